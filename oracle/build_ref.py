@@ -1,0 +1,220 @@
+#!/usr/bin/env python3
+"""Builds the REAL reference (refresh-bio/fqsqueezer 1.1) into oracle/_ref/ -- test infrastructure only.
+
+Nothing from /root/reference is copied into the repository: sources are compiled where they lie
+(or from a scratch copy under /tmp when a tap has to be patched in), and only binaries land in
+oracle/_ref/ (git-ignored, but shipped to the GPU box by gpurun like our own .so files).
+
+Products
+  oracle/_ref/fqs-1.1          unmodified reference compressor (CPU baseline `kind: "reference"`,
+                               .fqs byte-identity and decode checks)
+  oracle/_ref/fqs-1.1-tap      same sources + a build-time tap: after the count-vector resolution of
+                               every coded base (dna.cpp:736) it appends one 28-byte record to $FQS_TAP,
+                               one marker per read and one per sync; at exit it dumps the k-mer tables to
+                               $FQS_TAP_DUMP.  Its .fqs output must equal the untapped one (checked by
+                               oracle/make_golden.py).
+  oracle/_ref/libfqs_ref.so    harness TU (oracle/ref_harness.cpp) over the reference's own
+                               kmer.h / ht_kmer.h / bit_vec.h / utils.h for unit-level pinning.
+
+The reference needs `-include cstdint` (defs.h:15 uses uint32_t without it).
+This script is a no-op (exit 0) where /root/reference does not exist (the GPU box).
+"""
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("FQS_REFERENCE", "/root/reference")
+SRC = os.path.join(REF, "fqs")
+OUT = os.path.join(HERE, "_ref")
+CXXFLAGS = ["-O3", "-m64", "-std=c++14", "-pthread", "-mavx", "-include", "cstdint", "-w"]
+
+
+def run(cmd, **kw):
+    subprocess.run(cmd, check=True, **kw)
+
+
+def compile_dir(src_dir, build_dir, exe):
+    os.makedirs(build_dir, exist_ok=True)
+    cpps = sorted(f for f in os.listdir(src_dir) if f.endswith(".cpp"))
+
+    def one(f):
+        o = os.path.join(build_dir, f[:-4] + ".o")
+        run(["g++", *CXXFLAGS, "-I", src_dir, "-c", os.path.join(src_dir, f), "-o", o])
+        return o
+
+    with ThreadPoolExecutor(8) as ex:
+        objs = list(ex.map(one, cpps))
+    run(["g++", "-O3", "-pthread", "-o", exe, *objs, "-lm"])
+
+
+def patch(path, anchor, insertion, before=False, count=1):
+    s = open(path, encoding='latin-1').read()
+    assert s.count(anchor) >= 1, f"anchor not found in {path}: {anchor!r}"
+    if before:
+        s = s.replace(anchor, insertion + anchor, count)
+    else:
+        s = s.replace(anchor, anchor + insertion, count)
+    open(path, 'w', encoding='latin-1').write(s)
+
+
+TAP_H = r'''
+#pragma once
+// build-time tap (oracle/build_ref.py) -- not part of the reference
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+struct fqs_tap_rec { uint32_t pos; uint32_t c[4]; uint32_t cor_pos; uint8_t level; uint8_t rough; uint16_t pad; };
+inline FILE *fqs_tap_file() {
+	static FILE *f = nullptr; static bool init = false;
+	if (!init) { init = true; const char *p = getenv("FQS_TAP"); if (p) f = fopen(p, "wb"); }
+	return f;
+}
+inline void fqs_tap_emit(uint32_t pos, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t cor_pos, uint8_t level, uint8_t rough) {
+	FILE *f = fqs_tap_file(); if (!f) return;
+	fqs_tap_rec r{pos, {c0, c1, c2, c3}, cor_pos, level, rough, 0};
+	fwrite(&r, sizeof(r), 1, f);
+}
+inline void fqs_tap_flush() { FILE *f = fqs_tap_file(); if (f) fflush(f); }
+'''
+
+HT_FOREACH = r'''
+	// build-time tap: visit every stored (k-mer, count)
+	template<typename F> void tap_for_each(F f) const
+	{
+		for (uint64_t i = 0; i < tab_size; ++i)
+			for (uint64_t j = 0; j < ht_desc[i].size; ++j)
+				if (ht_desc[i].ht[j] != EMPTY)
+					f(join_kmer((uint32_t) i, ht_desc[i].ht[j] >> (8 * sizeof(item_t) - 2 * (kmer_len - prefix_len))), get_count(ht_desc[i].ht[j]));
+	}
+'''
+
+PAIR_FOREACH = r'''
+	template<typename F> void tap_for_each(F f) const
+	{
+		for (uint64_t i = 0; i < no_parts; ++i)
+			for (uint64_t j = 0; j < ht_desc[i].size; ++j)
+				if (ht_desc[i].ht[j] != EMPTY)
+					f(ht_desc[i].ht[j].first, ht_desc[i].ht[j].second);
+	}
+'''
+
+SIV_FOREACH = r'''
+	template<typename F> void tap_for_each(F f) const
+	{
+		for (uint64_t w = 0; w < data_size; ++w)
+			if (data[w])
+				for (uint64_t r = 0; r < divider; ++r)
+				{
+					uint64_t v = (data[w] >> (FIELD_SIZE * r)) & mask;
+					if (v) f(w * divider + r, v);
+				}
+	}
+'''
+
+APP_DUMP = r'''
+	// build-time tap: dump the k-mer tables (sorted by the test harness, not here)
+	if (const char *dump_path = getenv("FQS_TAP_DUMP"))
+	{
+		FILE *df = fopen(dump_path, "wb");
+		auto put = [&](uint64_t tag, uint64_t a, uint64_t b) { uint64_t r[3] = {tag, a, b}; fwrite(r, 8, 3, df); };
+		siv_pmer->tap_for_each([&](uint64_t idx, uint64_t v) { put(0, idx, v); });
+		ht_smer->tap_for_each([&](uint64_t k, uint32_t c) { put(1, k, c); });
+		ht_bmer->tap_for_each([&](uint64_t k, uint32_t c) { put(2, k, c); });
+		ht_pe_mers->tap_for_each([&](uint64_t k, uint64_t vc) { put(3, k, vc); });
+		put(4, siv_pmer->get_no_pmers(), siv_pmer->get_no_updates());
+		fclose(df);
+	}
+	fqs_tap_flush();
+'''
+
+
+def patch_headers(d):
+    """Adds read-only visitors to the three table classes (scratch copy only)."""
+    patch(os.path.join(d, "ht_kmer.h"),
+          "public:\n\t// ************************************************************************************\n\tCHT_kmer(uint64_t _kmer_len",
+          HT_FOREACH + "\n", before=True)
+    patch(os.path.join(d, "ht_kmer.h"), "public:\n\tCHT_pair_kmers(uint32_t _kmer_size, uint64_t _no_parts);", PAIR_FOREACH)
+    patch(os.path.join(d, "bit_vec.h"), "public:\n\tTSmallIntVector(const uint32_t _key_size)", SIV_FOREACH + "\n", before=True)
+    # the visitor sits in the private section of CHT_kmer / TSmallIntVector -> re-open as public
+    s = open(os.path.join(d, "ht_kmer.h"), encoding="latin-1").read()
+    s = s.replace(HT_FOREACH, "public:" + HT_FOREACH + "private:\n", 1)
+    open(os.path.join(d, "ht_kmer.h"), "w", encoding="latin-1").write(s)
+    s = open(os.path.join(d, "bit_vec.h"), encoding="latin-1").read()
+    s = s.replace(SIV_FOREACH, "public:" + SIV_FOREACH + "private:\n", 1)
+    open(os.path.join(d, "bit_vec.h"), "w", encoding="latin-1").write(s)
+
+
+def build_tap(scratch):
+    d = os.path.join(scratch, "tap_src")
+    if os.path.exists(d):
+        shutil.rmtree(d)
+    os.makedirs(d)
+    for f in os.listdir(SRC):
+        if f.endswith((".h", ".cpp")):
+            shutil.copy(os.path.join(SRC, f), d)
+    open(os.path.join(d, "fqs_tap.h"), "w").write(TAP_H)
+    patch_headers(d)
+    dna = os.path.join(d, "dna.cpp")
+    patch(dna, '#include "dna.h"\n', '#include "fqs_tap.h"\n')
+    # per coded base: after find_counts + bmer_unc rewrite + rough resolution (dna.cpp:736)
+    patch(dna, "\t\tif (counts_level != counts_level_t::none && N_run_len < 2)\n\t\t{\n\t\t\tint cor_dist",
+          "\t\tfqs_tap_emit(i, counts[0], counts[1], counts[2], counts[3], cor_pos, (uint8_t) counts_level, (uint8_t) rough_counts);\n",
+          before=True)
+    # per read markers (dna.cpp:1517, 1559, 1716): pos = 0xFFFFFFFF, c0 = size, c1 = kind
+    patch(dna, "bool CDNACompressor::CompressDirect(uint8_t *p, uint32_t size, uint8_t *q, bool first_read_of_pair)\n{\n",
+          "\tfqs_tap_emit(0xFFFFFFFFu, size, 0, first_read_of_pair, 0, 0, 0, 0);\n")
+    patch(dna, "bool CDNACompressor::CompressDirectWithMinim(uint8_t *p, uint32_t size, uint32_t minim_pos)\n{\n",
+          "\tfqs_tap_emit(0xFFFFFFFFu, size, 1, minim_pos, 0, 0, 0, 0);\n")
+    patch(dna, "bool CDNACompressor::CompressSorted(uint8_t *p, uint32_t size, bool first_read_of_pair)\n{\n",
+          "\tfqs_tap_emit(0xFFFFFFFFu, size, 2, first_read_of_pair, 0, 0, 0, 0);\n")
+    # duplicate flag: emitted right where the reference codes it
+    patch(dna, "\t\tif (same_read)\n\t\t\treturn true;", "\t\tif (same_read) fqs_tap_emit(0xFFFFFFFDu, 0, 0, 0, 0, 0, 0, 0);\n", before=True, count=2)
+    # per sync marker (dna.cpp:2393)
+    patch(dna, "void CDNACompressor::InsertKmersToHT()\n{\n", "\tfqs_tap_emit(0xFFFFFFFEu, 0, 0, 0, 0, 0, 0, 0);\n")
+    app = os.path.join(d, "application.cpp")
+    patch(app, '#include "application.h"\n', '#include "fqs_tap.h"\n')
+    # dump the tables when the SE / PE compress loops are done (application.cpp:762, 1310)
+    s = open(app, encoding="latin-1").read()
+    anchor = "\tv_thr_compress.clear();\n"
+    assert s.count(anchor) == 2, s.count(anchor)
+    s = s.replace(anchor, anchor + APP_DUMP)
+    open(app, "w", encoding="latin-1").write(s)
+    compile_dir(d, os.path.join(scratch, "tap_obj"), os.path.join(OUT, "fqs-1.1-tap"))
+
+
+def build_harness(scratch):
+    d = os.path.join(scratch, "hdr_src")
+    if os.path.exists(d):
+        shutil.rmtree(d)
+    os.makedirs(d)
+    for f in ("defs.h", "kmer.h", "ht_kmer.h", "ht_kmer.cpp", "bit_vec.h", "utils.h", "utils.cpp"):
+        shutil.copy(os.path.join(SRC, f), d)
+    patch_headers(d)
+    run(["g++", *CXXFLAGS, "-fPIC", "-shared", "-I", d,
+         os.path.join(HERE, "ref_harness.cpp"), os.path.join(d, "ht_kmer.cpp"), os.path.join(d, "utils.cpp"),
+         "-o", os.path.join(OUT, "libfqs_ref.so")])
+
+
+def main():
+    if not os.path.isdir(SRC):
+        print(f"[build_ref] {SRC} not present -- keeping prebuilt oracle/_ref (if any)")
+        return 0
+    os.makedirs(OUT, exist_ok=True)
+    scratch = os.environ.get("FQS_REF_SCRATCH", "/tmp/fqs_ref_build")
+    os.makedirs(scratch, exist_ok=True)
+    what = sys.argv[1:] or ["plain", "tap", "harness"]
+    if "plain" in what:
+        compile_dir(SRC, os.path.join(scratch, "plain_obj"), os.path.join(OUT, "fqs-1.1"))
+    if "tap" in what:
+        build_tap(scratch)
+    if "harness" in what:
+        build_harness(scratch)
+    print("[build_ref] ok:", sorted(os.listdir(OUT)))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,75 @@
+#!/usr/bin/env python3
+"""Generates tests/golden/*.npz from the REAL reference (tapped fqs-1.1 built by oracle/build_ref.py).
+
+Run in the build container (needs /root/reference for build_ref.py; afterwards only oracle/_ref binaries).
+Each fixture holds: the FASTQ bytes, the reference options, the per-base tap records, the sync positions and the
+final table dumps.  Also asserts that the tapped binary's .fqs equals the untapped one and that it decodes.
+"""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path[:] = [x for x in sys.path if os.path.abspath(x or '.') != HERE]
+sys.path.insert(0, ROOT)
+from fqsqueezer_b200 import synth  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def run_ref(fastq_path, gs, extra, tmp):
+    plain = os.path.join(tmp, "plain.fqs")
+    tapd = os.path.join(tmp, "tap.fqs")
+    tap = os.path.join(tmp, "tap.bin")
+    dump = os.path.join(tmp, "dump.bin")
+    base = ["e", "-s", "-qm", "o", "-im", "o", "-t", "1", "-gs", str(gs), "-v", "0", *extra]
+    subprocess.run([O.REF_BIN, *base, "-out", plain, fastq_path], check=True, cwd=tmp, stdout=subprocess.DEVNULL)
+    env = dict(os.environ, FQS_TAP=tap, FQS_TAP_DUMP=dump)
+    subprocess.run([O.REF_TAP_BIN, *base, "-out", tapd, fastq_path], check=True, cwd=tmp, env=env, stdout=subprocess.DEVNULL)
+    assert open(plain, "rb").read() == open(tapd, "rb").read(), "tap changed the .fqs bytes"
+    dec = os.path.join(tmp, "dec.fastq")
+    subprocess.run([O.REF_BIN, "d", "-out", dec, plain], check=True, cwd=tmp, stdout=subprocess.DEVNULL)
+    recs = np.fromfile(tap, dtype=O.REC_DTYPE)
+    d = np.fromfile(dump, dtype="<u8").reshape(-1, 3)
+    return recs, d, open(plain, "rb").read(), open(dec, "rb").read()
+
+
+def make_case(name, G, n_reads, L, gs, seed, n_frac=0.0, dup_frac=0.0, extra=("-om", "o")):
+    genome = synth.make_genome(G, seed)
+    codes, err = synth.make_reads(genome, n_reads, L=L, seed=seed, n_frac=n_frac, dup_frac=dup_frac)
+    with tempfile.TemporaryDirectory() as tmp:
+        fq = os.path.join(tmp, "in.fastq")
+        synth.write_fastq(fq, codes, err, seed=seed)
+        recs, d, fqs, dec = run_ref(fq, gs, list(extra), tmp)
+        fastq = np.fromfile(fq, dtype=np.uint8)
+        if tuple(extra) == ("-om", "o"):
+            assert dec == fastq.tobytes(), "reference round trip failed"
+    dumps = {}
+    for tag, nm in ((0, "siv"), (1, "smer"), (2, "bmer"), (3, "pair")):
+        x = d[d[:, 0] == tag]
+        o = np.lexsort((x[:, 2], x[:, 1]))
+        dumps[nm + "_keys"] = x[o, 1]
+        dumps[nm + "_vals"] = x[o, 2]
+    stat = d[d[:, 0] == 4][0]
+    out = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(out, fastq=fastq, gs=np.int64(gs), extra=np.array(list(extra)), recs=recs,
+                        siv_no_filled=stat[1], siv_no_updates=stat[2], fqs_size=np.int64(len(fqs)), **dumps)
+    print(name, "reads", n_reads, "records", len(recs), "file", os.path.getsize(out))
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    # SE original order, tiny k (gs 1: prefix 9, p14/s17/b19), high coverage so that repairs, rough searches,
+    # probabilistic counters (> 7) and the avg_filling_factor >= 7 gate all fire; Ns and duplicate reads included.
+    make_case("se_orig_gs1", G=6000, n_reads=1500, L=80, gs=1, seed=7, n_frac=0.002, dup_frac=0.01)
+    # same options as BASELINE config 2 (-gs 100: prefix 12, p17/s20/b24), small input
+    make_case("se_orig_gs100", G=20000, n_reads=1200, L=100, gs=100, seed=43)
+
+
+if __name__ == "__main__":
+    main()
