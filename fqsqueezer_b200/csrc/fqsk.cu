@@ -1,0 +1,905 @@
+// fqsk.cu -- host orchestration + C-ABI (include/fqsk.h) of the B200 k-mer statistics engine.
+//
+// The reference (refresh-bio/fqsqueezer 1.1) runs its k-mer engine sequentially, read after read, with three kinds of
+// order-dependent state inside a sync segment: the thread-local delta tables, the mt19937 streams behind the approximate
+// counters, and the running A/C/G/T totals.  Here a segment is replayed for all reads in parallel against
+//   (a) the frozen global tables in HBM,
+//   (b) a delta built from the PREVIOUS iteration's pushes (sorted by k-mer, then push index), and
+//   (c) per-read draw offsets obtained by an exclusive scan of the PREVIOUS iteration's per-read draw counts,
+// and iterated until pushes and draw counts reproduce themselves: at that fixed point every read has seen exactly the state
+// the sequential reference would have shown it, so records, pushes and PRNG positions are bit-exact.
+// There is no CPU fallback anywhere in this file.
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "fqsk_kernels.cuh"
+
+using namespace fqsk;
+
+static thread_local std::string g_create_error;
+
+namespace {
+
+struct DevBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+	cudaError_t ensure(size_t bytes) {
+		if (bytes <= cap) return cudaSuccess;
+		if (p) cudaFree(p);
+		p = nullptr; cap = 0;
+		size_t want = bytes + bytes / 4 + 256;
+		cudaError_t e = cudaMalloc(&p, want);
+		if (e == cudaSuccess) cap = want;
+		return e;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+	template <typename T> T *as() const { return (T *) p; }
+};
+
+struct Stream {            // one mt19937 stream (utils.h:257, seeded 5481 at utils.h:298), tempered outputs kept in HBM
+	uint32_t *buf = nullptr;
+	uint32_t *state = nullptr;
+	uint64_t cap = 0, base = 0, generated = 0, consumed = 0;
+};
+
+struct Table {
+	HtDev d{};
+	MixInv inv{};
+	CIncP ci{};
+};
+
+enum { ST_B = 0, ST_S = 1, ST_LB = 2, ST_LS = 3 };
+
+}  // namespace
+
+struct fqsk_handle {
+	fqsk_params P{};
+	cudaStream_t st = nullptr;
+	std::string err;
+	Table tb, ts;
+	SivDev siv{};
+	Stream rng[4];
+	int *d_flags = nullptr;              // 8 ints
+	unsigned long long *d_counters = nullptr;  // [0,1] b items main/stash, [2,3] s items, [4] siv new, [5] dump count
+	fqsk_stats S{};
+	unsigned long long sl_base[4] = {0, 0, 0, 0};   // s_letters (dna.h:92, dna.cpp:2047-2057)
+	uint64_t hidden_p = 0;                           // no_pmer_hidden_updates (dna.cpp:850, 2417)
+	// previous read / previous prefix p-mer carried across segments
+	DevBuf prev_read; uint32_t prev_len = 0;
+	unsigned long long pprev_dir = 0; uint32_t pprev_valid = 0;
+	// segment buffers
+	DevBuf dna, off, len, dup, n_coded, letters, rec_off, sl_prefix, recs, push_b, push_s, push_p, cnt_b, cnt_s, cnt_p, hidden,
+	       draw_cnt, draw_cnt_prev, draw_scan, off_b[2], off_s[2], off_p, row_b[2], row_s[2], row_p, dk_b, di_b, dk_s, di_s, iota, cub_tmp,
+	       slot, val, slot_sorted, val_sorted, flag8, draw_off, final_cnt, dump_k, dump_v, q0, q1, q2, q3, q4, sflag, sdif, hid_scan;
+	uint32_t iota_n = 0;
+	// pending rows (device), valid after fqsk_segment until fqsk_sync
+	bool pending = false;
+	int cur = 0;                          // which of row_b/row_s/off_b/off_s holds the converged iteration
+	uint32_t pend_b = 0, pend_s = 0, pend_p = 0;
+	uint64_t n_recs = 0;
+	uint32_t seg_reads = 0;
+	// pinned staging
+	uint8_t *h_stage = nullptr; size_t h_stage_cap = 0;
+	void *h_small = nullptr;              // pinned scratch for small D2H reads
+	// profiling
+	bool prof = false;
+	double ph_ms[FQSK_PH_COUNT] = {0};
+	struct Ev { cudaEvent_t a, b; int ph; };
+	std::vector<Ev> evs;
+	std::vector<cudaEvent_t> ev_pool;
+};
+
+namespace {
+
+int fail(fqsk_handle *h, int code, const char *fmt, ...) {
+	char b[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(b, sizeof b, fmt, ap);
+	va_end(ap);
+	if (h) h->err = b; else g_create_error = b;
+	return code;
+}
+#define CK(call)                                                                                            \
+	do {                                                                                                    \
+		cudaError_t e_ = (call);                                                                            \
+		if (e_ != cudaSuccess) return fail(h, e_ == cudaErrorMemoryAllocation ? FQSK_E_NOMEM : FQSK_E_CUDA, \
+			"%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));                             \
+	} while (0)
+#define CKR(expr) do { int r_ = (expr); if (r_ != FQSK_OK) return r_; } while (0)
+#define LAUNCHED(h) (++(h)->S.kernel_launches)
+
+inline uint32_t nblk(uint64_t n, uint32_t t) { return (uint32_t) ((n + t - 1) / t); }
+
+struct Phase {   // optional CUDA-event bracket on the engine's stream
+	fqsk_handle *h; int ph; cudaEvent_t a = nullptr;
+	Phase(fqsk_handle *h_, int ph_) : h(h_), ph(ph_) {
+		if (!h->prof) return;
+		a = take(); cudaEventRecord(a, h->st);
+	}
+	~Phase() {
+		if (!h->prof) return;
+		cudaEvent_t b = take(); cudaEventRecord(b, h->st);
+		h->evs.push_back({a, b, ph});
+	}
+	cudaEvent_t take() {
+		if (!h->ev_pool.empty()) { cudaEvent_t e = h->ev_pool.back(); h->ev_pool.pop_back(); return e; }
+		cudaEvent_t e; cudaEventCreate(&e); return e;
+	}
+};
+void resolve_phases(fqsk_handle *h) {   // call after a stream synchronize
+	for (auto &e : h->evs) {
+		float ms = 0;
+		if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) h->ph_ms[e.ph] += ms;
+		h->ev_pool.push_back(e.a); h->ev_pool.push_back(e.b);
+	}
+	h->evs.clear();
+}
+
+uint64_t mod_inverse(uint64_t x) { uint64_t inv = x; for (int i = 0; i < 6; ++i) inv *= 2 - x * inv; return inv; }
+
+int table_alloc(fqsk_handle *h, Table &t, uint32_t k, uint32_t cbits, uint32_t B, unsigned long long *counters) {
+	HtDev &d = t.d;
+	d.k = k; d.cbits = cbits; d.W = 2 * k - 8; d.top = (1u << cbits) - 1;
+	uint32_t bmin = d.W + cbits > 24 ? d.W + cbits - 24 : 1;
+	if (B < bmin) B = bmin;
+	if (B >= d.W) B = d.W - 1;
+	if (B > 28) return fail(h, FQSK_E_INVAL, "table with k=%u needs 2^%u buckets; this build addresses slots with 32 bits (max 2^28 buckets)", k, B);
+	d.B = B; d.rem_bits = d.W - B;
+	if (d.rem_bits + 8 + cbits > 32) return fail(h, FQSK_E_INVAL, "k=%u, %u counter bits do not fit a 32-bit item with 2^%u buckets", k, cbits, B);
+	d.maskW = d.W >= 64 ? ~0ull : ((1ull << d.W) - 1);
+	d.mix_sh = (d.W + 1) / 2;
+	d.stash_log2 = B + 3 >= 5 + 12 ? B + 3 - 5 : 12;
+	d.n_items = counters;
+	t.inv.inv1 = mod_inverse(MIX_C1); t.inv.inv2 = mod_inverse(MIX_C2);
+	size_t mb = (size_t) 32 << B, sb = (size_t) 8 << d.stash_log2;
+	CK(cudaMalloc(&d.main, mb));
+	CK(cudaMalloc(&d.stash, sb));
+	CK(cudaMemsetAsync(d.main, 0, mb, h->st));
+	CK(cudaMemsetAsync(d.stash, 0, sb, h->st));
+	CK(cudaMemsetAsync(counters, 0, 16, h->st));
+	return FQSK_OK;
+}
+
+int stream_init(fqsk_handle *h, Stream &s) {
+	uint32_t st[624];
+	st[0] = 5481u;
+	for (int i = 1; i < 624; ++i) st[i] = 1812433253u * (st[i - 1] ^ (st[i - 1] >> 30)) + (uint32_t) i;
+	CK(cudaMalloc(&s.state, 624 * 4));
+	CK(cudaMemcpy(s.state, st, 624 * 4, cudaMemcpyHostToDevice));
+	s.cap = 0; s.base = s.generated = s.consumed = 0; s.buf = nullptr;
+	return FQSK_OK;
+}
+// make outputs [consumed, consumed + need) available
+int stream_ensure(fqsk_handle *h, Stream &s, uint64_t need) {
+	uint64_t want_abs = s.consumed + need;
+	if (want_abs <= s.generated) return FQSK_OK;
+	Phase ph(h, FQSK_PH_MT);
+	uint64_t blocks = (want_abs - s.generated + 623) / 624;
+	if (blocks < 2048) blocks = 2048;
+	uint64_t new_gen = s.generated + blocks * 624;
+	if (new_gen - s.base > s.cap) {
+		uint64_t live = s.generated - s.consumed;
+		uint64_t new_cap = std::max<uint64_t>(2 * (new_gen - s.consumed), 1u << 22);
+		uint32_t *nb = nullptr;
+		CK(cudaMalloc(&nb, new_cap * 4));
+		if (live) CK(cudaMemcpyAsync(nb, s.buf + (s.consumed - s.base), live * 4, cudaMemcpyDeviceToDevice, h->st));
+		CK(cudaStreamSynchronize(h->st));
+		if (s.buf) cudaFree(s.buf);
+		s.buf = nb; s.cap = new_cap; s.base = s.consumed;
+	}
+	while (blocks) {
+		uint32_t nb = (uint32_t) std::min<uint64_t>(blocks, 1u << 20);
+		k_mt_extend<<<1, 256, 0, h->st>>>(s.state, s.buf + (s.generated - s.base), nb);
+		LAUNCHED(h);
+		s.generated += (uint64_t) nb * 624; blocks -= nb;
+	}
+	CK(cudaGetLastError());
+	return FQSK_OK;
+}
+inline const uint32_t *stream_ptr(const Stream &s) { return s.buf ? s.buf + (s.consumed - s.base) : nullptr; }
+inline uint64_t stream_avail(const Stream &s) { return s.generated - s.consumed; }
+
+int ensure_iota(fqsk_handle *h, uint32_t n) {
+	if (n <= h->iota_n) return FQSK_OK;
+	uint32_t want = n + n / 2 + 1024;
+	CK(h->iota.ensure((size_t) want * 4));
+	k_iota<<<nblk(want, 256), 256, 0, h->st>>>(h->iota.as<uint32_t>(), want);
+	LAUNCHED(h);
+	h->iota_n = want;
+	return FQSK_OK;
+}
+
+template <typename InT, typename OutT>
+int scan_excl(fqsk_handle *h, const InT *in, OutT *out, uint32_t n, OutT init) {
+	size_t bytes = 0;
+	CK(cub::DeviceScan::ExclusiveScan(nullptr, bytes, in, out, cub::Sum(), init, (int) n, h->st));
+	CK(h->cub_tmp.ensure(bytes));
+	CK(cub::DeviceScan::ExclusiveScan(h->cub_tmp.p, bytes, in, out, cub::Sum(), init, (int) n, h->st));
+	return FQSK_OK;
+}
+
+int sort_pairs_u64_u32(fqsk_handle *h, const unsigned long long *kin, unsigned long long *kout, const uint32_t *vin, uint32_t *vout, uint32_t n, int b0, int b1) {
+	size_t bytes = 0;
+	CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int) n, b0, b1, h->st));
+	CK(h->cub_tmp.ensure(bytes));
+	CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, kin, kout, vin, vout, (int) n, b0, b1, h->st));
+	return FQSK_OK;
+}
+int sort_pairs_u32_u32(fqsk_handle *h, const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, uint32_t n, int b1) {
+	size_t bytes = 0;
+	CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int) n, 0, b1, h->st));
+	CK(h->cub_tmp.ensure(bytes));
+	CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, kin, kout, vin, vout, (int) n, 0, b1, h->st));
+	return FQSK_OK;
+}
+
+int read_flags(fqsk_handle *h, int *out, int n) {
+	CK(cudaMemcpyAsync(h->h_small, h->d_flags, n * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+	CK(cudaStreamSynchronize(h->st));
+	memcpy(out, h->h_small, n * sizeof(int));
+	resolve_phases(h);
+	return FQSK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dump / growth
+// ---------------------------------------------------------------------------------------------------------------
+int table_dump_device(fqsk_handle *h, Table &t, uint64_t *n_out) {   // into h->dump_k / dump_v (unsorted)
+	uint64_t total = (8ull << t.d.B) + (1ull << t.d.stash_log2);
+	unsigned long long items[2];
+	CK(cudaMemcpyAsync(items, t.d.n_items, 16, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaStreamSynchronize(h->st));
+	uint64_t n = items[0] + items[1];
+	CK(h->dump_k.ensure((n + 1) * 8));
+	CK(h->dump_v.ensure((n + 1) * 8));
+	CK(cudaMemsetAsync(h->d_counters + 5, 0, 8, h->st));
+	k_dump_ht<<<nblk(total, 256), 256, 0, h->st>>>(t.d, t.inv, h->dump_k.as<unsigned long long>(), h->dump_v.as<unsigned long long>(), n, h->d_counters + 5);
+	LAUNCHED(h);
+	unsigned long long got = 0;
+	CK(cudaMemcpyAsync(&got, h->d_counters + 5, 8, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaStreamSynchronize(h->st));
+	if (got != n) return fail(h, FQSK_E_CUDA, "table dump found %llu items, counters say %llu", got, (unsigned long long) n);
+	*n_out = n;
+	return FQSK_OK;
+}
+
+int table_grow_if_needed(fqsk_handle *h, Table &t) {
+	unsigned long long items[2];
+	CK(cudaMemcpyAsync(items, t.d.n_items, 16, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaStreamSynchronize(h->st));
+	while (items[0] > (4ull << t.d.B) || items[1] > (1ull << t.d.stash_log2) / 2) {
+		uint64_t n = 0;
+		CKR(table_dump_device(h, t, &n));
+		unsigned long long *counters = t.d.n_items;
+		CK(cudaFree(t.d.main)); CK(cudaFree(t.d.stash));
+		uint32_t k = t.d.k, cb = t.d.cbits, B = t.d.B + 1;
+		CKR(table_alloc(h, t, k, cb, B, counters));
+		if (n) { k_reinsert<<<nblk(n, 256), 256, 0, h->st>>>(t.d, h->dump_k.as<unsigned long long>(), h->dump_v.as<unsigned long long>(), n); LAUNCHED(h); }
+		CK(cudaMemcpyAsync(items, t.d.n_items, 16, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaStreamSynchronize(h->st));
+		if (items[0] + items[1] != n) return fail(h, FQSK_E_CUDA, "table growth lost items (%llu -> %llu)", (unsigned long long) n, items[0] + items[1]);
+	}
+	return FQSK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// ordered insert of a row of k-mers into one table (CHT_kmer::insert in push order with one PRNG stream)
+// ---------------------------------------------------------------------------------------------------------------
+int apply_inserts(fqsk_handle *h, Table &t, Stream &rng, const unsigned long long *d_kmers, uint32_t n) {
+	if (!n) return FQSK_OK;
+	if (n >= 0x80000000u) return fail(h, FQSK_E_INVAL, "more than 2^31 k-mers in one sync row");
+	CK(h->slot.ensure((size_t) n * 4)); CK(h->val.ensure((size_t) n * 4));
+	CK(h->slot_sorted.ensure((size_t) n * 4)); CK(h->val_sorted.ensure((size_t) n * 4));
+	CK(h->flag8.ensure((size_t) n + 4)); CK(h->draw_off.ensure(((size_t) n + 1) * 4)); CK(h->final_cnt.ensure((size_t) n * 4));
+	{
+		Phase ph(h, FQSK_PH_SYNC_LOCATE);
+		k_locate<<<nblk(n, 256), 256, 0, h->st>>>(t.d, d_kmers, n, h->slot.as<uint32_t>(), h->val.as<uint32_t>());
+		LAUNCHED(h);
+	}
+	{
+		Phase ph(h, FQSK_PH_SYNC_SORT);
+		CKR(sort_pairs_u32_u32(h, h->slot.as<uint32_t>(), h->slot_sorted.as<uint32_t>(), h->val.as<uint32_t>(), h->val_sorted.as<uint32_t>(), n, (int) t.d.B + 4));
+	}
+	Phase ph(h, FQSK_PH_SYNC_APPLY);
+	CK(cudaMemsetAsync(h->flag8.p, 0, (size_t) n + 4, h->st));
+	CK(cudaMemsetAsync(h->draw_off.p, 0, ((size_t) n + 1) * 4, h->st));
+	uint32_t total_draws = 0;
+	for (int it = 0;; ++it) {
+		if (it > 64) return fail(h, FQSK_E_NO_CONVERGE, "sync insert: draw flags did not settle");
+		CK(cudaMemsetAsync(h->d_flags, 0, 4 * sizeof(int), h->st));
+		k_apply<<<nblk(n, 256), 256, 0, h->st>>>(t.d, t.ci, h->slot_sorted.as<uint32_t>(), h->val_sorted.as<uint32_t>(), n, h->flag8.as<uint8_t>(),
+		                                          h->draw_off.as<uint32_t>(), stream_ptr(rng), stream_avail(rng), h->final_cnt.as<uint32_t>(), h->d_flags);
+		LAUNCHED(h);
+		int fl[4];
+		CKR(read_flags(h, fl, 4));
+		if (!fl[2] && !fl[0]) break;
+		// flags changed (or the draw window was short): rescan the draw indices in push order and make the window long enough
+		CKR((scan_excl<uint8_t, uint32_t>(h, h->flag8.as<uint8_t>(), h->draw_off.as<uint32_t>(), n + 1, 0u)));
+		CK(cudaMemcpyAsync(h->h_small, h->draw_off.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaStreamSynchronize(h->st));
+		total_draws = *(uint32_t *) h->h_small;
+		CKR(stream_ensure(h, rng, total_draws));
+	}
+	k_commit<<<nblk(n, 256), 256, 0, h->st>>>(t.d, h->slot_sorted.as<uint32_t>(), n, h->final_cnt.as<uint32_t>());
+	LAUNCHED(h);
+	rng.consumed += total_draws;
+	return FQSK_OK;
+}
+
+EngineDev make_engine_dev(fqsk_handle *h) {
+	EngineDev E{};
+	E.hb = h->tb.d; E.hs = h->ts.d; E.siv = h->siv; E.cib = h->tb.ci; E.cis = h->ts.ci;
+	E.p = h->P.pmer_len; E.s = h->P.smer_len; E.b = h->P.bmer_len; E.prefix_len = h->P.prefix_len;
+	E.sorted = (h->P.mode == FQSK_MODE_SE_SORTED || h->P.mode == FQSK_MODE_PE_SORTED);
+	double aff = h->S.siv_no_filled ? (double) h->S.siv_no_updates / (double) h->S.siv_no_filled : 0.0;   // bit_vec.h:204-210
+	E.gate_missing = aff >= 7.0;
+	for (int i = 0; i < 4; ++i) { E.draws[i] = stream_ptr(h->rng[i]); E.avail[i] = stream_avail(h->rng[i]); }
+	E.flags = h->d_flags;
+	return E;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// one sync segment, reads resident on the device
+// ---------------------------------------------------------------------------------------------------------------
+int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes, const unsigned long long *d_off, const uint32_t *d_len, uint32_t n) {
+	if (h->pending) return fail(h, FQSK_E_INVAL, "fqsk_segment called twice without fqsk_sync (the reference syncs after every segment, application.cpp:643-662)");
+	const uint32_t first = (h->P.mode == FQSK_MODE_SE_SORTED || h->P.mode == FQSK_MODE_PE_SORTED) ? h->P.pmer_len : h->P.prefix_len;
+	h->seg_reads = n; h->n_recs = 0; h->pend_b = h->pend_s = h->pend_p = 0;
+	++h->S.n_segments;
+	if (n == 0) { h->pending = true; return FQSK_OK; }
+	if (dna_bytes >= (1ull << 30)) return fail(h, FQSK_E_INVAL, "segment larger than 1 GiB of DNA");
+	const size_t n1 = (size_t) n + 1;
+	CK(h->dup.ensure(n)); CK(h->n_coded.ensure(n1 * 4)); CK(h->letters.ensure(n1 * 32)); CK(h->rec_off.ensure(n1 * 8)); CK(h->sl_prefix.ensure(n1 * 32));
+	CK(h->recs.ensure((dna_bytes + 1) * sizeof(fqsk_base_rec)));
+	CK(h->push_b.ensure((2 * dna_bytes + 2) * 8)); CK(h->push_s.ensure((dna_bytes + 1) * 8)); CK(h->push_p.ensure((2 * dna_bytes + 2 * n1) * 8));
+	CK(h->cnt_b.ensure(n1 * 4)); CK(h->cnt_s.ensure(n1 * 4)); CK(h->cnt_p.ensure(n1 * 4)); CK(h->hidden.ensure(n1 * 4));
+	CK(h->draw_cnt.ensure(n1 * 32)); CK(h->draw_cnt_prev.ensure(n1 * 32)); CK(h->draw_scan.ensure(n1 * 32));
+	for (int i = 0; i < 2; ++i) {
+		CK(h->off_b[i].ensure(n1 * 4)); CK(h->off_s[i].ensure(n1 * 4));
+		CK(h->row_b[i].ensure((2 * dna_bytes + 2) * 8)); CK(h->row_s[i].ensure((dna_bytes + 1) * 8));
+	}
+	CK(h->off_p.ensure(n1 * 4)); CK(h->row_p.ensure((2 * dna_bytes + 2 * n1) * 8));
+	CK(h->dk_b.ensure((2 * dna_bytes + 2) * 8)); CK(h->di_b.ensure((2 * dna_bytes + 2) * 4));
+	CK(h->dk_s.ensure((dna_bytes + 1) * 8)); CK(h->di_s.ensure((dna_bytes + 1) * 4));
+	CK(h->sflag.ensure(n1 * 4)); CK(h->sdif.ensure(n1 * 8)); CK(h->hid_scan.ensure(n1 * 4));
+
+	SegDev S{};
+	S.dna = d_dna; S.off = d_off; S.len = d_len; S.n_reads = n;
+	S.prev_read = h->prev_read.as<uint8_t>(); S.prev_len = h->prev_len;
+	S.pprev_dir = h->pprev_dir; S.pprev_valid = h->pprev_valid;
+	S.dup = h->dup.as<uint8_t>(); S.n_coded = h->n_coded.as<uint32_t>(); S.letters = h->letters.as<U64x4>();
+	S.rec_off = h->rec_off.as<unsigned long long>(); S.sl_prefix = h->sl_prefix.as<U64x4>();
+	for (int i = 0; i < 4; ++i) S.sl_base.v[i] = h->sl_base[i];
+	S.recs = h->recs.as<fqsk_base_rec>();
+	S.push_b = h->push_b.as<unsigned long long>(); S.push_s = h->push_s.as<unsigned long long>(); S.push_p = h->push_p.as<unsigned long long>();
+	S.cnt_b = h->cnt_b.as<uint32_t>(); S.cnt_s = h->cnt_s.as<uint32_t>(); S.cnt_p = h->cnt_p.as<uint32_t>(); S.hidden = h->hidden.as<uint32_t>();
+	S.draw_cnt = h->draw_cnt.as<U64x4>(); S.draw_guess = h->draw_scan.as<U64x4>();
+	S.sorted_flag = h->sflag.as<uint32_t>(); S.sorted_dif = h->sdif.as<unsigned long long>();
+
+	{
+		Phase ph(h, FQSK_PH_PREP);
+		CK(cudaMemsetAsync(h->n_coded.p, 0, n1 * 4, h->st));
+		CK(cudaMemsetAsync(h->letters.p, 0, n1 * 32, h->st));
+		k_prep<<<nblk(n, 128), 128, 0, h->st>>>(S, first);
+		LAUNCHED(h);
+		CKR((scan_excl<uint32_t, unsigned long long>(h, h->n_coded.as<uint32_t>(), h->rec_off.as<unsigned long long>(), n + 1, 0ull)));
+		U64x4 z{}; z.v[0] = z.v[1] = z.v[2] = z.v[3] = 0;
+		CKR((scan_excl<U64x4, U64x4>(h, h->letters.as<U64x4>(), h->sl_prefix.as<U64x4>(), n + 1, z)));
+		CK(cudaMemsetAsync(h->draw_scan.p, 0, n1 * 32, h->st));       // iteration 0 guesses: every read starts at the stream position
+		CK(cudaMemsetAsync(h->draw_cnt_prev.p, 0, n1 * 32, h->st));
+	}
+	// make sure some draws exist before the first replay (the overflow flag covers the rest)
+	for (int i = 0; i < 4; ++i) CKR(stream_ensure(h, h->rng[i], i == 0 ? std::max<uint64_t>(dna_bytes, 1u << 16) : i == 1 ? (1u << 16) : (1u << 12)));
+
+	const uint32_t max_it = h->P.max_iterations ? h->P.max_iterations : 16;
+	int cur = 0;
+	uint32_t tot_b_prev = 0, tot_s_prev = 0;
+	S.base_b = nullptr; S.base_s = nullptr;
+	S.delta_b = DeltaDev{nullptr, nullptr, 0, h->tb.ci.thr + 1};
+	S.delta_s = DeltaDev{nullptr, nullptr, 0, h->ts.ci.thr + 1};
+	uint32_t tot_b = 0, tot_s = 0, tot_p = 0;
+	U64x4 tot_draws{};
+	for (uint32_t it = 0;; ++it) {
+		if (it >= max_it) return fail(h, FQSK_E_NO_CONVERGE, "segment replay did not reach its fixed point in %u iterations", max_it);
+		EngineDev E = make_engine_dev(h);
+		CK(cudaMemsetAsync(h->d_flags, 0, 4 * sizeof(int), h->st));
+		{
+			Phase ph(h, FQSK_PH_REPLAY);
+			k_replay<<<nblk(n, 128), 128, 0, h->st>>>(E, S);
+			LAUNCHED(h);
+			++h->S.n_replays;
+		}
+		{
+			Phase ph(h, FQSK_PH_COMPACT);
+			// totals ride in slot n of the count arrays
+			CK(cudaMemsetAsync(h->cnt_b.as<uint32_t>() + n, 0, 4, h->st)); CK(cudaMemsetAsync(h->cnt_s.as<uint32_t>() + n, 0, 4, h->st));
+			CK(cudaMemsetAsync(h->cnt_p.as<uint32_t>() + n, 0, 4, h->st)); CK(cudaMemsetAsync(h->draw_cnt.as<U64x4>() + n, 0, 32, h->st));
+			CKR((scan_excl<uint32_t, uint32_t>(h, h->cnt_b.as<uint32_t>(), h->off_b[cur].as<uint32_t>(), n + 1, 0u)));
+			CKR((scan_excl<uint32_t, uint32_t>(h, h->cnt_s.as<uint32_t>(), h->off_s[cur].as<uint32_t>(), n + 1, 0u)));
+			CKR((scan_excl<uint32_t, uint32_t>(h, h->cnt_p.as<uint32_t>(), h->off_p.as<uint32_t>(), n + 1, 0u)));
+			k_compact<<<n, 64, 0, h->st>>>(S, h->off_b[cur].as<uint32_t>(), h->off_s[cur].as<uint32_t>(), h->off_p.as<uint32_t>(),
+			                              h->row_b[cur].as<unsigned long long>(), h->row_s[cur].as<unsigned long long>(), h->row_p.as<unsigned long long>());
+			LAUNCHED(h);
+			uint32_t *hs = (uint32_t *) h->h_small;
+			CK(cudaMemcpyAsync(hs + 0, h->off_b[cur].as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, h->st));
+			CK(cudaMemcpyAsync(hs + 1, h->off_s[cur].as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, h->st));
+			CK(cudaMemcpyAsync(hs + 2, h->off_p.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, h->st));
+			CK(cudaMemcpyAsync(hs + 4, h->d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+			CK(cudaStreamSynchronize(h->st));
+			tot_b = hs[0]; tot_s = hs[1]; tot_p = hs[2];
+			int fl[4]; memcpy(fl, hs + 4, sizeof fl);
+			resolve_phases(h);
+			if (fl[1]) return fail(h, FQSK_E_UNSUPPORTED, "segment needs the thread-local PRNG streams (a k-mer occurs more than %u times inside one sync segment and is looked up there); not implemented yet", h->tb.ci.thr + 1);
+			if (fl[0]) {   // draw window too short: extend all streams generously and redo this iteration
+				for (int i = 0; i < 4; ++i) CKR(stream_ensure(h, h->rng[i], 2 * stream_avail(h->rng[i]) + (1u << 16)));
+				--it;
+				continue;
+			}
+		}
+		// did this iteration reproduce the state it was run against?
+		bool changed = (tot_b != tot_b_prev) || (tot_s != tot_s_prev);
+		if (!changed) {
+			CK(cudaMemsetAsync(h->d_flags + 2, 0, sizeof(int), h->st));
+			if (tot_b) { k_compare_u64<<<nblk(tot_b, 256), 256, 0, h->st>>>(h->row_b[cur].as<unsigned long long>(), h->row_b[cur ^ 1].as<unsigned long long>(), tot_b, h->d_flags + 2); LAUNCHED(h); }
+			if (tot_s) { k_compare_u64<<<nblk(tot_s, 256), 256, 0, h->st>>>(h->row_s[cur].as<unsigned long long>(), h->row_s[cur ^ 1].as<unsigned long long>(), tot_s, h->d_flags + 2); LAUNCHED(h); }
+			if (it > 0) {
+				k_compare_u32<<<nblk(n, 256), 256, 0, h->st>>>(h->off_b[cur].as<uint32_t>(), h->off_b[cur ^ 1].as<uint32_t>(), n, h->d_flags + 2); LAUNCHED(h);
+				k_compare_u32<<<nblk(n, 256), 256, 0, h->st>>>(h->off_s[cur].as<uint32_t>(), h->off_s[cur ^ 1].as<uint32_t>(), n, h->d_flags + 2); LAUNCHED(h);
+			}
+			k_compare_u64<<<nblk((uint64_t) n * 4, 256), 256, 0, h->st>>>((const unsigned long long *) h->draw_cnt.p, (const unsigned long long *) h->draw_cnt_prev.p, (uint64_t) n * 4, h->d_flags + 2);
+			LAUNCHED(h);
+			int fl[4];
+			CKR(read_flags(h, fl, 4));
+			changed = fl[2] != 0;
+		}
+		if (!changed) { h->cur = cur; break; }
+		// next iteration runs against this one's pushes and draw counts
+		{
+			Phase ph(h, FQSK_PH_DELTA);
+			U64x4 z{}; z.v[0] = z.v[1] = z.v[2] = z.v[3] = 0;
+			CKR((scan_excl<U64x4, U64x4>(h, h->draw_cnt.as<U64x4>(), h->draw_scan.as<U64x4>(), n + 1, z)));
+			CK(cudaMemcpyAsync(h->draw_cnt_prev.p, h->draw_cnt.p, n1 * 32, cudaMemcpyDeviceToDevice, h->st));
+			CKR(ensure_iota(h, std::max(tot_b, tot_s)));
+			if (tot_b) CKR(sort_pairs_u64_u32(h, h->row_b[cur].as<unsigned long long>(), h->dk_b.as<unsigned long long>(), h->iota.as<uint32_t>(), h->di_b.as<uint32_t>(), tot_b, 64 - 2 * (int) h->P.bmer_len, 64));
+			if (tot_s) CKR(sort_pairs_u64_u32(h, h->row_s[cur].as<unsigned long long>(), h->dk_s.as<unsigned long long>(), h->iota.as<uint32_t>(), h->di_s.as<uint32_t>(), tot_s, 64 - 2 * (int) h->P.smer_len, 64));
+			S.delta_b = DeltaDev{h->dk_b.as<unsigned long long>(), h->di_b.as<uint32_t>(), tot_b, h->tb.ci.thr + 1};
+			S.delta_s = DeltaDev{h->dk_s.as<unsigned long long>(), h->di_s.as<uint32_t>(), tot_s, h->ts.ci.thr + 1};
+			S.base_b = h->off_b[cur].as<uint32_t>(); S.base_s = h->off_s[cur].as<uint32_t>();
+		}
+		tot_b_prev = tot_b; tot_s_prev = tot_s;
+		cur ^= 1;
+	}
+	// converged: totals
+	{
+		U64x4 z{}; z.v[0] = z.v[1] = z.v[2] = z.v[3] = 0;
+		CKR((scan_excl<U64x4, U64x4>(h, h->draw_cnt.as<U64x4>(), h->draw_scan.as<U64x4>(), n + 1, z)));
+		CK(cudaMemsetAsync(h->hidden.as<uint32_t>() + n, 0, 4, h->st));
+		CKR((scan_excl<uint32_t, uint32_t>(h, h->hidden.as<uint32_t>(), h->hid_scan.as<uint32_t>(), n + 1, 0u)));
+		uint8_t *hs = (uint8_t *) h->h_small;
+		CK(cudaMemcpyAsync(hs, h->draw_scan.as<U64x4>() + n, 32, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaMemcpyAsync(hs + 32, h->sl_prefix.as<U64x4>() + n, 32, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaMemcpyAsync(hs + 64, h->hid_scan.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaMemcpyAsync(hs + 72, h->rec_off.as<unsigned long long>() + n, 8, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaStreamSynchronize(h->st));
+		resolve_phases(h);
+		memcpy(&tot_draws, hs, 32);
+		U64x4 letters; memcpy(&letters, hs + 32, 32);
+		uint32_t hid; memcpy(&hid, hs + 64, 4);
+		unsigned long long nrec; memcpy(&nrec, hs + 72, 8);
+		for (int i = 0; i < 4; ++i) { h->rng[i].consumed += tot_draws.v[i]; h->S.draws[i] = h->rng[i].consumed; h->sl_base[i] += letters.v[i]; }
+		h->hidden_p += hid;
+		h->n_recs = nrec;
+	}
+	h->pend_b = tot_b; h->pend_s = tot_s; h->pend_p = tot_p;
+	h->pending = true;
+	h->S.n_reads += n; h->S.n_bases += dna_bytes;
+	return FQSK_OK;
+}
+
+}  // namespace
+
+// =================================================================================================================
+// C-ABI
+// =================================================================================================================
+extern "C" {
+
+const char *fqsk_last_error(fqsk_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
+	fqsk_handle *h = nullptr;
+	if (!p || !out) return fail(h, FQSK_E_INVAL, "null argument");
+	*out = nullptr;
+	if (p->abi_version != FQSK_ABI_VERSION) return fail(h, FQSK_E_INVAL, "ABI version %u, library is %u", p->abi_version, FQSK_ABI_VERSION);
+	if (p->n_workers != 1) return fail(h, FQSK_E_INVAL, "only n_workers == 1 (the bit-exact `-t 1` configuration) is supported");
+	if (!(p->pmer_len >= 5 && p->pmer_len < p->smer_len && p->smer_len < p->bmer_len && p->bmer_len <= 31)) return fail(h, FQSK_E_INVAL, "need 5 <= p < s < b <= 31");
+	if (p->pmer_len > 18) return fail(h, FQSK_E_INVAL, "pmer_len > 18 not supported");
+	if (p->mode != FQSK_MODE_SE_ORIGINAL && p->mode != FQSK_MODE_SE_SORTED) return fail(h, FQSK_E_UNSUPPORTED, "paired-end modes are not implemented yet");
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(h, FQSK_E_NO_DEVICE, "no CUDA device: this library has no CPU path");
+	if (p->device < 0 || p->device >= ndev) return fail(h, FQSK_E_INVAL, "device %d out of range (%d devices)", p->device, ndev);
+	{
+		cudaError_t e = cudaSetDevice(p->device);
+		if (e != cudaSuccess) return fail(h, FQSK_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+	}
+	h = new fqsk_handle();
+	h->P = *p;
+	h->prof = (p->flags & FQSK_F_PROFILE) != 0;
+	int rc = [&]() -> int {
+		CK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+		CK(cudaMalloc(&h->d_flags, 8 * sizeof(int)));
+		CK(cudaMalloc(&h->d_counters, 8 * 8));
+		CK(cudaMemset(h->d_counters, 0, 64));
+		CK(cudaMallocHost(&h->h_small, 256));
+		uint64_t expect = p->expected_kmers ? p->expected_kmers : (1ull << 22);
+		uint32_t Bauto = 1;
+		while ((4ull << Bauto) < expect && Bauto < 28) ++Bauto;    // <= 50 % of 8 << B slots
+		CKR(table_alloc(h, h->tb, p->bmer_len, p->bmer_counter_bits ? p->bmer_counter_bits : 6, p->bmer_log2_buckets ? p->bmer_log2_buckets : Bauto, h->d_counters + 0));
+		CKR(table_alloc(h, h->ts, p->smer_len, p->smer_counter_bits ? p->smer_counter_bits : 12, p->smer_log2_buckets ? p->smer_log2_buckets : Bauto, h->d_counters + 2));
+		h->tb.ci = CIncP{7, 2, h->tb.d.top};                                  // cinc_b.Reset(7, 2, 63)            dna.cpp:162
+		h->ts.ci = CIncP{h->ts.d.top / 2, 1, h->ts.d.top};                    // cinc_s.Reset(4095 / 2, 1, 4095)   dna.cpp:163
+		if (h->tb.ci.thr > h->tb.ci.top) h->tb.ci.thr = h->tb.ci.top;
+		h->siv.key_bits = 2 * p->pmer_len;                                    // application.cpp:88
+		size_t sb = ((size_t) 1 << h->siv.key_bits) / 4;
+		CK(cudaMalloc(&h->siv.w, sb));
+		CK(cudaMemsetAsync(h->siv.w, 0, sb, h->st));
+		for (int i = 0; i < 4; ++i) CKR(stream_init(h, h->rng[i]));
+		CK(h->prev_read.ensure(1 << 16));
+		CK(cudaStreamSynchronize(h->st));
+		return FQSK_OK;
+	}();
+	if (rc != FQSK_OK) { g_create_error = h->err; fqsk_destroy(h); return rc; }
+	*out = h;
+	return FQSK_OK;
+}
+
+void fqsk_destroy(fqsk_handle *h) {
+	if (!h) return;
+	cudaSetDevice(h->P.device);
+	if (h->st) cudaStreamSynchronize(h->st);
+	for (Table *t : {&h->tb, &h->ts}) { if (t->d.main) cudaFree(t->d.main); if (t->d.stash) cudaFree(t->d.stash); }
+	if (h->siv.w) cudaFree(h->siv.w);
+	for (auto &s : h->rng) { if (s.buf) cudaFree(s.buf); if (s.state) cudaFree(s.state); }
+	if (h->d_flags) cudaFree(h->d_flags);
+	if (h->d_counters) cudaFree(h->d_counters);
+	DevBuf *bufs[] = {&h->prev_read, &h->dna, &h->off, &h->len, &h->dup, &h->n_coded, &h->letters, &h->rec_off, &h->sl_prefix, &h->recs, &h->push_b, &h->push_s,
+	                  &h->push_p, &h->cnt_b, &h->cnt_s, &h->cnt_p, &h->hidden, &h->draw_cnt, &h->draw_cnt_prev, &h->draw_scan, &h->off_b[0], &h->off_b[1], &h->off_s[0],
+	                  &h->off_s[1], &h->off_p, &h->row_b[0], &h->row_b[1], &h->row_s[0], &h->row_s[1], &h->row_p, &h->dk_b, &h->di_b, &h->dk_s, &h->di_s, &h->iota,
+	                  &h->cub_tmp, &h->slot, &h->val, &h->slot_sorted, &h->val_sorted, &h->flag8, &h->draw_off, &h->final_cnt, &h->dump_k, &h->dump_v, &h->q0, &h->q1,
+	                  &h->q2, &h->q3, &h->q4, &h->sflag, &h->sdif, &h->hid_scan};
+	for (DevBuf *b : bufs) b->release();
+	if (h->h_stage) cudaFreeHost(h->h_stage);
+	if (h->h_small) cudaFreeHost(h->h_small);
+	for (auto &e : h->evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+	for (auto e : h->ev_pool) cudaEventDestroy(e);
+	if (h->st) cudaStreamDestroy(h->st);
+	delete h;
+}
+
+int fqsk_block_start(fqsk_handle *h) {
+	if (!h) return FQSK_E_INVAL;
+	h->prev_len = 0;   // read_prev.clear(), application.cpp:624
+	return FQSK_OK;
+}
+
+static int after_segment_state(fqsk_handle *h, const uint8_t *d_dna, const unsigned long long *d_off_last, uint64_t last_off, uint32_t last_len) {
+	// read_prev (dna.cpp:1550-1551) and, in sorted mode, pmer_can_prev (dna.cpp:655) follow the last read of the segment
+	CK(h->prev_read.ensure((size_t) last_len + 64));
+	if (last_len) CK(cudaMemcpyAsync(h->prev_read.p, d_dna + last_off, last_len, cudaMemcpyDeviceToDevice, h->st));
+	h->prev_len = last_len;
+	return FQSK_OK;
+}
+
+int fqsk_segment_device(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes, const uint64_t *d_off, const uint32_t *d_len, uint32_t n_reads, uint64_t *n_recs) {
+	if (!h) return FQSK_E_INVAL;
+	CK(cudaSetDevice(h->P.device));
+	CKR(run_segment(h, d_dna, dna_bytes, (const unsigned long long *) d_off, d_len, n_reads));
+	if (n_reads) {
+		unsigned long long lo; uint32_t ll;
+		CK(cudaMemcpyAsync(&lo, d_off + (n_reads - 1), 8, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaMemcpyAsync(&ll, d_len + (n_reads - 1), 4, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaStreamSynchronize(h->st));
+		CKR(after_segment_state(h, d_dna, nullptr, lo, ll));
+		if (h->P.mode == FQSK_MODE_SE_SORTED) {
+			std::vector<uint8_t> tmp(h->P.pmer_len);
+			CK(cudaMemcpyAsync(tmp.data(), d_dna + lo, h->P.pmer_len, cudaMemcpyDeviceToHost, h->st));
+			CK(cudaStreamSynchronize(h->st));
+			unsigned long long d = 0;
+			for (uint32_t i = 0; i < h->P.pmer_len; ++i) { uint8_t ch = tmp[i]; uint64_t s = ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : 3; d |= s << (62 - 2 * i); }
+			h->pprev_dir = d; h->pprev_valid = 1;
+		}
+	}
+	if (n_recs) *n_recs = h->n_recs;
+	return FQSK_OK;
+}
+
+int fqsk_device_recs(fqsk_handle *h, const fqsk_base_rec **d_recs, uint64_t *n_recs) {
+	if (!h || !d_recs) return FQSK_E_INVAL;
+	*d_recs = h->recs.as<fqsk_base_rec>();
+	if (n_recs) *n_recs = h->n_recs;
+	return FQSK_OK;
+}
+
+int fqsk_segment(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const fqsk_read_desc *reads, uint32_t n_reads,
+                 fqsk_base_rec *recs, uint64_t rec_cap, uint64_t *n_recs, uint8_t *dup, uint64_t *rec_off) {
+	if (!h || (!slab && n_reads) || (!reads && n_reads)) return FQSK_E_INVAL;
+	CK(cudaSetDevice(h->P.device));
+	const uint32_t first = h->P.mode == FQSK_MODE_SE_SORTED ? h->P.pmer_len : h->P.prefix_len;
+	// pack the DNA bytes of the segment (plus the few bytes the reference also reads when a read is shorter than the
+	// directly coded prefix, dna.cpp:518-521) into pinned memory: [dna bytes | off u64 | len u32]
+	uint64_t total = 0;
+	for (uint32_t i = 0; i < n_reads; ++i) total += std::max(reads[i].dna_len, first);
+	size_t need = total + 64 + (size_t) n_reads * 12 + 64;
+	if (need > h->h_stage_cap) {
+		if (h->h_stage) cudaFreeHost(h->h_stage);
+		h->h_stage = nullptr; h->h_stage_cap = 0;
+		CK(cudaMallocHost(&h->h_stage, need + need / 4));
+		h->h_stage_cap = need + need / 4;
+	}
+	size_t off_pos = (total + 63) & ~(size_t) 63;
+	unsigned long long *h_off = (unsigned long long *) (h->h_stage + off_pos);
+	uint32_t *h_len = (uint32_t *) (h->h_stage + off_pos + (size_t) n_reads * 8);
+	uint64_t at = 0;
+	for (uint32_t i = 0; i < n_reads; ++i) {
+		uint32_t plen = std::max(reads[i].dna_len, first);
+		uint64_t o = reads[i].dna_off;
+		if (o > slab_size) return fail(h, FQSK_E_INVAL, "read %u starts outside the slab", i);
+		uint64_t avail = std::min<uint64_t>(plen, slab_size - o);
+		memcpy(h->h_stage + at, slab + o, avail);
+		if (avail < plen) memset(h->h_stage + at + avail, 0, plen - avail);
+		h_off[i] = at; h_len[i] = reads[i].dna_len;
+		at += plen;
+	}
+	CK(h->dna.ensure(total + 64)); CK(h->off.ensure((size_t) n_reads * 8 + 8)); CK(h->len.ensure((size_t) n_reads * 4 + 4));
+	if (n_reads) {
+		CK(cudaMemcpyAsync(h->dna.p, h->h_stage, total, cudaMemcpyHostToDevice, h->st));
+		CK(cudaMemcpyAsync(h->off.p, h_off, (size_t) n_reads * 8, cudaMemcpyHostToDevice, h->st));
+		CK(cudaMemcpyAsync(h->len.p, h_len, (size_t) n_reads * 4, cudaMemcpyHostToDevice, h->st));
+	}
+	CKR(run_segment(h, h->dna.as<uint8_t>(), total, h->off.as<unsigned long long>(), h->len.as<uint32_t>(), n_reads));
+	if (n_reads) {
+		CKR(after_segment_state(h, h->dna.as<uint8_t>(), nullptr, h_off[n_reads - 1], h_len[n_reads - 1]));
+		if (h->P.mode == FQSK_MODE_SE_SORTED) {
+			const uint8_t *lp = h->h_stage + h_off[n_reads - 1];
+			unsigned long long d = 0;
+			for (uint32_t i = 0; i < h->P.pmer_len; ++i) { uint8_t ch = lp[i]; uint64_t s = ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : 3; d |= s << (62 - 2 * i); }
+			h->pprev_dir = d; h->pprev_valid = 1;
+		}
+	}
+	if (h->n_recs > rec_cap) return fail(h, FQSK_E_CAPACITY, "record buffer holds %llu, segment produced %llu", (unsigned long long) rec_cap, (unsigned long long) h->n_recs);
+	if (h->n_recs && recs) CK(cudaMemcpyAsync(recs, h->recs.p, h->n_recs * sizeof(fqsk_base_rec), cudaMemcpyDeviceToHost, h->st));
+	if (n_reads && dup) CK(cudaMemcpyAsync(dup, h->dup.p, n_reads, cudaMemcpyDeviceToHost, h->st));
+	if (n_reads && rec_off) CK(cudaMemcpyAsync(rec_off, h->rec_off.p, ((size_t) n_reads + 1) * 8, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaStreamSynchronize(h->st));
+	if (n_recs) *n_recs = h->n_recs;
+	return FQSK_OK;
+}
+
+int fqsk_sync(fqsk_handle *h) {
+	if (!h) return FQSK_E_INVAL;
+	CK(cudaSetDevice(h->P.device));
+	++h->S.n_syncs;
+	if (h->pending && h->seg_reads) {
+		// p-mers (dna.cpp:2401-2418)
+		if (h->pend_p) {
+			Phase ph(h, FQSK_PH_SYNC_SIV);
+			CK(cudaMemsetAsync(h->d_counters + 4, 0, 8, h->st));
+			k_siv_increment<<<nblk(h->pend_p, 256), 256, 0, h->st>>>(h->siv, h->row_p.as<unsigned long long>(), h->pend_p, h->d_counters + 4);
+			LAUNCHED(h);
+			CK(cudaMemcpyAsync(h->h_small, h->d_counters + 4, 8, cudaMemcpyDeviceToHost, h->st));
+			CK(cudaStreamSynchronize(h->st));
+			h->S.siv_no_filled += *(unsigned long long *) h->h_small;
+		}
+		h->S.siv_no_updates += h->pend_p + h->hidden_p;
+		h->hidden_p = 0;
+		// s-mers, then b-mers (dna.cpp:2425-2446)
+		CKR(apply_inserts(h, h->ts, h->rng[ST_S], h->row_s[h->cur].as<unsigned long long>(), h->pend_s));
+		CKR(apply_inserts(h, h->tb, h->rng[ST_B], h->row_b[h->cur].as<unsigned long long>(), h->pend_b));
+		CKR(table_grow_if_needed(h, h->ts));
+		CKR(table_grow_if_needed(h, h->tb));
+	} else {
+		h->S.siv_no_updates += h->hidden_p;
+		h->hidden_p = 0;
+	}
+	for (int i = 0; i < 4; ++i) h->S.draws[i] = h->rng[i].consumed;
+	h->pending = false; h->pend_b = h->pend_s = h->pend_p = 0; h->seg_reads = 0;
+	CK(cudaStreamSynchronize(h->st));
+	resolve_phases(h);
+	return FQSK_OK;
+}
+
+static int dump_sorted(fqsk_handle *h, uint64_t n, uint64_t *keys, uint64_t *vals) {
+	std::vector<unsigned long long> k(n), v(n);
+	if (n) {
+		CK(cudaMemcpyAsync(k.data(), h->dump_k.p, n * 8, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaMemcpyAsync(v.data(), h->dump_v.p, n * 8, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaStreamSynchronize(h->st));
+	}
+	std::vector<uint64_t> order(n);
+	for (uint64_t i = 0; i < n; ++i) order[i] = i;
+	std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return k[a] < k[b]; });
+	for (uint64_t i = 0; i < n; ++i) { keys[i] = k[order[i]]; vals[i] = v[order[i]]; }
+	return FQSK_OK;
+}
+
+int fqsk_dump(fqsk_handle *h, int table, uint64_t *keys, uint64_t *vals, uint64_t cap, uint64_t *n) {
+	if (!h || !n) return FQSK_E_INVAL;
+	CK(cudaSetDevice(h->P.device));
+	if (table == FQSK_TABLE_SMER || table == FQSK_TABLE_BMER) {
+		Table &t = table == FQSK_TABLE_SMER ? h->ts : h->tb;
+		uint64_t cnt = 0;
+		CKR(table_dump_device(h, t, &cnt));
+		*n = cnt;
+		if (!keys) return FQSK_OK;
+		if (cnt > cap) return fail(h, FQSK_E_CAPACITY, "dump needs %llu entries", (unsigned long long) cnt);
+		return dump_sorted(h, cnt, keys, vals);
+	}
+	if (table == FQSK_TABLE_SIV) {
+		uint64_t cnt = h->S.siv_no_filled;
+		*n = cnt;
+		if (!keys) return FQSK_OK;
+		if (cnt > cap) return fail(h, FQSK_E_CAPACITY, "dump needs %llu entries", (unsigned long long) cnt);
+		CK(h->dump_k.ensure((cnt + 1) * 8)); CK(h->dump_v.ensure((cnt + 1) * 8));
+		CK(cudaMemsetAsync(h->d_counters + 5, 0, 8, h->st));
+		uint64_t nw = (1ull << h->siv.key_bits) >> 4;
+		k_dump_siv<<<nblk(nw, 256), 256, 0, h->st>>>(h->siv, h->dump_k.as<unsigned long long>(), h->dump_v.as<unsigned long long>(), cnt, h->d_counters + 5);
+		LAUNCHED(h);
+		unsigned long long got = 0;
+		CK(cudaMemcpyAsync(&got, h->d_counters + 5, 8, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaStreamSynchronize(h->st));
+		if (got != cnt) return fail(h, FQSK_E_CUDA, "p-mer dump found %llu fields, no_filled says %llu", got, (unsigned long long) cnt);
+		return dump_sorted(h, cnt, keys, vals);
+	}
+	return fail(h, FQSK_E_UNSUPPORTED, "table %d cannot be dumped", table);
+}
+
+int fqsk_stats_get(fqsk_handle *h, fqsk_stats *out) {
+	if (!h || !out) return FQSK_E_INVAL;
+	CK(cudaSetDevice(h->P.device));
+	unsigned long long c[4];
+	CK(cudaMemcpyAsync(c, h->d_counters, 32, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaStreamSynchronize(h->st));
+	h->S.n_bmers = c[0] + c[1]; h->S.bmer_stash_used = c[1];
+	h->S.n_smers = c[2] + c[3]; h->S.smer_stash_used = c[3];
+	h->S.bmer_buckets = 1ull << h->tb.d.B; h->S.smer_buckets = 1ull << h->ts.d.B;
+	for (int i = 0; i < 4; ++i) h->S.draws[i] = h->rng[i].consumed;
+	*out = h->S;
+	return FQSK_OK;
+}
+
+int fqsk_profile(fqsk_handle *h, double *ms, uint32_t n) {
+	if (!h || !ms) return FQSK_E_INVAL;
+	for (uint32_t i = 0; i < n && i < FQSK_PH_COUNT; ++i) ms[i] = h->ph_ms[i];
+	return FQSK_OK;
+}
+
+// ---- table-level batch mirrors ----------------------------------------------------------------------------------
+static Table *pick(fqsk_handle *h, int table) { return table == FQSK_TABLE_SMER ? &h->ts : table == FQSK_TABLE_BMER ? &h->tb : nullptr; }
+
+int fqsk_ht_insert(fqsk_handle *h, int table, const uint64_t *kmers, uint64_t n) {
+	if (!h) return FQSK_E_INVAL;
+	Table *t = pick(h, table);
+	if (!t) return fail(h, FQSK_E_INVAL, "bad table");
+	CK(cudaSetDevice(h->P.device));
+	if (!n) return FQSK_OK;
+	CK(h->q3.ensure(n * 8));
+	CK(cudaMemcpyAsync(h->q3.p, kmers, n * 8, cudaMemcpyHostToDevice, h->st));
+	CKR(apply_inserts(h, *t, h->rng[table == FQSK_TABLE_SMER ? ST_S : ST_B], h->q3.as<unsigned long long>(), (uint32_t) n));
+	CKR(table_grow_if_needed(h, *t));
+	CK(cudaStreamSynchronize(h->st));
+	return FQSK_OK;
+}
+
+int fqsk_ht_find(fqsk_handle *h, int table, const uint64_t *kmer_dir, const uint64_t *kmer_rc, const uint32_t *cur_size, uint64_t n, uint32_t *counts) {
+	if (!h) return FQSK_E_INVAL;
+	Table *t = pick(h, table);
+	if (!t) return fail(h, FQSK_E_INVAL, "bad table");
+	CK(cudaSetDevice(h->P.device));
+	if (!n) return FQSK_OK;
+	Stream &rng = h->rng[table == FQSK_TABLE_SMER ? ST_S : ST_B];
+	CK(h->q0.ensure((n + 1) * 8)); CK(h->q1.ensure((n + 1) * 8)); CK(h->q2.ensure((n + 1) * 8)); CK(h->q3.ensure((n + 1) * 16)); CK(h->q4.ensure((n + 1) * 8));
+	unsigned long long *d_dir = h->q0.as<unsigned long long>(), *d_rc = h->q1.as<unsigned long long>(), *d_guess = h->q2.as<unsigned long long>();
+	uint32_t *d_counts = h->q3.as<uint32_t>();
+	uint32_t *d_cur = h->q4.as<uint32_t>(), *d_used = h->q4.as<uint32_t>() + (n + 1);
+	CK(cudaMemcpyAsync(d_dir, kmer_dir, n * 8, cudaMemcpyHostToDevice, h->st));
+	CK(cudaMemcpyAsync(d_rc, kmer_rc, n * 8, cudaMemcpyHostToDevice, h->st));
+	CK(cudaMemcpyAsync(d_cur, cur_size, n * 4, cudaMemcpyHostToDevice, h->st));
+	CK(cudaMemsetAsync(d_guess, 0, (n + 1) * 8, h->st));
+	CKR(stream_ensure(h, rng, 1u << 16));
+	std::vector<unsigned long long> prev(n + 1, 0), now(n + 1, 0);
+	for (int it = 0;; ++it) {
+		if (it > 32) return fail(h, FQSK_E_NO_CONVERGE, "find: draw offsets did not settle");
+		CK(cudaMemsetAsync(h->d_flags, 0, 4 * sizeof(int), h->st));
+		CK(cudaMemsetAsync(d_used + n, 0, 4, h->st));
+		k_find<<<nblk(n, 128), 128, 0, h->st>>>(t->d, t->ci, d_dir, d_rc, d_cur, (uint32_t) n, d_counts, stream_ptr(rng), stream_avail(rng), d_guess, d_used, h->d_flags);
+		LAUNCHED(h);
+		int fl[4];
+		CKR(read_flags(h, fl, 4));
+		if (fl[0]) { CKR(stream_ensure(h, rng, 2 * stream_avail(rng))); --it; continue; }
+		CKR((scan_excl<uint32_t, unsigned long long>(h, d_used, d_guess, (uint32_t) n + 1, 0ull)));
+		CK(cudaMemcpyAsync(now.data(), d_guess, (n + 1) * 8, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaStreamSynchronize(h->st));
+		if (now == prev) break;
+		prev = now;
+	}
+	rng.consumed += now[n];
+	CK(cudaMemcpyAsync(counts, d_counts, n * 16, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaStreamSynchronize(h->st));
+	return FQSK_OK;
+}
+
+int fqsk_ht_count(fqsk_handle *h, int table, const uint64_t *kmers, uint64_t n, uint32_t *out) {
+	if (!h) return FQSK_E_INVAL;
+	Table *t = pick(h, table);
+	if (!t) return fail(h, FQSK_E_INVAL, "bad table");
+	CK(cudaSetDevice(h->P.device));
+	if (!n) return FQSK_OK;
+	CK(h->q0.ensure(n * 8)); CK(h->q1.ensure(n * 4));
+	CK(cudaMemcpyAsync(h->q0.p, kmers, n * 8, cudaMemcpyHostToDevice, h->st));
+	k_count<<<nblk(n, 256), 256, 0, h->st>>>(t->d, h->q0.as<unsigned long long>(), (uint32_t) n, h->q1.as<uint32_t>());
+	LAUNCHED(h);
+	CK(cudaMemcpyAsync(out, h->q1.p, n * 4, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaStreamSynchronize(h->st));
+	return FQSK_OK;
+}
+
+int fqsk_siv_increment(fqsk_handle *h, const uint64_t *idx, uint64_t n, uint64_t *n_new) {
+	if (!h) return FQSK_E_INVAL;
+	CK(cudaSetDevice(h->P.device));
+	unsigned long long fresh = 0;
+	if (n) {
+		CK(h->q0.ensure(n * 8));
+		CK(cudaMemcpyAsync(h->q0.p, idx, n * 8, cudaMemcpyHostToDevice, h->st));
+		CK(cudaMemsetAsync(h->d_counters + 4, 0, 8, h->st));
+		k_siv_increment<<<nblk(n, 256), 256, 0, h->st>>>(h->siv, h->q0.as<unsigned long long>(), n, h->d_counters + 4);
+		LAUNCHED(h);
+		CK(cudaMemcpyAsync(&fresh, h->d_counters + 4, 8, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaStreamSynchronize(h->st));
+	}
+	h->S.siv_no_filled += fresh; h->S.siv_no_updates += n;
+	if (n_new) *n_new = fresh;
+	return FQSK_OK;
+}
+
+static int siv_query(fqsk_handle *h, int what, const uint64_t *idx, const uint32_t *bits, uint64_t n, void *out) {
+	CK(cudaSetDevice(h->P.device));
+	if (!n) return FQSK_OK;
+	CK(h->q0.ensure(n * 8)); CK(h->q1.ensure(n * 16)); CK(h->q2.ensure(n * 4));
+	CK(cudaMemcpyAsync(h->q0.p, idx, n * 8, cudaMemcpyHostToDevice, h->st));
+	if (bits) CK(cudaMemcpyAsync(h->q2.p, bits, n * 4, cudaMemcpyHostToDevice, h->st));
+	size_t ob;
+	if (what == 0) { k_siv_test<<<nblk(n, 256), 256, 0, h->st>>>(h->siv, h->q0.as<unsigned long long>(), (uint32_t) n, h->q1.as<uint32_t>()); ob = n * 4; }
+	else if (what == 1) { k_siv_counts<<<nblk(n, 256), 256, 0, h->st>>>(h->siv, h->q0.as<unsigned long long>(), (uint32_t) n, h->q1.as<uint32_t>()); ob = n * 16; }
+	else { k_siv_prefix<<<nblk(n, 256), 256, 0, h->st>>>(h->siv, h->q0.as<unsigned long long>(), h->q2.as<uint32_t>(), (uint32_t) n, h->q1.as<unsigned long long>()); ob = n * 8; }
+	LAUNCHED(h);
+	CK(cudaMemcpyAsync(out, h->q1.p, ob, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaStreamSynchronize(h->st));
+	return FQSK_OK;
+}
+int fqsk_siv_test(fqsk_handle *h, const uint64_t *idx, uint64_t n, uint32_t *out) { return h ? siv_query(h, 0, idx, nullptr, n, out) : FQSK_E_INVAL; }
+int fqsk_siv_counts(fqsk_handle *h, const uint64_t *idx, uint64_t n, uint32_t *out4) { return h ? siv_query(h, 1, idx, nullptr, n, out4) : FQSK_E_INVAL; }
+int fqsk_siv_test_shorter(fqsk_handle *h, const uint64_t *idx, const uint32_t *size_bits, uint64_t n, uint64_t *out) { return h ? siv_query(h, 2, idx, size_bits, n, out) : FQSK_E_INVAL; }
+
+int fqsk_mt_stream(fqsk_handle *h, uint64_t n, uint32_t *out) {
+	if (!h) return FQSK_E_INVAL;
+	CK(cudaSetDevice(h->P.device));
+	// a scratch stream: same seed, generated from scratch so the engine's own streams are untouched
+	Stream s;
+	CKR(stream_init(h, s));
+	int rc = stream_ensure(h, s, n);
+	if (rc == FQSK_OK && n) {
+		cudaError_t e = cudaMemcpyAsync(out, s.buf, n * 4, cudaMemcpyDeviceToHost, h->st);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+		if (e != cudaSuccess) rc = fail(h, FQSK_E_CUDA, "mt_stream copy: %s", cudaGetErrorString(e));
+	}
+	if (s.buf) cudaFree(s.buf);
+	if (s.state) cudaFree(s.state);
+	return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,295 @@
+// fqsk_dev.cuh -- device-side primitives of the B200 k-mer statistics engine (sm_100a).
+//
+// Data layout in HBM:
+//   * b-/s-mer tables: 2^B buckets of 8 x u32 (one 32-byte sector). A k-mer lives in the bucket chosen by a bijective
+//     mix of its KERNEL (symbols s2..s(k-3), kmer.h:199-202) so the 4 next-symbol siblings of a context -- which differ
+//     only in s(k-1) (dir-oriented) or s0 (rc-oriented) -- share one sector, and one sector read answers
+//     CHT_kmer::find_full (ht_kmer.h:205-263).  item = [rem | s0 s1 s(k-2) s(k-1) | counter]; 0 = empty.
+//     Buckets only hold native items; a k-mer whose bucket is full goes to a small u64 open-addressing stash.
+//     Reference lookups depend only on table CONTENTS, so this layout is free to differ from ht_kmer.h:49-76.
+//   * p-mer array: 2-bit saturating fields, 16 per u32, direct-addressed (bit_vec.h:17-231).
+// `reference:` citations are relative to /root/reference/fqs/.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define FQSK_DEV __device__ __forceinline__
+#define FQSK_HD __host__ __device__ __forceinline__
+
+namespace fqsk {
+
+// ------------------------------------------------------------------------------------------------------------------
+// canonical rolling register (reference: kmer.h:18-540).  cur (symbols held) is tracked by the caller: all six
+// registers of a read advance in lock-step (dna.cpp:687-693, 810-816), so cur = min(k, symbols pushed).
+// ------------------------------------------------------------------------------------------------------------------
+struct KReg { uint64_t dir, rc; };
+
+FQSK_HD uint64_t kr_top_mask(uint32_t k) { return ~0ull << (64 - 2 * k); }
+FQSK_HD uint64_t kr_kernel_mask(uint32_t k) { return ((1ull << (2 * k - 8)) - 1ull) << (64 - 2 * k + 4); }
+// kmer.h:73-108 (insert_zero == insert of symbol 0: the rc side receives T)
+FQSK_HD void kr_push(KReg &r, uint32_t k, uint32_t cur_before, uint64_t s) {
+	r.rc = ((r.rc >> 2) + ((3 - s) << 62)) & kr_top_mask(k);
+	if (cur_before >= k) r.dir = (r.dir << 2) + (s << (64 - 2 * k));
+	else r.dir += s << (62 - 2 * cur_before);
+}
+FQSK_HD void kr_set_last(KReg &r, uint32_t cur, uint64_t s) {  // kmer.h:153-174
+	uint32_t sh = 64 - 2 * cur;
+	r.dir = (r.dir & ~(3ull << sh)) + (s << sh);
+	r.rc = ((r.rc << 2) >> 2) + ((3 - s) << 62);
+}
+FQSK_HD void kr_set(KReg &r, uint32_t cur, uint64_t s, uint32_t pos) {  // kmer.h:144-167
+	uint32_t sh = 62 - 2 * pos;
+	r.dir = (r.dir & ~(3ull << sh)) + (s << sh);
+	sh = 64 - 2 * cur + 2 * pos;
+	r.rc = (r.rc & ~(3ull << sh)) + ((3 - s) << sh);
+}
+FQSK_HD uint64_t kr_sym(const KReg &r, uint32_t pos) { return (r.dir >> (62 - 2 * pos)) & 3; }
+FQSK_HD bool kr_is_dir(const KReg &r, uint32_t k) { uint64_t m = kr_kernel_mask(k); return (r.dir & m) < (r.rc & m); }  // kmer.h:380-385
+FQSK_HD uint64_t kr_norm(const KReg &r, uint32_t k) { return kr_is_dir(r, k) ? r.dir : r.rc; }  // kmer.h:366-377
+
+// ------------------------------------------------------------------------------------------------------------------
+// approximate counters (reference: utils.h:256-335).  v_mapping has the closed form thr + mult * n(n+1)/2.
+// ------------------------------------------------------------------------------------------------------------------
+struct CIncP { uint32_t thr, mult, top; };
+
+FQSK_HD uint32_t ci_real_of(const CIncP &p, uint32_t c) {
+	if (c <= p.thr) return c;
+	if (c > p.top) c = p.top;  // guard entry v_mapping[max+1] = v_mapping[max] (utils.h:312)
+	uint32_t n = c - p.thr;
+	return p.thr + p.mult * (n * (n + 1) / 2);
+}
+FQSK_HD uint32_t ci_to_real(const CIncP &p, uint32_t c) { return c <= p.thr ? c : (ci_real_of(p, c) + ci_real_of(p, c + 1)) / 2; }  // utils.h:264-270
+// utils.h:272-291; *need_draw tells the caller whether one mt19937 output is consumed; `draw` is that output.
+FQSK_HD uint32_t ci_code_floor(const CIncP &p, uint32_t r) {  // largest code in [thr, top] with real_of(code) <= r
+	uint32_t d = (r - p.thr) / p.mult;  // n(n+1)/2 <= d
+	uint32_t n = (uint32_t) ((sqrt(8.0 * (double) d + 1.0) - 1.0) * 0.5);
+	while ((uint64_t) (n + 1) * (n + 2) / 2 <= d) ++n;
+	while (n > 0 && (uint64_t) n * (n + 1) / 2 > d) --n;
+	uint32_t code = p.thr + n;
+	return code > p.top ? p.top : code;
+}
+
+// A cursor into one pre-generated mt19937 stream (tempered 32-bit outputs in HBM).  `next` is relative to the read's
+// guessed starting offset; the fix point in fqsk.cu makes guess == truth before results are released.
+struct DrawCursor {
+	const uint32_t *buf;   // already offset to the stream's `consumed` position
+	uint64_t avail;        // outputs generated beyond that position
+	uint64_t base;         // guessed offset of this read
+	uint32_t used;         // draws consumed by this read so far
+	int *overflow;         // set when the pre-generated window is too short (host extends and replays)
+	__device__ uint32_t next() {
+		uint64_t i = base + used++;
+		if (i >= avail) { *overflow = 1; return 0; }
+		return buf[i];
+	}
+};
+
+FQSK_DEV uint32_t ci_from_real(const CIncP &p, uint32_t r, DrawCursor &dc) {
+	if (r <= p.thr) return r;
+	uint32_t code = ci_code_floor(p, r);
+	if (code >= p.top) return p.top;
+	uint32_t rest = r - ci_real_of(p, code);
+	uint32_t width = ci_real_of(p, code + 1) - ci_real_of(p, code);
+	if (dc.next() % width < rest) ++code;
+	return code;
+}
+FQSK_DEV uint32_t ci_plus(const CIncP &p, uint32_t c, uint32_t inc, DrawCursor &dc) { return ci_from_real(p, ci_to_real(p, c) + ci_to_real(p, inc), dc); }  // utils.h:328-334
+
+// ------------------------------------------------------------------------------------------------------------------
+// bucketed k-mer table
+// ------------------------------------------------------------------------------------------------------------------
+struct HtDev {
+	uint32_t *main;                 // 8 << B items
+	unsigned long long *stash;      // 1 << stash_log2 items: (aligned k-mer << cbits) | counter, 0 = empty
+	uint32_t k, cbits, W, B, rem_bits, top, stash_log2, mix_sh;
+	uint64_t maskW;
+	unsigned long long *n_items;    // device counters: [0] main items, [1] stash items
+};
+
+static const uint64_t MIX_C1 = 0x9E3779B97F4A7C15ull, MIX_C2 = 0xD6E8FEB86659FD93ull;
+
+FQSK_HD uint64_t ht_mix(const HtDev &t, uint64_t x) {  // bijection on W-bit words
+	x = (x * MIX_C1) & t.maskW; x ^= x >> t.mix_sh;
+	x = (x * MIX_C2) & t.maskW; x ^= x >> t.mix_sh;
+	return x;
+}
+FQSK_HD uint64_t ht_kernel(const HtDev &t, uint64_t x) { return (x >> (64 - 2 * t.k + 4)) & t.maskW; }
+FQSK_HD uint32_t ht_ends(const HtDev &t, uint64_t x) { return (uint32_t) (((x >> 60) & 0xF) << 4 | ((x >> (64 - 2 * t.k)) & 0xF)); }
+FQSK_HD uint64_t ht_slot_count() { return 8; }
+
+struct HtKey { uint64_t bucket; uint32_t q; uint64_t kal; uint64_t h; };  // q = item without counter
+FQSK_HD HtKey ht_key(const HtDev &t, uint64_t x) {
+	HtKey k;
+	k.h = ht_mix(t, ht_kernel(t, x));
+	k.bucket = k.h >> t.rem_bits;
+	uint32_t rem = (uint32_t) (k.h & ((1ull << t.rem_bits) - 1));
+	k.q = (rem << (8 + t.cbits)) | (ht_ends(t, x) << t.cbits);
+	k.kal = x >> (64 - 2 * t.k);
+	return k;
+}
+FQSK_HD uint64_t ht_stash_pos(const HtDev &t, uint64_t h) { return (h * 0xC2B2AE3D27D4EB4Full) >> (64 - t.stash_log2); }
+
+struct Bucket { uint4 lo, hi; };
+FQSK_DEV Bucket ht_load_bucket(const HtDev &t, uint64_t b) {
+	const uint4 *p = reinterpret_cast<const uint4 *>(t.main + b * 8);
+	Bucket r;
+	r.lo = __ldg(p);
+	r.hi = __ldg(p + 1);
+	return r;
+}
+FQSK_DEV uint32_t bucket_item(const Bucket &b, int i) {
+	switch (i) { case 0: return b.lo.x; case 1: return b.lo.y; case 2: return b.lo.z; case 3: return b.lo.w;
+	             case 4: return b.hi.x; case 5: return b.hi.y; case 6: return b.hi.z; default: return b.hi.w; }
+}
+
+// The 4 next-symbol counters of a context (ht_kmer.h:205-263) from an already loaded bucket; falls through to the
+// stash only when the bucket is full.  x = normalised register (context + placeholder), is_dir = its orientation.
+FQSK_DEV void ht_ctx_counts_from(const HtDev &t, const HtKey &key, bool is_dir, const Bucket &bk, uint32_t c[4]) {
+	uint32_t unk = is_dir ? (3u << t.cbits) : (3u << (t.cbits + 6));
+	uint32_t mm = ~(t.top | unk);
+	uint32_t sh = is_dir ? t.cbits : t.cbits + 6;
+	bool full = true;
+#pragma unroll
+	for (int i = 0; i < 8; ++i) {
+		uint32_t it = bucket_item(bk, i);
+		if (it == 0) { full = false; break; }
+		if (((it ^ key.q) & mm) == 0) { uint32_t f = (it >> sh) & 3; c[is_dir ? f : 3 - f] += it & t.top; }
+	}
+	if (!full) return;
+	uint64_t ush = is_dir ? 0 : 2 * t.k - 2;  // unknown symbol inside the aligned k-mer
+	uint64_t m64 = ~(3ull << ush);
+	uint64_t smask = (1ull << t.stash_log2) - 1;
+	for (uint64_t p = ht_stash_pos(t, key.h);; p = (p + 1) & smask) {
+		unsigned long long it = t.stash[p];
+		if (it == 0) break;
+		uint64_t kal = it >> t.cbits;
+		if (((kal ^ key.kal) & m64) == 0) { uint32_t f = (uint32_t) ((kal >> ush) & 3); c[is_dir ? f : 3 - f] += (uint32_t) (it & t.top); }
+	}
+}
+FQSK_DEV void ht_ctx_counts(const HtDev &t, uint64_t x, bool is_dir, uint32_t c[4]) {
+	HtKey key = ht_key(t, x);
+	Bucket bk = ht_load_bucket(t, key.bucket);
+	ht_ctx_counts_from(t, key, is_dir, bk, c);
+}
+// CHT_kmer::count(uint64_t): exact match (ht_kmer.h:441-454)
+FQSK_DEV uint32_t ht_count(const HtDev &t, uint64_t x) {
+	HtKey key = ht_key(t, x);
+	Bucket bk = ht_load_bucket(t, key.bucket);
+	bool full = true;
+#pragma unroll
+	for (int i = 0; i < 8; ++i) {
+		uint32_t it = bucket_item(bk, i);
+		if (it == 0) { full = false; break; }
+		if ((it & ~t.top) == key.q) return it & t.top;
+	}
+	if (!full) return 0;
+	uint64_t smask = (1ull << t.stash_log2) - 1;
+	for (uint64_t p = ht_stash_pos(t, key.h);; p = (p + 1) & smask) {
+		unsigned long long it = t.stash[p];
+		if (it == 0) return 0;
+		if ((it >> t.cbits) == key.kal) return (uint32_t) (it & t.top);
+	}
+}
+// find-or-create for the sync step (ht_kmer.h:330-362).  New slots are claimed with counter 1; the group pass of the sync
+// step turns that into the reference's "start at 0, then Increment".  Returns a slot id (main: index, stash: 8<<B + index).
+FQSK_DEV uint64_t ht_locate(const HtDev &t, uint64_t x, bool &created) {
+	HtKey key = ht_key(t, x);
+	uint32_t *bp = t.main + key.bucket * 8;
+	created = false;
+	for (int i = 0; i < 8; ++i) {
+		uint32_t it = *((volatile uint32_t *) (bp + i));
+		if (it == 0) {
+			uint32_t old = atomicCAS(bp + i, 0u, key.q | 1u);
+			if (old == 0) { created = true; atomicAdd(t.n_items, 1ull); return key.bucket * 8 + i; }
+			it = old;
+		}
+		if ((it & ~t.top) == key.q) return key.bucket * 8 + i;
+	}
+	uint64_t smask = (1ull << t.stash_log2) - 1;
+	unsigned long long fresh = (key.kal << t.cbits) | 1ull;
+	for (uint64_t p = ht_stash_pos(t, key.h);; p = (p + 1) & smask) {
+		unsigned long long it = *((volatile unsigned long long *) (t.stash + p));
+		if (it == 0) {
+			unsigned long long old = atomicCAS(t.stash + p, 0ull, fresh);
+			if (old == 0) { created = true; atomicAdd(t.n_items + 1, 1ull); return (8ull << t.B) + p; }
+			it = old;
+		}
+		if ((it >> t.cbits) == key.kal) return (8ull << t.B) + p;
+	}
+}
+FQSK_DEV uint32_t ht_slot_get(const HtDev &t, uint64_t slot) {
+	uint64_t nm = 8ull << t.B;
+	return slot < nm ? (t.main[slot] & t.top) : (uint32_t) (t.stash[slot - nm] & t.top);
+}
+FQSK_DEV void ht_slot_set(const HtDev &t, uint64_t slot, uint32_t cnt) {
+	uint64_t nm = 8ull << t.B;
+	if (slot < nm) t.main[slot] = (t.main[slot] & ~t.top) | cnt;
+	else t.stash[slot - nm] = (t.stash[slot - nm] & ~(unsigned long long) t.top) | cnt;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// p-mer array (reference: bit_vec.h:17-231), u32 words of 16 two-bit fields
+// ------------------------------------------------------------------------------------------------------------------
+struct SivDev { uint32_t *w; uint32_t key_bits; };
+
+FQSK_DEV uint32_t siv_test(const SivDev &s, uint64_t idx) { return (__ldg(s.w + (idx >> 4)) >> (2 * (idx & 15))) & 3; }  // bit_vec.h:69-81
+FQSK_DEV void siv_counts(const SivDev &s, uint64_t idx, uint32_t c[4], bool accumulate) {  // bit_vec.h:83-111
+	uint32_t d = __ldg(s.w + (idx >> 4)) >> (2 * ((idx & 15) & ~3ull));
+#pragma unroll
+	for (int i = 0; i < 4; ++i) { uint32_t v = (d >> (2 * i)) & 3; c[i] = accumulate ? c[i] + v : v; }
+}
+FQSK_DEV uint32_t siv_word_sum(uint32_t w) {
+	uint32_t x = (w & 0x33333333u) + ((w >> 2) & 0x33333333u);
+	x = (x + (x >> 4)) & 0x0F0F0F0Fu;
+	return (x * 0x01010101u) >> 24;
+}
+FQSK_DEV uint64_t siv_prefix_sum(const SivDev &s, uint64_t prefix, uint32_t prefix_bits) {  // bit_vec.h:113-166
+	uint32_t sh = s.key_bits - prefix_bits;
+	uint64_t start = prefix << sh, n = 1ull << sh;
+	if (n == 1) return siv_test(s, start);
+	if (n < 16) { uint32_t d = __ldg(s.w + (start >> 4)) >> (2 * (start & 15)); return siv_word_sum(d & ((1u << (2 * n)) - 1)); }
+	uint64_t r = 0;
+	for (uint64_t wd = start >> 4, e = (start + n) >> 4; wd < e; ++wd) r += siv_word_sum(__ldg(s.w + wd));
+	return r;
+}
+// bit_vec.h:53-67, order-independent form: saturate at 3, return 1 when the field was zero
+FQSK_DEV uint32_t siv_increment(const SivDev &s, uint64_t idx) {
+	uint32_t *p = s.w + (idx >> 4);
+	uint32_t sh = 2 * (idx & 15);
+	uint32_t old = *((volatile uint32_t *) p);
+	for (;;) {
+		uint32_t f = (old >> sh) & 3;
+		if (f == 3) return 0;
+		uint32_t seen = atomicCAS(p, old, old + (1u << sh));
+		if (seen == old) return f == 0;
+		old = seen;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// intra-segment delta (the reference's thread-local CHT_kmer<uint64_t>, dna.cpp:99-103, 826, 837, 862, 872): the segment's
+// pushes sorted by (k-mer, push index).  A lookup at push-time T sees the entries with index < T.
+// ------------------------------------------------------------------------------------------------------------------
+struct DeltaDev { const unsigned long long *keys; const uint32_t *idx; uint32_t n; uint32_t exact_limit; };
+
+FQSK_DEV uint32_t delta_count(const DeltaDev &d, uint64_t key, uint32_t T, int *unsupported) {
+	if (d.n == 0) return 0;
+	uint32_t lo = 0, hi = d.n;
+	while (lo < hi) { uint32_t m = (lo + hi) >> 1; if (d.keys[m] < key) lo = m + 1; else hi = m; }
+	if (lo >= d.n || d.keys[lo] != key) return 0;
+	uint32_t first = lo;
+	// first entry of this key with idx >= T
+	uint32_t a = first, b = d.n;
+	while (a < b) { uint32_t m = (a + b) >> 1; if (d.keys[m] == key && d.idx[m] < T) a = m + 1; else b = m; }
+	uint32_t cnt = a - first;
+	if (cnt > d.exact_limit) { *unsupported = 1; cnt = d.exact_limit; }  // would need the local PRNG stream (cinc_lb / cinc_ls)
+	return cnt;
+}
+FQSK_DEV void delta_ctx_counts(const DeltaDev &d, uint32_t k, uint64_t x, bool is_dir, uint32_t T, uint32_t c[4], int *unsupported) {
+	uint32_t sh = is_dir ? 64 - 2 * k : 62;
+	uint64_t base = x & ~(3ull << sh);
+#pragma unroll
+	for (uint64_t f = 0; f < 4; ++f) c[is_dir ? f : 3 - f] += delta_count(d, base | (f << sh), T, unsupported);
+}
+
+}  // namespace fqsk

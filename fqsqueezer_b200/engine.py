@@ -1,0 +1,236 @@
+"""ctypes host mirror of include/fqsk.h.
+
+`KmerEngine` keeps the vocabulary of the reference's host code for this path: block_start (application.cpp:624),
+segment (the k-mer half of CDNACompressor::CompressDirect / CompressSorted for the reads between two syncs),
+sync (InsertKmersToHT + ClearKmersToHT, dna.cpp:2393-2488), dump / stats, and the table-level batch mirrors of
+CHT_kmer<T> and TSmallIntVector<2>.  Everything computes on the GPU; failures raise FqskError."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libfqsk.so")
+
+REC_DTYPE = np.dtype([("pos", "<u4"), ("c", "<u4", 4), ("cor_pos", "<u4"), ("level", "u1"), ("rough", "u1"), ("pad", "<u2")])
+READ_DESC_DTYPE = np.dtype([("dna_off", "<u8"), ("dna_len", "<u4"), ("flags", "<u4")])
+TABLE_SIV, TABLE_SMER, TABLE_BMER, TABLE_PAIR = 0, 1, 2, 3
+MODE_SE_ORIGINAL, MODE_SE_SORTED, MODE_PE_ORIGINAL, MODE_PE_SORTED = 0, 1, 2, 3
+F_PROFILE = 1
+PHASES = ["prep", "replay", "compact", "delta", "sync_locate", "sync_sort", "sync_apply", "sync_siv", "mt"]
+
+
+class FqskError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"fqsk error {code}: {msg}")
+        self.code = code
+
+
+class _Params(C.Structure):
+    _fields_ = [("abi_version", C.c_uint32), ("pmer_len", C.c_uint32), ("smer_len", C.c_uint32), ("bmer_len", C.c_uint32),
+                ("prefix_len", C.c_uint32), ("smer_counter_bits", C.c_uint32), ("bmer_counter_bits", C.c_uint32), ("mode", C.c_uint32),
+                ("n_workers", C.c_uint32), ("device", C.c_int32), ("bmer_log2_buckets", C.c_uint32), ("smer_log2_buckets", C.c_uint32),
+                ("expected_kmers", C.c_uint64), ("world_size", C.c_uint32), ("rank", C.c_uint32), ("max_iterations", C.c_uint32),
+                ("flags", C.c_uint32)]
+
+
+class _Stats(C.Structure):
+    _fields_ = [("siv_no_filled", C.c_uint64), ("siv_no_updates", C.c_uint64), ("n_smers", C.c_uint64), ("n_bmers", C.c_uint64),
+                ("draws", C.c_uint64 * 4), ("n_segments", C.c_uint64), ("n_syncs", C.c_uint64), ("n_replays", C.c_uint64),
+                ("n_bases", C.c_uint64), ("n_reads", C.c_uint64), ("kernel_launches", C.c_uint64), ("bmer_buckets", C.c_uint64),
+                ("smer_buckets", C.c_uint64), ("bmer_stash_used", C.c_uint64), ("smer_stash_used", C.c_uint64)]
+
+
+EXPORTS = ["fqsk_create", "fqsk_destroy", "fqsk_last_error", "fqsk_block_start", "fqsk_segment", "fqsk_segment_device",
+           "fqsk_device_recs", "fqsk_sync", "fqsk_dump", "fqsk_stats_get", "fqsk_profile", "fqsk_ht_insert", "fqsk_ht_find",
+           "fqsk_ht_count", "fqsk_siv_increment", "fqsk_siv_test", "fqsk_siv_counts", "fqsk_siv_test_shorter", "fqsk_mt_stream"]
+
+_lib = None
+
+
+def load_library():
+    """Loads libfqsk.so (built in-tree by fqsqueezer_b200/build.py).  Raises if it is missing: there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FqskError(-2, f"{LIB_PATH} not built (run `python -m fqsqueezer_b200.build`); there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    vp, u64p, u32p, u8p = C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)
+    lib.fqsk_create.argtypes = [C.POINTER(_Params), C.POINTER(vp)]
+    lib.fqsk_destroy.argtypes = [vp]
+    lib.fqsk_destroy.restype = None
+    lib.fqsk_last_error.argtypes = [vp]
+    lib.fqsk_last_error.restype = C.c_char_p
+    lib.fqsk_block_start.argtypes = [vp]
+    lib.fqsk_segment.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint32, vp, C.c_uint64, u64p, vp, vp]
+    lib.fqsk_segment_device.argtypes = [vp, vp, C.c_uint64, vp, vp, C.c_uint32, u64p]
+    lib.fqsk_device_recs.argtypes = [vp, C.POINTER(vp), u64p]
+    lib.fqsk_sync.argtypes = [vp]
+    lib.fqsk_dump.argtypes = [vp, C.c_int, vp, vp, C.c_uint64, u64p]
+    lib.fqsk_stats_get.argtypes = [vp, C.POINTER(_Stats)]
+    lib.fqsk_profile.argtypes = [vp, C.POINTER(C.c_double), C.c_uint32]
+    lib.fqsk_ht_insert.argtypes = [vp, C.c_int, vp, C.c_uint64]
+    lib.fqsk_ht_find.argtypes = [vp, C.c_int, vp, vp, vp, C.c_uint64, vp]
+    lib.fqsk_ht_count.argtypes = [vp, C.c_int, vp, C.c_uint64, vp]
+    lib.fqsk_siv_increment.argtypes = [vp, vp, C.c_uint64, u64p]
+    lib.fqsk_siv_test.argtypes = [vp, vp, C.c_uint64, vp]
+    lib.fqsk_siv_counts.argtypes = [vp, vp, C.c_uint64, vp]
+    lib.fqsk_siv_test_shorter.argtypes = [vp, vp, vp, C.c_uint64, vp]
+    lib.fqsk_mt_stream.argtypes = [vp, C.c_uint64, vp]
+    for n in EXPORTS:
+        if n not in ("fqsk_destroy", "fqsk_last_error"):
+            getattr(lib, n).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def kmer_params(genome_size_mb: int):
+    """-gs -> (prefix_len, pmer, smer, bmer), CParams::adjust_kmer_sizes (params.h:131-155)."""
+    table = [(1, 9, 14, 17, 19), (4, 9, 15, 18, 20), (16, 10, 15, 18, 21), (64, 11, 16, 18, 23), (256, 12, 17, 20, 24),
+             (1024, 12, 17, 21, 26), (4096, 13, 18, 21, 27), (16384, 14, 18, 22, 27), (65536, 15, 18, 22, 27)]
+    for gs, pref, p, s, b in table:
+        if genome_size_mb <= gs:
+            return pref, p, s, b
+    return 14, 13, 15, 26
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class KmerEngine:
+    def __init__(self, p, s, b, prefix_len, mode=MODE_SE_ORIGINAL, device=0, expected_kmers=0, bmer_log2_buckets=0,
+                 smer_log2_buckets=0, profile=False, max_iterations=0):
+        self.lib = load_library()
+        prm = _Params(abi_version=1, pmer_len=p, smer_len=s, bmer_len=b, prefix_len=prefix_len, smer_counter_bits=12,
+                      bmer_counter_bits=6, mode=mode, n_workers=1, device=device, bmer_log2_buckets=bmer_log2_buckets,
+                      smer_log2_buckets=smer_log2_buckets, expected_kmers=expected_kmers, world_size=1, rank=0,
+                      max_iterations=max_iterations, flags=F_PROFILE if profile else 0)
+        h = C.c_void_p()
+        rc = self.lib.fqsk_create(C.byref(prm), C.byref(h))
+        if rc != 0:
+            raise FqskError(rc, self.lib.fqsk_last_error(None).decode())
+        self.h = h
+        self.p, self.s, self.b, self.prefix_len, self.mode = p, s, b, prefix_len, mode
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.fqsk_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise FqskError(rc, self.lib.fqsk_last_error(self.h).decode())
+
+    # ---- segment-level API ----
+    def block_start(self):
+        self._ck(self.lib.fqsk_block_start(self.h))
+
+    def segment(self, slab: np.ndarray, off: np.ndarray, length: np.ndarray, kind: int = 0, want_rec_off=False):
+        slab = np.ascontiguousarray(slab, np.uint8)
+        n = len(off)
+        desc = np.zeros(n, READ_DESC_DTYPE)
+        desc["dna_off"] = off
+        desc["dna_len"] = length
+        cap = int(np.asarray(length, np.int64).sum()) + 16
+        recs = np.zeros(cap, REC_DTYPE)
+        dup = np.zeros(max(n, 1), np.uint8)
+        rec_off = np.zeros(n + 1, np.uint64)
+        n_recs = C.c_uint64(0)
+        self._ck(self.lib.fqsk_segment(self.h, _ptr(slab), slab.size, _ptr(desc), n, _ptr(recs), cap, C.byref(n_recs), _ptr(dup), _ptr(rec_off)))
+        out = recs[: n_recs.value]
+        if want_rec_off:
+            return out, dup[:n], rec_off
+        return out, dup[:n]
+
+    def segment_device(self, d_dna_ptr: int, dna_bytes: int, d_off_ptr: int, d_len_ptr: int, n_reads: int) -> int:
+        n_recs = C.c_uint64(0)
+        self._ck(self.lib.fqsk_segment_device(self.h, C.c_void_p(d_dna_ptr), dna_bytes, C.c_void_p(d_off_ptr), C.c_void_p(d_len_ptr), n_reads, C.byref(n_recs)))
+        return n_recs.value
+
+    def device_recs(self):
+        p = C.c_void_p()
+        n = C.c_uint64(0)
+        self._ck(self.lib.fqsk_device_recs(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def sync(self):
+        self._ck(self.lib.fqsk_sync(self.h))
+
+    def dump(self, which):
+        n = C.c_uint64(0)
+        self._ck(self.lib.fqsk_dump(self.h, which, None, None, 0, C.byref(n)))
+        k = np.zeros(max(n.value, 1), np.uint64)
+        v = np.zeros(max(n.value, 1), np.uint64)
+        self._ck(self.lib.fqsk_dump(self.h, which, _ptr(k), _ptr(v), n.value, C.byref(n)))
+        return k[: n.value], v[: n.value]
+
+    def stats(self):
+        st = _Stats()
+        self._ck(self.lib.fqsk_stats_get(self.h, C.byref(st)))
+        d = {f: getattr(st, f) for f, _ in _Stats._fields_ if f != "draws"}
+        d.update(draws_b=st.draws[0], draws_s=st.draws[1], draws_lb=st.draws[2], draws_ls=st.draws[3])
+        return d
+
+    def profile(self):
+        ms = (C.c_double * len(PHASES))()
+        self._ck(self.lib.fqsk_profile(self.h, ms, len(PHASES)))
+        return dict(zip(PHASES, list(ms)))
+
+    # ---- table-level batch mirrors (CHT_kmer<T>, TSmallIntVector<2>) ----
+    def ht_insert(self, table, kmers):
+        kmers = np.ascontiguousarray(kmers, np.uint64)
+        self._ck(self.lib.fqsk_ht_insert(self.h, table, _ptr(kmers), len(kmers)))
+
+    def ht_find(self, table, d, rc, cur):
+        d = np.ascontiguousarray(d, np.uint64)
+        rc = np.ascontiguousarray(rc, np.uint64)
+        cur = np.ascontiguousarray(cur, np.uint32)
+        out = np.zeros(4 * max(len(d), 1), np.uint32)
+        self._ck(self.lib.fqsk_ht_find(self.h, table, _ptr(d), _ptr(rc), _ptr(cur), len(d), _ptr(out)))
+        return out[: 4 * len(d)].reshape(-1, 4)
+
+    def ht_count(self, table, kmers):
+        kmers = np.ascontiguousarray(kmers, np.uint64)
+        out = np.zeros(max(len(kmers), 1), np.uint32)
+        self._ck(self.lib.fqsk_ht_count(self.h, table, _ptr(kmers), len(kmers), _ptr(out)))
+        return out[: len(kmers)]
+
+    def siv_increment(self, idx):
+        idx = np.ascontiguousarray(idx, np.uint64)
+        nn = C.c_uint64(0)
+        self._ck(self.lib.fqsk_siv_increment(self.h, _ptr(idx), len(idx), C.byref(nn)))
+        return nn.value
+
+    def siv_test(self, idx):
+        idx = np.ascontiguousarray(idx, np.uint64)
+        out = np.zeros(max(len(idx), 1), np.uint32)
+        self._ck(self.lib.fqsk_siv_test(self.h, _ptr(idx), len(idx), _ptr(out)))
+        return out[: len(idx)]
+
+    def siv_counts(self, idx):
+        idx = np.ascontiguousarray(idx, np.uint64)
+        out = np.zeros(4 * max(len(idx), 1), np.uint32)
+        self._ck(self.lib.fqsk_siv_counts(self.h, _ptr(idx), len(idx), _ptr(out)))
+        return out[: 4 * len(idx)].reshape(-1, 4)
+
+    def siv_test_shorter(self, idx, size_bits):
+        idx = np.ascontiguousarray(idx, np.uint64)
+        size_bits = np.ascontiguousarray(size_bits, np.uint32)
+        out = np.zeros(max(len(idx), 1), np.uint64)
+        self._ck(self.lib.fqsk_siv_test_shorter(self.h, _ptr(idx), _ptr(size_bits), len(idx), _ptr(out)))
+        return out[: len(idx)]
+
+    def mt_stream(self, n):
+        out = np.zeros(n, np.uint32)
+        self._ck(self.lib.fqsk_mt_stream(self.h, n, _ptr(out)))
+        return out

@@ -1,0 +1,151 @@
+/* fqsk.h -- C-ABI of the B200 k-mer statistics engine for FQSqueezer (libfqsk.so).
+ *
+ * Drop-in boundary for ONE path of refresh-bio/fqsqueezer 1.1: the k-mer statistics engine behind
+ * CDNACompressor (dna.cpp) -- CKmer (kmer.h), CHT_kmer<T> (ht_kmer.h), TSmallIntVector<2> (bit_vec.h),
+ * CCounterIncrementer (utils.h:256-335).  The reference calls those classes ~13 times per base; a per-call
+ * mirror cannot be fast, so the boundary is lifted to what CDNACompressor::compress_suffix (dna.cpp:674-877)
+ * needs per sync segment.  Everything below is plain C: pointers and sizes only.
+ *
+ * All `reference:` citations are relative to /root/reference/fqs/.
+ * Every function returns 0 on success or a negative FQSK_E_* code; nothing throws across the ABI.
+ * There is NO CPU fallback: without a CUDA device fqsk_create fails with FQSK_E_NO_DEVICE.
+ */
+#ifndef FQSK_H
+#define FQSK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FQSK_ABI_VERSION 1
+
+enum {
+	FQSK_OK = 0,
+	FQSK_E_INVAL = -1,        /* bad argument */
+	FQSK_E_NO_DEVICE = -2,    /* no usable CUDA device */
+	FQSK_E_CUDA = -3,         /* CUDA runtime error, see fqsk_last_error() */
+	FQSK_E_NOMEM = -4,        /* device allocation failed */
+	FQSK_E_CAPACITY = -5,     /* caller's output buffer too small */
+	FQSK_E_UNSUPPORTED = -6,  /* input needs a path that is not implemented yet (reported, never silently approximated) */
+	FQSK_E_NO_CONVERGE = -7   /* ordered-replay fix point did not settle within the iteration limit */
+};
+
+/* dna_mode_t, reference: params.h:18 */
+enum { FQSK_MODE_SE_ORIGINAL = 0, FQSK_MODE_SE_SORTED = 1, FQSK_MODE_PE_ORIGINAL = 2, FQSK_MODE_PE_SORTED = 3 };
+/* counts_level_t, reference: defs.h:46 */
+enum { FQSK_LEVEL_NONE = 0, FQSK_LEVEL_PMER = 1, FQSK_LEVEL_SMER = 2, FQSK_LEVEL_BMER = 3, FQSK_LEVEL_MIXED = 4, FQSK_LEVEL_BMER_UNC = 5 };
+/* tables, for fqsk_dump / fqsk_ht_* */
+enum { FQSK_TABLE_SIV = 0, FQSK_TABLE_SMER = 1, FQSK_TABLE_BMER = 2, FQSK_TABLE_PAIR = 3 };
+
+/* Replaces the constructor arguments of the reference's tables (application.cpp:86-91, ht_kmer.h:366-399,
+ * bit_vec.h:29-40) and the k-mer lengths chosen by CParams::adjust_kmer_sizes (params.h:131-155). */
+typedef struct fqsk_params {
+	uint32_t abi_version;        /* FQSK_ABI_VERSION */
+	uint32_t pmer_len, smer_len, bmer_len, prefix_len;
+	uint32_t smer_counter_bits;  /* 12, defs.h:26 */
+	uint32_t bmer_counter_bits;  /* 6,  defs.h:27 */
+	uint32_t mode;               /* FQSK_MODE_* */
+	uint32_t n_workers;          /* reference -t; only 1 is bit-exact with `fqs-1.1 -t 1` and only 1 is accepted */
+	int32_t device;              /* CUDA ordinal */
+	uint32_t bmer_log2_buckets;  /* 0 = choose from expected_kmers; 8 slots of 4 bytes per bucket */
+	uint32_t smer_log2_buckets;
+	uint64_t expected_kmers;     /* hint for initial table sizes (distinct b-mers); tables grow when half full */
+	/* hash sharding across the GPUs of one box: this handle owns the k-mers whose owner key == rank */
+	uint32_t world_size, rank;
+	uint32_t max_iterations;     /* fix-point limit per segment, 0 = default (16) */
+	uint32_t flags;              /* FQSK_F_* */
+} fqsk_params;
+
+#define FQSK_F_PROFILE 1u        /* record CUDA-event timings per internal phase (fqsk_profile) */
+
+typedef struct fqsk_handle fqsk_handle;
+
+/* One read of a reads_block slab: replaces read_desc_t::dna / read_len() (defs.h:58-85). */
+typedef struct fqsk_read_desc {
+	uint64_t dna_off;            /* byte offset of the first DNA symbol inside the slab */
+	uint32_t dna_len;            /* number of DNA symbols */
+	uint32_t flags;              /* reserved (PE: bit0 = second mate) */
+} fqsk_read_desc;
+
+/* One record per coded suffix base, in the order compress_suffix visits them: exactly the values the host-side
+ * context model consumes at dna.cpp:737-760 (counts, level after the bmer_unc->bmer and rough->pmer rewrites at
+ * 697-735, the rough flag, and cor_pos as used by the cor_zone formula at 741).  28 bytes, little endian. */
+typedef struct fqsk_base_rec {
+	uint32_t pos;
+	uint32_t counts[4];
+	uint32_t cor_pos;
+	uint8_t level;
+	uint8_t rough;
+	uint16_t pad;
+} fqsk_base_rec;
+
+typedef struct fqsk_stats {
+	uint64_t siv_no_filled, siv_no_updates;  /* bit_vec.h:25-26, 204-220: feed avg_filling_factor (dna.cpp:376) */
+	uint64_t n_smers, n_bmers;               /* ht_kmer.h:46, 531-534 */
+	uint64_t draws[4];                       /* mt19937 outputs consumed so far: cinc_b, cinc_s, cinc_lb, cinc_ls (dna.cpp:162-165) */
+	uint64_t n_segments, n_syncs, n_replays; /* engine counters: replays / segments = fix-point cost */
+	uint64_t n_bases, n_reads;
+	uint64_t kernel_launches;                /* launches of this library's own kernels */
+	uint64_t bmer_buckets, smer_buckets, bmer_stash_used, smer_stash_used;
+} fqsk_stats;
+
+/* Named phases of fqsk_profile(): device milliseconds accumulated since create (only with FQSK_F_PROFILE). */
+enum { FQSK_PH_PREP = 0, FQSK_PH_REPLAY, FQSK_PH_COMPACT, FQSK_PH_DELTA, FQSK_PH_SYNC_LOCATE, FQSK_PH_SYNC_SORT, FQSK_PH_SYNC_APPLY,
+       FQSK_PH_SYNC_SIV, FQSK_PH_MT, FQSK_PH_COUNT };
+
+int fqsk_create(const fqsk_params *p, fqsk_handle **out);
+void fqsk_destroy(fqsk_handle *h);
+const char *fqsk_last_error(fqsk_handle *h);   /* also valid with h == NULL after a failed create */
+
+/* application.cpp:624 (ResetReadPrev at the start of every reads_block). */
+int fqsk_block_start(fqsk_handle *h);
+
+/* Replaces, for the reads [0, n_reads) of one sync segment (application.cpp:630-655), every k-mer-engine call made by
+ * CDNACompressor::CompressDirect / CompressSorted (dna.cpp:1517-1556, 1716-1754): register updates, find_counts,
+ * rough searches, repairs, pushes to the to_add rows and to the intra-segment delta tables.
+ *   slab/reads : the CReadsBlock slab (reads_block.h:18-215) and the reads of this segment (host memory)
+ *   recs       : out, capacity rec_cap records; *n_recs = records written (sum of coded suffix bases)
+ *   dup        : out, n_reads bytes, 1 = duplicate of the previous read (coded as a flag, no k-mer work; dna.cpp:1523-1533)
+ *   rec_off    : out (optional, may be NULL), n_reads + 1 entries: first record of every read
+ * Side effect: the segment's pending table updates are kept on the device until fqsk_sync. */
+int fqsk_segment(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const fqsk_read_desc *reads, uint32_t n_reads,
+                 fqsk_base_rec *recs, uint64_t rec_cap, uint64_t *n_recs, uint8_t *dup, uint64_t *rec_off);
+
+/* Same, with the reads already resident in HBM (bench `value`): d_dna is a device pointer to the concatenated DNA bytes
+ * (ASCII), d_off/d_len device arrays (u64 / u32); records stay on the device in the handle (fqsk_device_recs). */
+int fqsk_segment_device(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes, const uint64_t *d_off, const uint32_t *d_len,
+                        uint32_t n_reads, uint64_t *n_recs);
+int fqsk_device_recs(fqsk_handle *h, const fqsk_base_rec **d_recs, uint64_t *n_recs);
+
+/* Replaces CDNACompressor::InsertKmersToHT + ClearKmersToHT (dna.cpp:2393-2488) and the three barriers around them
+ * (application.cpp:645-654): p-mers, then s-mers, then b-mers, in push order, with the reference's PRNG draw order. */
+int fqsk_sync(fqsk_handle *h);
+
+/* Sorted (key, value) contents: FQSK_TABLE_SIV -> (p-mer index, 2-bit field); SMER/BMER -> (normalised k-mer, counter).
+ * Call with keys == NULL to get the count in *n.  Replaces nothing in the reference; parity check 1. */
+int fqsk_dump(fqsk_handle *h, int table, uint64_t *keys, uint64_t *vals, uint64_t cap, uint64_t *n);
+int fqsk_stats_get(fqsk_handle *h, fqsk_stats *out);
+int fqsk_profile(fqsk_handle *h, double *ms, uint32_t n);   /* n <= FQSK_PH_COUNT */
+
+/* ---- table-level batch mirrors (unit parity with the reference classes; also the multi-GPU exchange building blocks) ---- */
+/* CHT_kmer<T>::insert for a list in order, with the table's CCounterIncrementer stream (ht_kmer.h:420-438). */
+int fqsk_ht_insert(fqsk_handle *h, int table, const uint64_t *kmers_normalized, uint64_t n);
+/* CHT_kmer<T>::find on n registers in order (ht_kmer.h:504-510): full registers -> find_full, front-truncated -> find_partial
+ * with the ordered PRNG-aware merge.  counts: 4 x u32 per query. */
+int fqsk_ht_find(fqsk_handle *h, int table, const uint64_t *kmer_dir, const uint64_t *kmer_rc, const uint32_t *cur_size, uint64_t n, uint32_t *counts);
+/* CHT_kmer<T>::count(uint64_t) (ht_kmer.h:441-454). */
+int fqsk_ht_count(fqsk_handle *h, int table, const uint64_t *kmers_normalized, uint64_t n, uint32_t *out);
+/* TSmallIntVector<2>::increment / test / counts / test_shorter (bit_vec.h:53-123). */
+int fqsk_siv_increment(fqsk_handle *h, const uint64_t *idx, uint64_t n, uint64_t *n_new);
+int fqsk_siv_test(fqsk_handle *h, const uint64_t *idx, uint64_t n, uint32_t *out);
+int fqsk_siv_counts(fqsk_handle *h, const uint64_t *idx, uint64_t n, uint32_t *out4);
+int fqsk_siv_test_shorter(fqsk_handle *h, const uint64_t *idx, const uint32_t *size_bits, uint64_t n, uint64_t *out);
+/* First n outputs of std::mt19937 seeded 5481 as generated on the device (utils.h:298). */
+int fqsk_mt_stream(fqsk_handle *h, uint64_t n, uint32_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FQSK_H */
