@@ -35,8 +35,10 @@ def run_se(engine, slab, kind=0, max_blocks=None):
 def assert_recs_equal(got, want):
     want = want[want["pos"] != O.POS_SYNC]
     assert len(got) == len(want), (len(got), len(want))
-    a = got.view(np.uint8).reshape(len(got), -1)
-    b = want.view(np.uint8).reshape(len(want), -1)
+    if len(got) == 0:
+        return
+    a = np.ascontiguousarray(got).view(np.uint8).reshape(len(got), -1)
+    b = np.ascontiguousarray(want).view(np.uint8).reshape(len(want), -1)
     bad = np.flatnonzero((a != b).any(axis=1))
     assert len(bad) == 0, f"{len(bad)} records differ, first at {bad[0]}: got {got[bad[0]]} want {want[bad[0]]}"
 
