@@ -17,7 +17,7 @@
 #include <string>
 #include <vector>
 
-#include "fqsk_kernels.cuh"
+#include "fqsk_pipeline.cuh"
 
 using namespace fqsk;
 
@@ -75,7 +75,12 @@ struct fqsk_handle {
 	// segment buffers
 	DevBuf dna, off, len, dup, n_coded, letters, rec_off, sl_prefix, recs, push_b, push_s, push_p, cnt_b, cnt_s, cnt_p, hidden,
 	       draw_cnt, draw_cnt_prev, draw_scan, off_b[2], off_s[2], off_p, row_b[2], row_s[2], row_p, dk_b, di_b, dk_s, di_s, iota, cub_tmp,
-	       slot, val, slot_sorted, val_sorted, flag8, draw_off, final_cnt, dump_k, dump_v, q0, q1, q2, q3, q4, sflag, sdif, hid_scan;
+	       flag8, draw_off, final_cnt, slot_of, dump_k, dump_v, q0, q1, q2, q3, q4, sflag, sdif, hid_scan,
+	       prov, pflags, pscripts, rscripts, rreqs, pool, miss, draws_b16, draws_s16, doff_b, doff_s, time_b, time_s, rt_b[2], rt_s[2],
+	       sidx_b, sidx_s, stime_b, stime_s, sort_k, sort_v;
+	uint32_t miss_cap = 0, rreq_cap = 0, pool_cap = 1u << 18;
+	uint32_t *d_u32 = nullptr;            // [0] n_miss [1] n_rreq [2] pool_used
+	bool delta_b_valid = false, delta_s_valid = false;   // dk_b/sidx_b (dk_s/sidx_s) hold the pending row sorted by k-mer
 	uint32_t iota_n = 0;
 	// pending rows (device), valid after fqsk_segment until fqsk_sync
 	bool pending = false;
@@ -289,22 +294,17 @@ int table_grow_if_needed(fqsk_handle *h, Table &t) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// ordered insert of a row of k-mers into one table (CHT_kmer::insert in push order with one PRNG stream)
+// ordered insert of a row of k-mers into one table (CHT_kmer::insert in push order with one PRNG stream).
+// Input: the row sorted by k-mer (stable) + the push index of every sorted occurrence.
 // ---------------------------------------------------------------------------------------------------------------
-int apply_inserts(fqsk_handle *h, Table &t, Stream &rng, const unsigned long long *d_kmers, uint32_t n) {
+int apply_sorted(fqsk_handle *h, Table &t, Stream &rng, const unsigned long long *skeys, const uint32_t *sidx, uint32_t n) {
 	if (!n) return FQSK_OK;
-	if (n >= 0x80000000u) return fail(h, FQSK_E_INVAL, "more than 2^31 k-mers in one sync row");
-	CK(h->slot.ensure((size_t) n * 4)); CK(h->val.ensure((size_t) n * 4));
-	CK(h->slot_sorted.ensure((size_t) n * 4)); CK(h->val_sorted.ensure((size_t) n * 4));
+	CK(h->slot_of.ensure((size_t) n * 8));
 	CK(h->flag8.ensure((size_t) n + 4)); CK(h->draw_off.ensure(((size_t) n + 1) * 4)); CK(h->final_cnt.ensure((size_t) n * 4));
 	{
 		Phase ph(h, FQSK_PH_SYNC_LOCATE);
-		k_locate<<<nblk(n, 256), 256, 0, h->st>>>(t.d, d_kmers, n, h->slot.as<uint32_t>(), h->val.as<uint32_t>());
+		k_locate_heads<<<nblk(n, 256), 256, 0, h->st>>>(t.d, skeys, n, h->slot_of.as<unsigned long long>());
 		LAUNCHED(h);
-	}
-	{
-		Phase ph(h, FQSK_PH_SYNC_SORT);
-		CKR(sort_pairs_u32_u32(h, h->slot.as<uint32_t>(), h->slot_sorted.as<uint32_t>(), h->val.as<uint32_t>(), h->val_sorted.as<uint32_t>(), n, (int) t.d.B + 4));
 	}
 	Phase ph(h, FQSK_PH_SYNC_APPLY);
 	CK(cudaMemsetAsync(h->flag8.p, 0, (size_t) n + 4, h->st));
@@ -312,12 +312,12 @@ int apply_inserts(fqsk_handle *h, Table &t, Stream &rng, const unsigned long lon
 	uint32_t total_draws = 0;
 	for (int it = 0;; ++it) {
 		if (it > 64) return fail(h, FQSK_E_NO_CONVERGE, "sync insert: draw flags did not settle");
-		CK(cudaMemsetAsync(h->d_flags, 0, 4 * sizeof(int), h->st));
-		k_apply<<<nblk(n, 256), 256, 0, h->st>>>(t.d, t.ci, h->slot_sorted.as<uint32_t>(), h->val_sorted.as<uint32_t>(), n, h->flag8.as<uint8_t>(),
-		                                          h->draw_off.as<uint32_t>(), stream_ptr(rng), stream_avail(rng), h->final_cnt.as<uint32_t>(), h->d_flags);
+		CK(cudaMemsetAsync(h->d_flags, 0, 8 * sizeof(int), h->st));
+		k_apply_keys<<<nblk(n, 256), 256, 0, h->st>>>(t.d, t.ci, skeys, sidx, n, h->slot_of.as<unsigned long long>(), h->flag8.as<uint8_t>(),
+		                                               h->draw_off.as<uint32_t>(), stream_ptr(rng), stream_avail(rng), h->final_cnt.as<uint32_t>(), h->d_flags);
 		LAUNCHED(h);
-		int fl[4];
-		CKR(read_flags(h, fl, 4));
+		int fl[8];
+		CKR(read_flags(h, fl, 8));
 		if (!fl[2] && !fl[0]) break;
 		// flags changed (or the draw window was short): rescan the draw indices in push order and make the window long enough
 		CKR((scan_excl<uint8_t, uint32_t>(h, h->flag8.as<uint8_t>(), h->draw_off.as<uint32_t>(), n + 1, 0u)));
@@ -326,10 +326,27 @@ int apply_inserts(fqsk_handle *h, Table &t, Stream &rng, const unsigned long lon
 		total_draws = *(uint32_t *) h->h_small;
 		CKR(stream_ensure(h, rng, total_draws));
 	}
-	k_commit<<<nblk(n, 256), 256, 0, h->st>>>(t.d, h->slot_sorted.as<uint32_t>(), n, h->final_cnt.as<uint32_t>());
+	k_commit_keys<<<nblk(n, 256), 256, 0, h->st>>>(t.d, skeys, n, h->slot_of.as<unsigned long long>(), h->final_cnt.as<uint32_t>());
 	LAUNCHED(h);
 	rng.consumed += total_draws;
 	return FQSK_OK;
+}
+
+// sort a row by k-mer (stable): out keys + push indices
+int sort_row(fqsk_handle *h, const unsigned long long *row, uint32_t n, uint32_t k, DevBuf &keys_out, DevBuf &idx_out) {
+	if (!n) return FQSK_OK;
+	Phase ph(h, FQSK_PH_SYNC_SORT);
+	CK(keys_out.ensure((size_t) n * 8)); CK(idx_out.ensure((size_t) n * 4));
+	CKR(ensure_iota(h, n));
+	CKR(sort_pairs_u64_u32(h, row, keys_out.as<unsigned long long>(), h->iota.as<uint32_t>(), idx_out.as<uint32_t>(), n, 64 - 2 * (int) k, 64));
+	return FQSK_OK;
+}
+
+int apply_inserts(fqsk_handle *h, Table &t, Stream &rng, const unsigned long long *d_kmers, uint32_t n) {
+	if (!n) return FQSK_OK;
+	if (n >= 0x80000000u) return fail(h, FQSK_E_INVAL, "more than 2^31 k-mers in one sync row");
+	CKR(sort_row(h, d_kmers, n, t.d.k, h->sort_k, h->sort_v));
+	return apply_sorted(h, t, rng, h->sort_k.as<unsigned long long>(), h->sort_v.as<uint32_t>(), n);
 }
 
 EngineDev make_engine_dev(fqsk_handle *h) {
@@ -344,9 +361,172 @@ EngineDev make_engine_dev(fqsk_handle *h) {
 	return E;
 }
 
+const int RC_RETRY = 1;   // internal: a capacity was too small, grow and redo the segment
+
 // ---------------------------------------------------------------------------------------------------------------
-// one sync segment, reads resident on the device
+// one sync segment, reads resident on the device (DESIGN.md section 5)
 // ---------------------------------------------------------------------------------------------------------------
+int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes, uint32_t n_rec, uint32_t first) {
+	const size_t n1 = (size_t) n + 1, r1 = (size_t) n_rec + 1;
+	const uint32_t pslots = h->P.bmer_len - h->P.pmer_len + 1;
+	CK(h->prov.ensure(r1 * sizeof(fqsk_base_rec))); CK(h->recs.ensure(r1 * sizeof(fqsk_base_rec))); CK(h->pflags.ensure(r1));
+	CK(h->pscripts.ensure(n1 * pslots * sizeof(Script)));
+	CK(h->rscripts.ensure(((size_t) h->rreq_cap + 1) * sizeof(Script))); CK(h->rreqs.ensure(((size_t) h->rreq_cap + 1) * sizeof(RoughReq)));
+	CK(h->pool.ensure(((size_t) h->pool_cap + 1) * 8)); CK(h->miss.ensure(((size_t) h->miss_cap + 1) * sizeof(MissEntry)));
+	CK(h->draws_b16.ensure(r1 * 2)); CK(h->draws_s16.ensure(r1 * 2)); CK(h->doff_b.ensure(r1 * 8)); CK(h->doff_s.ensure(r1 * 8));
+	CK(h->time_b.ensure((2 * dna_bytes + 2) * 4)); CK(h->time_s.ensure((dna_bytes + 1) * 4));
+	for (int i = 0; i < 2; ++i) { CK(h->rt_b[i].ensure((2 * dna_bytes + 2) * 4)); CK(h->rt_s[i].ensure((dna_bytes + 1) * 4)); }
+
+	PipeDev P{};
+	P.n_rec = n_rec; P.start = first; P.rec_off = S.rec_off;
+	P.prov = h->prov.as<fqsk_base_rec>(); P.recs = h->recs.as<fqsk_base_rec>(); P.pflags = h->pflags.as<uint8_t>();
+	P.pscripts = h->pscripts.as<Script>(); P.pslots = pslots; P.pfirst_n = h->P.pmer_len - 1;
+	P.rscripts = h->rscripts.as<Script>(); P.rreqs = h->rreqs.as<RoughReq>(); P.n_rreq = h->d_u32 + 1; P.rreq_cap = h->rreq_cap;
+	P.pool = h->pool.as<unsigned short>(); P.pool_used = h->d_u32 + 2; P.pool_cap = h->pool_cap;
+	P.miss = h->miss.as<MissEntry>(); P.n_miss = h->d_u32 + 0; P.miss_cap = h->miss_cap;
+	P.draws_b = h->draws_b16.as<unsigned short>(); P.draws_s = h->draws_s16.as<unsigned short>();
+	P.doff_b = h->doff_b.as<unsigned long long>(); P.doff_s = h->doff_s.as<unsigned long long>();
+	P.time_b = h->time_b.as<uint32_t>(); P.time_s = h->time_s.as<uint32_t>();
+	P.flags = h->d_flags;
+	S.recs = P.recs;
+
+	EngineDev E = make_engine_dev(h);
+	CK(cudaMemsetAsync(h->d_u32, 0, 8 * 4, h->st));
+	CK(cudaMemsetAsync(h->d_flags, 0, 8 * sizeof(int), h->st));
+	if (n_rec) {
+		Phase ph(h, FQSK_PH_REPLAY);
+		k_lookup<<<nblk(n_rec, 256), 256, 0, h->st>>>(E, S, P); LAUNCHED(h);
+		k_partial<<<nblk((uint64_t) n * pslots * 32, 128), 128, 0, h->st>>>(E, S, P); LAUNCHED(h);
+	}
+	S.delta_b = DeltaDev{nullptr, nullptr, 0, h->tb.ci.thr + 1};
+	S.delta_s = DeltaDev{nullptr, nullptr, 0, h->ts.ci.thr + 1};
+	h->delta_b_valid = h->delta_s_valid = false;
+	const uint32_t max_it = h->P.max_iterations ? h->P.max_iterations : 16;
+	int cur = 0;
+	uint32_t tot_b = 0, tot_s = 0, tot_p = 0, tot_b_prev = 0, tot_s_prev = 0, n_miss = 0, n_rreq = 0;
+	bool window_local_it0 = false;
+	auto build_delta = [&](int c) -> int {
+		Phase ph(h, FQSK_PH_DELTA);
+		CKR(sort_row(h, h->row_b[c].as<unsigned long long>(), tot_b, h->P.bmer_len, h->dk_b, h->sidx_b));
+		CKR(sort_row(h, h->row_s[c].as<unsigned long long>(), tot_s, h->P.smer_len, h->dk_s, h->sidx_s));
+		CK(h->stime_b.ensure((size_t) tot_b * 4 + 4)); CK(h->stime_s.ensure((size_t) tot_s * 4 + 4));
+		if (tot_b) { k_gather_u32<<<nblk(tot_b, 256), 256, 0, h->st>>>(h->rt_b[c].as<uint32_t>(), h->sidx_b.as<uint32_t>(), tot_b, h->stime_b.as<uint32_t>()); LAUNCHED(h); }
+		if (tot_s) { k_gather_u32<<<nblk(tot_s, 256), 256, 0, h->st>>>(h->rt_s[c].as<uint32_t>(), h->sidx_s.as<uint32_t>(), tot_s, h->stime_s.as<uint32_t>()); LAUNCHED(h); }
+		S.delta_b = DeltaDev{h->dk_b.as<unsigned long long>(), h->stime_b.as<uint32_t>(), tot_b, h->tb.ci.thr + 1};
+		S.delta_s = DeltaDev{h->dk_s.as<unsigned long long>(), h->stime_s.as<uint32_t>(), tot_s, h->ts.ci.thr + 1};
+		h->delta_b_valid = h->delta_s_valid = true;
+		return FQSK_OK;
+	};
+	for (uint32_t it = 0;; ++it) {
+		if (it >= max_it) return fail(h, FQSK_E_NO_CONVERGE, "segment did not reach its fixed point in %u iterations", max_it);
+		CK(cudaMemsetAsync(h->d_u32 + 1, 0, 4, h->st));          // rough requests are re-issued by every walk
+		CK(cudaMemsetAsync(h->d_flags + 3, 0, sizeof(int), h->st));
+		{
+			Phase ph(h, FQSK_PH_REPLAY);
+			k_walk<<<nblk(n, 128), 128, 0, h->st>>>(E, S, P); LAUNCHED(h);
+			++h->S.n_replays;
+		}
+		{
+			Phase ph(h, FQSK_PH_COMPACT);
+			CK(cudaMemsetAsync(h->cnt_b.as<uint32_t>() + n, 0, 4, h->st)); CK(cudaMemsetAsync(h->cnt_s.as<uint32_t>() + n, 0, 4, h->st));
+			CK(cudaMemsetAsync(h->cnt_p.as<uint32_t>() + n, 0, 4, h->st));
+			CKR((scan_excl<uint32_t, uint32_t>(h, h->cnt_b.as<uint32_t>(), h->off_b[cur].as<uint32_t>(), n + 1, 0u)));
+			CKR((scan_excl<uint32_t, uint32_t>(h, h->cnt_s.as<uint32_t>(), h->off_s[cur].as<uint32_t>(), n + 1, 0u)));
+			CKR((scan_excl<uint32_t, uint32_t>(h, h->cnt_p.as<uint32_t>(), h->off_p.as<uint32_t>(), n + 1, 0u)));
+			k_compact2<<<n, 64, 0, h->st>>>(S, P, h->off_b[cur].as<uint32_t>(), h->off_s[cur].as<uint32_t>(), h->off_p.as<uint32_t>(),
+			                               h->row_b[cur].as<unsigned long long>(), h->row_s[cur].as<unsigned long long>(), h->row_p.as<unsigned long long>(),
+			                               h->rt_b[cur].as<uint32_t>(), h->rt_s[cur].as<uint32_t>());
+			LAUNCHED(h);
+			uint32_t *hs = (uint32_t *) h->h_small;
+			CK(cudaMemcpyAsync(hs + 0, h->off_b[cur].as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, h->st));
+			CK(cudaMemcpyAsync(hs + 1, h->off_s[cur].as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, h->st));
+			CK(cudaMemcpyAsync(hs + 2, h->off_p.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, h->st));
+			CK(cudaMemcpyAsync(hs + 4, h->d_u32, 3 * 4, cudaMemcpyDeviceToHost, h->st));
+			CK(cudaMemcpyAsync(hs + 8, h->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+			CK(cudaStreamSynchronize(h->st));
+			resolve_phases(h);
+			tot_b = hs[0]; tot_s = hs[1]; tot_p = hs[2]; n_miss = hs[4]; n_rreq = hs[5];
+			int fl[8]; memcpy(fl, hs + 8, sizeof fl);
+			if (fl[4]) {
+				if (n_miss > h->miss_cap) h->miss_cap = n_miss + n_miss / 4 + 1024;
+				if (n_rreq > h->rreq_cap) h->rreq_cap = n_rreq + n_rreq / 4 + 1024;
+				if (hs[6] > h->pool_cap) h->pool_cap = hs[6] + hs[6] / 2 + 1024;
+				return RC_RETRY;
+			}
+			if (fl[5]) return fail(h, FQSK_E_CUDA, "internal error: a draw was requested on a path that must not draw");
+			if (fl[1]) return fail(h, FQSK_E_UNSUPPORTED, "segment needs the thread-local PRNG streams (a k-mer occurs more than %u times inside one sync segment and is looked up there, or a thread-local merge exceeds the deterministic range); not implemented yet", h->tb.ci.thr + 1);
+			if (it == 0) window_local_it0 = fl[3] != 0;
+		}
+		bool need_more;
+		if (it == 0) {
+			need_more = (n_miss > 0 || window_local_it0) && (tot_b + tot_s > 0);
+			if (need_more) {
+				CKR(build_delta(cur));
+				CK(cudaMemsetAsync(h->d_flags + 6, 0, sizeof(int), h->st));
+				if (n_miss) { Phase ph(h, FQSK_PH_DELTA); k_local<<<nblk(n_miss, 128), 128, 0, h->st>>>(E, S, P, n_miss); LAUNCHED(h); }
+				int fl[8];
+				CKR(read_flags(h, fl, 8));
+				if (fl[1]) return fail(h, FQSK_E_UNSUPPORTED, "segment needs the thread-local PRNG streams; not implemented yet");
+				if (!fl[6] && !window_local_it0) need_more = false;   // nobody saw anything in the thread-local tables: the walk stands
+			}
+		} else {
+			bool changed = (tot_b != tot_b_prev) || (tot_s != tot_s_prev);
+			if (!changed) {
+				CK(cudaMemsetAsync(h->d_flags + 2, 0, sizeof(int), h->st));
+				if (tot_b) {
+					k_compare_u64<<<nblk(tot_b, 256), 256, 0, h->st>>>(h->row_b[cur].as<unsigned long long>(), h->row_b[cur ^ 1].as<unsigned long long>(), tot_b, h->d_flags + 2); LAUNCHED(h);
+					k_compare_u32<<<nblk(tot_b, 256), 256, 0, h->st>>>(h->rt_b[cur].as<uint32_t>(), h->rt_b[cur ^ 1].as<uint32_t>(), tot_b, h->d_flags + 2); LAUNCHED(h);
+				}
+				if (tot_s) {
+					k_compare_u64<<<nblk(tot_s, 256), 256, 0, h->st>>>(h->row_s[cur].as<unsigned long long>(), h->row_s[cur ^ 1].as<unsigned long long>(), tot_s, h->d_flags + 2); LAUNCHED(h);
+					k_compare_u32<<<nblk(tot_s, 256), 256, 0, h->st>>>(h->rt_s[cur].as<uint32_t>(), h->rt_s[cur ^ 1].as<uint32_t>(), tot_s, h->d_flags + 2); LAUNCHED(h);
+				}
+				int fl[8];
+				CKR(read_flags(h, fl, 8));
+				changed = fl[2] != 0;
+			}
+			need_more = changed;
+			if (need_more) {
+				CKR(build_delta(cur));
+				if (n_miss) { Phase ph(h, FQSK_PH_DELTA); k_local<<<nblk(n_miss, 128), 128, 0, h->st>>>(E, S, P, n_miss); LAUNCHED(h); }
+			}
+		}
+		if (!need_more) { h->cur = cur; break; }
+		tot_b_prev = tot_b; tot_s_prev = tot_s;
+		cur ^= 1;
+	}
+	// rough searches requested by the final walk, then the ordered merges of every script
+	if (n_rec) {
+		Phase ph(h, FQSK_PH_REPLAY);
+		if (n_rreq) { k_rough<<<nblk((uint64_t) n_rreq * 32, 128), 128, 0, h->st>>>(E, P, n_rreq); LAUNCHED(h); }
+		uint32_t n_ps = n * pslots;
+		k_fold<<<nblk(n_ps, 128), 128, 0, h->st>>>(E, P, P.pscripts, n_ps, 0); LAUNCHED(h);
+		if (n_rreq) { k_fold<<<nblk(n_rreq, 128), 128, 0, h->st>>>(E, P, P.rscripts, n_rreq, 0); LAUNCHED(h); }
+		for (int it = 0;; ++it) {
+			if (it > 32) return fail(h, FQSK_E_NO_CONVERGE, "draw offsets of the merge scripts did not settle");
+			CK(cudaMemsetAsync(h->draws_b16.as<unsigned short>() + n_rec, 0, 2, h->st)); CK(cudaMemsetAsync(h->draws_s16.as<unsigned short>() + n_rec, 0, 2, h->st));
+			CKR((scan_excl<unsigned short, unsigned long long>(h, h->draws_b16.as<unsigned short>(), h->doff_b.as<unsigned long long>(), n_rec + 1, 0ull)));
+			CKR((scan_excl<unsigned short, unsigned long long>(h, h->draws_s16.as<unsigned short>(), h->doff_s.as<unsigned long long>(), n_rec + 1, 0ull)));
+			unsigned long long *hs = (unsigned long long *) h->h_small;
+			CK(cudaMemcpyAsync(hs + 0, h->doff_b.as<unsigned long long>() + n_rec, 8, cudaMemcpyDeviceToHost, h->st));
+			CK(cudaMemcpyAsync(hs + 1, h->doff_s.as<unsigned long long>() + n_rec, 8, cudaMemcpyDeviceToHost, h->st));
+			CK(cudaStreamSynchronize(h->st));
+			unsigned long long db = hs[0], ds = hs[1];
+			CKR(stream_ensure(h, h->rng[ST_B], db)); CKR(stream_ensure(h, h->rng[ST_S], ds));
+			E = make_engine_dev(h);
+			CK(cudaMemsetAsync(h->d_flags, 0, 8 * sizeof(int), h->st));
+			k_fold<<<nblk(n_ps, 128), 128, 0, h->st>>>(E, P, P.pscripts, n_ps, 1); LAUNCHED(h);
+			if (n_rreq) { k_fold<<<nblk(n_rreq, 128), 128, 0, h->st>>>(E, P, P.rscripts, n_rreq, 1); LAUNCHED(h); }
+			int fl[8];
+			CKR(read_flags(h, fl, 8));
+			if (fl[0]) return fail(h, FQSK_E_CUDA, "internal error: draw window shorter than the scanned total");
+			if (!fl[2]) { h->rng[ST_B].consumed += db; h->rng[ST_S].consumed += ds; break; }
+		}
+	}
+	h->pend_b = tot_b; h->pend_s = tot_s; h->pend_p = tot_p;
+	return FQSK_OK;
+}
+
 int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes, const unsigned long long *d_off, const uint32_t *d_len, uint32_t n) {
 	if (h->pending) return fail(h, FQSK_E_INVAL, "fqsk_segment called twice without fqsk_sync (the reference syncs after every segment, application.cpp:643-662)");
 	const uint32_t first = (h->P.mode == FQSK_MODE_SE_SORTED || h->P.mode == FQSK_MODE_PE_SORTED) ? h->P.pmer_len : h->P.prefix_len;
@@ -356,17 +536,13 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes, const 
 	if (dna_bytes >= (1ull << 30)) return fail(h, FQSK_E_INVAL, "segment larger than 1 GiB of DNA");
 	const size_t n1 = (size_t) n + 1;
 	CK(h->dup.ensure(n)); CK(h->n_coded.ensure(n1 * 4)); CK(h->letters.ensure(n1 * 32)); CK(h->rec_off.ensure(n1 * 8)); CK(h->sl_prefix.ensure(n1 * 32));
-	CK(h->recs.ensure((dna_bytes + 1) * sizeof(fqsk_base_rec)));
 	CK(h->push_b.ensure((2 * dna_bytes + 2) * 8)); CK(h->push_s.ensure((dna_bytes + 1) * 8)); CK(h->push_p.ensure((2 * dna_bytes + 2 * n1) * 8));
 	CK(h->cnt_b.ensure(n1 * 4)); CK(h->cnt_s.ensure(n1 * 4)); CK(h->cnt_p.ensure(n1 * 4)); CK(h->hidden.ensure(n1 * 4));
-	CK(h->draw_cnt.ensure(n1 * 32)); CK(h->draw_cnt_prev.ensure(n1 * 32)); CK(h->draw_scan.ensure(n1 * 32));
 	for (int i = 0; i < 2; ++i) {
 		CK(h->off_b[i].ensure(n1 * 4)); CK(h->off_s[i].ensure(n1 * 4));
 		CK(h->row_b[i].ensure((2 * dna_bytes + 2) * 8)); CK(h->row_s[i].ensure((dna_bytes + 1) * 8));
 	}
 	CK(h->off_p.ensure(n1 * 4)); CK(h->row_p.ensure((2 * dna_bytes + 2 * n1) * 8));
-	CK(h->dk_b.ensure((2 * dna_bytes + 2) * 8)); CK(h->di_b.ensure((2 * dna_bytes + 2) * 4));
-	CK(h->dk_s.ensure((dna_bytes + 1) * 8)); CK(h->di_s.ensure((dna_bytes + 1) * 4));
 	CK(h->sflag.ensure(n1 * 4)); CK(h->sdif.ensure(n1 * 8)); CK(h->hid_scan.ensure(n1 * 4));
 
 	SegDev S{};
@@ -376,12 +552,11 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes, const 
 	S.dup = h->dup.as<uint8_t>(); S.n_coded = h->n_coded.as<uint32_t>(); S.letters = h->letters.as<U64x4>();
 	S.rec_off = h->rec_off.as<unsigned long long>(); S.sl_prefix = h->sl_prefix.as<U64x4>();
 	for (int i = 0; i < 4; ++i) S.sl_base.v[i] = h->sl_base[i];
-	S.recs = h->recs.as<fqsk_base_rec>();
 	S.push_b = h->push_b.as<unsigned long long>(); S.push_s = h->push_s.as<unsigned long long>(); S.push_p = h->push_p.as<unsigned long long>();
 	S.cnt_b = h->cnt_b.as<uint32_t>(); S.cnt_s = h->cnt_s.as<uint32_t>(); S.cnt_p = h->cnt_p.as<uint32_t>(); S.hidden = h->hidden.as<uint32_t>();
-	S.draw_cnt = h->draw_cnt.as<U64x4>(); S.draw_guess = h->draw_scan.as<U64x4>();
 	S.sorted_flag = h->sflag.as<uint32_t>(); S.sorted_dif = h->sdif.as<unsigned long long>();
 
+	unsigned long long n_rec64 = 0;
 	{
 		Phase ph(h, FQSK_PH_PREP);
 		CK(cudaMemsetAsync(h->n_coded.p, 0, n1 * 4, h->st));
@@ -391,112 +566,40 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes, const 
 		CKR((scan_excl<uint32_t, unsigned long long>(h, h->n_coded.as<uint32_t>(), h->rec_off.as<unsigned long long>(), n + 1, 0ull)));
 		U64x4 z{}; z.v[0] = z.v[1] = z.v[2] = z.v[3] = 0;
 		CKR((scan_excl<U64x4, U64x4>(h, h->letters.as<U64x4>(), h->sl_prefix.as<U64x4>(), n + 1, z)));
-		CK(cudaMemsetAsync(h->draw_scan.p, 0, n1 * 32, h->st));       // iteration 0 guesses: every read starts at the stream position
-		CK(cudaMemsetAsync(h->draw_cnt_prev.p, 0, n1 * 32, h->st));
+		CK(cudaMemcpyAsync(h->h_small, h->rec_off.as<unsigned long long>() + n, 8, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaStreamSynchronize(h->st));
+		n_rec64 = *(unsigned long long *) h->h_small;
 	}
-	// make sure some draws exist before the first replay (the overflow flag covers the rest)
-	for (int i = 0; i < 4; ++i) CKR(stream_ensure(h, h->rng[i], i == 0 ? std::max<uint64_t>(dna_bytes, 1u << 16) : i == 1 ? (1u << 16) : (1u << 12)));
-
-	const uint32_t max_it = h->P.max_iterations ? h->P.max_iterations : 16;
-	int cur = 0;
-	uint32_t tot_b_prev = 0, tot_s_prev = 0;
-	S.base_b = nullptr; S.base_s = nullptr;
-	S.delta_b = DeltaDev{nullptr, nullptr, 0, h->tb.ci.thr + 1};
-	S.delta_s = DeltaDev{nullptr, nullptr, 0, h->ts.ci.thr + 1};
-	uint32_t tot_b = 0, tot_s = 0, tot_p = 0;
-	U64x4 tot_draws{};
-	for (uint32_t it = 0;; ++it) {
-		if (it >= max_it) return fail(h, FQSK_E_NO_CONVERGE, "segment replay did not reach its fixed point in %u iterations", max_it);
-		EngineDev E = make_engine_dev(h);
-		CK(cudaMemsetAsync(h->d_flags, 0, 4 * sizeof(int), h->st));
-		{
-			Phase ph(h, FQSK_PH_REPLAY);
-			k_replay<<<nblk(n, 128), 128, 0, h->st>>>(E, S);
-			LAUNCHED(h);
-			++h->S.n_replays;
-		}
-		{
-			Phase ph(h, FQSK_PH_COMPACT);
-			// totals ride in slot n of the count arrays
-			CK(cudaMemsetAsync(h->cnt_b.as<uint32_t>() + n, 0, 4, h->st)); CK(cudaMemsetAsync(h->cnt_s.as<uint32_t>() + n, 0, 4, h->st));
-			CK(cudaMemsetAsync(h->cnt_p.as<uint32_t>() + n, 0, 4, h->st)); CK(cudaMemsetAsync(h->draw_cnt.as<U64x4>() + n, 0, 32, h->st));
-			CKR((scan_excl<uint32_t, uint32_t>(h, h->cnt_b.as<uint32_t>(), h->off_b[cur].as<uint32_t>(), n + 1, 0u)));
-			CKR((scan_excl<uint32_t, uint32_t>(h, h->cnt_s.as<uint32_t>(), h->off_s[cur].as<uint32_t>(), n + 1, 0u)));
-			CKR((scan_excl<uint32_t, uint32_t>(h, h->cnt_p.as<uint32_t>(), h->off_p.as<uint32_t>(), n + 1, 0u)));
-			k_compact<<<n, 64, 0, h->st>>>(S, h->off_b[cur].as<uint32_t>(), h->off_s[cur].as<uint32_t>(), h->off_p.as<uint32_t>(),
-			                              h->row_b[cur].as<unsigned long long>(), h->row_s[cur].as<unsigned long long>(), h->row_p.as<unsigned long long>());
-			LAUNCHED(h);
-			uint32_t *hs = (uint32_t *) h->h_small;
-			CK(cudaMemcpyAsync(hs + 0, h->off_b[cur].as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, h->st));
-			CK(cudaMemcpyAsync(hs + 1, h->off_s[cur].as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, h->st));
-			CK(cudaMemcpyAsync(hs + 2, h->off_p.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, h->st));
-			CK(cudaMemcpyAsync(hs + 4, h->d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
-			CK(cudaStreamSynchronize(h->st));
-			tot_b = hs[0]; tot_s = hs[1]; tot_p = hs[2];
-			int fl[4]; memcpy(fl, hs + 4, sizeof fl);
-			resolve_phases(h);
-			if (fl[1]) return fail(h, FQSK_E_UNSUPPORTED, "segment needs the thread-local PRNG streams (a k-mer occurs more than %u times inside one sync segment and is looked up there); not implemented yet", h->tb.ci.thr + 1);
-			if (fl[0]) {   // draw window too short: extend all streams generously and redo this iteration
-				for (int i = 0; i < 4; ++i) CKR(stream_ensure(h, h->rng[i], 2 * stream_avail(h->rng[i]) + (1u << 16)));
-				--it;
-				continue;
-			}
-		}
-		// did this iteration reproduce the state it was run against?
-		bool changed = (tot_b != tot_b_prev) || (tot_s != tot_s_prev);
-		if (!changed) {
-			CK(cudaMemsetAsync(h->d_flags + 2, 0, sizeof(int), h->st));
-			if (tot_b) { k_compare_u64<<<nblk(tot_b, 256), 256, 0, h->st>>>(h->row_b[cur].as<unsigned long long>(), h->row_b[cur ^ 1].as<unsigned long long>(), tot_b, h->d_flags + 2); LAUNCHED(h); }
-			if (tot_s) { k_compare_u64<<<nblk(tot_s, 256), 256, 0, h->st>>>(h->row_s[cur].as<unsigned long long>(), h->row_s[cur ^ 1].as<unsigned long long>(), tot_s, h->d_flags + 2); LAUNCHED(h); }
-			if (it > 0) {
-				k_compare_u32<<<nblk(n, 256), 256, 0, h->st>>>(h->off_b[cur].as<uint32_t>(), h->off_b[cur ^ 1].as<uint32_t>(), n, h->d_flags + 2); LAUNCHED(h);
-				k_compare_u32<<<nblk(n, 256), 256, 0, h->st>>>(h->off_s[cur].as<uint32_t>(), h->off_s[cur ^ 1].as<uint32_t>(), n, h->d_flags + 2); LAUNCHED(h);
-			}
-			k_compare_u64<<<nblk((uint64_t) n * 4, 256), 256, 0, h->st>>>((const unsigned long long *) h->draw_cnt.p, (const unsigned long long *) h->draw_cnt_prev.p, (uint64_t) n * 4, h->d_flags + 2);
-			LAUNCHED(h);
-			int fl[4];
-			CKR(read_flags(h, fl, 4));
-			changed = fl[2] != 0;
-		}
-		if (!changed) { h->cur = cur; break; }
-		// next iteration runs against this one's pushes and draw counts
-		{
-			Phase ph(h, FQSK_PH_DELTA);
-			U64x4 z{}; z.v[0] = z.v[1] = z.v[2] = z.v[3] = 0;
-			CKR((scan_excl<U64x4, U64x4>(h, h->draw_cnt.as<U64x4>(), h->draw_scan.as<U64x4>(), n + 1, z)));
-			CK(cudaMemcpyAsync(h->draw_cnt_prev.p, h->draw_cnt.p, n1 * 32, cudaMemcpyDeviceToDevice, h->st));
-			CKR(ensure_iota(h, std::max(tot_b, tot_s)));
-			if (tot_b) CKR(sort_pairs_u64_u32(h, h->row_b[cur].as<unsigned long long>(), h->dk_b.as<unsigned long long>(), h->iota.as<uint32_t>(), h->di_b.as<uint32_t>(), tot_b, 64 - 2 * (int) h->P.bmer_len, 64));
-			if (tot_s) CKR(sort_pairs_u64_u32(h, h->row_s[cur].as<unsigned long long>(), h->dk_s.as<unsigned long long>(), h->iota.as<uint32_t>(), h->di_s.as<uint32_t>(), tot_s, 64 - 2 * (int) h->P.smer_len, 64));
-			S.delta_b = DeltaDev{h->dk_b.as<unsigned long long>(), h->di_b.as<uint32_t>(), tot_b, h->tb.ci.thr + 1};
-			S.delta_s = DeltaDev{h->dk_s.as<unsigned long long>(), h->di_s.as<uint32_t>(), tot_s, h->ts.ci.thr + 1};
-			S.base_b = h->off_b[cur].as<uint32_t>(); S.base_s = h->off_s[cur].as<uint32_t>();
-		}
-		tot_b_prev = tot_b; tot_s_prev = tot_s;
-		cur ^= 1;
+	resolve_phases(h);
+	if (n_rec64 >= 0xFFFFFFF0ull) return fail(h, FQSK_E_INVAL, "segment too large");
+	const uint32_t n_rec = (uint32_t) n_rec64;
+	if (h->miss_cap < std::min<uint32_t>(n_rec, 1u << 20)) h->miss_cap = std::min<uint32_t>(n_rec, 1u << 20);
+	if (h->miss_cap < n_rec / 4) h->miss_cap = n_rec / 4 + 1024;
+	if (h->rreq_cap < std::min<uint32_t>(n_rec, 1u << 20)) h->rreq_cap = std::min<uint32_t>(n_rec, 1u << 20);
+	if (h->rreq_cap < n_rec / 4) h->rreq_cap = n_rec / 4 + 1024;
+	CKR(stream_ensure(h, h->rng[ST_B], 1u << 16)); CKR(stream_ensure(h, h->rng[ST_S], 1u << 12));
+	for (int attempt = 0;; ++attempt) {
+		if (attempt > 8) return fail(h, FQSK_E_NOMEM, "segment buffers kept overflowing");
+		int rc = segment_attempt(h, S, n, dna_bytes, n_rec, first);
+		if (rc == RC_RETRY) continue;
+		if (rc != FQSK_OK) return rc;
+		break;
 	}
 	// converged: totals
 	{
-		U64x4 z{}; z.v[0] = z.v[1] = z.v[2] = z.v[3] = 0;
-		CKR((scan_excl<U64x4, U64x4>(h, h->draw_cnt.as<U64x4>(), h->draw_scan.as<U64x4>(), n + 1, z)));
 		CK(cudaMemsetAsync(h->hidden.as<uint32_t>() + n, 0, 4, h->st));
 		CKR((scan_excl<uint32_t, uint32_t>(h, h->hidden.as<uint32_t>(), h->hid_scan.as<uint32_t>(), n + 1, 0u)));
 		uint8_t *hs = (uint8_t *) h->h_small;
-		CK(cudaMemcpyAsync(hs, h->draw_scan.as<U64x4>() + n, 32, cudaMemcpyDeviceToHost, h->st));
 		CK(cudaMemcpyAsync(hs + 32, h->sl_prefix.as<U64x4>() + n, 32, cudaMemcpyDeviceToHost, h->st));
 		CK(cudaMemcpyAsync(hs + 64, h->hid_scan.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, h->st));
-		CK(cudaMemcpyAsync(hs + 72, h->rec_off.as<unsigned long long>() + n, 8, cudaMemcpyDeviceToHost, h->st));
 		CK(cudaStreamSynchronize(h->st));
 		resolve_phases(h);
-		memcpy(&tot_draws, hs, 32);
 		U64x4 letters; memcpy(&letters, hs + 32, 32);
 		uint32_t hid; memcpy(&hid, hs + 64, 4);
-		unsigned long long nrec; memcpy(&nrec, hs + 72, 8);
-		for (int i = 0; i < 4; ++i) { h->rng[i].consumed += tot_draws.v[i]; h->S.draws[i] = h->rng[i].consumed; h->sl_base[i] += letters.v[i]; }
+		for (int i = 0; i < 4; ++i) { h->S.draws[i] = h->rng[i].consumed; h->sl_base[i] += letters.v[i]; }
 		h->hidden_p += hid;
-		h->n_recs = nrec;
+		h->n_recs = n_rec;
 	}
-	h->pend_b = tot_b; h->pend_s = tot_s; h->pend_p = tot_p;
 	h->pending = true;
 	h->S.n_reads += n; h->S.n_bases += dna_bytes;
 	return FQSK_OK;
@@ -534,6 +637,7 @@ int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
 		CK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
 		CK(cudaMalloc(&h->d_flags, 8 * sizeof(int)));
 		CK(cudaMalloc(&h->d_counters, 8 * 8));
+		CK(cudaMalloc(&h->d_u32, 8 * 4));
 		CK(cudaMemset(h->d_counters, 0, 64));
 		CK(cudaMallocHost(&h->h_small, 256));
 		uint64_t expect = p->expected_kmers ? p->expected_kmers : (1ull << 22);
@@ -570,8 +674,11 @@ void fqsk_destroy(fqsk_handle *h) {
 	DevBuf *bufs[] = {&h->prev_read, &h->dna, &h->off, &h->len, &h->dup, &h->n_coded, &h->letters, &h->rec_off, &h->sl_prefix, &h->recs, &h->push_b, &h->push_s,
 	                  &h->push_p, &h->cnt_b, &h->cnt_s, &h->cnt_p, &h->hidden, &h->draw_cnt, &h->draw_cnt_prev, &h->draw_scan, &h->off_b[0], &h->off_b[1], &h->off_s[0],
 	                  &h->off_s[1], &h->off_p, &h->row_b[0], &h->row_b[1], &h->row_s[0], &h->row_s[1], &h->row_p, &h->dk_b, &h->di_b, &h->dk_s, &h->di_s, &h->iota,
-	                  &h->cub_tmp, &h->slot, &h->val, &h->slot_sorted, &h->val_sorted, &h->flag8, &h->draw_off, &h->final_cnt, &h->dump_k, &h->dump_v, &h->q0, &h->q1,
-	                  &h->q2, &h->q3, &h->q4, &h->sflag, &h->sdif, &h->hid_scan};
+	                  &h->cub_tmp, &h->flag8, &h->draw_off, &h->final_cnt, &h->slot_of, &h->dump_k, &h->dump_v, &h->q0, &h->q1,
+	                  &h->q2, &h->q3, &h->q4, &h->sflag, &h->sdif, &h->hid_scan, &h->prov, &h->pflags, &h->pscripts, &h->rscripts, &h->rreqs, &h->pool, &h->miss,
+	                  &h->draws_b16, &h->draws_s16, &h->doff_b, &h->doff_s, &h->time_b, &h->time_s, &h->rt_b[0], &h->rt_b[1], &h->rt_s[0], &h->rt_s[1],
+	                  &h->sidx_b, &h->sidx_s, &h->stime_b, &h->stime_s, &h->sort_k, &h->sort_v};
+	if (h->d_u32) cudaFree(h->d_u32);
 	for (DevBuf *b : bufs) b->release();
 	if (h->h_stage) cudaFreeHost(h->h_stage);
 	if (h->h_small) cudaFreeHost(h->h_small);
@@ -698,8 +805,11 @@ int fqsk_sync(fqsk_handle *h) {
 		h->S.siv_no_updates += h->pend_p + h->hidden_p;
 		h->hidden_p = 0;
 		// s-mers, then b-mers (dna.cpp:2425-2446)
-		CKR(apply_inserts(h, h->ts, h->rng[ST_S], h->row_s[h->cur].as<unsigned long long>(), h->pend_s));
-		CKR(apply_inserts(h, h->tb, h->rng[ST_B], h->row_b[h->cur].as<unsigned long long>(), h->pend_b));
+		if (h->delta_s_valid) CKR(apply_sorted(h, h->ts, h->rng[ST_S], h->dk_s.as<unsigned long long>(), h->sidx_s.as<uint32_t>(), h->pend_s));
+		else CKR(apply_inserts(h, h->ts, h->rng[ST_S], h->row_s[h->cur].as<unsigned long long>(), h->pend_s));
+		if (h->delta_b_valid) CKR(apply_sorted(h, h->tb, h->rng[ST_B], h->dk_b.as<unsigned long long>(), h->sidx_b.as<uint32_t>(), h->pend_b));
+		else CKR(apply_inserts(h, h->tb, h->rng[ST_B], h->row_b[h->cur].as<unsigned long long>(), h->pend_b));
+		h->delta_b_valid = h->delta_s_valid = false;
 		CKR(table_grow_if_needed(h, h->ts));
 		CKR(table_grow_if_needed(h, h->tb));
 	} else {

@@ -3,9 +3,8 @@
 // Kernel inventory:
 //   k_mt_extend        mt19937 block recurrence, one CTA, state in shared memory        (utils.h:257, 298)
 //   k_prep             per read: duplicate flag, A/C/G/T totals, number of coded bases  (dna.cpp:1521-1533, 2047-2057)
-//   k_replay           per read: the k-mer half of CompressDirect/CompressSorted        (dna.cpp:457-877, 1517-1754)
-//   k_compact          per-read push regions -> contiguous to_add rows in push order    (dna.cpp:822-873)
-//   k_locate/k_apply/k_commit   InsertKmersToHT for s-/b-mers with ordered PRNG draws   (dna.cpp:2420-2446, ht_kmer.h:420-438)
+//   (segment pipeline: k_lookup / k_partial / k_local / k_walk / k_rough / k_fold live in fqsk_pipeline.cuh)
+//   k_locate_heads/k_apply_keys/k_commit_keys   InsertKmersToHT for s-/b-mers with ordered PRNG draws   (dna.cpp:2420-2446, ht_kmer.h:420-438)
 //   k_siv_increment    InsertKmersToHT for p-mers                                        (dna.cpp:2401-2418)
 //   k_find / k_count / k_siv_*   table-level batch mirrors                               (ht_kmer.h:441-510, bit_vec.h:53-123)
 #pragma once
@@ -158,52 +157,8 @@ __device__ bool ht_find(const HtDev &t, const CIncP &ci, const KReg &r, uint32_t
 	return any4(c);
 }
 
-// find_counts_rough_{s,b} (dna.cpp:257-330): every single substitution at positions 0..k-2 (the original included once per
-// position); a non-empty neighbour is merged for ALL four symbols.
-__device__ bool rough_ht(const HtDev &t, const CIncP &ci, const KReg &base, uint32_t c[4], DrawCursor &dc) {
-	c[0] = c[1] = c[2] = c[3] = 0;
-	for (uint32_t i = 0; i + 1 < t.k; ++i) {
-		HtKey key[4]; Bucket bk[4]; bool isd[4];
-#pragma unroll
-		for (int j = 0; j < 4; ++j) {
-			KReg tr = base;
-			kr_set(tr, t.k, j, i);
-			isd[j] = kr_is_dir(tr, t.k);
-			key[j] = ht_key(t, isd[j] ? tr.dir : tr.rc);
-			bk[j] = ht_load_bucket(t, key[j].bucket);
-		}
-#pragma unroll
-		for (int j = 0; j < 4; ++j) {
-			uint32_t loc[4] = {0, 0, 0, 0};
-			ht_ctx_counts_from(t, key[j], isd[j], bk[j], loc);
-			if (any4(loc)) for (int q = 0; q < 4; ++q) c[q] = ci_plus(ci, c[q], loc[q], dc);
-		}
-	}
-	return any4(c);
-}
-
-// thread-local table lookups (dna.cpp:485, 495) against the segment delta
-__device__ bool local_find(const DeltaDev &d, uint32_t k, const CIncP &ci, const KReg &r, uint32_t cur, uint32_t T, uint32_t c[4], DrawCursor &dc, int *unsupported) {
-	c[0] = c[1] = c[2] = c[3] = 0;
-	if (d.n == 0) return false;
-	if (cur >= k) {
-		bool dd = kr_is_dir(r, k);
-		delta_ctx_counts(d, k, dd ? r.dir : r.rc, dd, T, c, unsupported);
-		return any4(c);
-	}
-	uint32_t m = k - cur, trials = 1u << (2 * m);
-	for (uint32_t n = 0; n < trials; ++n) {
-		KReg tr = partial_trial(r, k, m, n);
-		bool dd = kr_is_dir(tr, k);
-		uint32_t loc[4] = {0, 0, 0, 0};
-		delta_ctx_counts(d, k, dd ? tr.dir : tr.rc, dd, T, loc, unsupported);
-		for (int i = 0; i < 4; ++i) if (loc[i]) c[i] = ci_plus(ci, c[i], loc[i], dc);
-	}
-	return any4(c);
-}
-
 // ------------------------------------------------------------------------------------------------------------------
-// k_replay: one thread replays one read through the reference's per-base state machine.
+// per-read register state shared by the pipeline kernels
 // ------------------------------------------------------------------------------------------------------------------
 struct ReadState {
 	KReg pc, sc, bc, pu, su, bu;
@@ -217,197 +172,6 @@ __device__ __forceinline__ void rs_push_all(ReadState &R, const EngineDev &E, ui
 	++R.n;
 }
 __device__ __forceinline__ uint32_t cur_of(uint32_t k, uint32_t n) { return n < k ? n : k; }
-
-__global__ void __launch_bounds__(128) k_replay(EngineDev E, SegDev S) {
-	uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-	if (r >= S.n_reads) return;
-	U64x4 zero4; zero4.v[0] = zero4.v[1] = zero4.v[2] = zero4.v[3] = 0;
-	if (S.dup[r]) { S.cnt_b[r] = S.cnt_s[r] = S.cnt_p[r] = S.hidden[r] = 0; S.draw_cnt[r] = zero4; if (E.sorted) { S.sorted_flag[r] = 0; S.sorted_dif[r] = 0; } return; }
-	const uint8_t *p = S.dna + S.off[r];
-	const uint32_t size = S.len[r];
-	unsigned long long *out_b = S.push_b + 2 * S.off[r];
-	unsigned long long *out_s = S.push_s + S.off[r];
-	unsigned long long *out_p = S.push_p + 2 * S.off[r] + 2ull * r;
-	fqsk_base_rec *rec = S.recs + S.rec_off[r];
-	uint32_t nb = 0, ns = 0, np = 0, hidden = 0;
-	unsigned long long sl[4];
-	for (int i = 0; i < 4; ++i) sl[i] = S.sl_base.v[i] + S.sl_prefix[r].v[i];
-	DrawCursor dc[4];
-	for (int i = 0; i < 4; ++i) { dc[i].buf = E.draws[i]; dc[i].avail = E.avail[i]; dc[i].base = S.draw_guess[r].v[i]; dc[i].used = 0; dc[i].overflow = E.flags + 0; }
-	int *unsupported = E.flags + 1;
-	const uint32_t Tb0 = S.base_b ? S.base_b[r] : 0, Ts0 = S.base_s ? S.base_s[r] : 0;
-	const CIncP cil_b = E.cib, cil_s = E.cis;
-
-	ReadState R;
-	R.pc = R.sc = R.bc = R.pu = R.su = R.bu = KReg{0, 0};
-	R.n = 0; R.cor_pos = 0; R.n_run = 0;
-
-	uint32_t start;
-	if (!E.sorted) {
-		// compress_prefix_direct, register half (dna.cpp:518-545)
-		for (uint32_t i = 0; i < E.prefix_len; ++i) {
-			uint32_t sym = dna_code(p[i]);
-			if (sym == 4) { sym = 0; R.cor_pos = i; }
-			rs_push_all(R, E, sym);
-		}
-		start = E.prefix_len;
-	} else {
-		// compress_prefix_sorted, siv half (dna.cpp:555-605, 655-660)
-		for (uint32_t i = 0; i < E.p; ++i) {
-			uint32_t sym = dna_code(p[i]);
-			if (sym == 4) { sym = 3; ++R.n_run; } else R.n_run = 0;
-			rs_push_all(R, E, sym);
-		}
-		unsigned long long prev_dir; bool prev_valid;
-		if (r == 0) { prev_dir = S.pprev_dir; prev_valid = S.pprev_valid != 0; }
-		else {
-			const uint8_t *q = S.dna + S.off[r - 1];
-			prev_dir = 0;
-			for (uint32_t i = 0; i < E.p; ++i) { uint32_t sym = dna_code(q[i]); if (sym == 4) sym = 3; prev_dir |= (unsigned long long) sym << (62 - 2 * i); }
-			prev_valid = true;
-		}
-		uint64_t cur_al = R.pc.dir >> (64 - 2 * E.p);
-		uint64_t prev_al = prev_valid ? prev_dir >> (64 - 2 * E.p) : 0;
-		uint32_t flag; unsigned long long dif = 0;
-		if (R.pc.dir == prev_dir) flag = 4;   // an unset pmer_can_prev has kmer_dir == 0 (kmer.h:233-237), same comparison
-		else flag = siv_test(E.siv, cur_al);
-		if (flag < 4) for (uint64_t i = prev_al + 1; i < cur_al; ++i) dif += siv_test(E.siv, i) == flag;
-		S.sorted_flag[r] = flag; S.sorted_dif[r] = dif;
-		out_p[np++] = cur_al;
-		out_p[np++] = R.pc.rc >> (64 - 2 * E.p);
-		start = E.p;
-	}
-
-	const uint32_t b_margin = E.b - E.s - 1, s_margin = E.s - E.p + 1;
-	uint32_t c[4] = {0, 0, 0, 0};
-	for (uint32_t i = start; i < size; ++i) {
-		const uint32_t sym = dna_code(p[i]);
-		const uint64_t ks = sym == 4 ? 0 : sym;
-		rs_push_all(R, E, 0);   // placeholder (dna.cpp:687-693)
-		const uint32_t cb = cur_of(E.b, R.n), cs = cur_of(E.s, R.n), cp = cur_of(E.p, R.n);
-
-		// ---- find_counts (dna.cpp:457-502)
-		uint32_t lev = FQSK_LEVEL_NONE;
-		c[0] = c[1] = c[2] = c[3] = 0;
-		bool done = false;
-		if (cb + b_margin >= E.b) {
-			if (ht_find(E.hb, E.cib, R.bc, cb, c, dc[0])) {
-				int sat = (c[0] == E.hb.top) + (c[1] == E.hb.top) + (c[2] == E.hb.top) + (c[3] == E.hb.top);
-				if (sat > 1) {
-					uint32_t c2[4];
-					ht_find(E.hs, E.cis, R.sc, cs, c2, dc[1]);
-					for (int q = 0; q < 4; ++q) c[q] += c2[q];
-					lev = FQSK_LEVEL_MIXED;
-				} else lev = FQSK_LEVEL_BMER;
-				done = true;
-			} else if (local_find(S.delta_b, E.b, cil_b, R.bc, cb, Tb0 + nb, c, dc[2], unsupported)) { lev = FQSK_LEVEL_BMER; done = true; }
-			else if (R.bc.dir != R.bu.dir && ht_find(E.hb, E.cib, R.bu, cb, c, dc[0])) { lev = FQSK_LEVEL_BMER_UNC; done = true; }
-		}
-		if (!done) {
-			if (cs + s_margin >= E.s) {
-				if (ht_find(E.hs, E.cis, R.sc, cs, c, dc[1])) lev = FQSK_LEVEL_SMER;
-				else if (local_find(S.delta_s, E.s, cil_s, R.sc, cs, Ts0 + ns, c, dc[3], unsupported)) lev = FQSK_LEVEL_SMER;
-			} else {
-				// find_counts_p (dna.cpp:210-226)
-				if (cp < E.p) {
-					for (uint64_t j = 0; j < 4; ++j) {
-						KReg t = R.pc;
-						kr_set_last(t, cp, j);
-						c[j] = (uint32_t) siv_prefix_sum(E.siv, t.rc >> (64 - 2 * cp), 2 * cp);
-					}
-				} else siv_counts(E.siv, R.pc.dir >> (64 - 2 * E.p), c, false);
-				if (any4(c)) lev = FQSK_LEVEL_PMER;
-			}
-		}
-		if (lev == FQSK_LEVEL_BMER_UNC) { R.bc = R.bu; R.sc = R.su; R.pc = R.pu; R.cor_pos = 0; lev = FQSK_LEVEL_BMER; }  // dna.cpp:697-705
-		uint32_t rough = 0;
-		if (lev == FQSK_LEVEL_NONE) {   // dna.cpp:709-735
-			if (cb == E.b) { if (rough_ht(E.hb, E.cib, R.bc, c, dc[0])) { lev = FQSK_LEVEL_PMER; rough = 1; } }
-			else if (cs == E.s) { if (rough_ht(E.hs, E.cis, R.sc, c, dc[1])) { lev = FQSK_LEVEL_PMER; rough = 1; } }
-			else if (cp == E.p) {
-				c[0] = c[1] = c[2] = c[3] = 0;   // find_counts_rough_p (dna.cpp:229-254)
-				for (uint32_t q = 0; q + 1 < E.p; ++q)
-					for (uint64_t j = 0; j < 4; ++j) { KReg t = R.pc; kr_set(t, E.p, j, q); siv_counts(E.siv, t.dir >> (64 - 2 * E.p), c, true); }
-				if (any4(c)) { lev = FQSK_LEVEL_PMER; rough = 1; }
-			}
-		}
-		{
-			fqsk_base_rec o;
-			o.pos = i; o.counts[0] = c[0]; o.counts[1] = c[1]; o.counts[2] = c[2]; o.counts[3] = c[3];
-			o.cor_pos = R.cor_pos; o.level = (uint8_t) lev; o.rough = (uint8_t) rough; o.pad = 0;
-			rec[i - start] = o;
-		}
-		R.n_run = sym == 4 ? R.n_run + 1 : 0;
-		kr_set_last(R.pc, cp, ks); kr_set_last(R.sc, cs, ks); kr_set_last(R.bc, cb, ks);
-		kr_set_last(R.pu, cp, ks); kr_set_last(R.su, cs, ks); kr_set_last(R.bu, cb, ks);
-		if (sym < 4) {   // dna.cpp:818-852
-			bool p_insert = true;
-			if (cb == E.b) {
-				out_b[nb++] = kr_norm(R.bc, E.b);
-				if ((lev == FQSK_LEVEL_SMER || lev == FQSK_LEVEL_BMER || lev == FQSK_LEVEL_MIXED) && c[sym] >= 3) p_insert = false;
-			}
-			if (cs == E.s) out_s[ns++] = kr_norm(R.sc, E.s);
-			if (cp == E.p && i - R.cor_pos >= E.p - 1) {
-				if (p_insert) { out_p[np++] = R.pc.dir >> (64 - 2 * E.p); out_p[np++] = R.pc.rc >> (64 - 2 * E.p); }
-				else hidden += 2;
-			}
-		}
-		if (cb == E.b) {   // dna.cpp:854-875
-			bool repaired = false;
-			if (lev == FQSK_LEVEL_BMER || lev == FQSK_LEVEL_MIXED) {
-				// repair_kmers_existing (dna.cpp:333-370)
-				uint32_t best = 0;
-				for (uint32_t q = 1; q < 4; ++q) if (c[q] > c[best] || (c[q] == c[best] && sl[q] > sl[best])) best = q;
-				bool ok = true;
-				if (sym != 4) ok = best != sym && c[sym] == 0 && c[best] > 3;
-				if (ok) { kr_set_last(R.pc, cp, best); kr_set_last(R.sc, cs, best); kr_set_last(R.bc, cb, best); R.cor_pos = i; repaired = true; }
-			} else if ((lev == FQSK_LEVEL_NONE || lev == FQSK_LEVEL_PMER) && E.gate_missing) {
-				// repair_kmers_missing (dna.cpp:374-454)
-				int best_c = 4, best_count = 0, best_j = 0;
-				for (int j = 1; j < 6; ++j) {
-					uint32_t cnts[4];
-					uint64_t orig = kr_sym(R.bc, cb - 1 - j);
-#pragma unroll
-					for (uint64_t q = 0; q < 4; ++q) {
-						cnts[q] = 0;
-						if (q == orig) continue;
-						KReg t = R.bc;
-						kr_set(t, cb, q, cb - 1 - j);
-						cnts[q] = ht_count(E.hb, kr_norm(t, E.b));
-					}
-					for (int q = 0; q < 4; ++q) {
-						if ((uint64_t) q == orig) continue;
-						int cnt = (int) cnts[q];
-						if (cnt >= best_count && cnt >= 2) { best_c = q; best_count = cnt; best_j = j; }
-					}
-				}
-				if (best_j) {
-					kr_set(R.bc, cb, best_c, cb - 1 - best_j);
-					if (best_j < (int) cs) kr_set(R.sc, cs, best_c, cs - 1 - best_j);
-					if (best_j < (int) cp) kr_set(R.pc, cp, best_c, cp - 1 - best_j);
-					uint32_t np2 = i - (uint32_t) best_j;
-					R.cor_pos = R.cor_pos > np2 ? R.cor_pos : np2;
-					repaired = true;
-				}
-			}
-			if (repaired) out_b[nb++] = kr_norm(R.bc, E.b);
-		}
-	}
-	S.cnt_b[r] = nb; S.cnt_s[r] = ns; S.cnt_p[r] = np; S.hidden[r] = hidden;
-	U64x4 d; for (int i = 0; i < 4; ++i) d.v[i] = dc[i].used;
-	S.draw_cnt[r] = d;
-}
-
-// per-read regions -> contiguous rows (push order == read order, then base order)
-__global__ void k_compact(SegDev S, const uint32_t *off_b, const uint32_t *off_s, const uint32_t *off_p,
-                          unsigned long long *row_b, unsigned long long *row_s, unsigned long long *row_p) {
-	uint32_t r = blockIdx.x;
-	if (r >= S.n_reads) return;
-	const unsigned long long *sb = S.push_b + 2 * S.off[r], *ss = S.push_s + S.off[r], *sp = S.push_p + 2 * S.off[r] + 2ull * r;
-	for (uint32_t i = threadIdx.x; i < S.cnt_b[r]; i += blockDim.x) row_b[off_b[r] + i] = sb[i];
-	for (uint32_t i = threadIdx.x; i < S.cnt_s[r]; i += blockDim.x) row_s[off_s[r] + i] = ss[i];
-	for (uint32_t i = threadIdx.x; i < S.cnt_p[r]; i += blockDim.x) row_p[off_p[r] + i] = sp[i];
-}
 
 __global__ void k_compare_u64(const unsigned long long *a, const unsigned long long *b, uint64_t n, int *changed) {
 	uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -423,30 +187,30 @@ __global__ void k_iota(uint32_t *a, uint32_t n) { uint32_t i = blockIdx.x * bloc
 // sync step for one hash table: InsertKmersToHT (dna.cpp:2420-2446) == for every pushed k-mer, in push order,
 // CHT_kmer::insert(x, cinc) (ht_kmer.h:420-438).
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void k_locate(HtDev t, const unsigned long long *kmers, uint32_t n, uint32_t *slot, uint32_t *val) {
-	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= n) return;
-	bool created;
-	uint64_t s = ht_locate(t, kmers[j], created);
-	slot[j] = (uint32_t) s;
-	val[j] = j | (created ? 0x80000000u : 0u);
-}
-// One thread per group of equal slots (sorted stably, so occurrences are in push order).  flag[j] says whether occurrence j
-// consumes a draw; the kernel recomputes that from the counter it sees and reports a change (fix point over the ordered
-// draw indices; changes can only come from counters saturating inside the batch).
-__global__ void k_apply(HtDev t, CIncP ci, const uint32_t *slot_sorted, const uint32_t *val_sorted, uint32_t n,
-                        uint8_t *flag, const uint32_t *draw_off, const uint32_t *draws, unsigned long long avail,
-                        uint32_t *final_cnt, int *flags) {
+// Input: the row sorted by k-mer (stable, so equal k-mers stay in push order) with the push index of every occurrence.
+// k_locate_heads: one find-or-create per DISTINCT k-mer.
+__global__ void k_locate_heads(HtDev t, const unsigned long long *skeys, uint32_t n, unsigned long long *slot_of) {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
-	uint32_t sl = slot_sorted[i];
-	if (i > 0 && slot_sorted[i - 1] == sl) return;   // not a group head
-	uint32_t e = i;
-	uint32_t created = 0;
-	while (e < n && slot_sorted[e] == sl) { created |= val_sorted[e] >> 31; ++e; }
-	uint32_t c = ht_slot_get(t, sl) - created;       // counter before this sync (a fresh slot was claimed with 1)
-	for (uint32_t q = i; q < e; ++q) {
-		uint32_t j = val_sorted[q] & 0x7fffffffu;
+	unsigned long long key = skeys[i];
+	if (i > 0 && skeys[i - 1] == key) return;   // not a group head
+	bool created;
+	uint64_t s = ht_locate(t, key, created);
+	slot_of[i] = s | (created ? (1ull << 63) : 0ull);
+}
+// k_apply_keys: one thread per group walks its occurrences in push order.  flag[j] says whether occurrence j consumes a
+// draw; the kernel recomputes that from the counter it sees and reports a change (fix point over the ordered draw indices;
+// after the first pass changes can only come from counters saturating inside the batch).
+__global__ void k_apply_keys(HtDev t, CIncP ci, const unsigned long long *skeys, const uint32_t *sidx, uint32_t n, const unsigned long long *slot_of,
+                             uint8_t *flag, const uint32_t *draw_off, const uint32_t *draws, unsigned long long avail, uint32_t *final_cnt, int *flags) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	unsigned long long key = skeys[i];
+	if (i > 0 && skeys[i - 1] == key) return;
+	unsigned long long so = slot_of[i];
+	uint32_t c = ht_slot_get(t, so & ~(1ull << 63)) - (uint32_t) (so >> 63);   // counter before this sync (fresh slots were claimed with 1)
+	for (uint32_t q = i; q < n && skeys[q] == key; ++q) {
+		uint32_t j = sidx[q];
 		if (c >= t.top) { if (flag[j]) { flag[j] = 0; flags[2] = 1; } continue; }   // ht_kmer.h:435: cnt < counter_max
 		if (c <= ci.thr) { if (flag[j]) { flag[j] = 0; flags[2] = 1; } ++c; continue; }
 		if (!flag[j]) { flag[j] = 1; flags[2] = 1; continue; }                      // needs a draw it was not given yet
@@ -456,12 +220,11 @@ __global__ void k_apply(HtDev t, CIncP ci, const uint32_t *slot_sorted, const ui
 	}
 	final_cnt[i] = c;
 }
-__global__ void k_commit(HtDev t, const uint32_t *slot_sorted, uint32_t n, const uint32_t *final_cnt) {
+__global__ void k_commit_keys(HtDev t, const unsigned long long *skeys, uint32_t n, const unsigned long long *slot_of, const uint32_t *final_cnt) {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
-	uint32_t sl = slot_sorted[i];
-	if (i > 0 && slot_sorted[i - 1] == sl) return;
-	ht_slot_set(t, sl, final_cnt[i]);
+	if (i > 0 && skeys[i - 1] == skeys[i]) return;
+	ht_slot_set(t, slot_of[i] & ~(1ull << 63), final_cnt[i]);
 }
 
 __global__ void k_siv_increment(SivDev s, const unsigned long long *idx, uint64_t n, unsigned long long *n_new) {

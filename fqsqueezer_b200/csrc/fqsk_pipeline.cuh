@@ -1,0 +1,602 @@
+// fqsk_pipeline.cuh -- the position-parallel segment pipeline.
+//
+// The reference walks a read base by base and, per base, walks a cascade of table lookups (dna.cpp:457-502, 674-877).
+// Three facts of that algorithm make it parallel without changing a bit of its output:
+//   (1) the corrected registers equal the uncorrected ones except in the b-1 positions after a repair
+//       (dna.cpp:363-365, 442-446, 697-705), and the uncorrected ones are a pure function of the read;
+//   (2) repairs, pushes and the level of a position depend only on lookups of FULL contexts, which draw no random numbers
+//       (ht_kmer.h:189-196); PRNG-dependent values (merges of front-truncated and of rough lookups, ht_kmer.h:321-323,
+//       dna.cpp:285-287, 323-325) only reach the emitted counts;
+//   (3) rough results never feed back into the registers (dna.cpp:707-735 vs 854-875).
+// So:  k_lookup    one thread per (read, position): the whole cascade for the uncorrected registers, global tables only
+//      k_partial   one warp per front-truncated lookup: 4^m completions across lanes -> ordered merge script
+//      k_local     one thread per position the global tables could not answer: the segment delta (thread-local tables)
+//      k_walk      one thread per read: registers, repairs, cor_pos, pushes; table traffic only inside repair windows
+//      k_rough     one warp per rough request: 4(k-1) neighbours across lanes -> ordered merge script
+//      k_fold      one thread per script: approximate-counter merges with the read-ordered mt19937 draw indices
+#pragma once
+#include "fqsk_kernels.cuh"
+
+namespace fqsk {
+
+// per-position flags kept beside the provisional record
+enum : uint8_t {
+	PF_MISS_B = 1,        // b-mer context consulted and absent from the global table -> thread-local b table is next (dna.cpp:485)
+	PF_MISS_S = 2,        // s-mer context consulted and absent from the global table -> thread-local s table is next (dna.cpp:495)
+	PF_PARTIAL_B = 4,     // front-truncated b lookup (ordered merge script pending)
+	PF_PARTIAL_S = 8,     // front-truncated s lookup
+	PF_GLOBAL_S_HIT = 16, // the global s-mer lookup succeeded (its counts are stored in the miss entry)
+};
+
+struct Script {              // ordered list of per-trial count vectors to be merged with CCounterIncrementer::Increment(a, b)
+	uint32_t rec;            // record index of the position
+	uint8_t kind;            // 0 partial b, 1 partial s, 2 rough b, 3 rough s
+	uint8_t valid;
+	uint16_t n;              // entries (inline up to 8, the rest in the overflow pool)
+	uint32_t overflow;       // first overflow entry
+	uint16_t c2[4];          // s-mer counts for the `mixed` rule when a partial b merge ends with two saturated counters (dna.cpp:470-478)
+	uint16_t e[8][4];
+};
+static const uint32_t SCRIPT_INLINE = 8;
+
+struct MissEntry {           // a position whose uncorrected cascade needs the thread-local tables
+	uint32_t rec, time;      // record index; position id (byte offset of the base inside the packed DNA) used as push time
+	KReg breg;               // uncorrected b register with the placeholder (s register is derived from it)
+	uint32_t cb;             // symbols held by the b register
+	uint8_t flags;           // PF_*
+	uint8_t glevel;          // level of the global-only cascade (SMER or NONE)
+	uint16_t gs[4];          // its counts (global s-mer hit)
+};
+
+struct RoughReq { uint32_t rec; uint32_t kind; KReg reg; };   // kind 2 = b, 3 = s, 4 = p
+
+struct PipeDev {
+	// geometry
+	uint32_t n_rec, start;          // coded positions of the segment; first coded position of a read
+	const unsigned long long *rec_off;
+	// provisional / final records and per-position flags
+	fqsk_base_rec *prov;            // find_counts result for the UNCORRECTED registers (k_lookup / k_partial / k_local)
+	fqsk_base_rec *recs; uint8_t *pflags;   // final records (k_walk, then k_rough / k_fold)
+	// scripts: partial ones are addressed densely (read * slots + slot); rough ones are appended
+	Script *pscripts; uint32_t pslots; uint32_t pfirst_n; // slot = (i + 1) - pfirst_n
+	Script *rscripts; RoughReq *rreqs; uint32_t *n_rreq; uint32_t rreq_cap;
+	unsigned short *pool; uint32_t *pool_used; uint32_t pool_cap;   // overflow entries (4 x u16 each)
+	MissEntry *miss; uint32_t *n_miss; uint32_t miss_cap;
+	// per-position draw counts and their exclusive scans (stream b, stream s)
+	unsigned short *draws_b, *draws_s; const unsigned long long *doff_b, *doff_s;
+	// pushes
+	uint32_t *time_b, *time_s;      // per-read regions parallel to push_b / push_s
+	int *flags;                     // [0] draw overflow [1] unsupported [2] changed [3] window consulted the local tables
+	                                // [4] capacity overflow (pool / miss / rough lists) [5] internal: draw in a no-draw path [6] k_local hit
+};
+
+__device__ __forceinline__ uint32_t sym_at(const SegDev &S, const EngineDev &E, const uint8_t *p, uint32_t j) {
+	uint32_t c = dna_code(p[j]);
+	if (c == 4) c = (E.sorted && j < E.p) ? 3u : 0u;   // dna.cpp:532-536 / 560-565 / 684
+	return c;
+}
+// uncorrected b register (with placeholder) in front of position i; cb = min(b, i + 1)
+__device__ __forceinline__ KReg build_breg(const SegDev &S, const EngineDev &E, const uint8_t *p, uint32_t i, uint32_t cb) {
+	KReg r{0, 0};
+	// symbols p[i - cb + 1 .. i - 1] then the placeholder (dir: A, rc: T)
+	for (uint32_t t = 0; t + 1 < cb; ++t) {
+		uint64_t s = sym_at(S, E, p, i + 1 - cb + t);
+		r.dir |= s << (62 - 2 * t);
+		r.rc |= (3 - s) << (64 - 2 * cb + 2 * t);     // complement lands mirrored: symbol t -> rc position cb-1-t
+	}
+	r.rc |= 3ull << 62;                                // placeholder complement at rc position 0
+	// rc position of symbol t is cb-1-t: shift = 62 - 2*(cb-1-t) = 64 - 2cb + 2t  (done above)
+	return r;
+}
+// suffix register of length c (c <= cb) taken from a register holding cb symbols
+__device__ __forceinline__ KReg suffix_reg(const KReg &r, uint32_t cb, uint32_t c) {
+	KReg o;
+	o.dir = r.dir << (2 * (cb - c));
+	o.rc = r.rc & (~0ull << (64 - 2 * c));
+	return o;
+}
+__device__ __forceinline__ uint32_t find_read(const unsigned long long *rec_off, uint32_t n_reads, uint32_t g) {
+	uint32_t lo = 0, hi = n_reads;     // last r with rec_off[r] <= g
+	while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (rec_off[m] <= g) lo = m; else hi = m; }
+	return lo;
+}
+__device__ __forceinline__ void put_rec(fqsk_base_rec *rec, uint32_t pos, const uint32_t c[4], uint32_t lev) {
+	fqsk_base_rec o;
+	o.pos = pos; o.counts[0] = c[0]; o.counts[1] = c[1]; o.counts[2] = c[2]; o.counts[3] = c[3];
+	o.cor_pos = 0; o.level = (uint8_t) lev; o.rough = 0; o.pad = 0;
+	*rec = o;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_lookup: the find_counts cascade (dna.cpp:457-502) for the uncorrected registers of every coded position, global
+// tables only.  Front-truncated table lookups are left to k_partial (flagged here).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_lookup(EngineDev E, SegDev S, PipeDev P) {
+	uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= P.n_rec) return;
+	uint32_t r = find_read(S.rec_off, S.n_reads, g);
+	uint32_t i = P.start + (g - (uint32_t) S.rec_off[r]);
+	const uint8_t *p = S.dna + S.off[r];
+	const uint32_t n = i + 1;
+	const uint32_t cb = n < E.b ? n : E.b, cs = n < E.s ? n : E.s, cp = n < E.p ? n : E.p;
+	const uint32_t b_margin = E.b - E.s - 1, s_margin = E.s - E.p + 1;
+	uint32_t c[4] = {0, 0, 0, 0};
+	uint32_t lev = FQSK_LEVEL_NONE;
+	uint8_t fl = 0;
+	KReg br = build_breg(S, E, p, i, cb);
+	if (cb + b_margin >= E.b) {
+		if (cb == E.b) {
+			bool d = kr_is_dir(br, E.b);
+			ht_ctx_counts(E.hb, d ? br.dir : br.rc, d, c);
+			KReg sr = suffix_reg(br, cb, cs);
+			if (any4(c)) {
+				int sat = (c[0] == E.hb.top) + (c[1] == E.hb.top) + (c[2] == E.hb.top) + (c[3] == E.hb.top);
+				lev = FQSK_LEVEL_BMER;
+				if (sat > 1) {
+					uint32_t c2[4] = {0, 0, 0, 0};
+					bool d2 = kr_is_dir(sr, E.s);
+					ht_ctx_counts(E.hs, d2 ? sr.dir : sr.rc, d2, c2);
+					for (int q = 0; q < 4; ++q) c[q] += c2[q];
+					lev = FQSK_LEVEL_MIXED;
+				}
+			} else {
+				fl |= PF_MISS_B;
+				bool d2 = kr_is_dir(sr, E.s);
+				ht_ctx_counts(E.hs, d2 ? sr.dir : sr.rc, d2, c);
+				if (any4(c)) { lev = FQSK_LEVEL_SMER; fl |= PF_GLOBAL_S_HIT; } else fl |= PF_MISS_S;
+			}
+		} else fl |= PF_PARTIAL_B;     // k_partial runs the rest of the cascade for this position
+	} else if (cs + s_margin >= E.s) {
+		if (cs == E.s) {
+			KReg sr = suffix_reg(br, cb, cs);
+			bool d2 = kr_is_dir(sr, E.s);
+			ht_ctx_counts(E.hs, d2 ? sr.dir : sr.rc, d2, c);
+			if (any4(c)) { lev = FQSK_LEVEL_SMER; fl |= PF_GLOBAL_S_HIT; } else fl |= PF_MISS_S;
+		} else fl |= PF_PARTIAL_S;
+	} else {
+		KReg pr = suffix_reg(br, cb, cp);      // find_counts_p (dna.cpp:210-226)
+		if (cp < E.p) {
+			for (uint64_t j = 0; j < 4; ++j) { KReg t = pr; kr_set_last(t, cp, j); c[j] = (uint32_t) siv_prefix_sum(E.siv, t.rc >> (64 - 2 * cp), 2 * cp); }
+		} else siv_counts(E.siv, pr.dir >> (64 - 2 * E.p), c, false);
+		if (any4(c)) lev = FQSK_LEVEL_PMER;
+	}
+	put_rec(P.prov + g, i, c, lev);
+	P.pflags[g] = fl;
+	P.draws_b[g] = 0; P.draws_s[g] = 0;
+	if ((fl & (PF_MISS_B | PF_MISS_S)) && !(fl & (PF_PARTIAL_B | PF_PARTIAL_S))) {
+		uint32_t m = atomicAdd(P.n_miss, 1u);
+		if (m >= P.miss_cap) P.flags[4] = 1;
+		if (m < P.miss_cap) {
+			MissEntry e;
+			e.rec = g; e.time = (uint32_t) S.off[r] + i; e.breg = br; e.cb = cb; e.flags = fl; e.glevel = (uint8_t) lev;
+			for (int q = 0; q < 4; ++q) e.gs[q] = (uint16_t) c[q];
+			P.miss[m] = e;
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_partial: one warp per front-truncated position.  Lanes evaluate the 4^m completions (ht_kmer.h:276-310) 32 at a time;
+// non-empty trials are appended, in trial order, to the position's merge script (ht_kmer.h:312-324 is replayed by k_fold).
+// Then the warp finishes the cascade for that position: s-mer fallback and miss bookkeeping.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void script_append(PipeDev &P, Script &sc, uint32_t &n, uint32_t &ovf, const uint32_t loc[4], bool have, uint32_t remaining_upper) {
+	// warp-collective: lanes with have==true append in lane order
+	unsigned m = __ballot_sync(0xffffffffu, have);
+	if (!m) return;
+	uint32_t lane = threadIdx.x & 31;
+	uint32_t pos = n + __popc(m & ((1u << lane) - 1));
+	uint32_t total = n + __popc(m);
+	if (total > SCRIPT_INLINE && ovf == 0xFFFFFFFFu) {
+		// first spill: reserve room for everything that can still come
+		uint32_t o = 0;
+		if (lane == 0) o = atomicAdd(P.pool_used, remaining_upper);
+		ovf = __shfl_sync(0xffffffffu, o, 0);
+		if (ovf + remaining_upper > P.pool_cap) { if (lane == 0) P.flags[4] = 1; ovf = 0xFFFFFFFEu; }
+	}
+	if (have) {
+		if (pos < SCRIPT_INLINE) { for (int q = 0; q < 4; ++q) sc.e[pos][q] = (uint16_t) loc[q]; }
+		else if (ovf < 0xFFFFFFFEu) { unsigned short *d = P.pool + 4ull * (ovf + (pos - SCRIPT_INLINE)); for (int q = 0; q < 4; ++q) d[q] = (unsigned short) loc[q]; }
+	}
+	n = total;
+}
+
+__global__ void __launch_bounds__(128) k_partial(EngineDev E, SegDev S, PipeDev P) {
+	// one warp per (read, partial slot); slot -> n = pfirst_n + slot symbols in the registers (placeholder included)
+	uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	uint32_t lane = threadIdx.x & 31;
+	uint32_t r = w / P.pslots, slot = w % P.pslots;
+	if (r >= S.n_reads) return;
+	Script *scp = P.pscripts + (size_t) r * P.pslots + slot;
+	if (lane == 0) scp->valid = 0;
+	if (S.dup[r]) return;
+	uint32_t n = P.pfirst_n + slot, i = n - 1;
+	if (i < P.start || i >= S.len[r]) return;
+	uint32_t g = (uint32_t) S.rec_off[r] + (i - P.start);
+	uint8_t fl = P.pflags[g];
+	if (!(fl & (PF_PARTIAL_B | PF_PARTIAL_S))) return;
+	const uint8_t *p = S.dna + S.off[r];
+	const uint32_t cb = n < E.b ? n : E.b, cs = n < E.s ? n : E.s;
+	KReg br = build_breg(S, E, p, i, cb);
+	const bool is_b = (fl & PF_PARTIAL_B) != 0;
+	const HtDev &t = is_b ? E.hb : E.hs;
+	KReg reg = is_b ? br : suffix_reg(br, cb, cs);
+	uint32_t cur = is_b ? cb : cs;
+	uint32_t m = t.k - cur, trials = 1u << (2 * m);
+	// the script lives in registers of lane 0 .. written through a shared staging copy
+	__shared__ Script stage[4];
+	Script &sc = stage[threadIdx.x >> 5];
+	uint32_t n_ent = 0, ovf = 0xFFFFFFFFu;
+	bool found = false;
+	for (uint32_t n0 = 0; n0 < trials; n0 += 32) {
+		uint32_t tn = n0 + lane;
+		uint32_t loc[4] = {0, 0, 0, 0};
+		if (tn < trials) {
+			KReg tr = partial_trial(reg, t.k, m, tn);
+			bool d = kr_is_dir(tr, t.k);
+			ht_ctx_counts(t, d ? tr.dir : tr.rc, d, loc);
+		}
+		bool have = any4(loc);
+		script_append(P, sc, n_ent, ovf, loc, have, trials - n0);
+		found |= __any_sync(0xffffffffu, have);
+	}
+	__syncwarp();
+	// rest of the cascade (lane 0): s-mer fallback after a partial-b miss (cs == s there), miss entry for the local tables
+	if (lane == 0) {
+		uint32_t c[4] = {0, 0, 0, 0};
+		uint32_t lev = FQSK_LEVEL_NONE;
+		uint8_t nf = fl;
+		uint16_t c2[4] = {0, 0, 0, 0};
+		if (is_b) {
+			KReg sr = suffix_reg(br, cb, cs);
+			bool d2 = kr_is_dir(sr, E.s);
+			uint32_t cc[4] = {0, 0, 0, 0};
+			ht_ctx_counts(E.hs, d2 ? sr.dir : sr.rc, d2, cc);     // needed for `mixed` (hit) or as the s fallback (miss)
+			if (found) { lev = FQSK_LEVEL_BMER; for (int q = 0; q < 4; ++q) c2[q] = (uint16_t) cc[q]; }
+			else {
+				nf |= PF_MISS_B;
+				for (int q = 0; q < 4; ++q) c[q] = cc[q];
+				if (any4(cc)) { lev = FQSK_LEVEL_SMER; nf |= PF_GLOBAL_S_HIT; } else nf |= PF_MISS_S;
+			}
+		} else {
+			if (found) lev = FQSK_LEVEL_SMER; else nf |= PF_MISS_S;
+		}
+		sc.rec = g; sc.kind = is_b ? 0 : 1; sc.valid = found ? 1 : 0; sc.n = (uint16_t) n_ent; sc.overflow = ovf;
+		for (int q = 0; q < 4; ++q) sc.c2[q] = c2[q];
+		*scp = sc;
+		put_rec(P.prov + g, i, c, lev);
+		P.pflags[g] = nf;
+		if (nf & (PF_MISS_B | PF_MISS_S)) {
+			uint32_t mi = atomicAdd(P.n_miss, 1u);
+			if (mi >= P.miss_cap) P.flags[4] = 1;
+			if (mi < P.miss_cap) {
+				MissEntry e;
+				e.rec = g; e.time = (uint32_t) S.off[r] + i; e.breg = br; e.cb = cb; e.flags = nf; e.glevel = (uint8_t) lev;
+				for (int q = 0; q < 4; ++q) e.gs[q] = (uint16_t) c[q];
+				P.miss[mi] = e;
+			}
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_local: thread-local table lookups (dna.cpp:485, 495) for the positions listed by k_lookup / k_partial, against the
+// delta of the previous iteration.  Idempotent: always starts from the stored global-only result.
+// Merges that would draw from the thread-local PRNG streams are reported as unsupported.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ bool local_find_nodraw(const DeltaDev &d, uint32_t k, const CIncP &ci, const KReg &r, uint32_t cur, uint32_t T, uint32_t c[4], int *unsupported) {
+	c[0] = c[1] = c[2] = c[3] = 0;
+	if (d.n == 0) return false;
+	if (cur >= k) {
+		bool dd = kr_is_dir(r, k);
+		delta_ctx_counts(d, k, dd ? r.dir : r.rc, dd, T, c, unsupported);
+		return any4(c);
+	}
+	uint32_t m = k - cur, trials = 1u << (2 * m);
+	for (uint32_t n = 0; n < trials; ++n) {
+		KReg tr = partial_trial(r, k, m, n);
+		bool dd = kr_is_dir(tr, k);
+		uint32_t loc[4] = {0, 0, 0, 0};
+		delta_ctx_counts(d, k, dd ? tr.dir : tr.rc, dd, T, loc, unsupported);
+		for (int i = 0; i < 4; ++i) if (loc[i]) {
+			uint32_t sum = ci_to_real(ci, c[i]) + ci_to_real(ci, loc[i]);
+			if (sum > ci.thr) { *unsupported = 1; sum = ci.thr; }   // would need cinc_lb / cinc_ls draws
+			c[i] = sum;
+		}
+	}
+	return any4(c);
+}
+
+__global__ void __launch_bounds__(128) k_local(EngineDev E, SegDev S, PipeDev P, uint32_t n_miss) {
+	uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+	if (m >= n_miss) return;
+	MissEntry e = P.miss[m];
+	uint32_t c[4] = {e.gs[0], e.gs[1], e.gs[2], e.gs[3]};
+	uint32_t lev = e.glevel;
+	const uint32_t cs = e.cb < E.s ? e.cb : E.s;
+	bool hit = false;
+	if (e.flags & PF_MISS_B) {
+		uint32_t lc[4];
+		if (local_find_nodraw(S.delta_b, E.b, E.cib, e.breg, e.cb, e.time, lc, P.flags + 1)) { for (int q = 0; q < 4; ++q) c[q] = lc[q]; lev = FQSK_LEVEL_BMER; hit = true; }
+	}
+	if (!hit && (e.flags & PF_MISS_S)) {
+		KReg sr = suffix_reg(e.breg, e.cb, cs);
+		uint32_t lc[4];
+		if (local_find_nodraw(S.delta_s, E.s, E.cis, sr, cs, e.time, lc, P.flags + 1)) { for (int q = 0; q < 4; ++q) c[q] = lc[q]; lev = FQSK_LEVEL_SMER; hit = true; }
+	}
+	fqsk_base_rec *rec = P.prov + e.rec;
+	if (hit) P.flags[6] = 1;
+	rec->counts[0] = c[0]; rec->counts[1] = c[1]; rec->counts[2] = c[2]; rec->counts[3] = c[3];
+	rec->level = (uint8_t) lev;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_walk: one thread per read.  Keeps the six registers, decides repairs, tracks cor_pos, produces the pushes.  Outside
+// repair windows (corrected == uncorrected registers) every count vector comes from the provisional records; inside a
+// window the cascade is evaluated here with the corrected registers (the slow path of the reference's own hot loop).
+// Rough searches are only REQUESTED here: their result never feeds back into the registers (dna.cpp:707-735).
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rough_request(PipeDev &P, uint32_t g, uint32_t kind, const KReg &reg) {
+	uint32_t q = atomicAdd(P.n_rreq, 1u);
+	if (q >= P.rreq_cap) P.flags[4] = 1;
+	if (q < P.rreq_cap) { RoughReq rq; rq.rec = g; rq.kind = kind; rq.reg = reg; P.rreqs[q] = rq; }
+}
+
+__global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P) {
+	uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= S.n_reads) return;
+	if (S.dup[r]) { S.cnt_b[r] = S.cnt_s[r] = S.cnt_p[r] = S.hidden[r] = 0; if (E.sorted) { S.sorted_flag[r] = 0; S.sorted_dif[r] = 0; } return; }
+	const uint8_t *p = S.dna + S.off[r];
+	const uint32_t size = S.len[r];
+	const uint32_t tbase = (uint32_t) S.off[r];
+	unsigned long long *out_b = S.push_b + 2 * S.off[r];
+	unsigned long long *out_s = S.push_s + S.off[r];
+	unsigned long long *out_p = S.push_p + 2 * S.off[r] + 2ull * r;
+	uint32_t *tim_b = P.time_b + 2 * S.off[r], *tim_s = P.time_s + S.off[r];
+	const uint32_t g0 = (uint32_t) S.rec_off[r];
+	uint32_t nb = 0, ns = 0, np = 0, hidden = 0;
+	unsigned long long sl[4];
+	for (int i = 0; i < 4; ++i) sl[i] = S.sl_base.v[i] + S.sl_prefix[r].v[i];
+	int *unsupported = E.flags + 1;
+	DrawCursor nodraw; nodraw.buf = nullptr; nodraw.avail = 0; nodraw.base = 0; nodraw.used = 0; nodraw.overflow = E.flags + 5;
+
+	ReadState R;
+	R.pc = R.sc = R.bc = R.pu = R.su = R.bu = KReg{0, 0};
+	R.n = 0; R.cor_pos = 0; R.n_run = 0;
+	uint32_t start;
+	if (!E.sorted) {
+		for (uint32_t i = 0; i < E.prefix_len; ++i) {
+			uint32_t sym = dna_code(p[i]);
+			if (sym == 4) { sym = 0; R.cor_pos = i; }
+			rs_push_all(R, E, sym);
+		}
+		start = E.prefix_len;
+	} else {
+		for (uint32_t i = 0; i < E.p; ++i) { uint32_t sym = dna_code(p[i]); if (sym == 4) sym = 3; rs_push_all(R, E, sym); }
+		unsigned long long prev_dir; bool prev_valid;
+		if (r == 0) { prev_dir = S.pprev_dir; prev_valid = S.pprev_valid != 0; }
+		else {
+			const uint8_t *q = S.dna + S.off[r - 1];
+			prev_dir = 0;
+			for (uint32_t i = 0; i < E.p; ++i) { uint32_t sym = dna_code(q[i]); if (sym == 4) sym = 3; prev_dir |= (unsigned long long) sym << (62 - 2 * i); }
+			prev_valid = true;
+		}
+		uint64_t cur_al = R.pc.dir >> (64 - 2 * E.p);
+		uint64_t prev_al = prev_valid ? prev_dir >> (64 - 2 * E.p) : 0;
+		uint32_t flag; unsigned long long dif = 0;
+		if (R.pc.dir == prev_dir) flag = 4; else flag = siv_test(E.siv, cur_al);
+		if (flag < 4) for (uint64_t i = prev_al + 1; i < cur_al; ++i) dif += siv_test(E.siv, i) == flag;
+		S.sorted_flag[r] = flag; S.sorted_dif[r] = dif;
+		out_p[np++] = cur_al;
+		out_p[np++] = R.pc.rc >> (64 - 2 * E.p);
+		start = E.p;
+	}
+	const uint32_t s_margin = E.s - E.p + 1;
+	for (uint32_t i = start; i < size; ++i) {
+		const uint32_t g = g0 + (i - start);
+		const uint32_t sym = dna_code(p[i]);
+		const uint64_t ks = sym == 4 ? 0 : sym;
+		rs_push_all(R, E, 0);
+		const uint32_t cb = cur_of(E.b, R.n), cs = cur_of(E.s, R.n), cp = cur_of(E.p, R.n);
+		fqsk_base_rec *rec = P.recs + g;
+		uint32_t lev, c[4];
+		if (R.bc.dir == R.bu.dir) {
+			// fast path: the provisional record is the reference's find_counts result
+			const fqsk_base_rec *pv = P.prov + g;
+			lev = pv->level; c[0] = pv->counts[0]; c[1] = pv->counts[1]; c[2] = pv->counts[2]; c[3] = pv->counts[3];
+		} else {
+			// repair window: cascade with the corrected registers (only reachable with a full b register)
+			c[0] = c[1] = c[2] = c[3] = 0;
+			lev = FQSK_LEVEL_NONE;
+			bool done = false;
+			if (ht_find(E.hb, E.cib, R.bc, cb, c, nodraw)) {
+				int sat = (c[0] == E.hb.top) + (c[1] == E.hb.top) + (c[2] == E.hb.top) + (c[3] == E.hb.top);
+				if (sat > 1) { uint32_t c2[4]; ht_find(E.hs, E.cis, R.sc, cs, c2, nodraw); for (int q = 0; q < 4; ++q) c[q] += c2[q]; lev = FQSK_LEVEL_MIXED; }
+				else lev = FQSK_LEVEL_BMER;
+				done = true;
+			} else {
+				if (S.delta_b.n) { P.flags[3] = 1; if (local_find_nodraw(S.delta_b, E.b, E.cib, R.bc, cb, tbase + i, c, unsupported)) { lev = FQSK_LEVEL_BMER; done = true; } }
+				else P.flags[3] = 1;   // a window lookup of the thread-local table happened: one more iteration must confirm it
+				if (!done && ht_find(E.hb, E.cib, R.bu, cb, c, nodraw)) { lev = FQSK_LEVEL_BMER_UNC; done = true; }
+			}
+			if (!done) {
+				if (ht_find(E.hs, E.cis, R.sc, cs, c, nodraw)) lev = FQSK_LEVEL_SMER;
+				else if (S.delta_s.n && local_find_nodraw(S.delta_s, E.s, E.cis, R.sc, cs, tbase + i, c, unsupported)) lev = FQSK_LEVEL_SMER;
+			}
+			if (lev == FQSK_LEVEL_BMER_UNC) { R.bc = R.bu; R.sc = R.su; R.pc = R.pu; R.cor_pos = 0; lev = FQSK_LEVEL_BMER; }
+		}
+		{
+			fqsk_base_rec o;
+			o.pos = i; o.counts[0] = c[0]; o.counts[1] = c[1]; o.counts[2] = c[2]; o.counts[3] = c[3];
+			o.cor_pos = R.cor_pos; o.level = (uint8_t) lev; o.rough = 0; o.pad = 0;
+			*rec = o;
+		}
+		if (lev == FQSK_LEVEL_NONE) {   // dna.cpp:709-735, deferred
+			if (cb == E.b) rough_request(P, g, 2, R.bc);
+			else if (cs == E.s) rough_request(P, g, 3, R.sc);
+			else if (cp == E.p) rough_request(P, g, 4, R.pc);
+		}
+		kr_set_last(R.pc, cp, ks); kr_set_last(R.sc, cs, ks); kr_set_last(R.bc, cb, ks);
+		kr_set_last(R.pu, cp, ks); kr_set_last(R.su, cs, ks); kr_set_last(R.bu, cb, ks);
+		if (sym < 4) {
+			bool p_insert = true;
+			if (cb == E.b) {
+				tim_b[nb] = tbase + i; out_b[nb++] = kr_norm(R.bc, E.b);
+				if ((lev == FQSK_LEVEL_SMER || lev == FQSK_LEVEL_BMER || lev == FQSK_LEVEL_MIXED) && c[sym] >= 3) p_insert = false;
+			}
+			if (cs == E.s) { tim_s[ns] = tbase + i; out_s[ns++] = kr_norm(R.sc, E.s); }
+			if (cp == E.p && i - R.cor_pos >= E.p - 1) {
+				if (p_insert) { out_p[np++] = R.pc.dir >> (64 - 2 * E.p); out_p[np++] = R.pc.rc >> (64 - 2 * E.p); }
+				else hidden += 2;
+			}
+		}
+		if (cb == E.b) {
+			bool repaired = false;
+			if (lev == FQSK_LEVEL_BMER || lev == FQSK_LEVEL_MIXED) {
+				uint32_t best = 0;
+				for (uint32_t q = 1; q < 4; ++q) if (c[q] > c[best] || (c[q] == c[best] && sl[q] > sl[best])) best = q;
+				bool ok = true;
+				if (sym != 4) ok = best != sym && c[sym] == 0 && c[best] > 3;
+				if (ok) { kr_set_last(R.pc, cp, best); kr_set_last(R.sc, cs, best); kr_set_last(R.bc, cb, best); R.cor_pos = i; repaired = true; }
+			} else if ((lev == FQSK_LEVEL_NONE || lev == FQSK_LEVEL_PMER) && E.gate_missing) {
+				int best_c = 4, best_count = 0, best_j = 0;
+				for (int j = 1; j < 6; ++j) {
+					uint32_t cnts[4];
+					uint64_t orig = kr_sym(R.bc, cb - 1 - j);
+#pragma unroll
+					for (uint64_t q = 0; q < 4; ++q) {
+						cnts[q] = 0;
+						if (q == orig) continue;
+						KReg t = R.bc;
+						kr_set(t, cb, q, cb - 1 - j);
+						cnts[q] = ht_count(E.hb, kr_norm(t, E.b));
+					}
+					for (int q = 0; q < 4; ++q) {
+						if ((uint64_t) q == orig) continue;
+						int cnt = (int) cnts[q];
+						if (cnt >= best_count && cnt >= 2) { best_c = q; best_count = cnt; best_j = j; }
+					}
+				}
+				if (best_j) {
+					kr_set(R.bc, cb, best_c, cb - 1 - best_j);
+					if (best_j < (int) cs) kr_set(R.sc, cs, best_c, cs - 1 - best_j);
+					if (best_j < (int) cp) kr_set(R.pc, cp, best_c, cp - 1 - best_j);
+					uint32_t np2 = i - (uint32_t) best_j;
+					R.cor_pos = R.cor_pos > np2 ? R.cor_pos : np2;
+					repaired = true;
+				}
+			}
+			if (repaired) { tim_b[nb] = tbase + i; out_b[nb++] = kr_norm(R.bc, E.b); }
+		}
+	}
+	S.cnt_b[r] = nb; S.cnt_s[r] = ns; S.cnt_p[r] = np; S.hidden[r] = hidden;
+	(void) s_margin;
+}
+
+__global__ void k_compact2(SegDev S, PipeDev P, const uint32_t *off_b, const uint32_t *off_s, const uint32_t *off_p,
+                           unsigned long long *row_b, unsigned long long *row_s, unsigned long long *row_p, uint32_t *rt_b, uint32_t *rt_s) {
+	uint32_t r = blockIdx.x;
+	if (r >= S.n_reads) return;
+	const unsigned long long *sb = S.push_b + 2 * S.off[r], *ss = S.push_s + S.off[r], *sp = S.push_p + 2 * S.off[r] + 2ull * r;
+	const uint32_t *tb = P.time_b + 2 * S.off[r], *ts = P.time_s + S.off[r];
+	for (uint32_t i = threadIdx.x; i < S.cnt_b[r]; i += blockDim.x) { row_b[off_b[r] + i] = sb[i]; rt_b[off_b[r] + i] = tb[i]; }
+	for (uint32_t i = threadIdx.x; i < S.cnt_s[r]; i += blockDim.x) { row_s[off_s[r] + i] = ss[i]; rt_s[off_s[r] + i] = ts[i]; }
+	for (uint32_t i = threadIdx.x; i < S.cnt_p[r]; i += blockDim.x) row_p[off_p[r] + i] = sp[i];
+}
+__global__ void k_gather_u32(const uint32_t *src, const uint32_t *idx, uint32_t n, uint32_t *dst) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) dst[i] = src[idx[i]];
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_rough: one warp per request.  find_counts_rough_{s,b} (dna.cpp:257-330): 4(k-1) single-substitution neighbours across the
+// lanes, non-empty ones appended in trial order to a merge script; find_counts_rough_p (dna.cpp:229-254) is a plain sum.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_rough(EngineDev E, PipeDev P, uint32_t n_req) {
+	uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	uint32_t lane = threadIdx.x & 31;
+	if (w >= n_req) return;
+	RoughReq rq = P.rreqs[w];
+	__shared__ Script stage[4];
+	Script &sc = stage[threadIdx.x >> 5];
+	if (rq.kind == 4) {
+		uint32_t c[4] = {0, 0, 0, 0};
+		uint32_t trials = 4 * (E.p - 1);
+		for (uint32_t t = lane; t < trials; t += 32) {
+			KReg tr = rq.reg;
+			kr_set(tr, E.p, t & 3, t >> 2);
+			siv_counts(E.siv, tr.dir >> (64 - 2 * E.p), c, true);
+		}
+		for (int q = 0; q < 4; ++q) for (int o = 16; o; o >>= 1) c[q] += __shfl_xor_sync(0xffffffffu, c[q], o);
+		if (lane == 0) {
+			Script *out = P.rscripts + w;
+			out->valid = 0; out->rec = rq.rec; out->n = 0; out->kind = 4;
+			if (any4(c)) {
+				fqsk_base_rec *rec = P.recs + rq.rec;
+				rec->counts[0] = c[0]; rec->counts[1] = c[1]; rec->counts[2] = c[2]; rec->counts[3] = c[3];
+				rec->level = FQSK_LEVEL_PMER; rec->rough = 1;
+			}
+		}
+		return;
+	}
+	const HtDev &t = rq.kind == 2 ? E.hb : E.hs;
+	uint32_t trials = 4 * (t.k - 1);
+	uint32_t n_ent = 0, ovf = 0xFFFFFFFFu;
+	for (uint32_t n0 = 0; n0 < trials; n0 += 32) {
+		uint32_t tn = n0 + lane;
+		uint32_t loc[4] = {0, 0, 0, 0};
+		if (tn < trials) {
+			KReg tr = rq.reg;
+			kr_set(tr, t.k, tn & 3, tn >> 2);
+			bool d = kr_is_dir(tr, t.k);
+			ht_ctx_counts(t, d ? tr.dir : tr.rc, d, loc);
+		}
+		script_append(P, sc, n_ent, ovf, loc, any4(loc), trials - n0);
+	}
+	__syncwarp();
+	if (lane == 0) {
+		sc.rec = rq.rec; sc.kind = (uint8_t) rq.kind; sc.valid = n_ent ? 1 : 0; sc.n = (uint16_t) n_ent; sc.overflow = ovf;
+		for (int q = 0; q < 4; ++q) sc.c2[q] = 0;
+		P.rscripts[w] = sc;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_fold: replay the ordered approximate-counter merges of one script with its exact position in the mt19937 stream.
+// pass 0 only counts draws (offset-independent unless a counter saturates), pass 1 evaluates with the scanned offsets,
+// writes the final counts and re-reports the draw count so the host can confirm the offsets.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_fold(EngineDev E, PipeDev P, const Script *scripts, uint32_t n_scripts, int pass) {
+	uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+	if (w >= n_scripts) return;
+	const Script &sc = scripts[w];
+	if (!sc.valid) return;
+	const bool is_b = (sc.kind == 0 || sc.kind == 2);
+	const bool rough = sc.kind >= 2;
+	const CIncP ci = is_b ? E.cib : E.cis;
+	DrawCursor dc;
+	dc.buf = E.draws[is_b ? 0 : 1]; dc.avail = E.avail[is_b ? 0 : 1]; dc.used = 0; dc.overflow = E.flags + 0;
+	dc.base = pass ? (is_b ? P.doff_b[sc.rec] : P.doff_s[sc.rec]) : 0;
+	uint32_t c[4] = {0, 0, 0, 0};
+	for (uint32_t n = 0; n < sc.n; ++n) {
+		uint32_t loc[4];
+		if (n < SCRIPT_INLINE) { for (int q = 0; q < 4; ++q) loc[q] = sc.e[n][q]; }
+		else { const unsigned short *d = P.pool + 4ull * (sc.overflow + (n - SCRIPT_INLINE)); for (int q = 0; q < 4; ++q) loc[q] = d[q]; }
+		for (int q = 0; q < 4; ++q) if (rough || loc[q]) c[q] = ci_plus(ci, c[q], loc[q], dc);
+	}
+	unsigned short *dcount = is_b ? P.draws_b : P.draws_s;
+	if (pass == 0) { dcount[sc.rec] = (unsigned short) dc.used; return; }
+	if (dcount[sc.rec] != (unsigned short) dc.used) { dcount[sc.rec] = (unsigned short) dc.used; P.flags[2] = 1; }
+	fqsk_base_rec *rec = P.recs + sc.rec;
+	uint32_t lev = rec->level;
+	if (rough) { if (any4(c)) { lev = FQSK_LEVEL_PMER; rec->rough = 1; } }
+	else if (sc.kind == 0) {
+		int sat = (c[0] == ci.top) + (c[1] == ci.top) + (c[2] == ci.top) + (c[3] == ci.top);
+		if (sat > 1) { for (int q = 0; q < 4; ++q) c[q] += sc.c2[q]; lev = FQSK_LEVEL_MIXED; }
+	}
+	if (rough && !any4(c)) return;
+	rec->counts[0] = c[0]; rec->counts[1] = c[1]; rec->counts[2] = c[2]; rec->counts[3] = c[3];
+	rec->level = (uint8_t) lev;
+}
+
+}  // namespace fqsk
