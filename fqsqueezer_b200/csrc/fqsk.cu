@@ -97,6 +97,7 @@ struct fqsk_handle {
 	struct Ev { cudaEvent_t a, b; int ph; };
 	std::vector<Ev> evs;
 	std::vector<cudaEvent_t> ev_pool;
+	cudaEvent_t t0 = nullptr, t1 = nullptr;
 };
 
 namespace {
@@ -335,7 +336,7 @@ int apply_sorted(fqsk_handle *h, Table &t, Stream &rng, const unsigned long long
 // sort a row by k-mer (stable): out keys + push indices
 int sort_row(fqsk_handle *h, const unsigned long long *row, uint32_t n, uint32_t k, DevBuf &keys_out, DevBuf &idx_out) {
 	if (!n) return FQSK_OK;
-	Phase ph(h, FQSK_PH_SYNC_SORT);
+	Phase ph(h, FQSK_PH_SORT);
 	CK(keys_out.ensure((size_t) n * 8)); CK(idx_out.ensure((size_t) n * 4));
 	CKR(ensure_iota(h, n));
 	CKR(sort_pairs_u64_u32(h, row, keys_out.as<unsigned long long>(), h->iota.as<uint32_t>(), idx_out.as<uint32_t>(), n, 64 - 2 * (int) k, 64));
@@ -394,9 +395,8 @@ int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes, u
 	CK(cudaMemsetAsync(h->d_u32, 0, 8 * 4, h->st));
 	CK(cudaMemsetAsync(h->d_flags, 0, 8 * sizeof(int), h->st));
 	if (n_rec) {
-		Phase ph(h, FQSK_PH_REPLAY);
-		k_lookup<<<nblk(n_rec, 256), 256, 0, h->st>>>(E, S, P); LAUNCHED(h);
-		k_partial<<<nblk((uint64_t) n * pslots * 32, 128), 128, 0, h->st>>>(E, S, P); LAUNCHED(h);
+		{ Phase ph(h, FQSK_PH_LOOKUP); k_lookup<<<nblk(n_rec, 256), 256, 0, h->st>>>(E, S, P); LAUNCHED(h); }
+		{ Phase ph(h, FQSK_PH_PARTIAL); k_partial<<<nblk((uint64_t) n * pslots * 32, 128), 128, 0, h->st>>>(E, S, P); LAUNCHED(h); }
 	}
 	S.delta_b = DeltaDev{nullptr, nullptr, 0, h->tb.ci.thr + 1};
 	S.delta_s = DeltaDev{nullptr, nullptr, 0, h->ts.ci.thr + 1};
@@ -406,7 +406,6 @@ int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes, u
 	uint32_t tot_b = 0, tot_s = 0, tot_p = 0, tot_b_prev = 0, tot_s_prev = 0, n_miss = 0, n_rreq = 0;
 	bool window_local_it0 = false;
 	auto build_delta = [&](int c) -> int {
-		Phase ph(h, FQSK_PH_DELTA);
 		CKR(sort_row(h, h->row_b[c].as<unsigned long long>(), tot_b, h->P.bmer_len, h->dk_b, h->sidx_b));
 		CKR(sort_row(h, h->row_s[c].as<unsigned long long>(), tot_s, h->P.smer_len, h->dk_s, h->sidx_s));
 		CK(h->stime_b.ensure((size_t) tot_b * 4 + 4)); CK(h->stime_s.ensure((size_t) tot_s * 4 + 4));
@@ -422,7 +421,7 @@ int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes, u
 		CK(cudaMemsetAsync(h->d_u32 + 1, 0, 4, h->st));          // rough requests are re-issued by every walk
 		CK(cudaMemsetAsync(h->d_flags + 3, 0, sizeof(int), h->st));
 		{
-			Phase ph(h, FQSK_PH_REPLAY);
+			Phase ph(h, FQSK_PH_WALK);
 			k_walk<<<nblk(n, 128), 128, 0, h->st>>>(E, S, P); LAUNCHED(h);
 			++h->S.n_replays;
 		}
@@ -463,7 +462,7 @@ int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes, u
 			if (need_more) {
 				CKR(build_delta(cur));
 				CK(cudaMemsetAsync(h->d_flags + 6, 0, sizeof(int), h->st));
-				if (n_miss) { Phase ph(h, FQSK_PH_DELTA); k_local<<<nblk(n_miss, 128), 128, 0, h->st>>>(E, S, P, n_miss); LAUNCHED(h); }
+				if (n_miss) { Phase ph(h, FQSK_PH_LOCAL); k_local<<<nblk(n_miss, 128), 128, 0, h->st>>>(E, S, P, n_miss); LAUNCHED(h); }
 				int fl[8];
 				CKR(read_flags(h, fl, 8));
 				if (fl[1]) return fail(h, FQSK_E_UNSUPPORTED, "segment needs the thread-local PRNG streams; not implemented yet");
@@ -488,7 +487,7 @@ int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes, u
 			need_more = changed;
 			if (need_more) {
 				CKR(build_delta(cur));
-				if (n_miss) { Phase ph(h, FQSK_PH_DELTA); k_local<<<nblk(n_miss, 128), 128, 0, h->st>>>(E, S, P, n_miss); LAUNCHED(h); }
+				if (n_miss) { Phase ph(h, FQSK_PH_LOCAL); k_local<<<nblk(n_miss, 128), 128, 0, h->st>>>(E, S, P, n_miss); LAUNCHED(h); }
 			}
 		}
 		if (!need_more) { h->cur = cur; break; }
@@ -497,8 +496,8 @@ int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes, u
 	}
 	// rough searches requested by the final walk, then the ordered merges of every script
 	if (n_rec) {
-		Phase ph(h, FQSK_PH_REPLAY);
-		if (n_rreq) { k_rough<<<nblk((uint64_t) n_rreq * 32, 128), 128, 0, h->st>>>(E, P, n_rreq); LAUNCHED(h); }
+		if (n_rreq) { Phase ph(h, FQSK_PH_ROUGH); k_rough<<<nblk((uint64_t) n_rreq * 32, 128), 128, 0, h->st>>>(E, P, n_rreq); LAUNCHED(h); }
+		Phase ph(h, FQSK_PH_FOLD);
 		uint32_t n_ps = n * pslots;
 		k_fold<<<nblk(n_ps, 128), 128, 0, h->st>>>(E, P, P.pscripts, n_ps, 0); LAUNCHED(h);
 		if (n_rreq) { k_fold<<<nblk(n_rreq, 128), 128, 0, h->st>>>(E, P, P.rscripts, n_rreq, 0); LAUNCHED(h); }
@@ -684,6 +683,7 @@ void fqsk_destroy(fqsk_handle *h) {
 	if (h->h_small) cudaFreeHost(h->h_small);
 	for (auto &e : h->evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
 	for (auto e : h->ev_pool) cudaEventDestroy(e);
+	if (h->t0) { cudaEventDestroy(h->t0); cudaEventDestroy(h->t1); }
 	if (h->st) cudaStreamDestroy(h->st);
 	delete h;
 }
@@ -879,6 +879,24 @@ int fqsk_stats_get(fqsk_handle *h, fqsk_stats *out) {
 	h->S.bmer_buckets = 1ull << h->tb.d.B; h->S.smer_buckets = 1ull << h->ts.d.B;
 	for (int i = 0; i < 4; ++i) h->S.draws[i] = h->rng[i].consumed;
 	*out = h->S;
+	return FQSK_OK;
+}
+
+int fqsk_timer_begin(fqsk_handle *h) {
+	if (!h) return FQSK_E_INVAL;
+	CK(cudaSetDevice(h->P.device));
+	if (!h->t0) { CK(cudaEventCreate(&h->t0)); CK(cudaEventCreate(&h->t1)); }
+	CK(cudaStreamSynchronize(h->st));
+	CK(cudaEventRecord(h->t0, h->st));
+	return FQSK_OK;
+}
+int fqsk_timer_end(fqsk_handle *h, double *ms) {
+	if (!h || !ms || !h->t0) return FQSK_E_INVAL;
+	CK(cudaEventRecord(h->t1, h->st));
+	CK(cudaEventSynchronize(h->t1));
+	float f = 0;
+	CK(cudaEventElapsedTime(&f, h->t0, h->t1));
+	*ms = f;
 	return FQSK_OK;
 }
 

@@ -19,7 +19,7 @@ READ_DESC_DTYPE = np.dtype([("dna_off", "<u8"), ("dna_len", "<u4"), ("flags", "<
 TABLE_SIV, TABLE_SMER, TABLE_BMER, TABLE_PAIR = 0, 1, 2, 3
 MODE_SE_ORIGINAL, MODE_SE_SORTED, MODE_PE_ORIGINAL, MODE_PE_SORTED = 0, 1, 2, 3
 F_PROFILE = 1
-PHASES = ["prep", "replay", "compact", "delta", "sync_locate", "sync_sort", "sync_apply", "sync_siv", "mt"]
+PHASES = ["prep", "lookup", "partial", "walk", "compact", "sort", "local", "rough", "fold", "sync_locate", "sync_apply", "sync_siv", "mt"]
 
 
 class FqskError(RuntimeError):
@@ -45,7 +45,7 @@ class _Stats(C.Structure):
 
 EXPORTS = ["fqsk_create", "fqsk_destroy", "fqsk_last_error", "fqsk_block_start", "fqsk_segment", "fqsk_segment_device",
            "fqsk_device_recs", "fqsk_sync", "fqsk_dump", "fqsk_stats_get", "fqsk_profile", "fqsk_ht_insert", "fqsk_ht_find",
-           "fqsk_ht_count", "fqsk_siv_increment", "fqsk_siv_test", "fqsk_siv_counts", "fqsk_siv_test_shorter", "fqsk_mt_stream"]
+           "fqsk_ht_count", "fqsk_timer_begin", "fqsk_timer_end", "fqsk_siv_increment", "fqsk_siv_test", "fqsk_siv_counts", "fqsk_siv_test_shorter", "fqsk_mt_stream"]
 
 _lib = None
 
@@ -72,6 +72,8 @@ def load_library():
     lib.fqsk_dump.argtypes = [vp, C.c_int, vp, vp, C.c_uint64, u64p]
     lib.fqsk_stats_get.argtypes = [vp, C.POINTER(_Stats)]
     lib.fqsk_profile.argtypes = [vp, C.POINTER(C.c_double), C.c_uint32]
+    lib.fqsk_timer_begin.argtypes = [vp]
+    lib.fqsk_timer_end.argtypes = [vp, C.POINTER(C.c_double)]
     lib.fqsk_ht_insert.argtypes = [vp, C.c_int, vp, C.c_uint64]
     lib.fqsk_ht_find.argtypes = [vp, C.c_int, vp, vp, vp, C.c_uint64, vp]
     lib.fqsk_ht_count.argtypes = [vp, C.c_int, vp, C.c_uint64, vp]
@@ -180,6 +182,14 @@ class KmerEngine:
         d = {f: getattr(st, f) for f, _ in _Stats._fields_ if f != "draws"}
         d.update(draws_b=st.draws[0], draws_s=st.draws[1], draws_lb=st.draws[2], draws_ls=st.draws[3])
         return d
+
+    def timer_begin(self):
+        self._ck(self.lib.fqsk_timer_begin(self.h))
+
+    def timer_end(self) -> float:
+        ms = C.c_double(0)
+        self._ck(self.lib.fqsk_timer_end(self.h, C.byref(ms)))
+        return ms.value
 
     def profile(self):
         ms = (C.c_double * len(PHASES))()

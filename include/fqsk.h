@@ -92,8 +92,8 @@ typedef struct fqsk_stats {
 } fqsk_stats;
 
 /* Named phases of fqsk_profile(): device milliseconds accumulated since create (only with FQSK_F_PROFILE). */
-enum { FQSK_PH_PREP = 0, FQSK_PH_REPLAY, FQSK_PH_COMPACT, FQSK_PH_DELTA, FQSK_PH_SYNC_LOCATE, FQSK_PH_SYNC_SORT, FQSK_PH_SYNC_APPLY,
-       FQSK_PH_SYNC_SIV, FQSK_PH_MT, FQSK_PH_COUNT };
+enum { FQSK_PH_PREP = 0, FQSK_PH_LOOKUP, FQSK_PH_PARTIAL, FQSK_PH_WALK, FQSK_PH_COMPACT, FQSK_PH_SORT, FQSK_PH_LOCAL, FQSK_PH_ROUGH, FQSK_PH_FOLD,
+       FQSK_PH_SYNC_LOCATE, FQSK_PH_SYNC_APPLY, FQSK_PH_SYNC_SIV, FQSK_PH_MT, FQSK_PH_COUNT };
 
 int fqsk_create(const fqsk_params *p, fqsk_handle **out);
 void fqsk_destroy(fqsk_handle *h);
@@ -128,6 +128,10 @@ int fqsk_sync(fqsk_handle *h);
 int fqsk_dump(fqsk_handle *h, int table, uint64_t *keys, uint64_t *vals, uint64_t cap, uint64_t *n);
 int fqsk_stats_get(fqsk_handle *h, fqsk_stats *out);
 int fqsk_profile(fqsk_handle *h, double *ms, uint32_t n);   /* n <= FQSK_PH_COUNT */
+/* CUDA-event stopwatch on the engine's own stream (bench.py times steps on the device with it): begin records an event,
+ * end records a second one, waits for it and returns the elapsed device milliseconds. */
+int fqsk_timer_begin(fqsk_handle *h);
+int fqsk_timer_end(fqsk_handle *h, double *ms);
 
 /* ---- table-level batch mirrors (unit parity with the reference classes; also the multi-GPU exchange building blocks) ---- */
 /* CHT_kmer<T>::insert for a list in order, with the table's CCounterIncrementer stream (ht_kmer.h:420-438). */
