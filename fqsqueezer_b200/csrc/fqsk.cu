@@ -41,10 +41,12 @@ struct DevBuf {
 	template <typename T> T *as() const { return (T *) p; }
 };
 
-struct Stream {            // one mt19937 stream (utils.h:257, seeded 5481 at utils.h:298), tempered outputs kept in HBM
-	uint32_t *buf = nullptr;
+struct Stream {            // one mt19937 stream (utils.h:257, seeded 5481 at utils.h:298): tempered outputs in an HBM ring buffer,
+	uint32_t *buf = nullptr;   // generated ahead of use on a side CUDA stream
 	uint32_t *state = nullptr;
-	uint64_t cap = 0, base = 0, generated = 0, consumed = 0;
+	uint64_t cap = 0, generated = 0, consumed = 0;   // cap is a power of two; absolute positions
+	cudaEvent_t ev = nullptr;  // completion of the latest generation launch
+	bool ev_pending = false;   // the main stream has not waited for `ev` yet
 };
 
 struct Table {
@@ -59,7 +61,7 @@ enum { ST_B = 0, ST_S = 1, ST_LB = 2, ST_LS = 3 };
 
 struct fqsk_handle {
 	fqsk_params P{};
-	cudaStream_t st = nullptr;
+	cudaStream_t st = nullptr, st_mt = nullptr;
 	std::string err;
 	Table tb, ts;
 	SivDev siv{};
@@ -172,43 +174,63 @@ int table_alloc(fqsk_handle *h, Table &t, uint32_t k, uint32_t cbits, uint32_t B
 	return FQSK_OK;
 }
 
-int stream_init(fqsk_handle *h, Stream &s) {
+inline uint64_t stream_avail_of(const Stream &s) { return s.generated - s.consumed; }
+int stream_init(fqsk_handle *h, Stream &s, uint64_t cap) {
 	uint32_t st[624];
 	st[0] = 5481u;
 	for (int i = 1; i < 624; ++i) st[i] = 1812433253u * (st[i - 1] ^ (st[i - 1] >> 30)) + (uint32_t) i;
 	CK(cudaMalloc(&s.state, 624 * 4));
 	CK(cudaMemcpy(s.state, st, 624 * 4, cudaMemcpyHostToDevice));
-	s.cap = 0; s.base = s.generated = s.consumed = 0; s.buf = nullptr;
+	CK(cudaMalloc(&s.buf, cap * 4));
+	CK(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+	s.cap = cap; s.generated = s.consumed = 0; s.ev_pending = false;
 	return FQSK_OK;
 }
-// make outputs [consumed, consumed + need) available
-int stream_ensure(fqsk_handle *h, Stream &s, uint64_t need) {
-	uint64_t want_abs = s.consumed + need;
-	if (want_abs <= s.generated) return FQSK_OK;
-	Phase ph(h, FQSK_PH_MT);
-	uint64_t blocks = (want_abs - s.generated + 623) / 624;
-	if (blocks < 2048) blocks = 2048;
-	uint64_t new_gen = s.generated + blocks * 624;
-	if (new_gen - s.base > s.cap) {
+// enqueue generation up to absolute position `upto` (rounded up to 624-blocks) on the side stream
+int stream_generate(fqsk_handle *h, Stream &s, uint64_t upto) {
+	if (upto <= s.generated) return FQSK_OK;
+	uint64_t blocks = (upto - s.generated + 623) / 624;
+	if (s.generated + blocks * 624 - s.consumed > s.cap) {
+		// the ring must never overwrite unconsumed outputs: enlarge it (rare: a single call needing more than the ring holds)
 		uint64_t live = s.generated - s.consumed;
-		uint64_t new_cap = std::max<uint64_t>(2 * (new_gen - s.consumed), 1u << 22);
+		uint64_t ncap = s.cap;
+		while (s.generated + blocks * 624 - s.consumed > ncap) ncap <<= 1;
+		CK(cudaStreamSynchronize(h->st_mt)); CK(cudaStreamSynchronize(h->st));
 		uint32_t *nb = nullptr;
-		CK(cudaMalloc(&nb, new_cap * 4));
-		if (live) CK(cudaMemcpyAsync(nb, s.buf + (s.consumed - s.base), live * 4, cudaMemcpyDeviceToDevice, h->st));
-		CK(cudaStreamSynchronize(h->st));
-		if (s.buf) cudaFree(s.buf);
-		s.buf = nb; s.cap = new_cap; s.base = s.consumed;
+		CK(cudaMalloc(&nb, ncap * 4));
+		for (uint64_t done = 0; done < live;) {   // copy the live window, re-based to the new mask
+			uint64_t from = (s.consumed + done) & (s.cap - 1), to = (s.consumed + done) & (ncap - 1);
+			uint64_t len = std::min(std::min(live - done, s.cap - from), ncap - to);
+			CK(cudaMemcpy(nb + to, s.buf + from, len * 4, cudaMemcpyDeviceToDevice));
+			done += len;
+		}
+		cudaFree(s.buf);
+		s.buf = nb; s.cap = ncap;
 	}
+	Phase ph(h, FQSK_PH_MT);
 	while (blocks) {
 		uint32_t nb = (uint32_t) std::min<uint64_t>(blocks, 1u << 20);
-		k_mt_extend<<<1, 256, 0, h->st>>>(s.state, s.buf + (s.generated - s.base), nb);
+		k_mt_extend<<<1, 256, 0, h->st_mt>>>(s.state, s.buf, s.cap - 1, s.generated, nb);
 		LAUNCHED(h);
 		s.generated += (uint64_t) nb * 624; blocks -= nb;
 	}
 	CK(cudaGetLastError());
+	CK(cudaEventRecord(s.ev, h->st_mt));
+	s.ev_pending = true;
 	return FQSK_OK;
 }
-inline const uint32_t *stream_ptr(const Stream &s) { return s.buf ? s.buf + (s.consumed - s.base) : nullptr; }
+// make outputs [consumed, consumed + need) available to kernels launched on the main stream after this call
+int stream_ensure(fqsk_handle *h, Stream &s, uint64_t need) {
+	if (s.consumed + need > s.generated) CKR(stream_generate(h, s, s.consumed + need + (need < (1u << 20) ? (1u << 20) : need / 2)));
+	if (s.ev_pending) { CK(cudaStreamWaitEvent(h->st, s.ev, 0)); s.ev_pending = false; }
+	return FQSK_OK;
+}
+// keep the generator ahead of the consumer without blocking anybody
+int stream_prefetch(fqsk_handle *h, Stream &s, uint64_t ahead) {
+	if (stream_avail_of(s) * 2 < ahead) return stream_generate(h, s, s.consumed + ahead);
+	return FQSK_OK;
+}
+inline const uint32_t *stream_ptr(const Stream &s) { return s.buf; }
 inline uint64_t stream_avail(const Stream &s) { return s.generated - s.consumed; }
 
 int ensure_iota(fqsk_handle *h, uint32_t n) {
@@ -315,7 +337,7 @@ int apply_sorted(fqsk_handle *h, Table &t, Stream &rng, const unsigned long long
 		if (it > 64) return fail(h, FQSK_E_NO_CONVERGE, "sync insert: draw flags did not settle");
 		CK(cudaMemsetAsync(h->d_flags, 0, 8 * sizeof(int), h->st));
 		k_apply_keys<<<nblk(n, 256), 256, 0, h->st>>>(t.d, t.ci, skeys, sidx, n, h->slot_of.as<unsigned long long>(), h->flag8.as<uint8_t>(),
-		                                               h->draw_off.as<uint32_t>(), stream_ptr(rng), stream_avail(rng), h->final_cnt.as<uint32_t>(), h->d_flags);
+		                                               h->draw_off.as<uint32_t>(), rng.buf, rng.cap - 1, rng.consumed, stream_avail(rng), h->final_cnt.as<uint32_t>(), h->d_flags);
 		LAUNCHED(h);
 		int fl[8];
 		CKR(read_flags(h, fl, 8));
@@ -357,7 +379,7 @@ EngineDev make_engine_dev(fqsk_handle *h) {
 	E.sorted = (h->P.mode == FQSK_MODE_SE_SORTED || h->P.mode == FQSK_MODE_PE_SORTED);
 	double aff = h->S.siv_no_filled ? (double) h->S.siv_no_updates / (double) h->S.siv_no_filled : 0.0;   // bit_vec.h:204-210
 	E.gate_missing = aff >= 7.0;
-	for (int i = 0; i < 4; ++i) { E.draws[i] = stream_ptr(h->rng[i]); E.avail[i] = stream_avail(h->rng[i]); }
+	for (int i = 0; i < 4; ++i) { E.draws[i] = h->rng[i].buf; E.dmask[i] = h->rng[i].cap - 1; E.dpos[i] = h->rng[i].consumed; E.avail[i] = stream_avail(h->rng[i]); }
 	E.flags = h->d_flags;
 	return E;
 }
@@ -398,22 +420,27 @@ int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes, u
 		{ Phase ph(h, FQSK_PH_LOOKUP); k_lookup<<<nblk(n_rec, 256), 256, 0, h->st>>>(E, S, P); LAUNCHED(h); }
 		{ Phase ph(h, FQSK_PH_PARTIAL); k_partial<<<nblk((uint64_t) n * pslots * 32, 128), 128, 0, h->st>>>(E, S, P); LAUNCHED(h); }
 	}
-	S.delta_b = DeltaDev{nullptr, nullptr, 0, h->tb.ci.thr + 1};
-	S.delta_s = DeltaDev{nullptr, nullptr, 0, h->ts.ci.thr + 1};
+	S.delta_b = DeltaDev{nullptr, nullptr, 0, 0, h->P.bmer_len, 1, h->tb.ci.thr + 1};
+	S.delta_s = DeltaDev{nullptr, nullptr, 0, 0, h->P.smer_len, 1, h->ts.ci.thr + 1};
 	h->delta_b_valid = h->delta_s_valid = false;
 	const uint32_t max_it = h->P.max_iterations ? h->P.max_iterations : 16;
 	int cur = 0;
 	uint32_t tot_b = 0, tot_s = 0, tot_p = 0, tot_b_prev = 0, tot_s_prev = 0, n_miss = 0, n_rreq = 0;
 	bool window_local_it0 = false;
+	const uint32_t t_b = std::max<uint32_t>(h->P.bmer_len - h->P.smer_len - 1, 1), t_s = std::max<uint32_t>(h->P.smer_len - h->P.pmer_len + 1, 1);
+	auto build_one = [&](DevBuf &kbuf, DevBuf &tbuf, const unsigned long long *row, const uint32_t *rt, uint32_t tot, uint32_t k, uint32_t t, uint32_t limit, DeltaDev &out) -> int {
+		uint32_t slots = 1024;
+		while (slots < 2 * tot) slots <<= 1;
+		CK(kbuf.ensure((size_t) slots * 8)); CK(tbuf.ensure((size_t) slots * 4));
+		CK(cudaMemsetAsync(tbuf.p, 0xFF, (size_t) slots * 4, h->st));
+		if (tot) { k_delta_build<<<nblk(tot, 256), 256, 0, h->st>>>(kbuf.as<unsigned long long>(), tbuf.as<uint32_t>(), slots - 1, k, t, row, rt, tot); LAUNCHED(h); }
+		out = DeltaDev{kbuf.as<unsigned long long>(), tbuf.as<uint32_t>(), slots - 1, tot, k, t, limit};
+		return FQSK_OK;
+	};
 	auto build_delta = [&](int c) -> int {
-		CKR(sort_row(h, h->row_b[c].as<unsigned long long>(), tot_b, h->P.bmer_len, h->dk_b, h->sidx_b));
-		CKR(sort_row(h, h->row_s[c].as<unsigned long long>(), tot_s, h->P.smer_len, h->dk_s, h->sidx_s));
-		CK(h->stime_b.ensure((size_t) tot_b * 4 + 4)); CK(h->stime_s.ensure((size_t) tot_s * 4 + 4));
-		if (tot_b) { k_gather_u32<<<nblk(tot_b, 256), 256, 0, h->st>>>(h->rt_b[c].as<uint32_t>(), h->sidx_b.as<uint32_t>(), tot_b, h->stime_b.as<uint32_t>()); LAUNCHED(h); }
-		if (tot_s) { k_gather_u32<<<nblk(tot_s, 256), 256, 0, h->st>>>(h->rt_s[c].as<uint32_t>(), h->sidx_s.as<uint32_t>(), tot_s, h->stime_s.as<uint32_t>()); LAUNCHED(h); }
-		S.delta_b = DeltaDev{h->dk_b.as<unsigned long long>(), h->stime_b.as<uint32_t>(), tot_b, h->tb.ci.thr + 1};
-		S.delta_s = DeltaDev{h->dk_s.as<unsigned long long>(), h->stime_s.as<uint32_t>(), tot_s, h->ts.ci.thr + 1};
-		h->delta_b_valid = h->delta_s_valid = true;
+		Phase ph(h, FQSK_PH_SORT);
+		CKR(build_one(h->dk_b, h->stime_b, h->row_b[c].as<unsigned long long>(), h->rt_b[c].as<uint32_t>(), tot_b, h->P.bmer_len, t_b, h->tb.ci.thr + 1, S.delta_b));
+		CKR(build_one(h->dk_s, h->stime_s, h->row_s[c].as<unsigned long long>(), h->rt_s[c].as<uint32_t>(), tot_s, h->P.smer_len, t_s, h->ts.ci.thr + 1, S.delta_s));
 		return FQSK_OK;
 	};
 	for (uint32_t it = 0;; ++it) {
@@ -634,6 +661,7 @@ int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
 	h->prof = (p->flags & FQSK_F_PROFILE) != 0;
 	int rc = [&]() -> int {
 		CK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+		CK(cudaStreamCreateWithFlags(&h->st_mt, cudaStreamNonBlocking));
 		CK(cudaMalloc(&h->d_flags, 8 * sizeof(int)));
 		CK(cudaMalloc(&h->d_counters, 8 * 8));
 		CK(cudaMalloc(&h->d_u32, 8 * 4));
@@ -651,7 +679,8 @@ int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
 		size_t sb = ((size_t) 1 << h->siv.key_bits) / 4;
 		CK(cudaMalloc(&h->siv.w, sb));
 		CK(cudaMemsetAsync(h->siv.w, 0, sb, h->st));
-		for (int i = 0; i < 4; ++i) CKR(stream_init(h, h->rng[i]));
+		for (int i = 0; i < 4; ++i) CKR(stream_init(h, h->rng[i], i == ST_B ? (1ull << 25) : i == ST_S ? (1ull << 21) : (1ull << 16)));
+		CKR(stream_generate(h, h->rng[ST_B], 1u << 22)); CKR(stream_generate(h, h->rng[ST_S], 1u << 18));
 		CK(h->prev_read.ensure(1 << 16));
 		CK(cudaStreamSynchronize(h->st));
 		return FQSK_OK;
@@ -667,7 +696,8 @@ void fqsk_destroy(fqsk_handle *h) {
 	if (h->st) cudaStreamSynchronize(h->st);
 	for (Table *t : {&h->tb, &h->ts}) { if (t->d.main) cudaFree(t->d.main); if (t->d.stash) cudaFree(t->d.stash); }
 	if (h->siv.w) cudaFree(h->siv.w);
-	for (auto &s : h->rng) { if (s.buf) cudaFree(s.buf); if (s.state) cudaFree(s.state); }
+	if (h->st_mt) cudaStreamSynchronize(h->st_mt);
+	for (auto &s : h->rng) { if (s.buf) cudaFree(s.buf); if (s.state) cudaFree(s.state); if (s.ev) cudaEventDestroy(s.ev); }
 	if (h->d_flags) cudaFree(h->d_flags);
 	if (h->d_counters) cudaFree(h->d_counters);
 	DevBuf *bufs[] = {&h->prev_read, &h->dna, &h->off, &h->len, &h->dup, &h->n_coded, &h->letters, &h->rec_off, &h->sl_prefix, &h->recs, &h->push_b, &h->push_s,
@@ -685,6 +715,7 @@ void fqsk_destroy(fqsk_handle *h) {
 	for (auto e : h->ev_pool) cudaEventDestroy(e);
 	if (h->t0) { cudaEventDestroy(h->t0); cudaEventDestroy(h->t1); }
 	if (h->st) cudaStreamDestroy(h->st);
+	if (h->st_mt) cudaStreamDestroy(h->st_mt);
 	delete h;
 }
 
@@ -817,6 +848,7 @@ int fqsk_sync(fqsk_handle *h) {
 		h->hidden_p = 0;
 	}
 	for (int i = 0; i < 4; ++i) h->S.draws[i] = h->rng[i].consumed;
+	CKR(stream_prefetch(h, h->rng[ST_B], 1u << 23)); CKR(stream_prefetch(h, h->rng[ST_S], 1u << 18));
 	h->pending = false; h->pend_b = h->pend_s = h->pend_p = 0; h->seg_reads = 0;
 	CK(cudaStreamSynchronize(h->st));
 	resolve_phases(h);
@@ -944,7 +976,7 @@ int fqsk_ht_find(fqsk_handle *h, int table, const uint64_t *kmer_dir, const uint
 		if (it > 32) return fail(h, FQSK_E_NO_CONVERGE, "find: draw offsets did not settle");
 		CK(cudaMemsetAsync(h->d_flags, 0, 4 * sizeof(int), h->st));
 		CK(cudaMemsetAsync(d_used + n, 0, 4, h->st));
-		k_find<<<nblk(n, 128), 128, 0, h->st>>>(t->d, t->ci, d_dir, d_rc, d_cur, (uint32_t) n, d_counts, stream_ptr(rng), stream_avail(rng), d_guess, d_used, h->d_flags);
+		k_find<<<nblk(n, 128), 128, 0, h->st>>>(t->d, t->ci, d_dir, d_rc, d_cur, (uint32_t) n, d_counts, rng.buf, rng.cap - 1, rng.consumed, stream_avail(rng), d_guess, d_used, h->d_flags);
 		LAUNCHED(h);
 		int fl[4];
 		CKR(read_flags(h, fl, 4));
@@ -1018,15 +1050,19 @@ int fqsk_mt_stream(fqsk_handle *h, uint64_t n, uint32_t *out) {
 	CK(cudaSetDevice(h->P.device));
 	// a scratch stream: same seed, generated from scratch so the engine's own streams are untouched
 	Stream s;
-	CKR(stream_init(h, s));
+	uint64_t cap = 1u << 16;
+	while (cap < n + 1248) cap <<= 1;
+	CKR(stream_init(h, s, cap));
 	int rc = stream_ensure(h, s, n);
 	if (rc == FQSK_OK && n) {
 		cudaError_t e = cudaMemcpyAsync(out, s.buf, n * 4, cudaMemcpyDeviceToHost, h->st);
 		if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
 		if (e != cudaSuccess) rc = fail(h, FQSK_E_CUDA, "mt_stream copy: %s", cudaGetErrorString(e));
 	}
+	cudaStreamSynchronize(h->st_mt);
 	if (s.buf) cudaFree(s.buf);
 	if (s.state) cudaFree(s.state);
+	if (s.ev) cudaEventDestroy(s.ev);
 	return rc;
 }
 

@@ -72,15 +72,17 @@ FQSK_HD uint32_t ci_code_floor(const CIncP &p, uint32_t r) {  // largest code in
 // A cursor into one pre-generated mt19937 stream (tempered 32-bit outputs in HBM).  `next` is relative to the read's
 // guessed starting offset; the fix point in fqsk.cu makes guess == truth before results are released.
 struct DrawCursor {
-	const uint32_t *buf;   // already offset to the stream's `consumed` position
+	const uint32_t *ring;  // ring buffer of tempered outputs
+	uint64_t mask;         // ring size - 1
+	uint64_t pos0;         // absolute index of the stream's `consumed` position
 	uint64_t avail;        // outputs generated beyond that position
-	uint64_t base;         // guessed offset of this read
-	uint32_t used;         // draws consumed by this read so far
+	uint64_t base;         // guessed offset of this consumer
+	uint32_t used;         // draws consumed by this consumer so far
 	int *overflow;         // set when the pre-generated window is too short (host extends and replays)
 	__device__ uint32_t next() {
 		uint64_t i = base + used++;
 		if (i >= avail) { *overflow = 1; return 0; }
-		return buf[i];
+		return ring[(pos0 + i) & mask];
 	}
 };
 
@@ -267,29 +269,66 @@ FQSK_DEV uint32_t siv_increment(const SivDev &s, uint64_t idx) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// intra-segment delta (the reference's thread-local CHT_kmer<uint64_t>, dna.cpp:99-103, 826, 837, 862, 872): the segment's
-// pushes sorted by (k-mer, push index).  A lookup at push-time T sees the entries with index < T.
+// intra-segment delta (the reference's thread-local CHT_kmer<uint64_t>, dna.cpp:99-103, 826, 837, 862, 872): every push of
+// the segment as a (k-mer, push time) entry of an open-addressing table whose probe run is chosen by the CANONICAL INNER
+// CORE of the k-mer (symbols t..k-1-t, min with its reverse complement).  All 4^m front completions, both orientations
+// and the 4 next-symbol siblings of a context share that core, so one probe run answers a thread-local find() -- full or
+// front-truncated (ht_kmer.h:266-327 needs 4^m probe runs for the same answer).  A lookup at time T sees entries < T.
 // ------------------------------------------------------------------------------------------------------------------
-struct DeltaDev { const unsigned long long *keys; const uint32_t *idx; uint32_t n; uint32_t exact_limit; };
+struct DeltaDev {
+	const unsigned long long *keys; const uint32_t *times;
+	uint32_t mask, n;         // slots - 1; number of pushes (0 = empty delta)
+	uint32_t k, t;            // k-mer length; symbols trimmed on each side to get the core
+	uint32_t exact_limit;     // thr + 1: highest counter value reachable without the thread-local PRNG
+};
+static const uint32_t DELTA_EMPTY = 0xFFFFFFFFu;
 
-FQSK_DEV uint32_t delta_count(const DeltaDev &d, uint64_t key, uint32_t T, int *unsupported) {
-	if (d.n == 0) return 0;
-	uint32_t lo = 0, hi = d.n;
-	while (lo < hi) { uint32_t m = (lo + hi) >> 1; if (d.keys[m] < key) lo = m + 1; else hi = m; }
-	if (lo >= d.n || d.keys[lo] != key) return 0;
-	uint32_t first = lo;
-	// first entry of this key with idx >= T
-	uint32_t a = first, b = d.n;
-	while (a < b) { uint32_t m = (a + b) >> 1; if (d.keys[m] == key && d.idx[m] < T) a = m + 1; else b = m; }
-	uint32_t cnt = a - first;
-	if (cnt > d.exact_limit) { *unsupported = 1; cnt = d.exact_limit; }  // would need the local PRNG stream (cinc_lb / cinc_ls)
-	return cnt;
+FQSK_HD uint64_t fmix64(uint64_t x) { x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33; return x; }
+FQSK_DEV uint64_t rc_kmer(uint64_t x, uint32_t k) {   // reverse complement of a left-aligned k-mer
+	uint64_t y = __brevll(x);                                            // symbols reversed, bits inside each symbol swapped
+	y = ((y >> 1) & 0x5555555555555555ull) | ((y & 0x5555555555555555ull) << 1);
+	return (~(y << (64 - 2 * k))) & (~0ull << (64 - 2 * k));
 }
-FQSK_DEV void delta_ctx_counts(const DeltaDev &d, uint32_t k, uint64_t x, bool is_dir, uint32_t T, uint32_t c[4], int *unsupported) {
-	uint32_t sh = is_dir ? 64 - 2 * k : 62;
-	uint64_t base = x & ~(3ull << sh);
-#pragma unroll
-	for (uint64_t f = 0; f < 4; ++f) c[is_dir ? f : 3 - f] += delta_count(d, base | (f << sh), T, unsupported);
+FQSK_DEV uint64_t delta_slot_of_key(uint64_t x, uint32_t k, uint32_t t, uint32_t mask) {
+	uint32_t cl = k - 2 * t;
+	uint64_t c1 = (x << (2 * t)) >> (64 - 2 * cl);
+	uint64_t c2 = (rc_kmer(x, k) << (2 * t)) >> (64 - 2 * cl);
+	return fmix64(c1 < c2 ? c1 : c2) & mask;
+}
+// Raw occurrence counts (before time T) of every k-mer that completes the context held in `r` (cur symbols, the last one is
+// the placeholder; k - cur leading symbols unknown), accumulated per next symbol exactly as the reference's trial loop
+// would find them: a stored key X counts for the trial Y in {X, rc(X)} whose known symbols match and whose normalised form
+// is X (kmer.h:366-385).
+FQSK_DEV void delta_query(const DeltaDev &D, const KReg &r, uint32_t cur, uint32_t T, uint32_t c[4]) {
+	if (D.n == 0) return;
+	const uint32_t k = D.k, m = k - cur, cl = k - 2 * D.t;
+	uint64_t c1 = (r.dir << (2 * (D.t - m))) >> (64 - 2 * cl);
+	uint64_t c2 = (r.rc << (2 * D.t)) >> (64 - 2 * cl);
+	const uint64_t qd = r.dir >> (2 * m);
+	const uint64_t kmask = (cur >= 2 ? ((1ull << (2 * (cur - 1))) - 1ull) : 0ull) << (64 - 2 * k + 2);
+	const uint64_t km = kr_kernel_mask(k);
+	const uint32_t lsh = 64 - 2 * k;
+	for (uint64_t slot = fmix64(c1 < c2 ? c1 : c2) & D.mask;; slot = (slot + 1) & D.mask) {
+		uint32_t tm = D.times[slot];
+		if (tm == DELTA_EMPTY) break;
+		if (tm >= T) continue;
+		uint64_t X = D.keys[slot];
+		uint64_t Xr = rc_kmer(X, k);
+		uint64_t kx = X & km, kxr = Xr & km;
+		bool pal = X == Xr;
+		if (((X ^ qd) & kmask) == 0 && (kx < kxr || pal)) ++c[(X >> lsh) & 3];
+		if (!pal && ((Xr ^ qd) & kmask) == 0 && !(kxr < kx)) ++c[(Xr >> lsh) & 3];
+	}
+}
+// thread-local find(): true when anything was found.  Counter values that would need the thread-local PRNG stream
+// (cinc_lb / cinc_ls, dna.cpp:164-165) are reported through *unsupported instead of being approximated.
+FQSK_DEV bool delta_find(const DeltaDev &D, const CIncP &ci, const KReg &r, uint32_t cur, uint32_t T, uint32_t c[4], int *unsupported) {
+	c[0] = c[1] = c[2] = c[3] = 0;
+	if (D.n == 0) return false;
+	delta_query(D, r, cur, T, c);
+	uint32_t lim = cur >= D.k ? D.exact_limit : ci.thr;   // a merge of several completions must stay in the exact range
+	for (int i = 0; i < 4; ++i) if (c[i] > lim) { *unsupported = 1; c[i] = lim; }
+	return (c[0] | c[1] | c[2] | c[3]) != 0;
 }
 
 }  // namespace fqsk

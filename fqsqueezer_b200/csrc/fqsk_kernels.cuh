@@ -25,7 +25,7 @@ __device__ __forceinline__ uint32_t mt_twist(uint32_t a, uint32_t b, uint32_t fa
 	uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
 	return far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
 }
-__global__ void __launch_bounds__(256) k_mt_extend(uint32_t *state, uint32_t *out, uint32_t n_blocks) {
+__global__ void __launch_bounds__(256) k_mt_extend(uint32_t *state, uint32_t *ring, unsigned long long mask, unsigned long long pos, uint32_t n_blocks) {
 	__shared__ uint32_t st[624];
 	const int t = threadIdx.x;
 	for (int i = t; i < 624; i += 256) st[i] = state[i];
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) k_mt_extend(uint32_t *state, uint32_t *ou
 		for (int i = t; i < 624; i += 256) {
 			uint32_t y = st[i];
 			y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
-			out[(uint64_t) blk * 624 + i] = y;
+			ring[(pos + (uint64_t) blk * 624 + i) & mask] = y;
 		}
 	}
 	__syncthreads();
@@ -66,8 +66,8 @@ struct EngineDev {
 	CIncP cib, cis;                 // cinc_b / cinc_s; the local incrementers have the same parameters (dna.cpp:162-165)
 	uint32_t p, s, b, prefix_len, sorted;
 	uint32_t gate_missing;          // siv_pmer->avg_filling_factor() >= 7.0 (dna.cpp:376), constant inside a segment
-	const uint32_t *draws[4];       // streams cinc_b, cinc_s, cinc_lb, cinc_ls at their consumed position
-	unsigned long long avail[4];
+	const uint32_t *draws[4];       // ring buffers of the streams cinc_b, cinc_s, cinc_lb, cinc_ls
+	unsigned long long dmask[4], dpos[4], avail[4];   // ring size - 1, absolute consumed position, outputs available beyond it
 	int *flags;                     // [0] draw window overflow, [1] unsupported path, [2] changed, [3] scratch
 };
 
@@ -202,7 +202,7 @@ __global__ void k_locate_heads(HtDev t, const unsigned long long *skeys, uint32_
 // draw; the kernel recomputes that from the counter it sees and reports a change (fix point over the ordered draw indices;
 // after the first pass changes can only come from counters saturating inside the batch).
 __global__ void k_apply_keys(HtDev t, CIncP ci, const unsigned long long *skeys, const uint32_t *sidx, uint32_t n, const unsigned long long *slot_of,
-                             uint8_t *flag, const uint32_t *draw_off, const uint32_t *draws, unsigned long long avail, uint32_t *final_cnt, int *flags) {
+                             uint8_t *flag, const uint32_t *draw_off, const uint32_t *draws, unsigned long long dmask, unsigned long long dpos, unsigned long long avail, uint32_t *final_cnt, int *flags) {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	unsigned long long key = skeys[i];
@@ -216,7 +216,7 @@ __global__ void k_apply_keys(HtDev t, CIncP ci, const unsigned long long *skeys,
 		if (!flag[j]) { flag[j] = 1; flags[2] = 1; continue; }                      // needs a draw it was not given yet
 		uint32_t di = draw_off[j];
 		if (di >= avail) { flags[0] = 1; continue; }
-		if (draws[di] % (ci.mult * (c - ci.thr)) == 0) ++c;
+		if (draws[(dpos + di) & dmask] % (ci.mult * (c - ci.thr)) == 0) ++c;
 	}
 	final_cnt[i] = c;
 }
@@ -239,10 +239,10 @@ __global__ void k_siv_increment(SivDev s, const unsigned long long *idx, uint64_
 // table-level batch mirrors
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void k_find(HtDev t, CIncP ci, const unsigned long long *dir, const unsigned long long *rc, const uint32_t *cur, uint32_t n,
-                       uint32_t *counts, const uint32_t *draws, unsigned long long avail, const unsigned long long *guess, uint32_t *used, int *flags) {
+                       uint32_t *counts, const uint32_t *draws, unsigned long long dmask, unsigned long long dpos, unsigned long long avail, const unsigned long long *guess, uint32_t *used, int *flags) {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
-	DrawCursor dc; dc.buf = draws; dc.avail = avail; dc.base = guess ? guess[i] : 0; dc.used = 0; dc.overflow = flags;
+	DrawCursor dc; dc.ring = draws; dc.mask = dmask; dc.pos0 = dpos; dc.avail = avail; dc.base = guess ? guess[i] : 0; dc.used = 0; dc.overflow = flags;
 	KReg r{dir[i], rc[i]};
 	uint32_t c[4];
 	ht_find(t, ci, r, cur[i], c, dc);

@@ -284,29 +284,6 @@ __global__ void __launch_bounds__(128) k_partial(EngineDev E, SegDev S, PipeDev 
 // delta of the previous iteration.  Idempotent: always starts from the stored global-only result.
 // Merges that would draw from the thread-local PRNG streams are reported as unsupported.
 // ------------------------------------------------------------------------------------------------------------------
-__device__ bool local_find_nodraw(const DeltaDev &d, uint32_t k, const CIncP &ci, const KReg &r, uint32_t cur, uint32_t T, uint32_t c[4], int *unsupported) {
-	c[0] = c[1] = c[2] = c[3] = 0;
-	if (d.n == 0) return false;
-	if (cur >= k) {
-		bool dd = kr_is_dir(r, k);
-		delta_ctx_counts(d, k, dd ? r.dir : r.rc, dd, T, c, unsupported);
-		return any4(c);
-	}
-	uint32_t m = k - cur, trials = 1u << (2 * m);
-	for (uint32_t n = 0; n < trials; ++n) {
-		KReg tr = partial_trial(r, k, m, n);
-		bool dd = kr_is_dir(tr, k);
-		uint32_t loc[4] = {0, 0, 0, 0};
-		delta_ctx_counts(d, k, dd ? tr.dir : tr.rc, dd, T, loc, unsupported);
-		for (int i = 0; i < 4; ++i) if (loc[i]) {
-			uint32_t sum = ci_to_real(ci, c[i]) + ci_to_real(ci, loc[i]);
-			if (sum > ci.thr) { *unsupported = 1; sum = ci.thr; }   // would need cinc_lb / cinc_ls draws
-			c[i] = sum;
-		}
-	}
-	return any4(c);
-}
-
 __global__ void __launch_bounds__(128) k_local(EngineDev E, SegDev S, PipeDev P, uint32_t n_miss) {
 	uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
 	if (m >= n_miss) return;
@@ -317,12 +294,12 @@ __global__ void __launch_bounds__(128) k_local(EngineDev E, SegDev S, PipeDev P,
 	bool hit = false;
 	if (e.flags & PF_MISS_B) {
 		uint32_t lc[4];
-		if (local_find_nodraw(S.delta_b, E.b, E.cib, e.breg, e.cb, e.time, lc, P.flags + 1)) { for (int q = 0; q < 4; ++q) c[q] = lc[q]; lev = FQSK_LEVEL_BMER; hit = true; }
+		if (delta_find(S.delta_b, E.cib, e.breg, e.cb, e.time, lc, P.flags + 1)) { for (int q = 0; q < 4; ++q) c[q] = lc[q]; lev = FQSK_LEVEL_BMER; hit = true; }
 	}
 	if (!hit && (e.flags & PF_MISS_S)) {
 		KReg sr = suffix_reg(e.breg, e.cb, cs);
 		uint32_t lc[4];
-		if (local_find_nodraw(S.delta_s, E.s, E.cis, sr, cs, e.time, lc, P.flags + 1)) { for (int q = 0; q < 4; ++q) c[q] = lc[q]; lev = FQSK_LEVEL_SMER; hit = true; }
+		if (delta_find(S.delta_s, E.cis, sr, cs, e.time, lc, P.flags + 1)) { for (int q = 0; q < 4; ++q) c[q] = lc[q]; lev = FQSK_LEVEL_SMER; hit = true; }
 	}
 	fqsk_base_rec *rec = P.prov + e.rec;
 	if (hit) P.flags[6] = 1;
@@ -358,7 +335,7 @@ __global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P) 
 	unsigned long long sl[4];
 	for (int i = 0; i < 4; ++i) sl[i] = S.sl_base.v[i] + S.sl_prefix[r].v[i];
 	int *unsupported = E.flags + 1;
-	DrawCursor nodraw; nodraw.buf = nullptr; nodraw.avail = 0; nodraw.base = 0; nodraw.used = 0; nodraw.overflow = E.flags + 5;
+	DrawCursor nodraw; nodraw.ring = nullptr; nodraw.mask = 0; nodraw.pos0 = 0; nodraw.avail = 0; nodraw.base = 0; nodraw.used = 0; nodraw.overflow = E.flags + 5;
 
 	ReadState R;
 	R.pc = R.sc = R.bc = R.pu = R.su = R.bu = KReg{0, 0};
@@ -415,13 +392,13 @@ __global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P) 
 				else lev = FQSK_LEVEL_BMER;
 				done = true;
 			} else {
-				if (S.delta_b.n) { P.flags[3] = 1; if (local_find_nodraw(S.delta_b, E.b, E.cib, R.bc, cb, tbase + i, c, unsupported)) { lev = FQSK_LEVEL_BMER; done = true; } }
+				if (S.delta_b.n) { P.flags[3] = 1; if (delta_find(S.delta_b, E.cib, R.bc, cb, tbase + i, c, unsupported)) { lev = FQSK_LEVEL_BMER; done = true; } }
 				else P.flags[3] = 1;   // a window lookup of the thread-local table happened: one more iteration must confirm it
 				if (!done && ht_find(E.hb, E.cib, R.bu, cb, c, nodraw)) { lev = FQSK_LEVEL_BMER_UNC; done = true; }
 			}
 			if (!done) {
 				if (ht_find(E.hs, E.cis, R.sc, cs, c, nodraw)) lev = FQSK_LEVEL_SMER;
-				else if (S.delta_s.n && local_find_nodraw(S.delta_s, E.s, E.cis, R.sc, cs, tbase + i, c, unsupported)) lev = FQSK_LEVEL_SMER;
+				else if (S.delta_s.n && delta_find(S.delta_s, E.cis, R.sc, cs, tbase + i, c, unsupported)) lev = FQSK_LEVEL_SMER;
 			}
 			if (lev == FQSK_LEVEL_BMER_UNC) { R.bc = R.bu; R.sc = R.su; R.pc = R.pu; R.cor_pos = 0; lev = FQSK_LEVEL_BMER; }
 		}
@@ -503,9 +480,15 @@ __global__ void k_compact2(SegDev S, PipeDev P, const uint32_t *off_b, const uin
 	for (uint32_t i = threadIdx.x; i < S.cnt_s[r]; i += blockDim.x) { row_s[off_s[r] + i] = ss[i]; rt_s[off_s[r] + i] = ts[i]; }
 	for (uint32_t i = threadIdx.x; i < S.cnt_p[r]; i += blockDim.x) row_p[off_p[r] + i] = sp[i];
 }
-__global__ void k_gather_u32(const uint32_t *src, const uint32_t *idx, uint32_t n, uint32_t *dst) {
-	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n) dst[i] = src[idx[i]];
+// delta build: one entry per push, placed by the canonical inner core of its k-mer
+__global__ void k_delta_build(unsigned long long *keys, uint32_t *times, uint32_t mask, uint32_t k, uint32_t t, const unsigned long long *row, const uint32_t *rt, uint32_t n) {
+	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n) return;
+	unsigned long long x = row[j];
+	uint32_t tm = rt[j];
+	for (uint64_t slot = delta_slot_of_key(x, k, t, mask);; slot = (slot + 1) & mask) {
+		if (atomicCAS(times + slot, DELTA_EMPTY, tm) == DELTA_EMPTY) { keys[slot] = x; return; }
+	}
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -575,7 +558,7 @@ __global__ void __launch_bounds__(128) k_fold(EngineDev E, PipeDev P, const Scri
 	const bool rough = sc.kind >= 2;
 	const CIncP ci = is_b ? E.cib : E.cis;
 	DrawCursor dc;
-	dc.buf = E.draws[is_b ? 0 : 1]; dc.avail = E.avail[is_b ? 0 : 1]; dc.used = 0; dc.overflow = E.flags + 0;
+	dc.ring = E.draws[is_b ? 0 : 1]; dc.mask = E.dmask[is_b ? 0 : 1]; dc.pos0 = E.dpos[is_b ? 0 : 1]; dc.avail = E.avail[is_b ? 0 : 1]; dc.used = 0; dc.overflow = E.flags + 0;
 	dc.base = pass ? (is_b ? P.doff_b[sc.rec] : P.doff_s[sc.rec]) : 0;
 	uint32_t c[4] = {0, 0, 0, 0};
 	for (uint32_t n = 0; n < sc.n; ++n) {
