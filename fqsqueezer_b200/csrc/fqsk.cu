@@ -79,7 +79,7 @@ struct fqsk_handle {
 	       draw_cnt, draw_cnt_prev, draw_scan, off_b[2], off_s[2], off_p, row_b[2], row_s[2], row_p, dk_b, di_b, dk_s, di_s, iota, cub_tmp,
 	       flag8, draw_off, final_cnt, slot_of, dump_k, dump_v, q0, q1, q2, q3, q4, sflag, sdif, hid_scan,
 	       prov, pflags, pscripts, rscripts, rreqs, pool, miss, draws_b16, draws_s16, doff_b, doff_s, time_b, time_s, rt_b[2], rt_s[2],
-	       sidx_b, sidx_s, stime_b, stime_s, sort_k, sort_v;
+	       sidx_b, sidx_s, stime_b, stime_s, sort_k, sort_v, rkind, rreg, rslot, dirty, rdraws_b, rdraws_s, totals;
 	uint32_t miss_cap = 0, rreq_cap = 0, pool_cap = 1u << 18;
 	uint32_t *d_u32 = nullptr;            // [0] n_miss [1] n_rreq [2] pool_used
 	bool delta_b_valid = false, delta_s_valid = false;   // dk_b/sidx_b (dk_s/sidx_s) hold the pending row sorted by k-mer
@@ -387,169 +387,146 @@ EngineDev make_engine_dev(fqsk_handle *h) {
 const int RC_RETRY = 1;   // internal: a capacity was too small, grow and redo the segment
 
 // ---------------------------------------------------------------------------------------------------------------
-// one sync segment, reads resident on the device
+// one sync segment, reads resident on the device.  All counts stay on the device; kernels are
+// launched from host-side upper bounds and the host looks at the device twice per segment.
 // ---------------------------------------------------------------------------------------------------------------
-int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes, uint32_t n_rec, uint32_t first) {
-	const size_t n1 = (size_t) n + 1, r1 = (size_t) n_rec + 1;
+int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes, uint32_t first) {
+	const size_t n1 = (size_t) n + 1;
+	const uint32_t rec_bound = (uint32_t) dna_bytes;                 // coded positions <= DNA bytes
+	const size_t r1 = (size_t) rec_bound + 1;
 	const uint32_t pslots = h->P.bmer_len - h->P.pmer_len + 1;
 	CK(h->prov.ensure(r1 * sizeof(fqsk_base_rec))); CK(h->recs.ensure(r1 * sizeof(fqsk_base_rec))); CK(h->pflags.ensure(r1));
+	CK(h->rkind.ensure(r1)); CK(h->rreg.ensure(r1 * sizeof(KReg))); CK(h->rslot.ensure(r1 * 4)); CK(h->dirty.ensure(n1));
 	CK(h->pscripts.ensure(n1 * pslots * sizeof(Script)));
-	CK(h->rscripts.ensure(((size_t) h->rreq_cap + 1) * sizeof(Script))); CK(h->rreqs.ensure(((size_t) h->rreq_cap + 1) * sizeof(RoughReq)));
+	CK(h->rscripts.ensure(((size_t) h->rreq_cap + 1) * sizeof(Script)));
 	CK(h->pool.ensure(((size_t) h->pool_cap + 1) * 8)); CK(h->miss.ensure(((size_t) h->miss_cap + 1) * sizeof(MissEntry)));
-	CK(h->draws_b16.ensure(r1 * 2)); CK(h->draws_s16.ensure(r1 * 2)); CK(h->doff_b.ensure(r1 * 8)); CK(h->doff_s.ensure(r1 * 8));
+	CK(h->rdraws_b.ensure(n1 * 4)); CK(h->rdraws_s.ensure(n1 * 4)); CK(h->doff_b.ensure(n1 * 8)); CK(h->doff_s.ensure(n1 * 8));
 	CK(h->time_b.ensure((2 * dna_bytes + 2) * 4)); CK(h->time_s.ensure((dna_bytes + 1) * 4));
-	for (int i = 0; i < 2; ++i) { CK(h->rt_b[i].ensure((2 * dna_bytes + 2) * 4)); CK(h->rt_s[i].ensure((dna_bytes + 1) * 4)); }
+	CK(h->rt_b[0].ensure((2 * dna_bytes + 2) * 4)); CK(h->rt_s[0].ensure((dna_bytes + 1) * 4));
+	CK(h->totals.ensure(256));
 
 	PipeDev P{};
-	P.n_rec = n_rec; P.start = first; P.rec_off = S.rec_off;
+	P.n_rec = rec_bound; P.start = first; P.rec_off = S.rec_off;
 	P.prov = h->prov.as<fqsk_base_rec>(); P.recs = h->recs.as<fqsk_base_rec>(); P.pflags = h->pflags.as<uint8_t>();
 	P.pscripts = h->pscripts.as<Script>(); P.pslots = pslots; P.pfirst_n = h->P.pmer_len - 1;
-	P.rscripts = h->rscripts.as<Script>(); P.rreqs = h->rreqs.as<RoughReq>(); P.n_rreq = h->d_u32 + 1; P.rreq_cap = h->rreq_cap;
+	P.rscripts = h->rscripts.as<Script>(); P.n_rscript = h->d_u32 + 1; P.rscript_cap = h->rreq_cap;
+	P.rkind = h->rkind.as<uint8_t>(); P.rreg = h->rreg.as<KReg>(); P.rslot = h->rslot.as<uint32_t>(); P.dirty = h->dirty.as<uint8_t>();
 	P.pool = h->pool.as<unsigned short>(); P.pool_used = h->d_u32 + 2; P.pool_cap = h->pool_cap;
 	P.miss = h->miss.as<MissEntry>(); P.n_miss = h->d_u32 + 0; P.miss_cap = h->miss_cap;
-	P.draws_b = h->draws_b16.as<unsigned short>(); P.draws_s = h->draws_s16.as<unsigned short>();
+	P.rdraws_b = h->rdraws_b.as<uint32_t>(); P.rdraws_s = h->rdraws_s.as<uint32_t>();
 	P.doff_b = h->doff_b.as<unsigned long long>(); P.doff_s = h->doff_s.as<unsigned long long>();
 	P.time_b = h->time_b.as<uint32_t>(); P.time_s = h->time_s.as<uint32_t>();
-	P.flags = h->d_flags;
+	P.flags = h->d_flags; P.n_rec_dev = h->d_u32 + 3;
 	S.recs = P.recs;
+	SegTotals *d_tot = h->totals.as<SegTotals>();
+	uint32_t *d_tot4 = (uint32_t *) (h->totals.as<uint8_t>() + 128);          // tot_b, tot_s, tot_p, hidden
+	unsigned long long *d_draw2 = (unsigned long long *) (h->totals.as<uint8_t>() + 160);
 
 	EngineDev E = make_engine_dev(h);
-	CK(cudaMemsetAsync(h->d_u32, 0, 8 * 4, h->st));
+	CK(cudaMemsetAsync(h->d_u32, 0, 3 * 4, h->st));
 	CK(cudaMemsetAsync(h->d_flags, 0, 8 * sizeof(int), h->st));
-	if (n_rec) {
-		{ Phase ph(h, FQSK_PH_LOOKUP); k_lookup<<<nblk(n_rec, 256), 256, 0, h->st>>>(E, S, P); LAUNCHED(h); }
-		{ Phase ph(h, FQSK_PH_PARTIAL); k_partial<<<nblk((uint64_t) n * pslots * 32, 128), 128, 0, h->st>>>(E, S, P); LAUNCHED(h); }
-	}
+	{ Phase ph(h, FQSK_PH_LOOKUP); k_lookup<<<nblk(rec_bound, 256), 256, 0, h->st>>>(E, S, P); LAUNCHED(h); }
+	{ Phase ph(h, FQSK_PH_PARTIAL); k_partial<<<nblk((uint64_t) n * pslots * 32, 128), 128, 0, h->st>>>(E, S, P); LAUNCHED(h); }
 	S.delta_b = DeltaDev{nullptr, nullptr, 0, 0, h->P.bmer_len, 1, h->tb.ci.thr + 1};
 	S.delta_s = DeltaDev{nullptr, nullptr, 0, 0, h->P.smer_len, 1, h->ts.ci.thr + 1};
 	h->delta_b_valid = h->delta_s_valid = false;
-	const uint32_t max_it = h->P.max_iterations ? h->P.max_iterations : 16;
-	int cur = 0;
-	uint32_t tot_b = 0, tot_s = 0, tot_p = 0, tot_b_prev = 0, tot_s_prev = 0, n_miss = 0, n_rreq = 0;
-	bool window_local_it0 = false;
 	const uint32_t t_b = std::max<uint32_t>(h->P.bmer_len - h->P.smer_len - 1, 1), t_s = std::max<uint32_t>(h->P.smer_len - h->P.pmer_len + 1, 1);
-	auto build_one = [&](DevBuf &kbuf, DevBuf &tbuf, const unsigned long long *row, const uint32_t *rt, uint32_t tot, uint32_t k, uint32_t t, uint32_t limit, DeltaDev &out) -> int {
-		uint32_t slots = 1024;
-		while (slots < 2 * tot) slots <<= 1;
-		CK(kbuf.ensure((size_t) slots * 8)); CK(tbuf.ensure((size_t) slots * 4));
-		CK(cudaMemsetAsync(tbuf.p, 0xFF, (size_t) slots * 4, h->st));
-		if (tot) { k_delta_build<<<nblk(tot, 256), 256, 0, h->st>>>(kbuf.as<unsigned long long>(), tbuf.as<uint32_t>(), slots - 1, k, t, row, rt, tot); LAUNCHED(h); }
-		out = DeltaDev{kbuf.as<unsigned long long>(), tbuf.as<uint32_t>(), slots - 1, tot, k, t, limit};
-		return FQSK_OK;
-	};
-	auto build_delta = [&](int c) -> int {
+	uint32_t slots_b = 1024, slots_s = 1024;
+	while (slots_b < 4 * dna_bytes) slots_b <<= 1;      // at most 2 b pushes per base, half-full table
+	while (slots_s < 2 * dna_bytes) slots_s <<= 1;
+	auto build_delta = [&]() -> int {
 		Phase ph(h, FQSK_PH_SORT);
-		CKR(build_one(h->dk_b, h->stime_b, h->row_b[c].as<unsigned long long>(), h->rt_b[c].as<uint32_t>(), tot_b, h->P.bmer_len, t_b, h->tb.ci.thr + 1, S.delta_b));
-		CKR(build_one(h->dk_s, h->stime_s, h->row_s[c].as<unsigned long long>(), h->rt_s[c].as<uint32_t>(), tot_s, h->P.smer_len, t_s, h->ts.ci.thr + 1, S.delta_s));
+		CK(h->dk_b.ensure((size_t) slots_b * 8)); CK(h->stime_b.ensure((size_t) slots_b * 4));
+		CK(h->dk_s.ensure((size_t) slots_s * 8)); CK(h->stime_s.ensure((size_t) slots_s * 4));
+		CK(cudaMemsetAsync(h->stime_b.p, 0xFF, (size_t) slots_b * 4, h->st));
+		CK(cudaMemsetAsync(h->stime_s.p, 0xFF, (size_t) slots_s * 4, h->st));
+		k_delta_build<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(S, P, h->dk_b.as<unsigned long long>(), h->stime_b.as<uint32_t>(), slots_b - 1, h->P.bmer_len, t_b,
+		                                                             h->dk_s.as<unsigned long long>(), h->stime_s.as<uint32_t>(), slots_s - 1, h->P.smer_len, t_s);
+		LAUNCHED(h);
+		S.delta_b = DeltaDev{h->dk_b.as<unsigned long long>(), h->stime_b.as<uint32_t>(), slots_b - 1, 1, h->P.bmer_len, t_b, h->tb.ci.thr + 1};
+		S.delta_s = DeltaDev{h->dk_s.as<unsigned long long>(), h->stime_s.as<uint32_t>(), slots_s - 1, 1, h->P.smer_len, t_s, h->ts.ci.thr + 1};
 		return FQSK_OK;
 	};
-	for (uint32_t it = 0;; ++it) {
+	const uint32_t max_it = h->P.max_iterations ? h->P.max_iterations : 16;
+	int fl[8];
+	uint32_t cnt[4];
+	// walk 0 on every read, then (speculatively) the thread-local pass: delta, k_local, walk 1 on the reads it touched
+	{ Phase ph(h, FQSK_PH_WALK); k_walk<<<nblk(n, 128), 128, 0, h->st>>>(E, S, P, 0); LAUNCHED(h); ++h->S.n_replays; }
+	for (uint32_t it = 1;; ++it) {
 		if (it >= max_it) return fail(h, FQSK_E_NO_CONVERGE, "segment did not reach its fixed point in %u iterations", max_it);
-		CK(cudaMemsetAsync(h->d_u32 + 1, 0, 4, h->st));          // rough requests are re-issued by every walk
-		CK(cudaMemsetAsync(h->d_flags + 3, 0, sizeof(int), h->st));
-		{
-			Phase ph(h, FQSK_PH_WALK);
-			k_walk<<<nblk(n, 128), 128, 0, h->st>>>(E, S, P); LAUNCHED(h);
-			++h->S.n_replays;
+		CK(cudaMemsetAsync(h->d_flags + 2, 0, sizeof(int), h->st));
+		CKR(build_delta());
+		{ Phase ph(h, FQSK_PH_LOCAL); k_local<<<std::min<uint32_t>(nblk(std::max<uint32_t>(h->miss_cap, 1), 128), 148 * 16), 128, 0, h->st>>>(E, S, P); LAUNCHED(h); }
+		{ Phase ph(h, FQSK_PH_WALK); k_walk<<<nblk(n, 128), 128, 0, h->st>>>(E, S, P, it); LAUNCHED(h); ++h->S.n_replays; }
+		uint32_t *hs = (uint32_t *) h->h_small;
+		CK(cudaMemcpyAsync(hs, h->d_u32, 4 * 4, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaMemcpyAsync(hs + 8, h->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+		CK(cudaStreamSynchronize(h->st));
+		resolve_phases(h);
+		memcpy(cnt, hs, sizeof cnt); memcpy(fl, hs + 8, sizeof fl);
+		if (fl[4]) {
+			if (cnt[0] > h->miss_cap) h->miss_cap = cnt[0] + cnt[0] / 4 + 1024;
+			if (cnt[2] > h->pool_cap) h->pool_cap = cnt[2] + cnt[2] / 2 + 1024;
+			return RC_RETRY;
 		}
-		{
-			Phase ph(h, FQSK_PH_COMPACT);
-			CK(cudaMemsetAsync(h->cnt_b.as<uint32_t>() + n, 0, 4, h->st)); CK(cudaMemsetAsync(h->cnt_s.as<uint32_t>() + n, 0, 4, h->st));
-			CK(cudaMemsetAsync(h->cnt_p.as<uint32_t>() + n, 0, 4, h->st));
-			CKR((scan_excl<uint32_t, uint32_t>(h, h->cnt_b.as<uint32_t>(), h->off_b[cur].as<uint32_t>(), n + 1, 0u)));
-			CKR((scan_excl<uint32_t, uint32_t>(h, h->cnt_s.as<uint32_t>(), h->off_s[cur].as<uint32_t>(), n + 1, 0u)));
-			CKR((scan_excl<uint32_t, uint32_t>(h, h->cnt_p.as<uint32_t>(), h->off_p.as<uint32_t>(), n + 1, 0u)));
-			k_compact2<<<n, 64, 0, h->st>>>(S, P, h->off_b[cur].as<uint32_t>(), h->off_s[cur].as<uint32_t>(), h->off_p.as<uint32_t>(),
-			                               h->row_b[cur].as<unsigned long long>(), h->row_s[cur].as<unsigned long long>(), h->row_p.as<unsigned long long>(),
-			                               h->rt_b[cur].as<uint32_t>(), h->rt_s[cur].as<uint32_t>());
-			LAUNCHED(h);
-			uint32_t *hs = (uint32_t *) h->h_small;
-			CK(cudaMemcpyAsync(hs + 0, h->off_b[cur].as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, h->st));
-			CK(cudaMemcpyAsync(hs + 1, h->off_s[cur].as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, h->st));
-			CK(cudaMemcpyAsync(hs + 2, h->off_p.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, h->st));
-			CK(cudaMemcpyAsync(hs + 4, h->d_u32, 3 * 4, cudaMemcpyDeviceToHost, h->st));
-			CK(cudaMemcpyAsync(hs + 8, h->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
-			CK(cudaStreamSynchronize(h->st));
-			resolve_phases(h);
-			tot_b = hs[0]; tot_s = hs[1]; tot_p = hs[2]; n_miss = hs[4]; n_rreq = hs[5];
-			int fl[8]; memcpy(fl, hs + 8, sizeof fl);
-			if (fl[4]) {
-				if (n_miss > h->miss_cap) h->miss_cap = n_miss + n_miss / 4 + 1024;
-				if (n_rreq > h->rreq_cap) h->rreq_cap = n_rreq + n_rreq / 4 + 1024;
-				if (hs[6] > h->pool_cap) h->pool_cap = hs[6] + hs[6] / 2 + 1024;
-				return RC_RETRY;
-			}
-			if (fl[5]) return fail(h, FQSK_E_CUDA, "internal error: a draw was requested on a path that must not draw");
-			if (fl[1]) return fail(h, FQSK_E_UNSUPPORTED, "segment needs the thread-local PRNG streams (a k-mer occurs more than %u times inside one sync segment and is looked up there, or a thread-local merge exceeds the deterministic range); not implemented yet", h->tb.ci.thr + 1);
-			if (it == 0) window_local_it0 = fl[3] != 0;
-		}
-		bool need_more;
-		if (it == 0) {
-			need_more = (n_miss > 0 || window_local_it0) && (tot_b + tot_s > 0);
-			if (need_more) {
-				CKR(build_delta(cur));
-				CK(cudaMemsetAsync(h->d_flags + 6, 0, sizeof(int), h->st));
-				if (n_miss) { Phase ph(h, FQSK_PH_LOCAL); k_local<<<nblk(n_miss, 128), 128, 0, h->st>>>(E, S, P, n_miss); LAUNCHED(h); }
-				int fl[8];
-				CKR(read_flags(h, fl, 8));
-				if (fl[1]) return fail(h, FQSK_E_UNSUPPORTED, "segment needs the thread-local PRNG streams; not implemented yet");
-				if (!fl[6] && !window_local_it0) need_more = false;   // nobody saw anything in the thread-local tables: the walk stands
-			}
-		} else {
-			bool changed = (tot_b != tot_b_prev) || (tot_s != tot_s_prev);
-			if (!changed) {
-				CK(cudaMemsetAsync(h->d_flags + 2, 0, sizeof(int), h->st));
-				if (tot_b) {
-					k_compare_u64<<<nblk(tot_b, 256), 256, 0, h->st>>>(h->row_b[cur].as<unsigned long long>(), h->row_b[cur ^ 1].as<unsigned long long>(), tot_b, h->d_flags + 2); LAUNCHED(h);
-					k_compare_u32<<<nblk(tot_b, 256), 256, 0, h->st>>>(h->rt_b[cur].as<uint32_t>(), h->rt_b[cur ^ 1].as<uint32_t>(), tot_b, h->d_flags + 2); LAUNCHED(h);
-				}
-				if (tot_s) {
-					k_compare_u64<<<nblk(tot_s, 256), 256, 0, h->st>>>(h->row_s[cur].as<unsigned long long>(), h->row_s[cur ^ 1].as<unsigned long long>(), tot_s, h->d_flags + 2); LAUNCHED(h);
-					k_compare_u32<<<nblk(tot_s, 256), 256, 0, h->st>>>(h->rt_s[cur].as<uint32_t>(), h->rt_s[cur ^ 1].as<uint32_t>(), tot_s, h->d_flags + 2); LAUNCHED(h);
-				}
-				int fl[8];
-				CKR(read_flags(h, fl, 8));
-				changed = fl[2] != 0;
-			}
-			need_more = changed;
-			if (need_more) {
-				CKR(build_delta(cur));
-				if (n_miss) { Phase ph(h, FQSK_PH_LOCAL); k_local<<<nblk(n_miss, 128), 128, 0, h->st>>>(E, S, P, n_miss); LAUNCHED(h); }
-			}
-		}
-		if (!need_more) { h->cur = cur; break; }
-		tot_b_prev = tot_b; tot_s_prev = tot_s;
-		cur ^= 1;
+		if (fl[5]) return fail(h, FQSK_E_CUDA, "internal error: a draw was requested on a path that must not draw");
+		if (fl[1]) return fail(h, FQSK_E_UNSUPPORTED, "segment needs the thread-local PRNG streams (a k-mer occurs more than %u times inside one sync segment and is looked up there, or a thread-local merge exceeds the deterministic range); not implemented yet", h->tb.ci.thr + 1);
+		if (!fl[2]) break;        // the re-walked reads reproduced their pushes: fixed point
 	}
-	// rough searches requested by the final walk, then the ordered merges of every script
-	if (n_rec) {
-		if (n_rreq) { Phase ph(h, FQSK_PH_ROUGH); k_rough<<<nblk((uint64_t) n_rreq * 32, 128), 128, 0, h->st>>>(E, P, n_rreq); LAUNCHED(h); }
+	// compaction of the converged pushes, rough searches, ordered merges
+	{
+		Phase ph(h, FQSK_PH_COMPACT);
+		k_scan_u32x4<<<1, 1024, 0, h->st>>>(n, h->cnt_b.as<uint32_t>(), h->off_b[0].as<uint32_t>(), h->cnt_s.as<uint32_t>(), h->off_s[0].as<uint32_t>(),
+		                                     h->cnt_p.as<uint32_t>(), h->off_p.as<uint32_t>(), h->hidden.as<uint32_t>(), nullptr, d_tot4);
+		LAUNCHED(h);
+		k_compact2<<<n, 64, 0, h->st>>>(S, P, h->off_b[0].as<uint32_t>(), h->off_s[0].as<uint32_t>(), h->off_p.as<uint32_t>(),
+		                               h->row_b[0].as<unsigned long long>(), h->row_s[0].as<unsigned long long>(), h->row_p.as<unsigned long long>(),
+		                               h->rt_b[0].as<uint32_t>(), h->rt_s[0].as<uint32_t>());
+		LAUNCHED(h);
+	}
+	h->cur = 0;
+	{ Phase ph(h, FQSK_PH_ROUGH); k_rough<<<148 * 8, 128, 0, h->st>>>(E, P); LAUNCHED(h); }
+	unsigned long long draws2[2] = {0, 0};
+	{
 		Phase ph(h, FQSK_PH_FOLD);
-		uint32_t n_ps = n * pslots;
-		k_fold<<<nblk(n_ps, 128), 128, 0, h->st>>>(E, P, P.pscripts, n_ps, 0); LAUNCHED(h);
-		if (n_rreq) { k_fold<<<nblk(n_rreq, 128), 128, 0, h->st>>>(E, P, P.rscripts, n_rreq, 0); LAUNCHED(h); }
+		k_fold<<<nblk(n, 128), 128, 0, h->st>>>(E, S, P, 0); LAUNCHED(h);
 		for (int it = 0;; ++it) {
 			if (it > 32) return fail(h, FQSK_E_NO_CONVERGE, "draw offsets of the merge scripts did not settle");
-			CK(cudaMemsetAsync(h->draws_b16.as<unsigned short>() + n_rec, 0, 2, h->st)); CK(cudaMemsetAsync(h->draws_s16.as<unsigned short>() + n_rec, 0, 2, h->st));
-			CKR((scan_excl<unsigned short, unsigned long long>(h, h->draws_b16.as<unsigned short>(), h->doff_b.as<unsigned long long>(), n_rec + 1, 0ull)));
-			CKR((scan_excl<unsigned short, unsigned long long>(h, h->draws_s16.as<unsigned short>(), h->doff_s.as<unsigned long long>(), n_rec + 1, 0ull)));
-			unsigned long long *hs = (unsigned long long *) h->h_small;
-			CK(cudaMemcpyAsync(hs + 0, h->doff_b.as<unsigned long long>() + n_rec, 8, cudaMemcpyDeviceToHost, h->st));
-			CK(cudaMemcpyAsync(hs + 1, h->doff_s.as<unsigned long long>() + n_rec, 8, cudaMemcpyDeviceToHost, h->st));
+			k_scan_draws<<<1, 1024, 0, h->st>>>(n, P.rdraws_b, h->doff_b.as<unsigned long long>(), P.rdraws_s, h->doff_s.as<unsigned long long>(), d_draw2); LAUNCHED(h);
+			CK(cudaMemsetAsync(h->d_flags, 0, 4 * sizeof(int), h->st));
+			k_fold<<<nblk(n, 128), 128, 0, h->st>>>(E, S, P, 1); LAUNCHED(h);
+			uint8_t *hs = (uint8_t *) h->h_small;
+			CK(cudaMemcpyAsync(hs, h->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+			CK(cudaMemcpyAsync(hs + 32, d_draw2, 16, cudaMemcpyDeviceToHost, h->st));
+			CK(cudaMemcpyAsync(hs + 48, d_tot4, 16, cudaMemcpyDeviceToHost, h->st));
+			CK(cudaMemcpyAsync(hs + 64, d_tot, 48, cudaMemcpyDeviceToHost, h->st));
+			CK(cudaMemcpyAsync(hs + 128, h->d_u32, 16, cudaMemcpyDeviceToHost, h->st));
 			CK(cudaStreamSynchronize(h->st));
-			unsigned long long db = hs[0], ds = hs[1];
-			CKR(stream_ensure(h, h->rng[ST_B], db)); CKR(stream_ensure(h, h->rng[ST_S], ds));
-			E = make_engine_dev(h);
-			CK(cudaMemsetAsync(h->d_flags, 0, 8 * sizeof(int), h->st));
-			k_fold<<<nblk(n_ps, 128), 128, 0, h->st>>>(E, P, P.pscripts, n_ps, 1); LAUNCHED(h);
-			if (n_rreq) { k_fold<<<nblk(n_rreq, 128), 128, 0, h->st>>>(E, P, P.rscripts, n_rreq, 1); LAUNCHED(h); }
-			int fl[8];
-			CKR(read_flags(h, fl, 8));
-			if (fl[0]) return fail(h, FQSK_E_CUDA, "internal error: draw window shorter than the scanned total");
-			if (!fl[2]) { h->rng[ST_B].consumed += db; h->rng[ST_S].consumed += ds; break; }
+			resolve_phases(h);
+			memcpy(fl, hs, sizeof fl); memcpy(draws2, hs + 32, 16); memcpy(cnt, hs + 128, 16);
+			if (fl[4]) {   // rough script list or overflow pool too small
+				if (cnt[1] > h->rreq_cap) h->rreq_cap = cnt[1] + cnt[1] / 4 + 1024;
+				if (cnt[2] > h->pool_cap) h->pool_cap = cnt[2] + cnt[2] / 2 + 1024;
+				return RC_RETRY;
+			}
+			if (fl[0]) {   // the pre-generated draw window was too short: extend and evaluate again
+				CKR(stream_ensure(h, h->rng[ST_B], draws2[0] + (1u << 16))); CKR(stream_ensure(h, h->rng[ST_S], draws2[1] + (1u << 12)));
+				E = make_engine_dev(h);
+				continue;
+			}
+			if (!fl[2]) break;
 		}
 	}
-	h->pend_b = tot_b; h->pend_s = tot_s; h->pend_p = tot_p;
+	{
+		uint8_t *hs = (uint8_t *) h->h_small;
+		uint32_t t4[4]; memcpy(t4, hs + 48, 16);
+		SegTotals tt; memcpy(&tt, hs + 64, 48);
+		h->pend_b = t4[0]; h->pend_s = t4[1]; h->pend_p = t4[2];
+		h->hidden_p += t4[3];
+		for (int i = 0; i < 4; ++i) h->sl_base[i] += tt.letters.v[i];
+		h->n_recs = tt.n_rec;
+		h->rng[ST_B].consumed += draws2[0]; h->rng[ST_S].consumed += draws2[1];
+	}
 	return FQSK_OK;
 }
 
@@ -564,12 +541,10 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes, const 
 	CK(h->dup.ensure(n)); CK(h->n_coded.ensure(n1 * 4)); CK(h->letters.ensure(n1 * 32)); CK(h->rec_off.ensure(n1 * 8)); CK(h->sl_prefix.ensure(n1 * 32));
 	CK(h->push_b.ensure((2 * dna_bytes + 2) * 8)); CK(h->push_s.ensure((dna_bytes + 1) * 8)); CK(h->push_p.ensure((2 * dna_bytes + 2 * n1) * 8));
 	CK(h->cnt_b.ensure(n1 * 4)); CK(h->cnt_s.ensure(n1 * 4)); CK(h->cnt_p.ensure(n1 * 4)); CK(h->hidden.ensure(n1 * 4));
-	for (int i = 0; i < 2; ++i) {
-		CK(h->off_b[i].ensure(n1 * 4)); CK(h->off_s[i].ensure(n1 * 4));
-		CK(h->row_b[i].ensure((2 * dna_bytes + 2) * 8)); CK(h->row_s[i].ensure((dna_bytes + 1) * 8));
-	}
+	CK(h->off_b[0].ensure(n1 * 4)); CK(h->off_s[0].ensure(n1 * 4));
+	CK(h->row_b[0].ensure((2 * dna_bytes + 2) * 8)); CK(h->row_s[0].ensure((dna_bytes + 1) * 8));
 	CK(h->off_p.ensure(n1 * 4)); CK(h->row_p.ensure((2 * dna_bytes + 2 * n1) * 8));
-	CK(h->sflag.ensure(n1 * 4)); CK(h->sdif.ensure(n1 * 8)); CK(h->hid_scan.ensure(n1 * 4));
+	CK(h->sflag.ensure(n1 * 4)); CK(h->sdif.ensure(n1 * 8)); CK(h->totals.ensure(256));
 
 	SegDev S{};
 	S.dna = d_dna; S.off = d_off; S.len = d_len; S.n_reads = n;
@@ -581,51 +556,25 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes, const 
 	S.push_b = h->push_b.as<unsigned long long>(); S.push_s = h->push_s.as<unsigned long long>(); S.push_p = h->push_p.as<unsigned long long>();
 	S.cnt_b = h->cnt_b.as<uint32_t>(); S.cnt_s = h->cnt_s.as<uint32_t>(); S.cnt_p = h->cnt_p.as<uint32_t>(); S.hidden = h->hidden.as<uint32_t>();
 	S.sorted_flag = h->sflag.as<uint32_t>(); S.sorted_dif = h->sdif.as<unsigned long long>();
-
-	unsigned long long n_rec64 = 0;
 	{
 		Phase ph(h, FQSK_PH_PREP);
-		CK(cudaMemsetAsync(h->n_coded.p, 0, n1 * 4, h->st));
-		CK(cudaMemsetAsync(h->letters.p, 0, n1 * 32, h->st));
-		k_prep<<<nblk(n, 128), 128, 0, h->st>>>(S, first);
-		LAUNCHED(h);
-		CKR((scan_excl<uint32_t, unsigned long long>(h, h->n_coded.as<uint32_t>(), h->rec_off.as<unsigned long long>(), n + 1, 0ull)));
-		U64x4 z{}; z.v[0] = z.v[1] = z.v[2] = z.v[3] = 0;
-		CKR((scan_excl<U64x4, U64x4>(h, h->letters.as<U64x4>(), h->sl_prefix.as<U64x4>(), n + 1, z)));
-		CK(cudaMemcpyAsync(h->h_small, h->rec_off.as<unsigned long long>() + n, 8, cudaMemcpyDeviceToHost, h->st));
-		CK(cudaStreamSynchronize(h->st));
-		n_rec64 = *(unsigned long long *) h->h_small;
+		k_prep<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(S, first); LAUNCHED(h);
+		k_scan_reads<<<1, 1024, 0, h->st>>>(S, h->rec_off.as<unsigned long long>(), h->sl_prefix.as<U64x4>(), h->totals.as<SegTotals>(), h->d_u32 + 3); LAUNCHED(h);
 	}
-	resolve_phases(h);
-	if (n_rec64 >= 0xFFFFFFF0ull) return fail(h, FQSK_E_INVAL, "segment too large");
-	const uint32_t n_rec = (uint32_t) n_rec64;
-	if (h->miss_cap < std::min<uint32_t>(n_rec, 1u << 20)) h->miss_cap = std::min<uint32_t>(n_rec, 1u << 20);
-	if (h->miss_cap < n_rec / 4) h->miss_cap = n_rec / 4 + 1024;
-	if (h->rreq_cap < std::min<uint32_t>(n_rec, 1u << 20)) h->rreq_cap = std::min<uint32_t>(n_rec, 1u << 20);
-	if (h->rreq_cap < n_rec / 4) h->rreq_cap = n_rec / 4 + 1024;
+	const uint32_t rec_bound = (uint32_t) dna_bytes;
+	if (h->miss_cap < std::min<uint32_t>(rec_bound, 1u << 20)) h->miss_cap = std::min<uint32_t>(rec_bound, 1u << 20);
+	if (h->miss_cap < rec_bound / 4) h->miss_cap = rec_bound / 4 + 1024;
+	if (h->rreq_cap < std::min<uint32_t>(rec_bound, 1u << 20)) h->rreq_cap = std::min<uint32_t>(rec_bound, 1u << 20);
+	if (h->rreq_cap < rec_bound / 8) h->rreq_cap = rec_bound / 8 + 1024;
 	CKR(stream_ensure(h, h->rng[ST_B], 1u << 16)); CKR(stream_ensure(h, h->rng[ST_S], 1u << 12));
 	for (int attempt = 0;; ++attempt) {
 		if (attempt > 8) return fail(h, FQSK_E_NOMEM, "segment buffers kept overflowing");
-		int rc = segment_attempt(h, S, n, dna_bytes, n_rec, first);
+		int rc = segment_attempt(h, S, n, dna_bytes, first);
 		if (rc == RC_RETRY) continue;
 		if (rc != FQSK_OK) return rc;
 		break;
 	}
-	// converged: totals
-	{
-		CK(cudaMemsetAsync(h->hidden.as<uint32_t>() + n, 0, 4, h->st));
-		CKR((scan_excl<uint32_t, uint32_t>(h, h->hidden.as<uint32_t>(), h->hid_scan.as<uint32_t>(), n + 1, 0u)));
-		uint8_t *hs = (uint8_t *) h->h_small;
-		CK(cudaMemcpyAsync(hs + 32, h->sl_prefix.as<U64x4>() + n, 32, cudaMemcpyDeviceToHost, h->st));
-		CK(cudaMemcpyAsync(hs + 64, h->hid_scan.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, h->st));
-		CK(cudaStreamSynchronize(h->st));
-		resolve_phases(h);
-		U64x4 letters; memcpy(&letters, hs + 32, 32);
-		uint32_t hid; memcpy(&hid, hs + 64, 4);
-		for (int i = 0; i < 4; ++i) { h->S.draws[i] = h->rng[i].consumed; h->sl_base[i] += letters.v[i]; }
-		h->hidden_p += hid;
-		h->n_recs = n_rec;
-	}
+	for (int i = 0; i < 4; ++i) h->S.draws[i] = h->rng[i].consumed;
 	h->pending = true;
 	h->S.n_reads += n; h->S.n_bases += dna_bytes;
 	return FQSK_OK;
@@ -706,7 +655,7 @@ void fqsk_destroy(fqsk_handle *h) {
 	                  &h->cub_tmp, &h->flag8, &h->draw_off, &h->final_cnt, &h->slot_of, &h->dump_k, &h->dump_v, &h->q0, &h->q1,
 	                  &h->q2, &h->q3, &h->q4, &h->sflag, &h->sdif, &h->hid_scan, &h->prov, &h->pflags, &h->pscripts, &h->rscripts, &h->rreqs, &h->pool, &h->miss,
 	                  &h->draws_b16, &h->draws_s16, &h->doff_b, &h->doff_s, &h->time_b, &h->time_s, &h->rt_b[0], &h->rt_b[1], &h->rt_s[0], &h->rt_s[1],
-	                  &h->sidx_b, &h->sidx_s, &h->stime_b, &h->stime_s, &h->sort_k, &h->sort_v};
+	                  &h->sidx_b, &h->sidx_s, &h->stime_b, &h->stime_s, &h->sort_k, &h->sort_v, &h->rkind, &h->rreg, &h->rslot, &h->dirty, &h->rdraws_b, &h->rdraws_s, &h->totals};
 	if (h->d_u32) cudaFree(h->d_u32);
 	for (DevBuf *b : bufs) b->release();
 	if (h->h_stage) cudaFreeHost(h->h_stage);

@@ -90,29 +90,29 @@ __device__ __forceinline__ uint32_t dna_code(uint8_t ch) {  // dna.cpp:18-23
 	return ch == 'A' ? 0u : ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : 4u;
 }
 
-__global__ void k_prep(SegDev S, uint32_t first_len_bytes) {
-	uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) k_prep(SegDev S, uint32_t first_len_bytes) {   // one warp per read
+	uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (r >= S.n_reads) return;
 	const uint8_t *p = S.dna + S.off[r];
 	uint32_t n = S.len[r];
-	bool same;
-	if (r == 0) {
-		same = (S.prev_len == n);
-		for (uint32_t i = 0; same && i < n; ++i) same = S.prev_read[i] == p[i];
-	} else {
-		const uint8_t *q = S.dna + S.off[r - 1];
-		same = (S.len[r - 1] == n);
-		for (uint32_t i = 0; same && i < n; ++i) same = q[i] == p[i];
+	const uint8_t *q; uint32_t qn;
+	if (r == 0) { q = S.prev_read; qn = S.prev_len; } else { q = S.dna + S.off[r - 1]; qn = S.len[r - 1]; }
+	bool same = qn == n;
+	uint32_t cnt[4] = {0, 0, 0, 0};
+	for (uint32_t i = lane; i < n; i += 32) {
+		uint8_t ch = p[i];
+		if (same && q[i] != ch) same = false;
+		uint32_t c = dna_code(ch);
+		if (c < 4) { ++cnt[c]; ++cnt[3 - c]; }
 	}
-	S.dup[r] = same;
-	U64x4 L; L.v[0] = L.v[1] = L.v[2] = L.v[3] = 0;
-	uint32_t coded = 0;
-	if (!same) {
-		for (uint32_t i = 0; i < n; ++i) { uint32_t c = dna_code(p[i]); if (c < 4) { ++L.v[c]; ++L.v[3 - c]; } }
-		coded = n > first_len_bytes ? n - first_len_bytes : 0;
+	same = __all_sync(0xffffffffu, same);
+	for (int k = 0; k < 4; ++k) for (int o = 16; o; o >>= 1) cnt[k] += __shfl_xor_sync(0xffffffffu, cnt[k], o);
+	if (lane == 0) {
+		S.dup[r] = same;
+		U64x4 L; for (int k = 0; k < 4; ++k) L.v[k] = same ? 0 : cnt[k];
+		S.letters[r] = L;
+		S.n_coded[r] = (!same && n > first_len_bytes) ? n - first_len_bytes : 0;
 	}
-	S.letters[r] = L;
-	S.n_coded[r] = coded;
 }
 
 // ------------------------------------------------------------------------------------------------------------------

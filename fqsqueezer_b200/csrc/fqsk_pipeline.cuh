@@ -41,6 +41,7 @@ static const uint32_t SCRIPT_INLINE = 8;
 
 struct MissEntry {           // a position whose uncorrected cascade needs the thread-local tables
 	uint32_t rec, time;      // record index; position id (byte offset of the base inside the packed DNA) used as push time
+	uint32_t read;           // owning read (marked dirty when the thread-local answer changes)
 	KReg breg;               // uncorrected b register with the placeholder (s register is derived from it)
 	uint32_t cb;             // symbols held by the b register
 	uint8_t flags;           // PF_*
@@ -48,7 +49,6 @@ struct MissEntry {           // a position whose uncorrected cascade needs the t
 	uint16_t gs[4];          // its counts (global s-mer hit)
 };
 
-struct RoughReq { uint32_t rec; uint32_t kind; KReg reg; };   // kind 2 = b, 3 = s, 4 = p
 
 struct PipeDev {
 	// geometry
@@ -59,11 +59,14 @@ struct PipeDev {
 	fqsk_base_rec *recs; uint8_t *pflags;   // final records (k_walk, then k_rough / k_fold)
 	// scripts: partial ones are addressed densely (read * slots + slot); rough ones are appended
 	Script *pscripts; uint32_t pslots; uint32_t pfirst_n; // slot = (i + 1) - pfirst_n
-	Script *rscripts; RoughReq *rreqs; uint32_t *n_rreq; uint32_t rreq_cap;
+	Script *rscripts; uint32_t *n_rscript; uint32_t rscript_cap;   // rough scripts, allocated by k_rough
+	uint8_t *rkind; KReg *rreg; uint32_t *rslot;                   // per position: rough request kind (0/2/3/4), its register, its script
+	uint8_t *dirty;                                                // per read: must be walked again
 	unsigned short *pool; uint32_t *pool_used; uint32_t pool_cap;   // overflow entries (4 x u16 each)
 	MissEntry *miss; uint32_t *n_miss; uint32_t miss_cap;
-	// per-position draw counts and their exclusive scans (stream b, stream s)
-	unsigned short *draws_b, *draws_s; const unsigned long long *doff_b, *doff_s;
+	// per-read draw counts of the merge scripts (stream b, stream s) and their exclusive scans
+	uint32_t *rdraws_b, *rdraws_s; const unsigned long long *doff_b, *doff_s;
+	const uint32_t *n_rec_dev;      // number of coded positions, device copy (grids are sized from host-side upper bounds)
 	// pushes
 	uint32_t *time_b, *time_s;      // per-read regions parallel to push_b / push_s
 	int *flags;                     // [0] draw overflow [1] unsupported [2] changed [3] window consulted the local tables
@@ -113,7 +116,7 @@ __device__ __forceinline__ void put_rec(fqsk_base_rec *rec, uint32_t pos, const 
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_lookup(EngineDev E, SegDev S, PipeDev P) {
 	uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-	if (g >= P.n_rec) return;
+	if (g >= *P.n_rec_dev) return;
 	uint32_t r = find_read(S.rec_off, S.n_reads, g);
 	uint32_t i = P.start + (g - (uint32_t) S.rec_off[r]);
 	const uint8_t *p = S.dna + S.off[r];
@@ -162,13 +165,12 @@ __global__ void __launch_bounds__(256) k_lookup(EngineDev E, SegDev S, PipeDev P
 	}
 	put_rec(P.prov + g, i, c, lev);
 	P.pflags[g] = fl;
-	P.draws_b[g] = 0; P.draws_s[g] = 0;
 	if ((fl & (PF_MISS_B | PF_MISS_S)) && !(fl & (PF_PARTIAL_B | PF_PARTIAL_S))) {
 		uint32_t m = atomicAdd(P.n_miss, 1u);
 		if (m >= P.miss_cap) P.flags[4] = 1;
 		if (m < P.miss_cap) {
 			MissEntry e;
-			e.rec = g; e.time = (uint32_t) S.off[r] + i; e.breg = br; e.cb = cb; e.flags = fl; e.glevel = (uint8_t) lev;
+			e.rec = g; e.time = (uint32_t) S.off[r] + i; e.read = r; e.breg = br; e.cb = cb; e.flags = fl; e.glevel = (uint8_t) lev;
 			for (int q = 0; q < 4; ++q) e.gs[q] = (uint16_t) c[q];
 			P.miss[m] = e;
 		}
@@ -271,7 +273,7 @@ __global__ void __launch_bounds__(128) k_partial(EngineDev E, SegDev S, PipeDev 
 			if (mi >= P.miss_cap) P.flags[4] = 1;
 			if (mi < P.miss_cap) {
 				MissEntry e;
-				e.rec = g; e.time = (uint32_t) S.off[r] + i; e.breg = br; e.cb = cb; e.flags = nf; e.glevel = (uint8_t) lev;
+				e.rec = g; e.time = (uint32_t) S.off[r] + i; e.read = r; e.breg = br; e.cb = cb; e.flags = nf; e.glevel = (uint8_t) lev;
 				for (int q = 0; q < 4; ++q) e.gs[q] = (uint16_t) c[q];
 				P.miss[mi] = e;
 			}
@@ -284,27 +286,33 @@ __global__ void __launch_bounds__(128) k_partial(EngineDev E, SegDev S, PipeDev 
 // delta of the previous iteration.  Idempotent: always starts from the stored global-only result.
 // Merges that would draw from the thread-local PRNG streams are reported as unsupported.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_local(EngineDev E, SegDev S, PipeDev P, uint32_t n_miss) {
-	uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
-	if (m >= n_miss) return;
-	MissEntry e = P.miss[m];
-	uint32_t c[4] = {e.gs[0], e.gs[1], e.gs[2], e.gs[3]};
-	uint32_t lev = e.glevel;
-	const uint32_t cs = e.cb < E.s ? e.cb : E.s;
-	bool hit = false;
-	if (e.flags & PF_MISS_B) {
-		uint32_t lc[4];
-		if (delta_find(S.delta_b, E.cib, e.breg, e.cb, e.time, lc, P.flags + 1)) { for (int q = 0; q < 4; ++q) c[q] = lc[q]; lev = FQSK_LEVEL_BMER; hit = true; }
+__global__ void __launch_bounds__(128) k_local(EngineDev E, SegDev S, PipeDev P) {
+	if (S.delta_b.n == 0 && S.delta_s.n == 0) return;
+	uint32_t n_miss = *P.n_miss;
+	if (n_miss > P.miss_cap) n_miss = P.miss_cap;
+	for (uint32_t m = blockIdx.x * blockDim.x + threadIdx.x; m < n_miss; m += gridDim.x * blockDim.x) {
+		MissEntry e = P.miss[m];
+		uint32_t c[4] = {e.gs[0], e.gs[1], e.gs[2], e.gs[3]};
+		uint32_t lev = e.glevel;
+		const uint32_t cs = e.cb < E.s ? e.cb : E.s;
+		bool hit = false;
+		if (e.flags & PF_MISS_B) {
+			uint32_t lc[4];
+			if (delta_find(S.delta_b, E.cib, e.breg, e.cb, e.time, lc, P.flags + 1)) { for (int q = 0; q < 4; ++q) c[q] = lc[q]; lev = FQSK_LEVEL_BMER; hit = true; }
+		}
+		if (!hit && (e.flags & PF_MISS_S)) {
+			KReg sr = suffix_reg(e.breg, e.cb, cs);
+			uint32_t lc[4];
+			if (delta_find(S.delta_s, E.cis, sr, cs, e.time, lc, P.flags + 1)) { for (int q = 0; q < 4; ++q) c[q] = lc[q]; lev = FQSK_LEVEL_SMER; hit = true; }
+		}
+		fqsk_base_rec *rec = P.prov + e.rec;
+		if (rec->level != lev || rec->counts[0] != c[0] || rec->counts[1] != c[1] || rec->counts[2] != c[2] || rec->counts[3] != c[3]) {
+			rec->counts[0] = c[0]; rec->counts[1] = c[1]; rec->counts[2] = c[2]; rec->counts[3] = c[3];
+			rec->level = (uint8_t) lev;
+			P.dirty[e.read] = 1;      // the walk of this read consumed a different answer
+			P.flags[6] = 1;
+		}
 	}
-	if (!hit && (e.flags & PF_MISS_S)) {
-		KReg sr = suffix_reg(e.breg, e.cb, cs);
-		uint32_t lc[4];
-		if (delta_find(S.delta_s, E.cis, sr, cs, e.time, lc, P.flags + 1)) { for (int q = 0; q < 4; ++q) c[q] = lc[q]; lev = FQSK_LEVEL_SMER; hit = true; }
-	}
-	fqsk_base_rec *rec = P.prov + e.rec;
-	if (hit) P.flags[6] = 1;
-	rec->counts[0] = c[0]; rec->counts[1] = c[1]; rec->counts[2] = c[2]; rec->counts[3] = c[3];
-	rec->level = (uint8_t) lev;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -313,16 +321,21 @@ __global__ void __launch_bounds__(128) k_local(EngineDev E, SegDev S, PipeDev P,
 // window the cascade is evaluated here with the corrected registers (the slow path of the reference's own hot loop).
 // Rough searches are only REQUESTED here: their result never feeds back into the registers (dna.cpp:707-735).
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void rough_request(PipeDev &P, uint32_t g, uint32_t kind, const KReg &reg) {
-	uint32_t q = atomicAdd(P.n_rreq, 1u);
-	if (q >= P.rreq_cap) P.flags[4] = 1;
-	if (q < P.rreq_cap) { RoughReq rq; rq.rec = g; rq.kind = kind; rq.reg = reg; P.rreqs[q] = rq; }
+template <bool CHECK>
+__device__ __forceinline__ void push_u64(unsigned long long *dst, uint32_t *tdst, uint32_t idx, unsigned long long v, uint32_t t, bool &changed) {
+	if (CHECK) changed |= (dst[idx] != v) | (tdst[idx] != t);
+	dst[idx] = v; tdst[idx] = t;
 }
 
-__global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P) {
+// it == 0: every read; it > 0: only reads marked dirty, and any difference to the previous walk's pushes raises flags[2].
+__global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P, uint32_t it) {
 	uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= S.n_reads) return;
+	if (it > 0) { if (!P.dirty[r]) return; }
+	P.dirty[r] = 0;
 	if (S.dup[r]) { S.cnt_b[r] = S.cnt_s[r] = S.cnt_p[r] = S.hidden[r] = 0; if (E.sorted) { S.sorted_flag[r] = 0; S.sorted_dif[r] = 0; } return; }
+	const bool check = it > 0;
+	bool changed = false, window_local = false;
 	const uint8_t *p = S.dna + S.off[r];
 	const uint32_t size = S.len[r];
 	const uint32_t tbase = (uint32_t) S.off[r];
@@ -368,19 +381,22 @@ __global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P) 
 		out_p[np++] = R.pc.rc >> (64 - 2 * E.p);
 		start = E.p;
 	}
-	const uint32_t s_margin = E.s - E.p + 1;
+	// software pipeline: the provisional record and the read symbol of the NEXT position are loaded one step ahead
+	fqsk_base_rec pv_next;
+	uint32_t ch_next = 0;
+	if (start < size) { pv_next = P.prov[g0]; ch_next = p[start]; }
 	for (uint32_t i = start; i < size; ++i) {
 		const uint32_t g = g0 + (i - start);
-		const uint32_t sym = dna_code(p[i]);
+		const fqsk_base_rec pv = pv_next;
+		const uint32_t sym = dna_code((uint8_t) ch_next);
+		if (i + 1 < size) { pv_next = P.prov[g + 1]; ch_next = p[i + 1]; }
 		const uint64_t ks = sym == 4 ? 0 : sym;
 		rs_push_all(R, E, 0);
 		const uint32_t cb = cur_of(E.b, R.n), cs = cur_of(E.s, R.n), cp = cur_of(E.p, R.n);
-		fqsk_base_rec *rec = P.recs + g;
 		uint32_t lev, c[4];
 		if (R.bc.dir == R.bu.dir) {
 			// fast path: the provisional record is the reference's find_counts result
-			const fqsk_base_rec *pv = P.prov + g;
-			lev = pv->level; c[0] = pv->counts[0]; c[1] = pv->counts[1]; c[2] = pv->counts[2]; c[3] = pv->counts[3];
+			lev = pv.level; c[0] = pv.counts[0]; c[1] = pv.counts[1]; c[2] = pv.counts[2]; c[3] = pv.counts[3];
 		} else {
 			// repair window: cascade with the corrected registers (only reachable with a full b register)
 			c[0] = c[1] = c[2] = c[3] = 0;
@@ -392,13 +408,13 @@ __global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P) 
 				else lev = FQSK_LEVEL_BMER;
 				done = true;
 			} else {
-				if (S.delta_b.n) { P.flags[3] = 1; if (delta_find(S.delta_b, E.cib, R.bc, cb, tbase + i, c, unsupported)) { lev = FQSK_LEVEL_BMER; done = true; } }
-				else P.flags[3] = 1;   // a window lookup of the thread-local table happened: one more iteration must confirm it
+				window_local = true;   // the thread-local table is consulted here: this read must be re-walked once the delta exists / changes
+				if (delta_find(S.delta_b, E.cib, R.bc, cb, tbase + i, c, unsupported)) { lev = FQSK_LEVEL_BMER; done = true; }
 				if (!done && ht_find(E.hb, E.cib, R.bu, cb, c, nodraw)) { lev = FQSK_LEVEL_BMER_UNC; done = true; }
 			}
 			if (!done) {
 				if (ht_find(E.hs, E.cis, R.sc, cs, c, nodraw)) lev = FQSK_LEVEL_SMER;
-				else if (S.delta_s.n && delta_find(S.delta_s, E.cis, R.sc, cs, tbase + i, c, unsupported)) lev = FQSK_LEVEL_SMER;
+				else if (delta_find(S.delta_s, E.cis, R.sc, cs, tbase + i, c, unsupported)) lev = FQSK_LEVEL_SMER;
 			}
 			if (lev == FQSK_LEVEL_BMER_UNC) { R.bc = R.bu; R.sc = R.su; R.pc = R.pu; R.cor_pos = 0; lev = FQSK_LEVEL_BMER; }
 		}
@@ -406,22 +422,28 @@ __global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P) 
 			fqsk_base_rec o;
 			o.pos = i; o.counts[0] = c[0]; o.counts[1] = c[1]; o.counts[2] = c[2]; o.counts[3] = c[3];
 			o.cor_pos = R.cor_pos; o.level = (uint8_t) lev; o.rough = 0; o.pad = 0;
-			*rec = o;
+			P.recs[g] = o;
 		}
-		if (lev == FQSK_LEVEL_NONE) {   // dna.cpp:709-735, deferred
-			if (cb == E.b) rough_request(P, g, 2, R.bc);
-			else if (cs == E.s) rough_request(P, g, 3, R.sc);
-			else if (cp == E.p) rough_request(P, g, 4, R.pc);
+		uint8_t rk = 0;
+		if (lev == FQSK_LEVEL_NONE) {   // dna.cpp:709-735, deferred to k_rough
+			if (cb == E.b) { rk = 2; P.rreg[g] = R.bc; }
+			else if (cs == E.s) { rk = 3; P.rreg[g] = R.sc; }
+			else if (cp == E.p) { rk = 4; P.rreg[g] = R.pc; }
 		}
+		P.rkind[g] = rk;
 		kr_set_last(R.pc, cp, ks); kr_set_last(R.sc, cs, ks); kr_set_last(R.bc, cb, ks);
 		kr_set_last(R.pu, cp, ks); kr_set_last(R.su, cs, ks); kr_set_last(R.bu, cb, ks);
 		if (sym < 4) {
 			bool p_insert = true;
 			if (cb == E.b) {
-				tim_b[nb] = tbase + i; out_b[nb++] = kr_norm(R.bc, E.b);
+				if (check) push_u64<true>(out_b, tim_b, nb, kr_norm(R.bc, E.b), tbase + i, changed); else push_u64<false>(out_b, tim_b, nb, kr_norm(R.bc, E.b), tbase + i, changed);
+				++nb;
 				if ((lev == FQSK_LEVEL_SMER || lev == FQSK_LEVEL_BMER || lev == FQSK_LEVEL_MIXED) && c[sym] >= 3) p_insert = false;
 			}
-			if (cs == E.s) { tim_s[ns] = tbase + i; out_s[ns++] = kr_norm(R.sc, E.s); }
+			if (cs == E.s) {
+				if (check) push_u64<true>(out_s, tim_s, ns, kr_norm(R.sc, E.s), tbase + i, changed); else push_u64<false>(out_s, tim_s, ns, kr_norm(R.sc, E.s), tbase + i, changed);
+				++ns;
+			}
 			if (cp == E.p && i - R.cor_pos >= E.p - 1) {
 				if (p_insert) { out_p[np++] = R.pc.dir >> (64 - 2 * E.p); out_p[np++] = R.pc.rc >> (64 - 2 * E.p); }
 				else hidden += 2;
@@ -463,11 +485,15 @@ __global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P) 
 					repaired = true;
 				}
 			}
-			if (repaired) { tim_b[nb] = tbase + i; out_b[nb++] = kr_norm(R.bc, E.b); }
+			if (repaired) {
+				if (check) push_u64<true>(out_b, tim_b, nb, kr_norm(R.bc, E.b), tbase + i, changed); else push_u64<false>(out_b, tim_b, nb, kr_norm(R.bc, E.b), tbase + i, changed);
+				++nb;
+			}
 		}
 	}
+	if (check && (changed || S.cnt_b[r] != nb || S.cnt_s[r] != ns)) P.flags[2] = 1;
 	S.cnt_b[r] = nb; S.cnt_s[r] = ns; S.cnt_p[r] = np; S.hidden[r] = hidden;
-	(void) s_margin;
+	if (window_local) { P.dirty[r] = 1; if (it == 0) P.flags[3] = 1; }
 }
 
 __global__ void k_compact2(SegDev S, PipeDev P, const uint32_t *off_b, const uint32_t *off_s, const uint32_t *off_p,
@@ -480,14 +506,23 @@ __global__ void k_compact2(SegDev S, PipeDev P, const uint32_t *off_b, const uin
 	for (uint32_t i = threadIdx.x; i < S.cnt_s[r]; i += blockDim.x) { row_s[off_s[r] + i] = ss[i]; rt_s[off_s[r] + i] = ts[i]; }
 	for (uint32_t i = threadIdx.x; i < S.cnt_p[r]; i += blockDim.x) row_p[off_p[r] + i] = sp[i];
 }
-// delta build: one entry per push, placed by the canonical inner core of its k-mer
-__global__ void k_delta_build(unsigned long long *keys, uint32_t *times, uint32_t mask, uint32_t k, uint32_t t, const unsigned long long *row, const uint32_t *rt, uint32_t n) {
-	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= n) return;
-	unsigned long long x = row[j];
-	uint32_t tm = rt[j];
-	for (uint64_t slot = delta_slot_of_key(x, k, t, mask);; slot = (slot + 1) & mask) {
-		if (atomicCAS(times + slot, DELTA_EMPTY, tm) == DELTA_EMPTY) { keys[slot] = x; return; }
+// delta build straight from the per-read push regions: one warp per read, one entry per push, placed by the canonical
+// inner core of its k-mer
+__global__ void __launch_bounds__(128) k_delta_build(SegDev S, PipeDev P, unsigned long long *kb, uint32_t *tb, uint32_t mask_b, uint32_t k_b, uint32_t t_b,
+                                                     unsigned long long *ks, uint32_t *ts, uint32_t mask_s, uint32_t k_s, uint32_t t_s) {
+	uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if (r >= S.n_reads) return;
+	const unsigned long long *sb = S.push_b + 2 * S.off[r], *ss = S.push_s + S.off[r];
+	const uint32_t *qb = P.time_b + 2 * S.off[r], *qs = P.time_s + S.off[r];
+	for (uint32_t j = lane; j < S.cnt_b[r]; j += 32) {
+		unsigned long long x = sb[j];
+		for (uint64_t slot = delta_slot_of_key(x, k_b, t_b, mask_b);; slot = (slot + 1) & mask_b)
+			if (atomicCAS(tb + slot, DELTA_EMPTY, qb[j]) == DELTA_EMPTY) { kb[slot] = x; break; }
+	}
+	for (uint32_t j = lane; j < S.cnt_s[r]; j += 32) {
+		unsigned long long x = ss[j];
+		for (uint64_t slot = delta_slot_of_key(x, k_s, t_s, mask_s);; slot = (slot + 1) & mask_s)
+			if (atomicCAS(ts + slot, DELTA_EMPTY, qs[j]) == DELTA_EMPTY) { ks[slot] = x; break; }
 	}
 }
 
@@ -495,71 +530,85 @@ __global__ void k_delta_build(unsigned long long *keys, uint32_t *times, uint32_
 // k_rough: one warp per request.  find_counts_rough_{s,b} (dna.cpp:257-330): 4(k-1) single-substitution neighbours across the
 // lanes, non-empty ones appended in trial order to a merge script; find_counts_rough_p (dna.cpp:229-254) is a plain sum.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_rough(EngineDev E, PipeDev P, uint32_t n_req) {
-	uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	uint32_t lane = threadIdx.x & 31;
-	if (w >= n_req) return;
-	RoughReq rq = P.rreqs[w];
+__global__ void __launch_bounds__(128) k_rough(EngineDev E, PipeDev P) {
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t n_rec = *P.n_rec_dev;
+	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
 	__shared__ Script stage[4];
 	Script &sc = stage[threadIdx.x >> 5];
-	if (rq.kind == 4) {
-		uint32_t c[4] = {0, 0, 0, 0};
-		uint32_t trials = 4 * (E.p - 1);
-		for (uint32_t t = lane; t < trials; t += 32) {
-			KReg tr = rq.reg;
-			kr_set(tr, E.p, t & 3, t >> 2);
-			siv_counts(E.siv, tr.dir >> (64 - 2 * E.p), c, true);
-		}
-		for (int q = 0; q < 4; ++q) for (int o = 16; o; o >>= 1) c[q] += __shfl_xor_sync(0xffffffffu, c[q], o);
-		if (lane == 0) {
-			Script *out = P.rscripts + w;
-			out->valid = 0; out->rec = rq.rec; out->n = 0; out->kind = 4;
-			if (any4(c)) {
-				fqsk_base_rec *rec = P.recs + rq.rec;
-				rec->counts[0] = c[0]; rec->counts[1] = c[1]; rec->counts[2] = c[2]; rec->counts[3] = c[3];
-				rec->level = FQSK_LEVEL_PMER; rec->rough = 1;
+	for (uint32_t g0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; g0 < n_rec; g0 += warps * 32) {
+		// each warp owns 32 consecutive positions: find the flagged ones, then work on them one at a time with all lanes
+		uint32_t mine = g0 + lane < n_rec ? P.rkind[g0 + lane] : 0;
+		unsigned todo = __ballot_sync(0xffffffffu, mine != 0);
+		while (todo) {
+			uint32_t q = __ffs(todo) - 1;
+			todo &= todo - 1;
+			const uint32_t g = g0 + q;
+			const uint32_t kind = __shfl_sync(0xffffffffu, mine, q);
+			const KReg reg = P.rreg[g];
+			if (kind == 4) {
+				uint32_t c[4] = {0, 0, 0, 0};
+				uint32_t trials = 4 * (E.p - 1);
+				for (uint32_t t = lane; t < trials; t += 32) {
+					KReg tr = reg;
+					kr_set(tr, E.p, t & 3, t >> 2);
+					siv_counts(E.siv, tr.dir >> (64 - 2 * E.p), c, true);
+				}
+				for (int qq = 0; qq < 4; ++qq) for (int o = 16; o; o >>= 1) c[qq] += __shfl_xor_sync(0xffffffffu, c[qq], o);
+				if (lane == 0) {
+					P.rslot[g] = 0xFFFFFFFFu;
+					if (any4(c)) {
+						fqsk_base_rec *rec = P.recs + g;
+						rec->counts[0] = c[0]; rec->counts[1] = c[1]; rec->counts[2] = c[2]; rec->counts[3] = c[3];
+						rec->level = FQSK_LEVEL_PMER; rec->rough = 1;
+					}
+				}
+				continue;
 			}
+			const HtDev &t = kind == 2 ? E.hb : E.hs;
+			uint32_t trials = 4 * (t.k - 1);
+			uint32_t n_ent = 0, ovf = 0xFFFFFFFFu;
+			for (uint32_t n0 = 0; n0 < trials; n0 += 32) {
+				uint32_t tn = n0 + lane;
+				uint32_t loc[4] = {0, 0, 0, 0};
+				if (tn < trials) {
+					KReg tr = reg;
+					kr_set(tr, t.k, tn & 3, tn >> 2);
+					bool d = kr_is_dir(tr, t.k);
+					ht_ctx_counts(t, d ? tr.dir : tr.rc, d, loc);
+				}
+				script_append(P, sc, n_ent, ovf, loc, any4(loc), trials - n0);
+			}
+			__syncwarp();
+			if (lane == 0) {
+				uint32_t slot = 0xFFFFFFFFu;
+				if (n_ent) {
+					slot = atomicAdd(P.n_rscript, 1u);
+					if (slot >= P.rscript_cap) { P.flags[4] = 1; slot = 0xFFFFFFFFu; }
+					else {
+						sc.rec = g; sc.kind = (uint8_t) kind; sc.valid = 1; sc.n = (uint16_t) n_ent; sc.overflow = ovf;
+						for (int qq = 0; qq < 4; ++qq) sc.c2[qq] = 0;
+						P.rscripts[slot] = sc;
+					}
+				}
+				P.rslot[g] = slot;
+			}
+			__syncwarp();
 		}
-		return;
-	}
-	const HtDev &t = rq.kind == 2 ? E.hb : E.hs;
-	uint32_t trials = 4 * (t.k - 1);
-	uint32_t n_ent = 0, ovf = 0xFFFFFFFFu;
-	for (uint32_t n0 = 0; n0 < trials; n0 += 32) {
-		uint32_t tn = n0 + lane;
-		uint32_t loc[4] = {0, 0, 0, 0};
-		if (tn < trials) {
-			KReg tr = rq.reg;
-			kr_set(tr, t.k, tn & 3, tn >> 2);
-			bool d = kr_is_dir(tr, t.k);
-			ht_ctx_counts(t, d ? tr.dir : tr.rc, d, loc);
-		}
-		script_append(P, sc, n_ent, ovf, loc, any4(loc), trials - n0);
-	}
-	__syncwarp();
-	if (lane == 0) {
-		sc.rec = rq.rec; sc.kind = (uint8_t) rq.kind; sc.valid = n_ent ? 1 : 0; sc.n = (uint16_t) n_ent; sc.overflow = ovf;
-		for (int q = 0; q < 4; ++q) sc.c2[q] = 0;
-		P.rscripts[w] = sc;
 	}
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// k_fold: replay the ordered approximate-counter merges of one script with its exact position in the mt19937 stream.
-// pass 0 only counts draws (offset-independent unless a counter saturates), pass 1 evaluates with the scanned offsets,
-// writes the final counts and re-reports the draw count so the host can confirm the offsets.
+// k_fold: one thread per read replays the ordered approximate-counter merges of that read's scripts (front-truncated
+// lookups first, then the rough searches, each in position order = the reference's program order per PRNG stream) with
+// their exact positions in the mt19937 streams.  pass 0 counts the draws of the read (offset-independent unless a counter
+// saturates); after a scan over reads pass 1 evaluates with the true offsets, writes the final counts and re-reports the
+// totals so the host can confirm the offsets.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_fold(EngineDev E, PipeDev P, const Script *scripts, uint32_t n_scripts, int pass) {
-	uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-	if (w >= n_scripts) return;
-	const Script &sc = scripts[w];
-	if (!sc.valid) return;
+__device__ void fold_script(const EngineDev &E, const PipeDev &P, const Script &sc, DrawCursor &dc, bool write) {
 	const bool is_b = (sc.kind == 0 || sc.kind == 2);
 	const bool rough = sc.kind >= 2;
 	const CIncP ci = is_b ? E.cib : E.cis;
-	DrawCursor dc;
-	dc.ring = E.draws[is_b ? 0 : 1]; dc.mask = E.dmask[is_b ? 0 : 1]; dc.pos0 = E.dpos[is_b ? 0 : 1]; dc.avail = E.avail[is_b ? 0 : 1]; dc.used = 0; dc.overflow = E.flags + 0;
-	dc.base = pass ? (is_b ? P.doff_b[sc.rec] : P.doff_s[sc.rec]) : 0;
 	uint32_t c[4] = {0, 0, 0, 0};
 	for (uint32_t n = 0; n < sc.n; ++n) {
 		uint32_t loc[4];
@@ -567,19 +616,170 @@ __global__ void __launch_bounds__(128) k_fold(EngineDev E, PipeDev P, const Scri
 		else { const unsigned short *d = P.pool + 4ull * (sc.overflow + (n - SCRIPT_INLINE)); for (int q = 0; q < 4; ++q) loc[q] = d[q]; }
 		for (int q = 0; q < 4; ++q) if (rough || loc[q]) c[q] = ci_plus(ci, c[q], loc[q], dc);
 	}
-	unsigned short *dcount = is_b ? P.draws_b : P.draws_s;
-	if (pass == 0) { dcount[sc.rec] = (unsigned short) dc.used; return; }
-	if (dcount[sc.rec] != (unsigned short) dc.used) { dcount[sc.rec] = (unsigned short) dc.used; P.flags[2] = 1; }
+	if (!write) return;
 	fqsk_base_rec *rec = P.recs + sc.rec;
 	uint32_t lev = rec->level;
-	if (rough) { if (any4(c)) { lev = FQSK_LEVEL_PMER; rec->rough = 1; } }
+	if (rough) { if (!any4(c)) return; lev = FQSK_LEVEL_PMER; rec->rough = 1; }
 	else if (sc.kind == 0) {
 		int sat = (c[0] == ci.top) + (c[1] == ci.top) + (c[2] == ci.top) + (c[3] == ci.top);
 		if (sat > 1) { for (int q = 0; q < 4; ++q) c[q] += sc.c2[q]; lev = FQSK_LEVEL_MIXED; }
 	}
-	if (rough && !any4(c)) return;
 	rec->counts[0] = c[0]; rec->counts[1] = c[1]; rec->counts[2] = c[2]; rec->counts[3] = c[3];
 	rec->level = (uint8_t) lev;
+}
+
+__global__ void __launch_bounds__(128) k_fold(EngineDev E, SegDev S, PipeDev P, int pass) {
+	uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= S.n_reads) return;
+	DrawCursor db, ds;
+	db.ring = E.draws[0]; db.mask = E.dmask[0]; db.pos0 = E.dpos[0]; db.avail = E.avail[0]; db.used = 0; db.overflow = E.flags + 0;
+	ds.ring = E.draws[1]; ds.mask = E.dmask[1]; ds.pos0 = E.dpos[1]; ds.avail = E.avail[1]; ds.used = 0; ds.overflow = E.flags + 0;
+	db.base = pass ? P.doff_b[r] : 0;
+	ds.base = pass ? P.doff_s[r] : 0;
+	if (!S.dup[r]) {
+		// front-truncated lookups: slots are in position order
+		const Script *ps = P.pscripts + (size_t) r * P.pslots;
+		for (uint32_t sl = 0; sl < P.pslots; ++sl) {
+			const Script &sc = ps[sl];
+			if (!sc.valid) continue;
+			fold_script(E, P, sc, sc.kind == 0 ? db : ds, pass != 0);
+		}
+		// rough searches of this read, in position order
+		uint32_t g0 = (uint32_t) S.rec_off[r], g1 = (uint32_t) S.rec_off[r + 1];
+		for (uint32_t g = g0; g < g1; ++g) {
+			uint8_t k = P.rkind[g];
+			if (k != 2 && k != 3) continue;
+			uint32_t slot = P.rslot[g];
+			if (slot == 0xFFFFFFFFu) continue;
+			fold_script(E, P, P.rscripts[slot], k == 2 ? db : ds, pass != 0);
+		}
+	}
+	if (pass == 0) { P.rdraws_b[r] = db.used; P.rdraws_s[r] = ds.used; return; }
+	if (P.rdraws_b[r] != db.used || P.rdraws_s[r] != ds.used) { P.rdraws_b[r] = db.used; P.rdraws_s[r] = ds.used; P.flags[2] = 1; }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// single-CTA scans over per-read arrays (n_reads is at most a few 10^4: one CTA beats a chain of library launches)
+// ------------------------------------------------------------------------------------------------------------------
+struct SegTotals {        // written by the scan kernels, read by the host once per segment
+	unsigned long long n_rec; U64x4 letters;
+	uint32_t tot_b, tot_s, tot_p, hidden;
+	unsigned long long draws_b, draws_s;
+};
+
+__global__ void __launch_bounds__(1024) k_scan_reads(SegDev S, unsigned long long *rec_off, U64x4 *sl_prefix, SegTotals *tot, uint32_t *n_rec_dev) {
+	__shared__ unsigned long long sh[5][32];
+	__shared__ unsigned long long carry[5];
+	const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5;
+	if (t < 5) carry[t] = 0;
+	__syncthreads();
+	for (uint32_t base = 0; base < S.n_reads; base += 1024) {
+		uint32_t r = base + t;
+		unsigned long long v[5] = {0, 0, 0, 0, 0};
+		if (r < S.n_reads) { v[0] = S.n_coded[r]; U64x4 L = S.letters[r]; v[1] = L.v[0]; v[2] = L.v[1]; v[3] = L.v[2]; v[4] = L.v[3]; }
+		unsigned long long inc[5];
+		for (int q = 0; q < 5; ++q) {
+			unsigned long long x = v[q];
+			for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+			inc[q] = x;
+			if (lane == 31) sh[q][w] = x;
+		}
+		__syncthreads();
+		if (w == 0) {
+			for (int q = 0; q < 5; ++q) {
+				unsigned long long x = sh[q][lane];
+				for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+				sh[q][lane] = x;
+			}
+		}
+		__syncthreads();
+		unsigned long long ex[5];
+		for (int q = 0; q < 5; ++q) ex[q] = carry[q] + (w ? sh[q][w - 1] : 0) + inc[q] - v[q];
+		if (r < S.n_reads) { rec_off[r] = ex[0]; U64x4 o; o.v[0] = ex[1]; o.v[1] = ex[2]; o.v[2] = ex[3]; o.v[3] = ex[4]; sl_prefix[r] = o; }
+		__syncthreads();
+		if (t < 5) carry[t] += sh[t][31];
+		__syncthreads();
+	}
+	if (t == 0) {
+		rec_off[S.n_reads] = carry[0];
+		U64x4 o; o.v[0] = carry[1]; o.v[1] = carry[2]; o.v[2] = carry[3]; o.v[3] = carry[4];
+		sl_prefix[S.n_reads] = o;
+		tot->n_rec = carry[0]; tot->letters = o;
+		*n_rec_dev = (uint32_t) carry[0];
+	}
+}
+
+// up to 4 u32 arrays -> exclusive scans (u32) + totals
+__global__ void __launch_bounds__(1024) k_scan_u32x4(uint32_t n, const uint32_t *a0, uint32_t *o0, const uint32_t *a1, uint32_t *o1,
+                                                     const uint32_t *a2, uint32_t *o2, const uint32_t *a3, uint32_t *o3, uint32_t *totals) {
+	__shared__ uint32_t sh[4][32];
+	__shared__ uint32_t carry[4];
+	const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5;
+	const uint32_t *in[4] = {a0, a1, a2, a3};
+	uint32_t *out[4] = {o0, o1, o2, o3};
+	if (t < 4) carry[t] = 0;
+	__syncthreads();
+	for (uint32_t base = 0; base < n; base += 1024) {
+		uint32_t r = base + t;
+		uint32_t v[4], inc[4];
+		for (int q = 0; q < 4; ++q) {
+			v[q] = (in[q] && r < n) ? in[q][r] : 0;
+			uint32_t x = v[q];
+			for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+			inc[q] = x;
+			if (lane == 31) sh[q][w] = x;
+		}
+		__syncthreads();
+		if (w == 0) {
+			for (int q = 0; q < 4; ++q) {
+				uint32_t x = sh[q][lane];
+				for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+				sh[q][lane] = x;
+			}
+		}
+		__syncthreads();
+		for (int q = 0; q < 4; ++q) if (out[q] && r < n) out[q][r] = carry[q] + (w ? sh[q][w - 1] : 0) + inc[q] - v[q];
+		__syncthreads();
+		if (t < 4) carry[t] += sh[t][31];
+		__syncthreads();
+	}
+	if (t < 4) { if (out[t]) out[t][n] = carry[t]; totals[t] = carry[t]; }
+}
+
+// per-read draw counts (u32) -> exclusive scans (u64) + totals
+__global__ void __launch_bounds__(1024) k_scan_draws(uint32_t n, const uint32_t *a0, unsigned long long *o0, const uint32_t *a1, unsigned long long *o1, unsigned long long *totals) {
+	__shared__ unsigned long long sh[2][32];
+	__shared__ unsigned long long carry[2];
+	const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5;
+	const uint32_t *in[2] = {a0, a1};
+	unsigned long long *out[2] = {o0, o1};
+	if (t < 2) carry[t] = 0;
+	__syncthreads();
+	for (uint32_t base = 0; base < n; base += 1024) {
+		uint32_t r = base + t;
+		unsigned long long v[2], inc[2];
+		for (int q = 0; q < 2; ++q) {
+			v[q] = r < n ? in[q][r] : 0;
+			unsigned long long x = v[q];
+			for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+			inc[q] = x;
+			if (lane == 31) sh[q][w] = x;
+		}
+		__syncthreads();
+		if (w == 0) {
+			for (int q = 0; q < 2; ++q) {
+				unsigned long long x = sh[q][lane];
+				for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+				sh[q][lane] = x;
+			}
+		}
+		__syncthreads();
+		for (int q = 0; q < 2; ++q) if (r < n) out[q][r] = carry[q] + (w ? sh[q][w - 1] : 0) + inc[q] - v[q];
+		__syncthreads();
+		if (t < 2) carry[t] += sh[t][31];
+		__syncthreads();
+	}
+	if (t < 2) { out[t][n] = carry[t]; totals[t] = carry[t]; }
 }
 
 }  // namespace fqsk
