@@ -451,13 +451,13 @@ int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes, u
 	int fl[8];
 	uint32_t cnt[4];
 	// walk 0 on every read, then (speculatively) the thread-local pass: delta, k_local, walk 1 on the reads it touched
-	{ Phase ph(h, FQSK_PH_WALK); k_walk<<<nblk(n, 128), 128, 0, h->st>>>(E, S, P, 0); LAUNCHED(h); ++h->S.n_replays; }
+	{ Phase ph(h, FQSK_PH_WALK); k_walk<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(E, S, P, 0); LAUNCHED(h); ++h->S.n_replays; }
 	for (uint32_t it = 1;; ++it) {
 		if (it >= max_it) return fail(h, FQSK_E_NO_CONVERGE, "segment did not reach its fixed point in %u iterations", max_it);
 		CK(cudaMemsetAsync(h->d_flags + 2, 0, sizeof(int), h->st));
 		CKR(build_delta());
 		{ Phase ph(h, FQSK_PH_LOCAL); k_local<<<std::min<uint32_t>(nblk(std::max<uint32_t>(h->miss_cap, 1), 128), 148 * 16), 128, 0, h->st>>>(E, S, P); LAUNCHED(h); }
-		{ Phase ph(h, FQSK_PH_WALK); k_walk<<<nblk(n, 128), 128, 0, h->st>>>(E, S, P, it); LAUNCHED(h); ++h->S.n_replays; }
+		{ Phase ph(h, FQSK_PH_WALK); k_walk<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(E, S, P, it); LAUNCHED(h); ++h->S.n_replays; }
 		uint32_t *hs = (uint32_t *) h->h_small;
 		CK(cudaMemcpyAsync(hs, h->d_u32, 4 * 4, cudaMemcpyDeviceToHost, h->st));
 		CK(cudaMemcpyAsync(hs + 8, h->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->st));

@@ -321,19 +321,41 @@ __global__ void __launch_bounds__(128) k_local(EngineDev E, SegDev S, PipeDev P)
 // window the cascade is evaluated here with the corrected registers (the slow path of the reference's own hot loop).
 // Rough searches are only REQUESTED here: their result never feeds back into the registers (dna.cpp:707-735).
 // ------------------------------------------------------------------------------------------------------------------
-template <bool CHECK>
-__device__ __forceinline__ void push_u64(unsigned long long *dst, uint32_t *tdst, uint32_t idx, unsigned long long v, uint32_t t, bool &changed) {
-	if (CHECK) changed |= (dst[idx] != v) | (tdst[idx] != t);
-	dst[idx] = v; tdst[idx] = t;
+// ------------------------------------------------------------------------------------------------------------------
+// k_walk: one WARP per read, "speculative chunks with commit-prefix".
+// The corrected registers of the reference are the registers of a CORRECTED READ: the original symbols with the patches
+// made by repair_kmers_existing / repair_kmers_missing (dna.cpp:363-365, 442-446); a bmer_unc hit (dna.cpp:697-705) drops
+// the patches that are still inside the b-mer window.  The warp keeps the last 64 corrected and original symbols in two
+// shared-memory rings.  Each iteration the 32 lanes evaluate 32 consecutive positions in parallel from the rings as they
+// are (registers, find_counts -- from the provisional record when corrected == uncorrected, from the tables otherwise --,
+// pushes, repair decision).  The first lane whose position changes the rings (a repair or a bmer_unc revert) is the
+// commit point: lanes up to it write their records and pushes, its event is applied to the ring, and the next chunk starts
+// right behind it.  Everything a lane needs besides the rings (cor_pos, push counters) is constant up to the commit point,
+// so committed lanes are exactly the reference's sequential steps.
+// it == 0: every read; it > 0: only reads marked dirty, and any difference to the previous walk's pushes raises flags[2].
+// ------------------------------------------------------------------------------------------------------------------
+struct LaneRegs { KReg b; uint32_t cb; };
+
+__device__ __forceinline__ KReg ring_breg(const uint8_t *ring, uint32_t i, uint32_t cb) {
+	KReg r{0, 0};
+	for (uint32_t t = 0; t + 1 < cb; ++t) {
+		uint64_t sy = ring[(i + 1 - cb + t) & 63];
+		r.dir |= sy << (62 - 2 * t);
+		r.rc |= (3 - sy) << (64 - 2 * cb + 2 * t);
+	}
+	r.rc |= 3ull << 62;
+	return r;
 }
 
-// it == 0: every read; it > 0: only reads marked dirty, and any difference to the previous walk's pushes raises flags[2].
 __global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P, uint32_t it) {
-	uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (r >= S.n_reads) return;
 	if (it > 0) { if (!P.dirty[r]) return; }
-	P.dirty[r] = 0;
-	if (S.dup[r]) { S.cnt_b[r] = S.cnt_s[r] = S.cnt_p[r] = S.hidden[r] = 0; if (E.sorted) { S.sorted_flag[r] = 0; S.sorted_dif[r] = 0; } return; }
+	__syncwarp();
+	if (lane == 0) P.dirty[r] = 0;
+	if (S.dup[r]) { if (lane == 0) { S.cnt_b[r] = S.cnt_s[r] = S.cnt_p[r] = S.hidden[r] = 0; if (E.sorted) { S.sorted_flag[r] = 0; S.sorted_dif[r] = 0; } } return; }
+	__shared__ uint8_t ringC_all[4][64], ringU_all[4][64];
+	uint8_t *ringC = ringC_all[threadIdx.x >> 5], *ringU = ringU_all[threadIdx.x >> 5];
 	const bool check = it > 0;
 	bool changed = false, window_local = false;
 	const uint8_t *p = S.dna + S.off[r];
@@ -350,150 +372,217 @@ __global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P, 
 	int *unsupported = E.flags + 1;
 	DrawCursor nodraw; nodraw.ring = nullptr; nodraw.mask = 0; nodraw.pos0 = 0; nodraw.avail = 0; nodraw.base = 0; nodraw.used = 0; nodraw.overflow = E.flags + 5;
 
-	ReadState R;
-	R.pc = R.sc = R.bc = R.pu = R.su = R.bu = KReg{0, 0};
-	R.n = 0; R.cor_pos = 0; R.n_run = 0;
-	uint32_t start;
-	if (!E.sorted) {
-		for (uint32_t i = 0; i < E.prefix_len; ++i) {
-			uint32_t sym = dna_code(p[i]);
-			if (sym == 4) { sym = 0; R.cor_pos = i; }
-			rs_push_all(R, E, sym);
-		}
-		start = E.prefix_len;
-	} else {
-		for (uint32_t i = 0; i < E.p; ++i) { uint32_t sym = dna_code(p[i]); if (sym == 4) sym = 3; rs_push_all(R, E, sym); }
-		unsigned long long prev_dir; bool prev_valid;
-		if (r == 0) { prev_dir = S.pprev_dir; prev_valid = S.pprev_valid != 0; }
-		else {
-			const uint8_t *q = S.dna + S.off[r - 1];
-			prev_dir = 0;
-			for (uint32_t i = 0; i < E.p; ++i) { uint32_t sym = dna_code(q[i]); if (sym == 4) sym = 3; prev_dir |= (unsigned long long) sym << (62 - 2 * i); }
-			prev_valid = true;
-		}
-		uint64_t cur_al = R.pc.dir >> (64 - 2 * E.p);
-		uint64_t prev_al = prev_valid ? prev_dir >> (64 - 2 * E.p) : 0;
-		uint32_t flag; unsigned long long dif = 0;
-		if (R.pc.dir == prev_dir) flag = 4; else flag = siv_test(E.siv, cur_al);
-		if (flag < 4) for (uint64_t i = prev_al + 1; i < cur_al; ++i) dif += siv_test(E.siv, i) == flag;
-		S.sorted_flag[r] = flag; S.sorted_dif[r] = dif;
-		out_p[np++] = cur_al;
-		out_p[np++] = R.pc.rc >> (64 - 2 * E.p);
-		start = E.p;
+	const uint32_t start = E.sorted ? E.p : E.prefix_len;
+	uint32_t cor_pos = 0;
+	// prefix: symbols enter the registers with N -> A (direct, cor_pos = position of the last N, dna.cpp:532-536) or N -> T (sorted, 560-565)
+	{
+		uint32_t npos = 0;
+		for (uint32_t j = lane; j < start; j += 32) if (dna_code(p[j]) == 4) npos = j + 1;
+		for (int o = 16; o; o >>= 1) { uint32_t y = __shfl_xor_sync(0xffffffffu, npos, o); npos = npos > y ? npos : y; }
+		if (!E.sorted && npos) cor_pos = npos - 1;
 	}
-	// software pipeline: the provisional record and the read symbol of the NEXT position are loaded one step ahead
-	fqsk_base_rec pv_next;
-	uint32_t ch_next = 0;
-	if (start < size) { pv_next = P.prov[g0]; ch_next = p[start]; }
-	for (uint32_t i = start; i < size; ++i) {
-		const uint32_t g = g0 + (i - start);
-		const fqsk_base_rec pv = pv_next;
-		const uint32_t sym = dna_code((uint8_t) ch_next);
-		if (i + 1 < size) { pv_next = P.prov[g + 1]; ch_next = p[i + 1]; }
-		const uint64_t ks = sym == 4 ? 0 : sym;
-		rs_push_all(R, E, 0);
-		const uint32_t cb = cur_of(E.b, R.n), cs = cur_of(E.s, R.n), cp = cur_of(E.p, R.n);
-		uint32_t lev, c[4];
-		if (R.bc.dir == R.bu.dir) {
-			// fast path: the provisional record is the reference's find_counts result
-			lev = pv.level; c[0] = pv.counts[0]; c[1] = pv.counts[1]; c[2] = pv.counts[2]; c[3] = pv.counts[3];
-		} else {
-			// repair window: cascade with the corrected registers (only reachable with a full b register)
-			c[0] = c[1] = c[2] = c[3] = 0;
-			lev = FQSK_LEVEL_NONE;
-			bool done = false;
-			if (ht_find(E.hb, E.cib, R.bc, cb, c, nodraw)) {
-				int sat = (c[0] == E.hb.top) + (c[1] == E.hb.top) + (c[2] == E.hb.top) + (c[3] == E.hb.top);
-				if (sat > 1) { uint32_t c2[4]; ht_find(E.hs, E.cis, R.sc, cs, c2, nodraw); for (int q = 0; q < 4; ++q) c[q] += c2[q]; lev = FQSK_LEVEL_MIXED; }
-				else lev = FQSK_LEVEL_BMER;
-				done = true;
-			} else {
-				window_local = true;   // the thread-local table is consulted here: this read must be re-walked once the delta exists / changes
-				if (delta_find(S.delta_b, E.cib, R.bc, cb, tbase + i, c, unsupported)) { lev = FQSK_LEVEL_BMER; done = true; }
-				if (!done && ht_find(E.hb, E.cib, R.bu, cb, c, nodraw)) { lev = FQSK_LEVEL_BMER_UNC; done = true; }
+	if (E.sorted) {
+		if (lane == 0) {
+			unsigned long long cur_dir = 0;
+			for (uint32_t i = 0; i < E.p; ++i) cur_dir |= (unsigned long long) sym_at(S, E, p, i) << (62 - 2 * i);
+			unsigned long long cur_rc = 0;
+			for (uint32_t i = 0; i < E.p; ++i) cur_rc |= (unsigned long long) (3 - sym_at(S, E, p, E.p - 1 - i)) << (62 - 2 * i);
+			unsigned long long prev_dir; bool prev_valid;
+			if (r == 0) { prev_dir = S.pprev_dir; prev_valid = S.pprev_valid != 0; }
+			else {
+				const uint8_t *q = S.dna + S.off[r - 1];
+				prev_dir = 0;
+				for (uint32_t i = 0; i < E.p; ++i) { uint32_t sy = dna_code(q[i]); if (sy == 4) sy = 3; prev_dir |= (unsigned long long) sy << (62 - 2 * i); }
+				prev_valid = true;
 			}
-			if (!done) {
-				if (ht_find(E.hs, E.cis, R.sc, cs, c, nodraw)) lev = FQSK_LEVEL_SMER;
-				else if (delta_find(S.delta_s, E.cis, R.sc, cs, tbase + i, c, unsupported)) lev = FQSK_LEVEL_SMER;
-			}
-			if (lev == FQSK_LEVEL_BMER_UNC) { R.bc = R.bu; R.sc = R.su; R.pc = R.pu; R.cor_pos = 0; lev = FQSK_LEVEL_BMER; }
+			uint64_t cur_al = cur_dir >> (64 - 2 * E.p);
+			uint64_t prev_al = prev_valid ? prev_dir >> (64 - 2 * E.p) : 0;
+			uint32_t flag; unsigned long long dif = 0;
+			if (cur_dir == prev_dir) flag = 4; else flag = siv_test(E.siv, cur_al);
+			if (flag < 4) for (uint64_t i = prev_al + 1; i < cur_al; ++i) dif += siv_test(E.siv, i) == flag;
+			S.sorted_flag[r] = flag; S.sorted_dif[r] = dif;
+			out_p[0] = cur_al; out_p[1] = cur_rc >> (64 - 2 * E.p);
 		}
-		{
+		np = 2;
+	}
+	// rings: positions [0, start + 32) that exist
+	for (uint32_t j = lane; j < 64; j += 32) { ringC[j] = 0; ringU[j] = 0; }
+	__syncwarp();
+	uint32_t filled = 0;            // positions [.., filled) are in the rings
+	uint32_t i0 = start;
+	while (i0 < size) {
+		// bring the rings up to position i0 + 31 (never more than 64 behind)
+		uint32_t want = i0 + 32 < size ? i0 + 32 : size;
+		uint32_t from = filled > (i0 >= 31 ? i0 - 31 : 0) ? filled : (i0 >= 31 ? i0 - 31 : 0);
+		for (uint32_t j = from + lane; j < want; j += 32) { uint8_t sy = (uint8_t) sym_at(S, E, p, j); ringU[j & 63] = sy; ringC[j & 63] = sy; }
+		filled = want;
+		__syncwarp();
+		const uint32_t i = i0 + lane;
+		const bool valid = i < size;
+		// ---- per-lane evaluation of position i
+		uint32_t lev = FQSK_LEVEL_NONE, c[4] = {0, 0, 0, 0};
+		uint32_t sym = 4, cb = 0, cs = 0, cp = 0, lane_cor = cor_pos;
+		bool ev_revert = false, ev_patch = false, repaired = false, lane_wl = false;
+		int lane_unsup = 0;   // discarded (speculative) lanes must not raise global flags
+		uint32_t patch_pos = 0, patch_sym = 0, new_cor = cor_pos;
+		KReg bc{0, 0}, bu{0, 0};
+		uint8_t rk = 0;
+		bool push_b0 = false, push_s0 = false, push_p0 = false;
+		uint32_t hid = 0;
+		unsigned long long key_b0 = 0, key_s0 = 0, key_p0 = 0, key_p1 = 0, key_b1 = 0;
+		if (valid) {
+			const uint32_t n = i + 1;
+			cb = n < E.b ? n : E.b; cs = n < E.s ? n : E.s; cp = n < E.p ? n : E.p;
+			sym = dna_code(p[i]);
+			const uint64_t ks = sym == 4 ? 0 : sym;
+			bu = ring_breg(ringU, i, cb);
+			bc = ring_breg(ringC, i, cb);
+			const fqsk_base_rec pv = P.prov[g0 + (i - start)];
+			if (bc.dir == bu.dir) {
+				lev = pv.level; c[0] = pv.counts[0]; c[1] = pv.counts[1]; c[2] = pv.counts[2]; c[3] = pv.counts[3];
+			} else {
+				// repair window: cascade with the corrected registers (only reachable with a full b register)
+				KReg sc = suffix_reg(bc, cb, cs);
+				bool done = false;
+				if (ht_find(E.hb, E.cib, bc, cb, c, nodraw)) {
+					int sat = (c[0] == E.hb.top) + (c[1] == E.hb.top) + (c[2] == E.hb.top) + (c[3] == E.hb.top);
+					if (sat > 1) { uint32_t c2[4]; ht_find(E.hs, E.cis, sc, cs, c2, nodraw); for (int q = 0; q < 4; ++q) c[q] += c2[q]; lev = FQSK_LEVEL_MIXED; }
+					else lev = FQSK_LEVEL_BMER;
+					done = true;
+				} else {
+					lane_wl = true;   // the thread-local table is consulted here: this read is re-walked when the delta exists / changes
+					if (delta_find(S.delta_b, E.cib, bc, cb, tbase + i, c, &lane_unsup)) { lev = FQSK_LEVEL_BMER; done = true; }
+					if (!done && ht_find(E.hb, E.cib, bu, cb, c, nodraw)) { lev = FQSK_LEVEL_BMER_UNC; done = true; }
+				}
+				if (!done) {
+					if (ht_find(E.hs, E.cis, sc, cs, c, nodraw)) lev = FQSK_LEVEL_SMER;
+					else if (delta_find(S.delta_s, E.cis, sc, cs, tbase + i, c, &lane_unsup)) lev = FQSK_LEVEL_SMER;
+				}
+				if (lev == FQSK_LEVEL_BMER_UNC) { bc = bu; ev_revert = true; lane_cor = 0; new_cor = 0; lev = FQSK_LEVEL_BMER; }   // dna.cpp:697-705
+			}
+			KReg sc = suffix_reg(bc, cb, cs), pc = suffix_reg(bc, cb, cp);
+			if (lev == FQSK_LEVEL_NONE) {   // dna.cpp:709-735, deferred to k_rough
+				if (cb == E.b) rk = 2; else if (cs == E.s) rk = 3; else if (cp == E.p) rk = 4;
+			}
+			KReg rq = rk == 2 ? bc : rk == 3 ? sc : pc;
+			// the symbol becomes known (dna.cpp:810-816)
+			kr_set_last(bc, cb, ks); kr_set_last(sc, cs, ks); kr_set_last(pc, cp, ks);
+			if (sym < 4) {   // dna.cpp:818-852
+				bool p_insert = true;
+				if (cb == E.b) {
+					push_b0 = true; key_b0 = kr_norm(bc, E.b);
+					if ((lev == FQSK_LEVEL_SMER || lev == FQSK_LEVEL_BMER || lev == FQSK_LEVEL_MIXED) && c[sym] >= 3) p_insert = false;
+				}
+				if (cs == E.s) { push_s0 = true; key_s0 = kr_norm(sc, E.s); }
+				if (cp == E.p && i - lane_cor >= E.p - 1) {
+					if (p_insert) { push_p0 = true; key_p0 = pc.dir >> (64 - 2 * E.p); key_p1 = pc.rc >> (64 - 2 * E.p); }
+					else hid = 2;
+				}
+			}
+			if (cb == E.b) {   // dna.cpp:854-875
+				if (lev == FQSK_LEVEL_BMER || lev == FQSK_LEVEL_MIXED) {
+					uint32_t best = 0;
+					for (uint32_t q = 1; q < 4; ++q) if (c[q] > c[best] || (c[q] == c[best] && sl[q] > sl[best])) best = q;
+					bool ok = true;
+					if (sym != 4) ok = best != sym && c[sym] == 0 && c[best] > 3;
+					if (ok) { kr_set_last(bc, cb, best); ev_patch = true; patch_pos = i; patch_sym = best; new_cor = i; repaired = true; }
+				} else if ((lev == FQSK_LEVEL_NONE || lev == FQSK_LEVEL_PMER) && E.gate_missing) {
+					int best_c = 4, best_count = 0, best_j = 0;
+					for (int j = 1; j < 6; ++j) {
+						uint32_t cnts[4];
+						uint64_t orig = kr_sym(bc, cb - 1 - j);
+#pragma unroll
+						for (uint64_t q = 0; q < 4; ++q) {
+							cnts[q] = 0;
+							if (q == orig) continue;
+							KReg t = bc;
+							kr_set(t, cb, q, cb - 1 - j);
+							cnts[q] = ht_count(E.hb, kr_norm(t, E.b));
+						}
+						for (int q = 0; q < 4; ++q) {
+							if ((uint64_t) q == orig) continue;
+							int cnt = (int) cnts[q];
+							if (cnt >= best_count && cnt >= 2) { best_c = q; best_count = cnt; best_j = j; }
+						}
+					}
+					if (best_j) {
+						kr_set(bc, cb, best_c, cb - 1 - best_j);
+						ev_patch = true; patch_pos = i - (uint32_t) best_j; patch_sym = (uint32_t) best_c;
+						uint32_t np2 = i - (uint32_t) best_j;
+						new_cor = lane_cor > np2 ? lane_cor : np2;
+						repaired = true;
+					}
+				}
+				if (repaired) key_b1 = kr_norm(bc, E.b);
+			}
+			(void) rq;
+		}
+		// ---- commit point (all 32 lanes participate in the collectives)
+		const bool ev = valid && (ev_revert || ev_patch);
+		const unsigned evm = __ballot_sync(0xffffffffu, ev);
+		const unsigned vm = __ballot_sync(0xffffffffu, valid);
+		const uint32_t last_valid = 31 - __clz(vm);
+		const uint32_t f = evm ? (uint32_t) (__ffs(evm) - 1) : last_valid;
+		const bool commit = valid && lane <= f;
+		const unsigned below = (1u << lane) - 1u;
+		const unsigned mb0 = __ballot_sync(0xffffffffu, commit && push_b0), mb1 = __ballot_sync(0xffffffffu, commit && repaired);
+		const unsigned ms0 = __ballot_sync(0xffffffffu, commit && push_s0), mp0 = __ballot_sync(0xffffffffu, commit && push_p0);
+		if (commit) {
+			if (lane_unsup) *unsupported = 1;
+			window_local |= lane_wl;
+			const uint32_t g = g0 + (i - start);
 			fqsk_base_rec o;
 			o.pos = i; o.counts[0] = c[0]; o.counts[1] = c[1]; o.counts[2] = c[2]; o.counts[3] = c[3];
-			o.cor_pos = R.cor_pos; o.level = (uint8_t) lev; o.rough = 0; o.pad = 0;
+			o.cor_pos = lane_cor; o.level = (uint8_t) lev; o.rough = 0; o.pad = 0;
 			P.recs[g] = o;
+			P.rkind[g] = rk;
+			if (rk) {
+				// register before the symbol became known: rebuild from the (possibly reverted) corrected view
+				KReg bq = ev_revert ? ring_breg(ringU, i, cb) : ring_breg(ringC, i, cb);
+				P.rreg[g] = rk == 2 ? bq : rk == 3 ? suffix_reg(bq, cb, cs) : suffix_reg(bq, cb, cp);
+			}
+			// pushes: positions of earlier lanes first; inside a position: b, [repaired b]
+			uint32_t ib = nb + __popc(mb0 & below) + __popc(mb1 & below);
+			if (push_b0) { if (check) changed |= (out_b[ib] != key_b0) | (tim_b[ib] != tbase + i); out_b[ib] = key_b0; tim_b[ib] = tbase + i; ++ib; }
+			if (repaired) { if (check) changed |= (out_b[ib] != key_b1) | (tim_b[ib] != tbase + i); out_b[ib] = key_b1; tim_b[ib] = tbase + i; }
+			uint32_t is = ns + __popc(ms0 & below);
+			if (push_s0) { if (check) changed |= (out_s[is] != key_s0) | (tim_s[is] != tbase + i); out_s[is] = key_s0; tim_s[is] = tbase + i; }
+			uint32_t ip = np + 2 * __popc(mp0 & below);
+			if (push_p0) { out_p[ip] = key_p0; out_p[ip + 1] = key_p1; }
 		}
-		uint8_t rk = 0;
-		if (lev == FQSK_LEVEL_NONE) {   // dna.cpp:709-735, deferred to k_rough
-			if (cb == E.b) { rk = 2; P.rreg[g] = R.bc; }
-			else if (cs == E.s) { rk = 3; P.rreg[g] = R.sc; }
-			else if (cp == E.p) { rk = 4; P.rreg[g] = R.pc; }
+		nb += __popc(mb0) + __popc(mb1); ns += __popc(ms0); np += 2 * __popc(mp0);
+		{
+			uint32_t hsum = commit ? hid : 0;
+			for (int o = 16; o; o >>= 1) hsum += __shfl_xor_sync(0xffffffffu, hsum, o);
+			hidden += hsum;
 		}
-		P.rkind[g] = rk;
-		kr_set_last(R.pc, cp, ks); kr_set_last(R.sc, cs, ks); kr_set_last(R.bc, cb, ks);
-		kr_set_last(R.pu, cp, ks); kr_set_last(R.su, cs, ks); kr_set_last(R.bu, cb, ks);
-		if (sym < 4) {
-			bool p_insert = true;
-			if (cb == E.b) {
-				if (check) push_u64<true>(out_b, tim_b, nb, kr_norm(R.bc, E.b), tbase + i, changed); else push_u64<false>(out_b, tim_b, nb, kr_norm(R.bc, E.b), tbase + i, changed);
-				++nb;
-				if ((lev == FQSK_LEVEL_SMER || lev == FQSK_LEVEL_BMER || lev == FQSK_LEVEL_MIXED) && c[sym] >= 3) p_insert = false;
+		// ---- apply the event of lane f to the corrected ring and continue right behind it
+		if (evm) {
+			const uint32_t e_rev = __shfl_sync(0xffffffffu, (uint32_t) ev_revert, f);
+			const uint32_t e_pat = __shfl_sync(0xffffffffu, (uint32_t) ev_patch, f);
+			const uint32_t e_pos = __shfl_sync(0xffffffffu, patch_pos, f), e_sym = __shfl_sync(0xffffffffu, patch_sym, f);
+			cor_pos = __shfl_sync(0xffffffffu, new_cor, f);
+			const uint32_t i_f = i0 + f;
+			__syncwarp();
+			if (e_rev) {   // corrected registers := uncorrected ones: drop every patch inside the b window of position i_f
+				uint32_t lo = i_f + 1 >= E.b ? i_f + 1 - E.b : 0;
+				for (uint32_t j = lo + lane; j <= i_f; j += 32) ringC[j & 63] = ringU[j & 63];
 			}
-			if (cs == E.s) {
-				if (check) push_u64<true>(out_s, tim_s, ns, kr_norm(R.sc, E.s), tbase + i, changed); else push_u64<false>(out_s, tim_s, ns, kr_norm(R.sc, E.s), tbase + i, changed);
-				++ns;
-			}
-			if (cp == E.p && i - R.cor_pos >= E.p - 1) {
-				if (p_insert) { out_p[np++] = R.pc.dir >> (64 - 2 * E.p); out_p[np++] = R.pc.rc >> (64 - 2 * E.p); }
-				else hidden += 2;
-			}
-		}
-		if (cb == E.b) {
-			bool repaired = false;
-			if (lev == FQSK_LEVEL_BMER || lev == FQSK_LEVEL_MIXED) {
-				uint32_t best = 0;
-				for (uint32_t q = 1; q < 4; ++q) if (c[q] > c[best] || (c[q] == c[best] && sl[q] > sl[best])) best = q;
-				bool ok = true;
-				if (sym != 4) ok = best != sym && c[sym] == 0 && c[best] > 3;
-				if (ok) { kr_set_last(R.pc, cp, best); kr_set_last(R.sc, cs, best); kr_set_last(R.bc, cb, best); R.cor_pos = i; repaired = true; }
-			} else if ((lev == FQSK_LEVEL_NONE || lev == FQSK_LEVEL_PMER) && E.gate_missing) {
-				int best_c = 4, best_count = 0, best_j = 0;
-				for (int j = 1; j < 6; ++j) {
-					uint32_t cnts[4];
-					uint64_t orig = kr_sym(R.bc, cb - 1 - j);
-#pragma unroll
-					for (uint64_t q = 0; q < 4; ++q) {
-						cnts[q] = 0;
-						if (q == orig) continue;
-						KReg t = R.bc;
-						kr_set(t, cb, q, cb - 1 - j);
-						cnts[q] = ht_count(E.hb, kr_norm(t, E.b));
-					}
-					for (int q = 0; q < 4; ++q) {
-						if ((uint64_t) q == orig) continue;
-						int cnt = (int) cnts[q];
-						if (cnt >= best_count && cnt >= 2) { best_c = q; best_count = cnt; best_j = j; }
-					}
-				}
-				if (best_j) {
-					kr_set(R.bc, cb, best_c, cb - 1 - best_j);
-					if (best_j < (int) cs) kr_set(R.sc, cs, best_c, cs - 1 - best_j);
-					if (best_j < (int) cp) kr_set(R.pc, cp, best_c, cp - 1 - best_j);
-					uint32_t np2 = i - (uint32_t) best_j;
-					R.cor_pos = R.cor_pos > np2 ? R.cor_pos : np2;
-					repaired = true;
-				}
-			}
-			if (repaired) {
-				if (check) push_u64<true>(out_b, tim_b, nb, kr_norm(R.bc, E.b), tbase + i, changed); else push_u64<false>(out_b, tim_b, nb, kr_norm(R.bc, E.b), tbase + i, changed);
-				++nb;
-			}
+			__syncwarp();
+			if (e_pat && lane == 0) ringC[e_pos & 63] = (uint8_t) e_sym;
+			__syncwarp();
+			i0 = i_f + 1;
+		} else {
+			i0 += 32;
 		}
 	}
-	if (check && (changed || S.cnt_b[r] != nb || S.cnt_s[r] != ns)) P.flags[2] = 1;
-	S.cnt_b[r] = nb; S.cnt_s[r] = ns; S.cnt_p[r] = np; S.hidden[r] = hidden;
-	if (window_local) { P.dirty[r] = 1; if (it == 0) P.flags[3] = 1; }
+	changed = __any_sync(0xffffffffu, changed);
+	window_local = __any_sync(0xffffffffu, window_local);
+	if (lane == 0) {
+		if (check && (changed || S.cnt_b[r] != nb || S.cnt_s[r] != ns)) P.flags[2] = 1;
+		S.cnt_b[r] = nb; S.cnt_s[r] = ns; S.cnt_p[r] = np; S.hidden[r] = hidden;
+		if (window_local) { P.dirty[r] = 1; if (it == 0) P.flags[3] = 1; }
+	}
 }
 
 __global__ void k_compact2(SegDev S, PipeDev P, const uint32_t *off_b, const uint32_t *off_s, const uint32_t *off_p,
