@@ -82,6 +82,7 @@ struct fqsk_handle {
 	       sidx_b, sidx_s, stime_b, stime_s, sort_k, sort_v, rkind, rreg, rslot, dirty, rdraws_b, rdraws_s, totals;
 	uint32_t miss_cap = 0, rreq_cap = 0, pool_cap = 1u << 18;
 	uint32_t *d_u32 = nullptr;            // [0] n_miss [1] n_rreq [2] pool_used
+	bool fast_ok[2] = {true, true};     // [0] s-mers, [1] b-mers: the atomic fast path has not been refuted yet
 	bool delta_b_valid = false, delta_s_valid = false;   // dk_b/sidx_b (dk_s/sidx_s) hold the pending row sorted by k-mer
 	uint32_t iota_n = 0;
 	// pending rows (device), valid after fqsk_segment until fqsk_sync
@@ -154,12 +155,12 @@ uint64_t mod_inverse(uint64_t x) { uint64_t inv = x; for (int i = 0; i < 6; ++i)
 int table_alloc(fqsk_handle *h, Table &t, uint32_t k, uint32_t cbits, uint32_t B, unsigned long long *counters) {
 	HtDev &d = t.d;
 	d.k = k; d.cbits = cbits; d.W = 2 * k - 8; d.top = (1u << cbits) - 1;
-	uint32_t bmin = d.W + cbits > 24 ? d.W + cbits - 24 : 1;
+	uint32_t bmin = d.W + cbits > 23 ? d.W + cbits - 23 : 1;   // rem + 8 end bits + counter + the occupied bit fit 32 bits
 	if (B < bmin) B = bmin;
 	if (B >= d.W) B = d.W - 1;
-	if (B > 28) return fail(h, FQSK_E_INVAL, "table with k=%u needs 2^%u buckets; this build addresses slots with 32 bits (max 2^28 buckets)", k, B);
+	if (B > 30) return fail(h, FQSK_E_INVAL, "table with k=%u needs 2^%u buckets (more than 2^30 is not supported)", k, B);
 	d.B = B; d.rem_bits = d.W - B;
-	if (d.rem_bits + 8 + cbits > 32) return fail(h, FQSK_E_INVAL, "k=%u, %u counter bits do not fit a 32-bit item with 2^%u buckets", k, cbits, B);
+	if (d.rem_bits + 8 + cbits > 31) return fail(h, FQSK_E_INVAL, "k=%u, %u counter bits do not fit a 32-bit item with 2^%u buckets", k, cbits, B);
 	d.maskW = d.W >= 64 ? ~0ull : ((1ull << d.W) - 1);
 	d.mix_sh = (d.W + 1) / 2;
 	d.stash_log2 = B + 3 >= 5 + 12 ? B + 3 - 5 : 12;
@@ -365,9 +366,21 @@ int sort_row(fqsk_handle *h, const unsigned long long *row, uint32_t n, uint32_t
 	return FQSK_OK;
 }
 
-int apply_inserts(fqsk_handle *h, Table &t, Stream &rng, const unsigned long long *d_kmers, uint32_t n) {
+int apply_inserts(fqsk_handle *h, Table &t, Stream &rng, const unsigned long long *d_kmers, uint32_t n, bool *fast_ok = nullptr) {
 	if (!n) return FQSK_OK;
 	if (n >= 0x80000000u) return fail(h, FQSK_E_INVAL, "more than 2^31 k-mers in one sync row");
+	if (fast_ok && *fast_ok) {
+		Phase ph(h, FQSK_PH_SYNC_APPLY);
+		CK(cudaMemsetAsync(h->d_flags, 0, 8 * sizeof(int), h->st));
+		k_insert_fast<<<nblk(n, 256), 256, 0, h->st>>>(t.d, t.ci, d_kmers, n, h->d_flags); LAUNCHED(h);
+		int fl[8];
+		CKR(read_flags(h, fl, 8));
+		if (!fl[2]) return FQSK_OK;
+		// some counter left the deterministic range: undo (claimed slots stay as zero-count items == the reference's fresh slot) and
+		// take the ordered path from now on for this table (once counters are above thr they stay there)
+		k_insert_undo<<<nblk(n, 256), 256, 0, h->st>>>(t.d, d_kmers, n); LAUNCHED(h);
+		*fast_ok = false;
+	}
 	CKR(sort_row(h, d_kmers, n, t.d.k, h->sort_k, h->sort_v));
 	return apply_sorted(h, t, rng, h->sort_k.as<unsigned long long>(), h->sort_v.as<uint32_t>(), n);
 }
@@ -489,12 +502,12 @@ int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes, u
 	unsigned long long draws2[2] = {0, 0};
 	{
 		Phase ph(h, FQSK_PH_FOLD);
-		k_fold<<<nblk(n, 128), 128, 0, h->st>>>(E, S, P, 0); LAUNCHED(h);
+		k_fold<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(E, S, P, 0); LAUNCHED(h);
 		for (int it = 0;; ++it) {
 			if (it > 32) return fail(h, FQSK_E_NO_CONVERGE, "draw offsets of the merge scripts did not settle");
 			k_scan_draws<<<1, 1024, 0, h->st>>>(n, P.rdraws_b, h->doff_b.as<unsigned long long>(), P.rdraws_s, h->doff_s.as<unsigned long long>(), d_draw2); LAUNCHED(h);
 			CK(cudaMemsetAsync(h->d_flags, 0, 4 * sizeof(int), h->st));
-			k_fold<<<nblk(n, 128), 128, 0, h->st>>>(E, S, P, 1); LAUNCHED(h);
+			k_fold<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(E, S, P, 1); LAUNCHED(h);
 			uint8_t *hs = (uint8_t *) h->h_small;
 			CK(cudaMemcpyAsync(hs, h->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
 			CK(cudaMemcpyAsync(hs + 32, d_draw2, 16, cudaMemcpyDeviceToHost, h->st));
@@ -618,7 +631,7 @@ int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
 		CK(cudaMallocHost(&h->h_small, 256));
 		uint64_t expect = p->expected_kmers ? p->expected_kmers : (1ull << 22);
 		uint32_t Bauto = 1;
-		while ((4ull << Bauto) < expect && Bauto < 28) ++Bauto;    // <= 50 % of 8 << B slots
+		while ((4ull << Bauto) < expect && Bauto < 30) ++Bauto;    // <= 50 % of 8 << B slots
 		CKR(table_alloc(h, h->tb, p->bmer_len, p->bmer_counter_bits ? p->bmer_counter_bits : 6, p->bmer_log2_buckets ? p->bmer_log2_buckets : Bauto, h->d_counters + 0));
 		CKR(table_alloc(h, h->ts, p->smer_len, p->smer_counter_bits ? p->smer_counter_bits : 12, p->smer_log2_buckets ? p->smer_log2_buckets : Bauto, h->d_counters + 2));
 		h->tb.ci = CIncP{7, 2, h->tb.d.top};                                  // cinc_b.Reset(7, 2, 63)            dna.cpp:162
@@ -786,9 +799,9 @@ int fqsk_sync(fqsk_handle *h) {
 		h->hidden_p = 0;
 		// s-mers, then b-mers (dna.cpp:2425-2446)
 		if (h->delta_s_valid) CKR(apply_sorted(h, h->ts, h->rng[ST_S], h->dk_s.as<unsigned long long>(), h->sidx_s.as<uint32_t>(), h->pend_s));
-		else CKR(apply_inserts(h, h->ts, h->rng[ST_S], h->row_s[h->cur].as<unsigned long long>(), h->pend_s));
+		else CKR(apply_inserts(h, h->ts, h->rng[ST_S], h->row_s[h->cur].as<unsigned long long>(), h->pend_s, &h->fast_ok[0]));
 		if (h->delta_b_valid) CKR(apply_sorted(h, h->tb, h->rng[ST_B], h->dk_b.as<unsigned long long>(), h->sidx_b.as<uint32_t>(), h->pend_b));
-		else CKR(apply_inserts(h, h->tb, h->rng[ST_B], h->row_b[h->cur].as<unsigned long long>(), h->pend_b));
+		else CKR(apply_inserts(h, h->tb, h->rng[ST_B], h->row_b[h->cur].as<unsigned long long>(), h->pend_b, &h->fast_ok[1]));
 		h->delta_b_valid = h->delta_s_valid = false;
 		CKR(table_grow_if_needed(h, h->ts));
 		CKR(table_grow_if_needed(h, h->tb));

@@ -4,7 +4,8 @@
 //   * b-/s-mer tables: 2^B buckets of 8 x u32 (one 32-byte sector). A k-mer lives in the bucket chosen by a bijective
 //     mix of its KERNEL (symbols s2..s(k-3), kmer.h:199-202) so the 4 next-symbol siblings of a context -- which differ
 //     only in s(k-1) (dir-oriented) or s0 (rc-oriented) -- share one sector, and one sector read answers
-//     CHT_kmer::find_full (ht_kmer.h:205-263).  item = [rem | s0 s1 s(k-2) s(k-1) | counter]; 0 = empty.
+//     CHT_kmer::find_full (ht_kmer.h:205-263).  item = [1 | rem | s0 s1 s(k-2) s(k-1) | counter]; 0 = empty (bit 31 marks an
+//     occupied slot, so an item stays distinguishable from an empty slot whatever its counter is).
 //     Buckets only hold native items; a k-mer whose bucket is full goes to a small u64 open-addressing stash.
 //     Reference lookups depend only on table CONTENTS, so this layout is free to differ from ht_kmer.h:49-76.
 //   * p-mer array: 2-bit saturating fields, 16 per u32, direct-addressed (bit_vec.h:17-231).
@@ -102,7 +103,7 @@ FQSK_DEV uint32_t ci_plus(const CIncP &p, uint32_t c, uint32_t inc, DrawCursor &
 // ------------------------------------------------------------------------------------------------------------------
 struct HtDev {
 	uint32_t *main;                 // 8 << B items
-	unsigned long long *stash;      // 1 << stash_log2 items: (aligned k-mer << cbits) | counter, 0 = empty
+	unsigned long long *stash;      // 1 << stash_log2 items: ((aligned k-mer + 1) << cbits) | counter, 0 = empty
 	uint32_t k, cbits, W, B, rem_bits, top, stash_log2, mix_sh;
 	uint64_t maskW;
 	unsigned long long *n_items;    // device counters: [0] main items, [1] stash items
@@ -125,7 +126,7 @@ FQSK_HD HtKey ht_key(const HtDev &t, uint64_t x) {
 	k.h = ht_mix(t, ht_kernel(t, x));
 	k.bucket = k.h >> t.rem_bits;
 	uint32_t rem = (uint32_t) (k.h & ((1ull << t.rem_bits) - 1));
-	k.q = (rem << (8 + t.cbits)) | (ht_ends(t, x) << t.cbits);
+	k.q = 0x80000000u | (rem << (8 + t.cbits)) | (ht_ends(t, x) << t.cbits);
 	k.kal = x >> (64 - 2 * t.k);
 	return k;
 }
@@ -164,7 +165,7 @@ FQSK_DEV void ht_ctx_counts_from(const HtDev &t, const HtKey &key, bool is_dir, 
 	for (uint64_t p = ht_stash_pos(t, key.h);; p = (p + 1) & smask) {
 		unsigned long long it = t.stash[p];
 		if (it == 0) break;
-		uint64_t kal = it >> t.cbits;
+		uint64_t kal = (it >> t.cbits) - 1;
 		if (((kal ^ key.kal) & m64) == 0) { uint32_t f = (uint32_t) ((kal >> ush) & 3); c[is_dir ? f : 3 - f] += (uint32_t) (it & t.top); }
 	}
 }
@@ -189,7 +190,7 @@ FQSK_DEV uint32_t ht_count(const HtDev &t, uint64_t x) {
 	for (uint64_t p = ht_stash_pos(t, key.h);; p = (p + 1) & smask) {
 		unsigned long long it = t.stash[p];
 		if (it == 0) return 0;
-		if ((it >> t.cbits) == key.kal) return (uint32_t) (it & t.top);
+		if ((it >> t.cbits) == key.kal + 1) return (uint32_t) (it & t.top);
 	}
 }
 // find-or-create for the sync step (ht_kmer.h:330-362).  New slots are claimed with counter 1; the group pass of the sync
@@ -208,7 +209,7 @@ FQSK_DEV uint64_t ht_locate(const HtDev &t, uint64_t x, bool &created) {
 		if ((it & ~t.top) == key.q) return key.bucket * 8 + i;
 	}
 	uint64_t smask = (1ull << t.stash_log2) - 1;
-	unsigned long long fresh = (key.kal << t.cbits) | 1ull;
+	unsigned long long fresh = ((key.kal + 1) << t.cbits) | 1ull;
 	for (uint64_t p = ht_stash_pos(t, key.h);; p = (p + 1) & smask) {
 		unsigned long long it = *((volatile unsigned long long *) (t.stash + p));
 		if (it == 0) {
@@ -216,7 +217,7 @@ FQSK_DEV uint64_t ht_locate(const HtDev &t, uint64_t x, bool &created) {
 			if (old == 0) { created = true; atomicAdd(t.n_items + 1, 1ull); return (8ull << t.B) + p; }
 			it = old;
 		}
-		if ((it >> t.cbits) == key.kal) return (8ull << t.B) + p;
+		if ((it >> t.cbits) == key.kal + 1) return (8ull << t.B) + p;
 	}
 }
 FQSK_DEV uint32_t ht_slot_get(const HtDev &t, uint64_t slot) {

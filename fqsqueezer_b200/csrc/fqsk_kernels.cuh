@@ -227,6 +227,29 @@ __global__ void k_commit_keys(HtDev t, const unsigned long long *skeys, uint32_t
 	ht_slot_set(t, slot_of[i] & ~(1ull << 63), final_cnt[i]);
 }
 
+// Fast path of the sync step: every occurrence does find-or-create and one atomic +1.  That equals the reference's ordered
+// Increment()s exactly when no counter leaves the deterministic range (pre-count <= thr for every occurrence, utils.h:317-318);
+// any occurrence that sees a pre-count above thr raises flags[2] and the host undoes the pass (k_insert_undo: the adds are
+// plain arithmetic on the item, so subtracting them restores every bit) and runs the ordered path instead.
+__global__ void k_insert_fast(HtDev t, CIncP ci, const unsigned long long *kmers, uint32_t n, int *flags) {
+	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n) return;
+	bool created;
+	uint64_t s = ht_locate(t, kmers[j], created);
+	if (created) return;            // claimed with counter 1 == Increment(0)
+	uint64_t nm = 8ull << t.B;
+	uint32_t old = s < nm ? (atomicAdd(t.main + s, 1u) & t.top) : (uint32_t) (atomicAdd(t.stash + (s - nm), 1ull) & t.top);
+	if (old > ci.thr) flags[2] = 1;
+}
+__global__ void k_insert_undo(HtDev t, const unsigned long long *kmers, uint32_t n) {
+	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n) return;
+	bool created;
+	uint64_t s = ht_locate(t, kmers[j], created);   // every key exists now
+	uint64_t nm = 8ull << t.B;
+	if (s < nm) atomicSub(t.main + s, 1u); else atomicAdd(t.stash + (s - nm), ~0ull);
+}
+
 __global__ void k_siv_increment(SivDev s, const unsigned long long *idx, uint64_t n, unsigned long long *n_new) {
 	uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	uint32_t fresh = 0;
@@ -285,7 +308,7 @@ __global__ void k_dump_ht(HtDev t, MixInv mi, unsigned long long *keys, unsigned
 	if (i < nm) {
 		uint32_t it = t.main[i];
 		if (!it) return;
-		uint64_t rem = it >> (8 + t.cbits);
+		uint64_t rem = (it & 0x7fffffffu) >> (8 + t.cbits);
 		uint64_t h = ((i >> 3) << t.rem_bits) | rem;
 		uint64_t kernel = ht_unmix(t, mi, h);
 		uint64_t ends = (it >> t.cbits) & 0xFF;
@@ -294,7 +317,7 @@ __global__ void k_dump_ht(HtDev t, MixInv mi, unsigned long long *keys, unsigned
 	} else {
 		unsigned long long it = t.stash[i - nm];
 		if (!it) return;
-		x = (it >> t.cbits) << (64 - 2 * t.k);
+		x = ((it >> t.cbits) - 1) << (64 - 2 * t.k);
 		cnt = it & t.top;
 	}
 	unsigned long long o = atomicAdd(n_out, 1ull);

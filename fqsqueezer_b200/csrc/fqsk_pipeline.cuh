@@ -717,32 +717,40 @@ __device__ void fold_script(const EngineDev &E, const PipeDev &P, const Script &
 	rec->level = (uint8_t) lev;
 }
 
-__global__ void __launch_bounds__(128) k_fold(EngineDev E, SegDev S, PipeDev P, int pass) {
-	uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) k_fold(EngineDev E, SegDev S, PipeDev P, int pass) {   // one warp per read
+	const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (r >= S.n_reads) return;
+	// the cursors are replicated in every lane (uniform control flow); lane 0 writes
 	DrawCursor db, ds;
 	db.ring = E.draws[0]; db.mask = E.dmask[0]; db.pos0 = E.dpos[0]; db.avail = E.avail[0]; db.used = 0; db.overflow = E.flags + 0;
 	ds.ring = E.draws[1]; ds.mask = E.dmask[1]; ds.pos0 = E.dpos[1]; ds.avail = E.avail[1]; ds.used = 0; ds.overflow = E.flags + 0;
 	db.base = pass ? P.doff_b[r] : 0;
 	ds.base = pass ? P.doff_s[r] : 0;
+	const bool write = pass != 0 && lane == 0;
 	if (!S.dup[r]) {
 		// front-truncated lookups: slots are in position order
 		const Script *ps = P.pscripts + (size_t) r * P.pslots;
-		for (uint32_t sl = 0; sl < P.pslots; ++sl) {
+		unsigned vm = __ballot_sync(0xffffffffu, lane < P.pslots && ps[lane].valid);
+		while (vm) {
+			uint32_t sl = __ffs(vm) - 1; vm &= vm - 1;
 			const Script &sc = ps[sl];
-			if (!sc.valid) continue;
-			fold_script(E, P, sc, sc.kind == 0 ? db : ds, pass != 0);
+			fold_script(E, P, sc, sc.kind == 0 ? db : ds, write);
 		}
 		// rough searches of this read, in position order
-		uint32_t g0 = (uint32_t) S.rec_off[r], g1 = (uint32_t) S.rec_off[r + 1];
-		for (uint32_t g = g0; g < g1; ++g) {
-			uint8_t k = P.rkind[g];
-			if (k != 2 && k != 3) continue;
-			uint32_t slot = P.rslot[g];
-			if (slot == 0xFFFFFFFFu) continue;
-			fold_script(E, P, P.rscripts[slot], k == 2 ? db : ds, pass != 0);
+		const uint32_t g0 = (uint32_t) S.rec_off[r], g1 = (uint32_t) S.rec_off[r + 1];
+		for (uint32_t gb = g0; gb < g1; gb += 32) {
+			uint32_t g = gb + lane;
+			uint32_t k = g < g1 ? P.rkind[g] : 0;
+			uint32_t slot = (k == 2 || k == 3) ? P.rslot[g] : 0xFFFFFFFFu;
+			unsigned hm = __ballot_sync(0xffffffffu, slot != 0xFFFFFFFFu);
+			while (hm) {
+				uint32_t q = __ffs(hm) - 1; hm &= hm - 1;
+				uint32_t sq = __shfl_sync(0xffffffffu, slot, q), kq = __shfl_sync(0xffffffffu, k, q);
+				fold_script(E, P, P.rscripts[sq], kq == 2 ? db : ds, write);
+			}
 		}
 	}
+	if (lane) return;
 	if (pass == 0) { P.rdraws_b[r] = db.used; P.rdraws_s[r] = ds.used; return; }
 	if (P.rdraws_b[r] != db.used || P.rdraws_s[r] != ds.used) { P.rdraws_b[r] = db.used; P.rdraws_s[r] = ds.used; P.flags[2] = 1; }
 }
