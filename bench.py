@@ -166,6 +166,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-reads", type=int, default=40_000)
+    ap.add_argument("--trace-blocks", type=int, default=0, help="print per-block phase ms every N blocks to stderr")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -204,7 +205,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- value: reads resident in HBM ----------------
-    eng = E.KmerEngine(p, s, b, pref, device=local_rank, expected_kmers=1 << 28, profile=True)
+    eng = E.KmerEngine(p, s, b, pref, device=local_rank, expected_kmers=1 << 29, profile=True, reserve_reads=READS_PER_BLOCK, reserve_bytes=READS_PER_BLOCK * L)
     d_blocks = []
     off_np = (np.arange(READS_PER_BLOCK, dtype=np.int64) * L)
     d_off = torch.from_numpy(off_np).to(dev)                      # same offsets for every block
@@ -231,8 +232,15 @@ def main():
     barrier()
     eng.timer_begin()
     t_wall = time.time()
+    prev_prof, t_prev = eng.profile(), time.time()
     for g in range(args.warmup, n_blocks):
         run_block_device(g)
+        if args.trace_blocks and (g % args.trace_blocks == 0 or g == n_blocks - 1):
+            pr = eng.profile()
+            print(f"block {g} ({len(sched[g])} segments): wall {1e3 * (time.time() - t_prev):.1f} ms " +
+                  str({k: round(pr[k] - prev_prof[k], 2) for k in pr}), file=sys.stderr, flush=True)
+        if args.trace_blocks:
+            prev_prof, t_prev = eng.profile(), time.time()
     dev_ms = eng.timer_end()
     barrier()
     wall_ms = (time.time() - t_wall) * 1e3
@@ -255,7 +263,7 @@ def main():
     # ---------------- e2e: host buffers through fqsk_segment ----------------
     e2e = None
     if not args.no_e2e:
-        eng2 = E.KmerEngine(p, s, b, pref, device=local_rank, expected_kmers=1 << 28)
+        eng2 = E.KmerEngine(p, s, b, pref, device=local_rank, expected_kmers=1 << 29, reserve_reads=READS_PER_BLOCK, reserve_bytes=READS_PER_BLOCK * (L + 1))
         slabs = []
         for g in range(n_blocks):
             slabs.append(codes_to_slab(block_codes(genome, g, rank)))

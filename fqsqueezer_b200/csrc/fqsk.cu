@@ -32,7 +32,7 @@ struct DevBuf {
 		if (bytes <= cap) return cudaSuccess;
 		if (p) cudaFree(p);
 		p = nullptr; cap = 0;
-		size_t want = bytes + bytes / 4 + 256;
+		size_t want = bytes + bytes / 2 + 256;
 		cudaError_t e = cudaMalloc(&p, want);
 		if (e == cudaSuccess) cap = want;
 		return e;
@@ -79,7 +79,9 @@ struct fqsk_handle {
 	       draw_cnt, draw_cnt_prev, draw_scan, off_b[2], off_s[2], off_p, row_b[2], row_s[2], row_p, dk_b, di_b, dk_s, di_s, iota, cub_tmp,
 	       flag8, draw_off, final_cnt, slot_of, dump_k, dump_v, q0, q1, q2, q3, q4, sflag, sdif, hid_scan,
 	       prov, pflags, pscripts, rscripts, rreqs, pool, miss, draws_b16, draws_s16, doff_b, doff_s, time_b, time_s, rt_b[2], rt_s[2],
-	       sidx_b, sidx_s, stime_b, stime_s, sort_k, sort_v, rkind, rreg, rslot, dirty, rdraws_b, rdraws_s, totals;
+	       sidx_b, sidx_s, stime_b, stime_s, sort_k, sort_v, rkind, rreg, rslot, dirty, rdraws_b, rdraws_s, totals,
+	       y_tslot, y_c0, y_m, y_draw, y_j, y_final, y_flag_at, y_own, y_lead, y_rank, y_flag, y_doff, idx_k, idx_t, idx_rt;
+	DeltaDev seg_delta_b{}, seg_delta_s{};   // the converged segment's delta tables (valid while `pending`)
 	uint32_t miss_cap = 0, rreq_cap = 0, pool_cap = 1u << 18;
 	uint32_t *d_u32 = nullptr;            // [0] n_miss [1] n_rreq [2] pool_used
 	bool fast_ok[2] = {true, true};     // [0] s-mers, [1] b-mers: the atomic fast path has not been refuted yet
@@ -385,6 +387,69 @@ int apply_inserts(fqsk_handle *h, Table &t, Stream &rng, const unsigned long lon
 	return apply_sorted(h, t, rng, h->sort_k.as<unsigned long long>(), h->sort_v.as<uint32_t>(), n);
 }
 
+// ordered insert of a row using a (k-mer, time) index whose probe runs group equal k-mers (the segment's delta table, or an
+// index built from the row).  One host sync; falls back to the sorted path when a hot group is too large for one thread.
+int apply_indexed(fqsk_handle *h, Table &t, Stream &rng, const DeltaDev &D, const unsigned long long *row, const uint32_t *rt, uint32_t n) {
+	if (!n) return FQSK_OK;
+	const size_t slots = (size_t) D.mask + 1;
+	CK(h->y_tslot.ensure(slots * 8)); CK(h->y_c0.ensure(slots * 4)); CK(h->y_m.ensure(slots * 4)); CK(h->y_draw.ensure(slots * 4));
+	CK(h->y_j.ensure(slots * 4)); CK(h->y_final.ensure(slots * 4)); CK(h->y_flag_at.ensure(slots));
+	CK(h->y_own.ensure((size_t) n * 4)); CK(h->y_lead.ensure((size_t) n * 4)); CK(h->y_rank.ensure((size_t) n * 4));
+	CK(h->y_flag.ensure((size_t) n + 4)); CK(h->y_doff.ensure(((size_t) n + 1) * 4));
+	SyncDev Y{};
+	Y.D = D;
+	Y.lead_tslot = h->y_tslot.as<unsigned long long>(); Y.lead_c0 = h->y_c0.as<uint32_t>(); Y.lead_m = h->y_m.as<uint32_t>();
+	Y.draw_at = h->y_draw.as<uint32_t>(); Y.j_at = h->y_j.as<uint32_t>(); Y.final_at = h->y_final.as<uint32_t>(); Y.flag_at = h->y_flag_at.as<uint8_t>();
+	Y.own = h->y_own.as<uint32_t>(); Y.lead = h->y_lead.as<uint32_t>(); Y.rank = h->y_rank.as<uint32_t>();
+	Y.flag = h->y_flag.as<uint8_t>(); Y.draw_off = h->y_doff.as<uint32_t>(); Y.flags = h->d_flags;
+	const uint32_t g = nblk(n, 256);
+	{
+		Phase ph(h, FQSK_PH_SYNC_LOCATE);
+		CK(cudaMemsetAsync(h->d_flags, 0, 8 * sizeof(int), h->st));
+		CK(cudaMemsetAsync(h->y_flag.p, 0, (size_t) n + 4, h->st));
+		k_sync_rank<<<g, 256, 0, h->st>>>(t.d, Y, row, rt, n); LAUNCHED(h);
+		k_sync_flags<<<g, 256, 0, h->st>>>(t.d, t.ci, Y, n); LAUNCHED(h);
+	}
+	Phase ph(h, FQSK_PH_SYNC_APPLY);
+	uint32_t total_draws = 0;
+	for (int it = 0;; ++it) {
+		if (it > 64) return fail(h, FQSK_E_NO_CONVERGE, "sync insert: draw flags did not settle");
+		CKR((scan_excl<uint8_t, uint32_t>(h, h->y_flag.as<uint8_t>(), h->y_doff.as<uint32_t>(), n + 1, 0u)));
+		CKR(stream_ensure(h, rng, 0));     // wait for the generator if it is still running
+		k_sync_scatter<<<g, 256, 0, h->st>>>(t.ci, Y, n); LAUNCHED(h);
+		CK(cudaMemsetAsync(h->d_flags, 0, 4 * sizeof(int), h->st));
+		k_sync_apply<<<g, 256, 0, h->st>>>(t.d, t.ci, Y, row, n, rng.buf, rng.cap - 1, rng.consumed, stream_avail(rng)); LAUNCHED(h);
+		k_sync_commit<<<g, 256, 0, h->st>>>(t.d, Y, n); LAUNCHED(h);
+		uint32_t *hs = (uint32_t *) h->h_small;
+		CK(cudaMemcpyAsync(hs, h->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+		CK(cudaMemcpyAsync(hs + 8, h->y_doff.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaStreamSynchronize(h->st));
+		resolve_phases(h);
+		int fl[8]; memcpy(fl, hs, sizeof fl);
+		total_draws = hs[8];
+		if (fl[7]) {   // a hot k-mer occurs more than SYNC_GROUP_CAP times in this row: sorted path for the whole row
+			k_sync_unclaim<<<g, 256, 0, h->st>>>(t.d, Y, n); LAUNCHED(h);
+			return apply_inserts(h, t, rng, row, n);
+		}
+		if (fl[0]) { CKR(stream_ensure(h, rng, (uint64_t) total_draws + (1u << 16))); continue; }
+		if (!fl[2]) break;
+	}
+	rng.consumed += total_draws;
+	return FQSK_OK;
+}
+
+// build an index for a plain row (no segment behind it) and insert it
+int apply_row(fqsk_handle *h, Table &t, Stream &rng, const unsigned long long *row, uint32_t n) {
+	if (!n) return FQSK_OK;
+	uint32_t slots = 1024;
+	while (slots < 2 * n) slots <<= 1;
+	CK(h->idx_k.ensure((size_t) slots * 8)); CK(h->idx_t.ensure((size_t) slots * 4)); CK(h->idx_rt.ensure((size_t) n * 4));
+	CK(cudaMemsetAsync(h->idx_t.p, 0xFF, (size_t) slots * 4, h->st));
+	k_row_index_build<<<nblk(n, 256), 256, 0, h->st>>>(h->idx_k.as<unsigned long long>(), h->idx_t.as<uint32_t>(), slots - 1, t.d.k, 1, row, n, h->idx_rt.as<uint32_t>()); LAUNCHED(h);
+	DeltaDev D{h->idx_k.as<unsigned long long>(), h->idx_t.as<uint32_t>(), slots - 1, n, t.d.k, 1, t.ci.thr + 1};
+	return apply_indexed(h, t, rng, D, row, h->idx_rt.as<uint32_t>(), n);
+}
+
 EngineDev make_engine_dev(fqsk_handle *h) {
 	EngineDev E{};
 	E.hb = h->tb.d; E.hs = h->ts.d; E.siv = h->siv; E.cib = h->tb.ci; E.cis = h->ts.ci;
@@ -397,16 +462,18 @@ EngineDev make_engine_dev(fqsk_handle *h) {
 	return E;
 }
 
+const uint32_t SYNC_INDEXED_MAX = 400000;
 const int RC_RETRY = 1;   // internal: a capacity was too small, grow and redo the segment
 
 // ---------------------------------------------------------------------------------------------------------------
 // one sync segment, reads resident on the device.  All counts stay on the device; kernels are
 // launched from host-side upper bounds and the host looks at the device twice per segment.
 // ---------------------------------------------------------------------------------------------------------------
-int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes, uint32_t first) {
-	const size_t n1 = (size_t) n + 1;
-	const uint32_t rec_bound = (uint32_t) dna_bytes;                 // coded positions <= DNA bytes
-	const size_t r1 = (size_t) rec_bound + 1;
+int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes_actual, uint32_t first) {
+	const uint64_t dna_bytes = std::max<uint64_t>(dna_bytes_actual, h->P.reserve_bytes);   // scratch sized once for the largest segment
+	const size_t n1 = (size_t) std::max<uint32_t>(n, h->P.reserve_reads) + 1;
+	const uint32_t rec_bound = (uint32_t) dna_bytes_actual;          // coded positions <= DNA bytes
+	const size_t r1 = (size_t) dna_bytes + 1;
 	const uint32_t pslots = h->P.bmer_len - h->P.pmer_len + 1;
 	CK(h->prov.ensure(r1 * sizeof(fqsk_base_rec))); CK(h->recs.ensure(r1 * sizeof(fqsk_base_rec))); CK(h->pflags.ensure(r1));
 	CK(h->rkind.ensure(r1)); CK(h->rreg.ensure(r1 * sizeof(KReg))); CK(h->rslot.ensure(r1 * 4)); CK(h->dirty.ensure(n1));
@@ -445,8 +512,14 @@ int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes, u
 	h->delta_b_valid = h->delta_s_valid = false;
 	const uint32_t t_b = std::max<uint32_t>(h->P.bmer_len - h->P.smer_len - 1, 1), t_s = std::max<uint32_t>(h->P.smer_len - h->P.pmer_len + 1, 1);
 	uint32_t slots_b = 1024, slots_s = 1024;
-	while (slots_b < 4 * dna_bytes) slots_b <<= 1;      // at most 2 b pushes per base, half-full table
-	while (slots_s < 2 * dna_bytes) slots_s <<= 1;
+	while (slots_b < 4 * dna_bytes_actual) slots_b <<= 1;      // at most 2 b pushes per base, half-full table
+	while (slots_s < 2 * dna_bytes_actual) slots_s <<= 1;
+	{
+		size_t rb = 1024, rs = 1024;
+		while (rb < 4 * dna_bytes) rb <<= 1;
+		while (rs < 2 * dna_bytes) rs <<= 1;
+		CK(h->dk_b.ensure(rb * 8)); CK(h->stime_b.ensure(rb * 4)); CK(h->dk_s.ensure(rs * 8)); CK(h->stime_s.ensure(rs * 4));
+	}
 	auto build_delta = [&]() -> int {
 		Phase ph(h, FQSK_PH_SORT);
 		CK(h->dk_b.ensure((size_t) slots_b * 8)); CK(h->stime_b.ensure((size_t) slots_b * 4));
@@ -463,73 +536,73 @@ int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes, u
 	const uint32_t max_it = h->P.max_iterations ? h->P.max_iterations : 16;
 	int fl[8];
 	uint32_t cnt[4];
-	// walk 0 on every read, then (speculatively) the thread-local pass: delta, k_local, walk 1 on the reads it touched
+	unsigned long long draws2[2] = {0, 0};
+	// Fixed launch schedule, ONE host look at the end: walk 0 on every read, the thread-local pass (delta, k_local, walk 1 on
+	// the reads it touched), compaction, rough searches, ordered merges.  If the look shows that walk 1 changed pushes
+	// (rare) the thread-local pass and everything after it is repeated; if only the merge offsets moved, only the merges.
 	{ Phase ph(h, FQSK_PH_WALK); k_walk<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(E, S, P, 0); LAUNCHED(h); ++h->S.n_replays; }
-	for (uint32_t it = 1;; ++it) {
-		if (it >= max_it) return fail(h, FQSK_E_NO_CONVERGE, "segment did not reach its fixed point in %u iterations", max_it);
-		CK(cudaMemsetAsync(h->d_flags + 2, 0, sizeof(int), h->st));
-		CKR(build_delta());
-		{ Phase ph(h, FQSK_PH_LOCAL); k_local<<<std::min<uint32_t>(nblk(std::max<uint32_t>(h->miss_cap, 1), 128), 148 * 16), 128, 0, h->st>>>(E, S, P); LAUNCHED(h); }
-		{ Phase ph(h, FQSK_PH_WALK); k_walk<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(E, S, P, it); LAUNCHED(h); ++h->S.n_replays; }
-		uint32_t *hs = (uint32_t *) h->h_small;
-		CK(cudaMemcpyAsync(hs, h->d_u32, 4 * 4, cudaMemcpyDeviceToHost, h->st));
-		CK(cudaMemcpyAsync(hs + 8, h->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+	uint32_t it = 0;
+	bool redo_walk = true, redo_tail = true;
+	for (uint32_t pass = 0;; ++pass) {
+		if (pass > 64) return fail(h, FQSK_E_NO_CONVERGE, "segment did not settle");
+		if (redo_walk) {
+			if (++it >= max_it) return fail(h, FQSK_E_NO_CONVERGE, "segment did not reach its fixed point in %u iterations", max_it);
+			CK(cudaMemsetAsync(h->d_flags + 2, 0, sizeof(int), h->st));
+			CKR(build_delta());
+			{ Phase ph(h, FQSK_PH_LOCAL); k_local<<<std::min<uint32_t>(nblk(std::max<uint32_t>(h->miss_cap, 1), 128), 148 * 16), 128, 0, h->st>>>(E, S, P); LAUNCHED(h); }
+			{ Phase ph(h, FQSK_PH_WALK); k_walk<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(E, S, P, it); LAUNCHED(h); ++h->S.n_replays; }
+		}
+		if (redo_tail) {
+			{
+				Phase ph(h, FQSK_PH_COMPACT);
+				k_scan_u32x4<<<1, 1024, 0, h->st>>>(n, h->cnt_b.as<uint32_t>(), h->off_b[0].as<uint32_t>(), h->cnt_s.as<uint32_t>(), h->off_s[0].as<uint32_t>(),
+				                                     h->cnt_p.as<uint32_t>(), h->off_p.as<uint32_t>(), h->hidden.as<uint32_t>(), nullptr, d_tot4);
+				LAUNCHED(h);
+				k_compact2<<<n, 64, 0, h->st>>>(S, P, h->off_b[0].as<uint32_t>(), h->off_s[0].as<uint32_t>(), h->off_p.as<uint32_t>(),
+				                               h->row_b[0].as<unsigned long long>(), h->row_s[0].as<unsigned long long>(), h->row_p.as<unsigned long long>(),
+				                               h->rt_b[0].as<uint32_t>(), h->rt_s[0].as<uint32_t>());
+				LAUNCHED(h);
+			}
+			CK(cudaMemsetAsync(h->d_u32 + 1, 0, 4, h->st));      // rough scripts are rebuilt
+			{ Phase ph(h, FQSK_PH_ROUGH); k_rough<<<148 * 8, 128, 0, h->st>>>(E, P); LAUNCHED(h); }
+			{ Phase ph(h, FQSK_PH_FOLD); k_fold<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(E, S, P, 0); LAUNCHED(h); }
+		}
+		{
+			Phase ph(h, FQSK_PH_FOLD);
+			k_scan_draws<<<1, 1024, 0, h->st>>>(n, P.rdraws_b, h->doff_b.as<unsigned long long>(), P.rdraws_s, h->doff_s.as<unsigned long long>(), d_draw2); LAUNCHED(h);
+			CK(cudaMemsetAsync(h->d_flags + 0, 0, sizeof(int), h->st)); CK(cudaMemsetAsync(h->d_flags + 7, 0, sizeof(int), h->st));
+			k_fold<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(E, S, P, 1); LAUNCHED(h);
+		}
+		uint8_t *hs = (uint8_t *) h->h_small;
+		CK(cudaMemcpyAsync(hs, h->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+		CK(cudaMemcpyAsync(hs + 32, d_draw2, 16, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaMemcpyAsync(hs + 48, d_tot4, 16, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaMemcpyAsync(hs + 64, d_tot, 48, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaMemcpyAsync(hs + 128, h->d_u32, 16, cudaMemcpyDeviceToHost, h->st));
 		CK(cudaStreamSynchronize(h->st));
 		resolve_phases(h);
-		memcpy(cnt, hs, sizeof cnt); memcpy(fl, hs + 8, sizeof fl);
+		memcpy(fl, hs, sizeof fl); memcpy(draws2, hs + 32, 16); memcpy(cnt, hs + 128, 16);
 		if (fl[4]) {
 			if (cnt[0] > h->miss_cap) h->miss_cap = cnt[0] + cnt[0] / 4 + 1024;
+			if (cnt[1] > h->rreq_cap) h->rreq_cap = cnt[1] + cnt[1] / 4 + 1024;
 			if (cnt[2] > h->pool_cap) h->pool_cap = cnt[2] + cnt[2] / 2 + 1024;
 			return RC_RETRY;
 		}
 		if (fl[5]) return fail(h, FQSK_E_CUDA, "internal error: a draw was requested on a path that must not draw");
 		if (fl[1]) return fail(h, FQSK_E_UNSUPPORTED, "segment needs the thread-local PRNG streams (a k-mer occurs more than %u times inside one sync segment and is looked up there, or a thread-local merge exceeds the deterministic range); not implemented yet", h->tb.ci.thr + 1);
-		if (!fl[2]) break;        // the re-walked reads reproduced their pushes: fixed point
-	}
-	// compaction of the converged pushes, rough searches, ordered merges
-	{
-		Phase ph(h, FQSK_PH_COMPACT);
-		k_scan_u32x4<<<1, 1024, 0, h->st>>>(n, h->cnt_b.as<uint32_t>(), h->off_b[0].as<uint32_t>(), h->cnt_s.as<uint32_t>(), h->off_s[0].as<uint32_t>(),
-		                                     h->cnt_p.as<uint32_t>(), h->off_p.as<uint32_t>(), h->hidden.as<uint32_t>(), nullptr, d_tot4);
-		LAUNCHED(h);
-		k_compact2<<<n, 64, 0, h->st>>>(S, P, h->off_b[0].as<uint32_t>(), h->off_s[0].as<uint32_t>(), h->off_p.as<uint32_t>(),
-		                               h->row_b[0].as<unsigned long long>(), h->row_s[0].as<unsigned long long>(), h->row_p.as<unsigned long long>(),
-		                               h->rt_b[0].as<uint32_t>(), h->rt_s[0].as<uint32_t>());
-		LAUNCHED(h);
-	}
-	h->cur = 0;
-	{ Phase ph(h, FQSK_PH_ROUGH); k_rough<<<148 * 8, 128, 0, h->st>>>(E, P); LAUNCHED(h); }
-	unsigned long long draws2[2] = {0, 0};
-	{
-		Phase ph(h, FQSK_PH_FOLD);
-		k_fold<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(E, S, P, 0); LAUNCHED(h);
-		for (int it = 0;; ++it) {
-			if (it > 32) return fail(h, FQSK_E_NO_CONVERGE, "draw offsets of the merge scripts did not settle");
-			k_scan_draws<<<1, 1024, 0, h->st>>>(n, P.rdraws_b, h->doff_b.as<unsigned long long>(), P.rdraws_s, h->doff_s.as<unsigned long long>(), d_draw2); LAUNCHED(h);
-			CK(cudaMemsetAsync(h->d_flags, 0, 4 * sizeof(int), h->st));
-			k_fold<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(E, S, P, 1); LAUNCHED(h);
-			uint8_t *hs = (uint8_t *) h->h_small;
-			CK(cudaMemcpyAsync(hs, h->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
-			CK(cudaMemcpyAsync(hs + 32, d_draw2, 16, cudaMemcpyDeviceToHost, h->st));
-			CK(cudaMemcpyAsync(hs + 48, d_tot4, 16, cudaMemcpyDeviceToHost, h->st));
-			CK(cudaMemcpyAsync(hs + 64, d_tot, 48, cudaMemcpyDeviceToHost, h->st));
-			CK(cudaMemcpyAsync(hs + 128, h->d_u32, 16, cudaMemcpyDeviceToHost, h->st));
-			CK(cudaStreamSynchronize(h->st));
-			resolve_phases(h);
-			memcpy(fl, hs, sizeof fl); memcpy(draws2, hs + 32, 16); memcpy(cnt, hs + 128, 16);
-			if (fl[4]) {   // rough script list or overflow pool too small
-				if (cnt[1] > h->rreq_cap) h->rreq_cap = cnt[1] + cnt[1] / 4 + 1024;
-				if (cnt[2] > h->pool_cap) h->pool_cap = cnt[2] + cnt[2] / 2 + 1024;
-				return RC_RETRY;
-			}
-			if (fl[0]) {   // the pre-generated draw window was too short: extend and evaluate again
-				CKR(stream_ensure(h, h->rng[ST_B], draws2[0] + (1u << 16))); CKR(stream_ensure(h, h->rng[ST_S], draws2[1] + (1u << 12)));
-				E = make_engine_dev(h);
-				continue;
-			}
-			if (!fl[2]) break;
+		if (fl[2]) { redo_walk = true; redo_tail = true; continue; }      // walk `it` changed pushes: one more thread-local pass
+		redo_walk = false;
+		if (fl[0]) {   // the pre-generated draw window was too short: extend and evaluate the merges again
+			CKR(stream_ensure(h, h->rng[ST_B], draws2[0] + (1u << 16))); CKR(stream_ensure(h, h->rng[ST_S], draws2[1] + (1u << 12)));
+			E = make_engine_dev(h);
+			redo_tail = false;
+			continue;
 		}
+		if (fl[7]) { redo_tail = false; continue; }                     // a counter saturated inside a merge: offsets moved, merge again
+		break;
 	}
+	h->seg_delta_b = S.delta_b; h->seg_delta_s = S.delta_s;
+	h->cur = 0;
 	{
 		uint8_t *hs = (uint8_t *) h->h_small;
 		uint32_t t4[4]; memcpy(t4, hs + 48, 16);
@@ -543,15 +616,16 @@ int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes, u
 	return FQSK_OK;
 }
 
-int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes, const unsigned long long *d_off, const uint32_t *d_len, uint32_t n) {
+int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual, const unsigned long long *d_off, const uint32_t *d_len, uint32_t n) {
+	const uint64_t dna_bytes = std::max<uint64_t>(dna_bytes_actual, h->P.reserve_bytes);
 	if (h->pending) return fail(h, FQSK_E_INVAL, "fqsk_segment called twice without fqsk_sync (the reference syncs after every segment, application.cpp:643-662)");
 	const uint32_t first = (h->P.mode == FQSK_MODE_SE_SORTED || h->P.mode == FQSK_MODE_PE_SORTED) ? h->P.pmer_len : h->P.prefix_len;
 	h->seg_reads = n; h->n_recs = 0; h->pend_b = h->pend_s = h->pend_p = 0;
 	++h->S.n_segments;
 	if (n == 0) { h->pending = true; return FQSK_OK; }
 	if (dna_bytes >= (1ull << 30)) return fail(h, FQSK_E_INVAL, "segment larger than 1 GiB of DNA");
-	const size_t n1 = (size_t) n + 1;
-	CK(h->dup.ensure(n)); CK(h->n_coded.ensure(n1 * 4)); CK(h->letters.ensure(n1 * 32)); CK(h->rec_off.ensure(n1 * 8)); CK(h->sl_prefix.ensure(n1 * 32));
+	const size_t n1 = (size_t) std::max<uint32_t>(n, h->P.reserve_reads) + 1;
+	CK(h->dup.ensure(n1)); CK(h->n_coded.ensure(n1 * 4)); CK(h->letters.ensure(n1 * 32)); CK(h->rec_off.ensure(n1 * 8)); CK(h->sl_prefix.ensure(n1 * 32));
 	CK(h->push_b.ensure((2 * dna_bytes + 2) * 8)); CK(h->push_s.ensure((dna_bytes + 1) * 8)); CK(h->push_p.ensure((2 * dna_bytes + 2 * n1) * 8));
 	CK(h->cnt_b.ensure(n1 * 4)); CK(h->cnt_s.ensure(n1 * 4)); CK(h->cnt_p.ensure(n1 * 4)); CK(h->hidden.ensure(n1 * 4));
 	CK(h->off_b[0].ensure(n1 * 4)); CK(h->off_s[0].ensure(n1 * 4));
@@ -574,7 +648,7 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes, const 
 		k_prep<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(S, first); LAUNCHED(h);
 		k_scan_reads<<<1, 1024, 0, h->st>>>(S, h->rec_off.as<unsigned long long>(), h->sl_prefix.as<U64x4>(), h->totals.as<SegTotals>(), h->d_u32 + 3); LAUNCHED(h);
 	}
-	const uint32_t rec_bound = (uint32_t) dna_bytes;
+	const uint32_t rec_bound = (uint32_t) dna_bytes;   // capacities follow the reserve as well
 	if (h->miss_cap < std::min<uint32_t>(rec_bound, 1u << 20)) h->miss_cap = std::min<uint32_t>(rec_bound, 1u << 20);
 	if (h->miss_cap < rec_bound / 4) h->miss_cap = rec_bound / 4 + 1024;
 	if (h->rreq_cap < std::min<uint32_t>(rec_bound, 1u << 20)) h->rreq_cap = std::min<uint32_t>(rec_bound, 1u << 20);
@@ -582,14 +656,14 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes, const 
 	CKR(stream_ensure(h, h->rng[ST_B], 1u << 16)); CKR(stream_ensure(h, h->rng[ST_S], 1u << 12));
 	for (int attempt = 0;; ++attempt) {
 		if (attempt > 8) return fail(h, FQSK_E_NOMEM, "segment buffers kept overflowing");
-		int rc = segment_attempt(h, S, n, dna_bytes, first);
+		int rc = segment_attempt(h, S, n, dna_bytes_actual, first);
 		if (rc == RC_RETRY) continue;
 		if (rc != FQSK_OK) return rc;
 		break;
 	}
 	for (int i = 0; i < 4; ++i) h->S.draws[i] = h->rng[i].consumed;
 	h->pending = true;
-	h->S.n_reads += n; h->S.n_bases += dna_bytes;
+	h->S.n_reads += n; h->S.n_bases += dna_bytes_actual;
 	return FQSK_OK;
 }
 
@@ -668,7 +742,9 @@ void fqsk_destroy(fqsk_handle *h) {
 	                  &h->cub_tmp, &h->flag8, &h->draw_off, &h->final_cnt, &h->slot_of, &h->dump_k, &h->dump_v, &h->q0, &h->q1,
 	                  &h->q2, &h->q3, &h->q4, &h->sflag, &h->sdif, &h->hid_scan, &h->prov, &h->pflags, &h->pscripts, &h->rscripts, &h->rreqs, &h->pool, &h->miss,
 	                  &h->draws_b16, &h->draws_s16, &h->doff_b, &h->doff_s, &h->time_b, &h->time_s, &h->rt_b[0], &h->rt_b[1], &h->rt_s[0], &h->rt_s[1],
-	                  &h->sidx_b, &h->sidx_s, &h->stime_b, &h->stime_s, &h->sort_k, &h->sort_v, &h->rkind, &h->rreg, &h->rslot, &h->dirty, &h->rdraws_b, &h->rdraws_s, &h->totals};
+	                  &h->sidx_b, &h->sidx_s, &h->stime_b, &h->stime_s, &h->sort_k, &h->sort_v, &h->rkind, &h->rreg, &h->rslot, &h->dirty, &h->rdraws_b, &h->rdraws_s, &h->totals,
+	                  &h->y_tslot, &h->y_c0, &h->y_m, &h->y_draw, &h->y_j, &h->y_final, &h->y_flag_at, &h->y_own, &h->y_lead, &h->y_rank, &h->y_flag, &h->y_doff,
+	                  &h->idx_k, &h->idx_t, &h->idx_rt};
 	if (h->d_u32) cudaFree(h->d_u32);
 	for (DevBuf *b : bufs) b->release();
 	if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -798,10 +874,11 @@ int fqsk_sync(fqsk_handle *h) {
 		h->S.siv_no_updates += h->pend_p + h->hidden_p;
 		h->hidden_p = 0;
 		// s-mers, then b-mers (dna.cpp:2425-2446)
-		if (h->delta_s_valid) CKR(apply_sorted(h, h->ts, h->rng[ST_S], h->dk_s.as<unsigned long long>(), h->sidx_s.as<uint32_t>(), h->pend_s));
-		else CKR(apply_inserts(h, h->ts, h->rng[ST_S], h->row_s[h->cur].as<unsigned long long>(), h->pend_s, &h->fast_ok[0]));
-		if (h->delta_b_valid) CKR(apply_sorted(h, h->tb, h->rng[ST_B], h->dk_b.as<unsigned long long>(), h->sidx_b.as<uint32_t>(), h->pend_b));
-		else CKR(apply_inserts(h, h->tb, h->rng[ST_B], h->row_b[h->cur].as<unsigned long long>(), h->pend_b, &h->fast_ok[1]));
+		// small rows: sort-free grouping through the segment's delta table (few launches); large rows: one radix sort is cheaper
+		if (h->pend_s <= SYNC_INDEXED_MAX) CKR(apply_indexed(h, h->ts, h->rng[ST_S], h->seg_delta_s, h->row_s[0].as<unsigned long long>(), h->rt_s[0].as<uint32_t>(), h->pend_s));
+		else CKR(apply_inserts(h, h->ts, h->rng[ST_S], h->row_s[0].as<unsigned long long>(), h->pend_s));
+		if (h->pend_b <= SYNC_INDEXED_MAX) CKR(apply_indexed(h, h->tb, h->rng[ST_B], h->seg_delta_b, h->row_b[0].as<unsigned long long>(), h->rt_b[0].as<uint32_t>(), h->pend_b));
+		else CKR(apply_inserts(h, h->tb, h->rng[ST_B], h->row_b[0].as<unsigned long long>(), h->pend_b));
 		h->delta_b_valid = h->delta_s_valid = false;
 		CKR(table_grow_if_needed(h, h->ts));
 		CKR(table_grow_if_needed(h, h->tb));
@@ -911,7 +988,7 @@ int fqsk_ht_insert(fqsk_handle *h, int table, const uint64_t *kmers, uint64_t n)
 	if (!n) return FQSK_OK;
 	CK(h->q3.ensure(n * 8));
 	CK(cudaMemcpyAsync(h->q3.p, kmers, n * 8, cudaMemcpyHostToDevice, h->st));
-	CKR(apply_inserts(h, *t, h->rng[table == FQSK_TABLE_SMER ? ST_S : ST_B], h->q3.as<unsigned long long>(), (uint32_t) n));
+	CKR(apply_row(h, *t, h->rng[table == FQSK_TABLE_SMER ? ST_S : ST_B], h->q3.as<unsigned long long>(), (uint32_t) n));
 	CKR(table_grow_if_needed(h, *t));
 	CK(cudaStreamSynchronize(h->st));
 	return FQSK_OK;

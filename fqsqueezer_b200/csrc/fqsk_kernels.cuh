@@ -227,6 +227,135 @@ __global__ void k_commit_keys(HtDev t, const unsigned long long *skeys, uint32_t
 	ht_slot_set(t, slot_of[i] & ~(1ull << 63), final_cnt[i]);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// sort-free ordered insert: the segment's delta table already holds every push as (k-mer, push time) with all entries of
+// one k-mer in one probe run, so an occurrence gets its group size m and its exact push-order rank from that run.
+//   k_sync_rank   per occurrence: m, rank, own / leader entry; the leader (rank 0) does the ONE find-or-create of the group
+//   k_sync_flags  per occurrence: cold group (c0 + m <= thr + 1: all increments deterministic) -> leader records c0 + m;
+//                 hot group -> draw flag in push order (pre-count c0 + rank > thr)
+//   (exclusive scan of the flags = absolute draw indices in push order)
+//   k_sync_scatter  per hot occurrence: draw index / flag stored at its delta entry
+//   k_sync_apply  per hot leader: members in time order, Increment() with the scanned draws; verifies the flags against the
+//                 counters it sees (they differ only when a counter saturates inside the batch) and reports a change
+//   k_sync_commit leaders write the final counters
+// ------------------------------------------------------------------------------------------------------------------
+struct SyncDev {
+	DeltaDev D;
+	unsigned long long *lead_tslot; uint32_t *lead_c0, *lead_m, *draw_at, *j_at, *final_at; uint8_t *flag_at;   // per delta slot
+	uint32_t *own, *lead, *rank; uint8_t *flag; const uint32_t *draw_off;                                       // per occurrence
+	int *flags;   // [2] changed, [0] draw window short, [7] a hot group is too large for the in-thread path
+};
+static const uint32_t SYNC_GROUP_CAP = 48;
+
+__global__ void k_sync_rank(HtDev t, SyncDev Y, const unsigned long long *row, const uint32_t *rt, uint32_t n) {
+	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n) return;
+	const unsigned long long x = row[j];
+	const uint32_t tm = rt[j];
+	uint32_t m = 0, rank = 0, own = 0xFFFFFFFFu, lead = 0xFFFFFFFFu, lead_t = 0xFFFFFFFFu;
+	for (uint64_t slot = delta_slot_of_key(x, Y.D.k, Y.D.t, Y.D.mask);; slot = (slot + 1) & Y.D.mask) {
+		uint32_t et = Y.D.times[slot];
+		if (et == DELTA_EMPTY) break;
+		if (Y.D.keys[slot] != x) continue;
+		++m;
+		if (et < tm) ++rank;
+		if (et == tm) own = (uint32_t) slot;
+		if (et < lead_t) { lead_t = et; lead = (uint32_t) slot; }
+	}
+	Y.own[j] = own; Y.lead[j] = lead; Y.rank[j] = rank;
+	Y.j_at[own] = j;
+	if (rank == 0) {
+		bool created;
+		uint64_t ts = ht_locate(t, x, created);
+		Y.lead_tslot[own] = ts | (created ? (1ull << 63) : 0ull);
+		Y.lead_c0[own] = created ? 0u : ht_slot_get(t, ts);
+		Y.lead_m[own] = m;
+	}
+}
+__global__ void k_sync_flags(HtDev t, CIncP ci, SyncDev Y, uint32_t n) {
+	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n) return;
+	const uint32_t L = Y.lead[j], c0 = Y.lead_c0[L], m = Y.lead_m[L], rank = Y.rank[j];
+	uint8_t f = 0;
+	if (c0 + m <= ci.thr + 1) { if (rank == 0) Y.final_at[L] = c0 + m; }    // cold group
+	else {
+		f = (c0 + rank > ci.thr) ? 1 : 0;
+		if (rank == 0 && m > SYNC_GROUP_CAP) Y.flags[7] = 1;
+	}
+	Y.flag[j] = f;
+}
+__global__ void k_sync_scatter(CIncP ci, SyncDev Y, uint32_t n) {
+	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n) return;
+	const uint32_t L = Y.lead[j];
+	if (Y.lead_c0[L] + Y.lead_m[L] <= ci.thr + 1) return;
+	const uint32_t own = Y.own[j];
+	Y.draw_at[own] = Y.draw_off[j];
+	Y.flag_at[own] = Y.flag[j];
+}
+__global__ void k_sync_apply(HtDev t, CIncP ci, SyncDev Y, const unsigned long long *row, uint32_t n,
+                             const uint32_t *draws, unsigned long long dmask, unsigned long long dpos, unsigned long long avail) {
+	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n) return;
+	if (Y.rank[j] != 0) return;
+	const uint32_t L = Y.own[j];
+	const uint32_t c0 = Y.lead_c0[L], m = Y.lead_m[L];
+	if (c0 + m <= ci.thr + 1 || m > SYNC_GROUP_CAP) return;
+	// members of the group in time order
+	const unsigned long long x = row[j];
+	uint32_t mt[SYNC_GROUP_CAP], ms[SYNC_GROUP_CAP];
+	uint32_t k = 0;
+	for (uint64_t slot = delta_slot_of_key(x, Y.D.k, Y.D.t, Y.D.mask);; slot = (slot + 1) & Y.D.mask) {
+		uint32_t et = Y.D.times[slot];
+		if (et == DELTA_EMPTY) break;
+		if (Y.D.keys[slot] != x) continue;
+		uint32_t q = k++;
+		while (q > 0 && mt[q - 1] > et) { mt[q] = mt[q - 1]; ms[q] = ms[q - 1]; --q; }
+		mt[q] = et; ms[q] = (uint32_t) slot;
+	}
+	uint32_t c = c0;
+	for (uint32_t q = 0; q < k; ++q) {
+		const uint32_t ds = ms[q];
+		uint8_t fl = Y.flag_at[ds];
+		uint8_t want;
+		if (c >= t.top) want = 0;                       // ht_kmer.h:435: cnt < counter_max
+		else if (c <= ci.thr) want = 0;
+		else want = 1;
+		if (fl != want) { Y.flag[Y.j_at[ds]] = want; Y.flags[2] = 1; if (c < t.top && c <= ci.thr) ++c; continue; }
+		if (c >= t.top) continue;
+		if (c <= ci.thr) { ++c; continue; }
+		uint32_t di = Y.draw_at[ds];
+		if (di >= avail) { Y.flags[0] = 1; continue; }
+		if (draws[(dpos + di) & dmask] % (ci.mult * (c - ci.thr)) == 0) ++c;
+	}
+	Y.final_at[L] = c;
+}
+__global__ void k_sync_commit(HtDev t, SyncDev Y, uint32_t n) {
+	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n) return;
+	if (Y.rank[j] != 0) return;
+	if (Y.flags[7] || Y.flags[2] || Y.flags[0]) return;     // not settled: the host iterates or falls back, nothing is written
+	const uint32_t L = Y.own[j];
+	ht_slot_set(t, Y.lead_tslot[L] & ~(1ull << 63), Y.final_at[L]);
+}
+// fallback preparation: slots claimed by k_sync_rank (counter 1) become zero-count items, i.e. the reference's fresh slot
+__global__ void k_sync_unclaim(HtDev t, SyncDev Y, uint32_t n) {
+	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n) return;
+	if (Y.rank[j] != 0) return;
+	unsigned long long ts = Y.lead_tslot[Y.own[j]];
+	if (ts >> 63) ht_slot_set(t, ts & ~(1ull << 63), 0);
+}
+// index of a plain row (table-level API): entry time = push index
+__global__ void k_row_index_build(unsigned long long *keys, uint32_t *times, uint32_t mask, uint32_t k, uint32_t t, const unsigned long long *row, uint32_t n, uint32_t *rt) {
+	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n) return;
+	unsigned long long x = row[j];
+	rt[j] = j;
+	for (uint64_t slot = delta_slot_of_key(x, k, t, mask);; slot = (slot + 1) & mask)
+		if (atomicCAS(times + slot, DELTA_EMPTY, j) == DELTA_EMPTY) { keys[slot] = x; return; }
+}
+
 // Fast path of the sync step: every occurrence does find-or-create and one atomic +1.  That equals the reference's ordered
 // Increment()s exactly when no counter leaves the deterministic range (pre-count <= thr for every occurrence, utils.h:317-318);
 // any occurrence that sees a pre-count above thr raises flags[2] and the host undoes the pass (k_insert_undo: the adds are

@@ -71,6 +71,7 @@ struct PipeDev {
 	uint32_t *time_b, *time_s;      // per-read regions parallel to push_b / push_s
 	int *flags;                     // [0] draw overflow [1] unsupported [2] changed [3] window consulted the local tables
 	                                // [4] capacity overflow (pool / miss / rough lists) [5] internal: draw in a no-draw path [6] k_local hit
+	                                // [7] k_fold: a read's draw count differs from the scanned one
 };
 
 __device__ __forceinline__ uint32_t sym_at(const SegDev &S, const EngineDev &E, const uint8_t *p, uint32_t j) {
@@ -752,7 +753,7 @@ __global__ void __launch_bounds__(128) k_fold(EngineDev E, SegDev S, PipeDev P, 
 	}
 	if (lane) return;
 	if (pass == 0) { P.rdraws_b[r] = db.used; P.rdraws_s[r] = ds.used; return; }
-	if (P.rdraws_b[r] != db.used || P.rdraws_s[r] != ds.used) { P.rdraws_b[r] = db.used; P.rdraws_s[r] = ds.used; P.flags[2] = 1; }
+	if (P.rdraws_b[r] != db.used || P.rdraws_s[r] != ds.used) { P.rdraws_b[r] = db.used; P.rdraws_s[r] = ds.used; P.flags[7] = 1; }
 }
 
 // ------------------------------------------------------------------------------------------------------------------

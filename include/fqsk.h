@@ -56,6 +56,8 @@ typedef struct fqsk_params {
 	uint32_t world_size, rank;
 	uint32_t max_iterations;     /* fix-point limit per segment, 0 = default (16) */
 	uint32_t flags;              /* FQSK_F_* */
+	uint32_t reserve_reads;      /* optional: largest segment the caller will submit (reads / DNA bytes); scratch is allocated once */
+	uint32_t reserve_bytes;
 } fqsk_params;
 
 #define FQSK_F_PROFILE 1u        /* record CUDA-event timings per internal phase (fqsk_profile) */
