@@ -66,6 +66,7 @@ struct fqsk_handle {
 	Table tb, ts;
 	SivDev siv{};
 	Stream rng[4];
+	uint8_t *d_status = nullptr;         // one 512-byte block read by the host in ONE copy: flags | counters | segment totals
 	int *d_flags = nullptr;              // 8 ints
 	unsigned long long *d_counters = nullptr;  // [0,1] b items main/stash, [2,3] s items, [4] siv new, [5] dump count
 	fqsk_stats S{};
@@ -498,9 +499,9 @@ int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes_ac
 	P.time_b = h->time_b.as<uint32_t>(); P.time_s = h->time_s.as<uint32_t>();
 	P.flags = h->d_flags; P.n_rec_dev = h->d_u32 + 3;
 	S.recs = P.recs;
-	SegTotals *d_tot = h->totals.as<SegTotals>();
-	uint32_t *d_tot4 = (uint32_t *) (h->totals.as<uint8_t>() + 128);          // tot_b, tot_s, tot_p, hidden
-	unsigned long long *d_draw2 = (unsigned long long *) (h->totals.as<uint8_t>() + 160);
+	SegTotals *d_tot = (SegTotals *) (h->d_status + 64);                       // +64  : SegTotals (72 bytes)
+	uint32_t *d_tot4 = (uint32_t *) (h->d_status + 192);                        // +192 : tot_b, tot_s, tot_p, hidden
+	unsigned long long *d_draw2 = (unsigned long long *) (h->d_status + 208);   // +208 : draws b, s
 
 	EngineDev E = make_engine_dev(h);
 	CK(cudaMemsetAsync(h->d_u32, 0, 3 * 4, h->st));
@@ -574,14 +575,10 @@ int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes_ac
 			k_fold<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(E, S, P, 1); LAUNCHED(h);
 		}
 		uint8_t *hs = (uint8_t *) h->h_small;
-		CK(cudaMemcpyAsync(hs, h->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
-		CK(cudaMemcpyAsync(hs + 32, d_draw2, 16, cudaMemcpyDeviceToHost, h->st));
-		CK(cudaMemcpyAsync(hs + 48, d_tot4, 16, cudaMemcpyDeviceToHost, h->st));
-		CK(cudaMemcpyAsync(hs + 64, d_tot, 48, cudaMemcpyDeviceToHost, h->st));
-		CK(cudaMemcpyAsync(hs + 128, h->d_u32, 16, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaMemcpyAsync(hs, h->d_status, 256, cudaMemcpyDeviceToHost, h->st));
 		CK(cudaStreamSynchronize(h->st));
 		resolve_phases(h);
-		memcpy(fl, hs, sizeof fl); memcpy(draws2, hs + 32, 16); memcpy(cnt, hs + 128, 16);
+		memcpy(fl, hs, sizeof fl); memcpy(draws2, hs + 208, 16); memcpy(cnt, hs + 32, 16);
 		if (fl[4]) {
 			if (cnt[0] > h->miss_cap) h->miss_cap = cnt[0] + cnt[0] / 4 + 1024;
 			if (cnt[1] > h->rreq_cap) h->rreq_cap = cnt[1] + cnt[1] / 4 + 1024;
@@ -605,8 +602,8 @@ int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes_ac
 	h->cur = 0;
 	{
 		uint8_t *hs = (uint8_t *) h->h_small;
-		uint32_t t4[4]; memcpy(t4, hs + 48, 16);
-		SegTotals tt; memcpy(&tt, hs + 64, 48);
+		uint32_t t4[4]; memcpy(t4, hs + 192, 16);
+		SegTotals tt; memcpy(&tt, hs + 64, sizeof tt);
 		h->pend_b = t4[0]; h->pend_s = t4[1]; h->pend_p = t4[2];
 		h->hidden_p += t4[3];
 		for (int i = 0; i < 4; ++i) h->sl_base[i] += tt.letters.v[i];
@@ -646,7 +643,7 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 	{
 		Phase ph(h, FQSK_PH_PREP);
 		k_prep<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(S, first); LAUNCHED(h);
-		k_scan_reads<<<1, 1024, 0, h->st>>>(S, h->rec_off.as<unsigned long long>(), h->sl_prefix.as<U64x4>(), h->totals.as<SegTotals>(), h->d_u32 + 3); LAUNCHED(h);
+		k_scan_reads<<<1, 1024, 0, h->st>>>(S, h->rec_off.as<unsigned long long>(), h->sl_prefix.as<U64x4>(), (SegTotals *) (h->d_status + 64), h->d_u32 + 3); LAUNCHED(h);
 	}
 	const uint32_t rec_bound = (uint32_t) dna_bytes;   // capacities follow the reserve as well
 	if (h->miss_cap < std::min<uint32_t>(rec_bound, 1u << 20)) h->miss_cap = std::min<uint32_t>(rec_bound, 1u << 20);
@@ -698,11 +695,12 @@ int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
 	int rc = [&]() -> int {
 		CK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
 		CK(cudaStreamCreateWithFlags(&h->st_mt, cudaStreamNonBlocking));
-		CK(cudaMalloc(&h->d_flags, 8 * sizeof(int)));
+		CK(cudaMalloc(&h->d_status, 512)); CK(cudaMemset(h->d_status, 0, 512));
+		h->d_flags = (int *) h->d_status;                       // +0   : 8 ints
+		h->d_u32 = (uint32_t *) (h->d_status + 32);              // +32  : 8 counters
 		CK(cudaMalloc(&h->d_counters, 8 * 8));
-		CK(cudaMalloc(&h->d_u32, 8 * 4));
 		CK(cudaMemset(h->d_counters, 0, 64));
-		CK(cudaMallocHost(&h->h_small, 256));
+		CK(cudaMallocHost(&h->h_small, 1024));
 		uint64_t expect = p->expected_kmers ? p->expected_kmers : (1ull << 22);
 		uint32_t Bauto = 1;
 		while ((4ull << Bauto) < expect && Bauto < 30) ++Bauto;    // <= 50 % of 8 << B slots
@@ -734,7 +732,7 @@ void fqsk_destroy(fqsk_handle *h) {
 	if (h->siv.w) cudaFree(h->siv.w);
 	if (h->st_mt) cudaStreamSynchronize(h->st_mt);
 	for (auto &s : h->rng) { if (s.buf) cudaFree(s.buf); if (s.state) cudaFree(s.state); if (s.ev) cudaEventDestroy(s.ev); }
-	if (h->d_flags) cudaFree(h->d_flags);
+	if (h->d_status) cudaFree(h->d_status);
 	if (h->d_counters) cudaFree(h->d_counters);
 	DevBuf *bufs[] = {&h->prev_read, &h->dna, &h->off, &h->len, &h->dup, &h->n_coded, &h->letters, &h->rec_off, &h->sl_prefix, &h->recs, &h->push_b, &h->push_s,
 	                  &h->push_p, &h->cnt_b, &h->cnt_s, &h->cnt_p, &h->hidden, &h->draw_cnt, &h->draw_cnt_prev, &h->draw_scan, &h->off_b[0], &h->off_b[1], &h->off_s[0],
@@ -745,7 +743,7 @@ void fqsk_destroy(fqsk_handle *h) {
 	                  &h->sidx_b, &h->sidx_s, &h->stime_b, &h->stime_s, &h->sort_k, &h->sort_v, &h->rkind, &h->rreg, &h->rslot, &h->dirty, &h->rdraws_b, &h->rdraws_s, &h->totals,
 	                  &h->y_tslot, &h->y_c0, &h->y_m, &h->y_draw, &h->y_j, &h->y_final, &h->y_flag_at, &h->y_own, &h->y_lead, &h->y_rank, &h->y_flag, &h->y_doff,
 	                  &h->idx_k, &h->idx_t, &h->idx_rt};
-	if (h->d_u32) cudaFree(h->d_u32);
+
 	for (DevBuf *b : bufs) b->release();
 	if (h->h_stage) cudaFreeHost(h->h_stage);
 	if (h->h_small) cudaFreeHost(h->h_small);
@@ -861,27 +859,30 @@ int fqsk_sync(fqsk_handle *h) {
 	CK(cudaSetDevice(h->P.device));
 	++h->S.n_syncs;
 	if (h->pending && h->seg_reads) {
-		// p-mers (dna.cpp:2401-2418)
+		// p-mers (dna.cpp:2401-2418): order-independent saturating increments; the fresh-field count is read with the next look
+		CK(cudaMemsetAsync(h->d_counters + 4, 0, 8, h->st));
 		if (h->pend_p) {
 			Phase ph(h, FQSK_PH_SYNC_SIV);
-			CK(cudaMemsetAsync(h->d_counters + 4, 0, 8, h->st));
 			k_siv_increment<<<nblk(h->pend_p, 256), 256, 0, h->st>>>(h->siv, h->row_p.as<unsigned long long>(), h->pend_p, h->d_counters + 4);
 			LAUNCHED(h);
-			CK(cudaMemcpyAsync(h->h_small, h->d_counters + 4, 8, cudaMemcpyDeviceToHost, h->st));
-			CK(cudaStreamSynchronize(h->st));
-			h->S.siv_no_filled += *(unsigned long long *) h->h_small;
 		}
-		h->S.siv_no_updates += h->pend_p + h->hidden_p;
-		h->hidden_p = 0;
 		// s-mers, then b-mers (dna.cpp:2425-2446)
 		// small rows: sort-free grouping through the segment's delta table (few launches); large rows: one radix sort is cheaper
 		if (h->pend_s <= SYNC_INDEXED_MAX) CKR(apply_indexed(h, h->ts, h->rng[ST_S], h->seg_delta_s, h->row_s[0].as<unsigned long long>(), h->rt_s[0].as<uint32_t>(), h->pend_s));
 		else CKR(apply_inserts(h, h->ts, h->rng[ST_S], h->row_s[0].as<unsigned long long>(), h->pend_s));
 		if (h->pend_b <= SYNC_INDEXED_MAX) CKR(apply_indexed(h, h->tb, h->rng[ST_B], h->seg_delta_b, h->row_b[0].as<unsigned long long>(), h->rt_b[0].as<uint32_t>(), h->pend_b));
 		else CKR(apply_inserts(h, h->tb, h->rng[ST_B], h->row_b[0].as<unsigned long long>(), h->pend_b));
-		h->delta_b_valid = h->delta_s_valid = false;
-		CKR(table_grow_if_needed(h, h->ts));
-		CKR(table_grow_if_needed(h, h->tb));
+		// one look: fresh p-mer fields and the item counters of both tables (growth check)
+		unsigned long long *hc = (unsigned long long *) h->h_small;
+		CK(cudaMemcpyAsync(hc, h->d_counters, 48, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaStreamSynchronize(h->st));
+		h->S.siv_no_filled += hc[4];
+		h->S.siv_no_updates += h->pend_p + h->hidden_p;
+		h->hidden_p = 0;
+		for (int k = 0; k < 2; ++k) {
+			Table &t = k ? h->tb : h->ts;
+			if (hc[2 - 2 * k] > (4ull << t.d.B) || hc[3 - 2 * k] > (1ull << t.d.stash_log2) / 2) CKR(table_grow_if_needed(h, t));
+		}
 	} else {
 		h->S.siv_no_updates += h->hidden_p;
 		h->hidden_p = 0;
@@ -889,7 +890,6 @@ int fqsk_sync(fqsk_handle *h) {
 	for (int i = 0; i < 4; ++i) h->S.draws[i] = h->rng[i].consumed;
 	CKR(stream_prefetch(h, h->rng[ST_B], 1u << 23)); CKR(stream_prefetch(h, h->rng[ST_S], 1u << 18));
 	h->pending = false; h->pend_b = h->pend_s = h->pend_p = 0; h->seg_reads = 0;
-	CK(cudaStreamSynchronize(h->st));
 	resolve_phases(h);
 	return FQSK_OK;
 }

@@ -626,9 +626,10 @@ __global__ void __launch_bounds__(128) k_rough(EngineDev E, PipeDev P) {
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
 	__shared__ Script stage[4];
 	Script &sc = stage[threadIdx.x >> 5];
-	for (uint32_t g0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; g0 < n_rec; g0 += warps * 32) {
-		// each warp owns 32 consecutive positions: find the flagged ones, then work on them one at a time with all lanes
-		uint32_t mine = g0 + lane < n_rec ? P.rkind[g0 + lane] : 0;
+	const uint32_t RCHUNK = 4;      // positions per warp iteration: small, so that a tiny segment still spreads over every SM
+	for (uint32_t g0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * RCHUNK; g0 < n_rec; g0 += warps * RCHUNK) {
+		// each warp owns RCHUNK consecutive positions: find the flagged ones, then work on them one at a time with all lanes
+		uint32_t mine = (lane < RCHUNK && g0 + lane < n_rec) ? P.rkind[g0 + lane] : 0;
 		unsigned todo = __ballot_sync(0xffffffffu, mine != 0);
 		while (todo) {
 			uint32_t q = __ffs(todo) - 1;
