@@ -375,14 +375,15 @@ int apply_inserts(fqsk_handle *h, Table &t, Stream &rng, const unsigned long lon
 	if (fast_ok && *fast_ok) {
 		Phase ph(h, FQSK_PH_SYNC_APPLY);
 		CK(cudaMemsetAsync(h->d_flags, 0, 8 * sizeof(int), h->st));
-		k_insert_fast<<<nblk(n, 256), 256, 0, h->st>>>(t.d, t.ci, d_kmers, n, h->d_flags); LAUNCHED(h);
+		CK(h->y_flag.ensure((size_t) n + 4));
+		k_insert_fast<<<nblk(n, 256), 256, 0, h->st>>>(t.d, t.ci, d_kmers, n, h->y_flag.as<uint8_t>(), h->d_flags); LAUNCHED(h);
 		int fl[8];
 		CKR(read_flags(h, fl, 8));
 		if (!fl[2]) return FQSK_OK;
 		// some counter left the deterministic range: undo (claimed slots stay as zero-count items == the reference's fresh slot) and
 		// take the ordered path from now on for this table (once counters are above thr they stay there)
-		k_insert_undo<<<nblk(n, 256), 256, 0, h->st>>>(t.d, d_kmers, n); LAUNCHED(h);
-		*fast_ok = false;
+		k_insert_undo<<<nblk(n, 256), 256, 0, h->st>>>(t.d, d_kmers, n, h->y_flag.as<uint8_t>()); LAUNCHED(h);
+		// this row goes through the ordered path; the next row tries the fast path again
 	}
 	CKR(sort_row(h, d_kmers, n, t.d.k, h->sort_k, h->sort_v));
 	return apply_sorted(h, t, rng, h->sort_k.as<unsigned long long>(), h->sort_v.as<uint32_t>(), n);
@@ -868,7 +869,9 @@ int fqsk_sync(fqsk_handle *h) {
 		}
 		// s-mers, then b-mers (dna.cpp:2425-2446)
 		// small rows: sort-free grouping through the segment's delta table (few launches); large rows: one radix sort is cheaper
-		if (h->pend_s <= SYNC_INDEXED_MAX) CKR(apply_indexed(h, h->ts, h->rng[ST_S], h->seg_delta_s, h->row_s[0].as<unsigned long long>(), h->rt_s[0].as<uint32_t>(), h->pend_s));
+		// s-mers: counters stay far below thr = 2047, so the single-kernel atomic path is (almost) always exact; it checks itself
+		if (h->fast_ok[0]) CKR(apply_inserts(h, h->ts, h->rng[ST_S], h->row_s[0].as<unsigned long long>(), h->pend_s, &h->fast_ok[0]));
+		else if (h->pend_s <= SYNC_INDEXED_MAX) CKR(apply_indexed(h, h->ts, h->rng[ST_S], h->seg_delta_s, h->row_s[0].as<unsigned long long>(), h->rt_s[0].as<uint32_t>(), h->pend_s));
 		else CKR(apply_inserts(h, h->ts, h->rng[ST_S], h->row_s[0].as<unsigned long long>(), h->pend_s));
 		if (h->pend_b <= SYNC_INDEXED_MAX) CKR(apply_indexed(h, h->tb, h->rng[ST_B], h->seg_delta_b, h->row_b[0].as<unsigned long long>(), h->rt_b[0].as<uint32_t>(), h->pend_b));
 		else CKR(apply_inserts(h, h->tb, h->rng[ST_B], h->row_b[0].as<unsigned long long>(), h->pend_b));
@@ -988,7 +991,10 @@ int fqsk_ht_insert(fqsk_handle *h, int table, const uint64_t *kmers, uint64_t n)
 	if (!n) return FQSK_OK;
 	CK(h->q3.ensure(n * 8));
 	CK(cudaMemcpyAsync(h->q3.p, kmers, n * 8, cudaMemcpyHostToDevice, h->st));
-	CKR(apply_row(h, *t, h->rng[table == FQSK_TABLE_SMER ? ST_S : ST_B], h->q3.as<unsigned long long>(), (uint32_t) n));
+	if (table == FQSK_TABLE_SMER) {   // same route as fqsk_sync: atomic fast path that checks itself, ordered path as the fallback
+		bool fast = true;
+		CKR(apply_inserts(h, *t, h->rng[ST_S], h->q3.as<unsigned long long>(), (uint32_t) n, &fast));
+	} else CKR(apply_row(h, *t, h->rng[ST_B], h->q3.as<unsigned long long>(), (uint32_t) n));
 	CKR(table_grow_if_needed(h, *t));
 	CK(cudaStreamSynchronize(h->st));
 	return FQSK_OK;

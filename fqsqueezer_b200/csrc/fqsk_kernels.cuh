@@ -360,22 +360,43 @@ __global__ void k_row_index_build(unsigned long long *keys, uint32_t *times, uin
 // Increment()s exactly when no counter leaves the deterministic range (pre-count <= thr for every occurrence, utils.h:317-318);
 // any occurrence that sees a pre-count above thr raises flags[2] and the host undoes the pass (k_insert_undo: the adds are
 // plain arithmetic on the item, so subtracting them restores every bit) and runs the ordered path instead.
-__global__ void k_insert_fast(HtDev t, CIncP ci, const unsigned long long *kmers, uint32_t n, int *flags) {
+__global__ void k_insert_fast(HtDev t, CIncP ci, const unsigned long long *kmers, uint32_t n, uint8_t *added, int *flags) {
 	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
 	if (j >= n) return;
 	bool created;
 	uint64_t s = ht_locate(t, kmers[j], created);
-	if (created) return;            // claimed with counter 1 == Increment(0)
+	added[j] = created ? 2 : 0;     // 2: this occurrence claimed the slot (counter 1 == Increment(0)), 1: it added one, 0: nothing
+	if (created) return;
+	// +1 unless the counter field is full (a carry would corrupt the key bits other lookups are comparing right now)
 	uint64_t nm = 8ull << t.B;
-	uint32_t old = s < nm ? (atomicAdd(t.main + s, 1u) & t.top) : (uint32_t) (atomicAdd(t.stash + (s - nm), 1ull) & t.top);
-	if (old > ci.thr) flags[2] = 1;
+	if (s < nm) {
+		uint32_t *p = t.main + s;
+		uint32_t old = *((volatile uint32_t *) p);
+		for (;;) {
+			if ((old & t.top) > ci.thr) { flags[2] = 1; if ((old & t.top) >= t.top) return; }
+			uint32_t seen = atomicCAS(p, old, old + 1);
+			if (seen == old) { added[j] = 1; return; }
+			old = seen;
+		}
+	} else {
+		unsigned long long *p = t.stash + (s - nm);
+		unsigned long long old = *((volatile unsigned long long *) p);
+		for (;;) {
+			if ((uint32_t) (old & t.top) > ci.thr) { flags[2] = 1; if ((uint32_t) (old & t.top) >= t.top) return; }
+			unsigned long long seen = atomicCAS(p, old, old + 1);
+			if (seen == old) { added[j] = 1; return; }
+			old = seen;
+		}
+	}
 }
-__global__ void k_insert_undo(HtDev t, const unsigned long long *kmers, uint32_t n) {
+__global__ void k_insert_undo(HtDev t, const unsigned long long *kmers, uint32_t n, const uint8_t *added) {
 	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
 	if (j >= n) return;
 	bool created;
 	uint64_t s = ht_locate(t, kmers[j], created);   // every key exists now
 	uint64_t nm = 8ull << t.B;
+	if (!added[j]) return;      // met a full counter: nothing to take back
+	// an add, or the claim of a new slot (counter 1 -> zero-count item == the reference's fresh slot)
 	if (s < nm) atomicSub(t.main + s, 1u); else atomicAdd(t.stash + (s - nm), ~0ull);
 }
 
