@@ -800,6 +800,17 @@ int fqsk_device_recs(fqsk_handle *h, const fqsk_base_rec **d_recs, uint64_t *n_r
 	return FQSK_OK;
 }
 
+int fqsk_sorted_prefix(fqsk_handle *h, uint32_t *flag, uint64_t *dif, uint32_t n_reads) {
+	if (!h || !flag || !dif) return FQSK_E_INVAL;
+	CK(cudaSetDevice(h->P.device));
+	if (n_reads > h->seg_reads) return fail(h, FQSK_E_INVAL, "last segment had %u reads", h->seg_reads);
+	if (!n_reads) return FQSK_OK;
+	CK(cudaMemcpyAsync(flag, h->sflag.p, (size_t) n_reads * 4, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaMemcpyAsync(dif, h->sdif.p, (size_t) n_reads * 8, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaStreamSynchronize(h->st));
+	return FQSK_OK;
+}
+
 int fqsk_segment(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const fqsk_read_desc *reads, uint32_t n_reads,
                  fqsk_base_rec *recs, uint64_t rec_cap, uint64_t *n_recs, uint8_t *dup, uint64_t *rec_off) {
 	if (!h || (!slab && n_reads) || (!reads && n_reads)) return FQSK_E_INVAL;

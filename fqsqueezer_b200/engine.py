@@ -44,7 +44,7 @@ class _Stats(C.Structure):
 
 
 EXPORTS = ["fqsk_create", "fqsk_destroy", "fqsk_last_error", "fqsk_block_start", "fqsk_segment", "fqsk_segment_device",
-           "fqsk_device_recs", "fqsk_sync", "fqsk_dump", "fqsk_stats_get", "fqsk_profile", "fqsk_ht_insert", "fqsk_ht_find",
+           "fqsk_device_recs", "fqsk_sorted_prefix", "fqsk_sync", "fqsk_dump", "fqsk_stats_get", "fqsk_profile", "fqsk_ht_insert", "fqsk_ht_find",
            "fqsk_ht_count", "fqsk_timer_begin", "fqsk_timer_end", "fqsk_siv_increment", "fqsk_siv_test", "fqsk_siv_counts", "fqsk_siv_test_shorter", "fqsk_mt_stream"]
 
 _lib = None
@@ -68,6 +68,7 @@ def load_library():
     lib.fqsk_segment.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint32, vp, C.c_uint64, u64p, vp, vp]
     lib.fqsk_segment_device.argtypes = [vp, vp, C.c_uint64, vp, vp, C.c_uint32, u64p]
     lib.fqsk_device_recs.argtypes = [vp, C.POINTER(vp), u64p]
+    lib.fqsk_sorted_prefix.argtypes = [vp, vp, vp, C.c_uint32]
     lib.fqsk_sync.argtypes = [vp]
     lib.fqsk_dump.argtypes = [vp, C.c_int, vp, vp, C.c_uint64, u64p]
     lib.fqsk_stats_get.argtypes = [vp, C.POINTER(_Stats)]
@@ -164,6 +165,13 @@ class KmerEngine:
         n = C.c_uint64(0)
         self._ck(self.lib.fqsk_device_recs(self.h, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    def sorted_prefix(self, n_reads):
+        """(flag, dif) per read of the last segment -- compress_prefix_sorted, dna.cpp:589-605."""
+        flag = np.zeros(max(n_reads, 1), np.uint32)
+        dif = np.zeros(max(n_reads, 1), np.uint64)
+        self._ck(self.lib.fqsk_sorted_prefix(self.h, _ptr(flag), _ptr(dif), n_reads))
+        return flag[:n_reads], dif[:n_reads]
 
     def sync(self):
         self._ck(self.lib.fqsk_sync(self.h))

@@ -120,6 +120,9 @@ int fqsk_segment(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const 
 int fqsk_segment_device(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes, const uint64_t *d_off, const uint32_t *d_len,
                         uint32_t n_reads, uint64_t *n_recs);
 int fqsk_device_recs(fqsk_handle *h, const fqsk_base_rec **d_recs, uint64_t *n_recs);
+/* Sorted-order modes: what compress_prefix_sorted (dna.cpp:589-605) codes per read of the last segment -- flag = siv.test(p-mer)
+ * or 4 when the p-mer equals the previous read's, dif = number of p-mers with that flag between the previous and this p-mer. */
+int fqsk_sorted_prefix(fqsk_handle *h, uint32_t *flag, uint64_t *dif, uint32_t n_reads);
 
 /* Replaces CDNACompressor::InsertKmersToHT + ClearKmersToHT (dna.cpp:2393-2488) and the three barriers around them
  * (application.cpp:645-654): p-mers, then s-mers, then b-mers, in push order, with the reference's PRNG draw order. */

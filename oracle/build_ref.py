@@ -170,6 +170,9 @@ def build_tap(scratch):
           "\tfqs_tap_emit(0xFFFFFFFFu, size, 1, minim_pos, 0, 0, 0, 0);\n")
     patch(dna, "bool CDNACompressor::CompressSorted(uint8_t *p, uint32_t size, bool first_read_of_pair)\n{\n",
           "\tfqs_tap_emit(0xFFFFFFFFu, size, 2, first_read_of_pair, 0, 0, 0, 0);\n")
+    # sorted-order prefix (dna.cpp:589-605): flag and, when present, the dif count -- pos = 0xFFFFFFFC, c0 = flag, c1/c2 = dif lo/hi
+    patch(dna, "\tif (flag < max_prefix_sorted_flag_value)\n\t{\n\t\tdif = 0;", "\tif (flag >= max_prefix_sorted_flag_value) fqs_tap_emit(0xFFFFFFFCu, (uint32_t) flag, 0, 0, 0, 0, 0, 0);\n", before=True)
+    patch(dna, "\t\tdif_no_bytes = no_bytes(dif);", "\t\tfqs_tap_emit(0xFFFFFFFCu, (uint32_t) flag, (uint32_t) dif, (uint32_t) (dif >> 32), 0, 0, 0, 0);\n", before=True)
     # duplicate flag: emitted right where the reference codes it
     patch(dna, "\t\tif (same_read)\n\t\t\treturn true;", "\t\tif (same_read) fqs_tap_emit(0xFFFFFFFDu, 0, 0, 0, 0, 0, 0, 0);\n", before=True, count=2)
     # per sync marker (dna.cpp:2393)

@@ -49,6 +49,10 @@ def make_case(name, G, n_reads, L, gs, seed, n_frac=0.0, dup_frac=0.0, extra=("-
         fastq = np.fromfile(fq, dtype=np.uint8)
         if tuple(extra) == ("-om", "o"):
             assert dec == fastq.tobytes(), "reference round trip failed"
+        else:
+            # sorted order: the decoder writes the reads in the order they were coded -> that IS the engine's input order
+            assert sorted(dec.split(b"\n")[1::4]) == sorted(fastq.tobytes().split(b"\n")[1::4]), "reference round trip lost reads"
+            fastq = np.frombuffer(dec, dtype=np.uint8).copy()
     dumps = {}
     for tag, nm in ((0, "siv"), (1, "smer"), (2, "bmer"), (3, "pair")):
         x = d[d[:, 0] == tag]
@@ -69,6 +73,8 @@ def main():
     make_case("se_orig_gs1", G=6000, n_reads=1500, L=80, gs=1, seed=7, n_frac=0.002, dup_frac=0.01)
     # same options as BASELINE config 2 (-gs 100: prefix 12, p17/s20/b24), small input
     make_case("se_orig_gs100", G=20000, n_reads=1200, L=100, gs=100, seed=43)
+    # sorted order (-om s): bins by 4-symbol prefix, std::sort inside a bin, sorted-prefix coding (flag / dif) + suffix from p_len
+    make_case("se_sorted_gs1", G=5000, n_reads=2500, L=70, gs=1, seed=45, n_frac=0.002, dup_frac=0.01, extra=("-om", "s"))
 
 
 if __name__ == "__main__":

@@ -51,3 +51,47 @@ def assert_dump_equal(engine, gold):
     st = engine.stats()
     assert st["siv_no_filled"] == int(gold["siv_no_filled"])
     assert st["siv_no_updates"] == int(gold["siv_no_updates"])
+
+
+def run_sorted(engine, slab, is_gpu):
+    """Sorted-order driver: the reference feeds one temp file per 4-symbol bin (N -> T) through the same block / sync
+    loop (application.cpp:198-219, 349-412, 538-570), so blocks never span bins and the block generation keeps counting.
+    `slab` must already be in the reference's processing order (its decoder writes reads in that order).
+    Returns (records without markers, flags, difs) -- for the oracle the (flag, dif) values ride in 0xFFFFFFFC records."""
+    off, ln, roff, rsz = S.parse_fastq(slab)
+    lut = np.full(256, 3, np.int64)
+    lut[ord("A")], lut[ord("C")], lut[ord("G")], lut[ord("T")] = 0, 1, 2, 3
+    first4 = np.stack([lut[slab[off.astype(np.int64) + k]] for k in range(4)], axis=1)
+    bins = first4[:, 0] * 64 + first4[:, 1] * 16 + first4[:, 2] * 4 + first4[:, 3]
+    cuts = [0] + list(np.flatnonzero(np.diff(bins)) + 1) + [len(off)]
+    out, flags, difs = [], [], []
+    gen = 0
+    for a0, a1 in zip(cuts[:-1], cuts[1:]):
+        for f, l in S.split_blocks(rsz[a0:a1]):
+            f += a0; l += a0
+            ns = S.calc_no_synchronizations(gen, l - f, 1)
+            engine.block_start()
+            for a, b in S.segments(f, l, ns):
+                recs, dup = engine.segment(slab, off[a:b], ln[a:b], 2)
+                if is_gpu:
+                    fl, df = engine.sorted_prefix(b - a)
+                    keep = dup == 0
+                    flags.append(fl[keep]); difs.append(df[keep])
+                out.append(recs)
+                engine.sync()
+            gen += 1
+    recs = np.concatenate(out) if out else np.zeros(0, O.REC_DTYPE)
+    if not is_gpu:
+        sp = recs[recs["pos"] == O.POS_SORTED]
+        flags = [sp["c"][:, 0].astype(np.uint32)]
+        difs = [sp["c"][:, 1].astype(np.uint64) | (sp["c"][:, 2].astype(np.uint64) << np.uint64(32))]
+    recs = recs[recs["pos"] < 0xFFFFFFF0]
+    return recs, np.concatenate(flags) if flags else np.zeros(0, np.uint32), np.concatenate(difs) if difs else np.zeros(0, np.uint64)
+
+
+def golden_sorted_expect(gold):
+    r = gold["recs"]
+    sp = r[r["pos"] == O.POS_SORTED]
+    flags = sp["c"][:, 0].astype(np.uint32)
+    difs = sp["c"][:, 1].astype(np.uint64) | (sp["c"][:, 2].astype(np.uint64) << np.uint64(32))
+    return r[r["pos"] < 0xFFFFFFF0], flags, difs

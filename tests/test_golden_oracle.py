@@ -19,3 +19,18 @@ def test_oracle_matches_reference_tap(name):
         assert st["draws_b"] > 1000 and st["rough_b"] > 100 and st["repair_existing"] > 10 and st["local_hits"] > 10
         assert (recs["pos"] == O.POS_DUP).sum() > 0
     e.close()
+
+
+def test_oracle_matches_reference_tap_sorted_order():
+    """-om s: sorted-prefix (flag, dif) values, suffix records from p_len and final tables vs the tapped reference."""
+    g = H.load_golden("se_sorted_gs1")
+    pref, p, s, b = O.kmer_params(int(g["gs"]))
+    e = O.OracleEngine(p, s, b, pref, mode=1)
+    recs, flags, difs = H.run_sorted(e, g["fastq"], is_gpu=False)
+    want, wflags, wdifs = H.golden_sorted_expect(g)
+    H.assert_recs_equal(recs, want)
+    import numpy as np
+    assert np.array_equal(flags, wflags) and np.array_equal(difs, wdifs)
+    assert (wflags == 4).sum() > 0 and (wdifs > 0).sum() > 100
+    H.assert_dump_equal(e, g)
+    e.close()

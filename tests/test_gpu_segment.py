@@ -97,3 +97,16 @@ def test_edge_cases_empty_and_ragged():
         ko, vo = o.dump(which)
         assert np.array_equal(kg, ko) and np.array_equal(vg, vo)
     e.close(); o.close()
+
+
+def test_engine_matches_reference_golden_sorted_order():
+    """-om s (row a15): compress_prefix_sorted's siv test + linear scan, p-mer pushes of the prefix, suffix from p_len."""
+    g = H.load_golden("se_sorted_gs1")
+    pref, p, s, b = E.kmer_params(int(g["gs"]))
+    e = E.KmerEngine(p, s, b, pref, mode=E.MODE_SE_SORTED)
+    recs, flags, difs = H.run_sorted(e, g["fastq"], is_gpu=True)
+    want, wflags, wdifs = H.golden_sorted_expect(g)
+    H.assert_recs_equal(recs, want)
+    assert np.array_equal(flags, wflags) and np.array_equal(difs, wdifs)
+    H.assert_dump_equal(e, g)
+    e.close()
