@@ -81,7 +81,10 @@ struct fqsk_handle {
 	       flag8, draw_off, final_cnt, slot_of, dump_k, dump_v, q0, q1, q2, q3, q4, sflag, sdif, hid_scan,
 	       prov, pflags, pscripts, rscripts, rreqs, pool, miss, draws_b16, draws_s16, doff_b, doff_s, time_b, time_s, rt_b[2], rt_s[2],
 	       sidx_b, sidx_s, stime_b, stime_s, sort_k, sort_v, rkind, rreg, rslot, dirty, rdraws_b, rdraws_s, totals,
-	       y_tslot, y_c0, y_m, y_draw, y_j, y_final, y_flag_at, y_own, y_lead, y_rank, y_flag, y_doff, idx_k, idx_t, idx_rt;
+	       y_tslot, y_c0, y_m, y_draw, y_j, y_final, y_flag_at, y_own, y_lead, y_rank, y_flag, y_doff, idx_k, idx_t, idx_rt,
+	       miss_fold, hr_b[3], hr_s[3], evk[2], evv[2], evk_s[2], evv_s[2];
+	bool hot = false;                        // the current segment is being redone with the ordered thread-local evaluator
+	bool hot_seen[2] = {false, false};       // [0] s, [1] b: the last sync saw a k-mer pushed more than thr + 1 times in its row
 	DeltaDev seg_delta_b{}, seg_delta_s{};   // the converged segment's delta tables (valid while `pending`)
 	uint32_t miss_cap = 0, rreq_cap = 0, pool_cap = 1u << 18;
 	uint32_t *d_u32 = nullptr;            // [0] n_miss [1] n_rreq [2] pool_used
@@ -345,6 +348,7 @@ int apply_sorted(fqsk_handle *h, Table &t, Stream &rng, const unsigned long long
 		LAUNCHED(h);
 		int fl[8];
 		CKR(read_flags(h, fl, 8));
+		if (fl[6]) h->hot_seen[&t == &h->tb ? 1 : 0] = true;
 		if (!fl[2] && !fl[0]) break;
 		// flags changed (or the draw window was short): rescan the draw indices in push order and make the window long enough
 		CKR((scan_excl<uint8_t, uint32_t>(h, h->flag8.as<uint8_t>(), h->draw_off.as<uint32_t>(), n + 1, 0u)));
@@ -429,6 +433,7 @@ int apply_indexed(fqsk_handle *h, Table &t, Stream &rng, const DeltaDev &D, cons
 		resolve_phases(h);
 		int fl[8]; memcpy(fl, hs, sizeof fl);
 		total_draws = hs[8];
+		if (fl[6]) h->hot_seen[&t == &h->tb ? 1 : 0] = true;
 		if (fl[7]) {   // a hot k-mer occurs more than SYNC_GROUP_CAP times in this row: sorted path for the whole row
 			k_sync_unclaim<<<g, 256, 0, h->st>>>(t.d, Y, n); LAUNCHED(h);
 			return apply_inserts(h, t, rng, row, n);
@@ -482,6 +487,7 @@ int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes_ac
 	CK(h->pscripts.ensure(n1 * pslots * sizeof(Script)));
 	CK(h->rscripts.ensure(((size_t) h->rreq_cap + 1) * sizeof(Script)));
 	CK(h->pool.ensure(((size_t) h->pool_cap + 1) * 8)); CK(h->miss.ensure(((size_t) h->miss_cap + 1) * sizeof(MissEntry)));
+	CK(h->miss_fold.ensure((size_t) h->miss_cap + 1)); CK(cudaMemsetAsync(h->miss_fold.p, 0, (size_t) h->miss_cap + 1, h->st));
 	CK(h->rdraws_b.ensure(n1 * 4)); CK(h->rdraws_s.ensure(n1 * 4)); CK(h->doff_b.ensure(n1 * 8)); CK(h->doff_s.ensure(n1 * 8));
 	CK(h->time_b.ensure((2 * dna_bytes + 2) * 4)); CK(h->time_s.ensure((dna_bytes + 1) * 4));
 	CK(h->rt_b[0].ensure((2 * dna_bytes + 2) * 4)); CK(h->rt_s[0].ensure((dna_bytes + 1) * 4));
@@ -494,7 +500,8 @@ int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes_ac
 	P.rscripts = h->rscripts.as<Script>(); P.n_rscript = h->d_u32 + 1; P.rscript_cap = h->rreq_cap;
 	P.rkind = h->rkind.as<uint8_t>(); P.rreg = h->rreg.as<KReg>(); P.rslot = h->rslot.as<uint32_t>(); P.dirty = h->dirty.as<uint8_t>();
 	P.pool = h->pool.as<unsigned short>(); P.pool_used = h->d_u32 + 2; P.pool_cap = h->pool_cap;
-	P.miss = h->miss.as<MissEntry>(); P.n_miss = h->d_u32 + 0; P.miss_cap = h->miss_cap;
+	P.miss = h->miss.as<MissEntry>(); P.n_miss = h->d_u32 + 0; P.miss_cap = h->miss_cap; P.miss_fold = h->miss_fold.as<uint8_t>();
+	P.ev_n = h->d_u32 + 4; P.hot_draws = h->d_u32 + 6; P.ev_cap = 0;
 	P.rdraws_b = h->rdraws_b.as<uint32_t>(); P.rdraws_s = h->rdraws_s.as<uint32_t>();
 	P.doff_b = h->doff_b.as<unsigned long long>(); P.doff_s = h->doff_s.as<unsigned long long>();
 	P.time_b = h->time_b.as<uint32_t>(); P.time_s = h->time_s.as<uint32_t>();
@@ -506,11 +513,12 @@ int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes_ac
 
 	EngineDev E = make_engine_dev(h);
 	CK(cudaMemsetAsync(h->d_u32, 0, 3 * 4, h->st));
+	CK(cudaMemsetAsync(h->d_u32 + 4, 0, 4 * 4, h->st));
 	CK(cudaMemsetAsync(h->d_flags, 0, 8 * sizeof(int), h->st));
 	{ Phase ph(h, FQSK_PH_LOOKUP); k_lookup<<<nblk(rec_bound, 256), 256, 0, h->st>>>(E, S, P); LAUNCHED(h); }
 	{ Phase ph(h, FQSK_PH_PARTIAL); k_partial<<<nblk((uint64_t) n * pslots * 32, 128), 128, 0, h->st>>>(E, S, P); LAUNCHED(h); }
-	S.delta_b = DeltaDev{nullptr, nullptr, 0, 0, h->P.bmer_len, 1, h->tb.ci.thr + 1};
-	S.delta_s = DeltaDev{nullptr, nullptr, 0, 0, h->P.smer_len, 1, h->ts.ci.thr + 1};
+	S.delta_b = DeltaDev{nullptr, nullptr, 0, 0, h->P.bmer_len, 1, h->tb.ci.thr + 1, nullptr, nullptr, nullptr};
+	S.delta_s = DeltaDev{nullptr, nullptr, 0, 0, h->P.smer_len, 1, h->ts.ci.thr + 1, nullptr, nullptr, nullptr};
 	h->delta_b_valid = h->delta_s_valid = false;
 	const uint32_t t_b = std::max<uint32_t>(h->P.bmer_len - h->P.smer_len - 1, 1), t_s = std::max<uint32_t>(h->P.smer_len - h->P.pmer_len + 1, 1);
 	uint32_t slots_b = 1024, slots_s = 1024;
@@ -531,8 +539,36 @@ int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes_ac
 		k_delta_build<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(S, P, h->dk_b.as<unsigned long long>(), h->stime_b.as<uint32_t>(), slots_b - 1, h->P.bmer_len, t_b,
 		                                                             h->dk_s.as<unsigned long long>(), h->stime_s.as<uint32_t>(), slots_s - 1, h->P.smer_len, t_s);
 		LAUNCHED(h);
-		S.delta_b = DeltaDev{h->dk_b.as<unsigned long long>(), h->stime_b.as<uint32_t>(), slots_b - 1, 1, h->P.bmer_len, t_b, h->tb.ci.thr + 1};
-		S.delta_s = DeltaDev{h->dk_s.as<unsigned long long>(), h->stime_s.as<uint32_t>(), slots_s - 1, 1, h->P.smer_len, t_s, h->ts.ci.thr + 1};
+		S.delta_b = DeltaDev{h->dk_b.as<unsigned long long>(), h->stime_b.as<uint32_t>(), slots_b - 1, 1, h->P.bmer_len, t_b, h->tb.ci.thr + 1, nullptr, nullptr, nullptr};
+		S.delta_s = DeltaDev{h->dk_s.as<unsigned long long>(), h->stime_s.as<uint32_t>(), slots_s - 1, 1, h->P.smer_len, t_s, h->ts.ci.thr + 1, nullptr, nullptr, nullptr};
+		if (!h->hot) return FQSK_OK;
+		// hot mode: ranks, queued events (inserts above thr + thread-local merges), time order, sequential evaluation
+		Phase ph2(h, FQSK_PH_LOCAL);
+		for (int q = 0; q < 3; ++q) { CK(h->hr_b[q].ensure((size_t) slots_b * 4)); CK(h->hr_s[q].ensure((size_t) slots_s * 4)); }
+		const uint32_t ev_cap = (uint32_t) std::min<uint64_t>(2 * dna_bytes_actual + 1024, 1u << 30);
+		for (int q = 0; q < 2; ++q) { CK(h->evk[q].ensure((size_t) ev_cap * 8)); CK(h->evv[q].ensure((size_t) ev_cap * 4)); CK(h->evk_s[q].ensure((size_t) ev_cap * 8)); CK(h->evv_s[q].ensure((size_t) ev_cap * 4)); }
+		S.delta_b.rank_at = h->hr_b[0].as<uint32_t>(); S.delta_b.prev_at = h->hr_b[1].as<uint32_t>(); S.delta_b.cnt_at = h->hr_b[2].as<uint32_t>();
+		S.delta_s.rank_at = h->hr_s[0].as<uint32_t>(); S.delta_s.prev_at = h->hr_s[1].as<uint32_t>(); S.delta_s.cnt_at = h->hr_s[2].as<uint32_t>();
+		for (int q = 0; q < 2; ++q) { P.ev_key[q] = h->evk[q].as<unsigned long long>(); P.ev_val[q] = h->evv[q].as<uint32_t>(); }
+		P.ev_n = h->d_u32 + 4; P.ev_cap = ev_cap; P.hot_draws = h->d_u32 + 6;
+		CK(cudaMemsetAsync(h->d_u32 + 4, 0, 4 * 4, h->st));
+		k_delta_rank<<<148 * 8, 256, 0, h->st>>>(S.delta_b, P, 0); LAUNCHED(h);
+		k_delta_rank<<<148 * 8, 256, 0, h->st>>>(S.delta_s, P, 1); LAUNCHED(h);
+		k_local<<<std::min<uint32_t>(nblk(std::max<uint32_t>(h->miss_cap, 1), 128), 148 * 16), 128, 0, h->st>>>(E, S, P, 0); LAUNCHED(h);
+		uint32_t *hs = (uint32_t *) h->h_small;
+		CK(cudaMemcpyAsync(hs, h->d_status, 64, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaStreamSynchronize(h->st));
+		if (((int *) hs)[4]) return RC_RETRY + 1;     // event list too small (cannot happen with the bound above)
+		uint32_t en[2] = {hs[8 + 4], hs[8 + 5]};
+		for (int q = 0; q < 2; ++q) if (en[q]) {
+			size_t bytes = 0;
+			CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, h->evk[q].as<unsigned long long>(), h->evk_s[q].as<unsigned long long>(), h->evv[q].as<uint32_t>(), h->evv_s[q].as<uint32_t>(), (int) en[q], 0, 34, h->st));
+			CK(h->cub_tmp.ensure(bytes));
+			CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, h->evk[q].as<unsigned long long>(), h->evk_s[q].as<unsigned long long>(), h->evv[q].as<uint32_t>(), h->evv_s[q].as<uint32_t>(), (int) en[q], 0, 34, h->st));
+		}
+		CKR(stream_ensure(h, h->rng[ST_LB], (uint64_t) en[0] * 8 + 1024)); CKR(stream_ensure(h, h->rng[ST_LS], (uint64_t) en[1] * 8 + 1024));
+		E = make_engine_dev(h);
+		k_hot_eval<<<1, 64, 0, h->st>>>(E, S, P, h->evk_s[0].as<unsigned long long>(), h->evv_s[0].as<uint32_t>(), en[0], h->evk_s[1].as<unsigned long long>(), h->evv_s[1].as<uint32_t>(), en[1]); LAUNCHED(h);
 		return FQSK_OK;
 	};
 	const uint32_t max_it = h->P.max_iterations ? h->P.max_iterations : 16;
@@ -550,8 +586,8 @@ int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes_ac
 		if (redo_walk) {
 			if (++it >= max_it) return fail(h, FQSK_E_NO_CONVERGE, "segment did not reach its fixed point in %u iterations", max_it);
 			CK(cudaMemsetAsync(h->d_flags + 2, 0, sizeof(int), h->st));
-			CKR(build_delta());
-			{ Phase ph(h, FQSK_PH_LOCAL); k_local<<<std::min<uint32_t>(nblk(std::max<uint32_t>(h->miss_cap, 1), 128), 148 * 16), 128, 0, h->st>>>(E, S, P); LAUNCHED(h); }
+			{ int rc_ = build_delta(); if (rc_ != FQSK_OK) return rc_ == RC_RETRY + 1 ? fail(h, FQSK_E_NOMEM, "hot-mode event list overflow") : rc_; }
+			{ Phase ph(h, FQSK_PH_LOCAL); k_local<<<std::min<uint32_t>(nblk(std::max<uint32_t>(h->miss_cap, 1), 128), 148 * 16), 128, 0, h->st>>>(E, S, P, 1); LAUNCHED(h); }
 			{ Phase ph(h, FQSK_PH_WALK); k_walk<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(E, S, P, it); LAUNCHED(h); ++h->S.n_replays; }
 		}
 		if (redo_tail) {
@@ -587,7 +623,11 @@ int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes_ac
 			return RC_RETRY;
 		}
 		if (fl[5]) return fail(h, FQSK_E_CUDA, "internal error: a draw was requested on a path that must not draw");
-		if (fl[1]) return fail(h, FQSK_E_UNSUPPORTED, "segment needs the thread-local PRNG streams (a k-mer occurs more than %u times inside one sync segment and is looked up there, or a thread-local merge exceeds the deterministic range); not implemented yet", h->tb.ci.thr + 1);
+		if (fl[1]) {
+			// a thread-local counter left the deterministic range: redo the segment with the ordered evaluator
+			if (!h->hot) { h->hot = true; ++h->S.n_hot_segments; return RC_RETRY; }
+			return fail(h, FQSK_E_UNSUPPORTED, "a front-truncated thread-local lookup matched more than %u entries; not supported", DeltaCollect::CAP);
+		}
 		if (fl[2]) { redo_walk = true; redo_tail = true; continue; }      // walk `it` changed pushes: one more thread-local pass
 		redo_walk = false;
 		if (fl[0]) {   // the pre-generated draw window was too short: extend and evaluate the merges again
@@ -610,6 +650,7 @@ int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes_ac
 		for (int i = 0; i < 4; ++i) h->sl_base[i] += tt.letters.v[i];
 		h->n_recs = tt.n_rec;
 		h->rng[ST_B].consumed += draws2[0]; h->rng[ST_S].consumed += draws2[1];
+		if (h->hot) { uint32_t hd[2]; memcpy(hd, hs + 32 + 6 * 4, 8); h->rng[ST_LB].consumed += hd[0]; h->rng[ST_LS].consumed += hd[1]; }
 	}
 	return FQSK_OK;
 }
@@ -619,9 +660,10 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 	if (h->pending) return fail(h, FQSK_E_INVAL, "fqsk_segment called twice without fqsk_sync (the reference syncs after every segment, application.cpp:643-662)");
 	const uint32_t first = (h->P.mode == FQSK_MODE_SE_SORTED || h->P.mode == FQSK_MODE_PE_SORTED) ? h->P.pmer_len : h->P.prefix_len;
 	h->seg_reads = n; h->n_recs = 0; h->pend_b = h->pend_s = h->pend_p = 0;
+	h->hot = false;
 	++h->S.n_segments;
 	if (n == 0) { h->pending = true; return FQSK_OK; }
-	if (dna_bytes >= (1ull << 30)) return fail(h, FQSK_E_INVAL, "segment larger than 1 GiB of DNA");
+	if (dna_bytes >= (1ull << 30)) return fail(h, FQSK_E_INVAL, "segment larger than 1 GiB of DNA");   // push times are 2 * byte offset (+1) in 32 bits
 	const size_t n1 = (size_t) std::max<uint32_t>(n, h->P.reserve_reads) + 1;
 	CK(h->dup.ensure(n1)); CK(h->n_coded.ensure(n1 * 4)); CK(h->letters.ensure(n1 * 32)); CK(h->rec_off.ensure(n1 * 8)); CK(h->sl_prefix.ensure(n1 * 32));
 	CK(h->push_b.ensure((2 * dna_bytes + 2) * 8)); CK(h->push_s.ensure((dna_bytes + 1) * 8)); CK(h->push_p.ensure((2 * dna_bytes + 2 * n1) * 8));
@@ -662,6 +704,49 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 	for (int i = 0; i < 4; ++i) h->S.draws[i] = h->rng[i].consumed;
 	h->pending = true;
 	h->S.n_reads += n; h->S.n_bases += dna_bytes_actual;
+	return FQSK_OK;
+}
+
+// The reference's thread-local tables draw from cinc_lb / cinc_ls on every insert whose counter is above thr, looked up or
+// not (ht_kmer.h:433-436 via dna.cpp:826, 837, 862, 872).  When a sync row shows such a k-mer and the segment was not
+// evaluated in hot mode, the ordered evaluator runs in accounting mode to advance the stream position exactly.
+int hot_account(fqsk_handle *h, int stream) {
+	DeltaDev D = stream ? h->seg_delta_s : h->seg_delta_b;
+	if (!D.keys) return FQSK_OK;
+	const size_t slots = (size_t) D.mask + 1;
+	DevBuf *hr = stream ? h->hr_s : h->hr_b;
+	for (int q = 0; q < 3; ++q) CK(hr[q].ensure(slots * 4));
+	D.rank_at = hr[0].as<uint32_t>(); D.prev_at = hr[1].as<uint32_t>(); D.cnt_at = hr[2].as<uint32_t>();
+	const uint32_t ev_cap = (uint32_t) std::min<size_t>(slots, 1u << 30);
+	CK(h->evk[stream].ensure((size_t) ev_cap * 8)); CK(h->evv[stream].ensure((size_t) ev_cap * 4));
+	CK(h->evk_s[stream].ensure((size_t) ev_cap * 8)); CK(h->evv_s[stream].ensure((size_t) ev_cap * 4));
+	PipeDev P{};
+	for (int q = 0; q < 2; ++q) { P.ev_key[q] = h->evk[q].as<unsigned long long>(); P.ev_val[q] = h->evv[q].as<uint32_t>(); }
+	P.ev_n = h->d_u32 + 4; P.ev_cap = ev_cap; P.hot_draws = h->d_u32 + 6; P.flags = h->d_flags;
+	CK(cudaMemsetAsync(h->d_u32 + 4, 0, 4 * 4, h->st));
+	CK(cudaMemsetAsync(h->d_flags, 0, 8 * sizeof(int), h->st));
+	k_delta_rank<<<148 * 8, 256, 0, h->st>>>(D, P, (uint32_t) stream); LAUNCHED(h);
+	uint32_t *hs = (uint32_t *) h->h_small;
+	CK(cudaMemcpyAsync(hs, h->d_status, 64, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaStreamSynchronize(h->st));
+	uint32_t en = hs[8 + 4 + stream];
+	if (!en) return FQSK_OK;
+	size_t bytes = 0;
+	CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, h->evk[stream].as<unsigned long long>(), h->evk_s[stream].as<unsigned long long>(), h->evv[stream].as<uint32_t>(), h->evv_s[stream].as<uint32_t>(), (int) en, 0, 34, h->st));
+	CK(h->cub_tmp.ensure(bytes));
+	CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, h->evk[stream].as<unsigned long long>(), h->evk_s[stream].as<unsigned long long>(), h->evv[stream].as<uint32_t>(), h->evv_s[stream].as<uint32_t>(), (int) en, 0, 34, h->st));
+	Stream &rng = h->rng[stream ? ST_LS : ST_LB];
+	CKR(stream_ensure(h, rng, (uint64_t) en + 1024));
+	EngineDev E = make_engine_dev(h);
+	SegDev S{};
+	S.delta_b = stream ? DeltaDev{} : D; S.delta_s = stream ? D : DeltaDev{};
+	k_hot_eval<<<1, 64, 0, h->st>>>(E, S, P, h->evk_s[0].as<unsigned long long>(), h->evv_s[0].as<uint32_t>(), stream ? 0 : en,
+	                               h->evk_s[1].as<unsigned long long>(), h->evv_s[1].as<uint32_t>(), stream ? en : 0);
+	LAUNCHED(h);
+	CK(cudaMemcpyAsync(hs, h->d_status, 64, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaStreamSynchronize(h->st));
+	if (((int *) hs)[0]) return fail(h, FQSK_E_CUDA, "internal error: thread-local draw window too short");
+	rng.consumed += hs[8 + 6 + stream];
 	return FQSK_OK;
 }
 
@@ -743,7 +828,8 @@ void fqsk_destroy(fqsk_handle *h) {
 	                  &h->draws_b16, &h->draws_s16, &h->doff_b, &h->doff_s, &h->time_b, &h->time_s, &h->rt_b[0], &h->rt_b[1], &h->rt_s[0], &h->rt_s[1],
 	                  &h->sidx_b, &h->sidx_s, &h->stime_b, &h->stime_s, &h->sort_k, &h->sort_v, &h->rkind, &h->rreg, &h->rslot, &h->dirty, &h->rdraws_b, &h->rdraws_s, &h->totals,
 	                  &h->y_tslot, &h->y_c0, &h->y_m, &h->y_draw, &h->y_j, &h->y_final, &h->y_flag_at, &h->y_own, &h->y_lead, &h->y_rank, &h->y_flag, &h->y_doff,
-	                  &h->idx_k, &h->idx_t, &h->idx_rt};
+	                  &h->idx_k, &h->idx_t, &h->idx_rt, &h->miss_fold, &h->hr_b[0], &h->hr_b[1], &h->hr_b[2], &h->hr_s[0], &h->hr_s[1], &h->hr_s[2],
+	                  &h->evk[0], &h->evk[1], &h->evv[0], &h->evv[1], &h->evk_s[0], &h->evk_s[1], &h->evv_s[0], &h->evv_s[1]};
 
 	for (DevBuf *b : bufs) b->release();
 	if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -872,6 +958,7 @@ int fqsk_sync(fqsk_handle *h) {
 	++h->S.n_syncs;
 	if (h->pending && h->seg_reads) {
 		// p-mers (dna.cpp:2401-2418): order-independent saturating increments; the fresh-field count is read with the next look
+		h->hot_seen[0] = h->hot_seen[1] = false;
 		CK(cudaMemsetAsync(h->d_counters + 4, 0, 8, h->st));
 		if (h->pend_p) {
 			Phase ph(h, FQSK_PH_SYNC_SIV);
@@ -886,6 +973,11 @@ int fqsk_sync(fqsk_handle *h) {
 		else CKR(apply_inserts(h, h->ts, h->rng[ST_S], h->row_s[0].as<unsigned long long>(), h->pend_s));
 		if (h->pend_b <= SYNC_INDEXED_MAX) CKR(apply_indexed(h, h->tb, h->rng[ST_B], h->seg_delta_b, h->row_b[0].as<unsigned long long>(), h->rt_b[0].as<uint32_t>(), h->pend_b));
 		else CKR(apply_inserts(h, h->tb, h->rng[ST_B], h->row_b[0].as<unsigned long long>(), h->pend_b));
+		if (!h->hot) {   // hot segments already advanced the thread-local streams
+			if (h->hot_seen[0]) CKR(hot_account(h, 1));
+			if (h->hot_seen[1]) CKR(hot_account(h, 0));
+		}
+		h->hot_seen[0] = h->hot_seen[1] = false;
 		// one look: fresh p-mer fields and the item counters of both tables (growth check)
 		unsigned long long *hc = (unsigned long long *) h->h_small;
 		CK(cudaMemcpyAsync(hc, h->d_counters, 48, cudaMemcpyDeviceToHost, h->st));

@@ -281,6 +281,9 @@ struct DeltaDev {
 	uint32_t mask, n;         // slots - 1; number of pushes (0 = empty delta)
 	uint32_t k, t;            // k-mer length; symbols trimmed on each side to get the core
 	uint32_t exact_limit;     // thr + 1: highest counter value reachable without the thread-local PRNG
+	// hot mode only (a k-mer is pushed more than exact_limit times inside the segment): per entry, its push-order rank among
+	// equal k-mers, the previous equal entry, and the counter after this push as evaluated with the cinc_lb / cinc_ls stream
+	uint32_t *rank_at, *prev_at, *cnt_at;
 };
 static const uint32_t DELTA_EMPTY = 0xFFFFFFFFu;
 
@@ -296,11 +299,13 @@ FQSK_DEV uint64_t delta_slot_of_key(uint64_t x, uint32_t k, uint32_t t, uint32_t
 	uint64_t c2 = (rc_kmer(x, k) << (2 * t)) >> (64 - 2 * cl);
 	return fmix64(c1 < c2 ? c1 : c2) & mask;
 }
-// Raw occurrence counts (before time T) of every k-mer that completes the context held in `r` (cur symbols, the last one is
-// the placeholder; k - cur leading symbols unknown), accumulated per next symbol exactly as the reference's trial loop
-// would find them: a stored key X counts for the trial Y in {X, rc(X)} whose known symbols match and whose normalised form
-// is X (kmer.h:366-385).
-FQSK_DEV void delta_query(const DeltaDev &D, const KReg &r, uint32_t cur, uint32_t T, uint32_t c[4]) {
+// Visits every entry older than T whose k-mer completes the context held in `r` (cur symbols, the last one is the
+// placeholder; k - cur leading symbols unknown), exactly as the reference's trial loop would find it: a stored key X counts
+// for the trial Y in {X, rc(X)} whose known symbols match and whose normalised form is X (kmer.h:366-385).
+// f(Y, time, slot): Y = the trial k-mer (dir form, left-aligned): its last symbol is the next symbol, its first k - cur
+// symbols are the front completion.
+template <typename F>
+FQSK_DEV void delta_scan(const DeltaDev &D, const KReg &r, uint32_t cur, uint32_t T, F &f) {
 	if (D.n == 0) return;
 	const uint32_t k = D.k, m = k - cur, cl = k - 2 * D.t;
 	uint64_t c1 = (r.dir << (2 * (D.t - m))) >> (64 - 2 * cl);
@@ -308,7 +313,6 @@ FQSK_DEV void delta_query(const DeltaDev &D, const KReg &r, uint32_t cur, uint32
 	const uint64_t qd = r.dir >> (2 * m);
 	const uint64_t kmask = (cur >= 2 ? ((1ull << (2 * (cur - 1))) - 1ull) : 0ull) << (64 - 2 * k + 2);
 	const uint64_t km = kr_kernel_mask(k);
-	const uint32_t lsh = 64 - 2 * k;
 	for (uint64_t slot = fmix64(c1 < c2 ? c1 : c2) & D.mask;; slot = (slot + 1) & D.mask) {
 		uint32_t tm = D.times[slot];
 		if (tm == DELTA_EMPTY) break;
@@ -317,19 +321,49 @@ FQSK_DEV void delta_query(const DeltaDev &D, const KReg &r, uint32_t cur, uint32
 		uint64_t Xr = rc_kmer(X, k);
 		uint64_t kx = X & km, kxr = Xr & km;
 		bool pal = X == Xr;
-		if (((X ^ qd) & kmask) == 0 && (kx < kxr || pal)) ++c[(X >> lsh) & 3];
-		if (!pal && ((Xr ^ qd) & kmask) == 0 && !(kxr < kx)) ++c[(Xr >> lsh) & 3];
+		if (((X ^ qd) & kmask) == 0 && (kx < kxr || pal)) f(X, tm, (uint32_t) slot);
+		if (!pal && ((Xr ^ qd) & kmask) == 0 && !(kxr < kx)) f(Xr, tm, (uint32_t) slot);
 	}
 }
-// thread-local find(): true when anything was found.  Counter values that would need the thread-local PRNG stream
-// (cinc_lb / cinc_ls, dna.cpp:164-165) are reported through *unsupported instead of being approximated.
-FQSK_DEV bool delta_find(const DeltaDev &D, const CIncP &ci, const KReg &r, uint32_t cur, uint32_t T, uint32_t c[4], int *unsupported) {
+struct DeltaCount {      // plain occurrence counts per next symbol
+	uint32_t c[4]; uint32_t lsh;
+	FQSK_DEV void operator()(uint64_t Y, uint32_t, uint32_t) { ++c[(Y >> lsh) & 3]; }
+};
+struct DeltaLatest {     // latest entry per next symbol (full contexts: one k-mer per symbol)
+	uint32_t t[4], s[4]; uint32_t lsh;
+	FQSK_DEV void operator()(uint64_t Y, uint32_t tm, uint32_t slot) { uint32_t q = (Y >> lsh) & 3; if (s[q] == 0xFFFFFFFFu || tm > t[q]) { t[q] = tm; s[q] = slot; } }
+};
+FQSK_DEV uint32_t delta_count_at(const DeltaDev &D, uint32_t slot) {   // counter after the push stored at `slot` (hot mode)
+	uint32_t rk = D.rank_at[slot];
+	return rk < D.exact_limit ? rk + 1 : D.cnt_at[slot];
+}
+// thread-local find(): true when anything was found.
+// Normal mode: counter values that would need the thread-local PRNG stream (cinc_lb / cinc_ls, dna.cpp:164-165) are reported
+// through *unsupported (the host then redoes the segment in hot mode).
+// Hot mode (D.rank_at != nullptr): full contexts read the evaluated counters; front-truncated contexts with any match are
+// left to the ordered evaluator (*need_fold).
+FQSK_DEV bool delta_find(const DeltaDev &D, const CIncP &ci, const KReg &r, uint32_t cur, uint32_t T, uint32_t c[4], int *unsupported, int *need_fold = nullptr) {
 	c[0] = c[1] = c[2] = c[3] = 0;
 	if (D.n == 0) return false;
-	delta_query(D, r, cur, T, c);
+	const uint32_t lsh = 64 - 2 * D.k;
+	if (D.rank_at && cur >= D.k) {
+		DeltaLatest L; L.lsh = lsh;
+		for (int i = 0; i < 4; ++i) { L.t[i] = 0; L.s[i] = 0xFFFFFFFFu; }
+		delta_scan(D, r, cur, T, L);
+		for (int i = 0; i < 4; ++i) if (L.s[i] != 0xFFFFFFFFu) c[i] = delta_count_at(D, L.s[i]);
+		return (c[0] | c[1] | c[2] | c[3]) != 0;
+	}
+	DeltaCount C; C.lsh = lsh; C.c[0] = C.c[1] = C.c[2] = C.c[3] = 0;
+	delta_scan(D, r, cur, T, C);
+	for (int i = 0; i < 4; ++i) c[i] = C.c[i];
+	bool any = (c[0] | c[1] | c[2] | c[3]) != 0;
+	if (D.rank_at) {   // hot mode, front-truncated context
+		if (any && need_fold) *need_fold = 1;
+		return any;
+	}
 	uint32_t lim = cur >= D.k ? D.exact_limit : ci.thr;   // a merge of several completions must stay in the exact range
 	for (int i = 0; i < 4; ++i) if (c[i] > lim) { *unsupported = 1; c[i] = lim; }
-	return (c[0] | c[1] | c[2] | c[3]) != 0;
+	return any;
 }
 
 }  // namespace fqsk

@@ -209,7 +209,9 @@ __global__ void k_apply_keys(HtDev t, CIncP ci, const unsigned long long *skeys,
 	if (i > 0 && skeys[i - 1] == key) return;
 	unsigned long long so = slot_of[i];
 	uint32_t c = ht_slot_get(t, so & ~(1ull << 63)) - (uint32_t) (so >> 63);   // counter before this sync (fresh slots were claimed with 1)
+	uint32_t gsize = 0;
 	for (uint32_t q = i; q < n && skeys[q] == key; ++q) {
+		++gsize;
 		uint32_t j = sidx[q];
 		if (c >= t.top) { if (flag[j]) { flag[j] = 0; flags[2] = 1; } continue; }   // ht_kmer.h:435: cnt < counter_max
 		if (c <= ci.thr) { if (flag[j]) { flag[j] = 0; flags[2] = 1; } ++c; continue; }
@@ -218,6 +220,7 @@ __global__ void k_apply_keys(HtDev t, CIncP ci, const unsigned long long *skeys,
 		if (di >= avail) { flags[0] = 1; continue; }
 		if (draws[(dpos + di) & dmask] % (ci.mult * (c - ci.thr)) == 0) ++c;
 	}
+	if (gsize > ci.thr + 1) flags[6] = 1;   // the thread-local table of the reference drew from its own stream for this k-mer
 	final_cnt[i] = c;
 }
 __global__ void k_commit_keys(HtDev t, const unsigned long long *skeys, uint32_t n, const unsigned long long *slot_of, const uint32_t *final_cnt) {
@@ -277,6 +280,7 @@ __global__ void k_sync_flags(HtDev t, CIncP ci, SyncDev Y, uint32_t n) {
 	if (j >= n) return;
 	const uint32_t L = Y.lead[j], c0 = Y.lead_c0[L], m = Y.lead_m[L], rank = Y.rank[j];
 	uint8_t f = 0;
+	if (rank == 0 && m > ci.thr + 1) Y.flags[6] = 1;   // the thread-local table of the reference drew from its own stream for this k-mer
 	if (c0 + m <= ci.thr + 1) { if (rank == 0) Y.final_at[L] = c0 + m; }    // cold group
 	else {
 		f = (c0 + rank > ci.thr) ? 1 : 0;

@@ -40,7 +40,7 @@ struct Script {              // ordered list of per-trial count vectors to be me
 static const uint32_t SCRIPT_INLINE = 8;
 
 struct MissEntry {           // a position whose uncorrected cascade needs the thread-local tables
-	uint32_t rec, time;      // record index; position id (byte offset of the base inside the packed DNA) used as push time
+	uint32_t rec, time;      // record index; lookup time = 2 * position id (byte offset of the base inside the packed DNA)
 	uint32_t read;           // owning read (marked dirty when the thread-local answer changes)
 	KReg breg;               // uncorrected b register with the placeholder (s register is derived from it)
 	uint32_t cb;             // symbols held by the b register
@@ -64,6 +64,9 @@ struct PipeDev {
 	uint8_t *dirty;                                                // per read: must be walked again
 	unsigned short *pool; uint32_t *pool_used; uint32_t pool_cap;   // overflow entries (4 x u16 each)
 	MissEntry *miss; uint32_t *n_miss; uint32_t miss_cap;
+	uint8_t *miss_fold;             // hot mode: 1 / 2 = this entry's thread-local merge (b / s) is done by the ordered evaluator
+	unsigned long long *ev_key[2]; uint32_t *ev_val[2]; uint32_t *ev_n; uint32_t ev_cap;   // hot mode: time-ordered events of the cinc_lb / cinc_ls streams
+	uint32_t *hot_draws;            // hot mode: draws consumed from cinc_lb, cinc_ls
 	// per-read draw counts of the merge scripts (stream b, stream s) and their exclusive scans
 	uint32_t *rdraws_b, *rdraws_s; const unsigned long long *doff_b, *doff_s;
 	const uint32_t *n_rec_dev;      // number of coded positions, device copy (grids are sized from host-side upper bounds)
@@ -171,7 +174,7 @@ __global__ void __launch_bounds__(256) k_lookup(EngineDev E, SegDev S, PipeDev P
 		if (m >= P.miss_cap) P.flags[4] = 1;
 		if (m < P.miss_cap) {
 			MissEntry e;
-			e.rec = g; e.time = (uint32_t) S.off[r] + i; e.read = r; e.breg = br; e.cb = cb; e.flags = fl; e.glevel = (uint8_t) lev;
+			e.rec = g; e.time = 2 * ((uint32_t) S.off[r] + i); e.read = r; e.breg = br; e.cb = cb; e.flags = fl; e.glevel = (uint8_t) lev;
 			for (int q = 0; q < 4; ++q) e.gs[q] = (uint16_t) c[q];
 			P.miss[m] = e;
 		}
@@ -274,7 +277,7 @@ __global__ void __launch_bounds__(128) k_partial(EngineDev E, SegDev S, PipeDev 
 			if (mi >= P.miss_cap) P.flags[4] = 1;
 			if (mi < P.miss_cap) {
 				MissEntry e;
-				e.rec = g; e.time = (uint32_t) S.off[r] + i; e.read = r; e.breg = br; e.cb = cb; e.flags = nf; e.glevel = (uint8_t) lev;
+				e.rec = g; e.time = 2 * ((uint32_t) S.off[r] + i); e.read = r; e.breg = br; e.cb = cb; e.flags = nf; e.glevel = (uint8_t) lev;
 				for (int q = 0; q < 4; ++q) e.gs[q] = (uint16_t) c[q];
 				P.miss[mi] = e;
 			}
@@ -287,15 +290,37 @@ __global__ void __launch_bounds__(128) k_partial(EngineDev E, SegDev S, PipeDev 
 // delta of the previous iteration.  Idempotent: always starts from the stored global-only result.
 // Merges that would draw from the thread-local PRNG streams are reported as unsupported.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_local(EngineDev E, SegDev S, PipeDev P) {
+// phase 1 (always): evaluate the entries; phase 0 (hot mode only): find the front-truncated entries whose thread-local merge
+// has to go through the ordered evaluator and queue them as events of their PRNG stream.
+__global__ void __launch_bounds__(128) k_local(EngineDev E, SegDev S, PipeDev P, int phase) {
 	if (S.delta_b.n == 0 && S.delta_s.n == 0) return;
 	uint32_t n_miss = *P.n_miss;
 	if (n_miss > P.miss_cap) n_miss = P.miss_cap;
 	for (uint32_t m = blockIdx.x * blockDim.x + threadIdx.x; m < n_miss; m += gridDim.x * blockDim.x) {
 		MissEntry e = P.miss[m];
+		const uint32_t cs = e.cb < E.s ? e.cb : E.s;
+		if (phase == 0) {
+			uint8_t fold = 0;
+			uint32_t lc[4];
+			int nf = 0;
+			if ((e.flags & PF_MISS_B) && e.cb < E.b) { delta_find(S.delta_b, E.cib, e.breg, e.cb, e.time, lc, P.flags + 1, &nf); if (nf) fold = 1; }
+			if (!fold && (e.flags & PF_MISS_S) && cs < E.s) {
+				bool b_hit = false;
+				if (e.flags & PF_MISS_B) { int dummy = 0; b_hit = delta_find(S.delta_b, E.cib, e.breg, e.cb, e.time, lc, P.flags + 1, &dummy); }
+				if (!b_hit) { KReg sr = suffix_reg(e.breg, e.cb, cs); nf = 0; delta_find(S.delta_s, E.cis, sr, cs, e.time, lc, P.flags + 1, &nf); if (nf) fold = 2; }
+			}
+			P.miss_fold[m] = fold;
+			if (fold) {
+				uint32_t st = fold - 1;
+				uint32_t q = atomicAdd(P.ev_n + st, 1u);
+				if (q >= P.ev_cap) P.flags[4] = 1;
+				else { P.ev_key[st][q] = (unsigned long long) e.time << 1; P.ev_val[st][q] = m | 0x80000000u; }
+			}
+			continue;
+		}
+		if (P.miss_fold[m]) continue;      // written by the ordered evaluator
 		uint32_t c[4] = {e.gs[0], e.gs[1], e.gs[2], e.gs[3]};
 		uint32_t lev = e.glevel;
-		const uint32_t cs = e.cb < E.s ? e.cb : E.s;
 		bool hit = false;
 		if (e.flags & PF_MISS_B) {
 			uint32_t lc[4];
@@ -317,11 +342,103 @@ __global__ void __launch_bounds__(128) k_local(EngineDev E, SegDev S, PipeDev P)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// k_walk: one thread per read.  Keeps the six registers, decides repairs, tracks cor_pos, produces the pushes.  Outside
-// repair windows (corrected == uncorrected registers) every count vector comes from the provisional records; inside a
-// window the cascade is evaluated here with the corrected registers (the slow path of the reference's own hot loop).
-// Rough searches are only REQUESTED here: their result never feeds back into the registers (dna.cpp:707-735).
+// hot mode (a k-mer is pushed more than thr + 1 times inside the segment and looked up there): the thread-local counters
+// leave the deterministic range, so the reference's cinc_lb / cinc_ls draws -- one per thread-local insert above thr
+// (ht_kmer.h:433-436) and the draws of thread-local front-truncated merges (ht_kmer.h:321-323), in program order -- are
+// replayed by an ordered evaluator: k_delta_rank finds every entry's push-order rank and queues the inserts that draw,
+// k_local(phase 0) queues the merges, the events are sorted by time and k_hot_eval walks them sequentially (one thread per
+// stream).  Rare by construction: only segments that raised the flag are redone this way.
 // ------------------------------------------------------------------------------------------------------------------
+__global__ void k_delta_rank(DeltaDev D, PipeDev P, uint32_t stream) {
+	const uint64_t slots = (uint64_t) D.mask + 1;
+	for (uint64_t sidx = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; sidx < slots; sidx += (uint64_t) gridDim.x * blockDim.x) {
+		const uint32_t tm = D.times[sidx];
+		if (tm == DELTA_EMPTY) continue;
+		const unsigned long long x = D.keys[sidx];
+		uint32_t rank = 0, prev = 0xFFFFFFFFu, prev_t = 0;
+		for (uint64_t slot = delta_slot_of_key(x, D.k, D.t, D.mask);; slot = (slot + 1) & D.mask) {
+			uint32_t et = D.times[slot];
+			if (et == DELTA_EMPTY) break;
+			if (et >= tm || D.keys[slot] != x) continue;
+			++rank;
+			if (prev == 0xFFFFFFFFu || et > prev_t) { prev_t = et; prev = (uint32_t) slot; }
+		}
+		D.rank_at[sidx] = rank; D.prev_at[sidx] = prev; D.cnt_at[sidx] = 0;
+		if (rank >= D.exact_limit) {
+			uint32_t q = atomicAdd(P.ev_n + stream, 1u);
+			if (q >= P.ev_cap) P.flags[4] = 1;
+			else { P.ev_key[stream][q] = ((unsigned long long) tm << 1) | 1ull; P.ev_val[stream][q] = (uint32_t) sidx; }
+		}
+	}
+}
+
+struct DeltaCollect {    // matches of a front-truncated context: (trial index, next symbol, latest entry)
+	static const uint32_t CAP = 128;
+	uint32_t key[CAP], tm[CAP], slot[CAP]; uint32_t n, m, lsh; bool overflow;
+	FQSK_DEV void operator()(uint64_t Y, uint32_t t, uint32_t s) {
+		uint32_t trial = 0;
+		for (uint32_t j = 0; j < m; ++j) trial |= (uint32_t) ((Y >> (62 - 2 * j)) & 3) << (2 * j);    // front symbol 0 is the fastest digit (ht_kmer.h:291-310)
+		uint32_t kk = (trial << 2) | (uint32_t) ((Y >> lsh) & 3);
+		for (uint32_t q = 0; q < n; ++q) if (key[q] == kk) { if (t > tm[q]) { tm[q] = t; slot[q] = s; } return; }
+		if (n >= CAP) { overflow = true; return; }
+		key[n] = kk; tm[n] = t; slot[n] = s; ++n;
+	}
+};
+
+__global__ void k_hot_eval(EngineDev E, SegDev S, PipeDev P, const unsigned long long *ek0, const uint32_t *ev0, uint32_t n0,
+                           const unsigned long long *ek1, const uint32_t *ev1, uint32_t n1) {
+	if ((threadIdx.x & 31) != 0) return;
+	const uint32_t st = threadIdx.x >> 5;     // 0: b / cinc_lb, 1: s / cinc_ls
+	if (st > 1) return;
+	const DeltaDev &D = st ? S.delta_s : S.delta_b;
+	const CIncP ci = st ? E.cis : E.cib;
+	const uint32_t top = st ? E.hs.top : E.hb.top;
+	const unsigned long long *ek = st ? ek1 : ek0;
+	const uint32_t *ev = st ? ev1 : ev0;
+	const uint32_t n = st ? n1 : n0;
+	DrawCursor dc;
+	dc.ring = E.draws[2 + st]; dc.mask = E.dmask[2 + st]; dc.pos0 = E.dpos[2 + st]; dc.avail = E.avail[2 + st]; dc.base = 0; dc.used = 0; dc.overflow = E.flags + 0;
+	for (uint32_t i = 0; i < n; ++i) {
+		const uint32_t v = ev[i];
+		if (ek[i] & 1ull) {
+			// a thread-local insert whose counter is above thr: one draw unless the counter is full (ht_kmer.h:433-436)
+			const uint32_t rank = D.rank_at[v];
+			uint32_t c = rank == D.exact_limit ? D.exact_limit : D.cnt_at[D.prev_at[v]];
+			if (c < top && dc.next() % (ci.mult * (c - ci.thr)) == 0) ++c;
+			D.cnt_at[v] = c;
+			continue;
+		}
+		// a thread-local front-truncated lookup: completions in odometer order, merged with the approximate addition
+		const uint32_t mi = v & 0x7fffffffu;
+		const MissEntry e = P.miss[mi];
+		const uint32_t cs = e.cb < E.s ? e.cb : E.s;
+		const KReg reg = st ? suffix_reg(e.breg, e.cb, cs) : e.breg;
+		const uint32_t cur = st ? cs : e.cb;
+		DeltaCollect M; M.n = 0; M.m = D.k - cur; M.lsh = 64 - 2 * D.k; M.overflow = false;
+		delta_scan(D, reg, cur, e.time, M);
+		if (M.overflow) { P.flags[1] = 1; continue; }
+		for (uint32_t a = 1; a < M.n; ++a) {   // insertion sort by (trial, symbol)
+			uint32_t kk = M.key[a], tt = M.tm[a], ss = M.slot[a]; uint32_t b = a;
+			while (b > 0 && M.key[b - 1] > kk) { M.key[b] = M.key[b - 1]; M.tm[b] = M.tm[b - 1]; M.slot[b] = M.slot[b - 1]; --b; }
+			M.key[b] = kk; M.tm[b] = tt; M.slot[b] = ss;
+		}
+		uint32_t c[4] = {0, 0, 0, 0};
+		for (uint32_t a = 0; a < M.n; ++a) {
+			uint32_t sym = M.key[a] & 3, loc = delta_count_at(D, M.slot[a]);
+			if (loc) c[sym] = ci_plus(ci, c[sym], loc, dc);
+		}
+		const uint32_t lev = st ? FQSK_LEVEL_SMER : FQSK_LEVEL_BMER;
+		fqsk_base_rec *rec = P.prov + e.rec;
+		if (rec->level != lev || rec->counts[0] != c[0] || rec->counts[1] != c[1] || rec->counts[2] != c[2] || rec->counts[3] != c[3]) {
+			rec->counts[0] = c[0]; rec->counts[1] = c[1]; rec->counts[2] = c[2]; rec->counts[3] = c[3];
+			rec->level = (uint8_t) lev;
+			P.dirty[e.read] = 1;
+			P.flags[6] = 1;
+		}
+	}
+	P.hot_draws[st] = dc.used;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // k_walk: one WARP per read, "speculative chunks with commit-prefix".
 // The corrected registers of the reference are the registers of a CORRECTED READ: the original symbols with the patches
@@ -452,12 +569,12 @@ __global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P, 
 					done = true;
 				} else {
 					lane_wl = true;   // the thread-local table is consulted here: this read is re-walked when the delta exists / changes
-					if (delta_find(S.delta_b, E.cib, bc, cb, tbase + i, c, &lane_unsup)) { lev = FQSK_LEVEL_BMER; done = true; }
+					if (delta_find(S.delta_b, E.cib, bc, cb, 2 * (tbase + i), c, &lane_unsup)) { lev = FQSK_LEVEL_BMER; done = true; }
 					if (!done && ht_find(E.hb, E.cib, bu, cb, c, nodraw)) { lev = FQSK_LEVEL_BMER_UNC; done = true; }
 				}
 				if (!done) {
 					if (ht_find(E.hs, E.cis, sc, cs, c, nodraw)) lev = FQSK_LEVEL_SMER;
-					else if (delta_find(S.delta_s, E.cis, sc, cs, tbase + i, c, &lane_unsup)) lev = FQSK_LEVEL_SMER;
+					else if (delta_find(S.delta_s, E.cis, sc, cs, 2 * (tbase + i), c, &lane_unsup)) lev = FQSK_LEVEL_SMER;
 				}
 				if (lev == FQSK_LEVEL_BMER_UNC) { bc = bu; ev_revert = true; lane_cor = 0; new_cor = 0; lev = FQSK_LEVEL_BMER; }   // dna.cpp:697-705
 			}
@@ -544,10 +661,12 @@ __global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P, 
 			}
 			// pushes: positions of earlier lanes first; inside a position: b, [repaired b]
 			uint32_t ib = nb + __popc(mb0 & below) + __popc(mb1 & below);
-			if (push_b0) { if (check) changed |= (out_b[ib] != key_b0) | (tim_b[ib] != tbase + i); out_b[ib] = key_b0; tim_b[ib] = tbase + i; ++ib; }
-			if (repaired) { if (check) changed |= (out_b[ib] != key_b1) | (tim_b[ib] != tbase + i); out_b[ib] = key_b1; tim_b[ib] = tbase + i; }
+			// push time = 2 * position (+1 for the repaired b-mer, which the reference pushes second: dna.cpp:822-826 vs 858-873)
+			const uint32_t tpos = 2 * (tbase + i);
+			if (push_b0) { if (check) changed |= (out_b[ib] != key_b0) | (tim_b[ib] != tpos); out_b[ib] = key_b0; tim_b[ib] = tpos; ++ib; }
+			if (repaired) { if (check) changed |= (out_b[ib] != key_b1) | (tim_b[ib] != tpos + 1); out_b[ib] = key_b1; tim_b[ib] = tpos + 1; }
 			uint32_t is = ns + __popc(ms0 & below);
-			if (push_s0) { if (check) changed |= (out_s[is] != key_s0) | (tim_s[is] != tbase + i); out_s[is] = key_s0; tim_s[is] = tbase + i; }
+			if (push_s0) { if (check) changed |= (out_s[is] != key_s0) | (tim_s[is] != tpos); out_s[is] = key_s0; tim_s[is] = tpos; }
 			uint32_t ip = np + 2 * __popc(mp0 & below);
 			if (push_p0) { out_p[ip] = key_p0; out_p[ip + 1] = key_p1; }
 		}

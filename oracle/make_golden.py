@@ -39,8 +39,17 @@ def run_ref(fastq_path, gs, extra, tmp):
     return recs, d, open(plain, "rb").read(), open(dec, "rb").read()
 
 
-def make_case(name, G, n_reads, L, gs, seed, n_frac=0.0, dup_frac=0.0, extra=("-om", "o")):
+def make_case(name, G, n_reads, L, gs, seed, n_frac=0.0, dup_frac=0.0, extra=("-om", "o"), repeats=False):
     genome = synth.make_genome(G, seed)
+    if repeats:
+        # low-complexity stretches (homopolymers, di-/tri-nucleotide repeats, a tandem duplication): k-mers that occur far more
+        # than 8 times inside one sync segment, so the thread-local counters run on the cinc_lb / cinc_ls PRNG streams
+        rng = np.random.default_rng(seed + 99)
+        for a in range(200, G - 400, 900):
+            kind = rng.integers(0, 4)
+            unit = [np.array([rng.integers(0, 4)]), rng.integers(0, 4, 2), rng.integers(0, 4, 3), rng.integers(0, 4, 31)][kind]
+            ln = int(rng.integers(60, 220))
+            genome[a:a + ln] = np.resize(unit, ln)
     codes, err = synth.make_reads(genome, n_reads, L=L, seed=seed, n_frac=n_frac, dup_frac=dup_frac)
     with tempfile.TemporaryDirectory() as tmp:
         fq = os.path.join(tmp, "in.fastq")
@@ -73,6 +82,8 @@ def main():
     make_case("se_orig_gs1", G=6000, n_reads=1500, L=80, gs=1, seed=7, n_frac=0.002, dup_frac=0.01)
     # same options as BASELINE config 2 (-gs 100: prefix 12, p17/s20/b24), small input
     make_case("se_orig_gs100", G=20000, n_reads=1200, L=100, gs=100, seed=43)
+    # repeats: thread-local counters above the deterministic range (cinc_lb / cinc_ls draws) inside a segment
+    make_case("se_orig_repeats_gs1", G=8000, n_reads=1600, L=90, gs=1, seed=51, n_frac=0.001, repeats=True)
     # sorted order (-om s): bins by 4-symbol prefix, std::sort inside a bin, sorted-prefix coding (flag / dif) + suffix from p_len
     make_case("se_sorted_gs1", G=5000, n_reads=2500, L=70, gs=1, seed=45, n_frac=0.002, dup_frac=0.01, extra=("-om", "s"))
 

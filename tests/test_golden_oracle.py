@@ -6,7 +6,7 @@ from oracle import oracle as O
 from tests import helpers as H
 
 
-@pytest.mark.parametrize("name", ["se_orig_gs1", "se_orig_gs100"])
+@pytest.mark.parametrize("name", ["se_orig_gs1", "se_orig_gs100", "se_orig_repeats_gs1"])
 def test_oracle_matches_reference_tap(name):
     g = H.load_golden(name)
     pref, p, s, b = O.kmer_params(int(g["gs"]))
@@ -18,6 +18,8 @@ def test_oracle_matches_reference_tap(name):
     if name == "se_orig_gs1":   # the fixture must exercise the hard paths, otherwise it pins nothing
         assert st["draws_b"] > 1000 and st["rough_b"] > 100 and st["repair_existing"] > 10 and st["local_hits"] > 10
         assert (recs["pos"] == O.POS_DUP).sum() > 0
+    if name == "se_orig_repeats_gs1":
+        assert st["draws_lb"] > 1000    # thread-local counters above thr: cinc_lb in use
     e.close()
 
 

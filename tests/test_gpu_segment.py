@@ -12,7 +12,7 @@ from tests import helpers as H
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", ["se_orig_gs1", "se_orig_gs100"])
+@pytest.mark.parametrize("name", ["se_orig_gs1", "se_orig_gs100", "se_orig_repeats_gs1"])
 def test_engine_matches_reference_golden(name):
     g = H.load_golden(name)
     pref, p, s, b = E.kmer_params(int(g["gs"]))
@@ -22,6 +22,9 @@ def test_engine_matches_reference_golden(name):
     want = want[want["pos"] < 0xFFFFFFF0]
     H.assert_recs_equal(recs, want)
     H.assert_dump_equal(e, g)
+    if name == "se_orig_repeats_gs1":    # low-complexity reads: the thread-local PRNG streams (cinc_lb) must have been used
+        st = e.stats()
+        assert st["n_hot_segments"] > 0 and st["draws_lb"] > 0
     e.close()
 
 
