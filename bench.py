@@ -167,6 +167,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-reads", type=int, default=40_000)
     ap.add_argument("--trace-blocks", type=int, default=0, help="print per-block phase ms every N blocks to stderr")
+    ap.add_argument("--profile-block", type=int, default=-1, help="cudaProfilerStart/Stop around this block (for ncu --profile-from-start off)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -234,7 +235,11 @@ def main():
     t_wall = time.time()
     prev_prof, t_prev = eng.profile(), time.time()
     for g in range(args.warmup, n_blocks):
+        if g == args.profile_block:
+            torch.cuda.cudart().cudaProfilerStart()
         run_block_device(g)
+        if g == args.profile_block:
+            torch.cuda.cudart().cudaProfilerStop()
         if args.trace_blocks and (g % args.trace_blocks == 0 or g == n_blocks - 1):
             pr = eng.profile()
             print(f"block {g} ({len(sched[g])} segments): wall {1e3 * (time.time() - t_prev):.1f} ms " +
