@@ -45,6 +45,7 @@ struct Stream {            // one mt19937 stream (utils.h:257, seeded 5481 at ut
 	uint32_t *buf = nullptr;   // generated ahead of use on a side CUDA stream
 	uint32_t *state = nullptr;
 	uint64_t cap = 0, generated = 0, consumed = 0;   // cap is a power of two; absolute positions
+	uint64_t safe = 0;         // outputs below this position are known to be complete for the main stream (it waited for them)
 	cudaEvent_t ev = nullptr;  // completion of the latest generation launch
 	bool ev_pending = false;   // the main stream has not waited for `ev` yet
 };
@@ -181,7 +182,7 @@ int table_alloc(fqsk_handle *h, Table &t, uint32_t k, uint32_t cbits, uint32_t B
 	return FQSK_OK;
 }
 
-inline uint64_t stream_avail_of(const Stream &s) { return s.generated - s.consumed; }
+inline uint64_t stream_avail_of(const Stream &s) { return s.generated - s.consumed; }   // generated (maybe still in flight) ahead of the consumer
 int stream_init(fqsk_handle *h, Stream &s, uint64_t cap) {
 	uint32_t st[624];
 	st[0] = 5481u;
@@ -190,7 +191,7 @@ int stream_init(fqsk_handle *h, Stream &s, uint64_t cap) {
 	CK(cudaMemcpy(s.state, st, 624 * 4, cudaMemcpyHostToDevice));
 	CK(cudaMalloc(&s.buf, cap * 4));
 	CK(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
-	s.cap = cap; s.generated = s.consumed = 0; s.ev_pending = false;
+	s.cap = cap; s.generated = s.consumed = 0; s.safe = 0; s.ev_pending = false;
 	return FQSK_OK;
 }
 // enqueue generation up to absolute position `upto` (rounded up to 624-blocks) on the side stream
@@ -229,7 +230,9 @@ int stream_generate(fqsk_handle *h, Stream &s, uint64_t upto) {
 // make outputs [consumed, consumed + need) available to kernels launched on the main stream after this call
 int stream_ensure(fqsk_handle *h, Stream &s, uint64_t need) {
 	if (s.consumed + need > s.generated) CKR(stream_generate(h, s, s.consumed + need + (need < (1u << 20) ? (1u << 20) : need / 2)));
-	if (s.ev_pending) { CK(cudaStreamWaitEvent(h->st, s.ev, 0)); s.ev_pending = false; }
+	// wait for the generator only when the requested range reaches into outputs the main stream has not waited for yet
+	if (s.consumed + need > s.safe && s.ev_pending) { CK(cudaStreamWaitEvent(h->st, s.ev, 0)); s.ev_pending = false; s.safe = s.generated; }
+	else if (!s.ev_pending) s.safe = s.generated;
 	return FQSK_OK;
 }
 // keep the generator ahead of the consumer without blocking anybody
@@ -238,7 +241,7 @@ int stream_prefetch(fqsk_handle *h, Stream &s, uint64_t ahead) {
 	return FQSK_OK;
 }
 inline const uint32_t *stream_ptr(const Stream &s) { return s.buf; }
-inline uint64_t stream_avail(const Stream &s) { return s.generated - s.consumed; }
+inline uint64_t stream_avail(const Stream &s) { return (s.safe > s.consumed ? s.safe : s.consumed) - s.consumed; }
 
 int ensure_iota(fqsk_handle *h, uint32_t n) {
 	if (n <= h->iota_n) return FQSK_OK;
@@ -331,34 +334,58 @@ int apply_sorted(fqsk_handle *h, Table &t, Stream &rng, const unsigned long long
 	if (!n) return FQSK_OK;
 	CK(h->slot_of.ensure((size_t) n * 8));
 	CK(h->flag8.ensure((size_t) n + 4)); CK(h->draw_off.ensure(((size_t) n + 1) * 4)); CK(h->final_cnt.ensure((size_t) n * 4));
+	const uint32_t g = nblk(n, 256);
+	uint8_t *flag = h->flag8.as<uint8_t>();
+	uint32_t *doff = h->draw_off.as<uint32_t>(), *c0_of = h->final_cnt.as<uint32_t>();
+	unsigned long long *slot_of = h->slot_of.as<unsigned long long>();
 	{
 		Phase ph(h, FQSK_PH_SYNC_LOCATE);
-		k_locate_heads<<<nblk(n, 256), 256, 0, h->st>>>(t.d, skeys, n, h->slot_of.as<unsigned long long>());
-		LAUNCHED(h);
+		CK(cudaMemsetAsync(h->d_flags, 0, 8 * sizeof(int), h->st));
+		CK(cudaMemsetAsync(flag + n, 0, 4, h->st));
+		k_locate_heads<<<g, 256, 0, h->st>>>(t.d, t.ci, skeys, sidx, n, slot_of, c0_of, flag, h->d_flags); LAUNCHED(h);
 	}
 	Phase ph(h, FQSK_PH_SYNC_APPLY);
-	CK(cudaMemsetAsync(h->flag8.p, 0, (size_t) n + 4, h->st));
-	CK(cudaMemsetAsync(h->draw_off.p, 0, ((size_t) n + 1) * 4, h->st));
 	uint32_t total_draws = 0;
+	bool safe_done = false;
 	for (int it = 0;; ++it) {
 		if (it > 64) return fail(h, FQSK_E_NO_CONVERGE, "sync insert: draw flags did not settle");
-		CK(cudaMemsetAsync(h->d_flags, 0, 8 * sizeof(int), h->st));
-		k_apply_keys<<<nblk(n, 256), 256, 0, h->st>>>(t.d, t.ci, skeys, sidx, n, h->slot_of.as<unsigned long long>(), h->flag8.as<uint8_t>(),
-		                                               h->draw_off.as<uint32_t>(), rng.buf, rng.cap - 1, rng.consumed, stream_avail(rng), h->final_cnt.as<uint32_t>(), h->d_flags);
-		LAUNCHED(h);
-		int fl[8];
-		CKR(read_flags(h, fl, 8));
-		if (fl[6]) h->hot_seen[&t == &h->tb ? 1 : 0] = true;
-		if (!fl[2] && !fl[0]) break;
-		// flags changed (or the draw window was short): rescan the draw indices in push order and make the window long enough
-		CKR((scan_excl<uint8_t, uint32_t>(h, h->flag8.as<uint8_t>(), h->draw_off.as<uint32_t>(), n + 1, 0u)));
-		CK(cudaMemcpyAsync(h->h_small, h->draw_off.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, h->st));
+		CKR((scan_excl<uint8_t, uint32_t>(h, flag, doff, n + 1, 0u)));
+		CKR(stream_ensure(h, rng, 0));
+		CK(cudaMemsetAsync(h->d_flags, 0, 3 * sizeof(int), h->st));      // [0] draw window short, [2] corrected a flag; [3] unsafe seen / [6] hot seen stay
+		if (!safe_done) { k_apply_keys<<<g, 256, 0, h->st>>>(t.d, t.ci, skeys, sidx, n, slot_of, c0_of, flag, doff, rng.buf, rng.cap - 1, rng.consumed, stream_avail(rng), 0, 0, h->d_flags); LAUNCHED(h); }
+		uint32_t *hs = (uint32_t *) h->h_small;
+		CK(cudaMemcpyAsync(hs, h->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+		CK(cudaMemcpyAsync(hs + 8, doff + n, 4, cudaMemcpyDeviceToHost, h->st));
 		CK(cudaStreamSynchronize(h->st));
-		total_draws = *(uint32_t *) h->h_small;
-		CKR(stream_ensure(h, rng, total_draws));
+		resolve_phases(h);
+		int fl[8]; memcpy(fl, hs, sizeof fl);
+		total_draws = hs[8];
+		if (fl[6]) h->hot_seen[&t == &h->tb ? 1 : 0] = true;
+		if (fl[0]) { CKR(stream_ensure(h, rng, (uint64_t) total_draws + (1u << 16))); continue; }   // safe groups rewrite the same values
+		if (!fl[3]) break;                    // no group can saturate: done with one pass
+		// unsafe groups: verify their flags until a pass makes no correction, then commit them; safe groups are committed again
+		// by the final pass only if the indices moved (a correction shifts every later draw index)
+		bool moved = false;
+		for (int vit = 0;; ++vit) {
+			if (vit > 64) return fail(h, FQSK_E_NO_CONVERGE, "sync insert: draw flags did not settle");
+			CK(cudaMemsetAsync(h->d_flags, 0, 3 * sizeof(int), h->st));
+			k_apply_keys<<<g, 256, 0, h->st>>>(t.d, t.ci, skeys, sidx, n, slot_of, c0_of, flag, doff, rng.buf, rng.cap - 1, rng.consumed, stream_avail(rng), 1, 0, h->d_flags); LAUNCHED(h);
+			CKR(read_flags(h, fl, 8));
+			if (fl[0]) { CKR(stream_ensure(h, rng, 2 * stream_avail(rng) + (1u << 16))); continue; }
+			if (!fl[2]) break;
+			moved = true;
+			CKR((scan_excl<uint8_t, uint32_t>(h, flag, doff, n + 1, 0u)));
+		}
+		CK(cudaMemcpyAsync(hs + 8, doff + n, 4, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaStreamSynchronize(h->st));
+		total_draws = hs[8];
+		CKR(stream_ensure(h, rng, (uint64_t) total_draws));
+		if (moved) { k_apply_keys<<<g, 256, 0, h->st>>>(t.d, t.ci, skeys, sidx, n, slot_of, c0_of, flag, doff, rng.buf, rng.cap - 1, rng.consumed, stream_avail(rng), 0, 0, h->d_flags); LAUNCHED(h); }
+		k_apply_keys<<<g, 256, 0, h->st>>>(t.d, t.ci, skeys, sidx, n, slot_of, c0_of, flag, doff, rng.buf, rng.cap - 1, rng.consumed, stream_avail(rng), 1, 1, h->d_flags); LAUNCHED(h);
+		CKR(read_flags(h, fl, 8));
+		if (fl[0] || fl[2]) return fail(h, FQSK_E_CUDA, "internal error: unsafe-group commit pass was not clean");
+		break;
 	}
-	k_commit_keys<<<nblk(n, 256), 256, 0, h->st>>>(t.d, skeys, n, h->slot_of.as<unsigned long long>(), h->final_cnt.as<uint32_t>());
-	LAUNCHED(h);
 	rng.consumed += total_draws;
 	return FQSK_OK;
 }
@@ -1128,7 +1155,7 @@ int fqsk_ht_find(fqsk_handle *h, int table, const uint64_t *kmer_dir, const uint
 		LAUNCHED(h);
 		int fl[4];
 		CKR(read_flags(h, fl, 4));
-		if (fl[0]) { CKR(stream_ensure(h, rng, 2 * stream_avail(rng))); --it; continue; }
+		if (fl[0]) { CKR(stream_ensure(h, rng, 2 * stream_avail(rng) + (1u << 16))); --it; continue; }
 		CKR((scan_excl<uint32_t, unsigned long long>(h, d_used, d_guess, (uint32_t) n + 1, 0ull)));
 		CK(cudaMemcpyAsync(now.data(), d_guess, (n + 1) * 8, cudaMemcpyDeviceToHost, h->st));
 		CK(cudaStreamSynchronize(h->st));

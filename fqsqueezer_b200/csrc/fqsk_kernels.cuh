@@ -188,46 +188,60 @@ __global__ void k_iota(uint32_t *a, uint32_t n) { uint32_t i = blockIdx.x * bloc
 // CHT_kmer::insert(x, cinc) (ht_kmer.h:420-438).
 // ------------------------------------------------------------------------------------------------------------------
 // Input: the row sorted by k-mer (stable, so equal k-mers stay in push order) with the push index of every occurrence.
-// k_locate_heads: one find-or-create per DISTINCT k-mer.
-__global__ void k_locate_heads(HtDev t, const unsigned long long *skeys, uint32_t n, unsigned long long *slot_of) {
+// k_locate_heads: one find-or-create per DISTINCT k-mer; it also sizes the group, reads the counter before the sync (c0) and
+// writes the draw flag of every member in push order (pre-count c0 + r > thr, the counter cannot move otherwise below top).
+// Groups that cannot reach the top of the counter (c0 + m < top) are final with those flags; the others are marked unsafe
+// and go through the verifying passes (k_apply_keys with verify = 1) -- only there can a flag be wrong.
+__global__ void k_locate_heads(HtDev t, CIncP ci, const unsigned long long *skeys, const uint32_t *sidx, uint32_t n, unsigned long long *slot_of, uint32_t *c0_of,
+                               uint8_t *flag, int *flags) {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	unsigned long long key = skeys[i];
 	if (i > 0 && skeys[i - 1] == key) return;   // not a group head
 	bool created;
 	uint64_t s = ht_locate(t, key, created);
-	slot_of[i] = s | (created ? (1ull << 63) : 0ull);
+	uint32_t c0 = created ? 0u : ht_slot_get(t, s);
+	uint32_t m = 0;
+	for (uint32_t q = i; q < n && skeys[q] == key; ++q, ++m) flag[sidx[q]] = (c0 + m > ci.thr) ? 1 : 0;
+	bool unsafe = c0 + m >= t.top;
+	if (unsafe) flags[3] = 1;
+	if (m > ci.thr + 1) flags[6] = 1;           // the thread-local table of the reference drew from its own stream for this k-mer
+	slot_of[i] = s | (unsafe ? (1ull << 63) : 0ull);
+	c0_of[i] = c0;
 }
-// k_apply_keys: one thread per group walks its occurrences in push order.  flag[j] says whether occurrence j consumes a
-// draw; the kernel recomputes that from the counter it sees and reports a change (fix point over the ordered draw indices;
-// after the first pass changes can only come from counters saturating inside the batch).
-__global__ void k_apply_keys(HtDev t, CIncP ci, const unsigned long long *skeys, const uint32_t *sidx, uint32_t n, const unsigned long long *slot_of,
-                             uint8_t *flag, const uint32_t *draw_off, const uint32_t *draws, unsigned long long dmask, unsigned long long dpos, unsigned long long avail, uint32_t *final_cnt, int *flags) {
+// k_apply_keys: one thread per group walks its occurrences in push order and applies Increment() with the scanned draw
+// indices.  verify == 0: only safe groups, the final counter is written straight to the table (blind write: the item's key
+// bits are known).  verify == 1: only unsafe groups; flags are checked against the counters seen (a counter reaching the
+// top stops drawing, ht_kmer.h:435), a mismatch is corrected and reported (flags[2]); nothing is written until the host has
+// seen a pass without corrections (commit == 1).
+__global__ void k_apply_keys(HtDev t, CIncP ci, const unsigned long long *skeys, const uint32_t *sidx, uint32_t n, const unsigned long long *slot_of, const uint32_t *c0_of,
+                             uint8_t *flag, const uint32_t *draw_off, const uint32_t *draws, unsigned long long dmask, unsigned long long dpos, unsigned long long avail,
+                             int verify, int commit, int *flags) {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	unsigned long long key = skeys[i];
 	if (i > 0 && skeys[i - 1] == key) return;
 	unsigned long long so = slot_of[i];
-	uint32_t c = ht_slot_get(t, so & ~(1ull << 63)) - (uint32_t) (so >> 63);   // counter before this sync (fresh slots were claimed with 1)
-	uint32_t gsize = 0;
+	const bool unsafe = (so >> 63) != 0;
+	if (unsafe != (verify != 0)) return;
+	uint32_t c = c0_of[i];
 	for (uint32_t q = i; q < n && skeys[q] == key; ++q) {
-		++gsize;
 		uint32_t j = sidx[q];
-		if (c >= t.top) { if (flag[j]) { flag[j] = 0; flags[2] = 1; } continue; }   // ht_kmer.h:435: cnt < counter_max
-		if (c <= ci.thr) { if (flag[j]) { flag[j] = 0; flags[2] = 1; } ++c; continue; }
-		if (!flag[j]) { flag[j] = 1; flags[2] = 1; continue; }                      // needs a draw it was not given yet
+		if (verify) {
+			uint8_t want = (c < t.top && c > ci.thr) ? 1 : 0;
+			if (flag[j] != want) { flag[j] = want; flags[2] = 1; if (c <= ci.thr) ++c; continue; }
+		}
+		if (c >= t.top) continue;                  // ht_kmer.h:435: cnt < counter_max
+		if (c <= ci.thr) { ++c; continue; }
 		uint32_t di = draw_off[j];
 		if (di >= avail) { flags[0] = 1; continue; }
 		if (draws[(dpos + di) & dmask] % (ci.mult * (c - ci.thr)) == 0) ++c;
 	}
-	if (gsize > ci.thr + 1) flags[6] = 1;   // the thread-local table of the reference drew from its own stream for this k-mer
-	final_cnt[i] = c;
-}
-__global__ void k_commit_keys(HtDev t, const unsigned long long *skeys, uint32_t n, const unsigned long long *slot_of, const uint32_t *final_cnt) {
-	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	if (i > 0 && skeys[i - 1] == skeys[i]) return;
-	ht_slot_set(t, slot_of[i] & ~(1ull << 63), final_cnt[i]);
+	if (verify && !commit) return;
+	// blind write of the item: [occupied | rem | ends | counter] resp. [(k-mer + 1) | counter]
+	uint64_t slot = so & ~(1ull << 63), nm = 8ull << t.B;
+	HtKey hk = ht_key(t, key);
+	if (slot < nm) t.main[slot] = hk.q | c; else t.stash[slot - nm] = ((hk.kal + 1) << t.cbits) | c;
 }
 
 // ------------------------------------------------------------------------------------------------------------------

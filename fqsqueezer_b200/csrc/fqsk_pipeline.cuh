@@ -876,47 +876,65 @@ __global__ void __launch_bounds__(128) k_fold(EngineDev E, SegDev S, PipeDev P, 
 	if (P.rdraws_b[r] != db.used || P.rdraws_s[r] != ds.used) { P.rdraws_b[r] = db.used; P.rdraws_s[r] = ds.used; P.flags[7] = 1; }
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// single-CTA scans over per-read arrays (n_reads is at most a few 10^4: one CTA beats a chain of library launches)
-// ------------------------------------------------------------------------------------------------------------------
+// Block-wide exclusive scan helper: every thread owns ITEMS consecutive elements (serial), warp shuffles + one smem round
+// combine the per-thread sums; `carry` threads the running total through the chunks of a long array.
+template <typename T, int NQ, int ITEMS>
+__device__ __forceinline__ void block_scan_chunk(T (&v)[NQ][ITEMS], T (&ex)[NQ][ITEMS], T (*sh)[32], T *carry) {
+	const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5;
+	T tsum[NQ], inc[NQ];
+	for (int q = 0; q < NQ; ++q) {
+		T run = 0;
+		for (int e = 0; e < ITEMS; ++e) { ex[q][e] = run; run += v[q][e]; }
+		tsum[q] = run;
+		T x = run;
+		for (int o = 1; o < 32; o <<= 1) { T y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+		inc[q] = x;
+		if (lane == 31) sh[q][w] = x;
+	}
+	__syncthreads();
+	if (w == 0) {
+		for (int q = 0; q < NQ; ++q) {
+			T x = sh[q][lane];
+			for (int o = 1; o < 32; o <<= 1) { T y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+			sh[q][lane] = x;
+		}
+	}
+	__syncthreads();
+	for (int q = 0; q < NQ; ++q) {
+		T base = carry[q] + (w ? sh[q][w - 1] : 0) + inc[q] - tsum[q];
+		for (int e = 0; e < ITEMS; ++e) ex[q][e] += base;
+	}
+	__syncthreads();
+	if (t < NQ) carry[t] += sh[t][31];
+	__syncthreads();
+}
+
 struct SegTotals {        // written by the scan kernels, read by the host once per segment
 	unsigned long long n_rec; U64x4 letters;
 	uint32_t tot_b, tot_s, tot_p, hidden;
 	unsigned long long draws_b, draws_s;
 };
 
+// single-CTA scans over per-read arrays (n_reads is at most a few 10^4: one CTA beats a chain of library launches)
 __global__ void __launch_bounds__(1024) k_scan_reads(SegDev S, unsigned long long *rec_off, U64x4 *sl_prefix, SegTotals *tot, uint32_t *n_rec_dev) {
+	const int IT = 4;
 	__shared__ unsigned long long sh[5][32];
 	__shared__ unsigned long long carry[5];
-	const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5;
+	const uint32_t t = threadIdx.x;
 	if (t < 5) carry[t] = 0;
 	__syncthreads();
-	for (uint32_t base = 0; base < S.n_reads; base += 1024) {
-		uint32_t r = base + t;
-		unsigned long long v[5] = {0, 0, 0, 0, 0};
-		if (r < S.n_reads) { v[0] = S.n_coded[r]; U64x4 L = S.letters[r]; v[1] = L.v[0]; v[2] = L.v[1]; v[3] = L.v[2]; v[4] = L.v[3]; }
-		unsigned long long inc[5];
-		for (int q = 0; q < 5; ++q) {
-			unsigned long long x = v[q];
-			for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-			inc[q] = x;
-			if (lane == 31) sh[q][w] = x;
+	for (uint32_t base = 0; base < S.n_reads; base += 1024 * IT) {
+		unsigned long long v[5][IT], ex[5][IT];
+		for (int e = 0; e < IT; ++e) {
+			uint32_t r = base + t * IT + e;
+			if (r < S.n_reads) { v[0][e] = S.n_coded[r]; U64x4 L = S.letters[r]; v[1][e] = L.v[0]; v[2][e] = L.v[1]; v[3][e] = L.v[2]; v[4][e] = L.v[3]; }
+			else { v[0][e] = v[1][e] = v[2][e] = v[3][e] = v[4][e] = 0; }
 		}
-		__syncthreads();
-		if (w == 0) {
-			for (int q = 0; q < 5; ++q) {
-				unsigned long long x = sh[q][lane];
-				for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-				sh[q][lane] = x;
-			}
+		block_scan_chunk<unsigned long long, 5, IT>(v, ex, sh, carry);
+		for (int e = 0; e < IT; ++e) {
+			uint32_t r = base + t * IT + e;
+			if (r < S.n_reads) { rec_off[r] = ex[0][e]; U64x4 o; o.v[0] = ex[1][e]; o.v[1] = ex[2][e]; o.v[2] = ex[3][e]; o.v[3] = ex[4][e]; sl_prefix[r] = o; }
 		}
-		__syncthreads();
-		unsigned long long ex[5];
-		for (int q = 0; q < 5; ++q) ex[q] = carry[q] + (w ? sh[q][w - 1] : 0) + inc[q] - v[q];
-		if (r < S.n_reads) { rec_off[r] = ex[0]; U64x4 o; o.v[0] = ex[1]; o.v[1] = ex[2]; o.v[2] = ex[3]; o.v[3] = ex[4]; sl_prefix[r] = o; }
-		__syncthreads();
-		if (t < 5) carry[t] += sh[t][31];
-		__syncthreads();
 	}
 	if (t == 0) {
 		rec_off[S.n_reads] = carry[0];
@@ -930,72 +948,38 @@ __global__ void __launch_bounds__(1024) k_scan_reads(SegDev S, unsigned long lon
 // up to 4 u32 arrays -> exclusive scans (u32) + totals
 __global__ void __launch_bounds__(1024) k_scan_u32x4(uint32_t n, const uint32_t *a0, uint32_t *o0, const uint32_t *a1, uint32_t *o1,
                                                      const uint32_t *a2, uint32_t *o2, const uint32_t *a3, uint32_t *o3, uint32_t *totals) {
+	const int IT = 8;
 	__shared__ uint32_t sh[4][32];
 	__shared__ uint32_t carry[4];
-	const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5;
+	const uint32_t t = threadIdx.x;
 	const uint32_t *in[4] = {a0, a1, a2, a3};
 	uint32_t *out[4] = {o0, o1, o2, o3};
 	if (t < 4) carry[t] = 0;
 	__syncthreads();
-	for (uint32_t base = 0; base < n; base += 1024) {
-		uint32_t r = base + t;
-		uint32_t v[4], inc[4];
-		for (int q = 0; q < 4; ++q) {
-			v[q] = (in[q] && r < n) ? in[q][r] : 0;
-			uint32_t x = v[q];
-			for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-			inc[q] = x;
-			if (lane == 31) sh[q][w] = x;
-		}
-		__syncthreads();
-		if (w == 0) {
-			for (int q = 0; q < 4; ++q) {
-				uint32_t x = sh[q][lane];
-				for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-				sh[q][lane] = x;
-			}
-		}
-		__syncthreads();
-		for (int q = 0; q < 4; ++q) if (out[q] && r < n) out[q][r] = carry[q] + (w ? sh[q][w - 1] : 0) + inc[q] - v[q];
-		__syncthreads();
-		if (t < 4) carry[t] += sh[t][31];
-		__syncthreads();
+	for (uint32_t base = 0; base < n; base += 1024 * IT) {
+		uint32_t v[4][IT], ex[4][IT];
+		for (int q = 0; q < 4; ++q) for (int e = 0; e < IT; ++e) { uint32_t r = base + t * IT + e; v[q][e] = (in[q] && r < n) ? in[q][r] : 0; }
+		block_scan_chunk<uint32_t, 4, IT>(v, ex, sh, carry);
+		for (int q = 0; q < 4; ++q) if (out[q]) for (int e = 0; e < IT; ++e) { uint32_t r = base + t * IT + e; if (r < n) out[q][r] = ex[q][e]; }
 	}
 	if (t < 4) { if (out[t]) out[t][n] = carry[t]; totals[t] = carry[t]; }
 }
 
 // per-read draw counts (u32) -> exclusive scans (u64) + totals
 __global__ void __launch_bounds__(1024) k_scan_draws(uint32_t n, const uint32_t *a0, unsigned long long *o0, const uint32_t *a1, unsigned long long *o1, unsigned long long *totals) {
+	const int IT = 8;
 	__shared__ unsigned long long sh[2][32];
 	__shared__ unsigned long long carry[2];
-	const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5;
+	const uint32_t t = threadIdx.x;
 	const uint32_t *in[2] = {a0, a1};
 	unsigned long long *out[2] = {o0, o1};
 	if (t < 2) carry[t] = 0;
 	__syncthreads();
-	for (uint32_t base = 0; base < n; base += 1024) {
-		uint32_t r = base + t;
-		unsigned long long v[2], inc[2];
-		for (int q = 0; q < 2; ++q) {
-			v[q] = r < n ? in[q][r] : 0;
-			unsigned long long x = v[q];
-			for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-			inc[q] = x;
-			if (lane == 31) sh[q][w] = x;
-		}
-		__syncthreads();
-		if (w == 0) {
-			for (int q = 0; q < 2; ++q) {
-				unsigned long long x = sh[q][lane];
-				for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-				sh[q][lane] = x;
-			}
-		}
-		__syncthreads();
-		for (int q = 0; q < 2; ++q) if (r < n) out[q][r] = carry[q] + (w ? sh[q][w - 1] : 0) + inc[q] - v[q];
-		__syncthreads();
-		if (t < 2) carry[t] += sh[t][31];
-		__syncthreads();
+	for (uint32_t base = 0; base < n; base += 1024 * IT) {
+		unsigned long long v[2][IT], ex[2][IT];
+		for (int q = 0; q < 2; ++q) for (int e = 0; e < IT; ++e) { uint32_t r = base + t * IT + e; v[q][e] = r < n ? in[q][r] : 0; }
+		block_scan_chunk<unsigned long long, 2, IT>(v, ex, sh, carry);
+		for (int q = 0; q < 2; ++q) for (int e = 0; e < IT; ++e) { uint32_t r = base + t * IT + e; if (r < n) out[q][r] = ex[q][e]; }
 	}
 	if (t < 2) { out[t][n] = carry[t]; totals[t] = carry[t]; }
 }
