@@ -243,7 +243,9 @@ def main():
         if args.trace_blocks and (g % args.trace_blocks == 0 or g == n_blocks - 1):
             pr = eng.profile()
             print(f"block {g} ({len(sched[g])} segments): wall {1e3 * (time.time() - t_prev):.1f} ms " +
-                  str({k: round(pr[k] - prev_prof[k], 2) for k in pr}), file=sys.stderr, flush=True)
+                  str({k: round(pr[k] - prev_prof[k], 2) for k in pr}) + " " +
+                  str({k: v for k, v in eng.stats().items() if k in ("n_hot_segments", "n_replays", "bmer_buckets", "smer_buckets", "bmer_stash_used", "n_bmers", "n_smers", "draws_b")}),
+                  file=sys.stderr, flush=True)
         if args.trace_blocks:
             prev_prof, t_prev = eng.profile(), time.time()
     dev_ms = eng.timer_end()

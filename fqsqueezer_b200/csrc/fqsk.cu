@@ -37,6 +37,16 @@ struct DevBuf {
 		if (e == cudaSuccess) cap = want;
 		return e;
 	}
+	cudaError_t ensure_keep(size_t bytes, cudaStream_t st) {   // grows without losing the contents
+		if (bytes <= cap) return cudaSuccess;
+		size_t want = bytes + bytes / 2 + 256;
+		void *np = nullptr;
+		cudaError_t e = cudaMalloc(&np, want);
+		if (e != cudaSuccess) return e;
+		if (p) { cudaMemcpyAsync(np, p, cap, cudaMemcpyDeviceToDevice, st); cudaStreamSynchronize(st); cudaFree(p); }
+		p = np; cap = want;
+		return cudaSuccess;
+	}
 	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 	template <typename T> T *as() const { return (T *) p; }
 };
@@ -74,8 +84,8 @@ struct fqsk_handle {
 	unsigned long long sl_base[4] = {0, 0, 0, 0};   // s_letters (dna.h:92, dna.cpp:2047-2057)
 	uint64_t hidden_p = 0;                           // no_pmer_hidden_updates (dna.cpp:850, 2417)
 	// previous read / previous prefix p-mer carried across segments
-	DevBuf prev_read; uint32_t prev_len = 0;
-	unsigned long long pprev_dir = 0; uint32_t pprev_valid = 0;
+	DevBuf prev_read;
+	Carry *d_carry = nullptr;            // inside d_status: prev read length + pmer_can_prev (written by k_save_carry)
 	// segment buffers
 	DevBuf dna, off, len, dup, n_coded, letters, rec_off, sl_prefix, recs, push_b, push_s, push_p, cnt_b, cnt_s, cnt_p, hidden,
 	       draw_cnt, draw_cnt_prev, draw_scan, off_b[2], off_s[2], off_p, row_b[2], row_s[2], row_p, dk_b, di_b, dk_s, di_s, iota, cub_tmp,
@@ -84,6 +94,8 @@ struct fqsk_handle {
 	       sidx_b, sidx_s, stime_b, stime_s, sort_k, sort_v, rkind, rreg, rslot, dirty, rdraws_b, rdraws_s, totals,
 	       y_tslot, y_c0, y_m, y_draw, y_j, y_final, y_flag_at, y_own, y_lead, y_rank, y_flag, y_doff, idx_k, idx_t, idx_rt,
 	       miss_fold, hr_b[3], hr_s[3], evk[2], evv[2], evk_s[2], evv_s[2];
+	bool look_fresh = false;                 // h_small holds the status block + counters as of the end of everything enqueued so far
+	int *d_sfast = nullptr;                  // inside d_status: the s-mer fast path saw a counter above thr
 	bool hot = false;                        // the current segment is being redone with the ordered thread-local evaluator
 	bool hot_seen[2] = {false, false};       // [0] s, [1] b: the last sync saw a k-mer pushed more than thr + 1 times in its row
 	DeltaDev seg_delta_b{}, seg_delta_s{};   // the converged segment's delta tables (valid while `pending`)
@@ -332,6 +344,7 @@ int table_grow_if_needed(fqsk_handle *h, Table &t) {
 // ---------------------------------------------------------------------------------------------------------------
 int apply_sorted(fqsk_handle *h, Table &t, Stream &rng, const unsigned long long *skeys, const uint32_t *sidx, uint32_t n) {
 	if (!n) return FQSK_OK;
+	h->look_fresh = false;
 	CK(h->slot_of.ensure((size_t) n * 8));
 	CK(h->flag8.ensure((size_t) n + 4)); CK(h->draw_off.ensure(((size_t) n + 1) * 4)); CK(h->final_cnt.ensure((size_t) n * 4));
 	const uint32_t g = nblk(n, 256);
@@ -403,11 +416,12 @@ int sort_row(fqsk_handle *h, const unsigned long long *row, uint32_t n, uint32_t
 int apply_inserts(fqsk_handle *h, Table &t, Stream &rng, const unsigned long long *d_kmers, uint32_t n, bool *fast_ok = nullptr) {
 	if (!n) return FQSK_OK;
 	if (n >= 0x80000000u) return fail(h, FQSK_E_INVAL, "more than 2^31 k-mers in one sync row");
+	h->look_fresh = false;
 	if (fast_ok && *fast_ok) {
 		Phase ph(h, FQSK_PH_SYNC_APPLY);
 		CK(cudaMemsetAsync(h->d_flags, 0, 8 * sizeof(int), h->st));
 		CK(h->y_flag.ensure((size_t) n + 4));
-		k_insert_fast<<<nblk(n, 256), 256, 0, h->st>>>(t.d, t.ci, d_kmers, n, h->y_flag.as<uint8_t>(), h->d_flags); LAUNCHED(h);
+		k_insert_fast<<<nblk(n, 256), 256, 0, h->st>>>(t.d, t.ci, d_kmers, n, h->y_flag.as<uint8_t>(), h->d_flags + 2); LAUNCHED(h);
 		int fl[8];
 		CKR(read_flags(h, fl, 8));
 		if (!fl[2]) return FQSK_OK;
@@ -454,12 +468,14 @@ int apply_indexed(fqsk_handle *h, Table &t, Stream &rng, const DeltaDev &D, cons
 		k_sync_apply<<<g, 256, 0, h->st>>>(t.d, t.ci, Y, row, n, rng.buf, rng.cap - 1, rng.consumed, stream_avail(rng)); LAUNCHED(h);
 		k_sync_commit<<<g, 256, 0, h->st>>>(t.d, Y, n); LAUNCHED(h);
 		uint32_t *hs = (uint32_t *) h->h_small;
-		CK(cudaMemcpyAsync(hs, h->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
-		CK(cudaMemcpyAsync(hs + 8, h->y_doff.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaMemcpyAsync(hs, h->d_status, 256, cudaMemcpyDeviceToHost, h->st));                          // flags | ... | s-mer fast-path verdict
+		CK(cudaMemcpyAsync(hs + 64, h->y_doff.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaMemcpyAsync(hs + 72, h->d_counters, 48, cudaMemcpyDeviceToHost, h->st));                    // item counters, fresh p-mer fields
 		CK(cudaStreamSynchronize(h->st));
 		resolve_phases(h);
+		h->look_fresh = true;
 		int fl[8]; memcpy(fl, hs, sizeof fl);
-		total_draws = hs[8];
+		total_draws = hs[64];
 		if (fl[6]) h->hot_seen[&t == &h->tb ? 1 : 0] = true;
 		if (fl[7]) {   // a hot k-mer occurs more than SYNC_GROUP_CAP times in this row: sorted path for the whole row
 			k_sync_unclaim<<<g, 256, 0, h->st>>>(t.d, Y, n); LAUNCHED(h);
@@ -629,7 +645,7 @@ int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes_ac
 				LAUNCHED(h);
 			}
 			CK(cudaMemsetAsync(h->d_u32 + 1, 0, 4, h->st));      // rough scripts are rebuilt
-			{ Phase ph(h, FQSK_PH_ROUGH); k_rough<<<148 * 8, 128, 0, h->st>>>(E, P); LAUNCHED(h); }
+			{ Phase ph(h, FQSK_PH_ROUGH); k_rough<<<std::max<uint32_t>(148, std::min<uint32_t>(nblk(rec_bound, 16), 148 * 32)), 128, 0, h->st>>>(E, P); LAUNCHED(h); }
 			{ Phase ph(h, FQSK_PH_FOLD); k_fold<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(E, S, P, 0); LAUNCHED(h); }
 		}
 		{
@@ -702,8 +718,8 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 
 	SegDev S{};
 	S.dna = d_dna; S.off = d_off; S.len = d_len; S.n_reads = n;
-	S.prev_read = h->prev_read.as<uint8_t>(); S.prev_len = h->prev_len;
-	S.pprev_dir = h->pprev_dir; S.pprev_valid = h->pprev_valid;
+	CK(h->prev_read.ensure_keep((size_t) dna_bytes_actual + 64, h->st));     // a read is never longer than its segment
+	S.prev_read = h->prev_read.as<uint8_t>(); S.carry = h->d_carry;
 	S.dup = h->dup.as<uint8_t>(); S.n_coded = h->n_coded.as<uint32_t>(); S.letters = h->letters.as<U64x4>();
 	S.rec_off = h->rec_off.as<unsigned long long>(); S.sl_prefix = h->sl_prefix.as<U64x4>();
 	for (int i = 0; i < 4; ++i) S.sl_base.v[i] = h->sl_base[i];
@@ -729,6 +745,7 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 		break;
 	}
 	for (int i = 0; i < 4; ++i) h->S.draws[i] = h->rng[i].consumed;
+	k_save_carry<<<1, 256, 0, h->st>>>(S, h->prev_read.as<uint8_t>(), h->d_carry, h->P.mode == FQSK_MODE_SE_SORTED || h->P.mode == FQSK_MODE_PE_SORTED, h->P.pmer_len); LAUNCHED(h);
 	h->pending = true;
 	h->S.n_reads += n; h->S.n_bases += dna_bytes_actual;
 	return FQSK_OK;
@@ -811,6 +828,8 @@ int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
 		CK(cudaMalloc(&h->d_status, 512)); CK(cudaMemset(h->d_status, 0, 512));
 		h->d_flags = (int *) h->d_status;                       // +0   : 8 ints
 		h->d_u32 = (uint32_t *) (h->d_status + 32);              // +32  : 8 counters
+		h->d_carry = (Carry *) (h->d_status + 232);              // +232 : Carry (16 bytes)
+		h->d_sfast = (int *) (h->d_status + 224);                // +224 : s-mer fast-path verdict
 		CK(cudaMalloc(&h->d_counters, 8 * 8));
 		CK(cudaMemset(h->d_counters, 0, 64));
 		CK(cudaMallocHost(&h->h_small, 1024));
@@ -871,15 +890,8 @@ void fqsk_destroy(fqsk_handle *h) {
 
 int fqsk_block_start(fqsk_handle *h) {
 	if (!h) return FQSK_E_INVAL;
-	h->prev_len = 0;   // read_prev.clear(), application.cpp:624
-	return FQSK_OK;
-}
-
-static int after_segment_state(fqsk_handle *h, const uint8_t *d_dna, const unsigned long long *d_off_last, uint64_t last_off, uint32_t last_len) {
-	// read_prev (dna.cpp:1550-1551) and, in sorted mode, pmer_can_prev (dna.cpp:655) follow the last read of the segment
-	CK(h->prev_read.ensure((size_t) last_len + 64));
-	if (last_len) CK(cudaMemcpyAsync(h->prev_read.p, d_dna + last_off, last_len, cudaMemcpyDeviceToDevice, h->st));
-	h->prev_len = last_len;
+	CK(cudaSetDevice(h->P.device));
+	CK(cudaMemsetAsync(&h->d_carry->prev_len, 0, 4, h->st));   // read_prev.clear(), application.cpp:624
 	return FQSK_OK;
 }
 
@@ -887,21 +899,6 @@ int fqsk_segment_device(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes
 	if (!h) return FQSK_E_INVAL;
 	CK(cudaSetDevice(h->P.device));
 	CKR(run_segment(h, d_dna, dna_bytes, (const unsigned long long *) d_off, d_len, n_reads));
-	if (n_reads) {
-		unsigned long long lo; uint32_t ll;
-		CK(cudaMemcpyAsync(&lo, d_off + (n_reads - 1), 8, cudaMemcpyDeviceToHost, h->st));
-		CK(cudaMemcpyAsync(&ll, d_len + (n_reads - 1), 4, cudaMemcpyDeviceToHost, h->st));
-		CK(cudaStreamSynchronize(h->st));
-		CKR(after_segment_state(h, d_dna, nullptr, lo, ll));
-		if (h->P.mode == FQSK_MODE_SE_SORTED) {
-			std::vector<uint8_t> tmp(h->P.pmer_len);
-			CK(cudaMemcpyAsync(tmp.data(), d_dna + lo, h->P.pmer_len, cudaMemcpyDeviceToHost, h->st));
-			CK(cudaStreamSynchronize(h->st));
-			unsigned long long d = 0;
-			for (uint32_t i = 0; i < h->P.pmer_len; ++i) { uint8_t ch = tmp[i]; uint64_t s = ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : 3; d |= s << (62 - 2 * i); }
-			h->pprev_dir = d; h->pprev_valid = 1;
-		}
-	}
 	if (n_recs) *n_recs = h->n_recs;
 	return FQSK_OK;
 }
@@ -961,15 +958,6 @@ int fqsk_segment(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const 
 		CK(cudaMemcpyAsync(h->len.p, h_len, (size_t) n_reads * 4, cudaMemcpyHostToDevice, h->st));
 	}
 	CKR(run_segment(h, h->dna.as<uint8_t>(), total, h->off.as<unsigned long long>(), h->len.as<uint32_t>(), n_reads));
-	if (n_reads) {
-		CKR(after_segment_state(h, h->dna.as<uint8_t>(), nullptr, h_off[n_reads - 1], h_len[n_reads - 1]));
-		if (h->P.mode == FQSK_MODE_SE_SORTED) {
-			const uint8_t *lp = h->h_stage + h_off[n_reads - 1];
-			unsigned long long d = 0;
-			for (uint32_t i = 0; i < h->P.pmer_len; ++i) { uint8_t ch = lp[i]; uint64_t s = ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : 3; d |= s << (62 - 2 * i); }
-			h->pprev_dir = d; h->pprev_valid = 1;
-		}
-	}
 	if (h->n_recs > rec_cap) return fail(h, FQSK_E_CAPACITY, "record buffer holds %llu, segment produced %llu", (unsigned long long) rec_cap, (unsigned long long) h->n_recs);
 	if (h->n_recs && recs) CK(cudaMemcpyAsync(recs, h->recs.p, h->n_recs * sizeof(fqsk_base_rec), cudaMemcpyDeviceToHost, h->st));
 	if (n_reads && dup) CK(cudaMemcpyAsync(dup, h->dup.p, n_reads, cudaMemcpyDeviceToHost, h->st));
@@ -992,23 +980,46 @@ int fqsk_sync(fqsk_handle *h) {
 			k_siv_increment<<<nblk(h->pend_p, 256), 256, 0, h->st>>>(h->siv, h->row_p.as<unsigned long long>(), h->pend_p, h->d_counters + 4);
 			LAUNCHED(h);
 		}
-		// s-mers, then b-mers (dna.cpp:2425-2446)
-		// small rows: sort-free grouping through the segment's delta table (few launches); large rows: one radix sort is cheaper
-		// s-mers: counters stay far below thr = 2047, so the single-kernel atomic path is (almost) always exact; it checks itself
-		if (h->fast_ok[0]) CKR(apply_inserts(h, h->ts, h->rng[ST_S], h->row_s[0].as<unsigned long long>(), h->pend_s, &h->fast_ok[0]));
+		// s-mers and b-mers (dna.cpp:2425-2446) live in different tables and use different PRNG streams, so their rows are
+		// independent of each other.  Small rows: the s-mers go through the self-checking atomic path and the b-mers through the
+		// sort-free grouping over the segment's delta table, all enqueued back to back with ONE host look for the whole sync;
+		// large rows: one radix sort per row is cheaper.
+		bool s_fast_pending = false;
+		h->look_fresh = false;
+		if (h->fast_ok[0] && h->pend_s) {
+			Phase ph(h, FQSK_PH_SYNC_APPLY);
+			CK(cudaMemsetAsync(h->d_sfast, 0, sizeof(int), h->st));
+			CK(h->q4.ensure((size_t) h->pend_s + 4));
+			k_insert_fast<<<nblk(h->pend_s, 256), 256, 0, h->st>>>(h->ts.d, h->ts.ci, h->row_s[0].as<unsigned long long>(), h->pend_s, h->q4.as<uint8_t>(), h->d_sfast); LAUNCHED(h);
+			s_fast_pending = true;
+		}
 		else if (h->pend_s <= SYNC_INDEXED_MAX) CKR(apply_indexed(h, h->ts, h->rng[ST_S], h->seg_delta_s, h->row_s[0].as<unsigned long long>(), h->rt_s[0].as<uint32_t>(), h->pend_s));
 		else CKR(apply_inserts(h, h->ts, h->rng[ST_S], h->row_s[0].as<unsigned long long>(), h->pend_s));
+		h->look_fresh = false;
 		if (h->pend_b <= SYNC_INDEXED_MAX) CKR(apply_indexed(h, h->tb, h->rng[ST_B], h->seg_delta_b, h->row_b[0].as<unsigned long long>(), h->rt_b[0].as<uint32_t>(), h->pend_b));
 		else CKR(apply_inserts(h, h->tb, h->rng[ST_B], h->row_b[0].as<unsigned long long>(), h->pend_b));
+		unsigned long long *hc = (unsigned long long *) ((uint32_t *) h->h_small + 72);
+		if (!h->look_fresh) {
+			CK(cudaMemcpyAsync(h->h_small, h->d_status, 256, cudaMemcpyDeviceToHost, h->st));
+			CK(cudaMemcpyAsync(hc, h->d_counters, 48, cudaMemcpyDeviceToHost, h->st));
+			CK(cudaStreamSynchronize(h->st));
+		}
+		unsigned long long counters[6]; memcpy(counters, hc, 48);
+		if (s_fast_pending && *(int *) ((uint8_t *) h->h_small + 224)) {
+			// some s-mer counter left the deterministic range: undo (claimed slots stay as zero-count items == the reference's fresh
+			// slot) and insert the row in order
+			k_insert_undo<<<nblk(h->pend_s, 256), 256, 0, h->st>>>(h->ts.d, h->row_s[0].as<unsigned long long>(), h->pend_s, h->q4.as<uint8_t>()); LAUNCHED(h);
+			CKR(apply_inserts(h, h->ts, h->rng[ST_S], h->row_s[0].as<unsigned long long>(), h->pend_s));
+			CK(cudaMemcpyAsync(hc, h->d_counters, 48, cudaMemcpyDeviceToHost, h->st));
+			CK(cudaStreamSynchronize(h->st));
+			counters[2] = hc[2]; counters[3] = hc[3];
+		}
 		if (!h->hot) {   // hot segments already advanced the thread-local streams
 			if (h->hot_seen[0]) CKR(hot_account(h, 1));
 			if (h->hot_seen[1]) CKR(hot_account(h, 0));
 		}
 		h->hot_seen[0] = h->hot_seen[1] = false;
-		// one look: fresh p-mer fields and the item counters of both tables (growth check)
-		unsigned long long *hc = (unsigned long long *) h->h_small;
-		CK(cudaMemcpyAsync(hc, h->d_counters, 48, cudaMemcpyDeviceToHost, h->st));
-		CK(cudaStreamSynchronize(h->st));
+		hc = counters;
 		h->S.siv_no_filled += hc[4];
 		h->S.siv_no_updates += h->pend_p + h->hidden_p;
 		h->hidden_p = 0;

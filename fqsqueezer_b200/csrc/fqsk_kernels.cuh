@@ -71,10 +71,16 @@ struct EngineDev {
 	int *flags;                     // [0] draw window overflow, [1] unsupported path, [2] changed, [3] scratch
 };
 
+struct Carry {             // state a segment hands to the next one without a host round trip (k_save_carry)
+	uint32_t prev_len;     // read_prev.size(), 0 after ResetReadPrev (application.cpp:624)
+	uint32_t pprev_valid;
+	unsigned long long pprev_dir;   // pmer_can_prev (dna.cpp:167, 655): prefix p-mer of the last read, left-aligned
+};
+
 struct SegDev {
 	const uint8_t *dna; const unsigned long long *off; const uint32_t *len; uint32_t n_reads;
-	const uint8_t *prev_read; uint32_t prev_len;      // last read of the previous segment of this block (read_prev, dna.cpp:1550)
-	unsigned long long pprev_dir; uint32_t pprev_valid; // pmer_can_prev carried across segments (dna.cpp:167, 655)
+	const uint8_t *prev_read;                         // last read of the previous segment of this block (read_prev, dna.cpp:1550)
+	const struct Carry *carry;                        // its length and pmer_can_prev, kept on the device between segments
 	uint8_t *dup; uint32_t *n_coded; U64x4 *letters;  // k_prep outputs
 	const unsigned long long *rec_off; const U64x4 *sl_prefix; U64x4 sl_base;
 	fqsk_base_rec *recs;
@@ -96,7 +102,7 @@ __global__ void __launch_bounds__(128) k_prep(SegDev S, uint32_t first_len_bytes
 	const uint8_t *p = S.dna + S.off[r];
 	uint32_t n = S.len[r];
 	const uint8_t *q; uint32_t qn;
-	if (r == 0) { q = S.prev_read; qn = S.prev_len; } else { q = S.dna + S.off[r - 1]; qn = S.len[r - 1]; }
+	if (r == 0) { q = S.prev_read; qn = S.carry->prev_len; } else { q = S.dna + S.off[r - 1]; qn = S.len[r - 1]; }
 	bool same = qn == n;
 	uint32_t cnt[4] = {0, 0, 0, 0};
 	for (uint32_t i = lane; i < n; i += 32) {
@@ -112,6 +118,22 @@ __global__ void __launch_bounds__(128) k_prep(SegDev S, uint32_t first_len_bytes
 		U64x4 L; for (int k = 0; k < 4; ++k) L.v[k] = same ? 0 : cnt[k];
 		S.letters[r] = L;
 		S.n_coded[r] = (!same && n > first_len_bytes) ? n - first_len_bytes : 0;
+	}
+}
+
+// read_prev (dna.cpp:1550-1551) and, in sorted order, pmer_can_prev (dna.cpp:655) follow the last read of the segment
+__global__ void __launch_bounds__(256) k_save_carry(SegDev S, uint8_t *prev_read, Carry *carry, uint32_t sorted, uint32_t p) {
+	if (S.n_reads == 0) return;
+	const uint8_t *q = S.dna + S.off[S.n_reads - 1];
+	const uint32_t n = S.len[S.n_reads - 1];
+	for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) prev_read[i] = q[i];
+	if (threadIdx.x == 0) {
+		carry->prev_len = n;
+		if (sorted) {
+			unsigned long long d = 0;
+			for (uint32_t i = 0; i < p; ++i) { uint32_t sy = dna_code(q[i]); if (sy == 4) sy = 3; d |= (unsigned long long) sy << (62 - 2 * i); }
+			carry->pprev_dir = d; carry->pprev_valid = 1;
+		}
 	}
 }
 
@@ -378,7 +400,7 @@ __global__ void k_row_index_build(unsigned long long *keys, uint32_t *times, uin
 // Increment()s exactly when no counter leaves the deterministic range (pre-count <= thr for every occurrence, utils.h:317-318);
 // any occurrence that sees a pre-count above thr raises flags[2] and the host undoes the pass (k_insert_undo: the adds are
 // plain arithmetic on the item, so subtracting them restores every bit) and runs the ordered path instead.
-__global__ void k_insert_fast(HtDev t, CIncP ci, const unsigned long long *kmers, uint32_t n, uint8_t *added, int *flags) {
+__global__ void k_insert_fast(HtDev t, CIncP ci, const unsigned long long *kmers, uint32_t n, uint8_t *added, int *refuted) {
 	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
 	if (j >= n) return;
 	bool created;
@@ -391,7 +413,7 @@ __global__ void k_insert_fast(HtDev t, CIncP ci, const unsigned long long *kmers
 		uint32_t *p = t.main + s;
 		uint32_t old = *((volatile uint32_t *) p);
 		for (;;) {
-			if ((old & t.top) > ci.thr) { flags[2] = 1; if ((old & t.top) >= t.top) return; }
+			if ((old & t.top) > ci.thr) { *refuted = 1; if ((old & t.top) >= t.top) return; }
 			uint32_t seen = atomicCAS(p, old, old + 1);
 			if (seen == old) { added[j] = 1; return; }
 			old = seen;
@@ -400,7 +422,7 @@ __global__ void k_insert_fast(HtDev t, CIncP ci, const unsigned long long *kmers
 		unsigned long long *p = t.stash + (s - nm);
 		unsigned long long old = *((volatile unsigned long long *) p);
 		for (;;) {
-			if ((uint32_t) (old & t.top) > ci.thr) { flags[2] = 1; if ((uint32_t) (old & t.top) >= t.top) return; }
+			if ((uint32_t) (old & t.top) > ci.thr) { *refuted = 1; if ((uint32_t) (old & t.top) >= t.top) return; }
 			unsigned long long seen = atomicCAS(p, old, old + 1);
 			if (seen == old) { added[j] = 1; return; }
 			old = seen;

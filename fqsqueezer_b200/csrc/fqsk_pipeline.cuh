@@ -36,6 +36,7 @@ struct Script {              // ordered list of per-trial count vectors to be me
 	uint32_t overflow;       // first overflow entry
 	uint16_t c2[4];          // s-mer counts for the `mixed` rule when a partial b merge ends with two saturated counters (dna.cpp:470-478)
 	uint16_t e[8][4];
+	uint32_t draws;          // mt19937 outputs this script's merge consumes (k_fold pass 0; confirmed by pass 1)
 };
 static const uint32_t SCRIPT_INLINE = 8;
 
@@ -506,7 +507,7 @@ __global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P, 
 			unsigned long long cur_rc = 0;
 			for (uint32_t i = 0; i < E.p; ++i) cur_rc |= (unsigned long long) (3 - sym_at(S, E, p, E.p - 1 - i)) << (62 - 2 * i);
 			unsigned long long prev_dir; bool prev_valid;
-			if (r == 0) { prev_dir = S.pprev_dir; prev_valid = S.pprev_valid != 0; }
+			if (r == 0) { prev_dir = S.carry->pprev_dir; prev_valid = S.carry->pprev_valid != 0; }
 			else {
 				const uint8_t *q = S.dna + S.off[r - 1];
 				prev_dir = 0;
@@ -778,16 +779,28 @@ __global__ void __launch_bounds__(128) k_rough(EngineDev E, PipeDev P) {
 			const HtDev &t = kind == 2 ? E.hb : E.hs;
 			uint32_t trials = 4 * (t.k - 1);
 			uint32_t n_ent = 0, ovf = 0xFFFFFFFFu;
-			for (uint32_t n0 = 0; n0 < trials; n0 += 32) {
-				uint32_t tn = n0 + lane;
-				uint32_t loc[4] = {0, 0, 0, 0};
-				if (tn < trials) {
+			// all sector reads of the request are issued before the first one is consumed (4(k-1) <= 128 trials: up to 4 per lane)
+			HtKey key[4]; Bucket bk[4]; bool isd[4], live[4];
+#pragma unroll
+			for (int u = 0; u < 4; ++u) {
+				uint32_t tn = u * 32 + lane;
+				// a trial that puts the original symbol back is the context itself, which the global table has just failed to
+				// answer (the level is `none`): known empty, no read
+				live[u] = tn < trials && (tn & 3) != kr_sym(reg, tn >> 2);
+				if (live[u]) {
 					KReg tr = reg;
 					kr_set(tr, t.k, tn & 3, tn >> 2);
-					bool d = kr_is_dir(tr, t.k);
-					ht_ctx_counts(t, d ? tr.dir : tr.rc, d, loc);
+					isd[u] = kr_is_dir(tr, t.k);
+					key[u] = ht_key(t, isd[u] ? tr.dir : tr.rc);
+					bk[u] = ht_load_bucket(t, key[u].bucket);
 				}
-				script_append(P, sc, n_ent, ovf, loc, any4(loc), trials - n0);
+			}
+#pragma unroll
+			for (int u = 0; u < 4; ++u) {
+				if ((uint32_t) u * 32 >= trials) break;
+				uint32_t loc[4] = {0, 0, 0, 0};
+				if (live[u]) ht_ctx_counts_from(t, key[u], isd[u], bk[u], loc);
+				script_append(P, sc, n_ent, ovf, loc, any4(loc), trials - u * 32);
 			}
 			__syncwarp();
 			if (lane == 0) {
@@ -838,24 +851,52 @@ __device__ void fold_script(const EngineDev &E, const PipeDev &P, const Script &
 	rec->level = (uint8_t) lev;
 }
 
-__global__ void __launch_bounds__(128) k_fold(EngineDev E, SegDev S, PipeDev P, int pass) {   // one warp per read
+__device__ __forceinline__ uint32_t warp_excl_sum(uint32_t v, uint32_t lane, uint32_t &total) {
+	uint32_t x = v;
+	for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+	total = __shfl_sync(0xffffffffu, x, 31);
+	return x - v;
+}
+
+// One warp per read, one LANE per script: the scripts of a read are visited in program order (front-truncated lookups by
+// position, then rough searches by position) 32 at a time.  pass 0 folds every script from offset 0 to count its draws;
+// pass 1 gives every script its exact offset (read offset from the scan over reads + the counts of the scripts before it)
+// and writes the final counts.  A count that differs from the stored one (a counter saturated) raises flags[7]: the host
+// scans and runs pass 1 again.
+__global__ void __launch_bounds__(128) k_fold(EngineDev E, SegDev S, PipeDev P, int pass) {
 	const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (r >= S.n_reads) return;
-	// the cursors are replicated in every lane (uniform control flow); lane 0 writes
-	DrawCursor db, ds;
-	db.ring = E.draws[0]; db.mask = E.dmask[0]; db.pos0 = E.dpos[0]; db.avail = E.avail[0]; db.used = 0; db.overflow = E.flags + 0;
-	ds.ring = E.draws[1]; ds.mask = E.dmask[1]; ds.pos0 = E.dpos[1]; ds.avail = E.avail[1]; ds.used = 0; ds.overflow = E.flags + 0;
-	db.base = pass ? P.doff_b[r] : 0;
-	ds.base = pass ? P.doff_s[r] : 0;
-	const bool write = pass != 0 && lane == 0;
+	uint32_t used[2] = {0, 0};          // draws of the scripts visited so far, per stream (b, s), as assumed by the offsets
+	uint32_t now[2] = {0, 0};           // ... as consumed by this pass
+	bool mismatch = false;
+	const unsigned long long base[2] = {pass ? P.doff_b[r] : 0ull, pass ? P.doff_s[r] : 0ull};
+	auto batch = [&](Script *sp) {      // warp-collective; sp == nullptr for idle lanes
+		uint32_t st = 0, stored = 0;
+		if (sp) { st = (sp->kind == 0 || sp->kind == 2) ? 0 : 1; stored = pass ? sp->draws : 0; }
+		uint32_t tot0, tot1;
+		uint32_t ex0 = warp_excl_sum(sp && st == 0 ? stored : 0, lane, tot0);
+		uint32_t ex1 = warp_excl_sum(sp && st == 1 ? stored : 0, lane, tot1);
+		uint32_t cnt = 0;
+		if (sp) {
+			DrawCursor dc;
+			dc.ring = E.draws[st]; dc.mask = E.dmask[st]; dc.pos0 = E.dpos[st]; dc.avail = E.avail[st]; dc.used = 0; dc.overflow = E.flags + 0;
+			dc.base = base[st] + used[st] + (st ? ex1 : ex0);
+			fold_script(E, P, *sp, dc, pass != 0);
+			cnt = dc.used;
+			if (pass == 0) sp->draws = cnt;
+			else if (cnt != stored) { sp->draws = cnt; mismatch = true; }
+		}
+		uint32_t c0 = sp && st == 0 ? cnt : 0, c1 = sp && st == 1 ? cnt : 0;
+		for (int o = 16; o; o >>= 1) { c0 += __shfl_xor_sync(0xffffffffu, c0, o); c1 += __shfl_xor_sync(0xffffffffu, c1, o); }
+		now[0] += c0; now[1] += c1;
+		if (pass == 0) { used[0] += c0; used[1] += c1; } else { used[0] += tot0; used[1] += tot1; }
+	};
 	if (!S.dup[r]) {
 		// front-truncated lookups: slots are in position order
-		const Script *ps = P.pscripts + (size_t) r * P.pslots;
-		unsigned vm = __ballot_sync(0xffffffffu, lane < P.pslots && ps[lane].valid);
-		while (vm) {
-			uint32_t sl = __ffs(vm) - 1; vm &= vm - 1;
-			const Script &sc = ps[sl];
-			fold_script(E, P, sc, sc.kind == 0 ? db : ds, write);
+		Script *ps = P.pscripts + (size_t) r * P.pslots;
+		for (uint32_t s0 = 0; s0 < P.pslots; s0 += 32) {
+			Script *sp = (s0 + lane < P.pslots && ps[s0 + lane].valid) ? ps + s0 + lane : nullptr;
+			if (__any_sync(0xffffffffu, sp != nullptr)) batch(sp);
 		}
 		// rough searches of this read, in position order
 		const uint32_t g0 = (uint32_t) S.rec_off[r], g1 = (uint32_t) S.rec_off[r + 1];
@@ -863,17 +904,13 @@ __global__ void __launch_bounds__(128) k_fold(EngineDev E, SegDev S, PipeDev P, 
 			uint32_t g = gb + lane;
 			uint32_t k = g < g1 ? P.rkind[g] : 0;
 			uint32_t slot = (k == 2 || k == 3) ? P.rslot[g] : 0xFFFFFFFFu;
-			unsigned hm = __ballot_sync(0xffffffffu, slot != 0xFFFFFFFFu);
-			while (hm) {
-				uint32_t q = __ffs(hm) - 1; hm &= hm - 1;
-				uint32_t sq = __shfl_sync(0xffffffffu, slot, q), kq = __shfl_sync(0xffffffffu, k, q);
-				fold_script(E, P, P.rscripts[sq], kq == 2 ? db : ds, write);
-			}
+			if (__any_sync(0xffffffffu, slot != 0xFFFFFFFFu)) batch(slot != 0xFFFFFFFFu ? P.rscripts + slot : nullptr);
 		}
 	}
+	mismatch = __any_sync(0xffffffffu, mismatch);
 	if (lane) return;
-	if (pass == 0) { P.rdraws_b[r] = db.used; P.rdraws_s[r] = ds.used; return; }
-	if (P.rdraws_b[r] != db.used || P.rdraws_s[r] != ds.used) { P.rdraws_b[r] = db.used; P.rdraws_s[r] = ds.used; P.flags[7] = 1; }
+	if (pass == 0 || mismatch) { P.rdraws_b[r] = now[0]; P.rdraws_s[r] = now[1]; }
+	if (pass && mismatch) P.flags[7] = 1;
 }
 
 // Block-wide exclusive scan helper: every thread owns ITEMS consecutive elements (serial), warp shuffles + one smem round
