@@ -165,6 +165,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-phase-events", action="store_true", help="do not bracket the internal phases with CUDA events (fewer host API calls per segment)")
     ap.add_argument("--cpu-sample-reads", type=int, default=40_000)
     ap.add_argument("--trace-blocks", type=int, default=0, help="print per-block phase ms every N blocks to stderr")
     ap.add_argument("--profile-block", type=int, default=-1, help="cudaProfilerStart/Stop around this block (for ncu --profile-from-start off)")
@@ -206,7 +207,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- value: reads resident in HBM ----------------
-    eng = E.KmerEngine(p, s, b, pref, device=local_rank, expected_kmers=1 << 29, profile=True, reserve_reads=READS_PER_BLOCK, reserve_bytes=READS_PER_BLOCK * L)
+    eng = E.KmerEngine(p, s, b, pref, device=local_rank, expected_kmers=1 << 29, profile=not args.no_phase_events, reserve_reads=READS_PER_BLOCK, reserve_bytes=READS_PER_BLOCK * L)
     d_blocks = []
     off_np = (np.arange(READS_PER_BLOCK, dtype=np.int64) * L)
     d_off = torch.from_numpy(off_np).to(dev)                      # same offsets for every block
@@ -221,7 +222,7 @@ def main():
         base = d_blocks[g].data_ptr()
         for a, bb in sched[g]:
             n = bb - a
-            eng.segment_device(base + a * L, n * L, d_off.data_ptr(), d_len.data_ptr(), n)   # offsets are relative to the segment's first read
+            eng.segment_device(base + a * L, n * L, d_off.data_ptr(), d_len.data_ptr(), n, want_n_recs=False)   # offsets are relative to the segment's first read
             eng.sync()
 
     for g in range(args.warmup):

@@ -68,6 +68,13 @@ struct Table {
 
 enum { ST_B = 0, ST_S = 1, ST_LB = 2, ST_LS = 3 };
 
+struct SegCtx {            // everything the passes of one segment share (host side)
+	SegDev S{}; PipeDev P{}; EngineDev E{};
+	uint32_t n = 0, first = 0, it = 0, pass = 0, slots_b = 0, slots_s = 0, t_b = 0, t_s = 0;
+	uint64_t dna_bytes_actual = 0;
+	bool redo_walk = true, redo_tail = true;
+};
+
 }  // namespace
 
 struct fqsk_handle {
@@ -96,6 +103,12 @@ struct fqsk_handle {
 	       miss_fold, hr_b[3], hr_s[3], evk[2], evv[2], evk_s[2], evv_s[2];
 	bool look_fresh = false;                 // h_small holds the status block + counters as of the end of everything enqueued so far
 	int *d_sfast = nullptr;                  // inside d_status: the s-mer fast path saw a counter above thr
+	int *d_sflags = nullptr;                 // inside d_status: flags of the ordered insert ([0] window short [2] flag corrected [6] hot k-mer [7] group too large)
+	SyncIn *d_syncin = nullptr, *d_syncin2 = nullptr;   // inside d_status: inputs of the sync enqueued behind its segment / of a plain ordered insert
+	SegCtx ctx;                              // the segment being evaluated
+	bool unsettled = false;                  // its first pass is enqueued, nobody has looked at the outcome yet
+	bool miss_fold_dirty = true; void *miss_fold_seen = nullptr;
+	DevBuf scan_part; uint32_t scan_epoch = 0;   // published CTA sums of k_scan_flags, tagged with the launch epoch
 	bool hot = false;                        // the current segment is being redone with the ordered thread-local evaluator
 	bool hot_seen[2] = {false, false};       // [0] s, [1] b: the last sync saw a k-mer pushed more than thr + 1 times in its row
 	DeltaDev seg_delta_b{}, seg_delta_s{};   // the converged segment's delta tables (valid while `pending`)
@@ -413,6 +426,10 @@ int sort_row(fqsk_handle *h, const unsigned long long *row, uint32_t n, uint32_t
 	return FQSK_OK;
 }
 
+const uint32_t SYNC_INDEXED_MAX = 400000;
+const uint64_t SPEC_MAX_BYTES = 420000;   // segments up to this many DNA bytes get their sync enqueued without a host look in between
+const int RC_RETRY = 1;   // internal: a capacity was too small, grow and redo the segment
+
 int apply_inserts(fqsk_handle *h, Table &t, Stream &rng, const unsigned long long *d_kmers, uint32_t n, bool *fast_ok = nullptr) {
 	if (!n) return FQSK_OK;
 	if (n >= 0x80000000u) return fail(h, FQSK_E_INVAL, "more than 2^31 k-mers in one sync row");
@@ -435,51 +452,77 @@ int apply_inserts(fqsk_handle *h, Table &t, Stream &rng, const unsigned long lon
 }
 
 // ordered insert of a row using a (k-mer, time) index whose probe runs group equal k-mers (the segment's delta table, or an
-// index built from the row).  One host sync; falls back to the sorted path when a hot group is too large for one thread.
-int apply_indexed(fqsk_handle *h, Table &t, Stream &rng, const DeltaDev &D, const unsigned long long *row, const uint32_t *rt, uint32_t n) {
-	if (!n) return FQSK_OK;
-	const size_t slots = (size_t) D.mask + 1;
+// index built from the row).  Row length and stream position are read from a SyncIn block on the device, so the same launch
+// sequence serves a sync that is enqueued right behind its segment (no host look in between) and the plain call below.
+int indexed_setup(fqsk_handle *h, const DeltaDev &D, uint32_t n_bound, SyncIn *in, bool is_b, SyncDev &Y) {
+	const size_t slots = std::max<size_t>((size_t) D.mask + 1, (size_t) 1 << 21);    // generous floors: no reallocation while segments grow
+	const size_t nb = std::max<size_t>(n_bound, SYNC_INDEXED_MAX) + 64;
 	CK(h->y_tslot.ensure(slots * 8)); CK(h->y_c0.ensure(slots * 4)); CK(h->y_m.ensure(slots * 4)); CK(h->y_draw.ensure(slots * 4));
 	CK(h->y_j.ensure(slots * 4)); CK(h->y_final.ensure(slots * 4)); CK(h->y_flag_at.ensure(slots));
-	CK(h->y_own.ensure((size_t) n * 4)); CK(h->y_lead.ensure((size_t) n * 4)); CK(h->y_rank.ensure((size_t) n * 4));
-	CK(h->y_flag.ensure((size_t) n + 4)); CK(h->y_doff.ensure(((size_t) n + 1) * 4));
-	SyncDev Y{};
+	CK(h->y_own.ensure(nb * 4)); CK(h->y_lead.ensure(nb * 4)); CK(h->y_rank.ensure(nb * 4));
+	CK(h->y_flag.ensure(nb + 64)); CK(h->y_doff.ensure((nb + 1) * 4));
+	if (!h->scan_part.p) { CK(h->scan_part.ensure(4096 * 8)); CK(cudaMemsetAsync(h->scan_part.p, 0, h->scan_part.cap, h->st)); }
+	if (nblk(nb, SCANF_TILE) > 1024) return fail(h, FQSK_E_INVAL, "row too long for the indexed ordered insert");
+	Y = SyncDev{};
 	Y.D = D;
+	Y.in = in; Y.n_dev = is_b ? &in->n_b : &in->n_s; Y.dpos_dev = is_b ? &in->dpos_b : &in->dpos_s; Y.total_draws = &in->draws_b;
 	Y.lead_tslot = h->y_tslot.as<unsigned long long>(); Y.lead_c0 = h->y_c0.as<uint32_t>(); Y.lead_m = h->y_m.as<uint32_t>();
 	Y.draw_at = h->y_draw.as<uint32_t>(); Y.j_at = h->y_j.as<uint32_t>(); Y.final_at = h->y_final.as<uint32_t>(); Y.flag_at = h->y_flag_at.as<uint8_t>();
 	Y.own = h->y_own.as<uint32_t>(); Y.lead = h->y_lead.as<uint32_t>(); Y.rank = h->y_rank.as<uint32_t>();
-	Y.flag = h->y_flag.as<uint8_t>(); Y.draw_off = h->y_doff.as<uint32_t>(); Y.flags = h->d_flags;
+	Y.flag = h->y_flag.as<uint8_t>(); Y.draw_off = h->y_doff.as<uint32_t>(); Y.flags = h->d_sflags;
+	return FQSK_OK;
+}
+inline unsigned long long stream_safe_abs(const Stream &s) { return s.safe > s.consumed ? s.safe : s.consumed; }
+int indexed_head(fqsk_handle *h, Table &t, const SyncDev &Y, const unsigned long long *row, const uint32_t *rt, uint32_t g) {
+	Phase ph(h, FQSK_PH_SYNC_LOCATE);
+	CK(cudaMemsetAsync(h->d_sflags, 0, 8 * sizeof(int), h->st));
+	k_sync_rank<<<g, 256, 0, h->st>>>(t.d, Y, row, rt); LAUNCHED(h);
+	k_sync_flags<<<g, 256, 0, h->st>>>(t.d, t.ci, Y); LAUNCHED(h);
+	return FQSK_OK;
+}
+int indexed_tail(fqsk_handle *h, Table &t, Stream &rng, const SyncDev &Y, const unsigned long long *row, uint32_t g, uint32_t n_bound) {
+	k_scan_flags<<<nblk(n_bound, SCANF_TILE), 256, 0, h->st>>>(Y.in, Y.n_dev, Y.flag, h->y_doff.as<uint32_t>(), Y.total_draws, h->scan_part.as<unsigned long long>(), ++h->scan_epoch); LAUNCHED(h);
+	k_sync_scatter<<<g, 256, 0, h->st>>>(t.ci, Y); LAUNCHED(h);
+	CK(cudaMemsetAsync(h->d_sflags, 0, 4 * sizeof(int), h->st));      // [0] draw window short, [2] corrected a flag; [6] hot seen / [7] group too large stay
+	k_sync_apply<<<g, 256, 0, h->st>>>(t.d, t.ci, Y, row, rng.buf, rng.cap - 1, stream_safe_abs(rng)); LAUNCHED(h);
+	k_sync_commit<<<g, 256, 0, h->st>>>(t.d, Y); LAUNCHED(h);
+	return FQSK_OK;
+}
+// one look at the device: the whole status block, the item counters and the fresh p-mer field count
+int look(fqsk_handle *h) {
+	uint8_t *hs = (uint8_t *) h->h_small;
+	CK(cudaMemcpyAsync(hs, h->d_status, 512, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaMemcpyAsync(hs + 512, h->d_counters, 48, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaStreamSynchronize(h->st));
+	resolve_phases(h);
+	h->look_fresh = true;
+	return FQSK_OK;
+}
+inline const int *looked_sflags(fqsk_handle *h) { return (const int *) ((uint8_t *) h->h_small + ((uint8_t *) h->d_sflags - h->d_status)); }
+inline const SyncIn *looked_syncin(fqsk_handle *h, const SyncIn *d) { return (const SyncIn *) ((uint8_t *) h->h_small + ((const uint8_t *) d - h->d_status)); }
+
+int apply_indexed(fqsk_handle *h, Table &t, Stream &rng, const DeltaDev &D, const unsigned long long *row, const uint32_t *rt, uint32_t n) {
+	if (!n) return FQSK_OK;
+	const bool is_b = &t == &h->tb;
+	SyncIn *in = h->d_syncin2;
+	k_set_syncin<<<1, 32, 0, h->st>>>(in, is_b ? n : 0, is_b ? 0 : n, 0, is_b ? rng.consumed : 0, is_b ? 0 : rng.consumed); LAUNCHED(h);
+	SyncDev Y;
+	CKR(indexed_setup(h, D, n, in, is_b, Y));
 	const uint32_t g = nblk(n, 256);
-	{
-		Phase ph(h, FQSK_PH_SYNC_LOCATE);
-		CK(cudaMemsetAsync(h->d_flags, 0, 8 * sizeof(int), h->st));
-		CK(cudaMemsetAsync(h->y_flag.p, 0, (size_t) n + 4, h->st));
-		k_sync_rank<<<g, 256, 0, h->st>>>(t.d, Y, row, rt, n); LAUNCHED(h);
-		k_sync_flags<<<g, 256, 0, h->st>>>(t.d, t.ci, Y, n); LAUNCHED(h);
-	}
+	CKR(indexed_head(h, t, Y, row, rt, g));
 	Phase ph(h, FQSK_PH_SYNC_APPLY);
 	uint32_t total_draws = 0;
 	for (int it = 0;; ++it) {
 		if (it > 64) return fail(h, FQSK_E_NO_CONVERGE, "sync insert: draw flags did not settle");
-		CKR((scan_excl<uint8_t, uint32_t>(h, h->y_flag.as<uint8_t>(), h->y_doff.as<uint32_t>(), n + 1, 0u)));
 		CKR(stream_ensure(h, rng, 0));     // wait for the generator if it is still running
-		k_sync_scatter<<<g, 256, 0, h->st>>>(t.ci, Y, n); LAUNCHED(h);
-		CK(cudaMemsetAsync(h->d_flags, 0, 4 * sizeof(int), h->st));
-		k_sync_apply<<<g, 256, 0, h->st>>>(t.d, t.ci, Y, row, n, rng.buf, rng.cap - 1, rng.consumed, stream_avail(rng)); LAUNCHED(h);
-		k_sync_commit<<<g, 256, 0, h->st>>>(t.d, Y, n); LAUNCHED(h);
-		uint32_t *hs = (uint32_t *) h->h_small;
-		CK(cudaMemcpyAsync(hs, h->d_status, 256, cudaMemcpyDeviceToHost, h->st));                          // flags | ... | s-mer fast-path verdict
-		CK(cudaMemcpyAsync(hs + 64, h->y_doff.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, h->st));
-		CK(cudaMemcpyAsync(hs + 72, h->d_counters, 48, cudaMemcpyDeviceToHost, h->st));                    // item counters, fresh p-mer fields
-		CK(cudaStreamSynchronize(h->st));
-		resolve_phases(h);
-		h->look_fresh = true;
-		int fl[8]; memcpy(fl, hs, sizeof fl);
-		total_draws = hs[64];
-		if (fl[6]) h->hot_seen[&t == &h->tb ? 1 : 0] = true;
+		CKR(indexed_tail(h, t, rng, Y, row, g, n));
+		CKR(look(h));
+		const int *fl = looked_sflags(h);
+		total_draws = looked_syncin(h, in)->draws_b;
+		if (fl[6]) h->hot_seen[is_b ? 1 : 0] = true;
 		if (fl[7]) {   // a hot k-mer occurs more than SYNC_GROUP_CAP times in this row: sorted path for the whole row
-			k_sync_unclaim<<<g, 256, 0, h->st>>>(t.d, Y, n); LAUNCHED(h);
-			return apply_inserts(h, t, rng, row, n);
+			k_sync_unclaim<<<g, 256, 0, h->st>>>(t.d, Y); LAUNCHED(h);
+			return apply_inserts(h, t, rng, row, n, nullptr);
 		}
 		if (fl[0]) { CKR(stream_ensure(h, rng, (uint64_t) total_draws + (1u << 16))); continue; }
 		if (!fl[2]) break;
@@ -491,6 +534,7 @@ int apply_indexed(fqsk_handle *h, Table &t, Stream &rng, const DeltaDev &D, cons
 // build an index for a plain row (no segment behind it) and insert it
 int apply_row(fqsk_handle *h, Table &t, Stream &rng, const unsigned long long *row, uint32_t n) {
 	if (!n) return FQSK_OK;
+	if (n > (1u << 21)) return apply_inserts(h, t, rng, row, n);     // long rows: one radix sort is cheaper (and k_scan_flags stays co-resident)
 	uint32_t slots = 1024;
 	while (slots < 2 * n) slots <<= 1;
 	CK(h->idx_k.ensure((size_t) slots * 8)); CK(h->idx_t.ensure((size_t) slots * 4)); CK(h->idx_rt.ensure((size_t) n * 4));
@@ -512,17 +556,19 @@ EngineDev make_engine_dev(fqsk_handle *h) {
 	return E;
 }
 
-const uint32_t SYNC_INDEXED_MAX = 400000;
-const int RC_RETRY = 1;   // internal: a capacity was too small, grow and redo the segment
-
 // ---------------------------------------------------------------------------------------------------------------
 // one sync segment, reads resident on the device.  All counts stay on the device; kernels are
-// launched from host-side upper bounds and the host looks at the device twice per segment.
+// launched from host-side upper bounds.  seg_setup + seg_pass enqueue the first pass of the fixed launch schedule; the host
+// does not look at the device until somebody needs the outcome (seg_settle): the sync that follows a small segment is
+// enqueued behind it unseen, predicated on the device-side verdict of the pass (k_seg_verdict).
 // ---------------------------------------------------------------------------------------------------------------
-int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes_actual, uint32_t first) {
-	const uint64_t dna_bytes = std::max<uint64_t>(dna_bytes_actual, h->P.reserve_bytes);   // scratch sized once for the largest segment
+int seg_setup(fqsk_handle *h) {
+	SegCtx &C = h->ctx;
+	SegDev &S = C.S;
+	const uint32_t n = C.n;
+	const uint64_t dna_bytes = std::max<uint64_t>(C.dna_bytes_actual, h->P.reserve_bytes);   // scratch sized once for the largest segment
 	const size_t n1 = (size_t) std::max<uint32_t>(n, h->P.reserve_reads) + 1;
-	const uint32_t rec_bound = (uint32_t) dna_bytes_actual;          // coded positions <= DNA bytes
+	const uint32_t rec_bound = (uint32_t) C.dna_bytes_actual;          // coded positions <= DNA bytes
 	const size_t r1 = (size_t) dna_bytes + 1;
 	const uint32_t pslots = h->P.bmer_len - h->P.pmer_len + 1;
 	CK(h->prov.ensure(r1 * sizeof(fqsk_base_rec))); CK(h->recs.ensure(r1 * sizeof(fqsk_base_rec))); CK(h->pflags.ensure(r1));
@@ -530,14 +576,18 @@ int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes_ac
 	CK(h->pscripts.ensure(n1 * pslots * sizeof(Script)));
 	CK(h->rscripts.ensure(((size_t) h->rreq_cap + 1) * sizeof(Script)));
 	CK(h->pool.ensure(((size_t) h->pool_cap + 1) * 8)); CK(h->miss.ensure(((size_t) h->miss_cap + 1) * sizeof(MissEntry)));
-	CK(h->miss_fold.ensure((size_t) h->miss_cap + 1)); CK(cudaMemsetAsync(h->miss_fold.p, 0, (size_t) h->miss_cap + 1, h->st));
+	CK(h->miss_fold.ensure((size_t) h->miss_cap + 1));
+	if (h->hot || h->miss_fold_dirty || h->miss_fold.p != h->miss_fold_seen) {   // only the ordered evaluator (hot mode) ever marks entries
+		CK(cudaMemsetAsync(h->miss_fold.p, 0, h->miss_fold.cap, h->st));
+		h->miss_fold_dirty = h->hot; h->miss_fold_seen = h->miss_fold.p;
+	}
 	CK(h->rdraws_b.ensure(n1 * 4)); CK(h->rdraws_s.ensure(n1 * 4)); CK(h->doff_b.ensure(n1 * 8)); CK(h->doff_s.ensure(n1 * 8));
 	CK(h->time_b.ensure((2 * dna_bytes + 2) * 4)); CK(h->time_s.ensure((dna_bytes + 1) * 4));
 	CK(h->rt_b[0].ensure((2 * dna_bytes + 2) * 4)); CK(h->rt_s[0].ensure((dna_bytes + 1) * 4));
-	CK(h->totals.ensure(256));
 
-	PipeDev P{};
-	P.n_rec = rec_bound; P.start = first; P.rec_off = S.rec_off;
+	PipeDev &P = C.P;
+	P = PipeDev{};
+	P.n_rec = rec_bound; P.start = C.first; P.rec_off = S.rec_off;
 	P.prov = h->prov.as<fqsk_base_rec>(); P.recs = h->recs.as<fqsk_base_rec>(); P.pflags = h->pflags.as<uint8_t>();
 	P.pscripts = h->pscripts.as<Script>(); P.pslots = pslots; P.pfirst_n = h->P.pmer_len - 1;
 	P.rscripts = h->rscripts.as<Script>(); P.n_rscript = h->d_u32 + 1; P.rscript_cap = h->rreq_cap;
@@ -550,114 +600,128 @@ int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes_ac
 	P.time_b = h->time_b.as<uint32_t>(); P.time_s = h->time_s.as<uint32_t>();
 	P.flags = h->d_flags; P.n_rec_dev = h->d_u32 + 3;
 	S.recs = P.recs;
-	SegTotals *d_tot = (SegTotals *) (h->d_status + 64);                       // +64  : SegTotals (72 bytes)
-	uint32_t *d_tot4 = (uint32_t *) (h->d_status + 192);                        // +192 : tot_b, tot_s, tot_p, hidden
-	unsigned long long *d_draw2 = (unsigned long long *) (h->d_status + 208);   // +208 : draws b, s
 
-	EngineDev E = make_engine_dev(h);
-	CK(cudaMemsetAsync(h->d_u32, 0, 3 * 4, h->st));
+	C.E = make_engine_dev(h);
+	CK(cudaMemsetAsync(h->d_status, 0, 44, h->st));                 // flags[8] | n_miss, n_rscript, pool_used (n_rec_dev stays: k_scan_reads wrote it)
 	CK(cudaMemsetAsync(h->d_u32 + 4, 0, 4 * 4, h->st));
-	CK(cudaMemsetAsync(h->d_flags, 0, 8 * sizeof(int), h->st));
-	{ Phase ph(h, FQSK_PH_LOOKUP); k_lookup<<<nblk(rec_bound, 256), 256, 0, h->st>>>(E, S, P); LAUNCHED(h); }
-	{ Phase ph(h, FQSK_PH_PARTIAL); k_partial<<<nblk((uint64_t) n * pslots * 32, 128), 128, 0, h->st>>>(E, S, P); LAUNCHED(h); }
+	{ Phase ph(h, FQSK_PH_LOOKUP); k_lookup<<<nblk(rec_bound, 256), 256, 0, h->st>>>(C.E, S, P); LAUNCHED(h); }
+	{ Phase ph(h, FQSK_PH_PARTIAL); k_partial<<<nblk((uint64_t) n * pslots * 32, 128), 128, 0, h->st>>>(C.E, S, P); LAUNCHED(h); }
 	S.delta_b = DeltaDev{nullptr, nullptr, 0, 0, h->P.bmer_len, 1, h->tb.ci.thr + 1, nullptr, nullptr, nullptr};
 	S.delta_s = DeltaDev{nullptr, nullptr, 0, 0, h->P.smer_len, 1, h->ts.ci.thr + 1, nullptr, nullptr, nullptr};
 	h->delta_b_valid = h->delta_s_valid = false;
-	const uint32_t t_b = std::max<uint32_t>(h->P.bmer_len - h->P.smer_len - 1, 1), t_s = std::max<uint32_t>(h->P.smer_len - h->P.pmer_len + 1, 1);
-	uint32_t slots_b = 1024, slots_s = 1024;
-	while (slots_b < 4 * dna_bytes_actual) slots_b <<= 1;      // at most 2 b pushes per base, half-full table
-	while (slots_s < 2 * dna_bytes_actual) slots_s <<= 1;
+	C.t_b = std::max<uint32_t>(h->P.bmer_len - h->P.smer_len - 1, 1); C.t_s = std::max<uint32_t>(h->P.smer_len - h->P.pmer_len + 1, 1);
+	C.slots_b = 1024; C.slots_s = 1024;
+	while (C.slots_b < 4 * C.dna_bytes_actual) C.slots_b <<= 1;      // at most 2 b pushes per base, half-full table
+	while (C.slots_s < 2 * C.dna_bytes_actual) C.slots_s <<= 1;
 	{
 		size_t rb = 1024, rs = 1024;
 		while (rb < 4 * dna_bytes) rb <<= 1;
 		while (rs < 2 * dna_bytes) rs <<= 1;
 		CK(h->dk_b.ensure(rb * 8)); CK(h->stime_b.ensure(rb * 4)); CK(h->dk_s.ensure(rs * 8)); CK(h->stime_s.ensure(rs * 4));
 	}
-	auto build_delta = [&]() -> int {
-		Phase ph(h, FQSK_PH_SORT);
-		CK(h->dk_b.ensure((size_t) slots_b * 8)); CK(h->stime_b.ensure((size_t) slots_b * 4));
-		CK(h->dk_s.ensure((size_t) slots_s * 8)); CK(h->stime_s.ensure((size_t) slots_s * 4));
-		CK(cudaMemsetAsync(h->stime_b.p, 0xFF, (size_t) slots_b * 4, h->st));
-		CK(cudaMemsetAsync(h->stime_s.p, 0xFF, (size_t) slots_s * 4, h->st));
-		k_delta_build<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(S, P, h->dk_b.as<unsigned long long>(), h->stime_b.as<uint32_t>(), slots_b - 1, h->P.bmer_len, t_b,
-		                                                             h->dk_s.as<unsigned long long>(), h->stime_s.as<uint32_t>(), slots_s - 1, h->P.smer_len, t_s);
-		LAUNCHED(h);
-		S.delta_b = DeltaDev{h->dk_b.as<unsigned long long>(), h->stime_b.as<uint32_t>(), slots_b - 1, 1, h->P.bmer_len, t_b, h->tb.ci.thr + 1, nullptr, nullptr, nullptr};
-		S.delta_s = DeltaDev{h->dk_s.as<unsigned long long>(), h->stime_s.as<uint32_t>(), slots_s - 1, 1, h->P.smer_len, t_s, h->ts.ci.thr + 1, nullptr, nullptr, nullptr};
-		if (!h->hot) return FQSK_OK;
-		// hot mode: ranks, queued events (inserts above thr + thread-local merges), time order, sequential evaluation
-		Phase ph2(h, FQSK_PH_LOCAL);
-		for (int q = 0; q < 3; ++q) { CK(h->hr_b[q].ensure((size_t) slots_b * 4)); CK(h->hr_s[q].ensure((size_t) slots_s * 4)); }
-		const uint32_t ev_cap = (uint32_t) std::min<uint64_t>(2 * dna_bytes_actual + 1024, 1u << 30);
-		for (int q = 0; q < 2; ++q) { CK(h->evk[q].ensure((size_t) ev_cap * 8)); CK(h->evv[q].ensure((size_t) ev_cap * 4)); CK(h->evk_s[q].ensure((size_t) ev_cap * 8)); CK(h->evv_s[q].ensure((size_t) ev_cap * 4)); }
-		S.delta_b.rank_at = h->hr_b[0].as<uint32_t>(); S.delta_b.prev_at = h->hr_b[1].as<uint32_t>(); S.delta_b.cnt_at = h->hr_b[2].as<uint32_t>();
-		S.delta_s.rank_at = h->hr_s[0].as<uint32_t>(); S.delta_s.prev_at = h->hr_s[1].as<uint32_t>(); S.delta_s.cnt_at = h->hr_s[2].as<uint32_t>();
-		for (int q = 0; q < 2; ++q) { P.ev_key[q] = h->evk[q].as<unsigned long long>(); P.ev_val[q] = h->evv[q].as<uint32_t>(); }
-		P.ev_n = h->d_u32 + 4; P.ev_cap = ev_cap; P.hot_draws = h->d_u32 + 6;
-		CK(cudaMemsetAsync(h->d_u32 + 4, 0, 4 * 4, h->st));
-		k_delta_rank<<<148 * 8, 256, 0, h->st>>>(S.delta_b, P, 0); LAUNCHED(h);
-		k_delta_rank<<<148 * 8, 256, 0, h->st>>>(S.delta_s, P, 1); LAUNCHED(h);
-		k_local<<<std::min<uint32_t>(nblk(std::max<uint32_t>(h->miss_cap, 1), 128), 148 * 16), 128, 0, h->st>>>(E, S, P, 0); LAUNCHED(h);
-		uint32_t *hs = (uint32_t *) h->h_small;
-		CK(cudaMemcpyAsync(hs, h->d_status, 64, cudaMemcpyDeviceToHost, h->st));
-		CK(cudaStreamSynchronize(h->st));
-		if (((int *) hs)[4]) return RC_RETRY + 1;     // event list too small (cannot happen with the bound above)
-		uint32_t en[2] = {hs[8 + 4], hs[8 + 5]};
-		for (int q = 0; q < 2; ++q) if (en[q]) {
-			size_t bytes = 0;
-			CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, h->evk[q].as<unsigned long long>(), h->evk_s[q].as<unsigned long long>(), h->evv[q].as<uint32_t>(), h->evv_s[q].as<uint32_t>(), (int) en[q], 0, 34, h->st));
-			CK(h->cub_tmp.ensure(bytes));
-			CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, h->evk[q].as<unsigned long long>(), h->evk_s[q].as<unsigned long long>(), h->evv[q].as<uint32_t>(), h->evv_s[q].as<uint32_t>(), (int) en[q], 0, 34, h->st));
-		}
-		CKR(stream_ensure(h, h->rng[ST_LB], (uint64_t) en[0] * 8 + 1024)); CKR(stream_ensure(h, h->rng[ST_LS], (uint64_t) en[1] * 8 + 1024));
-		E = make_engine_dev(h);
-		k_hot_eval<<<1, 64, 0, h->st>>>(E, S, P, h->evk_s[0].as<unsigned long long>(), h->evv_s[0].as<uint32_t>(), en[0], h->evk_s[1].as<unsigned long long>(), h->evv_s[1].as<uint32_t>(), en[1]); LAUNCHED(h);
-		return FQSK_OK;
-	};
+	{ Phase ph(h, FQSK_PH_WALK); k_walk<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(C.E, S, P, 0); LAUNCHED(h); ++h->S.n_replays; }
+	C.it = 0; C.pass = 0; C.redo_walk = true; C.redo_tail = true;
+	return FQSK_OK;
+}
+
+int seg_build_delta(fqsk_handle *h) {
+	SegCtx &C = h->ctx;
+	SegDev &S = C.S; PipeDev &P = C.P;
+	const uint32_t n = C.n, slots_b = C.slots_b, slots_s = C.slots_s;
+	Phase ph(h, FQSK_PH_SORT);
+	CK(h->dk_b.ensure((size_t) slots_b * 8)); CK(h->stime_b.ensure((size_t) slots_b * 4));
+	CK(h->dk_s.ensure((size_t) slots_s * 8)); CK(h->stime_s.ensure((size_t) slots_s * 4));
+	CK(cudaMemsetAsync(h->stime_b.p, 0xFF, (size_t) slots_b * 4, h->st));
+	CK(cudaMemsetAsync(h->stime_s.p, 0xFF, (size_t) slots_s * 4, h->st));
+	k_delta_build<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(S, P, h->dk_b.as<unsigned long long>(), h->stime_b.as<uint32_t>(), slots_b - 1, h->P.bmer_len, C.t_b,
+	                                                             h->dk_s.as<unsigned long long>(), h->stime_s.as<uint32_t>(), slots_s - 1, h->P.smer_len, C.t_s);
+	LAUNCHED(h);
+	S.delta_b = DeltaDev{h->dk_b.as<unsigned long long>(), h->stime_b.as<uint32_t>(), slots_b - 1, 1, h->P.bmer_len, C.t_b, h->tb.ci.thr + 1, nullptr, nullptr, nullptr};
+	S.delta_s = DeltaDev{h->dk_s.as<unsigned long long>(), h->stime_s.as<uint32_t>(), slots_s - 1, 1, h->P.smer_len, C.t_s, h->ts.ci.thr + 1, nullptr, nullptr, nullptr};
+	if (!h->hot) return FQSK_OK;
+	// hot mode: ranks, queued events (inserts above thr + thread-local merges), time order, sequential evaluation
+	Phase ph2(h, FQSK_PH_LOCAL);
+	for (int q = 0; q < 3; ++q) { CK(h->hr_b[q].ensure((size_t) slots_b * 4)); CK(h->hr_s[q].ensure((size_t) slots_s * 4)); }
+	const uint32_t ev_cap = (uint32_t) std::min<uint64_t>(2 * C.dna_bytes_actual + 1024, 1u << 30);
+	for (int q = 0; q < 2; ++q) { CK(h->evk[q].ensure((size_t) ev_cap * 8)); CK(h->evv[q].ensure((size_t) ev_cap * 4)); CK(h->evk_s[q].ensure((size_t) ev_cap * 8)); CK(h->evv_s[q].ensure((size_t) ev_cap * 4)); }
+	S.delta_b.rank_at = h->hr_b[0].as<uint32_t>(); S.delta_b.prev_at = h->hr_b[1].as<uint32_t>(); S.delta_b.cnt_at = h->hr_b[2].as<uint32_t>();
+	S.delta_s.rank_at = h->hr_s[0].as<uint32_t>(); S.delta_s.prev_at = h->hr_s[1].as<uint32_t>(); S.delta_s.cnt_at = h->hr_s[2].as<uint32_t>();
+	for (int q = 0; q < 2; ++q) { P.ev_key[q] = h->evk[q].as<unsigned long long>(); P.ev_val[q] = h->evv[q].as<uint32_t>(); }
+	P.ev_n = h->d_u32 + 4; P.ev_cap = ev_cap; P.hot_draws = h->d_u32 + 6;
+	CK(cudaMemsetAsync(h->d_u32 + 4, 0, 4 * 4, h->st));
+	k_delta_rank<<<148 * 8, 256, 0, h->st>>>(S.delta_b, P, 0); LAUNCHED(h);
+	k_delta_rank<<<148 * 8, 256, 0, h->st>>>(S.delta_s, P, 1); LAUNCHED(h);
+	k_local<<<std::min<uint32_t>(nblk(std::max<uint32_t>(h->miss_cap, 1), 128), 148 * 16), 128, 0, h->st>>>(C.E, S, P, 0); LAUNCHED(h);
+	uint32_t *hs = (uint32_t *) h->h_small;
+	CK(cudaMemcpyAsync(hs, h->d_status, 64, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaStreamSynchronize(h->st));
+	if (((int *) hs)[4]) return fail(h, FQSK_E_NOMEM, "hot-mode event list overflow");     // cannot happen with the bound above
+	uint32_t en[2] = {hs[8 + 4], hs[8 + 5]};
+	for (int q = 0; q < 2; ++q) if (en[q]) {
+		size_t bytes = 0;
+		CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, h->evk[q].as<unsigned long long>(), h->evk_s[q].as<unsigned long long>(), h->evv[q].as<uint32_t>(), h->evv_s[q].as<uint32_t>(), (int) en[q], 0, 34, h->st));
+		CK(h->cub_tmp.ensure(bytes));
+		CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, h->evk[q].as<unsigned long long>(), h->evk_s[q].as<unsigned long long>(), h->evv[q].as<uint32_t>(), h->evv_s[q].as<uint32_t>(), (int) en[q], 0, 34, h->st));
+	}
+	CKR(stream_ensure(h, h->rng[ST_LB], (uint64_t) en[0] * 8 + 1024)); CKR(stream_ensure(h, h->rng[ST_LS], (uint64_t) en[1] * 8 + 1024));
+	C.E = make_engine_dev(h);
+	k_hot_eval<<<1, 64, 0, h->st>>>(C.E, S, P, h->evk_s[0].as<unsigned long long>(), h->evv_s[0].as<uint32_t>(), en[0], h->evk_s[1].as<unsigned long long>(), h->evv_s[1].as<uint32_t>(), en[1]); LAUNCHED(h);
+	return FQSK_OK;
+}
+
+// Fixed launch schedule of one pass: the thread-local pass (delta, k_local, walk `it` on the reads it touched), compaction,
+// rough searches, ordered merges.  If the look shows that the walk changed pushes (rare) the thread-local pass and everything
+// after it is repeated; if only the merge offsets moved, only the merges.
+int seg_pass(fqsk_handle *h) {
+	SegCtx &C = h->ctx;
+	SegDev &S = C.S; PipeDev &P = C.P; EngineDev &E = C.E;
+	const uint32_t n = C.n, rec_bound = (uint32_t) C.dna_bytes_actual;
 	const uint32_t max_it = h->P.max_iterations ? h->P.max_iterations : 16;
+	uint32_t *d_tot4 = (uint32_t *) (h->d_status + 192);                        // +192 : tot_b, tot_s, tot_p, hidden
+	unsigned long long *d_draw2 = (unsigned long long *) (h->d_status + 208);   // +208 : draws b, s
+	if (++C.pass > 64) return fail(h, FQSK_E_NO_CONVERGE, "segment did not settle");
+	if (C.redo_walk) {
+		if (++C.it >= max_it) return fail(h, FQSK_E_NO_CONVERGE, "segment did not reach its fixed point in %u iterations", max_it);
+		CK(cudaMemsetAsync(h->d_flags + 2, 0, sizeof(int), h->st));
+		CKR(seg_build_delta(h));
+		{ Phase ph(h, FQSK_PH_LOCAL); k_local<<<std::min<uint32_t>(nblk(std::max<uint32_t>(h->miss_cap, 1), 128), 148 * 16), 128, 0, h->st>>>(E, S, P, 1); LAUNCHED(h); }
+		{ Phase ph(h, FQSK_PH_WALK); k_walk<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(E, S, P, C.it); LAUNCHED(h); ++h->S.n_replays; }
+	}
+	if (C.redo_tail) {
+		{
+			Phase ph(h, FQSK_PH_COMPACT);
+			k_scan_u32x4<<<1, 1024, 0, h->st>>>(n, h->cnt_b.as<uint32_t>(), h->off_b[0].as<uint32_t>(), h->cnt_s.as<uint32_t>(), h->off_s[0].as<uint32_t>(),
+			                                     h->cnt_p.as<uint32_t>(), h->off_p.as<uint32_t>(), h->hidden.as<uint32_t>(), nullptr, d_tot4);
+			LAUNCHED(h);
+			k_compact2<<<n, 64, 0, h->st>>>(S, P, h->off_b[0].as<uint32_t>(), h->off_s[0].as<uint32_t>(), h->off_p.as<uint32_t>(),
+			                               h->row_b[0].as<unsigned long long>(), h->row_s[0].as<unsigned long long>(), h->row_p.as<unsigned long long>(),
+			                               h->rt_b[0].as<uint32_t>(), h->rt_s[0].as<uint32_t>());
+			LAUNCHED(h);
+		}
+		CK(cudaMemsetAsync(h->d_u32 + 1, 0, 4, h->st));      // rough scripts are rebuilt
+		{ Phase ph(h, FQSK_PH_ROUGH); k_rough<<<std::max<uint32_t>(148, std::min<uint32_t>(nblk(rec_bound, 16), 148 * 32)), 128, 0, h->st>>>(E, P); LAUNCHED(h); }
+		{ Phase ph(h, FQSK_PH_FOLD); k_fold<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(E, S, P, 0); LAUNCHED(h); }
+	}
+	{
+		Phase ph(h, FQSK_PH_FOLD);
+		k_scan_draws<<<1, 1024, 0, h->st>>>(n, P.rdraws_b, h->doff_b.as<unsigned long long>(), P.rdraws_s, h->doff_s.as<unsigned long long>(), d_draw2); LAUNCHED(h);
+		CK(cudaMemsetAsync(h->d_flags + 0, 0, sizeof(int), h->st)); CK(cudaMemsetAsync(h->d_flags + 7, 0, sizeof(int), h->st));
+		k_fold<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(E, S, P, 1); LAUNCHED(h);
+	}
+	return FQSK_OK;
+}
+
+// Look at the enqueued pass (unless the caller has just done so) and iterate until the segment is settled; then take the
+// totals over to the host side.  Returns RC_RETRY when the whole segment has to be set up again.
+int seg_finish(fqsk_handle *h, bool have_look) {
+	SegCtx &C = h->ctx;
 	int fl[8];
 	uint32_t cnt[4];
 	unsigned long long draws2[2] = {0, 0};
-	// Fixed launch schedule, ONE host look at the end: walk 0 on every read, the thread-local pass (delta, k_local, walk 1 on
-	// the reads it touched), compaction, rough searches, ordered merges.  If the look shows that walk 1 changed pushes
-	// (rare) the thread-local pass and everything after it is repeated; if only the merge offsets moved, only the merges.
-	{ Phase ph(h, FQSK_PH_WALK); k_walk<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(E, S, P, 0); LAUNCHED(h); ++h->S.n_replays; }
-	uint32_t it = 0;
-	bool redo_walk = true, redo_tail = true;
-	for (uint32_t pass = 0;; ++pass) {
-		if (pass > 64) return fail(h, FQSK_E_NO_CONVERGE, "segment did not settle");
-		if (redo_walk) {
-			if (++it >= max_it) return fail(h, FQSK_E_NO_CONVERGE, "segment did not reach its fixed point in %u iterations", max_it);
-			CK(cudaMemsetAsync(h->d_flags + 2, 0, sizeof(int), h->st));
-			{ int rc_ = build_delta(); if (rc_ != FQSK_OK) return rc_ == RC_RETRY + 1 ? fail(h, FQSK_E_NOMEM, "hot-mode event list overflow") : rc_; }
-			{ Phase ph(h, FQSK_PH_LOCAL); k_local<<<std::min<uint32_t>(nblk(std::max<uint32_t>(h->miss_cap, 1), 128), 148 * 16), 128, 0, h->st>>>(E, S, P, 1); LAUNCHED(h); }
-			{ Phase ph(h, FQSK_PH_WALK); k_walk<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(E, S, P, it); LAUNCHED(h); ++h->S.n_replays; }
-		}
-		if (redo_tail) {
-			{
-				Phase ph(h, FQSK_PH_COMPACT);
-				k_scan_u32x4<<<1, 1024, 0, h->st>>>(n, h->cnt_b.as<uint32_t>(), h->off_b[0].as<uint32_t>(), h->cnt_s.as<uint32_t>(), h->off_s[0].as<uint32_t>(),
-				                                     h->cnt_p.as<uint32_t>(), h->off_p.as<uint32_t>(), h->hidden.as<uint32_t>(), nullptr, d_tot4);
-				LAUNCHED(h);
-				k_compact2<<<n, 64, 0, h->st>>>(S, P, h->off_b[0].as<uint32_t>(), h->off_s[0].as<uint32_t>(), h->off_p.as<uint32_t>(),
-				                               h->row_b[0].as<unsigned long long>(), h->row_s[0].as<unsigned long long>(), h->row_p.as<unsigned long long>(),
-				                               h->rt_b[0].as<uint32_t>(), h->rt_s[0].as<uint32_t>());
-				LAUNCHED(h);
-			}
-			CK(cudaMemsetAsync(h->d_u32 + 1, 0, 4, h->st));      // rough scripts are rebuilt
-			{ Phase ph(h, FQSK_PH_ROUGH); k_rough<<<std::max<uint32_t>(148, std::min<uint32_t>(nblk(rec_bound, 16), 148 * 32)), 128, 0, h->st>>>(E, P); LAUNCHED(h); }
-			{ Phase ph(h, FQSK_PH_FOLD); k_fold<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(E, S, P, 0); LAUNCHED(h); }
-		}
-		{
-			Phase ph(h, FQSK_PH_FOLD);
-			k_scan_draws<<<1, 1024, 0, h->st>>>(n, P.rdraws_b, h->doff_b.as<unsigned long long>(), P.rdraws_s, h->doff_s.as<unsigned long long>(), d_draw2); LAUNCHED(h);
-			CK(cudaMemsetAsync(h->d_flags + 0, 0, sizeof(int), h->st)); CK(cudaMemsetAsync(h->d_flags + 7, 0, sizeof(int), h->st));
-			k_fold<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(E, S, P, 1); LAUNCHED(h);
-		}
-		uint8_t *hs = (uint8_t *) h->h_small;
-		CK(cudaMemcpyAsync(hs, h->d_status, 256, cudaMemcpyDeviceToHost, h->st));
-		CK(cudaStreamSynchronize(h->st));
-		resolve_phases(h);
+	uint8_t *hs = (uint8_t *) h->h_small;
+	for (;;) {
+		if (!have_look) CKR(look(h));
+		have_look = false;
 		memcpy(fl, hs, sizeof fl); memcpy(draws2, hs + 208, 16); memcpy(cnt, hs + 32, 16);
 		if (fl[4]) {
 			if (cnt[0] > h->miss_cap) h->miss_cap = cnt[0] + cnt[0] / 4 + 1024;
@@ -671,21 +735,21 @@ int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes_ac
 			if (!h->hot) { h->hot = true; ++h->S.n_hot_segments; return RC_RETRY; }
 			return fail(h, FQSK_E_UNSUPPORTED, "a front-truncated thread-local lookup matched more than %u entries; not supported", DeltaCollect::CAP);
 		}
-		if (fl[2]) { redo_walk = true; redo_tail = true; continue; }      // walk `it` changed pushes: one more thread-local pass
-		redo_walk = false;
+		if (fl[2]) { C.redo_walk = true; C.redo_tail = true; CKR(seg_pass(h)); continue; }      // walk `it` changed pushes: one more thread-local pass
+		C.redo_walk = false;
 		if (fl[0]) {   // the pre-generated draw window was too short: extend and evaluate the merges again
 			CKR(stream_ensure(h, h->rng[ST_B], draws2[0] + (1u << 16))); CKR(stream_ensure(h, h->rng[ST_S], draws2[1] + (1u << 12)));
-			E = make_engine_dev(h);
-			redo_tail = false;
+			C.E = make_engine_dev(h);
+			C.redo_tail = false;
+			CKR(seg_pass(h));
 			continue;
 		}
-		if (fl[7]) { redo_tail = false; continue; }                     // a counter saturated inside a merge: offsets moved, merge again
+		if (fl[7]) { C.redo_tail = false; CKR(seg_pass(h)); continue; }                     // a counter saturated inside a merge: offsets moved, merge again
 		break;
 	}
-	h->seg_delta_b = S.delta_b; h->seg_delta_s = S.delta_s;
+	h->seg_delta_b = C.S.delta_b; h->seg_delta_s = C.S.delta_s;
 	h->cur = 0;
 	{
-		uint8_t *hs = (uint8_t *) h->h_small;
 		uint32_t t4[4]; memcpy(t4, hs + 192, 16);
 		SegTotals tt; memcpy(&tt, hs + 64, sizeof tt);
 		h->pend_b = t4[0]; h->pend_s = t4[1]; h->pend_p = t4[2];
@@ -695,7 +759,21 @@ int segment_attempt(fqsk_handle *h, SegDev &S, uint32_t n, uint64_t dna_bytes_ac
 		h->rng[ST_B].consumed += draws2[0]; h->rng[ST_S].consumed += draws2[1];
 		if (h->hot) { uint32_t hd[2]; memcpy(hd, hs + 32 + 6 * 4, 8); h->rng[ST_LB].consumed += hd[0]; h->rng[ST_LS].consumed += hd[1]; }
 	}
+	for (int i = 0; i < 4; ++i) h->S.draws[i] = h->rng[i].consumed;
+	h->unsettled = false;
 	return FQSK_OK;
+}
+
+// make the outcome of the last fqsk_segment* call final on the host side (records, pending rows, stream positions)
+int seg_settle(fqsk_handle *h, bool have_look = false) {
+	if (!h->unsettled) return FQSK_OK;
+	for (int attempt = 0;; ++attempt) {
+		if (attempt > 8) return fail(h, FQSK_E_NOMEM, "segment buffers kept overflowing");
+		int rc = seg_finish(h, have_look);
+		have_look = false;
+		if (rc == RC_RETRY) { CKR(seg_setup(h)); CKR(seg_pass(h)); continue; }
+		return rc;
+	}
 }
 
 int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual, const unsigned long long *d_off, const uint32_t *d_len, uint32_t n) {
@@ -716,7 +794,10 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 	CK(h->off_p.ensure(n1 * 4)); CK(h->row_p.ensure((2 * dna_bytes + 2 * n1) * 8));
 	CK(h->sflag.ensure(n1 * 4)); CK(h->sdif.ensure(n1 * 8)); CK(h->totals.ensure(256));
 
-	SegDev S{};
+	SegCtx &C = h->ctx;
+	C.n = n; C.dna_bytes_actual = dna_bytes_actual; C.first = first;
+	SegDev &S = C.S;
+	S = SegDev{};
 	S.dna = d_dna; S.off = d_off; S.len = d_len; S.n_reads = n;
 	CK(h->prev_read.ensure_keep((size_t) dna_bytes_actual + 64, h->st));     // a read is never longer than its segment
 	S.prev_read = h->prev_read.as<uint8_t>(); S.carry = h->d_carry;
@@ -736,16 +817,15 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 	if (h->miss_cap < rec_bound / 4) h->miss_cap = rec_bound / 4 + 1024;
 	if (h->rreq_cap < std::min<uint32_t>(rec_bound, 1u << 20)) h->rreq_cap = std::min<uint32_t>(rec_bound, 1u << 20);
 	if (h->rreq_cap < rec_bound / 8) h->rreq_cap = rec_bound / 8 + 1024;
-	CKR(stream_ensure(h, h->rng[ST_B], 1u << 16)); CKR(stream_ensure(h, h->rng[ST_S], 1u << 12));
-	for (int attempt = 0;; ++attempt) {
-		if (attempt > 8) return fail(h, FQSK_E_NOMEM, "segment buffers kept overflowing");
-		int rc = segment_attempt(h, S, n, dna_bytes_actual, first);
-		if (rc == RC_RETRY) continue;
-		if (rc != FQSK_OK) return rc;
-		break;
-	}
-	for (int i = 0; i < 4; ++i) h->S.draws[i] = h->rng[i].consumed;
+	// draw windows: the merges of the segment and, for a sync enqueued unseen, the ordered inserts of its b-mers
+	CKR(stream_ensure(h, h->rng[ST_B], (1u << 16) + (dna_bytes_actual <= SPEC_MAX_BYTES ? 2 * dna_bytes_actual : 0))); CKR(stream_ensure(h, h->rng[ST_S], 1u << 12));
+	CKR(seg_setup(h));
+	CKR(seg_pass(h));
+	// verdict of the first pass for a sync enqueued unseen, and the state the next segment inherits (both are inputs only)
+	k_seg_verdict<<<1, 32, 0, h->st>>>(h->d_flags, (const uint32_t *) (h->d_status + 192), (const unsigned long long *) (h->d_status + 208),
+	                                   h->rng[ST_B].consumed, h->rng[ST_S].consumed, SYNC_INDEXED_MAX, h->d_syncin); LAUNCHED(h);
 	k_save_carry<<<1, 256, 0, h->st>>>(S, h->prev_read.as<uint8_t>(), h->d_carry, h->P.mode == FQSK_MODE_SE_SORTED || h->P.mode == FQSK_MODE_PE_SORTED, h->P.pmer_len); LAUNCHED(h);
+	h->unsettled = true;
 	h->pending = true;
 	h->S.n_reads += n; h->S.n_bases += dna_bytes_actual;
 	return FQSK_OK;
@@ -830,6 +910,9 @@ int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
 		h->d_u32 = (uint32_t *) (h->d_status + 32);              // +32  : 8 counters
 		h->d_carry = (Carry *) (h->d_status + 232);              // +232 : Carry (16 bytes)
 		h->d_sfast = (int *) (h->d_status + 224);                // +224 : s-mer fast-path verdict
+		h->d_syncin = (SyncIn *) (h->d_status + 256);            // +256 : SyncIn (40 bytes) of the sync enqueued behind its segment
+		h->d_sflags = (int *) (h->d_status + 304);               // +304 : 8 ints, flags of the ordered insert
+		h->d_syncin2 = (SyncIn *) (h->d_status + 352);           // +352 : SyncIn of a plain ordered insert
 		CK(cudaMalloc(&h->d_counters, 8 * 8));
 		CK(cudaMemset(h->d_counters, 0, 64));
 		CK(cudaMallocHost(&h->h_small, 1024));
@@ -875,7 +958,7 @@ void fqsk_destroy(fqsk_handle *h) {
 	                  &h->sidx_b, &h->sidx_s, &h->stime_b, &h->stime_s, &h->sort_k, &h->sort_v, &h->rkind, &h->rreg, &h->rslot, &h->dirty, &h->rdraws_b, &h->rdraws_s, &h->totals,
 	                  &h->y_tslot, &h->y_c0, &h->y_m, &h->y_draw, &h->y_j, &h->y_final, &h->y_flag_at, &h->y_own, &h->y_lead, &h->y_rank, &h->y_flag, &h->y_doff,
 	                  &h->idx_k, &h->idx_t, &h->idx_rt, &h->miss_fold, &h->hr_b[0], &h->hr_b[1], &h->hr_b[2], &h->hr_s[0], &h->hr_s[1], &h->hr_s[2],
-	                  &h->evk[0], &h->evk[1], &h->evv[0], &h->evv[1], &h->evk_s[0], &h->evk_s[1], &h->evv_s[0], &h->evv_s[1]};
+	                  &h->evk[0], &h->evk[1], &h->evv[0], &h->evv[1], &h->evk_s[0], &h->evk_s[1], &h->evv_s[0], &h->evv_s[1], &h->scan_part};
 
 	for (DevBuf *b : bufs) b->release();
 	if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -899,12 +982,14 @@ int fqsk_segment_device(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes
 	if (!h) return FQSK_E_INVAL;
 	CK(cudaSetDevice(h->P.device));
 	CKR(run_segment(h, d_dna, dna_bytes, (const unsigned long long *) d_off, d_len, n_reads));
-	if (n_recs) *n_recs = h->n_recs;
+	if (n_recs) { CKR(seg_settle(h)); *n_recs = h->n_recs; }    // pass NULL to leave the look to fqsk_sync / fqsk_device_recs
 	return FQSK_OK;
 }
 
 int fqsk_device_recs(fqsk_handle *h, const fqsk_base_rec **d_recs, uint64_t *n_recs) {
 	if (!h || !d_recs) return FQSK_E_INVAL;
+	CK(cudaSetDevice(h->P.device));
+	CKR(seg_settle(h));
 	*d_recs = h->recs.as<fqsk_base_rec>();
 	if (n_recs) *n_recs = h->n_recs;
 	return FQSK_OK;
@@ -915,6 +1000,7 @@ int fqsk_sorted_prefix(fqsk_handle *h, uint32_t *flag, uint64_t *dif, uint32_t n
 	CK(cudaSetDevice(h->P.device));
 	if (n_reads > h->seg_reads) return fail(h, FQSK_E_INVAL, "last segment had %u reads", h->seg_reads);
 	if (!n_reads) return FQSK_OK;
+	CKR(seg_settle(h));
 	CK(cudaMemcpyAsync(flag, h->sflag.p, (size_t) n_reads * 4, cudaMemcpyDeviceToHost, h->st));
 	CK(cudaMemcpyAsync(dif, h->sdif.p, (size_t) n_reads * 8, cudaMemcpyDeviceToHost, h->st));
 	CK(cudaStreamSynchronize(h->st));
@@ -958,6 +1044,7 @@ int fqsk_segment(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const 
 		CK(cudaMemcpyAsync(h->len.p, h_len, (size_t) n_reads * 4, cudaMemcpyHostToDevice, h->st));
 	}
 	CKR(run_segment(h, h->dna.as<uint8_t>(), total, h->off.as<unsigned long long>(), h->len.as<uint32_t>(), n_reads));
+	CKR(seg_settle(h));
 	if (h->n_recs > rec_cap) return fail(h, FQSK_E_CAPACITY, "record buffer holds %llu, segment produced %llu", (unsigned long long) rec_cap, (unsigned long long) h->n_recs);
 	if (h->n_recs && recs) CK(cudaMemcpyAsync(recs, h->recs.p, h->n_recs * sizeof(fqsk_base_rec), cudaMemcpyDeviceToHost, h->st));
 	if (n_reads && dup) CK(cudaMemcpyAsync(dup, h->dup.p, n_reads, cudaMemcpyDeviceToHost, h->st));
@@ -967,67 +1054,129 @@ int fqsk_segment(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const 
 	return FQSK_OK;
 }
 
+// The sync of a small segment, enqueued right behind the segment's first pass without a host look in between: every kernel is
+// predicated on the device-side verdict of that pass and takes row lengths and stream positions from the device (SyncIn).
+// One look then settles the segment AND the sync.  *applied = false: the caller runs the plain path (nothing was changed).
+static int sync_speculative(fqsk_handle *h, bool *applied, unsigned long long counters[6]) {
+	*applied = false;
+	SegCtx &C = h->ctx;
+	SyncIn *in = h->d_syncin;
+	const uint32_t bound_b = (uint32_t) (2 * C.dna_bytes_actual + 2), bound_s = (uint32_t) (C.dna_bytes_actual + 1);
+	const uint64_t bound_p = 2 * C.dna_bytes_actual + 2ull * C.n;
+	CK(cudaMemsetAsync(h->d_counters + 4, 0, 8, h->st));
+	{
+		Phase ph(h, FQSK_PH_SYNC_SIV);
+		k_siv_increment<<<nblk(bound_p, 256), 256, 0, h->st>>>(h->siv, h->row_p.as<unsigned long long>(), 0, h->d_counters + 4, in); LAUNCHED(h);
+	}
+	{
+		Phase ph(h, FQSK_PH_SYNC_APPLY);
+		CK(cudaMemsetAsync(h->d_sfast, 0, sizeof(int), h->st));
+		CK(h->q4.ensure((size_t) bound_s + 4));
+		k_insert_fast<<<nblk(bound_s, 256), 256, 0, h->st>>>(h->ts.d, h->ts.ci, h->row_s[0].as<unsigned long long>(), 0, h->q4.as<uint8_t>(), h->d_sfast, in); LAUNCHED(h);
+	}
+	SyncDev Y;
+	CKR(indexed_setup(h, C.S.delta_b, bound_b, in, true, Y));
+	const uint32_t g = nblk(bound_b, 256);
+	const unsigned long long *row_b = h->row_b[0].as<unsigned long long>();
+	CKR(indexed_head(h, h->tb, Y, row_b, h->rt_b[0].as<uint32_t>(), g));
+	{
+		Phase ph(h, FQSK_PH_SYNC_APPLY);
+		CKR(stream_ensure(h, h->rng[ST_B], 0));
+		CKR(indexed_tail(h, h->tb, h->rng[ST_B], Y, row_b, g, bound_b));
+	}
+	CKR(look(h));
+	const SyncIn li = *looked_syncin(h, in);
+	int fl[8]; memcpy(fl, looked_sflags(h), sizeof fl);
+	const int s_refuted = *(const int *) ((uint8_t *) h->h_small + 224);
+	memcpy(counters, (uint8_t *) h->h_small + 512, 48);
+	CKR(seg_settle(h, true));      // the same look carries the segment's flags and totals
+	if (!li.ok) return FQSK_OK;    // the first pass was not the last one (or the rows are large): nothing was applied
+	*applied = true;
+	bool relook = false;
+	if (fl[6]) h->hot_seen[1] = true;
+	if (fl[7] || fl[0] || fl[2]) {
+		// a counter saturated inside the batch, the draw window was short or a group is too large: nothing was committed; release
+		// the claimed slots and take the plain ordered path for this row
+		k_sync_unclaim<<<g, 256, 0, h->st>>>(h->tb.d, Y); LAUNCHED(h);
+		CKR(apply_indexed(h, h->tb, h->rng[ST_B], h->seg_delta_b, row_b, h->rt_b[0].as<uint32_t>(), h->pend_b));
+		relook = true;
+	} else h->rng[ST_B].consumed += li.draws_b;
+	if (s_refuted) {
+		k_insert_undo<<<nblk(h->pend_s, 256), 256, 0, h->st>>>(h->ts.d, h->row_s[0].as<unsigned long long>(), h->pend_s, h->q4.as<uint8_t>()); LAUNCHED(h);
+		CKR(apply_inserts(h, h->ts, h->rng[ST_S], h->row_s[0].as<unsigned long long>(), h->pend_s));
+		relook = true;
+	}
+	if (relook) {
+		unsigned long long *hc = (unsigned long long *) ((uint8_t *) h->h_small + 512);
+		CK(cudaMemcpyAsync(hc, h->d_counters, 48, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaStreamSynchronize(h->st));
+		for (int i = 0; i < 4; ++i) counters[i] = hc[i];      // [4] (fresh p-mer fields) is from the first look: the p-mers were applied once
+	}
+	return FQSK_OK;
+}
+
 int fqsk_sync(fqsk_handle *h) {
 	if (!h) return FQSK_E_INVAL;
 	CK(cudaSetDevice(h->P.device));
 	++h->S.n_syncs;
 	if (h->pending && h->seg_reads) {
-		// p-mers (dna.cpp:2401-2418): order-independent saturating increments; the fresh-field count is read with the next look
 		h->hot_seen[0] = h->hot_seen[1] = false;
-		CK(cudaMemsetAsync(h->d_counters + 4, 0, 8, h->st));
-		if (h->pend_p) {
-			Phase ph(h, FQSK_PH_SYNC_SIV);
-			k_siv_increment<<<nblk(h->pend_p, 256), 256, 0, h->st>>>(h->siv, h->row_p.as<unsigned long long>(), h->pend_p, h->d_counters + 4);
-			LAUNCHED(h);
-		}
-		// s-mers and b-mers (dna.cpp:2425-2446) live in different tables and use different PRNG streams, so their rows are
-		// independent of each other.  Small rows: the s-mers go through the self-checking atomic path and the b-mers through the
-		// sort-free grouping over the segment's delta table, all enqueued back to back with ONE host look for the whole sync;
-		// large rows: one radix sort per row is cheaper.
-		bool s_fast_pending = false;
-		h->look_fresh = false;
-		if (h->fast_ok[0] && h->pend_s) {
-			Phase ph(h, FQSK_PH_SYNC_APPLY);
-			CK(cudaMemsetAsync(h->d_sfast, 0, sizeof(int), h->st));
-			CK(h->q4.ensure((size_t) h->pend_s + 4));
-			k_insert_fast<<<nblk(h->pend_s, 256), 256, 0, h->st>>>(h->ts.d, h->ts.ci, h->row_s[0].as<unsigned long long>(), h->pend_s, h->q4.as<uint8_t>(), h->d_sfast); LAUNCHED(h);
-			s_fast_pending = true;
-		}
-		else if (h->pend_s <= SYNC_INDEXED_MAX) CKR(apply_indexed(h, h->ts, h->rng[ST_S], h->seg_delta_s, h->row_s[0].as<unsigned long long>(), h->rt_s[0].as<uint32_t>(), h->pend_s));
-		else CKR(apply_inserts(h, h->ts, h->rng[ST_S], h->row_s[0].as<unsigned long long>(), h->pend_s));
-		h->look_fresh = false;
-		if (h->pend_b <= SYNC_INDEXED_MAX) CKR(apply_indexed(h, h->tb, h->rng[ST_B], h->seg_delta_b, h->row_b[0].as<unsigned long long>(), h->rt_b[0].as<uint32_t>(), h->pend_b));
-		else CKR(apply_inserts(h, h->tb, h->rng[ST_B], h->row_b[0].as<unsigned long long>(), h->pend_b));
-		unsigned long long *hc = (unsigned long long *) ((uint32_t *) h->h_small + 72);
-		if (!h->look_fresh) {
-			CK(cudaMemcpyAsync(h->h_small, h->d_status, 256, cudaMemcpyDeviceToHost, h->st));
-			CK(cudaMemcpyAsync(hc, h->d_counters, 48, cudaMemcpyDeviceToHost, h->st));
-			CK(cudaStreamSynchronize(h->st));
-		}
-		unsigned long long counters[6]; memcpy(counters, hc, 48);
-		if (s_fast_pending && *(int *) ((uint8_t *) h->h_small + 224)) {
-			// some s-mer counter left the deterministic range: undo (claimed slots stay as zero-count items == the reference's fresh
-			// slot) and insert the row in order
-			k_insert_undo<<<nblk(h->pend_s, 256), 256, 0, h->st>>>(h->ts.d, h->row_s[0].as<unsigned long long>(), h->pend_s, h->q4.as<uint8_t>()); LAUNCHED(h);
-			CKR(apply_inserts(h, h->ts, h->rng[ST_S], h->row_s[0].as<unsigned long long>(), h->pend_s));
-			CK(cudaMemcpyAsync(hc, h->d_counters, 48, cudaMemcpyDeviceToHost, h->st));
-			CK(cudaStreamSynchronize(h->st));
-			counters[2] = hc[2]; counters[3] = hc[3];
+		unsigned long long counters[6] = {0, 0, 0, 0, 0, 0};
+		bool applied = false;
+		if (h->unsettled && h->fast_ok[0] && h->ctx.dna_bytes_actual <= SPEC_MAX_BYTES) CKR(sync_speculative(h, &applied, counters));
+		CKR(seg_settle(h));
+		if (!applied) {
+			// p-mers (dna.cpp:2401-2418): order-independent saturating increments; the fresh-field count is read with the next look
+			CK(cudaMemsetAsync(h->d_counters + 4, 0, 8, h->st));
+			if (h->pend_p) {
+				Phase ph(h, FQSK_PH_SYNC_SIV);
+				k_siv_increment<<<nblk(h->pend_p, 256), 256, 0, h->st>>>(h->siv, h->row_p.as<unsigned long long>(), h->pend_p, h->d_counters + 4);
+				LAUNCHED(h);
+			}
+			// s-mers and b-mers (dna.cpp:2425-2446) live in different tables and use different PRNG streams, so their rows are
+			// independent of each other.  The s-mers go through the self-checking atomic path (counters stay far below thr = 2047);
+			// b-mers: small rows through the sort-free grouping over the segment's delta table, large rows through one radix sort.
+			bool s_fast_pending = false;
+			h->look_fresh = false;
+			if (h->fast_ok[0] && h->pend_s) {
+				Phase ph(h, FQSK_PH_SYNC_APPLY);
+				CK(cudaMemsetAsync(h->d_sfast, 0, sizeof(int), h->st));
+				CK(h->q4.ensure((size_t) h->pend_s + 4));
+				k_insert_fast<<<nblk(h->pend_s, 256), 256, 0, h->st>>>(h->ts.d, h->ts.ci, h->row_s[0].as<unsigned long long>(), h->pend_s, h->q4.as<uint8_t>(), h->d_sfast); LAUNCHED(h);
+				s_fast_pending = true;
+			}
+			else if (h->pend_s <= SYNC_INDEXED_MAX) CKR(apply_indexed(h, h->ts, h->rng[ST_S], h->seg_delta_s, h->row_s[0].as<unsigned long long>(), h->rt_s[0].as<uint32_t>(), h->pend_s));
+			else CKR(apply_inserts(h, h->ts, h->rng[ST_S], h->row_s[0].as<unsigned long long>(), h->pend_s));
+			h->look_fresh = false;
+			if (h->pend_b <= SYNC_INDEXED_MAX) CKR(apply_indexed(h, h->tb, h->rng[ST_B], h->seg_delta_b, h->row_b[0].as<unsigned long long>(), h->rt_b[0].as<uint32_t>(), h->pend_b));
+			else CKR(apply_inserts(h, h->tb, h->rng[ST_B], h->row_b[0].as<unsigned long long>(), h->pend_b));
+			if (!h->look_fresh) CKR(look(h));
+			memcpy(counters, (uint8_t *) h->h_small + 512, 48);
+			if (s_fast_pending && *(int *) ((uint8_t *) h->h_small + 224)) {
+				// some s-mer counter left the deterministic range: undo (claimed slots stay as zero-count items == the reference's fresh
+				// slot) and insert the row in order
+				k_insert_undo<<<nblk(h->pend_s, 256), 256, 0, h->st>>>(h->ts.d, h->row_s[0].as<unsigned long long>(), h->pend_s, h->q4.as<uint8_t>()); LAUNCHED(h);
+				CKR(apply_inserts(h, h->ts, h->rng[ST_S], h->row_s[0].as<unsigned long long>(), h->pend_s));
+				unsigned long long *hc = (unsigned long long *) ((uint8_t *) h->h_small + 512);
+				CK(cudaMemcpyAsync(hc, h->d_counters, 48, cudaMemcpyDeviceToHost, h->st));
+				CK(cudaStreamSynchronize(h->st));
+				counters[2] = hc[2]; counters[3] = hc[3];
+			}
 		}
 		if (!h->hot) {   // hot segments already advanced the thread-local streams
 			if (h->hot_seen[0]) CKR(hot_account(h, 1));
 			if (h->hot_seen[1]) CKR(hot_account(h, 0));
 		}
 		h->hot_seen[0] = h->hot_seen[1] = false;
-		hc = counters;
-		h->S.siv_no_filled += hc[4];
+		h->S.siv_no_filled += counters[4];
 		h->S.siv_no_updates += h->pend_p + h->hidden_p;
 		h->hidden_p = 0;
 		for (int k = 0; k < 2; ++k) {
 			Table &t = k ? h->tb : h->ts;
-			if (hc[2 - 2 * k] > (4ull << t.d.B) || hc[3 - 2 * k] > (1ull << t.d.stash_log2) / 2) CKR(table_grow_if_needed(h, t));
+			if (counters[2 - 2 * k] > (4ull << t.d.B) || counters[3 - 2 * k] > (1ull << t.d.stash_log2) / 2) CKR(table_grow_if_needed(h, t));
 		}
 	} else {
+		CKR(seg_settle(h));
 		h->S.siv_no_updates += h->hidden_p;
 		h->hidden_p = 0;
 	}
@@ -1055,6 +1204,7 @@ static int dump_sorted(fqsk_handle *h, uint64_t n, uint64_t *keys, uint64_t *val
 int fqsk_dump(fqsk_handle *h, int table, uint64_t *keys, uint64_t *vals, uint64_t cap, uint64_t *n) {
 	if (!h || !n) return FQSK_E_INVAL;
 	CK(cudaSetDevice(h->P.device));
+	CKR(seg_settle(h));
 	if (table == FQSK_TABLE_SMER || table == FQSK_TABLE_BMER) {
 		Table &t = table == FQSK_TABLE_SMER ? h->ts : h->tb;
 		uint64_t cnt = 0;
@@ -1086,6 +1236,7 @@ int fqsk_dump(fqsk_handle *h, int table, uint64_t *keys, uint64_t *vals, uint64_
 int fqsk_stats_get(fqsk_handle *h, fqsk_stats *out) {
 	if (!h || !out) return FQSK_E_INVAL;
 	CK(cudaSetDevice(h->P.device));
+	CKR(seg_settle(h));
 	unsigned long long c[4];
 	CK(cudaMemcpyAsync(c, h->d_counters, 32, cudaMemcpyDeviceToHost, h->st));
 	CK(cudaStreamSynchronize(h->st));

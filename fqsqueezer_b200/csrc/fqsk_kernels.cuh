@@ -278,17 +278,25 @@ __global__ void k_apply_keys(HtDev t, CIncP ci, const unsigned long long *skeys,
 //                 counters it sees (they differ only when a counter saturates inside the batch) and reports a change
 //   k_sync_commit leaders write the final counters
 // ------------------------------------------------------------------------------------------------------------------
+struct SyncIn {             // inputs of a sync that only the device knows when the sync is enqueued right behind its segment
+	uint32_t ok;            // the segment settled on its first pass (k_seg_verdict); 0 = every sync kernel is a no-op
+	uint32_t n_b, n_s, n_p; // rows to apply (dna.cpp:2401-2446)
+	unsigned long long dpos_b, dpos_s;   // absolute positions of the cinc_b / cinc_s streams after the segment's lookups
+	uint32_t draws_b, pad;  // out: mt19937 outputs consumed by the b-mer inserts of this sync
+};
+
 struct SyncDev {
 	DeltaDev D;
+	const SyncIn *in; const uint32_t *n_dev; const unsigned long long *dpos_dev; uint32_t *total_draws;
 	unsigned long long *lead_tslot; uint32_t *lead_c0, *lead_m, *draw_at, *j_at, *final_at; uint8_t *flag_at;   // per delta slot
 	uint32_t *own, *lead, *rank; uint8_t *flag; const uint32_t *draw_off;                                       // per occurrence
 	int *flags;   // [2] changed, [0] draw window short, [7] a hot group is too large for the in-thread path
 };
 static const uint32_t SYNC_GROUP_CAP = 48;
 
-__global__ void k_sync_rank(HtDev t, SyncDev Y, const unsigned long long *row, const uint32_t *rt, uint32_t n) {
+__global__ void k_sync_rank(HtDev t, SyncDev Y, const unsigned long long *row, const uint32_t *rt) {
 	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= n) return;
+	if (!Y.in->ok || j >= *Y.n_dev) return;
 	const unsigned long long x = row[j];
 	const uint32_t tm = rt[j];
 	uint32_t m = 0, rank = 0, own = 0xFFFFFFFFu, lead = 0xFFFFFFFFu, lead_t = 0xFFFFFFFFu;
@@ -311,9 +319,9 @@ __global__ void k_sync_rank(HtDev t, SyncDev Y, const unsigned long long *row, c
 		Y.lead_m[own] = m;
 	}
 }
-__global__ void k_sync_flags(HtDev t, CIncP ci, SyncDev Y, uint32_t n) {
+__global__ void k_sync_flags(HtDev t, CIncP ci, SyncDev Y) {
 	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= n) return;
+	if (!Y.in->ok || j >= *Y.n_dev) return;
 	const uint32_t L = Y.lead[j], c0 = Y.lead_c0[L], m = Y.lead_m[L], rank = Y.rank[j];
 	uint8_t f = 0;
 	if (rank == 0 && m > ci.thr + 1) Y.flags[6] = 1;   // the thread-local table of the reference drew from its own stream for this k-mer
@@ -324,20 +332,22 @@ __global__ void k_sync_flags(HtDev t, CIncP ci, SyncDev Y, uint32_t n) {
 	}
 	Y.flag[j] = f;
 }
-__global__ void k_sync_scatter(CIncP ci, SyncDev Y, uint32_t n) {
+__global__ void k_sync_scatter(CIncP ci, SyncDev Y) {
 	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= n) return;
+	if (!Y.in->ok || j >= *Y.n_dev) return;
 	const uint32_t L = Y.lead[j];
 	if (Y.lead_c0[L] + Y.lead_m[L] <= ci.thr + 1) return;
 	const uint32_t own = Y.own[j];
 	Y.draw_at[own] = Y.draw_off[j];
 	Y.flag_at[own] = Y.flag[j];
 }
-__global__ void k_sync_apply(HtDev t, CIncP ci, SyncDev Y, const unsigned long long *row, uint32_t n,
-                             const uint32_t *draws, unsigned long long dmask, unsigned long long dpos, unsigned long long avail) {
+__global__ void k_sync_apply(HtDev t, CIncP ci, SyncDev Y, const unsigned long long *row,
+                             const uint32_t *draws, unsigned long long dmask, unsigned long long safe_abs) {
 	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= n) return;
+	if (!Y.in->ok || j >= *Y.n_dev) return;
 	if (Y.rank[j] != 0) return;
+	const unsigned long long dpos = *Y.dpos_dev;
+	const unsigned long long avail = safe_abs > dpos ? safe_abs - dpos : 0;
 	const uint32_t L = Y.own[j];
 	const uint32_t c0 = Y.lead_c0[L], m = Y.lead_m[L];
 	if (c0 + m <= ci.thr + 1 || m > SYNC_GROUP_CAP) return;
@@ -370,18 +380,18 @@ __global__ void k_sync_apply(HtDev t, CIncP ci, SyncDev Y, const unsigned long l
 	}
 	Y.final_at[L] = c;
 }
-__global__ void k_sync_commit(HtDev t, SyncDev Y, uint32_t n) {
+__global__ void k_sync_commit(HtDev t, SyncDev Y) {
 	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= n) return;
+	if (!Y.in->ok || j >= *Y.n_dev) return;
 	if (Y.rank[j] != 0) return;
 	if (Y.flags[7] || Y.flags[2] || Y.flags[0]) return;     // not settled: the host iterates or falls back, nothing is written
 	const uint32_t L = Y.own[j];
 	ht_slot_set(t, Y.lead_tslot[L] & ~(1ull << 63), Y.final_at[L]);
 }
 // fallback preparation: slots claimed by k_sync_rank (counter 1) become zero-count items, i.e. the reference's fresh slot
-__global__ void k_sync_unclaim(HtDev t, SyncDev Y, uint32_t n) {
+__global__ void k_sync_unclaim(HtDev t, SyncDev Y) {
 	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= n) return;
+	if (!Y.in->ok || j >= *Y.n_dev) return;
 	if (Y.rank[j] != 0) return;
 	unsigned long long ts = Y.lead_tslot[Y.own[j]];
 	if (ts >> 63) ht_slot_set(t, ts & ~(1ull << 63), 0);
@@ -400,8 +410,9 @@ __global__ void k_row_index_build(unsigned long long *keys, uint32_t *times, uin
 // Increment()s exactly when no counter leaves the deterministic range (pre-count <= thr for every occurrence, utils.h:317-318);
 // any occurrence that sees a pre-count above thr raises flags[2] and the host undoes the pass (k_insert_undo: the adds are
 // plain arithmetic on the item, so subtracting them restores every bit) and runs the ordered path instead.
-__global__ void k_insert_fast(HtDev t, CIncP ci, const unsigned long long *kmers, uint32_t n, uint8_t *added, int *refuted) {
+__global__ void k_insert_fast(HtDev t, CIncP ci, const unsigned long long *kmers, uint32_t n, uint8_t *added, int *refuted, const SyncIn *in = nullptr) {
 	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (in) { if (!in->ok) return; n = in->n_s; }
 	if (j >= n) return;
 	bool created;
 	uint64_t s = ht_locate(t, kmers[j], created);
@@ -440,8 +451,9 @@ __global__ void k_insert_undo(HtDev t, const unsigned long long *kmers, uint32_t
 	if (s < nm) atomicSub(t.main + s, 1u); else atomicAdd(t.stash + (s - nm), ~0ull);
 }
 
-__global__ void k_siv_increment(SivDev s, const unsigned long long *idx, uint64_t n, unsigned long long *n_new) {
+__global__ void k_siv_increment(SivDev s, const unsigned long long *idx, uint64_t n, unsigned long long *n_new, const SyncIn *in = nullptr) {
 	uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (in) n = in->ok ? in->n_p : 0;
 	uint32_t fresh = 0;
 	if (i < n) fresh = siv_increment(s, idx[i]);
 	unsigned mask = __ballot_sync(0xffffffffu, fresh);

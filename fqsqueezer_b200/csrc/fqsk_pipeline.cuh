@@ -1021,4 +1021,83 @@ __global__ void __launch_bounds__(1024) k_scan_draws(uint32_t n, const uint32_t 
 	if (t < 2) { out[t][n] = carry[t]; totals[t] = carry[t]; }
 }
 
+// draw flags (u8, push order) -> exclusive scan = draw index of every occurrence; n lives on the device.  Chained scan: every
+// CTA scans 4096 flags, publishes its sum tagged with the launch epoch and adds up the sums of the CTAs before it.  The grid
+// comes from a host-side bound and is small enough to be co-resident (rows that take this path are at most SYNC_INDEXED_MAX
+// long), so waiting on lower-numbered CTAs cannot deadlock.
+static const uint32_t SCANF_TILE = 4096;
+__global__ void __launch_bounds__(256) k_scan_flags(const SyncIn *in, const uint32_t *n_dev, const uint8_t *flag, uint32_t *out, uint32_t *total,
+                                                    unsigned long long *partials, uint32_t epoch) {
+	const uint32_t n = in->ok ? *n_dev : 0;
+	const uint32_t b = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+	const uint32_t base = b * SCANF_TILE;
+	if (base >= n) { if (b == 0 && t == 0) { out[0] = 0; *total = 0; } return; }
+	__shared__ uint32_t wsum[8];
+	__shared__ uint32_t bprefix;
+	const uint32_t r0 = base + t * 16;
+	uint32_t v[16];
+	if (r0 + 16 <= n) {
+		const uint4 q = *reinterpret_cast<const uint4 *>(flag + r0);     // flag arrays are 16-byte aligned, r0 is a multiple of 16
+		const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+		for (int e = 0; e < 16; ++e) v[e] = (wd[e >> 2] >> (8 * (e & 3))) & 0xFF;
+	} else {
+#pragma unroll
+		for (int e = 0; e < 16; ++e) v[e] = r0 + e < n ? flag[r0 + e] : 0;
+	}
+	uint32_t run = 0;
+#pragma unroll
+	for (int e = 0; e < 16; ++e) { uint32_t x = v[e]; v[e] = run; run += x; }
+	uint32_t inc = run;
+	for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+	if (lane == 31) wsum[w] = inc;
+	__syncthreads();
+	uint32_t woff = 0, bsum = 0;
+#pragma unroll
+	for (int q = 0; q < 8; ++q) { if (q < (int) w) woff += wsum[q]; bsum += wsum[q]; }
+	if (t == 0) {
+		__threadfence();
+		atomicExch(partials + b, ((unsigned long long) epoch << 32) | bsum);
+	}
+	// prefix of the CTAs before this one
+	uint32_t pre = 0;
+	for (uint32_t q = t; q < b; q += 256) {
+		unsigned long long x;
+		do { x = *((volatile unsigned long long *) (partials + q)); } while ((uint32_t) (x >> 32) != epoch);
+		pre += (uint32_t) x;
+	}
+	for (int o = 16; o; o >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, o);
+	__syncthreads();
+	if (lane == 0) wsum[w] = pre;
+	__syncthreads();
+	if (t == 0) { uint32_t x = 0; for (int q = 0; q < 8; ++q) x += wsum[q]; bprefix = x; }
+	__syncthreads();
+	const uint32_t off = bprefix + woff + inc - run;
+	if (r0 + 16 <= n) {
+		uint4 *o4 = reinterpret_cast<uint4 *>(out + r0);
+#pragma unroll
+		for (int e = 0; e < 4; ++e) o4[e] = make_uint4(off + v[4 * e], off + v[4 * e + 1], off + v[4 * e + 2], off + v[4 * e + 3]);
+	} else {
+		for (int e = 0; e < 16; ++e) if (r0 + e < n) out[r0 + e] = off + v[e];
+	}
+	if (base + SCANF_TILE >= n && t == 0) { out[n] = bprefix + bsum; *total = bprefix + bsum; }
+}
+
+// Verdict of a segment's first pass, for the sync that is enqueued right behind it without a host look: the pass settled when
+// no flag asks for another iteration, a retry or the ordered thread-local evaluator.
+__global__ void k_seg_verdict(const int *flags, const uint32_t *tot4, const unsigned long long *draws2, unsigned long long consumed_b, unsigned long long consumed_s,
+                              uint32_t row_cap, SyncIn *in) {
+	if (threadIdx.x || blockIdx.x) return;
+	bool ok = !(flags[0] | flags[1] | flags[2] | flags[4] | flags[5] | flags[7]);
+	if (tot4[0] > row_cap || tot4[1] > row_cap) ok = false;
+	in->n_b = tot4[0]; in->n_s = tot4[1]; in->n_p = tot4[2];
+	in->dpos_b = consumed_b + draws2[0]; in->dpos_s = consumed_s + draws2[1];
+	in->draws_b = 0;
+	in->ok = ok ? 1u : 0u;
+}
+__global__ void k_set_syncin(SyncIn *in, uint32_t n_b, uint32_t n_s, uint32_t n_p, unsigned long long dpos_b, unsigned long long dpos_s) {
+	if (threadIdx.x || blockIdx.x) return;
+	in->ok = 1; in->n_b = n_b; in->n_s = n_s; in->n_p = n_p; in->dpos_b = dpos_b; in->dpos_s = dpos_s; in->draws_b = 0;
+}
+
 }  // namespace fqsk

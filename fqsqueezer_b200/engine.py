@@ -155,7 +155,12 @@ class KmerEngine:
             return out, dup[:n], rec_off
         return out, dup[:n]
 
-    def segment_device(self, d_dna_ptr: int, dna_bytes: int, d_off_ptr: int, d_len_ptr: int, n_reads: int) -> int:
+    def segment_device(self, d_dna_ptr: int, dna_bytes: int, d_off_ptr: int, d_len_ptr: int, n_reads: int, want_n_recs: bool = True):
+        """Reads already in HBM.  want_n_recs=False only enqueues the segment: the library looks at the outcome when the
+        following sync (or device_recs / stats) needs it, which saves one host round trip per segment."""
+        if not want_n_recs:
+            self._ck(self.lib.fqsk_segment_device(self.h, C.c_void_p(d_dna_ptr), dna_bytes, C.c_void_p(d_off_ptr), C.c_void_p(d_len_ptr), n_reads, None))
+            return None
         n_recs = C.c_uint64(0)
         self._ck(self.lib.fqsk_segment_device(self.h, C.c_void_p(d_dna_ptr), dna_bytes, C.c_void_p(d_off_ptr), C.c_void_p(d_len_ptr), n_reads, C.byref(n_recs)))
         return n_recs.value
