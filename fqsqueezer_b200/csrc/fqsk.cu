@@ -1382,6 +1382,15 @@ int fqsk_siv_test(fqsk_handle *h, const uint64_t *idx, uint64_t n, uint32_t *out
 int fqsk_siv_counts(fqsk_handle *h, const uint64_t *idx, uint64_t n, uint32_t *out4) { return h ? siv_query(h, 1, idx, nullptr, n, out4) : FQSK_E_INVAL; }
 int fqsk_siv_test_shorter(fqsk_handle *h, const uint64_t *idx, const uint32_t *size_bits, uint64_t n, uint64_t *out) { return h ? siv_query(h, 2, idx, size_bits, n, out) : FQSK_E_INVAL; }
 
+int fqsk_host_alloc(uint64_t bytes, void **out) {
+	if (!out) return FQSK_E_INVAL;
+	*out = nullptr;
+	cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+	if (e != cudaSuccess) { g_create_error = std::string("cudaMallocHost: ") + cudaGetErrorString(e); return e == cudaErrorMemoryAllocation ? FQSK_E_NOMEM : FQSK_E_CUDA; }
+	return FQSK_OK;
+}
+void fqsk_host_free(void *p) { if (p) cudaFreeHost(p); }
+
 int fqsk_mt_stream(fqsk_handle *h, uint64_t n, uint32_t *out) {
 	if (!h) return FQSK_E_INVAL;
 	CK(cudaSetDevice(h->P.device));

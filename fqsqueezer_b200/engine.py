@@ -45,7 +45,7 @@ class _Stats(C.Structure):
 
 EXPORTS = ["fqsk_create", "fqsk_destroy", "fqsk_last_error", "fqsk_block_start", "fqsk_segment", "fqsk_segment_device",
            "fqsk_device_recs", "fqsk_sorted_prefix", "fqsk_sync", "fqsk_dump", "fqsk_stats_get", "fqsk_profile", "fqsk_ht_insert", "fqsk_ht_find",
-           "fqsk_ht_count", "fqsk_timer_begin", "fqsk_timer_end", "fqsk_siv_increment", "fqsk_siv_test", "fqsk_siv_counts", "fqsk_siv_test_shorter", "fqsk_mt_stream"]
+           "fqsk_ht_count", "fqsk_timer_begin", "fqsk_timer_end", "fqsk_siv_increment", "fqsk_siv_test", "fqsk_siv_counts", "fqsk_siv_test_shorter", "fqsk_mt_stream", "fqsk_host_alloc", "fqsk_host_free"]
 
 _lib = None
 
@@ -83,8 +83,11 @@ def load_library():
     lib.fqsk_siv_counts.argtypes = [vp, vp, C.c_uint64, vp]
     lib.fqsk_siv_test_shorter.argtypes = [vp, vp, vp, C.c_uint64, vp]
     lib.fqsk_mt_stream.argtypes = [vp, C.c_uint64, vp]
+    lib.fqsk_host_alloc.argtypes = [C.c_uint64, C.POINTER(vp)]
+    lib.fqsk_host_free.argtypes = [vp]
+    lib.fqsk_host_free.restype = None
     for n in EXPORTS:
-        if n not in ("fqsk_destroy", "fqsk_last_error"):
+        if n not in ("fqsk_destroy", "fqsk_last_error", "fqsk_host_free"):
             getattr(lib, n).restype = C.c_int
     _lib = lib
     return lib
@@ -120,9 +123,26 @@ class KmerEngine:
         self.p, self.s, self.b, self.prefix_len, self.mode = p, s, b, prefix_len, mode
 
     def close(self):
+        for ptr, _ in getattr(self, "_pinned", {}).values():
+            self.lib.fqsk_host_free(ptr)
+        self._pinned = {}
         if getattr(self, "h", None):
             self.lib.fqsk_destroy(self.h)
             self.h = None
+
+    def _pinned_array(self, name: str, nbytes: int) -> np.ndarray:
+        """A reusable page-locked byte buffer (fqsk_host_alloc) of at least nbytes, as a numpy uint8 view."""
+        if not hasattr(self, "_pinned"):
+            self._pinned = {}
+        cur = self._pinned.get(name)
+        if cur is None or cur[1] < nbytes:
+            if cur is not None:
+                self.lib.fqsk_host_free(cur[0])
+            cap = max(int(nbytes * 1.25) + 4096, 1 << 16)
+            ptr = C.c_void_p()
+            self._ck(self.lib.fqsk_host_alloc(cap, C.byref(ptr)))
+            self._pinned[name] = cur = (ptr, cap)
+        return np.ctypeslib.as_array(C.cast(cur[0], C.POINTER(C.c_uint8)), shape=(cur[1],))
 
     def __del__(self):
         try:
@@ -138,16 +158,23 @@ class KmerEngine:
     def block_start(self):
         self._ck(self.lib.fqsk_block_start(self.h))
 
-    def segment(self, slab: np.ndarray, off: np.ndarray, length: np.ndarray, kind: int = 0, want_rec_off=False):
+    def segment(self, slab: np.ndarray, off: np.ndarray, length: np.ndarray, kind: int = 0, want_rec_off=False, pinned=False):
+        """One sync segment from host memory.  pinned=True returns views into reusable page-locked buffers owned by the engine
+        (valid until the next call): the records then come back by DMA without a staging copy."""
         slab = np.ascontiguousarray(slab, np.uint8)
         n = len(off)
         desc = np.zeros(n, READ_DESC_DTYPE)
         desc["dna_off"] = off
         desc["dna_len"] = length
         cap = int(np.asarray(length, np.int64).sum()) + 16
-        recs = np.zeros(cap, REC_DTYPE)
-        dup = np.zeros(max(n, 1), np.uint8)
-        rec_off = np.zeros(n + 1, np.uint64)
+        if pinned:
+            recs = self._pinned_array("recs", cap * REC_DTYPE.itemsize)[: cap * REC_DTYPE.itemsize].view(REC_DTYPE)
+            dup = self._pinned_array("dup", max(n, 1))[: max(n, 1)]
+            rec_off = self._pinned_array("rec_off", (n + 1) * 8)[: (n + 1) * 8].view(np.uint64)
+        else:
+            recs = np.zeros(cap, REC_DTYPE)
+            dup = np.zeros(max(n, 1), np.uint8)
+            rec_off = np.zeros(n + 1, np.uint64)
         n_recs = C.c_uint64(0)
         self._ck(self.lib.fqsk_segment(self.h, _ptr(slab), slab.size, _ptr(desc), n, _ptr(recs), cap, C.byref(n_recs), _ptr(dup), _ptr(rec_off)))
         out = recs[: n_recs.value]

@@ -152,6 +152,11 @@ int fqsk_siv_increment(fqsk_handle *h, const uint64_t *idx, uint64_t n, uint64_t
 int fqsk_siv_test(fqsk_handle *h, const uint64_t *idx, uint64_t n, uint32_t *out);
 int fqsk_siv_counts(fqsk_handle *h, const uint64_t *idx, uint64_t n, uint32_t *out4);
 int fqsk_siv_test_shorter(fqsk_handle *h, const uint64_t *idx, const uint32_t *size_bits, uint64_t n, uint64_t *out);
+/* Page-locked host memory for the caller's slab / record buffers (fqsk_segment copies to and from them with DMA; pageable
+ * buffers work too, only slower).  Replaces nothing in the reference: its buffers are plain heap memory. */
+int fqsk_host_alloc(uint64_t bytes, void **out);
+void fqsk_host_free(void *p);
+
 /* First n outputs of std::mt19937 seeded 5481 as generated on the device (utils.h:298). */
 int fqsk_mt_stream(fqsk_handle *h, uint64_t n, uint32_t *out);
 

@@ -13,6 +13,11 @@ Products
                                one marker per read and one per sync; at exit it dumps the k-mer tables to
                                $FQS_TAP_DUMP.  Its .fqs output must equal the untapped one (checked by
                                oracle/make_golden.py).
+  oracle/_ref/fqs-1.1-replay   same sources, but compress_suffix (dna.cpp:674-877) takes counts / level / rough flag / cor_pos of
+                               every coded base from the record stream in $FQS_REPLAY instead of calling its own k-mer engine
+                               (find_counts, rough searches, pushes, repairs are all bypassed): the reference's untouched
+                               context model + range coders consuming OUR records.  Its .fqs must be byte-identical to the
+                               plain binary's -- north-star check 3 (tests/test_fqs_bytes.py).  Original order only.
   oracle/_ref/libfqs_ref.so    harness TU (oracle/ref_harness.cpp) over the reference's own
                                kmer.h / ht_kmer.h / bit_vec.h / utils.h for unit-level pinning.
 
@@ -188,6 +193,61 @@ def build_tap(scratch):
     compile_dir(d, os.path.join(scratch, "tap_obj"), os.path.join(OUT, "fqs-1.1-tap"))
 
 
+REPLAY_H = r'''
+#pragma once
+// build-time record replay (oracle/build_ref.py) -- not part of the reference
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+struct fqs_rp_rec { uint32_t pos; uint32_t c[4]; uint32_t cor_pos; uint8_t level; uint8_t rough; uint16_t pad; };
+inline FILE *fqs_rp_file() {
+	static FILE *f = nullptr; static bool init = false;
+	if (!init) { init = true; const char *p = getenv("FQS_REPLAY"); if (p) { f = fopen(p, "rb"); if (!f) { fprintf(stderr, "replay: cannot open %s\n", p); exit(3); } } }
+	return f;
+}
+inline bool fqs_rp_on() { return fqs_rp_file() != nullptr; }
+inline fqs_rp_rec fqs_rp_next(uint32_t expect_pos) {
+	fqs_rp_rec r;
+	if (fread(&r, sizeof(r), 1, fqs_rp_file()) != 1) { fprintf(stderr, "replay: record stream ended early (position %u)\n", expect_pos); exit(3); }
+	if (r.pos != expect_pos) { fprintf(stderr, "replay: record for position %u where %u is being coded\n", r.pos, expect_pos); exit(3); }
+	return r;
+}
+'''
+
+
+def build_replay(scratch):
+    d = os.path.join(scratch, "replay_src")
+    if os.path.exists(d):
+        shutil.rmtree(d)
+    os.makedirs(d)
+    for f in os.listdir(SRC):
+        if f.endswith((".h", ".cpp")):
+            shutil.copy(os.path.join(SRC, f), d)
+    open(os.path.join(d, "fqs_replay.h"), "w").write(REPLAY_H)
+    dna = os.path.join(d, "dna.cpp")
+    patch(dna, '#include "dna.h"\n', '#include "fqs_replay.h"\n')
+    s = open(dna, encoding="latin-1").read()
+    # (1) the count vector of a coded base comes from the record stream (dna.cpp:695)
+    a = "\t\tcounts_level_t counts_level = find_counts(counts);\n"
+    assert s.count(a) >= 1   # the decoder repeats these lines further down: the first hit is compress_suffix
+    s = s.replace(a, "\t\tconst bool rp = fqs_rp_on();\n\t\tfqs_rp_rec rp_rec{};\n\t\tcounts_level_t counts_level;\n"
+                     "\t\tif (rp) { rp_rec = fqs_rp_next(i); for (int q = 0; q < 4; ++q) counts[q] = rp_rec.c[q]; counts_level = (counts_level_t) rp_rec.level; cor_pos = rp_rec.cor_pos; }\n"
+                     "\t\telse counts_level = find_counts(counts);\n", 1)
+    # (2) no rough searches of its own (dna.cpp:709-735); the rough flag rides in the record
+    a = "\t\tif (counts_level == counts_level_t::none)\n\t\t{\n\t\t\tif (bmer_can.is_full())\n\t\t\t{\n\t\t\t\tif (find_counts_rough_b(counts))"
+    assert s.count(a) >= 1   # the decoder repeats these lines further down: the first hit is compress_suffix
+    s = s.replace(a, a.replace("if (counts_level == counts_level_t::none)", "if (!rp && counts_level == counts_level_t::none)"), 1)
+    a = "\t\tif (counts_level != counts_level_t::none && N_run_len < 2)\n\t\t{\n\t\t\tint cor_dist"
+    assert s.count(a) >= 1   # the decoder repeats these lines further down: the first hit is compress_suffix
+    s = s.replace(a, "\t\tif (rp) rough_counts = rp_rec.rough != 0;\n" + a, 1)
+    # (3) no pushes, no thread-local inserts, no repairs (dna.cpp:810-876): the registers are not needed any more
+    a = "\t\tpmer_can.replace_last(sym_to_kmers);\n\t\tsmer_can.replace_last(sym_to_kmers);\n\t\tbmer_can.replace_last(sym_to_kmers);\n"
+    assert s.count(a) >= 1   # the decoder repeats these lines further down: the first hit is compress_suffix
+    s = s.replace(a, "\t\tif (rp) continue;\n" + a, 1)
+    open(dna, "w", encoding="latin-1").write(s)
+    compile_dir(d, os.path.join(scratch, "replay_obj"), os.path.join(OUT, "fqs-1.1-replay"))
+
+
 def build_harness(scratch):
     d = os.path.join(scratch, "hdr_src")
     if os.path.exists(d):
@@ -208,11 +268,13 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     scratch = os.environ.get("FQS_REF_SCRATCH", "/tmp/fqs_ref_build")
     os.makedirs(scratch, exist_ok=True)
-    what = sys.argv[1:] or ["plain", "tap", "harness"]
+    what = sys.argv[1:] or ["plain", "tap", "replay", "harness"]
     if "plain" in what:
         compile_dir(SRC, os.path.join(scratch, "plain_obj"), os.path.join(OUT, "fqs-1.1"))
     if "tap" in what:
         build_tap(scratch)
+    if "replay" in what:
+        build_replay(scratch)
     if "harness" in what:
         build_harness(scratch)
     print("[build_ref] ok:", sorted(os.listdir(OUT)))
