@@ -68,21 +68,28 @@ def patch(path, anchor, insertion, before=False, count=1):
 TAP_H = r'''
 #pragma once
 // build-time tap (oracle/build_ref.py) -- not part of the reference
+// One file per worker thread: $FQS_TAP for worker 0, $FQS_TAP.t<i> for worker i (the workers announce themselves with
+// fqs_tap_set_thread; other threads never emit).
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
+#include <string>
 struct fqs_tap_rec { uint32_t pos; uint32_t c[4]; uint32_t cor_pos; uint8_t level; uint8_t rough; uint16_t pad; };
-inline FILE *fqs_tap_file() {
-	static FILE *f = nullptr; static bool init = false;
-	if (!init) { init = true; const char *p = getenv("FQS_TAP"); if (p) f = fopen(p, "wb"); }
-	return f;
+inline FILE **fqs_tap_files() { static FILE *f[64] = {nullptr}; return f; }
+inline int &fqs_tap_tid() { static thread_local int tid = -1; return tid; }
+inline void fqs_tap_set_thread(int tid) {
+	if (tid < 0 || tid >= 64) return;
+	fqs_tap_tid() = tid;
+	const char *p = getenv("FQS_TAP");
+	if (p && !fqs_tap_files()[tid]) { std::string n(p); if (tid) n += ".t" + std::to_string(tid); fqs_tap_files()[tid] = fopen(n.c_str(), "wb"); }
 }
 inline void fqs_tap_emit(uint32_t pos, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t cor_pos, uint8_t level, uint8_t rough) {
-	FILE *f = fqs_tap_file(); if (!f) return;
+	int tid = fqs_tap_tid(); if (tid < 0) return;
+	FILE *f = fqs_tap_files()[tid]; if (!f) return;
 	fqs_tap_rec r{pos, {c0, c1, c2, c3}, cor_pos, level, rough, 0};
 	fwrite(&r, sizeof(r), 1, f);
 }
-inline void fqs_tap_flush() { FILE *f = fqs_tap_file(); if (f) fflush(f); }
+inline void fqs_tap_flush() { for (int i = 0; i < 64; ++i) if (fqs_tap_files()[i]) fflush(fqs_tap_files()[i]); }
 '''
 
 HT_FOREACH = r'''
@@ -186,6 +193,10 @@ def build_tap(scratch):
     patch(app, '#include "application.h"\n', '#include "fqs_tap.h"\n')
     # dump the tables when the SE / PE compress loops are done (application.cpp:762, 1310)
     s = open(app, encoding="latin-1").read()
+    # every worker thread announces its id to the tap (application.cpp:588, 1117: right where it picks its CDNACompressor)
+    anchor = "\t\t\tCDNACompressor &dna_comp = v_dna_comp[thread_id];\n"
+    assert s.count(anchor) >= 2, s.count(anchor)
+    s = s.replace(anchor, anchor + "\t\t\tfqs_tap_set_thread((int) thread_id);\n")
     anchor = "\tv_thr_compress.clear();\n"
     assert s.count(anchor) == 2, s.count(anchor)
     s = s.replace(anchor, anchor + APP_DUMP)

@@ -22,12 +22,12 @@ from oracle import oracle as O  # noqa: E402
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
-def run_ref(fastq_path, gs, extra, tmp):
+def run_ref(fastq_path, gs, extra, tmp, threads=1):
     plain = os.path.join(tmp, "plain.fqs")
     tapd = os.path.join(tmp, "tap.fqs")
     tap = os.path.join(tmp, "tap.bin")
     dump = os.path.join(tmp, "dump.bin")
-    base = ["e", "-s", "-qm", "o", "-im", "o", "-t", "1", "-gs", str(gs), "-v", "0", *extra]
+    base = ["e", "-s", "-qm", "o", "-im", "o", "-t", str(threads), "-gs", str(gs), "-v", "0", *extra]
     subprocess.run([O.REF_BIN, *base, "-out", plain, fastq_path], check=True, cwd=tmp, stdout=subprocess.DEVNULL)
     env = dict(os.environ, FQS_TAP=tap, FQS_TAP_DUMP=dump)
     subprocess.run([O.REF_TAP_BIN, *base, "-out", tapd, fastq_path], check=True, cwd=tmp, env=env, stdout=subprocess.DEVNULL)
@@ -35,11 +35,13 @@ def run_ref(fastq_path, gs, extra, tmp):
     dec = os.path.join(tmp, "dec.fastq")
     subprocess.run([O.REF_BIN, "d", "-out", dec, plain], check=True, cwd=tmp, stdout=subprocess.DEVNULL)
     recs = np.fromfile(tap, dtype=O.REC_DTYPE)
+    if threads > 1:     # one tap file per worker thread ($FQS_TAP, $FQS_TAP.t1, ...)
+        recs = [recs] + [np.fromfile(tap + ".t%d" % i, dtype=O.REC_DTYPE) for i in range(1, threads)]
     d = np.fromfile(dump, dtype="<u8").reshape(-1, 3)
     return recs, d, open(plain, "rb").read(), open(dec, "rb").read()
 
 
-def make_case(name, G, n_reads, L, gs, seed, n_frac=0.0, dup_frac=0.0, extra=("-om", "o"), repeats=False):
+def make_case(name, G, n_reads, L, gs, seed, n_frac=0.0, dup_frac=0.0, extra=("-om", "o"), repeats=False, threads=1):
     genome = synth.make_genome(G, seed)
     if repeats:
         # low-complexity stretches (homopolymers, di-/tri-nucleotide repeats, a tandem duplication): k-mers that occur far more
@@ -54,7 +56,7 @@ def make_case(name, G, n_reads, L, gs, seed, n_frac=0.0, dup_frac=0.0, extra=("-
     with tempfile.TemporaryDirectory() as tmp:
         fq = os.path.join(tmp, "in.fastq")
         synth.write_fastq(fq, codes, err, seed=seed)
-        recs, d, fqs, dec = run_ref(fq, gs, list(extra), tmp)
+        recs, d, fqs, dec = run_ref(fq, gs, list(extra), tmp, threads)
         fastq = np.fromfile(fq, dtype=np.uint8)
         if tuple(extra) == ("-om", "o"):
             assert dec == fastq.tobytes(), "reference round trip failed"
@@ -70,13 +72,21 @@ def make_case(name, G, n_reads, L, gs, seed, n_frac=0.0, dup_frac=0.0, extra=("-
         dumps[nm + "_vals"] = x[o, 2]
     stat = d[d[:, 0] == 4][0]
     out = os.path.join(GOLD, name + ".npz")
-    np.savez_compressed(out, fastq=fastq, gs=np.int64(gs), extra=np.array(list(extra)), recs=recs,
+    if threads > 1:
+        dumps.update({"recs_t%d" % i: r for i, r in enumerate(recs)})
+        recs = recs[0]
+    np.savez_compressed(out, fastq=fastq, gs=np.int64(gs), extra=np.array(list(extra)), recs=recs, threads=np.int64(threads),
                         siv_no_filled=stat[1], siv_no_updates=stat[2], fqs_size=np.int64(len(fqs)), **dumps)
     print(name, "reads", n_reads, "records", len(recs), "file", os.path.getsize(out))
 
 
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    only = sys.argv[1:]
+    global make_case
+    if only:
+        _mk = make_case
+        make_case = lambda name, **kw: _mk(name, **kw) if name in only else None
     # SE original order, tiny k (gs 1: prefix 9, p14/s17/b19), high coverage so that repairs, rough searches,
     # probabilistic counters (> 7) and the avg_filling_factor >= 7 gate all fire; Ns and duplicate reads included.
     make_case("se_orig_gs1", G=6000, n_reads=1500, L=80, gs=1, seed=7, n_frac=0.002, dup_frac=0.01)
@@ -86,6 +96,9 @@ def main():
     make_case("se_orig_repeats_gs1", G=8000, n_reads=1600, L=90, gs=1, seed=51, n_frac=0.001, repeats=True)
     # sorted order (-om s): bins by 4-symbol prefix, std::sort inside a bin, sorted-prefix coding (flag / dif) + suffix from p_len
     make_case("se_sorted_gs1", G=5000, n_reads=2500, L=70, gs=1, seed=45, n_frac=0.002, dup_frac=0.01, extra=("-om", "s"))
+    # two / three worker threads (-t 2, -t 3): per-worker PRNG streams, owner-routed exchange rows, global gate statistics
+    make_case("se_orig_gs1_t2", G=6000, n_reads=1800, L=80, gs=1, seed=61, n_frac=0.002, dup_frac=0.01, threads=2)
+    make_case("se_orig_gs16_t3", G=9000, n_reads=1500, L=100, gs=16, seed=62, threads=3)
 
 
 if __name__ == "__main__":

@@ -225,6 +225,9 @@ def oracle_lib():
         lib.fqso_stats.argtypes = [C.c_void_p, _u64p]
         lib.fqso_pending.restype = C.c_uint64
         lib.fqso_pending.argtypes = [C.c_void_p, C.c_uint32, _u64p, C.c_uint64]
+        lib.fqso_create_worker.restype = C.c_void_p
+        lib.fqso_create_worker.argtypes = [C.c_void_p]
+        lib.fqso_sync_group.argtypes = [C.POINTER(C.c_void_p), C.c_uint32]
         _oracle_lib = lib
     return _oracle_lib
 
@@ -304,6 +307,37 @@ class OracleEngine:
         n = self.lib.fqso_pending(self.h, which, o, cap)
         assert n <= cap
         return o[:n].copy()
+
+
+class OracleGroup:
+    """Sequential CPU model of the reference at -t T: T workers (one CDNACompressor each: own PRNG streams, thread-local tables,
+    s_letters, read_prev) on shared global tables; `sync` is InsertKmersToHT + ClearKmersToHT of all of them with the
+    reference's owner routing (dna.cpp:2393-2488).  workers[i] has the OracleEngine interface for that worker's reads."""
+
+    def __init__(self, p, s, b, prefix_len, n_workers, mode=0):
+        self.workers = [OracleEngine(p, s, b, prefix_len, mode)]
+        lib = self.workers[0].lib
+        for _ in range(1, n_workers):
+            w = OracleEngine.__new__(OracleEngine)
+            w.lib = lib
+            w.h = lib.fqso_create_worker(self.workers[0].h)
+            w.p, w.s, w.b, w.prefix_len, w.mode = p, s, b, prefix_len, mode
+            self.workers.append(w)
+        self.lib = lib
+
+    def sync(self):
+        arr = (C.c_void_p * len(self.workers))(*[w.h for w in self.workers])
+        self.lib.fqso_sync_group(arr, len(self.workers))
+
+    def dump(self, which):
+        return self.workers[0].dump(which)
+
+    def stats(self):
+        return self.workers[0].stats()
+
+    def close(self):
+        for w in reversed(self.workers):     # worker 0 owns the shared tables: free it last
+            w.close()
 
 
 def kmer_params(genome_size_mb: int):

@@ -32,6 +32,32 @@ def run_se(engine, slab, kind=0, max_blocks=None):
     return recs[recs["pos"] != O.POS_SYNC]
 
 
+def run_se_workers(group, slab, n_workers, kind=0):
+    """The reference at -t T (application.cpp:575-671): every block is partitioned among the workers (reads_block.h:197-214),
+    all of them run the same number of sync segments and meet at every sync.  `group.workers[i]` codes worker i's reads,
+    `group.sync()` is the exchange + table update of all workers.  Returns one record stream per worker."""
+    off, ln, roff, rsz = S.parse_fastq(slab)
+    out = [[] for _ in range(n_workers)]
+    for gen, (f, l) in enumerate(S.split_blocks(rsz)):
+        ns = S.calc_no_synchronizations(gen, l - f, n_workers)
+        ranges = S.partition_for_workers(l - f, n_workers)
+        segs = [list(S.segments(f + a, f + b, ns)) for a, b in ranges]
+        assert len({len(x) for x in segs}) == 1, "workers disagree on the number of syncs"
+        for w in group.workers:
+            w.block_start()
+        for q in range(len(segs[0])):
+            for wi, w in enumerate(group.workers):
+                a, b = segs[wi][q]
+                recs, dup = w.segment(slab, off[a:b], ln[a:b], kind)
+                out[wi].append(recs)
+            group.sync()
+    res = []
+    for wi in range(n_workers):
+        r = np.concatenate(out[wi]) if out[wi] else np.zeros(0, O.REC_DTYPE)
+        res.append(r[r["pos"] < 0xFFFFFFF0])
+    return res
+
+
 def assert_recs_equal(got, want):
     want = want[want["pos"] != O.POS_SYNC]
     assert len(got) == len(want), (len(got), len(want))

@@ -36,3 +36,19 @@ def test_oracle_matches_reference_tap_sorted_order():
     assert (wflags == 4).sum() > 0 and (wdifs > 0).sum() > 100
     H.assert_dump_equal(e, g)
     e.close()
+
+
+@pytest.mark.parametrize("name", ["se_orig_gs1_t2", "se_orig_gs16_t3"])
+def test_oracle_group_matches_reference_tap_multithread(name):
+    """-t 2 / -t 3: per-worker record streams (each worker has its own PRNG streams and thread-local tables), owner-routed
+    exchange rows and the shared tables after all syncs vs the tapped reference run with that many threads."""
+    g = H.load_golden(name)
+    T = int(g["threads"])
+    pref, p, s, b = O.kmer_params(int(g["gs"]))
+    grp = O.OracleGroup(p, s, b, pref, T)
+    per_worker = H.run_se_workers(grp, g["fastq"], T)
+    for w in range(T):
+        want = g["recs_t%d" % w]
+        H.assert_recs_equal(per_worker[w], want[want["pos"] < 0xFFFFFFF0])
+    H.assert_dump_equal(grp, g)
+    grp.close()
