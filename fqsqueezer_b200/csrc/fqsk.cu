@@ -108,6 +108,14 @@ struct fqsk_handle {
 	SegCtx ctx;                              // the segment being evaluated
 	bool unsettled = false;                  // its first pass is enqueued, nobody has looked at the outcome yet
 	bool miss_fold_dirty = true; void *miss_fold_seen = nullptr;
+	uint32_t world = 1, rank = 0;            // reference worker `rank` of `world` (one per GPU)
+	unsigned long long *inbox = nullptr; uint64_t inbox_cap = 0;      // this rank's inbox: header + [3 tables][world sources][inbox_cap]
+	unsigned long long *peer_inbox[8] = {nullptr};
+	void *peer_ptrs[8][6] = {{nullptr}};     // IPC mappings to close
+	uint32_t attached = 0;                   // bit i: rank i's shard is mapped
+	DevBuf route_keys, route_keys2, route_sorted, route_hist;
+	uint64_t sync_fresh = 0, sync_updates = 0; bool routed = false, applied = false;
+	uint64_t siv_local_filled = 0;           // non-zero fields of THIS rank's p-mer shard (S.siv_no_filled is the global statistic)
 	DevBuf scan_part; uint32_t scan_epoch = 0;   // published CTA sums of k_scan_flags, tagged with the launch epoch
 	bool hot = false;                        // the current segment is being redone with the ordered thread-local evaluator
 	bool hot_seen[2] = {false, false};       // [0] s, [1] b: the last sync saw a k-mer pushed more than thr + 1 times in its row
@@ -204,6 +212,9 @@ int table_alloc(fqsk_handle *h, Table &t, uint32_t k, uint32_t cbits, uint32_t B
 	CK(cudaMemsetAsync(d.main, 0, mb, h->st));
 	CK(cudaMemsetAsync(d.stash, 0, sb, h->st));
 	CK(cudaMemsetAsync(counters, 0, 16, h->st));
+	d.world = h->world; d.rank = h->rank;
+	for (uint32_t i = 0; i < FQSK_MAX_WORLD; ++i) { d.peer_main[i] = nullptr; d.peer_stash[i] = nullptr; }
+	d.peer_main[h->rank] = d.main; d.peer_stash[h->rank] = d.stash;
 	return FQSK_OK;
 }
 
@@ -336,6 +347,8 @@ int table_grow_if_needed(fqsk_handle *h, Table &t) {
 	unsigned long long items[2];
 	CK(cudaMemcpyAsync(items, t.d.n_items, 16, cudaMemcpyDeviceToHost, h->st));
 	CK(cudaStreamSynchronize(h->st));
+	if (h->world > 1 && (items[0] > (4ull << t.d.B) || items[1] > (1ull << t.d.stash_log2) / 2))
+		return fail(h, FQSK_E_CAPACITY, "a table shard is more than half full and tables cannot grow in sharded mode: create the engines with a larger expected_kmers");
 	while (items[0] > (4ull << t.d.B) || items[1] > (1ull << t.d.stash_log2) / 2) {
 		uint64_t n = 0;
 		CKR(table_dump_device(h, t, &n));
@@ -779,6 +792,7 @@ int seg_settle(fqsk_handle *h, bool have_look = false) {
 int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual, const unsigned long long *d_off, const uint32_t *d_len, uint32_t n) {
 	const uint64_t dna_bytes = std::max<uint64_t>(dna_bytes_actual, h->P.reserve_bytes);
 	if (h->pending) return fail(h, FQSK_E_INVAL, "fqsk_segment called twice without fqsk_sync (the reference syncs after every segment, application.cpp:643-662)");
+	if (h->world > 1 && h->attached != (1u << h->world) - 1) return fail(h, FQSK_E_INVAL, "sharded engine: not every peer shard is attached (fqsk_shard_attach)");
 	const uint32_t first = (h->P.mode == FQSK_MODE_SE_SORTED || h->P.mode == FQSK_MODE_PE_SORTED) ? h->P.pmer_len : h->P.prefix_len;
 	h->seg_reads = n; h->n_recs = 0; h->pend_b = h->pend_s = h->pend_p = 0;
 	h->hot = false;
@@ -888,7 +902,10 @@ int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
 	if (!p || !out) return fail(h, FQSK_E_INVAL, "null argument");
 	*out = nullptr;
 	if (p->abi_version != FQSK_ABI_VERSION) return fail(h, FQSK_E_INVAL, "ABI version %u, library is %u", p->abi_version, FQSK_ABI_VERSION);
-	if (p->n_workers != 1) return fail(h, FQSK_E_INVAL, "only n_workers == 1 (the bit-exact `-t 1` configuration) is supported");
+	const uint32_t world = p->world_size ? p->world_size : 1;
+	if (world > FQSK_MAX_WORLD || p->rank >= world) return fail(h, FQSK_E_INVAL, "need rank < world_size <= %u", FQSK_MAX_WORLD);
+	if (p->n_workers != world) return fail(h, FQSK_E_INVAL, "n_workers must equal world_size: one reference worker thread (-t) per GPU");
+	if (world > 1 && p->mode != FQSK_MODE_SE_ORIGINAL) return fail(h, FQSK_E_UNSUPPORTED, "sharded operation is implemented for original-order SE only");
 	if (!(p->pmer_len >= 5 && p->pmer_len < p->smer_len && p->smer_len < p->bmer_len && p->bmer_len <= 31)) return fail(h, FQSK_E_INVAL, "need 5 <= p < s < b <= 31");
 	if (p->pmer_len > 18) return fail(h, FQSK_E_INVAL, "pmer_len > 18 not supported");
 	if (p->mode != FQSK_MODE_SE_ORIGINAL && p->mode != FQSK_MODE_SE_SORTED) return fail(h, FQSK_E_UNSUPPORTED, "paired-end modes are not implemented yet");
@@ -901,6 +918,7 @@ int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
 	}
 	h = new fqsk_handle();
 	h->P = *p;
+	h->world = world; h->rank = p->rank;
 	h->prof = (p->flags & FQSK_F_PROFILE) != 0;
 	int rc = [&]() -> int {
 		CK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
@@ -925,9 +943,22 @@ int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
 		h->ts.ci = CIncP{h->ts.d.top / 2, 1, h->ts.d.top};                    // cinc_s.Reset(4095 / 2, 1, 4095)   dna.cpp:163
 		if (h->tb.ci.thr > h->tb.ci.top) h->tb.ci.thr = h->tb.ci.top;
 		h->siv.key_bits = 2 * p->pmer_len;                                    // application.cpp:88
-		size_t sb = ((size_t) 1 << h->siv.key_bits) / 4;
+		h->siv.world = world; h->siv.rank = p->rank; h->siv.top_shift = h->siv.key_bits - 12;
+		size_t sb = world > 1 ? ((((size_t) 4096 + world - 1) / world) << h->siv.top_shift) / 4 : ((size_t) 1 << h->siv.key_bits) / 4;
 		CK(cudaMalloc(&h->siv.w, sb));
 		CK(cudaMemsetAsync(h->siv.w, 0, sb, h->st));
+		for (uint32_t i = 0; i < FQSK_MAX_WORLD; ++i) h->siv.peer_w[i] = nullptr;
+		h->siv.peer_w[p->rank] = h->siv.w;
+		if (world > 1) {
+			// inbox: [64-word header: posted slot lengths][3 tables][world sources][cap k-mers]; a source never sends more than its own rows
+			const uint64_t rb = p->reserve_bytes ? p->reserve_bytes : (1u << 23), rr = p->reserve_reads ? p->reserve_reads : (1u << 16);
+			h->inbox_cap = 2 * rb + 2 * rr + 1024;
+			size_t ib = (INBOX_HDR + 3ull * world * h->inbox_cap) * 8;
+			CK(cudaMalloc(&h->inbox, ib));
+			CK(cudaMemsetAsync(h->inbox, 0, INBOX_HDR * 8, h->st));
+			h->peer_inbox[p->rank] = h->inbox;
+			h->attached = 1u << p->rank;
+		}
 		for (int i = 0; i < 4; ++i) CKR(stream_init(h, h->rng[i], i == ST_B ? (1ull << 25) : i == ST_S ? (1ull << 21) : (1ull << 16)));
 		CKR(stream_generate(h, h->rng[ST_B], 1u << 22)); CKR(stream_generate(h, h->rng[ST_S], 1u << 18));
 		CK(h->prev_read.ensure(1 << 16));
@@ -945,6 +976,8 @@ void fqsk_destroy(fqsk_handle *h) {
 	if (h->st) cudaStreamSynchronize(h->st);
 	for (Table *t : {&h->tb, &h->ts}) { if (t->d.main) cudaFree(t->d.main); if (t->d.stash) cudaFree(t->d.stash); }
 	if (h->siv.w) cudaFree(h->siv.w);
+	for (uint32_t i = 0; i < FQSK_MAX_WORLD; ++i) for (int q = 0; q < 6; ++q) if (h->peer_ptrs[i][q]) cudaIpcCloseMemHandle(h->peer_ptrs[i][q]);
+	if (h->inbox) cudaFree(h->inbox);
 	if (h->st_mt) cudaStreamSynchronize(h->st_mt);
 	for (auto &s : h->rng) { if (s.buf) cudaFree(s.buf); if (s.state) cudaFree(s.state); if (s.ev) cudaEventDestroy(s.ev); }
 	if (h->d_status) cudaFree(h->d_status);
@@ -958,7 +991,8 @@ void fqsk_destroy(fqsk_handle *h) {
 	                  &h->sidx_b, &h->sidx_s, &h->stime_b, &h->stime_s, &h->sort_k, &h->sort_v, &h->rkind, &h->rreg, &h->rslot, &h->dirty, &h->rdraws_b, &h->rdraws_s, &h->totals,
 	                  &h->y_tslot, &h->y_c0, &h->y_m, &h->y_draw, &h->y_j, &h->y_final, &h->y_flag_at, &h->y_own, &h->y_lead, &h->y_rank, &h->y_flag, &h->y_doff,
 	                  &h->idx_k, &h->idx_t, &h->idx_rt, &h->miss_fold, &h->hr_b[0], &h->hr_b[1], &h->hr_b[2], &h->hr_s[0], &h->hr_s[1], &h->hr_s[2],
-	                  &h->evk[0], &h->evk[1], &h->evv[0], &h->evv[1], &h->evk_s[0], &h->evk_s[1], &h->evv_s[0], &h->evv_s[1], &h->scan_part};
+	                  &h->evk[0], &h->evk[1], &h->evv[0], &h->evv[1], &h->evk_s[0], &h->evk_s[1], &h->evv_s[0], &h->evv_s[1], &h->scan_part,
+	                  &h->route_keys, &h->route_keys2, &h->route_sorted, &h->route_hist};
 
 	for (DevBuf *b : bufs) b->release();
 	if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -1118,6 +1152,7 @@ static int sync_speculative(fqsk_handle *h, bool *applied, unsigned long long co
 int fqsk_sync(fqsk_handle *h) {
 	if (!h) return FQSK_E_INVAL;
 	CK(cudaSetDevice(h->P.device));
+	if (h->world > 1) return fail(h, FQSK_E_INVAL, "sharded engine: use fqsk_sync_route / fqsk_sync_apply / fqsk_sync_finish");
 	++h->S.n_syncs;
 	if (h->pending && h->seg_reads) {
 		h->hot_seen[0] = h->hot_seen[1] = false;
@@ -1187,6 +1222,146 @@ int fqsk_sync(fqsk_handle *h) {
 	return FQSK_OK;
 }
 
+// ---- sharded operation --------------------------------------------------------------------------------------------
+int fqsk_shard_export(fqsk_handle *h, fqsk_shard_desc *out) {
+	if (!h || !out) return FQSK_E_INVAL;
+	CK(cudaSetDevice(h->P.device));
+	if (h->world <= 1) return fail(h, FQSK_E_INVAL, "not a sharded engine");
+	memset(out, 0, sizeof *out);
+	out->rank = h->rank; out->world_size = h->world;
+	out->geometry[0] = h->tb.d.B; out->geometry[1] = h->tb.d.stash_log2; out->geometry[2] = h->ts.d.B; out->geometry[3] = h->ts.d.stash_log2;
+	out->geometry[4] = h->siv.key_bits;
+	out->inbox_cap = h->inbox_cap;
+	void *ptrs[6] = {h->tb.d.main, h->tb.d.stash, h->ts.d.main, h->ts.d.stash, h->siv.w, h->inbox};
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+	for (int q = 0; q < 6; ++q) CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t *) out->ipc[q], ptrs[q]));
+	CK(cudaStreamSynchronize(h->st));      // the shards are zero-filled before anybody maps them
+	return FQSK_OK;
+}
+
+int fqsk_shard_attach(fqsk_handle *h, const fqsk_shard_desc *peer) {
+	if (!h || !peer) return FQSK_E_INVAL;
+	CK(cudaSetDevice(h->P.device));
+	if (h->world <= 1 || peer->world_size != h->world || peer->rank >= h->world) return fail(h, FQSK_E_INVAL, "descriptor of rank %u / %u does not belong to this group", peer->rank, peer->world_size);
+	if (peer->rank == h->rank) return FQSK_OK;
+	if (peer->geometry[0] != h->tb.d.B || peer->geometry[1] != h->tb.d.stash_log2 || peer->geometry[2] != h->ts.d.B || peer->geometry[3] != h->ts.d.stash_log2 ||
+	    peer->geometry[4] != h->siv.key_bits || peer->inbox_cap != h->inbox_cap)
+		return fail(h, FQSK_E_INVAL, "rank %u was created with a different table geometry", peer->rank);
+	const uint32_t r = peer->rank;
+	for (int q = 0; q < 6; ++q) {
+		if (h->peer_ptrs[r][q]) continue;
+		cudaIpcMemHandle_t hd; memcpy(&hd, peer->ipc[q], 64);
+		CK(cudaIpcOpenMemHandle(&h->peer_ptrs[r][q], hd, cudaIpcMemLazyEnablePeerAccess));
+	}
+	h->tb.d.peer_main[r] = (const uint32_t *) h->peer_ptrs[r][0]; h->tb.d.peer_stash[r] = (const unsigned long long *) h->peer_ptrs[r][1];
+	h->ts.d.peer_main[r] = (const uint32_t *) h->peer_ptrs[r][2]; h->ts.d.peer_stash[r] = (const unsigned long long *) h->peer_ptrs[r][3];
+	h->siv.peer_w[r] = (const uint32_t *) h->peer_ptrs[r][4];
+	h->peer_inbox[r] = (unsigned long long *) h->peer_ptrs[r][5];
+	h->attached |= 1u << r;
+	return FQSK_OK;
+}
+
+int fqsk_sync_route(fqsk_handle *h) {
+	if (!h) return FQSK_E_INVAL;
+	CK(cudaSetDevice(h->P.device));
+	if (h->world <= 1) return fail(h, FQSK_E_INVAL, "not a sharded engine");
+	CKR(seg_settle(h));
+	++h->S.n_syncs;
+	InboxDev I{};
+	for (uint32_t i = 0; i < h->world; ++i) I.base[i] = h->peer_inbox[i];
+	I.cap = h->inbox_cap; I.world = h->world; I.rank = h->rank;
+	const bool have = h->pending && h->seg_reads;
+	const unsigned long long *rows[3] = {h->row_p.as<unsigned long long>(), h->row_s[0].as<unsigned long long>(), h->row_b[0].as<unsigned long long>()};
+	const uint32_t ns[3] = {have ? h->pend_p : 0, have ? h->pend_s : 0, have ? h->pend_b : 0};
+	CK(h->route_hist.ensure(3 * 8 * 4));
+	CK(cudaMemsetAsync(h->route_hist.p, 0, 3 * 8 * 4, h->st));
+	CK(cudaMemsetAsync(h->d_flags, 0, 8 * sizeof(int), h->st));
+	for (int t = 0; t < 3; ++t) {
+		const uint32_t n = ns[t];
+		uint32_t *hist = h->route_hist.as<uint32_t>() + 8 * t;
+		if (n) {
+			CK(h->route_keys.ensure(n)); CK(h->route_keys2.ensure(n)); CK(h->route_sorted.ensure((size_t) n * 8));
+			k_owner_keys<<<nblk(n, 256), 256, 0, h->st>>>(rows[t], n, t == 0 ? 0u : 1u, 2 * h->P.pmer_len - 12, h->world, h->route_keys.as<uint8_t>(), hist); LAUNCHED(h);
+			size_t bytes = 0;   // stable: push order survives inside every owner group
+			CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, h->route_keys.as<uint8_t>(), h->route_keys2.as<uint8_t>(), rows[t], h->route_sorted.as<unsigned long long>(), (int) n, 0, 3, h->st));
+			CK(h->cub_tmp.ensure(bytes));
+			CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, h->route_keys.as<uint8_t>(), h->route_keys2.as<uint8_t>(), rows[t], h->route_sorted.as<unsigned long long>(), (int) n, 0, 3, h->st));
+		}
+		k_route_scatter<<<nblk(std::max<uint32_t>(n, 8), 256), 256, 0, h->st>>>(h->route_sorted.as<unsigned long long>(), n, hist, I, (uint32_t) t, h->d_flags); LAUNCHED(h);
+	}
+	int fl[8];
+	CKR(read_flags(h, fl, 8));      // also drains the stream: the peer stores are complete when the caller enters its barrier
+	if (fl[4]) return fail(h, FQSK_E_CAPACITY, "an exchange row is longer than the inbox slot (%llu k-mers): create the engines with a larger reserve_bytes", (unsigned long long) h->inbox_cap);
+	h->routed = true;
+	return FQSK_OK;
+}
+
+int fqsk_sync_apply(fqsk_handle *h, uint64_t *fresh, uint64_t *updates) {
+	if (!h) return FQSK_E_INVAL;
+	CK(cudaSetDevice(h->P.device));
+	if (h->world <= 1 || !h->routed) return fail(h, FQSK_E_INVAL, "fqsk_sync_apply needs fqsk_sync_route on a sharded engine first");
+	// posted slot lengths (every source wrote its own entry before the barrier)
+	unsigned long long cnt[24];
+	CK(cudaMemcpyAsync(cnt, h->inbox, sizeof cnt, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaStreamSynchronize(h->st));
+	uint64_t tot[3] = {0, 0, 0};
+	for (int t = 0; t < 3; ++t) for (uint32_t i = 0; i < h->world; ++i) tot[t] += cnt[t * 8 + i];
+	for (int t = 0; t < 3; ++t) if (tot[t] >= 0x80000000ull) return fail(h, FQSK_E_INVAL, "more than 2^31 k-mers in one sync row");
+	// rows [*][rank] in source order: one contiguous row per table
+	CK(h->row_p.ensure((tot[0] + 1) * 8)); CK(h->row_s[0].ensure((tot[1] + 1) * 8)); CK(h->row_b[0].ensure((tot[2] + 1) * 8));
+	unsigned long long *dst[3] = {h->row_p.as<unsigned long long>(), h->row_s[0].as<unsigned long long>(), h->row_b[0].as<unsigned long long>()};
+	// (the segment's own rows lived in these buffers; fqsk_sync_route has copied them out)
+	for (int t = 0; t < 3; ++t) {
+		uint64_t at = 0;
+		for (uint32_t i = 0; i < h->world; ++i) {
+			const uint64_t c = cnt[t * 8 + i];
+			if (c) CK(cudaMemcpyAsync(dst[t] + at, inbox_slot(h->inbox, h->inbox_cap, h->world, (uint32_t) t, i), c * 8, cudaMemcpyDeviceToDevice, h->st));
+			at += c;
+		}
+	}
+	// the thread-local PRNG streams of THIS worker advance with its own pushes, whoever owns them (ht_kmer.h:433-436 via
+	// dna.cpp:826, 837, 862, 872): account for them from the segment's delta before it is dropped
+	if (h->pending && h->seg_reads && !h->hot) { CKR(hot_account(h, 1)); CKR(hot_account(h, 0)); }
+	h->hot_seen[0] = h->hot_seen[1] = false;
+	CK(cudaMemsetAsync(h->d_counters + 4, 0, 8, h->st));
+	if (tot[0]) {
+		Phase ph(h, FQSK_PH_SYNC_SIV);
+		k_siv_increment<<<nblk(tot[0], 256), 256, 0, h->st>>>(h->siv, dst[0], tot[0], h->d_counters + 4); LAUNCHED(h);
+	}
+	if (tot[1]) { bool fast = true; CKR(apply_inserts(h, h->ts, h->rng[ST_S], dst[1], (uint32_t) tot[1], &fast)); }
+	if (tot[2]) CKR(apply_row(h, h->tb, h->rng[ST_B], dst[2], (uint32_t) tot[2]));
+	unsigned long long hc[6];
+	CK(cudaMemcpyAsync(hc, h->d_counters, 48, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaStreamSynchronize(h->st));
+	resolve_phases(h);
+	for (int k = 0; k < 2; ++k) {
+		Table &t = k ? h->tb : h->ts;
+		if (hc[2 - 2 * k] > (4ull << t.d.B) || hc[3 - 2 * k] > (1ull << t.d.stash_log2) / 2) CKR(table_grow_if_needed(h, t));
+	}
+	h->sync_fresh = hc[4];
+	h->siv_local_filled += hc[4];
+	h->sync_updates = tot[0] + h->hidden_p;
+	h->hidden_p = 0;
+	if (fresh) *fresh = h->sync_fresh;
+	if (updates) *updates = h->sync_updates;
+	h->applied = true;
+	return FQSK_OK;
+}
+
+int fqsk_sync_finish(fqsk_handle *h, uint64_t fresh_all, uint64_t updates_all) {
+	if (!h) return FQSK_E_INVAL;
+	CK(cudaSetDevice(h->P.device));
+	if (h->world <= 1 || !h->applied) return fail(h, FQSK_E_INVAL, "fqsk_sync_finish needs fqsk_sync_apply on a sharded engine first");
+	h->S.siv_no_filled += fresh_all;       // bit_vec.h:212-220: global atomics in the reference, read by every worker (dna.cpp:376)
+	h->S.siv_no_updates += updates_all;
+	for (int i = 0; i < 4; ++i) h->S.draws[i] = h->rng[i].consumed;
+	CKR(stream_prefetch(h, h->rng[ST_B], 1u << 23)); CKR(stream_prefetch(h, h->rng[ST_S], 1u << 18));
+	h->pending = false; h->pend_b = h->pend_s = h->pend_p = 0; h->seg_reads = 0;
+	h->routed = h->applied = false;
+	resolve_phases(h);
+	return FQSK_OK;
+}
+
 static int dump_sorted(fqsk_handle *h, uint64_t n, uint64_t *keys, uint64_t *vals) {
 	std::vector<unsigned long long> k(n), v(n);
 	if (n) {
@@ -1215,13 +1390,13 @@ int fqsk_dump(fqsk_handle *h, int table, uint64_t *keys, uint64_t *vals, uint64_
 		return dump_sorted(h, cnt, keys, vals);
 	}
 	if (table == FQSK_TABLE_SIV) {
-		uint64_t cnt = h->S.siv_no_filled;
+		uint64_t cnt = h->world > 1 ? h->siv_local_filled : h->S.siv_no_filled;
 		*n = cnt;
 		if (!keys) return FQSK_OK;
 		if (cnt > cap) return fail(h, FQSK_E_CAPACITY, "dump needs %llu entries", (unsigned long long) cnt);
 		CK(h->dump_k.ensure((cnt + 1) * 8)); CK(h->dump_v.ensure((cnt + 1) * 8));
 		CK(cudaMemsetAsync(h->d_counters + 5, 0, 8, h->st));
-		uint64_t nw = (1ull << h->siv.key_bits) >> 4;
+		uint64_t nw = h->world > 1 ? ((((uint64_t) 4096 + h->world - 1) / h->world) << h->siv.top_shift) >> 4 : (1ull << h->siv.key_bits) >> 4;
 		k_dump_siv<<<nblk(nw, 256), 256, 0, h->st>>>(h->siv, h->dump_k.as<unsigned long long>(), h->dump_v.as<unsigned long long>(), cnt, h->d_counters + 5);
 		LAUNCHED(h);
 		unsigned long long got = 0;

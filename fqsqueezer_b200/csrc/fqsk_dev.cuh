@@ -107,7 +107,15 @@ struct HtDev {
 	uint32_t k, cbits, W, B, rem_bits, top, stash_log2, mix_sh;
 	uint64_t maskW;
 	unsigned long long *n_items;    // device counters: [0] main items, [1] stash items
+	// hash sharding over the GPUs of one box: the table is split by the reference's own owner key of a k-mer,
+	// ((x >> 46) & 0x3fff) % world (dna.cpp:825, 836, 2382-2388) -- bits of symbols s2..s8, i.e. of the kernel, so the 4
+	// siblings of a context share the owner.  All shards have the same geometry; main / stash are THIS rank's shard (the only
+	// one it ever writes), peer_* are every rank's shard (NVLink peer mappings, [rank] = own) for lookups.
+	uint32_t world, rank;
+	const uint32_t *peer_main[8];
+	const unsigned long long *peer_stash[8];
 };
+static const uint32_t FQSK_MAX_WORLD = 8;
 
 static const uint64_t MIX_C1 = 0x9E3779B97F4A7C15ull, MIX_C2 = 0xD6E8FEB86659FD93ull;
 
@@ -120,7 +128,8 @@ FQSK_HD uint64_t ht_kernel(const HtDev &t, uint64_t x) { return (x >> (64 - 2 * 
 FQSK_HD uint32_t ht_ends(const HtDev &t, uint64_t x) { return (uint32_t) (((x >> 60) & 0xF) << 4 | ((x >> (64 - 2 * t.k)) & 0xF)); }
 FQSK_HD uint64_t ht_slot_count() { return 8; }
 
-struct HtKey { uint64_t bucket; uint32_t q; uint64_t kal; uint64_t h; };  // q = item without counter
+struct HtKey { uint64_t bucket; uint32_t q; uint32_t owner; uint64_t kal; uint64_t h; };  // q = item without counter; owner = rank holding the k-mer
+FQSK_HD uint32_t ht_owner(uint32_t world, uint64_t x) { return world > 1 ? (uint32_t) (((x >> 46) & 0x3fff) % world) : 0u; }
 FQSK_HD HtKey ht_key(const HtDev &t, uint64_t x) {
 	HtKey k;
 	k.h = ht_mix(t, ht_kernel(t, x));
@@ -128,13 +137,14 @@ FQSK_HD HtKey ht_key(const HtDev &t, uint64_t x) {
 	uint32_t rem = (uint32_t) (k.h & ((1ull << t.rem_bits) - 1));
 	k.q = 0x80000000u | (rem << (8 + t.cbits)) | (ht_ends(t, x) << t.cbits);
 	k.kal = x >> (64 - 2 * t.k);
+	k.owner = ht_owner(t.world, x);
 	return k;
 }
 FQSK_HD uint64_t ht_stash_pos(const HtDev &t, uint64_t h) { return (h * 0xC2B2AE3D27D4EB4Full) >> (64 - t.stash_log2); }
 
 struct Bucket { uint4 lo, hi; };
-FQSK_DEV Bucket ht_load_bucket(const HtDev &t, uint64_t b) {
-	const uint4 *p = reinterpret_cast<const uint4 *>(t.main + b * 8);
+FQSK_DEV Bucket ht_load_bucket(const HtDev &t, const HtKey &key) {
+	const uint4 *p = reinterpret_cast<const uint4 *>(t.peer_main[key.owner] + key.bucket * 8);
 	Bucket r;
 	r.lo = __ldg(p);
 	r.hi = __ldg(p + 1);
@@ -162,8 +172,9 @@ FQSK_DEV void ht_ctx_counts_from(const HtDev &t, const HtKey &key, bool is_dir, 
 	uint64_t ush = is_dir ? 0 : 2 * t.k - 2;  // unknown symbol inside the aligned k-mer
 	uint64_t m64 = ~(3ull << ush);
 	uint64_t smask = (1ull << t.stash_log2) - 1;
+	const unsigned long long *stash = t.peer_stash[key.owner];
 	for (uint64_t p = ht_stash_pos(t, key.h);; p = (p + 1) & smask) {
-		unsigned long long it = t.stash[p];
+		unsigned long long it = stash[p];
 		if (it == 0) break;
 		uint64_t kal = (it >> t.cbits) - 1;
 		if (((kal ^ key.kal) & m64) == 0) { uint32_t f = (uint32_t) ((kal >> ush) & 3); c[is_dir ? f : 3 - f] += (uint32_t) (it & t.top); }
@@ -171,13 +182,13 @@ FQSK_DEV void ht_ctx_counts_from(const HtDev &t, const HtKey &key, bool is_dir, 
 }
 FQSK_DEV void ht_ctx_counts(const HtDev &t, uint64_t x, bool is_dir, uint32_t c[4]) {
 	HtKey key = ht_key(t, x);
-	Bucket bk = ht_load_bucket(t, key.bucket);
+	Bucket bk = ht_load_bucket(t, key);
 	ht_ctx_counts_from(t, key, is_dir, bk, c);
 }
 // CHT_kmer::count(uint64_t): exact match (ht_kmer.h:441-454)
 FQSK_DEV uint32_t ht_count(const HtDev &t, uint64_t x) {
 	HtKey key = ht_key(t, x);
-	Bucket bk = ht_load_bucket(t, key.bucket);
+	Bucket bk = ht_load_bucket(t, key);
 	bool full = true;
 #pragma unroll
 	for (int i = 0; i < 8; ++i) {
@@ -187,8 +198,9 @@ FQSK_DEV uint32_t ht_count(const HtDev &t, uint64_t x) {
 	}
 	if (!full) return 0;
 	uint64_t smask = (1ull << t.stash_log2) - 1;
+	const unsigned long long *stash = t.peer_stash[key.owner];
 	for (uint64_t p = ht_stash_pos(t, key.h);; p = (p + 1) & smask) {
-		unsigned long long it = t.stash[p];
+		unsigned long long it = stash[p];
 		if (it == 0) return 0;
 		if ((it >> t.cbits) == key.kal + 1) return (uint32_t) (it & t.top);
 	}
@@ -233,11 +245,23 @@ FQSK_DEV void ht_slot_set(const HtDev &t, uint64_t slot, uint32_t cnt) {
 // ------------------------------------------------------------------------------------------------------------------
 // p-mer array (reference: bit_vec.h:17-231), u32 words of 16 two-bit fields
 // ------------------------------------------------------------------------------------------------------------------
-struct SivDev { uint32_t *w; uint32_t key_bits; };
+// Sharding: the owner of a p-mer is (x >> (2p - 12)) % world (dna.cpp:658, 845, 2381), i.e. its top 12 bits pick the rank; a
+// rank stores the fields of its own top values densely (local top = top / world).  w is THIS rank's shard, peer_w every rank's.
+struct SivDev { uint32_t *w; uint32_t key_bits; uint32_t world, rank, top_shift; const uint32_t *peer_w[8]; };
 
-FQSK_DEV uint32_t siv_test(const SivDev &s, uint64_t idx) { return (__ldg(s.w + (idx >> 4)) >> (2 * (idx & 15))) & 3; }  // bit_vec.h:69-81
+FQSK_HD uint32_t siv_owner(const SivDev &s, uint64_t idx) { return s.world > 1 ? (uint32_t) ((idx >> s.top_shift) % s.world) : 0u; }
+// owner's array for the field `idx`; idx becomes the index inside that shard
+FQSK_DEV const uint32_t *siv_shard(const SivDev &s, uint64_t &idx) {
+	if (s.world <= 1) return s.w;
+	const uint64_t top = idx >> s.top_shift;
+	const uint32_t owner = (uint32_t) (top % s.world);
+	idx = ((top / s.world) << s.top_shift) | (idx & ((1ull << s.top_shift) - 1ull));
+	return s.peer_w[owner];
+}
+FQSK_DEV uint32_t siv_test(const SivDev &s, uint64_t idx) { const uint32_t *w = siv_shard(s, idx); return (__ldg(w + (idx >> 4)) >> (2 * (idx & 15))) & 3; }  // bit_vec.h:69-81
 FQSK_DEV void siv_counts(const SivDev &s, uint64_t idx, uint32_t c[4], bool accumulate) {  // bit_vec.h:83-111
-	uint32_t d = __ldg(s.w + (idx >> 4)) >> (2 * ((idx & 15) & ~3ull));
+	const uint32_t *w = siv_shard(s, idx);
+	uint32_t d = __ldg(w + (idx >> 4)) >> (2 * ((idx & 15) & ~3ull));
 #pragma unroll
 	for (int i = 0; i < 4; ++i) { uint32_t v = (d >> (2 * i)) & 3; c[i] = accumulate ? c[i] + v : v; }
 }
@@ -250,13 +274,15 @@ FQSK_DEV uint64_t siv_prefix_sum(const SivDev &s, uint64_t prefix, uint32_t pref
 	uint32_t sh = s.key_bits - prefix_bits;
 	uint64_t start = prefix << sh, n = 1ull << sh;
 	if (n == 1) return siv_test(s, start);
-	if (n < 16) { uint32_t d = __ldg(s.w + (start >> 4)) >> (2 * (start & 15)); return siv_word_sum(d & ((1u << (2 * n)) - 1)); }
+	const uint32_t *w = siv_shard(s, start);      // prefixes are at least 12 bits long (prefix_len >= 9 symbols): one owner per range
+	if (n < 16) { uint32_t d = __ldg(w + (start >> 4)) >> (2 * (start & 15)); return siv_word_sum(d & ((1u << (2 * n)) - 1)); }
 	uint64_t r = 0;
-	for (uint64_t wd = start >> 4, e = (start + n) >> 4; wd < e; ++wd) r += siv_word_sum(__ldg(s.w + wd));
+	for (uint64_t wd = start >> 4, e = (start + n) >> 4; wd < e; ++wd) r += siv_word_sum(__ldg(w + wd));
 	return r;
 }
 // bit_vec.h:53-67, order-independent form: saturate at 3, return 1 when the field was zero
-FQSK_DEV uint32_t siv_increment(const SivDev &s, uint64_t idx) {
+FQSK_DEV uint32_t siv_increment(const SivDev &s, uint64_t idx) {   // idx is owned by this rank (routing happened before)
+	siv_shard(s, idx);
 	uint32_t *p = s.w + (idx >> 4);
 	uint32_t sh = 2 * (idx & 15);
 	uint32_t old = *((volatile uint32_t *) p);

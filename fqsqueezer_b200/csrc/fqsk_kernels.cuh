@@ -167,7 +167,7 @@ __device__ bool ht_find(const HtDev &t, const CIncP &ci, const KReg &r, uint32_t
 			KReg tr = partial_trial(r, t.k, m, n0 + u);
 			isd[u] = kr_is_dir(tr, t.k);
 			key[u] = ht_key(t, isd[u] ? tr.dir : tr.rc);
-			bk[u] = ht_load_bucket(t, key[u].bucket);
+			bk[u] = ht_load_bucket(t, key[u]);
 		}
 #pragma unroll
 		for (int u = 0; u < 4; ++u) {
@@ -461,6 +461,53 @@ __global__ void k_siv_increment(SivDev s, const unsigned long long *idx, uint64_
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// sharded sync (reference -t N: X_to_add[src][dst] + three barriers, dna.cpp:2393-2488).  The exchange matrix is written
+// straight into the owners' inboxes with NVLink peer stores: k_owner_keys tags every pending k-mer with its owner and
+// counts, a stable 3-bit radix sort groups the row by owner without disturbing push order, k_route_scatter copies group j
+// into slot [table][src = this rank] of rank j's inbox and posts its length there.  The owners then apply the slots in
+// source order with their own PRNG streams.
+// ------------------------------------------------------------------------------------------------------------------
+struct InboxDev {
+	unsigned long long *base[8];     // every rank's inbox (peer mapping; [rank] = own)
+	unsigned long long cap;          // entries per (table, source) slot
+	uint32_t world, rank;
+};
+static const uint32_t INBOX_HDR = 64;    // u64 words: counts[3 tables][8 sources], then padding
+FQSK_HD unsigned long long *inbox_slot(unsigned long long *base, unsigned long long cap, uint32_t world, uint32_t table, uint32_t src) {
+	return base + INBOX_HDR + ((unsigned long long) table * world + src) * cap;
+}
+// kind 0: p-mers (aligned index, owner by its top 12 bits), 1: s-/b-mers (normalised k-mer)
+__global__ void k_owner_keys(const unsigned long long *row, uint32_t n, uint32_t kind, uint32_t pshift, uint32_t world, uint8_t *keys, uint32_t *hist) {
+	__shared__ uint32_t sh[8];
+	if (threadIdx.x < 8) sh[threadIdx.x] = 0;
+	__syncthreads();
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) {
+		unsigned long long x = row[i];
+		uint32_t o = kind == 0 ? (uint32_t) ((x >> pshift) % world) : ht_owner(world, x);
+		keys[i] = (uint8_t) o;
+		atomicAdd(sh + o, 1u);
+	}
+	__syncthreads();
+	if (threadIdx.x < 8 && sh[threadIdx.x]) atomicAdd(hist + threadIdx.x, sh[threadIdx.x]);
+}
+__global__ void k_route_scatter(const unsigned long long *sorted, uint32_t n, const uint32_t *hist, InboxDev I, uint32_t table, int *flags) {
+	uint32_t off[9];
+	off[0] = 0;
+	for (uint32_t o = 0; o < 8; ++o) off[o + 1] = off[o] + (o < I.world ? hist[o] : 0);
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < I.world) {
+		if (hist[i] > I.cap) flags[4] = 1;
+		I.base[i][table * 8 + I.rank] = hist[i];      // posted length of slot [table][src = rank] at owner i
+	}
+	if (i >= n) return;
+	uint32_t o = 0;
+	while (i >= off[o + 1]) ++o;
+	if (hist[o] > I.cap) return;
+	inbox_slot(I.base[o], I.cap, I.world, table, I.rank)[i - off[o]] = sorted[i];
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // table-level batch mirrors
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void k_find(HtDev t, CIncP ci, const unsigned long long *dir, const unsigned long long *rc, const uint32_t *cur, uint32_t n,
@@ -527,13 +574,18 @@ __global__ void k_dump_ht(HtDev t, MixInv mi, unsigned long long *keys, unsigned
 }
 __global__ void k_dump_siv(SivDev s, unsigned long long *keys, unsigned long long *vals, unsigned long long cap, unsigned long long *n_out) {
 	uint64_t w = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
-	uint64_t nw = (1ull << s.key_bits) >> 4;
+	uint64_t tops = s.world > 1 ? (4096 + s.world - 1) / s.world : 4096;      // this rank's shard: ceil(4096 / world) top values
+	uint64_t nw = s.world > 1 ? (tops << s.top_shift) >> 4 : (1ull << s.key_bits) >> 4;
 	if (w >= nw) return;
 	uint32_t d = s.w[w];
 	if (!d) return;
 	for (uint32_t r = 0; r < 16; ++r) {
 		uint32_t f = (d >> (2 * r)) & 3;
-		if (f) { unsigned long long o = atomicAdd(n_out, 1ull); if (o < cap) { keys[o] = w * 16 + r; vals[o] = f; } }
+		if (!f) continue;
+		uint64_t li = w * 16 + r, gi = li;
+		if (s.world > 1) gi = (((li >> s.top_shift) * s.world + s.rank) << s.top_shift) | (li & ((1ull << s.top_shift) - 1ull));
+		unsigned long long o = atomicAdd(n_out, 1ull);
+		if (o < cap) { keys[o] = gi; vals[o] = f; }
 	}
 }
 // re-insert dumped (k-mer, counter) pairs into a fresh, larger table

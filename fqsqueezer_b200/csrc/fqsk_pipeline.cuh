@@ -792,7 +792,7 @@ __global__ void __launch_bounds__(128) k_rough(EngineDev E, PipeDev P) {
 					kr_set(tr, t.k, tn & 3, tn >> 2);
 					isd[u] = kr_is_dir(tr, t.k);
 					key[u] = ht_key(t, isd[u] ? tr.dir : tr.rc);
-					bk[u] = ht_load_bucket(t, key[u].bucket);
+					bk[u] = ht_load_bucket(t, key[u]);
 				}
 			}
 #pragma unroll

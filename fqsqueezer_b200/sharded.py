@@ -1,0 +1,103 @@
+"""Sharded operation over the GPUs of one box: one process per GPU, reference `-t N` semantics.
+
+Rank r is the reference's worker thread r (application.cpp:575-671): it codes its own slice of every reads_block with its
+own PRNG streams and thread-local tables, and it OWNS the k-mers whose routing key maps to it (dna.cpp:825, 836, 845,
+2381-2388).  Lookups read every rank's shard through NVLink peer mappings (CUDA IPC, set up once here); at a sync the
+exchange matrices X_to_add[src][dst] are written straight into the owners' inboxes by the routing kernel (peer stores), and
+torch.distributed (NCCL) carries what is left of the reference's three barriers: one barrier and one all-reduce of the global
+p-mer statistics per sync.
+
+    grp = ShardedKmerEngine(p, s, b, prefix_len, rank, world, device=local_rank)   # after dist.init_process_group
+    grp.block_start(); recs, dup = grp.segment(slab, off, ln); grp.sync()
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import engine as E
+
+
+class _ShardDesc(C.Structure):
+    _fields_ = [("rank", C.c_uint32), ("world_size", C.c_uint32), ("geometry", C.c_uint32 * 6), ("inbox_cap", C.c_uint64), ("ipc", (C.c_uint8 * 64) * 6)]
+
+
+def owner_of_kmer(x: np.ndarray, world: int) -> np.ndarray:
+    """Owner of normalised s-/b-mers: ((x >> 46) & 0x3fff) % T (dna.cpp:825, 836, 2382-2388)."""
+    return ((np.asarray(x, np.uint64) >> np.uint64(46)) & np.uint64(0x3FFF)) % np.uint64(world)
+
+
+def owner_of_pmer(idx: np.ndarray, pmer_len: int, world: int) -> np.ndarray:
+    """Owner of aligned p-mers: (x >> (2p - 12)) % T (dna.cpp:658, 845, 2381)."""
+    return (np.asarray(idx, np.uint64) >> np.uint64(2 * pmer_len - 12)) % np.uint64(world)
+
+
+class ShardedKmerEngine(E.KmerEngine):
+    """KmerEngine of one rank of a sharded group.  `dist` is torch.distributed (initialised by the caller, NCCL on GPU boxes)."""
+
+    def __init__(self, p, s, b, prefix_len, rank, world, device=0, dist=None, expected_kmers=0, reserve_reads=0, reserve_bytes=0, **kw):
+        self.rank, self.world, self.dist = rank, world, dist
+        self.lib = E.load_library()
+        self._bind()
+        prm = E._Params(abi_version=1, pmer_len=p, smer_len=s, bmer_len=b, prefix_len=prefix_len, smer_counter_bits=12, bmer_counter_bits=6,
+                        mode=E.MODE_SE_ORIGINAL, n_workers=world, device=device, bmer_log2_buckets=kw.get("bmer_log2_buckets", 0),
+                        smer_log2_buckets=kw.get("smer_log2_buckets", 0), expected_kmers=expected_kmers, world_size=world, rank=rank,
+                        max_iterations=0, flags=E.F_PROFILE if kw.get("profile") else 0, reserve_reads=reserve_reads, reserve_bytes=reserve_bytes)
+        h = C.c_void_p()
+        rc = self.lib.fqsk_create(C.byref(prm), C.byref(h))
+        if rc != 0:
+            raise E.FqskError(rc, self.lib.fqsk_last_error(None).decode())
+        self.h = h
+        self.p, self.s, self.b, self.prefix_len, self.mode = p, s, b, prefix_len, E.MODE_SE_ORIGINAL
+        if world > 1:
+            self._attach_peers()
+
+    def _bind(self):
+        lib = self.lib
+        vp = C.c_void_p
+        lib.fqsk_shard_export.argtypes = [vp, C.POINTER(_ShardDesc)]
+        lib.fqsk_shard_attach.argtypes = [vp, C.POINTER(_ShardDesc)]
+        lib.fqsk_sync_route.argtypes = [vp]
+        lib.fqsk_sync_apply.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        lib.fqsk_sync_finish.argtypes = [vp, C.c_uint64, C.c_uint64]
+        for n in ("fqsk_shard_export", "fqsk_shard_attach", "fqsk_sync_route", "fqsk_sync_apply", "fqsk_sync_finish"):
+            getattr(lib, n).restype = C.c_int
+
+    def _attach_peers(self):
+        d = _ShardDesc()
+        self._ck(self.lib.fqsk_shard_export(self.h, C.byref(d)))
+        blobs = [None] * self.world
+        self.dist.all_gather_object(blobs, bytes(d))
+        for r, blob in enumerate(blobs):
+            if r == self.rank:
+                continue
+            peer = _ShardDesc.from_buffer_copy(blob)
+            self._ck(self.lib.fqsk_shard_attach(self.h, C.byref(peer)))
+        self.dist.barrier()
+
+    def sync(self):
+        """InsertKmersToHT + ClearKmersToHT of all workers (dna.cpp:2393-2488) around the reference's barriers."""
+        if self.world == 1:
+            return super().sync()
+        import torch
+        self._ck(self.lib.fqsk_sync_route(self.h))
+        self.dist.barrier()                                     # every row [src][dst] is in its owner's inbox
+        fresh, upd = C.c_uint64(0), C.c_uint64(0)
+        self._ck(self.lib.fqsk_sync_apply(self.h, C.byref(fresh), C.byref(upd)))
+        dev = torch.device("cuda", torch.cuda.current_device()) if self.dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.tensor([fresh.value, upd.value], dtype=torch.int64, device=dev)
+        self.dist.all_reduce(t)                                 # global p-mer statistics; also: every owner has finished its inserts
+        tot = t.tolist()
+        self._ck(self.lib.fqsk_sync_finish(self.h, int(tot[0]), int(tot[1])))
+
+    def dump_all(self, which):
+        """Sorted contents of the whole (sharded) table, gathered on every rank -- parity check 1."""
+        k, v = self.dump(which)
+        if self.world == 1:
+            return k, v
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, (k, v))
+        kk = np.concatenate([x[0] for x in parts]); vv = np.concatenate([x[1] for x in parts])
+        o = np.argsort(kk, kind="stable")
+        return kk[o], vv[o]

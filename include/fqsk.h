@@ -47,12 +47,15 @@ typedef struct fqsk_params {
 	uint32_t smer_counter_bits;  /* 12, defs.h:26 */
 	uint32_t bmer_counter_bits;  /* 6,  defs.h:27 */
 	uint32_t mode;               /* FQSK_MODE_* */
-	uint32_t n_workers;          /* reference -t; only 1 is bit-exact with `fqs-1.1 -t 1` and only 1 is accepted */
+	uint32_t n_workers;          /* reference -t: 1, or world_size (one reference worker thread per GPU; bit-exact with `fqs-1.1 -t N`) */
 	int32_t device;              /* CUDA ordinal */
 	uint32_t bmer_log2_buckets;  /* 0 = choose from expected_kmers; 8 slots of 4 bytes per bucket */
 	uint32_t smer_log2_buckets;
 	uint64_t expected_kmers;     /* hint for initial table sizes (distinct b-mers); tables grow when half full */
-	/* hash sharding across the GPUs of one box: this handle owns the k-mers whose owner key == rank */
+	/* hash sharding across the GPUs of one box, at most 8 ranks: this handle is reference worker `rank` of
+	 * `world_size` and owns the k-mers whose owner key == rank -- ((x >> 46) & 0x3fff) % world_size for s-/b-mers
+	 * (dna.cpp:825, 836), (x >> (2p - 12)) % world_size for p-mers (dna.cpp:845) -- exactly the rows [*][rank] of the
+	 * reference's X_to_add exchange matrices (application.h:56-59) */
 	uint32_t world_size, rank;
 	uint32_t max_iterations;     /* fix-point limit per segment, 0 = default (16) */
 	uint32_t flags;              /* FQSK_F_* */
@@ -128,6 +131,33 @@ int fqsk_sorted_prefix(fqsk_handle *h, uint32_t *flag, uint64_t *dif, uint32_t n
 /* Replaces CDNACompressor::InsertKmersToHT + ClearKmersToHT (dna.cpp:2393-2488) and the three barriers around them
  * (application.cpp:645-654): p-mers, then s-mers, then b-mers, in push order, with the reference's PRNG draw order. */
 int fqsk_sync(fqsk_handle *h);
+
+/* ---- sharded operation (world_size > 1): one handle per GPU / process, reference `-t world_size` semantics --------------------
+ * Replaces the shared-memory coupling of the reference's worker threads: global tables read by everybody between barriers
+ * (application.cpp:645-654), X_to_add[src][dst] exchange matrices + InsertKmersToHT on the owner (dna.cpp:2393-2472).
+ * Set-up: every rank calls fqsk_shard_export, the descriptors are exchanged by the caller (any transport) and every rank calls
+ * fqsk_shard_attach for each peer: tables and inboxes become NVLink peer mappings (CUDA IPC).
+ * Per sync, instead of fqsk_sync:  fqsk_sync_route  -> BARRIER ->  fqsk_sync_apply  -> ALL-REDUCE(sum) of (fresh, updates) ->
+ * fqsk_sync_finish.  The barrier / all-reduce are the caller's (NCCL in fqsqueezer_b200/sharded.py); the payload itself moves
+ * inside fqsk_sync_route as peer stores into the owners' inboxes.  Table growth is not supported in this mode: size the
+ * tables with expected_kmers / *_log2_buckets. */
+typedef struct fqsk_shard_desc {
+	uint32_t rank, world_size;
+	uint32_t geometry[6];        /* b: log2 buckets, log2 stash; s: same; p-mer key bits; reserved -- must agree on all ranks */
+	uint64_t inbox_cap;
+	uint8_t ipc[6][64];          /* cudaIpcMemHandle_t of: b main, b stash, s main, s stash, p-mer shard, inbox */
+} fqsk_shard_desc;
+int fqsk_shard_export(fqsk_handle *h, fqsk_shard_desc *out);
+int fqsk_shard_attach(fqsk_handle *h, const fqsk_shard_desc *peer);
+/* Routes this worker's pending rows (p, s, b) to their owners: rows [rank][*] of the exchange matrices, written into the owners'
+ * inboxes.  Call on every rank, then synchronise all ranks (barrier). */
+int fqsk_sync_route(fqsk_handle *h);
+/* Owner side of InsertKmersToHT: applies the rows [*][rank] in source order (p-mers, s-mers, b-mers; this rank's cinc_s / cinc_b).
+ * fresh = p-mer fields that became non-zero here, updates = p-mers applied here + this worker's hidden updates (dna.cpp:2416-2418). */
+int fqsk_sync_apply(fqsk_handle *h, uint64_t *fresh, uint64_t *updates);
+/* After the all-reduce: the global p-mer statistics (bit_vec.h:204-220 -- they gate repair_kmers_missing on every worker) and
+ * ClearKmersToHT.  The call sequence must be completed on all ranks before any of them starts its next segment. */
+int fqsk_sync_finish(fqsk_handle *h, uint64_t fresh_all_ranks, uint64_t updates_all_ranks);
 
 /* Sorted (key, value) contents: FQSK_TABLE_SIV -> (p-mer index, 2-bit field); SMER/BMER -> (normalised k-mer, counter).
  * Call with keys == NULL to get the count in *n.  Replaces nothing in the reference; parity check 1. */

@@ -1,0 +1,56 @@
+"""One rank of the sharded GPU parity run (launched by tests/test_gpu_sharded.py through torch.distributed.run):
+rank r plays the reference's worker thread r on fixture <name> (produced by the tapped reference at -t world) and checks
+its per-base records, and -- merged over the ranks -- the final tables, bit for bit."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from fqsqueezer_b200 import engine as E  # noqa: E402
+from fqsqueezer_b200 import schedule as S  # noqa: E402
+from fqsqueezer_b200 import sharded  # noqa: E402
+from tests import helpers as H  # noqa: E402
+
+
+def main():
+    name = sys.argv[1]
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    g = H.load_golden(name)
+    assert int(g["threads"]) == world, (int(g["threads"]), world)
+    pref, p, s, b = E.kmer_params(int(g["gs"]))
+    slab = g["fastq"]
+    eng = sharded.ShardedKmerEngine(p, s, b, pref, rank, world, device=local, dist=dist, reserve_bytes=1 << 20, reserve_reads=1 << 14)
+    off, ln, roff, rsz = S.parse_fastq(slab)
+    out = []
+    for gen, (f, l) in enumerate(S.split_blocks(rsz)):
+        ns = S.calc_no_synchronizations(gen, l - f, world)
+        a0, b0 = S.partition_for_workers(l - f, world)[rank]
+        eng.block_start()
+        for a, bb in S.segments(f + a0, f + b0, ns):
+            recs, dup = eng.segment(slab, off[a:bb], ln[a:bb])
+            out.append(recs)
+            eng.sync()
+    recs = np.concatenate(out)
+    want = g["recs_t%d" % rank]
+    H.assert_recs_equal(recs, want[want["pos"] < 0xFFFFFFF0])
+    for which, nm in ((0, "siv"), (1, "smer"), (2, "bmer")):
+        k, v = eng.dump_all(which)
+        assert np.array_equal(k, g[nm + "_keys"]), (nm, len(k), len(g[nm + "_keys"]))
+        assert np.array_equal(v, g[nm + "_vals"]), nm
+    st = eng.stats()
+    assert st["siv_no_filled"] == int(g["siv_no_filled"]) and st["siv_no_updates"] == int(g["siv_no_updates"]), (st["siv_no_filled"], st["siv_no_updates"])
+    assert st["kernel_launches"] > 0
+    print(f"rank {rank}/{world}: {len(recs)} records and the merged tables bit-exact vs fqs-1.1 -t {world} ({st['kernel_launches']} launches)", flush=True)
+    eng.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
