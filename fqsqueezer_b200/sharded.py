@@ -33,6 +33,24 @@ def owner_of_pmer(idx: np.ndarray, pmer_len: int, world: int) -> np.ndarray:
     return (np.asarray(idx, np.uint64) >> np.uint64(2 * pmer_len - 12)) % np.uint64(world)
 
 
+def gather_descs(dist, my_blob: bytes, world: int):
+    """Every rank's shard descriptor, in rank order (the descriptors are plain bytes: any transport would do)."""
+    blobs = [None] * world
+    dist.all_gather_object(blobs, my_blob)
+    assert all(isinstance(x, (bytes, bytearray)) and len(x) == C.sizeof(_ShardDesc) for x in blobs)
+    return [_ShardDesc.from_buffer_copy(x) for x in blobs]
+
+
+def allreduce_stats(dist, fresh: int, updates: int):
+    """Sum over the ranks of (fresh p-mer fields, p-mer updates): TSmallIntVector's global atomics (bit_vec.h:212-220)."""
+    import torch
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.tensor([fresh, updates], dtype=torch.int64, device=dev)
+    dist.all_reduce(t)
+    a, b = t.tolist()
+    return int(a), int(b)
+
+
 class ShardedKmerEngine(E.KmerEngine):
     """KmerEngine of one rank of a sharded group.  `dist` is torch.distributed (initialised by the caller, NCCL on GPU boxes)."""
 
@@ -67,29 +85,22 @@ class ShardedKmerEngine(E.KmerEngine):
     def _attach_peers(self):
         d = _ShardDesc()
         self._ck(self.lib.fqsk_shard_export(self.h, C.byref(d)))
-        blobs = [None] * self.world
-        self.dist.all_gather_object(blobs, bytes(d))
-        for r, blob in enumerate(blobs):
-            if r == self.rank:
-                continue
-            peer = _ShardDesc.from_buffer_copy(blob)
-            self._ck(self.lib.fqsk_shard_attach(self.h, C.byref(peer)))
+        for r, peer in enumerate(gather_descs(self.dist, bytes(d), self.world)):
+            if r != self.rank:
+                self._ck(self.lib.fqsk_shard_attach(self.h, C.byref(peer)))
         self.dist.barrier()
 
     def sync(self):
         """InsertKmersToHT + ClearKmersToHT of all workers (dna.cpp:2393-2488) around the reference's barriers."""
         if self.world == 1:
             return super().sync()
-        import torch
         self._ck(self.lib.fqsk_sync_route(self.h))
         self.dist.barrier()                                     # every row [src][dst] is in its owner's inbox
         fresh, upd = C.c_uint64(0), C.c_uint64(0)
         self._ck(self.lib.fqsk_sync_apply(self.h, C.byref(fresh), C.byref(upd)))
-        dev = torch.device("cuda", torch.cuda.current_device()) if self.dist.get_backend() == "nccl" else torch.device("cpu")
-        t = torch.tensor([fresh.value, upd.value], dtype=torch.int64, device=dev)
-        self.dist.all_reduce(t)                                 # global p-mer statistics; also: every owner has finished its inserts
-        tot = t.tolist()
-        self._ck(self.lib.fqsk_sync_finish(self.h, int(tot[0]), int(tot[1])))
+        # global p-mer statistics; also the second barrier: every owner has finished its inserts before anybody looks up again
+        f_all, u_all = allreduce_stats(self.dist, fresh.value, upd.value)
+        self._ck(self.lib.fqsk_sync_finish(self.h, f_all, u_all))
 
     def dump_all(self, which):
         """Sorted contents of the whole (sharded) table, gathered on every rank -- parity check 1."""

@@ -29,10 +29,8 @@ def main():
     off, ln, roff, rsz = S.parse_fastq(slab)
     out = []
     for gen, (f, l) in enumerate(S.split_blocks(rsz)):
-        ns = S.calc_no_synchronizations(gen, l - f, world)
-        a0, b0 = S.partition_for_workers(l - f, world)[rank]
         eng.block_start()
-        for a, bb in S.segments(f + a0, f + b0, ns):
+        for a, bb in S.worker_segments(f, l, gen, world, rank):
             recs, dup = eng.segment(slab, off[a:bb], ln[a:bb])
             out.append(recs)
             eng.sync()
