@@ -49,12 +49,12 @@ def make_reads(genome: np.ndarray, n_reads: int, L: int = 150, p_err: float = 0.
     return codes, err
 
 
-def make_pairs(genome: np.ndarray, n_pairs: int, L: int = 150, p_err: float = 0.005, seed: int = 0):
+def make_pairs(genome: np.ndarray, n_pairs: int, L: int = 150, p_err: float = 0.005, seed: int = 0, ins_mean: float = 400, ins_sd: float = 40):
     """Returns (codes1, err1, codes2, err2); mate 2 is the reverse complement of the fragment end."""
     rng = np.random.default_rng(seed + 2)
     G = genome.shape[0]
-    ins = np.clip(np.rint(rng.normal(400, 40, n_pairs)), L, 2000).astype(np.int64)
-    starts = rng.integers(0, G - 2000, n_pairs)
+    ins = np.clip(np.rint(rng.normal(ins_mean, ins_sd, n_pairs)), L, 2000).astype(np.int64)
+    starts = rng.integers(0, G - min(2000, G // 2), n_pairs)
     strand = rng.integers(0, 2, n_pairs).astype(bool)
     ar = np.arange(L)[None, :]
     left = genome[starts[:, None] + ar]

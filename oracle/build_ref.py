@@ -187,6 +187,9 @@ def build_tap(scratch):
     patch(dna, "\t\tdif_no_bytes = no_bytes(dif);", "\t\tfqs_tap_emit(0xFFFFFFFCu, (uint32_t) flag, (uint32_t) dif, (uint32_t) (dif >> 32), 0, 0, 0, 0);\n", before=True)
     # duplicate flag: emitted right where the reference codes it
     patch(dna, "\t\tif (same_read)\n\t\t\treturn true;", "\t\tif (same_read) fqs_tap_emit(0xFFFFFFFDu, 0, 0, 0, 0, 0, 0, 0);\n", before=True, count=2)
+    # per pair (dna.cpp:1848): what CompressPE decided for mate 2 -- pos = 0xFFFFFFFB, c0 = minim_found, c1 = minim2_id, c2 = minim2_pos
+    patch(dna, "\tif (minim2_id < 0)\n\t\tCompressDirect(p2, size2, nullptr, false);",
+          "\tfqs_tap_emit(0xFFFFFFFBu, (uint32_t) minim_found, minim_found ? (uint32_t) minim2_id : 0u, (minim_found && minim2_id < 15) ? minim2_pos : 0u, 0, 0, 0, 0);\n", before=True)
     # per sync marker (dna.cpp:2393)
     patch(dna, "void CDNACompressor::InsertKmersToHT()\n{\n", "\tfqs_tap_emit(0xFFFFFFFEu, 0, 0, 0, 0, 0, 0, 0);\n")
     app = os.path.join(d, "application.cpp")

@@ -80,6 +80,47 @@ def make_case(name, G, n_reads, L, gs, seed, n_frac=0.0, dup_frac=0.0, extra=("-
     print(name, "reads", n_reads, "records", len(recs), "file", os.path.getsize(out))
 
 
+def make_case_pe(name, G, n_pairs, L, gs, seed, threads=1):
+    """Paired-end, original order (-p -om o): two FASTQ files; the fixture keeps them interleaved (mate 1, mate 2, ...), which is
+    how the reference lays the pairs out inside a reads_block (reads_block.h:144-169)."""
+    genome = synth.make_genome(G, seed)
+    c1, e1, c2, e2 = synth.make_pairs(genome, n_pairs, L=L, seed=seed, ins_mean=2.2 * L, ins_sd=0.2 * L)
+    with tempfile.TemporaryDirectory() as tmp:
+        f1, f2 = os.path.join(tmp, "in_1.fastq"), os.path.join(tmp, "in_2.fastq")
+        synth.write_fastq(f1, c1, e1, mate=1, seed=seed)
+        synth.write_fastq(f2, c2, e2, mate=2, seed=seed + 1)
+        plain, tapd, tap, dump = (os.path.join(tmp, x) for x in ("plain.fqs", "tap.fqs", "tap.bin", "dump.bin"))
+        base = ["e", "-p", "-om", "o", "-qm", "o", "-im", "o", "-t", str(threads), "-gs", str(gs), "-v", "0"]
+        subprocess.run([O.REF_BIN, *base, "-out", plain, f1, f2], check=True, cwd=tmp, stdout=subprocess.DEVNULL)
+        subprocess.run([O.REF_TAP_BIN, *base, "-out", tapd, f1, f2], check=True, cwd=tmp, env=dict(os.environ, FQS_TAP=tap, FQS_TAP_DUMP=dump), stdout=subprocess.DEVNULL)
+        assert open(plain, "rb").read() == open(tapd, "rb").read(), "tap changed the .fqs bytes"
+        d1, d2 = os.path.join(tmp, "d1.fastq"), os.path.join(tmp, "d2.fastq")
+        subprocess.run([O.REF_BIN, "d", "-out", d1, "-out2", d2, plain], check=True, cwd=tmp, stdout=subprocess.DEVNULL)
+        assert open(d1, "rb").read() == open(f1, "rb").read() and open(d2, "rb").read() == open(f2, "rb").read(), "reference PE round trip failed"
+        recs = np.fromfile(tap, dtype=O.REC_DTYPE)
+        d = np.fromfile(dump, dtype="<u8").reshape(-1, 3)
+        r1 = open(f1, "rb").read().split(b"\n")
+        r2 = open(f2, "rb").read().split(b"\n")
+        inter = []
+        for i in range(n_pairs):
+            inter += r1[4 * i:4 * i + 4] + r2[4 * i:4 * i + 4]
+        fastq = np.frombuffer(b"\n".join(inter) + b"\n", dtype=np.uint8).copy()
+        fqs_size = os.path.getsize(plain)
+    dumps = {}
+    for tag, nm in ((0, "siv"), (1, "smer"), (2, "bmer"), (3, "pair")):
+        x = d[d[:, 0] == tag]
+        o = np.lexsort((x[:, 2], x[:, 1]))
+        dumps[nm + "_keys"] = x[o, 1]
+        dumps[nm + "_vals"] = x[o, 2]
+    stat = d[d[:, 0] == 4][0]
+    out = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(out, fastq=fastq, gs=np.int64(gs), extra=np.array(["-p", "-om", "o"]), recs=recs, threads=np.int64(threads),
+                        siv_no_filled=stat[1], siv_no_updates=stat[2], fqs_size=np.int64(fqs_size), **dumps)
+    pi = recs[recs["pos"] == 0xFFFFFFFB]
+    print(name, "pairs", n_pairs, "records", len(recs), "pairs with a minimizer hit", int((pi["c"][:, 0] == 1).sum()), "coded from a minimizer", int(((pi["c"][:, 0] == 1) & (pi["c"][:, 1] < 15)).sum()),
+          "file", os.path.getsize(out))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     only = sys.argv[1:]
@@ -99,6 +140,9 @@ def main():
     # two / three worker threads (-t 2, -t 3): per-worker PRNG streams, owner-routed exchange rows, global gate statistics
     make_case("se_orig_gs1_t2", G=6000, n_reads=1800, L=80, gs=1, seed=61, n_frac=0.002, dup_frac=0.01, threads=2)
     make_case("se_orig_gs16_t3", G=9000, n_reads=1500, L=100, gs=16, seed=62, threads=3)
+    # paired end, original order: pair table, minimizer candidates, mate 2 coded from a shared minimizer (forward + reversed part)
+    if not only or "pe_orig_gs1" in only:
+        make_case_pe("pe_orig_gs1", G=5000, n_pairs=1200, L=80, gs=1, seed=71)
 
 
 if __name__ == "__main__":

@@ -58,6 +58,36 @@ def run_se_workers(group, slab, n_workers, kind=0):
     return res
 
 
+POS_PAIR = 0xFFFFFFFB    # per pair: c0 = a candidate list exists, c1 = minimizer id (0..14, 15 = none usable), c2 = its position in mate 2
+
+
+def run_pe(engine, slab, is_gpu=False):
+    """Paired-end driver (application.cpp:1020-1331): the slab holds the pairs interleaved (mate 1, mate 2, ...); blocks close
+    on pair boundaries with twice the margin, syncs step by pairs (`i >= next_synchro`).  Returns (records, pair_info[n, 3])."""
+    off, ln, roff, rsz = S.parse_fastq(slab)
+    out, info = [], []
+    for gen, (f, l) in enumerate(S.split_blocks(rsz, paired=True)):
+        ns = S.calc_no_synchronizations(gen, l - f, 1)
+        engine.block_start()
+        for a, b in S.segments(f, l, ns, paired=True):
+            recs, dup = engine.segment(slab, off[a:b], ln[a:b], 3)
+            out.append(recs)
+            if is_gpu:
+                info.append(engine.pair_info((b - a) // 2))
+            engine.sync()
+    recs = np.concatenate(out) if out else np.zeros(0, O.REC_DTYPE)
+    if not is_gpu:
+        pi = recs[recs["pos"] == POS_PAIR]
+        info = [pi["c"][:, :3].astype(np.uint32)]
+    return recs[recs["pos"] < 0xFFFFFFF0], (np.concatenate(info) if info else np.zeros((0, 3), np.uint32))
+
+
+def golden_pe_expect(gold):
+    r = gold["recs"]
+    pi = r[r["pos"] == POS_PAIR]
+    return r[r["pos"] < 0xFFFFFFF0], pi["c"][:, :3].astype(np.uint32)
+
+
 def assert_recs_equal(got, want):
     want = want[want["pos"] != O.POS_SYNC]
     assert len(got) == len(want), (len(got), len(want))
@@ -69,8 +99,8 @@ def assert_recs_equal(got, want):
     assert len(bad) == 0, f"{len(bad)} records differ, first at {bad[0]}: got {got[bad[0]]} want {want[bad[0]]}"
 
 
-def assert_dump_equal(engine, gold):
-    for which, nm in ((0, "siv"), (1, "smer"), (2, "bmer")):
+def assert_dump_equal(engine, gold, pairs=False):
+    for which, nm in ((0, "siv"), (1, "smer"), (2, "bmer")) + (((3, "pair"),) if pairs else ()):
         k, v = engine.dump(which)
         assert np.array_equal(k, gold[nm + "_keys"]), nm
         assert np.array_equal(v, gold[nm + "_vals"]), nm

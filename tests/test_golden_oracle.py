@@ -52,3 +52,19 @@ def test_oracle_group_matches_reference_tap_multithread(name):
         H.assert_recs_equal(per_worker[w], want[want["pos"] < 0xFFFFFFF0])
     H.assert_dump_equal(grp, g)
     grp.close()
+
+
+def test_oracle_matches_reference_tap_paired_end():
+    """-p -om o: mate 1 as a single read, minimizer candidates from the pair tables (global + thread-local), mate 2 coded
+    forward + reversed from a shared minimizer, 14 pair-table pushes per pair -- records, per-pair decisions and all four tables."""
+    import numpy as np
+    g = H.load_golden("pe_orig_gs1")
+    pref, p, s, b = O.kmer_params(int(g["gs"]))
+    e = O.OracleEngine(p, s, b, pref, mode=2)
+    recs, info = H.run_pe(e, g["fastq"])
+    want, winfo = H.golden_pe_expect(g)
+    assert np.array_equal(info, winfo), np.flatnonzero((info != winfo).any(axis=1))[:5]
+    H.assert_recs_equal(recs, want)
+    assert (winfo[:, 0] == 1).sum() > 500 and ((winfo[:, 0] == 1) & (winfo[:, 1] < 15)).sum() > 500 and (winfo[:, 1] == 15).sum() > 0
+    H.assert_dump_equal(e, g, pairs=True)
+    e.close()
