@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "fqsk_pipeline.cuh"
+#include "fqsk_pe.cuh"
 
 using namespace fqsk;
 
@@ -131,6 +132,12 @@ struct fqsk_handle {
 	uint32_t pend_b = 0, pend_s = 0, pend_p = 0;
 	uint64_t n_recs = 0;
 	uint32_t seg_reads = 0;
+	// paired-end (fqsk_pe.cuh): the global pair table, the segment's sorted triples, the per-pair decisions and the work items
+	PairDev pair{}; uint64_t pair_items = 0;
+	uint32_t *d_pe = nullptr;                // [0] pool_used [1] overflow [2..5] scan totals [6,7] items in the pair table (u64)
+	DevBuf pe_tk, pe_tv, pe_q, pe_sk, pe_sv, pe_sidx, pe_t1, pe_t2, pe_pool, pe_info, it_src, it_len, it_bytes, it_first, it_bias, it_dupprev,
+	       it_flags, it_off32, it_off64, it_dna;
+	uint32_t pe_pool_cap = 1u << 20, pe_pairs = 0, pe_nt = 0, seg_reads_in = 0;
 	// pinned staging
 	uint8_t *h_stage = nullptr; size_t h_stage_cap = 0;
 	void *h_small = nullptr;              // pinned scratch for small D2H reads
@@ -789,9 +796,98 @@ int seg_settle(fqsk_handle *h, bool have_look = false) {
 	}
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// paired-end front end (fqsk_pe.cuh): pair table, decisions, work items
+// ---------------------------------------------------------------------------------------------------------------
+int pair_alloc(fqsk_handle *h, PairDev &t, uint64_t slots) {
+	t = PairDev{};
+	t.b = h->P.bmer_len; t.vm = (1ull << (2 * t.b)) - 1; t.top = ~0ull >> (2 * t.b); t.mask = slots - 1;
+	CK(cudaMalloc(&t.keys, slots * 8)); CK(cudaMalloc(&t.vcs, slots * 8));
+	CK(cudaMemsetAsync(t.keys, 0xFF, slots * 8, h->st)); CK(cudaMemsetAsync(t.vcs, 0xFF, slots * 8, h->st));
+	return FQSK_OK;
+}
+int pair_reserve(fqsk_handle *h, uint64_t incoming) {     // keep the table at most half full (contents, not layout, are the contract)
+	uint64_t slots = h->pair.mask + 1;
+	if ((h->pair_items + incoming) * 2 <= slots) return FQSK_OK;
+	while ((h->pair_items + incoming) * 2 > slots) slots <<= 1;
+	PairDev nt;
+	CKR(pair_alloc(h, nt, slots));
+	k_pair_rehash<<<148 * 8, 256, 0, h->st>>>(h->pair, nt); LAUNCHED(h);
+	CK(cudaStreamSynchronize(h->st));
+	cudaFree(h->pair.keys); cudaFree(h->pair.vcs);
+	h->pair = nt;
+	return FQSK_OK;
+}
+PeSeg pe_seg(fqsk_handle *h) { return PeSeg{h->pe_sk.as<unsigned long long>(), h->pe_sv.as<unsigned long long>(), h->pe_sidx.as<uint32_t>(), h->pe_nt}; }
+
+// Turns the n_pairs pairs of a segment into 3 * n_pairs work items (texts in it_dna, descriptors in it_*).
+int pe_front(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes, const unsigned long long *d_off, const uint32_t *d_len, uint32_t np, uint64_t *item_bytes_bound) {
+	const uint32_t nt = 14 * np, ni = 3 * np, b = h->P.bmer_len;
+	*item_bytes_bound = dna_bytes + (uint64_t) np * (b + 2ull * h->P.prefix_len) + 64;
+	CK(h->pe_tk.ensure((size_t) nt * 8)); CK(h->pe_tv.ensure((size_t) nt * 8)); CK(h->pe_q.ensure((size_t) np * 32));
+	CK(h->pe_sk.ensure((size_t) nt * 8)); CK(h->pe_sv.ensure((size_t) nt * 8)); CK(h->pe_sidx.ensure((size_t) nt * 4));
+	CK(h->pe_t1.ensure((size_t) nt * 8)); CK(h->pe_t2.ensure((size_t) nt * 8)); CK(h->pe_info.ensure((size_t) np * 12));
+	CK(h->it_src.ensure((size_t) ni * 8)); CK(h->it_len.ensure((size_t) ni * 4 + 4)); CK(h->it_bytes.ensure((size_t) ni * 4)); CK(h->it_first.ensure((size_t) ni * 4));
+	CK(h->it_bias.ensure((size_t) ni * 4)); CK(h->it_dupprev.ensure((size_t) ni * 4)); CK(h->it_flags.ensure(ni));
+	CK(h->it_off32.ensure((size_t) ni * 4 + 4)); CK(h->it_off64.ensure((size_t) ni * 8 + 8)); CK(h->it_dna.ensure(*item_bytes_bound));
+	unsigned long long *tk = h->pe_tk.as<unsigned long long>(), *tv = h->pe_tv.as<unsigned long long>(), *q = h->pe_q.as<unsigned long long>();
+	k_pe_minim<<<nblk((uint64_t) np * 32, 128), 128, 0, h->st>>>(d_dna, d_off, d_len, np, b, tk, tv, q); LAUNCHED(h);
+	// stable two-pass sort of the triples by (key, value): value first, then key
+	CKR(ensure_iota(h, nt));
+	uint32_t *i1 = (uint32_t *) h->pe_t2.as<uint32_t>();
+	CKR(sort_pairs_u64_u32(h, tv, h->pe_t1.as<unsigned long long>(), h->iota.as<uint32_t>(), i1, nt, 0, 2 * (int) b));
+	k_pe_gather<<<nblk(nt, 256), 256, 0, h->st>>>(tk, i1, h->pe_t1.as<unsigned long long>(), nt); LAUNCHED(h);
+	CKR(sort_pairs_u64_u32(h, h->pe_t1.as<unsigned long long>(), h->pe_sk.as<unsigned long long>(), i1, h->pe_sidx.as<uint32_t>(), nt, 0, 2 * (int) b + 1));
+	k_pe_gather<<<nblk(nt, 256), 256, 0, h->st>>>(tv, h->pe_sidx.as<uint32_t>(), h->pe_sv.as<unsigned long long>(), nt); LAUNCHED(h);
+	h->pe_nt = nt; h->pe_pairs = np;
+	PeItems I{h->it_src.as<unsigned long long>(), h->it_len.as<uint32_t>(), h->it_bytes.as<uint32_t>(), h->it_first.as<uint32_t>(), h->it_bias.as<uint32_t>(),
+	          h->it_dupprev.as<uint32_t>(), h->it_flags.as<uint8_t>()};
+	for (int attempt = 0;; ++attempt) {
+		if (attempt > 12) return fail(h, FQSK_E_NOMEM, "pair candidate pool kept overflowing");
+		if (h->pe_pool_cap < 64 * np) h->pe_pool_cap = 64 * np;
+		CK(h->pe_pool.ensure((size_t) h->pe_pool_cap * 8));
+		CK(cudaMemsetAsync(h->d_pe, 0, 8, h->st));
+		k_pe_decide<<<nblk((uint64_t) np * 32, 128), 128, 0, h->st>>>(h->pair, pe_seg(h), q, d_dna, d_off, d_len, np, h->P.prefix_len, h->pe_pool.as<unsigned long long>(),
+		                                                             h->d_pe, h->pe_pool_cap, (int *) (h->d_pe + 1), h->pe_info.as<uint32_t>(), I); LAUNCHED(h);
+		uint32_t *hs = (uint32_t *) ((uint8_t *) h->h_small + 960);
+		CK(cudaMemcpyAsync(hs, h->d_pe, 8, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaStreamSynchronize(h->st));
+		if (!hs[1]) break;
+		h->pe_pool_cap = h->pe_pool_cap < (1u << 29) ? h->pe_pool_cap * 4 : h->pe_pool_cap;
+	}
+	k_scan_u32x4<<<1, 1024, 0, h->st>>>(ni, h->it_bytes.as<uint32_t>(), h->it_off32.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, h->d_pe + 2); LAUNCHED(h);
+	k_pe_fill<<<nblk((uint64_t) (ni + 1) * 32, 128), 128, 0, h->st>>>(d_dna, I, h->it_off32.as<uint32_t>(), ni, h->it_dna.as<uint8_t>(), h->it_off64.as<unsigned long long>()); LAUNCHED(h);
+	return FQSK_OK;
+}
+
+// sync: the segment's triples into the global pair table (dna.cpp:2448-2468)
+int pe_sync(fqsk_handle *h) {
+	if (!h->pe_nt) return FQSK_OK;
+	CKR(pair_reserve(h, h->pe_nt));
+	unsigned long long *d_items = (unsigned long long *) (h->d_pe + 6);
+	k_pair_insert<<<nblk(h->pe_nt, 256), 256, 0, h->st>>>(h->pair, pe_seg(h), d_items); LAUNCHED(h);
+	unsigned long long *hs = (unsigned long long *) ((uint8_t *) h->h_small + 968);
+	CK(cudaMemcpyAsync(hs, d_items, 8, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaStreamSynchronize(h->st));
+	h->pair_items = *hs;
+	h->pe_nt = 0;
+	return FQSK_OK;
+}
+
 int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual, const unsigned long long *d_off, const uint32_t *d_len, uint32_t n) {
-	const uint64_t dna_bytes = std::max<uint64_t>(dna_bytes_actual, h->P.reserve_bytes);
 	if (h->pending) return fail(h, FQSK_E_INVAL, "fqsk_segment called twice without fqsk_sync (the reference syncs after every segment, application.cpp:643-662)");
+	const bool pe = h->P.mode == FQSK_MODE_PE_ORIGINAL;
+	const uint32_t n_in = n;
+	const uint64_t bytes_in = dna_bytes_actual;
+	h->seg_reads_in = n_in; h->pe_nt = 0; h->pe_pairs = 0;
+	if (pe && (n & 1)) return fail(h, FQSK_E_INVAL, "paired-end segment with an odd number of reads");
+	if (pe && n) {   // pairs -> work items: mate 1, mate 2 (whole or right of the shared minimizer), reversed left part
+		uint64_t bound = 0;
+		CKR(pe_front(h, d_dna, dna_bytes_actual, d_off, d_len, n / 2, &bound));
+		d_dna = h->it_dna.as<uint8_t>(); d_off = h->it_off64.as<unsigned long long>(); d_len = h->it_len.as<uint32_t>();
+		n = 3 * (n / 2); dna_bytes_actual = bound;
+	}
+	const uint64_t dna_bytes = std::max<uint64_t>(dna_bytes_actual, pe ? (uint64_t) h->P.reserve_bytes + h->P.reserve_bytes / 4 : h->P.reserve_bytes);
 	if (h->world > 1 && h->attached != (1u << h->world) - 1) return fail(h, FQSK_E_INVAL, "sharded engine: not every peer shard is attached (fqsk_shard_attach)");
 	const uint32_t first = (h->P.mode == FQSK_MODE_SE_SORTED || h->P.mode == FQSK_MODE_PE_SORTED) ? h->P.pmer_len : h->P.prefix_len;
 	h->seg_reads = n; h->n_recs = 0; h->pend_b = h->pend_s = h->pend_p = 0;
@@ -799,7 +895,7 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 	++h->S.n_segments;
 	if (n == 0) { h->pending = true; return FQSK_OK; }
 	if (dna_bytes >= (1ull << 30)) return fail(h, FQSK_E_INVAL, "segment larger than 1 GiB of DNA");   // push times are 2 * byte offset (+1) in 32 bits
-	const size_t n1 = (size_t) std::max<uint32_t>(n, h->P.reserve_reads) + 1;
+	const size_t n1 = (size_t) std::max<uint32_t>(n, pe ? h->P.reserve_reads / 2 * 3 : h->P.reserve_reads) + 1;
 	CK(h->dup.ensure(n1)); CK(h->n_coded.ensure(n1 * 4)); CK(h->letters.ensure(n1 * 32)); CK(h->rec_off.ensure(n1 * 8)); CK(h->sl_prefix.ensure(n1 * 32));
 	CK(h->push_b.ensure((2 * dna_bytes + 2) * 8)); CK(h->push_s.ensure((dna_bytes + 1) * 8)); CK(h->push_p.ensure((2 * dna_bytes + 2 * n1) * 8));
 	CK(h->cnt_b.ensure(n1 * 4)); CK(h->cnt_s.ensure(n1 * 4)); CK(h->cnt_p.ensure(n1 * 4)); CK(h->hidden.ensure(n1 * 4));
@@ -813,6 +909,7 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 	SegDev &S = C.S;
 	S = SegDev{};
 	S.dna = d_dna; S.off = d_off; S.len = d_len; S.n_reads = n;
+	if (pe) { S.first_a = h->it_first.as<uint32_t>(); S.bias_a = h->it_bias.as<uint32_t>(); S.dup_prev = h->it_dupprev.as<uint32_t>(); S.iflags = h->it_flags.as<uint8_t>(); }
 	CK(h->prev_read.ensure_keep((size_t) dna_bytes_actual + 64, h->st));     // a read is never longer than its segment
 	S.prev_read = h->prev_read.as<uint8_t>(); S.carry = h->d_carry;
 	S.dup = h->dup.as<uint8_t>(); S.n_coded = h->n_coded.as<uint32_t>(); S.letters = h->letters.as<U64x4>();
@@ -823,7 +920,7 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 	S.sorted_flag = h->sflag.as<uint32_t>(); S.sorted_dif = h->sdif.as<unsigned long long>();
 	{
 		Phase ph(h, FQSK_PH_PREP);
-		k_prep<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(S, first); LAUNCHED(h);
+		k_prep<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(S, first, h->P.bmer_len); LAUNCHED(h);
 		k_scan_reads<<<1, 1024, 0, h->st>>>(S, h->rec_off.as<unsigned long long>(), h->sl_prefix.as<U64x4>(), (SegTotals *) (h->d_status + 64), h->d_u32 + 3); LAUNCHED(h);
 	}
 	const uint32_t rec_bound = (uint32_t) dna_bytes;   // capacities follow the reserve as well
@@ -838,10 +935,10 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 	// verdict of the first pass for a sync enqueued unseen, and the state the next segment inherits (both are inputs only)
 	k_seg_verdict<<<1, 32, 0, h->st>>>(h->d_flags, (const uint32_t *) (h->d_status + 192), (const unsigned long long *) (h->d_status + 208),
 	                                   h->rng[ST_B].consumed, h->rng[ST_S].consumed, SYNC_INDEXED_MAX, h->d_syncin); LAUNCHED(h);
-	k_save_carry<<<1, 256, 0, h->st>>>(S, h->prev_read.as<uint8_t>(), h->d_carry, h->P.mode == FQSK_MODE_SE_SORTED || h->P.mode == FQSK_MODE_PE_SORTED, h->P.pmer_len); LAUNCHED(h);
+	k_save_carry<<<1, 256, 0, h->st>>>(S, pe ? n - 3 : n - 1, h->prev_read.as<uint8_t>(), h->d_carry, h->P.mode == FQSK_MODE_SE_SORTED || h->P.mode == FQSK_MODE_PE_SORTED, h->P.pmer_len); LAUNCHED(h);
 	h->unsettled = true;
 	h->pending = true;
-	h->S.n_reads += n; h->S.n_bases += dna_bytes_actual;
+	h->S.n_reads += n_in; h->S.n_bases += bytes_in;
 	return FQSK_OK;
 }
 
@@ -908,7 +1005,7 @@ int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
 	if (world > 1 && p->mode != FQSK_MODE_SE_ORIGINAL) return fail(h, FQSK_E_UNSUPPORTED, "sharded operation is implemented for original-order SE only");
 	if (!(p->pmer_len >= 5 && p->pmer_len < p->smer_len && p->smer_len < p->bmer_len && p->bmer_len <= 31)) return fail(h, FQSK_E_INVAL, "need 5 <= p < s < b <= 31");
 	if (p->pmer_len > 18) return fail(h, FQSK_E_INVAL, "pmer_len > 18 not supported");
-	if (p->mode != FQSK_MODE_SE_ORIGINAL && p->mode != FQSK_MODE_SE_SORTED) return fail(h, FQSK_E_UNSUPPORTED, "paired-end modes are not implemented yet");
+	if (p->mode == FQSK_MODE_PE_SORTED || p->mode > FQSK_MODE_PE_SORTED) return fail(h, FQSK_E_UNSUPPORTED, "paired-end sorted order (-p -om s) is not implemented");
 	int ndev = 0;
 	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(h, FQSK_E_NO_DEVICE, "no CUDA device: this library has no CPU path");
 	if (p->device < 0 || p->device >= ndev) return fail(h, FQSK_E_INVAL, "device %d out of range (%d devices)", p->device, ndev);
@@ -962,6 +1059,10 @@ int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
 		for (int i = 0; i < 4; ++i) CKR(stream_init(h, h->rng[i], i == ST_B ? (1ull << 25) : i == ST_S ? (1ull << 21) : (1ull << 16)));
 		CKR(stream_generate(h, h->rng[ST_B], 1u << 22)); CKR(stream_generate(h, h->rng[ST_S], 1u << 18));
 		CK(h->prev_read.ensure(1 << 16));
+		if (p->mode == FQSK_MODE_PE_ORIGINAL) {          // CHT_pair_kmers(bmer_len, ...), application.cpp:91
+			CK(cudaMalloc(&h->d_pe, 64)); CK(cudaMemsetAsync(h->d_pe, 0, 64, h->st));
+			CKR(pair_alloc(h, h->pair, 1ull << 16));
+		}
 		CK(cudaStreamSynchronize(h->st));
 		return FQSK_OK;
 	}();
@@ -978,6 +1079,9 @@ void fqsk_destroy(fqsk_handle *h) {
 	if (h->siv.w) cudaFree(h->siv.w);
 	for (uint32_t i = 0; i < FQSK_MAX_WORLD; ++i) for (int q = 0; q < 6; ++q) if (h->peer_ptrs[i][q]) cudaIpcCloseMemHandle(h->peer_ptrs[i][q]);
 	if (h->inbox) cudaFree(h->inbox);
+	if (h->pair.keys) cudaFree(h->pair.keys);
+	if (h->pair.vcs) cudaFree(h->pair.vcs);
+	if (h->d_pe) cudaFree(h->d_pe);
 	if (h->st_mt) cudaStreamSynchronize(h->st_mt);
 	for (auto &s : h->rng) { if (s.buf) cudaFree(s.buf); if (s.state) cudaFree(s.state); if (s.ev) cudaEventDestroy(s.ev); }
 	if (h->d_status) cudaFree(h->d_status);
@@ -992,7 +1096,9 @@ void fqsk_destroy(fqsk_handle *h) {
 	                  &h->y_tslot, &h->y_c0, &h->y_m, &h->y_draw, &h->y_j, &h->y_final, &h->y_flag_at, &h->y_own, &h->y_lead, &h->y_rank, &h->y_flag, &h->y_doff,
 	                  &h->idx_k, &h->idx_t, &h->idx_rt, &h->miss_fold, &h->hr_b[0], &h->hr_b[1], &h->hr_b[2], &h->hr_s[0], &h->hr_s[1], &h->hr_s[2],
 	                  &h->evk[0], &h->evk[1], &h->evv[0], &h->evv[1], &h->evk_s[0], &h->evk_s[1], &h->evv_s[0], &h->evv_s[1], &h->scan_part,
-	                  &h->route_keys, &h->route_keys2, &h->route_sorted, &h->route_hist};
+	                  &h->route_keys, &h->route_keys2, &h->route_sorted, &h->route_hist,
+	                  &h->pe_tk, &h->pe_tv, &h->pe_q, &h->pe_sk, &h->pe_sv, &h->pe_sidx, &h->pe_t1, &h->pe_t2, &h->pe_pool, &h->pe_info, &h->it_src, &h->it_len,
+	                  &h->it_bytes, &h->it_first, &h->it_bias, &h->it_dupprev, &h->it_flags, &h->it_off32, &h->it_off64, &h->it_dna};
 
 	for (DevBuf *b : bufs) b->release();
 	if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -1041,6 +1147,17 @@ int fqsk_sorted_prefix(fqsk_handle *h, uint32_t *flag, uint64_t *dif, uint32_t n
 	return FQSK_OK;
 }
 
+int fqsk_pair_info(fqsk_handle *h, uint32_t *info, uint32_t n_pairs) {
+	if (!h || (!info && n_pairs)) return FQSK_E_INVAL;
+	CK(cudaSetDevice(h->P.device));
+	if (h->P.mode != FQSK_MODE_PE_ORIGINAL) return fail(h, FQSK_E_INVAL, "not a paired-end engine");
+	if (n_pairs > h->pe_pairs) return fail(h, FQSK_E_INVAL, "last segment had %u pairs", h->pe_pairs);
+	if (!n_pairs) return FQSK_OK;
+	CK(cudaMemcpyAsync(info, h->pe_info.p, (size_t) n_pairs * 12, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaStreamSynchronize(h->st));
+	return FQSK_OK;
+}
+
 int fqsk_segment(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const fqsk_read_desc *reads, uint32_t n_reads,
                  fqsk_base_rec *recs, uint64_t rec_cap, uint64_t *n_recs, uint8_t *dup, uint64_t *rec_off) {
 	if (!h || (!slab && n_reads) || (!reads && n_reads)) return FQSK_E_INVAL;
@@ -1081,6 +1198,24 @@ int fqsk_segment(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const 
 	CKR(seg_settle(h));
 	if (h->n_recs > rec_cap) return fail(h, FQSK_E_CAPACITY, "record buffer holds %llu, segment produced %llu", (unsigned long long) rec_cap, (unsigned long long) h->n_recs);
 	if (h->n_recs && recs) CK(cudaMemcpyAsync(recs, h->recs.p, h->n_recs * sizeof(fqsk_base_rec), cudaMemcpyDeviceToHost, h->st));
+	if (h->P.mode == FQSK_MODE_PE_ORIGINAL) {
+		// per-read views of the per-item arrays: mate 1 = item 3i, mate 2 = items 3i+1 (+ 3i+2, contiguous records)
+		const uint32_t ni = n_reads / 2 * 3;
+		std::vector<uint8_t> idup(ni + 1);
+		std::vector<unsigned long long> ioff(ni + 1);
+		if (ni) {
+			CK(cudaMemcpyAsync(idup.data(), h->dup.p, ni, cudaMemcpyDeviceToHost, h->st));
+			CK(cudaMemcpyAsync(ioff.data(), h->rec_off.p, ((size_t) ni + 1) * 8, cudaMemcpyDeviceToHost, h->st));
+		}
+		CK(cudaStreamSynchronize(h->st));
+		for (uint32_t i = 0; i < n_reads / 2; ++i) {
+			if (dup) { dup[2 * i] = idup[3 * i]; dup[2 * i + 1] = 0; }
+			if (rec_off) { rec_off[2 * i] = ioff[3 * i]; rec_off[2 * i + 1] = ioff[3 * i + 1]; }
+		}
+		if (rec_off) rec_off[n_reads] = ni ? ioff[ni] : 0;
+		if (n_recs) *n_recs = h->n_recs;
+		return FQSK_OK;
+	}
 	if (n_reads && dup) CK(cudaMemcpyAsync(dup, h->dup.p, n_reads, cudaMemcpyDeviceToHost, h->st));
 	if (n_reads && rec_off) CK(cudaMemcpyAsync(rec_off, h->rec_off.p, ((size_t) n_reads + 1) * 8, cudaMemcpyDeviceToHost, h->st));
 	CK(cudaStreamSynchronize(h->st));
@@ -1160,6 +1295,7 @@ int fqsk_sync(fqsk_handle *h) {
 		bool applied = false;
 		if (h->unsettled && h->fast_ok[0] && h->ctx.dna_bytes_actual <= SPEC_MAX_BYTES) CKR(sync_speculative(h, &applied, counters));
 		CKR(seg_settle(h));
+		if (h->P.mode == FQSK_MODE_PE_ORIGINAL) CKR(pe_sync(h));
 		if (!applied) {
 			// p-mers (dna.cpp:2401-2418): order-independent saturating increments; the fresh-field count is read with the next look
 			CK(cudaMemsetAsync(h->d_counters + 4, 0, 8, h->st));
@@ -1376,6 +1512,23 @@ static int dump_sorted(fqsk_handle *h, uint64_t n, uint64_t *keys, uint64_t *val
 	return FQSK_OK;
 }
 
+static int dump_pairs(fqsk_handle *h, uint64_t *keys, uint64_t *vals, uint64_t cap, uint64_t *n) {
+	if (!h->pair.keys) return fail(h, FQSK_E_INVAL, "not a paired-end engine");
+	const uint64_t slots = h->pair.mask + 1;
+	std::vector<unsigned long long> k(slots), v(slots);
+	CK(cudaMemcpyAsync(k.data(), h->pair.keys, slots * 8, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaMemcpyAsync(v.data(), h->pair.vcs, slots * 8, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaStreamSynchronize(h->st));
+	std::vector<std::pair<unsigned long long, unsigned long long>> items;
+	for (uint64_t i = 0; i < slots; ++i) if (k[i] != PAIR_EMPTY) items.emplace_back(k[i], v[i]);
+	*n = items.size();
+	if (!keys) return FQSK_OK;
+	if (items.size() > cap) return fail(h, FQSK_E_CAPACITY, "dump buffer holds %llu, table has %llu", (unsigned long long) cap, (unsigned long long) items.size());
+	std::sort(items.begin(), items.end());
+	for (size_t i = 0; i < items.size(); ++i) { keys[i] = items[i].first; vals[i] = items[i].second; }
+	return FQSK_OK;
+}
+
 int fqsk_dump(fqsk_handle *h, int table, uint64_t *keys, uint64_t *vals, uint64_t cap, uint64_t *n) {
 	if (!h || !n) return FQSK_E_INVAL;
 	CK(cudaSetDevice(h->P.device));
@@ -1405,6 +1558,7 @@ int fqsk_dump(fqsk_handle *h, int table, uint64_t *keys, uint64_t *vals, uint64_
 		if (got != cnt) return fail(h, FQSK_E_CUDA, "p-mer dump found %llu fields, no_filled says %llu", got, (unsigned long long) cnt);
 		return dump_sorted(h, cnt, keys, vals);
 	}
+	if (table == FQSK_TABLE_PAIR) return dump_pairs(h, keys, vals, cap, n);
 	return fail(h, FQSK_E_UNSUPPORTED, "table %d cannot be dumped", table);
 }
 

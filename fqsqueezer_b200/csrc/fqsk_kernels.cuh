@@ -90,20 +90,37 @@ struct SegDev {
 	const uint32_t *base_b, *base_s;                  // push-index base of every read in the delta's numbering
 	DeltaDev delta_b, delta_s;
 	uint32_t *sorted_flag; unsigned long long *sorted_dif;
+	// paired-end: the "reads" of the segment are work ITEMS (mate 1, mate 2 or its forward part, its reversed part), each with its
+	// own first coded position, position bias and flags; all null for single-end segments
+	const uint32_t *first_a, *bias_a, *dup_prev; const uint8_t *iflags;
 };
+enum : uint8_t {
+	IF_SKIP = 1,          // empty slot (a mate 2 coded in one piece has no reversed part)
+	IF_NO_DUPCHECK = 2,   // only first-of-pair reads are compared with read_prev (dna.cpp:1523)
+	IF_SEEDED = 4,        // registers seeded from a minimizer (dna.cpp:1579-1594, 1616-1631): no cor_pos from Ns in the preload
+	IF_NO_LETTERS = 8,    // right part of a split mate 2: update_s_letters runs once, after the left part (dna.cpp:1635)
+	IF_LETTERS_PREV = 16, // left part of a split mate 2: its own symbols plus those of the previous item beyond the shared b-mer
+	IF_REVCOMP = 32,      // text = reverse complement of the source range (dna.cpp:1598-1602)
+};
+__device__ __forceinline__ uint32_t item_first(const SegDev &S, uint32_t dflt, uint32_t r) { return S.first_a ? S.first_a[r] : dflt; }
+__device__ __forceinline__ uint32_t item_flags(const SegDev &S, uint32_t r) { return S.iflags ? S.iflags[r] : 0u; }
 
 __device__ __forceinline__ uint32_t dna_code(uint8_t ch) {  // dna.cpp:18-23
 	return ch == 'A' ? 0u : ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : 4u;
 }
 
-__global__ void __launch_bounds__(128) k_prep(SegDev S, uint32_t first_len_bytes) {   // one warp per read
+__global__ void __launch_bounds__(128) k_prep(SegDev S, uint32_t first_len_bytes, uint32_t b) {   // one warp per read
 	uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (r >= S.n_reads) return;
 	const uint8_t *p = S.dna + S.off[r];
 	uint32_t n = S.len[r];
+	const uint32_t ifl = item_flags(S, r);
+	first_len_bytes = item_first(S, first_len_bytes, r);
 	const uint8_t *q; uint32_t qn;
-	if (r == 0) { q = S.prev_read; qn = S.carry->prev_len; } else { q = S.dna + S.off[r - 1]; qn = S.len[r - 1]; }
-	bool same = qn == n;
+	uint32_t pr = S.dup_prev ? S.dup_prev[r] : (r ? r - 1 : 0xFFFFFFFFu);     // the read this one is compared with (read_prev)
+	if (pr == 0xFFFFFFFFu) { q = S.prev_read; qn = S.carry->prev_len; } else { q = S.dna + S.off[pr]; qn = S.len[pr]; }
+	bool same = qn == n && !(ifl & IF_NO_DUPCHECK);
+	if (ifl & IF_SKIP) { same = true; n = 0; }
 	uint32_t cnt[4] = {0, 0, 0, 0};
 	for (uint32_t i = lane; i < n; i += 32) {
 		uint8_t ch = p[i];
@@ -112,20 +129,25 @@ __global__ void __launch_bounds__(128) k_prep(SegDev S, uint32_t first_len_bytes
 		if (c < 4) { ++cnt[c]; ++cnt[3 - c]; }
 	}
 	same = __all_sync(0xffffffffu, same);
+	if (ifl & IF_LETTERS_PREV) {      // symbol + complement are counted (dna.cpp:2047-2057), so the reversed text counts like the original
+		const uint8_t *pp = S.dna + S.off[r - 1];
+		const uint32_t pn = S.len[r - 1];
+		for (uint32_t i = b + lane; i < pn; i += 32) { uint32_t c = dna_code(pp[i]); if (c < 4) { ++cnt[c]; ++cnt[3 - c]; } }
+	}
 	for (int k = 0; k < 4; ++k) for (int o = 16; o; o >>= 1) cnt[k] += __shfl_xor_sync(0xffffffffu, cnt[k], o);
 	if (lane == 0) {
 		S.dup[r] = same;
-		U64x4 L; for (int k = 0; k < 4; ++k) L.v[k] = same ? 0 : cnt[k];
+		U64x4 L; for (int k = 0; k < 4; ++k) L.v[k] = (same || (ifl & IF_NO_LETTERS)) ? 0 : cnt[k];
 		S.letters[r] = L;
 		S.n_coded[r] = (!same && n > first_len_bytes) ? n - first_len_bytes : 0;
 	}
 }
 
 // read_prev (dna.cpp:1550-1551) and, in sorted order, pmer_can_prev (dna.cpp:655) follow the last read of the segment
-__global__ void __launch_bounds__(256) k_save_carry(SegDev S, uint8_t *prev_read, Carry *carry, uint32_t sorted, uint32_t p) {
+__global__ void __launch_bounds__(256) k_save_carry(SegDev S, uint32_t last, uint8_t *prev_read, Carry *carry, uint32_t sorted, uint32_t p) {
 	if (S.n_reads == 0) return;
-	const uint8_t *q = S.dna + S.off[S.n_reads - 1];
-	const uint32_t n = S.len[S.n_reads - 1];
+	const uint8_t *q = S.dna + S.off[last];      // paired-end: only first-of-pair reads replace read_prev (dna.cpp:1550-1551)
+	const uint32_t n = S.len[last];
 	for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) prev_read[i] = q[i];
 	if (threadIdx.x == 0) {
 		carry->prev_len = n;

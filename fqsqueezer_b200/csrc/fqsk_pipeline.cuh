@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(256) k_lookup(EngineDev E, SegDev S, PipeDev P
 	uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
 	if (g >= *P.n_rec_dev) return;
 	uint32_t r = find_read(S.rec_off, S.n_reads, g);
-	uint32_t i = P.start + (g - (uint32_t) S.rec_off[r]);
+	uint32_t i = item_first(S, P.start, r) + (g - (uint32_t) S.rec_off[r]);
 	const uint8_t *p = S.dna + S.off[r];
 	const uint32_t n = i + 1;
 	const uint32_t cb = n < E.b ? n : E.b, cs = n < E.s ? n : E.s, cp = n < E.p ? n : E.p;
@@ -218,8 +218,9 @@ __global__ void __launch_bounds__(128) k_partial(EngineDev E, SegDev S, PipeDev 
 	if (lane == 0) scp->valid = 0;
 	if (S.dup[r]) return;
 	uint32_t n = P.pfirst_n + slot, i = n - 1;
-	if (i < P.start || i >= S.len[r]) return;
-	uint32_t g = (uint32_t) S.rec_off[r] + (i - P.start);
+	const uint32_t first_r = item_first(S, P.start, r);
+	if (i < first_r || i >= S.len[r]) return;
+	uint32_t g = (uint32_t) S.rec_off[r] + (i - first_r);
 	uint8_t fl = P.pflags[g];
 	if (!(fl & (PF_PARTIAL_B | PF_PARTIAL_S))) return;
 	const uint8_t *p = S.dna + S.off[r];
@@ -491,14 +492,16 @@ __global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P, 
 	int *unsupported = E.flags + 1;
 	DrawCursor nodraw; nodraw.ring = nullptr; nodraw.mask = 0; nodraw.pos0 = 0; nodraw.avail = 0; nodraw.base = 0; nodraw.used = 0; nodraw.overflow = E.flags + 5;
 
-	const uint32_t start = E.sorted ? E.p : E.prefix_len;
+	const uint32_t start = item_first(S, E.sorted ? E.p : E.prefix_len, r);
+	const uint32_t bias = S.bias_a ? S.bias_a[r] : 0;      // record positions and cor_pos are in the frame of the whole mate (dna.cpp:1596)
+	const bool seeded = (item_flags(S, r) & IF_SEEDED) != 0;
 	uint32_t cor_pos = 0;
 	// prefix: symbols enter the registers with N -> A (direct, cor_pos = position of the last N, dna.cpp:532-536) or N -> T (sorted, 560-565)
 	{
 		uint32_t npos = 0;
 		for (uint32_t j = lane; j < start; j += 32) if (dna_code(p[j]) == 4) npos = j + 1;
 		for (int o = 16; o; o >>= 1) { uint32_t y = __shfl_xor_sync(0xffffffffu, npos, o); npos = npos > y ? npos : y; }
-		if (!E.sorted && npos) cor_pos = npos - 1;
+		if (!E.sorted && npos && !seeded) cor_pos = npos - 1;
 	}
 	if (E.sorted) {
 		if (lane == 0) {
@@ -593,7 +596,7 @@ __global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P, 
 					if ((lev == FQSK_LEVEL_SMER || lev == FQSK_LEVEL_BMER || lev == FQSK_LEVEL_MIXED) && c[sym] >= 3) p_insert = false;
 				}
 				if (cs == E.s) { push_s0 = true; key_s0 = kr_norm(sc, E.s); }
-				if (cp == E.p && i - lane_cor >= E.p - 1) {
+				if (cp == E.p && (i + bias) - lane_cor >= E.p - 1) {
 					if (p_insert) { push_p0 = true; key_p0 = pc.dir >> (64 - 2 * E.p); key_p1 = pc.rc >> (64 - 2 * E.p); }
 					else hid = 2;
 				}
@@ -604,7 +607,7 @@ __global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P, 
 					for (uint32_t q = 1; q < 4; ++q) if (c[q] > c[best] || (c[q] == c[best] && sl[q] > sl[best])) best = q;
 					bool ok = true;
 					if (sym != 4) ok = best != sym && c[sym] == 0 && c[best] > 3;
-					if (ok) { kr_set_last(bc, cb, best); ev_patch = true; patch_pos = i; patch_sym = best; new_cor = i; repaired = true; }
+					if (ok) { kr_set_last(bc, cb, best); ev_patch = true; patch_pos = i; patch_sym = best; new_cor = i + bias; repaired = true; }
 				} else if ((lev == FQSK_LEVEL_NONE || lev == FQSK_LEVEL_PMER) && E.gate_missing) {
 					int best_c = 4, best_count = 0, best_j = 0;
 					for (int j = 1; j < 6; ++j) {
@@ -627,7 +630,7 @@ __global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P, 
 					if (best_j) {
 						kr_set(bc, cb, best_c, cb - 1 - best_j);
 						ev_patch = true; patch_pos = i - (uint32_t) best_j; patch_sym = (uint32_t) best_c;
-						uint32_t np2 = i - (uint32_t) best_j;
+						uint32_t np2 = i + bias - (uint32_t) best_j;
 						new_cor = lane_cor > np2 ? lane_cor : np2;
 						repaired = true;
 					}
@@ -651,7 +654,7 @@ __global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P, 
 			window_local |= lane_wl;
 			const uint32_t g = g0 + (i - start);
 			fqsk_base_rec o;
-			o.pos = i; o.counts[0] = c[0]; o.counts[1] = c[1]; o.counts[2] = c[2]; o.counts[3] = c[3];
+			o.pos = i + bias; o.counts[0] = c[0]; o.counts[1] = c[1]; o.counts[2] = c[2]; o.counts[3] = c[3];
 			o.cor_pos = lane_cor; o.level = (uint8_t) lev; o.rough = 0; o.pad = 0;
 			P.recs[g] = o;
 			P.rkind[g] = rk;

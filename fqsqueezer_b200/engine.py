@@ -44,7 +44,7 @@ class _Stats(C.Structure):
 
 
 EXPORTS = ["fqsk_create", "fqsk_destroy", "fqsk_last_error", "fqsk_block_start", "fqsk_segment", "fqsk_segment_device",
-           "fqsk_device_recs", "fqsk_sorted_prefix", "fqsk_sync", "fqsk_dump", "fqsk_stats_get", "fqsk_profile", "fqsk_ht_insert", "fqsk_ht_find",
+           "fqsk_device_recs", "fqsk_sorted_prefix", "fqsk_pair_info", "fqsk_sync", "fqsk_dump", "fqsk_stats_get", "fqsk_profile", "fqsk_ht_insert", "fqsk_ht_find",
            "fqsk_ht_count", "fqsk_timer_begin", "fqsk_timer_end", "fqsk_siv_increment", "fqsk_siv_test", "fqsk_siv_counts", "fqsk_siv_test_shorter", "fqsk_mt_stream", "fqsk_host_alloc", "fqsk_host_free",
            "fqsk_shard_export", "fqsk_shard_attach", "fqsk_sync_route", "fqsk_sync_apply", "fqsk_sync_finish"]
 
@@ -70,6 +70,7 @@ def load_library():
     lib.fqsk_segment_device.argtypes = [vp, vp, C.c_uint64, vp, vp, C.c_uint32, u64p]
     lib.fqsk_device_recs.argtypes = [vp, C.POINTER(vp), u64p]
     lib.fqsk_sorted_prefix.argtypes = [vp, vp, vp, C.c_uint32]
+    lib.fqsk_pair_info.argtypes = [vp, vp, C.c_uint32]
     lib.fqsk_sync.argtypes = [vp]
     lib.fqsk_dump.argtypes = [vp, C.c_int, vp, vp, C.c_uint64, u64p]
     lib.fqsk_stats_get.argtypes = [vp, C.POINTER(_Stats)]
@@ -205,6 +206,12 @@ class KmerEngine:
         dif = np.zeros(max(n_reads, 1), np.uint64)
         self._ck(self.lib.fqsk_sorted_prefix(self.h, _ptr(flag), _ptr(dif), n_reads))
         return flag[:n_reads], dif[:n_reads]
+
+    def pair_info(self, n_pairs):
+        """(found, minim2_id, minim2_pos) per pair of the last segment -- what CompressPE codes, dna.cpp:1790-1880."""
+        out = np.zeros((max(n_pairs, 1), 3), np.uint32)
+        self._ck(self.lib.fqsk_pair_info(self.h, _ptr(out), n_pairs))
+        return out[:n_pairs]
 
     def sync(self):
         self._ck(self.lib.fqsk_sync(self.h))

@@ -128,6 +128,15 @@ int fqsk_device_recs(fqsk_handle *h, const fqsk_base_rec **d_recs, uint64_t *n_r
  * or 4 when the p-mer equals the previous read's, dif = number of p-mers with that flag between the previous and this p-mer. */
 int fqsk_sorted_prefix(fqsk_handle *h, uint32_t *flag, uint64_t *dif, uint32_t n_reads);
 
+/* Paired-end (FQSK_MODE_PE_ORIGINAL): fqsk_segment / fqsk_segment_device take the pairs interleaved (mate 1, mate 2, ...), an even
+ * number of reads; the records of a pair come in the order CompressPE codes them (dna.cpp:1790-1880): mate 1, then mate 2 --
+ * either whole, or from the shared minimizer to the end followed by the reverse complement of the part left of it
+ * (CompressDirectWithMinim, dna.cpp:1559-1638; `pos` of a record is the index inside the text compress_suffix was given).
+ * fqsk_pair_info returns what CompressPE codes per pair of the last segment, 3 words each: [0] a candidate list exists
+ * (find_minim_cand, dna.cpp:1757-1787), [1] minim2_id (0..14, 15 = no usable candidate; 0 when [0] == 0), [2] minim2_pos (0 unless
+ * [1] < 15).  The 14 pushes of append_pe_mers3 (dna.cpp:1058-1136) go to the pair table at the next fqsk_sync. */
+int fqsk_pair_info(fqsk_handle *h, uint32_t *info, uint32_t n_pairs);
+
 /* Replaces CDNACompressor::InsertKmersToHT + ClearKmersToHT (dna.cpp:2393-2488) and the three barriers around them
  * (application.cpp:645-654): p-mers, then s-mers, then b-mers, in push order, with the reference's PRNG draw order. */
 int fqsk_sync(fqsk_handle *h);
@@ -159,7 +168,8 @@ int fqsk_sync_apply(fqsk_handle *h, uint64_t *fresh, uint64_t *updates);
  * ClearKmersToHT.  The call sequence must be completed on all ranks before any of them starts its next segment. */
 int fqsk_sync_finish(fqsk_handle *h, uint64_t fresh_all_ranks, uint64_t updates_all_ranks);
 
-/* Sorted (key, value) contents: FQSK_TABLE_SIV -> (p-mer index, 2-bit field); SMER/BMER -> (normalised k-mer, counter).
+/* Sorted (key, value) contents: FQSK_TABLE_SIV -> (p-mer index, 2-bit field); SMER/BMER -> (normalised k-mer, counter);
+ * PAIR -> (key minimizer, value minimizer | count << 2b), the items of CHT_pair_kmers (ht_kmer.h:566-571).
  * Call with keys == NULL to get the count in *n.  Replaces nothing in the reference; parity check 1. */
 int fqsk_dump(fqsk_handle *h, int table, uint64_t *keys, uint64_t *vals, uint64_t cap, uint64_t *n);
 int fqsk_stats_get(fqsk_handle *h, fqsk_stats *out);

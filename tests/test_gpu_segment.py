@@ -113,3 +113,63 @@ def test_engine_matches_reference_golden_sorted_order():
     assert np.array_equal(flags, wflags) and np.array_equal(difs, wdifs)
     H.assert_dump_equal(e, g)
     e.close()
+
+
+def test_engine_matches_reference_golden_paired_end():
+    """-p -om o (rows a10, a17): pair table, window minimizers, candidate ranking, mate 2 coded from a shared minimizer
+    (forward part + reversed left part) -- records, per-pair (found, id, pos) and all four tables vs the tapped reference."""
+    g = H.load_golden("pe_orig_gs1")
+    pref, p, s, b = E.kmer_params(int(g["gs"]))
+    e = E.KmerEngine(p, s, b, pref, mode=E.MODE_PE_ORIGINAL)
+    recs, info = H.run_pe(e, g["fastq"], is_gpu=True)
+    want, winfo = H.golden_pe_expect(g)
+    assert np.array_equal(info, winfo), np.flatnonzero((info != winfo).any(axis=1))[:5]
+    H.assert_recs_equal(recs, want)
+    H.assert_dump_equal(e, g, pairs=True)
+    e.close()
+
+
+def _pe_slab(genome, n_pairs, L, seed, nfrac=0.0, dup_every=0):
+    """Interleaved FASTQ slab of synthetic pairs: mate 2 = reverse complement of the fragment end."""
+    rng = np.random.default_rng(seed)
+    G = len(genome)
+    frag = np.clip(rng.normal(2.6 * L, 0.25 * L, n_pairs).astype(np.int64), L, G - 1)
+    start = rng.integers(0, G - frag)
+    idx = np.arange(L)
+    m1 = genome[start[:, None] + idx[None, :]]
+    m2 = 3 - genome[(start + frag)[:, None] - 1 - idx[None, :]]
+    for m in (m1, m2):
+        err = rng.random(m.shape) < 0.005
+        m[err] = (m[err] + rng.integers(1, 4, int(err.sum()))) & 3
+    codes = np.empty((2 * n_pairs, L), np.int64)
+    codes[0::2] = m1; codes[1::2] = m2
+    if nfrac:
+        codes[rng.random(codes.shape) < nfrac] = 4
+    if dup_every:
+        codes[2 * dup_every::2 * dup_every] = codes[2 * dup_every - 2:-2:2 * dup_every]    # mate 1 equal to the previous mate 1
+    return _fastq_slab(codes)
+
+
+@pytest.mark.parametrize("gs,G,n_pairs,L,seed,nfrac,dup_every", [
+    (1, 6000, 2500, 70, 21, 0.002, 40),       # heavy coverage: long candidate lists, saturating pair counters, duplicates, Ns
+    (100, 40000, 1500, 150, 22, 0.0, 0),      # BASELINE config-3 k-mer lengths
+])
+def test_engine_matches_oracle_paired_end(gs, G, n_pairs, L, seed, nfrac, dup_every):
+    genome = synth.make_genome(G, seed)
+    slab = _pe_slab(genome, n_pairs, L, seed, nfrac, dup_every)
+    pref, p, s, b = E.kmer_params(gs)
+    e = E.KmerEngine(p, s, b, pref, mode=E.MODE_PE_ORIGINAL, bmer_log2_buckets=12, smer_log2_buckets=12)
+    o = O.OracleEngine(p, s, b, pref, mode=2)
+    got, ginfo = H.run_pe(e, slab, is_gpu=True)
+    want, winfo = H.run_pe(o, slab)
+    assert np.array_equal(ginfo, winfo), np.flatnonzero((ginfo != winfo).any(axis=1))[:5]
+    assert (winfo[:, 0] == 1).sum() > n_pairs // 4 and ((winfo[:, 0] == 1) & (winfo[:, 1] < 15)).sum() > n_pairs // 8
+    H.assert_recs_equal(got, want)
+    for which in (0, 1, 2, 3):
+        kg, vg = e.dump(which)
+        ko, vo = o.dump(which)
+        assert np.array_equal(kg, ko) and np.array_equal(vg, vo), which
+    sg, so = e.stats(), o.stats()
+    for key in ("siv_no_filled", "siv_no_updates", "n_smers", "n_bmers", "draws_b", "draws_s", "draws_lb", "draws_ls"):
+        assert sg[key] == so[key], key
+    e.close(); o.close()
