@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -29,8 +30,10 @@ namespace {
 struct DevBuf {
 	void *p = nullptr;
 	size_t cap = 0;
-	cudaError_t ensure(size_t bytes) {
+	cudaError_t ensure(size_t bytes, int line = __builtin_LINE()) {
 		if (bytes <= cap) return cudaSuccess;
+		static const bool trace = getenv("FQSK_TRACE_ALLOC") != nullptr;
+		if (trace) fprintf(stderr, "[fqsk alloc] line %d: %zu -> %zu bytes\n", line, cap, bytes);
 		if (p) cudaFree(p);
 		p = nullptr; cap = 0;
 		size_t want = bytes + bytes / 2 + 256;
@@ -117,6 +120,7 @@ struct fqsk_handle {
 	DevBuf route_keys, route_keys2, route_sorted, route_hist;
 	uint64_t sync_fresh = 0, sync_updates = 0; bool routed = false, applied = false;
 	uint64_t siv_local_filled = 0;           // non-zero fields of THIS rank's p-mer shard (S.siv_no_filled is the global statistic)
+	DevBuf scan_vals; uint32_t scan_epoch2 = 0;
 	DevBuf scan_part; uint32_t scan_epoch = 0;   // published CTA sums of k_scan_flags, tagged with the launch epoch
 	bool hot = false;                        // the current segment is being redone with the ordered thread-local evaluator
 	bool hot_seen[2] = {false, false};       // [0] s, [1] b: the last sync saw a k-mer pushed more than thr + 1 times in its row
@@ -169,6 +173,22 @@ int fail(fqsk_handle *h, int code, const char *fmt, ...) {
 	} while (0)
 #define CKR(expr) do { int r_ = (expr); if (r_ != FQSK_OK) return r_; } while (0)
 #define LAUNCHED(h) (++(h)->S.kernel_launches)
+
+
+// Every kernel of the engine starts with pdl_enter() (griddepcontrol.launch_dependents + griddepcontrol.wait) and is launched with
+// programmatic stream serialization: the next kernel of the stream is scheduled while the last wave of this one is still running
+// and waits, before touching memory, until this one has completed and flushed.  Semantics are those of plain stream order; what is
+// saved is the launch latency between the ~25 small dependent kernels of a sync segment.
+template <typename... KArgs, typename... Args>
+inline cudaError_t pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args &&...args) {
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+	cudaLaunchAttribute at[1];
+	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	at[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = at; cfg.numAttrs = 1;
+	return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 inline uint32_t nblk(uint64_t n, uint32_t t) { return (uint32_t) ((n + t - 1) / t); }
 
@@ -286,11 +306,20 @@ int stream_prefetch(fqsk_handle *h, Stream &s, uint64_t ahead) {
 inline const uint32_t *stream_ptr(const Stream &s) { return s.buf; }
 inline uint64_t stream_avail(const Stream &s) { return (s.safe > s.consumed ? s.safe : s.consumed) - s.consumed; }
 
+// published chunk totals of the multi-CTA scans (k_scan_reads / k_scan_u32x4 / k_scan_draws), tagged with a per-launch epoch
+int scan_chain(fqsk_handle *h, ScanChain &C) {
+	if (!h->scan_vals.p) {
+		CK(h->scan_vals.ensure((size_t) SCAN_CHAIN_MAX * 8 * 8 + (size_t) SCAN_CHAIN_MAX * 4));
+		CK(cudaMemsetAsync(h->scan_vals.p, 0, h->scan_vals.cap, h->st));
+	}
+	C.vals = h->scan_vals.as<unsigned long long>(); C.flags = (uint32_t *) (C.vals + (size_t) SCAN_CHAIN_MAX * 8); C.epoch = ++h->scan_epoch2;
+	return FQSK_OK;
+}
 int ensure_iota(fqsk_handle *h, uint32_t n) {
 	if (n <= h->iota_n) return FQSK_OK;
 	uint32_t want = n + n / 2 + 1024;
 	CK(h->iota.ensure((size_t) want * 4));
-	k_iota<<<nblk(want, 256), 256, 0, h->st>>>(h->iota.as<uint32_t>(), want);
+	CK(pdl(k_iota, nblk(want, 256), 256, h->st, h->iota.as<uint32_t>(), want));
 	LAUNCHED(h);
 	h->iota_n = want;
 	return FQSK_OK;
@@ -305,10 +334,16 @@ int scan_excl(fqsk_handle *h, const InT *in, OutT *out, uint32_t n, OutT init) {
 	return FQSK_OK;
 }
 
+// rows of a sync are at most this long when the caller announced its largest segment: buffers sized once, not as segments grow
+inline size_t row_reserve(const fqsk_handle *h, size_t n) {
+	const size_t r = h->P.reserve_bytes ? 2 * (size_t) h->P.reserve_bytes + 2 * (size_t) h->P.reserve_reads + 64 : 0;
+	return n > r ? n : r;
+}
 int sort_pairs_u64_u32(fqsk_handle *h, const unsigned long long *kin, unsigned long long *kout, const uint32_t *vin, uint32_t *vout, uint32_t n, int b0, int b1) {
 	size_t bytes = 0;
-	CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int) n, b0, b1, h->st));
+	CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int) row_reserve(h, n), b0, b1, h->st));
 	CK(h->cub_tmp.ensure(bytes));
+	CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int) n, b0, b1, h->st));
 	CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, kin, kout, vin, vout, (int) n, b0, b1, h->st));
 	return FQSK_OK;
 }
@@ -340,7 +375,7 @@ int table_dump_device(fqsk_handle *h, Table &t, uint64_t *n_out) {   // into h->
 	CK(h->dump_k.ensure((n + 1) * 8));
 	CK(h->dump_v.ensure((n + 1) * 8));
 	CK(cudaMemsetAsync(h->d_counters + 5, 0, 8, h->st));
-	k_dump_ht<<<nblk(total, 256), 256, 0, h->st>>>(t.d, t.inv, h->dump_k.as<unsigned long long>(), h->dump_v.as<unsigned long long>(), n, h->d_counters + 5);
+	CK(pdl(k_dump_ht, nblk(total, 256), 256, h->st, t.d, t.inv, h->dump_k.as<unsigned long long>(), h->dump_v.as<unsigned long long>(), n, h->d_counters + 5));
 	LAUNCHED(h);
 	unsigned long long got = 0;
 	CK(cudaMemcpyAsync(&got, h->d_counters + 5, 8, cudaMemcpyDeviceToHost, h->st));
@@ -363,7 +398,7 @@ int table_grow_if_needed(fqsk_handle *h, Table &t) {
 		CK(cudaFree(t.d.main)); CK(cudaFree(t.d.stash));
 		uint32_t k = t.d.k, cb = t.d.cbits, B = t.d.B + 1;
 		CKR(table_alloc(h, t, k, cb, B, counters));
-		if (n) { k_reinsert<<<nblk(n, 256), 256, 0, h->st>>>(t.d, h->dump_k.as<unsigned long long>(), h->dump_v.as<unsigned long long>(), n); LAUNCHED(h); }
+		if (n) { CK(pdl(k_reinsert, nblk(n, 256), 256, h->st, t.d, h->dump_k.as<unsigned long long>(), h->dump_v.as<unsigned long long>(), n)); LAUNCHED(h); }
 		CK(cudaMemcpyAsync(items, t.d.n_items, 16, cudaMemcpyDeviceToHost, h->st));
 		CK(cudaStreamSynchronize(h->st));
 		if (items[0] + items[1] != n) return fail(h, FQSK_E_CUDA, "table growth lost items (%llu -> %llu)", (unsigned long long) n, items[0] + items[1]);
@@ -378,8 +413,11 @@ int table_grow_if_needed(fqsk_handle *h, Table &t) {
 int apply_sorted(fqsk_handle *h, Table &t, Stream &rng, const unsigned long long *skeys, const uint32_t *sidx, uint32_t n) {
 	if (!n) return FQSK_OK;
 	h->look_fresh = false;
-	CK(h->slot_of.ensure((size_t) n * 8));
-	CK(h->flag8.ensure((size_t) n + 4)); CK(h->draw_off.ensure(((size_t) n + 1) * 4)); CK(h->final_cnt.ensure((size_t) n * 4));
+	{
+		const size_t nr = row_reserve(h, n);
+		CK(h->slot_of.ensure(nr * 8));
+		CK(h->flag8.ensure(nr + 4)); CK(h->draw_off.ensure((nr + 1) * 4)); CK(h->final_cnt.ensure(nr * 4));
+	}
 	const uint32_t g = nblk(n, 256);
 	uint8_t *flag = h->flag8.as<uint8_t>();
 	uint32_t *doff = h->draw_off.as<uint32_t>(), *c0_of = h->final_cnt.as<uint32_t>();
@@ -388,7 +426,7 @@ int apply_sorted(fqsk_handle *h, Table &t, Stream &rng, const unsigned long long
 		Phase ph(h, FQSK_PH_SYNC_LOCATE);
 		CK(cudaMemsetAsync(h->d_flags, 0, 8 * sizeof(int), h->st));
 		CK(cudaMemsetAsync(flag + n, 0, 4, h->st));
-		k_locate_heads<<<g, 256, 0, h->st>>>(t.d, t.ci, skeys, sidx, n, slot_of, c0_of, flag, h->d_flags); LAUNCHED(h);
+		CK(pdl(k_locate_heads, g, 256, h->st, t.d, t.ci, skeys, sidx, n, slot_of, c0_of, flag, h->d_flags)); LAUNCHED(h);
 	}
 	Phase ph(h, FQSK_PH_SYNC_APPLY);
 	uint32_t total_draws = 0;
@@ -398,7 +436,7 @@ int apply_sorted(fqsk_handle *h, Table &t, Stream &rng, const unsigned long long
 		CKR((scan_excl<uint8_t, uint32_t>(h, flag, doff, n + 1, 0u)));
 		CKR(stream_ensure(h, rng, 0));
 		CK(cudaMemsetAsync(h->d_flags, 0, 3 * sizeof(int), h->st));      // [0] draw window short, [2] corrected a flag; [3] unsafe seen / [6] hot seen stay
-		if (!safe_done) { k_apply_keys<<<g, 256, 0, h->st>>>(t.d, t.ci, skeys, sidx, n, slot_of, c0_of, flag, doff, rng.buf, rng.cap - 1, rng.consumed, stream_avail(rng), 0, 0, h->d_flags); LAUNCHED(h); }
+		if (!safe_done) { CK(pdl(k_apply_keys, g, 256, h->st, t.d, t.ci, skeys, sidx, n, slot_of, c0_of, flag, doff, rng.buf, rng.cap - 1, rng.consumed, stream_avail(rng), 0, 0, h->d_flags)); LAUNCHED(h); }
 		uint32_t *hs = (uint32_t *) h->h_small;
 		CK(cudaMemcpyAsync(hs, h->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
 		CK(cudaMemcpyAsync(hs + 8, doff + n, 4, cudaMemcpyDeviceToHost, h->st));
@@ -415,7 +453,7 @@ int apply_sorted(fqsk_handle *h, Table &t, Stream &rng, const unsigned long long
 		for (int vit = 0;; ++vit) {
 			if (vit > 64) return fail(h, FQSK_E_NO_CONVERGE, "sync insert: draw flags did not settle");
 			CK(cudaMemsetAsync(h->d_flags, 0, 3 * sizeof(int), h->st));
-			k_apply_keys<<<g, 256, 0, h->st>>>(t.d, t.ci, skeys, sidx, n, slot_of, c0_of, flag, doff, rng.buf, rng.cap - 1, rng.consumed, stream_avail(rng), 1, 0, h->d_flags); LAUNCHED(h);
+			CK(pdl(k_apply_keys, g, 256, h->st, t.d, t.ci, skeys, sidx, n, slot_of, c0_of, flag, doff, rng.buf, rng.cap - 1, rng.consumed, stream_avail(rng), 1, 0, h->d_flags)); LAUNCHED(h);
 			CKR(read_flags(h, fl, 8));
 			if (fl[0]) { CKR(stream_ensure(h, rng, 2 * stream_avail(rng) + (1u << 16))); continue; }
 			if (!fl[2]) break;
@@ -426,8 +464,8 @@ int apply_sorted(fqsk_handle *h, Table &t, Stream &rng, const unsigned long long
 		CK(cudaStreamSynchronize(h->st));
 		total_draws = hs[8];
 		CKR(stream_ensure(h, rng, (uint64_t) total_draws));
-		if (moved) { k_apply_keys<<<g, 256, 0, h->st>>>(t.d, t.ci, skeys, sidx, n, slot_of, c0_of, flag, doff, rng.buf, rng.cap - 1, rng.consumed, stream_avail(rng), 0, 0, h->d_flags); LAUNCHED(h); }
-		k_apply_keys<<<g, 256, 0, h->st>>>(t.d, t.ci, skeys, sidx, n, slot_of, c0_of, flag, doff, rng.buf, rng.cap - 1, rng.consumed, stream_avail(rng), 1, 1, h->d_flags); LAUNCHED(h);
+		if (moved) { CK(pdl(k_apply_keys, g, 256, h->st, t.d, t.ci, skeys, sidx, n, slot_of, c0_of, flag, doff, rng.buf, rng.cap - 1, rng.consumed, stream_avail(rng), 0, 0, h->d_flags)); LAUNCHED(h); }
+		CK(pdl(k_apply_keys, g, 256, h->st, t.d, t.ci, skeys, sidx, n, slot_of, c0_of, flag, doff, rng.buf, rng.cap - 1, rng.consumed, stream_avail(rng), 1, 1, h->d_flags)); LAUNCHED(h);
 		CKR(read_flags(h, fl, 8));
 		if (fl[0] || fl[2]) return fail(h, FQSK_E_CUDA, "internal error: unsafe-group commit pass was not clean");
 		break;
@@ -440,8 +478,8 @@ int apply_sorted(fqsk_handle *h, Table &t, Stream &rng, const unsigned long long
 int sort_row(fqsk_handle *h, const unsigned long long *row, uint32_t n, uint32_t k, DevBuf &keys_out, DevBuf &idx_out) {
 	if (!n) return FQSK_OK;
 	Phase ph(h, FQSK_PH_SORT);
-	CK(keys_out.ensure((size_t) n * 8)); CK(idx_out.ensure((size_t) n * 4));
-	CKR(ensure_iota(h, n));
+	CK(keys_out.ensure(row_reserve(h, n) * 8)); CK(idx_out.ensure(row_reserve(h, n) * 4));
+	CKR(ensure_iota(h, (uint32_t) row_reserve(h, n)));
 	CKR(sort_pairs_u64_u32(h, row, keys_out.as<unsigned long long>(), h->iota.as<uint32_t>(), idx_out.as<uint32_t>(), n, 64 - 2 * (int) k, 64));
 	return FQSK_OK;
 }
@@ -458,13 +496,13 @@ int apply_inserts(fqsk_handle *h, Table &t, Stream &rng, const unsigned long lon
 		Phase ph(h, FQSK_PH_SYNC_APPLY);
 		CK(cudaMemsetAsync(h->d_flags, 0, 8 * sizeof(int), h->st));
 		CK(h->y_flag.ensure((size_t) n + 4));
-		k_insert_fast<<<nblk(n, 256), 256, 0, h->st>>>(t.d, t.ci, d_kmers, n, h->y_flag.as<uint8_t>(), h->d_flags + 2); LAUNCHED(h);
+		CK(pdl(k_insert_fast, nblk(n, 256), 256, h->st, t.d, t.ci, d_kmers, n, h->y_flag.as<uint8_t>(), h->d_flags + 2, (const SyncIn *) nullptr)); LAUNCHED(h);
 		int fl[8];
 		CKR(read_flags(h, fl, 8));
 		if (!fl[2]) return FQSK_OK;
 		// some counter left the deterministic range: undo (claimed slots stay as zero-count items == the reference's fresh slot) and
 		// take the ordered path from now on for this table (once counters are above thr they stay there)
-		k_insert_undo<<<nblk(n, 256), 256, 0, h->st>>>(t.d, d_kmers, n, h->y_flag.as<uint8_t>()); LAUNCHED(h);
+		CK(pdl(k_insert_undo, nblk(n, 256), 256, h->st, t.d, d_kmers, n, h->y_flag.as<uint8_t>())); LAUNCHED(h);
 		// this row goes through the ordered path; the next row tries the fast path again
 	}
 	CKR(sort_row(h, d_kmers, n, t.d.k, h->sort_k, h->sort_v));
@@ -476,7 +514,7 @@ int apply_inserts(fqsk_handle *h, Table &t, Stream &rng, const unsigned long lon
 // sequence serves a sync that is enqueued right behind its segment (no host look in between) and the plain call below.
 int indexed_setup(fqsk_handle *h, const DeltaDev &D, uint32_t n_bound, SyncIn *in, bool is_b, SyncDev &Y) {
 	const size_t slots = std::max<size_t>((size_t) D.mask + 1, (size_t) 1 << 21);    // generous floors: no reallocation while segments grow
-	const size_t nb = std::max<size_t>(n_bound, SYNC_INDEXED_MAX) + 64;
+	const size_t nb = std::max<size_t>(n_bound, 2 * SPEC_MAX_BYTES + 2) + 64;
 	CK(h->y_tslot.ensure(slots * 8)); CK(h->y_c0.ensure(slots * 4)); CK(h->y_m.ensure(slots * 4)); CK(h->y_draw.ensure(slots * 4));
 	CK(h->y_j.ensure(slots * 4)); CK(h->y_final.ensure(slots * 4)); CK(h->y_flag_at.ensure(slots));
 	CK(h->y_own.ensure(nb * 4)); CK(h->y_lead.ensure(nb * 4)); CK(h->y_rank.ensure(nb * 4));
@@ -493,19 +531,19 @@ int indexed_setup(fqsk_handle *h, const DeltaDev &D, uint32_t n_bound, SyncIn *i
 	return FQSK_OK;
 }
 inline unsigned long long stream_safe_abs(const Stream &s) { return s.safe > s.consumed ? s.safe : s.consumed; }
-int indexed_head(fqsk_handle *h, Table &t, const SyncDev &Y, const unsigned long long *row, const uint32_t *rt, uint32_t g) {
+int indexed_head(fqsk_handle *h, Table &t, const SyncDev &Y, const unsigned long long *row, const uint32_t *rt, uint32_t g, bool reset = true) {
 	Phase ph(h, FQSK_PH_SYNC_LOCATE);
-	CK(cudaMemsetAsync(h->d_sflags, 0, 8 * sizeof(int), h->st));
-	k_sync_rank<<<g, 256, 0, h->st>>>(t.d, Y, row, rt); LAUNCHED(h);
-	k_sync_flags<<<g, 256, 0, h->st>>>(t.d, t.ci, Y); LAUNCHED(h);
+	if (reset) CK(cudaMemsetAsync(h->d_sflags, 0, 8 * sizeof(int), h->st));
+	CK(pdl(k_sync_rank, g, 256, h->st, t.d, Y, row, rt)); LAUNCHED(h);
+	CK(pdl(k_sync_flags, g, 256, h->st, t.d, t.ci, Y)); LAUNCHED(h);
 	return FQSK_OK;
 }
-int indexed_tail(fqsk_handle *h, Table &t, Stream &rng, const SyncDev &Y, const unsigned long long *row, uint32_t g, uint32_t n_bound) {
-	k_scan_flags<<<nblk(n_bound, SCANF_TILE), 256, 0, h->st>>>(Y.in, Y.n_dev, Y.flag, h->y_doff.as<uint32_t>(), Y.total_draws, h->scan_part.as<unsigned long long>(), ++h->scan_epoch); LAUNCHED(h);
-	k_sync_scatter<<<g, 256, 0, h->st>>>(t.ci, Y); LAUNCHED(h);
-	CK(cudaMemsetAsync(h->d_sflags, 0, 4 * sizeof(int), h->st));      // [0] draw window short, [2] corrected a flag; [6] hot seen / [7] group too large stay
-	k_sync_apply<<<g, 256, 0, h->st>>>(t.d, t.ci, Y, row, rng.buf, rng.cap - 1, stream_safe_abs(rng)); LAUNCHED(h);
-	k_sync_commit<<<g, 256, 0, h->st>>>(t.d, Y); LAUNCHED(h);
+int indexed_tail(fqsk_handle *h, Table &t, Stream &rng, const SyncDev &Y, const unsigned long long *row, uint32_t g, uint32_t n_bound, bool reset = true) {
+	CK(pdl(k_scan_flags, nblk(n_bound, SCANF_TILE), 256, h->st, Y.in, Y.n_dev, Y.flag, h->y_doff.as<uint32_t>(), Y.total_draws, h->scan_part.as<unsigned long long>(), ++h->scan_epoch)); LAUNCHED(h);
+	CK(pdl(k_sync_scatter, g, 256, h->st, t.ci, Y)); LAUNCHED(h);
+	if (reset) CK(cudaMemsetAsync(h->d_sflags, 0, 4 * sizeof(int), h->st));      // [0] draw window short, [2] corrected a flag; [6] hot seen / [7] group too large stay
+	CK(pdl(k_sync_apply, g, 256, h->st, t.d, t.ci, Y, row, rng.buf, rng.cap - 1, stream_safe_abs(rng))); LAUNCHED(h);
+	CK(pdl(k_sync_commit, g, 256, h->st, t.d, Y)); LAUNCHED(h);
 	return FQSK_OK;
 }
 // one look at the device: the whole status block, the item counters and the fresh p-mer field count
@@ -525,7 +563,7 @@ int apply_indexed(fqsk_handle *h, Table &t, Stream &rng, const DeltaDev &D, cons
 	if (!n) return FQSK_OK;
 	const bool is_b = &t == &h->tb;
 	SyncIn *in = h->d_syncin2;
-	k_set_syncin<<<1, 32, 0, h->st>>>(in, is_b ? n : 0, is_b ? 0 : n, 0, is_b ? rng.consumed : 0, is_b ? 0 : rng.consumed); LAUNCHED(h);
+	CK(pdl(k_set_syncin, 1, 32, h->st, in, is_b ? n : 0, is_b ? 0 : n, 0, is_b ? rng.consumed : 0, is_b ? 0 : rng.consumed)); LAUNCHED(h);
 	SyncDev Y;
 	CKR(indexed_setup(h, D, n, in, is_b, Y));
 	const uint32_t g = nblk(n, 256);
@@ -541,7 +579,7 @@ int apply_indexed(fqsk_handle *h, Table &t, Stream &rng, const DeltaDev &D, cons
 		total_draws = looked_syncin(h, in)->draws_b;
 		if (fl[6]) h->hot_seen[is_b ? 1 : 0] = true;
 		if (fl[7]) {   // a hot k-mer occurs more than SYNC_GROUP_CAP times in this row: sorted path for the whole row
-			k_sync_unclaim<<<g, 256, 0, h->st>>>(t.d, Y); LAUNCHED(h);
+			CK(pdl(k_sync_unclaim, g, 256, h->st, t.d, Y)); LAUNCHED(h);
 			return apply_inserts(h, t, rng, row, n, nullptr);
 		}
 		if (fl[0]) { CKR(stream_ensure(h, rng, (uint64_t) total_draws + (1u << 16))); continue; }
@@ -559,7 +597,7 @@ int apply_row(fqsk_handle *h, Table &t, Stream &rng, const unsigned long long *r
 	while (slots < 2 * n) slots <<= 1;
 	CK(h->idx_k.ensure((size_t) slots * 8)); CK(h->idx_t.ensure((size_t) slots * 4)); CK(h->idx_rt.ensure((size_t) n * 4));
 	CK(cudaMemsetAsync(h->idx_t.p, 0xFF, (size_t) slots * 4, h->st));
-	k_row_index_build<<<nblk(n, 256), 256, 0, h->st>>>(h->idx_k.as<unsigned long long>(), h->idx_t.as<uint32_t>(), slots - 1, t.d.k, 1, row, n, h->idx_rt.as<uint32_t>()); LAUNCHED(h);
+	CK(pdl(k_row_index_build, nblk(n, 256), 256, h->st, h->idx_k.as<unsigned long long>(), h->idx_t.as<uint32_t>(), slots - 1, t.d.k, 1, row, n, h->idx_rt.as<uint32_t>())); LAUNCHED(h);
 	DeltaDev D{h->idx_k.as<unsigned long long>(), h->idx_t.as<uint32_t>(), slots - 1, n, t.d.k, 1, t.ci.thr + 1};
 	return apply_indexed(h, t, rng, D, row, h->idx_rt.as<uint32_t>(), n);
 }
@@ -622,10 +660,11 @@ int seg_setup(fqsk_handle *h) {
 	S.recs = P.recs;
 
 	C.E = make_engine_dev(h);
-	CK(cudaMemsetAsync(h->d_status, 0, 44, h->st));                 // flags[8] | n_miss, n_rscript, pool_used (n_rec_dev stays: k_scan_reads wrote it)
-	CK(cudaMemsetAsync(h->d_u32 + 4, 0, 4 * 4, h->st));
-	{ Phase ph(h, FQSK_PH_LOOKUP); k_lookup<<<nblk(rec_bound, 256), 256, 0, h->st>>>(C.E, S, P); LAUNCHED(h); }
-	{ Phase ph(h, FQSK_PH_PARTIAL); k_partial<<<nblk((uint64_t) n * pslots * 32, 128), 128, 0, h->st>>>(C.E, S, P); LAUNCHED(h); }
+	// one launch clears every status word the segment and a sync enqueued behind it start from: flags[8] | n_miss, n_rscript, pool_used
+	// (n_rec_dev stays: k_scan_reads wrote it) | hot-mode counters | fresh p-mer fields | s fast-path verdict | ordered-insert flags
+	CK(pdl(k_seg_reset, 1, 64, h->st, h->d_status, h->d_counters)); LAUNCHED(h);
+	{ Phase ph(h, FQSK_PH_LOOKUP); CK(pdl(k_lookup, nblk(rec_bound, 256), 256, h->st, C.E, S, P)); LAUNCHED(h); }
+	{ Phase ph(h, FQSK_PH_PARTIAL); CK(pdl(k_partial, nblk((uint64_t) n * pslots * 32, 128), 128, h->st, C.E, S, P)); LAUNCHED(h); }
 	S.delta_b = DeltaDev{nullptr, nullptr, 0, 0, h->P.bmer_len, 1, h->tb.ci.thr + 1, nullptr, nullptr, nullptr};
 	S.delta_s = DeltaDev{nullptr, nullptr, 0, 0, h->P.smer_len, 1, h->ts.ci.thr + 1, nullptr, nullptr, nullptr};
 	h->delta_b_valid = h->delta_s_valid = false;
@@ -637,9 +676,9 @@ int seg_setup(fqsk_handle *h) {
 		size_t rb = 1024, rs = 1024;
 		while (rb < 4 * dna_bytes) rb <<= 1;
 		while (rs < 2 * dna_bytes) rs <<= 1;
-		CK(h->dk_b.ensure(rb * 8)); CK(h->stime_b.ensure(rb * 4)); CK(h->dk_s.ensure(rs * 8)); CK(h->stime_s.ensure(rs * 4));
+		CK(h->dk_b.ensure(rb * 8)); CK(h->stime_b.ensure((rb + rs) * 4)); CK(h->dk_s.ensure(rs * 8));     // both time arrays in one allocation: one fill
 	}
-	{ Phase ph(h, FQSK_PH_WALK); k_walk<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(C.E, S, P, 0); LAUNCHED(h); ++h->S.n_replays; }
+	{ Phase ph(h, FQSK_PH_WALK); CK(pdl(k_walk, nblk((uint64_t) n * 32, 128), 128, h->st, C.E, S, P, 0)); LAUNCHED(h); ++h->S.n_replays; }
 	C.it = 0; C.pass = 0; C.redo_walk = true; C.redo_tail = true;
 	return FQSK_OK;
 }
@@ -649,15 +688,19 @@ int seg_build_delta(fqsk_handle *h) {
 	SegDev &S = C.S; PipeDev &P = C.P;
 	const uint32_t n = C.n, slots_b = C.slots_b, slots_s = C.slots_s;
 	Phase ph(h, FQSK_PH_SORT);
-	CK(h->dk_b.ensure((size_t) slots_b * 8)); CK(h->stime_b.ensure((size_t) slots_b * 4));
-	CK(h->dk_s.ensure((size_t) slots_s * 8)); CK(h->stime_s.ensure((size_t) slots_s * 4));
-	CK(cudaMemsetAsync(h->stime_b.p, 0xFF, (size_t) slots_b * 4, h->st));
-	CK(cudaMemsetAsync(h->stime_s.p, 0xFF, (size_t) slots_s * 4, h->st));
-	k_delta_build<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(S, P, h->dk_b.as<unsigned long long>(), h->stime_b.as<uint32_t>(), slots_b - 1, h->P.bmer_len, C.t_b,
-	                                                             h->dk_s.as<unsigned long long>(), h->stime_s.as<uint32_t>(), slots_s - 1, h->P.smer_len, C.t_s);
+	CK(h->dk_b.ensure((size_t) slots_b * 8)); CK(h->stime_b.ensure(((size_t) slots_b + slots_s) * 4));
+	CK(h->dk_s.ensure((size_t) slots_s * 8));
+	uint32_t *stime_s = h->stime_b.as<uint32_t>() + slots_b;
+	CK(cudaMemsetAsync(h->stime_b.p, 0xFF, ((size_t) slots_b + slots_s) * 4, h->st));
+	if (n < 8192 && C.dna_bytes_actual < (1u << 22))
+		CK(pdl(k_delta_build_flat, nblk(3 * C.dna_bytes_actual, 256), 256, h->st, S, P, (uint32_t) C.dna_bytes_actual, h->dk_b.as<unsigned long long>(), h->stime_b.as<uint32_t>(), slots_b - 1,
+		       h->P.bmer_len, C.t_b, h->dk_s.as<unsigned long long>(), stime_s, slots_s - 1, h->P.smer_len, C.t_s));
+	else
+	CK(pdl(k_delta_build, nblk((uint64_t) n * 32, 128), 128, h->st, S, P, h->dk_b.as<unsigned long long>(), h->stime_b.as<uint32_t>(), slots_b - 1, h->P.bmer_len, C.t_b,
+	                                                             h->dk_s.as<unsigned long long>(), stime_s, slots_s - 1, h->P.smer_len, C.t_s));
 	LAUNCHED(h);
 	S.delta_b = DeltaDev{h->dk_b.as<unsigned long long>(), h->stime_b.as<uint32_t>(), slots_b - 1, 1, h->P.bmer_len, C.t_b, h->tb.ci.thr + 1, nullptr, nullptr, nullptr};
-	S.delta_s = DeltaDev{h->dk_s.as<unsigned long long>(), h->stime_s.as<uint32_t>(), slots_s - 1, 1, h->P.smer_len, C.t_s, h->ts.ci.thr + 1, nullptr, nullptr, nullptr};
+	S.delta_s = DeltaDev{h->dk_s.as<unsigned long long>(), stime_s, slots_s - 1, 1, h->P.smer_len, C.t_s, h->ts.ci.thr + 1, nullptr, nullptr, nullptr};
 	if (!h->hot) return FQSK_OK;
 	// hot mode: ranks, queued events (inserts above thr + thread-local merges), time order, sequential evaluation
 	Phase ph2(h, FQSK_PH_LOCAL);
@@ -669,9 +712,9 @@ int seg_build_delta(fqsk_handle *h) {
 	for (int q = 0; q < 2; ++q) { P.ev_key[q] = h->evk[q].as<unsigned long long>(); P.ev_val[q] = h->evv[q].as<uint32_t>(); }
 	P.ev_n = h->d_u32 + 4; P.ev_cap = ev_cap; P.hot_draws = h->d_u32 + 6;
 	CK(cudaMemsetAsync(h->d_u32 + 4, 0, 4 * 4, h->st));
-	k_delta_rank<<<148 * 8, 256, 0, h->st>>>(S.delta_b, P, 0); LAUNCHED(h);
-	k_delta_rank<<<148 * 8, 256, 0, h->st>>>(S.delta_s, P, 1); LAUNCHED(h);
-	k_local<<<std::min<uint32_t>(nblk(std::max<uint32_t>(h->miss_cap, 1), 128), 148 * 16), 128, 0, h->st>>>(C.E, S, P, 0); LAUNCHED(h);
+	CK(pdl(k_delta_rank, 148 * 8, 256, h->st, S.delta_b, P, 0)); LAUNCHED(h);
+	CK(pdl(k_delta_rank, 148 * 8, 256, h->st, S.delta_s, P, 1)); LAUNCHED(h);
+	CK(pdl(k_local, std::min<uint32_t>(nblk(std::max<uint32_t>(h->miss_cap, 1), 128), 148 * 16), 128, h->st, C.E, S, P, 0)); LAUNCHED(h);
 	uint32_t *hs = (uint32_t *) h->h_small;
 	CK(cudaMemcpyAsync(hs, h->d_status, 64, cudaMemcpyDeviceToHost, h->st));
 	CK(cudaStreamSynchronize(h->st));
@@ -685,7 +728,7 @@ int seg_build_delta(fqsk_handle *h) {
 	}
 	CKR(stream_ensure(h, h->rng[ST_LB], (uint64_t) en[0] * 8 + 1024)); CKR(stream_ensure(h, h->rng[ST_LS], (uint64_t) en[1] * 8 + 1024));
 	C.E = make_engine_dev(h);
-	k_hot_eval<<<1, 64, 0, h->st>>>(C.E, S, P, h->evk_s[0].as<unsigned long long>(), h->evv_s[0].as<uint32_t>(), en[0], h->evk_s[1].as<unsigned long long>(), h->evv_s[1].as<uint32_t>(), en[1]); LAUNCHED(h);
+	CK(pdl(k_hot_eval, 1, 64, h->st, C.E, S, P, h->evk_s[0].as<unsigned long long>(), h->evv_s[0].as<uint32_t>(), en[0], h->evk_s[1].as<unsigned long long>(), h->evv_s[1].as<uint32_t>(), en[1])); LAUNCHED(h);
 	return FQSK_OK;
 }
 
@@ -702,31 +745,31 @@ int seg_pass(fqsk_handle *h) {
 	if (++C.pass > 64) return fail(h, FQSK_E_NO_CONVERGE, "segment did not settle");
 	if (C.redo_walk) {
 		if (++C.it >= max_it) return fail(h, FQSK_E_NO_CONVERGE, "segment did not reach its fixed point in %u iterations", max_it);
-		CK(cudaMemsetAsync(h->d_flags + 2, 0, sizeof(int), h->st));
+		if (C.pass > 1) CK(cudaMemsetAsync(h->d_flags + 2, 0, sizeof(int), h->st));     // first pass: still clear from k_seg_reset
 		CKR(seg_build_delta(h));
-		{ Phase ph(h, FQSK_PH_LOCAL); k_local<<<std::min<uint32_t>(nblk(std::max<uint32_t>(h->miss_cap, 1), 128), 148 * 16), 128, 0, h->st>>>(E, S, P, 1); LAUNCHED(h); }
-		{ Phase ph(h, FQSK_PH_WALK); k_walk<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(E, S, P, C.it); LAUNCHED(h); ++h->S.n_replays; }
+		{ Phase ph(h, FQSK_PH_LOCAL); CK(pdl(k_local, std::min<uint32_t>(nblk(std::max<uint32_t>(h->miss_cap, 1), 128), 148 * 16), 128, h->st, E, S, P, 1)); LAUNCHED(h); }
+		{ Phase ph(h, FQSK_PH_WALK); CK(pdl(k_walk, nblk((uint64_t) n * 32, 128), 128, h->st, E, S, P, C.it)); LAUNCHED(h); ++h->S.n_replays; }
 	}
 	if (C.redo_tail) {
 		{
 			Phase ph(h, FQSK_PH_COMPACT);
-			k_scan_u32x4<<<1, 1024, 0, h->st>>>(n, h->cnt_b.as<uint32_t>(), h->off_b[0].as<uint32_t>(), h->cnt_s.as<uint32_t>(), h->off_s[0].as<uint32_t>(),
-			                                     h->cnt_p.as<uint32_t>(), h->off_p.as<uint32_t>(), h->hidden.as<uint32_t>(), nullptr, d_tot4);
+			ScanChain sc; CKR(scan_chain(h, sc));
+			CK(pdl(k_scan_u32x4, std::max<uint32_t>(nblk(n, SCAN_U32_CHUNK), 1), 1024, h->st, n, h->cnt_b.as<uint32_t>(), h->off_b[0].as<uint32_t>(), h->cnt_s.as<uint32_t>(), h->off_s[0].as<uint32_t>(),
+			                                     h->cnt_p.as<uint32_t>(), h->off_p.as<uint32_t>(), h->hidden.as<uint32_t>(), (uint32_t *) nullptr, d_tot4, h->d_u32 + 1, sc));   // + rough scripts are rebuilt
 			LAUNCHED(h);
-			k_compact2<<<n, 64, 0, h->st>>>(S, P, h->off_b[0].as<uint32_t>(), h->off_s[0].as<uint32_t>(), h->off_p.as<uint32_t>(),
+			CK(pdl(k_compact2, n, 64, h->st, S, P, h->off_b[0].as<uint32_t>(), h->off_s[0].as<uint32_t>(), h->off_p.as<uint32_t>(),
 			                               h->row_b[0].as<unsigned long long>(), h->row_s[0].as<unsigned long long>(), h->row_p.as<unsigned long long>(),
-			                               h->rt_b[0].as<uint32_t>(), h->rt_s[0].as<uint32_t>());
+			                               h->rt_b[0].as<uint32_t>(), h->rt_s[0].as<uint32_t>()));
 			LAUNCHED(h);
 		}
-		CK(cudaMemsetAsync(h->d_u32 + 1, 0, 4, h->st));      // rough scripts are rebuilt
-		{ Phase ph(h, FQSK_PH_ROUGH); k_rough<<<std::max<uint32_t>(148, std::min<uint32_t>(nblk(rec_bound, 16), 148 * 32)), 128, 0, h->st>>>(E, P); LAUNCHED(h); }
-		{ Phase ph(h, FQSK_PH_FOLD); k_fold<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(E, S, P, 0); LAUNCHED(h); }
+		{ Phase ph(h, FQSK_PH_ROUGH); CK(pdl(k_rough, std::max<uint32_t>(148, std::min<uint32_t>(nblk(rec_bound, 16), 148 * 32)), 128, h->st, E, P)); LAUNCHED(h); }
+		{ Phase ph(h, FQSK_PH_FOLD); CK(pdl(k_fold, nblk((uint64_t) n * 32, 128), 128, h->st, E, S, P, 0)); LAUNCHED(h); }
 	}
 	{
 		Phase ph(h, FQSK_PH_FOLD);
-		k_scan_draws<<<1, 1024, 0, h->st>>>(n, P.rdraws_b, h->doff_b.as<unsigned long long>(), P.rdraws_s, h->doff_s.as<unsigned long long>(), d_draw2); LAUNCHED(h);
-		CK(cudaMemsetAsync(h->d_flags + 0, 0, sizeof(int), h->st)); CK(cudaMemsetAsync(h->d_flags + 7, 0, sizeof(int), h->st));
-		k_fold<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(E, S, P, 1); LAUNCHED(h);
+		ScanChain sc; CKR(scan_chain(h, sc));
+		CK(pdl(k_scan_draws, std::max<uint32_t>(nblk(n, SCAN_U32_CHUNK), 1), 1024, h->st, n, P.rdraws_b, h->doff_b.as<unsigned long long>(), P.rdraws_s, h->doff_s.as<unsigned long long>(), d_draw2, h->d_flags, sc)); LAUNCHED(h);   // + clears flags[0], flags[7]
+		CK(pdl(k_fold, nblk((uint64_t) n * 32, 128), 128, h->st, E, S, P, 1)); LAUNCHED(h);
 	}
 	return FQSK_OK;
 }
@@ -812,7 +855,7 @@ int pair_reserve(fqsk_handle *h, uint64_t incoming) {     // keep the table at m
 	while ((h->pair_items + incoming) * 2 > slots) slots <<= 1;
 	PairDev nt;
 	CKR(pair_alloc(h, nt, slots));
-	k_pair_rehash<<<148 * 8, 256, 0, h->st>>>(h->pair, nt); LAUNCHED(h);
+	CK(pdl(k_pair_rehash, 148 * 8, 256, h->st, h->pair, nt)); LAUNCHED(h);
 	CK(cudaStreamSynchronize(h->st));
 	cudaFree(h->pair.keys); cudaFree(h->pair.vcs);
 	h->pair = nt;
@@ -831,14 +874,14 @@ int pe_front(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes, const uns
 	CK(h->it_bias.ensure((size_t) ni * 4)); CK(h->it_dupprev.ensure((size_t) ni * 4)); CK(h->it_flags.ensure(ni));
 	CK(h->it_off32.ensure((size_t) ni * 4 + 4)); CK(h->it_off64.ensure((size_t) ni * 8 + 8)); CK(h->it_dna.ensure(*item_bytes_bound));
 	unsigned long long *tk = h->pe_tk.as<unsigned long long>(), *tv = h->pe_tv.as<unsigned long long>(), *q = h->pe_q.as<unsigned long long>();
-	k_pe_minim<<<nblk((uint64_t) np * 32, 128), 128, 0, h->st>>>(d_dna, d_off, d_len, np, b, tk, tv, q); LAUNCHED(h);
+	CK(pdl(k_pe_minim, nblk((uint64_t) np * 32, 128), 128, h->st, d_dna, d_off, d_len, np, b, tk, tv, q)); LAUNCHED(h);
 	// stable two-pass sort of the triples by (key, value): value first, then key
 	CKR(ensure_iota(h, nt));
 	uint32_t *i1 = (uint32_t *) h->pe_t2.as<uint32_t>();
 	CKR(sort_pairs_u64_u32(h, tv, h->pe_t1.as<unsigned long long>(), h->iota.as<uint32_t>(), i1, nt, 0, 2 * (int) b));
-	k_pe_gather<<<nblk(nt, 256), 256, 0, h->st>>>(tk, i1, h->pe_t1.as<unsigned long long>(), nt); LAUNCHED(h);
+	CK(pdl(k_pe_gather, nblk(nt, 256), 256, h->st, tk, i1, h->pe_t1.as<unsigned long long>(), nt)); LAUNCHED(h);
 	CKR(sort_pairs_u64_u32(h, h->pe_t1.as<unsigned long long>(), h->pe_sk.as<unsigned long long>(), i1, h->pe_sidx.as<uint32_t>(), nt, 0, 2 * (int) b + 1));
-	k_pe_gather<<<nblk(nt, 256), 256, 0, h->st>>>(tv, h->pe_sidx.as<uint32_t>(), h->pe_sv.as<unsigned long long>(), nt); LAUNCHED(h);
+	CK(pdl(k_pe_gather, nblk(nt, 256), 256, h->st, tv, h->pe_sidx.as<uint32_t>(), h->pe_sv.as<unsigned long long>(), nt)); LAUNCHED(h);
 	h->pe_nt = nt; h->pe_pairs = np;
 	PeItems I{h->it_src.as<unsigned long long>(), h->it_len.as<uint32_t>(), h->it_bytes.as<uint32_t>(), h->it_first.as<uint32_t>(), h->it_bias.as<uint32_t>(),
 	          h->it_dupprev.as<uint32_t>(), h->it_flags.as<uint8_t>()};
@@ -847,16 +890,17 @@ int pe_front(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes, const uns
 		if (h->pe_pool_cap < 64 * np) h->pe_pool_cap = 64 * np;
 		CK(h->pe_pool.ensure((size_t) h->pe_pool_cap * 8));
 		CK(cudaMemsetAsync(h->d_pe, 0, 8, h->st));
-		k_pe_decide<<<nblk((uint64_t) np * 32, 128), 128, 0, h->st>>>(h->pair, pe_seg(h), q, d_dna, d_off, d_len, np, h->P.prefix_len, h->pe_pool.as<unsigned long long>(),
-		                                                             h->d_pe, h->pe_pool_cap, (int *) (h->d_pe + 1), h->pe_info.as<uint32_t>(), I); LAUNCHED(h);
+		CK(pdl(k_pe_decide, nblk((uint64_t) np * 32, 128), 128, h->st, h->pair, pe_seg(h), q, d_dna, d_off, d_len, np, h->P.prefix_len, h->pe_pool.as<unsigned long long>(),
+		                                                             h->d_pe, h->pe_pool_cap, (int *) (h->d_pe + 1), h->pe_info.as<uint32_t>(), I)); LAUNCHED(h);
 		uint32_t *hs = (uint32_t *) ((uint8_t *) h->h_small + 960);
 		CK(cudaMemcpyAsync(hs, h->d_pe, 8, cudaMemcpyDeviceToHost, h->st));
 		CK(cudaStreamSynchronize(h->st));
 		if (!hs[1]) break;
 		h->pe_pool_cap = h->pe_pool_cap < (1u << 29) ? h->pe_pool_cap * 4 : h->pe_pool_cap;
 	}
-	k_scan_u32x4<<<1, 1024, 0, h->st>>>(ni, h->it_bytes.as<uint32_t>(), h->it_off32.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, h->d_pe + 2); LAUNCHED(h);
-	k_pe_fill<<<nblk((uint64_t) (ni + 1) * 32, 128), 128, 0, h->st>>>(d_dna, I, h->it_off32.as<uint32_t>(), ni, h->it_dna.as<uint8_t>(), h->it_off64.as<unsigned long long>()); LAUNCHED(h);
+	ScanChain sc; CKR(scan_chain(h, sc));
+	CK(pdl(k_scan_u32x4, std::max<uint32_t>(nblk(ni, SCAN_U32_CHUNK), 1), 1024, h->st, ni, h->it_bytes.as<uint32_t>(), h->it_off32.as<uint32_t>(), (const uint32_t *) nullptr, (uint32_t *) nullptr, (const uint32_t *) nullptr, (uint32_t *) nullptr, (const uint32_t *) nullptr, (uint32_t *) nullptr, h->d_pe + 2, (uint32_t *) nullptr, sc)); LAUNCHED(h);
+	CK(pdl(k_pe_fill, nblk((uint64_t) (ni + 1) * 32, 128), 128, h->st, d_dna, I, h->it_off32.as<uint32_t>(), ni, h->it_dna.as<uint8_t>(), h->it_off64.as<unsigned long long>())); LAUNCHED(h);
 	return FQSK_OK;
 }
 
@@ -865,7 +909,7 @@ int pe_sync(fqsk_handle *h) {
 	if (!h->pe_nt) return FQSK_OK;
 	CKR(pair_reserve(h, h->pe_nt));
 	unsigned long long *d_items = (unsigned long long *) (h->d_pe + 6);
-	k_pair_insert<<<nblk(h->pe_nt, 256), 256, 0, h->st>>>(h->pair, pe_seg(h), d_items); LAUNCHED(h);
+	CK(pdl(k_pair_insert, nblk(h->pe_nt, 256), 256, h->st, h->pair, pe_seg(h), d_items)); LAUNCHED(h);
 	unsigned long long *hs = (unsigned long long *) ((uint8_t *) h->h_small + 968);
 	CK(cudaMemcpyAsync(hs, d_items, 8, cudaMemcpyDeviceToHost, h->st));
 	CK(cudaStreamSynchronize(h->st));
@@ -920,8 +964,10 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 	S.sorted_flag = h->sflag.as<uint32_t>(); S.sorted_dif = h->sdif.as<unsigned long long>();
 	{
 		Phase ph(h, FQSK_PH_PREP);
-		k_prep<<<nblk((uint64_t) n * 32, 128), 128, 0, h->st>>>(S, first, h->P.bmer_len); LAUNCHED(h);
-		k_scan_reads<<<1, 1024, 0, h->st>>>(S, h->rec_off.as<unsigned long long>(), h->sl_prefix.as<U64x4>(), (SegTotals *) (h->d_status + 64), h->d_u32 + 3); LAUNCHED(h);
+		CK(pdl(k_prep, nblk((uint64_t) n * 32, 128), 128, h->st, S, first, h->P.bmer_len)); LAUNCHED(h);
+		if (n > SCAN_CHAIN_MAX * SCAN_READS_CHUNK) return fail(h, FQSK_E_INVAL, "more than %u reads in one segment", SCAN_CHAIN_MAX * SCAN_READS_CHUNK);
+		ScanChain sc; CKR(scan_chain(h, sc));
+		CK(pdl(k_scan_reads, std::max<uint32_t>(nblk(n, SCAN_READS_CHUNK), 1), 1024, h->st, S, h->rec_off.as<unsigned long long>(), h->sl_prefix.as<U64x4>(), (SegTotals *) (h->d_status + 64), h->d_u32 + 3, sc)); LAUNCHED(h);
 	}
 	const uint32_t rec_bound = (uint32_t) dna_bytes;   // capacities follow the reserve as well
 	if (h->miss_cap < std::min<uint32_t>(rec_bound, 1u << 20)) h->miss_cap = std::min<uint32_t>(rec_bound, 1u << 20);
@@ -933,9 +979,9 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 	CKR(seg_setup(h));
 	CKR(seg_pass(h));
 	// verdict of the first pass for a sync enqueued unseen, and the state the next segment inherits (both are inputs only)
-	k_seg_verdict<<<1, 32, 0, h->st>>>(h->d_flags, (const uint32_t *) (h->d_status + 192), (const unsigned long long *) (h->d_status + 208),
-	                                   h->rng[ST_B].consumed, h->rng[ST_S].consumed, SYNC_INDEXED_MAX, h->d_syncin); LAUNCHED(h);
-	k_save_carry<<<1, 256, 0, h->st>>>(S, pe ? n - 3 : n - 1, h->prev_read.as<uint8_t>(), h->d_carry, h->P.mode == FQSK_MODE_SE_SORTED || h->P.mode == FQSK_MODE_PE_SORTED, h->P.pmer_len); LAUNCHED(h);
+	CK(pdl(k_seg_verdict, 1, 32, h->st, h->d_flags, (const uint32_t *) (h->d_status + 192), (const unsigned long long *) (h->d_status + 208),
+	                                   h->rng[ST_B].consumed, h->rng[ST_S].consumed, SYNC_INDEXED_MAX, h->d_syncin)); LAUNCHED(h);
+	CK(pdl(k_save_carry, 1, 256, h->st, S, pe ? n - 3 : n - 1, h->prev_read.as<uint8_t>(), h->d_carry, h->P.mode == FQSK_MODE_SE_SORTED || h->P.mode == FQSK_MODE_PE_SORTED, h->P.pmer_len)); LAUNCHED(h);
 	h->unsettled = true;
 	h->pending = true;
 	h->S.n_reads += n_in; h->S.n_bases += bytes_in;
@@ -960,7 +1006,7 @@ int hot_account(fqsk_handle *h, int stream) {
 	P.ev_n = h->d_u32 + 4; P.ev_cap = ev_cap; P.hot_draws = h->d_u32 + 6; P.flags = h->d_flags;
 	CK(cudaMemsetAsync(h->d_u32 + 4, 0, 4 * 4, h->st));
 	CK(cudaMemsetAsync(h->d_flags, 0, 8 * sizeof(int), h->st));
-	k_delta_rank<<<148 * 8, 256, 0, h->st>>>(D, P, (uint32_t) stream); LAUNCHED(h);
+	CK(pdl(k_delta_rank, 148 * 8, 256, h->st, D, P, (uint32_t) stream)); LAUNCHED(h);
 	uint32_t *hs = (uint32_t *) h->h_small;
 	CK(cudaMemcpyAsync(hs, h->d_status, 64, cudaMemcpyDeviceToHost, h->st));
 	CK(cudaStreamSynchronize(h->st));
@@ -975,8 +1021,8 @@ int hot_account(fqsk_handle *h, int stream) {
 	EngineDev E = make_engine_dev(h);
 	SegDev S{};
 	S.delta_b = stream ? DeltaDev{} : D; S.delta_s = stream ? D : DeltaDev{};
-	k_hot_eval<<<1, 64, 0, h->st>>>(E, S, P, h->evk_s[0].as<unsigned long long>(), h->evv_s[0].as<uint32_t>(), stream ? 0 : en,
-	                               h->evk_s[1].as<unsigned long long>(), h->evv_s[1].as<uint32_t>(), stream ? en : 0);
+	CK(pdl(k_hot_eval, 1, 64, h->st, E, S, P, h->evk_s[0].as<unsigned long long>(), h->evv_s[0].as<uint32_t>(), stream ? 0 : en,
+	                               h->evk_s[1].as<unsigned long long>(), h->evv_s[1].as<uint32_t>(), stream ? en : 0));
 	LAUNCHED(h);
 	CK(cudaMemcpyAsync(hs, h->d_status, 64, cudaMemcpyDeviceToHost, h->st));
 	CK(cudaStreamSynchronize(h->st));
@@ -1095,7 +1141,7 @@ void fqsk_destroy(fqsk_handle *h) {
 	                  &h->sidx_b, &h->sidx_s, &h->stime_b, &h->stime_s, &h->sort_k, &h->sort_v, &h->rkind, &h->rreg, &h->rslot, &h->dirty, &h->rdraws_b, &h->rdraws_s, &h->totals,
 	                  &h->y_tslot, &h->y_c0, &h->y_m, &h->y_draw, &h->y_j, &h->y_final, &h->y_flag_at, &h->y_own, &h->y_lead, &h->y_rank, &h->y_flag, &h->y_doff,
 	                  &h->idx_k, &h->idx_t, &h->idx_rt, &h->miss_fold, &h->hr_b[0], &h->hr_b[1], &h->hr_b[2], &h->hr_s[0], &h->hr_s[1], &h->hr_s[2],
-	                  &h->evk[0], &h->evk[1], &h->evv[0], &h->evv[1], &h->evk_s[0], &h->evk_s[1], &h->evv_s[0], &h->evv_s[1], &h->scan_part,
+	                  &h->evk[0], &h->evk[1], &h->evv[0], &h->evv[1], &h->evk_s[0], &h->evk_s[1], &h->evv_s[0], &h->evv_s[1], &h->scan_part, &h->scan_vals,
 	                  &h->route_keys, &h->route_keys2, &h->route_sorted, &h->route_hist,
 	                  &h->pe_tk, &h->pe_tv, &h->pe_q, &h->pe_sk, &h->pe_sv, &h->pe_sidx, &h->pe_t1, &h->pe_t2, &h->pe_pool, &h->pe_info, &h->it_src, &h->it_len,
 	                  &h->it_bytes, &h->it_first, &h->it_bias, &h->it_dupprev, &h->it_flags, &h->it_off32, &h->it_off64, &h->it_dna};
@@ -1232,26 +1278,24 @@ static int sync_speculative(fqsk_handle *h, bool *applied, unsigned long long co
 	SyncIn *in = h->d_syncin;
 	const uint32_t bound_b = (uint32_t) (2 * C.dna_bytes_actual + 2), bound_s = (uint32_t) (C.dna_bytes_actual + 1);
 	const uint64_t bound_p = 2 * C.dna_bytes_actual + 2ull * C.n;
-	CK(cudaMemsetAsync(h->d_counters + 4, 0, 8, h->st));
-	{
+	{   // d_counters[4], d_sfast and the ordered-insert flags are still clear from k_seg_reset
 		Phase ph(h, FQSK_PH_SYNC_SIV);
-		k_siv_increment<<<nblk(bound_p, 256), 256, 0, h->st>>>(h->siv, h->row_p.as<unsigned long long>(), 0, h->d_counters + 4, in); LAUNCHED(h);
+		CK(pdl(k_siv_increment, nblk(bound_p, 256), 256, h->st, h->siv, h->row_p.as<unsigned long long>(), 0, h->d_counters + 4, (const SyncIn *) in)); LAUNCHED(h);
 	}
 	{
 		Phase ph(h, FQSK_PH_SYNC_APPLY);
-		CK(cudaMemsetAsync(h->d_sfast, 0, sizeof(int), h->st));
-		CK(h->q4.ensure((size_t) bound_s + 4));
-		k_insert_fast<<<nblk(bound_s, 256), 256, 0, h->st>>>(h->ts.d, h->ts.ci, h->row_s[0].as<unsigned long long>(), 0, h->q4.as<uint8_t>(), h->d_sfast, in); LAUNCHED(h);
+		CK(h->q4.ensure(row_reserve(h, bound_s) + 4));
+		CK(pdl(k_insert_fast, nblk(bound_s, 256), 256, h->st, h->ts.d, h->ts.ci, h->row_s[0].as<unsigned long long>(), 0, h->q4.as<uint8_t>(), h->d_sfast, (const SyncIn *) in)); LAUNCHED(h);
 	}
 	SyncDev Y;
 	CKR(indexed_setup(h, C.S.delta_b, bound_b, in, true, Y));
 	const uint32_t g = nblk(bound_b, 256);
 	const unsigned long long *row_b = h->row_b[0].as<unsigned long long>();
-	CKR(indexed_head(h, h->tb, Y, row_b, h->rt_b[0].as<uint32_t>(), g));
+	CKR(indexed_head(h, h->tb, Y, row_b, h->rt_b[0].as<uint32_t>(), g, false));
 	{
 		Phase ph(h, FQSK_PH_SYNC_APPLY);
 		CKR(stream_ensure(h, h->rng[ST_B], 0));
-		CKR(indexed_tail(h, h->tb, h->rng[ST_B], Y, row_b, g, bound_b));
+		CKR(indexed_tail(h, h->tb, h->rng[ST_B], Y, row_b, g, bound_b, false));
 	}
 	CKR(look(h));
 	const SyncIn li = *looked_syncin(h, in);
@@ -1266,12 +1310,12 @@ static int sync_speculative(fqsk_handle *h, bool *applied, unsigned long long co
 	if (fl[7] || fl[0] || fl[2]) {
 		// a counter saturated inside the batch, the draw window was short or a group is too large: nothing was committed; release
 		// the claimed slots and take the plain ordered path for this row
-		k_sync_unclaim<<<g, 256, 0, h->st>>>(h->tb.d, Y); LAUNCHED(h);
+		CK(pdl(k_sync_unclaim, g, 256, h->st, h->tb.d, Y)); LAUNCHED(h);
 		CKR(apply_indexed(h, h->tb, h->rng[ST_B], h->seg_delta_b, row_b, h->rt_b[0].as<uint32_t>(), h->pend_b));
 		relook = true;
 	} else h->rng[ST_B].consumed += li.draws_b;
 	if (s_refuted) {
-		k_insert_undo<<<nblk(h->pend_s, 256), 256, 0, h->st>>>(h->ts.d, h->row_s[0].as<unsigned long long>(), h->pend_s, h->q4.as<uint8_t>()); LAUNCHED(h);
+		CK(pdl(k_insert_undo, nblk(h->pend_s, 256), 256, h->st, h->ts.d, h->row_s[0].as<unsigned long long>(), h->pend_s, h->q4.as<uint8_t>())); LAUNCHED(h);
 		CKR(apply_inserts(h, h->ts, h->rng[ST_S], h->row_s[0].as<unsigned long long>(), h->pend_s));
 		relook = true;
 	}
@@ -1301,7 +1345,7 @@ int fqsk_sync(fqsk_handle *h) {
 			CK(cudaMemsetAsync(h->d_counters + 4, 0, 8, h->st));
 			if (h->pend_p) {
 				Phase ph(h, FQSK_PH_SYNC_SIV);
-				k_siv_increment<<<nblk(h->pend_p, 256), 256, 0, h->st>>>(h->siv, h->row_p.as<unsigned long long>(), h->pend_p, h->d_counters + 4);
+				CK(pdl(k_siv_increment, nblk(h->pend_p, 256), 256, h->st, h->siv, h->row_p.as<unsigned long long>(), h->pend_p, h->d_counters + 4, (const SyncIn *) nullptr));
 				LAUNCHED(h);
 			}
 			// s-mers and b-mers (dna.cpp:2425-2446) live in different tables and use different PRNG streams, so their rows are
@@ -1312,8 +1356,8 @@ int fqsk_sync(fqsk_handle *h) {
 			if (h->fast_ok[0] && h->pend_s) {
 				Phase ph(h, FQSK_PH_SYNC_APPLY);
 				CK(cudaMemsetAsync(h->d_sfast, 0, sizeof(int), h->st));
-				CK(h->q4.ensure((size_t) h->pend_s + 4));
-				k_insert_fast<<<nblk(h->pend_s, 256), 256, 0, h->st>>>(h->ts.d, h->ts.ci, h->row_s[0].as<unsigned long long>(), h->pend_s, h->q4.as<uint8_t>(), h->d_sfast); LAUNCHED(h);
+				CK(h->q4.ensure(row_reserve(h, h->pend_s) + 4));
+				CK(pdl(k_insert_fast, nblk(h->pend_s, 256), 256, h->st, h->ts.d, h->ts.ci, h->row_s[0].as<unsigned long long>(), h->pend_s, h->q4.as<uint8_t>(), h->d_sfast, (const SyncIn *) nullptr)); LAUNCHED(h);
 				s_fast_pending = true;
 			}
 			else if (h->pend_s <= SYNC_INDEXED_MAX) CKR(apply_indexed(h, h->ts, h->rng[ST_S], h->seg_delta_s, h->row_s[0].as<unsigned long long>(), h->rt_s[0].as<uint32_t>(), h->pend_s));
@@ -1326,7 +1370,7 @@ int fqsk_sync(fqsk_handle *h) {
 			if (s_fast_pending && *(int *) ((uint8_t *) h->h_small + 224)) {
 				// some s-mer counter left the deterministic range: undo (claimed slots stay as zero-count items == the reference's fresh
 				// slot) and insert the row in order
-				k_insert_undo<<<nblk(h->pend_s, 256), 256, 0, h->st>>>(h->ts.d, h->row_s[0].as<unsigned long long>(), h->pend_s, h->q4.as<uint8_t>()); LAUNCHED(h);
+				CK(pdl(k_insert_undo, nblk(h->pend_s, 256), 256, h->st, h->ts.d, h->row_s[0].as<unsigned long long>(), h->pend_s, h->q4.as<uint8_t>())); LAUNCHED(h);
 				CKR(apply_inserts(h, h->ts, h->rng[ST_S], h->row_s[0].as<unsigned long long>(), h->pend_s));
 				unsigned long long *hc = (unsigned long long *) ((uint8_t *) h->h_small + 512);
 				CK(cudaMemcpyAsync(hc, h->d_counters, 48, cudaMemcpyDeviceToHost, h->st));
@@ -1417,13 +1461,13 @@ int fqsk_sync_route(fqsk_handle *h) {
 		uint32_t *hist = h->route_hist.as<uint32_t>() + 8 * t;
 		if (n) {
 			CK(h->route_keys.ensure(n)); CK(h->route_keys2.ensure(n)); CK(h->route_sorted.ensure((size_t) n * 8));
-			k_owner_keys<<<nblk(n, 256), 256, 0, h->st>>>(rows[t], n, t == 0 ? 0u : 1u, 2 * h->P.pmer_len - 12, h->world, h->route_keys.as<uint8_t>(), hist); LAUNCHED(h);
+			CK(pdl(k_owner_keys, nblk(n, 256), 256, h->st, rows[t], n, t == 0 ? 0u : 1u, 2 * h->P.pmer_len - 12, h->world, h->route_keys.as<uint8_t>(), hist)); LAUNCHED(h);
 			size_t bytes = 0;   // stable: push order survives inside every owner group
 			CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, h->route_keys.as<uint8_t>(), h->route_keys2.as<uint8_t>(), rows[t], h->route_sorted.as<unsigned long long>(), (int) n, 0, 3, h->st));
 			CK(h->cub_tmp.ensure(bytes));
 			CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, h->route_keys.as<uint8_t>(), h->route_keys2.as<uint8_t>(), rows[t], h->route_sorted.as<unsigned long long>(), (int) n, 0, 3, h->st));
 		}
-		k_route_scatter<<<nblk(std::max<uint32_t>(n, 8), 256), 256, 0, h->st>>>(h->route_sorted.as<unsigned long long>(), n, hist, I, (uint32_t) t, h->d_flags); LAUNCHED(h);
+		CK(pdl(k_route_scatter, nblk(std::max<uint32_t>(n, 8), 256), 256, h->st, h->route_sorted.as<unsigned long long>(), n, hist, I, (uint32_t) t, h->d_flags)); LAUNCHED(h);
 	}
 	int fl[8];
 	CKR(read_flags(h, fl, 8));      // also drains the stream: the peer stores are complete when the caller enters its barrier
@@ -1462,7 +1506,7 @@ int fqsk_sync_apply(fqsk_handle *h, uint64_t *fresh, uint64_t *updates) {
 	CK(cudaMemsetAsync(h->d_counters + 4, 0, 8, h->st));
 	if (tot[0]) {
 		Phase ph(h, FQSK_PH_SYNC_SIV);
-		k_siv_increment<<<nblk(tot[0], 256), 256, 0, h->st>>>(h->siv, dst[0], tot[0], h->d_counters + 4); LAUNCHED(h);
+		CK(pdl(k_siv_increment, nblk(tot[0], 256), 256, h->st, h->siv, dst[0], tot[0], h->d_counters + 4, (const SyncIn *) nullptr)); LAUNCHED(h);
 	}
 	if (tot[1]) { bool fast = true; CKR(apply_inserts(h, h->ts, h->rng[ST_S], dst[1], (uint32_t) tot[1], &fast)); }
 	if (tot[2]) CKR(apply_row(h, h->tb, h->rng[ST_B], dst[2], (uint32_t) tot[2]));
@@ -1550,7 +1594,7 @@ int fqsk_dump(fqsk_handle *h, int table, uint64_t *keys, uint64_t *vals, uint64_
 		CK(h->dump_k.ensure((cnt + 1) * 8)); CK(h->dump_v.ensure((cnt + 1) * 8));
 		CK(cudaMemsetAsync(h->d_counters + 5, 0, 8, h->st));
 		uint64_t nw = h->world > 1 ? ((((uint64_t) 4096 + h->world - 1) / h->world) << h->siv.top_shift) >> 4 : (1ull << h->siv.key_bits) >> 4;
-		k_dump_siv<<<nblk(nw, 256), 256, 0, h->st>>>(h->siv, h->dump_k.as<unsigned long long>(), h->dump_v.as<unsigned long long>(), cnt, h->d_counters + 5);
+		CK(pdl(k_dump_siv, nblk(nw, 256), 256, h->st, h->siv, h->dump_k.as<unsigned long long>(), h->dump_v.as<unsigned long long>(), cnt, h->d_counters + 5));
 		LAUNCHED(h);
 		unsigned long long got = 0;
 		CK(cudaMemcpyAsync(&got, h->d_counters + 5, 8, cudaMemcpyDeviceToHost, h->st));
@@ -1642,7 +1686,7 @@ int fqsk_ht_find(fqsk_handle *h, int table, const uint64_t *kmer_dir, const uint
 		if (it > 32) return fail(h, FQSK_E_NO_CONVERGE, "find: draw offsets did not settle");
 		CK(cudaMemsetAsync(h->d_flags, 0, 4 * sizeof(int), h->st));
 		CK(cudaMemsetAsync(d_used + n, 0, 4, h->st));
-		k_find<<<nblk(n, 128), 128, 0, h->st>>>(t->d, t->ci, d_dir, d_rc, d_cur, (uint32_t) n, d_counts, rng.buf, rng.cap - 1, rng.consumed, stream_avail(rng), d_guess, d_used, h->d_flags);
+		CK(pdl(k_find, nblk(n, 128), 128, h->st, t->d, t->ci, d_dir, d_rc, d_cur, (uint32_t) n, d_counts, rng.buf, rng.cap - 1, rng.consumed, stream_avail(rng), d_guess, d_used, h->d_flags));
 		LAUNCHED(h);
 		int fl[4];
 		CKR(read_flags(h, fl, 4));
@@ -1667,7 +1711,7 @@ int fqsk_ht_count(fqsk_handle *h, int table, const uint64_t *kmers, uint64_t n, 
 	if (!n) return FQSK_OK;
 	CK(h->q0.ensure(n * 8)); CK(h->q1.ensure(n * 4));
 	CK(cudaMemcpyAsync(h->q0.p, kmers, n * 8, cudaMemcpyHostToDevice, h->st));
-	k_count<<<nblk(n, 256), 256, 0, h->st>>>(t->d, h->q0.as<unsigned long long>(), (uint32_t) n, h->q1.as<uint32_t>());
+	CK(pdl(k_count, nblk(n, 256), 256, h->st, t->d, h->q0.as<unsigned long long>(), (uint32_t) n, h->q1.as<uint32_t>()));
 	LAUNCHED(h);
 	CK(cudaMemcpyAsync(out, h->q1.p, n * 4, cudaMemcpyDeviceToHost, h->st));
 	CK(cudaStreamSynchronize(h->st));
@@ -1682,7 +1726,7 @@ int fqsk_siv_increment(fqsk_handle *h, const uint64_t *idx, uint64_t n, uint64_t
 		CK(h->q0.ensure(n * 8));
 		CK(cudaMemcpyAsync(h->q0.p, idx, n * 8, cudaMemcpyHostToDevice, h->st));
 		CK(cudaMemsetAsync(h->d_counters + 4, 0, 8, h->st));
-		k_siv_increment<<<nblk(n, 256), 256, 0, h->st>>>(h->siv, h->q0.as<unsigned long long>(), n, h->d_counters + 4);
+		CK(pdl(k_siv_increment, nblk(n, 256), 256, h->st, h->siv, h->q0.as<unsigned long long>(), n, h->d_counters + 4, (const SyncIn *) nullptr));
 		LAUNCHED(h);
 		CK(cudaMemcpyAsync(&fresh, h->d_counters + 4, 8, cudaMemcpyDeviceToHost, h->st));
 		CK(cudaStreamSynchronize(h->st));
@@ -1699,9 +1743,9 @@ static int siv_query(fqsk_handle *h, int what, const uint64_t *idx, const uint32
 	CK(cudaMemcpyAsync(h->q0.p, idx, n * 8, cudaMemcpyHostToDevice, h->st));
 	if (bits) CK(cudaMemcpyAsync(h->q2.p, bits, n * 4, cudaMemcpyHostToDevice, h->st));
 	size_t ob;
-	if (what == 0) { k_siv_test<<<nblk(n, 256), 256, 0, h->st>>>(h->siv, h->q0.as<unsigned long long>(), (uint32_t) n, h->q1.as<uint32_t>()); ob = n * 4; }
-	else if (what == 1) { k_siv_counts<<<nblk(n, 256), 256, 0, h->st>>>(h->siv, h->q0.as<unsigned long long>(), (uint32_t) n, h->q1.as<uint32_t>()); ob = n * 16; }
-	else { k_siv_prefix<<<nblk(n, 256), 256, 0, h->st>>>(h->siv, h->q0.as<unsigned long long>(), h->q2.as<uint32_t>(), (uint32_t) n, h->q1.as<unsigned long long>()); ob = n * 8; }
+	if (what == 0) { CK(pdl(k_siv_test, nblk(n, 256), 256, h->st, h->siv, h->q0.as<unsigned long long>(), (uint32_t) n, h->q1.as<uint32_t>())); ob = n * 4; }
+	else if (what == 1) { CK(pdl(k_siv_counts, nblk(n, 256), 256, h->st, h->siv, h->q0.as<unsigned long long>(), (uint32_t) n, h->q1.as<uint32_t>())); ob = n * 16; }
+	else { CK(pdl(k_siv_prefix, nblk(n, 256), 256, h->st, h->siv, h->q0.as<unsigned long long>(), h->q2.as<uint32_t>(), (uint32_t) n, h->q1.as<unsigned long long>())); ob = n * 8; }
 	LAUNCHED(h);
 	CK(cudaMemcpyAsync(out, h->q1.p, ob, cudaMemcpyDeviceToHost, h->st));
 	CK(cudaStreamSynchronize(h->st));

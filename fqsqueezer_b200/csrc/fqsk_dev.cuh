@@ -23,6 +23,13 @@ namespace fqsk {
 // canonical rolling register (reference: kmer.h:18-540).  cur (symbols held) is tracked by the caller: all six
 // registers of a read advance in lock-step (dna.cpp:687-693, 810-816), so cur = min(k, symbols pushed).
 // ------------------------------------------------------------------------------------------------------------------
+// programmatic dependent launch (see pdl() in fqsk.cu): let the next kernel of the stream be scheduled now, then wait until the
+// previous one has completed and its writes are visible.  First statement of every kernel; a no-op for plain launches.
+FQSK_DEV void pdl_enter() {
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 struct KReg { uint64_t dir, rc; };
 
 FQSK_HD uint64_t kr_top_mask(uint32_t k) { return ~0ull << (64 - 2 * k); }

@@ -109,7 +109,7 @@ __device__ __forceinline__ uint32_t dna_code(uint8_t ch) {  // dna.cpp:18-23
 	return ch == 'A' ? 0u : ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : 4u;
 }
 
-__global__ void __launch_bounds__(128) k_prep(SegDev S, uint32_t first_len_bytes, uint32_t b) {   // one warp per read
+__global__ void __launch_bounds__(128) k_prep(SegDev S, uint32_t first_len_bytes, uint32_t b) { pdl_enter();   // one warp per read
 	uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (r >= S.n_reads) return;
 	const uint8_t *p = S.dna + S.off[r];
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(128) k_prep(SegDev S, uint32_t first_len_bytes
 }
 
 // read_prev (dna.cpp:1550-1551) and, in sorted order, pmer_can_prev (dna.cpp:655) follow the last read of the segment
-__global__ void __launch_bounds__(256) k_save_carry(SegDev S, uint32_t last, uint8_t *prev_read, Carry *carry, uint32_t sorted, uint32_t p) {
+__global__ void __launch_bounds__(256) k_save_carry(SegDev S, uint32_t last, uint8_t *prev_read, Carry *carry, uint32_t sorted, uint32_t p) { pdl_enter();
 	if (S.n_reads == 0) return;
 	const uint8_t *q = S.dna + S.off[last];      // paired-end: only first-of-pair reads replace read_prev (dna.cpp:1550-1551)
 	const uint32_t n = S.len[last];
@@ -217,15 +217,15 @@ __device__ __forceinline__ void rs_push_all(ReadState &R, const EngineDev &E, ui
 }
 __device__ __forceinline__ uint32_t cur_of(uint32_t k, uint32_t n) { return n < k ? n : k; }
 
-__global__ void k_compare_u64(const unsigned long long *a, const unsigned long long *b, uint64_t n, int *changed) {
+__global__ void k_compare_u64(const unsigned long long *a, const unsigned long long *b, uint64_t n, int *changed) { pdl_enter();
 	uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n && a[i] != b[i]) *changed = 1;
 }
-__global__ void k_compare_u32(const uint32_t *a, const uint32_t *b, uint64_t n, int *changed) {
+__global__ void k_compare_u32(const uint32_t *a, const uint32_t *b, uint64_t n, int *changed) { pdl_enter();
 	uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n && a[i] != b[i]) *changed = 1;
 }
-__global__ void k_iota(uint32_t *a, uint32_t n) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = i; }
+__global__ void k_iota(uint32_t *a, uint32_t n) { pdl_enter(); uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = i; }
 
 // ------------------------------------------------------------------------------------------------------------------
 // sync step for one hash table: InsertKmersToHT (dna.cpp:2420-2446) == for every pushed k-mer, in push order,
@@ -237,7 +237,7 @@ __global__ void k_iota(uint32_t *a, uint32_t n) { uint32_t i = blockIdx.x * bloc
 // Groups that cannot reach the top of the counter (c0 + m < top) are final with those flags; the others are marked unsafe
 // and go through the verifying passes (k_apply_keys with verify = 1) -- only there can a flag be wrong.
 __global__ void k_locate_heads(HtDev t, CIncP ci, const unsigned long long *skeys, const uint32_t *sidx, uint32_t n, unsigned long long *slot_of, uint32_t *c0_of,
-                               uint8_t *flag, int *flags) {
+                               uint8_t *flag, int *flags) { pdl_enter();
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	unsigned long long key = skeys[i];
@@ -260,7 +260,7 @@ __global__ void k_locate_heads(HtDev t, CIncP ci, const unsigned long long *skey
 // seen a pass without corrections (commit == 1).
 __global__ void k_apply_keys(HtDev t, CIncP ci, const unsigned long long *skeys, const uint32_t *sidx, uint32_t n, const unsigned long long *slot_of, const uint32_t *c0_of,
                              uint8_t *flag, const uint32_t *draw_off, const uint32_t *draws, unsigned long long dmask, unsigned long long dpos, unsigned long long avail,
-                             int verify, int commit, int *flags) {
+                             int verify, int commit, int *flags) { pdl_enter();
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	unsigned long long key = skeys[i];
@@ -316,7 +316,7 @@ struct SyncDev {
 };
 static const uint32_t SYNC_GROUP_CAP = 48;
 
-__global__ void k_sync_rank(HtDev t, SyncDev Y, const unsigned long long *row, const uint32_t *rt) {
+__global__ void k_sync_rank(HtDev t, SyncDev Y, const unsigned long long *row, const uint32_t *rt) { pdl_enter();
 	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
 	if (!Y.in->ok || j >= *Y.n_dev) return;
 	const unsigned long long x = row[j];
@@ -341,7 +341,7 @@ __global__ void k_sync_rank(HtDev t, SyncDev Y, const unsigned long long *row, c
 		Y.lead_m[own] = m;
 	}
 }
-__global__ void k_sync_flags(HtDev t, CIncP ci, SyncDev Y) {
+__global__ void k_sync_flags(HtDev t, CIncP ci, SyncDev Y) { pdl_enter();
 	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
 	if (!Y.in->ok || j >= *Y.n_dev) return;
 	const uint32_t L = Y.lead[j], c0 = Y.lead_c0[L], m = Y.lead_m[L], rank = Y.rank[j];
@@ -354,7 +354,7 @@ __global__ void k_sync_flags(HtDev t, CIncP ci, SyncDev Y) {
 	}
 	Y.flag[j] = f;
 }
-__global__ void k_sync_scatter(CIncP ci, SyncDev Y) {
+__global__ void k_sync_scatter(CIncP ci, SyncDev Y) { pdl_enter();
 	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
 	if (!Y.in->ok || j >= *Y.n_dev) return;
 	const uint32_t L = Y.lead[j];
@@ -364,7 +364,7 @@ __global__ void k_sync_scatter(CIncP ci, SyncDev Y) {
 	Y.flag_at[own] = Y.flag[j];
 }
 __global__ void k_sync_apply(HtDev t, CIncP ci, SyncDev Y, const unsigned long long *row,
-                             const uint32_t *draws, unsigned long long dmask, unsigned long long safe_abs) {
+                             const uint32_t *draws, unsigned long long dmask, unsigned long long safe_abs) { pdl_enter();
 	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
 	if (!Y.in->ok || j >= *Y.n_dev) return;
 	if (Y.rank[j] != 0) return;
@@ -402,7 +402,7 @@ __global__ void k_sync_apply(HtDev t, CIncP ci, SyncDev Y, const unsigned long l
 	}
 	Y.final_at[L] = c;
 }
-__global__ void k_sync_commit(HtDev t, SyncDev Y) {
+__global__ void k_sync_commit(HtDev t, SyncDev Y) { pdl_enter();
 	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
 	if (!Y.in->ok || j >= *Y.n_dev) return;
 	if (Y.rank[j] != 0) return;
@@ -411,7 +411,7 @@ __global__ void k_sync_commit(HtDev t, SyncDev Y) {
 	ht_slot_set(t, Y.lead_tslot[L] & ~(1ull << 63), Y.final_at[L]);
 }
 // fallback preparation: slots claimed by k_sync_rank (counter 1) become zero-count items, i.e. the reference's fresh slot
-__global__ void k_sync_unclaim(HtDev t, SyncDev Y) {
+__global__ void k_sync_unclaim(HtDev t, SyncDev Y) { pdl_enter();
 	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
 	if (!Y.in->ok || j >= *Y.n_dev) return;
 	if (Y.rank[j] != 0) return;
@@ -419,7 +419,7 @@ __global__ void k_sync_unclaim(HtDev t, SyncDev Y) {
 	if (ts >> 63) ht_slot_set(t, ts & ~(1ull << 63), 0);
 }
 // index of a plain row (table-level API): entry time = push index
-__global__ void k_row_index_build(unsigned long long *keys, uint32_t *times, uint32_t mask, uint32_t k, uint32_t t, const unsigned long long *row, uint32_t n, uint32_t *rt) {
+__global__ void k_row_index_build(unsigned long long *keys, uint32_t *times, uint32_t mask, uint32_t k, uint32_t t, const unsigned long long *row, uint32_t n, uint32_t *rt) { pdl_enter();
 	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
 	if (j >= n) return;
 	unsigned long long x = row[j];
@@ -432,7 +432,7 @@ __global__ void k_row_index_build(unsigned long long *keys, uint32_t *times, uin
 // Increment()s exactly when no counter leaves the deterministic range (pre-count <= thr for every occurrence, utils.h:317-318);
 // any occurrence that sees a pre-count above thr raises flags[2] and the host undoes the pass (k_insert_undo: the adds are
 // plain arithmetic on the item, so subtracting them restores every bit) and runs the ordered path instead.
-__global__ void k_insert_fast(HtDev t, CIncP ci, const unsigned long long *kmers, uint32_t n, uint8_t *added, int *refuted, const SyncIn *in = nullptr) {
+__global__ void k_insert_fast(HtDev t, CIncP ci, const unsigned long long *kmers, uint32_t n, uint8_t *added, int *refuted, const SyncIn *in = nullptr) { pdl_enter();
 	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
 	if (in) { if (!in->ok) return; n = in->n_s; }
 	if (j >= n) return;
@@ -462,7 +462,7 @@ __global__ void k_insert_fast(HtDev t, CIncP ci, const unsigned long long *kmers
 		}
 	}
 }
-__global__ void k_insert_undo(HtDev t, const unsigned long long *kmers, uint32_t n, const uint8_t *added) {
+__global__ void k_insert_undo(HtDev t, const unsigned long long *kmers, uint32_t n, const uint8_t *added) { pdl_enter();
 	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
 	if (j >= n) return;
 	bool created;
@@ -473,7 +473,7 @@ __global__ void k_insert_undo(HtDev t, const unsigned long long *kmers, uint32_t
 	if (s < nm) atomicSub(t.main + s, 1u); else atomicAdd(t.stash + (s - nm), ~0ull);
 }
 
-__global__ void k_siv_increment(SivDev s, const unsigned long long *idx, uint64_t n, unsigned long long *n_new, const SyncIn *in = nullptr) {
+__global__ void k_siv_increment(SivDev s, const unsigned long long *idx, uint64_t n, unsigned long long *n_new, const SyncIn *in = nullptr) { pdl_enter();
 	uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	if (in) n = in->ok ? in->n_p : 0;
 	uint32_t fresh = 0;
@@ -499,7 +499,7 @@ FQSK_HD unsigned long long *inbox_slot(unsigned long long *base, unsigned long l
 	return base + INBOX_HDR + ((unsigned long long) table * world + src) * cap;
 }
 // kind 0: p-mers (aligned index, owner by its top 12 bits), 1: s-/b-mers (normalised k-mer)
-__global__ void k_owner_keys(const unsigned long long *row, uint32_t n, uint32_t kind, uint32_t pshift, uint32_t world, uint8_t *keys, uint32_t *hist) {
+__global__ void k_owner_keys(const unsigned long long *row, uint32_t n, uint32_t kind, uint32_t pshift, uint32_t world, uint8_t *keys, uint32_t *hist) { pdl_enter();
 	__shared__ uint32_t sh[8];
 	if (threadIdx.x < 8) sh[threadIdx.x] = 0;
 	__syncthreads();
@@ -513,7 +513,7 @@ __global__ void k_owner_keys(const unsigned long long *row, uint32_t n, uint32_t
 	__syncthreads();
 	if (threadIdx.x < 8 && sh[threadIdx.x]) atomicAdd(hist + threadIdx.x, sh[threadIdx.x]);
 }
-__global__ void k_route_scatter(const unsigned long long *sorted, uint32_t n, const uint32_t *hist, InboxDev I, uint32_t table, int *flags) {
+__global__ void k_route_scatter(const unsigned long long *sorted, uint32_t n, const uint32_t *hist, InboxDev I, uint32_t table, int *flags) { pdl_enter();
 	uint32_t off[9];
 	off[0] = 0;
 	for (uint32_t o = 0; o < 8; ++o) off[o + 1] = off[o] + (o < I.world ? hist[o] : 0);
@@ -533,7 +533,7 @@ __global__ void k_route_scatter(const unsigned long long *sorted, uint32_t n, co
 // table-level batch mirrors
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void k_find(HtDev t, CIncP ci, const unsigned long long *dir, const unsigned long long *rc, const uint32_t *cur, uint32_t n,
-                       uint32_t *counts, const uint32_t *draws, unsigned long long dmask, unsigned long long dpos, unsigned long long avail, const unsigned long long *guess, uint32_t *used, int *flags) {
+                       uint32_t *counts, const uint32_t *draws, unsigned long long dmask, unsigned long long dpos, unsigned long long avail, const unsigned long long *guess, uint32_t *used, int *flags) { pdl_enter();
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	DrawCursor dc; dc.ring = draws; dc.mask = dmask; dc.pos0 = dpos; dc.avail = avail; dc.base = guess ? guess[i] : 0; dc.used = 0; dc.overflow = flags;
@@ -543,19 +543,19 @@ __global__ void k_find(HtDev t, CIncP ci, const unsigned long long *dir, const u
 	for (int q = 0; q < 4; ++q) counts[4 * i + q] = c[q];
 	used[i] = dc.used;
 }
-__global__ void k_count(HtDev t, const unsigned long long *kmers, uint32_t n, uint32_t *out) {
+__global__ void k_count(HtDev t, const unsigned long long *kmers, uint32_t n, uint32_t *out) { pdl_enter();
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n) out[i] = ht_count(t, kmers[i]);
 }
-__global__ void k_siv_test(SivDev s, const unsigned long long *idx, uint32_t n, uint32_t *out) {
+__global__ void k_siv_test(SivDev s, const unsigned long long *idx, uint32_t n, uint32_t *out) { pdl_enter();
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n) out[i] = siv_test(s, idx[i]);
 }
-__global__ void k_siv_counts(SivDev s, const unsigned long long *idx, uint32_t n, uint32_t *out) {
+__global__ void k_siv_counts(SivDev s, const unsigned long long *idx, uint32_t n, uint32_t *out) { pdl_enter();
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n) { uint32_t c[4]; siv_counts(s, idx[i], c, false); for (int q = 0; q < 4; ++q) out[4 * i + q] = c[q]; }
 }
-__global__ void k_siv_prefix(SivDev s, const unsigned long long *idx, const uint32_t *bits, uint32_t n, unsigned long long *out) {
+__global__ void k_siv_prefix(SivDev s, const unsigned long long *idx, const uint32_t *bits, uint32_t n, unsigned long long *out) { pdl_enter();
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n) out[i] = siv_prefix_sum(s, idx[i], bits[i]);
 }
@@ -571,7 +571,7 @@ __device__ __forceinline__ uint64_t ht_unmix(const HtDev &t, const MixInv &mi, u
 	x = (x * mi.inv1) & t.maskW;
 	return x;
 }
-__global__ void k_dump_ht(HtDev t, MixInv mi, unsigned long long *keys, unsigned long long *vals, unsigned long long cap, unsigned long long *n_out) {
+__global__ void k_dump_ht(HtDev t, MixInv mi, unsigned long long *keys, unsigned long long *vals, unsigned long long cap, unsigned long long *n_out) { pdl_enter();
 	uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	uint64_t nm = 8ull << t.B, ns = 1ull << t.stash_log2;
 	if (i >= nm + ns) return;
@@ -594,7 +594,7 @@ __global__ void k_dump_ht(HtDev t, MixInv mi, unsigned long long *keys, unsigned
 	unsigned long long o = atomicAdd(n_out, 1ull);
 	if (o < cap) { keys[o] = x; vals[o] = cnt; }
 }
-__global__ void k_dump_siv(SivDev s, unsigned long long *keys, unsigned long long *vals, unsigned long long cap, unsigned long long *n_out) {
+__global__ void k_dump_siv(SivDev s, unsigned long long *keys, unsigned long long *vals, unsigned long long cap, unsigned long long *n_out) { pdl_enter();
 	uint64_t w = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	uint64_t tops = s.world > 1 ? (4096 + s.world - 1) / s.world : 4096;      // this rank's shard: ceil(4096 / world) top values
 	uint64_t nw = s.world > 1 ? (tops << s.top_shift) >> 4 : (1ull << s.key_bits) >> 4;
@@ -611,7 +611,7 @@ __global__ void k_dump_siv(SivDev s, unsigned long long *keys, unsigned long lon
 	}
 }
 // re-insert dumped (k-mer, counter) pairs into a fresh, larger table
-__global__ void k_reinsert(HtDev t, const unsigned long long *keys, const unsigned long long *vals, uint64_t n) {
+__global__ void k_reinsert(HtDev t, const unsigned long long *keys, const unsigned long long *vals, uint64_t n) { pdl_enter();
 	uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	bool created;

@@ -59,7 +59,7 @@ __constant__ uint8_t PE_TRI_C[14] = {2, 4, 1, 3, 3, 4, 2, 2, 4, 1, 3, 4, 4, 2};
 // get a key above every real key) and the 4 look-up keys.
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_pe_minim(const uint8_t *dna, const unsigned long long *off, const uint32_t *len, uint32_t n_pairs, uint32_t b,
-                                                  unsigned long long *tri_key, unsigned long long *tri_val, unsigned long long *qkeys) {
+                                                  unsigned long long *tri_key, unsigned long long *tri_val, unsigned long long *qkeys) { pdl_enter();
 	const uint32_t pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (pair >= n_pairs) return;
 	__shared__ unsigned long long vals_all[4][8];
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(128) k_pe_minim(const uint8_t *dna, const unsi
 	}
 }
 
-__global__ void k_pe_gather(const unsigned long long *src, const uint32_t *idx, unsigned long long *dst, uint32_t n) {
+__global__ void k_pe_gather(const unsigned long long *src, const uint32_t *idx, unsigned long long *dst, uint32_t n) { pdl_enter();
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n) dst[i] = src[idx[i]];
 }
@@ -160,7 +160,7 @@ FQSK_DEV bool pe_before(unsigned long long x, unsigned long long y, uint32_t sh,
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_pe_decide(PairDev G, PeSeg L, const unsigned long long *qkeys, const uint8_t *dna, const unsigned long long *off, const uint32_t *len,
                                                    uint32_t n_pairs, uint32_t prefix_len, unsigned long long *pool, uint32_t *pool_used, uint32_t pool_cap, int *overflow,
-                                                   uint32_t *info, PeItems I) {
+                                                   uint32_t *info, PeItems I) { pdl_enter();
 	const uint32_t pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (pair >= n_pairs) return;
 	__shared__ unsigned long long top_all[4][48];
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(128) k_pe_decide(PairDev G, PeSeg L, const uns
 
 // item texts, one warp per item: a copy of the mate (or of its right part), or the reverse complement of its left part
 // (dna.cpp:1598-1602; reverse_complement_alhpa, utils.h:105-116)
-__global__ void __launch_bounds__(128) k_pe_fill(const uint8_t *dna, PeItems I, const uint32_t *off32, uint32_t n_items, uint8_t *out, unsigned long long *off64) {
+__global__ void __launch_bounds__(128) k_pe_fill(const uint8_t *dna, PeItems I, const uint32_t *off32, uint32_t n_items, uint8_t *out, unsigned long long *off64) { pdl_enter();
 	const uint32_t it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (it > n_items) return;
 	if (lane == 0) off64[it] = off32[it];
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(128) k_pe_fill(const uint8_t *dna, PeItems I, 
 // pair is inserted once: no two threads ever work on the same item.  A slot claimed by another new pair shows an unwritten
 // value part (value_mask) until its owner stores it, which no real value equals -- so it is skipped, as it must be.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void k_pair_insert(PairDev G, PeSeg L, unsigned long long *n_items) {
+__global__ void k_pair_insert(PairDev G, PeSeg L, unsigned long long *n_items) { pdl_enter();
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= L.n) return;
 	const unsigned long long key = L.skey[i], val = L.sval[i];
@@ -300,7 +300,7 @@ __global__ void k_pair_insert(PairDev G, PeSeg L, unsigned long long *n_items) {
 	}
 }
 
-__global__ void k_pair_rehash(PairDev old_t, PairDev new_t) {
+__global__ void k_pair_rehash(PairDev old_t, PairDev new_t) { pdl_enter();
 	const unsigned long long slots = old_t.mask + 1;
 	for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < slots; i += (unsigned long long) gridDim.x * blockDim.x) {
 		const unsigned long long key = old_t.keys[i];

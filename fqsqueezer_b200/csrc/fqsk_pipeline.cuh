@@ -119,7 +119,7 @@ __device__ __forceinline__ void put_rec(fqsk_base_rec *rec, uint32_t pos, const 
 // k_lookup: the find_counts cascade (dna.cpp:457-502) for the uncorrected registers of every coded position, global
 // tables only.  Front-truncated table lookups are left to k_partial (flagged here).
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_lookup(EngineDev E, SegDev S, PipeDev P) {
+__global__ void __launch_bounds__(256) k_lookup(EngineDev E, SegDev S, PipeDev P) { pdl_enter();
 	uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
 	if (g >= *P.n_rec_dev) return;
 	uint32_t r = find_read(S.rec_off, S.n_reads, g);
@@ -171,7 +171,12 @@ __global__ void __launch_bounds__(256) k_lookup(EngineDev E, SegDev S, PipeDev P
 	put_rec(P.prov + g, i, c, lev);
 	P.pflags[g] = fl;
 	if ((fl & (PF_MISS_B | PF_MISS_S)) && !(fl & (PF_PARTIAL_B | PF_PARTIAL_S))) {
-		uint32_t m = atomicAdd(P.n_miss, 1u);
+		// warp-aggregated append: misses come in runs (an uncovered stretch, the b positions after an error), one atomic per warp
+		const unsigned am = __activemask();
+		const uint32_t lane = threadIdx.x & 31, leader = (uint32_t) __ffs(am) - 1;
+		uint32_t m = 0;
+		if (lane == leader) m = atomicAdd(P.n_miss, (uint32_t) __popc(am));
+		m = __shfl_sync(am, m, leader) + __popc(am & ((1u << lane) - 1u));
 		if (m >= P.miss_cap) P.flags[4] = 1;
 		if (m < P.miss_cap) {
 			MissEntry e;
@@ -208,7 +213,7 @@ __device__ __forceinline__ void script_append(PipeDev &P, Script &sc, uint32_t &
 	n = total;
 }
 
-__global__ void __launch_bounds__(128) k_partial(EngineDev E, SegDev S, PipeDev P) {
+__global__ void __launch_bounds__(128) k_partial(EngineDev E, SegDev S, PipeDev P) { pdl_enter();
 	// one warp per (read, partial slot); slot -> n = pfirst_n + slot symbols in the registers (placeholder included)
 	uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	uint32_t lane = threadIdx.x & 31;
@@ -294,7 +299,7 @@ __global__ void __launch_bounds__(128) k_partial(EngineDev E, SegDev S, PipeDev 
 // ------------------------------------------------------------------------------------------------------------------
 // phase 1 (always): evaluate the entries; phase 0 (hot mode only): find the front-truncated entries whose thread-local merge
 // has to go through the ordered evaluator and queue them as events of their PRNG stream.
-__global__ void __launch_bounds__(128) k_local(EngineDev E, SegDev S, PipeDev P, int phase) {
+__global__ void __launch_bounds__(128) k_local(EngineDev E, SegDev S, PipeDev P, int phase) { pdl_enter();
 	if (S.delta_b.n == 0 && S.delta_s.n == 0) return;
 	uint32_t n_miss = *P.n_miss;
 	if (n_miss > P.miss_cap) n_miss = P.miss_cap;
@@ -351,7 +356,7 @@ __global__ void __launch_bounds__(128) k_local(EngineDev E, SegDev S, PipeDev P,
 // k_local(phase 0) queues the merges, the events are sorted by time and k_hot_eval walks them sequentially (one thread per
 // stream).  Rare by construction: only segments that raised the flag are redone this way.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void k_delta_rank(DeltaDev D, PipeDev P, uint32_t stream) {
+__global__ void k_delta_rank(DeltaDev D, PipeDev P, uint32_t stream) { pdl_enter();
 	const uint64_t slots = (uint64_t) D.mask + 1;
 	for (uint64_t sidx = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; sidx < slots; sidx += (uint64_t) gridDim.x * blockDim.x) {
 		const uint32_t tm = D.times[sidx];
@@ -388,7 +393,7 @@ struct DeltaCollect {    // matches of a front-truncated context: (trial index, 
 };
 
 __global__ void k_hot_eval(EngineDev E, SegDev S, PipeDev P, const unsigned long long *ek0, const uint32_t *ev0, uint32_t n0,
-                           const unsigned long long *ek1, const uint32_t *ev1, uint32_t n1) {
+                           const unsigned long long *ek1, const uint32_t *ev1, uint32_t n1) { pdl_enter();
 	if ((threadIdx.x & 31) != 0) return;
 	const uint32_t st = threadIdx.x >> 5;     // 0: b / cinc_lb, 1: s / cinc_ls
 	if (st > 1) return;
@@ -467,7 +472,7 @@ __device__ __forceinline__ KReg ring_breg(const uint8_t *ring, uint32_t i, uint3
 	return r;
 }
 
-__global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P, uint32_t it) {
+__global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P, uint32_t it) { pdl_enter();
 	const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (r >= S.n_reads) return;
 	if (it > 0) { if (!P.dirty[r]) return; }
@@ -710,7 +715,7 @@ __global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P, 
 }
 
 __global__ void k_compact2(SegDev S, PipeDev P, const uint32_t *off_b, const uint32_t *off_s, const uint32_t *off_p,
-                           unsigned long long *row_b, unsigned long long *row_s, unsigned long long *row_p, uint32_t *rt_b, uint32_t *rt_s) {
+                           unsigned long long *row_b, unsigned long long *row_s, unsigned long long *row_p, uint32_t *rt_b, uint32_t *rt_s) { pdl_enter();
 	uint32_t r = blockIdx.x;
 	if (r >= S.n_reads) return;
 	const unsigned long long *sb = S.push_b + 2 * S.off[r], *ss = S.push_s + S.off[r], *sp = S.push_p + 2 * S.off[r] + 2ull * r;
@@ -722,7 +727,7 @@ __global__ void k_compact2(SegDev S, PipeDev P, const uint32_t *off_b, const uin
 // delta build straight from the per-read push regions: one warp per read, one entry per push, placed by the canonical
 // inner core of its k-mer
 __global__ void __launch_bounds__(128) k_delta_build(SegDev S, PipeDev P, unsigned long long *kb, uint32_t *tb, uint32_t mask_b, uint32_t k_b, uint32_t t_b,
-                                                     unsigned long long *ks, uint32_t *ts, uint32_t mask_s, uint32_t k_s, uint32_t t_s) {
+                                                     unsigned long long *ks, uint32_t *ts, uint32_t mask_s, uint32_t k_s, uint32_t t_s) { pdl_enter();
 	uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (r >= S.n_reads) return;
 	const unsigned long long *sb = S.push_b + 2 * S.off[r], *ss = S.push_s + S.off[r];
@@ -739,11 +744,40 @@ __global__ void __launch_bounds__(128) k_delta_build(SegDev S, PipeDev P, unsign
 	}
 }
 
+// the same for small segments, one thread per slot of the push regions: a segment of a few hundred reads has too few warps to
+// hide the latency of a warp-per-read loop, but tens of thousands of pushes
+__global__ void __launch_bounds__(256) k_delta_build_flat(SegDev S, PipeDev P, uint32_t slots_total, unsigned long long *kb, uint32_t *tb, uint32_t mask_b, uint32_t k_b, uint32_t t_b,
+                                                          unsigned long long *ks, uint32_t *ts, uint32_t mask_s, uint32_t k_s, uint32_t t_s) { pdl_enter();
+	const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;      // slot of the b regions, then of the s regions: [0, 2T) [2T, 3T), T = bytes of the segment
+	if (g >= 3 * slots_total) return;
+	const bool is_b = g < 2 * slots_total;
+	const uint32_t j = is_b ? g : g - 2 * slots_total;
+	const uint32_t at = is_b ? j >> 1 : j;                           // byte offset whose read owns the slot (regions: b at 2 * off, s at off)
+	uint32_t lo = 0, hi = S.n_reads;                                 // last read with off <= at
+	while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if ((uint32_t) S.off[m] <= at) lo = m; else hi = m; }
+	const uint32_t r = lo;
+	if (is_b) {
+		const uint32_t i = j - 2 * (uint32_t) S.off[r];
+		if (i >= S.cnt_b[r]) return;
+		const unsigned long long x = S.push_b[j];
+		const uint32_t tm = P.time_b[j];
+		for (uint64_t slot = delta_slot_of_key(x, k_b, t_b, mask_b);; slot = (slot + 1) & mask_b)
+			if (atomicCAS(tb + slot, DELTA_EMPTY, tm) == DELTA_EMPTY) { kb[slot] = x; break; }
+	} else {
+		const uint32_t i = j - (uint32_t) S.off[r];
+		if (i >= S.cnt_s[r]) return;
+		const unsigned long long x = S.push_s[j];
+		const uint32_t tm = P.time_s[j];
+		for (uint64_t slot = delta_slot_of_key(x, k_s, t_s, mask_s);; slot = (slot + 1) & mask_s)
+			if (atomicCAS(ts + slot, DELTA_EMPTY, tm) == DELTA_EMPTY) { ks[slot] = x; break; }
+	}
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // k_rough: one warp per request.  find_counts_rough_{s,b} (dna.cpp:257-330): 4(k-1) single-substitution neighbours across the
 // lanes, non-empty ones appended in trial order to a merge script; find_counts_rough_p (dna.cpp:229-254) is a plain sum.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_rough(EngineDev E, PipeDev P) {
+__global__ void __launch_bounds__(128) k_rough(EngineDev E, PipeDev P) { pdl_enter();
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t n_rec = *P.n_rec_dev;
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
@@ -866,7 +900,7 @@ __device__ __forceinline__ uint32_t warp_excl_sum(uint32_t v, uint32_t lane, uin
 // pass 1 gives every script its exact offset (read offset from the scan over reads + the counts of the scripts before it)
 // and writes the final counts.  A count that differs from the stored one (a counter saturated) raises flags[7]: the host
 // scans and runs pass 1 again.
-__global__ void __launch_bounds__(128) k_fold(EngineDev E, SegDev S, PipeDev P, int pass) {
+__global__ void __launch_bounds__(128) k_fold(EngineDev E, SegDev S, PipeDev P, int pass) { pdl_enter();
 	const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (r >= S.n_reads) return;
 	uint32_t used[2] = {0, 0};          // draws of the scripts visited so far, per stream (b, s), as assumed by the offsets
@@ -955,58 +989,95 @@ struct SegTotals {        // written by the scan kernels, read by the host once 
 	unsigned long long draws_b, draws_s;
 };
 
-// single-CTA scans over per-read arrays (n_reads is at most a few 10^4: one CTA beats a chain of library launches)
-__global__ void __launch_bounds__(1024) k_scan_reads(SegDev S, unsigned long long *rec_off, U64x4 *sl_prefix, SegTotals *tot, uint32_t *n_rec_dev) {
+// Scans over per-read arrays, one CTA per chunk of 1024 * ITEMS reads (a single CTA is bound by what one SM can pull from
+// HBM: 0.28 ms for 51 000 reads).  Every CTA scans its chunk, publishes the chunk totals tagged with the launch epoch and adds
+// up the totals of the CTAs before it (cta_chain_prefix).  Grids are small (<= 2 CTAs per SM), so all CTAs are co-resident and
+// waiting for lower-numbered ones cannot deadlock.
+struct ScanChain { unsigned long long *vals; uint32_t *flags; uint32_t epoch; };     // vals[cta][8], flags[cta]
+static const uint32_t SCAN_CHAIN_MAX = 256;
+
+template <int NQ>
+__device__ __forceinline__ void cta_chain_prefix(const ScanChain &C, const unsigned long long *mine /* shared, [NQ] */, unsigned long long (&pre)[NQ], unsigned long long (*sh)[32]) {
+	const uint32_t b = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5, nw = blockDim.x >> 5;
+	if (t == 0) {
+		for (int q = 0; q < NQ; ++q) C.vals[b * 8 + q] = mine[q];
+		__threadfence();
+		atomicExch(C.flags + b, C.epoch);
+	}
+	unsigned long long acc[NQ];
+	for (int q = 0; q < NQ; ++q) acc[q] = 0;
+	for (uint32_t c = t; c < b; c += blockDim.x) {
+		while (*((volatile uint32_t *) (C.flags + c)) != C.epoch) { }
+		__threadfence();
+		for (int q = 0; q < NQ; ++q) acc[q] += *((volatile unsigned long long *) (C.vals + c * 8 + q));
+	}
+	for (int q = 0; q < NQ; ++q) {
+		for (int o = 16; o; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+		if (lane == 0) sh[q][w] = acc[q];
+	}
+	__syncthreads();
+	for (int q = 0; q < NQ; ++q) { unsigned long long x = 0; for (uint32_t i = 0; i < nw; ++i) x += sh[q][i]; pre[q] = x; }
+	__syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) k_scan_reads(SegDev S, unsigned long long *rec_off, U64x4 *sl_prefix, SegTotals *tot, uint32_t *n_rec_dev, ScanChain C) { pdl_enter();
 	const int IT = 4;
 	__shared__ unsigned long long sh[5][32];
 	__shared__ unsigned long long carry[5];
 	const uint32_t t = threadIdx.x;
 	if (t < 5) carry[t] = 0;
 	__syncthreads();
-	for (uint32_t base = 0; base < S.n_reads; base += 1024 * IT) {
-		unsigned long long v[5][IT], ex[5][IT];
-		for (int e = 0; e < IT; ++e) {
-			uint32_t r = base + t * IT + e;
-			if (r < S.n_reads) { v[0][e] = S.n_coded[r]; U64x4 L = S.letters[r]; v[1][e] = L.v[0]; v[2][e] = L.v[1]; v[3][e] = L.v[2]; v[4][e] = L.v[3]; }
-			else { v[0][e] = v[1][e] = v[2][e] = v[3][e] = v[4][e] = 0; }
-		}
-		block_scan_chunk<unsigned long long, 5, IT>(v, ex, sh, carry);
-		for (int e = 0; e < IT; ++e) {
-			uint32_t r = base + t * IT + e;
-			if (r < S.n_reads) { rec_off[r] = ex[0][e]; U64x4 o; o.v[0] = ex[1][e]; o.v[1] = ex[2][e]; o.v[2] = ex[3][e]; o.v[3] = ex[4][e]; sl_prefix[r] = o; }
-		}
+	const uint32_t base = blockIdx.x * 1024 * IT;
+	unsigned long long v[5][IT], ex[5][IT];
+	for (int e = 0; e < IT; ++e) {
+		uint32_t r = base + t * IT + e;
+		if (r < S.n_reads) { v[0][e] = S.n_coded[r]; U64x4 L = S.letters[r]; v[1][e] = L.v[0]; v[2][e] = L.v[1]; v[3][e] = L.v[2]; v[4][e] = L.v[3]; }
+		else { v[0][e] = v[1][e] = v[2][e] = v[3][e] = v[4][e] = 0; }
 	}
-	if (t == 0) {
-		rec_off[S.n_reads] = carry[0];
-		U64x4 o; o.v[0] = carry[1]; o.v[1] = carry[2]; o.v[2] = carry[3]; o.v[3] = carry[4];
+	block_scan_chunk<unsigned long long, 5, IT>(v, ex, sh, carry);      // carry = totals of this chunk
+	unsigned long long pre[5];
+	cta_chain_prefix<5>(C, carry, pre, sh);
+	for (int e = 0; e < IT; ++e) {
+		uint32_t r = base + t * IT + e;
+		if (r < S.n_reads) { rec_off[r] = pre[0] + ex[0][e]; U64x4 o; o.v[0] = pre[1] + ex[1][e]; o.v[1] = pre[2] + ex[2][e]; o.v[2] = pre[3] + ex[3][e]; o.v[3] = pre[4] + ex[4][e]; sl_prefix[r] = o; }
+	}
+	if (t == 0 && blockIdx.x == gridDim.x - 1) {
+		rec_off[S.n_reads] = pre[0] + carry[0];
+		U64x4 o; o.v[0] = pre[1] + carry[1]; o.v[1] = pre[2] + carry[2]; o.v[2] = pre[3] + carry[3]; o.v[3] = pre[4] + carry[4];
 		sl_prefix[S.n_reads] = o;
-		tot->n_rec = carry[0]; tot->letters = o;
-		*n_rec_dev = (uint32_t) carry[0];
+		tot->n_rec = pre[0] + carry[0]; tot->letters = o;
+		*n_rec_dev = (uint32_t) (pre[0] + carry[0]);
 	}
 }
 
 // up to 4 u32 arrays -> exclusive scans (u32) + totals
+static const uint32_t SCAN_U32_CHUNK = 1024 * 8, SCAN_READS_CHUNK = 1024 * 4;
 __global__ void __launch_bounds__(1024) k_scan_u32x4(uint32_t n, const uint32_t *a0, uint32_t *o0, const uint32_t *a1, uint32_t *o1,
-                                                     const uint32_t *a2, uint32_t *o2, const uint32_t *a3, uint32_t *o3, uint32_t *totals) {
+                                                     const uint32_t *a2, uint32_t *o2, const uint32_t *a3, uint32_t *o3, uint32_t *totals, uint32_t *zero_me, ScanChain C) { pdl_enter();
 	const int IT = 8;
-	__shared__ uint32_t sh[4][32];
-	__shared__ uint32_t carry[4];
+	__shared__ unsigned long long sh[4][32];
+	__shared__ unsigned long long carry[4];
 	const uint32_t t = threadIdx.x;
 	const uint32_t *in[4] = {a0, a1, a2, a3};
 	uint32_t *out[4] = {o0, o1, o2, o3};
 	if (t < 4) carry[t] = 0;
 	__syncthreads();
-	for (uint32_t base = 0; base < n; base += 1024 * IT) {
-		uint32_t v[4][IT], ex[4][IT];
-		for (int q = 0; q < 4; ++q) for (int e = 0; e < IT; ++e) { uint32_t r = base + t * IT + e; v[q][e] = (in[q] && r < n) ? in[q][r] : 0; }
-		block_scan_chunk<uint32_t, 4, IT>(v, ex, sh, carry);
-		for (int q = 0; q < 4; ++q) if (out[q]) for (int e = 0; e < IT; ++e) { uint32_t r = base + t * IT + e; if (r < n) out[q][r] = ex[q][e]; }
+	const uint32_t base = blockIdx.x * 1024 * IT;
+	unsigned long long v[4][IT], ex[4][IT];
+	for (int q = 0; q < 4; ++q) for (int e = 0; e < IT; ++e) { uint32_t r = base + t * IT + e; v[q][e] = (in[q] && r < n) ? in[q][r] : 0; }
+	block_scan_chunk<unsigned long long, 4, IT>(v, ex, sh, carry);
+	unsigned long long pre[4];
+	cta_chain_prefix<4>(C, carry, pre, sh);
+	for (int q = 0; q < 4; ++q) if (out[q]) for (int e = 0; e < IT; ++e) { uint32_t r = base + t * IT + e; if (r < n) out[q][r] = (uint32_t) (pre[q] + ex[q][e]); }
+	if (blockIdx.x == gridDim.x - 1) {
+		if (t < 4) { if (out[t]) out[t][n] = (uint32_t) (pre[t] + carry[t]); totals[t] = (uint32_t) (pre[t] + carry[t]); }
+		if (t == 0 && zero_me) *zero_me = 0;
 	}
-	if (t < 4) { if (out[t]) out[t][n] = carry[t]; totals[t] = carry[t]; }
 }
 
 // per-read draw counts (u32) -> exclusive scans (u64) + totals
-__global__ void __launch_bounds__(1024) k_scan_draws(uint32_t n, const uint32_t *a0, unsigned long long *o0, const uint32_t *a1, unsigned long long *o1, unsigned long long *totals) {
+__global__ void __launch_bounds__(1024) k_scan_draws(uint32_t n, const uint32_t *a0, unsigned long long *o0, const uint32_t *a1, unsigned long long *o1, unsigned long long *totals,
+                                                     int *flags, ScanChain C) { pdl_enter();
 	const int IT = 8;
 	__shared__ unsigned long long sh[2][32];
 	__shared__ unsigned long long carry[2];
@@ -1015,13 +1086,17 @@ __global__ void __launch_bounds__(1024) k_scan_draws(uint32_t n, const uint32_t 
 	unsigned long long *out[2] = {o0, o1};
 	if (t < 2) carry[t] = 0;
 	__syncthreads();
-	for (uint32_t base = 0; base < n; base += 1024 * IT) {
-		unsigned long long v[2][IT], ex[2][IT];
-		for (int q = 0; q < 2; ++q) for (int e = 0; e < IT; ++e) { uint32_t r = base + t * IT + e; v[q][e] = r < n ? in[q][r] : 0; }
-		block_scan_chunk<unsigned long long, 2, IT>(v, ex, sh, carry);
-		for (int q = 0; q < 2; ++q) for (int e = 0; e < IT; ++e) { uint32_t r = base + t * IT + e; if (r < n) out[q][r] = ex[q][e]; }
+	const uint32_t base = blockIdx.x * 1024 * IT;
+	unsigned long long v[2][IT], ex[2][IT];
+	for (int q = 0; q < 2; ++q) for (int e = 0; e < IT; ++e) { uint32_t r = base + t * IT + e; v[q][e] = r < n ? in[q][r] : 0; }
+	block_scan_chunk<unsigned long long, 2, IT>(v, ex, sh, carry);
+	unsigned long long pre[2];
+	cta_chain_prefix<2>(C, carry, pre, sh);
+	for (int q = 0; q < 2; ++q) for (int e = 0; e < IT; ++e) { uint32_t r = base + t * IT + e; if (r < n) out[q][r] = pre[q] + ex[q][e]; }
+	if (blockIdx.x == gridDim.x - 1) {
+		if (t < 2) { out[t][n] = pre[t] + carry[t]; totals[t] = pre[t] + carry[t]; }
+		if (t == 0 && flags) { flags[0] = 0; flags[7] = 0; }      // draw window short / offsets moved: k_fold pass 1 reports them afresh
 	}
-	if (t < 2) { out[t][n] = carry[t]; totals[t] = carry[t]; }
 }
 
 // draw flags (u8, push order) -> exclusive scan = draw index of every occurrence; n lives on the device.  Chained scan: every
@@ -1030,7 +1105,7 @@ __global__ void __launch_bounds__(1024) k_scan_draws(uint32_t n, const uint32_t 
 // long), so waiting on lower-numbered CTAs cannot deadlock.
 static const uint32_t SCANF_TILE = 4096;
 __global__ void __launch_bounds__(256) k_scan_flags(const SyncIn *in, const uint32_t *n_dev, const uint8_t *flag, uint32_t *out, uint32_t *total,
-                                                    unsigned long long *partials, uint32_t epoch) {
+                                                    unsigned long long *partials, uint32_t epoch) { pdl_enter();
 	const uint32_t n = in->ok ? *n_dev : 0;
 	const uint32_t b = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
 	const uint32_t base = b * SCANF_TILE;
@@ -1089,7 +1164,7 @@ __global__ void __launch_bounds__(256) k_scan_flags(const SyncIn *in, const uint
 // Verdict of a segment's first pass, for the sync that is enqueued right behind it without a host look: the pass settled when
 // no flag asks for another iteration, a retry or the ordered thread-local evaluator.
 __global__ void k_seg_verdict(const int *flags, const uint32_t *tot4, const unsigned long long *draws2, unsigned long long consumed_b, unsigned long long consumed_s,
-                              uint32_t row_cap, SyncIn *in) {
+                              uint32_t row_cap, SyncIn *in) { pdl_enter();
 	if (threadIdx.x || blockIdx.x) return;
 	bool ok = !(flags[0] | flags[1] | flags[2] | flags[4] | flags[5] | flags[7]);
 	if (tot4[0] > row_cap || tot4[1] > row_cap) ok = false;
@@ -1098,7 +1173,17 @@ __global__ void k_seg_verdict(const int *flags, const uint32_t *tot4, const unsi
 	in->draws_b = 0;
 	in->ok = ok ? 1u : 0u;
 }
-__global__ void k_set_syncin(SyncIn *in, uint32_t n_b, uint32_t n_s, uint32_t n_p, unsigned long long dpos_b, unsigned long long dpos_s) {
+// status words at their start-of-segment values (layout: fqsk_create)
+__global__ void k_seg_reset(uint8_t *status, unsigned long long *counters) { pdl_enter();
+	const uint32_t t = threadIdx.x;
+	uint32_t *w = reinterpret_cast<uint32_t *>(status);
+	if (t < 11) w[t] = 0;                                  // +0 flags[8], +32 n_miss, n_rscript, pool_used
+	if (t >= 12 && t < 16) w[t] = 0;                       // +48 hot-mode event counts / draws
+	if (t == 16) w[224 / 4] = 0;                           // s-mer fast-path verdict
+	if (t >= 32 && t < 40) w[304 / 4 + (t - 32)] = 0;      // flags of the ordered insert
+	if (t == 40) counters[4] = 0;                          // fresh p-mer fields
+}
+__global__ void k_set_syncin(SyncIn *in, uint32_t n_b, uint32_t n_s, uint32_t n_p, unsigned long long dpos_b, unsigned long long dpos_s) { pdl_enter();
 	if (threadIdx.x || blockIdx.x) return;
 	in->ok = 1; in->n_b = n_b; in->n_s = n_s; in->n_p = n_p; in->dpos_b = dpos_b; in->dpos_s = dpos_s; in->draws_b = 0;
 }

@@ -1,29 +1,35 @@
-import sys, time, numpy as np
-sys.path.insert(0, '.')
-from fqsqueezer_b200 import engine as E, synth, schedule as S
-pref,p,s,b = E.kmer_params(100)
-G = int(sys.argv[1]) if len(sys.argv)>1 else 100_000_000
-nblocks = int(sys.argv[2]) if len(sys.argv)>2 else 6
-steady_after = int(sys.argv[3]) if len(sys.argv)>3 else 10**9
-every = int(sys.argv[4]) if len(sys.argv)>4 else 1
-t=time.time(); genome = synth.make_genome(G, 43); print('genome', time.time()-t, flush=True)
-e = E.KmerEngine(p,s,b,pref, expected_kmers=1<<27, profile=True)
-print('engine', time.time()-t, flush=True)
-L=150; per_block=51000
-from tests.test_gpu_segment import _fastq_slab
-tot=0; t0=time.time(); prev={}
-for g in range(nblocks):
-    codes,_ = synth.make_reads(genome, per_block, L=L, seed=1000+g)
-    slab = _fastq_slab(codes)
-    off,ln,roff,rsz = S.parse_fastq(slab)
-    ns = S.calc_no_synchronizations(g if g < steady_after else 100, per_block, 1)
-    e.block_start()
-    tb=time.time()
-    for a,bb in S.segments(0, per_block, ns):
-        e.segment(slab, off[a:bb], ln[a:bb]); e.sync()
-    dt=time.time()-tb
-    st=e.stats()
-    if g % every == 0 or g == nblocks-1: print(f'block {g}: {dt*1e3:.1f} ms  {per_block*L/dt/1e6:.1f} Mbases/s  replays/seg={st["n_replays"]/st["n_segments"]:.2f} launches={st["kernel_launches"]} bmers={st["n_bmers"]} stash={st["bmer_stash_used"]}', flush=True)
-    pr=e.profile()
-    if g % every == 0 or g == nblocks-1: print('   ', {k: round(v-prev.get(k,0),1) for k,v in pr.items()}, flush=True)
-    prev=pr
+"""Scratch probe (not part of the product): host-side time per C-ABI call in the early, small-segment regime."""
+import sys, time, os
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import bench as B
+from fqsqueezer_b200 import engine as E, schedule as S, synth
+
+pref, p, s, b = E.kmer_params(B.GS)
+genome = synth.make_genome(B.GENOME, B.SEED)
+dev = torch.device("cuda", 0)
+NB = int(sys.argv[1]) if len(sys.argv) > 1 else 24
+eng = E.KmerEngine(p, s, b, pref, expected_kmers=1 << 29, reserve_reads=B.READS_PER_BLOCK, reserve_bytes=B.READS_PER_BLOCK * B.L)
+d_off = torch.from_numpy(np.arange(B.READS_PER_BLOCK, dtype=np.int64) * B.L).to(dev)
+d_len = torch.full((B.READS_PER_BLOCK,), B.L, dtype=torch.int32, device=dev)
+blocks = [torch.from_numpy(synth.codes_to_ascii(B.block_codes(genome, g, 0)).reshape(-1)).to(dev) for g in range(NB)]
+torch.cuda.synchronize()
+for g in range(NB):
+    sched = list(S.segments(0, B.READS_PER_BLOCK, S.calc_no_synchronizations(g, B.READS_PER_BLOCK, 1)))
+    eng.block_start()
+    base = blocks[g].data_ptr()
+    t_seg = t_sync = 0.0
+    t0 = time.perf_counter()
+    for a, bb in sched:
+        n = bb - a
+        t1 = time.perf_counter()
+        eng.segment_device(base + a * B.L, n * B.L, d_off.data_ptr(), d_len.data_ptr(), n, want_n_recs=False)
+        t2 = time.perf_counter()
+        eng.sync()
+        t3 = time.perf_counter()
+        t_seg += t2 - t1; t_sync += t3 - t2
+    tot = time.perf_counter() - t0
+    if g >= 4:
+        print(f"block {g}: {len(sched)} segs, per segment: total {1e6 * tot / len(sched):.0f} us, segment_device (enqueue only) {1e6 * t_seg / len(sched):.0f} us, sync (enqueue + look) {1e6 * t_sync / len(sched):.0f} us")
+st = eng.stats()
+print({k: st[k] for k in ("n_segments", "n_replays", "kernel_launches", "n_hot_segments")})
