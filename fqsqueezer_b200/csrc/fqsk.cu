@@ -142,6 +142,16 @@ struct fqsk_handle {
 	DevBuf pe_tk, pe_tv, pe_q, pe_sk, pe_sv, pe_sidx, pe_t1, pe_t2, pe_pool, pe_info, it_src, it_len, it_bytes, it_first, it_bias, it_dupprev,
 	       it_flags, it_off32, it_off64, it_dna;
 	uint32_t pe_pool_cap = 1u << 20, pe_pairs = 0, pe_nt = 0, seg_reads_in = 0;
+	// the sync enqueued behind its segment (sync_spec_enqueue / sync_spec_finish)
+	bool spec_enqueued = false; SyncDev spec_Y{}; uint32_t spec_g = 0;
+	bool seg_extra_pass = false;             // the last segment needed more than its first pass: records were rewritten after the pass
+	// fqsk_submit / fqsk_collect: double-buffered records, copies on their own stream
+	DevBuf recs_alt; int rec_par = 0;
+	cudaStream_t st_copy = nullptr; cudaEvent_t ev_recs = nullptr, ev_copied[2] = {nullptr, nullptr};
+	uint8_t *h_stage2 = nullptr; size_t h_stage2_cap = 0;       // second pinned staging buffer (H2D of segment n + 1 while n is still needed)
+	uint8_t *h_meta[2] = {nullptr, nullptr}; size_t h_meta_cap[2] = {0, 0};   // pinned per-ticket copies of dup / rec_off (item arrays in paired-end mode)
+	struct Ticket { bool open = false, done = false; fqsk_base_rec *recs = nullptr; uint64_t bound = 0, n_recs = 0; uint8_t *dup = nullptr; uint64_t *rec_off = nullptr; uint32_t n_reads = 0; int par = 0; uint64_t id = 0; } tk[2];
+	bool tk_open = false; int tk_cur = 0; uint64_t tk_next = 1;
 	// pinned staging
 	uint8_t *h_stage = nullptr; size_t h_stage_cap = 0;
 	void *h_small = nullptr;              // pinned scratch for small D2H reads
@@ -629,7 +639,7 @@ int seg_setup(fqsk_handle *h) {
 	const uint32_t rec_bound = (uint32_t) C.dna_bytes_actual;          // coded positions <= DNA bytes
 	const size_t r1 = (size_t) dna_bytes + 1;
 	const uint32_t pslots = h->P.bmer_len - h->P.pmer_len + 1;
-	CK(h->prov.ensure(r1 * sizeof(fqsk_base_rec))); CK(h->recs.ensure(r1 * sizeof(fqsk_base_rec))); CK(h->pflags.ensure(r1));
+	CK(h->prov.ensure(r1 * sizeof(fqsk_base_rec))); CK((h->rec_par ? h->recs_alt : h->recs).ensure(r1 * sizeof(fqsk_base_rec))); CK(h->pflags.ensure(r1));
 	CK(h->rkind.ensure(r1)); CK(h->rreg.ensure(r1 * sizeof(KReg))); CK(h->rslot.ensure(r1 * 4)); CK(h->dirty.ensure(n1));
 	CK(h->pscripts.ensure(n1 * pslots * sizeof(Script)));
 	CK(h->rscripts.ensure(((size_t) h->rreq_cap + 1) * sizeof(Script)));
@@ -646,7 +656,7 @@ int seg_setup(fqsk_handle *h) {
 	PipeDev &P = C.P;
 	P = PipeDev{};
 	P.n_rec = rec_bound; P.start = C.first; P.rec_off = S.rec_off;
-	P.prov = h->prov.as<fqsk_base_rec>(); P.recs = h->recs.as<fqsk_base_rec>(); P.pflags = h->pflags.as<uint8_t>();
+	P.prov = h->prov.as<fqsk_base_rec>(); P.recs = (h->rec_par ? h->recs_alt : h->recs).as<fqsk_base_rec>(); P.pflags = h->pflags.as<uint8_t>();
 	P.pscripts = h->pscripts.as<Script>(); P.pslots = pslots; P.pfirst_n = h->P.pmer_len - 1;
 	P.rscripts = h->rscripts.as<Script>(); P.n_rscript = h->d_u32 + 1; P.rscript_cap = h->rreq_cap;
 	P.rkind = h->rkind.as<uint8_t>(); P.rreg = h->rreg.as<KReg>(); P.rslot = h->rslot.as<uint32_t>(); P.dirty = h->dirty.as<uint8_t>();
@@ -790,14 +800,16 @@ int seg_finish(fqsk_handle *h, bool have_look) {
 			if (cnt[0] > h->miss_cap) h->miss_cap = cnt[0] + cnt[0] / 4 + 1024;
 			if (cnt[1] > h->rreq_cap) h->rreq_cap = cnt[1] + cnt[1] / 4 + 1024;
 			if (cnt[2] > h->pool_cap) h->pool_cap = cnt[2] + cnt[2] / 2 + 1024;
+			h->seg_extra_pass = true;
 			return RC_RETRY;
 		}
 		if (fl[5]) return fail(h, FQSK_E_CUDA, "internal error: a draw was requested on a path that must not draw");
 		if (fl[1]) {
 			// a thread-local counter left the deterministic range: redo the segment with the ordered evaluator
-			if (!h->hot) { h->hot = true; ++h->S.n_hot_segments; return RC_RETRY; }
+			if (!h->hot) { h->hot = true; ++h->S.n_hot_segments; h->seg_extra_pass = true; return RC_RETRY; }
 			return fail(h, FQSK_E_UNSUPPORTED, "a front-truncated thread-local lookup matched more than %u entries; not supported", DeltaCollect::CAP);
 		}
+		if (fl[2] || fl[0] || fl[7]) h->seg_extra_pass = true;
 		if (fl[2]) { C.redo_walk = true; C.redo_tail = true; CKR(seg_pass(h)); continue; }      // walk `it` changed pushes: one more thread-local pass
 		C.redo_walk = false;
 		if (fl[0]) {   // the pre-generated draw window was too short: extend and evaluate the merges again
@@ -935,7 +947,7 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 	if (h->world > 1 && h->attached != (1u << h->world) - 1) return fail(h, FQSK_E_INVAL, "sharded engine: not every peer shard is attached (fqsk_shard_attach)");
 	const uint32_t first = (h->P.mode == FQSK_MODE_SE_SORTED || h->P.mode == FQSK_MODE_PE_SORTED) ? h->P.pmer_len : h->P.prefix_len;
 	h->seg_reads = n; h->n_recs = 0; h->pend_b = h->pend_s = h->pend_p = 0;
-	h->hot = false;
+	h->hot = false; h->seg_extra_pass = false;
 	++h->S.n_segments;
 	if (n == 0) { h->pending = true; return FQSK_OK; }
 	if (dna_bytes >= (1ull << 30)) return fail(h, FQSK_E_INVAL, "segment larger than 1 GiB of DNA");   // push times are 2 * byte offset (+1) in 32 bits
@@ -1141,13 +1153,17 @@ void fqsk_destroy(fqsk_handle *h) {
 	                  &h->sidx_b, &h->sidx_s, &h->stime_b, &h->stime_s, &h->sort_k, &h->sort_v, &h->rkind, &h->rreg, &h->rslot, &h->dirty, &h->rdraws_b, &h->rdraws_s, &h->totals,
 	                  &h->y_tslot, &h->y_c0, &h->y_m, &h->y_draw, &h->y_j, &h->y_final, &h->y_flag_at, &h->y_own, &h->y_lead, &h->y_rank, &h->y_flag, &h->y_doff,
 	                  &h->idx_k, &h->idx_t, &h->idx_rt, &h->miss_fold, &h->hr_b[0], &h->hr_b[1], &h->hr_b[2], &h->hr_s[0], &h->hr_s[1], &h->hr_s[2],
-	                  &h->evk[0], &h->evk[1], &h->evv[0], &h->evv[1], &h->evk_s[0], &h->evk_s[1], &h->evv_s[0], &h->evv_s[1], &h->scan_part, &h->scan_vals,
+	                  &h->evk[0], &h->evk[1], &h->evv[0], &h->evv[1], &h->evk_s[0], &h->evk_s[1], &h->evv_s[0], &h->evv_s[1], &h->scan_part, &h->scan_vals, &h->recs_alt,
 	                  &h->route_keys, &h->route_keys2, &h->route_sorted, &h->route_hist,
 	                  &h->pe_tk, &h->pe_tv, &h->pe_q, &h->pe_sk, &h->pe_sv, &h->pe_sidx, &h->pe_t1, &h->pe_t2, &h->pe_pool, &h->pe_info, &h->it_src, &h->it_len,
 	                  &h->it_bytes, &h->it_first, &h->it_bias, &h->it_dupprev, &h->it_flags, &h->it_off32, &h->it_off64, &h->it_dna};
 
 	for (DevBuf *b : bufs) b->release();
 	if (h->h_stage) cudaFreeHost(h->h_stage);
+	if (h->h_stage2) cudaFreeHost(h->h_stage2);
+	for (int i = 0; i < 2; ++i) { if (h->h_meta[i]) cudaFreeHost(h->h_meta[i]); if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]); }
+	if (h->ev_recs) cudaEventDestroy(h->ev_recs);
+	if (h->st_copy) { cudaStreamSynchronize(h->st_copy); cudaStreamDestroy(h->st_copy); }
 	if (h->h_small) cudaFreeHost(h->h_small);
 	for (auto &e : h->evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
 	for (auto e : h->ev_pool) cudaEventDestroy(e);
@@ -1176,7 +1192,7 @@ int fqsk_device_recs(fqsk_handle *h, const fqsk_base_rec **d_recs, uint64_t *n_r
 	if (!h || !d_recs) return FQSK_E_INVAL;
 	CK(cudaSetDevice(h->P.device));
 	CKR(seg_settle(h));
-	*d_recs = h->recs.as<fqsk_base_rec>();
+	*d_recs = (h->rec_par ? h->recs_alt : h->recs).as<fqsk_base_rec>();
 	if (n_recs) *n_recs = h->n_recs;
 	return FQSK_OK;
 }
@@ -1204,46 +1220,63 @@ int fqsk_pair_info(fqsk_handle *h, uint32_t *info, uint32_t n_pairs) {
 	return FQSK_OK;
 }
 
-int fqsk_segment(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const fqsk_read_desc *reads, uint32_t n_reads,
-                 fqsk_base_rec *recs, uint64_t rec_cap, uint64_t *n_recs, uint8_t *dup, uint64_t *rec_off) {
-	if (!h || (!slab && n_reads) || (!reads && n_reads)) return FQSK_E_INVAL;
-	CK(cudaSetDevice(h->P.device));
+// pack the DNA bytes of the segment (plus the few bytes the reference also reads when a read is shorter than the directly coded
+// prefix, dna.cpp:518-521) into pinned memory -- [dna bytes | off u64 | len u32] -- and enqueue the copy to the device.
+// *rec_bound = upper bound of the records the segment produces (exact unless it holds duplicates).
+static int stage_segment(fqsk_handle *h, uint8_t *&stage, size_t &stage_cap, const uint8_t *slab, uint64_t slab_size, const fqsk_read_desc *reads, uint32_t n_reads,
+                         uint64_t *total_out, uint64_t *rec_bound) {
 	const uint32_t first = h->P.mode == FQSK_MODE_SE_SORTED ? h->P.pmer_len : h->P.prefix_len;
-	// pack the DNA bytes of the segment (plus the few bytes the reference also reads when a read is shorter than the
-	// directly coded prefix, dna.cpp:518-521) into pinned memory: [dna bytes | off u64 | len u32]
-	uint64_t total = 0;
-	for (uint32_t i = 0; i < n_reads; ++i) total += std::max(reads[i].dna_len, first);
+	uint64_t total = 0, bound = 0;
+	for (uint32_t i = 0; i < n_reads; ++i) { total += std::max(reads[i].dna_len, first); if (reads[i].dna_len > first) bound += reads[i].dna_len - first; }
 	size_t need = total + 64 + (size_t) n_reads * 12 + 64;
-	if (need > h->h_stage_cap) {
-		if (h->h_stage) cudaFreeHost(h->h_stage);
-		h->h_stage = nullptr; h->h_stage_cap = 0;
-		CK(cudaMallocHost(&h->h_stage, need + need / 4));
-		h->h_stage_cap = need + need / 4;
+	if (need > stage_cap) {
+		if (stage) cudaFreeHost(stage);
+		stage = nullptr; stage_cap = 0;
+		size_t want = std::max<size_t>(need + need / 4, (size_t) h->P.reserve_bytes + (size_t) h->P.reserve_reads * 16 + 4096);
+		CK(cudaMallocHost(&stage, want));
+		stage_cap = want;
 	}
 	size_t off_pos = (total + 63) & ~(size_t) 63;
-	unsigned long long *h_off = (unsigned long long *) (h->h_stage + off_pos);
-	uint32_t *h_len = (uint32_t *) (h->h_stage + off_pos + (size_t) n_reads * 8);
+	unsigned long long *h_off = (unsigned long long *) (stage + off_pos);
+	uint32_t *h_len = (uint32_t *) (stage + off_pos + (size_t) n_reads * 8);
 	uint64_t at = 0;
 	for (uint32_t i = 0; i < n_reads; ++i) {
 		uint32_t plen = std::max(reads[i].dna_len, first);
 		uint64_t o = reads[i].dna_off;
 		if (o > slab_size) return fail(h, FQSK_E_INVAL, "read %u starts outside the slab", i);
 		uint64_t avail = std::min<uint64_t>(plen, slab_size - o);
-		memcpy(h->h_stage + at, slab + o, avail);
-		if (avail < plen) memset(h->h_stage + at + avail, 0, plen - avail);
+		memcpy(stage + at, slab + o, avail);
+		if (avail < plen) memset(stage + at + avail, 0, plen - avail);
 		h_off[i] = at; h_len[i] = reads[i].dna_len;
 		at += plen;
 	}
-	CK(h->dna.ensure(total + 64)); CK(h->off.ensure((size_t) n_reads * 8 + 8)); CK(h->len.ensure((size_t) n_reads * 4 + 4));
+	*total_out = total; *rec_bound = bound;
+	return FQSK_OK;
+}
+static int upload_segment(fqsk_handle *h, const uint8_t *stage, uint64_t total, uint32_t n_reads) {
+	const size_t off_pos = (total + 63) & ~(size_t) 63;
+	CK(h->dna.ensure(std::max<uint64_t>(total, h->P.reserve_bytes) + 64)); CK(h->off.ensure((size_t) std::max(n_reads, h->P.reserve_reads) * 8 + 8));
+	CK(h->len.ensure((size_t) std::max(n_reads, h->P.reserve_reads) * 4 + 4));
 	if (n_reads) {
-		CK(cudaMemcpyAsync(h->dna.p, h->h_stage, total, cudaMemcpyHostToDevice, h->st));
-		CK(cudaMemcpyAsync(h->off.p, h_off, (size_t) n_reads * 8, cudaMemcpyHostToDevice, h->st));
-		CK(cudaMemcpyAsync(h->len.p, h_len, (size_t) n_reads * 4, cudaMemcpyHostToDevice, h->st));
+		CK(cudaMemcpyAsync(h->dna.p, stage, total, cudaMemcpyHostToDevice, h->st));
+		CK(cudaMemcpyAsync(h->off.p, stage + off_pos, (size_t) n_reads * 8, cudaMemcpyHostToDevice, h->st));
+		CK(cudaMemcpyAsync(h->len.p, stage + off_pos + (size_t) n_reads * 8, (size_t) n_reads * 4, cudaMemcpyHostToDevice, h->st));
 	}
+	return FQSK_OK;
+}
+
+int fqsk_segment(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const fqsk_read_desc *reads, uint32_t n_reads,
+                 fqsk_base_rec *recs, uint64_t rec_cap, uint64_t *n_recs, uint8_t *dup, uint64_t *rec_off) {
+	if (!h || (!slab && n_reads) || (!reads && n_reads)) return FQSK_E_INVAL;
+	CK(cudaSetDevice(h->P.device));
+	if (h->tk_open) return fail(h, FQSK_E_INVAL, "a submitted segment is in flight: fqsk_collect it first");
+	uint64_t total = 0, bound = 0;
+	CKR(stage_segment(h, h->h_stage, h->h_stage_cap, slab, slab_size, reads, n_reads, &total, &bound));
+	CKR(upload_segment(h, h->h_stage, total, n_reads));
 	CKR(run_segment(h, h->dna.as<uint8_t>(), total, h->off.as<unsigned long long>(), h->len.as<uint32_t>(), n_reads));
 	CKR(seg_settle(h));
 	if (h->n_recs > rec_cap) return fail(h, FQSK_E_CAPACITY, "record buffer holds %llu, segment produced %llu", (unsigned long long) rec_cap, (unsigned long long) h->n_recs);
-	if (h->n_recs && recs) CK(cudaMemcpyAsync(recs, h->recs.p, h->n_recs * sizeof(fqsk_base_rec), cudaMemcpyDeviceToHost, h->st));
+	if (h->n_recs && recs) CK(cudaMemcpyAsync(recs, (h->rec_par ? h->recs_alt : h->recs).p, h->n_recs * sizeof(fqsk_base_rec), cudaMemcpyDeviceToHost, h->st));
 	if (h->P.mode == FQSK_MODE_PE_ORIGINAL) {
 		// per-read views of the per-item arrays: mate 1 = item 3i, mate 2 = items 3i+1 (+ 3i+2, contiguous records)
 		const uint32_t ni = n_reads / 2 * 3;
@@ -1272,8 +1305,7 @@ int fqsk_segment(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const 
 // The sync of a small segment, enqueued right behind the segment's first pass without a host look in between: every kernel is
 // predicated on the device-side verdict of that pass and takes row lengths and stream positions from the device (SyncIn).
 // One look then settles the segment AND the sync.  *applied = false: the caller runs the plain path (nothing was changed).
-static int sync_speculative(fqsk_handle *h, bool *applied, unsigned long long counters[6]) {
-	*applied = false;
+static int sync_spec_enqueue(fqsk_handle *h) {
 	SegCtx &C = h->ctx;
 	SyncIn *in = h->d_syncin;
 	const uint32_t bound_b = (uint32_t) (2 * C.dna_bytes_actual + 2), bound_s = (uint32_t) (C.dna_bytes_actual + 1);
@@ -1287,9 +1319,9 @@ static int sync_speculative(fqsk_handle *h, bool *applied, unsigned long long co
 		CK(h->q4.ensure(row_reserve(h, bound_s) + 4));
 		CK(pdl(k_insert_fast, nblk(bound_s, 256), 256, h->st, h->ts.d, h->ts.ci, h->row_s[0].as<unsigned long long>(), 0, h->q4.as<uint8_t>(), h->d_sfast, (const SyncIn *) in)); LAUNCHED(h);
 	}
-	SyncDev Y;
+	SyncDev &Y = h->spec_Y;
 	CKR(indexed_setup(h, C.S.delta_b, bound_b, in, true, Y));
-	const uint32_t g = nblk(bound_b, 256);
+	const uint32_t g = h->spec_g = nblk(bound_b, 256);
 	const unsigned long long *row_b = h->row_b[0].as<unsigned long long>();
 	CKR(indexed_head(h, h->tb, Y, row_b, h->rt_b[0].as<uint32_t>(), g, false));
 	{
@@ -1297,6 +1329,16 @@ static int sync_speculative(fqsk_handle *h, bool *applied, unsigned long long co
 		CKR(stream_ensure(h, h->rng[ST_B], 0));
 		CKR(indexed_tail(h, h->tb, h->rng[ST_B], Y, row_b, g, bound_b, false));
 	}
+	h->spec_enqueued = true;
+	return FQSK_OK;
+}
+static int sync_spec_finish(fqsk_handle *h, bool *applied, unsigned long long counters[6]) {
+	*applied = false;
+	h->spec_enqueued = false;
+	SyncIn *in = h->d_syncin;
+	SyncDev &Y = h->spec_Y;
+	const uint32_t g = h->spec_g;
+	const unsigned long long *row_b = h->row_b[0].as<unsigned long long>();
 	CKR(look(h));
 	const SyncIn li = *looked_syncin(h, in);
 	int fl[8]; memcpy(fl, looked_sflags(h), sizeof fl);
@@ -1328,16 +1370,20 @@ static int sync_speculative(fqsk_handle *h, bool *applied, unsigned long long co
 	return FQSK_OK;
 }
 
-int fqsk_sync(fqsk_handle *h) {
-	if (!h) return FQSK_E_INVAL;
-	CK(cudaSetDevice(h->P.device));
-	if (h->world > 1) return fail(h, FQSK_E_INVAL, "sharded engine: use fqsk_sync_route / fqsk_sync_apply / fqsk_sync_finish");
+// fqsk_sync in two halves: sync_begin enqueues what can be enqueued without looking at the device (the predicated sync of a small
+// segment), sync_end looks, settles the segment and finishes the sync.  fqsk_submit calls the first half right behind the segment
+// and the second half when the caller comes back for the records.
+static int sync_begin(fqsk_handle *h) {
+	if (h->pending && h->seg_reads && h->unsettled && !h->spec_enqueued && h->fast_ok[0] && h->ctx.dna_bytes_actual <= SPEC_MAX_BYTES) CKR(sync_spec_enqueue(h));
+	return FQSK_OK;
+}
+static int sync_end(fqsk_handle *h) {
 	++h->S.n_syncs;
 	if (h->pending && h->seg_reads) {
 		h->hot_seen[0] = h->hot_seen[1] = false;
 		unsigned long long counters[6] = {0, 0, 0, 0, 0, 0};
 		bool applied = false;
-		if (h->unsettled && h->fast_ok[0] && h->ctx.dna_bytes_actual <= SPEC_MAX_BYTES) CKR(sync_speculative(h, &applied, counters));
+		if (h->spec_enqueued) CKR(sync_spec_finish(h, &applied, counters));
 		CKR(seg_settle(h));
 		if (h->P.mode == FQSK_MODE_PE_ORIGINAL) CKR(pe_sync(h));
 		if (!applied) {
@@ -1399,6 +1445,121 @@ int fqsk_sync(fqsk_handle *h) {
 	CKR(stream_prefetch(h, h->rng[ST_B], 1u << 23)); CKR(stream_prefetch(h, h->rng[ST_S], 1u << 18));
 	h->pending = false; h->pend_b = h->pend_s = h->pend_p = 0; h->seg_reads = 0;
 	resolve_phases(h);
+	return FQSK_OK;
+}
+
+int fqsk_sync(fqsk_handle *h) {
+	if (!h) return FQSK_E_INVAL;
+	CK(cudaSetDevice(h->P.device));
+	if (h->world > 1) return fail(h, FQSK_E_INVAL, "sharded engine: use fqsk_sync_route / fqsk_sync_apply / fqsk_sync_finish");
+	if (h->tk_open) return fail(h, FQSK_E_INVAL, "a submitted segment is in flight: fqsk_collect it first (fqsk_submit includes the sync)");
+	CKR(sync_begin(h));
+	return sync_end(h);
+}
+
+// ---- asynchronous, double-buffered segment + sync ---------------------------------------------------------------------
+static fqsk_base_rec *dev_recs(fqsk_handle *h, int par) { return (par ? h->recs_alt : h->recs).as<fqsk_base_rec>(); }
+
+// compute side of the ticket in flight: the sync (its look also settles the segment); if the segment needed more than its
+// first pass the records were rewritten after the copy was enqueued, so they are copied again (the copy stream is in order)
+static int submit_finish_compute(fqsk_handle *h) {
+	if (!h->tk_open) return FQSK_OK;
+	auto &T = h->tk[h->tk_cur];
+	if (!T.open || T.done) return FQSK_OK;
+	CKR(sync_end(h));
+	T.n_recs = h->n_recs;
+	if (T.n_recs > T.bound) return fail(h, FQSK_E_CAPACITY, "segment produced %llu records, more than its reads allow (%llu)", (unsigned long long) T.n_recs, (unsigned long long) T.bound);
+	if (h->seg_extra_pass && T.n_recs && T.recs) {
+		CK(cudaEventRecord(h->ev_recs, h->st)); CK(cudaStreamWaitEvent(h->st_copy, h->ev_recs, 0));
+		CK(cudaMemcpyAsync(T.recs, dev_recs(h, T.par), T.n_recs * sizeof(fqsk_base_rec), cudaMemcpyDeviceToHost, h->st_copy));
+		CK(cudaEventRecord(h->ev_copied[T.par], h->st_copy));
+	}
+	T.done = true;
+	return FQSK_OK;
+}
+
+int fqsk_submit(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const fqsk_read_desc *reads, uint32_t n_reads,
+                fqsk_base_rec *recs, uint64_t rec_cap, uint8_t *dup, uint64_t *rec_off, uint64_t *ticket) {
+	if (!h || !ticket || (!slab && n_reads) || (!reads && n_reads)) return FQSK_E_INVAL;
+	CK(cudaSetDevice(h->P.device));
+	if (h->world > 1) return fail(h, FQSK_E_UNSUPPORTED, "fqsk_submit: not available on a sharded engine");
+	if (!h->st_copy) {
+		CK(cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking));
+		CK(cudaEventCreateWithFlags(&h->ev_recs, cudaEventDisableTiming));
+		for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
+	}
+	const int par = h->tk_open ? h->tk_cur ^ 1 : h->rec_par ^ 1;
+	if (h->tk[par].open) return fail(h, FQSK_E_INVAL, "two segments are already in flight: fqsk_collect the older one first");
+	// host work first (the GPU is still busy with the previous segment): stage the reads in the pinned buffer of this parity
+	uint64_t total = 0, bound = 0;
+	uint8_t *&stage = par ? h->h_stage2 : h->h_stage;
+	size_t &stage_cap = par ? h->h_stage2_cap : h->h_stage_cap;
+	CKR(stage_segment(h, stage, stage_cap, slab, slab_size, reads, n_reads, &total, &bound));
+	if (bound > rec_cap) return fail(h, FQSK_E_CAPACITY, "record buffer holds %llu, the segment can produce %llu", (unsigned long long) rec_cap, (unsigned long long) bound);
+	CKR(submit_finish_compute(h));                                  // previous segment: settle + sync
+	CK(cudaStreamWaitEvent(h->st, h->ev_copied[par], 0));             // the device records of this parity have left for the host
+	h->rec_par = par;
+	CKR(upload_segment(h, stage, total, n_reads));
+	CKR(run_segment(h, h->dna.as<uint8_t>(), total, h->off.as<unsigned long long>(), h->len.as<uint32_t>(), n_reads));
+	const uint32_t ni = h->P.mode == FQSK_MODE_PE_ORIGINAL ? n_reads / 2 * 3 : n_reads;
+	if (ni) {   // duplicate flags and record offsets are final after k_prep / k_scan_reads: main stream, ahead of the look that ends the sync
+		const size_t need = (((size_t) ni + 8) & ~(size_t) 7) + ((size_t) ni + 1) * 8;
+		if (need > h->h_meta_cap[par]) {
+			if (h->h_meta[par]) cudaFreeHost(h->h_meta[par]);
+			h->h_meta[par] = nullptr; h->h_meta_cap[par] = 0;
+			const size_t want = std::max<size_t>(need + need / 4, (size_t) h->P.reserve_reads * 14 + 64);
+			CK(cudaMallocHost(&h->h_meta[par], want));
+			h->h_meta_cap[par] = want;
+		}
+		CK(cudaMemcpyAsync(h->h_meta[par], h->dup.p, ni, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaMemcpyAsync(h->h_meta[par] + (((size_t) ni + 8) & ~(size_t) 7), h->rec_off.p, ((size_t) ni + 1) * 8, cudaMemcpyDeviceToHost, h->st));
+	}
+	if (bound && recs && n_reads) {   // the records leave on their own stream while the sync and the next segment run
+		CK(cudaEventRecord(h->ev_recs, h->st)); CK(cudaStreamWaitEvent(h->st_copy, h->ev_recs, 0));
+		CK(cudaMemcpyAsync(recs, dev_recs(h, par), bound * sizeof(fqsk_base_rec), cudaMemcpyDeviceToHost, h->st_copy));
+		CK(cudaEventRecord(h->ev_copied[par], h->st_copy));
+	}
+	CKR(sync_begin(h));
+	auto &T = h->tk[par];
+	T = fqsk_handle::Ticket{};
+	T.open = true; T.done = false; T.recs = recs; T.bound = bound; T.dup = dup; T.rec_off = rec_off; T.n_reads = n_reads; T.par = par; T.id = h->tk_next++;
+	h->tk_open = true; h->tk_cur = par;
+	*ticket = T.id;
+	return FQSK_OK;
+}
+
+int fqsk_collect(fqsk_handle *h, uint64_t ticket, uint64_t *n_recs) {
+	if (!h) return FQSK_E_INVAL;
+	CK(cudaSetDevice(h->P.device));
+	int par = -1;
+	for (int i = 0; i < 2; ++i) if (h->tk[i].open && h->tk[i].id == ticket) par = i;
+	if (par < 0) return fail(h, FQSK_E_INVAL, "no such ticket in flight");
+	auto &T = h->tk[par];
+	if (!T.done) {
+		if (par != h->tk_cur) return fail(h, FQSK_E_CUDA, "internal error: an older ticket was left unfinished");
+		CKR(submit_finish_compute(h));
+	}
+	if (T.bound && T.recs && T.n_reads) CK(cudaEventSynchronize(h->ev_copied[par]));
+	const uint32_t n = T.n_reads;
+	if (n) {
+		const bool pe = h->P.mode == FQSK_MODE_PE_ORIGINAL;
+		const uint32_t ni = pe ? n / 2 * 3 : n;
+		const uint8_t *idup = h->h_meta[par];
+		const unsigned long long *ioff = (const unsigned long long *) (h->h_meta[par] + (((size_t) ni + 8) & ~(size_t) 7));
+		if (pe) {
+			for (uint32_t i = 0; i < n / 2; ++i) {
+				if (T.dup) { T.dup[2 * i] = idup[3 * i]; T.dup[2 * i + 1] = 0; }
+				if (T.rec_off) { T.rec_off[2 * i] = ioff[3 * i]; T.rec_off[2 * i + 1] = ioff[3 * i + 1]; }
+			}
+			if (T.rec_off) T.rec_off[n] = ioff[ni];
+		} else {
+			if (T.dup) memcpy(T.dup, idup, n);
+			if (T.rec_off) memcpy(T.rec_off, ioff, ((size_t) n + 1) * 8);
+		}
+	}
+	if (n_recs) *n_recs = T.n_recs;
+	T.open = false;
+	h->tk_open = h->tk[0].open || h->tk[1].open;
 	return FQSK_OK;
 }
 

@@ -44,7 +44,7 @@ class _Stats(C.Structure):
 
 
 EXPORTS = ["fqsk_create", "fqsk_destroy", "fqsk_last_error", "fqsk_block_start", "fqsk_segment", "fqsk_segment_device",
-           "fqsk_device_recs", "fqsk_sorted_prefix", "fqsk_pair_info", "fqsk_sync", "fqsk_dump", "fqsk_stats_get", "fqsk_profile", "fqsk_ht_insert", "fqsk_ht_find",
+           "fqsk_device_recs", "fqsk_sorted_prefix", "fqsk_pair_info", "fqsk_submit", "fqsk_collect", "fqsk_sync", "fqsk_dump", "fqsk_stats_get", "fqsk_profile", "fqsk_ht_insert", "fqsk_ht_find",
            "fqsk_ht_count", "fqsk_timer_begin", "fqsk_timer_end", "fqsk_siv_increment", "fqsk_siv_test", "fqsk_siv_counts", "fqsk_siv_test_shorter", "fqsk_mt_stream", "fqsk_host_alloc", "fqsk_host_free",
            "fqsk_shard_export", "fqsk_shard_attach", "fqsk_sync_route", "fqsk_sync_apply", "fqsk_sync_finish"]
 
@@ -71,6 +71,8 @@ def load_library():
     lib.fqsk_device_recs.argtypes = [vp, C.POINTER(vp), u64p]
     lib.fqsk_sorted_prefix.argtypes = [vp, vp, vp, C.c_uint32]
     lib.fqsk_pair_info.argtypes = [vp, vp, C.c_uint32]
+    lib.fqsk_submit.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint32, vp, C.c_uint64, vp, vp, u64p]
+    lib.fqsk_collect.argtypes = [vp, C.c_uint64, u64p]
     lib.fqsk_sync.argtypes = [vp]
     lib.fqsk_dump.argtypes = [vp, C.c_int, vp, vp, C.c_uint64, u64p]
     lib.fqsk_stats_get.argtypes = [vp, C.POINTER(_Stats)]
@@ -123,6 +125,7 @@ class KmerEngine:
             raise FqskError(rc, self.lib.fqsk_last_error(None).decode())
         self.h = h
         self.p, self.s, self.b, self.prefix_len, self.mode = p, s, b, prefix_len, mode
+        self.reserve_reads, self.reserve_bytes = reserve_reads, reserve_bytes
 
     def close(self):
         for ptr, _ in getattr(self, "_pinned", {}).values():
@@ -183,6 +186,35 @@ class KmerEngine:
         if want_rec_off:
             return out, dup[:n], rec_off
         return out, dup[:n]
+
+    def submit(self, slab: np.ndarray, off: np.ndarray, length: np.ndarray, first: int | None = None):
+        """Asynchronous segment + sync (fqsk_submit): returns a ticket; collect(ticket) -> (records, dup, rec_off).  The output
+        buffers are page-locked and owned by the engine, two sets used alternately: a ticket's arrays stay valid until the
+        second submit after it."""
+        slab = np.ascontiguousarray(slab, np.uint8)
+        n = len(off)
+        desc = np.zeros(n, READ_DESC_DTYPE)
+        desc["dna_off"] = off
+        desc["dna_len"] = length
+        cap = int(np.asarray(length, np.int64).sum()) + 16
+        slot = getattr(self, "_submit_slot", 0) ^ 1
+        self._submit_slot = slot
+        # page-locked buffers sized once for the largest announced segment (reallocating 200 MB of pinned memory costs ~0.1 s)
+        recs = self._pinned_array(f"srecs{slot}", max(cap, self.reserve_bytes + 16) * REC_DTYPE.itemsize)[: cap * REC_DTYPE.itemsize].view(REC_DTYPE)
+        dup = self._pinned_array(f"sdup{slot}", max(n, self.reserve_reads, 1))[: max(n, 1)]
+        rec_off = self._pinned_array(f"soff{slot}", (max(n, self.reserve_reads) + 1) * 8)[: (n + 1) * 8].view(np.uint64)
+        t = C.c_uint64(0)
+        self._ck(self.lib.fqsk_submit(self.h, _ptr(slab), slab.size, _ptr(desc), n, _ptr(recs), cap, _ptr(dup), _ptr(rec_off), C.byref(t)))
+        if not hasattr(self, "_tickets"):
+            self._tickets = {}
+        self._tickets[t.value] = (recs, dup, rec_off, n, (slab, desc))      # keep the inputs alive until the copy is staged (it is, on return)
+        return t.value
+
+    def collect(self, ticket: int):
+        recs, dup, rec_off, n, _ = self._tickets.pop(ticket)
+        n_recs = C.c_uint64(0)
+        self._ck(self.lib.fqsk_collect(self.h, ticket, C.byref(n_recs)))
+        return recs[: n_recs.value], dup[:n], rec_off
 
     def segment_device(self, d_dna_ptr: int, dna_bytes: int, d_off_ptr: int, d_len_ptr: int, n_reads: int, want_n_recs: bool = True):
         """Reads already in HBM.  want_n_recs=False only enqueues the segment: the library looks at the outcome when the

@@ -33,3 +33,29 @@ for g in range(NB):
         print(f"block {g}: {len(sched)} segs, per segment: total {1e6 * tot / len(sched):.0f} us, segment_device (enqueue only) {1e6 * t_seg / len(sched):.0f} us, sync (enqueue + look) {1e6 * t_sync / len(sched):.0f} us")
 st = eng.stats()
 print({k: st[k] for k in ("n_segments", "n_replays", "kernel_launches", "n_hot_segments")})
+
+# ---- e2e path (host buffers through fqsk_submit / fqsk_collect) ----
+eng.close()
+eng2 = E.KmerEngine(p, s, b, pref, expected_kmers=1 << 29, reserve_reads=B.READS_PER_BLOCK, reserve_bytes=B.READS_PER_BLOCK * (B.L + 1))
+pend = None
+for g in list(range(NB)) + [NB, NB + 1, NB + 2, NB + 3, NB + 4]:
+    steady = g >= NB
+    gg = 120 + g - NB if steady else g
+    slab, off, ln = B.codes_to_slab(B.block_codes(genome, gg, 0))
+    sched = [(0, B.READS_PER_BLOCK)] if steady else list(S.segments(0, B.READS_PER_BLOCK, S.calc_no_synchronizations(g, B.READS_PER_BLOCK, 1)))
+    eng2.block_start()
+    t_sub = t_col = 0.0
+    t0 = time.perf_counter()
+    for a, bb in sched:
+        t1 = time.perf_counter()
+        t = eng2.submit(slab, off[a:bb], ln[a:bb])
+        t2 = time.perf_counter()
+        if pend is not None:
+            eng2.collect(pend)
+        t3 = time.perf_counter()
+        pend = t
+        t_sub += t2 - t1; t_col += t3 - t2
+    tot = time.perf_counter() - t0
+    if g >= NB - 3:
+        print(f"e2e block {gg}: {len(sched)} segs, per segment: total {1e6 * tot / len(sched):.0f} us, submit {1e6 * t_sub / len(sched):.0f} us, collect {1e6 * t_col / len(sched):.0f} us")
+eng2.collect(pend)

@@ -141,6 +141,18 @@ int fqsk_pair_info(fqsk_handle *h, uint32_t *info, uint32_t n_pairs);
  * (application.cpp:645-654): p-mers, then s-mers, then b-mers, in push order, with the reference's PRNG draw order. */
 int fqsk_sync(fqsk_handle *h);
 
+/* Asynchronous, double-buffered form of fqsk_segment + fqsk_sync -- the pair the reference's worker loop executes for every sync
+ * segment (application.cpp:630-655).  fqsk_submit stages the reads, enqueues H2D, the segment, the copy of its records into the
+ * caller's buffers (page-locked memory from fqsk_host_alloc, on a second CUDA stream) and the sync, and returns a ticket;
+ * fqsk_collect blocks until that segment's records, duplicate flags and record offsets are in the caller's buffers.  Up to two
+ * tickets may be open: submit segment n + 1, then collect n and hand it to the host-side coder while the GPU works on n + 1 and
+ * the records of n + 1 travel behind it.  rec_cap must cover sum(max(dna_len - first coded position, 0)) of the segment (records
+ * beyond *n_recs are undefined).  Buffers of a ticket belong to the library until it is collected; fqsk_segment / fqsk_sync /
+ * fqsk_dump must not be called while a ticket is open. */
+int fqsk_submit(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const fqsk_read_desc *reads, uint32_t n_reads,
+                fqsk_base_rec *recs, uint64_t rec_cap, uint8_t *dup, uint64_t *rec_off, uint64_t *ticket);
+int fqsk_collect(fqsk_handle *h, uint64_t ticket, uint64_t *n_recs);
+
 /* ---- sharded operation (world_size > 1): one handle per GPU / process, reference `-t world_size` semantics --------------------
  * Replaces the shared-memory coupling of the reference's worker threads: global tables read by everybody between barriers
  * (application.cpp:645-654), X_to_add[src][dst] exchange matrices + InsertKmersToHT on the owner (dna.cpp:2393-2472).

@@ -58,6 +58,37 @@ def run_se_workers(group, slab, n_workers, kind=0):
     return res
 
 
+def run_async(engine, slab, paired=False):
+    """Same schedule through fqsk_submit / fqsk_collect, two segments in flight: segment n + 1 is submitted before n is collected
+    (the host-side coder would consume n meanwhile).  Returns (records, dup flags per read[, pair_info])."""
+    off, ln, roff, rsz = S.parse_fastq(slab)
+    out, dups, info = [], [], []
+    pend = None
+
+    def take(t):
+        recs, dup, rec_off = engine.collect(t)
+        assert int(rec_off[len(dup)]) == len(recs)
+        out.append(recs.copy()); dups.append(dup.copy())
+
+    for gen, (f, l) in enumerate(S.split_blocks(rsz, paired=paired)):
+        ns = S.calc_no_synchronizations(gen, l - f, 1)
+        engine.block_start()
+        for a, b in S.segments(f, l, ns, paired=paired):
+            t = engine.submit(slab, off[a:b], ln[a:b])
+            if paired:
+                info.append(engine.pair_info((b - a) // 2))      # decisions of the segment just submitted
+            if pend is not None:
+                take(pend)
+            pend = t
+    if pend is not None:
+        take(pend)
+    recs = np.concatenate(out) if out else np.zeros(0, O.REC_DTYPE)
+    dup = np.concatenate(dups) if dups else np.zeros(0, np.uint8)
+    if paired:
+        return recs, dup, (np.concatenate(info) if info else np.zeros((0, 3), np.uint32))
+    return recs, dup
+
+
 POS_PAIR = 0xFFFFFFFB    # per pair: c0 = a candidate list exists, c1 = minimizer id (0..14, 15 = none usable), c2 = its position in mate 2
 
 

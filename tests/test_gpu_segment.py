@@ -173,3 +173,34 @@ def test_engine_matches_oracle_paired_end(gs, G, n_pairs, L, seed, nfrac, dup_ev
     for key in ("siv_no_filled", "siv_no_updates", "n_smers", "n_bmers", "draws_b", "draws_s", "draws_lb", "draws_ls"):
         assert sg[key] == so[key], key
     e.close(); o.close()
+
+
+@pytest.mark.parametrize("name", ["se_orig_gs1", "se_orig_repeats_gs1"])
+def test_async_submit_collect_matches_reference_golden(name):
+    """fqsk_submit / fqsk_collect (double-buffered records on a copy stream, sync enqueued behind the segment, two tickets in
+    flight) must give the same bytes as the blocking calls: records, duplicate flags and tables vs the tapped reference.
+    The repeats fixture forces segments that need more than their first pass (records are copied a second time)."""
+    g = H.load_golden(name)
+    pref, p, s, b = E.kmer_params(int(g["gs"]))
+    e = E.KmerEngine(p, s, b, pref)
+    recs, dup = H.run_async(e, g["fastq"])
+    want = g["recs"]
+    n_dup_want = int((want["pos"] == O.POS_DUP).sum())
+    want = want[want["pos"] < 0xFFFFFFF0]
+    H.assert_recs_equal(recs, want)
+    assert int(dup.sum()) == n_dup_want
+    H.assert_dump_equal(e, g)
+    e.close()
+
+
+def test_async_submit_collect_paired_end():
+    g = H.load_golden("pe_orig_gs1")
+    pref, p, s, b = E.kmer_params(int(g["gs"]))
+    e = E.KmerEngine(p, s, b, pref, mode=E.MODE_PE_ORIGINAL)
+    recs, dup, info = H.run_async(e, g["fastq"], paired=True)
+    want, winfo = H.golden_pe_expect(g)
+    assert np.array_equal(info, winfo)
+    H.assert_recs_equal(recs, want)
+    assert dup[1::2].sum() == 0
+    H.assert_dump_equal(e, g, pairs=True)
+    e.close()
