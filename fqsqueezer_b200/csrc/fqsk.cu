@@ -549,11 +549,10 @@ int indexed_head(fqsk_handle *h, Table &t, const SyncDev &Y, const unsigned long
 	return FQSK_OK;
 }
 int indexed_tail(fqsk_handle *h, Table &t, Stream &rng, const SyncDev &Y, const unsigned long long *row, uint32_t g, uint32_t n_bound, bool reset = true) {
-	CK(pdl(k_scan_flags, nblk(n_bound, SCANF_TILE), 256, h->st, Y.in, Y.n_dev, Y.flag, h->y_doff.as<uint32_t>(), Y.total_draws, h->scan_part.as<unsigned long long>(), ++h->scan_epoch)); LAUNCHED(h);
-	CK(pdl(k_sync_scatter, g, 256, h->st, t.ci, Y)); LAUNCHED(h);
+	// scan of the draw flags (+ scatter of draw index / flag to the delta entries), then the leaders evaluate and write their groups
+	CK(pdl(k_scan_flags, nblk(n_bound, SCANF_TILE), 256, h->st, Y.in, Y.n_dev, (const uint8_t *) Y.flag, h->y_doff.as<uint32_t>(), Y.total_draws, h->scan_part.as<unsigned long long>(), ++h->scan_epoch, Y, t.ci)); LAUNCHED(h);
 	if (reset) CK(cudaMemsetAsync(h->d_sflags, 0, 4 * sizeof(int), h->st));      // [0] draw window short, [2] corrected a flag; [6] hot seen / [7] group too large stay
-	CK(pdl(k_sync_apply, g, 256, h->st, t.d, t.ci, Y, row, rng.buf, rng.cap - 1, stream_safe_abs(rng))); LAUNCHED(h);
-	CK(pdl(k_sync_commit, g, 256, h->st, t.d, Y)); LAUNCHED(h);
+	CK(pdl(k_sync_apply, g, 256, h->st, t.d, t.ci, Y, row, (const uint32_t *) rng.buf, (unsigned long long) (rng.cap - 1), stream_safe_abs(rng))); LAUNCHED(h);
 	return FQSK_OK;
 }
 // one look at the device: the whole status block, the item counters and the fresh p-mer field count
@@ -991,9 +990,10 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 	CKR(seg_setup(h));
 	CKR(seg_pass(h));
 	// verdict of the first pass for a sync enqueued unseen, and the state the next segment inherits (both are inputs only)
-	CK(pdl(k_seg_verdict, 1, 32, h->st, h->d_flags, (const uint32_t *) (h->d_status + 192), (const unsigned long long *) (h->d_status + 208),
-	                                   h->rng[ST_B].consumed, h->rng[ST_S].consumed, SYNC_INDEXED_MAX, h->d_syncin)); LAUNCHED(h);
-	CK(pdl(k_save_carry, 1, 256, h->st, S, pe ? n - 3 : n - 1, h->prev_read.as<uint8_t>(), h->d_carry, h->P.mode == FQSK_MODE_SE_SORTED || h->P.mode == FQSK_MODE_PE_SORTED, h->P.pmer_len)); LAUNCHED(h);
+	// one launch: verdict of the first pass + the state the next segment inherits (read_prev, pmer_can_prev)
+	CK(pdl(k_seg_tail, 1, 256, h->st, h->d_flags, (const uint32_t *) (h->d_status + 192), (const unsigned long long *) (h->d_status + 208),
+	       h->rng[ST_B].consumed, h->rng[ST_S].consumed, SYNC_INDEXED_MAX, h->d_syncin,
+	       S, pe ? n - 3 : n - 1, h->prev_read.as<uint8_t>(), h->d_carry, (uint32_t) (h->P.mode == FQSK_MODE_SE_SORTED || h->P.mode == FQSK_MODE_PE_SORTED), h->P.pmer_len)); LAUNCHED(h);
 	h->unsettled = true;
 	h->pending = true;
 	h->S.n_reads += n_in; h->S.n_bases += bytes_in;

@@ -372,7 +372,12 @@ __global__ void k_sync_apply(HtDev t, CIncP ci, SyncDev Y, const unsigned long l
 	const unsigned long long avail = safe_abs > dpos ? safe_abs - dpos : 0;
 	const uint32_t L = Y.own[j];
 	const uint32_t c0 = Y.lead_c0[L], m = Y.lead_m[L];
-	if (c0 + m <= ci.thr + 1 || m > SYNC_GROUP_CAP) return;
+	const unsigned long long tslot = Y.lead_tslot[L] & ~(1ull << 63);
+	// The leader writes the group's final counter right away (no separate commit launch).  If the row turns out not to be settled
+	// -- a flag was corrected, the draw window was short, a group is too large -- the host runs this kernel again (it always
+	// starts from the stored pre-sync counter c0, so rewriting is idempotent) or restores c0 with k_sync_unclaim and falls back.
+	if (c0 + m <= ci.thr + 1) { ht_slot_set(t, tslot, c0 + m); return; }    // cold group: every increment is deterministic
+	if (m > SYNC_GROUP_CAP) return;
 	// members of the group in time order
 	const unsigned long long x = row[j];
 	uint32_t mt[SYNC_GROUP_CAP], ms[SYNC_GROUP_CAP];
@@ -401,6 +406,7 @@ __global__ void k_sync_apply(HtDev t, CIncP ci, SyncDev Y, const unsigned long l
 		if (draws[(dpos + di) & dmask] % (ci.mult * (c - ci.thr)) == 0) ++c;
 	}
 	Y.final_at[L] = c;
+	ht_slot_set(t, tslot, c);
 }
 __global__ void k_sync_commit(HtDev t, SyncDev Y) { pdl_enter();
 	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -415,8 +421,10 @@ __global__ void k_sync_unclaim(HtDev t, SyncDev Y) { pdl_enter();
 	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
 	if (!Y.in->ok || j >= *Y.n_dev) return;
 	if (Y.rank[j] != 0) return;
+	// created slots stay as zero-count items (== the reference's fresh slot); existing ones get their pre-sync counter back
+	// (k_sync_apply writes final counters without waiting for the verdict of the whole row)
 	unsigned long long ts = Y.lead_tslot[Y.own[j]];
-	if (ts >> 63) ht_slot_set(t, ts & ~(1ull << 63), 0);
+	ht_slot_set(t, ts & ~(1ull << 63), (ts >> 63) ? 0u : Y.lead_c0[Y.own[j]]);
 }
 // index of a plain row (table-level API): entry time = push index
 __global__ void k_row_index_build(unsigned long long *keys, uint32_t *times, uint32_t mask, uint32_t k, uint32_t t, const unsigned long long *row, uint32_t n, uint32_t *rt) { pdl_enter();

@@ -103,8 +103,20 @@ __device__ __forceinline__ KReg suffix_reg(const KReg &r, uint32_t cb, uint32_t 
 	o.rc = r.rc & (~0ull << (64 - 2 * c));
 	return o;
 }
-__device__ __forceinline__ uint32_t find_read(const unsigned long long *rec_off, uint32_t n_reads, uint32_t g) {
-	uint32_t lo = 0, hi = n_reads;     // last r with rec_off[r] <= g
+__device__ __forceinline__ uint32_t find_read(const unsigned long long *rec_off, uint32_t n_reads, uint32_t g, uint32_t n_rec) {
+	// last r with rec_off[r] <= g.  Reads of a segment mostly have the same length, so interpolation lands on the read or next to
+	// it (2 dependent loads instead of log2(n) -- this search sits at the head of every position's latency chain); the bracket
+	// found by a few galloping steps is finished by bisection for ragged input.
+	uint32_t r = (uint32_t) (((unsigned long long) g * n_reads) / (n_rec ? n_rec : 1));
+	if (r >= n_reads) r = n_reads - 1;
+	uint32_t lo, hi;
+	if (rec_off[r] <= g) {
+		uint32_t step = 1; lo = r; hi = r + 1;
+		while (hi < n_reads && rec_off[hi] <= g) { lo = hi; hi = hi + step < n_reads ? hi + step : n_reads; step <<= 1; }
+	} else {
+		uint32_t step = 1; hi = r; lo = r >= 1 ? r - 1 : 0;
+		while (lo > 0 && rec_off[lo] > g) { hi = lo; lo = lo >= step ? lo - step : 0; step <<= 1; }
+	}
 	while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (rec_off[m] <= g) lo = m; else hi = m; }
 	return lo;
 }
@@ -121,8 +133,9 @@ __device__ __forceinline__ void put_rec(fqsk_base_rec *rec, uint32_t pos, const 
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_lookup(EngineDev E, SegDev S, PipeDev P) { pdl_enter();
 	uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-	if (g >= *P.n_rec_dev) return;
-	uint32_t r = find_read(S.rec_off, S.n_reads, g);
+	const uint32_t n_rec = *P.n_rec_dev;
+	if (g >= n_rec) return;
+	uint32_t r = find_read(S.rec_off, S.n_reads, g, n_rec);
 	uint32_t i = item_first(S, P.start, r) + (g - (uint32_t) S.rec_off[r]);
 	const uint8_t *p = S.dna + S.off[r];
 	const uint32_t n = i + 1;
@@ -777,7 +790,7 @@ __global__ void __launch_bounds__(256) k_delta_build_flat(SegDev S, PipeDev P, u
 // k_rough: one warp per request.  find_counts_rough_{s,b} (dna.cpp:257-330): 4(k-1) single-substitution neighbours across the
 // lanes, non-empty ones appended in trial order to a merge script; find_counts_rough_p (dna.cpp:229-254) is a plain sum.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_rough(EngineDev E, PipeDev P) { pdl_enter();
+__global__ void __launch_bounds__(128, 8) k_rough(EngineDev E, PipeDev P) { pdl_enter();
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t n_rec = *P.n_rec_dev;
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
@@ -817,7 +830,9 @@ __global__ void __launch_bounds__(128) k_rough(EngineDev E, PipeDev P) { pdl_ent
 			uint32_t trials = 4 * (t.k - 1);
 			uint32_t n_ent = 0, ovf = 0xFFFFFFFFu;
 			// all sector reads of the request are issued before the first one is consumed (4(k-1) <= 128 trials: up to 4 per lane)
-			HtKey key[4]; Bucket bk[4]; bool isd[4], live[4];
+			// Only the buckets stay live across the memory latency: the keys are recomputed when the sectors arrive, which keeps the
+			// kernel at 64 registers = 32 resident warps per SM (it is bound by the latency of one request's dependent steps).
+			Bucket bk[4]; bool live[4];
 #pragma unroll
 			for (int u = 0; u < 4; ++u) {
 				uint32_t tn = u * 32 + lane;
@@ -827,16 +842,21 @@ __global__ void __launch_bounds__(128) k_rough(EngineDev E, PipeDev P) { pdl_ent
 				if (live[u]) {
 					KReg tr = reg;
 					kr_set(tr, t.k, tn & 3, tn >> 2);
-					isd[u] = kr_is_dir(tr, t.k);
-					key[u] = ht_key(t, isd[u] ? tr.dir : tr.rc);
-					bk[u] = ht_load_bucket(t, key[u]);
+					const bool isd = kr_is_dir(tr, t.k);
+					bk[u] = ht_load_bucket(t, ht_key(t, isd ? tr.dir : tr.rc));
 				}
 			}
 #pragma unroll
 			for (int u = 0; u < 4; ++u) {
 				if ((uint32_t) u * 32 >= trials) break;
 				uint32_t loc[4] = {0, 0, 0, 0};
-				if (live[u]) ht_ctx_counts_from(t, key[u], isd[u], bk[u], loc);
+				if (live[u]) {
+					const uint32_t tn = u * 32 + lane;
+					KReg tr = reg;
+					kr_set(tr, t.k, tn & 3, tn >> 2);
+					const bool isd = kr_is_dir(tr, t.k);
+					ht_ctx_counts_from(t, ht_key(t, isd ? tr.dir : tr.rc), isd, bk[u], loc);
+				}
 				script_append(P, sc, n_ent, ovf, loc, any4(loc), trials - u * 32);
 			}
 			__syncwarp();
@@ -1105,7 +1125,7 @@ __global__ void __launch_bounds__(1024) k_scan_draws(uint32_t n, const uint32_t 
 // long), so waiting on lower-numbered CTAs cannot deadlock.
 static const uint32_t SCANF_TILE = 4096;
 __global__ void __launch_bounds__(256) k_scan_flags(const SyncIn *in, const uint32_t *n_dev, const uint8_t *flag, uint32_t *out, uint32_t *total,
-                                                    unsigned long long *partials, uint32_t epoch) { pdl_enter();
+                                                    unsigned long long *partials, uint32_t epoch, SyncDev Y, CIncP ci) { pdl_enter();
 	const uint32_t n = in->ok ? *n_dev : 0;
 	const uint32_t b = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
 	const uint32_t base = b * SCANF_TILE;
@@ -1159,6 +1179,17 @@ __global__ void __launch_bounds__(256) k_scan_flags(const SyncIn *in, const uint
 		for (int e = 0; e < 16; ++e) if (r0 + e < n) out[r0 + e] = off + v[e];
 	}
 	if (base + SCANF_TILE >= n && t == 0) { out[n] = bprefix + bsum; *total = bprefix + bsum; }
+	// former k_sync_scatter: every occurrence of a hot group leaves its draw index and flag at its own delta entry, where the
+	// group's leader reads them in time order (k_sync_apply)
+	for (int e = 0; e < 16; ++e) {
+		const uint32_t j = r0 + e;
+		if (j >= n) break;
+		const uint32_t L = Y.lead[j];
+		if (Y.lead_c0[L] + Y.lead_m[L] <= ci.thr + 1) continue;
+		const uint32_t own = Y.own[j];
+		Y.draw_at[own] = off + v[e];
+		Y.flag_at[own] = flag[j];
+	}
 }
 
 // Verdict of a segment's first pass, for the sync that is enqueued right behind it without a host look: the pass settled when
@@ -1182,6 +1213,30 @@ __global__ void k_seg_reset(uint8_t *status, unsigned long long *counters) { pdl
 	if (t == 16) w[224 / 4] = 0;                           // s-mer fast-path verdict
 	if (t >= 32 && t < 40) w[304 / 4 + (t - 32)] = 0;      // flags of the ordered insert
 	if (t == 40) counters[4] = 0;                          // fresh p-mer fields
+}
+// k_seg_verdict + k_save_carry in one launch (the chain of a small segment is launch-latency bound)
+__global__ void __launch_bounds__(256) k_seg_tail(const int *flags, const uint32_t *tot4, const unsigned long long *draws2, unsigned long long consumed_b, unsigned long long consumed_s,
+                                                  uint32_t row_cap, SyncIn *in, SegDev S, uint32_t last, uint8_t *prev_read, Carry *carry, uint32_t sorted, uint32_t p) { pdl_enter();
+	if (threadIdx.x == 0) {
+		bool ok = !(flags[0] | flags[1] | flags[2] | flags[4] | flags[5] | flags[7]);
+		if (tot4[0] > row_cap || tot4[1] > row_cap) ok = false;
+		in->n_b = tot4[0]; in->n_s = tot4[1]; in->n_p = tot4[2];
+		in->dpos_b = consumed_b + draws2[0]; in->dpos_s = consumed_s + draws2[1];
+		in->draws_b = 0;
+		in->ok = ok ? 1u : 0u;
+	}
+	if (S.n_reads == 0) return;
+	const uint8_t *q = S.dna + S.off[last];      // paired-end: only first-of-pair reads replace read_prev (dna.cpp:1550-1551)
+	const uint32_t n = S.len[last];
+	for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) prev_read[i] = q[i];
+	if (threadIdx.x == 32) {
+		carry->prev_len = n;
+		if (sorted) {
+			unsigned long long d = 0;
+			for (uint32_t i = 0; i < p; ++i) { uint32_t sy = dna_code(q[i]); if (sy == 4) sy = 3; d |= (unsigned long long) sy << (62 - 2 * i); }
+			carry->pprev_dir = d; carry->pprev_valid = 1;
+		}
+	}
 }
 __global__ void k_set_syncin(SyncIn *in, uint32_t n_b, uint32_t n_s, uint32_t n_p, unsigned long long dpos_b, unsigned long long dpos_s) { pdl_enter();
 	if (threadIdx.x || blockIdx.x) return;
