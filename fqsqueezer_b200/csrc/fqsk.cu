@@ -146,6 +146,7 @@ struct fqsk_handle {
 	bool spec_enqueued = false; SyncDev spec_Y{}; uint32_t spec_g = 0;
 	bool seg_extra_pass = false;             // the last segment needed more than its first pass: records were rewritten after the pass
 	// fqsk_submit / fqsk_collect: double-buffered records, copies on their own stream
+	DevBuf dfilter; bool delta_filtered = false;     // filter bits of the segment's delta (large segments), see seg_setup
 	DevBuf recs_alt; int rec_par = 0;
 	cudaStream_t st_copy = nullptr; cudaEvent_t ev_recs = nullptr, ev_copied[2] = {nullptr, nullptr};
 	uint8_t *h_stage2 = nullptr; size_t h_stage2_cap = 0;       // second pinned staging buffer (H2D of segment n + 1 while n is still needed)
@@ -669,15 +670,30 @@ int seg_setup(fqsk_handle *h) {
 	S.recs = P.recs;
 
 	C.E = make_engine_dev(h);
+	C.t_b = std::max<uint32_t>(h->P.bmer_len - h->P.smer_len - 1, 1); C.t_s = std::max<uint32_t>(h->P.smer_len - h->P.pmer_len + 1, 1);
+	{
+		// Large segments: the thread-local delta holds only the pushes a lookup can ask for (DeltaDev::filter).  Scattering all
+		// 13 M pushes of a 51 000-read segment into a 600 MB table cost 1.06 ms and 2.1 GB of DRAM traffic, although only the
+		// ~10 % of positions the global tables cannot answer ever look there.  Small segments keep the full delta: their sync
+		// groups equal k-mers through it (apply_indexed / sync_spec_enqueue); so does the ordered thread-local evaluator (hot mode).
+		const bool use_filter = !h->hot && h->world == 1 && C.dna_bytes_actual >= (1u << 20);
+		const uint32_t FBITS = 1u << 26;
+		uint32_t *fb = nullptr, *fs = nullptr;
+		if (use_filter) {
+			CK(h->dfilter.ensure((size_t) 2 * FBITS / 8));
+			CK(cudaMemsetAsync(h->dfilter.p, 0, (size_t) 2 * FBITS / 8, h->st));
+			fb = h->dfilter.as<uint32_t>(); fs = fb + FBITS / 32;
+		}
+		h->delta_filtered = use_filter;
+		S.delta_b = DeltaDev{nullptr, nullptr, 0, 0, h->P.bmer_len, C.t_b, h->tb.ci.thr + 1, nullptr, nullptr, nullptr, fb, FBITS - 1};
+		S.delta_s = DeltaDev{nullptr, nullptr, 0, 0, h->P.smer_len, C.t_s, h->ts.ci.thr + 1, nullptr, nullptr, nullptr, fs, FBITS - 1};
+	}
 	// one launch clears every status word the segment and a sync enqueued behind it start from: flags[8] | n_miss, n_rscript, pool_used
 	// (n_rec_dev stays: k_scan_reads wrote it) | hot-mode counters | fresh p-mer fields | s fast-path verdict | ordered-insert flags
 	CK(pdl(k_seg_reset, 1, 64, h->st, h->d_status, h->d_counters)); LAUNCHED(h);
 	{ Phase ph(h, FQSK_PH_LOOKUP); CK(pdl(k_lookup, nblk(rec_bound, 256), 256, h->st, C.E, S, P)); LAUNCHED(h); }
 	{ Phase ph(h, FQSK_PH_PARTIAL); CK(pdl(k_partial, nblk((uint64_t) n * pslots * 32, 128), 128, h->st, C.E, S, P)); LAUNCHED(h); }
-	S.delta_b = DeltaDev{nullptr, nullptr, 0, 0, h->P.bmer_len, 1, h->tb.ci.thr + 1, nullptr, nullptr, nullptr};
-	S.delta_s = DeltaDev{nullptr, nullptr, 0, 0, h->P.smer_len, 1, h->ts.ci.thr + 1, nullptr, nullptr, nullptr};
 	h->delta_b_valid = h->delta_s_valid = false;
-	C.t_b = std::max<uint32_t>(h->P.bmer_len - h->P.smer_len - 1, 1); C.t_s = std::max<uint32_t>(h->P.smer_len - h->P.pmer_len + 1, 1);
 	C.slots_b = 1024; C.slots_s = 1024;
 	while (C.slots_b < 4 * C.dna_bytes_actual) C.slots_b <<= 1;      // at most 2 b pushes per base, half-full table
 	while (C.slots_s < 2 * C.dna_bytes_actual) C.slots_s <<= 1;
@@ -692,9 +708,12 @@ int seg_setup(fqsk_handle *h) {
 	return FQSK_OK;
 }
 
-int seg_build_delta(fqsk_handle *h) {
+int seg_build_delta(fqsk_handle *h, bool force_full = false) {
 	SegCtx &C = h->ctx;
 	SegDev &S = C.S; PipeDev &P = C.P;
+	if (force_full) { S.delta_b.filter = nullptr; S.delta_s.filter = nullptr; }
+	uint32_t *const fb = S.delta_b.filter, *const fs = S.delta_s.filter;
+	const uint32_t fmask = S.delta_b.fmask;
 	const uint32_t n = C.n, slots_b = C.slots_b, slots_s = C.slots_s;
 	Phase ph(h, FQSK_PH_SORT);
 	CK(h->dk_b.ensure((size_t) slots_b * 8)); CK(h->stime_b.ensure(((size_t) slots_b + slots_s) * 4));
@@ -708,8 +727,8 @@ int seg_build_delta(fqsk_handle *h) {
 	CK(pdl(k_delta_build, nblk((uint64_t) n * 32, 128), 128, h->st, S, P, h->dk_b.as<unsigned long long>(), h->stime_b.as<uint32_t>(), slots_b - 1, h->P.bmer_len, C.t_b,
 	                                                             h->dk_s.as<unsigned long long>(), stime_s, slots_s - 1, h->P.smer_len, C.t_s));
 	LAUNCHED(h);
-	S.delta_b = DeltaDev{h->dk_b.as<unsigned long long>(), h->stime_b.as<uint32_t>(), slots_b - 1, 1, h->P.bmer_len, C.t_b, h->tb.ci.thr + 1, nullptr, nullptr, nullptr};
-	S.delta_s = DeltaDev{h->dk_s.as<unsigned long long>(), stime_s, slots_s - 1, 1, h->P.smer_len, C.t_s, h->ts.ci.thr + 1, nullptr, nullptr, nullptr};
+	S.delta_b = DeltaDev{h->dk_b.as<unsigned long long>(), h->stime_b.as<uint32_t>(), slots_b - 1, 1, h->P.bmer_len, C.t_b, h->tb.ci.thr + 1, nullptr, nullptr, nullptr, fb, fmask};
+	S.delta_s = DeltaDev{h->dk_s.as<unsigned long long>(), stime_s, slots_s - 1, 1, h->P.smer_len, C.t_s, h->ts.ci.thr + 1, nullptr, nullptr, nullptr, fs, fmask};
 	if (!h->hot) return FQSK_OK;
 	// hot mode: ranks, queued events (inserts above thr + thread-local merges), time order, sequential evaluation
 	Phase ph2(h, FQSK_PH_LOCAL);
@@ -988,6 +1007,7 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 	// draw windows: the merges of the segment and, for a sync enqueued unseen, the ordered inserts of its b-mers
 	CKR(stream_ensure(h, h->rng[ST_B], (1u << 16) + (dna_bytes_actual <= SPEC_MAX_BYTES ? 2 * dna_bytes_actual : 0))); CKR(stream_ensure(h, h->rng[ST_S], 1u << 12));
 	CKR(seg_setup(h));
+	if (h->delta_filtered) ++h->S.n_filtered_segments;
 	CKR(seg_pass(h));
 	// verdict of the first pass for a sync enqueued unseen, and the state the next segment inherits (both are inputs only)
 	// one launch: verdict of the first pass + the state the next segment inherits (read_prev, pmer_can_prev)
@@ -1004,6 +1024,11 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 // not (ht_kmer.h:433-436 via dna.cpp:826, 837, 862, 872).  When a sync row shows such a k-mer and the segment was not
 // evaluated in hot mode, the ordered evaluator runs in accounting mode to advance the stream position exactly.
 int hot_account(fqsk_handle *h, int stream) {
+	if (h->delta_filtered) {    // the accounting needs every push of the segment: build the unfiltered delta (rare: repeats inside one segment)
+		CKR(seg_build_delta(h, true));
+		h->seg_delta_b = h->ctx.S.delta_b; h->seg_delta_s = h->ctx.S.delta_s;
+		h->delta_filtered = false;
+	}
 	DeltaDev D = stream ? h->seg_delta_s : h->seg_delta_b;
 	if (!D.keys) return FQSK_OK;
 	const size_t slots = (size_t) D.mask + 1;
@@ -1153,7 +1178,7 @@ void fqsk_destroy(fqsk_handle *h) {
 	                  &h->sidx_b, &h->sidx_s, &h->stime_b, &h->stime_s, &h->sort_k, &h->sort_v, &h->rkind, &h->rreg, &h->rslot, &h->dirty, &h->rdraws_b, &h->rdraws_s, &h->totals,
 	                  &h->y_tslot, &h->y_c0, &h->y_m, &h->y_draw, &h->y_j, &h->y_final, &h->y_flag_at, &h->y_own, &h->y_lead, &h->y_rank, &h->y_flag, &h->y_doff,
 	                  &h->idx_k, &h->idx_t, &h->idx_rt, &h->miss_fold, &h->hr_b[0], &h->hr_b[1], &h->hr_b[2], &h->hr_s[0], &h->hr_s[1], &h->hr_s[2],
-	                  &h->evk[0], &h->evk[1], &h->evv[0], &h->evv[1], &h->evk_s[0], &h->evk_s[1], &h->evv_s[0], &h->evv_s[1], &h->scan_part, &h->scan_vals, &h->recs_alt,
+	                  &h->evk[0], &h->evk[1], &h->evv[0], &h->evv[1], &h->evk_s[0], &h->evk_s[1], &h->evv_s[0], &h->evv_s[1], &h->scan_part, &h->scan_vals, &h->recs_alt, &h->dfilter,
 	                  &h->route_keys, &h->route_keys2, &h->route_sorted, &h->route_hist,
 	                  &h->pe_tk, &h->pe_tv, &h->pe_q, &h->pe_sk, &h->pe_sv, &h->pe_sidx, &h->pe_t1, &h->pe_t2, &h->pe_pool, &h->pe_info, &h->it_src, &h->it_len,
 	                  &h->it_bytes, &h->it_first, &h->it_bias, &h->it_dupprev, &h->it_flags, &h->it_off32, &h->it_off64, &h->it_dna};
@@ -1406,10 +1431,10 @@ static int sync_end(fqsk_handle *h) {
 				CK(pdl(k_insert_fast, nblk(h->pend_s, 256), 256, h->st, h->ts.d, h->ts.ci, h->row_s[0].as<unsigned long long>(), h->pend_s, h->q4.as<uint8_t>(), h->d_sfast, (const SyncIn *) nullptr)); LAUNCHED(h);
 				s_fast_pending = true;
 			}
-			else if (h->pend_s <= SYNC_INDEXED_MAX) CKR(apply_indexed(h, h->ts, h->rng[ST_S], h->seg_delta_s, h->row_s[0].as<unsigned long long>(), h->rt_s[0].as<uint32_t>(), h->pend_s));
+			else if (h->pend_s <= SYNC_INDEXED_MAX && !h->delta_filtered) CKR(apply_indexed(h, h->ts, h->rng[ST_S], h->seg_delta_s, h->row_s[0].as<unsigned long long>(), h->rt_s[0].as<uint32_t>(), h->pend_s));
 			else CKR(apply_inserts(h, h->ts, h->rng[ST_S], h->row_s[0].as<unsigned long long>(), h->pend_s));
 			h->look_fresh = false;
-			if (h->pend_b <= SYNC_INDEXED_MAX) CKR(apply_indexed(h, h->tb, h->rng[ST_B], h->seg_delta_b, h->row_b[0].as<unsigned long long>(), h->rt_b[0].as<uint32_t>(), h->pend_b));
+			if (h->pend_b <= SYNC_INDEXED_MAX && !h->delta_filtered) CKR(apply_indexed(h, h->tb, h->rng[ST_B], h->seg_delta_b, h->row_b[0].as<unsigned long long>(), h->rt_b[0].as<uint32_t>(), h->pend_b));
 			else CKR(apply_inserts(h, h->tb, h->rng[ST_B], h->row_b[0].as<unsigned long long>(), h->pend_b));
 			if (!h->look_fresh) CKR(look(h));
 			memcpy(counters, (uint8_t *) h->h_small + 512, 48);

@@ -317,6 +317,11 @@ struct DeltaDev {
 	// hot mode only (a k-mer is pushed more than exact_limit times inside the segment): per entry, its push-order rank among
 	// equal k-mers, the previous equal entry, and the counter after this push as evaluated with the cinc_lb / cinc_ls stream
 	uint32_t *rank_at, *prev_at, *cnt_at;
+	// large segments: only the pushes somebody can ask for are inserted.  filter = one bit per hash of a canonical inner core, set
+	// for every context the miss list (k_lookup / k_partial) or a repair window (k_walk) looks up; k_delta_build skips a push whose
+	// bit is clear.  All k-mers a query can match share its core, so a query whose bit was set before the build sees exactly what
+	// the full table would show it; a query whose bit was clear sets it and asks for one more pass (delta_note).
+	uint32_t *filter; uint32_t fmask;
 };
 static const uint32_t DELTA_EMPTY = 0xFFFFFFFFu;
 
@@ -331,6 +336,26 @@ FQSK_DEV uint64_t delta_slot_of_key(uint64_t x, uint32_t k, uint32_t t, uint32_t
 	uint64_t c1 = (x << (2 * t)) >> (64 - 2 * cl);
 	uint64_t c2 = (rc_kmer(x, k) << (2 * t)) >> (64 - 2 * cl);
 	return fmix64(c1 < c2 ? c1 : c2) & mask;
+}
+FQSK_DEV uint32_t delta_fbit_of_key(uint64_t x, uint32_t k, uint32_t t, uint32_t fmask) {      // filter bit of a stored k-mer
+	uint32_t cl = k - 2 * t;
+	uint64_t c1 = (x << (2 * t)) >> (64 - 2 * cl);
+	uint64_t c2 = (rc_kmer(x, k) << (2 * t)) >> (64 - 2 * cl);
+	return (uint32_t) (fmix64(c1 < c2 ? c1 : c2) >> 34) & fmask;
+}
+FQSK_DEV uint32_t delta_fbit_of_query(const DeltaDev &D, const KReg &r, uint32_t cur) {            // ... of a context (cur symbols, placeholder last)
+	const uint32_t k = D.k, m = k - cur, cl = k - 2 * D.t;
+	uint64_t c1 = (r.dir << (2 * (D.t - m))) >> (64 - 2 * cl);
+	uint64_t c2 = (r.rc << (2 * D.t)) >> (64 - 2 * cl);
+	return (uint32_t) (fmix64(c1 < c2 ? c1 : c2) >> 34) & D.fmask;
+}
+// announce a thread-local lookup: sets the filter bit of the context; false when the bit was clear, i.e. the delta built so far
+// may lack entries this lookup must see
+FQSK_DEV bool delta_note(const DeltaDev &D, const KReg &r, uint32_t cur) {
+	if (!D.filter) return true;
+	const uint32_t fb = delta_fbit_of_query(D, r, cur), bit = 1u << (fb & 31);
+	if (D.filter[fb >> 5] & bit) return true;
+	return (atomicOr(D.filter + (fb >> 5), bit) & bit) != 0;
 }
 // Visits every entry older than T whose k-mer completes the context held in `r` (cur symbols, the last one is the
 // placeholder; k - cur leading symbols unknown), exactly as the reference's trial loop would find it: a stored key X counts

@@ -196,6 +196,8 @@ __global__ void __launch_bounds__(256) k_lookup(EngineDev E, SegDev S, PipeDev P
 			e.rec = g; e.time = 2 * ((uint32_t) S.off[r] + i); e.read = r; e.breg = br; e.cb = cb; e.flags = fl; e.glevel = (uint8_t) lev;
 			for (int q = 0; q < 4; ++q) e.gs[q] = (uint16_t) c[q];
 			P.miss[m] = e;
+			if (fl & PF_MISS_B) delta_note(S.delta_b, br, cb);
+			if (fl & PF_MISS_S) delta_note(S.delta_s, suffix_reg(br, cb, cs), cs);
 		}
 	}
 }
@@ -300,6 +302,8 @@ __global__ void __launch_bounds__(128) k_partial(EngineDev E, SegDev S, PipeDev 
 				e.rec = g; e.time = 2 * ((uint32_t) S.off[r] + i); e.read = r; e.breg = br; e.cb = cb; e.flags = nf; e.glevel = (uint8_t) lev;
 				for (int q = 0; q < 4; ++q) e.gs[q] = (uint16_t) c[q];
 				P.miss[mi] = e;
+				if (nf & PF_MISS_B) delta_note(S.delta_b, br, cb);
+				if (nf & PF_MISS_S) delta_note(S.delta_s, suffix_reg(br, cb, cs), cs);
 			}
 		}
 	}
@@ -562,7 +566,7 @@ __global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P, 
 		// ---- per-lane evaluation of position i
 		uint32_t lev = FQSK_LEVEL_NONE, c[4] = {0, 0, 0, 0};
 		uint32_t sym = 4, cb = 0, cs = 0, cp = 0, lane_cor = cor_pos;
-		bool ev_revert = false, ev_patch = false, repaired = false, lane_wl = false;
+		bool ev_revert = false, ev_patch = false, repaired = false, lane_wl = false, lane_fmiss = false;
 		int lane_unsup = 0;   // discarded (speculative) lanes must not raise global flags
 		uint32_t patch_pos = 0, patch_sym = 0, new_cor = cor_pos;
 		KReg bc{0, 0}, bu{0, 0};
@@ -591,12 +595,16 @@ __global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P, 
 					done = true;
 				} else {
 					lane_wl = true;   // the thread-local table is consulted here: this read is re-walked when the delta exists / changes
+					if (!delta_note(S.delta_b, bc, cb)) lane_fmiss = true;
 					if (delta_find(S.delta_b, E.cib, bc, cb, 2 * (tbase + i), c, &lane_unsup)) { lev = FQSK_LEVEL_BMER; done = true; }
 					if (!done && ht_find(E.hb, E.cib, bu, cb, c, nodraw)) { lev = FQSK_LEVEL_BMER_UNC; done = true; }
 				}
 				if (!done) {
 					if (ht_find(E.hs, E.cis, sc, cs, c, nodraw)) lev = FQSK_LEVEL_SMER;
-					else if (delta_find(S.delta_s, E.cis, sc, cs, 2 * (tbase + i), c, &lane_unsup)) lev = FQSK_LEVEL_SMER;
+					else {
+						if (!delta_note(S.delta_s, sc, cs)) lane_fmiss = true;
+						if (delta_find(S.delta_s, E.cis, sc, cs, 2 * (tbase + i), c, &lane_unsup)) lev = FQSK_LEVEL_SMER;
+					}
 				}
 				if (lev == FQSK_LEVEL_BMER_UNC) { bc = bu; ev_revert = true; lane_cor = 0; new_cor = 0; lev = FQSK_LEVEL_BMER; }   // dna.cpp:697-705
 			}
@@ -670,6 +678,7 @@ __global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P, 
 		if (commit) {
 			if (lane_unsup) *unsupported = 1;
 			window_local |= lane_wl;
+			if (lane_fmiss && S.delta_b.n) P.flags[2] = 1;   // the filtered delta was built without this context: one more pass (the bit is set now)
 			const uint32_t g = g0 + (i - start);
 			fqsk_base_rec o;
 			o.pos = i + bias; o.counts[0] = c[0]; o.counts[1] = c[1]; o.counts[2] = c[2]; o.counts[3] = c[3];
@@ -745,13 +754,16 @@ __global__ void __launch_bounds__(128) k_delta_build(SegDev S, PipeDev P, unsign
 	if (r >= S.n_reads) return;
 	const unsigned long long *sb = S.push_b + 2 * S.off[r], *ss = S.push_s + S.off[r];
 	const uint32_t *qb = P.time_b + 2 * S.off[r], *qs = P.time_s + S.off[r];
+	const uint32_t *fb = S.delta_b.filter, *fs = S.delta_s.filter;
 	for (uint32_t j = lane; j < S.cnt_b[r]; j += 32) {
 		unsigned long long x = sb[j];
+		if (fb) { const uint32_t q = delta_fbit_of_key(x, k_b, t_b, S.delta_b.fmask); if (!((__ldg(fb + (q >> 5)) >> (q & 31)) & 1u)) continue; }
 		for (uint64_t slot = delta_slot_of_key(x, k_b, t_b, mask_b);; slot = (slot + 1) & mask_b)
 			if (atomicCAS(tb + slot, DELTA_EMPTY, qb[j]) == DELTA_EMPTY) { kb[slot] = x; break; }
 	}
 	for (uint32_t j = lane; j < S.cnt_s[r]; j += 32) {
 		unsigned long long x = ss[j];
+		if (fs) { const uint32_t q = delta_fbit_of_key(x, k_s, t_s, S.delta_s.fmask); if (!((__ldg(fs + (q >> 5)) >> (q & 31)) & 1u)) continue; }
 		for (uint64_t slot = delta_slot_of_key(x, k_s, t_s, mask_s);; slot = (slot + 1) & mask_s)
 			if (atomicCAS(ts + slot, DELTA_EMPTY, qs[j]) == DELTA_EMPTY) { ks[slot] = x; break; }
 	}

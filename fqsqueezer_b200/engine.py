@@ -40,7 +40,8 @@ class _Stats(C.Structure):
     _fields_ = [("siv_no_filled", C.c_uint64), ("siv_no_updates", C.c_uint64), ("n_smers", C.c_uint64), ("n_bmers", C.c_uint64),
                 ("draws", C.c_uint64 * 4), ("n_segments", C.c_uint64), ("n_syncs", C.c_uint64), ("n_replays", C.c_uint64),
                 ("n_bases", C.c_uint64), ("n_reads", C.c_uint64), ("kernel_launches", C.c_uint64), ("bmer_buckets", C.c_uint64),
-                ("smer_buckets", C.c_uint64), ("bmer_stash_used", C.c_uint64), ("smer_stash_used", C.c_uint64), ("n_hot_segments", C.c_uint64)]
+                ("smer_buckets", C.c_uint64), ("bmer_stash_used", C.c_uint64), ("smer_stash_used", C.c_uint64), ("n_hot_segments", C.c_uint64),
+                ("n_filtered_segments", C.c_uint64)]
 
 
 EXPORTS = ["fqsk_create", "fqsk_destroy", "fqsk_last_error", "fqsk_block_start", "fqsk_segment", "fqsk_segment_device",

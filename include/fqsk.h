@@ -95,6 +95,7 @@ typedef struct fqsk_stats {
 	uint64_t kernel_launches;                /* launches of this library's own kernels */
 	uint64_t bmer_buckets, smer_buckets, bmer_stash_used, smer_stash_used;
 	uint64_t n_hot_segments;                 /* segments redone with the ordered thread-local evaluator (cinc_lb / cinc_ls in use) */
+	uint64_t n_filtered_segments;            /* large segments whose thread-local delta held only the pushes a lookup could ask for */
 } fqsk_stats;
 
 /* Named phases of fqsk_profile(): device milliseconds accumulated since create (only with FQSK_F_PROFILE). */

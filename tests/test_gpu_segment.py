@@ -204,3 +204,37 @@ def test_async_submit_collect_paired_end():
     assert dup[1::2].sum() == 0
     H.assert_dump_equal(e, g, pairs=True)
     e.close()
+
+
+@pytest.mark.parametrize("G,expect_hot", [(2_000_000, False), (300_000, True)])
+def test_large_segments_filtered_delta_matches_oracle(G, expect_hot):
+    """Segments above 1 MiB of DNA build their thread-local delta through the core filter (only pushes a lookup can ask for are
+    inserted) and sync through the radix-sort path: records, tables and PRNG positions vs the oracle, on reads with thread-local
+    hits, repairs, draws, duplicates and Ns.  The small genome pushes k-mers more than thr + 1 times inside one segment: the
+    filtered attempt must hand over to the ordered thread-local evaluator (full delta) without leaving a trace."""
+    genome = synth.make_genome(G, 31)
+    codes, _ = synth.make_reads(genome, 24_600, L=150, seed=31, n_frac=0.0005, dup_frac=0.002)
+    slab = _fastq_slab(codes)
+    off, ln, _, _ = __import__("fqsqueezer_b200.schedule", fromlist=["x"]).parse_fastq(slab)
+    pref, p, s, b = E.kmer_params(16)
+    e = E.KmerEngine(p, s, b, pref, expected_kmers=1 << 21)
+    o = O.OracleEngine(p, s, b, pref)
+    for eng in (e, o):
+        eng.block_start()
+    for a, bb in ((0, 8200), (8200, 16400), (16400, 24600)):
+        rg, dg = e.segment(slab, off[a:bb], ln[a:bb])
+        ro, do = o.segment(slab, off[a:bb], ln[a:bb])
+        ro = ro[ro["pos"] < 0xFFFFFFF0]
+        H.assert_recs_equal(rg, ro)
+        assert np.array_equal(dg, do)
+        e.sync(); o.sync()
+    for which in (0, 1, 2):
+        kg, vg = e.dump(which)
+        ko, vo = o.dump(which)
+        assert np.array_equal(kg, ko) and np.array_equal(vg, vo), which
+    sg, so = e.stats(), o.stats()
+    for key in ("siv_no_filled", "siv_no_updates", "n_smers", "n_bmers", "draws_b", "draws_s", "draws_lb", "draws_ls"):
+        assert sg[key] == so[key], key
+    assert sg["n_filtered_segments"] == 3 and so["local_hits"] > 100
+    assert (sg["n_hot_segments"] > 0) == expect_hot
+    e.close(); o.close()
