@@ -1031,6 +1031,7 @@ static const uint32_t SCAN_CHAIN_MAX = 256;
 template <int NQ>
 __device__ __forceinline__ void cta_chain_prefix(const ScanChain &C, const unsigned long long *mine /* shared, [NQ] */, unsigned long long (&pre)[NQ], unsigned long long (*sh)[32]) {
 	const uint32_t b = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5, nw = blockDim.x >> 5;
+	if (gridDim.x == 1) { for (int q = 0; q < NQ; ++q) pre[q] = 0; return; }      // small segments: one chunk, nothing to chain
 	if (t == 0) {
 		for (int q = 0; q < NQ; ++q) C.vals[b * 8 + q] = mine[q];
 		__threadfence();

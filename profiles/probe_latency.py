@@ -1,7 +1,10 @@
-"""Scratch probe (not part of the product): host-side time per C-ABI call in the early, small-segment regime."""
+"""Measurement helper (not part of the product): wall clock per C-ABI call in the small-segment regime of config 2, for the
+device-resident path (fqsk_segment_device + fqsk_sync) and the host-buffer path (fqsk_submit / fqsk_collect), plus a few
+full-size segments.  Run on the GPU box: `python profiles/probe_latency.py [n_blocks]`.  The numbers quoted in
+profiles/r01c_early_block_warm_summary.md and DESIGN.md section 6 come from it."""
 import sys, time, os
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench as B
 from fqsqueezer_b200 import engine as E, schedule as S, synth
 
