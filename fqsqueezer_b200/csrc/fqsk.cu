@@ -146,6 +146,7 @@ struct fqsk_handle {
 	bool spec_enqueued = false; SyncDev spec_Y{}; uint32_t spec_g = 0;
 	bool seg_extra_pass = false;             // the last segment needed more than its first pass: records were rewritten after the pass
 	// fqsk_submit / fqsk_collect: double-buffered records, copies on their own stream
+	DevBuf pk;                                       // 2-bit packed reads of the segment (k_prep)
 	DevBuf dfilter; bool delta_filtered = false;     // filter bits of the segment's delta (large segments), see seg_setup
 	DevBuf recs_alt; int rec_par = 0;
 	cudaStream_t st_copy = nullptr; cudaEvent_t ev_recs = nullptr, ev_copied[2] = {nullptr, nullptr};
@@ -992,9 +993,11 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 	S.push_b = h->push_b.as<unsigned long long>(); S.push_s = h->push_s.as<unsigned long long>(); S.push_p = h->push_p.as<unsigned long long>();
 	S.cnt_b = h->cnt_b.as<uint32_t>(); S.cnt_s = h->cnt_s.as<uint32_t>(); S.cnt_p = h->cnt_p.as<uint32_t>(); S.hidden = h->hidden.as<uint32_t>();
 	S.sorted_flag = h->sflag.as<uint32_t>(); S.sorted_dif = h->sdif.as<unsigned long long>();
+	CK(h->pk.ensure((dna_bytes / 32 + 2 * n1 + 8) * 8));
+	S.pk = h->pk.as<unsigned long long>();
 	{
 		Phase ph(h, FQSK_PH_PREP);
-		CK(pdl(k_prep, nblk((uint64_t) n * 32, 128), 128, h->st, S, first, h->P.bmer_len)); LAUNCHED(h);
+		CK(pdl(k_prep, nblk((uint64_t) n * 32, 128), 128, h->st, S, first, h->P.bmer_len, (uint32_t) (h->P.mode == FQSK_MODE_SE_SORTED))); LAUNCHED(h);
 		if (n > SCAN_CHAIN_MAX * SCAN_READS_CHUNK) return fail(h, FQSK_E_INVAL, "more than %u reads in one segment", SCAN_CHAIN_MAX * SCAN_READS_CHUNK);
 		ScanChain sc; CKR(scan_chain(h, sc));
 		CK(pdl(k_scan_reads, std::max<uint32_t>(nblk(n, SCAN_READS_CHUNK), 1), 1024, h->st, S, h->rec_off.as<unsigned long long>(), h->sl_prefix.as<U64x4>(), (SegTotals *) (h->d_status + 64), h->d_u32 + 3, sc)); LAUNCHED(h);
@@ -1178,7 +1181,7 @@ void fqsk_destroy(fqsk_handle *h) {
 	                  &h->sidx_b, &h->sidx_s, &h->stime_b, &h->stime_s, &h->sort_k, &h->sort_v, &h->rkind, &h->rreg, &h->rslot, &h->dirty, &h->rdraws_b, &h->rdraws_s, &h->totals,
 	                  &h->y_tslot, &h->y_c0, &h->y_m, &h->y_draw, &h->y_j, &h->y_final, &h->y_flag_at, &h->y_own, &h->y_lead, &h->y_rank, &h->y_flag, &h->y_doff,
 	                  &h->idx_k, &h->idx_t, &h->idx_rt, &h->miss_fold, &h->hr_b[0], &h->hr_b[1], &h->hr_b[2], &h->hr_s[0], &h->hr_s[1], &h->hr_s[2],
-	                  &h->evk[0], &h->evk[1], &h->evv[0], &h->evv[1], &h->evk_s[0], &h->evk_s[1], &h->evv_s[0], &h->evv_s[1], &h->scan_part, &h->scan_vals, &h->recs_alt, &h->dfilter,
+	                  &h->evk[0], &h->evk[1], &h->evv[0], &h->evv[1], &h->evk_s[0], &h->evk_s[1], &h->evv_s[0], &h->evv_s[1], &h->scan_part, &h->scan_vals, &h->recs_alt, &h->dfilter, &h->pk,
 	                  &h->route_keys, &h->route_keys2, &h->route_sorted, &h->route_hist,
 	                  &h->pe_tk, &h->pe_tv, &h->pe_q, &h->pe_sk, &h->pe_sv, &h->pe_sidx, &h->pe_t1, &h->pe_t2, &h->pe_pool, &h->pe_info, &h->it_src, &h->it_len,
 	                  &h->it_bytes, &h->it_first, &h->it_bias, &h->it_dupprev, &h->it_flags, &h->it_off32, &h->it_off64, &h->it_dna};

@@ -32,6 +32,26 @@ FQSK_DEV void pdl_enter() {
 
 struct KReg { uint64_t dir, rc; };
 
+// ---- 2-bit packed symbols: 32 per 64-bit word, symbol j of a word at bits 63-2j .. 62-2j (the layout of a left-aligned CKmer) ----
+// word of 32 symbols from two warp ballots (bit 1 / bit 0 of every lane's symbol); lane 0 = first symbol
+FQSK_DEV uint64_t pk_spread(uint32_t x) {            // bit j -> bit 2j
+	uint64_t v = x;
+	v = (v | (v << 16)) & 0x0000FFFF0000FFFFull;
+	v = (v | (v << 8)) & 0x00FF00FF00FF00FFull;
+	v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0Full;
+	v = (v | (v << 2)) & 0x3333333333333333ull;
+	v = (v | (v << 1)) & 0x5555555555555555ull;
+	return v;
+}
+FQSK_DEV uint64_t pk_from_ballots(unsigned b1, unsigned b0) { return (pk_spread(__brev(b1)) << 1) | pk_spread(__brev(b0)); }
+// len (< 32) symbols starting at symbol a of the sequence whose words are w[0], w[1], ...: hi = w[a >> 5], lo = w[(a >> 5) + 1]
+// (the sequence needs one word of slack); left-aligned, rest zero
+FQSK_DEV uint64_t pk_window(uint64_t hi, uint64_t lo, uint32_t a, uint32_t len) {
+	const uint32_t sh = 2 * (a & 31);
+	uint64_t x = sh ? (hi << sh) | (lo >> (64 - sh)) : hi;
+	return len ? x & (~0ull << (64 - 2 * len)) : 0ull;
+}
+
 FQSK_HD uint64_t kr_top_mask(uint32_t k) { return ~0ull << (64 - 2 * k); }
 FQSK_HD uint64_t kr_kernel_mask(uint32_t k) { return ((1ull << (2 * k - 8)) - 1ull) << (64 - 2 * k + 4); }
 // kmer.h:73-108 (insert_zero == insert of symbol 0: the rc side receives T)

@@ -93,7 +93,11 @@ struct SegDev {
 	// paired-end: the "reads" of the segment are work ITEMS (mate 1, mate 2 or its forward part, its reversed part), each with its
 	// own first coded position, position bias and flags; all null for single-end segments
 	const uint32_t *first_a, *bias_a, *dup_prev; const uint8_t *iflags;
+	// 2-bit packed symbols of every read (N -> A, in a sorted prefix N -> T: dna.cpp:532-536 / 560-565 / 684), written by k_prep:
+	// read r starts at word (off[r] >> 5) + 2 r and has one word of slack.  The registers of a position are two 64-bit loads.
+	unsigned long long *pk;
 };
+__device__ __forceinline__ unsigned long long *pk_of(const SegDev &S, uint32_t r) { return S.pk + (S.off[r] >> 5) + 2ull * r; }
 enum : uint8_t {
 	IF_SKIP = 1,          // empty slot (a mate 2 coded in one piece has no reversed part)
 	IF_NO_DUPCHECK = 2,   // only first-of-pair reads are compared with read_prev (dna.cpp:1523)
@@ -109,7 +113,7 @@ __device__ __forceinline__ uint32_t dna_code(uint8_t ch) {  // dna.cpp:18-23
 	return ch == 'A' ? 0u : ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : 4u;
 }
 
-__global__ void __launch_bounds__(128) k_prep(SegDev S, uint32_t first_len_bytes, uint32_t b) { pdl_enter();   // one warp per read
+__global__ void __launch_bounds__(128) k_prep(SegDev S, uint32_t first_len_bytes, uint32_t b, uint32_t sorted) { pdl_enter();   // one warp per read
 	uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (r >= S.n_reads) return;
 	const uint8_t *p = S.dna + S.off[r];
@@ -122,12 +126,21 @@ __global__ void __launch_bounds__(128) k_prep(SegDev S, uint32_t first_len_bytes
 	bool same = qn == n && !(ifl & IF_NO_DUPCHECK);
 	if (ifl & IF_SKIP) { same = true; n = 0; }
 	uint32_t cnt[4] = {0, 0, 0, 0};
-	for (uint32_t i = lane; i < n; i += 32) {
-		uint8_t ch = p[i];
-		if (same && q[i] != ch) same = false;
-		uint32_t c = dna_code(ch);
-		if (c < 4) { ++cnt[c]; ++cnt[3 - c]; }
+	unsigned long long *pkr = pk_of(S, r);
+	for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+		const uint32_t i = i0 + lane;
+		uint32_t c2 = 0;
+		if (i < n) {
+			uint8_t ch = p[i];
+			if (same && q[i] != ch) same = false;
+			uint32_t c = dna_code(ch);
+			if (c < 4) { ++cnt[c]; ++cnt[3 - c]; }
+			c2 = c < 4 ? c : ((sorted && i < first_len_bytes) ? 3u : 0u);
+		}
+		const unsigned b1 = __ballot_sync(0xffffffffu, c2 & 2u), b0 = __ballot_sync(0xffffffffu, c2 & 1u);
+		if (lane == 0) pkr[i0 >> 5] = pk_from_ballots(b1, b0);
 	}
+	if (lane == 0) pkr[(n + 31) >> 5] = 0;     // the word of slack pk_window reads
 	same = __all_sync(0xffffffffu, same);
 	if (ifl & IF_LETTERS_PREV) {      // symbol + complement are counted (dna.cpp:2047-2057), so the reversed text counts like the original
 		const uint8_t *pp = S.dna + S.off[r - 1];

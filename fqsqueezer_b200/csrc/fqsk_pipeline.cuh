@@ -83,18 +83,17 @@ __device__ __forceinline__ uint32_t sym_at(const SegDev &S, const EngineDev &E, 
 	if (c == 4) c = (E.sorted && j < E.p) ? 3u : 0u;   // dna.cpp:532-536 / 560-565 / 684
 	return c;
 }
-// uncorrected b register (with placeholder) in front of position i; cb = min(b, i + 1)
-__device__ __forceinline__ KReg build_breg(const SegDev &S, const EngineDev &E, const uint8_t *p, uint32_t i, uint32_t cb) {
-	KReg r{0, 0};
-	// symbols p[i - cb + 1 .. i - 1] then the placeholder (dir: A, rc: T)
-	for (uint32_t t = 0; t + 1 < cb; ++t) {
-		uint64_t s = sym_at(S, E, p, i + 1 - cb + t);
-		r.dir |= s << (62 - 2 * t);
-		r.rc |= (3 - s) << (64 - 2 * cb + 2 * t);     // complement lands mirrored: symbol t -> rc position cb-1-t
-	}
-	r.rc |= 3ull << 62;                                // placeholder complement at rc position 0
-	// rc position of symbol t is cb-1-t: shift = 62 - 2*(cb-1-t) = 64 - 2cb + 2t  (done above)
+// uncorrected b register (with placeholder) in front of position i; cb = min(b, i + 1): symbols i - cb + 1 .. i - 1 of the packed
+// read, then the placeholder (dir: A, rc: T at position 0, the complements mirrored behind it)
+__device__ __forceinline__ KReg breg_from_words(uint64_t hi, uint64_t lo, uint32_t a, uint32_t cb) {
+	KReg r;
+	r.dir = pk_window(hi, lo, a, cb - 1);
+	r.rc = (3ull << 62) | (cb > 1 ? rc_kmer(r.dir, cb - 1) >> 2 : 0ull);
 	return r;
+}
+__device__ __forceinline__ KReg build_breg(const unsigned long long *pkr, uint32_t i, uint32_t cb) {
+	const uint32_t a = i + 1 - cb;
+	return breg_from_words(pkr[a >> 5], pkr[(a >> 5) + 1], a, cb);
 }
 // suffix register of length c (c <= cb) taken from a register holding cb symbols
 __device__ __forceinline__ KReg suffix_reg(const KReg &r, uint32_t cb, uint32_t c) {
@@ -144,7 +143,7 @@ __global__ void __launch_bounds__(256) k_lookup(EngineDev E, SegDev S, PipeDev P
 	uint32_t c[4] = {0, 0, 0, 0};
 	uint32_t lev = FQSK_LEVEL_NONE;
 	uint8_t fl = 0;
-	KReg br = build_breg(S, E, p, i, cb);
+	KReg br = build_breg(pk_of(S, r), i, cb);
 	if (cb + b_margin >= E.b) {
 		if (cb == E.b) {
 			bool d = kr_is_dir(br, E.b);
@@ -245,7 +244,7 @@ __global__ void __launch_bounds__(128) k_partial(EngineDev E, SegDev S, PipeDev 
 	if (!(fl & (PF_PARTIAL_B | PF_PARTIAL_S))) return;
 	const uint8_t *p = S.dna + S.off[r];
 	const uint32_t cb = n < E.b ? n : E.b, cs = n < E.s ? n : E.s;
-	KReg br = build_breg(S, E, p, i, cb);
+	KReg br = build_breg(pk_of(S, r), i, cb);
 	const bool is_b = (fl & PF_PARTIAL_B) != 0;
 	const HtDev &t = is_b ? E.hb : E.hs;
 	KReg reg = is_b ? br : suffix_reg(br, cb, cs);
@@ -563,6 +562,18 @@ __global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P, 
 		__syncwarp();
 		const uint32_t i = i0 + lane;
 		const bool valid = i < size;
+		// the 64 ring symbols around the chunk as two packed words each (positions i0 - 32 .. i0 - 1 and i0 .. i0 + 31; positions that
+		// do not exist are never inside a register): a lane's register is a funnel shift instead of 2 x 24 shared-memory loads
+		uint64_t wU0, wU1, wC0, wC1;
+		{
+			const bool have_a = i0 + lane >= 32;
+			const uint32_t sa = have_a ? ringU[(i0 + lane - 32) & 63] : 0, sb = ringU[(i0 + lane) & 63];
+			const uint32_t ca = have_a ? ringC[(i0 + lane - 32) & 63] : 0, cbb = ringC[(i0 + lane) & 63];
+			wU0 = pk_from_ballots(__ballot_sync(0xffffffffu, sa & 2u), __ballot_sync(0xffffffffu, sa & 1u));
+			wU1 = pk_from_ballots(__ballot_sync(0xffffffffu, sb & 2u), __ballot_sync(0xffffffffu, sb & 1u));
+			wC0 = pk_from_ballots(__ballot_sync(0xffffffffu, ca & 2u), __ballot_sync(0xffffffffu, ca & 1u));
+			wC1 = pk_from_ballots(__ballot_sync(0xffffffffu, cbb & 2u), __ballot_sync(0xffffffffu, cbb & 1u));
+		}
 		// ---- per-lane evaluation of position i
 		uint32_t lev = FQSK_LEVEL_NONE, c[4] = {0, 0, 0, 0};
 		uint32_t sym = 4, cb = 0, cs = 0, cp = 0, lane_cor = cor_pos;
@@ -579,8 +590,9 @@ __global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P, 
 			cb = n < E.b ? n : E.b; cs = n < E.s ? n : E.s; cp = n < E.p ? n : E.p;
 			sym = dna_code(p[i]);
 			const uint64_t ks = sym == 4 ? 0 : sym;
-			bu = ring_breg(ringU, i, cb);
-			bc = ring_breg(ringC, i, cb);
+			const uint32_t a = 32 + lane + 1 - cb;                        // symbols i - cb + 1 .. i - 1 out of the 64 packed ones i0 - 32 .. i0 + 31
+			bu = a < 32 ? breg_from_words(wU0, wU1, a, cb) : breg_from_words(wU1, 0ull, a, cb);
+			bc = a < 32 ? breg_from_words(wC0, wC1, a, cb) : breg_from_words(wC1, 0ull, a, cb);
 			const fqsk_base_rec pv = P.prov[g0 + (i - start)];
 			if (bc.dir == bu.dir) {
 				lev = pv.level; c[0] = pv.counts[0]; c[1] = pv.counts[1]; c[2] = pv.counts[2]; c[3] = pv.counts[3];
