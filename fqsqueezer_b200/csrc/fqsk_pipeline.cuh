@@ -979,13 +979,20 @@ __global__ void __launch_bounds__(128) k_fold(EngineDev E, SegDev S, PipeDev P, 
 			Script *sp = (s0 + lane < P.pslots && ps[s0 + lane].valid) ? ps + s0 + lane : nullptr;
 			if (__any_sync(0xffffffffu, sp != nullptr)) batch(sp);
 		}
-		// rough searches of this read, in position order
+		// rough searches of this read, in position order.  The kind / script-slot loads of 8 chunks are issued together: a segment of
+		// a few hundred reads has one warp per read and nothing to hide the latency of chunk-by-chunk dependent loads behind.
 		const uint32_t g0 = (uint32_t) S.rec_off[r], g1 = (uint32_t) S.rec_off[r + 1];
-		for (uint32_t gb = g0; gb < g1; gb += 32) {
-			uint32_t g = gb + lane;
-			uint32_t k = g < g1 ? P.rkind[g] : 0;
-			uint32_t slot = (k == 2 || k == 3) ? P.rslot[g] : 0xFFFFFFFFu;
-			if (__any_sync(0xffffffffu, slot != 0xFFFFFFFFu)) batch(slot != 0xFFFFFFFFu ? P.rscripts + slot : nullptr);
+		for (uint32_t gs = g0; gs < g1; gs += 256) {
+			uint32_t kk[8], slot[8];
+#pragma unroll
+			for (int c = 0; c < 8; ++c) { const uint32_t g = gs + c * 32 + lane; kk[c] = g < g1 ? P.rkind[g] : 0; }
+#pragma unroll
+			for (int c = 0; c < 8; ++c) { const uint32_t g = gs + c * 32 + lane; slot[c] = (kk[c] == 2 || kk[c] == 3) ? P.rslot[g] : 0xFFFFFFFFu; }
+#pragma unroll
+			for (int c = 0; c < 8; ++c) {
+				if (gs + c * 32 >= g1) break;
+				if (__any_sync(0xffffffffu, slot[c] != 0xFFFFFFFFu)) batch(slot[c] != 0xFFFFFFFFu ? P.rscripts + slot[c] : nullptr);
+			}
 		}
 	}
 	mismatch = __any_sync(0xffffffffu, mismatch);
