@@ -783,7 +783,7 @@ int seg_pass(fqsk_handle *h) {
 		{
 			Phase ph(h, FQSK_PH_COMPACT);
 			ScanChain sc; CKR(scan_chain(h, sc));
-			CK(pdl(k_scan_u32x4, std::max<uint32_t>(nblk(n, SCAN_U32_CHUNK), 1), 1024, h->st, n, h->cnt_b.as<uint32_t>(), h->off_b[0].as<uint32_t>(), h->cnt_s.as<uint32_t>(), h->off_s[0].as<uint32_t>(),
+			CK(pdl(k_scan_u32x4, n <= 2048 ? 1u : nblk(n, SCAN_U32_CHUNK), n <= 2048 ? 256 : 1024, h->st, n, h->cnt_b.as<uint32_t>(), h->off_b[0].as<uint32_t>(), h->cnt_s.as<uint32_t>(), h->off_s[0].as<uint32_t>(),
 			                                     h->cnt_p.as<uint32_t>(), h->off_p.as<uint32_t>(), h->hidden.as<uint32_t>(), (uint32_t *) nullptr, d_tot4, h->d_u32 + 1, sc));   // + rough scripts are rebuilt
 			LAUNCHED(h);
 			CK(pdl(k_compact2, n, 64, h->st, S, P, h->off_b[0].as<uint32_t>(), h->off_s[0].as<uint32_t>(), h->off_p.as<uint32_t>(),
@@ -797,7 +797,7 @@ int seg_pass(fqsk_handle *h) {
 	{
 		Phase ph(h, FQSK_PH_FOLD);
 		ScanChain sc; CKR(scan_chain(h, sc));
-		CK(pdl(k_scan_draws, std::max<uint32_t>(nblk(n, SCAN_U32_CHUNK), 1), 1024, h->st, n, P.rdraws_b, h->doff_b.as<unsigned long long>(), P.rdraws_s, h->doff_s.as<unsigned long long>(), d_draw2, h->d_flags, sc)); LAUNCHED(h);   // + clears flags[0], flags[7]
+		CK(pdl(k_scan_draws, n <= 2048 ? 1u : nblk(n, SCAN_U32_CHUNK), n <= 2048 ? 256 : 1024, h->st, n, P.rdraws_b, h->doff_b.as<unsigned long long>(), P.rdraws_s, h->doff_s.as<unsigned long long>(), d_draw2, h->d_flags, sc)); LAUNCHED(h);   // + clears flags[0], flags[7]
 		CK(pdl(k_fold, nblk((uint64_t) n * 32, 128), 128, h->st, E, S, P, 1)); LAUNCHED(h);
 	}
 	return FQSK_OK;
@@ -1000,7 +1000,7 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 		CK(pdl(k_prep, nblk((uint64_t) n * 32, 128), 128, h->st, S, first, h->P.bmer_len, (uint32_t) (h->P.mode == FQSK_MODE_SE_SORTED))); LAUNCHED(h);
 		if (n > SCAN_CHAIN_MAX * SCAN_READS_CHUNK) return fail(h, FQSK_E_INVAL, "more than %u reads in one segment", SCAN_CHAIN_MAX * SCAN_READS_CHUNK);
 		ScanChain sc; CKR(scan_chain(h, sc));
-		CK(pdl(k_scan_reads, std::max<uint32_t>(nblk(n, SCAN_READS_CHUNK), 1), 1024, h->st, S, h->rec_off.as<unsigned long long>(), h->sl_prefix.as<U64x4>(), (SegTotals *) (h->d_status + 64), h->d_u32 + 3, sc)); LAUNCHED(h);
+		CK(pdl(k_scan_reads, n <= 1024 ? 1u : nblk(n, SCAN_READS_CHUNK), n <= 1024 ? 256 : 1024, h->st, S, h->rec_off.as<unsigned long long>(), h->sl_prefix.as<U64x4>(), (SegTotals *) (h->d_status + 64), h->d_u32 + 3, sc)); LAUNCHED(h);
 	}
 	const uint32_t rec_bound = (uint32_t) dna_bytes;   // capacities follow the reserve as well
 	if (h->miss_cap < std::min<uint32_t>(rec_bound, 1u << 20)) h->miss_cap = std::min<uint32_t>(rec_bound, 1u << 20);

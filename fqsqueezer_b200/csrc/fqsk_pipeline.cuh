@@ -1078,8 +1078,9 @@ __global__ void __launch_bounds__(1024) k_scan_reads(SegDev S, unsigned long lon
 	__shared__ unsigned long long carry[5];
 	const uint32_t t = threadIdx.x;
 	if (t < 5) carry[t] = 0;
+	if (t < 32) for (int q = 0; q < 5; ++q) sh[q][t] = 0;       // CTAs of fewer than 32 warps (small segments)
 	__syncthreads();
-	const uint32_t base = blockIdx.x * 1024 * IT;
+	const uint32_t base = blockIdx.x * blockDim.x * IT;
 	unsigned long long v[5][IT], ex[5][IT];
 	for (int e = 0; e < IT; ++e) {
 		uint32_t r = base + t * IT + e;
@@ -1113,8 +1114,9 @@ __global__ void __launch_bounds__(1024) k_scan_u32x4(uint32_t n, const uint32_t 
 	const uint32_t *in[4] = {a0, a1, a2, a3};
 	uint32_t *out[4] = {o0, o1, o2, o3};
 	if (t < 4) carry[t] = 0;
+	if (t < 32) for (int q = 0; q < 4; ++q) sh[q][t] = 0;       // CTAs of fewer than 32 warps (small segments)
 	__syncthreads();
-	const uint32_t base = blockIdx.x * 1024 * IT;
+	const uint32_t base = blockIdx.x * blockDim.x * IT;
 	unsigned long long v[4][IT], ex[4][IT];
 	for (int q = 0; q < 4; ++q) for (int e = 0; e < IT; ++e) { uint32_t r = base + t * IT + e; v[q][e] = (in[q] && r < n) ? in[q][r] : 0; }
 	block_scan_chunk<unsigned long long, 4, IT>(v, ex, sh, carry);
@@ -1137,8 +1139,9 @@ __global__ void __launch_bounds__(1024) k_scan_draws(uint32_t n, const uint32_t 
 	const uint32_t *in[2] = {a0, a1};
 	unsigned long long *out[2] = {o0, o1};
 	if (t < 2) carry[t] = 0;
+	if (t < 32) for (int q = 0; q < 2; ++q) sh[q][t] = 0;       // CTAs of fewer than 32 warps (small segments)
 	__syncthreads();
-	const uint32_t base = blockIdx.x * 1024 * IT;
+	const uint32_t base = blockIdx.x * blockDim.x * IT;
 	unsigned long long v[2][IT], ex[2][IT];
 	for (int q = 0; q < 2; ++q) for (int e = 0; e < IT; ++e) { uint32_t r = base + t * IT + e; v[q][e] = r < n ? in[q][r] : 0; }
 	block_scan_chunk<unsigned long long, 2, IT>(v, ex, sh, carry);
