@@ -143,6 +143,7 @@ struct fqsk_handle {
 	       it_flags, it_off32, it_off64, it_dna;
 	uint32_t pe_pool_cap = 1u << 20, pe_pairs = 0, pe_nt = 0, seg_reads_in = 0;
 	// the sync enqueued behind its segment (sync_spec_enqueue / sync_spec_finish)
+	unsigned long long items_main[2] = {0, 0};   // items in the buckets of the b / s table as of the last look (sparse -> k_rough tests occupancy bits)
 	bool spec_enqueued = false; SyncDev spec_Y{}; uint32_t spec_g = 0;
 	bool seg_extra_pass = false;             // the last segment needed more than its first pass: records were rewritten after the pass
 	// fqsk_submit / fqsk_collect: double-buffered records, copies on their own stream
@@ -248,6 +249,12 @@ int table_alloc(fqsk_handle *h, Table &t, uint32_t k, uint32_t cbits, uint32_t B
 	size_t mb = (size_t) 32 << B, sb = (size_t) 8 << d.stash_log2;
 	CK(cudaMalloc(&d.main, mb));
 	CK(cudaMalloc(&d.stash, sb));
+	{
+		const size_t ob = std::max<size_t>(((size_t) 1 << B) / 8, 4);
+		CK(cudaMalloc(&d.occ, ob));
+		CK(cudaMemsetAsync(d.occ, 0, ob, h->st));
+		d.occ_read = nullptr;
+	}
 	CK(cudaMemsetAsync(d.main, 0, mb, h->st));
 	CK(cudaMemsetAsync(d.stash, 0, sb, h->st));
 	CK(cudaMemsetAsync(counters, 0, 16, h->st));
@@ -407,7 +414,7 @@ int table_grow_if_needed(fqsk_handle *h, Table &t) {
 		uint64_t n = 0;
 		CKR(table_dump_device(h, t, &n));
 		unsigned long long *counters = t.d.n_items;
-		CK(cudaFree(t.d.main)); CK(cudaFree(t.d.stash));
+		CK(cudaFree(t.d.main)); CK(cudaFree(t.d.stash)); CK(cudaFree(t.d.occ));
 		uint32_t k = t.d.k, cb = t.d.cbits, B = t.d.B + 1;
 		CKR(table_alloc(h, t, k, cb, B, counters));
 		if (n) { CK(pdl(k_reinsert, nblk(n, 256), 256, h->st, t.d, h->dump_k.as<unsigned long long>(), h->dump_v.as<unsigned long long>(), n)); LAUNCHED(h); }
@@ -791,7 +798,10 @@ int seg_pass(fqsk_handle *h) {
 			                               h->rt_b[0].as<uint32_t>(), h->rt_s[0].as<uint32_t>()));
 			LAUNCHED(h);
 		}
-		{ Phase ph(h, FQSK_PH_ROUGH); CK(pdl(k_rough, std::max<uint32_t>(148, std::min<uint32_t>(nblk(rec_bound, 16), 148 * 32)), 128, h->st, E, P)); LAUNCHED(h); }
+		{ Phase ph(h, FQSK_PH_ROUGH); EngineDev Er = E;      // sparse tables (the first blocks of a file): k_rough tests the bucket-occupancy bit before reading a neighbour's bucket
+			if (h->world == 1 && h->items_main[0] < (1ull << h->tb.d.B)) Er.hb.occ_read = Er.hb.occ;
+			if (h->world == 1 && h->items_main[1] < (1ull << h->ts.d.B)) Er.hs.occ_read = Er.hs.occ;
+			CK(pdl(k_rough, std::max<uint32_t>(148, std::min<uint32_t>(nblk(rec_bound, 16), 148 * 32)), 128, h->st, Er, P)); LAUNCHED(h); }
 		{ Phase ph(h, FQSK_PH_FOLD); CK(pdl(k_fold, nblk((uint64_t) n * 32, 128), 128, h->st, E, S, P, 0)); LAUNCHED(h); }
 	}
 	{
@@ -1460,6 +1470,7 @@ static int sync_end(fqsk_handle *h) {
 		h->S.siv_no_filled += counters[4];
 		h->S.siv_no_updates += h->pend_p + h->hidden_p;
 		h->hidden_p = 0;
+		h->items_main[0] = counters[0]; h->items_main[1] = counters[2];
 		for (int k = 0; k < 2; ++k) {
 			Table &t = k ? h->tb : h->ts;
 			if (counters[2 - 2 * k] > (4ull << t.d.B) || counters[3 - 2 * k] > (1ull << t.d.stash_log2) / 2) CKR(table_grow_if_needed(h, t));

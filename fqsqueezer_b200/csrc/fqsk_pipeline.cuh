@@ -814,7 +814,7 @@ __global__ void __launch_bounds__(256) k_delta_build_flat(SegDev S, PipeDev P, u
 // k_rough: one warp per request.  find_counts_rough_{s,b} (dna.cpp:257-330): 4(k-1) single-substitution neighbours across the
 // lanes, non-empty ones appended in trial order to a merge script; find_counts_rough_p (dna.cpp:229-254) is a plain sum.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 8) k_rough(EngineDev E, PipeDev P) { pdl_enter();
+__global__ void __launch_bounds__(128, 8) k_rough(EngineDev E, PipeDev P) { pdl_enter();   // E.hb / E.hs carry occ_read while the tables are sparse (HtDev::occ)
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t n_rec = *P.n_rec_dev;
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
@@ -824,13 +824,16 @@ __global__ void __launch_bounds__(128, 8) k_rough(EngineDev E, PipeDev P) { pdl_
 	for (uint32_t g0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * RCHUNK; g0 < n_rec; g0 += warps * RCHUNK) {
 		// each warp owns RCHUNK consecutive positions: find the flagged ones, then work on them one at a time with all lanes
 		uint32_t mine = (lane < RCHUNK && g0 + lane < n_rec) ? P.rkind[g0 + lane] : 0;
+		KReg myreg{0, 0};
+		if (mine) myreg = P.rreg[g0 + lane];       // all registers of the chunk in one round trip, handed out by shuffles below
 		unsigned todo = __ballot_sync(0xffffffffu, mine != 0);
 		while (todo) {
 			uint32_t q = __ffs(todo) - 1;
 			todo &= todo - 1;
 			const uint32_t g = g0 + q;
 			const uint32_t kind = __shfl_sync(0xffffffffu, mine, q);
-			const KReg reg = P.rreg[g];
+			KReg reg;
+			reg.dir = __shfl_sync(0xffffffffu, myreg.dir, q); reg.rc = __shfl_sync(0xffffffffu, myreg.rc, q);
 			if (kind == 4) {
 				uint32_t c[4] = {0, 0, 0, 0};
 				uint32_t trials = 4 * (E.p - 1);
