@@ -115,7 +115,7 @@ struct fqsk_handle {
 	uint32_t world = 1, rank = 0;            // reference worker `rank` of `world` (one per GPU)
 	unsigned long long *inbox = nullptr; uint64_t inbox_cap = 0;      // this rank's inbox: header + [3 tables][world sources][inbox_cap]
 	unsigned long long *peer_inbox[8] = {nullptr};
-	void *peer_ptrs[8][6] = {{nullptr}};     // IPC mappings to close
+	void *peer_ptrs[8][8] = {{nullptr}};     // IPC mappings to close
 	uint32_t attached = 0;                   // bit i: rank i's shard is mapped
 	DevBuf route_keys, route_keys2, route_sorted, route_hist;
 	uint64_t sync_fresh = 0, sync_updates = 0; bool routed = false, applied = false;
@@ -139,6 +139,7 @@ struct fqsk_handle {
 	// paired-end (fqsk_pe.cuh): the global pair table, the segment's sorted triples, the per-pair decisions and the work items
 	PairDev pair{}; uint64_t pair_items = 0;
 	uint32_t *d_pe = nullptr;                // [0] pool_used [1] overflow [2..5] scan totals [6,7] items in the pair table (u64)
+	DevBuf pe_uk, pe_uv, pe_uc;              // sharded sync: distinct (key, value, weight) rows of the segment before routing
 	DevBuf pe_tk, pe_tv, pe_q, pe_sk, pe_sv, pe_sidx, pe_t1, pe_t2, pe_pool, pe_info, it_src, it_len, it_bytes, it_first, it_bias, it_dupprev,
 	       it_flags, it_off32, it_off64, it_dna;
 	uint32_t pe_pool_cap = 1u << 20, pe_pairs = 0, pe_nt = 0, seg_reads_in = 0;
@@ -888,11 +889,15 @@ int pair_alloc(fqsk_handle *h, PairDev &t, uint64_t slots) {
 	t.b = h->P.bmer_len; t.vm = (1ull << (2 * t.b)) - 1; t.top = ~0ull >> (2 * t.b); t.mask = slots - 1;
 	CK(cudaMalloc(&t.keys, slots * 8)); CK(cudaMalloc(&t.vcs, slots * 8));
 	CK(cudaMemsetAsync(t.keys, 0xFF, slots * 8, h->st)); CK(cudaMemsetAsync(t.vcs, 0xFF, slots * 8, h->st));
+	t.world = h->world;
+	for (uint32_t i = 0; i < 8; ++i) { t.peer_keys[i] = nullptr; t.peer_vcs[i] = nullptr; }
+	t.peer_keys[h->rank] = t.keys; t.peer_vcs[h->rank] = t.vcs;
 	return FQSK_OK;
 }
 int pair_reserve(fqsk_handle *h, uint64_t incoming) {     // keep the table at most half full (contents, not layout, are the contract)
 	uint64_t slots = h->pair.mask + 1;
 	if ((h->pair_items + incoming) * 2 <= slots) return FQSK_OK;
+	if (h->world > 1) return fail(h, FQSK_E_CAPACITY, "the pair-table shard would be more than half full and shards cannot grow: create the engines with a larger pair_log2_slots");
 	while ((h->pair_items + incoming) * 2 > slots) slots <<= 1;
 	PairDev nt;
 	CKR(pair_alloc(h, nt, slots));
@@ -1098,7 +1103,7 @@ int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
 	const uint32_t world = p->world_size ? p->world_size : 1;
 	if (world > FQSK_MAX_WORLD || p->rank >= world) return fail(h, FQSK_E_INVAL, "need rank < world_size <= %u", FQSK_MAX_WORLD);
 	if (p->n_workers != world) return fail(h, FQSK_E_INVAL, "n_workers must equal world_size: one reference worker thread (-t) per GPU");
-	if (world > 1 && p->mode != FQSK_MODE_SE_ORIGINAL) return fail(h, FQSK_E_UNSUPPORTED, "sharded operation is implemented for original-order SE only");
+	if (world > 1 && p->mode != FQSK_MODE_SE_ORIGINAL && p->mode != FQSK_MODE_PE_ORIGINAL) return fail(h, FQSK_E_UNSUPPORTED, "sharded operation is implemented for original order only (SE and PE)");
 	if (!(p->pmer_len >= 5 && p->pmer_len < p->smer_len && p->smer_len < p->bmer_len && p->bmer_len <= 31)) return fail(h, FQSK_E_INVAL, "need 5 <= p < s < b <= 31");
 	if (p->pmer_len > 18) return fail(h, FQSK_E_INVAL, "pmer_len > 18 not supported");
 	if (p->mode == FQSK_MODE_PE_SORTED || p->mode > FQSK_MODE_PE_SORTED) return fail(h, FQSK_E_UNSUPPORTED, "paired-end sorted order (-p -om s) is not implemented");
@@ -1146,7 +1151,7 @@ int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
 			// inbox: [64-word header: posted slot lengths][3 tables][world sources][cap k-mers]; a source never sends more than its own rows
 			const uint64_t rb = p->reserve_bytes ? p->reserve_bytes : (1u << 23), rr = p->reserve_reads ? p->reserve_reads : (1u << 16);
 			h->inbox_cap = 2 * rb + 2 * rr + 1024;
-			size_t ib = (INBOX_HDR + 3ull * world * h->inbox_cap) * 8;
+			size_t ib = (INBOX_HDR + 6ull * world * h->inbox_cap) * 8;      // tables 0-2: p / s / b rows; 3-5: key / value / weight planes of the pair rows
 			CK(cudaMalloc(&h->inbox, ib));
 			CK(cudaMemsetAsync(h->inbox, 0, INBOX_HDR * 8, h->st));
 			h->peer_inbox[p->rank] = h->inbox;
@@ -1157,7 +1162,7 @@ int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
 		CK(h->prev_read.ensure(1 << 16));
 		if (p->mode == FQSK_MODE_PE_ORIGINAL) {          // CHT_pair_kmers(bmer_len, ...), application.cpp:91
 			CK(cudaMalloc(&h->d_pe, 64)); CK(cudaMemsetAsync(h->d_pe, 0, 64, h->st));
-			CKR(pair_alloc(h, h->pair, 1ull << 16));
+			CKR(pair_alloc(h, h->pair, 1ull << (p->pair_log2_slots ? std::min<uint32_t>(std::max<uint32_t>(p->pair_log2_slots, 10), 34) : (world > 1 ? 22u : 16u))));
 		}
 		CK(cudaStreamSynchronize(h->st));
 		return FQSK_OK;
@@ -1173,7 +1178,7 @@ void fqsk_destroy(fqsk_handle *h) {
 	if (h->st) cudaStreamSynchronize(h->st);
 	for (Table *t : {&h->tb, &h->ts}) { if (t->d.main) cudaFree(t->d.main); if (t->d.stash) cudaFree(t->d.stash); }
 	if (h->siv.w) cudaFree(h->siv.w);
-	for (uint32_t i = 0; i < FQSK_MAX_WORLD; ++i) for (int q = 0; q < 6; ++q) if (h->peer_ptrs[i][q]) cudaIpcCloseMemHandle(h->peer_ptrs[i][q]);
+	for (uint32_t i = 0; i < FQSK_MAX_WORLD; ++i) for (int q = 0; q < 8; ++q) if (h->peer_ptrs[i][q]) cudaIpcCloseMemHandle(h->peer_ptrs[i][q]);
 	if (h->inbox) cudaFree(h->inbox);
 	if (h->pair.keys) cudaFree(h->pair.keys);
 	if (h->pair.vcs) cudaFree(h->pair.vcs);
@@ -1193,7 +1198,7 @@ void fqsk_destroy(fqsk_handle *h) {
 	                  &h->idx_k, &h->idx_t, &h->idx_rt, &h->miss_fold, &h->hr_b[0], &h->hr_b[1], &h->hr_b[2], &h->hr_s[0], &h->hr_s[1], &h->hr_s[2],
 	                  &h->evk[0], &h->evk[1], &h->evv[0], &h->evv[1], &h->evk_s[0], &h->evk_s[1], &h->evv_s[0], &h->evv_s[1], &h->scan_part, &h->scan_vals, &h->recs_alt, &h->dfilter, &h->pk,
 	                  &h->route_keys, &h->route_keys2, &h->route_sorted, &h->route_hist,
-	                  &h->pe_tk, &h->pe_tv, &h->pe_q, &h->pe_sk, &h->pe_sv, &h->pe_sidx, &h->pe_t1, &h->pe_t2, &h->pe_pool, &h->pe_info, &h->it_src, &h->it_len,
+	                  &h->pe_uk, &h->pe_uv, &h->pe_uc, &h->pe_tk, &h->pe_tv, &h->pe_q, &h->pe_sk, &h->pe_sv, &h->pe_sidx, &h->pe_t1, &h->pe_t2, &h->pe_pool, &h->pe_info, &h->it_src, &h->it_len,
 	                  &h->it_bytes, &h->it_first, &h->it_bias, &h->it_dupprev, &h->it_flags, &h->it_off32, &h->it_off64, &h->it_dna};
 
 	for (DevBuf *b : bufs) b->release();
@@ -1611,10 +1616,13 @@ int fqsk_shard_export(fqsk_handle *h, fqsk_shard_desc *out) {
 	out->rank = h->rank; out->world_size = h->world;
 	out->geometry[0] = h->tb.d.B; out->geometry[1] = h->tb.d.stash_log2; out->geometry[2] = h->ts.d.B; out->geometry[3] = h->ts.d.stash_log2;
 	out->geometry[4] = h->siv.key_bits;
+	uint32_t pl2 = 0;
+	if (h->pair.keys) while ((1ull << pl2) < h->pair.mask + 1) ++pl2;
+	out->geometry[5] = pl2;
 	out->inbox_cap = h->inbox_cap;
-	void *ptrs[6] = {h->tb.d.main, h->tb.d.stash, h->ts.d.main, h->ts.d.stash, h->siv.w, h->inbox};
+	void *ptrs[8] = {h->tb.d.main, h->tb.d.stash, h->ts.d.main, h->ts.d.stash, h->siv.w, h->inbox, h->pair.keys, h->pair.vcs};
 	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-	for (int q = 0; q < 6; ++q) CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t *) out->ipc[q], ptrs[q]));
+	for (int q = 0; q < (h->pair.keys ? 8 : 6); ++q) CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t *) out->ipc[q], ptrs[q]));
 	CK(cudaStreamSynchronize(h->st));      // the shards are zero-filled before anybody maps them
 	return FQSK_OK;
 }
@@ -1625,10 +1633,10 @@ int fqsk_shard_attach(fqsk_handle *h, const fqsk_shard_desc *peer) {
 	if (h->world <= 1 || peer->world_size != h->world || peer->rank >= h->world) return fail(h, FQSK_E_INVAL, "descriptor of rank %u / %u does not belong to this group", peer->rank, peer->world_size);
 	if (peer->rank == h->rank) return FQSK_OK;
 	if (peer->geometry[0] != h->tb.d.B || peer->geometry[1] != h->tb.d.stash_log2 || peer->geometry[2] != h->ts.d.B || peer->geometry[3] != h->ts.d.stash_log2 ||
-	    peer->geometry[4] != h->siv.key_bits || peer->inbox_cap != h->inbox_cap)
+	    peer->geometry[4] != h->siv.key_bits || peer->inbox_cap != h->inbox_cap || (h->pair.keys && (1ull << peer->geometry[5]) != h->pair.mask + 1))
 		return fail(h, FQSK_E_INVAL, "rank %u was created with a different table geometry", peer->rank);
 	const uint32_t r = peer->rank;
-	for (int q = 0; q < 6; ++q) {
+	for (int q = 0; q < (h->pair.keys ? 8 : 6); ++q) {
 		if (h->peer_ptrs[r][q]) continue;
 		cudaIpcMemHandle_t hd; memcpy(&hd, peer->ipc[q], 64);
 		CK(cudaIpcOpenMemHandle(&h->peer_ptrs[r][q], hd, cudaIpcMemLazyEnablePeerAccess));
@@ -1637,6 +1645,7 @@ int fqsk_shard_attach(fqsk_handle *h, const fqsk_shard_desc *peer) {
 	h->ts.d.peer_main[r] = (const uint32_t *) h->peer_ptrs[r][2]; h->ts.d.peer_stash[r] = (const unsigned long long *) h->peer_ptrs[r][3];
 	h->siv.peer_w[r] = (const uint32_t *) h->peer_ptrs[r][4];
 	h->peer_inbox[r] = (unsigned long long *) h->peer_ptrs[r][5];
+	if (h->pair.keys) { h->pair.peer_keys[r] = (const unsigned long long *) h->peer_ptrs[r][6]; h->pair.peer_vcs[r] = (const unsigned long long *) h->peer_ptrs[r][7]; }
 	h->attached |= 1u << r;
 	return FQSK_OK;
 }
@@ -1653,8 +1662,8 @@ int fqsk_sync_route(fqsk_handle *h) {
 	const bool have = h->pending && h->seg_reads;
 	const unsigned long long *rows[3] = {h->row_p.as<unsigned long long>(), h->row_s[0].as<unsigned long long>(), h->row_b[0].as<unsigned long long>()};
 	const uint32_t ns[3] = {have ? h->pend_p : 0, have ? h->pend_s : 0, have ? h->pend_b : 0};
-	CK(h->route_hist.ensure(3 * 8 * 4));
-	CK(cudaMemsetAsync(h->route_hist.p, 0, 3 * 8 * 4, h->st));
+	CK(h->route_hist.ensure(4 * 8 * 4));
+	CK(cudaMemsetAsync(h->route_hist.p, 0, 4 * 8 * 4, h->st));
 	CK(cudaMemsetAsync(h->d_flags, 0, 8 * sizeof(int), h->st));
 	for (int t = 0; t < 3; ++t) {
 		const uint32_t n = ns[t];
@@ -1669,6 +1678,37 @@ int fqsk_sync_route(fqsk_handle *h) {
 		}
 		CK(pdl(k_route_scatter, nblk(std::max<uint32_t>(n, 8), 256), 256, h->st, h->route_sorted.as<unsigned long long>(), n, hist, I, (uint32_t) t, h->d_flags)); LAUNCHED(h);
 	}
+	if (h->pair.keys) {
+		// paired end: the distinct (key, value) pairs of the segment with summed weights, routed by (fmix64(key) >> 48) % world as three
+		// planes (key / value / weight = inbox tables 3 / 4 / 5) sorted with the same owner keys (stable: the planes stay aligned)
+		uint32_t nu = 0;
+		uint32_t *hist = h->route_hist.as<uint32_t>() + 8 * 3;
+		const uint32_t nt = have ? h->pe_nt : 0;
+		if (nt) {
+			CK(h->pe_uk.ensure((size_t) nt * 8)); CK(h->pe_uv.ensure((size_t) nt * 8)); CK(h->pe_uc.ensure((size_t) nt * 8));
+			CK(cudaMemsetAsync(h->d_pe, 0, 4, h->st));
+			CK(pdl(k_pair_heads, nblk(nt, 256), 256, h->st, pe_seg(h), h->pair.vm, h->pe_uk.as<unsigned long long>(), h->pe_uv.as<unsigned long long>(), h->pe_uc.as<unsigned long long>(), h->d_pe)); LAUNCHED(h);
+			uint32_t *hs = (uint32_t *) ((uint8_t *) h->h_small + 960);
+			CK(cudaMemcpyAsync(hs, h->d_pe, 4, cudaMemcpyDeviceToHost, h->st));
+			CK(cudaStreamSynchronize(h->st));
+			nu = hs[0];
+		}
+		if (nu) {
+			CK(h->route_keys.ensure(nu)); CK(h->route_keys2.ensure(nu)); CK(h->route_sorted.ensure((size_t) nu * 8));
+			CK(pdl(k_pair_owner_keys, nblk(nu, 256), 256, h->st, (const unsigned long long *) h->pe_uk.as<unsigned long long>(), nu, h->world, h->route_keys.as<uint8_t>(), hist)); LAUNCHED(h);
+		}
+		const unsigned long long *planes[3] = {h->pe_uk.as<unsigned long long>(), h->pe_uv.as<unsigned long long>(), h->pe_uc.as<unsigned long long>()};
+		for (int q = 0; q < 3; ++q) {
+			if (nu) {
+				size_t bytes = 0;
+				CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, h->route_keys.as<uint8_t>(), h->route_keys2.as<uint8_t>(), planes[q], h->route_sorted.as<unsigned long long>(), (int) nu, 0, 3, h->st));
+				CK(h->cub_tmp.ensure(bytes));
+				CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, h->route_keys.as<uint8_t>(), h->route_keys2.as<uint8_t>(), planes[q], h->route_sorted.as<unsigned long long>(), (int) nu, 0, 3, h->st));
+			}
+			CK(pdl(k_route_scatter, nblk(std::max<uint32_t>(nu, 8), 256), 256, h->st, (const unsigned long long *) h->route_sorted.as<unsigned long long>(), nu, (const uint32_t *) hist, I, (uint32_t) (3 + q), h->d_flags)); LAUNCHED(h);
+		}
+		h->pe_nt = 0;
+	}
 	int fl[8];
 	CKR(read_flags(h, fl, 8));      // also drains the stream: the peer stores are complete when the caller enters its barrier
 	if (fl[4]) return fail(h, FQSK_E_CAPACITY, "an exchange row is longer than the inbox slot (%llu k-mers): create the engines with a larger reserve_bytes", (unsigned long long) h->inbox_cap);
@@ -1681,7 +1721,7 @@ int fqsk_sync_apply(fqsk_handle *h, uint64_t *fresh, uint64_t *updates) {
 	CK(cudaSetDevice(h->P.device));
 	if (h->world <= 1 || !h->routed) return fail(h, FQSK_E_INVAL, "fqsk_sync_apply needs fqsk_sync_route on a sharded engine first");
 	// posted slot lengths (every source wrote its own entry before the barrier)
-	unsigned long long cnt[24];
+	unsigned long long cnt[48];
 	CK(cudaMemcpyAsync(cnt, h->inbox, sizeof cnt, cudaMemcpyDeviceToHost, h->st));
 	CK(cudaStreamSynchronize(h->st));
 	uint64_t tot[3] = {0, 0, 0};
@@ -1710,6 +1750,22 @@ int fqsk_sync_apply(fqsk_handle *h, uint64_t *fresh, uint64_t *updates) {
 	}
 	if (tot[1]) { bool fast = true; CKR(apply_inserts(h, h->ts, h->rng[ST_S], dst[1], (uint32_t) tot[1], &fast)); }
 	if (tot[2]) CKR(apply_row(h, h->tb, h->rng[ST_B], dst[2], (uint32_t) tot[2]));
+	if (h->pair.keys) {   // pair rows [*][rank], one source after the other (each holds distinct pairs; the insertion is commutative)
+		uint64_t incoming = 0;
+		for (uint32_t i = 0; i < h->world; ++i) incoming += cnt[3 * 8 + i];
+		CKR(pair_reserve(h, incoming));
+		unsigned long long *d_items = (unsigned long long *) (h->d_pe + 6);
+		for (uint32_t i = 0; i < h->world; ++i) {
+			const uint32_t c = (uint32_t) cnt[3 * 8 + i];
+			if (!c) continue;
+			CK(pdl(k_pair_insert_list, nblk(c, 256), 256, h->st, h->pair, (const unsigned long long *) inbox_slot(h->inbox, h->inbox_cap, h->world, 3, i),
+			       (const unsigned long long *) inbox_slot(h->inbox, h->inbox_cap, h->world, 4, i), (const unsigned long long *) inbox_slot(h->inbox, h->inbox_cap, h->world, 5, i), c, d_items)); LAUNCHED(h);
+		}
+		unsigned long long *hsp = (unsigned long long *) ((uint8_t *) h->h_small + 968);
+		CK(cudaMemcpyAsync(hsp, d_items, 8, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaStreamSynchronize(h->st));
+		h->pair_items = *hsp;
+	}
 	unsigned long long hc[6];
 	CK(cudaMemcpyAsync(hc, h->d_counters, 48, cudaMemcpyDeviceToHost, h->st));
 	CK(cudaStreamSynchronize(h->st));

@@ -20,7 +20,13 @@ struct PairDev {                     // CHT_pair_kmers by contents: open address
 	unsigned long long mask;         // slots - 1
 	unsigned long long vm, top;      // value_mask = 4^b - 1 (ht_kmer.cpp:25), counter ceiling = ~0 >> 2b
 	uint32_t b;
+	// sharded operation: the pair table is split by the reference's own owner key (fmix64(key) >> 48) % world (ht_kmer.h:599-602,
+	// dna.cpp:1076-1081); keys / vcs are THIS rank's shard, peer_* every rank's (NVLink peer mappings, [rank] = own) for lookups.
+	// All shards have the same size.
+	const unsigned long long *peer_keys[8], *peer_vcs[8];
+	uint32_t world;
 };
+FQSK_HD uint32_t pair_owner(uint64_t key, uint32_t world) { return world > 1 ? (uint32_t) ((fmix64(key) >> 48) % world) : 0u; }
 static const unsigned long long PAIR_EMPTY = ~0ull;
 
 
@@ -123,10 +129,12 @@ FQSK_DEV uint32_t pe_collect(const PairDev &G, const PeSeg &L, uint32_t src, uns
 	uint32_t n = 0;
 	if (key >= G.vm) return 0;                    // "no minimizer" is never stored (ht_kmer.cpp:123-124)
 	if (src == 0) {
+		const uint32_t o = pair_owner(key, G.world);
+		const unsigned long long *K = G.peer_keys[o], *V = G.peer_vcs[o];
 		for (unsigned long long s = fmix64(key) & G.mask;; s = (s + 1) & G.mask) {
-			const unsigned long long k = G.keys[s];
+			const unsigned long long k = K[s];
 			if (k == PAIR_EMPTY) break;
-			if (k == key) { if (out) out[n] = G.vcs[s]; ++n; }
+			if (k == key) { if (out) out[n] = V[s]; ++n; }
 		}
 		return n;
 	}
@@ -272,14 +280,7 @@ __global__ void __launch_bounds__(128) k_pe_fill(const uint8_t *dna, PeItems I, 
 // pair is inserted once: no two threads ever work on the same item.  A slot claimed by another new pair shows an unwritten
 // value part (value_mask) until its owner stores it, which no real value equals -- so it is skipped, as it must be.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void k_pair_insert(PairDev G, PeSeg L, unsigned long long *n_items) { pdl_enter();
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= L.n) return;
-	const unsigned long long key = L.skey[i], val = L.sval[i];
-	if (key > G.vm) return;
-	if (i > 0 && L.skey[i - 1] == key && L.sval[i - 1] == val) return;
-	unsigned long long cnt = 0;
-	for (uint32_t j = i; j < L.n && L.skey[j] == key && L.sval[j] == val; ++j) cnt += PE_TRI_C[L.sidx[j] % 14];
+FQSK_DEV void pair_insert_one(const PairDev &G, unsigned long long key, unsigned long long val, unsigned long long cnt, unsigned long long *n_items) {
 	const uint32_t sh = 2 * G.b;
 	for (unsigned long long s = fmix64(key) & G.mask;; s = (s + 1) & G.mask) {
 		unsigned long long k = G.keys[s];
@@ -298,6 +299,43 @@ __global__ void k_pair_insert(PairDev G, PeSeg L, unsigned long long *n_items) {
 		G.vcs[s] = vc + (((c + cnt < G.top) ? cnt : G.top - c) << sh);
 		return;
 	}
+}
+__global__ void k_pair_insert(PairDev G, PeSeg L, unsigned long long *n_items) { pdl_enter();
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= L.n) return;
+	const unsigned long long key = L.skey[i], val = L.sval[i];
+	if (key > G.vm) return;
+	if (i > 0 && L.skey[i - 1] == key && L.sval[i - 1] == val) return;
+	unsigned long long cnt = 0;
+	for (uint32_t j = i; j < L.n && L.skey[j] == key && L.sval[j] == val; ++j) cnt += PE_TRI_C[L.sidx[j] % 14];
+	pair_insert_one(G, key, val, cnt, n_items);
+}
+// sharded sync, source side: the distinct (key, value) pairs of the segment with their summed weights, compacted (order is
+// irrelevant: the insertion is commutative) -- the rows [rank][*] of the reference's pe_mers_to_add matrix before routing
+__global__ void k_pair_heads(PeSeg L, unsigned long long vm, unsigned long long *okey, unsigned long long *oval, unsigned long long *ocnt, uint32_t *n_out) { pdl_enter();
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= L.n) return;
+	const unsigned long long key = L.skey[i], val = L.sval[i];
+	if (key > vm) return;
+	if (i > 0 && L.skey[i - 1] == key && L.sval[i - 1] == val) return;
+	unsigned long long cnt = 0;
+	for (uint32_t j = i; j < L.n && L.skey[j] == key && L.sval[j] == val; ++j) cnt += PE_TRI_C[L.sidx[j] % 14];
+	const uint32_t o = atomicAdd(n_out, 1u);
+	okey[o] = key; oval[o] = val; ocnt[o] = cnt;
+}
+__global__ void k_pair_owner_keys(const unsigned long long *keys, uint32_t n, uint32_t world, uint8_t *okeys, uint32_t *hist) { pdl_enter();
+	__shared__ uint32_t sh[8];
+	if (threadIdx.x < 8) sh[threadIdx.x] = 0;
+	__syncthreads();
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) { const uint32_t o = pair_owner(keys[i], world); okeys[i] = (uint8_t) o; atomicAdd(sh + o, 1u); }
+	__syncthreads();
+	if (threadIdx.x < 8 && sh[threadIdx.x]) atomicAdd(hist + threadIdx.x, sh[threadIdx.x]);
+}
+// sharded sync, owner side: one source's row (distinct pairs) into this rank's shard
+__global__ void k_pair_insert_list(PairDev G, const unsigned long long *keys, const unsigned long long *vals, const unsigned long long *cnts, uint32_t n, unsigned long long *n_items) { pdl_enter();
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) pair_insert_one(G, keys[i], vals[i], cnts[i], n_items);
 }
 
 __global__ void k_pair_rehash(PairDev old_t, PairDev new_t) { pdl_enter();

@@ -33,7 +33,7 @@ class _Params(C.Structure):
                 ("prefix_len", C.c_uint32), ("smer_counter_bits", C.c_uint32), ("bmer_counter_bits", C.c_uint32), ("mode", C.c_uint32),
                 ("n_workers", C.c_uint32), ("device", C.c_int32), ("bmer_log2_buckets", C.c_uint32), ("smer_log2_buckets", C.c_uint32),
                 ("expected_kmers", C.c_uint64), ("world_size", C.c_uint32), ("rank", C.c_uint32), ("max_iterations", C.c_uint32),
-                ("flags", C.c_uint32), ("reserve_reads", C.c_uint32), ("reserve_bytes", C.c_uint32)]
+                ("flags", C.c_uint32), ("reserve_reads", C.c_uint32), ("reserve_bytes", C.c_uint32), ("pair_log2_slots", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class _Stats(C.Structure):

@@ -88,10 +88,10 @@ def segments(first: int, last: int, n_sync: int, paired: bool = False) -> Iterat
     yield (a, last)       # end-of-block sync (possibly over an empty range)
 
 
-def worker_segments(first: int, last: int, generation: int, n_workers: int, worker: int) -> List[Tuple[int, int]]:
+def worker_segments(first: int, last: int, generation: int, n_workers: int, worker: int, paired: bool = False) -> List[Tuple[int, int]]:
     """Sync segments of worker `worker` for the block [first, last) with generation number `generation` at -t n_workers:
     PartitionForWorkers (reads_block.h:197-214) + the per-worker next_synchro arithmetic (application.cpp:617-662).
     Every worker gets the same number of segments (they all meet at every sync)."""
     ns = calc_no_synchronizations(generation, last - first, n_workers)
     a, b = partition_for_workers(last - first, n_workers)[worker]
-    return list(segments(first + a, first + b, ns))
+    return list(segments(first + a, first + b, ns, paired=paired))

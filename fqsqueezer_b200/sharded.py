@@ -20,7 +20,7 @@ from . import engine as E
 
 
 class _ShardDesc(C.Structure):
-    _fields_ = [("rank", C.c_uint32), ("world_size", C.c_uint32), ("geometry", C.c_uint32 * 6), ("inbox_cap", C.c_uint64), ("ipc", (C.c_uint8 * 64) * 6)]
+    _fields_ = [("rank", C.c_uint32), ("world_size", C.c_uint32), ("geometry", C.c_uint32 * 6), ("inbox_cap", C.c_uint64), ("ipc", (C.c_uint8 * 64) * 8)]
 
 
 def owner_of_kmer(x: np.ndarray, world: int) -> np.ndarray:
@@ -54,20 +54,22 @@ def allreduce_stats(dist, fresh: int, updates: int):
 class ShardedKmerEngine(E.KmerEngine):
     """KmerEngine of one rank of a sharded group.  `dist` is torch.distributed (initialised by the caller, NCCL on GPU boxes)."""
 
-    def __init__(self, p, s, b, prefix_len, rank, world, device=0, dist=None, expected_kmers=0, reserve_reads=0, reserve_bytes=0, **kw):
+    def __init__(self, p, s, b, prefix_len, rank, world, device=0, dist=None, expected_kmers=0, reserve_reads=0, reserve_bytes=0, mode=E.MODE_SE_ORIGINAL, **kw):
         self.rank, self.world, self.dist = rank, world, dist
         self.lib = E.load_library()
         self._bind()
         prm = E._Params(abi_version=1, pmer_len=p, smer_len=s, bmer_len=b, prefix_len=prefix_len, smer_counter_bits=12, bmer_counter_bits=6,
-                        mode=E.MODE_SE_ORIGINAL, n_workers=world, device=device, bmer_log2_buckets=kw.get("bmer_log2_buckets", 0),
+                        mode=mode, n_workers=world, device=device, bmer_log2_buckets=kw.get("bmer_log2_buckets", 0),
                         smer_log2_buckets=kw.get("smer_log2_buckets", 0), expected_kmers=expected_kmers, world_size=world, rank=rank,
-                        max_iterations=0, flags=E.F_PROFILE if kw.get("profile") else 0, reserve_reads=reserve_reads, reserve_bytes=reserve_bytes)
+                        max_iterations=0, flags=E.F_PROFILE if kw.get("profile") else 0, reserve_reads=reserve_reads, reserve_bytes=reserve_bytes,
+                        pair_log2_slots=kw.get("pair_log2_slots", 0))
         h = C.c_void_p()
         rc = self.lib.fqsk_create(C.byref(prm), C.byref(h))
         if rc != 0:
             raise E.FqskError(rc, self.lib.fqsk_last_error(None).decode())
         self.h = h
-        self.p, self.s, self.b, self.prefix_len, self.mode = p, s, b, prefix_len, E.MODE_SE_ORIGINAL
+        self.p, self.s, self.b, self.prefix_len, self.mode = p, s, b, prefix_len, mode
+        self.reserve_reads, self.reserve_bytes = reserve_reads, reserve_bytes
         if world > 1:
             self._attach_peers()
 
@@ -110,5 +112,5 @@ class ShardedKmerEngine(E.KmerEngine):
         parts = [None] * self.world
         self.dist.all_gather_object(parts, (k, v))
         kk = np.concatenate([x[0] for x in parts]); vv = np.concatenate([x[1] for x in parts])
-        o = np.argsort(kk, kind="stable")
+        o = np.lexsort((vv, kk))         # by key, then value (the pair table holds several values per key)
         return kk[o], vv[o]

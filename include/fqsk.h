@@ -61,6 +61,8 @@ typedef struct fqsk_params {
 	uint32_t flags;              /* FQSK_F_* */
 	uint32_t reserve_reads;      /* optional: largest segment the caller will submit (reads / DNA bytes); scratch is allocated once */
 	uint32_t reserve_bytes;
+	uint32_t pair_log2_slots;    /* paired-end: initial size of the pair table (0 = default); fixed on a sharded engine (shards cannot grow) */
+	uint32_t reserved;
 } fqsk_params;
 
 #define FQSK_F_PROFILE 1u        /* record CUDA-event timings per internal phase (fqsk_profile) */
@@ -162,12 +164,14 @@ int fqsk_collect(fqsk_handle *h, uint64_t ticket, uint64_t *n_recs);
  * Per sync, instead of fqsk_sync:  fqsk_sync_route  -> BARRIER ->  fqsk_sync_apply  -> ALL-REDUCE(sum) of (fresh, updates) ->
  * fqsk_sync_finish.  The barrier / all-reduce are the caller's (NCCL in fqsqueezer_b200/sharded.py); the payload itself moves
  * inside fqsk_sync_route as peer stores into the owners' inboxes.  Table growth is not supported in this mode: size the
- * tables with expected_kmers / *_log2_buckets. */
+ * tables with expected_kmers / *_log2_buckets / pair_log2_slots.  Paired-end (FQSK_MODE_PE_ORIGINAL): the pair table is
+ * sharded by (fmix64(key) >> 48) % world_size (ht_kmer.h:599-602, dna.cpp:1076-1081) and the distinct (key, value, weight)
+ * triples of a segment travel with the same exchange step. */
 typedef struct fqsk_shard_desc {
 	uint32_t rank, world_size;
-	uint32_t geometry[6];        /* b: log2 buckets, log2 stash; s: same; p-mer key bits; reserved -- must agree on all ranks */
+	uint32_t geometry[6];        /* b: log2 buckets, log2 stash; s: same; p-mer key bits; log2 pair-table slots (0: no pair table) -- must agree on all ranks */
 	uint64_t inbox_cap;
-	uint8_t ipc[6][64];          /* cudaIpcMemHandle_t of: b main, b stash, s main, s stash, p-mer shard, inbox */
+	uint8_t ipc[8][64];          /* cudaIpcMemHandle_t of: b main, b stash, s main, s stash, p-mer shard, inbox, pair keys, pair values (paired-end only) */
 } fqsk_shard_desc;
 int fqsk_shard_export(fqsk_handle *h, fqsk_shard_desc *out);
 int fqsk_shard_attach(fqsk_handle *h, const fqsk_shard_desc *peer);

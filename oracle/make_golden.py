@@ -98,6 +98,7 @@ def make_case_pe(name, G, n_pairs, L, gs, seed, threads=1):
         subprocess.run([O.REF_BIN, "d", "-out", d1, "-out2", d2, plain], check=True, cwd=tmp, stdout=subprocess.DEVNULL)
         assert open(d1, "rb").read() == open(f1, "rb").read() and open(d2, "rb").read() == open(f2, "rb").read(), "reference PE round trip failed"
         recs = np.fromfile(tap, dtype=O.REC_DTYPE)
+        per_thread = [recs] + [np.fromfile(tap + ".t%d" % i, dtype=O.REC_DTYPE) for i in range(1, threads)]   # one tap file per worker thread
         d = np.fromfile(dump, dtype="<u8").reshape(-1, 3)
         r1 = open(f1, "rb").read().split(b"\n")
         r2 = open(f2, "rb").read().split(b"\n")
@@ -114,6 +115,8 @@ def make_case_pe(name, G, n_pairs, L, gs, seed, threads=1):
         dumps[nm + "_vals"] = x[o, 2]
     stat = d[d[:, 0] == 4][0]
     out = os.path.join(GOLD, name + ".npz")
+    if threads > 1:
+        dumps.update({"recs_t%d" % i: r for i, r in enumerate(per_thread)})
     np.savez_compressed(out, fastq=fastq, gs=np.int64(gs), extra=np.array(["-p", "-om", "o"]), recs=recs, threads=np.int64(threads),
                         siv_no_filled=stat[1], siv_no_updates=stat[2], fqs_size=np.int64(fqs_size), **dumps)
     pi = recs[recs["pos"] == 0xFFFFFFFB]
@@ -143,6 +146,9 @@ def main():
     # paired end, original order: pair table, minimizer candidates, mate 2 coded from a shared minimizer (forward + reversed part)
     if not only or "pe_orig_gs1" in only:
         make_case_pe("pe_orig_gs1", G=5000, n_pairs=1200, L=80, gs=1, seed=71)
+    # paired end at -t 2: pair-table owners by (fmix64(key) >> 48) % T (dna.cpp:1076-1081), pair triples in the exchange matrix
+    if not only or "pe_orig_gs1_t2" in only:
+        make_case_pe("pe_orig_gs1_t2", G=5000, n_pairs=1400, L=80, gs=1, seed=72, threads=2)
 
 
 if __name__ == "__main__":

@@ -89,6 +89,30 @@ def run_async(engine, slab, paired=False):
     return recs, dup
 
 
+def run_pe_workers(group, slab, n_workers):
+    """Paired-end at -t T (application.cpp:1020-1331): blocks close on pair boundaries, PartitionForWorkers keeps pairs together,
+    every worker steps through its pairs with `i >= next_synchro`.  Returns per worker (records, pair_info)."""
+    off, ln, roff, rsz = S.parse_fastq(slab)
+    out = [[] for _ in range(n_workers)]
+    for gen, (f, l) in enumerate(S.split_blocks(rsz, paired=True)):
+        segs = [S.worker_segments(f, l, gen, n_workers, w, paired=True) for w in range(n_workers)]
+        assert len({len(x) for x in segs}) == 1, "workers disagree on the number of syncs"
+        for w in group.workers:
+            w.block_start()
+        for q in range(len(segs[0])):
+            for wi, w in enumerate(group.workers):
+                a, b = segs[wi][q]
+                recs, dup = w.segment(slab, off[a:b], ln[a:b], 3)
+                out[wi].append(recs)
+            group.sync()
+    res = []
+    for wi in range(n_workers):
+        r = np.concatenate(out[wi]) if out[wi] else np.zeros(0, O.REC_DTYPE)
+        pi = r[r["pos"] == POS_PAIR]
+        res.append((r[r["pos"] < 0xFFFFFFF0], pi["c"][:, :3].astype(np.uint32)))
+    return res
+
+
 POS_PAIR = 0xFFFFFFFB    # per pair: c0 = a candidate list exists, c1 = minimizer id (0..14, 15 = none usable), c2 = its position in mate 2
 
 

@@ -25,19 +25,26 @@ def main():
     assert int(g["threads"]) == world, (int(g["threads"]), world)
     pref, p, s, b = E.kmer_params(int(g["gs"]))
     slab = g["fastq"]
-    eng = sharded.ShardedKmerEngine(p, s, b, pref, rank, world, device=local, dist=dist, reserve_bytes=1 << 20, reserve_reads=1 << 14)
+    paired = "-p" in [str(x) for x in g["extra"]]
+    eng = sharded.ShardedKmerEngine(p, s, b, pref, rank, world, device=local, dist=dist, reserve_bytes=1 << 20, reserve_reads=1 << 14,
+                                    mode=E.MODE_PE_ORIGINAL if paired else E.MODE_SE_ORIGINAL)
     off, ln, roff, rsz = S.parse_fastq(slab)
-    out = []
-    for gen, (f, l) in enumerate(S.split_blocks(rsz)):
+    out, info = [], []
+    for gen, (f, l) in enumerate(S.split_blocks(rsz, paired=paired)):
         eng.block_start()
-        for a, bb in S.worker_segments(f, l, gen, world, rank):
+        for a, bb in S.worker_segments(f, l, gen, world, rank, paired=paired):
             recs, dup = eng.segment(slab, off[a:bb], ln[a:bb])
             out.append(recs)
+            if paired:
+                info.append(eng.pair_info((bb - a) // 2))
             eng.sync()
     recs = np.concatenate(out)
     want = g["recs_t%d" % rank]
     H.assert_recs_equal(recs, want[want["pos"] < 0xFFFFFFF0])
-    for which, nm in ((0, "siv"), (1, "smer"), (2, "bmer")):
+    if paired:      # what CompressPE codes per pair: (candidate list exists, minimizer id, its position in mate 2)
+        winfo = want[want["pos"] == H.POS_PAIR]["c"][:, :3].astype(np.uint32)
+        assert np.array_equal(np.concatenate(info), winfo)
+    for which, nm in ((0, "siv"), (1, "smer"), (2, "bmer")) + (((3, "pair"),) if paired else ()):
         k, v = eng.dump_all(which)
         assert np.array_equal(k, g[nm + "_keys"]), (nm, len(k), len(g[nm + "_keys"]))
         assert np.array_equal(v, g[nm + "_vals"]), nm

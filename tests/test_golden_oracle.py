@@ -68,3 +68,21 @@ def test_oracle_matches_reference_tap_paired_end():
     assert (winfo[:, 0] == 1).sum() > 500 and ((winfo[:, 0] == 1) & (winfo[:, 1] < 15)).sum() > 500 and (winfo[:, 1] == 15).sum() > 0
     H.assert_dump_equal(e, g, pairs=True)
     e.close()
+
+
+def test_oracle_group_matches_reference_tap_paired_end_two_threads():
+    """-p -t 2: per-worker records and pair decisions, pair triples routed to their owners ((fmix64(key) >> 48) % T), all four
+    shared tables after all syncs vs the tapped reference run with two threads."""
+    import numpy as np
+    g = H.load_golden("pe_orig_gs1_t2")
+    T = int(g["threads"])
+    pref, p, s, b = O.kmer_params(int(g["gs"]))
+    grp = O.OracleGroup(p, s, b, pref, T, mode=2)
+    per_worker = H.run_pe_workers(grp, g["fastq"], T)
+    for w in range(T):
+        want = g["recs_t%d" % w]
+        winfo = want[want["pos"] == H.POS_PAIR]["c"][:, :3].astype(np.uint32)
+        assert np.array_equal(per_worker[w][1], winfo), w
+        H.assert_recs_equal(per_worker[w][0], want[want["pos"] < 0xFFFFFFF0])
+    H.assert_dump_equal(grp, g, pairs=True)
+    grp.close()

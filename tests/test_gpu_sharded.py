@@ -15,7 +15,7 @@ def _n_gpus():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-@pytest.mark.parametrize("name,world", [("se_orig_gs1_t2", 2), ("se_orig_gs16_t3", 3)])
+@pytest.mark.parametrize("name,world", [("se_orig_gs1_t2", 2), ("pe_orig_gs1_t2", 2), ("se_orig_gs16_t3", 3)])
 def test_sharded_engine_matches_reference_threads(name, world):
     if _n_gpus() < world:
         pytest.skip(f"needs {world} GPUs")
