@@ -145,6 +145,7 @@ struct fqsk_handle {
 	uint32_t pe_pool_cap = 1u << 20, pe_pairs = 0, pe_nt = 0, seg_reads_in = 0;
 	// the sync enqueued behind its segment (sync_spec_enqueue / sync_spec_finish)
 	unsigned long long items_main[2] = {0, 0};   // items in the buckets of the b / s table as of the last look (sparse -> k_rough tests occupancy bits)
+	cudaStream_t st_side[2] = {nullptr, nullptr}; cudaEvent_t ev_side[2] = {nullptr, nullptr}, ev_fork = nullptr;   // p-mer / s-mer updates of a small sync
 	bool spec_enqueued = false; SyncDev spec_Y{}; uint32_t spec_g = 0;
 	bool seg_extra_pass = false;             // the last segment needed more than its first pass: records were rewritten after the pass
 	// fqsk_submit / fqsk_collect: double-buffered records, copies on their own stream
@@ -1206,6 +1207,8 @@ void fqsk_destroy(fqsk_handle *h) {
 	if (h->h_stage2) cudaFreeHost(h->h_stage2);
 	for (int i = 0; i < 2; ++i) { if (h->h_meta[i]) cudaFreeHost(h->h_meta[i]); if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]); }
 	if (h->ev_recs) cudaEventDestroy(h->ev_recs);
+	for (int i = 0; i < 2; ++i) { if (h->st_side[i]) { cudaStreamSynchronize(h->st_side[i]); cudaStreamDestroy(h->st_side[i]); } if (h->ev_side[i]) cudaEventDestroy(h->ev_side[i]); }
+	if (h->ev_fork) cudaEventDestroy(h->ev_fork);
 	if (h->st_copy) { cudaStreamSynchronize(h->st_copy); cudaStreamDestroy(h->st_copy); }
 	if (h->h_small) cudaFreeHost(h->h_small);
 	for (auto &e : h->evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -1353,15 +1356,26 @@ static int sync_spec_enqueue(fqsk_handle *h) {
 	SyncIn *in = h->d_syncin;
 	const uint32_t bound_b = (uint32_t) (2 * C.dna_bytes_actual + 2), bound_s = (uint32_t) (C.dna_bytes_actual + 1);
 	const uint64_t bound_p = 2 * C.dna_bytes_actual + 2ull * C.n;
+	// The three table updates are independent (p-mer array, s-mer table, b-mer table; separate status words): the p-mer and
+	// s-mer kernels run on two side streams next to the b-mer chain and join before the look.  With the phase brackets on
+	// (profiling) everything stays on the engine's stream so that the brackets measure what they say.
+	const bool fork = !h->prof;
+	if (fork && !h->st_side[0]) {
+		for (int i = 0; i < 2; ++i) { CK(cudaStreamCreateWithFlags(&h->st_side[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&h->ev_side[i], cudaEventDisableTiming)); }
+		CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+	}
+	cudaStream_t st_p = fork ? h->st_side[0] : h->st, st_s = fork ? h->st_side[1] : h->st;
+	CK(h->q4.ensure(row_reserve(h, bound_s) + 4));
+	if (fork) { CK(cudaEventRecord(h->ev_fork, h->st)); CK(cudaStreamWaitEvent(st_p, h->ev_fork, 0)); CK(cudaStreamWaitEvent(st_s, h->ev_fork, 0)); }
 	{   // d_counters[4], d_sfast and the ordered-insert flags are still clear from k_seg_reset
 		Phase ph(h, FQSK_PH_SYNC_SIV);
-		CK(pdl(k_siv_increment, nblk(bound_p, 256), 256, h->st, h->siv, h->row_p.as<unsigned long long>(), 0, h->d_counters + 4, (const SyncIn *) in)); LAUNCHED(h);
+		CK(pdl(k_siv_increment, nblk(bound_p, 256), 256, st_p, h->siv, h->row_p.as<unsigned long long>(), 0, h->d_counters + 4, (const SyncIn *) in)); LAUNCHED(h);
 	}
 	{
 		Phase ph(h, FQSK_PH_SYNC_APPLY);
-		CK(h->q4.ensure(row_reserve(h, bound_s) + 4));
-		CK(pdl(k_insert_fast, nblk(bound_s, 256), 256, h->st, h->ts.d, h->ts.ci, h->row_s[0].as<unsigned long long>(), 0, h->q4.as<uint8_t>(), h->d_sfast, (const SyncIn *) in)); LAUNCHED(h);
+		CK(pdl(k_insert_fast, nblk(bound_s, 256), 256, st_s, h->ts.d, h->ts.ci, h->row_s[0].as<unsigned long long>(), 0, h->q4.as<uint8_t>(), h->d_sfast, (const SyncIn *) in)); LAUNCHED(h);
 	}
+	if (fork) { CK(cudaEventRecord(h->ev_side[0], st_p)); CK(cudaEventRecord(h->ev_side[1], st_s)); }
 	SyncDev &Y = h->spec_Y;
 	CKR(indexed_setup(h, C.S.delta_b, bound_b, in, true, Y));
 	const uint32_t g = h->spec_g = nblk(bound_b, 256);
@@ -1372,6 +1386,7 @@ static int sync_spec_enqueue(fqsk_handle *h) {
 		CKR(stream_ensure(h, h->rng[ST_B], 0));
 		CKR(indexed_tail(h, h->tb, h->rng[ST_B], Y, row_b, g, bound_b, false));
 	}
+	if (fork) { CK(cudaStreamWaitEvent(h->st, h->ev_side[0], 0)); CK(cudaStreamWaitEvent(h->st, h->ev_side[1], 0)); }
 	h->spec_enqueued = true;
 	return FQSK_OK;
 }
