@@ -328,12 +328,14 @@ inline const uint32_t *stream_ptr(const Stream &s) { return s.buf; }
 inline uint64_t stream_avail(const Stream &s) { return (s.safe > s.consumed ? s.safe : s.consumed) - s.consumed; }
 
 // published chunk totals of the multi-CTA scans (k_scan_reads / k_scan_u32x4 / k_scan_draws), tagged with a per-launch epoch
-int scan_chain(fqsk_handle *h, ScanChain &C) {
+int scan_chain(fqsk_handle *h, ScanChain &C, int which = 0) {      // which = 1: a scan that may run next to another one (side stream)
+	const size_t one = (size_t) SCAN_CHAIN_MAX * 8 * 8 + (size_t) SCAN_CHAIN_MAX * 4 + 64;
 	if (!h->scan_vals.p) {
-		CK(h->scan_vals.ensure((size_t) SCAN_CHAIN_MAX * 8 * 8 + (size_t) SCAN_CHAIN_MAX * 4));
+		CK(h->scan_vals.ensure(2 * one));
 		CK(cudaMemsetAsync(h->scan_vals.p, 0, h->scan_vals.cap, h->st));
+		CK(cudaStreamSynchronize(h->st));
 	}
-	C.vals = h->scan_vals.as<unsigned long long>(); C.flags = (uint32_t *) (C.vals + (size_t) SCAN_CHAIN_MAX * 8); C.epoch = ++h->scan_epoch2;
+	C.vals = (unsigned long long *) (h->scan_vals.as<uint8_t>() + (which ? one : 0)); C.flags = (uint32_t *) (C.vals + (size_t) SCAN_CHAIN_MAX * 8); C.epoch = ++h->scan_epoch2;
 	return FQSK_OK;
 }
 int ensure_iota(fqsk_handle *h, uint32_t n) {
@@ -789,17 +791,28 @@ int seg_pass(fqsk_handle *h) {
 		{ Phase ph(h, FQSK_PH_WALK); CK(pdl(k_walk, nblk((uint64_t) n * 32, 128), 128, h->st, E, S, P, C.it)); LAUNCHED(h); ++h->S.n_replays; }
 	}
 	if (C.redo_tail) {
+		// The compaction of the pushes (rows of the sync) and the rough searches + merges (records) only meet again at the verdict:
+		// the two small compaction kernels run on a side stream next to k_rough / k_fold.  Profiling keeps one stream.
+		const bool fork = !h->prof;
+		if (fork && !h->st_side[0]) {
+			for (int i = 0; i < 2; ++i) { CK(cudaStreamCreateWithFlags(&h->st_side[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&h->ev_side[i], cudaEventDisableTiming)); }
+			CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+		}
+		cudaStream_t st_c = fork ? h->st_side[0] : h->st;
+		if (C.pass > 1) CK(cudaMemsetAsync(h->d_u32 + 1, 0, 4, h->st));      // rough scripts are rebuilt (first pass: still clear from k_seg_reset)
+		if (fork) { CK(cudaEventRecord(h->ev_fork, h->st)); CK(cudaStreamWaitEvent(st_c, h->ev_fork, 0)); }
 		{
 			Phase ph(h, FQSK_PH_COMPACT);
-			ScanChain sc; CKR(scan_chain(h, sc));
-			CK(pdl(k_scan_u32x4, n <= 2048 ? 1u : nblk(n, SCAN_U32_CHUNK), n <= 2048 ? 256 : 1024, h->st, n, h->cnt_b.as<uint32_t>(), h->off_b[0].as<uint32_t>(), h->cnt_s.as<uint32_t>(), h->off_s[0].as<uint32_t>(),
-			                                     h->cnt_p.as<uint32_t>(), h->off_p.as<uint32_t>(), h->hidden.as<uint32_t>(), (uint32_t *) nullptr, d_tot4, h->d_u32 + 1, sc));   // + rough scripts are rebuilt
+			ScanChain sc; CKR(scan_chain(h, sc, 1));
+			CK(pdl(k_scan_u32x4, n <= 2048 ? 1u : nblk(n, SCAN_U32_CHUNK), n <= 2048 ? 256 : 1024, st_c, n, h->cnt_b.as<uint32_t>(), h->off_b[0].as<uint32_t>(), h->cnt_s.as<uint32_t>(), h->off_s[0].as<uint32_t>(),
+			                                     h->cnt_p.as<uint32_t>(), h->off_p.as<uint32_t>(), h->hidden.as<uint32_t>(), (uint32_t *) nullptr, d_tot4, (uint32_t *) nullptr, sc));
 			LAUNCHED(h);
-			CK(pdl(k_compact2, n, 64, h->st, S, P, h->off_b[0].as<uint32_t>(), h->off_s[0].as<uint32_t>(), h->off_p.as<uint32_t>(),
+			CK(pdl(k_compact2, n, 64, st_c, S, P, h->off_b[0].as<uint32_t>(), h->off_s[0].as<uint32_t>(), h->off_p.as<uint32_t>(),
 			                               h->row_b[0].as<unsigned long long>(), h->row_s[0].as<unsigned long long>(), h->row_p.as<unsigned long long>(),
 			                               h->rt_b[0].as<uint32_t>(), h->rt_s[0].as<uint32_t>()));
 			LAUNCHED(h);
 		}
+		if (fork) CK(cudaEventRecord(h->ev_side[0], st_c));
 		{ Phase ph(h, FQSK_PH_ROUGH); EngineDev Er = E;      // sparse tables (the first blocks of a file): k_rough tests the bucket-occupancy bit before reading a neighbour's bucket
 			if (h->world == 1 && h->items_main[0] < (1ull << h->tb.d.B)) Er.hb.occ_read = Er.hb.occ;
 			if (h->world == 1 && h->items_main[1] < (1ull << h->ts.d.B)) Er.hs.occ_read = Er.hs.occ;
@@ -812,6 +825,7 @@ int seg_pass(fqsk_handle *h) {
 		CK(pdl(k_scan_draws, n <= 2048 ? 1u : nblk(n, SCAN_U32_CHUNK), n <= 2048 ? 256 : 1024, h->st, n, P.rdraws_b, h->doff_b.as<unsigned long long>(), P.rdraws_s, h->doff_s.as<unsigned long long>(), d_draw2, h->d_flags, sc)); LAUNCHED(h);   // + clears flags[0], flags[7]
 		CK(pdl(k_fold, nblk((uint64_t) n * 32, 128), 128, h->st, E, S, P, 1)); LAUNCHED(h);
 	}
+	if (C.redo_tail && !h->prof) CK(cudaStreamWaitEvent(h->st, h->ev_side[0], 0));      // join: the rows are compacted
 	return FQSK_OK;
 }
 
