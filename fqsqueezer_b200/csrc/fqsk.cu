@@ -703,8 +703,17 @@ int seg_setup(fqsk_handle *h) {
 	// one launch clears every status word the segment and a sync enqueued behind it start from: flags[8] | n_miss, n_rscript, pool_used
 	// (n_rec_dev stays: k_scan_reads wrote it) | hot-mode counters | fresh p-mer fields | s fast-path verdict | ordered-insert flags
 	CK(pdl(k_seg_reset, 1, 64, h->st, h->d_status, h->d_counters)); LAUNCHED(h);
+	// full and front-truncated lookups touch disjoint positions: k_partial runs on a side stream next to k_lookup (not when profiling)
+	const bool fork = !h->prof;
+	if (fork && !h->st_side[0]) {
+		for (int i = 0; i < 2; ++i) { CK(cudaStreamCreateWithFlags(&h->st_side[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&h->ev_side[i], cudaEventDisableTiming)); }
+		CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+	}
+	cudaStream_t st_pt = fork ? h->st_side[1] : h->st;
+	if (fork) { CK(cudaEventRecord(h->ev_fork, h->st)); CK(cudaStreamWaitEvent(st_pt, h->ev_fork, 0)); }
 	{ Phase ph(h, FQSK_PH_LOOKUP); CK(pdl(k_lookup, nblk(rec_bound, 256), 256, h->st, C.E, S, P)); LAUNCHED(h); }
-	{ Phase ph(h, FQSK_PH_PARTIAL); CK(pdl(k_partial, nblk((uint64_t) n * pslots * 32, 128), 128, h->st, C.E, S, P)); LAUNCHED(h); }
+	{ Phase ph(h, FQSK_PH_PARTIAL); CK(pdl(k_partial, nblk((uint64_t) n * pslots * 32, 128), 128, st_pt, C.E, S, P)); LAUNCHED(h); }
+	if (fork) { CK(cudaEventRecord(h->ev_side[1], st_pt)); CK(cudaStreamWaitEvent(h->st, h->ev_side[1], 0)); }
 	h->delta_b_valid = h->delta_s_valid = false;
 	C.slots_b = 1024; C.slots_s = 1024;
 	while (C.slots_b < 4 * C.dna_bytes_actual) C.slots_b <<= 1;      // at most 2 b pushes per base, half-full table

@@ -165,14 +165,14 @@ __global__ void __launch_bounds__(256) k_lookup(EngineDev E, SegDev S, PipeDev P
 				ht_ctx_counts(E.hs, d2 ? sr.dir : sr.rc, d2, c);
 				if (any4(c)) { lev = FQSK_LEVEL_SMER; fl |= PF_GLOBAL_S_HIT; } else fl |= PF_MISS_S;
 			}
-		} else fl |= PF_PARTIAL_B;     // k_partial runs the rest of the cascade for this position
+		} else return;                 // front-truncated b lookup: k_partial owns this position (it runs next to this kernel)
 	} else if (cs + s_margin >= E.s) {
 		if (cs == E.s) {
 			KReg sr = suffix_reg(br, cb, cs);
 			bool d2 = kr_is_dir(sr, E.s);
 			ht_ctx_counts(E.hs, d2 ? sr.dir : sr.rc, d2, c);
 			if (any4(c)) { lev = FQSK_LEVEL_SMER; fl |= PF_GLOBAL_S_HIT; } else fl |= PF_MISS_S;
-		} else fl |= PF_PARTIAL_S;
+		} else return;                 // front-truncated s lookup: k_partial
 	} else {
 		KReg pr = suffix_reg(br, cb, cp);      // find_counts_p (dna.cpp:210-226)
 		if (cp < E.p) {
@@ -240,10 +240,13 @@ __global__ void __launch_bounds__(128) k_partial(EngineDev E, SegDev S, PipeDev 
 	const uint32_t first_r = item_first(S, P.start, r);
 	if (i < first_r || i >= S.len[r]) return;
 	uint32_t g = (uint32_t) S.rec_off[r] + (i - first_r);
-	uint8_t fl = P.pflags[g];
-	if (!(fl & (PF_PARTIAL_B | PF_PARTIAL_S))) return;
-	const uint8_t *p = S.dna + S.off[r];
 	const uint32_t cb = n < E.b ? n : E.b, cs = n < E.s ? n : E.s;
+	// which positions are front-truncated table lookups is a function of the position alone (dna.cpp:461-466, 493): the same
+	// thresholds as in k_lookup, which leaves exactly these positions to this kernel
+	uint8_t fl = 0;
+	if (cb + (E.b - E.s - 1) >= E.b) { if (cb < E.b) fl = PF_PARTIAL_B; }
+	else if (cs + (E.s - E.p + 1) >= E.s) { if (cs < E.s) fl = PF_PARTIAL_S; }
+	if (!fl) return;
 	KReg br = build_breg(pk_of(S, r), i, cb);
 	const bool is_b = (fl & PF_PARTIAL_B) != 0;
 	const HtDev &t = is_b ? E.hb : E.hs;
