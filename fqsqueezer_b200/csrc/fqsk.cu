@@ -147,6 +147,7 @@ struct fqsk_handle {
 	unsigned long long items_main[2] = {0, 0};   // items in the buckets of the b / s table as of the last look (sparse -> k_rough tests occupancy bits)
 	cudaStream_t st_side[2] = {nullptr, nullptr}; cudaEvent_t ev_side[2] = {nullptr, nullptr}, ev_fork = nullptr;   // p-mer / s-mer updates of a small sync
 	bool spec_enqueued = false; SyncDev spec_Y{}; uint32_t spec_g = 0;
+	bool spec_prefix = false;                // the grouping half of the pending segment's b-mer sync was enqueued with the segment (seg_pass)
 	bool seg_extra_pass = false;             // the last segment needed more than its first pass: records were rewritten after the pass
 	// fqsk_submit / fqsk_collect: double-buffered records, copies on their own stream
 	DevBuf pk;                                       // 2-bit packed reads of the segment (k_prep)
@@ -554,19 +555,29 @@ int indexed_setup(fqsk_handle *h, const DeltaDev &D, uint32_t n_bound, SyncIn *i
 	return FQSK_OK;
 }
 inline unsigned long long stream_safe_abs(const Stream &s) { return s.safe > s.consumed ? s.safe : s.consumed; }
-int indexed_head(fqsk_handle *h, Table &t, const SyncDev &Y, const unsigned long long *row, const uint32_t *rt, uint32_t g, bool reset = true) {
+int indexed_head(fqsk_handle *h, Table &t, const SyncDev &Y, const unsigned long long *row, const uint32_t *rt, uint32_t g, bool reset = true, cudaStream_t st = nullptr) {
+	if (!st) st = h->st;
 	Phase ph(h, FQSK_PH_SYNC_LOCATE);
-	if (reset) CK(cudaMemsetAsync(h->d_sflags, 0, 8 * sizeof(int), h->st));
-	CK(pdl(k_sync_rank, g, 256, h->st, t.d, Y, row, rt)); LAUNCHED(h);
-	CK(pdl(k_sync_flags, g, 256, h->st, t.d, t.ci, Y)); LAUNCHED(h);
+	if (reset) CK(cudaMemsetAsync(h->d_sflags, 0, 8 * sizeof(int), st));
+	CK(pdl(k_sync_rank, g, 256, st, t.d, Y, row, rt)); LAUNCHED(h);
+	CK(pdl(k_sync_flags, g, 256, st, t.d, t.ci, Y)); LAUNCHED(h);
 	return FQSK_OK;
 }
-int indexed_tail(fqsk_handle *h, Table &t, Stream &rng, const SyncDev &Y, const unsigned long long *row, uint32_t g, uint32_t n_bound, bool reset = true) {
-	// scan of the draw flags (+ scatter of draw index / flag to the delta entries), then the leaders evaluate and write their groups
-	CK(pdl(k_scan_flags, nblk(n_bound, SCANF_TILE), 256, h->st, Y.in, Y.n_dev, (const uint8_t *) Y.flag, h->y_doff.as<uint32_t>(), Y.total_draws, h->scan_part.as<unsigned long long>(), ++h->scan_epoch, Y, t.ci)); LAUNCHED(h);
+// scan of the draw flags (+ scatter of draw index / flag to the delta entries)
+int indexed_scan(fqsk_handle *h, Table &t, const SyncDev &Y, uint32_t n_bound, cudaStream_t st = nullptr) {
+	if (!st) st = h->st;
+	CK(pdl(k_scan_flags, nblk(n_bound, SCANF_TILE), 256, st, Y.in, Y.n_dev, (const uint8_t *) Y.flag, h->y_doff.as<uint32_t>(), Y.total_draws, h->scan_part.as<unsigned long long>(), ++h->scan_epoch, Y, t.ci)); LAUNCHED(h);
+	return FQSK_OK;
+}
+// the leaders evaluate and write their groups
+int indexed_apply(fqsk_handle *h, Table &t, Stream &rng, const SyncDev &Y, const unsigned long long *row, uint32_t g, bool reset = true) {
 	if (reset) CK(cudaMemsetAsync(h->d_sflags, 0, 4 * sizeof(int), h->st));      // [0] draw window short, [2] corrected a flag; [6] hot seen / [7] group too large stay
 	CK(pdl(k_sync_apply, g, 256, h->st, t.d, t.ci, Y, row, (const uint32_t *) rng.buf, (unsigned long long) (rng.cap - 1), stream_safe_abs(rng))); LAUNCHED(h);
 	return FQSK_OK;
+}
+int indexed_tail(fqsk_handle *h, Table &t, Stream &rng, const SyncDev &Y, const unsigned long long *row, uint32_t g, uint32_t n_bound, bool reset = true) {
+	CKR(indexed_scan(h, t, Y, n_bound));
+	return indexed_apply(h, t, rng, Y, row, g, reset);
 }
 // one look at the device: the whole status block, the item counters and the fresh p-mer field count
 int look(fqsk_handle *h) {
@@ -601,7 +612,7 @@ int apply_indexed(fqsk_handle *h, Table &t, Stream &rng, const DeltaDev &D, cons
 		total_draws = looked_syncin(h, in)->draws_b;
 		if (fl[6]) h->hot_seen[is_b ? 1 : 0] = true;
 		if (fl[7]) {   // a hot k-mer occurs more than SYNC_GROUP_CAP times in this row: sorted path for the whole row
-			CK(pdl(k_sync_unclaim, g, 256, h->st, t.d, Y)); LAUNCHED(h);
+			CK(pdl(k_sync_unclaim, g, 256, h->st, t.d, Y, 0u)); LAUNCHED(h);
 			return apply_inserts(h, t, rng, row, n, nullptr);
 		}
 		if (fl[0]) { CKR(stream_ensure(h, rng, (uint64_t) total_draws + (1u << 16))); continue; }
@@ -784,7 +795,7 @@ int seg_build_delta(fqsk_handle *h, bool force_full = false) {
 // Fixed launch schedule of one pass: the thread-local pass (delta, k_local, walk `it` on the reads it touched), compaction,
 // rough searches, ordered merges.  If the look shows that the walk changed pushes (rare) the thread-local pass and everything
 // after it is repeated; if only the merge offsets moved, only the merges.
-int seg_pass(fqsk_handle *h) {
+int seg_pass(fqsk_handle *h, bool with_prefix = false) {
 	SegCtx &C = h->ctx;
 	SegDev &S = C.S; PipeDev &P = C.P; EngineDev &E = C.E;
 	const uint32_t n = C.n, rec_bound = (uint32_t) C.dna_bytes_actual;
@@ -820,6 +831,18 @@ int seg_pass(fqsk_handle *h) {
 			                               h->row_b[0].as<unsigned long long>(), h->row_s[0].as<unsigned long long>(), h->row_p.as<unsigned long long>(),
 			                               h->rt_b[0].as<uint32_t>(), h->rt_s[0].as<uint32_t>()));
 			LAUNCHED(h);
+		}
+		if (with_prefix) {
+			// grouping half of the b-mer sync (find-or-create per distinct k-mer, ranks, draw flags and their scan) right behind the
+			// compaction, on the same side stream: it runs while k_rough / k_fold work on the records.  Predicated on the walk-level
+			// verdict; if the merges then fail to settle, the claimed slots are released again (sync_end: k_sync_unclaim).
+			SyncIn *in = h->d_syncin;
+			const uint32_t bound_b = (uint32_t) (2 * C.dna_bytes_actual + 2);
+			CK(pdl(k_pre_verdict, 1, 32, st_c, (const int *) h->d_flags, (const uint32_t *) d_tot4, SYNC_INDEXED_MAX, in)); LAUNCHED(h);
+			CKR(indexed_setup(h, S.delta_b, bound_b, in, true, h->spec_Y));
+			h->spec_g = nblk(bound_b, 256);
+			CKR(indexed_head(h, h->tb, h->spec_Y, h->row_b[0].as<unsigned long long>(), h->rt_b[0].as<uint32_t>(), h->spec_g, false, st_c));
+			CKR(indexed_scan(h, h->tb, h->spec_Y, bound_b, st_c));
 		}
 		if (fork) CK(cudaEventRecord(h->ev_side[0], st_c));
 		{ Phase ph(h, FQSK_PH_ROUGH); EngineDev Er = E;      // sparse tables (the first blocks of a file): k_rough tests the bucket-occupancy bit before reading a neighbour's bucket
@@ -900,7 +923,11 @@ int seg_settle(fqsk_handle *h, bool have_look = false) {
 		if (attempt > 8) return fail(h, FQSK_E_NOMEM, "segment buffers kept overflowing");
 		int rc = seg_finish(h, have_look);
 		have_look = false;
-		if (rc == RC_RETRY) { CKR(seg_setup(h)); CKR(seg_pass(h)); continue; }
+		if (rc == RC_RETRY) {
+			// the segment is evaluated again from the tables: slots the early grouping (seg_pass with_prefix) claimed must not be seen
+			if (h->spec_prefix) { CK(pdl(k_sync_unclaim, h->spec_g, 256, h->st, h->tb.d, h->spec_Y, 1u)); LAUNCHED(h); h->spec_prefix = false; }
+			CKR(seg_setup(h)); CKR(seg_pass(h)); continue;
+		}
 		return rc;
 	}
 }
@@ -1005,7 +1032,7 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 	if (h->world > 1 && h->attached != (1u << h->world) - 1) return fail(h, FQSK_E_INVAL, "sharded engine: not every peer shard is attached (fqsk_shard_attach)");
 	const uint32_t first = (h->P.mode == FQSK_MODE_SE_SORTED || h->P.mode == FQSK_MODE_PE_SORTED) ? h->P.pmer_len : h->P.prefix_len;
 	h->seg_reads = n; h->n_recs = 0; h->pend_b = h->pend_s = h->pend_p = 0;
-	h->hot = false; h->seg_extra_pass = false;
+	h->hot = false; h->seg_extra_pass = false; h->spec_prefix = false;
 	++h->S.n_segments;
 	if (n == 0) { h->pending = true; return FQSK_OK; }
 	if (dna_bytes >= (1ull << 30)) return fail(h, FQSK_E_INVAL, "segment larger than 1 GiB of DNA");   // push times are 2 * byte offset (+1) in 32 bits
@@ -1050,12 +1077,14 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 	CKR(stream_ensure(h, h->rng[ST_B], (1u << 16) + (dna_bytes_actual <= SPEC_MAX_BYTES ? 2 * dna_bytes_actual : 0))); CKR(stream_ensure(h, h->rng[ST_S], 1u << 12));
 	CKR(seg_setup(h));
 	if (h->delta_filtered) ++h->S.n_filtered_segments;
-	CKR(seg_pass(h));
+	const bool prefix = h->world == 1 && h->fast_ok[0] && dna_bytes_actual <= SPEC_MAX_BYTES;     // the sync of this segment will be enqueued unseen
+	CKR(seg_pass(h, prefix));
+	h->spec_prefix = prefix;
 	// verdict of the first pass for a sync enqueued unseen, and the state the next segment inherits (both are inputs only)
 	// one launch: verdict of the first pass + the state the next segment inherits (read_prev, pmer_can_prev)
 	CK(pdl(k_seg_tail, 1, 256, h->st, h->d_flags, (const uint32_t *) (h->d_status + 192), (const unsigned long long *) (h->d_status + 208),
 	       h->rng[ST_B].consumed, h->rng[ST_S].consumed, SYNC_INDEXED_MAX, h->d_syncin,
-	       S, pe ? n - 3 : n - 1, h->prev_read.as<uint8_t>(), h->d_carry, (uint32_t) (h->P.mode == FQSK_MODE_SE_SORTED || h->P.mode == FQSK_MODE_PE_SORTED), h->P.pmer_len)); LAUNCHED(h);
+	       S, pe ? n - 3 : n - 1, h->prev_read.as<uint8_t>(), h->d_carry, (uint32_t) (h->P.mode == FQSK_MODE_SE_SORTED || h->P.mode == FQSK_MODE_PE_SORTED), h->P.pmer_len, (uint32_t) prefix)); LAUNCHED(h);
 	h->unsettled = true;
 	h->pending = true;
 	h->S.n_reads += n_in; h->S.n_bases += bytes_in;
@@ -1400,14 +1429,18 @@ static int sync_spec_enqueue(fqsk_handle *h) {
 	}
 	if (fork) { CK(cudaEventRecord(h->ev_side[0], st_p)); CK(cudaEventRecord(h->ev_side[1], st_s)); }
 	SyncDev &Y = h->spec_Y;
-	CKR(indexed_setup(h, C.S.delta_b, bound_b, in, true, Y));
-	const uint32_t g = h->spec_g = nblk(bound_b, 256);
 	const unsigned long long *row_b = h->row_b[0].as<unsigned long long>();
-	CKR(indexed_head(h, h->tb, Y, row_b, h->rt_b[0].as<uint32_t>(), g, false));
+	if (!h->spec_prefix) {
+		CKR(indexed_setup(h, C.S.delta_b, bound_b, in, true, Y));
+		h->spec_g = nblk(bound_b, 256);
+		CKR(indexed_head(h, h->tb, Y, row_b, h->rt_b[0].as<uint32_t>(), h->spec_g, false));
+	}
+	const uint32_t g = h->spec_g;
 	{
 		Phase ph(h, FQSK_PH_SYNC_APPLY);
 		CKR(stream_ensure(h, h->rng[ST_B], 0));
-		CKR(indexed_tail(h, h->tb, h->rng[ST_B], Y, row_b, g, bound_b, false));
+		if (!h->spec_prefix) CKR(indexed_scan(h, h->tb, Y, bound_b));
+		CKR(indexed_apply(h, h->tb, h->rng[ST_B], Y, row_b, g, false));
 	}
 	if (fork) { CK(cudaStreamWaitEvent(h->st, h->ev_side[0], 0)); CK(cudaStreamWaitEvent(h->st, h->ev_side[1], 0)); }
 	h->spec_enqueued = true;
@@ -1426,14 +1459,19 @@ static int sync_spec_finish(fqsk_handle *h, bool *applied, unsigned long long co
 	const int s_refuted = *(const int *) ((uint8_t *) h->h_small + 224);
 	memcpy(counters, (uint8_t *) h->h_small + 512, 48);
 	CKR(seg_settle(h, true));      // the same look carries the segment's flags and totals
-	if (!li.ok) return FQSK_OK;    // the first pass was not the last one (or the rows are large): nothing was applied
+	if (!li.ok) {                  // the first pass was not the last one (or the rows are large): nothing was applied ...
+		if (h->spec_prefix) { CK(pdl(k_sync_unclaim, g, 256, h->st, h->tb.d, Y, 1u)); LAUNCHED(h); }    // ... except slots claimed by the early grouping
+		h->spec_prefix = false;
+		return FQSK_OK;
+	}
+	h->spec_prefix = false;
 	*applied = true;
 	bool relook = false;
 	if (fl[6]) h->hot_seen[1] = true;
 	if (fl[7] || fl[0] || fl[2]) {
 		// a counter saturated inside the batch, the draw window was short or a group is too large: nothing was committed; release
 		// the claimed slots and take the plain ordered path for this row
-		CK(pdl(k_sync_unclaim, g, 256, h->st, h->tb.d, Y)); LAUNCHED(h);
+		CK(pdl(k_sync_unclaim, g, 256, h->st, h->tb.d, Y, 0u)); LAUNCHED(h);
 		CKR(apply_indexed(h, h->tb, h->rng[ST_B], h->seg_delta_b, row_b, h->rt_b[0].as<uint32_t>(), h->pend_b));
 		relook = true;
 	} else h->rng[ST_B].consumed += li.draws_b;
@@ -1466,6 +1504,10 @@ static int sync_end(fqsk_handle *h) {
 		bool applied = false;
 		if (h->spec_enqueued) CKR(sync_spec_finish(h, &applied, counters));
 		CKR(seg_settle(h));
+		if (h->spec_prefix) {      // the segment was looked at before its sync was enqueued: release what the early grouping claimed
+			CK(pdl(k_sync_unclaim, h->spec_g, 256, h->st, h->tb.d, h->spec_Y, 1u)); LAUNCHED(h);
+			h->spec_prefix = false;
+		}
 		if (h->P.mode == FQSK_MODE_PE_ORIGINAL) CKR(pe_sync(h));
 		if (!applied) {
 			// p-mers (dna.cpp:2401-2418): order-independent saturating increments; the fresh-field count is read with the next look
@@ -1870,6 +1912,7 @@ static int dump_pairs(fqsk_handle *h, uint64_t *keys, uint64_t *vals, uint64_t c
 int fqsk_dump(fqsk_handle *h, int table, uint64_t *keys, uint64_t *vals, uint64_t cap, uint64_t *n) {
 	if (!h || !n) return FQSK_E_INVAL;
 	CK(cudaSetDevice(h->P.device));
+	if (h->pending && h->spec_prefix) return fail(h, FQSK_E_INVAL, "fqsk_dump between a segment and its sync: call fqsk_sync first");
 	CKR(seg_settle(h));
 	if (table == FQSK_TABLE_SMER || table == FQSK_TABLE_BMER) {
 		Table &t = table == FQSK_TABLE_SMER ? h->ts : h->tb;

@@ -244,14 +244,14 @@ FQSK_DEV uint32_t ht_count(const HtDev &t, uint64_t x) {
 }
 // find-or-create for the sync step (ht_kmer.h:330-362).  New slots are claimed with counter 1; the group pass of the sync
 // step turns that into the reference's "start at 0, then Increment".  Returns a slot id (main: index, stash: 8<<B + index).
-FQSK_DEV uint64_t ht_locate(const HtDev &t, uint64_t x, bool &created) {
+FQSK_DEV uint64_t ht_locate(const HtDev &t, uint64_t x, bool &created, uint32_t claim = 1u) {      // claim: counter a new slot starts with
 	HtKey key = ht_key(t, x);
 	uint32_t *bp = t.main + key.bucket * 8;
 	created = false;
 	for (int i = 0; i < 8; ++i) {
 		uint32_t it = *((volatile uint32_t *) (bp + i));
 		if (it == 0) {
-			uint32_t old = atomicCAS(bp + i, 0u, key.q | 1u);
+			uint32_t old = atomicCAS(bp + i, 0u, key.q | claim);
 			if (old == 0) {
 				created = true; atomicAdd(t.n_items, 1ull);
 				if (t.occ) { const uint32_t bit = 1u << (key.bucket & 31); if (!(t.occ[key.bucket >> 5] & bit)) atomicOr(t.occ + (key.bucket >> 5), bit); }
@@ -262,7 +262,7 @@ FQSK_DEV uint64_t ht_locate(const HtDev &t, uint64_t x, bool &created) {
 		if ((it & ~t.top) == key.q) return key.bucket * 8 + i;
 	}
 	uint64_t smask = (1ull << t.stash_log2) - 1;
-	unsigned long long fresh = ((key.kal + 1) << t.cbits) | 1ull;
+	unsigned long long fresh = ((key.kal + 1) << t.cbits) | (unsigned long long) claim;
 	for (uint64_t p = ht_stash_pos(t, key.h);; p = (p + 1) & smask) {
 		unsigned long long it = *((volatile unsigned long long *) (t.stash + p));
 		if (it == 0) {

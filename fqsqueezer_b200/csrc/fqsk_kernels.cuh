@@ -317,7 +317,9 @@ struct SyncIn {             // inputs of a sync that only the device knows when 
 	uint32_t ok;            // the segment settled on its first pass (k_seg_verdict); 0 = every sync kernel is a no-op
 	uint32_t n_b, n_s, n_p; // rows to apply (dna.cpp:2401-2446)
 	unsigned long long dpos_b, dpos_s;   // absolute positions of the cinc_b / cinc_s streams after the segment's lookups
-	uint32_t draws_b, pad;  // out: mt19937 outputs consumed by the b-mer inserts of this sync
+	uint32_t draws_b;       // out: mt19937 outputs consumed by the b-mer inserts of this sync
+	uint32_t ok_pre;        // walk-level verdict (k_pre_verdict): the pushes are final, so the grouping half of the b-mer sync may run
+	                        // next to the rough searches and merges; `ok` (k_seg_tail) additionally needs the merges to have settled
 };
 
 struct SyncDev {
@@ -331,7 +333,7 @@ static const uint32_t SYNC_GROUP_CAP = 48;
 
 __global__ void k_sync_rank(HtDev t, SyncDev Y, const unsigned long long *row, const uint32_t *rt) { pdl_enter();
 	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-	if (!Y.in->ok || j >= *Y.n_dev) return;
+	if (!Y.in->ok_pre || j >= *Y.n_dev) return;
 	const unsigned long long x = row[j];
 	const uint32_t tm = rt[j];
 	uint32_t m = 0, rank = 0, own = 0xFFFFFFFFu, lead = 0xFFFFFFFFu, lead_t = 0xFFFFFFFFu;
@@ -348,7 +350,9 @@ __global__ void k_sync_rank(HtDev t, SyncDev Y, const unsigned long long *row, c
 	Y.j_at[own] = j;
 	if (rank == 0) {
 		bool created;
-		uint64_t ts = ht_locate(t, x, created);
+		// a new slot is claimed as a zero-count item (== the reference's fresh slot): this kernel may run next to kernels that still
+		// read the table for the segment (k_rough), and a zero counter adds nothing to any lookup
+		uint64_t ts = ht_locate(t, x, created, 0u);
 		Y.lead_tslot[own] = ts | (created ? (1ull << 63) : 0ull);
 		Y.lead_c0[own] = created ? 0u : ht_slot_get(t, ts);
 		Y.lead_m[own] = m;
@@ -356,7 +360,7 @@ __global__ void k_sync_rank(HtDev t, SyncDev Y, const unsigned long long *row, c
 }
 __global__ void k_sync_flags(HtDev t, CIncP ci, SyncDev Y) { pdl_enter();
 	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-	if (!Y.in->ok || j >= *Y.n_dev) return;
+	if (!Y.in->ok_pre || j >= *Y.n_dev) return;
 	const uint32_t L = Y.lead[j], c0 = Y.lead_c0[L], m = Y.lead_m[L], rank = Y.rank[j];
 	uint8_t f = 0;
 	if (rank == 0 && m > ci.thr + 1) Y.flags[6] = 1;   // the thread-local table of the reference drew from its own stream for this k-mer
@@ -430,9 +434,9 @@ __global__ void k_sync_commit(HtDev t, SyncDev Y) { pdl_enter();
 	ht_slot_set(t, Y.lead_tslot[L] & ~(1ull << 63), Y.final_at[L]);
 }
 // fallback preparation: slots claimed by k_sync_rank (counter 1) become zero-count items, i.e. the reference's fresh slot
-__global__ void k_sync_unclaim(HtDev t, SyncDev Y) { pdl_enter();
+__global__ void k_sync_unclaim(HtDev t, SyncDev Y, uint32_t use_pre) { pdl_enter();
 	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-	if (!Y.in->ok || j >= *Y.n_dev) return;
+	if (!(use_pre ? Y.in->ok_pre : Y.in->ok) || j >= *Y.n_dev) return;
 	if (Y.rank[j] != 0) return;
 	// created slots stay as zero-count items (== the reference's fresh slot); existing ones get their pre-sync counter back
 	// (k_sync_apply writes final counters without waiting for the verdict of the whole row)

@@ -1167,7 +1167,7 @@ __global__ void __launch_bounds__(1024) k_scan_draws(uint32_t n, const uint32_t 
 static const uint32_t SCANF_TILE = 4096;
 __global__ void __launch_bounds__(256) k_scan_flags(const SyncIn *in, const uint32_t *n_dev, const uint8_t *flag, uint32_t *out, uint32_t *total,
                                                     unsigned long long *partials, uint32_t epoch, SyncDev Y, CIncP ci) { pdl_enter();
-	const uint32_t n = in->ok ? *n_dev : 0;
+	const uint32_t n = in->ok_pre ? *n_dev : 0;
 	const uint32_t b = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
 	const uint32_t base = b * SCANF_TILE;
 	if (base >= n) { if (b == 0 && t == 0) { out[0] = 0; *total = 0; } return; }
@@ -1257,14 +1257,16 @@ __global__ void k_seg_reset(uint8_t *status, unsigned long long *counters) { pdl
 }
 // k_seg_verdict + k_save_carry in one launch (the chain of a small segment is launch-latency bound)
 __global__ void __launch_bounds__(256) k_seg_tail(const int *flags, const uint32_t *tot4, const unsigned long long *draws2, unsigned long long consumed_b, unsigned long long consumed_s,
-                                                  uint32_t row_cap, SyncIn *in, SegDev S, uint32_t last, uint8_t *prev_read, Carry *carry, uint32_t sorted, uint32_t p) { pdl_enter();
+                                                  uint32_t row_cap, SyncIn *in, SegDev S, uint32_t last, uint8_t *prev_read, Carry *carry, uint32_t sorted, uint32_t p,
+                                                  uint32_t have_prefix) { pdl_enter();
 	if (threadIdx.x == 0) {
 		bool ok = !(flags[0] | flags[1] | flags[2] | flags[4] | flags[5] | flags[7]);
 		if (tot4[0] > row_cap || tot4[1] > row_cap) ok = false;
 		in->n_b = tot4[0]; in->n_s = tot4[1]; in->n_p = tot4[2];
 		in->dpos_b = consumed_b + draws2[0]; in->dpos_s = consumed_s + draws2[1];
-		in->draws_b = 0;
 		in->ok = ok ? 1u : 0u;
+		if (!have_prefix) { in->ok_pre = ok ? 1u : 0u; in->draws_b = 0; }     // otherwise k_pre_verdict has set ok_pre and the early flag scan has
+		                                                                      // already left the row's draw total in draws_b
 	}
 	if (S.n_reads == 0) return;
 	const uint8_t *q = S.dna + S.off[last];      // paired-end: only first-of-pair reads replace read_prev (dna.cpp:1550-1551)
@@ -1279,9 +1281,21 @@ __global__ void __launch_bounds__(256) k_seg_tail(const int *flags, const uint32
 		}
 	}
 }
+// Walk-level verdict, available as soon as the pushes are compacted: no flag asks for another walk, a retry or the ordered
+// thread-local evaluator, and the rows fit the indexed ordered insert.  The pushes are final then (what can still fail -- the
+// merges of k_fold -- only touches records and draw counts), so k_sync_rank / k_sync_flags / k_scan_flags may run.
+__global__ void k_pre_verdict(const int *flags, const uint32_t *tot4, uint32_t row_cap, SyncIn *in) { pdl_enter();
+	if (threadIdx.x || blockIdx.x) return;
+	bool ok = !(flags[1] | flags[2] | flags[4] | flags[5]);
+	if (tot4[0] > row_cap || tot4[1] > row_cap) ok = false;
+	in->n_b = tot4[0]; in->n_s = tot4[1]; in->n_p = tot4[2];
+	in->draws_b = 0;
+	in->ok = 0;
+	in->ok_pre = ok ? 1u : 0u;
+}
 __global__ void k_set_syncin(SyncIn *in, uint32_t n_b, uint32_t n_s, uint32_t n_p, unsigned long long dpos_b, unsigned long long dpos_s) { pdl_enter();
 	if (threadIdx.x || blockIdx.x) return;
-	in->ok = 1; in->n_b = n_b; in->n_s = n_s; in->n_p = n_p; in->dpos_b = dpos_b; in->dpos_s = dpos_s; in->draws_b = 0;
+	in->ok = 1; in->ok_pre = 1; in->n_b = n_b; in->n_s = n_s; in->n_p = n_p; in->dpos_b = dpos_b; in->dpos_s = dpos_s; in->draws_b = 0;
 }
 
 }  // namespace fqsk
