@@ -147,6 +147,8 @@ struct fqsk_handle {
 	unsigned long long items_main[2] = {0, 0};   // items in the buckets of the b / s table as of the last look (sparse -> k_rough tests occupancy bits)
 	cudaStream_t st_side[2] = {nullptr, nullptr}; cudaEvent_t ev_side[2] = {nullptr, nullptr}, ev_fork = nullptr;   // p-mer / s-mer updates of a small sync
 	bool spec_enqueued = false; SyncDev spec_Y{}; uint32_t spec_g = 0;
+	uint32_t dbg_fail_every = 0, dbg_retry_every = 0, dbg_seg = 0;   // fault injection for tests (FQSK_DEBUG_FAIL_EVERY / FQSK_DEBUG_RETRY_EVERY): see fqsk_create
+	bool dbg_retry_armed = false;
 	bool spec_prefix = false;                // the grouping half of the pending segment's b-mer sync was enqueued with the segment (seg_pass)
 	bool seg_extra_pass = false;             // the last segment needed more than its first pass: records were rewritten after the pass
 	// fqsk_submit / fqsk_collect: double-buffered records, copies on their own stream
@@ -873,6 +875,7 @@ int seg_finish(fqsk_handle *h, bool have_look) {
 		if (!have_look) CKR(look(h));
 		have_look = false;
 		memcpy(fl, hs, sizeof fl); memcpy(draws2, hs + 208, 16); memcpy(cnt, hs + 32, 16);
+		if (h->dbg_retry_armed) { h->dbg_retry_armed = false; h->seg_extra_pass = true; return RC_RETRY; }     // fault injection (tests)
 		if (fl[4]) {
 			if (cnt[0] > h->miss_cap) h->miss_cap = cnt[0] + cnt[0] / 4 + 1024;
 			if (cnt[1] > h->rreq_cap) h->rreq_cap = cnt[1] + cnt[1] / 4 + 1024;
@@ -1084,7 +1087,10 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 	// one launch: verdict of the first pass + the state the next segment inherits (read_prev, pmer_can_prev)
 	CK(pdl(k_seg_tail, 1, 256, h->st, h->d_flags, (const uint32_t *) (h->d_status + 192), (const unsigned long long *) (h->d_status + 208),
 	       h->rng[ST_B].consumed, h->rng[ST_S].consumed, SYNC_INDEXED_MAX, h->d_syncin,
-	       S, pe ? n - 3 : n - 1, h->prev_read.as<uint8_t>(), h->d_carry, (uint32_t) (h->P.mode == FQSK_MODE_SE_SORTED || h->P.mode == FQSK_MODE_PE_SORTED), h->P.pmer_len, (uint32_t) prefix)); LAUNCHED(h);
+	       S, pe ? n - 3 : n - 1, h->prev_read.as<uint8_t>(), h->d_carry, (uint32_t) (h->P.mode == FQSK_MODE_SE_SORTED || h->P.mode == FQSK_MODE_PE_SORTED), h->P.pmer_len, (uint32_t) prefix,
+	       (uint32_t) ((h->dbg_fail_every && h->dbg_seg % h->dbg_fail_every == 0) || (h->dbg_retry_every && h->dbg_seg % h->dbg_retry_every == 1)))); LAUNCHED(h);
+	h->dbg_retry_armed = h->dbg_retry_every && h->dbg_seg % h->dbg_retry_every == 1;     // a retry always comes with a failed verdict (as flags[4] would give)
+	++h->dbg_seg;
 	h->unsettled = true;
 	h->pending = true;
 	h->S.n_reads += n_in; h->S.n_bases += bytes_in;
@@ -1171,6 +1177,11 @@ int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
 	h->P = *p;
 	h->world = world; h->rank = p->rank;
 	h->prof = (p->flags & FQSK_F_PROFILE) != 0;
+	// Fault injection (tests only; inert unless the variables are set): every N-th segment has its first-pass verdict forced to
+	// "not settled" after the early grouping has run (exercises k_sync_unclaim + the plain sync), resp. is evaluated a second time
+	// from scratch as after a capacity overflow (exercises the release of claimed slots before the tables are read again).
+	if (const char *e = getenv("FQSK_DEBUG_FAIL_EVERY")) h->dbg_fail_every = (uint32_t) atoi(e);
+	if (const char *e = getenv("FQSK_DEBUG_RETRY_EVERY")) h->dbg_retry_every = (uint32_t) atoi(e);
 	int rc = [&]() -> int {
 		CK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
 		CK(cudaStreamCreateWithFlags(&h->st_mt, cudaStreamNonBlocking));

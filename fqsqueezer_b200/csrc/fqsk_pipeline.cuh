@@ -1258,9 +1258,9 @@ __global__ void k_seg_reset(uint8_t *status, unsigned long long *counters) { pdl
 // k_seg_verdict + k_save_carry in one launch (the chain of a small segment is launch-latency bound)
 __global__ void __launch_bounds__(256) k_seg_tail(const int *flags, const uint32_t *tot4, const unsigned long long *draws2, unsigned long long consumed_b, unsigned long long consumed_s,
                                                   uint32_t row_cap, SyncIn *in, SegDev S, uint32_t last, uint8_t *prev_read, Carry *carry, uint32_t sorted, uint32_t p,
-                                                  uint32_t have_prefix) { pdl_enter();
+                                                  uint32_t have_prefix, uint32_t force_fail) { pdl_enter();
 	if (threadIdx.x == 0) {
-		bool ok = !(flags[0] | flags[1] | flags[2] | flags[4] | flags[5] | flags[7]);
+		bool ok = !(flags[0] | flags[1] | flags[2] | flags[4] | flags[5] | flags[7]) && !force_fail;      // force_fail: fault injection (tests)
 		if (tot4[0] > row_cap || tot4[1] > row_cap) ok = false;
 		in->n_b = tot4[0]; in->n_s = tot4[1]; in->n_p = tot4[2];
 		in->dpos_b = consumed_b + draws2[0]; in->dpos_s = consumed_s + draws2[1];
