@@ -512,6 +512,7 @@ int sort_row(fqsk_handle *h, const unsigned long long *row, uint32_t n, uint32_t
 
 const uint32_t SYNC_INDEXED_MAX = 400000;
 const uint64_t SPEC_MAX_BYTES = 420000;   // segments up to this many DNA bytes get their sync enqueued without a host look in between
+const uint32_t FORK_MAX_READS = 8192;  // segments below this size run independent kernels of their chain on side streams
 const int RC_RETRY = 1;   // internal: a capacity was too small, grow and redo the segment
 
 int apply_inserts(fqsk_handle *h, Table &t, Stream &rng, const unsigned long long *d_kmers, uint32_t n, bool *fast_ok = nullptr) {
@@ -717,7 +718,7 @@ int seg_setup(fqsk_handle *h) {
 	// (n_rec_dev stays: k_scan_reads wrote it) | hot-mode counters | fresh p-mer fields | s fast-path verdict | ordered-insert flags
 	CK(pdl(k_seg_reset, 1, 64, h->st, h->d_status, h->d_counters)); LAUNCHED(h);
 	// full and front-truncated lookups touch disjoint positions: k_partial runs on a side stream next to k_lookup (not when profiling)
-	const bool fork = !h->prof;
+	const bool fork = !h->prof && n < FORK_MAX_READS;      // side streams pay off where the chain is latency bound; large segments fill the GPU anyway
 	if (fork && !h->st_side[0]) {
 		for (int i = 0; i < 2; ++i) { CK(cudaStreamCreateWithFlags(&h->st_side[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&h->ev_side[i], cudaEventDisableTiming)); }
 		CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
@@ -815,7 +816,7 @@ int seg_pass(fqsk_handle *h, bool with_prefix = false) {
 	if (C.redo_tail) {
 		// The compaction of the pushes (rows of the sync) and the rough searches + merges (records) only meet again at the verdict:
 		// the two small compaction kernels run on a side stream next to k_rough / k_fold.  Profiling keeps one stream.
-		const bool fork = !h->prof;
+		const bool fork = !h->prof && n < FORK_MAX_READS;
 		if (fork && !h->st_side[0]) {
 			for (int i = 0; i < 2; ++i) { CK(cudaStreamCreateWithFlags(&h->st_side[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&h->ev_side[i], cudaEventDisableTiming)); }
 			CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
@@ -859,7 +860,7 @@ int seg_pass(fqsk_handle *h, bool with_prefix = false) {
 		CK(pdl(k_scan_draws, n <= 2048 ? 1u : nblk(n, SCAN_U32_CHUNK), n <= 2048 ? 256 : 1024, h->st, n, P.rdraws_b, h->doff_b.as<unsigned long long>(), P.rdraws_s, h->doff_s.as<unsigned long long>(), d_draw2, h->d_flags, sc)); LAUNCHED(h);   // + clears flags[0], flags[7]
 		CK(pdl(k_fold, nblk((uint64_t) n * 32, 128), 128, h->st, E, S, P, 1)); LAUNCHED(h);
 	}
-	if (C.redo_tail && !h->prof) CK(cudaStreamWaitEvent(h->st, h->ev_side[0], 0));      // join: the rows are compacted
+	if (C.redo_tail && !h->prof && n < FORK_MAX_READS) CK(cudaStreamWaitEvent(h->st, h->ev_side[0], 0));      // join: the rows are compacted
 	return FQSK_OK;
 }
 
