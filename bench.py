@@ -435,7 +435,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
-            "config": workload_config({"parallelism": "1 engine per GPU" + ("" if world == 1 else f" x {world} independent replicas (hash-sharded tables not implemented yet)"),
+            "config": workload_config({"parallelism": "1 engine per GPU" + ("" if world == 1 else f" x {world} independent replicas (ONE job over hash-sharded tables: --shard)"),
                                        "blocks": f"{args.warmup}..{n_blocks - 1} of the job", "segments_timed": n_seg}),
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": sampler.summary(), "wall_ms_per_step": wall_ms / args.steps}

@@ -1363,15 +1363,16 @@ static int stage_segment(fqsk_handle *h, uint8_t *&stage, size_t &stage_cap, con
 	*total_out = total; *rec_bound = bound;
 	return FQSK_OK;
 }
-static int upload_segment(fqsk_handle *h, const uint8_t *stage, uint64_t total, uint32_t n_reads) {
+// one H2D copy: the device buffer mirrors the staging layout [dna | off u64 | len u32]
+struct Uploaded { const uint8_t *dna; const unsigned long long *off; const uint32_t *len; };
+static int upload_segment(fqsk_handle *h, const uint8_t *stage, uint64_t total, uint32_t n_reads, Uploaded &U) {
 	const size_t off_pos = (total + 63) & ~(size_t) 63;
-	CK(h->dna.ensure(std::max<uint64_t>(total, h->P.reserve_bytes) + 64)); CK(h->off.ensure((size_t) std::max(n_reads, h->P.reserve_reads) * 8 + 8));
-	CK(h->len.ensure((size_t) std::max(n_reads, h->P.reserve_reads) * 4 + 4));
-	if (n_reads) {
-		CK(cudaMemcpyAsync(h->dna.p, stage, total, cudaMemcpyHostToDevice, h->st));
-		CK(cudaMemcpyAsync(h->off.p, stage + off_pos, (size_t) n_reads * 8, cudaMemcpyHostToDevice, h->st));
-		CK(cudaMemcpyAsync(h->len.p, stage + off_pos + (size_t) n_reads * 8, (size_t) n_reads * 4, cudaMemcpyHostToDevice, h->st));
-	}
+	const size_t bytes = off_pos + (size_t) n_reads * 12;
+	CK(h->dna.ensure(std::max<size_t>(bytes, (size_t) h->P.reserve_bytes + (size_t) h->P.reserve_reads * 12 + 128) + 64));
+	if (n_reads) CK(cudaMemcpyAsync(h->dna.p, stage, bytes, cudaMemcpyHostToDevice, h->st));
+	U.dna = h->dna.as<uint8_t>();
+	U.off = (const unsigned long long *) (h->dna.as<uint8_t>() + off_pos);
+	U.len = (const uint32_t *) (h->dna.as<uint8_t>() + off_pos + (size_t) n_reads * 8);
 	return FQSK_OK;
 }
 
@@ -1382,8 +1383,9 @@ int fqsk_segment(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const 
 	if (h->tk_open) return fail(h, FQSK_E_INVAL, "a submitted segment is in flight: fqsk_collect it first");
 	uint64_t total = 0, bound = 0;
 	CKR(stage_segment(h, h->h_stage, h->h_stage_cap, slab, slab_size, reads, n_reads, &total, &bound));
-	CKR(upload_segment(h, h->h_stage, total, n_reads));
-	CKR(run_segment(h, h->dna.as<uint8_t>(), total, h->off.as<unsigned long long>(), h->len.as<uint32_t>(), n_reads));
+	Uploaded U;
+	CKR(upload_segment(h, h->h_stage, total, n_reads, U));
+	CKR(run_segment(h, U.dna, total, U.off, U.len, n_reads));
 	CKR(seg_settle(h));
 	if (h->n_recs > rec_cap) return fail(h, FQSK_E_CAPACITY, "record buffer holds %llu, segment produced %llu", (unsigned long long) rec_cap, (unsigned long long) h->n_recs);
 	if (h->n_recs && recs) CK(cudaMemcpyAsync(recs, (h->rec_par ? h->recs_alt : h->recs).p, h->n_recs * sizeof(fqsk_base_rec), cudaMemcpyDeviceToHost, h->st));
@@ -1635,8 +1637,9 @@ int fqsk_submit(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const f
 	CKR(submit_finish_compute(h));                                  // previous segment: settle + sync
 	CK(cudaStreamWaitEvent(h->st, h->ev_copied[par], 0));             // the device records of this parity have left for the host
 	h->rec_par = par;
-	CKR(upload_segment(h, stage, total, n_reads));
-	CKR(run_segment(h, h->dna.as<uint8_t>(), total, h->off.as<unsigned long long>(), h->len.as<uint32_t>(), n_reads));
+	Uploaded U;
+	CKR(upload_segment(h, stage, total, n_reads, U));
+	CKR(run_segment(h, U.dna, total, U.off, U.len, n_reads));
 	const uint32_t ni = h->P.mode == FQSK_MODE_PE_ORIGINAL ? n_reads / 2 * 3 : n_reads;
 	if (ni) {   // duplicate flags and record offsets are final after k_prep / k_scan_reads: main stream, ahead of the look that ends the sync
 		const size_t need = (((size_t) ni + 8) & ~(size_t) 7) + ((size_t) ni + 1) * 8;
