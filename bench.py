@@ -412,7 +412,8 @@ def main():
     step_achieved = B_ALG * bases_rank / (dev_ms / 1e3) / 1e9
     roof = {"bound": "hbm", "achieved": step_achieved, "peak": peak, "unit": "GB/s", "frac": step_achieved / peak, "traffic": None,
             "peak_source": peak_src,
-            "kernel": "whole step (all kernels of fqsk_segment + fqsk_sync), 251.5 algorithmic B/base"}
+            "kernel": "whole step (all kernels of fqsk_segment + fqsk_sync), 251.5 algorithmic B/base",
+            "traffic_note": "ncu of one steady-state step (profiles/r01d_steady_block_summary.md): 8.5 GB of DRAM traffic per 7.65 Mbase segment = 4.4x the algorithmic bytes; the average step of the job mixes 1..95 segments, so no single per-launch figure exists"}
     if phases:
         dom = max(phases, key=lambda k: phases[k])
         dom_share = phases[dom] / max(sum(phases.values()), 1e-9)

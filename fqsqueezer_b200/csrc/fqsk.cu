@@ -96,7 +96,7 @@ struct fqsk_handle {
 	uint64_t hidden_p = 0;                           // no_pmer_hidden_updates (dna.cpp:850, 2417)
 	// previous read / previous prefix p-mer carried across segments
 	DevBuf prev_read;
-	Carry *d_carry = nullptr;            // inside d_status: prev read length + pmer_can_prev (written by k_save_carry)
+	Carry *d_carry = nullptr;            // inside d_status: prev read length + pmer_can_prev (written by k_seg_tail)
 	// segment buffers
 	DevBuf dna, off, len, dup, n_coded, letters, rec_off, sl_prefix, recs, push_b, push_s, push_p, cnt_b, cnt_s, cnt_p, hidden,
 	       draw_cnt, draw_cnt_prev, draw_scan, off_b[2], off_s[2], off_p, row_b[2], row_s[2], row_p, dk_b, di_b, dk_s, di_s, iota, cub_tmp,
@@ -654,7 +654,7 @@ EngineDev make_engine_dev(fqsk_handle *h) {
 // one sync segment, reads resident on the device.  All counts stay on the device; kernels are
 // launched from host-side upper bounds.  seg_setup + seg_pass enqueue the first pass of the fixed launch schedule; the host
 // does not look at the device until somebody needs the outcome (seg_settle): the sync that follows a small segment is
-// enqueued behind it unseen, predicated on the device-side verdict of the pass (k_seg_verdict).
+// enqueued behind it unseen, predicated on the device-side verdict of the pass (k_seg_tail).
 // ---------------------------------------------------------------------------------------------------------------
 int seg_setup(fqsk_handle *h) {
 	SegCtx &C = h->ctx;

@@ -71,7 +71,7 @@ struct EngineDev {
 	int *flags;                     // [0] draw window overflow, [1] unsupported path, [2] changed, [3] scratch
 };
 
-struct Carry {             // state a segment hands to the next one without a host round trip (k_save_carry)
+struct Carry {             // state a segment hands to the next one without a host round trip (k_seg_tail)
 	uint32_t prev_len;     // read_prev.size(), 0 after ResetReadPrev (application.cpp:624)
 	uint32_t pprev_valid;
 	unsigned long long pprev_dir;   // pmer_can_prev (dna.cpp:167, 655): prefix p-mer of the last read, left-aligned
@@ -153,22 +153,6 @@ __global__ void __launch_bounds__(128) k_prep(SegDev S, uint32_t first_len_bytes
 		U64x4 L; for (int k = 0; k < 4; ++k) L.v[k] = (same || (ifl & IF_NO_LETTERS)) ? 0 : cnt[k];
 		S.letters[r] = L;
 		S.n_coded[r] = (!same && n > first_len_bytes) ? n - first_len_bytes : 0;
-	}
-}
-
-// read_prev (dna.cpp:1550-1551) and, in sorted order, pmer_can_prev (dna.cpp:655) follow the last read of the segment
-__global__ void __launch_bounds__(256) k_save_carry(SegDev S, uint32_t last, uint8_t *prev_read, Carry *carry, uint32_t sorted, uint32_t p) { pdl_enter();
-	if (S.n_reads == 0) return;
-	const uint8_t *q = S.dna + S.off[last];      // paired-end: only first-of-pair reads replace read_prev (dna.cpp:1550-1551)
-	const uint32_t n = S.len[last];
-	for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) prev_read[i] = q[i];
-	if (threadIdx.x == 0) {
-		carry->prev_len = n;
-		if (sorted) {
-			unsigned long long d = 0;
-			for (uint32_t i = 0; i < p; ++i) { uint32_t sy = dna_code(q[i]); if (sy == 4) sy = 3; d |= (unsigned long long) sy << (62 - 2 * i); }
-			carry->pprev_dir = d; carry->pprev_valid = 1;
-		}
 	}
 }
 
@@ -308,13 +292,12 @@ __global__ void k_apply_keys(HtDev t, CIncP ci, const unsigned long long *skeys,
 //   k_sync_flags  per occurrence: cold group (c0 + m <= thr + 1: all increments deterministic) -> leader records c0 + m;
 //                 hot group -> draw flag in push order (pre-count c0 + rank > thr)
 //   (exclusive scan of the flags = absolute draw indices in push order)
-//   k_sync_scatter  per hot occurrence: draw index / flag stored at its delta entry
+//   (k_scan_flags, fqsk_pipeline.cuh, also leaves every hot occurrence's draw index / flag at its delta entry)
 //   k_sync_apply  per hot leader: members in time order, Increment() with the scanned draws; verifies the flags against the
 //                 counters it sees (they differ only when a counter saturates inside the batch) and reports a change
-//   k_sync_commit leaders write the final counters
 // ------------------------------------------------------------------------------------------------------------------
 struct SyncIn {             // inputs of a sync that only the device knows when the sync is enqueued right behind its segment
-	uint32_t ok;            // the segment settled on its first pass (k_seg_verdict); 0 = every sync kernel is a no-op
+	uint32_t ok;            // the segment settled on its first pass (k_seg_tail); 0 = every sync kernel is a no-op
 	uint32_t n_b, n_s, n_p; // rows to apply (dna.cpp:2401-2446)
 	unsigned long long dpos_b, dpos_s;   // absolute positions of the cinc_b / cinc_s streams after the segment's lookups
 	uint32_t draws_b;       // out: mt19937 outputs consumed by the b-mer inserts of this sync
@@ -371,15 +354,6 @@ __global__ void k_sync_flags(HtDev t, CIncP ci, SyncDev Y) { pdl_enter();
 	}
 	Y.flag[j] = f;
 }
-__global__ void k_sync_scatter(CIncP ci, SyncDev Y) { pdl_enter();
-	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-	if (!Y.in->ok || j >= *Y.n_dev) return;
-	const uint32_t L = Y.lead[j];
-	if (Y.lead_c0[L] + Y.lead_m[L] <= ci.thr + 1) return;
-	const uint32_t own = Y.own[j];
-	Y.draw_at[own] = Y.draw_off[j];
-	Y.flag_at[own] = Y.flag[j];
-}
 __global__ void k_sync_apply(HtDev t, CIncP ci, SyncDev Y, const unsigned long long *row,
                              const uint32_t *draws, unsigned long long dmask, unsigned long long safe_abs) { pdl_enter();
 	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -424,14 +398,6 @@ __global__ void k_sync_apply(HtDev t, CIncP ci, SyncDev Y, const unsigned long l
 	}
 	Y.final_at[L] = c;
 	ht_slot_set(t, tslot, c);
-}
-__global__ void k_sync_commit(HtDev t, SyncDev Y) { pdl_enter();
-	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-	if (!Y.in->ok || j >= *Y.n_dev) return;
-	if (Y.rank[j] != 0) return;
-	if (Y.flags[7] || Y.flags[2] || Y.flags[0]) return;     // not settled: the host iterates or falls back, nothing is written
-	const uint32_t L = Y.own[j];
-	ht_slot_set(t, Y.lead_tslot[L] & ~(1ull << 63), Y.final_at[L]);
 }
 // fallback preparation: slots claimed by k_sync_rank (counter 1) become zero-count items, i.e. the reference's fresh slot
 __global__ void k_sync_unclaim(HtDev t, SyncDev Y, uint32_t use_pre) { pdl_enter();

@@ -1233,18 +1233,6 @@ __global__ void __launch_bounds__(256) k_scan_flags(const SyncIn *in, const uint
 	}
 }
 
-// Verdict of a segment's first pass, for the sync that is enqueued right behind it without a host look: the pass settled when
-// no flag asks for another iteration, a retry or the ordered thread-local evaluator.
-__global__ void k_seg_verdict(const int *flags, const uint32_t *tot4, const unsigned long long *draws2, unsigned long long consumed_b, unsigned long long consumed_s,
-                              uint32_t row_cap, SyncIn *in) { pdl_enter();
-	if (threadIdx.x || blockIdx.x) return;
-	bool ok = !(flags[0] | flags[1] | flags[2] | flags[4] | flags[5] | flags[7]);
-	if (tot4[0] > row_cap || tot4[1] > row_cap) ok = false;
-	in->n_b = tot4[0]; in->n_s = tot4[1]; in->n_p = tot4[2];
-	in->dpos_b = consumed_b + draws2[0]; in->dpos_s = consumed_s + draws2[1];
-	in->draws_b = 0;
-	in->ok = ok ? 1u : 0u;
-}
 // status words at their start-of-segment values (layout: fqsk_create)
 __global__ void k_seg_reset(uint8_t *status, unsigned long long *counters) { pdl_enter();
 	const uint32_t t = threadIdx.x;
@@ -1255,7 +1243,9 @@ __global__ void k_seg_reset(uint8_t *status, unsigned long long *counters) { pdl
 	if (t >= 32 && t < 40) w[304 / 4 + (t - 32)] = 0;      // flags of the ordered insert
 	if (t == 40) counters[4] = 0;                          // fresh p-mer fields
 }
-// k_seg_verdict + k_save_carry in one launch (the chain of a small segment is launch-latency bound)
+// Verdict of a segment's first pass for the sync that is enqueued behind it without a host look + the state the next segment
+// inherits (read_prev, dna.cpp:1550-1551; in sorted order pmer_can_prev, dna.cpp:655), in one launch.  The pass settled when no
+// flag asks for another iteration, a retry or the ordered thread-local evaluator.
 __global__ void __launch_bounds__(256) k_seg_tail(const int *flags, const uint32_t *tot4, const unsigned long long *draws2, unsigned long long consumed_b, unsigned long long consumed_s,
                                                   uint32_t row_cap, SyncIn *in, SegDev S, uint32_t last, uint8_t *prev_read, Carry *carry, uint32_t sorted, uint32_t p,
                                                   uint32_t have_prefix, uint32_t force_fail) { pdl_enter();
