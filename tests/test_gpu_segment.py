@@ -258,3 +258,29 @@ def test_recovery_paths_of_the_enqueued_sync(var, mode, monkeypatch):
     H.assert_recs_equal(recs, want[want["pos"] < 0xFFFFFFF0])
     H.assert_dump_equal(e, g)
     e.close()
+
+
+def test_async_path_matches_oracle_config2_parameters_deep_coverage():
+    """BASELINE config-2 k-mer lengths (p17/s20/b24) at 20x coverage through the reference's schedule (100 sync segments), via
+    fqsk_submit / fqsk_collect: side streams, early grouping, enqueued syncs, saturating counters, the avg_filling_factor gate --
+    records, tables and all four PRNG positions against the oracle."""
+    genome = synth.make_genome(300_000, 77)
+    codes, _ = synth.make_reads(genome, 40_000, L=150, seed=77, n_frac=0.0005, dup_frac=0.001)
+    slab = _fastq_slab(codes)
+    pref, p, s, b = E.kmer_params(100)
+    e = E.KmerEngine(p, s, b, pref, expected_kmers=1 << 22)
+    o = O.OracleEngine(p, s, b, pref)
+    got, dup = H.run_async(e, slab)
+    want = H.run_se(o, slab)
+    n_dup = int((want["pos"] == O.POS_DUP).sum())
+    H.assert_recs_equal(got, want[want["pos"] < 0xFFFFFFF0])
+    assert int(dup.sum()) == n_dup and n_dup > 0
+    for which in (0, 1, 2):
+        kg, vg = e.dump(which)
+        ko, vo = o.dump(which)
+        assert np.array_equal(kg, ko) and np.array_equal(vg, vo), which
+    sg, so = e.stats(), o.stats()
+    for key in ("siv_no_filled", "siv_no_updates", "n_smers", "n_bmers", "draws_b", "draws_s", "draws_lb", "draws_ls"):
+        assert sg[key] == so[key], key
+    assert so["repair_missing"] > 0 and so["draws_b"] > 100_000 and so["local_hits"] > 1000
+    e.close(); o.close()
