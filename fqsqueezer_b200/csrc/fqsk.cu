@@ -1155,6 +1155,8 @@ extern "C" {
 
 const char *fqsk_last_error(fqsk_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
+static int prealloc_for_reserve(fqsk_handle *h);
+
 int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
 	fqsk_handle *h = nullptr;
 	if (!p || !out) return fail(h, FQSK_E_INVAL, "null argument");
@@ -1230,6 +1232,7 @@ int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
 			CKR(pair_alloc(h, h->pair, 1ull << (p->pair_log2_slots ? std::min<uint32_t>(std::max<uint32_t>(p->pair_log2_slots, 10), 34) : (world > 1 ? 22u : 16u))));
 		}
 		CK(cudaStreamSynchronize(h->st));
+		CKR(prealloc_for_reserve(h));
 		return FQSK_OK;
 	}();
 	if (rc != FQSK_OK) { g_create_error = h->err; fqsk_destroy(h); return rc; }
@@ -1281,6 +1284,27 @@ void fqsk_destroy(fqsk_handle *h) {
 	if (h->st) cudaStreamDestroy(h->st);
 	if (h->st_mt) cudaStreamDestroy(h->st_mt);
 	delete h;
+}
+
+// With a reserve hint everything a sync of the largest announced segment needs is allocated up front: cudaMalloc inside a run
+// costs anything from 0.1 to 600 ms depending on the state of the driver (measured: blocks 84-97 of the config-2 job, where the
+// radix-sort path, its scratch and the delta filter were first used, took 256-603 ms instead of 10 in some runs).
+static int prealloc_for_reserve(fqsk_handle *h) {
+	if (!h->P.reserve_bytes) return FQSK_OK;
+	const size_t nr = row_reserve(h, 0);
+	CK(h->sort_k.ensure(nr * 8)); CK(h->sort_v.ensure(nr * 4));
+	CKR(ensure_iota(h, (uint32_t) nr));
+	{
+		size_t bytes = 0;
+		CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned long long *) nullptr, (unsigned long long *) nullptr, (const uint32_t *) nullptr, (uint32_t *) nullptr, (int) nr, 0, 64, h->st));
+		CK(h->cub_tmp.ensure(bytes + bytes / 8));
+	}
+	CK(h->slot_of.ensure(nr * 8)); CK(h->flag8.ensure(nr + 4)); CK(h->draw_off.ensure((nr + 1) * 4)); CK(h->final_cnt.ensure(nr * 4));
+	CK(h->q4.ensure(nr + 4)); CK(h->y_flag.ensure(nr + 64));
+	if (h->world == 1 && h->P.reserve_bytes >= (1u << 20)) { CK(h->dfilter.ensure((size_t) 2 * (1u << 26) / 8)); }
+	if (h->P.mode == FQSK_MODE_PE_ORIGINAL) CK(h->pe_pool.ensure((size_t) std::max<uint32_t>(h->pe_pool_cap, 64 * (h->P.reserve_reads / 2 + 1)) * 8));
+	CK(cudaStreamSynchronize(h->st));
+	return FQSK_OK;
 }
 
 int fqsk_block_start(fqsk_handle *h) {
@@ -1524,11 +1548,20 @@ static int sync_end(fqsk_handle *h) {
 		}
 		if (h->P.mode == FQSK_MODE_PE_ORIGINAL) CKR(pe_sync(h));
 		if (!applied) {
+			// The three tables are independent (see sync_spec_enqueue): p-mer and s-mer updates run on side streams next to the ordered
+			// b-mer insert, which is a chain of sort / locate / apply launches with host looks in between.  Joined before the last look.
+			const bool fork = !h->prof && h->fast_ok[0] && h->pend_s;
+			if (fork && !h->st_side[0]) {
+				for (int i = 0; i < 2; ++i) { CK(cudaStreamCreateWithFlags(&h->st_side[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&h->ev_side[i], cudaEventDisableTiming)); }
+				CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+			}
+			cudaStream_t st_p = fork ? h->st_side[0] : h->st, st_s = fork ? h->st_side[1] : h->st;
 			// p-mers (dna.cpp:2401-2418): order-independent saturating increments; the fresh-field count is read with the next look
 			CK(cudaMemsetAsync(h->d_counters + 4, 0, 8, h->st));
+			if (fork) { CK(cudaEventRecord(h->ev_fork, h->st)); CK(cudaStreamWaitEvent(st_p, h->ev_fork, 0)); CK(cudaStreamWaitEvent(st_s, h->ev_fork, 0)); }
 			if (h->pend_p) {
 				Phase ph(h, FQSK_PH_SYNC_SIV);
-				CK(pdl(k_siv_increment, nblk(h->pend_p, 256), 256, h->st, h->siv, h->row_p.as<unsigned long long>(), h->pend_p, h->d_counters + 4, (const SyncIn *) nullptr));
+				CK(pdl(k_siv_increment, nblk(h->pend_p, 256), 256, st_p, h->siv, h->row_p.as<unsigned long long>(), h->pend_p, h->d_counters + 4, (const SyncIn *) nullptr));
 				LAUNCHED(h);
 			}
 			// s-mers and b-mers (dna.cpp:2425-2446) live in different tables and use different PRNG streams, so their rows are
@@ -1538,9 +1571,9 @@ static int sync_end(fqsk_handle *h) {
 			h->look_fresh = false;
 			if (h->fast_ok[0] && h->pend_s) {
 				Phase ph(h, FQSK_PH_SYNC_APPLY);
-				CK(cudaMemsetAsync(h->d_sfast, 0, sizeof(int), h->st));
 				CK(h->q4.ensure(row_reserve(h, h->pend_s) + 4));
-				CK(pdl(k_insert_fast, nblk(h->pend_s, 256), 256, h->st, h->ts.d, h->ts.ci, h->row_s[0].as<unsigned long long>(), h->pend_s, h->q4.as<uint8_t>(), h->d_sfast, (const SyncIn *) nullptr)); LAUNCHED(h);
+				CK(cudaMemsetAsync(h->d_sfast, 0, sizeof(int), st_s));
+				CK(pdl(k_insert_fast, nblk(h->pend_s, 256), 256, st_s, h->ts.d, h->ts.ci, h->row_s[0].as<unsigned long long>(), h->pend_s, h->q4.as<uint8_t>(), h->d_sfast, (const SyncIn *) nullptr)); LAUNCHED(h);
 				s_fast_pending = true;
 			}
 			else if (h->pend_s <= SYNC_INDEXED_MAX && !h->delta_filtered) CKR(apply_indexed(h, h->ts, h->rng[ST_S], h->seg_delta_s, h->row_s[0].as<unsigned long long>(), h->rt_s[0].as<uint32_t>(), h->pend_s));
@@ -1548,6 +1581,11 @@ static int sync_end(fqsk_handle *h) {
 			h->look_fresh = false;
 			if (h->pend_b <= SYNC_INDEXED_MAX && !h->delta_filtered) CKR(apply_indexed(h, h->tb, h->rng[ST_B], h->seg_delta_b, h->row_b[0].as<unsigned long long>(), h->rt_b[0].as<uint32_t>(), h->pend_b));
 			else CKR(apply_inserts(h, h->tb, h->rng[ST_B], h->row_b[0].as<unsigned long long>(), h->pend_b));
+			if (fork) {   // join: the looks of the b-mer path did not cover the side streams
+				CK(cudaEventRecord(h->ev_side[0], st_p)); CK(cudaEventRecord(h->ev_side[1], st_s));
+				CK(cudaStreamWaitEvent(h->st, h->ev_side[0], 0)); CK(cudaStreamWaitEvent(h->st, h->ev_side[1], 0));
+				h->look_fresh = false;
+			}
 			if (!h->look_fresh) CKR(look(h));
 			memcpy(counters, (uint8_t *) h->h_small + 512, 48);
 			if (s_fast_pending && *(int *) ((uint8_t *) h->h_small + 224)) {
