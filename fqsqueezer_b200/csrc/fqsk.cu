@@ -11,6 +11,7 @@
 // There is no CPU fallback anywhere in this file.
 #include <cub/cub.cuh>
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -105,6 +106,7 @@ struct fqsk_handle {
 	       sidx_b, sidx_s, stime_b, stime_s, sort_k, sort_v, rkind, rreg, rslot, dirty, rdraws_b, rdraws_s, totals,
 	       y_tslot, y_c0, y_m, y_draw, y_j, y_final, y_flag_at, y_own, y_lead, y_rank, y_flag, y_doff, idx_k, idx_t, idx_rt,
 	       miss_fold, hr_b[3], hr_s[3], evk[2], evv[2], evk_s[2], evv_s[2];
+	unsigned long long look_seq = 0;         // sequence number of the last published look (k_publish)
 	bool look_fresh = false;                 // h_small holds the status block + counters as of the end of everything enqueued so far
 	int *d_sfast = nullptr;                  // inside d_status: the s-mer fast path saw a counter above thr
 	int *d_sflags = nullptr;                 // inside d_status: flags of the ordered insert ([0] window short [2] flag corrected [6] hot k-mer [7] group too large)
@@ -585,10 +587,28 @@ int indexed_tail(fqsk_handle *h, Table &t, Stream &rng, const SyncDev &Y, const 
 // one look at the device: the whole status block, the item counters and the fresh p-mer field count
 int look(fqsk_handle *h) {
 	uint8_t *hs = (uint8_t *) h->h_small;
-	CK(cudaMemcpyAsync(hs, h->d_status, 512, cudaMemcpyDeviceToHost, h->st));
-	CK(cudaMemcpyAsync(hs + 512, h->d_counters, 48, cudaMemcpyDeviceToHost, h->st));
-	CK(cudaStreamSynchronize(h->st));
-	resolve_phases(h);
+	if (h->prof) {
+		CK(cudaMemcpyAsync(hs, h->d_status, 512, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaMemcpyAsync(hs + 512, h->d_counters, 48, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaStreamSynchronize(h->st));
+		resolve_phases(h);
+		h->look_fresh = true;
+		return FQSK_OK;
+	}
+	// One small kernel stores the status block and the counters into the page-locked look buffer (device-accessible under UVA) and
+	// then a sequence number; the host spins on that number.  Two copies and a stream synchronisation through the driver cost
+	// 10-20 us of wake-up latency per look -- once per sync segment, i.e. ~5 % of a small segment -- and jitter with the host load.
+	volatile unsigned long long *seq = (volatile unsigned long long *) (hs + 896);
+	const unsigned long long want = ++h->look_seq;
+	CK(pdl(k_publish, 1, 160, h->st, (const uint32_t *) h->d_status, (const unsigned long long *) h->d_counters, (uint32_t *) hs, (unsigned long long *) (hs + 896), want)); LAUNCHED(h);
+	for (uint64_t spins = 0; *seq != want; ++spins) {
+		if ((spins & 0xFFFF) == 0xFFFF) {      // a failed launch or a faulting kernel would never publish
+			cudaError_t e = cudaStreamQuery(h->st);
+			if (e != cudaSuccess && e != cudaErrorNotReady) return fail(h, FQSK_E_CUDA, "look: %s", cudaGetErrorString(e));
+			if (e == cudaSuccess && *seq != want) return fail(h, FQSK_E_CUDA, "look: the status block was not published");
+		}
+	}
+	std::atomic_thread_fence(std::memory_order_acquire);
 	h->look_fresh = true;
 	return FQSK_OK;
 }
@@ -1199,6 +1219,7 @@ int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
 		CK(cudaMalloc(&h->d_counters, 8 * 8));
 		CK(cudaMemset(h->d_counters, 0, 64));
 		CK(cudaMallocHost(&h->h_small, 1024));
+		memset(h->h_small, 0, 1024);
 		uint64_t expect = p->expected_kmers ? p->expected_kmers : (1ull << 22);
 		uint32_t Bauto = 1;
 		while ((4ull << Bauto) < expect && Bauto < 30) ++Bauto;    // <= 50 % of 8 << B slots

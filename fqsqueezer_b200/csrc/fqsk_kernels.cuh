@@ -25,36 +25,35 @@ __device__ __forceinline__ uint32_t mt_twist(uint32_t a, uint32_t b, uint32_t fa
 	uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
 	return far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
 }
+// Double-buffered: the three phases of a block read the previous state from one array and write the new one into the other, so
+// only the 3 true dependencies between the phases need a barrier (an in-place version needs 7 per block),
+// and every thread tempers and stores the word it has just produced.  The generator is one CTA on a side stream and late in a
+// file the b-mer counters consume ~6 M draws per 51 000-read block: its speed bounds the sync of the main stream.
 __global__ void __launch_bounds__(256) k_mt_extend(uint32_t *state, uint32_t *ring, unsigned long long mask, unsigned long long pos, uint32_t n_blocks) {
-	__shared__ uint32_t st[624];
+	__shared__ uint32_t st[2][624];
 	const int t = threadIdx.x;
-	for (int i = t; i < 624; i += 256) st[i] = state[i];
+	for (int i = t; i < 624; i += 256) st[0][i] = state[i];
 	__syncthreads();
+	int cur = 0;
 	for (uint32_t blk = 0; blk < n_blocks; ++blk) {
-		uint32_t v;
-		// phase A: i in [0, 227) uses old st[i], st[i+1], st[i+397]
-		if (t < 227) v = mt_twist(st[t], st[t + 1], st[t + 397]);
-		__syncthreads();
-		if (t < 227) st[t] = v;
-		__syncthreads();
-		// phase B: i in [227, 454) uses old st[i], st[i+1] and NEW st[i-227]
-		if (t < 227) v = mt_twist(st[t + 227], st[t + 228], st[t]);
-		__syncthreads();
-		if (t < 227) st[t + 227] = v;
-		__syncthreads();
-		// phase C: i in [454, 624): i < 623 uses old st[i], st[i+1], new st[i-227]; i = 623 wraps to new st[0]
-		if (t < 170) { int i = t + 454; v = mt_twist(st[i], i == 623 ? st[0] : st[i + 1], st[i - 227]); }
-		__syncthreads();
-		if (t < 170) st[t + 454] = v;
-		__syncthreads();
-		for (int i = t; i < 624; i += 256) {
-			uint32_t y = st[i];
+		const uint32_t *o = st[cur];
+		uint32_t *nw = st[cur ^ 1];
+		const unsigned long long base = pos + (unsigned long long) blk * 624;
+		auto emit = [&](int i, uint32_t v) {
+			nw[i] = v;
+			uint32_t y = v;
 			y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
-			ring[(pos + (uint64_t) blk * 624 + i) & mask] = y;
-		}
+			ring[(base + i) & mask] = y;
+		};
+		if (t < 227) emit(t, mt_twist(o[t], o[t + 1], o[t + 397]));                                   // i in [0, 227): old i, i+1, i+397
+		__syncthreads();
+		if (t < 227) emit(t + 227, mt_twist(o[t + 227], o[t + 228], nw[t]));                          // i in [227, 454): old i, i+1, NEW i-227
+		__syncthreads();
+		if (t < 170) { const int i = t + 454; emit(i, mt_twist(o[i], i == 623 ? nw[0] : o[i + 1], nw[i - 227])); }   // i in [454, 624)
+		__syncthreads();
+		cur ^= 1;
 	}
-	__syncthreads();
-	for (int i = t; i < 624; i += 256) state[i] = st[i];
+	for (int i = t; i < 624; i += 256) state[i] = st[cur][i];
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -1233,6 +1233,16 @@ __global__ void __launch_bounds__(256) k_scan_flags(const SyncIn *in, const uint
 	}
 }
 
+// the host's look at the device: status block (128 words) + counters (6 x u64) into the page-locked look buffer, then -- after a
+// system-wide fence -- the sequence number the host is spinning on
+__global__ void __launch_bounds__(160) k_publish(const uint32_t *status, const unsigned long long *counters, uint32_t *out, unsigned long long *seq, unsigned long long want) { pdl_enter();
+	const uint32_t t = threadIdx.x;
+	if (t < 128) out[t] = status[t];
+	else if (t < 134) reinterpret_cast<unsigned long long *>(out + 128)[t - 128] = counters[t - 128];
+	__threadfence_system();
+	__syncthreads();
+	if (t == 0) { *reinterpret_cast<volatile unsigned long long *>(seq) = want; __threadfence_system(); }
+}
 // status words at their start-of-segment values (layout: fqsk_create)
 __global__ void k_seg_reset(uint8_t *status, unsigned long long *counters) { pdl_enter();
 	const uint32_t t = threadIdx.x;
