@@ -185,7 +185,9 @@ int fqsk_sync_apply(fqsk_handle *h, uint64_t *fresh, uint64_t *updates);
  * ClearKmersToHT.  The call sequence must be completed on all ranks before any of them starts its next segment. */
 int fqsk_sync_finish(fqsk_handle *h, uint64_t fresh_all_ranks, uint64_t updates_all_ranks);
 
-/* Sorted (key, value) contents: FQSK_TABLE_SIV -> (p-mer index, 2-bit field); SMER/BMER -> (normalised k-mer, counter);
+/* Call after fqsk_sync, not between a segment and its sync (the grouping half of a small segment's sync may already be enqueued:
+ * FQSK_E_INVAL).
+ * Sorted (key, value) contents: FQSK_TABLE_SIV -> (p-mer index, 2-bit field); SMER/BMER -> (normalised k-mer, counter);
  * PAIR -> (key minimizer, value minimizer | count << 2b), the items of CHT_pair_kmers (ht_kmer.h:566-571).
  * Call with keys == NULL to get the count in *n.  Replaces nothing in the reference; parity check 1. */
 int fqsk_dump(fqsk_handle *h, int table, uint64_t *keys, uint64_t *vals, uint64_t cap, uint64_t *n);
