@@ -1,6 +1,6 @@
 """Measurement helper: throughput of the device mt19937 generator (k_mt_extend) through fqsk_mt_stream, incl. ring allocation and D2H."""
-import sys, time
-sys.path.insert(0, "/root/repo")
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from fqsqueezer_b200 import engine as E
 pref, p, s, b = E.kmer_params(100)

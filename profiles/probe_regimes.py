@@ -1,6 +1,9 @@
+"""Measurement helper: wall clock per block / per segment of the device-resident path (fqsk_segment_device + fqsk_sync) for a
+few block generations of config 2 -- 100 syncs per block, ..., one 51 000-read segment.  Tables stay young in this short run, so the
+large segments do more rough searches than in the real job; use bench.py --trace-blocks for the steady state."""
 import sys, time, os
 import numpy as np, torch
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench as B
 from fqsqueezer_b200 import engine as E, schedule as S, synth
 pref, p, s, b = E.kmer_params(B.GS)
