@@ -447,4 +447,14 @@ def main():
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    # stdout carries the ONE JSON line and nothing else: libraries that write to file descriptor 1 (NCCL prints its version
+    # there when the first communicator is created) are sent to stderr, the JSON line goes to the saved descriptor
+    sys.stdout.flush()
+    _real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = _real_stdout
+    try:
+        rc = main()
+    finally:
+        _real_stdout.flush()
+    sys.exit(rc)
