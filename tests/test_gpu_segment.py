@@ -284,3 +284,35 @@ def test_async_path_matches_oracle_config2_parameters_deep_coverage():
         assert sg[key] == so[key], key
     assert so["repair_missing"] > 0 and so["draws_b"] > 100_000 and so["local_hits"] > 1000
     e.close(); o.close()
+
+
+def test_large_paired_end_segments_match_oracle():
+    """Paired-end segments above 1 MiB of DNA (work items through the filtered delta, radix-sort sync, pair-table growth): records,
+    pair decisions and all four tables vs the oracle."""
+    genome = synth.make_genome(1_500_000, 41)
+    slab = _pe_slab(genome, 8_400, 150, 41, nfrac=0.0005, dup_every=500)
+    S_ = __import__("fqsqueezer_b200.schedule", fromlist=["x"])
+    off, ln, _, _ = S_.parse_fastq(slab)
+    pref, p, s, b = E.kmer_params(16)
+    e = E.KmerEngine(p, s, b, pref, mode=E.MODE_PE_ORIGINAL, expected_kmers=1 << 21)
+    o = O.OracleEngine(p, s, b, pref, mode=2)
+    for eng in (e, o):
+        eng.block_start()
+    for a, bb in ((0, 8400), (8400, 16800)):
+        rg, dg = e.segment(slab, off[a:bb], ln[a:bb])
+        ig = e.pair_info((bb - a) // 2)
+        ro, do = o.segment(slab, off[a:bb], ln[a:bb], 3)
+        io = ro[ro["pos"] == H.POS_PAIR]["c"][:, :3].astype(np.uint32)
+        assert np.array_equal(ig, io)
+        H.assert_recs_equal(rg, ro[ro["pos"] < 0xFFFFFFF0])
+        assert np.array_equal(dg, do)
+        e.sync(); o.sync()
+    for which in (0, 1, 2, 3):
+        kg, vg = e.dump(which)
+        ko, vo = o.dump(which)
+        assert np.array_equal(kg, ko) and np.array_equal(vg, vo), which
+    sg, so = e.stats(), o.stats()
+    for key in ("siv_no_filled", "siv_no_updates", "n_smers", "n_bmers", "draws_b", "draws_s", "draws_lb", "draws_ls"):
+        assert sg[key] == so[key], key
+    assert sg["n_filtered_segments"] == 2 and (io[:, 0] == 1).sum() > 100
+    e.close(); o.close()
