@@ -741,6 +741,7 @@ __global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P, 
 		} else {
 			i0 += 32;
 		}
+		__syncwarp();      // the next iteration refills ring slots that lanes of this one may still be reading (commit block)
 	}
 	changed = __any_sync(0xffffffffu, changed);
 	window_local = __any_sync(0xffffffffu, window_local);
