@@ -1,0 +1,140 @@
+#!/usr/bin/env python3
+"""Builds host/_bin/fqs-1.1-fqsk: the reference compressor (refresh-bio/fqsqueezer 1.1) with its k-mer engine replaced by
+libfqsk.so -- the drop-in of INTEGRATION.md, compiled, not sketched.
+
+The reference's own sources are compiled from a scratch copy under /tmp (nothing from /root/reference enters the repository;
+host/_bin/ is git-ignored and travels to the GPU box like our own .so files).  The patch below is the whole reference-side change:
+
+  application.cpp  AdjustToParams (86-91)      the engine is created in place of siv_pmer / ht_smer / ht_bmer (which shrink to stubs)
+                   SE worker loop (617-662)    fqsk_block_start per reads_block; ONE fqsk_segment before the worker codes the reads of a
+                                               sync segment; fqsk_sync in place of InsertKmersToHT + ClearKmersToHT
+  dna.cpp          compress_suffix (674-877)   counts / level / rough flag / cor_pos of every coded base come from the segment's records;
+                                               find_counts, the rough searches, repairs, pushes, thread-local inserts and prefetches are gone
+  everything else (context model, range coders, id / quality / meta streams, container, decompressor) is untouched.
+
+host/fqsk_live.h (ours) holds the binding itself (dlopen of $FQSK_LIB, descriptors, record cursor).
+Scope this round: -s -om o -t 1.  No-op (exit 0) where /root/reference does not exist (the GPU box uses the prebuilt binary).
+"""
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.environ.get("FQS_REFERENCE", "/root/reference")
+SRC = os.path.join(REF, "fqs")
+OUT = os.path.join(HERE, "_bin")
+EXE = os.path.join(OUT, "fqs-1.1-fqsk")
+CXXFLAGS = ["-O3", "-m64", "-std=c++14", "-pthread", "-mavx", "-include", "cstdint", "-w"]   # the reference's own flags (makefile) + cstdint (defs.h:15)
+
+
+def replace_once(s, old, new, where):
+    assert s.count(old) >= 1, f"anchor not found in {where}: {old!r}"
+    return s.replace(old, new, 1)
+
+
+def patch_application(path):
+    s = open(path, encoding="latin-1").read()
+    s = replace_once(s, '#include "application.h"\n', '#include "application.h"\n#include "fqsk_live.h"\n', path)
+    # application.cpp:86-91 -- the engine replaces the three global tables; the CPU objects stay as stubs nobody reads
+    s = replace_once(s, "\tsiv_pmer = new TSmallIntVector<SIV_FIELD_SIZE>(2 * params.pmer_len);\n"
+                        "\tht_smer = new CHT_kmer<uint32_t>(params.smer_len, SMER_COUNTER_BITS, params.ht_max_filling_factor);\n"
+                        "\tht_bmer = new CHT_kmer<uint32_t>(params.bmer_len, BMER_COUNTER_BITS, params.ht_max_filling_factor);\n",
+                     "\tCFqskLive::get().create(params.pmer_len, params.smer_len, params.bmer_len, params.prefix_len, params.genome_size,\n"
+                     "\t\tparams.dna_mode == dna_mode_t::se_original, (uint32_t) params.no_threads, params.duplicates_check);\n"
+                     "\tsiv_pmer = new TSmallIntVector<SIV_FIELD_SIZE>(8);\n"
+                     "\tht_smer = new CHT_kmer<uint32_t>(12, SMER_COUNTER_BITS, params.ht_max_filling_factor);\n"
+                     "\tht_bmer = new CHT_kmer<uint32_t>(12, BMER_COUNTER_BITS, params.ht_max_filling_factor);\n", path)
+    # application.cpp:624 -- start of a reads_block (first hit = the single-end compress loop)
+    s = replace_once(s, "\t\t\t\tdna_comp.ResetReadPrev();\n",
+                     "\t\t\t\tdna_comp.ResetReadPrev();\n"
+                     "\t\t\t\tCFqskLive::get().block_start(reads_block_cur->input_FASTQ, reads_block_cur->filled_size);\n"
+                     "\t\t\t\tuint64_t fqsk_seg_begin = my_first;\n", path)
+    # application.cpp:630 -- first read of a sync segment: the engine resolves the whole segment [i, next_synchro] (or the tail of the block)
+    s = replace_once(s, "\t\t\t\t\tauto &cur_read = reads_block_cur->v_reads[i];\n",
+                     "\t\t\t\t\tif (i == fqsk_seg_begin)\n\t\t\t\t\t{\n"
+                     "\t\t\t\t\t\tuint64_t fqsk_seg_last = (next_synchro >= i && next_synchro < my_last) ? next_synchro : my_last - 1;\n"
+                     "\t\t\t\t\t\tCFqskLive::get().segment(&reads_block_cur->v_reads[i], fqsk_seg_last - i + 1);\n"
+                     "\t\t\t\t\t}\n"
+                     "\t\t\t\t\tauto &cur_read = reads_block_cur->v_reads[i];\n", path)
+    # application.cpp:645-649 -- the sync inside a block
+    s = replace_once(s, "\t\t\t\t\t\tdna_comp.InsertKmersToHT();\n\t\t\t\t\t\tbar_synchro.count_down_and_wait();\n\t\t\t\t\t\tdna_comp.ClearKmersToHT();\n",
+                     "\t\t\t\t\t\tCFqskLive::get().sync();\n\t\t\t\t\t\tfqsk_seg_begin = i + 1;\n\t\t\t\t\t\tbar_synchro.count_down_and_wait();\n", path)
+    # application.cpp:657-661 -- the sync at the end of a block (over an empty segment when the last read closed one)
+    s = replace_once(s, "\t\t\t\tbar_synchro.count_down_and_wait();\n\t\t\t\tdna_comp.InsertKmersToHT();\n\t\t\t\tbar_synchro.count_down_and_wait();\n\t\t\t\tdna_comp.ClearKmersToHT();\n",
+                     "\t\t\t\tbar_synchro.count_down_and_wait();\n"
+                     "\t\t\t\tif (fqsk_seg_begin >= my_last)\n\t\t\t\t\tCFqskLive::get().segment(reads_block_cur->v_reads.data(), 0);\n"
+                     "\t\t\t\tCFqskLive::get().sync();\n\t\t\t\tbar_synchro.count_down_and_wait();\n", path)
+    # the workers have joined (application.cpp:762): engine statistics, release
+    s = replace_once(s, "\tv_thr_compress.clear();\n", "\tv_thr_compress.clear();\n\tCFqskLive::get().finish();\n", path)
+    open(path, "w", encoding="latin-1").write(s)
+
+
+def patch_dna(path):
+    s = open(path, encoding="latin-1").read()
+    s = replace_once(s, '#include "dna.h"\n', '#include "dna.h"\n#include "fqsk_live.h"\n', path)
+    a0 = s.index("void CDNACompressor::compress_suffix(")
+    a1 = s.index("\n//****", a0)
+    f = s[a0:a1]
+    # dna.cpp:695 -- the count vector of a coded base comes from the segment's records
+    f = replace_once(f, "\t\tcounts_level_t counts_level = find_counts(counts);\n",
+                     "\t\tconst fqs_rp_rec rp_rec = fqs_rp_next(i);\n"
+                     "\t\tfor (int q = 0; q < 4; ++q) counts[q] = rp_rec.c[q];\n"
+                     "\t\tcounts_level_t counts_level = (counts_level_t) rp_rec.level;\n"
+                     "\t\tcor_pos = rp_rec.cor_pos;\n", path)
+    # dna.cpp:709-735 -- no rough searches on the host; the rough flag rides in the record
+    a = "\t\tif (counts_level == counts_level_t::none)\n\t\t{\n\t\t\tif (bmer_can.is_full())\n\t\t\t{\n\t\t\t\tif (find_counts_rough_b(counts))"
+    f = replace_once(f, a, a.replace("if (counts_level == counts_level_t::none)", "if (false)"), path)
+    a = "\t\tif (counts_level != counts_level_t::none && N_run_len < 2)\n\t\t{\n\t\t\tint cor_dist"
+    f = replace_once(f, a, "\t\trough_counts = rp_rec.rough != 0;\n" + a, path)
+    # dna.cpp:765-773, 785-793 -- no table prefetches: the tables live in HBM
+    assert f.count("if(bmer_can.is_almost_full(1))") + f.count("if (bmer_can.is_almost_full(1))") == 2
+    f = f.replace("if(bmer_can.is_almost_full(1))", "if (false)").replace("if (bmer_can.is_almost_full(1))", "if (false)")
+    # dna.cpp:810-876 -- no register updates, pushes, thread-local inserts or repairs on the host
+    a = "\t\tpmer_can.replace_last(sym_to_kmers);\n\t\tsmer_can.replace_last(sym_to_kmers);\n\t\tbmer_can.replace_last(sym_to_kmers);\n"
+    f = replace_once(f, a, "\t\tcontinue;\n" + a, path)
+    # dna.cpp:684-693 -- the six register shifts at the top of the loop body have no reader left
+    a = ("\t\tpmer_can.insert_zero();\n\t\tsmer_can.insert_zero();\n\t\tbmer_can.insert_zero();\n\n"
+         "\t\tpmer_can_unc.insert_zero();\n\t\tsmer_can_unc.insert_zero();\n\t\tbmer_can_unc.insert_zero();\n")
+    f = replace_once(f, a, "", path)
+    s = s[:a0] + f + s[a1:]
+    open(path, "w", encoding="latin-1").write(s)
+
+
+def compile_dir(src_dir, build_dir, exe):
+    os.makedirs(build_dir, exist_ok=True)
+    cpps = sorted(f for f in os.listdir(src_dir) if f.endswith(".cpp"))
+
+    def one(f):
+        o = os.path.join(build_dir, f[:-4] + ".o")
+        subprocess.run(["g++", *CXXFLAGS, "-I", src_dir, "-I", os.path.join(ROOT, "include"), "-I", HERE, "-c", os.path.join(src_dir, f), "-o", o], check=True)
+        return o
+
+    with ThreadPoolExecutor(8) as ex:
+        objs = list(ex.map(one, cpps))
+    subprocess.run(["g++", "-O3", "-pthread", "-o", exe, *objs, "-lm", "-ldl"], check=True)
+
+
+def main():
+    if not os.path.isdir(SRC):
+        print(f"[build_host] {SRC} not present -- keeping prebuilt host/_bin (if any)")
+        return 0
+    scratch = os.path.join(os.environ.get("FQS_REF_SCRATCH", "/tmp/fqs_ref_build"), "host_src")
+    if os.path.exists(scratch):
+        shutil.rmtree(scratch)
+    os.makedirs(scratch)
+    os.makedirs(OUT, exist_ok=True)
+    for f in os.listdir(SRC):
+        if f.endswith((".h", ".cpp")):
+            shutil.copy(os.path.join(SRC, f), scratch)
+    patch_application(os.path.join(scratch, "application.cpp"))
+    patch_dna(os.path.join(scratch, "dna.cpp"))
+    compile_dir(scratch, os.path.join(os.path.dirname(scratch), "host_obj"), EXE)
+    print("[build_host] ok:", EXE)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

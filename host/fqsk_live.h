@@ -1,0 +1,164 @@
+// fqsk_live.h -- the reference-side binding of libfqsk.so: what a maintainer of refresh-bio/fqsqueezer adds to the tree so that
+// CApplication's worker loop (application.cpp:575-671) and CDNACompressor::compress_suffix (dna.cpp:674-877) take the k-mer
+// statistics of every coded base from the B200 engine instead of CHT_kmer / TSmallIntVector / CKmer.
+//
+// This file is OUR code (no reference source in it).  host/build_host.py compiles the reference's own sources -- where they lie,
+// patched in a scratch copy -- with this header into host/_bin/fqs-1.1-fqsk.  INTEGRATION.md walks through the patch.
+//
+// Scope of the live host this round: single-end, original order, -t 1 (the parity configuration of the north star).  Anything
+// else stops with a message: there is no CPU fallback for the k-mer path.
+//
+// The library is bound with dlopen ($FQSK_LIB, default "libfqsk.so") so that the binary has no link-time CUDA dependency and the
+// CPU test suite can point it at a mock built from the oracle (tests/mock_fqsk.cpp) to check the HOST half of the integration.
+#pragma once
+#include <dlfcn.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "fqsk.h"
+
+struct fqs_rp_rec { uint32_t pos; uint32_t c[4]; uint32_t cor_pos; uint8_t level; uint8_t rough; uint16_t pad; };
+static_assert(sizeof(fqs_rp_rec) == sizeof(fqsk_base_rec), "record layout");
+
+class CFqskLive {
+	void *lib = nullptr;
+	decltype(&fqsk_create) p_create = nullptr;
+	decltype(&fqsk_destroy) p_destroy = nullptr;
+	decltype(&fqsk_last_error) p_last_error = nullptr;
+	decltype(&fqsk_block_start) p_block_start = nullptr;
+	decltype(&fqsk_segment) p_segment = nullptr;
+	decltype(&fqsk_sync) p_sync = nullptr;
+	decltype(&fqsk_stats_get) p_stats = nullptr;
+	decltype(&fqsk_host_alloc) p_host_alloc = nullptr;
+	decltype(&fqsk_host_free) p_host_free = nullptr;
+
+	fqsk_handle *h = nullptr;
+	const uint8_t *slab = nullptr;
+	uint64_t slab_size = 0;
+	std::vector<fqsk_read_desc> descs;
+	fqsk_base_rec *recs = nullptr;
+	uint64_t rec_cap = 0, n_recs = 0, cursor = 0;
+	std::vector<uint8_t> dup;
+	uint64_t n_segments = 0, n_syncs = 0, n_bases = 0;
+	double engine_s = 0;
+
+	[[noreturn]] void die(const char *what, int rc = 0) {
+		fprintf(stderr, "fqsk: %s%s%s (rc %d)\n", what, (h || p_last_error) ? ": " : "", p_last_error ? p_last_error(h) : "", rc);
+		exit(3);
+	}
+	template <typename F> void sym(F &f, const char *name) {
+		f = (F) dlsym(lib, name);
+		if (!f) { fprintf(stderr, "fqsk: %s does not export %s\n", getenv("FQSK_LIB") ? getenv("FQSK_LIB") : "libfqsk.so", name); exit(3); }
+	}
+	static double now() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+
+public:
+	static CFqskLive &get() { static CFqskLive x; return x; }
+
+	// application.cpp:86-91 (AdjustToParams): the engine takes the place of siv_pmer / ht_smer / ht_bmer
+	void create(uint32_t pmer_len, uint32_t smer_len, uint32_t bmer_len, uint32_t prefix_len, uint64_t genome_mbp, bool se_original, uint32_t n_threads, bool dup_check) {
+		if (!se_original || n_threads != 1 || !dup_check) { fprintf(stderr, "fqsk: the live host covers -s -om o -t 1 with the duplicates check on; no CPU fallback for other modes\n"); exit(3); }
+		const char *path = getenv("FQSK_LIB");
+		lib = dlopen(path ? path : "libfqsk.so", RTLD_NOW | RTLD_LOCAL);
+		if (!lib) { fprintf(stderr, "fqsk: cannot load the k-mer engine (%s); set FQSK_LIB. There is no CPU fallback.\n", dlerror()); exit(3); }
+		sym(p_create, "fqsk_create"); sym(p_destroy, "fqsk_destroy"); sym(p_last_error, "fqsk_last_error"); sym(p_block_start, "fqsk_block_start");
+		sym(p_segment, "fqsk_segment"); sym(p_sync, "fqsk_sync"); sym(p_stats, "fqsk_stats_get"); sym(p_host_alloc, "fqsk_host_alloc"); sym(p_host_free, "fqsk_host_free");
+		fqsk_params P;
+		memset(&P, 0, sizeof(P));
+		P.abi_version = FQSK_ABI_VERSION;
+		P.pmer_len = pmer_len; P.smer_len = smer_len; P.bmer_len = bmer_len; P.prefix_len = prefix_len;
+		P.smer_counter_bits = 12; P.bmer_counter_bits = 6;                       // defs.h:26-27
+		P.mode = FQSK_MODE_SE_ORIGINAL;
+		P.n_workers = 1; P.world_size = 1; P.rank = 0;
+		P.device = getenv("FQSK_DEVICE") ? atoi(getenv("FQSK_DEVICE")) : 0;
+		uint64_t expect = genome_mbp * 3000000ull;                               // genomic + error k-mers; the tables grow when half full
+		if (const char *e = getenv("FQSK_EXPECTED_KMERS")) expect = strtoull(e, nullptr, 10);
+		P.expected_kmers = expect < (1ull << 22) ? (1ull << 22) : expect > (1ull << 30) ? (1ull << 30) : expect;
+		P.reserve_reads = 1u << 17; P.reserve_bytes = 16u << 20;                 // one reads_block (application.h:34) is the largest segment
+		int rc = p_create(&P, &h);
+		if (rc != FQSK_OK) { h = nullptr; die("fqsk_create", rc); }
+	}
+	bool on() const { return h != nullptr; }
+
+	// application.cpp:624 (dna_comp.ResetReadPrev() at the start of a reads_block)
+	void block_start(const uint8_t *input_FASTQ, uint64_t filled_size) {
+		slab = input_FASTQ; slab_size = filled_size;
+		int rc = p_block_start(h);
+		if (rc != FQSK_OK) die("fqsk_block_start", rc);
+	}
+
+	// One sync segment: reads[0 .. n) of the current block, i.e. the reads the worker codes before the next InsertKmersToHT.
+	// RD is the reference's read_desc_t (defs.h:58-85): only .dna and .read_len() are used.
+	template <typename RD> void segment(RD *reads, uint64_t n) {
+		descs.resize(n);
+		uint64_t total = 0;
+		for (uint64_t k = 0; k < n; ++k) {
+			descs[k].dna_off = (uint64_t) (reads[k].dna - slab);
+			descs[k].dna_len = reads[k].read_len();
+			descs[k].flags = 0;
+			total += descs[k].dna_len;
+		}
+		if (total + 1 > rec_cap) {
+			if (recs) p_host_free(recs);
+			rec_cap = total + total / 4 + 4096;
+			void *p = nullptr;
+			int rc = p_host_alloc(rec_cap * sizeof(fqsk_base_rec), &p);
+			if (rc != FQSK_OK) die("fqsk_host_alloc", rc);
+			recs = (fqsk_base_rec *) p;
+		}
+		dup.resize(n + 1);
+		const double t0 = now();
+		int rc = p_segment(h, slab, slab_size, descs.data(), (uint32_t) n, recs, rec_cap, &n_recs, dup.data(), nullptr);
+		engine_s += now() - t0;
+		if (rc != FQSK_OK) die("fqsk_segment", rc);
+		cursor = 0;
+		++n_segments; n_bases += total;
+	}
+
+	// dna.cpp:695 -- the record of the base compress_suffix is about to code
+	const fqsk_base_rec &next(uint32_t expect_pos) {
+		if (cursor >= n_recs) { fprintf(stderr, "fqsk: record stream of the segment ended early (position %u)\n", expect_pos); exit(3); }
+		const fqsk_base_rec &r = recs[cursor++];
+		if (r.pos != expect_pos) { fprintf(stderr, "fqsk: record for position %u where %u is being coded\n", r.pos, expect_pos); exit(3); }
+		return r;
+	}
+
+	// application.cpp:645-654 and 657-661: InsertKmersToHT + ClearKmersToHT between the barriers
+	void sync() {
+		if (cursor != n_recs) { fprintf(stderr, "fqsk: %llu records of the segment were not consumed\n", (unsigned long long) (n_recs - cursor)); exit(3); }
+		const double t0 = now();
+		int rc = p_sync(h);
+		engine_s += now() - t0;
+		if (rc != FQSK_OK) die("fqsk_sync", rc);
+		n_recs = cursor = 0;
+		++n_syncs;
+	}
+
+	void finish() {
+		if (!h) return;
+		if (getenv("FQSK_VERBOSE")) {
+			fqsk_stats st; memset(&st, 0, sizeof(st));
+			p_stats(h, &st);
+			fprintf(stderr, "fqsk: %llu segments, %llu syncs, %llu bases, %.3f s inside the engine calls, %llu kernel launches, %llu s-mers, %llu b-mers\n",
+			        (unsigned long long) n_segments, (unsigned long long) n_syncs, (unsigned long long) n_bases, engine_s,
+			        (unsigned long long) st.kernel_launches, (unsigned long long) st.n_smers, (unsigned long long) st.n_bmers);
+		}
+		if (recs) p_host_free(recs);
+		recs = nullptr;
+		p_destroy(h);
+		h = nullptr;
+	}
+};
+
+// names the dna.cpp patch uses (same as the file-replay build of oracle/build_ref.py, so the two patches stay one text)
+inline bool fqs_rp_on() { return true; }
+inline fqs_rp_rec fqs_rp_next(uint32_t expect_pos) {
+	const fqsk_base_rec &k = CFqskLive::get().next(expect_pos);
+	fqs_rp_rec r;
+	memcpy(&r, &k, sizeof(r));
+	return r;
+}

@@ -1,0 +1,94 @@
+"""The drop-in, compiled: host/_bin/fqs-1.1-fqsk is the reference compressor with its k-mer engine replaced by the C-ABI of
+include/fqsk.h (host/build_host.py + host/fqsk_live.h).  It binds the library with dlopen($FQSK_LIB).
+
+CPU leg : $FQSK_LIB = a mock built from the oracle (tests/mock_fqsk.cpp).  Checks the HOST half -- the patched worker loop
+          (segment boundaries, block starts, end-of-block syncs) and compress_suffix consuming records.
+GPU leg : $FQSK_LIB = fqsqueezer_b200/libfqsk.so.  The whole thing: reads_block slabs -> fqsk_segment / fqsk_sync on the B200 ->
+          the reference's context model and range coders.
+Both: the .fqs is byte-identical to the unmodified `fqs-1.1 -t 1` and the unmodified binary decodes it back to the input.
+The binaries are built from /root/reference by __graft_entry__.build() and travel to the GPU box (host/_bin, oracle/_ref)."""
+import os
+import subprocess
+import tempfile
+
+import pytest
+
+from fqsqueezer_b200 import synth
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIVE_BIN = os.path.join(ROOT, "host", "_bin", "fqs-1.1-fqsk")
+REAL_LIB = os.path.join(ROOT, "fqsqueezer_b200", "libfqsk.so")
+needs_bins = pytest.mark.skipif(not (os.path.exists(O.REF_BIN) and os.path.exists(LIVE_BIN)), reason="host/_bin or oracle/_ref not built")
+
+# (gs, genome, reads, read length, seed, N fraction, duplicate fraction)
+CASES = [(1, 6000, 4000, 100, 31, 0.002, 0.01), (100, 40000, 3000, 150, 32, 0.0, 0.0)]
+# > 1 reads_block (16 MiB slabs): block starts, decreasing sync counts, end-of-block syncs
+BIG = (100, 400000, 60000, 150, 33, 0.0005, 0.002)
+
+
+def _fastq(tmp, gs, G, n, L, seed, n_frac, dup_frac):
+    genome = synth.make_genome(G, seed)
+    codes, err = synth.make_reads(genome, n, L=L, seed=seed, n_frac=n_frac, dup_frac=dup_frac)
+    fq = os.path.join(tmp, "in.fastq")
+    synth.write_fastq(fq, codes, err, seed=seed)
+    return fq
+
+
+def _build_mock(tmp):
+    O.build_oracle()
+    so = os.path.join(tmp, "libfqsk_mock.so")
+    odir = os.path.dirname(O.ORACLE_SO)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", os.path.join(ROOT, "tests", "mock_fqsk.cpp"), "-I", os.path.join(ROOT, "include"),
+                    "-L", odir, "-l:libfqs_oracle.so", f"-Wl,-rpath,{odir}", "-o", so], check=True)
+    return so
+
+
+def _check(lib, gs, tmp, fq, decode=True):
+    base = ["e", "-s", "-om", "o", "-qm", "o", "-im", "o", "-t", "1", "-gs", str(gs), "-v", "0"]
+    plain, ours = os.path.join(tmp, "plain.fqs"), os.path.join(tmp, "ours.fqs")
+    subprocess.run([O.REF_BIN, *base, "-out", plain, fq], check=True, cwd=tmp, stdout=subprocess.DEVNULL)
+    r = subprocess.run([LIVE_BIN, *base, "-out", ours, fq], cwd=tmp, env=dict(os.environ, FQSK_LIB=lib, FQSK_VERBOSE="1"), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-600:]
+    a, b = open(plain, "rb").read(), open(ours, "rb").read()
+    assert len(a) > 1000
+    assert a == b, f".fqs differs: {len(a)} vs {len(b)} bytes, first difference at {next((i for i in range(min(len(a), len(b))) if a[i] != b[i]), -1)}"
+    if decode:
+        dec = os.path.join(tmp, "dec.fastq")
+        subprocess.run([O.REF_BIN, "d", "-out", dec, ours], check=True, cwd=tmp, stdout=subprocess.DEVNULL)
+        assert open(dec, "rb").read() == open(fq, "rb").read(), "the reference decompressor does not reproduce the input"
+    return r.stderr
+
+
+@needs_bins
+@pytest.mark.parametrize("case", CASES + [BIG])
+def test_live_host_with_oracle_records(case):
+    with tempfile.TemporaryDirectory() as tmp:
+        fq = _fastq(tmp, *case)
+        log = _check(_build_mock(tmp), case[0], tmp, fq, decode=case is not BIG)
+        assert "segments" in log
+
+
+@needs_bins
+def test_live_host_fails_loudly_without_engine():
+    """No CPU fallback: without a loadable library the compressor stops before it writes anything."""
+    with tempfile.TemporaryDirectory() as tmp:
+        fq = _fastq(tmp, *CASES[0])
+        r = subprocess.run([LIVE_BIN, "e", "-s", "-om", "o", "-t", "1", "-gs", "1", "-v", "0", "-out", os.path.join(tmp, "x.fqs"), fq], cwd=tmp,
+                           env=dict(os.environ, FQSK_LIB=os.path.join(tmp, "missing.so")), capture_output=True, text=True)
+        assert r.returncode == 3 and "no CPU fallback" in r.stderr.replace("There is no", "no")
+        # modes the live host does not cover stop the same way (never silently served by the CPU classes)
+        r = subprocess.run([LIVE_BIN, "e", "-s", "-om", "o", "-t", "2", "-gs", "1", "-v", "0", "-out", os.path.join(tmp, "x.fqs"), fq], cwd=tmp,
+                           env=dict(os.environ, FQSK_LIB=_build_mock(tmp)), capture_output=True, text=True)
+        assert r.returncode == 3 and "no CPU fallback" in r.stderr
+
+
+@needs_bins
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES + [BIG])
+def test_live_host_on_gpu(case):
+    assert os.path.exists(REAL_LIB), "fqsqueezer_b200/libfqsk.so is not built"
+    with tempfile.TemporaryDirectory() as tmp:
+        fq = _fastq(tmp, *case)
+        log = _check(REAL_LIB, case[0], tmp, fq, decode=case is not BIG)
+        assert "kernel launches" in log and " 0 kernel launches" not in log, log
