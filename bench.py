@@ -130,6 +130,44 @@ def run_reference(genome, n_reads, threads, seed_off=0):
     return {"bases": n_reads * L, "seconds": secs, "fastq_bytes": nbytes}
 
 
+def run_compress_e2e(genome, n_reads):
+    """BASELINE.json's second metric, `e2e compress MB/s`: the reference compressor with its k-mer engine bound to libfqsk.so
+    (host/_bin/fqs-1.1-fqsk: host/build_host.py + host/fqsk_live.h, the integration of INTEGRATION.md) against the unmodified
+    fqs-1.1 at -t 1 -- the parity configuration -- on the same FASTQ: FASTQ bytes / 'Processing time', and whether the two .fqs
+    files are byte-identical.  Bounded sample; everything outside the k-mer engine is the reference's own single-threaded host code."""
+    from oracle import oracle as O          # only to locate the unmodified reference binary (the baseline of this leg)
+    live = os.path.join(ROOT, "host", "_bin", "fqs-1.1-fqsk")
+    lib = os.path.join(ROOT, "fqsqueezer_b200", "libfqsk.so")
+    if not (os.path.exists(live) and os.path.exists(O.REF_BIN)):
+        return {"unavailable": "host/_bin/fqs-1.1-fqsk or oracle/_ref/fqs-1.1 not built"}
+    codes, err = synth.make_reads(genome, n_reads, L=L, seed=4242)
+    with tempfile.TemporaryDirectory() as tmp:
+        fq = os.path.join(tmp, "s.fastq")
+        nbytes = synth.write_fastq(fq, codes, err, seed=1)
+        base = ["e", "-s", "-om", "o", "-qm", "o", "-im", "o", "-gs", str(GS), "-t", "1", "-v", "0"]
+
+        def one(exe, out, env=None):
+            t = time.time()
+            r = subprocess.run([exe, *base, "-out", out, fq], capture_output=True, text=True, cwd=tmp, env=env)
+            wall = time.time() - t
+            if r.returncode != 0:
+                raise RuntimeError(f"{os.path.basename(exe)} exit {r.returncode}: {r.stderr[-300:]}")
+            m = re.search(r"Processing time:\s*([0-9.eE+-]+)", r.stdout + r.stderr)
+            return (float(m.group(1)) if m else wall), wall, r.stderr
+
+        env = dict(os.environ, FQSK_LIB=lib, FQSK_VERBOSE="1")
+        one(live, os.path.join(tmp, "w.fqs"), env)                     # warm-up: CUDA context, module load, page cache
+        t_live, wall_live, log = one(live, os.path.join(tmp, "a.fqs"), env)
+        t_ref, wall_ref, _ = one(O.REF_BIN, os.path.join(tmp, "b.fqs"))
+        same = open(os.path.join(tmp, "a.fqs"), "rb").read() == open(os.path.join(tmp, "b.fqs"), "rb").read()
+        fqs_bytes = os.path.getsize(os.path.join(tmp, "a.fqs"))
+    m = re.search(r"([0-9.]+) s inside the engine calls, (\d+) kernel launches", log)
+    return {"value": nbytes / 1e6 / t_live, "unit": "MB/s", "reference_t1": nbytes / 1e6 / t_ref, "speedup_vs_t1": t_ref / t_live,
+            "byte_identical": bool(same), "fastq_bytes": nbytes, "fqs_bytes": fqs_bytes, "seconds": t_live, "reference_seconds": t_ref,
+            "engine_call_seconds": float(m.group(1)) if m else None, "gpu_launches": int(m.group(2)) if m else None,
+            "sample": f"{n_reads} reads of a config-2 stream ({nbytes / 1e6:.1f} MB FASTQ), e -s -om o -qm o -im o -gs {GS} -t 1: fqs-1.1-fqsk (reference host code, k-mer engine on the GPU through the C-ABI, blocking fqsk_segment + fqsk_sync) vs the unmodified fqs-1.1; 'Processing time'"}
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -240,6 +278,8 @@ def main():
     ap.add_argument("--no-phase-events", action="store_true", help="do not bracket the internal phases with CUDA events (fewer host API calls per segment)")
     ap.add_argument("--no-box-warmup", action="store_true", help="skip the throw-away engine that warms the box up before the W warm-up steps")
     ap.add_argument("--cpu-sample-reads", type=int, default=40_000)
+    ap.add_argument("--no-compress-e2e", action="store_true", help="skip the whole-compressor leg (fqs-1.1-fqsk vs fqs-1.1 -t 1)")
+    ap.add_argument("--compress-sample-reads", type=int, default=60_000)
     ap.add_argument("--trace-blocks", type=int, default=0, help="print per-block phase ms every N blocks to stderr")
     ap.add_argument("--profile-block", type=int, default=-1, help="cudaProfilerStart/Stop around this block (for ncu --profile-from-start off)")
     args = ap.parse_args()
@@ -443,12 +483,20 @@ def main():
             cpu = {"value": res["bases"] / res["seconds"], "unit": UNIT, "cores": threads, "kind": "reference",
                    "sample": f"first {args.cpu_sample_reads} reads of a config-2 stream ({res['bases'] / 1e6:.1f} Mbases), fqs-1.1 e -s -om o -qm o -im o -gs {GS} -t {threads}, 'Processing time' = {res['seconds']:.2f} s (whole compressor, the k-mer engine is ~75% of it)"}
 
+    # ---------------- whole compressor through the drop-in (bounded sample, rank 0, N = 1 only) ----------------
+    compress = None
+    if not args.no_compress_e2e and world == 1:
+        try:
+            compress = run_compress_e2e(genome, args.compress_sample_reads)
+        except Exception as ex:              # never at the expense of the line itself
+            compress = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
             "config": workload_config({"parallelism": "1 engine per GPU" + ("" if world == 1 else f" x {world} independent replicas (ONE job over hash-sharded tables: --shard)"),
                                        "blocks": f"{args.warmup}..{n_blocks - 1} of the job", "segments_timed": n_seg}),
-            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "compress_e2e": compress, "gpu_launches": launches,
             "clocks": sampler.summary(), "wall_ms_per_step": wall_ms / args.steps}
     print(json.dumps(line))
     if dist is not None:
