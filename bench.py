@@ -148,7 +148,7 @@ def run_compress_e2e(genome, n_reads):
 
         def one(exe, out, env=None):
             t = time.time()
-            r = subprocess.run([exe, *base, "-out", out, fq], capture_output=True, text=True, cwd=tmp, env=env)
+            r = subprocess.run([exe, *base, "-out", out, fq], capture_output=True, text=True, cwd=tmp, env=env, timeout=300)
             wall = time.time() - t
             if r.returncode != 0:
                 raise RuntimeError(f"{os.path.basename(exe)} exit {r.returncode}: {r.stderr[-300:]}")

@@ -64,6 +64,10 @@ public:
 		if (!se_original || n_threads != 1 || !dup_check) { fprintf(stderr, "fqsk: the live host covers -s -om o -t 1 with the duplicates check on; no CPU fallback for other modes\n"); exit(3); }
 		const char *path = getenv("FQSK_LIB");
 		lib = dlopen(path ? path : "libfqsk.so", RTLD_NOW | RTLD_LOCAL);
+		if (!lib) {   // the library needs the CUDA runtime: when the loader's search path does not have it, take it from $FQSK_CUDART or the toolkit
+			const char *rt = getenv("FQSK_CUDART");
+			if (dlopen(rt ? rt : "/usr/local/cuda/lib64/libcudart.so.12", RTLD_NOW | RTLD_GLOBAL)) lib = dlopen(path ? path : "libfqsk.so", RTLD_NOW | RTLD_LOCAL);
+		}
 		if (!lib) { fprintf(stderr, "fqsk: cannot load the k-mer engine (%s); set FQSK_LIB. There is no CPU fallback.\n", dlerror()); exit(3); }
 		sym(p_create, "fqsk_create"); sym(p_destroy, "fqsk_destroy"); sym(p_last_error, "fqsk_last_error"); sym(p_block_start, "fqsk_block_start");
 		sym(p_segment, "fqsk_segment"); sym(p_sync, "fqsk_sync"); sym(p_stats, "fqsk_stats_get"); sym(p_host_alloc, "fqsk_host_alloc"); sym(p_host_free, "fqsk_host_free");
