@@ -6,14 +6,18 @@ The reference's own sources are compiled from a scratch copy under /tmp (nothing
 host/_bin/ is git-ignored and travels to the GPU box like our own .so files).  The patch below is the whole reference-side change:
 
   application.cpp  AdjustToParams (86-91)      the engine is created in place of siv_pmer / ht_smer / ht_bmer (which shrink to stubs)
-                   SE worker loop (617-662)    fqsk_block_start per reads_block; ONE fqsk_segment before the worker codes the reads of a
-                                               sync segment; fqsk_sync in place of InsertKmersToHT + ClearKmersToHT
+                   worker loops                fqsk_block_start per reads_block; ONE fqsk_segment before the worker codes the reads of a
+                   (617-662, 1145-1193)        sync segment; fqsk_sync in place of InsertKmersToHT + ClearKmersToHT
   dna.cpp          compress_suffix (674-877)   counts / level / rough flag / cor_pos of every coded base come from the segment's records;
                                                find_counts, the rough searches, repairs, pushes, thread-local inserts and prefetches are gone
+                   compress_prefix_sorted      (flag, dif) of the p-mer prefix from fqsk_sorted_prefix instead of siv_pmer->test + the linear
+                   (549-661)                   scan; no p-mer pushes
+                   CompressPE (1790-1880)      the shared-minimizer decision of mate 2 from fqsk_pair_info instead of find_minim_cand /
+                                               generate_read_bmers / the candidate search; no append_pe_mers3
   everything else (context model, range coders, id / quality / meta streams, container, decompressor) is untouched.
 
 host/fqsk_live.h (ours) holds the binding itself (dlopen of $FQSK_LIB, descriptors, record cursor).
-Scope this round: -s -om o -t 1.  No-op (exit 0) where /root/reference does not exist (the GPU box uses the prebuilt binary).
+Scope: -t 1; -s -om o, -s -om s, -p -om o.  No-op (exit 0) where /root/reference does not exist (the GPU box uses the prebuilt binary).
 """
 import os
 import shutil
@@ -35,6 +39,48 @@ def replace_once(s, old, new, where):
     return s.replace(old, new, 1)
 
 
+def in_range(s, start_marker, end_marker, fn, where):
+    """Applies fn to the text between two markers (one function of the reference) and splices the result back."""
+    a0 = s.index(start_marker)
+    a1 = s.index(end_marker, a0 + len(start_marker))
+    return s[:a0] + fn(s[a0:a1]) + s[a1:]
+
+
+def patch_worker_loop(f, first_read_anchor, paired, where):
+    """The compress worker loop of compress_se_files (application.cpp:617-662) / compress_pe_files (1145-1193)."""
+    step = 2 if paired else 1
+    # start of a reads_block (application.cpp:624 / 1152)
+    f = replace_once(f, "\t\t\t\tdna_comp.ResetReadPrev();\n",
+                     "\t\t\t\tdna_comp.ResetReadPrev();\n"
+                     "\t\t\t\tCFqskLive::get().block_start(reads_block_cur->input_FASTQ, reads_block_cur->filled_size);\n"
+                     "\t\t\t\tuint64_t fqsk_seg_begin = my_first;\n", where)
+    # first read of a sync segment: the engine resolves the whole segment -- the reads up to and including the one that triggers the
+    # next sync (SE: i == next_synchro, application.cpp:643; PE: the first pair with i >= next_synchro, 1170) or the tail of the block
+    if paired:
+        seg = ("\t\t\t\t\t\tuint64_t fqsk_seg_last = next_synchro > i ? next_synchro : i;\n"
+               "\t\t\t\t\t\tif ((fqsk_seg_last - my_first) & 1) ++fqsk_seg_last;\n"
+               "\t\t\t\t\t\tif (fqsk_seg_last + 2 > my_last) fqsk_seg_last = my_last - 2;\n"
+               "\t\t\t\t\t\tCFqskLive::get().segment(&reads_block_cur->v_reads[i], fqsk_seg_last + 2 - i);\n")
+    else:
+        seg = ("\t\t\t\t\t\tuint64_t fqsk_seg_last = (next_synchro >= i && next_synchro < my_last) ? next_synchro : my_last - 1;\n"
+               "\t\t\t\t\t\tCFqskLive::get().segment(&reads_block_cur->v_reads[i], fqsk_seg_last - i + 1);\n")
+    f = replace_once(f, first_read_anchor,
+                     "\t\t\t\t\tif (i == fqsk_seg_begin)\n\t\t\t\t\t{\n" + seg + "\t\t\t\t\t}\n"
+                     "\t\t\t\t\tCFqskLive::get().set_read(i - fqsk_seg_begin);\n" + first_read_anchor, where)
+    # the sync inside a block (application.cpp:645-649 / 1172-1176)
+    f = replace_once(f, "\t\t\t\t\t\tdna_comp.InsertKmersToHT();\n\t\t\t\t\t\tbar_synchro.count_down_and_wait();\n\t\t\t\t\t\tdna_comp.ClearKmersToHT();\n",
+                     f"\t\t\t\t\t\tCFqskLive::get().sync();\n\t\t\t\t\t\tfqsk_seg_begin = i + {step};\n\t\t\t\t\t\tbar_synchro.count_down_and_wait();\n", where)
+    # the sync at the end of a block (application.cpp:657-661 / 1184-1190), over an empty segment when the last read closed one
+    f = replace_once(f, "\t\t\t\tdna_comp.InsertKmersToHT();\n",
+                     "\t\t\t\tif (fqsk_seg_begin >= my_last)\n\t\t\t\t\tCFqskLive::get().segment(reads_block_cur->v_reads.data(), 0);\n"
+                     "\t\t\t\tCFqskLive::get().sync();\n", where)
+    f = replace_once(f, "\t\t\t\tdna_comp.ClearKmersToHT();\n", "", where)
+    assert "InsertKmersToHT" not in f and "ClearKmersToHT" not in f
+    # the workers have joined (application.cpp:762 / 1310): engine statistics, release
+    f = replace_once(f, "\tv_thr_compress.clear();\n", "\tv_thr_compress.clear();\n\tCFqskLive::get().finish();\n", where)
+    return f
+
+
 def patch_application(path):
     s = open(path, encoding="latin-1").read()
     s = replace_once(s, '#include "application.h"\n', '#include "application.h"\n#include "fqsk_live.h"\n', path)
@@ -43,41 +89,18 @@ def patch_application(path):
                         "\tht_smer = new CHT_kmer<uint32_t>(params.smer_len, SMER_COUNTER_BITS, params.ht_max_filling_factor);\n"
                         "\tht_bmer = new CHT_kmer<uint32_t>(params.bmer_len, BMER_COUNTER_BITS, params.ht_max_filling_factor);\n",
                      "\tCFqskLive::get().create(params.pmer_len, params.smer_len, params.bmer_len, params.prefix_len, params.genome_size,\n"
-                     "\t\tparams.dna_mode == dna_mode_t::se_original, (uint32_t) params.no_threads, params.duplicates_check);\n"
+                     "\t\t(uint32_t) params.dna_mode, (uint32_t) params.no_threads, params.duplicates_check);\n"
                      "\tsiv_pmer = new TSmallIntVector<SIV_FIELD_SIZE>(8);\n"
                      "\tht_smer = new CHT_kmer<uint32_t>(12, SMER_COUNTER_BITS, params.ht_max_filling_factor);\n"
                      "\tht_bmer = new CHT_kmer<uint32_t>(12, BMER_COUNTER_BITS, params.ht_max_filling_factor);\n", path)
-    # application.cpp:624 -- start of a reads_block (first hit = the single-end compress loop)
-    s = replace_once(s, "\t\t\t\tdna_comp.ResetReadPrev();\n",
-                     "\t\t\t\tdna_comp.ResetReadPrev();\n"
-                     "\t\t\t\tCFqskLive::get().block_start(reads_block_cur->input_FASTQ, reads_block_cur->filled_size);\n"
-                     "\t\t\t\tuint64_t fqsk_seg_begin = my_first;\n", path)
-    # application.cpp:630 -- first read of a sync segment: the engine resolves the whole segment [i, next_synchro] (or the tail of the block)
-    s = replace_once(s, "\t\t\t\t\tauto &cur_read = reads_block_cur->v_reads[i];\n",
-                     "\t\t\t\t\tif (i == fqsk_seg_begin)\n\t\t\t\t\t{\n"
-                     "\t\t\t\t\t\tuint64_t fqsk_seg_last = (next_synchro >= i && next_synchro < my_last) ? next_synchro : my_last - 1;\n"
-                     "\t\t\t\t\t\tCFqskLive::get().segment(&reads_block_cur->v_reads[i], fqsk_seg_last - i + 1);\n"
-                     "\t\t\t\t\t}\n"
-                     "\t\t\t\t\tauto &cur_read = reads_block_cur->v_reads[i];\n", path)
-    # application.cpp:645-649 -- the sync inside a block
-    s = replace_once(s, "\t\t\t\t\t\tdna_comp.InsertKmersToHT();\n\t\t\t\t\t\tbar_synchro.count_down_and_wait();\n\t\t\t\t\t\tdna_comp.ClearKmersToHT();\n",
-                     "\t\t\t\t\t\tCFqskLive::get().sync();\n\t\t\t\t\t\tfqsk_seg_begin = i + 1;\n\t\t\t\t\t\tbar_synchro.count_down_and_wait();\n", path)
-    # application.cpp:657-661 -- the sync at the end of a block (over an empty segment when the last read closed one)
-    s = replace_once(s, "\t\t\t\tbar_synchro.count_down_and_wait();\n\t\t\t\tdna_comp.InsertKmersToHT();\n\t\t\t\tbar_synchro.count_down_and_wait();\n\t\t\t\tdna_comp.ClearKmersToHT();\n",
-                     "\t\t\t\tbar_synchro.count_down_and_wait();\n"
-                     "\t\t\t\tif (fqsk_seg_begin >= my_last)\n\t\t\t\t\tCFqskLive::get().segment(reads_block_cur->v_reads.data(), 0);\n"
-                     "\t\t\t\tCFqskLive::get().sync();\n\t\t\t\tbar_synchro.count_down_and_wait();\n", path)
-    # the workers have joined (application.cpp:762): engine statistics, release
-    s = replace_once(s, "\tv_thr_compress.clear();\n", "\tv_thr_compress.clear();\n\tCFqskLive::get().finish();\n", path)
+    s = in_range(s, "bool CApplication::compress_se_files(", "bool CApplication::decompress_se_file(",
+                 lambda f: patch_worker_loop(f, "\t\t\t\t\tauto &cur_read = reads_block_cur->v_reads[i];\n", False, path), path)
+    s = in_range(s, "bool CApplication::compress_pe_files(", "bool CApplication::decompress_pe_file(",
+                 lambda f: patch_worker_loop(f, "\t\t\t\t\tauto &cur_read_1 = reads_block_cur->v_reads[i];\n", True, path), path)
     open(path, "w", encoding="latin-1").write(s)
 
 
-def patch_dna(path):
-    s = open(path, encoding="latin-1").read()
-    s = replace_once(s, '#include "dna.h"\n', '#include "dna.h"\n#include "fqsk_live.h"\n', path)
-    a0 = s.index("void CDNACompressor::compress_suffix(")
-    a1 = s.index("\n//****", a0)
-    f = s[a0:a1]
+def patch_suffix(f, path):
     # dna.cpp:695 -- the count vector of a coded base comes from the segment's records
     f = replace_once(f, "\t\tcounts_level_t counts_level = find_counts(counts);\n",
                      "\t\tconst fqs_rp_rec rp_rec = fqs_rp_next(i);\n"
@@ -98,8 +121,47 @@ def patch_dna(path):
     # dna.cpp:684-693 -- the six register shifts at the top of the loop body have no reader left
     a = ("\t\tpmer_can.insert_zero();\n\t\tsmer_can.insert_zero();\n\t\tbmer_can.insert_zero();\n\n"
          "\t\tpmer_can_unc.insert_zero();\n\t\tsmer_can_unc.insert_zero();\n\t\tbmer_can_unc.insert_zero();\n")
-    f = replace_once(f, a, "", path)
-    s = s[:a0] + f + s[a1:]
+    return replace_once(f, a, "", path)
+
+
+def patch_prefix_sorted(f, path):
+    # dna.cpp:589-592 -- flag: 4 when the p-mer equals the previous read's, else siv_pmer->test(p-mer)
+    f = replace_once(f, "\tif (pmer_can == pmer_can_prev)\n\t\tflag = max_prefix_sorted_flag_value;\n\telse\n\t\tflag = siv_pmer->test(pmer_can.data_aligned_dir());\n",
+                     "\tflag = CFqskLive::get().sorted_flag();\n", path)
+    # dna.cpp:600-605 -- dif: the linear scan over the p-mer array between the previous and this p-mer runs on the GPU
+    f = replace_once(f, "\t\tuint64_t max_i = pmer_can.data_aligned_dir();\n\n\t\tfor (uint64_t i = pmer_can_prev.data_aligned_dir() + 1; i < max_i; ++i)\n"
+                        "\t\t\tif (siv_pmer->test(i) == flag)\n\t\t\t\t++dif;\n",
+                     "\t\tdif = CFqskLive::get().sorted_dif();\n", path)
+    # dna.cpp:655-660 -- no p-mer pushes on the host
+    a = ("\tauto x = pmer_can.data_aligned_dir();\n\t(*my_pmers_to_add)[modulo_divisor(x >> pmer_mod_shift, no_threads)].push_back(x);\n"
+         "\tx = pmer_can.data_aligned_rc();\n\t(*my_pmers_to_add)[modulo_divisor(x >> pmer_mod_shift, no_threads)].push_back(x);\n")
+    return replace_once(f, a, "", path)
+
+
+def patch_compress_pe(f, path):
+    # dna.cpp:1798-1838 -- find_minim_cand, generate_read_bmers and the candidate search run on the GPU; the decision comes back per pair
+    a0 = f.index("\tbool minim_found = find_minim_cand(p1, size1);\n")
+    a1 = f.index("\tif (minim2_id < 0)\n\t\tCompressDirect(p2, size2, nullptr, false);")
+    f = (f[:a0] + "\tbool minim_found;\n\tuint32_t minim2_pos;\n\tint minim2_id;\n"
+         "\tCFqskLive::get().pair_decision(minim_found, minim2_id, minim2_pos);\n\n" + f[a1:])
+    # dna.cpp:1877 -- the 14 pair pushes of append_pe_mers3 are made by the engine
+    return replace_once(f, "\tappend_pe_mers3(p1, size1, p2, size2);\n", "", path)
+
+
+def patch_dup(f, path):
+    # dna.cpp:1525 / 1724 -- the host keeps its own duplicate test; the engine's flag must agree
+    return replace_once(f, "\t\tbool same_read = read_cur == read_prev;\n", "\t\tbool same_read = read_cur == read_prev;\n\t\tCFqskLive::get().check_dup(same_read);\n", path)
+
+
+def patch_dna(path):
+    s = open(path, encoding="latin-1").read()
+    s = replace_once(s, '#include "dna.h"\n', '#include "dna.h"\n#include "fqsk_live.h"\n', path)
+    sep = "\n//****"
+    s = in_range(s, "void CDNACompressor::compress_suffix(", sep, lambda f: patch_suffix(f, path), path)
+    s = in_range(s, "void CDNACompressor::compress_prefix_sorted(", sep, lambda f: patch_prefix_sorted(f, path), path)
+    s = in_range(s, "bool CDNACompressor::CompressPE(", sep, lambda f: patch_compress_pe(f, path), path)
+    s = in_range(s, "bool CDNACompressor::CompressDirect(", sep, lambda f: patch_dup(f, path), path)
+    s = in_range(s, "bool CDNACompressor::CompressSorted(", sep, lambda f: patch_dup(f, path), path)
     open(path, "w", encoding="latin-1").write(s)
 
 

@@ -5,8 +5,9 @@
 // This file is OUR code (no reference source in it).  host/build_host.py compiles the reference's own sources -- where they lie,
 // patched in a scratch copy -- with this header into host/_bin/fqs-1.1-fqsk.  INTEGRATION.md walks through the patch.
 //
-// Scope of the live host this round: single-end, original order, -t 1 (the parity configuration of the north star).  Anything
-// else stops with a message: there is no CPU fallback for the k-mer path.
+// Scope of the live host: -t 1 (the parity configuration of the north star; one engine = one reference worker thread), single-end in
+// original and sorted order (-s -om o / -om s) and paired-end in original order (-p -om o).  Anything else stops with a message:
+// there is no CPU fallback for the k-mer path.
 //
 // The library is bound with dlopen ($FQSK_LIB, default "libfqsk.so") so that the binary has no link-time CUDA dependency and the
 // CPU test suite can point it at a mock built from the oracle (tests/mock_fqsk.cpp) to check the HOST half of the integration.
@@ -33,6 +34,8 @@ class CFqskLive {
 	decltype(&fqsk_segment) p_segment = nullptr;
 	decltype(&fqsk_sync) p_sync = nullptr;
 	decltype(&fqsk_stats_get) p_stats = nullptr;
+	decltype(&fqsk_sorted_prefix) p_sorted_prefix = nullptr;
+	decltype(&fqsk_pair_info) p_pair_info = nullptr;
 	decltype(&fqsk_host_alloc) p_host_alloc = nullptr;
 	decltype(&fqsk_host_free) p_host_free = nullptr;
 
@@ -43,6 +46,10 @@ class CFqskLive {
 	fqsk_base_rec *recs = nullptr;
 	uint64_t rec_cap = 0, n_recs = 0, cursor = 0;
 	std::vector<uint8_t> dup;
+	uint32_t mode = FQSK_MODE_SE_ORIGINAL;
+	uint64_t n_seg_reads = 0, cur_read = 0;
+	std::vector<uint32_t> s_flag, pair_words;      // per read: compress_prefix_sorted's flag; per pair: what CompressPE codes for mate 2
+	std::vector<uint64_t> s_dif;
 	uint64_t n_segments = 0, n_syncs = 0, n_bases = 0;
 	double engine_s = 0;
 
@@ -60,8 +67,13 @@ public:
 	static CFqskLive &get() { static CFqskLive x; return x; }
 
 	// application.cpp:86-91 (AdjustToParams): the engine takes the place of siv_pmer / ht_smer / ht_bmer
-	void create(uint32_t pmer_len, uint32_t smer_len, uint32_t bmer_len, uint32_t prefix_len, uint64_t genome_mbp, bool se_original, uint32_t n_threads, bool dup_check) {
-		if (!se_original || n_threads != 1 || !dup_check) { fprintf(stderr, "fqsk: the live host covers -s -om o -t 1 with the duplicates check on; no CPU fallback for other modes\n"); exit(3); }
+	// dna_mode: params.h:18 (0 se_original, 1 se_sorted, 2 pe_original, 3 pe_sorted) = FQSK_MODE_*
+	void create(uint32_t pmer_len, uint32_t smer_len, uint32_t bmer_len, uint32_t prefix_len, uint64_t genome_mbp, uint32_t dna_mode, uint32_t n_threads, bool dup_check) {
+		if (dna_mode > FQSK_MODE_PE_ORIGINAL || n_threads != 1 || !dup_check) {
+			fprintf(stderr, "fqsk: the live host covers -t 1 with the duplicates check on, -s (-om o / -om s) and -p -om o; no CPU fallback for other modes\n");
+			exit(3);
+		}
+		mode = dna_mode;
 		const char *path = getenv("FQSK_LIB");
 		lib = dlopen(path ? path : "libfqsk.so", RTLD_NOW | RTLD_LOCAL);
 		if (!lib) {   // the library needs the CUDA runtime: when the loader's search path does not have it, take it from $FQSK_CUDART or the toolkit
@@ -71,12 +83,13 @@ public:
 		if (!lib) { fprintf(stderr, "fqsk: cannot load the k-mer engine (%s); set FQSK_LIB. There is no CPU fallback.\n", dlerror()); exit(3); }
 		sym(p_create, "fqsk_create"); sym(p_destroy, "fqsk_destroy"); sym(p_last_error, "fqsk_last_error"); sym(p_block_start, "fqsk_block_start");
 		sym(p_segment, "fqsk_segment"); sym(p_sync, "fqsk_sync"); sym(p_stats, "fqsk_stats_get"); sym(p_host_alloc, "fqsk_host_alloc"); sym(p_host_free, "fqsk_host_free");
+		sym(p_sorted_prefix, "fqsk_sorted_prefix"); sym(p_pair_info, "fqsk_pair_info");
 		fqsk_params P;
 		memset(&P, 0, sizeof(P));
 		P.abi_version = FQSK_ABI_VERSION;
 		P.pmer_len = pmer_len; P.smer_len = smer_len; P.bmer_len = bmer_len; P.prefix_len = prefix_len;
 		P.smer_counter_bits = 12; P.bmer_counter_bits = 6;                       // defs.h:26-27
-		P.mode = FQSK_MODE_SE_ORIGINAL;
+		P.mode = mode;
 		P.n_workers = 1; P.world_size = 1; P.rank = 0;
 		P.device = getenv("FQSK_DEVICE") ? atoi(getenv("FQSK_DEVICE")) : 0;
 		uint64_t expect = genome_mbp * 3000000ull;                               // genomic + error k-mers; the tables grow when half full
@@ -117,10 +130,41 @@ public:
 		dup.resize(n + 1);
 		const double t0 = now();
 		int rc = p_segment(h, slab, slab_size, descs.data(), (uint32_t) n, recs, rec_cap, &n_recs, dup.data(), nullptr);
-		engine_s += now() - t0;
 		if (rc != FQSK_OK) die("fqsk_segment", rc);
+		if (mode == FQSK_MODE_SE_SORTED) {            // dna.cpp:589-605: (flag, dif) of every read's p-mer prefix
+			s_flag.resize(n + 1); s_dif.resize(n + 1);
+			rc = p_sorted_prefix(h, s_flag.data(), s_dif.data(), (uint32_t) n);
+			if (rc != FQSK_OK) die("fqsk_sorted_prefix", rc);
+		}
+		if (mode == FQSK_MODE_PE_ORIGINAL) {          // dna.cpp:1798-1838: the shared-minimizer decision of every pair
+			if (n & 1) { fprintf(stderr, "fqsk: a paired-end segment with an odd number of reads\n"); exit(3); }
+			pair_words.resize(3 * (n / 2) + 3);
+			rc = p_pair_info(h, pair_words.data(), (uint32_t) (n / 2));
+			if (rc != FQSK_OK) die("fqsk_pair_info", rc);
+		}
+		engine_s += now() - t0;
+		n_seg_reads = n; cur_read = 0;
 		cursor = 0;
 		++n_segments; n_bases += total;
+	}
+
+	// the worker is about to code read `idx` of the segment (paired-end: its first mate)
+	void set_read(uint64_t idx) {
+		if (idx >= n_seg_reads) { fprintf(stderr, "fqsk: read %llu outside the segment of %llu reads\n", (unsigned long long) idx, (unsigned long long) n_seg_reads); exit(3); }
+		cur_read = idx;
+	}
+	// dna.cpp:1523-1533, 1722-1732: the host keeps its own duplicate test (it owns read_prev); the engine must agree
+	void check_dup(bool same_read) {
+		if ((dup[cur_read] != 0) != same_read) { fprintf(stderr, "fqsk: duplicate flag of read %llu disagrees with the host\n", (unsigned long long) cur_read); exit(3); }
+	}
+	uint64_t sorted_flag() const { return s_flag[cur_read]; }
+	uint64_t sorted_dif() const { return s_dif[cur_read]; }
+	// dna.cpp:1798-1838: minim_found, minim2_id (-1 when no candidate list exists, else 0..15), minim2_pos
+	void pair_decision(bool &minim_found, int &minim2_id, uint32_t &minim2_pos) const {
+		const uint32_t *w = pair_words.data() + 3 * (cur_read / 2);
+		minim_found = w[0] != 0;
+		minim2_id = minim_found ? (int) w[1] : -1;
+		minim2_pos = w[2];
 	}
 
 	// dna.cpp:695 -- the record of the base compress_suffix is about to code

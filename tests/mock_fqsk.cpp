@@ -19,14 +19,15 @@ void fqso_sync(void *h);
 void fqso_stats(void *h, uint64_t *o);
 }
 
-struct fqsk_handle { void *o; uint64_t n_segments = 0, n_syncs = 0; };
+struct fqsk_handle { void *o; uint32_t mode = 0; uint64_t n_segments = 0, n_syncs = 0; std::vector<uint32_t> s_flag, pair; std::vector<uint64_t> s_dif; };
 
 extern "C" {
 
 int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
-	if (!p || !out || p->abi_version != FQSK_ABI_VERSION || p->mode != FQSK_MODE_SE_ORIGINAL || p->n_workers != 1) return FQSK_E_INVAL;
+	if (!p || !out || p->abi_version != FQSK_ABI_VERSION || p->mode > FQSK_MODE_PE_ORIGINAL || p->n_workers != 1) return FQSK_E_INVAL;
 	fqsk_handle *h = new fqsk_handle();
-	h->o = fqso_create(p->pmer_len, p->smer_len, p->bmer_len, p->prefix_len, 0);
+	h->mode = p->mode;
+	h->o = fqso_create(p->pmer_len, p->smer_len, p->bmer_len, p->prefix_len, p->mode);   // dna_mode_t = FQSK_MODE_*
 	*out = h;
 	return FQSK_OK;
 }
@@ -41,13 +42,29 @@ int fqsk_segment(fqsk_handle *h, const uint8_t *slab, uint64_t, const fqsk_read_
 	for (uint32_t i = 0; i < n_reads; ++i) { off[i] = reads[i].dna_off; len[i] = reads[i].dna_len; total += len[i]; }
 	std::vector<fqsk_base_rec> tmp(total + 3 * (uint64_t) n_reads + 16);     // the oracle also emits per-read / duplicate markers (pos >= 0xFFFFFFF0)
 	std::vector<uint8_t> d(n_reads + 1);
-	uint64_t m = fqso_segment(h->o, slab, off.data(), len.data(), n_reads, 0, tmp.data(), tmp.size(), d.data());
+	const uint32_t kind = h->mode == FQSK_MODE_SE_SORTED ? 2 : h->mode == FQSK_MODE_PE_ORIGINAL ? 3 : 0;     // oracle: 0 CompressDirect, 2 CompressSorted, 3 CompressPE
+	uint64_t m = fqso_segment(h->o, slab, off.data(), len.data(), n_reads, kind, tmp.data(), tmp.size(), d.data());
 	if (m > tmp.size()) return FQSK_E_CAPACITY;
-	uint64_t k = 0;
-	for (uint64_t i = 0; i < m; ++i) if (tmp[i].pos < 0xFFFFFFF0u) { if (k >= rec_cap) return FQSK_E_CAPACITY; recs[k++] = tmp[i]; }
+	h->s_flag.assign(n_reads + 1, 0); h->s_dif.assign(n_reads + 1, 0); h->pair.assign(3 * (n_reads / 2) + 3, 0);
+	uint64_t k = 0, rd = 0, pr = 0;       // rd: reads started so far (one 0xFFFFFFFF marker each; a with-minimizer mate 2 emits kind 1), pr: pairs decided
+	for (uint64_t i = 0; i < m; ++i) {
+		const fqsk_base_rec &r = tmp[i];
+		if (r.pos < 0xFFFFFFF0u) { if (k >= rec_cap) return FQSK_E_CAPACITY; recs[k++] = r; }
+		else if (r.pos == 0xFFFFFFFFu) ++rd;
+		else if (r.pos == 0xFFFFFFFCu && rd >= 1 && rd <= n_reads) { h->s_flag[rd - 1] = r.counts[0]; h->s_dif[rd - 1] = r.counts[1] | ((uint64_t) r.counts[2] << 32); }
+		else if (r.pos == 0xFFFFFFFBu && pr < n_reads / 2) { for (int q = 0; q < 3; ++q) h->pair[3 * pr + q] = r.counts[q]; ++pr; }
+	}
 	*n_recs = k;
 	if (dup) memcpy(dup, d.data(), n_reads);
 	++h->n_segments;
+	return FQSK_OK;
+}
+int fqsk_sorted_prefix(fqsk_handle *h, uint32_t *flag, uint64_t *dif, uint32_t n_reads) {
+	for (uint32_t i = 0; i < n_reads; ++i) { flag[i] = h->s_flag[i]; dif[i] = h->s_dif[i]; }
+	return FQSK_OK;
+}
+int fqsk_pair_info(fqsk_handle *h, uint32_t *info, uint32_t n_pairs) {
+	for (uint32_t i = 0; i < 3 * n_pairs; ++i) info[i] = h->pair[i];
 	return FQSK_OK;
 }
 int fqsk_sync(fqsk_handle *h) { fqso_sync(h->o); ++h->n_syncs; return FQSK_OK; }

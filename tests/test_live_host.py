@@ -35,6 +35,15 @@ def _fastq(tmp, gs, G, n, L, seed, n_frac, dup_frac):
     return fq
 
 
+def _fastq_pe(tmp, gs, G, n_pairs, L, seed):
+    genome = synth.make_genome(G, seed)
+    c1, e1, c2, e2 = synth.make_pairs(genome, n_pairs, L=L, seed=seed, ins_mean=2.2 * L, ins_sd=0.2 * L)
+    f1, f2 = os.path.join(tmp, "in_1.fastq"), os.path.join(tmp, "in_2.fastq")
+    synth.write_fastq(f1, c1, e1, mate=1, seed=seed)
+    synth.write_fastq(f2, c2, e2, mate=2, seed=seed + 1)
+    return f1, f2
+
+
 def _build_mock(tmp):
     O.build_oracle()
     so = os.path.join(tmp, "libfqsk_mock.so")
@@ -44,20 +53,73 @@ def _build_mock(tmp):
     return so
 
 
-def _check(lib, gs, tmp, fq, decode=True):
-    base = ["e", "-s", "-om", "o", "-qm", "o", "-im", "o", "-t", "1", "-gs", str(gs), "-v", "0"]
+def _check(lib, gs, tmp, fq, decode=True, layout=("-s", "-om", "o")):
+    """fq: one FASTQ path (single-end) or a pair of paths (paired-end).  layout: the reference's read layout / order options."""
+    files = [fq] if isinstance(fq, str) else list(fq)
+    base = ["e", *layout, "-qm", "o", "-im", "o", "-t", "1", "-gs", str(gs), "-v", "0"]
     plain, ours = os.path.join(tmp, "plain.fqs"), os.path.join(tmp, "ours.fqs")
-    subprocess.run([O.REF_BIN, *base, "-out", plain, fq], check=True, cwd=tmp, stdout=subprocess.DEVNULL)
-    r = subprocess.run([LIVE_BIN, *base, "-out", ours, fq], cwd=tmp, env=dict(os.environ, FQSK_LIB=lib, FQSK_VERBOSE="1"), capture_output=True, text=True)
+    subprocess.run([O.REF_BIN, *base, "-out", plain, *files], check=True, cwd=tmp, stdout=subprocess.DEVNULL)
+    r = subprocess.run([LIVE_BIN, *base, "-out", ours, *files], cwd=tmp, env=dict(os.environ, FQSK_LIB=lib, FQSK_VERBOSE="1"), capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-600:]
     a, b = open(plain, "rb").read(), open(ours, "rb").read()
     assert len(a) > 1000
     assert a == b, f".fqs differs: {len(a)} vs {len(b)} bytes, first difference at {next((i for i in range(min(len(a), len(b))) if a[i] != b[i]), -1)}"
-    if decode:
+    if decode and len(files) == 1:
         dec = os.path.join(tmp, "dec.fastq")
         subprocess.run([O.REF_BIN, "d", "-out", dec, ours], check=True, cwd=tmp, stdout=subprocess.DEVNULL)
-        assert open(dec, "rb").read() == open(fq, "rb").read(), "the reference decompressor does not reproduce the input"
+        got, want = open(dec, "rb").read(), open(fq, "rb").read()
+        if "s" == layout[-1]:      # sorted order: the decoder returns the reads in the order they were coded
+            assert sorted(got.split(b"\n")[1::4]) == sorted(want.split(b"\n")[1::4]), "the reference decompressor lost reads"
+        else:
+            assert got == want, "the reference decompressor does not reproduce the input"
     return r.stderr
+
+
+# other modes of the live host: sorted order (-om s: compress_prefix_sorted's flag / dif from the engine) and paired end (-p:
+# CompressPE's shared-minimizer decision from the engine); (gs, genome, reads or pairs, read length, seed)
+SORTED = [(1, 5000, 2500, 70, 45), (16, 60000, 6000, 150, 46)]
+PAIRED = [(1, 5000, 1200, 80, 71), (100, 50000, 4000, 150, 72)]
+
+
+def _run_sorted(lib, case):
+    gs, G, n, L, seed = case
+    with tempfile.TemporaryDirectory() as tmp:
+        fq = _fastq(tmp, gs, G, n, L, seed, 0.002, 0.01)
+        return _check(lib(tmp), gs, tmp, fq, layout=("-s", "-om", "s"))
+
+
+def _run_paired(lib, case):
+    gs, G, n, L, seed = case
+    with tempfile.TemporaryDirectory() as tmp:
+        return _check(lib(tmp), gs, tmp, _fastq_pe(tmp, gs, G, n, L, seed), layout=("-p", "-om", "o"))
+
+
+@needs_bins
+@pytest.mark.parametrize("case", SORTED)
+def test_live_host_sorted_with_oracle_records(case):
+    assert "segments" in _run_sorted(_build_mock, case)
+
+
+@needs_bins
+@pytest.mark.parametrize("case", PAIRED)
+def test_live_host_paired_with_oracle_records(case):
+    assert "segments" in _run_paired(_build_mock, case)
+
+
+@needs_bins
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", SORTED)
+def test_live_host_sorted_on_gpu(case):
+    log = _run_sorted(lambda tmp: REAL_LIB, case)
+    assert "kernel launches" in log and " 0 kernel launches" not in log, log
+
+
+@needs_bins
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", PAIRED)
+def test_live_host_paired_on_gpu(case):
+    log = _run_paired(lambda tmp: REAL_LIB, case)
+    assert "kernel launches" in log and " 0 kernel launches" not in log, log
 
 
 @needs_bins
