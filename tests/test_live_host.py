@@ -11,6 +11,7 @@ import os
 import subprocess
 import tempfile
 
+import numpy as np
 import pytest
 
 from fqsqueezer_b200 import synth
@@ -129,6 +130,29 @@ def test_live_host_with_oracle_records(case):
         fq = _fastq(tmp, *case)
         log = _check(_build_mock(tmp), case[0], tmp, fq, decode=case is not BIG)
         assert "segments" in log
+
+
+def _make_ragged(fq, seed, lo):
+    """Cuts half of the reads to a random length in [lo, L] (DNA and quality lines alike)."""
+    rng = np.random.default_rng(seed)
+    lines = open(fq, "rb").read().split(b"\n")
+    out = []
+    for i in range(0, len(lines) - 1, 4):
+        L = len(lines[i + 1])
+        k = int(rng.integers(lo, L + 1)) if rng.random() < 0.5 else L
+        out += [lines[i], lines[i + 1][:k], lines[i + 2], lines[i + 3][:k]]
+    open(fq, "wb").write(b"\n".join(out) + b"\n")
+
+
+@needs_bins
+@pytest.mark.parametrize("lo", [25, 3])
+def test_live_host_ragged_reads_with_oracle_records(lo):
+    """Reads of unequal length, down to reads shorter than the directly coded prefix (prefix_len = 9 at -gs 1): descriptors,
+    record capacity and the record cursor of the binding must follow the reference's own walk over such reads."""
+    with tempfile.TemporaryDirectory() as tmp:
+        fq = _fastq(tmp, 1, 6000, 3000, 100, 77, 0.003, 0.01)
+        _make_ragged(fq, 5, lo)
+        assert "segments" in _check(_build_mock(tmp), 1, tmp, fq)
 
 
 @needs_bins
