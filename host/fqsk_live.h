@@ -99,7 +99,6 @@ public:
 		int rc = p_create(&P, &h);
 		if (rc != FQSK_OK) { h = nullptr; die("fqsk_create", rc); }
 	}
-	bool on() const { return h != nullptr; }
 
 	// application.cpp:624 (dna_comp.ResetReadPrev() at the start of a reads_block)
 	void block_start(const uint8_t *input_FASTQ, uint64_t filled_size) {
@@ -202,8 +201,7 @@ public:
 	}
 };
 
-// names the dna.cpp patch uses (same as the file-replay build of oracle/build_ref.py, so the two patches stay one text)
-inline bool fqs_rp_on() { return true; }
+// dna.cpp:695 as patched by host/build_host.py: the record of the base being coded, in the layout compress_suffix reads it
 inline fqs_rp_rec fqs_rp_next(uint32_t expect_pos) {
 	const fqsk_base_rec &k = CFqskLive::get().next(expect_pos);
 	fqs_rp_rec r;
