@@ -114,20 +114,29 @@ def measured_peak():
 # reference arm / cpu baseline: the unmodified fqs-1.1 compiled from /root/reference (oracle/_ref/fqs-1.1)
 # ------------------------------------------------------------------------------------------------------------------
 def run_reference(genome, n_reads, threads, seed_off=0):
+    """Times the unmodified fqs-1.1 on a bounded sample.  Its 'Processing time' starts with the construction of the CPU tables
+    (4 GiB p-mer array + 5 M sub-tables at -gs 100: seconds, independent of the input), which a 10 M-read job amortises and a
+    bounded sample does not: the same binary is therefore also timed on an 8-read file and that start-up is reported and taken off."""
     from oracle import oracle as O          # checker side only: this function never touches the product path
     if not os.path.exists(O.REF_BIN):
         return None
-    codes, err = synth.make_reads(genome, n_reads, L=L, seed=777 + seed_off)
-    with tempfile.TemporaryDirectory() as tmp:
-        fq = os.path.join(tmp, "s.fastq")
+
+    def one(codes, err, tmp, name):
+        fq = os.path.join(tmp, name + ".fastq")
         nbytes = synth.write_fastq(fq, codes, err, seed=1)
-        cmd = [O.REF_BIN, "e", "-s", "-om", "o", "-qm", "o", "-im", "o", "-gs", str(GS), "-t", str(threads), "-v", "0", "-out", os.path.join(tmp, "o.fqs"), fq]
+        cmd = [O.REF_BIN, "e", "-s", "-om", "o", "-qm", "o", "-im", "o", "-gs", str(GS), "-t", str(threads), "-v", "0", "-out", os.path.join(tmp, name + ".fqs"), fq]
         t = time.time()
         r = subprocess.run(cmd, capture_output=True, text=True, cwd=tmp)
         wall = time.time() - t
         m = re.search(r"Processing time:\s*([0-9.eE+-]+)", r.stdout + r.stderr)
-        secs = float(m.group(1)) if m else wall
-    return {"bases": n_reads * L, "seconds": secs, "fastq_bytes": nbytes}
+        return (float(m.group(1)) if m else wall), nbytes
+
+    codes, err = synth.make_reads(genome, n_reads, L=L, seed=777 + seed_off)
+    with tempfile.TemporaryDirectory() as tmp:
+        startup, _ = one(codes[:8], err[:8], tmp, "tiny")
+        secs, nbytes = one(codes, err, tmp, "s")
+    net = max(secs - startup, 0.05 * secs)
+    return {"bases": n_reads * L, "seconds": net, "seconds_total": secs, "startup_seconds": startup, "fastq_bytes": nbytes}
 
 
 def run_compress_e2e(genome, n_reads):
@@ -165,7 +174,7 @@ def run_compress_e2e(genome, n_reads):
     return {"value": nbytes / 1e6 / t_live, "unit": "MB/s", "reference_t1": nbytes / 1e6 / t_ref, "speedup_vs_t1": t_ref / t_live,
             "byte_identical": bool(same), "fastq_bytes": nbytes, "fqs_bytes": fqs_bytes, "seconds": t_live, "reference_seconds": t_ref,
             "engine_call_seconds": float(m.group(1)) if m else None, "gpu_launches": int(m.group(2)) if m else None,
-            "sample": f"{n_reads} reads of a config-2 stream ({nbytes / 1e6:.1f} MB FASTQ), e -s -om o -qm o -im o -gs {GS} -t 1: fqs-1.1-fqsk (reference host code, k-mer engine on the GPU through the C-ABI, blocking fqsk_segment + fqsk_sync) vs the unmodified fqs-1.1; 'Processing time'"}
+            "sample": f"{n_reads} reads of a config-2 stream ({nbytes / 1e6:.1f} MB FASTQ), e -s -om o -qm o -im o -gs {GS} -t 1: fqs-1.1-fqsk (reference host code, k-mer engine on the GPU through the C-ABI, blocking fqsk_segment + fqsk_sync) vs the unmodified fqs-1.1; 'Processing time' of each, start-up included (reference: construction of its CPU tables, several seconds; ours: CUDA context + HBM tables)"}
 
 
 def reference_arm(args):
@@ -182,7 +191,8 @@ def reference_arm(args):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/fqs-1.1 not built"}))
         return 0
     v = res["bases"] / res["seconds"]
-    sample = f"{per_step * args.steps} reads ({args.steps} steps x {per_step}) of the config-2 stream, fqs-1.1 e -s -om o -qm o -im o -gs {GS} -t {threads}, 'Processing time'"
+    sample = (f"{per_step * args.steps} reads ({args.steps} steps x {per_step}) of the config-2 stream, fqs-1.1 e -s -om o -qm o -im o -gs {GS} -t {threads}: "
+              f"'Processing time' {res['seconds_total']:.2f} s minus {res['startup_seconds']:.2f} s of table construction (same binary on an 8-read file)")
     line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * res["seconds"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic", "impl": "reference", "config": workload_config({"reads_per_step": per_step}),
@@ -481,7 +491,7 @@ def main():
         res = run_reference(genome, args.cpu_sample_reads, threads)
         if res is not None:
             cpu = {"value": res["bases"] / res["seconds"], "unit": UNIT, "cores": threads, "kind": "reference",
-                   "sample": f"first {args.cpu_sample_reads} reads of a config-2 stream ({res['bases'] / 1e6:.1f} Mbases), fqs-1.1 e -s -om o -qm o -im o -gs {GS} -t {threads}, 'Processing time' = {res['seconds']:.2f} s (whole compressor, the k-mer engine is ~75% of it)"}
+                   "sample": f"{args.cpu_sample_reads} reads of a config-2 stream ({res['bases'] / 1e6:.1f} Mbases), fqs-1.1 e -s -om o -qm o -im o -gs {GS} -t {threads}: 'Processing time' {res['seconds_total']:.2f} s minus {res['startup_seconds']:.2f} s of table construction (same binary on an 8-read file) = {res['seconds']:.2f} s (whole compressor, the k-mer engine is ~75% of it)"}
 
     # ---------------- whole compressor through the drop-in (bounded sample, rank 0, N = 1 only) ----------------
     compress = None
