@@ -156,6 +156,17 @@ def test_live_host_ragged_reads_with_oracle_records(lo):
 
 
 @needs_bins
+@pytest.mark.gpu
+@pytest.mark.parametrize("lo", [25, 3])
+def test_live_host_ragged_reads_on_gpu(lo):
+    with tempfile.TemporaryDirectory() as tmp:
+        fq = _fastq(tmp, 1, 6000, 3000, 100, 77, 0.003, 0.01)
+        _make_ragged(fq, 5, lo)
+        log = _check(REAL_LIB, 1, tmp, fq)
+        assert "kernel launches" in log and " 0 kernel launches" not in log, log
+
+
+@needs_bins
 def test_live_host_fails_loudly_without_engine():
     """No CPU fallback: without a loadable library the compressor stops before it writes anything."""
     with tempfile.TemporaryDirectory() as tmp:
