@@ -54,3 +54,19 @@ def test_product_package_does_not_import_oracle():
             assert not pat.search(open(os.path.join(ROOT, "fqsqueezer_b200", fn)).read()), fn
     for fn in os.listdir(os.path.join(ROOT, "fqsqueezer_b200", "csrc")):
         assert "oracle" not in open(os.path.join(ROOT, "fqsqueezer_b200", "csrc", fn)).read().lower(), fn
+
+
+def test_reference_side_binding_uses_only_the_declared_abi():
+    """host/fqsk_live.h (the binding compiled into the reference) resolves its entry points by name: every one of them must be
+    declared in include/fqsk.h and exported by libfqsk.so; the binding and its build recipe never reach for the oracle."""
+    from fqsqueezer_b200 import build
+    build.build()
+    src = open(os.path.join(ROOT, "host", "fqsk_live.h")).read()
+    bound = sorted(set(re.findall(r'sym\(p_[a-z_]+, "(fqsk_[a-z0-9_]+)"\)', src)))
+    assert len(bound) >= 9
+    lib = C.CDLL(E.LIB_PATH)
+    declared = _declared()
+    for n in bound:
+        assert n in declared and hasattr(lib, n), n
+    for fn in ("fqsk_live.h", "build_host.py"):
+        assert not re.search(r"libfqs_oracle|fqso_|oracle/|oracle\.|import\s+oracle|from\s+oracle", open(os.path.join(ROOT, "host", fn)).read()), fn
