@@ -108,6 +108,13 @@ def test_live_host_paired_with_oracle_records(case):
 
 
 @needs_bins
+def test_live_host_paired_multi_block_with_oracle_records():
+    """Paired end over more than one reads_block (two 16 MiB slabs per block, application.cpp:1057-1104): block starts, the
+    i >= next_synchro rule with i stepping by 2, end-of-block syncs."""
+    assert "segments" in _run_paired(_build_mock, (100, 400000, 35000, 150, 91))
+
+
+@needs_bins
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", SORTED)
 def test_live_host_sorted_on_gpu(case):
