@@ -183,7 +183,7 @@ def reference_arm(args):
         return 0
     threads = min(os.cpu_count() or 1, 64)
     genome = synth.make_genome(GENOME, SEED)
-    per_step = max(200, 60_000 // max(args.steps, 1))      # K steps of a bounded sample: ~60 k reads in total
+    per_step = max(200, 120_000 // max(args.steps, 1))     # K steps of a bounded sample: ~120 k reads in total (tens of seconds beyond the table construction)
     if args.warmup:
         run_reference(genome, min(per_step * args.warmup, 10_000), threads, seed_off=1)
     res = run_reference(genome, per_step * args.steps, threads)
@@ -287,7 +287,7 @@ def main():
     ap.add_argument("--shard", action="store_true", help="N > 1: ONE job with hash-sharded tables (reference -t N semantics, strong scaling) instead of N independent replicas")
     ap.add_argument("--no-phase-events", action="store_true", help="do not bracket the internal phases with CUDA events (fewer host API calls per segment)")
     ap.add_argument("--no-box-warmup", action="store_true", help="skip the throw-away engine that warms the box up before the W warm-up steps")
-    ap.add_argument("--cpu-sample-reads", type=int, default=40_000)
+    ap.add_argument("--cpu-sample-reads", type=int, default=120_000, help="bounded sample of the cpu_baseline leg: large enough that the reference spends tens of seconds beyond its table construction")
     ap.add_argument("--no-compress-e2e", action="store_true", help="skip the whole-compressor leg (fqs-1.1-fqsk vs fqs-1.1 -t 1)")
     ap.add_argument("--compress-sample-reads", type=int, default=60_000)
     ap.add_argument("--trace-blocks", type=int, default=0, help="print per-block phase ms every N blocks to stderr")
