@@ -176,6 +176,9 @@ struct fqsk_handle {
 
 namespace {
 
+inline bool mode_pe(uint32_t m) { return m == FQSK_MODE_PE_ORIGINAL || m == FQSK_MODE_PE_SORTED; }
+inline bool mode_sorted(uint32_t m) { return m == FQSK_MODE_SE_SORTED || m == FQSK_MODE_PE_SORTED; }
+
 int fail(fqsk_handle *h, int code, const char *fmt, ...) {
 	char b[512];
 	va_list ap;
@@ -662,7 +665,7 @@ EngineDev make_engine_dev(fqsk_handle *h) {
 	EngineDev E{};
 	E.hb = h->tb.d; E.hs = h->ts.d; E.siv = h->siv; E.cib = h->tb.ci; E.cis = h->ts.ci;
 	E.p = h->P.pmer_len; E.s = h->P.smer_len; E.b = h->P.bmer_len; E.prefix_len = h->P.prefix_len;
-	E.sorted = (h->P.mode == FQSK_MODE_SE_SORTED || h->P.mode == FQSK_MODE_PE_SORTED);
+	E.sorted = mode_sorted(h->P.mode);
 	double aff = h->S.siv_no_filled ? (double) h->S.siv_no_updates / (double) h->S.siv_no_filled : 0.0;   // bit_vec.h:204-210
 	E.gate_missing = aff >= 7.0;
 	for (int i = 0; i < 4; ++i) { E.draws[i] = h->rng[i].buf; E.dmask[i] = h->rng[i].cap - 1; E.dpos[i] = h->rng[i].consumed; E.avail[i] = stream_avail(h->rng[i]); }
@@ -987,7 +990,8 @@ PeSeg pe_seg(fqsk_handle *h) { return PeSeg{h->pe_sk.as<unsigned long long>(), h
 // Turns the n_pairs pairs of a segment into 3 * n_pairs work items (texts in it_dna, descriptors in it_*).
 int pe_front(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes, const unsigned long long *d_off, const uint32_t *d_len, uint32_t np, uint64_t *item_bytes_bound) {
 	const uint32_t nt = 14 * np, ni = 3 * np, b = h->P.bmer_len;
-	*item_bytes_bound = dna_bytes + (uint64_t) np * (b + 2ull * h->P.prefix_len) + 64;
+	const uint32_t first1 = h->P.mode == FQSK_MODE_PE_SORTED ? h->P.pmer_len : h->P.prefix_len;      // mate 1: CompressSorted codes from p_len (dna.cpp:1793-1796)
+	*item_bytes_bound = dna_bytes + (uint64_t) np * (b + (uint64_t) first1 + h->P.prefix_len) + 64;
 	CK(h->pe_tk.ensure((size_t) nt * 8)); CK(h->pe_tv.ensure((size_t) nt * 8)); CK(h->pe_q.ensure((size_t) np * 32));
 	CK(h->pe_sk.ensure((size_t) nt * 8)); CK(h->pe_sv.ensure((size_t) nt * 8)); CK(h->pe_sidx.ensure((size_t) nt * 4));
 	CK(h->pe_t1.ensure((size_t) nt * 8)); CK(h->pe_t2.ensure((size_t) nt * 8)); CK(h->pe_info.ensure((size_t) np * 12));
@@ -1011,7 +1015,7 @@ int pe_front(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes, const uns
 		if (h->pe_pool_cap < 64 * np) h->pe_pool_cap = 64 * np;
 		CK(h->pe_pool.ensure((size_t) h->pe_pool_cap * 8));
 		CK(cudaMemsetAsync(h->d_pe, 0, 8, h->st));
-		CK(pdl(k_pe_decide, nblk((uint64_t) np * 32, 128), 128, h->st, h->pair, pe_seg(h), q, d_dna, d_off, d_len, np, h->P.prefix_len, h->pe_pool.as<unsigned long long>(),
+		CK(pdl(k_pe_decide, nblk((uint64_t) np * 32, 128), 128, h->st, h->pair, pe_seg(h), q, d_dna, d_off, d_len, np, h->P.prefix_len, first1, h->pe_pool.as<unsigned long long>(),
 		                                                             h->d_pe, h->pe_pool_cap, (int *) (h->d_pe + 1), h->pe_info.as<uint32_t>(), I)); LAUNCHED(h);
 		uint32_t *hs = (uint32_t *) ((uint8_t *) h->h_small + 960);
 		CK(cudaMemcpyAsync(hs, h->d_pe, 8, cudaMemcpyDeviceToHost, h->st));
@@ -1041,7 +1045,7 @@ int pe_sync(fqsk_handle *h) {
 
 int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual, const unsigned long long *d_off, const uint32_t *d_len, uint32_t n) {
 	if (h->pending) return fail(h, FQSK_E_INVAL, "fqsk_segment called twice without fqsk_sync (the reference syncs after every segment, application.cpp:643-662)");
-	const bool pe = h->P.mode == FQSK_MODE_PE_ORIGINAL;
+	const bool pe = mode_pe(h->P.mode);
 	const uint32_t n_in = n;
 	const uint64_t bytes_in = dna_bytes_actual;
 	h->seg_reads_in = n_in; h->pe_nt = 0; h->pe_pairs = 0;
@@ -1054,7 +1058,7 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 	}
 	const uint64_t dna_bytes = std::max<uint64_t>(dna_bytes_actual, pe ? (uint64_t) h->P.reserve_bytes + h->P.reserve_bytes / 4 : h->P.reserve_bytes);
 	if (h->world > 1 && h->attached != (1u << h->world) - 1) return fail(h, FQSK_E_INVAL, "sharded engine: not every peer shard is attached (fqsk_shard_attach)");
-	const uint32_t first = (h->P.mode == FQSK_MODE_SE_SORTED || h->P.mode == FQSK_MODE_PE_SORTED) ? h->P.pmer_len : h->P.prefix_len;
+	const uint32_t first = mode_sorted(h->P.mode) ? h->P.pmer_len : h->P.prefix_len;
 	h->seg_reads = n; h->n_recs = 0; h->pend_b = h->pend_s = h->pend_p = 0;
 	h->hot = false; h->seg_extra_pass = false; h->spec_prefix = false;
 	++h->S.n_segments;
@@ -1087,7 +1091,7 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 	S.pk = h->pk.as<unsigned long long>();
 	{
 		Phase ph(h, FQSK_PH_PREP);
-		CK(pdl(k_prep, nblk((uint64_t) n * 32, 128), 128, h->st, S, first, h->P.bmer_len, (uint32_t) (h->P.mode == FQSK_MODE_SE_SORTED))); LAUNCHED(h);
+		CK(pdl(k_prep, nblk((uint64_t) n * 32, 128), 128, h->st, S, first, h->P.bmer_len, (uint32_t) mode_sorted(h->P.mode))); LAUNCHED(h);
 		if (n > SCAN_CHAIN_MAX * SCAN_READS_CHUNK) return fail(h, FQSK_E_INVAL, "more than %u reads in one segment", SCAN_CHAIN_MAX * SCAN_READS_CHUNK);
 		ScanChain sc; CKR(scan_chain(h, sc));
 		CK(pdl(k_scan_reads, n <= 1024 ? 1u : nblk(n, SCAN_READS_CHUNK), n <= 1024 ? 256 : 1024, h->st, S, h->rec_off.as<unsigned long long>(), h->sl_prefix.as<U64x4>(), (SegTotals *) (h->d_status + 64), h->d_u32 + 3, sc)); LAUNCHED(h);
@@ -1108,7 +1112,7 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 	// one launch: verdict of the first pass + the state the next segment inherits (read_prev, pmer_can_prev)
 	CK(pdl(k_seg_tail, 1, 256, h->st, h->d_flags, (const uint32_t *) (h->d_status + 192), (const unsigned long long *) (h->d_status + 208),
 	       h->rng[ST_B].consumed, h->rng[ST_S].consumed, SYNC_INDEXED_MAX, h->d_syncin,
-	       S, pe ? n - 3 : n - 1, h->prev_read.as<uint8_t>(), h->d_carry, (uint32_t) (h->P.mode == FQSK_MODE_SE_SORTED || h->P.mode == FQSK_MODE_PE_SORTED), h->P.pmer_len, (uint32_t) prefix,
+	       S, pe ? n - 3 : n - 1, h->prev_read.as<uint8_t>(), h->d_carry, (uint32_t) mode_sorted(h->P.mode), h->P.pmer_len, (uint32_t) prefix,
 	       (uint32_t) ((h->dbg_fail_every && h->dbg_seg % h->dbg_fail_every == 0) || (h->dbg_retry_every && h->dbg_seg % h->dbg_retry_every == 1)))); LAUNCHED(h);
 	h->dbg_retry_armed = h->dbg_retry_every && h->dbg_seg % h->dbg_retry_every == 1;     // a retry always comes with a failed verdict (as flags[4] would give)
 	++h->dbg_seg;
@@ -1188,7 +1192,7 @@ int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
 	if (world > 1 && p->mode != FQSK_MODE_SE_ORIGINAL && p->mode != FQSK_MODE_PE_ORIGINAL) return fail(h, FQSK_E_UNSUPPORTED, "sharded operation is implemented for original order only (SE and PE)");
 	if (!(p->pmer_len >= 5 && p->pmer_len < p->smer_len && p->smer_len < p->bmer_len && p->bmer_len <= 31)) return fail(h, FQSK_E_INVAL, "need 5 <= p < s < b <= 31");
 	if (p->pmer_len > 18) return fail(h, FQSK_E_INVAL, "pmer_len > 18 not supported");
-	if (p->mode == FQSK_MODE_PE_SORTED || p->mode > FQSK_MODE_PE_SORTED) return fail(h, FQSK_E_UNSUPPORTED, "paired-end sorted order (-p -om s) is not implemented");
+	if (p->mode > FQSK_MODE_PE_SORTED) return fail(h, FQSK_E_INVAL, "mode %u: not a dna_mode_t (params.h:18)", p->mode);
 	int ndev = 0;
 	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(h, FQSK_E_NO_DEVICE, "no CUDA device: this library has no CPU path");
 	if (p->device < 0 || p->device >= ndev) return fail(h, FQSK_E_INVAL, "device %d out of range (%d devices)", p->device, ndev);
@@ -1248,7 +1252,7 @@ int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
 		for (int i = 0; i < 4; ++i) CKR(stream_init(h, h->rng[i], i == ST_B ? (1ull << 25) : i == ST_S ? (1ull << 21) : (1ull << 16)));
 		CKR(stream_generate(h, h->rng[ST_B], 1u << 22)); CKR(stream_generate(h, h->rng[ST_S], 1u << 18));
 		CK(h->prev_read.ensure(1 << 16));
-		if (p->mode == FQSK_MODE_PE_ORIGINAL) {          // CHT_pair_kmers(bmer_len, ...), application.cpp:91
+		if (mode_pe(p->mode)) {          // CHT_pair_kmers(bmer_len, ...), application.cpp:91
 			CK(cudaMalloc(&h->d_pe, 64)); CK(cudaMemsetAsync(h->d_pe, 0, 64, h->st));
 			CKR(pair_alloc(h, h->pair, 1ull << (p->pair_log2_slots ? std::min<uint32_t>(std::max<uint32_t>(p->pair_log2_slots, 10), 34) : (world > 1 ? 22u : 16u))));
 		}
@@ -1323,7 +1327,7 @@ static int prealloc_for_reserve(fqsk_handle *h) {
 	CK(h->slot_of.ensure(nr * 8)); CK(h->flag8.ensure(nr + 4)); CK(h->draw_off.ensure((nr + 1) * 4)); CK(h->final_cnt.ensure(nr * 4));
 	CK(h->q4.ensure(nr + 4)); CK(h->y_flag.ensure(nr + 64));
 	if (h->world == 1 && h->P.reserve_bytes >= (1u << 20)) { CK(h->dfilter.ensure((size_t) 2 * (1u << 26) / 8)); }
-	if (h->P.mode == FQSK_MODE_PE_ORIGINAL) CK(h->pe_pool.ensure((size_t) std::max<uint32_t>(h->pe_pool_cap, 64 * (h->P.reserve_reads / 2 + 1)) * 8));
+	if (mode_pe(h->P.mode)) CK(h->pe_pool.ensure((size_t) std::max<uint32_t>(h->pe_pool_cap, 64 * (h->P.reserve_reads / 2 + 1)) * 8));
 	CK(cudaStreamSynchronize(h->st));
 	return FQSK_OK;
 }
@@ -1358,6 +1362,16 @@ int fqsk_sorted_prefix(fqsk_handle *h, uint32_t *flag, uint64_t *dif, uint32_t n
 	if (n_reads > h->seg_reads) return fail(h, FQSK_E_INVAL, "last segment had %u reads", h->seg_reads);
 	if (!n_reads) return FQSK_OK;
 	CKR(seg_settle(h));
+	if (mode_pe(h->P.mode)) {      // per read: the first mate of pair i is item 3i; second mates have no sorted prefix (zeros)
+		if (n_reads > h->seg_reads_in) return fail(h, FQSK_E_INVAL, "last segment had %u reads", h->seg_reads_in);
+		const uint32_t ni = (n_reads + 1) / 2 * 3;
+		std::vector<uint32_t> f(ni); std::vector<unsigned long long> d(ni);
+		CK(cudaMemcpyAsync(f.data(), h->sflag.p, (size_t) ni * 4, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaMemcpyAsync(d.data(), h->sdif.p, (size_t) ni * 8, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaStreamSynchronize(h->st));
+		for (uint32_t i = 0; i < n_reads; ++i) { flag[i] = (i & 1) ? 0u : f[3 * (i / 2)]; dif[i] = (i & 1) ? 0ull : d[3 * (i / 2)]; }
+		return FQSK_OK;
+	}
 	CK(cudaMemcpyAsync(flag, h->sflag.p, (size_t) n_reads * 4, cudaMemcpyDeviceToHost, h->st));
 	CK(cudaMemcpyAsync(dif, h->sdif.p, (size_t) n_reads * 8, cudaMemcpyDeviceToHost, h->st));
 	CK(cudaStreamSynchronize(h->st));
@@ -1367,7 +1381,7 @@ int fqsk_sorted_prefix(fqsk_handle *h, uint32_t *flag, uint64_t *dif, uint32_t n
 int fqsk_pair_info(fqsk_handle *h, uint32_t *info, uint32_t n_pairs) {
 	if (!h || (!info && n_pairs)) return FQSK_E_INVAL;
 	CK(cudaSetDevice(h->P.device));
-	if (h->P.mode != FQSK_MODE_PE_ORIGINAL) return fail(h, FQSK_E_INVAL, "not a paired-end engine");
+	if (!mode_pe(h->P.mode)) return fail(h, FQSK_E_INVAL, "not a paired-end engine");
 	if (n_pairs > h->pe_pairs) return fail(h, FQSK_E_INVAL, "last segment had %u pairs", h->pe_pairs);
 	if (!n_pairs) return FQSK_OK;
 	CK(cudaMemcpyAsync(info, h->pe_info.p, (size_t) n_pairs * 12, cudaMemcpyDeviceToHost, h->st));
@@ -1380,7 +1394,7 @@ int fqsk_pair_info(fqsk_handle *h, uint32_t *info, uint32_t n_pairs) {
 // *rec_bound = upper bound of the records the segment produces (exact unless it holds duplicates).
 static int stage_segment(fqsk_handle *h, uint8_t *&stage, size_t &stage_cap, const uint8_t *slab, uint64_t slab_size, const fqsk_read_desc *reads, uint32_t n_reads,
                          uint64_t *total_out, uint64_t *rec_bound) {
-	const uint32_t first = h->P.mode == FQSK_MODE_SE_SORTED ? h->P.pmer_len : h->P.prefix_len;
+	const uint32_t first = mode_sorted(h->P.mode) ? h->P.pmer_len : h->P.prefix_len;      // paired end, sorted order: only first mates need p symbols, padding the second ones is harmless
 	uint64_t total = 0, bound = 0;
 	for (uint32_t i = 0; i < n_reads; ++i) { total += std::max(reads[i].dna_len, first); if (reads[i].dna_len > first) bound += reads[i].dna_len - first; }
 	size_t need = total + 64 + (size_t) n_reads * 12 + 64;
@@ -1434,7 +1448,7 @@ int fqsk_segment(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const 
 	CKR(seg_settle(h));
 	if (h->n_recs > rec_cap) return fail(h, FQSK_E_CAPACITY, "record buffer holds %llu, segment produced %llu", (unsigned long long) rec_cap, (unsigned long long) h->n_recs);
 	if (h->n_recs && recs) CK(cudaMemcpyAsync(recs, (h->rec_par ? h->recs_alt : h->recs).p, h->n_recs * sizeof(fqsk_base_rec), cudaMemcpyDeviceToHost, h->st));
-	if (h->P.mode == FQSK_MODE_PE_ORIGINAL) {
+	if (mode_pe(h->P.mode)) {
 		// per-read views of the per-item arrays: mate 1 = item 3i, mate 2 = items 3i+1 (+ 3i+2, contiguous records)
 		const uint32_t ni = n_reads / 2 * 3;
 		std::vector<uint8_t> idup(ni + 1);
@@ -1567,7 +1581,7 @@ static int sync_end(fqsk_handle *h) {
 			CK(pdl(k_sync_unclaim, h->spec_g, 256, h->st, h->tb.d, h->spec_Y, 1u)); LAUNCHED(h);
 			h->spec_prefix = false;
 		}
-		if (h->P.mode == FQSK_MODE_PE_ORIGINAL) CKR(pe_sync(h));
+		if (mode_pe(h->P.mode)) CKR(pe_sync(h));
 		if (!applied) {
 			// The three tables are independent (see sync_spec_enqueue): p-mer and s-mer updates run on side streams next to the ordered
 			// b-mer insert, which is a chain of sort / locate / apply launches with host looks in between.  Joined before the last look.
@@ -1699,7 +1713,7 @@ int fqsk_submit(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const f
 	Uploaded U;
 	CKR(upload_segment(h, stage, total, n_reads, U));
 	CKR(run_segment(h, U.dna, total, U.off, U.len, n_reads));
-	const uint32_t ni = h->P.mode == FQSK_MODE_PE_ORIGINAL ? n_reads / 2 * 3 : n_reads;
+	const uint32_t ni = mode_pe(h->P.mode) ? n_reads / 2 * 3 : n_reads;
 	if (ni) {   // duplicate flags and record offsets are final after k_prep / k_scan_reads: main stream, ahead of the look that ends the sync
 		const size_t need = (((size_t) ni + 8) & ~(size_t) 7) + ((size_t) ni + 1) * 8;
 		if (need > h->h_meta_cap[par]) {
@@ -1740,7 +1754,7 @@ int fqsk_collect(fqsk_handle *h, uint64_t ticket, uint64_t *n_recs) {
 	if (T.bound && T.recs && T.n_reads) CK(cudaEventSynchronize(h->ev_copied[par]));
 	const uint32_t n = T.n_reads;
 	if (n) {
-		const bool pe = h->P.mode == FQSK_MODE_PE_ORIGINAL;
+		const bool pe = mode_pe(h->P.mode);
 		const uint32_t ni = pe ? n / 2 * 3 : n;
 		const uint8_t *idup = h->h_meta[par];
 		const unsigned long long *ioff = (const unsigned long long *) (h->h_meta[par] + (((size_t) ni + 8) & ~(size_t) 7));

@@ -104,9 +104,12 @@ enum : uint8_t {
 	IF_NO_LETTERS = 8,    // right part of a split mate 2: update_s_letters runs once, after the left part (dna.cpp:1635)
 	IF_LETTERS_PREV = 16, // left part of a split mate 2: its own symbols plus those of the previous item beyond the shared b-mer
 	IF_REVCOMP = 32,      // text = reverse complement of the source range (dna.cpp:1598-1602)
+	IF_SORTED = 64,       // paired end in sorted order: first mate, coded by CompressSorted (dna.cpp:1793-1796); the second mate is not
 };
 __device__ __forceinline__ uint32_t item_first(const SegDev &S, uint32_t dflt, uint32_t r) { return S.first_a ? S.first_a[r] : dflt; }
 __device__ __forceinline__ uint32_t item_flags(const SegDev &S, uint32_t r) { return S.iflags ? S.iflags[r] : 0u; }
+// is read / item r coded by CompressSorted?  single-end sorted order: every read; paired-end sorted order: the first mates only
+__device__ __forceinline__ bool item_sorted(const SegDev &S, uint32_t sorted_mode, uint32_t r) { return sorted_mode && (!S.iflags || (S.iflags[r] & IF_SORTED)); }
 
 __device__ __forceinline__ uint32_t dna_code(uint8_t ch) {  // dna.cpp:18-23
 	return ch == 'A' ? 0u : ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : 4u;
@@ -119,6 +122,7 @@ __global__ void __launch_bounds__(128) k_prep(SegDev S, uint32_t first_len_bytes
 	uint32_t n = S.len[r];
 	const uint32_t ifl = item_flags(S, r);
 	first_len_bytes = item_first(S, first_len_bytes, r);
+	sorted = item_sorted(S, sorted, r);
 	const uint8_t *q; uint32_t qn;
 	uint32_t pr = S.dup_prev ? S.dup_prev[r] : (r ? r - 1 : 0xFFFFFFFFu);     // the read this one is compared with (read_prev)
 	if (pr == 0xFFFFFFFFu) { q = S.prev_read; qn = S.carry->prev_len; } else { q = S.dna + S.off[pr]; qn = S.len[pr]; }

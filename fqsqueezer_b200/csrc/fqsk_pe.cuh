@@ -167,7 +167,7 @@ FQSK_DEV bool pe_before(unsigned long long x, unsigned long long y, uint32_t sh,
 // (1805-1822, generate_read_bmers 974-999): first candidate (of the first 15) present in mate 2, at its first position.
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_pe_decide(PairDev G, PeSeg L, const unsigned long long *qkeys, const uint8_t *dna, const unsigned long long *off, const uint32_t *len,
-                                                   uint32_t n_pairs, uint32_t prefix_len, unsigned long long *pool, uint32_t *pool_used, uint32_t pool_cap, int *overflow,
+                                                   uint32_t n_pairs, uint32_t prefix_len, uint32_t first1, unsigned long long *pool, uint32_t *pool_used, uint32_t pool_cap, int *overflow,
                                                    uint32_t *info, PeItems I) { pdl_enter();
 	const uint32_t pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (pair >= n_pairs) return;
@@ -244,7 +244,8 @@ __global__ void __launch_bounds__(128) k_pe_decide(PairDev G, PeSeg L, const uns
 	const bool split = found && id < 15;
 	info[3ull * pair] = found; info[3ull * pair + 1] = id; info[3ull * pair + 2] = split ? pos : 0;
 	const uint32_t a = 3 * pair;
-	I.src[a] = off[2 * pair]; I.len[a] = L1; I.bytes[a] = L1 > prefix_len ? L1 : prefix_len; I.first[a] = prefix_len; I.bias[a] = 0; I.flags[a] = 0;
+	// mate 1: CompressDirect, or -- in sorted order -- CompressSorted, which codes from p_len (first1 = p_len then; dna.cpp:1793-1796)
+	I.src[a] = off[2 * pair]; I.len[a] = L1; I.bytes[a] = L1 > first1 ? L1 : first1; I.first[a] = first1; I.bias[a] = 0; I.flags[a] = first1 != prefix_len ? IF_SORTED : 0;
 	I.dup_prev[a] = pair ? a - 3 : 0xFFFFFFFFu;
 	I.dup_prev[a + 1] = I.dup_prev[a + 2] = 0xFFFFFFFFu;
 	if (split) {

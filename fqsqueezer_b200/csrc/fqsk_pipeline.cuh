@@ -78,9 +78,9 @@ struct PipeDev {
 	                                // [7] k_fold: a read's draw count differs from the scanned one
 };
 
-__device__ __forceinline__ uint32_t sym_at(const SegDev &S, const EngineDev &E, const uint8_t *p, uint32_t j) {
+__device__ __forceinline__ uint32_t sym_at(bool sorted, const EngineDev &E, const uint8_t *p, uint32_t j) {
 	uint32_t c = dna_code(p[j]);
-	if (c == 4) c = (E.sorted && j < E.p) ? 3u : 0u;   // dna.cpp:532-536 / 560-565 / 684
+	if (c == 4) c = (sorted && j < E.p) ? 3u : 0u;   // dna.cpp:532-536 / 560-565 / 684
 	return c;
 }
 // uncorrected b register (with placeholder) in front of position i; cb = min(b, i + 1): symbols i - cb + 1 .. i - 1 of the packed
@@ -497,7 +497,9 @@ __global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P, 
 	if (it > 0) { if (!P.dirty[r]) return; }
 	__syncwarp();
 	if (lane == 0) P.dirty[r] = 0;
-	if (S.dup[r]) { if (lane == 0) { S.cnt_b[r] = S.cnt_s[r] = S.cnt_p[r] = S.hidden[r] = 0; if (E.sorted) { S.sorted_flag[r] = 0; S.sorted_dif[r] = 0; } } return; }
+	const bool sorted = item_sorted(S, E.sorted, r);      // this read goes through CompressSorted (dna.cpp:1716-1754)
+	if (S.dup[r] || (E.sorted && !sorted)) { if (lane == 0 && E.sorted) { S.sorted_flag[r] = 0; S.sorted_dif[r] = 0; } }
+	if (S.dup[r]) { if (lane == 0) { S.cnt_b[r] = S.cnt_s[r] = S.cnt_p[r] = S.hidden[r] = 0; } return; }
 	__shared__ uint8_t ringC_all[4][64], ringU_all[4][64];
 	uint8_t *ringC = ringC_all[threadIdx.x >> 5], *ringU = ringU_all[threadIdx.x >> 5];
 	const bool check = it > 0;
@@ -516,7 +518,7 @@ __global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P, 
 	int *unsupported = E.flags + 1;
 	DrawCursor nodraw; nodraw.ring = nullptr; nodraw.mask = 0; nodraw.pos0 = 0; nodraw.avail = 0; nodraw.base = 0; nodraw.used = 0; nodraw.overflow = E.flags + 5;
 
-	const uint32_t start = item_first(S, E.sorted ? E.p : E.prefix_len, r);
+	const uint32_t start = item_first(S, sorted ? E.p : E.prefix_len, r);
 	const uint32_t bias = S.bias_a ? S.bias_a[r] : 0;      // record positions and cor_pos are in the frame of the whole mate (dna.cpp:1596)
 	const bool seeded = (item_flags(S, r) & IF_SEEDED) != 0;
 	uint32_t cor_pos = 0;
@@ -525,18 +527,19 @@ __global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P, 
 		uint32_t npos = 0;
 		for (uint32_t j = lane; j < start; j += 32) if (dna_code(p[j]) == 4) npos = j + 1;
 		for (int o = 16; o; o >>= 1) { uint32_t y = __shfl_xor_sync(0xffffffffu, npos, o); npos = npos > y ? npos : y; }
-		if (!E.sorted && npos && !seeded) cor_pos = npos - 1;
+		if (!sorted && npos && !seeded) cor_pos = npos - 1;
 	}
-	if (E.sorted) {
+	if (sorted) {
 		if (lane == 0) {
 			unsigned long long cur_dir = 0;
-			for (uint32_t i = 0; i < E.p; ++i) cur_dir |= (unsigned long long) sym_at(S, E, p, i) << (62 - 2 * i);
+			for (uint32_t i = 0; i < E.p; ++i) cur_dir |= (unsigned long long) sym_at(sorted, E, p, i) << (62 - 2 * i);
 			unsigned long long cur_rc = 0;
-			for (uint32_t i = 0; i < E.p; ++i) cur_rc |= (unsigned long long) (3 - sym_at(S, E, p, E.p - 1 - i)) << (62 - 2 * i);
+			for (uint32_t i = 0; i < E.p; ++i) cur_rc |= (unsigned long long) (3 - sym_at(sorted, E, p, E.p - 1 - i)) << (62 - 2 * i);
 			unsigned long long prev_dir; bool prev_valid;
-			if (r == 0) { prev_dir = S.carry->pprev_dir; prev_valid = S.carry->pprev_valid != 0; }
+			const uint32_t back = S.iflags ? 3u : 1u;      // the previous read coded by CompressSorted: paired end -> the first mate of the previous pair
+			if (r < back) { prev_dir = S.carry->pprev_dir; prev_valid = S.carry->pprev_valid != 0; }
 			else {
-				const uint8_t *q = S.dna + S.off[r - 1];
+				const uint8_t *q = S.dna + S.off[r - back];
 				prev_dir = 0;
 				for (uint32_t i = 0; i < E.p; ++i) { uint32_t sy = dna_code(q[i]); if (sy == 4) sy = 3; prev_dir |= (unsigned long long) sy << (62 - 2 * i); }
 				prev_valid = true;
@@ -560,7 +563,7 @@ __global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P, 
 		// bring the rings up to position i0 + 31 (never more than 64 behind)
 		uint32_t want = i0 + 32 < size ? i0 + 32 : size;
 		uint32_t from = filled > (i0 >= 31 ? i0 - 31 : 0) ? filled : (i0 >= 31 ? i0 - 31 : 0);
-		for (uint32_t j = from + lane; j < want; j += 32) { uint8_t sy = (uint8_t) sym_at(S, E, p, j); ringU[j & 63] = sy; ringC[j & 63] = sy; }
+		for (uint32_t j = from + lane; j < want; j += 32) { uint8_t sy = (uint8_t) sym_at(sorted, E, p, j); ringU[j & 63] = sy; ringC[j & 63] = sy; }
 		filled = want;
 		__syncwarp();
 		const uint32_t i = i0 + lane;

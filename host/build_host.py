@@ -17,7 +17,7 @@ host/_bin/ is git-ignored and travels to the GPU box like our own .so files).  T
   everything else (context model, range coders, id / quality / meta streams, container, decompressor) is untouched.
 
 host/fqsk_live.h (ours) holds the binding itself (dlopen of $FQSK_LIB, descriptors, record cursor).
-Scope: -t 1; -s -om o, -s -om s, -p -om o.  No-op (exit 0) where /root/reference does not exist (the GPU box uses the prebuilt binary).
+Scope: -t 1; -s and -p, each with -om o and -om s.  No-op (exit 0) where /root/reference does not exist (the GPU box uses the prebuilt binary).
 """
 import os
 import shutil

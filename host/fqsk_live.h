@@ -5,9 +5,9 @@
 // This file is OUR code (no reference source in it).  host/build_host.py compiles the reference's own sources -- where they lie,
 // patched in a scratch copy -- with this header into host/_bin/fqs-1.1-fqsk.  INTEGRATION.md walks through the patch.
 //
-// Scope of the live host: -t 1 (the parity configuration of the north star; one engine = one reference worker thread), single-end in
-// original and sorted order (-s -om o / -om s) and paired-end in original order (-p -om o).  Anything else stops with a message:
-// there is no CPU fallback for the k-mer path.
+// Scope of the live host: -t 1 (the parity configuration of the north star; one engine = one reference worker thread), single-end and
+// paired-end, each in original and in sorted order (-s / -p with -om o / -om s; sorted is the reference's default, params.h:60).
+// Anything else stops with a message: there is no CPU fallback for the k-mer path.
 //
 // The library is bound with dlopen ($FQSK_LIB, default "libfqsk.so") so that the binary has no link-time CUDA dependency and the
 // CPU test suite can point it at a mock built from the oracle (tests/mock_fqsk.cpp) to check the HOST half of the integration.
@@ -69,8 +69,8 @@ public:
 	// application.cpp:86-91 (AdjustToParams): the engine takes the place of siv_pmer / ht_smer / ht_bmer
 	// dna_mode: params.h:18 (0 se_original, 1 se_sorted, 2 pe_original, 3 pe_sorted) = FQSK_MODE_*
 	void create(uint32_t pmer_len, uint32_t smer_len, uint32_t bmer_len, uint32_t prefix_len, uint64_t genome_mbp, uint32_t dna_mode, uint32_t n_threads, bool dup_check) {
-		if (dna_mode > FQSK_MODE_PE_ORIGINAL || n_threads != 1 || !dup_check) {
-			fprintf(stderr, "fqsk: the live host covers -t 1 with the duplicates check on, -s (-om o / -om s) and -p -om o; no CPU fallback for other modes\n");
+		if (dna_mode > FQSK_MODE_PE_SORTED || n_threads != 1 || !dup_check) {
+			fprintf(stderr, "fqsk: the live host covers -t 1 with the duplicates check on (-s / -p, -om o / -om s); no CPU fallback for other modes\n");
 			exit(3);
 		}
 		mode = dna_mode;
@@ -130,12 +130,12 @@ public:
 		const double t0 = now();
 		int rc = p_segment(h, slab, slab_size, descs.data(), (uint32_t) n, recs, rec_cap, &n_recs, dup.data(), nullptr);
 		if (rc != FQSK_OK) die("fqsk_segment", rc);
-		if (mode == FQSK_MODE_SE_SORTED) {            // dna.cpp:589-605: (flag, dif) of every read's p-mer prefix
+		if (mode == FQSK_MODE_SE_SORTED || mode == FQSK_MODE_PE_SORTED) {            // dna.cpp:589-605: (flag, dif) of every read's p-mer prefix (paired end: of the first mates)
 			s_flag.resize(n + 1); s_dif.resize(n + 1);
 			rc = p_sorted_prefix(h, s_flag.data(), s_dif.data(), (uint32_t) n);
 			if (rc != FQSK_OK) die("fqsk_sorted_prefix", rc);
 		}
-		if (mode == FQSK_MODE_PE_ORIGINAL) {          // dna.cpp:1798-1838: the shared-minimizer decision of every pair
+		if (mode == FQSK_MODE_PE_ORIGINAL || mode == FQSK_MODE_PE_SORTED) {          // dna.cpp:1798-1838: the shared-minimizer decision of every pair
 			if (n & 1) { fprintf(stderr, "fqsk: a paired-end segment with an odd number of reads\n"); exit(3); }
 			pair_words.resize(3 * (n / 2) + 3);
 			rc = p_pair_info(h, pair_words.data(), (uint32_t) (n / 2));

@@ -254,7 +254,7 @@ def ref_units() -> _Units:
 
 
 STAT_NAMES = ["siv_no_filled", "siv_no_updates", "n_smers", "n_bmers", "draws_b", "draws_s", "draws_lb", "draws_ls",
-              "rough_b", "rough_s", "rough_p", "repair_existing", "repair_missing", "local_hits", "probe_runs_s", "probe_runs_b"]
+              "rough_b", "rough_s", "rough_p", "repair_existing", "repair_missing", "local_hits", "probe_runs_s", "probe_runs_b", "mixed", "unc_reverts"]
 
 
 class OracleEngine:
@@ -298,7 +298,7 @@ class OracleEngine:
         return k[:n].copy(), v[:n].copy()
 
     def stats(self):
-        o = np.zeros(16, np.uint64)
+        o = np.zeros(len(STAT_NAMES), np.uint64)
         self.lib.fqso_stats(self.h, o)
         return dict(zip(STAT_NAMES, (int(x) for x in o)))
 

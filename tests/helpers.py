@@ -137,6 +137,53 @@ def run_pe(engine, slab, is_gpu=False):
     return recs[recs["pos"] < 0xFFFFFFF0], (np.concatenate(info) if info else np.zeros((0, 3), np.uint32))
 
 
+def run_pe_sorted(engine, slab, is_gpu=False):
+    """Paired-end in the reference's default order (-p -om s): preprocess_pe bins the pairs by the first 4 symbols of MATE 1 (N -> T,
+    application.cpp:415-506), each bin is one pair of temp files read through CSortedFASTQFile (pairs sorted by mate 1, io.h:499-528), so
+    reads_blocks never span bins while the block generation keeps counting (application.cpp:1048-1104).  `slab` holds the pairs
+    interleaved in the order the reference coded them.  Returns (records, pair_info[n, 3], flags, difs); the (flag, dif) of
+    compress_prefix_sorted exist for the first mate of every non-duplicate pair."""
+    off, ln, roff, rsz = S.parse_fastq(slab)
+    lut = np.full(256, 3, np.int64)
+    lut[ord("A")], lut[ord("C")], lut[ord("G")], lut[ord("T")] = 0, 1, 2, 3
+    o1 = off[0::2].astype(np.int64)
+    first4 = np.stack([lut[slab[o1 + k]] for k in range(4)], axis=1)
+    bins = first4[:, 0] * 64 + first4[:, 1] * 16 + first4[:, 2] * 4 + first4[:, 3]
+    cuts = [0] + list(2 * (np.flatnonzero(np.diff(bins)) + 1)) + [len(off)]
+    out, info, flags, difs = [], [], [], []
+    gen = 0
+    for a0, a1 in zip(cuts[:-1], cuts[1:]):
+        for f, l in S.split_blocks(rsz[a0:a1], paired=True):
+            f += a0; l += a0
+            ns = S.calc_no_synchronizations(gen, l - f, 1)
+            engine.block_start()
+            for a, b in S.segments(f, l, ns, paired=True):
+                recs, dup = engine.segment(slab, off[a:b], ln[a:b], 3)
+                out.append(recs)
+                if is_gpu:
+                    info.append(engine.pair_info((b - a) // 2))
+                    fl, df = engine.sorted_prefix(b - a)
+                    keep = (dup == 0) & (np.arange(b - a) % 2 == 0)
+                    flags.append(fl[keep]); difs.append(df[keep])
+                engine.sync()
+            gen += 1
+    recs = np.concatenate(out) if out else np.zeros(0, O.REC_DTYPE)
+    if not is_gpu:
+        pi = recs[recs["pos"] == POS_PAIR]
+        info = [pi["c"][:, :3].astype(np.uint32)]
+        sp = recs[recs["pos"] == O.POS_SORTED]
+        flags = [sp["c"][:, 0].astype(np.uint32)]
+        difs = [sp["c"][:, 1].astype(np.uint64) | (sp["c"][:, 2].astype(np.uint64) << np.uint64(32))]
+    cat = lambda v, dt, shape=(0,): np.concatenate(v) if v else np.zeros(shape, dt)
+    return recs[recs["pos"] < 0xFFFFFFF0], cat(info, np.uint32, (0, 3)), cat(flags, np.uint32), cat(difs, np.uint64)
+
+
+def golden_pe_sorted_expect(gold):
+    recs, info = golden_pe_expect(gold)
+    _, flags, difs = golden_sorted_expect(gold)
+    return recs, info, flags, difs
+
+
 def golden_pe_expect(gold):
     r = gold["recs"]
     pi = r[r["pos"] == POS_PAIR]

@@ -24,7 +24,7 @@ struct fqsk_handle { void *o; uint32_t mode = 0; uint64_t n_segments = 0, n_sync
 extern "C" {
 
 int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
-	if (!p || !out || p->abi_version != FQSK_ABI_VERSION || p->mode > FQSK_MODE_PE_ORIGINAL || p->n_workers != 1) return FQSK_E_INVAL;
+	if (!p || !out || p->abi_version != FQSK_ABI_VERSION || p->mode > FQSK_MODE_PE_SORTED || p->n_workers != 1) return FQSK_E_INVAL;
 	fqsk_handle *h = new fqsk_handle();
 	h->mode = p->mode;
 	h->o = fqso_create(p->pmer_len, p->smer_len, p->bmer_len, p->prefix_len, p->mode);   // dna_mode_t = FQSK_MODE_*
@@ -42,7 +42,7 @@ int fqsk_segment(fqsk_handle *h, const uint8_t *slab, uint64_t, const fqsk_read_
 	for (uint32_t i = 0; i < n_reads; ++i) { off[i] = reads[i].dna_off; len[i] = reads[i].dna_len; total += len[i]; }
 	std::vector<fqsk_base_rec> tmp(total + 3 * (uint64_t) n_reads + 16);     // the oracle also emits per-read / duplicate markers (pos >= 0xFFFFFFF0)
 	std::vector<uint8_t> d(n_reads + 1);
-	const uint32_t kind = h->mode == FQSK_MODE_SE_SORTED ? 2 : h->mode == FQSK_MODE_PE_ORIGINAL ? 3 : 0;     // oracle: 0 CompressDirect, 2 CompressSorted, 3 CompressPE
+	const uint32_t kind = h->mode == FQSK_MODE_SE_SORTED ? 2 : (h->mode == FQSK_MODE_PE_ORIGINAL || h->mode == FQSK_MODE_PE_SORTED) ? 3 : 0;     // oracle: 0 CompressDirect, 2 CompressSorted, 3 CompressPE
 	uint64_t m = fqso_segment(h->o, slab, off.data(), len.data(), n_reads, kind, tmp.data(), tmp.size(), d.data());
 	if (m > tmp.size()) return FQSK_E_CAPACITY;
 	h->s_flag.assign(n_reads + 1, 0); h->s_dif.assign(n_reads + 1, 0); h->pair.assign(3 * (n_reads / 2) + 3, 0);
@@ -69,7 +69,7 @@ int fqsk_pair_info(fqsk_handle *h, uint32_t *info, uint32_t n_pairs) {
 }
 int fqsk_sync(fqsk_handle *h) { fqso_sync(h->o); ++h->n_syncs; return FQSK_OK; }
 int fqsk_stats_get(fqsk_handle *h, fqsk_stats *out) {
-	uint64_t o[16];
+	uint64_t o[32];
 	fqso_stats(h->o, o);
 	memset(out, 0, sizeof(*out));
 	out->siv_no_filled = o[0]; out->siv_no_updates = o[1]; out->n_smers = o[2]; out->n_bmers = o[3];

@@ -6,7 +6,7 @@ from oracle import oracle as O
 from tests import helpers as H
 
 
-@pytest.mark.parametrize("name", ["se_orig_gs1", "se_orig_gs100", "se_orig_repeats_gs1"])
+@pytest.mark.parametrize("name", ["se_orig_gs1", "se_orig_gs100", "se_orig_repeats_gs1", "se_mixed_unc_gs1", "se_orig_gs3100"])
 def test_oracle_matches_reference_tap(name):
     g = H.load_golden(name)
     pref, p, s, b = O.kmer_params(int(g["gs"]))
@@ -20,6 +20,12 @@ def test_oracle_matches_reference_tap(name):
         assert (recs["pos"] == O.POS_DUP).sum() > 0
     if name == "se_orig_repeats_gs1":
         assert st["draws_lb"] > 1000    # thread-local counters above thr: cinc_lb in use
+    if name == "se_mixed_unc_gs1":      # `mixed` (dna.cpp:470-478) and the bmer_unc revert (dna.cpp:697-705) must both occur
+        assert (g["recs"]["level"][g["recs"]["pos"] < 0xFFFFFFF0] == 4).sum() > 1000 and st["mixed"] > 1000
+        assert st["unc_reverts"] >= 3
+    if name == "se_orig_gs3100":        # the reference's default k-mer lengths: front-truncated b-mer lookups with up to 5 missing symbols
+        assert (e.p, e.s, e.b, e.prefix_len) == (18, 21, 27, 13)
+        assert st["draws_b"] > 1000 and st["rough_b"] > 100 and st["repair_existing"] > 10 and st["probe_runs_b"] > 1364 * 1000
     e.close()
 
 
@@ -66,6 +72,39 @@ def test_oracle_matches_reference_tap_paired_end():
     assert np.array_equal(info, winfo), np.flatnonzero((info != winfo).any(axis=1))[:5]
     H.assert_recs_equal(recs, want)
     assert (winfo[:, 0] == 1).sum() > 500 and ((winfo[:, 0] == 1) & (winfo[:, 1] < 15)).sum() > 500 and (winfo[:, 1] == 15).sum() > 0
+    H.assert_dump_equal(e, g, pairs=True)
+    e.close()
+
+
+def test_oracle_matches_reference_tap_paired_end_default_kmer_lengths():
+    """-p -om o at the reference's default -gs 3100 (p18/s21/b27, prefix 13: BASELINE config 5's lengths)."""
+    import numpy as np
+    g = H.load_golden("pe_orig_gs3100")
+    pref, p, s, b = O.kmer_params(int(g["gs"]))
+    assert (pref, p, s, b) == (13, 18, 21, 27)
+    e = O.OracleEngine(p, s, b, pref, mode=2)
+    recs, info = H.run_pe(e, g["fastq"])
+    want, winfo = H.golden_pe_expect(g)
+    assert np.array_equal(info, winfo)
+    H.assert_recs_equal(recs, want)
+    assert ((winfo[:, 0] == 1) & (winfo[:, 1] < 15)).sum() > 300
+    H.assert_dump_equal(e, g, pairs=True)
+    e.close()
+
+
+def test_oracle_matches_reference_tap_paired_end_sorted_order():
+    """-p in the reference's DEFAULT order (-om s; params.h:60, BASELINE configs 3 and 5 as written): pairs binned and sorted by mate 1,
+    mate 1 through CompressSorted (dna.cpp:1793-1796: sorted prefix flag / dif, suffix from p_len), mate 2 as in original order."""
+    import numpy as np
+    g = H.load_golden("pe_sorted_gs1")
+    pref, p, s, b = O.kmer_params(int(g["gs"]))
+    e = O.OracleEngine(p, s, b, pref, mode=3)
+    recs, info, flags, difs = H.run_pe_sorted(e, g["fastq"])
+    want, winfo, wflags, wdifs = H.golden_pe_sorted_expect(g)
+    assert np.array_equal(info, winfo)
+    assert np.array_equal(flags, wflags) and np.array_equal(difs, wdifs)
+    H.assert_recs_equal(recs, want)
+    assert (wdifs > 0).sum() > 100 and ((winfo[:, 0] == 1) & (winfo[:, 1] < 15)).sum() > 500
     H.assert_dump_equal(e, g, pairs=True)
     e.close()
 

@@ -12,8 +12,10 @@ from tests import helpers as H
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", ["se_orig_gs1", "se_orig_gs100", "se_orig_repeats_gs1"])
+@pytest.mark.parametrize("name", ["se_orig_gs1", "se_orig_gs100", "se_orig_repeats_gs1", "se_mixed_unc_gs1", "se_orig_gs3100"])
 def test_engine_matches_reference_golden(name):
+    """se_mixed_unc_gs1: the fixture in which counts_level `mixed` (dna.cpp:470-478; > 5 000 records) and the bmer_unc revert
+    (dna.cpp:697-705) occur; se_orig_gs3100: the reference's default k-mer lengths (p18/s21/b27, prefix 13; BASELINE configs 1, 4, 5)."""
     g = H.load_golden(name)
     pref, p, s, b = E.kmer_params(int(g["gs"]))
     e = E.KmerEngine(p, s, b, pref)
@@ -25,6 +27,8 @@ def test_engine_matches_reference_golden(name):
     if name == "se_orig_repeats_gs1":    # low-complexity reads: the thread-local PRNG streams (cinc_lb) must have been used
         st = e.stats()
         assert st["n_hot_segments"] > 0 and st["draws_lb"] > 0
+    if name == "se_mixed_unc_gs1":
+        assert (recs["level"] == 4).sum() > 1000
     e.close()
 
 
@@ -124,6 +128,34 @@ def test_engine_matches_reference_golden_paired_end():
     recs, info = H.run_pe(e, g["fastq"], is_gpu=True)
     want, winfo = H.golden_pe_expect(g)
     assert np.array_equal(info, winfo), np.flatnonzero((info != winfo).any(axis=1))[:5]
+    H.assert_recs_equal(recs, want)
+    H.assert_dump_equal(e, g, pairs=True)
+    e.close()
+
+
+def test_engine_matches_reference_golden_paired_end_default_kmer_lengths():
+    """-p -om o at -gs 3100 (p18/s21/b27, prefix 13): BASELINE config 5's k-mer lengths."""
+    g = H.load_golden("pe_orig_gs3100")
+    pref, p, s, b = E.kmer_params(int(g["gs"]))
+    e = E.KmerEngine(p, s, b, pref, mode=E.MODE_PE_ORIGINAL)
+    recs, info = H.run_pe(e, g["fastq"], is_gpu=True)
+    want, winfo = H.golden_pe_expect(g)
+    assert np.array_equal(info, winfo), np.flatnonzero((info != winfo).any(axis=1))[:5]
+    H.assert_recs_equal(recs, want)
+    H.assert_dump_equal(e, g, pairs=True)
+    e.close()
+
+
+def test_engine_matches_reference_golden_paired_end_sorted_order():
+    """-p in the reference's default order (-om s; BASELINE configs 3 and 5 as written): mate 1 through the sorted prefix (flag / dif,
+    suffix from p_len: dna.cpp:1793-1796), mate 2 as in original order; pairs binned and sorted by mate 1."""
+    g = H.load_golden("pe_sorted_gs1")
+    pref, p, s, b = E.kmer_params(int(g["gs"]))
+    e = E.KmerEngine(p, s, b, pref, mode=E.MODE_PE_SORTED)
+    recs, info, flags, difs = H.run_pe_sorted(e, g["fastq"], is_gpu=True)
+    want, winfo, wflags, wdifs = H.golden_pe_sorted_expect(g)
+    assert np.array_equal(info, winfo), np.flatnonzero((info != winfo).any(axis=1))[:5]
+    assert np.array_equal(flags, wflags) and np.array_equal(difs, wdifs)
     H.assert_recs_equal(recs, want)
     H.assert_dump_equal(e, g, pairs=True)
     e.close()

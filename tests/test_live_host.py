@@ -80,6 +80,8 @@ def _check(lib, gs, tmp, fq, decode=True, layout=("-s", "-om", "o")):
 # CompressPE's shared-minimizer decision from the engine); (gs, genome, reads or pairs, read length, seed)
 SORTED = [(1, 5000, 2500, 70, 45), (16, 60000, 6000, 150, 46)]
 PAIRED = [(1, 5000, 1200, 80, 71), (100, 50000, 4000, 150, 72)]
+# -p in the reference's DEFAULT order (-om s, params.h:60): BASELINE configs 3 and 5 as literally written
+PAIRED_SORTED = [(1, 5000, 1500, 80, 73), (100, 50000, 4000, 150, 74)]
 
 
 def _run_sorted(lib, case):
@@ -89,10 +91,10 @@ def _run_sorted(lib, case):
         return _check(lib(tmp), gs, tmp, fq, layout=("-s", "-om", "s"))
 
 
-def _run_paired(lib, case):
+def _run_paired(lib, case, order="o"):
     gs, G, n, L, seed = case
     with tempfile.TemporaryDirectory() as tmp:
-        return _check(lib(tmp), gs, tmp, _fastq_pe(tmp, gs, G, n, L, seed), layout=("-p", "-om", "o"))
+        return _check(lib(tmp), gs, tmp, _fastq_pe(tmp, gs, G, n, L, seed), layout=("-p", "-om", order))
 
 
 @needs_bins
@@ -105,6 +107,20 @@ def test_live_host_sorted_with_oracle_records(case):
 @pytest.mark.parametrize("case", PAIRED)
 def test_live_host_paired_with_oracle_records(case):
     assert "segments" in _run_paired(_build_mock, case)
+
+
+@needs_bins
+@pytest.mark.parametrize("case", PAIRED_SORTED)
+def test_live_host_paired_sorted_with_oracle_records(case):
+    assert "segments" in _run_paired(_build_mock, case, order="s")
+
+
+@needs_bins
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", PAIRED_SORTED)
+def test_live_host_paired_sorted_on_gpu(case):
+    log = _run_paired(lambda tmp: REAL_LIB, case, order="s")
+    assert "kernel launches" in log and " 0 kernel launches" not in log, log
 
 
 @needs_bins
@@ -170,6 +186,50 @@ def test_live_host_ragged_reads_on_gpu(lo):
         fq = _fastq(tmp, 1, 6000, 3000, 100, 77, 0.003, 0.01)
         _make_ragged(fq, 5, lo)
         log = _check(REAL_LIB, 1, tmp, fq)
+        assert "kernel launches" in log and " 0 kernel launches" not in log, log
+
+
+def _run_golden_fqs(lib, name, tmp):
+    """The compiled drop-in on the FASTQ of a golden fixture; its .fqs must equal the reference's own, which rides in the fixture
+    (at -gs 3100 the reference needs 45 GB and a minute of table construction per run: it ran once, in oracle/make_golden.py)."""
+    from tests import helpers as H
+    g = H.load_golden(name)
+    extra = [str(x) for x in g["extra"]]
+    fq = os.path.join(tmp, "in.fastq")
+    lines = g["fastq"].tobytes().split(b"\n")
+    if "-p" in extra:      # the fixture holds the pairs interleaved
+        recs = [lines[i:i + 4] for i in range(0, len(lines) - 1, 4)]
+        f1, f2 = os.path.join(tmp, "in_1.fastq"), os.path.join(tmp, "in_2.fastq")
+        open(f1, "wb").write(b"".join(b"\n".join(r) + b"\n" for r in recs[0::2]))
+        open(f2, "wb").write(b"".join(b"\n".join(r) + b"\n" for r in recs[1::2]))
+        files, layout = [f1, f2], extra
+    else:
+        open(fq, "wb").write(g["fastq"].tobytes())
+        files, layout = [fq], ["-s", *extra]
+    ours = os.path.join(tmp, "ours.fqs")
+    base = ["e", *layout, "-qm", "o", "-im", "o", "-t", "1", "-gs", str(int(g["gs"])), "-v", "0"]
+    r = subprocess.run([LIVE_BIN, *base, "-out", ours, *files], cwd=tmp, env=dict(os.environ, FQSK_LIB=lib, FQSK_VERBOSE="1"), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-600:]
+    a, b = g["fqs"].tobytes(), open(ours, "rb").read()
+    assert len(a) > 1000
+    assert a == b, f".fqs differs: {len(a)} vs {len(b)} bytes, first difference at {next((i for i in range(min(len(a), len(b))) if a[i] != b[i]), -1)}"
+    return r.stderr
+
+
+@pytest.mark.skipif(not os.path.exists(LIVE_BIN), reason="host/_bin not built")
+@pytest.mark.parametrize("name", ["se_orig_gs3100", "pe_orig_gs3100"])
+def test_live_host_default_kmer_lengths_with_oracle_records(name):
+    """-gs 3100 (the reference's default: p18/s21/b27, prefix 13) through the compiled drop-in, oracle behind the ABI."""
+    with tempfile.TemporaryDirectory() as tmp:
+        assert "segments" in _run_golden_fqs(_build_mock(tmp), name, tmp)
+
+
+@pytest.mark.skipif(not os.path.exists(LIVE_BIN), reason="host/_bin not built")
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["se_orig_gs3100", "pe_orig_gs3100"])
+def test_live_host_default_kmer_lengths_on_gpu(name):
+    with tempfile.TemporaryDirectory() as tmp:
+        log = _run_golden_fqs(REAL_LIB, name, tmp)
         assert "kernel launches" in log and " 0 kernel launches" not in log, log
 
 
