@@ -3,17 +3,25 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-Workload (BASELINE.json configs[1]): synthetic 150 bp SE reads from a 100 Mbp random genome, 0.5 % substitutions,
-`-gs 100` k-mer lengths (prefix 12, p17/s20/b24), original order, one reference worker (`-t 1`).
-A STEP is one reads_block of that stream (16 MiB of FASTQ = 51 k reads, reads_block.h:121-169) pushed through the hot path
-exactly as the reference schedules it: block g is cut into calc_no_synchronizations(g)+1 sync segments
-(application.h:85-92) and every segment is one fqsk_segment + fqsk_sync.  Steps continue the same job, so the default
-W + K = 196 blocks is the whole 10 M-read configuration.
+Workload (BASELINE.json configs[1]): 10 M synthetic 150 bp SE reads from a 100 Mbp random genome, 0.5 % substitutions, `-gs 100`
+k-mer lengths (prefix 12, p17/s20/b24), original order.  The job is ONE stream of reads (fqsqueezer_b200/synth.py: job_chunk) cut
+into reads_blocks exactly where the reference cuts the corresponding FASTQ (16 MiB slabs, reads_block.h:121-169 -> 196 blocks) and
+every block into calc_no_synchronizations(g) + 1 sync segments (application.h:85-92); every segment is one fqsk_segment + fqsk_sync.
 
-value : bases/s with the reads already resident in HBM (fqsk_segment_device), timed with CUDA events on the engine's stream.
-e2e   : the same steps through the host-buffer C-ABI call (fqsk_segment): H2D of the reads and D2H of every per-base record
-        inside the timed region.
-roofline / cpu_baseline: see DESIGN.md section 7.
+A STEP is 1/K of that job: step j covers blocks [196 j / K, 196 (j + 1) / K), so any --steps spans both regimes of the job -- the
+EARLY one (blocks 0..99: 100 - g sync segments per block, latency bound) and the STEADY one (blocks 100+: one 51 k-read segment per
+block) -- which are also timed and reported separately (`regimes`).  The W warm-up steps run the first W steps of the job on a
+throw-away engine (same work, untimed).
+
+value  : bases/s with the reads already resident in HBM (fqsk_segment_device), timed with CUDA events on the engine's stream.
+e2e    : the same steps through the host-buffer C-ABI calls (fqsk_submit / fqsk_collect): H2D of the reads and D2H of every per-base
+         record inside the timed region.
+parity_check : device-side checksums (fqsk_recs_checksum) of every sync segment of the first blocks of the timed job against the
+         REAL reference's records for the same reads (tests/golden/bench_config2_ref_checksums.npz, produced once by
+         oracle/make_bench_golden.py from the tapped fqs-1.1 at -t 1).
+N > 1  : ONE job over N GPUs, tables hash-sharded by the reference's owner keys (reference `-t N` semantics; scaling "strong");
+         `--replicas` runs N independent engines instead (weak scaling, no exchange).
+roofline / cpu_baseline / compress_e2e: see DESIGN.md section 7.
 """
 from __future__ import annotations
 
@@ -41,25 +49,56 @@ L = 150
 GENOME = 100_000_000
 SEED = 43
 GS = 100
-READS_PER_BLOCK = 51_000            # 16 MiB / ~325 B per record, minus the 100 KiB margin (reads_block.h:25, 137)
+JOB_READS = 10_000_000
+RESERVE_READS = 52_000              # largest reads_block of the job (51 694 reads: the first one, short ids)
 B_ALG = 251.5                       # algorithmic bytes per base, SURVEY.md section 8d (config 2)
+EARLY_BLOCKS = 100                  # blocks 0..99 have intra-block syncs (application.h:85-92)
 PHASE_ALG = {"lookup": 127 * 32 / 150.0, "sync_apply": (127 + 131) * 64 / 150.0, "sync_siv": 134 * 128 / 150.0}
 PHASE_KERNEL = {"prep": "k_prep", "lookup": "k_lookup", "partial": "k_partial", "walk": "k_walk", "compact": "k_compact2+scans",
-                "sort": "cub radix sort", "local": "k_local", "rough": "k_rough", "fold": "k_fold", "sync_locate": "k_locate_heads",
-                "sync_apply": "k_apply_keys", "sync_siv": "k_siv_increment", "mt": "k_mt_extend"}
+                "sort": "k_delta_build / row grouping", "local": "k_local", "rough": "k_rough", "fold": "k_fold", "sync_locate": "k_locate_heads / k_sync_rank",
+                "sync_apply": "k_apply_keys / k_sync_apply / k_insert_fast", "sync_siv": "k_siv_increment", "mt": "k_mt_extend"}
+GOLDEN_SUMS = os.path.join(ROOT, "tests", "golden", "bench_config2_ref_checksums.npz")
 
 
-def workload_config(extra=None):
-    c = {"workload": "BASELINE config 2: 150bp SE reads, 100 Mbp random genome, 0.5% subs, -gs 100 (p17/s20/b24), -om o, -t 1 sync schedule",
-         "reads_per_step": READS_PER_BLOCK, "read_len": L, "l2": "tables (4 GiB p-mer array + GiB-scale b/s tables) are far larger than L2; no flush needed"}
-    if extra:
-        c.update(extra)
+def job_blocks():
+    """Read ranges [first, last) of the job's reads_blocks, cut where the reference cuts the FASTQ (reads_block.h:121-169)."""
+    return S.split_blocks(synth.fastq_record_sizes(1, JOB_READS, L))
+
+
+def workload_config(n_gpus, replicas=False):
+    """Identical for both arms (`--impl reference` prints the same dict): what is measured, not how."""
+    c = {"workload": "BASELINE config 2: 10 M 150bp SE reads, 100 Mbp random genome, 0.5% subs, -gs 100 (p17/s20/b24), -om o; the whole job, reads_blocks and sync schedule as the reference cuts them",
+         "job_reads": JOB_READS, "job_blocks": 196, "read_len": L, "step": "1/K of the job's blocks",
+         "l2": "tables (4 GiB p-mer array + GiB-scale b/s tables) are far larger than L2; no flush needed"}
+    if n_gpus > 1:
+        c["parallelism"] = (f"{n_gpus} independent replicas" if replicas else
+                            f"ONE job over {n_gpus} GPUs: every reads_block split among {n_gpus} workers, tables hash-sharded by the reference's owner keys (fqs-1.1 -t {n_gpus} semantics)")
     return c
 
 
-def block_codes(genome, g, rank=0):
-    codes, _ = synth.make_reads(genome, READS_PER_BLOCK, L=L, seed=1000 * (rank + 1) + g)
-    return codes
+class JobReads:
+    """The job's read stream, generated chunk by chunk (deterministic in the chunk number) and served block by block."""
+
+    def __init__(self, genome):
+        self.genome, self.chunks = genome, {}
+
+    def _chunk(self, c):
+        if c not in self.chunks:
+            self.chunks[c] = synth.job_chunk(self.genome, c, L)[0]
+            for k in [k for k in self.chunks if k < c - 2]:
+                del self.chunks[k]
+        return self.chunks[c]
+
+    def codes(self, first, last):
+        parts = []
+        a = first
+        while a < last:
+            c = a // synth.JOB_CHUNK
+            lo = a - c * synth.JOB_CHUNK
+            hi = min(synth.JOB_CHUNK, lo + (last - a))
+            parts.append(self._chunk(c)[lo:hi])
+            a += hi - lo
+        return parts[0] if len(parts) == 1 else np.concatenate(parts)
 
 
 def codes_to_slab(codes):
@@ -110,20 +149,33 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic():
+    """DRAM bytes of one steady-state step from the committed ncu capture of this round (profiles/r02_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            pass
+    return None
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the unmodified fqs-1.1 compiled from /root/reference (oracle/_ref/fqs-1.1)
 # ------------------------------------------------------------------------------------------------------------------
-def run_reference(genome, n_reads, threads, seed_off=0):
-    """Times the unmodified fqs-1.1 on a bounded sample.  Its 'Processing time' starts with the construction of the CPU tables
-    (4 GiB p-mer array + 5 M sub-tables at -gs 100: seconds, independent of the input), which a 10 M-read job amortises and a
-    bounded sample does not: the same binary is therefore also timed on an 8-read file and that start-up is reported and taken off."""
+def run_reference(reads: JobReads, n_reads, threads):
+    """Times the unmodified fqs-1.1 on the FIRST n_reads reads of the job (the same reads, ids and block cuts the GPU arm starts with).
+    Its 'Processing time' starts with the construction of the CPU tables (4 GiB p-mer array + 5 M sub-tables at -gs 100: seconds,
+    independent of the input), which the 10 M-read job amortises and a bounded sample does not: the same binary is therefore also
+    timed on an 8-read file and that start-up is reported and taken off -- as the GPU arm's table construction (fqsk_create) lies
+    outside its timed region too."""
     from oracle import oracle as O          # checker side only: this function never touches the product path
     if not os.path.exists(O.REF_BIN):
         return None
 
-    def one(codes, err, tmp, name):
+    def one(codes, tmp, name):
         fq = os.path.join(tmp, name + ".fastq")
-        nbytes = synth.write_fastq(fq, codes, err, seed=1)
+        nbytes = synth.write_fastq(fq, codes, np.zeros(codes.shape, bool), seed=1)
         cmd = [O.REF_BIN, "e", "-s", "-om", "o", "-qm", "o", "-im", "o", "-gs", str(GS), "-t", str(threads), "-v", "0", "-out", os.path.join(tmp, name + ".fqs"), fq]
         t = time.time()
         r = subprocess.run(cmd, capture_output=True, text=True, cwd=tmp)
@@ -131,33 +183,35 @@ def run_reference(genome, n_reads, threads, seed_off=0):
         m = re.search(r"Processing time:\s*([0-9.eE+-]+)", r.stdout + r.stderr)
         return (float(m.group(1)) if m else wall), nbytes
 
-    codes, err = synth.make_reads(genome, n_reads, L=L, seed=777 + seed_off)
+    codes = reads.codes(0, n_reads)
     with tempfile.TemporaryDirectory() as tmp:
-        startup, _ = one(codes[:8], err[:8], tmp, "tiny")
-        secs, nbytes = one(codes, err, tmp, "s")
+        startup, _ = one(codes[:8], tmp, "tiny")
+        secs, nbytes = one(codes, tmp, "s")
     net = max(secs - startup, 0.05 * secs)
     return {"bases": n_reads * L, "seconds": net, "seconds_total": secs, "startup_seconds": startup, "fastq_bytes": nbytes}
 
 
-def run_compress_e2e(genome, n_reads):
+def run_compress_e2e(reads: JobReads, n_reads):
     """BASELINE.json's second metric, `e2e compress MB/s`: the reference compressor with its k-mer engine bound to libfqsk.so
     (host/_bin/fqs-1.1-fqsk: host/build_host.py + host/fqsk_live.h, the integration of INTEGRATION.md) against the unmodified
-    fqs-1.1 at -t 1 -- the parity configuration -- on the same FASTQ: FASTQ bytes / 'Processing time', and whether the two .fqs
-    files are byte-identical.  Bounded sample; everything outside the k-mer engine is the reference's own single-threaded host code."""
+    fqs-1.1 at -t 1 -- the parity configuration -- on the same FASTQ (the first n_reads reads of the job): FASTQ bytes / seconds,
+    and whether the two .fqs files are byte-identical.  Everything outside the k-mer engine is the reference's own host code."""
     from oracle import oracle as O          # only to locate the unmodified reference binary (the baseline of this leg)
     live = os.path.join(ROOT, "host", "_bin", "fqs-1.1-fqsk")
     lib = os.path.join(ROOT, "fqsqueezer_b200", "libfqsk.so")
     if not (os.path.exists(live) and os.path.exists(O.REF_BIN)):
         return {"unavailable": "host/_bin/fqs-1.1-fqsk or oracle/_ref/fqs-1.1 not built"}
-    codes, err = synth.make_reads(genome, n_reads, L=L, seed=4242)
+    codes = reads.codes(0, n_reads)
+    rng = np.random.default_rng(4242)
+    err = rng.random(codes.shape) < 0.005          # only decides where the '#' qualities sit
     with tempfile.TemporaryDirectory() as tmp:
         fq = os.path.join(tmp, "s.fastq")
         nbytes = synth.write_fastq(fq, codes, err, seed=1)
         base = ["e", "-s", "-om", "o", "-qm", "o", "-im", "o", "-gs", str(GS), "-t", "1", "-v", "0"]
 
-        def one(exe, out, env=None):
+        def one(exe, out, env=None, files=None):
             t = time.time()
-            r = subprocess.run([exe, *base, "-out", out, fq], capture_output=True, text=True, cwd=tmp, env=env, timeout=300)
+            r = subprocess.run([exe, *base, "-out", out, *(files or [fq])], capture_output=True, text=True, cwd=tmp, env=env, timeout=600)
             wall = time.time() - t
             if r.returncode != 0:
                 raise RuntimeError(f"{os.path.basename(exe)} exit {r.returncode}: {r.stderr[-300:]}")
@@ -168,13 +222,22 @@ def run_compress_e2e(genome, n_reads):
         one(live, os.path.join(tmp, "w.fqs"), env)                     # warm-up: CUDA context, module load, page cache
         t_live, wall_live, log = one(live, os.path.join(tmp, "a.fqs"), env)
         t_ref, wall_ref, _ = one(O.REF_BIN, os.path.join(tmp, "b.fqs"))
+        # start-up of either binary (table construction: fqsk_create = CUDA context + 12 GiB of HBM tables; reference = its CPU tables)
+        # on an 8-read file, reported beside the totals
+        tiny = os.path.join(tmp, "tiny.fastq")
+        synth.write_fastq(tiny, codes[:8], err[:8], seed=1)
+        s_live, _, _ = one(live, os.path.join(tmp, "t1.fqs"), env, [tiny])
+        s_ref, _, _ = one(O.REF_BIN, os.path.join(tmp, "t2.fqs"), None, [tiny])
         same = open(os.path.join(tmp, "a.fqs"), "rb").read() == open(os.path.join(tmp, "b.fqs"), "rb").read()
         fqs_bytes = os.path.getsize(os.path.join(tmp, "a.fqs"))
     m = re.search(r"([0-9.]+) s inside the engine calls, (\d+) kernel launches", log)
+    mw = re.search(r"([0-9.]+) s waiting for the engine", log)
     return {"value": nbytes / 1e6 / t_live, "unit": "MB/s", "reference_t1": nbytes / 1e6 / t_ref, "speedup_vs_t1": t_ref / t_live,
             "byte_identical": bool(same), "fastq_bytes": nbytes, "fqs_bytes": fqs_bytes, "seconds": t_live, "reference_seconds": t_ref,
-            "engine_call_seconds": float(m.group(1)) if m else None, "gpu_launches": int(m.group(2)) if m else None,
-            "sample": f"{n_reads} reads of a config-2 stream ({nbytes / 1e6:.1f} MB FASTQ), e -s -om o -qm o -im o -gs {GS} -t 1: fqs-1.1-fqsk (reference host code, k-mer engine on the GPU through the C-ABI, blocking fqsk_segment + fqsk_sync) vs the unmodified fqs-1.1; 'Processing time' of each, start-up included (reference: construction of its CPU tables, several seconds; ours: CUDA context + HBM tables)"}
+            "startup_seconds": s_live, "reference_startup_seconds": s_ref,
+            "value_without_startup": nbytes / 1e6 / max(t_live - s_live, 1e-3), "reference_t1_without_startup": nbytes / 1e6 / max(t_ref - s_ref, 1e-3),
+            "engine_call_seconds": float(m.group(1)) if m else None, "engine_wait_seconds": float(mw.group(1)) if mw else None, "gpu_launches": int(m.group(2)) if m else None,
+            "sample": f"the first {n_reads} reads of the job ({nbytes / 1e6:.1f} MB FASTQ), e -s -om o -qm o -im o -gs {GS} -t 1: fqs-1.1-fqsk (reference host code, k-mer engine on the GPU through the C-ABI) vs the unmodified fqs-1.1; 'Processing time' of each, start-up included; the start-up of each binary (same options, 8-read file) is reported separately"}
 
 
 def reference_arm(args):
@@ -182,95 +245,68 @@ def reference_arm(args):
     if rank != 0:
         return 0
     threads = min(os.cpu_count() or 1, 64)
-    genome = synth.make_genome(GENOME, SEED)
-    per_step = max(200, 120_000 // max(args.steps, 1))     # K steps of a bounded sample: ~120 k reads in total (tens of seconds beyond the table construction)
+    reads = JobReads(synth.make_genome(GENOME, SEED))
+    per_step = max(200, args.ref_sample_reads // max(args.steps, 1))     # K steps of a bounded sample of the job's first reads
     if args.warmup:
-        run_reference(genome, min(per_step * args.warmup, 10_000), threads, seed_off=1)
-    res = run_reference(genome, per_step * args.steps, threads)
+        run_reference(reads, min(per_step * args.warmup, 10_000), threads)
+    res = run_reference(reads, per_step * args.steps, threads)
     if res is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/fqs-1.1 not built"}))
         return 0
+    t1 = run_reference(reads, args.ref_t1_reads, 1) if args.ref_t1_reads else None
     v = res["bases"] / res["seconds"]
-    sample = (f"{per_step * args.steps} reads ({args.steps} steps x {per_step}) of the config-2 stream, fqs-1.1 e -s -om o -qm o -im o -gs {GS} -t {threads}: "
-              f"'Processing time' {res['seconds_total']:.2f} s minus {res['startup_seconds']:.2f} s of table construction (same binary on an 8-read file)")
+    sample = (f"the first {per_step * args.steps} reads of the job ({args.steps} steps x {per_step}; the reads the GPU arm starts with), fqs-1.1 e -s -om o -qm o -im o -gs {GS} -t {threads}: "
+              f"'Processing time' {res['seconds_total']:.2f} s minus {res['startup_seconds']:.2f} s of table construction (same binary on an 8-read file); whole compressor")
+    cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample}
+    if t1:
+        cpu["t1_value"] = t1["bases"] / t1["seconds"]
+        cpu["t1_sample"] = f"-t 1 on the first {args.ref_t1_reads} reads: {t1['seconds_total']:.2f} s minus {t1['startup_seconds']:.2f} s of table construction"
     line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * res["seconds"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-            "data": "synthetic", "impl": "reference", "config": workload_config({"reads_per_step": per_step}),
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
+            "ms_per_step": 1e3 * res["seconds"] / args.steps, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 and not args.replicas else "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic", "impl": "reference", "config": workload_config(args.gpus, args.replicas),
+            "cpu_baseline": cpu,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
     return 0
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# sharded arm: ONE config-2 job over N GPUs, reference -t N semantics (tables sharded by owner key, rows routed at every sync)
+# parity check: device-side checksums of the first blocks' segments against the real reference's records
 # ------------------------------------------------------------------------------------------------------------------
-def sharded_arm(args, rank, world, local_rank, dist, dev):
+def parity_check(make_engine, reads: JobReads, blocks, max_blocks, dev):
     import torch
-    from fqsqueezer_b200 import engine as E
-    from fqsqueezer_b200 import sharded
-
-    pref, p, s, b = E.kmer_params(GS)
-    genome = synth.make_genome(GENOME, SEED)
-    n_blocks = args.warmup + args.steps
-    eng = sharded.ShardedKmerEngine(p, s, b, pref, rank, world, device=local_rank, dist=dist, expected_kmers=(1 << 29) // world,
-                                    reserve_reads=READS_PER_BLOCK // world + 16, reserve_bytes=(READS_PER_BLOCK // world + 16) * L)
-    segs, d_blocks = [], []
-    off_np = (np.arange(READS_PER_BLOCK, dtype=np.int64) * L)
-    d_off = torch.from_numpy(off_np).to(dev)
-    d_len = torch.full((READS_PER_BLOCK,), L, dtype=torch.int32, device=dev)
-    for g in range(n_blocks):
-        sg = S.worker_segments(0, READS_PER_BLOCK, g, world, rank)
-        segs.append(sg)
-        lo, hi = sg[0][0], sg[-1][1]
-        codes = block_codes(genome, g, 0)[lo:hi]               # every rank cuts ITS slice out of the same block
-        d_blocks.append((lo, torch.from_numpy(synth.codes_to_ascii(codes).reshape(-1)).to(dev)))
-    torch.cuda.synchronize()
-
-    def run_block(g):
-        eng.block_start()
-        lo, t = d_blocks[g]
-        for a, bb in segs[g]:
-            n = bb - a
-            eng.segment_device(t.data_ptr() + (a - lo) * L, n * L, d_off.data_ptr(), d_len.data_ptr(), n, want_n_recs=False)
-            eng.sync()
-
-    for g in range(args.warmup):
-        run_block(g)
-    st0 = eng.stats()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
-    eng.timer_begin()
+    if not os.path.exists(GOLDEN_SUMS):
+        return {"ok": None, "unavailable": "tests/golden/bench_config2_ref_checksums.npz missing"}
+    z = np.load(GOLDEN_SUMS)
+    nb = min(int(len(z["segs_per_block"])), max_blocks, len(blocks))
+    if (int(z["gs"]), int(z["genome"]), int(z["seed"]), int(z["read_len"])) != (GS, GENOME, SEED, L):
+        return {"ok": None, "unavailable": "golden checksums belong to another workload"}
+    eng = make_engine()
+    seg, n_rec, bad = 0, 0, []
     t0 = time.time()
-    for g in range(args.warmup, n_blocks):
-        run_block(g)
-    dev_ms = eng.timer_end()
-    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
-    wall_ms = (time.time() - t0) * 1e3
-    sampler.stop_flag = True
-    st1 = eng.stats()
-    ms = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    launches = torch.tensor([st1["kernel_launches"] - st0["kernel_launches"]], dtype=torch.int64, device=dev)
-    dist.all_reduce(launches)
-    dev_ms_max = float(ms.item())
-    bases = args.steps * READS_PER_BLOCK * L               # the whole job, all ranks together
+    for g in range(nb):
+        f, l = blocks[g]
+        if (int(z["block_first"][g]), int(z["block_last"][g])) != (f, l):
+            return {"ok": False, "error": f"block {g} is reads [{f}, {l}) here, [{int(z['block_first'][g])}, {int(z['block_last'][g])}) in the reference run"}
+        codes = reads.codes(f, l)
+        t = torch.from_numpy(synth.codes_to_ascii(codes).reshape(-1)).to(dev)
+        d_off = torch.arange(l - f, dtype=torch.int64, device=dev) * L
+        d_len = torch.full((l - f,), L, dtype=torch.int32, device=dev)
+        sched = list(S.segments(0, l - f, S.calc_no_synchronizations(g, l - f, 1)))
+        if len(sched) != int(z["segs_per_block"][g]):
+            return {"ok": False, "error": f"block {g}: {len(sched)} segments here, {int(z['segs_per_block'][g])} in the reference run"}
+        eng.block_start()
+        for a, b in sched:
+            eng.segment_device(t.data_ptr() + a * L, (b - a) * L, d_off.data_ptr(), d_len.data_ptr(), b - a, want_n_recs=False)
+            cs, n = eng.recs_checksum()
+            if n != int(z["seg_nrecs"][seg]) or cs != int(z["seg_sum"][seg]):
+                bad.append(seg)
+            n_rec += n
+            seg += 1
+            eng.sync()
     eng.close()
-    if rank == 0:
-        peak, peak_src = measured_peak()
-        achieved = B_ALG * bases / (dev_ms_max / 1e3) / 1e9
-        line = {"metric": METRIC, "value": bases / (dev_ms_max / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-                "config": workload_config({"parallelism": f"ONE job, tables hash-sharded over {world} GPUs by the reference's owner keys (-t {world} semantics): lookups through NVLink peer "
-                                                          f"mappings, exchange rows by peer stores into the owners' inboxes, NCCL barrier + all-reduce per sync",
-                                           "blocks": f"{args.warmup}..{n_blocks - 1} of the job", "segments_timed": (st1["n_segments"] - st0["n_segments"])}),
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world), "traffic": None, "peak_source": peak_src,
-                             "kernel": "whole step over all ranks, 251.5 algorithmic B/base"},
-                "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches.item()), "clocks": sampler.summary(), "wall_ms_per_step": wall_ms / args.steps}
-        print(json.dumps(line))
-    dist.destroy_process_group()
-    return 0
+    return {"ok": len(bad) == 0, "blocks": nb, "segments": seg, "records": n_rec, "mismatching_segments": bad[:8], "seconds": round(time.time() - t0, 2),
+            "checker": "per-segment record checksums of the REAL reference (tapped fqs-1.1 -t 1 on the same reads, oracle/make_bench_golden.py) vs fqsk_recs_checksum on the device"}
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -279,17 +315,21 @@ def sharded_arm(args, rank, world, local_rank, dist, dev):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=190)
-    ap.add_argument("--warmup", type=int, default=6)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--shard", action="store_true", help="N > 1: ONE job with hash-sharded tables (reference -t N semantics, strong scaling) instead of N independent replicas")
-    ap.add_argument("--no-phase-events", action="store_true", help="do not bracket the internal phases with CUDA events (fewer host API calls per segment)")
-    ap.add_argument("--no-box-warmup", action="store_true", help="skip the throw-away engine that warms the box up before the W warm-up steps")
-    ap.add_argument("--cpu-sample-reads", type=int, default=120_000, help="bounded sample of the cpu_baseline leg: large enough that the reference spends tens of seconds beyond its table construction")
+    ap.add_argument("--replicas", action="store_true", help="N > 1: N independent engines (weak scaling) instead of ONE job over hash-sharded tables")
+    ap.add_argument("--shard", action="store_true", help="(default at N > 1; kept for compatibility)")
+    ap.add_argument("--no-phase-events", action="store_true", help="skip the second pass that brackets the internal phases with CUDA events")
+    ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--parity-blocks", type=int, default=8, help="blocks of the job checked against the reference's golden checksums")
+    ap.add_argument("--ref-sample-reads", type=int, default=120_000, help="bounded sample of the reference legs (-t nproc)")
+    ap.add_argument("--ref-t1-reads", type=int, default=16_000, help="bounded sample of the reference's -t 1 figure (0 = skip)")
     ap.add_argument("--no-compress-e2e", action="store_true", help="skip the whole-compressor leg (fqs-1.1-fqsk vs fqs-1.1 -t 1)")
     ap.add_argument("--compress-sample-reads", type=int, default=60_000)
+    ap.add_argument("--max-blocks", type=int, default=0, help="debug: stop the job after this many blocks")
     ap.add_argument("--trace-blocks", type=int, default=0, help="print per-block phase ms every N blocks to stderr")
     ap.add_argument("--profile-block", type=int, default=-1, help="cudaProfilerStart/Stop around this block (for ncu --profile-from-start off)")
     args = ap.parse_args()
@@ -313,18 +353,36 @@ def main():
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
-
-    if args.shard and world > 1:
-        return sharded_arm(args, rank, world, local_rank, dist, dev)
+    sharded = world > 1 and not args.replicas
 
     pref, p, s, b = E.kmer_params(GS)
-    genome = synth.make_genome(GENOME, SEED)
-    n_blocks = args.warmup + args.steps
-    # every block's schedule: (#syncs, list of segments)
-    sched = []
-    for g in range(n_blocks):
-        ns = S.calc_no_synchronizations(g, READS_PER_BLOCK, 1)
-        sched.append(list(S.segments(0, READS_PER_BLOCK, ns)))
+    reads = JobReads(synth.make_genome(GENOME, SEED))
+    blocks = job_blocks()
+    if args.max_blocks:
+        blocks = blocks[: args.max_blocks]
+    NB = len(blocks)
+    K = args.steps
+    step_of_block = [min(K - 1, g * K // NB) for g in range(NB)] if K <= NB else list(range(NB))
+    warm_blocks = [g for g in range(NB) if step_of_block[g] < args.warmup]
+    n_early = min(EARLY_BLOCKS, NB)
+
+    # this rank's share of every block: everything (1 GPU / replicas) or worker `rank`'s slice (sharded: PartitionForWorkers)
+    def my_segments(g):
+        f, l = blocks[g]
+        if sharded:
+            return S.worker_segments(0, l - f, g, world, rank)
+        return list(S.segments(0, l - f, S.calc_no_synchronizations(g, l - f, 1)))
+
+    sched = [my_segments(g) for g in range(NB)]
+    if sharded:
+        from fqsqueezer_b200 import sharded as SH
+
+    def make_engine(profile=False, e2e=False):
+        rr, rb = RESERVE_READS, RESERVE_READS * (L + (1 if e2e else 0))
+        if sharded:
+            return SH.ShardedKmerEngine(p, s, b, pref, rank, world, device=local_rank, dist=dist, expected_kmers=(1 << 29) // world,
+                                        reserve_reads=rr // world + 16, reserve_bytes=(rr // world + 16) * (L + 1), profile=profile)
+        return E.KmerEngine(p, s, b, pref, device=local_rank, expected_kmers=1 << 29, profile=profile, reserve_reads=rr, reserve_bytes=rb)
 
     def barrier():
         torch.cuda.synchronize()
@@ -333,81 +391,95 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- value: reads resident in HBM ----------------
-    # Timed pass: no per-phase event brackets (they cost ~25 % in host API calls on the small early segments).  The phase
-    # shares come from a second, identical pass with the brackets on (below).
-    eng = E.KmerEngine(p, s, b, pref, device=local_rank, expected_kmers=1 << 29, profile=bool(args.trace_blocks), reserve_reads=READS_PER_BLOCK, reserve_bytes=READS_PER_BLOCK * L)
+    t_create = time.time()
+    eng = make_engine(profile=bool(args.trace_blocks))
+    torch.cuda.synchronize()
+    create_s = time.time() - t_create
+    d_off = torch.arange(RESERVE_READS + 16, dtype=torch.int64, device=dev) * L      # same offsets for every block (relative to the segment's first read)
+    d_len = torch.full((RESERVE_READS + 16,), L, dtype=torch.int32, device=dev)
     d_blocks = []
-    off_np = (np.arange(READS_PER_BLOCK, dtype=np.int64) * L)
-    d_off = torch.from_numpy(off_np).to(dev)                      # same offsets for every block
-    d_len = torch.full((READS_PER_BLOCK,), L, dtype=torch.int32, device=dev)
-    for g in range(n_blocks):
-        codes = block_codes(genome, g, rank)
-        d_blocks.append(torch.from_numpy(synth.codes_to_ascii(codes).reshape(-1)).to(dev))
+    for g in range(NB):
+        f, l = blocks[g]
+        lo, hi = sched[g][0][0], sched[g][-1][1]
+        codes = reads.codes(f + lo, f + hi) if (replica_shift := 0) == 0 else None
+        d_blocks.append((lo, torch.from_numpy(synth.codes_to_ascii(codes).reshape(-1)).to(dev)))
     torch.cuda.synchronize()
 
-    def run_block_device(g, eng):
-        eng.block_start()
-        base = d_blocks[g].data_ptr()
+    def run_block_device(g, e):
+        e.block_start()
+        lo, t = d_blocks[g]
+        base = t.data_ptr()
         for a, bb in sched[g]:
             n = bb - a
-            eng.segment_device(base + a * L, n * L, d_off.data_ptr(), d_len.data_ptr(), n, want_n_recs=False)   # offsets are relative to the segment's first read
-            eng.sync()
+            e.segment_device(base + (a - lo) * L, n * L, d_off.data_ptr(), d_len.data_ptr(), n, want_n_recs=False)
+            e.sync()
 
-    # Box warm-up (untimed, besides the W warm-up steps below): a fresh box starts with idle clocks and a cold driver, and this
-    # job is a chain of thousands of host-observed segments, so its first seconds run 20-30 % slower than the same blocks a few
-    # seconds later (measured: 609 vs 750 Mbases/s for the whole job).  A throw-away engine runs the first blocks of the job once.
-    if not args.no_box_warmup:
-        scratch = E.KmerEngine(p, s, b, pref, device=local_rank, expected_kmers=1 << 29, reserve_reads=READS_PER_BLOCK, reserve_bytes=READS_PER_BLOCK * L)
-        for g in range(min(24, n_blocks)):
-            run_block_device(g, scratch)
-        scratch.close()
-        del scratch
-    for g in range(args.warmup):
-        run_block_device(g, eng)
+    # warm-up: the first W steps of the job on a throw-away engine (a fresh box starts with idle clocks and a cold driver)
+    scratch = make_engine()
+    for g in warm_blocks:
+        run_block_device(g, scratch)
+    scratch.close()
+    del scratch
     st0 = eng.stats()
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
-    eng.timer_begin()
     t_wall = time.time()
     prev_prof, t_prev = eng.profile(), time.time()
-    for g in range(args.warmup, n_blocks):
-        if g == args.profile_block:
-            torch.cuda.cudart().cudaProfilerStart()
-        run_block_device(g, eng)
-        if g == args.profile_block:
-            torch.cuda.cudart().cudaProfilerStop()
-        if args.trace_blocks and (g % args.trace_blocks == 0 or g == n_blocks - 1):
-            pr = eng.profile()
-            print(f"block {g} ({len(sched[g])} segments): wall {1e3 * (time.time() - t_prev):.1f} ms " +
-                  str({k: round(pr[k] - prev_prof[k], 2) for k in pr}) + " " +
-                  str({k: v for k, v in eng.stats().items() if k in ("n_hot_segments", "n_replays", "bmer_buckets", "smer_buckets", "bmer_stash_used", "n_bmers", "n_smers", "draws_b")}),
-                  file=sys.stderr, flush=True)
-        if args.trace_blocks:
-            prev_prof, t_prev = eng.profile(), time.time()
-    dev_ms = eng.timer_end()
+    regime_ms = {"early": 0.0, "steady": 0.0}
+    seg_early = 0
+
+    def run_range(g0, g1, key):
+        nonlocal prev_prof, t_prev
+        if g0 >= g1:
+            return
+        eng.timer_begin()
+        for g in range(g0, g1):
+            if g == args.profile_block:
+                torch.cuda.cudart().cudaProfilerStart()
+            run_block_device(g, eng)
+            if g == args.profile_block:
+                torch.cuda.cudart().cudaProfilerStop()
+            if args.trace_blocks and (g % args.trace_blocks == 0 or g == NB - 1):
+                pr = eng.profile()
+                print(f"block {g} ({len(sched[g])} segments): wall {1e3 * (time.time() - t_prev):.1f} ms " +
+                      str({k: round(pr[k] - prev_prof[k], 2) for k in pr}) + " " +
+                      str({k: v for k, v in eng.stats().items() if k in ("n_hot_segments", "n_replays", "bmer_buckets", "smer_buckets", "bmer_stash_used", "n_bmers", "n_smers", "draws_b")}),
+                      file=sys.stderr, flush=True)
+            if args.trace_blocks:
+                prev_prof, t_prev = eng.profile(), time.time()
+        regime_ms[key] += eng.timer_end()
+
+    run_range(0, n_early, "early")
+    seg_early = eng.stats()["n_segments"] - st0["n_segments"]
+    run_range(n_early, NB, "steady")
     barrier()
     wall_ms = (time.time() - t_wall) * 1e3
     sampler.stop_flag = True
     st1 = eng.stats()
-    ms = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    dev_ms = regime_ms["early"] + regime_ms["steady"]
+    ms = torch.tensor([dev_ms, regime_ms["early"], regime_ms["steady"]], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    dev_ms_max = float(ms.item())
-    bases_rank = args.steps * READS_PER_BLOCK * L
-    value = world * bases_rank / (dev_ms_max / 1e3)
+    dev_ms_max, early_ms, steady_ms = (float(x) for x in ms.tolist())
+    job_bases = sum(l - f for f, l in blocks) * L
+    early_bases = sum(l - f for f, l in blocks[:n_early]) * L
+    total_bases = job_bases * (world if (world > 1 and not sharded) else 1)       # replicas: every rank runs the whole job
+    value = total_bases / (dev_ms_max / 1e3)
     n_seg = st1["n_segments"] - st0["n_segments"]
     launches = st1["kernel_launches"] - st0["kernel_launches"]
+    if dist is not None:
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
     eng.close()
 
     # ---------------- phase shares: the same pass again with CUDA-event brackets around the internal phases ----------------
     phases = None
-    if not args.no_phase_events:
-        engp = E.KmerEngine(p, s, b, pref, device=local_rank, expected_kmers=1 << 29, profile=True, reserve_reads=READS_PER_BLOCK, reserve_bytes=READS_PER_BLOCK * L)
-        for g in range(args.warmup):
-            run_block_device(g, engp)
+    if not args.no_phase_events and not sharded:
+        engp = make_engine(profile=True)
         prof0 = engp.profile()
-        for g in range(args.warmup, n_blocks):
+        for g in range(NB):
             run_block_device(g, engp)
         prof1 = engp.profile()
         phases = {k: prof1[k] - prof0[k] for k in prof1}
@@ -415,39 +487,44 @@ def main():
     del d_blocks
     torch.cuda.empty_cache()
 
-    # ---------------- e2e: host buffers through fqsk_segment ----------------
-    e2e = None
-    if not args.no_e2e:
-        eng2 = E.KmerEngine(p, s, b, pref, device=local_rank, expected_kmers=1 << 29, reserve_reads=READS_PER_BLOCK, reserve_bytes=READS_PER_BLOCK * (L + 1))
-        slabs = []
-        for g in range(n_blocks):
-            slabs.append(codes_to_slab(block_codes(genome, g, rank)))
+    # ---------------- parity: device-side checksums of the first blocks against the real reference ----------------
+    parity = None
+    if not args.no_parity_check and not sharded and rank == 0:
+        parity = parity_check(make_engine, reads, blocks, args.parity_blocks, dev)
 
-        def run_block_host(g, pend):
+    # ---------------- e2e: host buffers through fqsk_submit / fqsk_collect ----------------
+    e2e = None
+    if not args.no_e2e and not sharded:
+        eng2 = make_engine(e2e=True)
+        slabs = [codes_to_slab(reads.codes(*blocks[g])) for g in range(NB)]
+
+        def run_block_host(g, pend, e):
             """fqsk_submit / fqsk_collect, two segments in flight: segment n + 1 is submitted before n is collected -- the point where
             the reference's host-side coder would consume the records of n."""
             slab, off, ln = slabs[g]
-            eng2.block_start()
+            e.block_start()
             nb = 0
             for a, bb in sched[g]:
-                t = eng2.submit(slab, off[a:bb], ln[a:bb])
+                t = e.submit(slab, off[a:bb], ln[a:bb])
                 if pend is not None:
-                    recs, dup, _ = eng2.collect(pend)
+                    recs, dup, _ = e.collect(pend)
                     nb += recs.nbytes + dup.nbytes
                 pend = t
             return nb, pend
 
+        scratch = make_engine(e2e=True)
         pend = None
-        for g in range(args.warmup):
-            _, pend = run_block_host(g, pend)
+        for g in warm_blocks:
+            _, pend = run_block_host(g, pend, scratch)
         if pend is not None:
-            eng2.collect(pend)
+            scratch.collect(pend)
             pend = None
+        scratch.close()
         barrier()
         t0 = time.time()
         d2h = 0
-        for g in range(args.warmup, n_blocks):
-            nb, pend = run_block_host(g, pend)
+        for g in range(NB):
+            nb, pend = run_block_host(g, pend, eng2)
             d2h += nb
         if pend is not None:
             recs, dup, _ = eng2.collect(pend)
@@ -457,10 +534,11 @@ def main():
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * bases_rank / float(t.item()), "unit": UNIT,
-               "h2d_bytes_per_step": READS_PER_BLOCK * (L + 12), "d2h_bytes_per_step": d2h // args.steps,
+        e2e = {"value": total_bases / float(t.item()), "unit": UNIT,
+               "h2d_bytes_per_step": (JOB_READS if not args.max_blocks else blocks[-1][1]) * (L + 12) // K, "d2h_bytes_per_step": d2h // K,
                "note": "fqsk_submit / fqsk_collect with host slab + read descriptors (H2D inside), every per-base record (28 B) copied back into page-locked host memory on a second stream, two segments in flight; wall clock incl. ctypes/numpy host code"}
         eng2.close()
+        del slabs
 
     if rank != 0:
         if dist is not None:
@@ -469,45 +547,58 @@ def main():
 
     # ---------------- roofline ----------------
     peak, peak_src = measured_peak()
-    step_achieved = B_ALG * bases_rank / (dev_ms / 1e3) / 1e9
-    roof = {"bound": "hbm", "achieved": step_achieved, "peak": peak, "unit": "GB/s", "frac": step_achieved / peak, "traffic": None,
+    n_dev = world if sharded else 1
+    step_achieved = B_ALG * job_bases / (dev_ms_max / 1e3) / 1e9
+    traffic = measured_traffic()
+    roof = {"bound": "hbm", "achieved": step_achieved, "peak": peak * n_dev, "unit": "GB/s", "frac": step_achieved / (peak * n_dev),
+            "traffic": traffic.get("dram_bytes_per_steady_step") if traffic else None,
             "peak_source": peak_src,
             "kernel": "whole step (all kernels of fqsk_segment + fqsk_sync), 251.5 algorithmic B/base",
-            "traffic_note": "ncu of one steady-state step (profiles/r01d_steady_block_summary.md): 8.5 GB of DRAM traffic per 7.65 Mbase segment = 4.4x the algorithmic bytes; the average step of the job mixes 1..95 segments, so no single per-launch figure exists"}
+            "traffic_note": (traffic.get("note") if traffic else "no ncu capture of this round committed yet")}
+    regimes = {}
+    for key, ms_r, bases_r, blk, segs in (("early", early_ms, early_bases, f"0..{n_early - 1}", seg_early), ("steady", steady_ms, job_bases - early_bases, f"{n_early}..{NB - 1}", n_seg - seg_early)):
+        if ms_r > 0:
+            a = B_ALG * bases_r / (ms_r / 1e3) / 1e9
+            regimes[key] = {"blocks": blk, "segments": int(segs), "ms": round(ms_r, 2), "ms_per_block": round(ms_r / max(1, (n_early if key == "early" else NB - n_early)), 3),
+                            "bases_per_s": bases_r / (ms_r / 1e3), "achieved_GBps": a, "frac": a / (peak * n_dev)}
     if phases:
         dom = max(phases, key=lambda k: phases[k])
         dom_share = phases[dom] / max(sum(phases.values()), 1e-9)
-        dom_alg = PHASE_ALG.get(dom, 0.0) * bases_rank
-        roof["dominant_kernel"] = {"name": PHASE_KERNEL.get(dom, dom), "share_of_device_time": dom_share, "ms_per_step": phases[dom] / args.steps,
+        dom_alg = PHASE_ALG.get(dom, 0.0) * job_bases
+        roof["dominant_kernel"] = {"name": PHASE_KERNEL.get(dom, dom), "share_of_device_time": dom_share, "ms_per_step": phases[dom] / K,
                                    "algorithmic_GBps": (dom_alg / (phases[dom] / 1e3) / 1e9) if phases[dom] > 0 else None,
                                    "note": "phases without algorithmic bytes (walk, local, sort, fold, mt ...) are the cost of making the parallel order exact"}
-        roof["phase_ms_per_step"] = {k: round(v / args.steps, 4) for k, v in phases.items()}
+        roof["phase_ms_per_step"] = {k: round(v / K, 4) for k, v in phases.items()}
         roof["phase_note"] = "measured in a second identical pass with CUDA-event brackets on the engine's stream (the brackets are off in the timed pass)"
 
     # ---------------- cpu baseline (bounded sample, rank 0, N = 1 only) ----------------
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         threads = min(os.cpu_count() or 1, 64)
-        res = run_reference(genome, args.cpu_sample_reads, threads)
+        res = run_reference(reads, args.ref_sample_reads, threads)
         if res is not None:
             cpu = {"value": res["bases"] / res["seconds"], "unit": UNIT, "cores": threads, "kind": "reference",
-                   "sample": f"{args.cpu_sample_reads} reads of a config-2 stream ({res['bases'] / 1e6:.1f} Mbases), fqs-1.1 e -s -om o -qm o -im o -gs {GS} -t {threads}: 'Processing time' {res['seconds_total']:.2f} s minus {res['startup_seconds']:.2f} s of table construction (same binary on an 8-read file) = {res['seconds']:.2f} s (whole compressor, the k-mer engine is ~75% of it)"}
+                   "sample": f"the first {args.ref_sample_reads} reads of the job ({res['bases'] / 1e6:.1f} Mbases), fqs-1.1 e -s -om o -qm o -im o -gs {GS} -t {threads}: 'Processing time' {res['seconds_total']:.2f} s minus {res['startup_seconds']:.2f} s of table construction (same binary on an 8-read file) = {res['seconds']:.2f} s (whole compressor, the k-mer engine is ~75% of it)"}
+            if args.ref_t1_reads:
+                t1 = run_reference(reads, args.ref_t1_reads, 1)
+                cpu["t1_value"] = t1["bases"] / t1["seconds"]
+                cpu["t1_sample"] = f"-t 1 (the parity configuration) on the first {args.ref_t1_reads} reads: {t1['seconds_total']:.2f} s minus {t1['startup_seconds']:.2f} s of table construction"
 
     # ---------------- whole compressor through the drop-in (bounded sample, rank 0, N = 1 only) ----------------
     compress = None
     if not args.no_compress_e2e and world == 1:
         try:
-            compress = run_compress_e2e(genome, args.compress_sample_reads)
+            compress = run_compress_e2e(reads, args.compress_sample_reads)
         except Exception as ex:              # never at the expense of the line itself
             compress = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-            "data": "synthetic",
-            "config": workload_config({"parallelism": "1 engine per GPU" + ("" if world == 1 else f" x {world} independent replicas (ONE job over hash-sharded tables: --shard)"),
-                                       "blocks": f"{args.warmup}..{n_blocks - 1} of the job", "segments_timed": n_seg}),
-            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "compress_e2e": compress, "gpu_launches": launches,
-            "clocks": sampler.summary(), "wall_ms_per_step": wall_ms / args.steps}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+            "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic", "config": workload_config(world, args.replicas),
+            "job": {"blocks_timed": NB, "segments_timed": int(n_seg), "bases": job_bases, "device_ms": dev_ms_max, "wall_ms": wall_ms, "create_seconds": round(create_s, 3),
+                    "warmup_blocks": len(warm_blocks), "note": "table construction (fqsk_create) lies outside the timed region, as the reference's does in its arm"},
+            "regimes": regimes, "roofline": roof, "parity_check": parity, "cpu_baseline": cpu, "e2e": e2e, "compress_e2e": compress, "gpu_launches": int(launches),
+            "clocks": sampler.summary(), "wall_ms_per_step": wall_ms / K}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -1356,6 +1356,21 @@ int fqsk_device_recs(fqsk_handle *h, const fqsk_base_rec **d_recs, uint64_t *n_r
 	return FQSK_OK;
 }
 
+int fqsk_recs_checksum(fqsk_handle *h, uint64_t *sum, uint64_t *n_recs) {
+	if (!h || !sum) return FQSK_E_INVAL;
+	CK(cudaSetDevice(h->P.device));
+	CKR(seg_settle(h));
+	unsigned long long *d_sum = h->d_counters + 6;
+	CK(cudaMemsetAsync(d_sum, 0, 8, h->st));
+	if (h->n_recs) { CK(pdl(k_recs_checksum, std::min<uint32_t>(nblk(h->n_recs, 256), 148 * 8), 256, h->st, (const fqsk_base_rec *) (h->rec_par ? h->recs_alt : h->recs).as<fqsk_base_rec>(), (unsigned long long) h->n_recs, d_sum)); LAUNCHED(h); }
+	unsigned long long *hs = (unsigned long long *) ((uint8_t *) h->h_small + 976);
+	CK(cudaMemcpyAsync(hs, d_sum, 8, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaStreamSynchronize(h->st));
+	*sum = *hs;
+	if (n_recs) *n_recs = h->n_recs;
+	return FQSK_OK;
+}
+
 int fqsk_sorted_prefix(fqsk_handle *h, uint32_t *flag, uint64_t *dif, uint32_t n_reads) {
 	if (!h || !flag || !dif) return FQSK_E_INVAL;
 	CK(cudaSetDevice(h->P.device));

@@ -523,6 +523,18 @@ __global__ void k_route_scatter(const unsigned long long *sorted, uint32_t n, co
 	inbox_slot(I.base[o], I.cap, I.world, table, I.rank)[i - off[o]] = sorted[i];
 }
 
+// checksum of a record stream (fqsk_recs_checksum): position-dependent term per record, summed mod 2^64
+__global__ void __launch_bounds__(256) k_recs_checksum(const fqsk_base_rec *recs, unsigned long long n, unsigned long long *out) { pdl_enter();
+	unsigned long long acc = 0;
+	for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long) gridDim.x * blockDim.x) {
+		const uint32_t *w = reinterpret_cast<const uint32_t *>(recs + i);
+		const unsigned long long a = w[0] | ((unsigned long long) w[1] << 32), b = w[2] | ((unsigned long long) w[3] << 32), c = w[4] | ((unsigned long long) w[5] << 32), d = w[6];
+		acc += fmix64(a ^ fmix64(b ^ fmix64(c ^ fmix64(d + i))));
+	}
+	for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+	if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // table-level batch mirrors
 // ------------------------------------------------------------------------------------------------------------------

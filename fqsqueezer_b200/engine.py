@@ -45,7 +45,7 @@ class _Stats(C.Structure):
 
 
 EXPORTS = ["fqsk_create", "fqsk_destroy", "fqsk_last_error", "fqsk_block_start", "fqsk_segment", "fqsk_segment_device",
-           "fqsk_device_recs", "fqsk_sorted_prefix", "fqsk_pair_info", "fqsk_submit", "fqsk_collect", "fqsk_sync", "fqsk_dump", "fqsk_stats_get", "fqsk_profile", "fqsk_ht_insert", "fqsk_ht_find",
+           "fqsk_device_recs", "fqsk_recs_checksum", "fqsk_sorted_prefix", "fqsk_pair_info", "fqsk_submit", "fqsk_collect", "fqsk_sync", "fqsk_dump", "fqsk_stats_get", "fqsk_profile", "fqsk_ht_insert", "fqsk_ht_find",
            "fqsk_ht_count", "fqsk_timer_begin", "fqsk_timer_end", "fqsk_siv_increment", "fqsk_siv_test", "fqsk_siv_counts", "fqsk_siv_test_shorter", "fqsk_mt_stream", "fqsk_host_alloc", "fqsk_host_free",
            "fqsk_shard_export", "fqsk_shard_attach", "fqsk_sync_route", "fqsk_sync_apply", "fqsk_sync_finish"]
 
@@ -70,6 +70,7 @@ def load_library():
     lib.fqsk_segment.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint32, vp, C.c_uint64, u64p, vp, vp]
     lib.fqsk_segment_device.argtypes = [vp, vp, C.c_uint64, vp, vp, C.c_uint32, u64p]
     lib.fqsk_device_recs.argtypes = [vp, C.POINTER(vp), u64p]
+    lib.fqsk_recs_checksum.argtypes = [vp, u64p, u64p]
     lib.fqsk_sorted_prefix.argtypes = [vp, vp, vp, C.c_uint32]
     lib.fqsk_pair_info.argtypes = [vp, vp, C.c_uint32]
     lib.fqsk_submit.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint32, vp, C.c_uint64, vp, vp, u64p]
@@ -106,6 +107,23 @@ def kmer_params(genome_size_mb: int):
         if genome_size_mb <= gs:
             return pref, p, s, b
     return 14, 13, 15, 26
+
+
+def recs_checksum_host(recs: np.ndarray) -> int:
+    """fqsk_recs_checksum over a host-side record array (the oracle's records in bench.py's parity_check and in the tests)."""
+    n = len(recs)
+    if n == 0:
+        return 0
+    w = np.ascontiguousarray(recs).view(np.uint32).reshape(n, 7).astype(np.uint64)
+    m1, m2 = np.uint64(0xff51afd7ed558ccd), np.uint64(0xc4ceb9fe1a85ec53)
+
+    def fmix(x):
+        x = x ^ (x >> np.uint64(33)); x = x * m1; x = x ^ (x >> np.uint64(33)); x = x * m2; return x ^ (x >> np.uint64(33))
+
+    a, b, c, d = w[:, 0] | (w[:, 1] << np.uint64(32)), w[:, 2] | (w[:, 3] << np.uint64(32)), w[:, 4] | (w[:, 5] << np.uint64(32)), w[:, 6]
+    with np.errstate(over="ignore"):
+        h = fmix(a ^ fmix(b ^ fmix(c ^ fmix(d + np.arange(n, dtype=np.uint64)))))
+        return int(h.sum(dtype=np.uint64))
 
 
 def _ptr(a):
@@ -242,6 +260,12 @@ class KmerEngine:
         n = C.c_uint64(0)
         self._ck(self.lib.fqsk_device_recs(self.h, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    def recs_checksum(self):
+        """(checksum, number of records) of the last segment, computed on the device (fqsk_recs_checksum)."""
+        s, n = C.c_uint64(0), C.c_uint64(0)
+        self._ck(self.lib.fqsk_recs_checksum(self.h, C.byref(s), C.byref(n)))
+        return s.value, n.value
 
     def sorted_prefix(self, n_reads):
         """(flag, dif) per read of the last segment -- compress_prefix_sorted, dna.cpp:589-605."""

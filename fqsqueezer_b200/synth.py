@@ -73,7 +73,25 @@ def codes_to_ascii(codes: np.ndarray) -> np.ndarray:
     return lut[codes]
 
 
-def write_fastq(path: str, codes: np.ndarray, err: np.ndarray, mate: int = 1, seed: int = 0) -> int:
+# ---- the BASELINE config-2 job as ONE stream of reads (bench.py, oracle/make_bench_golden.py) -------------------------------
+JOB_CHUNK = 51_000          # reads are generated in chunks of this many, chunk c with seed 1000 + c; the job is their concatenation
+
+
+def job_chunk(genome: np.ndarray, c: int, L: int = 150):
+    """(codes, err) of chunk c of the job's read stream."""
+    return make_reads(genome, JOB_CHUNK, L=L, seed=1000 + c)
+
+
+def fastq_record_sizes(first_id: int, n: int, L: int = 150) -> np.ndarray:
+    """Bytes of the FASTQ records write_fastq produces for reads first_id .. first_id + n - 1 (ids count from 1):
+    '@SIM.<n> <n>/1' + DNA + '+' + qualities, four newlines.  The reference cuts its 16 MiB reads_blocks by these sizes
+    (reads_block.h:121-169), so they decide which reads share a block -- and with that the whole sync schedule."""
+    ids = np.arange(first_id, first_id + n, dtype=np.int64)
+    digits = np.floor(np.log10(ids)).astype(np.int64) + 1
+    return (9 + 2 * digits + 2 * (L + 1) + 2).astype(np.uint32)
+
+
+def write_fastq(path: str, codes: np.ndarray, err: np.ndarray, mate: int = 1, seed: int = 0, first_id: int = 1, append: bool = False) -> int:
     """Writes a FASTQ file in the §8d format; returns the number of bytes written."""
     rng = np.random.default_rng(seed + 3)
     n, L = codes.shape
@@ -81,13 +99,13 @@ def write_fastq(path: str, codes: np.ndarray, err: np.ndarray, mate: int = 1, se
     q = np.where(rng.random(codes.shape) < 0.1, ord("F"), ord("I")).astype(np.uint8)
     q = np.where(err, ord("#"), q).astype(np.uint8)
     total = 0
-    with open(path, "wb") as f:
+    with open(path, "ab" if append else "wb") as f:
         chunk = 100000
         for a in range(0, n, chunk):
             b = min(n, a + chunk)
             parts = []
             for i in range(a, b):
-                parts.append(b"@SIM.%d %d/%d\n" % (i + 1, i + 1, mate))
+                parts.append(b"@SIM.%d %d/%d\n" % (i + first_id, i + first_id, mate))
                 parts.append(seq[i].tobytes())
                 parts.append(b"\n+\n")
                 parts.append(q[i].tobytes())

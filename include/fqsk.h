@@ -127,6 +127,11 @@ int fqsk_segment(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const 
 int fqsk_segment_device(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes, const uint64_t *d_off, const uint32_t *d_len,
                         uint32_t n_reads, uint64_t *n_recs);
 int fqsk_device_recs(fqsk_handle *h, const fqsk_base_rec **d_recs, uint64_t *n_recs);
+/* Order-sensitive checksum of the last segment's records, computed on the device (no record leaves HBM): the sum over the records i of
+ * fmix64(a ^ fmix64(b ^ fmix64(c ^ fmix64(d + i)))) with a, b, c = the first three little-endian 64-bit words of record i, d = its last
+ * 32 bits and fmix64 = murmur3's finaliser.  bench.py compares it with the same sum over the oracle's records (BASELINE.md section 3:
+ * "count vectors verified on device").  Replaces nothing in the reference. */
+int fqsk_recs_checksum(fqsk_handle *h, uint64_t *sum, uint64_t *n_recs);
 /* Sorted-order modes: what compress_prefix_sorted (dna.cpp:589-605) codes per read of the last segment -- flag = siv.test(p-mer)
  * or 4 when the p-mer equals the previous read's, dif = number of p-mers with that flag between the previous and this p-mer. */
 int fqsk_sorted_prefix(fqsk_handle *h, uint32_t *flag, uint64_t *dif, uint32_t n_reads);
