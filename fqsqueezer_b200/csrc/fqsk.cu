@@ -21,6 +21,8 @@
 
 #include "fqsk_pipeline.cuh"
 #include "fqsk_pe.cuh"
+#include "fqsk_mtjump.h"
+#include <mutex>
 
 using namespace fqsk;
 
@@ -63,7 +65,9 @@ struct Stream {            // one mt19937 stream (utils.h:257, seeded 5481 at ut
 	uint64_t safe = 0;         // outputs below this position are known to be complete for the main stream (it waited for them)
 	cudaEvent_t ev = nullptr;  // completion of the latest generation launch
 	bool ev_pending = false;   // the main stream has not waited for `ev` yet
+	uint32_t *jstates = nullptr;   // parallel extension: the states MT_PAR chunks ahead (k_mt_jump)
 };
+const uint32_t MT_PAR = 32, MT_CHUNK_BLOCKS = 420;      // long extensions: 32 CTAs x 420 blocks x 624 outputs = 8.4 M outputs per launch
 
 struct Table {
 	HtDev d{};
@@ -162,6 +166,7 @@ struct fqsk_handle {
 	uint8_t *h_meta[2] = {nullptr, nullptr}; size_t h_meta_cap[2] = {0, 0};   // pinned per-ticket copies of dup / rec_off (item arrays in paired-end mode)
 	struct Ticket { bool open = false, done = false; fqsk_base_rec *recs = nullptr; uint64_t bound = 0, n_recs = 0; uint8_t *dup = nullptr; uint64_t *rec_off = nullptr; uint32_t n_reads = 0; int par = 0; uint64_t id = 0; } tk[2];
 	bool tk_open = false; int tk_cur = 0; uint64_t tk_next = 1;
+	int tk_info = -1;                        // ticket (parity) whose per-read extras (sorted prefix, pair decisions) fqsk_sorted_prefix / fqsk_pair_info serve; -1: the last blocking segment
 	// pinned staging
 	uint8_t *h_stage = nullptr; size_t h_stage_cap = 0;
 	void *h_small = nullptr;              // pinned scratch for small D2H reads
@@ -274,6 +279,26 @@ int table_alloc(fqsk_handle *h, Table &t, uint32_t k, uint32_t cbits, uint32_t B
 	return FQSK_OK;
 }
 
+// jump polynomials x^(j chunk) mod phi, j = 1 .. MT_PAR - 1: computed once per process on the host (~0.3 s), one copy per device
+int mt_jump_polys(fqsk_handle *h, const uint32_t **out) {
+	static std::mutex mu;
+	static std::vector<uint32_t> host;
+	static bool tried = false, ok = false;
+	static uint32_t *dev[64] = {nullptr};
+	std::lock_guard<std::mutex> lk(mu);
+	if (!tried) { tried = true; ok = fqsk_mtjump::jump_polys((uint64_t) MT_CHUNK_BLOCKS * 624, (int) MT_PAR - 1, host); }
+	if (!ok) return fail(h, FQSK_E_CUDA, "internal error: the characteristic polynomial of mt19937 was not recovered");
+	const int d = h->P.device;
+	if (d < 0 || d >= 64) return fail(h, FQSK_E_INVAL, "device ordinal %d", d);
+	if (!dev[d]) {
+		CK(cudaMalloc(&dev[d], host.size() * 4));
+		CK(cudaMemcpy(dev[d], host.data(), host.size() * 4, cudaMemcpyHostToDevice));
+		CK(cudaFuncSetAttribute(k_mt_jump, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (MT_JUMP_WORDS * 4)));
+	}
+	*out = dev[d];
+	return FQSK_OK;
+}
+
 inline uint64_t stream_avail_of(const Stream &s) { return s.generated - s.consumed; }   // generated (maybe still in flight) ahead of the consumer
 int stream_init(fqsk_handle *h, Stream &s, uint64_t cap) {
 	uint32_t st[624];
@@ -308,9 +333,19 @@ int stream_generate(fqsk_handle *h, Stream &s, uint64_t upto) {
 		s.buf = nb; s.cap = ncap;
 	}
 	Phase ph(h, FQSK_PH_MT);
+	// long extensions run as MT_PAR chunks side by side (jump-ahead, fqsk_mtjump.h); the rest sequentially
+	while (blocks >= (uint64_t) MT_PAR * MT_CHUNK_BLOCKS && (s.generated + (uint64_t) MT_PAR * MT_CHUNK_BLOCKS * 624 - s.consumed <= s.cap)) {
+		const uint32_t *polys = nullptr;
+		CKR(mt_jump_polys(h, &polys));
+		if (!s.jstates) CK(cudaMalloc(&s.jstates, (size_t) MT_PAR * 624 * 4));
+		k_mt_jump<<<MT_PAR, 640, MT_JUMP_WORDS * 4, h->st_mt>>>(s.state, polys, s.jstates);
+		k_mt_extend<<<MT_PAR, 256, 0, h->st_mt>>>(s.state, s.jstates, s.buf, s.cap - 1, s.generated, MT_CHUNK_BLOCKS);
+		LAUNCHED(h); LAUNCHED(h);
+		s.generated += (uint64_t) MT_PAR * MT_CHUNK_BLOCKS * 624; blocks -= (uint64_t) MT_PAR * MT_CHUNK_BLOCKS;
+	}
 	while (blocks) {
 		uint32_t nb = (uint32_t) std::min<uint64_t>(blocks, 1u << 20);
-		k_mt_extend<<<1, 256, 0, h->st_mt>>>(s.state, s.buf, s.cap - 1, s.generated, nb);
+		k_mt_extend<<<1, 256, 0, h->st_mt>>>(s.state, (const uint32_t *) nullptr, s.buf, s.cap - 1, s.generated, nb);
 		LAUNCHED(h);
 		s.generated += (uint64_t) nb * 624; blocks -= nb;
 	}
@@ -1250,7 +1285,7 @@ int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
 			h->attached = 1u << p->rank;
 		}
 		for (int i = 0; i < 4; ++i) CKR(stream_init(h, h->rng[i], i == ST_B ? (1ull << 25) : i == ST_S ? (1ull << 21) : (1ull << 16)));
-		CKR(stream_generate(h, h->rng[ST_B], 1u << 22)); CKR(stream_generate(h, h->rng[ST_S], 1u << 18));
+		CKR(stream_generate(h, h->rng[ST_B], h->P.expected_kmers >= (1ull << 26) ? (1u << 23) + 4096 : (1u << 22))); CKR(stream_generate(h, h->rng[ST_S], 1u << 18));      // large jobs: the parallel generator (and its polynomials) from the start
 		CK(h->prev_read.ensure(1 << 16));
 		if (mode_pe(p->mode)) {          // CHT_pair_kmers(bmer_len, ...), application.cpp:91
 			CK(cudaMalloc(&h->d_pe, 64)); CK(cudaMemsetAsync(h->d_pe, 0, 64, h->st));
@@ -1277,7 +1312,7 @@ void fqsk_destroy(fqsk_handle *h) {
 	if (h->pair.vcs) cudaFree(h->pair.vcs);
 	if (h->d_pe) cudaFree(h->d_pe);
 	if (h->st_mt) cudaStreamSynchronize(h->st_mt);
-	for (auto &s : h->rng) { if (s.buf) cudaFree(s.buf); if (s.state) cudaFree(s.state); if (s.ev) cudaEventDestroy(s.ev); }
+	for (auto &s : h->rng) { if (s.buf) cudaFree(s.buf); if (s.state) cudaFree(s.state); if (s.jstates) cudaFree(s.jstates); if (s.ev) cudaEventDestroy(s.ev); }
 	if (h->d_status) cudaFree(h->d_status);
 	if (h->d_counters) cudaFree(h->d_counters);
 	DevBuf *bufs[] = {&h->prev_read, &h->dna, &h->off, &h->len, &h->dup, &h->n_coded, &h->letters, &h->rec_off, &h->sl_prefix, &h->recs, &h->push_b, &h->push_s,
@@ -1342,6 +1377,7 @@ int fqsk_block_start(fqsk_handle *h) {
 int fqsk_segment_device(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes, const uint64_t *d_off, const uint32_t *d_len, uint32_t n_reads, uint64_t *n_recs) {
 	if (!h) return FQSK_E_INVAL;
 	CK(cudaSetDevice(h->P.device));
+	h->tk_info = -1;
 	CKR(run_segment(h, d_dna, dna_bytes, (const unsigned long long *) d_off, d_len, n_reads));
 	if (n_recs) { CKR(seg_settle(h)); *n_recs = h->n_recs; }    // pass NULL to leave the look to fqsk_sync / fqsk_device_recs
 	return FQSK_OK;
@@ -1374,6 +1410,20 @@ int fqsk_recs_checksum(fqsk_handle *h, uint64_t *sum, uint64_t *n_recs) {
 int fqsk_sorted_prefix(fqsk_handle *h, uint32_t *flag, uint64_t *dif, uint32_t n_reads) {
 	if (!h || !flag || !dif) return FQSK_E_INVAL;
 	CK(cudaSetDevice(h->P.device));
+	if (h->tk_info >= 0) {      // the segment of the ticket collected last: served from its page-locked copies
+		const auto &T = h->tk[h->tk_info];
+		if (n_reads > T.n_reads) return fail(h, FQSK_E_INVAL, "the collected segment had %u reads", T.n_reads);
+		const bool pe = mode_pe(h->P.mode);
+		const uint32_t ni = pe ? T.n_reads / 2 * 3 : T.n_reads;
+		const size_t o_off = ((size_t) ni + 8) & ~(size_t) 7, o_flag = o_off + ((size_t) ni + 1) * 8, o_dif = o_flag + ((((size_t) ni + 1) * 4 + 7) & ~(size_t) 7);
+		const uint32_t *f = (const uint32_t *) (h->h_meta[h->tk_info] + o_flag);
+		const unsigned long long *d = (const unsigned long long *) (h->h_meta[h->tk_info] + o_dif);
+		for (uint32_t i = 0; i < n_reads; ++i) {
+			const uint32_t it = pe ? 3 * (i / 2) : i;
+			flag[i] = (pe && (i & 1)) ? 0u : f[it]; dif[i] = (pe && (i & 1)) ? 0ull : d[it];
+		}
+		return FQSK_OK;
+	}
 	if (n_reads > h->seg_reads) return fail(h, FQSK_E_INVAL, "last segment had %u reads", h->seg_reads);
 	if (!n_reads) return FQSK_OK;
 	CKR(seg_settle(h));
@@ -1397,6 +1447,14 @@ int fqsk_pair_info(fqsk_handle *h, uint32_t *info, uint32_t n_pairs) {
 	if (!h || (!info && n_pairs)) return FQSK_E_INVAL;
 	CK(cudaSetDevice(h->P.device));
 	if (!mode_pe(h->P.mode)) return fail(h, FQSK_E_INVAL, "not a paired-end engine");
+	if (h->tk_info >= 0) {      // the segment of the ticket collected last
+		const auto &T = h->tk[h->tk_info];
+		if (n_pairs > T.n_reads / 2) return fail(h, FQSK_E_INVAL, "the collected segment had %u pairs", T.n_reads / 2);
+		const uint32_t ni = T.n_reads / 2 * 3;
+		const size_t o_off = ((size_t) ni + 8) & ~(size_t) 7, o_flag = o_off + ((size_t) ni + 1) * 8, o_dif = o_flag + ((((size_t) ni + 1) * 4 + 7) & ~(size_t) 7), o_pair = o_dif + (size_t) ni * 8;
+		if (n_pairs) memcpy(info, h->h_meta[h->tk_info] + o_pair, (size_t) n_pairs * 12);
+		return FQSK_OK;
+	}
 	if (n_pairs > h->pe_pairs) return fail(h, FQSK_E_INVAL, "last segment had %u pairs", h->pe_pairs);
 	if (!n_pairs) return FQSK_OK;
 	CK(cudaMemcpyAsync(info, h->pe_info.p, (size_t) n_pairs * 12, cudaMemcpyDeviceToHost, h->st));
@@ -1455,6 +1513,7 @@ int fqsk_segment(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const 
 	if (!h || (!slab && n_reads) || (!reads && n_reads)) return FQSK_E_INVAL;
 	CK(cudaSetDevice(h->P.device));
 	if (h->tk_open) return fail(h, FQSK_E_INVAL, "a submitted segment is in flight: fqsk_collect it first");
+	h->tk_info = -1;
 	uint64_t total = 0, bound = 0;
 	CKR(stage_segment(h, h->h_stage, h->h_stage_cap, slab, slab_size, reads, n_reads, &total, &bound));
 	Uploaded U;
@@ -1730,7 +1789,9 @@ int fqsk_submit(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const f
 	CKR(run_segment(h, U.dna, total, U.off, U.len, n_reads));
 	const uint32_t ni = mode_pe(h->P.mode) ? n_reads / 2 * 3 : n_reads;
 	if (ni) {   // duplicate flags and record offsets are final after k_prep / k_scan_reads: main stream, ahead of the look that ends the sync
-		const size_t need = (((size_t) ni + 8) & ~(size_t) 7) + ((size_t) ni + 1) * 8;
+		// layout: [dup: ni bytes, padded to 8][rec_off: (ni + 1) u64][sorted flag: ni u32, padded][sorted dif: ni u64][pair decisions: 3 u32 per pair]
+		const size_t o_off = ((size_t) ni + 8) & ~(size_t) 7, o_flag = o_off + ((size_t) ni + 1) * 8, o_dif = o_flag + ((((size_t) ni + 1) * 4 + 7) & ~(size_t) 7), o_pair = o_dif + (size_t) ni * 8;
+		const size_t need = o_pair + (size_t) (n_reads / 2 + 1) * 12;
 		if (need > h->h_meta_cap[par]) {
 			if (h->h_meta[par]) cudaFreeHost(h->h_meta[par]);
 			h->h_meta[par] = nullptr; h->h_meta_cap[par] = 0;
@@ -1739,7 +1800,14 @@ int fqsk_submit(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const f
 			h->h_meta_cap[par] = want;
 		}
 		CK(cudaMemcpyAsync(h->h_meta[par], h->dup.p, ni, cudaMemcpyDeviceToHost, h->st));
-		CK(cudaMemcpyAsync(h->h_meta[par] + (((size_t) ni + 8) & ~(size_t) 7), h->rec_off.p, ((size_t) ni + 1) * 8, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaMemcpyAsync(h->h_meta[par] + o_off, h->rec_off.p, ((size_t) ni + 1) * 8, cudaMemcpyDeviceToHost, h->st));
+		// what compress_prefix_sorted / CompressPE code per read / pair: functions of the reads and of the tables as they were when the
+		// segment started, so the values of the first pass are final
+		if (mode_sorted(h->P.mode)) {
+			CK(cudaMemcpyAsync(h->h_meta[par] + o_flag, h->sflag.p, (size_t) ni * 4, cudaMemcpyDeviceToHost, h->st));
+			CK(cudaMemcpyAsync(h->h_meta[par] + o_dif, h->sdif.p, (size_t) ni * 8, cudaMemcpyDeviceToHost, h->st));
+		}
+		if (mode_pe(h->P.mode) && n_reads >= 2) CK(cudaMemcpyAsync(h->h_meta[par] + o_pair, h->pe_info.p, (size_t) (n_reads / 2) * 12, cudaMemcpyDeviceToHost, h->st));
 	}
 	if (bound && recs && n_reads) {   // the records leave on their own stream while the sync and the next segment run
 		CK(cudaEventRecord(h->ev_recs, h->st)); CK(cudaStreamWaitEvent(h->st_copy, h->ev_recs, 0));
@@ -1772,7 +1840,7 @@ int fqsk_collect(fqsk_handle *h, uint64_t ticket, uint64_t *n_recs) {
 		const bool pe = mode_pe(h->P.mode);
 		const uint32_t ni = pe ? n / 2 * 3 : n;
 		const uint8_t *idup = h->h_meta[par];
-		const unsigned long long *ioff = (const unsigned long long *) (h->h_meta[par] + (((size_t) ni + 8) & ~(size_t) 7));
+		const unsigned long long *ioff = (const unsigned long long *) (h->h_meta[par] + (((size_t) ni + 8) & ~(size_t) 7));      // layout: fqsk_submit
 		if (pe) {
 			for (uint32_t i = 0; i < n / 2; ++i) {
 				if (T.dup) { T.dup[2 * i] = idup[3 * i]; T.dup[2 * i + 1] = 0; }
@@ -1787,6 +1855,7 @@ int fqsk_collect(fqsk_handle *h, uint64_t ticket, uint64_t *n_recs) {
 	if (n_recs) *n_recs = T.n_recs;
 	T.open = false;
 	h->tk_open = h->tk[0].open || h->tk[1].open;
+	h->tk_info = par;      // fqsk_sorted_prefix / fqsk_pair_info now describe this segment
 	return FQSK_OK;
 }
 
@@ -2221,6 +2290,7 @@ int fqsk_mt_stream(fqsk_handle *h, uint64_t n, uint32_t *out) {
 	cudaStreamSynchronize(h->st_mt);
 	if (s.buf) cudaFree(s.buf);
 	if (s.state) cudaFree(s.state);
+	if (s.jstates) cudaFree(s.jstates);
 	if (s.ev) cudaEventDestroy(s.ev);
 	return rc;
 }

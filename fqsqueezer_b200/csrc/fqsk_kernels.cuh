@@ -1,7 +1,8 @@
 // fqsk_kernels.cuh -- the kernels of the k-mer statistics engine (sm_100a).  Host orchestration lives in fqsk.cu.
 //
 // Kernel inventory:
-//   k_mt_extend        mt19937 block recurrence, one CTA, state in shared memory        (utils.h:257, 298)
+//   k_mt_extend        mt19937 block recurrence, one CTA per chunk, state in shared memory (utils.h:257, 298)
+//   k_mt_jump          mt19937 jump-ahead: the states j chunks ahead, so that G CTAs extend one stream side by side
 //   k_prep             per read: duplicate flag, A/C/G/T totals, number of coded bases  (dna.cpp:1521-1533, 2047-2057)
 //   (segment pipeline: k_lookup / k_partial / k_local / k_walk / k_rough / k_fold live in fqsk_pipeline.cuh)
 //   k_locate_heads/k_apply_keys/k_commit_keys   InsertKmersToHT for s-/b-mers with ordered PRNG draws   (dna.cpp:2420-2446, ht_kmer.h:420-438)
@@ -27,12 +28,16 @@ __device__ __forceinline__ uint32_t mt_twist(uint32_t a, uint32_t b, uint32_t fa
 }
 // Double-buffered: the three phases of a block read the previous state from one array and write the new one into the other, so
 // only the 3 true dependencies between the phases need a barrier (an in-place version needs 7 per block),
-// and every thread tempers and stores the word it has just produced.  The generator is one CTA on a side stream and late in a
-// file the b-mer counters consume ~6 M draws per 51 000-read block: its speed bounds the sync of the main stream.
-__global__ void __launch_bounds__(256) k_mt_extend(uint32_t *state, uint32_t *ring, unsigned long long mask, unsigned long long pos, uint32_t n_blocks) {
+// and every thread tempers and stores the word it has just produced.  One CTA is bound by the recurrence's dependency distance
+// (227 words): ~2 G outputs/s.  Late in a file the b-mer counters consume ~6 M draws per 51 000-read block, so long extensions
+// run as G chunks side by side: CTA j starts from the state j chunks ahead (states[j], from k_mt_jump) and writes its own
+// n_blocks x 624 outputs; the last CTA leaves the state the next launch continues from.  gridDim.x == 1: the plain sequential form.
+__global__ void __launch_bounds__(256) k_mt_extend(uint32_t *state, const uint32_t *states, uint32_t *ring, unsigned long long mask, unsigned long long pos, uint32_t n_blocks) {
 	__shared__ uint32_t st[2][624];
 	const int t = threadIdx.x;
-	for (int i = t; i < 624; i += 256) st[0][i] = state[i];
+	const uint32_t *src = gridDim.x > 1 ? states + 624u * blockIdx.x : state;
+	pos += (unsigned long long) blockIdx.x * n_blocks * 624ull;
+	for (int i = t; i < 624; i += 256) st[0][i] = src[i];
 	__syncthreads();
 	int cur = 0;
 	for (uint32_t blk = 0; blk < n_blocks; ++blk) {
@@ -53,7 +58,43 @@ __global__ void __launch_bounds__(256) k_mt_extend(uint32_t *state, uint32_t *ri
 		__syncthreads();
 		cur ^= 1;
 	}
-	for (int i = t; i < 624; i += 256) state[i] = st[cur][i];
+	if (blockIdx.x == gridDim.x - 1) for (int i = t; i < 624; i += 256) state[i] = st[cur][i];
+}
+
+// mt19937 jump-ahead (fqsk_mtjump.h): CTA j writes states[j] = the generator's state j chunks ahead of `state`, as the GF(2)
+// combination XOR_{i : g_i = 1} x[i + t] of the next 19937 + 623 raw words, g = x^(j chunk) mod the characteristic polynomial
+// (polys[j - 1]).  CTA 0 copies the state itself.  Dynamic shared memory: (624 + 33 * 624) words.
+static const uint32_t MT_JUMP_WORDS = 624 + 33 * 624;
+__global__ void __launch_bounds__(640) k_mt_jump(const uint32_t *state, const uint32_t *polys, uint32_t *states) {
+	extern __shared__ uint32_t X[];
+	const int t = threadIdx.x;
+	const uint32_t j = blockIdx.x;
+	if (j == 0) { if (t < 624) states[t] = state[t]; return; }
+	if (t < 624) X[t] = state[t];
+	__syncthreads();
+	for (uint32_t blk = 0; blk < 33; ++blk) {      // 33 x 624 = 20 592 >= 19 937 + 623 new words
+		const uint32_t *o = X + blk * 624;
+		uint32_t *nw = X + (blk + 1) * 624;
+		if (t < 227) nw[t] = mt_twist(o[t], o[t + 1], o[t + 397]);
+		__syncthreads();
+		if (t < 227) nw[t + 227] = mt_twist(o[t + 227], o[t + 228], nw[t]);
+		__syncthreads();
+		if (t < 170) { const int i = t + 454; nw[i] = mt_twist(o[i], i == 623 ? nw[0] : o[i + 1], nw[i - 227]); }
+		__syncthreads();
+	}
+	if (t >= 624) return;
+	const uint32_t *g = polys + (size_t) (j - 1) * 624;
+	uint32_t acc0 = 0, acc1 = 0;
+	for (uint32_t w = 0; w < 624; ++w) {
+		uint32_t bits = __ldg(g + w);
+		const uint32_t *xb = X + w * 32 + t;
+		while (bits) {
+			const uint32_t i = __ffs(bits) - 1; bits &= bits - 1;
+			acc0 ^= xb[i];
+			if (bits) { const uint32_t i2 = __ffs(bits) - 1; bits &= bits - 1; acc1 ^= xb[i2]; }
+		}
+	}
+	states[624u * j + t] = acc0 ^ acc1;
 }
 
 // ------------------------------------------------------------------------------------------------------------------

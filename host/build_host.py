@@ -52,8 +52,8 @@ def patch_worker_loop(f, first_read_anchor, paired, where):
     # start of a reads_block (application.cpp:624 / 1152)
     f = replace_once(f, "\t\t\t\tdna_comp.ResetReadPrev();\n",
                      "\t\t\t\tdna_comp.ResetReadPrev();\n"
-                     "\t\t\t\tCFqskLive::get().block_start(reads_block_cur->input_FASTQ, reads_block_cur->filled_size);\n"
-                     "\t\t\t\tuint64_t fqsk_seg_begin = my_first;\n", where)
+                     "\t\t\t\tCFqskLive::get().block_start(reads_block_cur->input_FASTQ, reads_block_cur->filled_size, reads_block_cur->v_reads.data(), my_first, my_last, no_synchronizations, %s);\n"
+                     "\t\t\t\tuint64_t fqsk_seg_begin = my_first;\n" % ("true" if paired else "false"), where)
     # first read of a sync segment: the engine resolves the whole segment -- the reads up to and including the one that triggers the
     # next sync (SE: i == next_synchro, application.cpp:643; PE: the first pair with i >= next_synchro, 1170) or the tail of the block
     if paired:
@@ -72,10 +72,33 @@ def patch_worker_loop(f, first_read_anchor, paired, where):
                      f"\t\t\t\t\t\tCFqskLive::get().sync();\n\t\t\t\t\t\tfqsk_seg_begin = i + {step};\n\t\t\t\t\t\tbar_synchro.count_down_and_wait();\n", where)
     # the sync at the end of a block (application.cpp:657-661 / 1184-1190), over an empty segment when the last read closed one
     f = replace_once(f, "\t\t\t\tdna_comp.InsertKmersToHT();\n",
-                     "\t\t\t\tif (fqsk_seg_begin >= my_last)\n\t\t\t\t\tCFqskLive::get().segment(reads_block_cur->v_reads.data(), 0);\n"
+                     "\t\t\t\tif (fqsk_seg_begin >= my_last)\n\t\t\t\t\tCFqskLive::get().segment(reads_block_cur->v_reads.data() + fqsk_seg_begin, 0);\n"
                      "\t\t\t\tCFqskLive::get().sync();\n", where)
     f = replace_once(f, "\t\t\t\tdna_comp.ClearKmersToHT();\n", "", where)
     assert "InsertKmersToHT" not in f and "ClearKmersToHT" not in f
+    # application.cpp:633-641 / 1161-1168 -- the four streams of a worker are independent (own models, own range coder, own output
+    # vector; their bytes are concatenated per block, 685-747): the read-length + id streams and the quality stream are coded by two
+    # helper threads over the same reads while this thread codes the DNA stream from the engine's records.  Same calls in the same order
+    # per stream, so every stream's bytes are unchanged.
+    if paired:
+        f = replace_once(f, "\t\t\t\t\tmeta_comp.CompressReadLenPE(cur_read_1.read_len(), cur_read_2.read_len());\n", "", where)
+        f = replace_once(f, "\t\t\t\t\tid_comp.CompressPE(cur_read_1.id, cur_read_1.id_len(), cur_read_2.id, cur_read_2.id_len());\n", "", where)
+        f = replace_once(f, "\t\t\t\t\tquality_comp.Compress(cur_read_1.quality, cur_read_1.read_len());\n\t\t\t\t\tquality_comp.Compress(cur_read_2.quality, cur_read_2.read_len());\n", "", where)
+        helpers = ("\t\t\t\tstd::thread fqsk_thr_ids([&] { for (uint64_t q = my_first; q < my_last; q += 2) { auto &r1 = reads_block_cur->v_reads[q]; auto &r2 = reads_block_cur->v_reads[q + 1];\n"
+                   "\t\t\t\t\tmeta_comp.CompressReadLenPE(r1.read_len(), r2.read_len()); id_comp.CompressPE(r1.id, r1.id_len(), r2.id, r2.id_len()); } });\n"
+                   "\t\t\t\tstd::thread fqsk_thr_qual([&] { for (uint64_t q = my_first; q < my_last; ++q) { auto &r = reads_block_cur->v_reads[q]; quality_comp.Compress(r.quality, r.read_len()); } });\n")
+        loop_head = "\t\t\t\tfor (uint64_t i = my_first; i < my_last; i += 2)\n"
+    else:
+        f = replace_once(f, "\t\t\t\t\tmeta_comp.CompressReadLen(cur_read.read_len());\n", "", where)
+        f = replace_once(f, "\t\t\t\t\tid_comp.Compress(cur_read.id, (uint32_t) cur_read.id_len());\n", "", where)
+        f = replace_once(f, "\t\t\t\t\tquality_comp.Compress(cur_read.quality, cur_read.read_len());\n", "", where)
+        helpers = ("\t\t\t\tstd::thread fqsk_thr_ids([&] { for (uint64_t q = my_first; q < my_last; ++q) { auto &r = reads_block_cur->v_reads[q];\n"
+                   "\t\t\t\t\tmeta_comp.CompressReadLen(r.read_len()); id_comp.Compress(r.id, (uint32_t) r.id_len()); } });\n"
+                   "\t\t\t\tstd::thread fqsk_thr_qual([&] { for (uint64_t q = my_first; q < my_last; ++q) { auto &r = reads_block_cur->v_reads[q]; quality_comp.Compress(r.quality, r.read_len()); } });\n")
+        loop_head = "\t\t\t\tfor (uint64_t i = my_first; i < my_last; ++i)\n"
+    f = replace_once(f, loop_head, helpers + loop_head, where)
+    # the helpers are done before the coders are flushed (application.cpp:663-664 / 1192-1193)
+    f = replace_once(f, "\t\t\t\tfor(auto &x : c_rc_enc)\n\t\t\t\t\tx.End();\n", "\t\t\t\tfqsk_thr_ids.join();\n\t\t\t\tfqsk_thr_qual.join();\n\t\t\t\tfor(auto &x : c_rc_enc)\n\t\t\t\t\tx.End();\n", where)
     # the workers have joined (application.cpp:762 / 1310): engine statistics, release
     f = replace_once(f, "\tv_thr_compress.clear();\n", "\tv_thr_compress.clear();\n\tCFqskLive::get().finish();\n", where)
     return f

@@ -31,8 +31,8 @@ class CFqskLive {
 	decltype(&fqsk_destroy) p_destroy = nullptr;
 	decltype(&fqsk_last_error) p_last_error = nullptr;
 	decltype(&fqsk_block_start) p_block_start = nullptr;
-	decltype(&fqsk_segment) p_segment = nullptr;
-	decltype(&fqsk_sync) p_sync = nullptr;
+	decltype(&fqsk_submit) p_submit = nullptr;
+	decltype(&fqsk_collect) p_collect = nullptr;
 	decltype(&fqsk_stats_get) p_stats = nullptr;
 	decltype(&fqsk_sorted_prefix) p_sorted_prefix = nullptr;
 	decltype(&fqsk_pair_info) p_pair_info = nullptr;
@@ -43,15 +43,22 @@ class CFqskLive {
 	const uint8_t *slab = nullptr;
 	uint64_t slab_size = 0;
 	std::vector<fqsk_read_desc> descs;
+	// two segments in flight (fqsk_submit / fqsk_collect): the engine works on segment n + 1 while the coder consumes segment n
+	struct Slot { fqsk_base_rec *recs = nullptr; uint64_t cap = 0; std::vector<uint8_t> dup; uint64_t ticket = 0; };
+	Slot slot[2];
+	struct Seg { uint64_t first, n; bool submitted; };     // the sync segments of the current reads_block, as the worker loop will cut them
+	std::vector<Seg> plan;
+	size_t plan_cur = 0;
+	void *plan_reads = nullptr; size_t plan_stride = 0;
 	fqsk_base_rec *recs = nullptr;
-	uint64_t rec_cap = 0, n_recs = 0, cursor = 0;
-	std::vector<uint8_t> dup;
+	uint64_t n_recs = 0, cursor = 0;
+	const uint8_t *dup = nullptr;
 	uint32_t mode = FQSK_MODE_SE_ORIGINAL;
 	uint64_t n_seg_reads = 0, cur_read = 0;
 	std::vector<uint32_t> s_flag, pair_words;      // per read: compress_prefix_sorted's flag; per pair: what CompressPE codes for mate 2
 	std::vector<uint64_t> s_dif;
 	uint64_t n_segments = 0, n_syncs = 0, n_bases = 0;
-	double engine_s = 0;
+	double engine_s = 0, wait_s = 0;
 
 	[[noreturn]] void die(const char *what, int rc = 0) {
 		fprintf(stderr, "fqsk: %s%s%s (rc %d)\n", what, (h || p_last_error) ? ": " : "", p_last_error ? p_last_error(h) : "", rc);
@@ -82,7 +89,7 @@ public:
 		}
 		if (!lib) { fprintf(stderr, "fqsk: cannot load the k-mer engine (%s); set FQSK_LIB. There is no CPU fallback.\n", dlerror()); exit(3); }
 		sym(p_create, "fqsk_create"); sym(p_destroy, "fqsk_destroy"); sym(p_last_error, "fqsk_last_error"); sym(p_block_start, "fqsk_block_start");
-		sym(p_segment, "fqsk_segment"); sym(p_sync, "fqsk_sync"); sym(p_stats, "fqsk_stats_get"); sym(p_host_alloc, "fqsk_host_alloc"); sym(p_host_free, "fqsk_host_free");
+		sym(p_submit, "fqsk_submit"); sym(p_collect, "fqsk_collect"); sym(p_stats, "fqsk_stats_get"); sym(p_host_alloc, "fqsk_host_alloc"); sym(p_host_free, "fqsk_host_free");
 		sym(p_sorted_prefix, "fqsk_sorted_prefix"); sym(p_pair_info, "fqsk_pair_info");
 		fqsk_params P;
 		memset(&P, 0, sizeof(P));
@@ -100,36 +107,73 @@ public:
 		if (rc != FQSK_OK) { h = nullptr; die("fqsk_create", rc); }
 	}
 
-	// application.cpp:624 (dna_comp.ResetReadPrev() at the start of a reads_block)
-	void block_start(const uint8_t *input_FASTQ, uint64_t filled_size) {
+	// application.cpp:617-624: start of a reads_block for this worker.  The block's sync segments are known up front -- they follow from
+	// my_first / my_last / no_synchronizations exactly as the worker loop computes next_synchro (SE: sync after read i == next_synchro,
+	// application.cpp:643; PE: after the first pair with i >= next_synchro, 1170; plus the sync at the end of the block, 657-661 /
+	// 1184-1190, possibly over an empty segment) -- so segment n + 1 can be handed to the engine before the coder starts on segment n.
+	template <typename RD> void block_start(const uint8_t *input_FASTQ, uint64_t filled_size, RD *reads, uint64_t my_first, uint64_t my_last, uint64_t no_synchronizations, bool paired) {
 		slab = input_FASTQ; slab_size = filled_size;
 		int rc = p_block_start(h);
 		if (rc != FQSK_OK) die("fqsk_block_start", rc);
+		plan.clear(); plan_cur = 0;
+		plan_reads = reads; plan_stride = sizeof(RD);
+		const uint64_t step = paired ? 2 : 1;
+		uint64_t gen = 0, a = my_first;
+		uint64_t next = (gen + 1) * (my_last - my_first) / (no_synchronizations + 1) + my_first;
+		for (uint64_t i = my_first; i < my_last; i += step)
+			if (paired ? i >= next : i == next) {
+				plan.push_back(Seg{a, i + step - a, false});
+				a = i + step;
+				++gen;
+				next = (gen + 1) * (my_last - my_first) / (no_synchronizations + 1) + my_first;
+			}
+		plan.push_back(Seg{a, my_last - a, false});
+	}
+
+	template <typename RD> void submit(size_t k) {
+		Seg &sg = plan[k];
+		Slot &sl = slot[k & 1];
+		RD *reads = (RD *) plan_reads + sg.first;      // read_desc_t::read_len() is not const-qualified (defs.h:58-85)
+		descs.resize(sg.n);
+		uint64_t total = 0;
+		for (uint64_t q = 0; q < sg.n; ++q) {
+			descs[q].dna_off = (uint64_t) (reads[q].dna - slab);
+			descs[q].dna_len = reads[q].read_len();
+			descs[q].flags = 0;
+			total += descs[q].dna_len;
+		}
+		if (total + 1 > sl.cap) {
+			if (sl.recs) p_host_free(sl.recs);
+			sl.cap = total + total / 4 + 4096;
+			void *p = nullptr;
+			int rc = p_host_alloc(sl.cap * sizeof(fqsk_base_rec), &p);
+			if (rc != FQSK_OK) die("fqsk_host_alloc", rc);
+			sl.recs = (fqsk_base_rec *) p;
+		}
+		sl.dup.resize(sg.n + 1);
+		int rc = p_submit(h, slab, slab_size, descs.data(), (uint32_t) sg.n, sl.recs, sl.cap, sl.dup.data(), nullptr, &sl.ticket);
+		if (rc != FQSK_OK) die("fqsk_submit", rc);
+		sg.submitted = true;
+		n_bases += total;
 	}
 
 	// One sync segment: reads[0 .. n) of the current block, i.e. the reads the worker codes before the next InsertKmersToHT.
-	// RD is the reference's read_desc_t (defs.h:58-85): only .dna and .read_len() are used.
+	// RD is the reference's read_desc_t (defs.h:58-85): only .dna and .read_len() are used.  The call must agree with the plan made at
+	// the start of the block (it is the worker loop's own arithmetic, checked here).  fqsk_submit = the segment + the sync behind it.
 	template <typename RD> void segment(RD *reads, uint64_t n) {
-		descs.resize(n);
-		uint64_t total = 0;
-		for (uint64_t k = 0; k < n; ++k) {
-			descs[k].dna_off = (uint64_t) (reads[k].dna - slab);
-			descs[k].dna_len = reads[k].read_len();
-			descs[k].flags = 0;
-			total += descs[k].dna_len;
+		if (plan_cur >= plan.size() || (RD *) plan_reads + plan[plan_cur].first != reads || plan[plan_cur].n != n) {
+			fprintf(stderr, "fqsk: the worker loop's segment %llu (%llu reads) is not the planned one\n", (unsigned long long) plan_cur, (unsigned long long) n);
+			exit(3);
 		}
-		if (total + 1 > rec_cap) {
-			if (recs) p_host_free(recs);
-			rec_cap = total + total / 4 + 4096;
-			void *p = nullptr;
-			int rc = p_host_alloc(rec_cap * sizeof(fqsk_base_rec), &p);
-			if (rc != FQSK_OK) die("fqsk_host_alloc", rc);
-			recs = (fqsk_base_rec *) p;
-		}
-		dup.resize(n + 1);
+		const size_t k = plan_cur++;
 		const double t0 = now();
-		int rc = p_segment(h, slab, slab_size, descs.data(), (uint32_t) n, recs, rec_cap, &n_recs, dup.data(), nullptr);
-		if (rc != FQSK_OK) die("fqsk_segment", rc);
+		if (!plan[k].submitted) submit<RD>(k);
+		if (k + 1 < plan.size() && !plan[k + 1].submitted) submit<RD>(k + 1);        // the engine runs ahead of the coder
+		const double t1 = now();
+		Slot &sl = slot[k & 1];
+		int rc = p_collect(h, sl.ticket, &n_recs);
+		if (rc != FQSK_OK) die("fqsk_collect", rc);
+		recs = sl.recs; dup = sl.dup.data();
 		if (mode == FQSK_MODE_SE_SORTED || mode == FQSK_MODE_PE_SORTED) {            // dna.cpp:589-605: (flag, dif) of every read's p-mer prefix (paired end: of the first mates)
 			s_flag.resize(n + 1); s_dif.resize(n + 1);
 			rc = p_sorted_prefix(h, s_flag.data(), s_dif.data(), (uint32_t) n);
@@ -141,10 +185,11 @@ public:
 			rc = p_pair_info(h, pair_words.data(), (uint32_t) (n / 2));
 			if (rc != FQSK_OK) die("fqsk_pair_info", rc);
 		}
-		engine_s += now() - t0;
+		const double t2 = now();
+		engine_s += t2 - t0; wait_s += t2 - t1;
 		n_seg_reads = n; cur_read = 0;
 		cursor = 0;
-		++n_segments; n_bases += total;
+		++n_segments;
 	}
 
 	// the worker is about to code read `idx` of the segment (paired-end: its first mate)
@@ -174,13 +219,10 @@ public:
 		return r;
 	}
 
-	// application.cpp:645-654 and 657-661: InsertKmersToHT + ClearKmersToHT between the barriers
+	// application.cpp:645-654 and 657-661: InsertKmersToHT + ClearKmersToHT between the barriers.  The engine has enqueued this sync right
+	// behind the segment (fqsk_submit); what is left to do here is the coder's side of the contract: every record was consumed.
 	void sync() {
 		if (cursor != n_recs) { fprintf(stderr, "fqsk: %llu records of the segment were not consumed\n", (unsigned long long) (n_recs - cursor)); exit(3); }
-		const double t0 = now();
-		int rc = p_sync(h);
-		engine_s += now() - t0;
-		if (rc != FQSK_OK) die("fqsk_sync", rc);
 		n_recs = cursor = 0;
 		++n_syncs;
 	}
@@ -190,11 +232,11 @@ public:
 		if (getenv("FQSK_VERBOSE")) {
 			fqsk_stats st; memset(&st, 0, sizeof(st));
 			p_stats(h, &st);
-			fprintf(stderr, "fqsk: %llu segments, %llu syncs, %llu bases, %.3f s inside the engine calls, %llu kernel launches, %llu s-mers, %llu b-mers\n",
+			fprintf(stderr, "fqsk: %llu segments, %llu syncs, %llu bases, %.3f s inside the engine calls, %llu kernel launches, %llu s-mers, %llu b-mers; %.3f s waiting for the engine\n",
 			        (unsigned long long) n_segments, (unsigned long long) n_syncs, (unsigned long long) n_bases, engine_s,
-			        (unsigned long long) st.kernel_launches, (unsigned long long) st.n_smers, (unsigned long long) st.n_bmers);
+			        (unsigned long long) st.kernel_launches, (unsigned long long) st.n_smers, (unsigned long long) st.n_bmers, wait_s);
 		}
-		if (recs) p_host_free(recs);
+		for (auto &sl : slot) { if (sl.recs) p_host_free(sl.recs); sl.recs = nullptr; }
 		recs = nullptr;
 		p_destroy(h);
 		h = nullptr;

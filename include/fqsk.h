@@ -133,10 +133,13 @@ int fqsk_device_recs(fqsk_handle *h, const fqsk_base_rec **d_recs, uint64_t *n_r
  * "count vectors verified on device").  Replaces nothing in the reference. */
 int fqsk_recs_checksum(fqsk_handle *h, uint64_t *sum, uint64_t *n_recs);
 /* Sorted-order modes: what compress_prefix_sorted (dna.cpp:589-605) codes per read of the last segment -- flag = siv.test(p-mer)
- * or 4 when the p-mer equals the previous read's, dif = number of p-mers with that flag between the previous and this p-mer. */
+ * or 4 when the p-mer equals the previous read's, dif = number of p-mers with that flag between the previous and this p-mer.
+ * Paired end in sorted order (FQSK_MODE_PE_SORTED): only first mates go through CompressSorted (dna.cpp:1793-1796); the entries of
+ * second mates are 0.  "The last segment" is the one of the most recent fqsk_segment / fqsk_segment_device call or -- with the
+ * asynchronous API -- of the most recent fqsk_collect (fqsk_pair_info likewise). */
 int fqsk_sorted_prefix(fqsk_handle *h, uint32_t *flag, uint64_t *dif, uint32_t n_reads);
 
-/* Paired-end (FQSK_MODE_PE_ORIGINAL): fqsk_segment / fqsk_segment_device take the pairs interleaved (mate 1, mate 2, ...), an even
+/* Paired-end (FQSK_MODE_PE_ORIGINAL, FQSK_MODE_PE_SORTED): fqsk_segment / fqsk_segment_device take the pairs interleaved (mate 1, mate 2, ...), an even
  * number of reads; the records of a pair come in the order CompressPE codes them (dna.cpp:1790-1880): mate 1, then mate 2 --
  * either whole, or from the shared minimizer to the end followed by the reverse complement of the part left of it
  * (CompressDirectWithMinim, dna.cpp:1559-1638; `pos` of a record is the index inside the text compress_suffix was given).

@@ -69,14 +69,14 @@ def run_async(engine, slab, paired=False):
         recs, dup, rec_off = engine.collect(t)
         assert int(rec_off[len(dup)]) == len(recs)
         out.append(recs.copy()); dups.append(dup.copy())
+        if paired:
+            info.append(engine.pair_info(len(dup) // 2))      # decisions of the segment just collected
 
     for gen, (f, l) in enumerate(S.split_blocks(rsz, paired=paired)):
         ns = S.calc_no_synchronizations(gen, l - f, 1)
         engine.block_start()
         for a, b in S.segments(f, l, ns, paired=paired):
             t = engine.submit(slab, off[a:b], ln[a:b])
-            if paired:
-                info.append(engine.pair_info((b - a) // 2))      # decisions of the segment just submitted
             if pend is not None:
                 take(pend)
             pend = t

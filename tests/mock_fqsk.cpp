@@ -19,7 +19,12 @@ void fqso_sync(void *h);
 void fqso_stats(void *h, uint64_t *o);
 }
 
-struct fqsk_handle { void *o; uint32_t mode = 0; uint64_t n_segments = 0, n_syncs = 0; std::vector<uint32_t> s_flag, pair; std::vector<uint64_t> s_dif; };
+struct fqsk_handle {
+	void *o; uint32_t mode = 0; uint64_t n_segments = 0, n_syncs = 0;
+	std::vector<uint32_t> s_flag, pair; std::vector<uint64_t> s_dif;      // the segment fqsk_sorted_prefix / fqsk_pair_info describe
+	struct Ticket { uint64_t id = 0, n_recs = 0; std::vector<uint32_t> s_flag, pair; std::vector<uint64_t> s_dif; } tk[2];
+	uint64_t next_ticket = 1;
+};
 
 extern "C" {
 
@@ -58,6 +63,26 @@ int fqsk_segment(fqsk_handle *h, const uint8_t *slab, uint64_t, const fqsk_read_
 	if (dup) memcpy(dup, d.data(), n_reads);
 	++h->n_segments;
 	return FQSK_OK;
+}
+int fqsk_sync(fqsk_handle *h);
+// fqsk_submit = segment + sync, served synchronously (the oracle has no stream to overlap with); the per-read extras of a ticket
+// become visible to fqsk_sorted_prefix / fqsk_pair_info when it is collected, as in the real library
+int fqsk_submit(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const fqsk_read_desc *reads, uint32_t n_reads, fqsk_base_rec *recs, uint64_t rec_cap, uint8_t *dup, uint64_t *rec_off,
+                uint64_t *ticket) {
+	fqsk_handle::Ticket &T = h->tk[h->next_ticket & 1];
+	std::vector<uint32_t> kf = h->s_flag, kp = h->pair; std::vector<uint64_t> kd = h->s_dif;
+	int rc = fqsk_segment(h, slab, slab_size, reads, n_reads, recs, rec_cap, &T.n_recs, dup, rec_off);
+	if (rc != FQSK_OK) return rc;
+	T.s_flag.swap(h->s_flag); T.s_dif.swap(h->s_dif); T.pair.swap(h->pair);
+	h->s_flag = kf; h->s_dif = kd; h->pair = kp;
+	fqsk_sync(h);
+	T.id = h->next_ticket++;
+	*ticket = T.id;
+	return FQSK_OK;
+}
+int fqsk_collect(fqsk_handle *h, uint64_t ticket, uint64_t *n_recs) {
+	for (auto &T : h->tk) if (T.id == ticket) { h->s_flag = T.s_flag; h->s_dif = T.s_dif; h->pair = T.pair; if (n_recs) *n_recs = T.n_recs; T.id = 0; return FQSK_OK; }
+	return FQSK_E_INVAL;
 }
 int fqsk_sorted_prefix(fqsk_handle *h, uint32_t *flag, uint64_t *dif, uint32_t n_reads) {
 	for (uint32_t i = 0; i < n_reads; ++i) { flag[i] = h->s_flag[i]; dif[i] = h->s_dif[i]; }

@@ -22,6 +22,20 @@ def test_mt19937_device_stream():
     e.close()
 
 
+def test_mt19937_device_stream_parallel_chunks():
+    """Long extensions run as 32 chunks side by side, each started from a jumped-ahead state (k_mt_jump: x^(j chunk) mod the
+    characteristic polynomial, fqsk_mtjump.h): 30 M outputs = three parallel launches + a sequential tail, against the sequential
+    generator of the oracle (= std::mt19937 seeded 5481, utils.h:298)."""
+    e = _engine()
+    n = 30_000_000
+    got = e.mt_stream(n)
+    want = O.oracle_units().mt_stream(5481, n)
+    bad = np.flatnonzero(got != want)
+    assert len(bad) == 0, (len(bad), bad[:4])
+    assert e.stats()["kernel_launches"] >= 6
+    e.close()
+
+
 @pytest.mark.parametrize("table,k,cbits,log2b", [(E.TABLE_BMER, 19, 6, 0), (E.TABLE_BMER, 24, 6, 0), (E.TABLE_SMER, 20, 12, 0),
                                                  (E.TABLE_BMER, 19, 6, 12), (E.TABLE_BMER, 27, 6, 0)])
 def test_insert_dump_find_count(table, k, cbits, log2b):
