@@ -30,13 +30,14 @@ static thread_local std::string g_create_error;
 
 namespace {
 
+static std::atomic<bool> g_trace_alloc{false};      // FQSK_F_TRACE_ALLOC of any live handle
+
 struct DevBuf {
 	void *p = nullptr;
 	size_t cap = 0;
 	cudaError_t ensure(size_t bytes, int line = __builtin_LINE()) {
 		if (bytes <= cap) return cudaSuccess;
-		static const bool trace = getenv("FQSK_TRACE_ALLOC") != nullptr;
-		if (trace) fprintf(stderr, "[fqsk alloc] line %d: %zu -> %zu bytes\n", line, cap, bytes);
+		if (g_trace_alloc.load(std::memory_order_relaxed)) fprintf(stderr, "[fqsk alloc] line %d: %zu -> %zu bytes\n", line, cap, bytes);
 		if (p) cudaFree(p);
 		p = nullptr; cap = 0;
 		size_t want = bytes + bytes / 2 + 256;
@@ -153,7 +154,7 @@ struct fqsk_handle {
 	unsigned long long items_main[2] = {0, 0};   // items in the buckets of the b / s table as of the last look (sparse -> k_rough tests occupancy bits)
 	cudaStream_t st_side[2] = {nullptr, nullptr}; cudaEvent_t ev_side[2] = {nullptr, nullptr}, ev_fork = nullptr;   // p-mer / s-mer updates of a small sync
 	bool spec_enqueued = false; SyncDev spec_Y{}; uint32_t spec_g = 0;
-	uint32_t dbg_fail_every = 0, dbg_retry_every = 0, dbg_seg = 0;   // fault injection for tests (FQSK_DEBUG_FAIL_EVERY / FQSK_DEBUG_RETRY_EVERY): see fqsk_create
+	uint32_t dbg_fail_every = 0, dbg_retry_every = 0, dbg_seg = 0;   // fault injection for tests (FQSK_F_TEST_HOOKS + fqsk_params.test_hooks): see fqsk_create
 	bool dbg_retry_armed = false;
 	bool spec_prefix = false;                // the grouping half of the pending segment's b-mer sync was enqueued with the segment (seg_pass)
 	bool seg_extra_pass = false;             // the last segment needed more than its first pass: records were rewritten after the pass
@@ -1227,6 +1228,7 @@ int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
 	if (world > 1 && p->mode != FQSK_MODE_SE_ORIGINAL && p->mode != FQSK_MODE_PE_ORIGINAL) return fail(h, FQSK_E_UNSUPPORTED, "sharded operation is implemented for original order only (SE and PE)");
 	if (!(p->pmer_len >= 5 && p->pmer_len < p->smer_len && p->smer_len < p->bmer_len && p->bmer_len <= 31)) return fail(h, FQSK_E_INVAL, "need 5 <= p < s < b <= 31");
 	if (p->pmer_len > 18) return fail(h, FQSK_E_INVAL, "pmer_len > 18 not supported");
+	if (p->test_hooks && !(p->flags & FQSK_F_TEST_HOOKS)) return fail(h, FQSK_E_INVAL, "test_hooks without FQSK_F_TEST_HOOKS");
 	if (p->mode > FQSK_MODE_PE_SORTED) return fail(h, FQSK_E_INVAL, "mode %u: not a dna_mode_t (params.h:18)", p->mode);
 	int ndev = 0;
 	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(h, FQSK_E_NO_DEVICE, "no CUDA device: this library has no CPU path");
@@ -1239,11 +1241,12 @@ int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
 	h->P = *p;
 	h->world = world; h->rank = p->rank;
 	h->prof = (p->flags & FQSK_F_PROFILE) != 0;
-	// Fault injection (tests only; inert unless the variables are set): every N-th segment has its first-pass verdict forced to
-	// "not settled" after the early grouping has run (exercises k_sync_unclaim + the plain sync), resp. is evaluated a second time
-	// from scratch as after a capacity overflow (exercises the release of claimed slots before the tables are read again).
-	if (const char *e = getenv("FQSK_DEBUG_FAIL_EVERY")) h->dbg_fail_every = (uint32_t) atoi(e);
-	if (const char *e = getenv("FQSK_DEBUG_RETRY_EVERY")) h->dbg_retry_every = (uint32_t) atoi(e);
+	// Fault injection (tests only; needs FQSK_F_TEST_HOOKS in the parameters, nothing is read from the environment): every N-th
+	// segment has its first-pass verdict forced to "not settled" after the early grouping has run (exercises k_sync_unclaim + the
+	// plain sync), resp. is evaluated a second time from scratch as after a capacity overflow (exercises the release of claimed
+	// slots before the tables are read again).
+	if (p->flags & FQSK_F_TEST_HOOKS) { h->dbg_fail_every = p->test_hooks & 0xFFFFu; h->dbg_retry_every = p->test_hooks >> 16; }
+	if (p->flags & FQSK_F_TRACE_ALLOC) g_trace_alloc.store(true);
 	int rc = [&]() -> int {
 		CK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
 		CK(cudaStreamCreateWithFlags(&h->st_mt, cudaStreamNonBlocking));
@@ -1469,7 +1472,12 @@ static int stage_segment(fqsk_handle *h, uint8_t *&stage, size_t &stage_cap, con
                          uint64_t *total_out, uint64_t *rec_bound) {
 	const uint32_t first = mode_sorted(h->P.mode) ? h->P.pmer_len : h->P.prefix_len;      // paired end, sorted order: only first mates need p symbols, padding the second ones is harmless
 	uint64_t total = 0, bound = 0;
-	for (uint32_t i = 0; i < n_reads; ++i) { total += std::max(reads[i].dna_len, first); if (reads[i].dna_len > first) bound += reads[i].dna_len - first; }
+	const bool pe_sorted = h->P.mode == FQSK_MODE_PE_SORTED;      // second mates are coded from prefix_len (CompressDirect), first mates from p_len
+	for (uint32_t i = 0; i < n_reads; ++i) {
+		total += std::max(reads[i].dna_len, first);
+		const uint32_t coded_from = (pe_sorted && (i & 1)) ? h->P.prefix_len : first;
+		if (reads[i].dna_len > coded_from) bound += reads[i].dna_len - coded_from;
+	}
 	size_t need = total + 64 + (size_t) n_reads * 12 + 64;
 	if (need > stage_cap) {
 		if (stage) cudaFreeHost(stage);
@@ -1485,7 +1493,7 @@ static int stage_segment(fqsk_handle *h, uint8_t *&stage, size_t &stage_cap, con
 	for (uint32_t i = 0; i < n_reads; ++i) {
 		uint32_t plen = std::max(reads[i].dna_len, first);
 		uint64_t o = reads[i].dna_off;
-		if (o > slab_size) return fail(h, FQSK_E_INVAL, "read %u starts outside the slab", i);
+		if (o > slab_size || reads[i].dna_len > slab_size - o) return fail(h, FQSK_E_INVAL, "read %u (offset %llu, %u symbols) does not lie inside the slab of %llu bytes", i, (unsigned long long) o, reads[i].dna_len, (unsigned long long) slab_size);
 		uint64_t avail = std::min<uint64_t>(plen, slab_size - o);
 		memcpy(stage + at, slab + o, avail);
 		if (avail < plen) memset(stage + at + avail, 0, plen - avail);
@@ -2157,11 +2165,20 @@ int fqsk_profile(fqsk_handle *h, double *ms, uint32_t n) {
 // ---- table-level batch mirrors ----------------------------------------------------------------------------------
 static Table *pick(fqsk_handle *h, int table) { return table == FQSK_TABLE_SMER ? &h->ts : table == FQSK_TABLE_BMER ? &h->tb : nullptr; }
 
+// the table-level calls work on the tables between segments: not while a segment's rows are pending or a ticket is open
+static int unit_call_ok(fqsk_handle *h, const void *a, const void *b, uint64_t n) {
+	if (h->pending || h->tk_open) return fail(h, FQSK_E_INVAL, "table-level call between a segment and its sync (or with a ticket open)");
+	if (n && (!a || !b)) return fail(h, FQSK_E_INVAL, "null array");
+	if (n > 0xFFFFFFFFull) return fail(h, FQSK_E_INVAL, "more than 2^32 - 1 elements in one call");
+	return FQSK_OK;
+}
+
 int fqsk_ht_insert(fqsk_handle *h, int table, const uint64_t *kmers, uint64_t n) {
 	if (!h) return FQSK_E_INVAL;
 	Table *t = pick(h, table);
 	if (!t) return fail(h, FQSK_E_INVAL, "bad table");
 	CK(cudaSetDevice(h->P.device));
+	CKR(unit_call_ok(h, kmers, kmers, n));
 	if (!n) return FQSK_OK;
 	CK(h->q3.ensure(n * 8));
 	CK(cudaMemcpyAsync(h->q3.p, kmers, n * 8, cudaMemcpyHostToDevice, h->st));
@@ -2179,6 +2196,7 @@ int fqsk_ht_find(fqsk_handle *h, int table, const uint64_t *kmer_dir, const uint
 	Table *t = pick(h, table);
 	if (!t) return fail(h, FQSK_E_INVAL, "bad table");
 	CK(cudaSetDevice(h->P.device));
+	CKR(unit_call_ok(h, kmer_dir, kmer_rc, n)); CKR(unit_call_ok(h, cur_size, counts, n));
 	if (!n) return FQSK_OK;
 	Stream &rng = h->rng[table == FQSK_TABLE_SMER ? ST_S : ST_B];
 	CK(h->q0.ensure((n + 1) * 8)); CK(h->q1.ensure((n + 1) * 8)); CK(h->q2.ensure((n + 1) * 8)); CK(h->q3.ensure((n + 1) * 16)); CK(h->q4.ensure((n + 1) * 8));
@@ -2217,6 +2235,7 @@ int fqsk_ht_count(fqsk_handle *h, int table, const uint64_t *kmers, uint64_t n, 
 	Table *t = pick(h, table);
 	if (!t) return fail(h, FQSK_E_INVAL, "bad table");
 	CK(cudaSetDevice(h->P.device));
+	CKR(unit_call_ok(h, kmers, out, n));
 	if (!n) return FQSK_OK;
 	CK(h->q0.ensure(n * 8)); CK(h->q1.ensure(n * 4));
 	CK(cudaMemcpyAsync(h->q0.p, kmers, n * 8, cudaMemcpyHostToDevice, h->st));
@@ -2230,6 +2249,11 @@ int fqsk_ht_count(fqsk_handle *h, int table, const uint64_t *kmers, uint64_t n, 
 int fqsk_siv_increment(fqsk_handle *h, const uint64_t *idx, uint64_t n, uint64_t *n_new) {
 	if (!h) return FQSK_E_INVAL;
 	CK(cudaSetDevice(h->P.device));
+	CKR(unit_call_ok(h, idx, idx, n));
+	for (uint64_t i = 0; i < n; ++i) {      // a p-mer index outside 4^p, or one another rank owns, would be written outside this rank's array
+		if (idx[i] >> h->siv.key_bits) return fail(h, FQSK_E_INVAL, "p-mer index %llu does not fit %u bits", (unsigned long long) idx[i], h->siv.key_bits);
+		if (h->world > 1 && (idx[i] >> h->siv.top_shift) % h->world != h->rank) return fail(h, FQSK_E_INVAL, "p-mer index %llu belongs to another rank's shard", (unsigned long long) idx[i]);
+	}
 	unsigned long long fresh = 0;
 	if (n) {
 		CK(h->q0.ensure(n * 8));
@@ -2247,6 +2271,12 @@ int fqsk_siv_increment(fqsk_handle *h, const uint64_t *idx, uint64_t n, uint64_t
 
 static int siv_query(fqsk_handle *h, int what, const uint64_t *idx, const uint32_t *bits, uint64_t n, void *out) {
 	CK(cudaSetDevice(h->P.device));
+	CKR(unit_call_ok(h, idx, out, n));
+	if (what == 2 && n && !bits) return fail(h, FQSK_E_INVAL, "null array");
+	for (uint64_t i = 0; i < n; ++i) {
+		const uint32_t kb = what == 2 ? bits[i] : h->siv.key_bits;
+		if (kb > h->siv.key_bits || (kb < 64 && (idx[i] >> kb)) || (what == 2 && h->world > 1 && kb < 12)) return fail(h, FQSK_E_INVAL, "p-mer index / prefix %llu out of range", (unsigned long long) idx[i]);
+	}
 	if (!n) return FQSK_OK;
 	CK(h->q0.ensure(n * 8)); CK(h->q1.ensure(n * 16)); CK(h->q2.ensure(n * 4));
 	CK(cudaMemcpyAsync(h->q0.p, idx, n * 8, cudaMemcpyHostToDevice, h->st));

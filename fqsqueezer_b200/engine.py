@@ -18,7 +18,7 @@ REC_DTYPE = np.dtype([("pos", "<u4"), ("c", "<u4", 4), ("cor_pos", "<u4"), ("lev
 READ_DESC_DTYPE = np.dtype([("dna_off", "<u8"), ("dna_len", "<u4"), ("flags", "<u4")])
 TABLE_SIV, TABLE_SMER, TABLE_BMER, TABLE_PAIR = 0, 1, 2, 3
 MODE_SE_ORIGINAL, MODE_SE_SORTED, MODE_PE_ORIGINAL, MODE_PE_SORTED = 0, 1, 2, 3
-F_PROFILE = 1
+F_PROFILE, F_TRACE_ALLOC, F_TEST_HOOKS = 1, 2, 4
 PHASES = ["prep", "lookup", "partial", "walk", "compact", "sort", "local", "rough", "fold", "sync_locate", "sync_apply", "sync_siv", "mt"]
 
 
@@ -33,7 +33,7 @@ class _Params(C.Structure):
                 ("prefix_len", C.c_uint32), ("smer_counter_bits", C.c_uint32), ("bmer_counter_bits", C.c_uint32), ("mode", C.c_uint32),
                 ("n_workers", C.c_uint32), ("device", C.c_int32), ("bmer_log2_buckets", C.c_uint32), ("smer_log2_buckets", C.c_uint32),
                 ("expected_kmers", C.c_uint64), ("world_size", C.c_uint32), ("rank", C.c_uint32), ("max_iterations", C.c_uint32),
-                ("flags", C.c_uint32), ("reserve_reads", C.c_uint32), ("reserve_bytes", C.c_uint32), ("pair_log2_slots", C.c_uint32), ("reserved", C.c_uint32)]
+                ("flags", C.c_uint32), ("reserve_reads", C.c_uint32), ("reserve_bytes", C.c_uint32), ("pair_log2_slots", C.c_uint32), ("test_hooks", C.c_uint32)]
 
 
 class _Stats(C.Structure):
@@ -132,12 +132,14 @@ def _ptr(a):
 
 class KmerEngine:
     def __init__(self, p, s, b, prefix_len, mode=MODE_SE_ORIGINAL, device=0, expected_kmers=0, bmer_log2_buckets=0,
-                 smer_log2_buckets=0, profile=False, max_iterations=0, reserve_reads=0, reserve_bytes=0):
+                 smer_log2_buckets=0, profile=False, max_iterations=0, reserve_reads=0, reserve_bytes=0, test_fail_every=0, test_retry_every=0):
         self.lib = load_library()
+        hooks = (test_fail_every & 0xFFFF) | ((test_retry_every & 0xFFFF) << 16)      # fault injection of the recovery paths (tests only)
         prm = _Params(abi_version=1, pmer_len=p, smer_len=s, bmer_len=b, prefix_len=prefix_len, smer_counter_bits=12,
                       bmer_counter_bits=6, mode=mode, n_workers=1, device=device, bmer_log2_buckets=bmer_log2_buckets,
                       smer_log2_buckets=smer_log2_buckets, expected_kmers=expected_kmers, world_size=1, rank=0,
-                      max_iterations=max_iterations, flags=F_PROFILE if profile else 0, reserve_reads=reserve_reads, reserve_bytes=reserve_bytes)
+                      max_iterations=max_iterations, flags=(F_PROFILE if profile else 0) | (F_TEST_HOOKS if hooks else 0), reserve_reads=reserve_reads, reserve_bytes=reserve_bytes,
+                      test_hooks=hooks)
         h = C.c_void_p()
         rc = self.lib.fqsk_create(C.byref(prm), C.byref(h))
         if rc != 0:

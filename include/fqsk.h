@@ -62,10 +62,13 @@ typedef struct fqsk_params {
 	uint32_t reserve_reads;      /* optional: largest segment the caller will submit (reads / DNA bytes); scratch is allocated once */
 	uint32_t reserve_bytes;
 	uint32_t pair_log2_slots;    /* paired-end: initial size of the pair table (0 = default); fixed on a sharded engine (shards cannot grow) */
-	uint32_t reserved;
+	uint32_t test_hooks;         /* only with FQSK_F_TEST_HOOKS, else must be 0: bits 0-15 = N -> every N-th segment's first-pass verdict is forced to
+	                              * "not settled"; bits 16-31 = M -> every M-th segment is evaluated a second time from scratch (fault injection) */
 } fqsk_params;
 
 #define FQSK_F_PROFILE 1u        /* record CUDA-event timings per internal phase (fqsk_profile) */
+#define FQSK_F_TRACE_ALLOC 2u    /* print every device allocation of the segment scratch to stderr */
+#define FQSK_F_TEST_HOOKS 4u     /* honour fqsk_params.test_hooks (tests of the recovery paths; never set by a host) */
 
 typedef struct fqsk_handle fqsk_handle;
 

@@ -272,16 +272,15 @@ def test_large_segments_filtered_delta_matches_oracle(G, expect_hot):
     e.close(); o.close()
 
 
-@pytest.mark.parametrize("var", ["FQSK_DEBUG_FAIL_EVERY", "FQSK_DEBUG_RETRY_EVERY"])
+@pytest.mark.parametrize("var", ["test_fail_every", "test_retry_every"])
 @pytest.mark.parametrize("mode", ["blocking", "async"])
-def test_recovery_paths_of_the_enqueued_sync(var, mode, monkeypatch):
+def test_recovery_paths_of_the_enqueued_sync(var, mode):
     """Fault injection: every 3rd segment has its first-pass verdict forced to 'not settled' AFTER the early grouping half of its
     b-mer sync has run (claimed slots must be released, the sync redone the plain way), resp. is evaluated again from scratch as
     after a capacity overflow (claimed slots must be released BEFORE the tables are read again).  Output must not change."""
-    monkeypatch.setenv(var, "3")
     g = H.load_golden("se_orig_gs1")
     pref, p, s, b = E.kmer_params(int(g["gs"]))
-    e = E.KmerEngine(p, s, b, pref)
+    e = E.KmerEngine(p, s, b, pref, **{var: 3})      # FQSK_F_TEST_HOOKS + fqsk_params.test_hooks
     if mode == "async":
         recs, _ = H.run_async(e, g["fastq"])
     else:
