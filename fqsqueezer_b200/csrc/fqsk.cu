@@ -9,7 +9,6 @@
 // and iterated until pushes and draw counts reproduce themselves: at that fixed point every read has seen exactly the state
 // the sequential reference would have shown it, so records, pushes and PRNG positions are bit-exact.
 // There is no CPU fallback anywhere in this file.
-#include <cub/cub.cuh>
 #include <algorithm>
 #include <atomic>
 #include <cstdarg>
@@ -124,11 +123,13 @@ struct fqsk_handle {
 	unsigned long long *peer_inbox[8] = {nullptr};
 	void *peer_ptrs[8][8] = {{nullptr}};     // IPC mappings to close
 	uint32_t attached = 0;                   // bit i: rank i's shard is mapped
-	DevBuf route_keys, route_keys2, route_sorted, route_hist;
+	DevBuf route_keys, route_keys2, route_sorted, route_hist, route_perm;
 	uint64_t sync_fresh = 0, sync_updates = 0; bool routed = false, applied = false;
 	uint64_t siv_local_filled = 0;           // non-zero fields of THIS rank's p-mer shard (S.siv_no_filled is the global statistic)
 	DevBuf scan_vals; uint32_t scan_epoch2 = 0;
 	DevBuf scan_part; uint32_t scan_epoch = 0;   // published CTA sums of k_scan_flags, tagged with the launch epoch
+	DevBuf scan8_part; uint32_t scan8_epoch = 0; // ... of k_scan_u8
+	DevBuf rdx_hist, rdx_k, rdx_v;               // radix partition (fqsk_sort.cuh): tile histograms + digit totals, ping-pong buffers
 	bool hot = false;                        // the current segment is being redone with the ordered thread-local evaluator
 	bool hot_seen[2] = {false, false};       // [0] s, [1] b: the last sync saw a k-mer pushed more than thr + 1 times in its row
 	DeltaDev seg_delta_b{}, seg_delta_s{};   // the converged segment's delta tables (valid while `pending`)
@@ -392,33 +393,67 @@ int ensure_iota(fqsk_handle *h, uint32_t n) {
 	return FQSK_OK;
 }
 
-template <typename InT, typename OutT>
-int scan_excl(fqsk_handle *h, const InT *in, OutT *out, uint32_t n, OutT init) {
-	size_t bytes = 0;
-	CK(cub::DeviceScan::ExclusiveScan(nullptr, bytes, in, out, cub::Sum(), init, (int) n, h->st));
-	CK(h->cub_tmp.ensure(bytes));
-	CK(cub::DeviceScan::ExclusiveScan(h->cub_tmp.p, bytes, in, out, cub::Sum(), init, (int) n, h->st));
-	return FQSK_OK;
-}
-
 // rows of a sync are at most this long when the caller announced its largest segment: buffers sized once, not as segments grow
 inline size_t row_reserve(const fqsk_handle *h, size_t n) {
 	const size_t r = h->P.reserve_bytes ? 2 * (size_t) h->P.reserve_bytes + 2 * (size_t) h->P.reserve_reads + 64 : 0;
 	return n > r ? n : r;
 }
-int sort_pairs_u64_u32(fqsk_handle *h, const unsigned long long *kin, unsigned long long *kout, const uint32_t *vin, uint32_t *vout, uint32_t n, int b0, int b1) {
-	size_t bytes = 0;
-	CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int) row_reserve(h, n), b0, b1, h->st));
-	CK(h->cub_tmp.ensure(bytes));
-	CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int) n, b0, b1, h->st));
-	CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, kin, kout, vin, vout, (int) n, b0, b1, h->st));
+
+// flags (u8) -> exclusive scan (u32), out[n] = total: the engine's own chained scan (fqsk_sort.cuh)
+int scan_flags_u8(fqsk_handle *h, const uint8_t *flag, uint32_t *out, uint32_t n) {
+	const uint32_t g = std::max<uint32_t>(nblk(n, SCAN8_TILE), 1);
+	const size_t need = (size_t) std::max<uint32_t>(g, nblk((uint32_t) row_reserve(h, n), SCAN8_TILE)) * 8 + 64;
+	if (h->scan8_part.cap < need) { CK(h->scan8_part.ensure(need)); CK(cudaMemsetAsync(h->scan8_part.p, 0, h->scan8_part.cap, h->st)); }
+	CK(pdl(k_scan_u8, g, 256, h->st, flag, n, out, h->scan8_part.as<unsigned long long>(), ++h->scan8_epoch)); LAUNCHED(h);
 	return FQSK_OK;
 }
-int sort_pairs_u32_u32(fqsk_handle *h, const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, uint32_t n, int b1) {
-	size_t bytes = 0;
-	CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int) n, 0, b1, h->st));
-	CK(h->cub_tmp.ensure(bytes));
-	CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, kin, kout, vin, vout, (int) n, 0, b1, h->st));
+
+// One stable LSD pass of the engine's radix partition (fqsk_sort.cuh): hist -> row scan -> scatter
+template <int NBITS, class Op>
+int rdx_pass(fqsk_handle *h, cudaStream_t st, const unsigned long long *kin, const uint32_t *vin, unsigned long long *kout, uint32_t *vout, uint32_t n, Op op) {
+	const uint32_t tiles = nblk(n, RDX_TILE);
+	uint32_t *hist = h->rdx_hist.as<uint32_t>(), *totals = hist + ((size_t) tiles << NBITS);
+	CK(pdl(k_rdx_hist<NBITS, Op>, tiles, RDX_THREADS, st, kin, n, tiles, hist, op)); LAUNCHED(h);
+	CK(pdl(k_rdx_rowscan, 1u << NBITS, 256, st, hist, tiles, totals)); LAUNCHED(h);
+	CK(pdl(k_rdx_scatter<NBITS, Op>, tiles, RDX_THREADS, st, kin, vin, kout, vout, n, tiles, (const uint32_t *) hist, (const uint32_t *) totals, op)); LAUNCHED(h);
+	return FQSK_OK;
+}
+int rdx_scratch(fqsk_handle *h, uint32_t n, bool need_tmp) {
+	const size_t nr = row_reserve(h, n);
+	CK(h->rdx_hist.ensure((((size_t) nblk((uint32_t) nr, RDX_TILE) + 1) << 9) * 4 + 4096));
+	if (need_tmp) { CK(h->rdx_k.ensure(nr * 8)); CK(h->rdx_v.ensure(nr * 4)); }
+	return FQSK_OK;
+}
+// stable sort of (key, value) pairs by the key bits [b0, b1); vin == nullptr: the values are the element indices.  kin is not modified.
+int sort_pairs_u64_u32(fqsk_handle *h, const unsigned long long *kin, unsigned long long *kout, const uint32_t *vin, uint32_t *vout, uint32_t n, int b0, int b1, cudaStream_t st = nullptr) {
+	if (!st) st = h->st;
+	if (!n) return FQSK_OK;
+	const int passes = std::max(1, (b1 - b0 + 7) / 8);
+	CKR(rdx_scratch(h, n, passes > 1));
+	const unsigned long long *ks = kin; const uint32_t *vs = vin;
+	for (int p = 0; p < passes; ++p) {
+		const bool to_out = ((passes - 1 - p) & 1) == 0;
+		unsigned long long *kd = to_out ? kout : h->rdx_k.as<unsigned long long>();
+		uint32_t *vd = to_out ? vout : h->rdx_v.as<uint32_t>();
+		const int lo = b0 + 8 * p, bits = std::min(8, b1 - lo);
+		CKR((rdx_pass<8, BitsOp>(h, st, ks, vs, kd, vd, n, BitsOp{(uint32_t) lo, (1u << bits) - 1u})));
+		ks = kd; vs = vd;
+	}
+	return FQSK_OK;
+}
+// the same by the table bucket of the k-mers (B bits, 9 per pass)
+int sort_by_bucket(fqsk_handle *h, const Table &t, const unsigned long long *kin, unsigned long long *kout, uint32_t *vout, uint32_t n) {
+	const int passes = ((int) t.d.B + 8) / 9;
+	CKR(rdx_scratch(h, n, passes > 1));
+	const unsigned long long *ks = kin; const uint32_t *vs = nullptr;
+	for (int p = 0; p < passes; ++p) {
+		const bool to_out = ((passes - 1 - p) & 1) == 0;
+		unsigned long long *kd = to_out ? kout : h->rdx_k.as<unsigned long long>();
+		uint32_t *vd = to_out ? vout : h->rdx_v.as<uint32_t>();
+		const int lo = 9 * p, bits = std::min(9, (int) t.d.B - lo);
+		CKR((rdx_pass<9, BucketOp>(h, h->st, ks, vs, kd, vd, n, BucketOp{t.d, (uint32_t) lo, (1u << bits) - 1u})));
+		ks = kd; vs = vd;
+	}
 	return FQSK_OK;
 }
 
@@ -500,7 +535,7 @@ int apply_sorted(fqsk_handle *h, Table &t, Stream &rng, const unsigned long long
 	bool safe_done = false;
 	for (int it = 0;; ++it) {
 		if (it > 64) return fail(h, FQSK_E_NO_CONVERGE, "sync insert: draw flags did not settle");
-		CKR((scan_excl<uint8_t, uint32_t>(h, flag, doff, n + 1, 0u)));
+		CKR(scan_flags_u8(h, flag, doff, n));
 		CKR(stream_ensure(h, rng, 0));
 		CK(cudaMemsetAsync(h->d_flags, 0, 3 * sizeof(int), h->st));      // [0] draw window short, [2] corrected a flag; [3] unsafe seen / [6] hot seen stay
 		if (!safe_done) { CK(pdl(k_apply_keys, g, 256, h->st, t.d, t.ci, skeys, sidx, n, slot_of, c0_of, flag, doff, rng.buf, rng.cap - 1, rng.consumed, stream_avail(rng), 0, 0, h->d_flags)); LAUNCHED(h); }
@@ -525,7 +560,7 @@ int apply_sorted(fqsk_handle *h, Table &t, Stream &rng, const unsigned long long
 			if (fl[0]) { CKR(stream_ensure(h, rng, 2 * stream_avail(rng) + (1u << 16))); continue; }
 			if (!fl[2]) break;
 			moved = true;
-			CKR((scan_excl<uint8_t, uint32_t>(h, flag, doff, n + 1, 0u)));
+			CKR(scan_flags_u8(h, flag, doff, n));
 		}
 		CK(cudaMemcpyAsync(hs + 8, doff + n, 4, cudaMemcpyDeviceToHost, h->st));
 		CK(cudaStreamSynchronize(h->st));
@@ -546,8 +581,7 @@ int sort_row(fqsk_handle *h, const unsigned long long *row, uint32_t n, uint32_t
 	if (!n) return FQSK_OK;
 	Phase ph(h, FQSK_PH_SORT);
 	CK(keys_out.ensure(row_reserve(h, n) * 8)); CK(idx_out.ensure(row_reserve(h, n) * 4));
-	CKR(ensure_iota(h, (uint32_t) row_reserve(h, n)));
-	CKR(sort_pairs_u64_u32(h, row, keys_out.as<unsigned long long>(), h->iota.as<uint32_t>(), idx_out.as<uint32_t>(), n, 64 - 2 * (int) k, 64));
+	CKR(sort_pairs_u64_u32(h, row, keys_out.as<unsigned long long>(), nullptr, idx_out.as<uint32_t>(), n, 64 - 2 * (int) k, 64));
 	return FQSK_OK;
 }
 
@@ -555,6 +589,42 @@ const uint32_t SYNC_INDEXED_MAX = 400000;
 const uint64_t SPEC_MAX_BYTES = 420000;   // segments up to this many DNA bytes get their sync enqueued without a host look in between
 const uint32_t FORK_MAX_READS = 8192;  // segments below this size run independent kernels of their chain on side streams
 const int RC_RETRY = 1;   // internal: a capacity was too small, grow and redo the segment
+
+// Ordered insert of a large row, grouped by table bucket (k_bucket_flags / k_bucket_apply): one stable partition by the bucket bits,
+// one read-only walk for the draw flags, their scan, one walk that applies the row sector by sector.  *done = false: a counter may
+// saturate inside the row or a bucket's run holds too many distinct k-mers -- nothing was written, the caller takes the general path.
+int apply_bucketed(fqsk_handle *h, Table &t, Stream &rng, const unsigned long long *row, uint32_t n, bool *done) {
+	*done = false;
+	const size_t nr = row_reserve(h, n);
+	CK(h->sort_k.ensure(nr * 8)); CK(h->sort_v.ensure(nr * 4)); CK(h->flag8.ensure(nr + 16)); CK(h->draw_off.ensure((nr + 1) * 4));
+	{ Phase ph(h, FQSK_PH_SORT); CKR(sort_by_bucket(h, t, row, h->sort_k.as<unsigned long long>(), h->sort_v.as<uint32_t>(), n)); }
+	const unsigned long long *sk = h->sort_k.as<unsigned long long>(); const uint32_t *sv = h->sort_v.as<uint32_t>();
+	uint8_t *flag = h->flag8.as<uint8_t>(); uint32_t *doff = h->draw_off.as<uint32_t>();
+	const uint32_t g = nblk(n, 256);
+	{
+		Phase ph(h, FQSK_PH_SYNC_LOCATE);
+		CK(cudaMemsetAsync(h->d_flags, 0, 8 * sizeof(int), h->st));
+		CK(pdl(k_bucket_flags, g, 256, h->st, t.d, t.ci, sk, sv, n, flag, h->d_flags)); LAUNCHED(h);
+		CKR(scan_flags_u8(h, flag, doff, n));
+	}
+	Phase ph(h, FQSK_PH_SYNC_APPLY);
+	CKR(stream_ensure(h, rng, n));      // every occurrence draws at most once
+	CK(pdl(k_bucket_apply, g, 256, h->st, t.d, t.ci, sk, sv, n, (const uint32_t *) doff, (const uint32_t *) rng.buf, (unsigned long long) (rng.cap - 1), (unsigned long long) rng.consumed,
+	       (unsigned long long) stream_avail(rng), h->d_flags)); LAUNCHED(h);
+	uint32_t *hs = (uint32_t *) h->h_small;
+	CK(cudaMemcpyAsync(hs, h->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+	CK(cudaMemcpyAsync(hs + 8, doff + n, 4, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaStreamSynchronize(h->st));
+	resolve_phases(h);
+	int fl[8]; memcpy(fl, hs, sizeof fl);
+	if (fl[3] || fl[7]) return FQSK_OK;
+	if (fl[0]) return fail(h, FQSK_E_CUDA, "internal error: the draw window of a bucket-grouped insert was too short");
+	if (fl[6]) h->hot_seen[&t == &h->tb ? 1 : 0] = true;
+	rng.consumed += hs[8];
+	h->look_fresh = false;
+	*done = true;
+	return FQSK_OK;
+}
 
 int apply_inserts(fqsk_handle *h, Table &t, Stream &rng, const unsigned long long *d_kmers, uint32_t n, bool *fast_ok = nullptr) {
 	if (!n) return FQSK_OK;
@@ -572,6 +642,11 @@ int apply_inserts(fqsk_handle *h, Table &t, Stream &rng, const unsigned long lon
 		// take the ordered path from now on for this table (once counters are above thr they stay there)
 		CK(pdl(k_insert_undo, nblk(n, 256), 256, h->st, t.d, d_kmers, n, h->y_flag.as<uint8_t>())); LAUNCHED(h);
 		// this row goes through the ordered path; the next row tries the fast path again
+	}
+	if (h->world == 1) {      // (a sharded table's buckets are this rank's own as well, but the exchange rows take the indexed path)
+		bool done = false;
+		CKR(apply_bucketed(h, t, rng, d_kmers, n, &done));
+		if (done) return FQSK_OK;
 	}
 	CKR(sort_row(h, d_kmers, n, t.d.k, h->sort_k, h->sort_v));
 	return apply_sorted(h, t, rng, h->sort_k.as<unsigned long long>(), h->sort_v.as<uint32_t>(), n);
@@ -843,10 +918,7 @@ int seg_build_delta(fqsk_handle *h, bool force_full = false) {
 	if (((int *) hs)[4]) return fail(h, FQSK_E_NOMEM, "hot-mode event list overflow");     // cannot happen with the bound above
 	uint32_t en[2] = {hs[8 + 4], hs[8 + 5]};
 	for (int q = 0; q < 2; ++q) if (en[q]) {
-		size_t bytes = 0;
-		CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, h->evk[q].as<unsigned long long>(), h->evk_s[q].as<unsigned long long>(), h->evv[q].as<uint32_t>(), h->evv_s[q].as<uint32_t>(), (int) en[q], 0, 34, h->st));
-		CK(h->cub_tmp.ensure(bytes));
-		CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, h->evk[q].as<unsigned long long>(), h->evk_s[q].as<unsigned long long>(), h->evv[q].as<uint32_t>(), h->evv_s[q].as<uint32_t>(), (int) en[q], 0, 34, h->st));
+		CKR(sort_pairs_u64_u32(h, h->evk[q].as<unsigned long long>(), h->evk_s[q].as<unsigned long long>(), h->evv[q].as<uint32_t>(), h->evv_s[q].as<uint32_t>(), en[q], 0, 34));      // by time
 	}
 	CKR(stream_ensure(h, h->rng[ST_LB], (uint64_t) en[0] * 8 + 1024)); CKR(stream_ensure(h, h->rng[ST_LS], (uint64_t) en[1] * 8 + 1024));
 	C.E = make_engine_dev(h);
@@ -1037,9 +1109,8 @@ int pe_front(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes, const uns
 	unsigned long long *tk = h->pe_tk.as<unsigned long long>(), *tv = h->pe_tv.as<unsigned long long>(), *q = h->pe_q.as<unsigned long long>();
 	CK(pdl(k_pe_minim, nblk((uint64_t) np * 32, 128), 128, h->st, d_dna, d_off, d_len, np, b, tk, tv, q)); LAUNCHED(h);
 	// stable two-pass sort of the triples by (key, value): value first, then key
-	CKR(ensure_iota(h, nt));
 	uint32_t *i1 = (uint32_t *) h->pe_t2.as<uint32_t>();
-	CKR(sort_pairs_u64_u32(h, tv, h->pe_t1.as<unsigned long long>(), h->iota.as<uint32_t>(), i1, nt, 0, 2 * (int) b));
+	CKR(sort_pairs_u64_u32(h, tv, h->pe_t1.as<unsigned long long>(), nullptr, i1, nt, 0, 2 * (int) b));
 	CK(pdl(k_pe_gather, nblk(nt, 256), 256, h->st, tk, i1, h->pe_t1.as<unsigned long long>(), nt)); LAUNCHED(h);
 	CKR(sort_pairs_u64_u32(h, h->pe_t1.as<unsigned long long>(), h->pe_sk.as<unsigned long long>(), i1, h->pe_sidx.as<uint32_t>(), nt, 0, 2 * (int) b + 1));
 	CK(pdl(k_pe_gather, nblk(nt, 256), 256, h->st, tv, h->pe_sidx.as<uint32_t>(), h->pe_sv.as<unsigned long long>(), nt)); LAUNCHED(h);
@@ -1187,10 +1258,7 @@ int hot_account(fqsk_handle *h, int stream) {
 	CK(cudaStreamSynchronize(h->st));
 	uint32_t en = hs[8 + 4 + stream];
 	if (!en) return FQSK_OK;
-	size_t bytes = 0;
-	CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, h->evk[stream].as<unsigned long long>(), h->evk_s[stream].as<unsigned long long>(), h->evv[stream].as<uint32_t>(), h->evv_s[stream].as<uint32_t>(), (int) en, 0, 34, h->st));
-	CK(h->cub_tmp.ensure(bytes));
-	CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, h->evk[stream].as<unsigned long long>(), h->evk_s[stream].as<unsigned long long>(), h->evv[stream].as<uint32_t>(), h->evv_s[stream].as<uint32_t>(), (int) en, 0, 34, h->st));
+	CKR(sort_pairs_u64_u32(h, h->evk[stream].as<unsigned long long>(), h->evk_s[stream].as<unsigned long long>(), h->evv[stream].as<uint32_t>(), h->evv_s[stream].as<uint32_t>(), en, 0, 34));      // by time
 	Stream &rng = h->rng[stream ? ST_LS : ST_LB];
 	CKR(stream_ensure(h, rng, (uint64_t) en + 1024));
 	EngineDev E = make_engine_dev(h);
@@ -1327,8 +1395,8 @@ void fqsk_destroy(fqsk_handle *h) {
 	                  &h->sidx_b, &h->sidx_s, &h->stime_b, &h->stime_s, &h->sort_k, &h->sort_v, &h->rkind, &h->rreg, &h->rslot, &h->dirty, &h->rdraws_b, &h->rdraws_s, &h->totals,
 	                  &h->y_tslot, &h->y_c0, &h->y_m, &h->y_draw, &h->y_j, &h->y_final, &h->y_flag_at, &h->y_own, &h->y_lead, &h->y_rank, &h->y_flag, &h->y_doff,
 	                  &h->idx_k, &h->idx_t, &h->idx_rt, &h->miss_fold, &h->hr_b[0], &h->hr_b[1], &h->hr_b[2], &h->hr_s[0], &h->hr_s[1], &h->hr_s[2],
-	                  &h->evk[0], &h->evk[1], &h->evv[0], &h->evv[1], &h->evk_s[0], &h->evk_s[1], &h->evv_s[0], &h->evv_s[1], &h->scan_part, &h->scan_vals, &h->recs_alt, &h->dfilter, &h->pk,
-	                  &h->route_keys, &h->route_keys2, &h->route_sorted, &h->route_hist,
+	                  &h->evk[0], &h->evk[1], &h->evv[0], &h->evv[1], &h->evk_s[0], &h->evk_s[1], &h->evv_s[0], &h->evv_s[1], &h->scan_part, &h->scan8_part, &h->rdx_hist, &h->rdx_k, &h->rdx_v, &h->scan_vals, &h->recs_alt, &h->dfilter, &h->pk,
+	                  &h->route_keys, &h->route_keys2, &h->route_sorted, &h->route_hist, &h->route_perm,
 	                  &h->pe_uk, &h->pe_uv, &h->pe_uc, &h->pe_tk, &h->pe_tv, &h->pe_q, &h->pe_sk, &h->pe_sv, &h->pe_sidx, &h->pe_t1, &h->pe_t2, &h->pe_pool, &h->pe_info, &h->it_src, &h->it_len,
 	                  &h->it_bytes, &h->it_first, &h->it_bias, &h->it_dupprev, &h->it_flags, &h->it_off32, &h->it_off64, &h->it_dna};
 
@@ -1356,12 +1424,8 @@ static int prealloc_for_reserve(fqsk_handle *h) {
 	if (!h->P.reserve_bytes) return FQSK_OK;
 	const size_t nr = row_reserve(h, 0);
 	CK(h->sort_k.ensure(nr * 8)); CK(h->sort_v.ensure(nr * 4));
-	CKR(ensure_iota(h, (uint32_t) nr));
-	{
-		size_t bytes = 0;
-		CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned long long *) nullptr, (unsigned long long *) nullptr, (const uint32_t *) nullptr, (uint32_t *) nullptr, (int) nr, 0, 64, h->st));
-		CK(h->cub_tmp.ensure(bytes + bytes / 8));
-	}
+	CKR(rdx_scratch(h, (uint32_t) nr, true));
+	{ const size_t need = (size_t) nblk((uint32_t) nr, SCAN8_TILE) * 8 + 64; CK(h->scan8_part.ensure(need)); CK(cudaMemsetAsync(h->scan8_part.p, 0, h->scan8_part.cap, h->st)); }
 	CK(h->slot_of.ensure(nr * 8)); CK(h->flag8.ensure(nr + 4)); CK(h->draw_off.ensure((nr + 1) * 4)); CK(h->final_cnt.ensure(nr * 4));
 	CK(h->q4.ensure(nr + 4)); CK(h->y_flag.ensure(nr + 64));
 	if (h->world == 1 && h->P.reserve_bytes >= (1u << 20)) { CK(h->dfilter.ensure((size_t) 2 * (1u << 26) / 8)); }
@@ -1931,10 +1995,9 @@ int fqsk_sync_route(fqsk_handle *h) {
 		if (n) {
 			CK(h->route_keys.ensure(n)); CK(h->route_keys2.ensure(n)); CK(h->route_sorted.ensure((size_t) n * 8));
 			CK(pdl(k_owner_keys, nblk(n, 256), 256, h->st, rows[t], n, t == 0 ? 0u : 1u, 2 * h->P.pmer_len - 12, h->world, h->route_keys.as<uint8_t>(), hist)); LAUNCHED(h);
-			size_t bytes = 0;   // stable: push order survives inside every owner group
-			CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, h->route_keys.as<uint8_t>(), h->route_keys2.as<uint8_t>(), rows[t], h->route_sorted.as<unsigned long long>(), (int) n, 0, 3, h->st));
-			CK(h->cub_tmp.ensure(bytes));
-			CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, h->route_keys.as<uint8_t>(), h->route_keys2.as<uint8_t>(), rows[t], h->route_sorted.as<unsigned long long>(), (int) n, 0, 3, h->st));
+			// one stable partition pass by owner: push order survives inside every owner group
+			CKR(rdx_scratch(h, n, false));
+			CKR((rdx_pass<3, OwnerOp>(h, h->st, rows[t], nullptr, h->route_sorted.as<unsigned long long>(), nullptr, n, OwnerOp{t == 0 ? 0u : 1u, 2 * h->P.pmer_len - 12, h->world})));
 		}
 		CK(pdl(k_route_scatter, nblk(std::max<uint32_t>(n, 8), 256), 256, h->st, h->route_sorted.as<unsigned long long>(), n, hist, I, (uint32_t) t, h->d_flags)); LAUNCHED(h);
 	}
@@ -1958,13 +2021,13 @@ int fqsk_sync_route(fqsk_handle *h) {
 			CK(pdl(k_pair_owner_keys, nblk(nu, 256), 256, h->st, (const unsigned long long *) h->pe_uk.as<unsigned long long>(), nu, h->world, h->route_keys.as<uint8_t>(), hist)); LAUNCHED(h);
 		}
 		const unsigned long long *planes[3] = {h->pe_uk.as<unsigned long long>(), h->pe_uv.as<unsigned long long>(), h->pe_uc.as<unsigned long long>()};
+		if (nu) {      // the permutation that groups the key plane by owner (stable), then every plane is gathered through it
+			CKR(rdx_scratch(h, nu, true));
+			CK(h->route_perm.ensure((size_t) nu * 4));
+			CKR((rdx_pass<3, OwnerOp>(h, h->st, planes[0], nullptr, h->rdx_k.as<unsigned long long>(), h->route_perm.as<uint32_t>(), nu, OwnerOp{2u, 0u, h->world})));
+		}
 		for (int q = 0; q < 3; ++q) {
-			if (nu) {
-				size_t bytes = 0;
-				CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, h->route_keys.as<uint8_t>(), h->route_keys2.as<uint8_t>(), planes[q], h->route_sorted.as<unsigned long long>(), (int) nu, 0, 3, h->st));
-				CK(h->cub_tmp.ensure(bytes));
-				CK(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, h->route_keys.as<uint8_t>(), h->route_keys2.as<uint8_t>(), planes[q], h->route_sorted.as<unsigned long long>(), (int) nu, 0, 3, h->st));
-			}
+			if (nu) { CK(pdl(k_pe_gather, nblk(nu, 256), 256, h->st, planes[q], (const uint32_t *) h->route_perm.as<uint32_t>(), h->route_sorted.as<unsigned long long>(), nu)); LAUNCHED(h); }
 			CK(pdl(k_route_scatter, nblk(std::max<uint32_t>(nu, 8), 256), 256, h->st, (const unsigned long long *) h->route_sorted.as<unsigned long long>(), nu, (const uint32_t *) hist, I, (uint32_t) (3 + q), h->d_flags)); LAUNCHED(h);
 		}
 		h->pe_nt = 0;
@@ -2199,8 +2262,9 @@ int fqsk_ht_find(fqsk_handle *h, int table, const uint64_t *kmer_dir, const uint
 	CKR(unit_call_ok(h, kmer_dir, kmer_rc, n)); CKR(unit_call_ok(h, cur_size, counts, n));
 	if (!n) return FQSK_OK;
 	Stream &rng = h->rng[table == FQSK_TABLE_SMER ? ST_S : ST_B];
-	CK(h->q0.ensure((n + 1) * 8)); CK(h->q1.ensure((n + 1) * 8)); CK(h->q2.ensure((n + 1) * 8)); CK(h->q3.ensure((n + 1) * 16)); CK(h->q4.ensure((n + 1) * 8));
-	unsigned long long *d_dir = h->q0.as<unsigned long long>(), *d_rc = h->q1.as<unsigned long long>(), *d_guess = h->q2.as<unsigned long long>();
+	if (n > (uint64_t) SCAN_CHAIN_MAX * SCAN_U32_CHUNK) return fail(h, FQSK_E_INVAL, "more than %u queries in one fqsk_ht_find call", SCAN_CHAIN_MAX * SCAN_U32_CHUNK);
+	CK(h->q0.ensure((n + 1) * 8)); CK(h->q1.ensure((n + 1) * 8)); CK(h->q2.ensure((n + 1) * 16)); CK(h->q3.ensure((n + 1) * 16)); CK(h->q4.ensure((n + 1) * 8));
+	unsigned long long *d_dir = h->q0.as<unsigned long long>(), *d_rc = h->q1.as<unsigned long long>(), *d_guess = h->q2.as<unsigned long long>(), *d_scan2 = h->q2.as<unsigned long long>() + (n + 1);
 	uint32_t *d_counts = h->q3.as<uint32_t>();
 	uint32_t *d_cur = h->q4.as<uint32_t>(), *d_used = h->q4.as<uint32_t>() + (n + 1);
 	CK(cudaMemcpyAsync(d_dir, kmer_dir, n * 8, cudaMemcpyHostToDevice, h->st));
@@ -2218,7 +2282,11 @@ int fqsk_ht_find(fqsk_handle *h, int table, const uint64_t *kmer_dir, const uint
 		int fl[4];
 		CKR(read_flags(h, fl, 4));
 		if (fl[0]) { CKR(stream_ensure(h, rng, 2 * stream_avail(rng) + (1u << 16))); --it; continue; }
-		CKR((scan_excl<uint32_t, unsigned long long>(h, d_used, d_guess, (uint32_t) n + 1, 0ull)));
+		{   // per-query draw counts -> exclusive offsets (d_guess[n] = total)
+			ScanChain sc; CKR(scan_chain(h, sc));
+			CK(pdl(k_scan_draws, std::max<uint32_t>(nblk((uint32_t) n, SCAN_U32_CHUNK), 1), 1024, h->st, (uint32_t) n, (const uint32_t *) d_used, d_guess, (const uint32_t *) d_used, d_scan2,
+			       (unsigned long long *) (h->d_counters + 6), (int *) nullptr, sc)); LAUNCHED(h);
+		}
 		CK(cudaMemcpyAsync(now.data(), d_guess, (n + 1) * 8, cudaMemcpyDeviceToHost, h->st));
 		CK(cudaStreamSynchronize(h->st));
 		if (now == prev) break;

@@ -10,6 +10,7 @@
 //   k_find / k_count / k_siv_*   table-level batch mirrors                               (ht_kmer.h:441-510, bit_vec.h:53-123)
 #pragma once
 #include "fqsk_dev.cuh"
+#include "fqsk_sort.cuh"
 #include "../../include/fqsk.h"
 
 namespace fqsk {
@@ -327,6 +328,132 @@ __global__ void k_apply_keys(HtDev t, CIncP ci, const unsigned long long *skeys,
 	uint64_t slot = so & ~(1ull << 63), nm = 8ull << t.B;
 	HtKey hk = ht_key(t, key);
 	if (slot < nm) t.main[slot] = hk.q | c; else t.stash[slot - nm] = ((hk.kal + 1) << t.cbits) | c;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// bucket-grouped ordered insert (large rows).  Input: the row partitioned by table BUCKET (stable: push order survives inside a
+// bucket's run; fqsk_sort.cuh) with the push index of every element.  One thread per run:
+//   k_bucket_flags  reads the bucket's sector once and walks the run in push order with a tiny model of the counters it will
+//                   touch: the draw flag of every occurrence is (counter before it > thr) -- exact as long as no counter can
+//                   reach the top inside the row, which the kernel checks (flags[3]) -- read-only;
+//   (k_scan_u8: flags in push order -> absolute draw indices)
+//   k_bucket_apply  walks the run again with the draws, creates missing items in the free slots of the same sector (stash when
+//                   the bucket is full) and writes the sector back once: one 32-byte read + one 32-byte write per touched
+//                   bucket instead of find-or-create + read-modify-write per k-mer through the sorted-by-k-mer path.
+// Runs with more than BUCKET_RUN_KEYS distinct k-mers, or rows in which a counter may saturate, are left to that path
+// (flags[3] / flags[7]: nothing has been written yet when the host sees them).
+// ------------------------------------------------------------------------------------------------------------------
+static const int BUCKET_RUN_KEYS = 12;
+struct BucketRun {
+	unsigned long long key[BUCKET_RUN_KEYS];
+	uint32_t cnt[BUCKET_RUN_KEYS], c0[BUCKET_RUN_KEYS], m[BUCKET_RUN_KEYS];      // running counter, counter before the row, occurrences in the row
+	int8_t slot[BUCKET_RUN_KEYS];      // item of the bucket (0..7), -1: not in the bucket yet, -2: lives in the stash
+	int n;
+};
+__device__ __forceinline__ uint64_t ht_bucket_of(const HtDev &t, unsigned long long x) { return ht_mix(t, ht_kernel(t, x)) >> t.rem_bits; }
+// entry of k-mer x in the run's model; created from the table's present contents on first sight.  -1: model full
+__device__ __forceinline__ int bucket_run_entry(const HtDev &t, BucketRun &R, const uint32_t it[8], unsigned long long x) {
+	for (int j = 0; j < R.n; ++j) if (R.key[j] == x) return j;
+	if (R.n >= BUCKET_RUN_KEYS) return -1;
+	const HtKey hk = ht_key(t, x);
+	const int j = R.n++;
+	R.key[j] = x; R.m[j] = 0; R.cnt[j] = 0; R.c0[j] = 0; R.slot[j] = -1;
+	bool full = true;
+#pragma unroll
+	for (int i = 0; i < 8; ++i) {
+		if (it[i] == 0) { full = false; break; }
+		if ((it[i] & ~t.top) == hk.q) { R.cnt[j] = R.c0[j] = it[i] & t.top; R.slot[j] = (int8_t) i; return j; }
+	}
+	if (full) {      // the k-mer may live in the stash
+		const uint64_t smask = (1ull << t.stash_log2) - 1;
+		for (uint64_t p = ht_stash_pos(t, hk.h);; p = (p + 1) & smask) {
+			const unsigned long long s = t.stash[p];
+			if (s == 0) break;
+			if ((s >> t.cbits) == hk.kal + 1) { R.cnt[j] = R.c0[j] = (uint32_t) (s & t.top); R.slot[j] = -2; break; }
+		}
+	}
+	return j;
+}
+__global__ void __launch_bounds__(256) k_bucket_flags(HtDev t, CIncP ci, const unsigned long long *skeys, const uint32_t *sidx, uint32_t n, uint8_t *flag, int *flags) { pdl_enter();
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const unsigned long long x0 = skeys[i];
+	const uint64_t bucket = ht_bucket_of(t, x0);
+	if (i > 0 && ht_bucket_of(t, skeys[i - 1]) == bucket) return;      // not the head of a run
+	const uint4 *bp = reinterpret_cast<const uint4 *>(t.main + bucket * 8);
+	const uint4 lo = __ldg(bp), hi = __ldg(bp + 1);
+	const uint32_t it[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+	BucketRun R; R.n = 0;
+	for (uint32_t q = i; q < n; ++q) {
+		const unsigned long long x = skeys[q];
+		if (q > i && ht_bucket_of(t, x) != bucket) break;
+		const int j = bucket_run_entry(t, R, it, x);
+		if (j < 0) { flags[7] = 1; return; }
+		const uint32_t c = R.cnt[j];
+		flag[sidx[q]] = c > ci.thr ? 1 : 0;
+		if (c <= ci.thr) R.cnt[j] = c + 1;      // above thr the counter stays above thr: all the flags need to know
+		++R.m[j];
+	}
+	for (int j = 0; j < R.n; ++j) {
+		if (R.c0[j] + R.m[j] >= t.top) flags[3] = 1;       // a counter could reach the top inside the row: the flags above may be wrong
+		if (R.m[j] > ci.thr + 1) flags[6] = 1;             // the thread-local table of the reference drew from its own stream for this k-mer
+	}
+}
+__global__ void __launch_bounds__(256) k_bucket_apply(HtDev t, CIncP ci, const unsigned long long *skeys, const uint32_t *sidx, uint32_t n, const uint32_t *draw_off,
+                                                     const uint32_t *draws, unsigned long long dmask, unsigned long long dpos, unsigned long long avail, int *flags) { pdl_enter();
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	if (flags[3] | flags[7]) return;      // the row goes through the sorted-by-k-mer path: nothing may be written here
+	const unsigned long long x0 = skeys[i];
+	const uint64_t bucket = ht_bucket_of(t, x0);
+	if (i > 0 && ht_bucket_of(t, skeys[i - 1]) == bucket) return;
+	uint4 *bp = reinterpret_cast<uint4 *>(t.main + bucket * 8);
+	const uint4 lo = bp[0], hi = bp[1];
+	uint32_t it[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+	BucketRun R; R.n = 0;
+	for (uint32_t q = i; q < n; ++q) {
+		const unsigned long long x = skeys[q];
+		if (q > i && ht_bucket_of(t, x) != bucket) break;
+		const int j = bucket_run_entry(t, R, it, x);
+		if (j < 0) return;      // cannot happen: k_bucket_flags saw the same run
+		uint32_t c = R.cnt[j];
+		++R.m[j];
+		if (c >= t.top) continue;                  // ht_kmer.h:435: cnt < counter_max
+		if (c <= ci.thr) { R.cnt[j] = c + 1; continue; }
+		const uint32_t di = draw_off[sidx[q]];
+		if (di >= avail) { flags[0] = 1; continue; }
+		if (draws[(dpos + di) & dmask] % (ci.mult * (c - ci.thr)) == 0) R.cnt[j] = c + 1;
+	}
+	// write the counters back: existing items in place, new k-mers into the free slots of the sector, the rest into the stash
+	uint32_t made_main = 0, made_stash = 0;
+	const bool was_empty = it[0] == 0;
+	for (int j = 0; j < R.n; ++j) {
+		const HtKey hk = ht_key(t, R.key[j]);
+		if (R.slot[j] >= 0) { it[R.slot[j]] = hk.q | R.cnt[j]; continue; }
+		if (R.slot[j] == -1) {
+			int f = -1;
+#pragma unroll
+			for (int s = 0; s < 8; ++s) if (f < 0 && it[s] == 0) f = s;
+			if (f >= 0) { it[f] = hk.q | R.cnt[j]; ++made_main; continue; }
+		}
+		// stash: find-or-create (another bucket's thread may claim slots next to ours)
+		const uint64_t smask = (1ull << t.stash_log2) - 1;
+		const unsigned long long item = ((hk.kal + 1) << t.cbits) | (unsigned long long) R.cnt[j];
+		for (uint64_t p = ht_stash_pos(t, hk.h);; p = (p + 1) & smask) {
+			unsigned long long s = *((volatile unsigned long long *) (t.stash + p));
+			if (s == 0) {
+				const unsigned long long old = atomicCAS(t.stash + p, 0ull, item);
+				if (old == 0) { ++made_stash; break; }
+				s = old;
+			}
+			if ((s >> t.cbits) == hk.kal + 1) { t.stash[p] = item; break; }
+		}
+	}
+	bp[0] = make_uint4(it[0], it[1], it[2], it[3]);
+	bp[1] = make_uint4(it[4], it[5], it[6], it[7]);
+	if (made_main) atomicAdd(t.n_items, (unsigned long long) made_main);
+	if (made_stash) atomicAdd(t.n_items + 1, (unsigned long long) made_stash);
+	if (t.occ && was_empty && it[0] != 0) atomicOr(t.occ + (bucket >> 5), 1u << (bucket & 31));
 }
 
 // ------------------------------------------------------------------------------------------------------------------

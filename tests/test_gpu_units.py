@@ -70,6 +70,41 @@ def test_insert_dump_find_count(table, k, cbits, log2b):
     e.close()
 
 
+@pytest.mark.parametrize("table,k,cbits,log2b,saturate", [(E.TABLE_BMER, 24, 6, 0, False), (E.TABLE_BMER, 19, 6, 14, False), (E.TABLE_BMER, 24, 6, 0, True),
+                                                          (E.TABLE_SMER, 20, 12, 0, False)])
+def test_large_row_insert_bucket_grouped(table, k, cbits, log2b, saturate):
+    """Rows of millions of k-mers (a steady-state sync): the engine's own radix partition by table bucket (fqsk_sort.cuh) + the
+    bucket-grouped ordered insert (k_bucket_flags / k_scan_u8 / k_bucket_apply); log2b = 14 crowds the buckets (stash, growth, runs
+    with many distinct k-mers).  saturate: one k-mer repeated far beyond the counter's ceiling -> the row must fall back to the
+    sorted-by-k-mer path (48-bit radix sort + k_locate_heads / k_apply_keys with their verifying passes).  Contents, counters and
+    the PRNG position against the oracle."""
+    rng = np.random.default_rng(77 * k + log2b + saturate)
+    p, s, b = (14, 17, k) if table == E.TABLE_BMER else (14, k, k + 4)
+    e = _engine(p, s, b, 9, bmer_log2_buckets=log2b, smer_log2_buckets=log2b)
+    ou = O.oracle_units()
+    thr, mult, top = (7, 2, 63) if cbits == 6 else (2047, 1, 4095)
+    to, co = ou.ht_new(k, cbits), ou.cinc_new(thr, mult, top)
+    d, rc, cur, _ = _rand_regs(rng, k, 400_000)
+    universe = np.unique(_normalize(d, rc, k))
+    for rnd in range(3):
+        # most k-mers once or twice, a hot core of 20 000 k-mers ~30 times each: counters far above thr, draws in push order
+        stream = np.concatenate([universe[rng.integers(0, len(universe), 2_000_000)], universe[rng.integers(0, 20_000, 600_000)]])
+        if saturate:
+            stream = np.concatenate([stream, np.repeat(universe[5:7], 6000)])
+        rng.shuffle(stream)
+        e.ht_insert(table, stream)
+        ou.ht_insert(to, co, stream)
+        kg, vg = e.dump(table)
+        ko, vo = ou.ht_dump(to, cap=1 << 22)
+        assert np.array_equal(kg, ko)
+        bad = np.flatnonzero(vg.astype(np.uint32) != vo)
+        assert len(bad) == 0, (rnd, len(bad), kg[bad[:3]], vg[bad[:3]], vo[bad[:3]])
+    assert (vo.max() == top) == (saturate or cbits == 6 and vo.max() == top)
+    st = e.stats()
+    assert st["draws_b" if table == E.TABLE_BMER else "draws_s"] == O.oracle_lib().fqso_cinc_draws(co)
+    e.close()
+
+
 @pytest.mark.parametrize("k,missing", [(19, 1), (19, 2), (24, 3), (27, 5)])
 def test_find_partial_ordered_merge(k, missing):
     """Front-truncated lookups: 4^m completions, merged in order with the PRNG-aware addition; draw offsets across
