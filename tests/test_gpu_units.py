@@ -99,7 +99,8 @@ def test_large_row_insert_bucket_grouped(table, k, cbits, log2b, saturate):
         assert np.array_equal(kg, ko)
         bad = np.flatnonzero(vg.astype(np.uint32) != vo)
         assert len(bad) == 0, (rnd, len(bad), kg[bad[:3]], vg[bad[:3]], vo[bad[:3]])
-    assert (vo.max() == top) == (saturate or cbits == 6 and vo.max() == top)
+    if saturate:
+        assert vo.max() == top
     st = e.stats()
     assert st["draws_b" if table == E.TABLE_BMER else "draws_s"] == O.oracle_lib().fqso_cinc_draws(co)
     e.close()
