@@ -163,10 +163,11 @@ struct fqsk_handle {
 	DevBuf pk;                                       // 2-bit packed reads of the segment (k_prep)
 	DevBuf dfilter; bool delta_filtered = false;     // filter bits of the segment's delta (large segments), see seg_setup
 	DevBuf recs_alt; int rec_par = 0;
+	DevBuf ctxrec[2];                                // fqsk_submit_ctx: the 16-byte context records of the segment in flight, per parity
 	cudaStream_t st_copy = nullptr; cudaEvent_t ev_recs = nullptr, ev_copied[2] = {nullptr, nullptr};
 	uint8_t *h_stage2 = nullptr; size_t h_stage2_cap = 0;       // second pinned staging buffer (H2D of segment n + 1 while n is still needed)
 	uint8_t *h_meta[2] = {nullptr, nullptr}; size_t h_meta_cap[2] = {0, 0};   // pinned per-ticket copies of dup / rec_off (item arrays in paired-end mode)
-	struct Ticket { bool open = false, done = false; fqsk_base_rec *recs = nullptr; uint64_t bound = 0, n_recs = 0; uint8_t *dup = nullptr; uint64_t *rec_off = nullptr; uint32_t n_reads = 0; int par = 0; uint64_t id = 0; } tk[2];
+	struct Ticket { bool open = false, done = false; fqsk_ctx_rec *ctx = nullptr; fqsk_base_rec *recs = nullptr; uint64_t bound = 0, n_recs = 0; uint8_t *dup = nullptr; uint64_t *rec_off = nullptr; uint32_t n_reads = 0; int par = 0; uint64_t id = 0; } tk[2];
 	bool tk_open = false; int tk_cur = 0; uint64_t tk_next = 1;
 	int tk_info = -1;                        // ticket (parity) whose per-read extras (sorted prefix, pair decisions) fqsk_sorted_prefix / fqsk_pair_info serve; -1: the last blocking segment
 	// pinned staging
@@ -262,6 +263,7 @@ int table_alloc(fqsk_handle *h, Table &t, uint32_t k, uint32_t cbits, uint32_t B
 	d.mix_sh = (d.W + 1) / 2;
 	d.stash_log2 = B + 3 >= 5 + 12 ? B + 3 - 5 : 12;
 	d.n_items = counters;
+	d.err = (int *) (h->d_status + 400);      // +400 : a table's stash ran full (sticky)
 	t.inv.inv1 = mod_inverse(MIX_C1); t.inv.inv2 = mod_inverse(MIX_C2);
 	size_t mb = (size_t) 32 << B, sb = (size_t) 8 << d.stash_log2;
 	CK(cudaMalloc(&d.main, mb));
@@ -457,11 +459,14 @@ int sort_by_bucket(fqsk_handle *h, const Table &t, const unsigned long long *kin
 	return FQSK_OK;
 }
 
+const char *const STASH_FULL = "a k-mer table ran full inside one sync (more new k-mers than it can take before it grows): create the engine with a larger expected_kmers / *_log2_buckets";
 int read_flags(fqsk_handle *h, int *out, int n) {
 	CK(cudaMemcpyAsync(h->h_small, h->d_flags, n * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+	CK(cudaMemcpyAsync((uint8_t *) h->h_small + 400, h->d_status + 400, 4, cudaMemcpyDeviceToHost, h->st));
 	CK(cudaStreamSynchronize(h->st));
 	memcpy(out, h->h_small, n * sizeof(int));
 	resolve_phases(h);
+	if (*(const int *) ((uint8_t *) h->h_small + 400)) return fail(h, FQSK_E_CAPACITY, "%s", STASH_FULL);
 	return FQSK_OK;
 }
 
@@ -614,9 +619,11 @@ int apply_bucketed(fqsk_handle *h, Table &t, Stream &rng, const unsigned long lo
 	uint32_t *hs = (uint32_t *) h->h_small;
 	CK(cudaMemcpyAsync(hs, h->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
 	CK(cudaMemcpyAsync(hs + 8, doff + n, 4, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaMemcpyAsync(hs + 100, h->d_status + 400, 4, cudaMemcpyDeviceToHost, h->st));
 	CK(cudaStreamSynchronize(h->st));
 	resolve_phases(h);
 	int fl[8]; memcpy(fl, hs, sizeof fl);
+	if (hs[100]) return fail(h, FQSK_E_CAPACITY, "%s", STASH_FULL);
 	if (fl[3] || fl[7]) return FQSK_OK;
 	if (fl[0]) return fail(h, FQSK_E_CUDA, "internal error: the draw window of a bucket-grouped insert was too short");
 	if (fl[6]) h->hot_seen[&t == &h->tb ? 1 : 0] = true;
@@ -707,6 +714,7 @@ int look(fqsk_handle *h) {
 		CK(cudaStreamSynchronize(h->st));
 		resolve_phases(h);
 		h->look_fresh = true;
+		if (*(const int *) (hs + 400)) return fail(h, FQSK_E_CAPACITY, "%s", STASH_FULL);
 		return FQSK_OK;
 	}
 	// One small kernel stores the status block and the counters into the page-locked look buffer (device-accessible under UVA) and
@@ -724,6 +732,7 @@ int look(fqsk_handle *h) {
 	}
 	std::atomic_thread_fence(std::memory_order_acquire);
 	h->look_fresh = true;
+	if (*(const int *) (hs + 400)) return fail(h, FQSK_E_CAPACITY, "%s", STASH_FULL);
 	return FQSK_OK;
 }
 inline const int *looked_sflags(fqsk_handle *h) { return (const int *) ((uint8_t *) h->h_small + ((uint8_t *) h->d_sflags - h->d_status)); }
@@ -1395,7 +1404,7 @@ void fqsk_destroy(fqsk_handle *h) {
 	                  &h->sidx_b, &h->sidx_s, &h->stime_b, &h->stime_s, &h->sort_k, &h->sort_v, &h->rkind, &h->rreg, &h->rslot, &h->dirty, &h->rdraws_b, &h->rdraws_s, &h->totals,
 	                  &h->y_tslot, &h->y_c0, &h->y_m, &h->y_draw, &h->y_j, &h->y_final, &h->y_flag_at, &h->y_own, &h->y_lead, &h->y_rank, &h->y_flag, &h->y_doff,
 	                  &h->idx_k, &h->idx_t, &h->idx_rt, &h->miss_fold, &h->hr_b[0], &h->hr_b[1], &h->hr_b[2], &h->hr_s[0], &h->hr_s[1], &h->hr_s[2],
-	                  &h->evk[0], &h->evk[1], &h->evv[0], &h->evv[1], &h->evk_s[0], &h->evk_s[1], &h->evv_s[0], &h->evv_s[1], &h->scan_part, &h->scan8_part, &h->rdx_hist, &h->rdx_k, &h->rdx_v, &h->scan_vals, &h->recs_alt, &h->dfilter, &h->pk,
+	                  &h->evk[0], &h->evk[1], &h->evv[0], &h->evv[1], &h->evk_s[0], &h->evk_s[1], &h->evv_s[0], &h->evv_s[1], &h->ctxrec[0], &h->ctxrec[1], &h->scan_part, &h->scan8_part, &h->rdx_hist, &h->rdx_k, &h->rdx_v, &h->scan_vals, &h->recs_alt, &h->dfilter, &h->pk,
 	                  &h->route_keys, &h->route_keys2, &h->route_sorted, &h->route_hist, &h->route_perm,
 	                  &h->pe_uk, &h->pe_uv, &h->pe_uc, &h->pe_tk, &h->pe_tv, &h->pe_q, &h->pe_sk, &h->pe_sv, &h->pe_sidx, &h->pe_t1, &h->pe_t2, &h->pe_pool, &h->pe_info, &h->it_src, &h->it_len,
 	                  &h->it_bytes, &h->it_first, &h->it_bias, &h->it_dupprev, &h->it_flags, &h->it_off32, &h->it_off64, &h->it_dna};
@@ -1817,6 +1826,16 @@ int fqsk_sync(fqsk_handle *h) {
 // ---- asynchronous, double-buffered segment + sync ---------------------------------------------------------------------
 static fqsk_base_rec *dev_recs(fqsk_handle *h, int par) { return (par ? h->recs_alt : h->recs).as<fqsk_base_rec>(); }
 
+// k_ctx_codes over the records of the segment being evaluated (h->ctx) into the context-record buffer of parity `par`
+static int enqueue_ctx_codes(fqsk_handle *h, int par) {
+	const SegCtx &C = h->ctx;
+	const uint32_t bound = (uint32_t) C.dna_bytes_actual;
+	if (!C.n || !bound) return FQSK_OK;
+	CK(h->ctxrec[par].ensure(((size_t) std::max<uint64_t>(bound, (uint64_t) h->P.reserve_bytes + h->P.reserve_bytes / 4) + 1) * sizeof(fqsk_ctx_rec)));
+	CK(pdl(k_ctx_codes, nblk(bound, 256), 256, h->st, C.E, C.S, C.P, h->ctxrec[par].as<fqsk_ctx_rec>())); LAUNCHED(h);
+	return FQSK_OK;
+}
+
 // compute side of the ticket in flight: the sync (its look also settles the segment); if the segment needed more than its
 // first pass the records were rewritten after the copy was enqueued, so they are copied again (the copy stream is in order)
 static int submit_finish_compute(fqsk_handle *h) {
@@ -1826,17 +1845,31 @@ static int submit_finish_compute(fqsk_handle *h) {
 	CKR(sync_end(h));
 	T.n_recs = h->n_recs;
 	if (T.n_recs > T.bound) return fail(h, FQSK_E_CAPACITY, "segment produced %llu records, more than its reads allow (%llu)", (unsigned long long) T.n_recs, (unsigned long long) T.bound);
-	if (h->seg_extra_pass && T.n_recs && T.recs) {
+	if (h->seg_extra_pass && T.n_recs && (T.recs || T.ctx)) {
+		if (T.ctx) CKR(enqueue_ctx_codes(h, T.par));      // the records were rewritten: build the context records again
 		CK(cudaEventRecord(h->ev_recs, h->st)); CK(cudaStreamWaitEvent(h->st_copy, h->ev_recs, 0));
-		CK(cudaMemcpyAsync(T.recs, dev_recs(h, T.par), T.n_recs * sizeof(fqsk_base_rec), cudaMemcpyDeviceToHost, h->st_copy));
+		if (T.ctx) CK(cudaMemcpyAsync(T.ctx, h->ctxrec[T.par].p, T.n_recs * sizeof(fqsk_ctx_rec), cudaMemcpyDeviceToHost, h->st_copy));
+		else CK(cudaMemcpyAsync(T.recs, dev_recs(h, T.par), T.n_recs * sizeof(fqsk_base_rec), cudaMemcpyDeviceToHost, h->st_copy));
 		CK(cudaEventRecord(h->ev_copied[T.par], h->st_copy));
 	}
 	T.done = true;
 	return FQSK_OK;
 }
 
+static int submit_impl(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const fqsk_read_desc *reads, uint32_t n_reads,
+                       fqsk_base_rec *recs, fqsk_ctx_rec *ctx, uint64_t rec_cap, uint8_t *dup, uint64_t *rec_off, uint64_t *ticket);
 int fqsk_submit(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const fqsk_read_desc *reads, uint32_t n_reads,
                 fqsk_base_rec *recs, uint64_t rec_cap, uint8_t *dup, uint64_t *rec_off, uint64_t *ticket) {
+	return submit_impl(h, slab, slab_size, reads, n_reads, recs, nullptr, rec_cap, dup, rec_off, ticket);
+}
+int fqsk_submit_ctx(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const fqsk_read_desc *reads, uint32_t n_reads,
+                    fqsk_ctx_rec *ctx, uint64_t rec_cap, uint8_t *dup, uint64_t *rec_off, uint64_t *ticket) {
+	if (h && !ctx && n_reads) return FQSK_E_INVAL;
+	if (h) for (uint32_t i = 0; reads && i < n_reads; ++i) if (reads[i].dna_len >= FQSK_CTX_MAX_READ) return fail(h, FQSK_E_UNSUPPORTED, "read %u has %u symbols: context records cover reads shorter than %u", i, reads[i].dna_len, FQSK_CTX_MAX_READ);
+	return submit_impl(h, slab, slab_size, reads, n_reads, nullptr, ctx, rec_cap, dup, rec_off, ticket);
+}
+static int submit_impl(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const fqsk_read_desc *reads, uint32_t n_reads,
+                       fqsk_base_rec *recs, fqsk_ctx_rec *ctx, uint64_t rec_cap, uint8_t *dup, uint64_t *rec_off, uint64_t *ticket) {
 	if (!h || !ticket || (!slab && n_reads) || (!reads && n_reads)) return FQSK_E_INVAL;
 	CK(cudaSetDevice(h->P.device));
 	if (h->world > 1) return fail(h, FQSK_E_UNSUPPORTED, "fqsk_submit: not available on a sharded engine");
@@ -1881,15 +1914,17 @@ int fqsk_submit(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const f
 		}
 		if (mode_pe(h->P.mode) && n_reads >= 2) CK(cudaMemcpyAsync(h->h_meta[par] + o_pair, h->pe_info.p, (size_t) (n_reads / 2) * 12, cudaMemcpyDeviceToHost, h->st));
 	}
-	if (bound && recs && n_reads) {   // the records leave on their own stream while the sync and the next segment run
+	if (bound && ctx && n_reads) CKR(enqueue_ctx_codes(h, par));      // the context ids of the segment's records, on the device
+	if (bound && (recs || ctx) && n_reads) {   // the records leave on their own stream while the sync and the next segment run
 		CK(cudaEventRecord(h->ev_recs, h->st)); CK(cudaStreamWaitEvent(h->st_copy, h->ev_recs, 0));
-		CK(cudaMemcpyAsync(recs, dev_recs(h, par), bound * sizeof(fqsk_base_rec), cudaMemcpyDeviceToHost, h->st_copy));
+		if (ctx) CK(cudaMemcpyAsync(ctx, h->ctxrec[par].p, bound * sizeof(fqsk_ctx_rec), cudaMemcpyDeviceToHost, h->st_copy));
+		else CK(cudaMemcpyAsync(recs, dev_recs(h, par), bound * sizeof(fqsk_base_rec), cudaMemcpyDeviceToHost, h->st_copy));
 		CK(cudaEventRecord(h->ev_copied[par], h->st_copy));
 	}
 	CKR(sync_begin(h));
 	auto &T = h->tk[par];
 	T = fqsk_handle::Ticket{};
-	T.open = true; T.done = false; T.recs = recs; T.bound = bound; T.dup = dup; T.rec_off = rec_off; T.n_reads = n_reads; T.par = par; T.id = h->tk_next++;
+	T.open = true; T.done = false; T.recs = recs; T.ctx = ctx; T.bound = bound; T.dup = dup; T.rec_off = rec_off; T.n_reads = n_reads; T.par = par; T.id = h->tk_next++;
 	h->tk_open = true; h->tk_cur = par;
 	*ticket = T.id;
 	return FQSK_OK;
@@ -1906,7 +1941,7 @@ int fqsk_collect(fqsk_handle *h, uint64_t ticket, uint64_t *n_recs) {
 		if (par != h->tk_cur) return fail(h, FQSK_E_CUDA, "internal error: an older ticket was left unfinished");
 		CKR(submit_finish_compute(h));
 	}
-	if (T.bound && T.recs && T.n_reads) CK(cudaEventSynchronize(h->ev_copied[par]));
+	if (T.bound && (T.recs || T.ctx) && T.n_reads) CK(cudaEventSynchronize(h->ev_copied[par]));
 	const uint32_t n = T.n_reads;
 	if (n) {
 		const bool pe = mode_pe(h->P.mode);

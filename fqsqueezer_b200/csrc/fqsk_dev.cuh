@@ -134,6 +134,8 @@ struct HtDev {
 	uint32_t k, cbits, W, B, rem_bits, top, stash_log2, mix_sh;
 	uint64_t maskW;
 	unsigned long long *n_items;    // device counters: [0] main items, [1] stash items
+	int *err;                       // set when an insert finds the stash full (a single sync brought more new k-mers than the table can take before it
+	                                // grows): the probe loops stay bounded, the host reports FQSK_E_CAPACITY at its next look
 	// one bit per bucket, set when the first item of the bucket is created and never cleared (16 MiB for 2^27 buckets: L2-resident).
 	// k_rough tests it before reading a neighbour's bucket while the table is sparse (occ_read != null): in the first blocks of a
 	// file nearly all of the 4(k-1) trials of a rough search land on empty buckets (measured on block 10 of config 2: DRAM reads of
@@ -210,7 +212,7 @@ FQSK_DEV void ht_ctx_counts_from(const HtDev &t, const HtKey &key, bool is_dir, 
 	uint64_t m64 = ~(3ull << ush);
 	uint64_t smask = (1ull << t.stash_log2) - 1;
 	const unsigned long long *stash = t.peer_stash[key.owner];
-	for (uint64_t p = ht_stash_pos(t, key.h);; p = (p + 1) & smask) {
+	for (uint64_t p = ht_stash_pos(t, key.h), guard = 0; guard <= smask; p = (p + 1) & smask, ++guard) {      // bounded: a full stash never spins
 		unsigned long long it = stash[p];
 		if (it == 0) break;
 		uint64_t kal = (it >> t.cbits) - 1;
@@ -236,11 +238,12 @@ FQSK_DEV uint32_t ht_count(const HtDev &t, uint64_t x) {
 	if (!full) return 0;
 	uint64_t smask = (1ull << t.stash_log2) - 1;
 	const unsigned long long *stash = t.peer_stash[key.owner];
-	for (uint64_t p = ht_stash_pos(t, key.h);; p = (p + 1) & smask) {
+	for (uint64_t p = ht_stash_pos(t, key.h), guard = 0; guard <= smask; p = (p + 1) & smask, ++guard) {
 		unsigned long long it = stash[p];
 		if (it == 0) return 0;
 		if ((it >> t.cbits) == key.kal + 1) return (uint32_t) (it & t.top);
 	}
+	return 0;
 }
 // find-or-create for the sync step (ht_kmer.h:330-362).  New slots are claimed with counter 1; the group pass of the sync
 // step turns that into the reference's "start at 0, then Increment".  Returns a slot id (main: index, stash: 8<<B + index).
@@ -263,7 +266,9 @@ FQSK_DEV uint64_t ht_locate(const HtDev &t, uint64_t x, bool &created, uint32_t 
 	}
 	uint64_t smask = (1ull << t.stash_log2) - 1;
 	unsigned long long fresh = ((key.kal + 1) << t.cbits) | (unsigned long long) claim;
+	uint64_t probes = 0;
 	for (uint64_t p = ht_stash_pos(t, key.h);; p = (p + 1) & smask) {
+		if (++probes > smask) { if (t.err) *t.err = 1; return (8ull << t.B) + p; }      // stash full: give up (the host fails the call), never spin
 		unsigned long long it = *((volatile unsigned long long *) (t.stash + p));
 		if (it == 0) {
 			unsigned long long old = atomicCAS(t.stash + p, 0ull, fresh);

@@ -366,7 +366,7 @@ __device__ __forceinline__ int bucket_run_entry(const HtDev &t, BucketRun &R, co
 	}
 	if (full) {      // the k-mer may live in the stash
 		const uint64_t smask = (1ull << t.stash_log2) - 1;
-		for (uint64_t p = ht_stash_pos(t, hk.h);; p = (p + 1) & smask) {
+		for (uint64_t p = ht_stash_pos(t, hk.h), guard = 0; guard <= smask; p = (p + 1) & smask, ++guard) {
 			const unsigned long long s = t.stash[p];
 			if (s == 0) break;
 			if ((s >> t.cbits) == hk.kal + 1) { R.cnt[j] = R.c0[j] = (uint32_t) (s & t.top); R.slot[j] = -2; break; }
@@ -439,7 +439,9 @@ __global__ void __launch_bounds__(256) k_bucket_apply(HtDev t, CIncP ci, const u
 		// stash: find-or-create (another bucket's thread may claim slots next to ours)
 		const uint64_t smask = (1ull << t.stash_log2) - 1;
 		const unsigned long long item = ((hk.kal + 1) << t.cbits) | (unsigned long long) R.cnt[j];
+		uint64_t probes = 0;
 		for (uint64_t p = ht_stash_pos(t, hk.h);; p = (p + 1) & smask) {
+			if (++probes > smask) { if (t.err) *t.err = 1; break; }      // stash full: the host fails the call
 			unsigned long long s = *((volatile unsigned long long *) (t.stash + p));
 			if (s == 0) {
 				const unsigned long long old = atomicCAS(t.stash + p, 0ull, item);

@@ -16,6 +16,7 @@
 //      k_fold      one thread per script: approximate-counter merges with the read-ordered mt19937 draw indices
 #pragma once
 #include "fqsk_kernels.cuh"
+#include "../../include/fqsk_ctx.h"
 
 namespace fqsk {
 
@@ -1235,6 +1236,55 @@ __global__ void __launch_bounds__(256) k_scan_flags(const SyncIn *in, const uint
 		Y.draw_at[own] = off + v[e];
 		Y.flag_at[own] = flag[j];
 	}
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_ctx_codes: the context ids of the DNA stream on the device.  One thread per coded base turns the final record
+// into the 16-byte fqsk_ctx_rec of include/fqsk_ctx.h: cor_zone, the counts quantised at the four resolutions of
+// determine_ctx_codes, let_max, the rank of the true symbol and the recent-rank history (the ranks of the 8 bases before it,
+// recomputed from their records: they are neighbours in memory), dna.cpp:737-774, code_ctx.cpp:257-338.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool ctx_base(const SegDev &S, const PipeDev &P, const EngineDev &E, uint32_t r, uint32_t g, uint32_t first, const uint8_t *p, uint32_t lb, const unsigned long long sl[4],
+                                         uint32_t &rsym, uint32_t &sym_out, uint32_t &n_run_out, fqsk_base_rec &rec) {
+	// coded with counts? (dna.cpp:737) + the rank; i = position inside the item's text
+	const uint32_t i = first + (g - (uint32_t) S.rec_off[r]);
+	rec = P.recs[g];
+	const uint32_t sym = dna_code(p[i]);
+	uint32_t n_run = 0;      // N_run_len: Ns right before i, counted from the first position this call walked (sorted prefix included)
+	for (uint32_t j = i; j > lb && dna_code(p[j - 1]) == 4 && n_run < 2; --j) ++n_run;
+	sym_out = sym; n_run_out = n_run;
+	const bool coded = rec.level != FQSK_LEVEL_NONE && n_run < 2;
+	uint64_t s64[4] = {sl[0], sl[1], sl[2], sl[3]};
+	rsym = coded ? fqsk_ctx_rank(rec.counts, s64, sym) : 4u;
+	return coded;
+}
+__global__ void __launch_bounds__(256) k_ctx_codes(EngineDev E, SegDev S, PipeDev P, fqsk_ctx_rec *out) { pdl_enter();
+	const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t n_rec = *P.n_rec_dev;
+	if (g >= n_rec) return;
+	const uint32_t r = find_read(S.rec_off, S.n_reads, g, n_rec);
+	const bool sorted = item_sorted(S, E.sorted, r);
+	const uint32_t first = item_first(S, sorted ? E.p : E.prefix_len, r);
+	const uint32_t g0 = (uint32_t) S.rec_off[r];
+	const uint8_t *p = S.dna + S.off[r];
+	const uint32_t lb = sorted ? 0u : first;
+	unsigned long long sl[4];
+	for (int q = 0; q < 4; ++q) sl[q] = S.sl_base.v[q] + S.sl_prefix[r].v[q];
+	// ctx_r_sym (dna.cpp:664-671, 774, 800): bit j = the base j + 1 positions back was coded with counts and ranked first
+	uint32_t r_hist = 0;
+	for (uint32_t j = 1; j <= 8 && g >= g0 + j; ++j) {
+		uint32_t rs, sy, nr; fqsk_base_rec pr;
+		if (ctx_base(S, P, E, r, g - j, first, p, lb, sl, rs, sy, nr, pr) && rs == 0) r_hist |= 1u << (j - 1);
+	}
+	uint32_t rs, sym, n_run; fqsk_base_rec rec;
+	ctx_base(S, P, E, r, g, first, p, lb, sl, rs, sym, n_run, rec);
+	const uint32_t fl = item_flags(S, r);
+	const uint32_t bias = S.bias_a ? S.bias_a[r] : 0;
+	const uint32_t i = rec.pos;                              // the coder's loop index (frame of the whole mate)
+	uint32_t pos = i, read_len = S.len[r] + bias;
+	if (fl & IF_REVCOMP) { pos = S.len[r] - (i - bias) - 1; read_len = 0xFFFFFFFFu; }      // dna.cpp:750-752
+	uint64_t s64[4] = {sl[0], sl[1], sl[2], sl[3]};
+	out[g] = fqsk_ctx_make(rec.counts, rec.level, rec.rough, rec.cor_pos, i, pos, read_len, sym, n_run, r_hist, s64, E.p, E.s, E.b);
 }
 
 // the host's look at the device: status block (128 words) + counters (6 x u64) into the page-locked look buffer, then -- after a

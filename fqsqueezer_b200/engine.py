@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(HERE, "libfqsk.so")
 
 REC_DTYPE = np.dtype([("pos", "<u4"), ("c", "<u4", 4), ("cor_pos", "<u4"), ("level", "u1"), ("rough", "u1"), ("pad", "<u2")])
 READ_DESC_DTYPE = np.dtype([("dna_off", "<u8"), ("dna_len", "<u4"), ("flags", "<u4")])
+CTX_REC_DTYPE = np.dtype([("a", "<u8"), ("b", "<u8")])      # fqsk_ctx_rec (include/fqsk_ctx.h)
 TABLE_SIV, TABLE_SMER, TABLE_BMER, TABLE_PAIR = 0, 1, 2, 3
 MODE_SE_ORIGINAL, MODE_SE_SORTED, MODE_PE_ORIGINAL, MODE_PE_SORTED = 0, 1, 2, 3
 F_PROFILE, F_TRACE_ALLOC, F_TEST_HOOKS = 1, 2, 4
@@ -45,7 +46,7 @@ class _Stats(C.Structure):
 
 
 EXPORTS = ["fqsk_create", "fqsk_destroy", "fqsk_last_error", "fqsk_block_start", "fqsk_segment", "fqsk_segment_device",
-           "fqsk_device_recs", "fqsk_recs_checksum", "fqsk_sorted_prefix", "fqsk_pair_info", "fqsk_submit", "fqsk_collect", "fqsk_sync", "fqsk_dump", "fqsk_stats_get", "fqsk_profile", "fqsk_ht_insert", "fqsk_ht_find",
+           "fqsk_device_recs", "fqsk_recs_checksum", "fqsk_sorted_prefix", "fqsk_pair_info", "fqsk_submit", "fqsk_submit_ctx", "fqsk_collect", "fqsk_sync", "fqsk_dump", "fqsk_stats_get", "fqsk_profile", "fqsk_ht_insert", "fqsk_ht_find",
            "fqsk_ht_count", "fqsk_timer_begin", "fqsk_timer_end", "fqsk_siv_increment", "fqsk_siv_test", "fqsk_siv_counts", "fqsk_siv_test_shorter", "fqsk_mt_stream", "fqsk_host_alloc", "fqsk_host_free",
            "fqsk_shard_export", "fqsk_shard_attach", "fqsk_sync_route", "fqsk_sync_apply", "fqsk_sync_finish"]
 
@@ -74,6 +75,7 @@ def load_library():
     lib.fqsk_sorted_prefix.argtypes = [vp, vp, vp, C.c_uint32]
     lib.fqsk_pair_info.argtypes = [vp, vp, C.c_uint32]
     lib.fqsk_submit.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint32, vp, C.c_uint64, vp, vp, u64p]
+    lib.fqsk_submit_ctx.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint32, vp, C.c_uint64, vp, vp, u64p]
     lib.fqsk_collect.argtypes = [vp, C.c_uint64, u64p]
     lib.fqsk_sync.argtypes = [vp]
     lib.fqsk_dump.argtypes = [vp, C.c_int, vp, vp, C.c_uint64, u64p]
@@ -153,6 +155,7 @@ class KmerEngine:
             self.lib.fqsk_host_free(ptr)
         self._pinned = {}
         self.__dict__.pop("_submit_cache", None)
+        self.__dict__.pop("_submit_cache_ctx", None)
         if getattr(self, "h", None):
             self.lib.fqsk_destroy(self.h)
             self.h = None
@@ -209,25 +212,27 @@ class KmerEngine:
             return out, dup[:n], rec_off
         return out, dup[:n]
 
-    def submit(self, slab: np.ndarray, off: np.ndarray, length: np.ndarray, first: int | None = None):
+    def submit(self, slab: np.ndarray, off: np.ndarray, length: np.ndarray, first: int | None = None, ctx: bool = False):
         """Asynchronous segment + sync (fqsk_submit): returns a ticket; collect(ticket) -> (records, dup, rec_off).  The output
         buffers are page-locked and owned by the engine, two sets used alternately: a ticket's arrays stay valid until the
-        second submit after it."""
+        second submit after it.  ctx=True: fqsk_submit_ctx -- the records are the 16-byte context records of include/fqsk_ctx.h
+        (CTX_REC_DTYPE) built on the device instead of the 28-byte per-base records."""
         if slab.dtype != np.uint8 or not slab.flags.c_contiguous:
             slab = np.ascontiguousarray(slab, np.uint8)
         n = len(off)
         slot = getattr(self, "_submit_slot", 0) ^ 1
         self._submit_slot = slot
+        dt = CTX_REC_DTYPE if ctx else REC_DTYPE
         # descriptor array and page-locked output buffers are kept per slot and reused (sized once for the largest announced
         # segment: reallocating 200 MB of pinned memory costs ~0.1 s, building numpy views ~10 us each)
-        cache = self.__dict__.setdefault("_submit_cache", {})
+        cache = self.__dict__.setdefault("_submit_cache_ctx" if ctx else "_submit_cache", {})
         ent = cache.get(slot)
         cap = int(length.sum(dtype=np.int64)) + 16
         n_cap = max(n, self.reserve_reads, 1)
         r_cap = max(cap, self.reserve_bytes + 16)
         if ent is None or ent[0] < n_cap or ent[1] < r_cap:
             ent = (n_cap, r_cap, np.zeros(n_cap, READ_DESC_DTYPE),
-                   self._pinned_array(f"srecs{slot}", r_cap * REC_DTYPE.itemsize)[: r_cap * REC_DTYPE.itemsize].view(REC_DTYPE),
+                   self._pinned_array(f"srecs{slot}{'c' if ctx else ''}", r_cap * dt.itemsize)[: r_cap * dt.itemsize].view(dt),
                    self._pinned_array(f"sdup{slot}", n_cap), self._pinned_array(f"soff{slot}", (n_cap + 1) * 8)[: (n_cap + 1) * 8].view(np.uint64))
             cache[slot] = ent
         desc = ent[2]
@@ -235,7 +240,8 @@ class KmerEngine:
         desc["dna_len"][:n] = length
         recs, dup, rec_off = ent[3][:cap], ent[4][: max(n, 1)], ent[5][: n + 1]
         t = C.c_uint64(0)
-        self._ck(self.lib.fqsk_submit(self.h, _ptr(slab), slab.size, _ptr(desc), n, _ptr(recs), cap, _ptr(dup), _ptr(rec_off), C.byref(t)))
+        fn = self.lib.fqsk_submit_ctx if ctx else self.lib.fqsk_submit
+        self._ck(fn(self.h, _ptr(slab), slab.size, _ptr(desc), n, _ptr(recs), cap, _ptr(dup), _ptr(rec_off), C.byref(t)))
         if not hasattr(self, "_tickets"):
             self._tickets = {}
         self._tickets[t.value] = (recs, dup, rec_off, n, (slab, desc))      # keep the inputs alive until the copy is staged (it is, on return)

@@ -125,11 +125,22 @@ def patch_application(path):
 
 def patch_suffix(f, path):
     # dna.cpp:695 -- the count vector of a coded base comes from the segment's records
+    # ... or, with fqsk_submit_ctx, the 16-byte context record: whether the base is coded with counts, the 7 context ids, the rank
     f = replace_once(f, "\t\tcounts_level_t counts_level = find_counts(counts);\n",
-                     "\t\tconst fqs_rp_rec rp_rec = fqs_rp_next(i);\n"
-                     "\t\tfor (int q = 0; q < 4; ++q) counts[q] = rp_rec.c[q];\n"
-                     "\t\tcounts_level_t counts_level = (counts_level_t) rp_rec.level;\n"
-                     "\t\tcor_pos = rp_rec.cor_pos;\n", path)
+                     "\t\tconst bool fqsk_cm = CFqskLive::get().ctx_mode();\n"
+                     "\t\tfqs_rp_rec rp_rec{};\n\t\tconst fqsk_ctx_rec *fqsk_cx = nullptr;\n\t\tcounts_level_t counts_level;\n"
+                     "\t\tif (fqsk_cm)\n\t\t{\n\t\t\tfqsk_cx = &CFqskLive::get().next_ctx();\n"
+                     "\t\t\tcounts_level = fqsk_ctx_coded(fqsk_cx) ? counts_level_t::bmer : counts_level_t::none;\t// only none / not none matters from here on\n\t\t}\n"
+                     "\t\telse\n\t\t{\n\t\t\trp_rec = fqs_rp_next(i);\n"
+                     "\t\t\tfor (int q = 0; q < 4; ++q) counts[q] = rp_rec.c[q];\n"
+                     "\t\t\tcounts_level = (counts_level_t) rp_rec.level;\n"
+                     "\t\t\tcor_pos = rp_rec.cor_pos;\n\t\t}\n", path)
+    # dna.cpp:746-752, 759 -- determine_ctx_codes and rank ran on the device (ctx mode)
+    f = replace_once(f, "\t\t\tcontext_levels_t ctx_lev_codes;\n\t\t\tif(!reversed_pe)\n",
+                     "\t\t\tcontext_levels_t ctx_lev_codes;\n"
+                     "\t\t\tif (fqsk_cm)\n\t\t\t{\n\t\t\t\tuint64_t fqsk_ids[7];\n\t\t\t\tfqsk_ctx_expand(fqsk_cx, fqsk_ids);\n"
+                     "\t\t\t\tfor (int q = 0; q < 7; ++q) ctx_lev_codes[q] = fqsk_ids[q];\n\t\t\t}\n\t\t\telse if(!reversed_pe)\n", path)
+    f = replace_once(f, "\t\t\tuint8_t r_sym = rank(counts, sym);\n", "\t\t\tuint8_t r_sym = fqsk_cm ? (uint8_t) fqsk_ctx_rsym(fqsk_cx) : rank(counts, sym);\n", path)
     # dna.cpp:709-735 -- no rough searches on the host; the rough flag rides in the record
     a = "\t\tif (counts_level == counts_level_t::none)\n\t\t{\n\t\t\tif (bmer_can.is_full())\n\t\t\t{\n\t\t\t\tif (find_counts_rough_b(counts))"
     f = replace_once(f, a, a.replace("if (counts_level == counts_level_t::none)", "if (false)"), path)

@@ -33,6 +33,8 @@ class CFqskLive {
 	decltype(&fqsk_block_start) p_block_start = nullptr;
 	decltype(&fqsk_submit) p_submit = nullptr;
 	decltype(&fqsk_collect) p_collect = nullptr;
+	decltype(&fqsk_submit_ctx) p_submit_ctx = nullptr;      // optional: context ids built on the device
+	bool ctx_on = false;
 	decltype(&fqsk_stats_get) p_stats = nullptr;
 	decltype(&fqsk_sorted_prefix) p_sorted_prefix = nullptr;
 	decltype(&fqsk_pair_info) p_pair_info = nullptr;
@@ -44,13 +46,14 @@ class CFqskLive {
 	uint64_t slab_size = 0;
 	std::vector<fqsk_read_desc> descs;
 	// two segments in flight (fqsk_submit / fqsk_collect): the engine works on segment n + 1 while the coder consumes segment n
-	struct Slot { fqsk_base_rec *recs = nullptr; uint64_t cap = 0; std::vector<uint8_t> dup; uint64_t ticket = 0; };
+	struct Slot { fqsk_base_rec *recs = nullptr; fqsk_ctx_rec *ctx = nullptr; uint64_t cap = 0; std::vector<uint8_t> dup; uint64_t ticket = 0; };
 	Slot slot[2];
 	struct Seg { uint64_t first, n; bool submitted; };     // the sync segments of the current reads_block, as the worker loop will cut them
 	std::vector<Seg> plan;
 	size_t plan_cur = 0;
 	void *plan_reads = nullptr; size_t plan_stride = 0;
 	fqsk_base_rec *recs = nullptr;
+	fqsk_ctx_rec *ctxs = nullptr;
 	uint64_t n_recs = 0, cursor = 0;
 	const uint8_t *dup = nullptr;
 	uint32_t mode = FQSK_MODE_SE_ORIGINAL;
@@ -91,6 +94,10 @@ public:
 		sym(p_create, "fqsk_create"); sym(p_destroy, "fqsk_destroy"); sym(p_last_error, "fqsk_last_error"); sym(p_block_start, "fqsk_block_start");
 		sym(p_submit, "fqsk_submit"); sym(p_collect, "fqsk_collect"); sym(p_stats, "fqsk_stats_get"); sym(p_host_alloc, "fqsk_host_alloc"); sym(p_host_free, "fqsk_host_free");
 		sym(p_sorted_prefix, "fqsk_sorted_prefix"); sym(p_pair_info, "fqsk_pair_info");
+		// with fqsk_submit_ctx the engine ships the 16-byte context records of include/fqsk_ctx.h instead of the 28-byte per-base records:
+		// cor_zone, determine_ctx_codes and rank (dna.cpp:739-760) have run on the device.  FQSK_CTX=0 keeps the per-base records.
+		p_submit_ctx = (decltype(p_submit_ctx)) dlsym(lib, "fqsk_submit_ctx");
+		ctx_on = p_submit_ctx && !(getenv("FQSK_CTX") && !strcmp(getenv("FQSK_CTX"), "0"));
 		fqsk_params P;
 		memset(&P, 0, sizeof(P));
 		P.abi_version = FQSK_ABI_VERSION;
@@ -144,15 +151,18 @@ public:
 		}
 		if (total + 1 > sl.cap) {
 			if (sl.recs) p_host_free(sl.recs);
+			if (sl.ctx) p_host_free(sl.ctx);
+			sl.recs = nullptr; sl.ctx = nullptr;
 			sl.cap = total + total / 4 + 4096;
 			void *p = nullptr;
-			int rc = p_host_alloc(sl.cap * sizeof(fqsk_base_rec), &p);
+			int rc = p_host_alloc(sl.cap * (ctx_on ? sizeof(fqsk_ctx_rec) : sizeof(fqsk_base_rec)), &p);
 			if (rc != FQSK_OK) die("fqsk_host_alloc", rc);
-			sl.recs = (fqsk_base_rec *) p;
+			if (ctx_on) sl.ctx = (fqsk_ctx_rec *) p; else sl.recs = (fqsk_base_rec *) p;
 		}
 		sl.dup.resize(sg.n + 1);
-		int rc = p_submit(h, slab, slab_size, descs.data(), (uint32_t) sg.n, sl.recs, sl.cap, sl.dup.data(), nullptr, &sl.ticket);
-		if (rc != FQSK_OK) die("fqsk_submit", rc);
+		int rc = ctx_on ? p_submit_ctx(h, slab, slab_size, descs.data(), (uint32_t) sg.n, sl.ctx, sl.cap, sl.dup.data(), nullptr, &sl.ticket)
+		                : p_submit(h, slab, slab_size, descs.data(), (uint32_t) sg.n, sl.recs, sl.cap, sl.dup.data(), nullptr, &sl.ticket);
+		if (rc != FQSK_OK) die(ctx_on ? "fqsk_submit_ctx" : "fqsk_submit", rc);
 		sg.submitted = true;
 		n_bases += total;
 	}
@@ -173,7 +183,7 @@ public:
 		Slot &sl = slot[k & 1];
 		int rc = p_collect(h, sl.ticket, &n_recs);
 		if (rc != FQSK_OK) die("fqsk_collect", rc);
-		recs = sl.recs; dup = sl.dup.data();
+		recs = sl.recs; ctxs = sl.ctx; dup = sl.dup.data();
 		if (mode == FQSK_MODE_SE_SORTED || mode == FQSK_MODE_PE_SORTED) {            // dna.cpp:589-605: (flag, dif) of every read's p-mer prefix (paired end: of the first mates)
 			s_flag.resize(n + 1); s_dif.resize(n + 1);
 			rc = p_sorted_prefix(h, s_flag.data(), s_dif.data(), (uint32_t) n);
@@ -211,6 +221,12 @@ public:
 		minim2_pos = w[2];
 	}
 
+	bool ctx_mode() const { return ctx_on; }
+	// dna.cpp:737-760 -- the context record of the base compress_suffix is about to code (ctx mode)
+	const fqsk_ctx_rec &next_ctx() {
+		if (cursor >= n_recs) { fprintf(stderr, "fqsk: record stream of the segment ended early\n"); exit(3); }
+		return ctxs[cursor++];
+	}
 	// dna.cpp:695 -- the record of the base compress_suffix is about to code
 	const fqsk_base_rec &next(uint32_t expect_pos) {
 		if (cursor >= n_recs) { fprintf(stderr, "fqsk: record stream of the segment ended early (position %u)\n", expect_pos); exit(3); }
@@ -236,7 +252,8 @@ public:
 			        (unsigned long long) n_segments, (unsigned long long) n_syncs, (unsigned long long) n_bases, engine_s,
 			        (unsigned long long) st.kernel_launches, (unsigned long long) st.n_smers, (unsigned long long) st.n_bmers, wait_s);
 		}
-		for (auto &sl : slot) { if (sl.recs) p_host_free(sl.recs); sl.recs = nullptr; }
+		if (getenv("FQSK_VERBOSE")) fprintf(stderr, "fqsk: per-base records: %s\n", ctx_on ? "16-byte context records built on the device (fqsk_submit_ctx)" : "28-byte count records (fqsk_submit)");
+		for (auto &sl : slot) { if (sl.recs) p_host_free(sl.recs); if (sl.ctx) p_host_free(sl.ctx); sl.recs = nullptr; sl.ctx = nullptr; }
 		recs = nullptr;
 		p_destroy(h);
 		h = nullptr;

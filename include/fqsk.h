@@ -15,6 +15,8 @@
 
 #include <stdint.h>
 
+#include "fqsk_ctx.h"   /* fqsk_ctx_rec: the 16-byte per-base record of fqsk_submit_ctx, and the functions that build / expand it */
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -166,6 +168,14 @@ int fqsk_sync(fqsk_handle *h);
 int fqsk_submit(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const fqsk_read_desc *reads, uint32_t n_reads,
                 fqsk_base_rec *recs, uint64_t rec_cap, uint8_t *dup, uint64_t *rec_off, uint64_t *ticket);
 int fqsk_collect(fqsk_handle *h, uint64_t ticket, uint64_t *n_recs);
+/* fqsk_submit with the context ids of the DNA stream built on the device: instead of fqsk_base_rec the
+ * caller receives one fqsk_ctx_rec (16 bytes, include/fqsk_ctx.h) per coded base -- what cor_zone (dna.cpp:739-744),
+ * CCodeContext::determine_ctx_codes (code_ctx.cpp:257-324), rank (dna.cpp:177-193) and update_ctx_r_sym (dna.cpp:664-671) compute on
+ * the host in the reference: fqsk_ctx_expand() gives the 7 context ids, fqsk_ctx_rsym() the rank to code, fqsk_ctx_coded() == 0 means
+ * plain-letter coding (dna.cpp:776-801).  Collected with fqsk_collect like any ticket.  Reads of FQSK_CTX_MAX_READ symbols or more
+ * are refused (FQSK_E_UNSUPPORTED): their positions would carry out of the 14-bit position field. */
+int fqsk_submit_ctx(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const fqsk_read_desc *reads, uint32_t n_reads,
+                    fqsk_ctx_rec *ctx, uint64_t rec_cap, uint8_t *dup, uint64_t *rec_off, uint64_t *ticket);
 
 /* ---- sharded operation (world_size > 1): one handle per GPU / process, reference `-t world_size` semantics --------------------
  * Replaces the shared-memory coupling of the reference's worker threads: global tables read by everybody between barriers

@@ -90,6 +90,17 @@ inline void fqs_tap_emit(uint32_t pos, uint32_t c0, uint32_t c1, uint32_t c2, ui
 	fwrite(&r, sizeof(r), 1, f);
 }
 inline void fqs_tap_flush() { for (int i = 0; i < 64; ++i) if (fqs_tap_files()[i]) fflush(fqs_tap_files()[i]); }
+// second tap ($FQS_TAP_CTX, worker 0 only): per base coded with counts, the 7 context ids of determine_ctx_codes and the rank of the
+// true symbol (dna.cpp:748-760) -- 8 x u64
+inline void fqs_tap_ctx(const uint64_t *ids, uint64_t r_sym) {
+	static FILE *f = nullptr; static bool init = false;
+	if (fqs_tap_tid() != 0) return;
+	if (!init) { init = true; const char *p = getenv("FQS_TAP_CTX"); if (p) f = fopen(p, "wb"); }
+	if (!f) return;
+	uint64_t r[8]; for (int i = 0; i < 7; ++i) r[i] = ids[i]; r[7] = r_sym;
+	fwrite(r, 8, 8, f);
+	fflush(f);
+}
 '''
 
 HT_FOREACH = r'''
@@ -175,6 +186,9 @@ def build_tap(scratch):
     patch(dna, "\t\tif (counts_level != counts_level_t::none && N_run_len < 2)\n\t\t{\n\t\t\tint cor_dist",
           "\t\tfqs_tap_emit(i, counts[0], counts[1], counts[2], counts[3], cor_pos, (uint8_t) counts_level, (uint8_t) rough_counts);\n",
           before=True)
+    # the context ids the coder looks up for this base and the rank it codes (dna.cpp:748-760; the decoder repeats these lines: first hit only)
+    patch(dna, "\t\t\tuint8_t r_sym = rank(counts, sym);\n\t\t\tp_rc5->Encode(r_sym);\n",
+          "\t\t\tfqs_tap_ctx(ctx_lev_codes.data(), r_sym);\n")
     # per read markers (dna.cpp:1517, 1559, 1716): pos = 0xFFFFFFFF, c0 = size, c1 = kind
     patch(dna, "bool CDNACompressor::CompressDirect(uint8_t *p, uint32_t size, uint8_t *q, bool first_read_of_pair)\n{\n",
           "\tfqs_tap_emit(0xFFFFFFFFu, size, 0, first_read_of_pair, 0, 0, 0, 0);\n")

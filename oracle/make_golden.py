@@ -29,7 +29,7 @@ def run_ref(fastq_path, gs, extra, tmp, threads=1):
     dump = os.path.join(tmp, "dump.bin")
     base = ["e", "-s", "-qm", "o", "-im", "o", "-t", str(threads), "-gs", str(gs), "-v", "0", *extra]
     subprocess.run([O.REF_BIN, *base, "-out", plain, fastq_path], check=True, cwd=tmp, stdout=subprocess.DEVNULL)
-    env = dict(os.environ, FQS_TAP=tap, FQS_TAP_DUMP=dump)
+    env = dict(os.environ, FQS_TAP=tap, FQS_TAP_DUMP=dump, FQS_TAP_CTX=os.path.join(tmp, "ctx.bin"))
     subprocess.run([O.REF_TAP_BIN, *base, "-out", tapd, fastq_path], check=True, cwd=tmp, env=env, stdout=subprocess.DEVNULL)
     assert open(plain, "rb").read() == open(tapd, "rb").read(), "tap changed the .fqs bytes"
     dec = os.path.join(tmp, "dec.fastq")
@@ -93,7 +93,7 @@ def write_fastq_ragged(path, reads, errs, seed):
             f.write(b"@SIM.%d %d/1\n" % (i + 1, i + 1) + lut[c].tobytes() + b"\n+\n" + q.tobytes() + b"\n")
 
 
-def make_case(name, G, n_reads, L, gs, seed, n_frac=0.0, dup_frac=0.0, extra=("-om", "o"), repeats=False, threads=1, custom=None, keep_fqs=False):
+def make_case(name, G, n_reads, L, gs, seed, n_frac=0.0, dup_frac=0.0, extra=("-om", "o"), repeats=False, threads=1, custom=None, keep_fqs=False, keep_ctx=False):
     genome = synth.make_genome(G, seed)
     if repeats:
         # low-complexity stretches (homopolymers, di-/tri-nucleotide repeats, a tandem duplication): k-mers that occur far more
@@ -114,6 +114,7 @@ def make_case(name, G, n_reads, L, gs, seed, n_frac=0.0, dup_frac=0.0, extra=("-
             write_fastq_ragged(fq, custom[0], custom[1], seed)
             n_reads = len(custom[0])
         recs, d, fqs, dec = run_ref(fq, gs, list(extra), tmp, threads)
+        ctx_ids = np.fromfile(os.path.join(tmp, "ctx.bin"), dtype="<u8").reshape(-1, 8) if keep_ctx else None
         fastq = np.fromfile(fq, dtype=np.uint8)
         if tuple(extra) == ("-om", "o"):
             assert dec == fastq.tobytes(), "reference round trip failed"
@@ -132,6 +133,8 @@ def make_case(name, G, n_reads, L, gs, seed, n_frac=0.0, dup_frac=0.0, extra=("-
     if threads > 1:
         dumps.update({"recs_t%d" % i: r for i, r in enumerate(recs)})
         recs = recs[0]
+    if keep_ctx:      # per base coded with counts: the 7 context ids + the coded rank, as the reference's coder saw them
+        dumps["ctx_ids"] = ctx_ids
     if keep_fqs:      # the reference's .fqs itself: the live-host test on the GPU box compares with it instead of running a 45 GB reference there
         dumps["fqs"] = np.frombuffer(fqs, dtype=np.uint8)
     np.savez_compressed(out, fastq=fastq, gs=np.int64(gs), extra=np.array(list(extra)), recs=recs, threads=np.int64(threads),
@@ -237,6 +240,8 @@ def main():
     # `mixed` (two saturated 6-bit counters in one context) and the bmer_unc revert: crafted reads, see mixed_unc_reads
     if not only or "se_mixed_unc_gs1" in only:
         make_case("se_mixed_unc_gs1", G=1000, n_reads=0, L=60, gs=1, seed=91, custom=mixed_unc_reads(91))
+    # device-side context ids (row f1): the 7 ids of determine_ctx_codes + the coded rank per base, tapped from the reference's coder
+    make_case("se_ctx_gs1", G=4000, n_reads=700, L=80, gs=1, seed=95, n_frac=0.004, dup_frac=0.01, keep_ctx=True)
     # paired end in the reference's default order (-p with -om s): mate 1 through the sorted prefix, bins and sort by mate 1
     if not only or "pe_sorted_gs1" in only:
         make_case_pe("pe_sorted_gs1", G=5000, n_pairs=1500, L=80, gs=1, seed=73, order="s", n_frac=0.002)

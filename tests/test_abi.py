@@ -13,7 +13,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared():
     src = open(os.path.join(ROOT, "include", "fqsk.h")).read()
-    return sorted(set(re.findall(r"\b(fqsk_[a-z0-9_]+)\s*\(", src)))
+    # prototypes only (a line that starts with the return type): inline helpers of fqsk_ctx.h mentioned in comments are not exports
+    return sorted(set(re.findall(r"^(?:int|void|const char \*)\s*(fqsk_[a-z0-9_]+)\s*\(", src, re.M)))
 
 
 def test_library_exports_every_declared_symbol():

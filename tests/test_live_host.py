@@ -249,6 +249,23 @@ def test_live_host_fails_loudly_without_engine():
 
 @needs_bins
 @pytest.mark.gpu
+@pytest.mark.parametrize("layout,case", [(("-s", "-om", "o"), CASES[0]), (("-p", "-om", "o"), PAIRED[0])])
+def test_live_host_count_records_on_gpu(layout, case, monkeypatch):
+    """The GPU legs of this file run with the 16-byte context records built on the device (fqsk_submit_ctx, the binding's default when
+    the library exports it: the log says so); this one keeps the 28-byte count-record path (FQSK_CTX=0, host-side determine_ctx_codes)
+    covered on the GPU as well.  Both must give the reference's bytes."""
+    monkeypatch.setenv("FQSK_CTX", "0")
+    with tempfile.TemporaryDirectory() as tmp:
+        if layout[0] == "-p":
+            gs, G, n, L, seed = case
+            log = _check(REAL_LIB, gs, tmp, _fastq_pe(tmp, gs, G, n, L, seed), layout=layout)
+        else:
+            log = _check(REAL_LIB, case[0], tmp, _fastq(tmp, *case), layout=layout)
+        assert "28-byte count records" in log, log
+
+
+@needs_bins
+@pytest.mark.gpu
 @pytest.mark.parametrize("case", CASES + [BIG])
 def test_live_host_on_gpu(case):
     assert os.path.exists(REAL_LIB), "fqsqueezer_b200/libfqsk.so is not built"
@@ -256,3 +273,4 @@ def test_live_host_on_gpu(case):
         fq = _fastq(tmp, *case)
         log = _check(REAL_LIB, case[0], tmp, fq, decode=case is not BIG)
         assert "kernel launches" in log and " 0 kernel launches" not in log, log
+        assert "16-byte context records built on the device" in log, log
