@@ -70,11 +70,11 @@ def test_insert_dump_find_count(table, k, cbits, log2b):
     e.close()
 
 
-@pytest.mark.parametrize("table,k,cbits,log2b,saturate", [(E.TABLE_BMER, 24, 6, 0, False), (E.TABLE_BMER, 19, 6, 17, False), (E.TABLE_BMER, 24, 6, 0, True),
+@pytest.mark.parametrize("table,k,cbits,log2b,saturate", [(E.TABLE_BMER, 24, 6, 0, False), (E.TABLE_BMER, 19, 6, 18, False), (E.TABLE_BMER, 24, 6, 0, True),
                                                           (E.TABLE_SMER, 20, 12, 0, False)])
 def test_large_row_insert_bucket_grouped(table, k, cbits, log2b, saturate):
     """Rows of millions of k-mers (a steady-state sync): the engine's own radix partition by table bucket (fqsk_sort.cuh) + the
-    bucket-grouped ordered insert (k_bucket_flags / k_scan_u8 / k_bucket_apply); log2b = 17 crowds the buckets (3 distinct k-mers per bucket on average: stash, growth, runs
+    bucket-grouped ordered insert (k_bucket_flags / k_scan_u8 / k_bucket_apply); log2b = 18 crowds the buckets (1.5 distinct k-mers per bucket on average: stash, growth, runs
     with many distinct k-mers).  saturate: one k-mer repeated far beyond the counter's ceiling -> the row must fall back to the
     sorted-by-k-mer path (48-bit radix sort + k_locate_heads / k_apply_keys with their verifying passes).  Contents, counters and
     the PRNG position against the oracle."""
