@@ -292,6 +292,7 @@ def parity_check(make_engine, reads: JobReads, blocks, max_blocks, dev):
         t = torch.from_numpy(synth.codes_to_ascii(codes).reshape(-1)).to(dev)
         d_off = torch.arange(l - f, dtype=torch.int64, device=dev) * L
         d_len = torch.full((l - f,), L, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()      # the engine works on its own non-blocking stream: torch's copies / fills must have landed before it reads them
         sched = list(S.segments(0, l - f, S.calc_no_synchronizations(g, l - f, 1)))
         if len(sched) != int(z["segs_per_block"][g]):
             return {"ok": False, "error": f"block {g}: {len(sched)} segments here, {int(z['segs_per_block'][g])} in the reference run"}

@@ -11,6 +11,7 @@
 // There is no CPU fallback anywhere in this file.
 #include <algorithm>
 #include <atomic>
+#include <cctype>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -153,7 +154,7 @@ struct fqsk_handle {
 	uint32_t pe_pool_cap = 1u << 20, pe_pairs = 0, pe_nt = 0, seg_reads_in = 0;
 	// the sync enqueued behind its segment (sync_spec_enqueue / sync_spec_finish)
 	unsigned long long items_main[2] = {0, 0};   // items in the buckets of the b / s table as of the last look (sparse -> k_rough tests occupancy bits)
-	cudaStream_t st_side[2] = {nullptr, nullptr}; cudaEvent_t ev_side[2] = {nullptr, nullptr}, ev_fork = nullptr;   // p-mer / s-mer updates of a small sync
+	cudaStream_t st_side[3] = {nullptr, nullptr, nullptr}; cudaEvent_t ev_side[3] = {nullptr, nullptr, nullptr}, ev_fork = nullptr, ev_aux = nullptr;   // p-mer / s-mer updates of a small sync
 	bool spec_enqueued = false; SyncDev spec_Y{}; uint32_t spec_g = 0;
 	uint32_t dbg_fail_every = 0, dbg_retry_every = 0, dbg_seg = 0;   // fault injection for tests (FQSK_F_TEST_HOOKS + fqsk_params.test_hooks): see fqsk_create
 	bool dbg_retry_armed = false;
@@ -175,6 +176,8 @@ struct fqsk_handle {
 	void *h_small = nullptr;              // pinned scratch for small D2H reads
 	// profiling
 	bool prof = false;
+	bool trace_launch = false;      // FQSK_F_TRACE_LAUNCH
+	bool serial = false;            // FQSK_F_SERIAL: no side streams
 	double ph_ms[FQSK_PH_COUNT] = {0};
 	struct Ev { cudaEvent_t a, b; int ph; };
 	std::vector<Ev> evs;
@@ -203,13 +206,26 @@ int fail(fqsk_handle *h, int code, const char *fmt, ...) {
 			"%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));                             \
 	} while (0)
 #define CKR(expr) do { int r_ = (expr); if (r_ != FQSK_OK) return r_; } while (0)
-#define LAUNCHED(h) (++(h)->S.kernel_launches)
+#define LAUNCHED(h) do { ++(h)->S.kernel_launches; if ((h)->trace_launch) trace_launch_sync(__LINE__); } while (0)
+// FQSK_F_TRACE_LAUNCH: every launch is followed by a device synchronisation and a line on stderr -- the last line printed names the
+// kernel that hangs or faults (debugging aid; serialises the side streams)
+inline void trace_launch_sync(int line) {
+	fprintf(stderr, "[fqsk launch] fqsk.cu:%d ...", line); fflush(stderr);
+	cudaError_t e = cudaDeviceSynchronize();
+	fprintf(stderr, " %s\n", e == cudaSuccess ? "ok" : cudaGetErrorString(e)); fflush(stderr);
+}
 
 
 // Every kernel of the engine starts with pdl_enter() (griddepcontrol.launch_dependents + griddepcontrol.wait) and is launched with
 // programmatic stream serialization: the next kernel of the stream is scheduled while the last wave of this one is still running
 // and waits, before touching memory, until this one has completed and flushed.  Semantics are those of plain stream order; what is
 // saved is the launch latency between the ~25 small dependent kernels of a sync segment.
+// fqsk_timeline (measurement aid): while a timeline is open every launch is bracketed by two timing events on ITS stream, so that the
+// fork / join structure of a segment can be read off a run that keeps its side streams (an event between two kernels costs the
+// programmatic overlap of that pair: read the structure, not the last microsecond)
+struct TimelineEntry { const void *fn; cudaStream_t st; cudaEvent_t a, b; };
+static std::vector<TimelineEntry> *g_timeline = nullptr;
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args &&...args) {
 	cudaLaunchConfig_t cfg = {};
@@ -218,6 +234,15 @@ inline cudaError_t pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream
 	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
 	at[0].val.programmaticStreamSerializationAllowed = 1;
 	cfg.attrs = at; cfg.numAttrs = 1;
+	if (g_timeline) {
+		TimelineEntry e{(const void *) kern, st, nullptr, nullptr};
+		cudaEventCreate(&e.a); cudaEventCreate(&e.b);
+		cudaEventRecord(e.a, st);
+		cudaError_t rc = cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+		cudaEventRecord(e.b, st);
+		g_timeline->push_back(e);
+		return rc;
+	}
 	return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
@@ -799,7 +824,21 @@ EngineDev make_engine_dev(fqsk_handle *h) {
 // does not look at the device until somebody needs the outcome (seg_settle): the sync that follows a small segment is
 // enqueued behind it unseen, predicated on the device-side verdict of the pass (k_seg_tail).
 // ---------------------------------------------------------------------------------------------------------------
-int seg_setup(fqsk_handle *h) {
+// side streams of the fork / join points (created on first use): [0] compaction + early grouping, p-mer updates; [1] k_partial, s-mer
+// inserts; [2] the rough searches that start behind walk 0
+int ensure_side(fqsk_handle *h) {
+	if (h->st_side[0]) return FQSK_OK;
+	// the chain of small dependent kernels is what a segment waits for: its streams get the highest priority, the long bandwidth-bound
+	// rough search that runs next to it the lowest (measured next to an unprioritised k_rough: k_delta_build_flat 67 us instead of 13)
+	int lo = 0, hi = 0;
+	CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+	for (int i = 0; i < 3; ++i) { CK(cudaStreamCreateWithPriority(&h->st_side[i], cudaStreamNonBlocking, i == 2 ? lo : hi)); CK(cudaEventCreateWithFlags(&h->ev_side[i], cudaEventDisableTiming)); }
+	CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+	CK(cudaEventCreateWithFlags(&h->ev_aux, cudaEventDisableTiming));
+	return FQSK_OK;
+}
+
+int seg_setup(fqsk_handle *h, bool reset_done = false) {      // reset_done: k_prep has just cleared the status words (first evaluation of the segment)
 	SegCtx &C = h->ctx;
 	SegDev &S = C.S;
 	const uint32_t n = C.n;
@@ -859,13 +898,12 @@ int seg_setup(fqsk_handle *h) {
 	}
 	// one launch clears every status word the segment and a sync enqueued behind it start from: flags[8] | n_miss, n_rscript, pool_used
 	// (n_rec_dev stays: k_scan_reads wrote it) | hot-mode counters | fresh p-mer fields | s fast-path verdict | ordered-insert flags
-	CK(pdl(k_seg_reset, 1, 64, h->st, h->d_status, h->d_counters)); LAUNCHED(h);
+	if (!reset_done) { CK(pdl(k_seg_reset, 1, 64, h->st, h->d_status, h->d_counters)); LAUNCHED(h); }
+	// sorted order: (flag, dif) of compress_prefix_sorted per read, against the p-mer array as it is before this segment's sync
+	if (mode_sorted(h->P.mode)) { CK(pdl(k_sorted_dif, n, 256, h->st, C.E, S)); LAUNCHED(h); }
 	// full and front-truncated lookups touch disjoint positions: k_partial runs on a side stream next to k_lookup (not when profiling)
-	const bool fork = !h->prof && n < FORK_MAX_READS;      // side streams pay off where the chain is latency bound; large segments fill the GPU anyway
-	if (fork && !h->st_side[0]) {
-		for (int i = 0; i < 2; ++i) { CK(cudaStreamCreateWithFlags(&h->st_side[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&h->ev_side[i], cudaEventDisableTiming)); }
-		CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-	}
+	const bool fork = !h->serial && n < FORK_MAX_READS;      // side streams pay off where the chain is latency bound; large segments fill the GPU anyway
+	if (fork) CKR(ensure_side(h));
 	cudaStream_t st_pt = fork ? h->st_side[1] : h->st;
 	if (fork) { CK(cudaEventRecord(h->ev_fork, h->st)); CK(cudaStreamWaitEvent(st_pt, h->ev_fork, 0)); }
 	{ Phase ph(h, FQSK_PH_LOOKUP); CK(pdl(k_lookup, nblk(rec_bound, 256), 256, h->st, C.E, S, P)); LAUNCHED(h); }
@@ -946,52 +984,78 @@ int seg_pass(fqsk_handle *h, bool with_prefix = false) {
 	uint32_t *d_tot4 = (uint32_t *) (h->d_status + 192);                        // +192 : tot_b, tot_s, tot_p, hidden
 	unsigned long long *d_draw2 = (unsigned long long *) (h->d_status + 208);   // +208 : draws b, s
 	if (++C.pass > 64) return fail(h, FQSK_E_NO_CONVERGE, "segment did not settle");
+	// sparse tables (the first blocks of a file): k_rough tests the bucket-occupancy bit before reading a neighbour's bucket
+	EngineDev Er = E;
+	if (h->world == 1 && h->items_main[0] < (1ull << h->tb.d.B)) Er.hb.occ_read = Er.hb.occ;
+	if (h->world == 1 && h->items_main[1] < (1ull << h->ts.d.B)) Er.hs.occ_read = Er.hs.occ;
+	const uint32_t rough_grid = std::max<uint32_t>(148, std::min<uint32_t>(nblk(rec_bound, 16), 148 * 32));
+	// First pass of a small segment: the rough searches -- the longest kernel of the chain -- start right behind walk 0 on a side stream,
+	// next to the thread-local pass (delta, k_local, walk 1).  The few positions walk 1 writes again carry a marker and are searched
+	// again below; k_rough writes scripts only (k_fold writes the records), so the two passes never race on a record.
+	const bool spec_rough = !h->serial && !h->hot && n < FORK_MAX_READS && C.pass == 1 && C.redo_walk && C.redo_tail;
+	// compaction of the pushes (+ the pre-verdict of the early grouping) on side stream 0
+	auto enqueue_compaction = [&](cudaStream_t st_c) -> int {
+		Phase ph(h, FQSK_PH_COMPACT);
+		ScanChain sc; CKR(scan_chain(h, sc, 1));
+		CK(pdl(k_scan_u32x4, n <= 2048 ? 1u : nblk(n, SCAN_U32_CHUNK), n <= 2048 ? 256 : 1024, st_c, n, h->cnt_b.as<uint32_t>(), h->off_b[0].as<uint32_t>(), h->cnt_s.as<uint32_t>(), h->off_s[0].as<uint32_t>(),
+		                                     h->cnt_p.as<uint32_t>(), h->off_p.as<uint32_t>(), h->hidden.as<uint32_t>(), (uint32_t *) nullptr, d_tot4, (uint32_t *) nullptr, sc));
+		LAUNCHED(h);
+		CK(pdl(k_compact2, n, 64, st_c, S, P, h->off_b[0].as<uint32_t>(), h->off_s[0].as<uint32_t>(), h->off_p.as<uint32_t>(),
+		                               h->row_b[0].as<unsigned long long>(), h->row_s[0].as<unsigned long long>(), h->row_p.as<unsigned long long>(),
+		                               h->rt_b[0].as<uint32_t>(), h->rt_s[0].as<uint32_t>()));
+		LAUNCHED(h);
+		if (with_prefix) { CK(pdl(k_pre_verdict, 1, 32, st_c, (const int *) h->d_flags, (const uint32_t *) d_tot4, SYNC_INDEXED_MAX, h->d_syncin)); LAUNCHED(h); }
+		return FQSK_OK;
+	};
+	// grouping half of the b-mer sync (find-or-create per distinct k-mer, ranks, draw flags and their scan) behind the compaction, on the
+	// same side stream: it runs while k_rough / k_fold work on the records.  Predicated on the walk-level verdict; if the pass then fails
+	// to settle, the claimed slots are released again (sync_end: k_sync_unclaim).  Needs the segment's delta table (seg_build_delta).
+	auto enqueue_grouping = [&](cudaStream_t st_c) -> int {
+		const uint32_t bound_b = (uint32_t) (2 * C.dna_bytes_actual + 2);
+		CKR(indexed_setup(h, S.delta_b, bound_b, h->d_syncin, true, h->spec_Y));
+		h->spec_g = nblk(bound_b, 256);
+		CKR(indexed_head(h, h->tb, h->spec_Y, h->row_b[0].as<unsigned long long>(), h->rt_b[0].as<uint32_t>(), h->spec_g, false, st_c));
+		CKR(indexed_scan(h, h->tb, h->spec_Y, bound_b, st_c));
+		return FQSK_OK;
+	};
+	if (spec_rough) {
+		// Walk 1 only re-walks the reads whose thread-local answers differ and almost never changes a push; when it does, flags[2] fails
+		// the pass and everything here is done again.  So all three consumers of walk 0 start behind it: the rough searches (side stream
+		// 2), the compaction + early grouping (side stream 0) and the thread-local pass (this stream).
+		CKR(ensure_side(h));
+		CK(cudaEventRecord(h->ev_fork, h->st));
+		CK(cudaStreamWaitEvent(h->st_side[2], h->ev_fork, 0)); CK(cudaStreamWaitEvent(h->st_side[0], h->ev_fork, 0));
+		CK(pdl(k_rough, rough_grid, 128, h->st_side[2], Er, P, 0u)); LAUNCHED(h);
+		CK(cudaEventRecord(h->ev_side[2], h->st_side[2]));
+		CKR(enqueue_compaction(h->st_side[0]));
+	}
 	if (C.redo_walk) {
 		if (++C.it >= max_it) return fail(h, FQSK_E_NO_CONVERGE, "segment did not reach its fixed point in %u iterations", max_it);
 		if (C.pass > 1) CK(cudaMemsetAsync(h->d_flags + 2, 0, sizeof(int), h->st));     // first pass: still clear from k_seg_reset
 		CKR(seg_build_delta(h));
+		if (spec_rough && with_prefix) {
+			CK(cudaEventRecord(h->ev_aux, h->st)); CK(cudaStreamWaitEvent(h->st_side[0], h->ev_aux, 0));      // the delta table is built
+			CKR(enqueue_grouping(h->st_side[0]));
+		}
 		{ Phase ph(h, FQSK_PH_LOCAL); CK(pdl(k_local, std::min<uint32_t>(nblk(std::max<uint32_t>(h->miss_cap, 1), 128), 148 * 16), 128, h->st, E, S, P, 1)); LAUNCHED(h); }
 		{ Phase ph(h, FQSK_PH_WALK); CK(pdl(k_walk, nblk((uint64_t) n * 32, 128), 128, h->st, E, S, P, C.it)); LAUNCHED(h); ++h->S.n_replays; }
 	}
 	if (C.redo_tail) {
 		// The compaction of the pushes (rows of the sync) and the rough searches + merges (records) only meet again at the verdict:
 		// the two small compaction kernels run on a side stream next to k_rough / k_fold.  Profiling keeps one stream.
-		const bool fork = !h->prof && n < FORK_MAX_READS;
-		if (fork && !h->st_side[0]) {
-			for (int i = 0; i < 2; ++i) { CK(cudaStreamCreateWithFlags(&h->st_side[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&h->ev_side[i], cudaEventDisableTiming)); }
-			CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-		}
+		const bool fork = !h->serial && n < FORK_MAX_READS;
+		if (fork) CKR(ensure_side(h));
 		cudaStream_t st_c = fork ? h->st_side[0] : h->st;
 		if (C.pass > 1) CK(cudaMemsetAsync(h->d_u32 + 1, 0, 4, h->st));      // rough scripts are rebuilt (first pass: still clear from k_seg_reset)
-		if (fork) { CK(cudaEventRecord(h->ev_fork, h->st)); CK(cudaStreamWaitEvent(st_c, h->ev_fork, 0)); }
-		{
-			Phase ph(h, FQSK_PH_COMPACT);
-			ScanChain sc; CKR(scan_chain(h, sc, 1));
-			CK(pdl(k_scan_u32x4, n <= 2048 ? 1u : nblk(n, SCAN_U32_CHUNK), n <= 2048 ? 256 : 1024, st_c, n, h->cnt_b.as<uint32_t>(), h->off_b[0].as<uint32_t>(), h->cnt_s.as<uint32_t>(), h->off_s[0].as<uint32_t>(),
-			                                     h->cnt_p.as<uint32_t>(), h->off_p.as<uint32_t>(), h->hidden.as<uint32_t>(), (uint32_t *) nullptr, d_tot4, (uint32_t *) nullptr, sc));
-			LAUNCHED(h);
-			CK(pdl(k_compact2, n, 64, st_c, S, P, h->off_b[0].as<uint32_t>(), h->off_s[0].as<uint32_t>(), h->off_p.as<uint32_t>(),
-			                               h->row_b[0].as<unsigned long long>(), h->row_s[0].as<unsigned long long>(), h->row_p.as<unsigned long long>(),
-			                               h->rt_b[0].as<uint32_t>(), h->rt_s[0].as<uint32_t>()));
-			LAUNCHED(h);
-		}
-		if (with_prefix) {
-			// grouping half of the b-mer sync (find-or-create per distinct k-mer, ranks, draw flags and their scan) right behind the
-			// compaction, on the same side stream: it runs while k_rough / k_fold work on the records.  Predicated on the walk-level
-			// verdict; if the merges then fail to settle, the claimed slots are released again (sync_end: k_sync_unclaim).
-			SyncIn *in = h->d_syncin;
-			const uint32_t bound_b = (uint32_t) (2 * C.dna_bytes_actual + 2);
-			CK(pdl(k_pre_verdict, 1, 32, st_c, (const int *) h->d_flags, (const uint32_t *) d_tot4, SYNC_INDEXED_MAX, in)); LAUNCHED(h);
-			CKR(indexed_setup(h, S.delta_b, bound_b, in, true, h->spec_Y));
-			h->spec_g = nblk(bound_b, 256);
-			CKR(indexed_head(h, h->tb, h->spec_Y, h->row_b[0].as<unsigned long long>(), h->rt_b[0].as<uint32_t>(), h->spec_g, false, st_c));
-			CKR(indexed_scan(h, h->tb, h->spec_Y, bound_b, st_c));
+		if (!spec_rough) {
+			if (fork) { CK(cudaEventRecord(h->ev_fork, h->st)); CK(cudaStreamWaitEvent(st_c, h->ev_fork, 0)); }
+			CKR(enqueue_compaction(st_c));
+			if (with_prefix) CKR(enqueue_grouping(st_c));
 		}
 		if (fork) CK(cudaEventRecord(h->ev_side[0], st_c));
-		{ Phase ph(h, FQSK_PH_ROUGH); EngineDev Er = E;      // sparse tables (the first blocks of a file): k_rough tests the bucket-occupancy bit before reading a neighbour's bucket
-			if (h->world == 1 && h->items_main[0] < (1ull << h->tb.d.B)) Er.hb.occ_read = Er.hb.occ;
-			if (h->world == 1 && h->items_main[1] < (1ull << h->ts.d.B)) Er.hs.occ_read = Er.hs.occ;
-			CK(pdl(k_rough, std::max<uint32_t>(148, std::min<uint32_t>(nblk(rec_bound, 16), 148 * 32)), 128, h->st, Er, P)); LAUNCHED(h); }
+		{ Phase ph(h, FQSK_PH_ROUGH);
+			if (spec_rough) CK(cudaStreamWaitEvent(h->st, h->ev_side[2], 0));      // join; then only the positions walk 1 wrote
+			CK(pdl(k_rough, rough_grid, 128, h->st, Er, P, spec_rough ? 1u : 0u)); LAUNCHED(h); }
 		{ Phase ph(h, FQSK_PH_FOLD); CK(pdl(k_fold, nblk((uint64_t) n * 32, 128), 128, h->st, E, S, P, 0)); LAUNCHED(h); }
 	}
 	{
@@ -1000,7 +1064,7 @@ int seg_pass(fqsk_handle *h, bool with_prefix = false) {
 		CK(pdl(k_scan_draws, n <= 2048 ? 1u : nblk(n, SCAN_U32_CHUNK), n <= 2048 ? 256 : 1024, h->st, n, P.rdraws_b, h->doff_b.as<unsigned long long>(), P.rdraws_s, h->doff_s.as<unsigned long long>(), d_draw2, h->d_flags, sc)); LAUNCHED(h);   // + clears flags[0], flags[7]
 		CK(pdl(k_fold, nblk((uint64_t) n * 32, 128), 128, h->st, E, S, P, 1)); LAUNCHED(h);
 	}
-	if (C.redo_tail && !h->prof && n < FORK_MAX_READS) CK(cudaStreamWaitEvent(h->st, h->ev_side[0], 0));      // join: the rows are compacted
+	if (C.redo_tail && !h->serial && n < FORK_MAX_READS) CK(cudaStreamWaitEvent(h->st, h->ev_side[0], 0));      // join: the rows are compacted
 	return FQSK_OK;
 }
 
@@ -1207,7 +1271,7 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 	S.pk = h->pk.as<unsigned long long>();
 	{
 		Phase ph(h, FQSK_PH_PREP);
-		CK(pdl(k_prep, nblk((uint64_t) n * 32, 128), 128, h->st, S, first, h->P.bmer_len, (uint32_t) mode_sorted(h->P.mode))); LAUNCHED(h);
+		CK(pdl(k_prep, nblk((uint64_t) n * 32, 128), 128, h->st, S, first, h->P.bmer_len, (uint32_t) mode_sorted(h->P.mode), h->d_status, h->d_counters)); LAUNCHED(h);      // + the segment's status words cleared
 		if (n > SCAN_CHAIN_MAX * SCAN_READS_CHUNK) return fail(h, FQSK_E_INVAL, "more than %u reads in one segment", SCAN_CHAIN_MAX * SCAN_READS_CHUNK);
 		ScanChain sc; CKR(scan_chain(h, sc));
 		CK(pdl(k_scan_reads, n <= 1024 ? 1u : nblk(n, SCAN_READS_CHUNK), n <= 1024 ? 256 : 1024, h->st, S, h->rec_off.as<unsigned long long>(), h->sl_prefix.as<U64x4>(), (SegTotals *) (h->d_status + 64), h->d_u32 + 3, sc)); LAUNCHED(h);
@@ -1219,7 +1283,7 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 	if (h->rreq_cap < rec_bound / 8) h->rreq_cap = rec_bound / 8 + 1024;
 	// draw windows: the merges of the segment and, for a sync enqueued unseen, the ordered inserts of its b-mers
 	CKR(stream_ensure(h, h->rng[ST_B], (1u << 16) + (dna_bytes_actual <= SPEC_MAX_BYTES ? 2 * dna_bytes_actual : 0))); CKR(stream_ensure(h, h->rng[ST_S], 1u << 12));
-	CKR(seg_setup(h));
+	CKR(seg_setup(h, true));
 	if (h->delta_filtered) ++h->S.n_filtered_segments;
 	const bool prefix = h->world == 1 && h->fast_ok[0] && dna_bytes_actual <= SPEC_MAX_BYTES;     // the sync of this segment will be enqueued unseen
 	CKR(seg_pass(h, prefix));
@@ -1318,6 +1382,8 @@ int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
 	h->P = *p;
 	h->world = world; h->rank = p->rank;
 	h->prof = (p->flags & FQSK_F_PROFILE) != 0;
+	h->trace_launch = (p->flags & FQSK_F_TRACE_LAUNCH) != 0;
+	h->serial = h->prof || h->trace_launch || (p->flags & FQSK_F_SERIAL) != 0;      // phase brackets measure what they say on one stream
 	// Fault injection (tests only; needs FQSK_F_TEST_HOOKS in the parameters, nothing is read from the environment): every N-th
 	// segment has its first-pass verdict forced to "not settled" after the early grouping has run (exercises k_sync_unclaim + the
 	// plain sync), resp. is evaluated a second time from scratch as after a capacity overflow (exercises the release of claimed
@@ -1325,8 +1391,10 @@ int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
 	if (p->flags & FQSK_F_TEST_HOOKS) { h->dbg_fail_every = p->test_hooks & 0xFFFFu; h->dbg_retry_every = p->test_hooks >> 16; }
 	if (p->flags & FQSK_F_TRACE_ALLOC) g_trace_alloc.store(true);
 	int rc = [&]() -> int {
-		CK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
-		CK(cudaStreamCreateWithFlags(&h->st_mt, cudaStreamNonBlocking));
+		int prio_lo = 0, prio_hi = 0;
+		CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+		CK(cudaStreamCreateWithPriority(&h->st, cudaStreamNonBlocking, prio_hi));         // see ensure_side
+		CK(cudaStreamCreateWithPriority(&h->st_mt, cudaStreamNonBlocking, prio_lo));      // the mt19937 generator works ahead: never in the way
 		CK(cudaMalloc(&h->d_status, 512)); CK(cudaMemset(h->d_status, 0, 512));
 		h->d_flags = (int *) h->d_status;                       // +0   : 8 ints
 		h->d_u32 = (uint32_t *) (h->d_status + 32);              // +32  : 8 counters
@@ -1414,8 +1482,9 @@ void fqsk_destroy(fqsk_handle *h) {
 	if (h->h_stage2) cudaFreeHost(h->h_stage2);
 	for (int i = 0; i < 2; ++i) { if (h->h_meta[i]) cudaFreeHost(h->h_meta[i]); if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]); }
 	if (h->ev_recs) cudaEventDestroy(h->ev_recs);
-	for (int i = 0; i < 2; ++i) { if (h->st_side[i]) { cudaStreamSynchronize(h->st_side[i]); cudaStreamDestroy(h->st_side[i]); } if (h->ev_side[i]) cudaEventDestroy(h->ev_side[i]); }
+	for (int i = 0; i < 3; ++i) { if (h->st_side[i]) { cudaStreamSynchronize(h->st_side[i]); cudaStreamDestroy(h->st_side[i]); } if (h->ev_side[i]) cudaEventDestroy(h->ev_side[i]); }
 	if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+	if (h->ev_aux) cudaEventDestroy(h->ev_aux);
 	if (h->st_copy) { cudaStreamSynchronize(h->st_copy); cudaStreamDestroy(h->st_copy); }
 	if (h->h_small) cudaFreeHost(h->h_small);
 	for (auto &e : h->evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -1639,11 +1708,8 @@ static int sync_spec_enqueue(fqsk_handle *h) {
 	// The three table updates are independent (p-mer array, s-mer table, b-mer table; separate status words): the p-mer and
 	// s-mer kernels run on two side streams next to the b-mer chain and join before the look.  With the phase brackets on
 	// (profiling) everything stays on the engine's stream so that the brackets measure what they say.
-	const bool fork = !h->prof;
-	if (fork && !h->st_side[0]) {
-		for (int i = 0; i < 2; ++i) { CK(cudaStreamCreateWithFlags(&h->st_side[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&h->ev_side[i], cudaEventDisableTiming)); }
-		CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-	}
+	const bool fork = !h->serial;
+	if (fork) CKR(ensure_side(h));
 	cudaStream_t st_p = fork ? h->st_side[0] : h->st, st_s = fork ? h->st_side[1] : h->st;
 	CK(h->q4.ensure(row_reserve(h, bound_s) + 4));
 	if (fork) { CK(cudaEventRecord(h->ev_fork, h->st)); CK(cudaStreamWaitEvent(st_p, h->ev_fork, 0)); CK(cudaStreamWaitEvent(st_s, h->ev_fork, 0)); }
@@ -1740,11 +1806,8 @@ static int sync_end(fqsk_handle *h) {
 		if (!applied) {
 			// The three tables are independent (see sync_spec_enqueue): p-mer and s-mer updates run on side streams next to the ordered
 			// b-mer insert, which is a chain of sort / locate / apply launches with host looks in between.  Joined before the last look.
-			const bool fork = !h->prof && h->fast_ok[0] && h->pend_s;
-			if (fork && !h->st_side[0]) {
-				for (int i = 0; i < 2; ++i) { CK(cudaStreamCreateWithFlags(&h->st_side[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&h->ev_side[i], cudaEventDisableTiming)); }
-				CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-			}
+			const bool fork = !h->serial && h->fast_ok[0] && h->pend_s;
+			if (fork) CKR(ensure_side(h));
 			cudaStream_t st_p = fork ? h->st_side[0] : h->st, st_s = fork ? h->st_side[1] : h->st;
 			// p-mers (dna.cpp:2401-2418): order-independent saturating increments; the fresh-field count is read with the next look
 			CK(cudaMemsetAsync(h->d_counters + 4, 0, 8, h->st));
@@ -2251,6 +2314,38 @@ int fqsk_timer_end(fqsk_handle *h, double *ms) {
 	float f = 0;
 	CK(cudaEventElapsedTime(&f, h->t0, h->t1));
 	*ms = f;
+	return FQSK_OK;
+}
+
+// on != 0: start collecting; on == 0: synchronise the device and print one line per launch since the start (kernel, stream, begin and
+// end in microseconds after the first launch) to stderr
+int fqsk_timeline(fqsk_handle *h, int on) {
+	if (!h) return FQSK_E_INVAL;
+	CK(cudaSetDevice(h->P.device));
+	static std::vector<TimelineEntry> store;
+	if (on) { CK(cudaDeviceSynchronize()); store.clear(); g_timeline = &store; return FQSK_OK; }
+	g_timeline = nullptr;
+	CK(cudaDeviceSynchronize());
+	std::vector<cudaStream_t> streams;
+	for (auto &e : store) {
+		float a = 0, b = 0;
+		cudaError_t ra = cudaEventElapsedTime(&a, store[0].a, e.a), rb = cudaEventElapsedTime(&b, store[0].a, e.b);
+		if (ra != cudaSuccess || rb != cudaSuccess) { fprintf(stderr, "[fqsk timeline] cudaEventElapsedTime: %s / %s\n", cudaGetErrorString(ra), cudaGetErrorString(rb)); cudaGetLastError(); }
+		size_t si = 0;
+		while (si < streams.size() && streams[si] != e.st) ++si;
+		if (si == streams.size()) streams.push_back(e.st);
+		const char *name = "?";
+		cudaFuncGetName(&name, e.fn);
+		char shortname[48]; size_t q = 0;
+		const char *k = strstr(name, "k_");      // mangled: ...<length>k_name<E or I>...
+		size_t len = 40;
+		if (k && k > name && isdigit((unsigned char) k[-1])) { const char *d = k; while (d > name && isdigit((unsigned char) d[-1])) --d; len = (size_t) atoi(d); }
+		for (const char *c = k ? k : name; *c && q < len && q + 1 < sizeof shortname; ++c) shortname[q++] = *c;
+		shortname[q] = 0;
+		fprintf(stderr, "[fqsk timeline] %-22s stream %zu  %9.1f %9.1f  (%.1f us)\n", shortname, si, 1e3 * a, 1e3 * b, 1e3 * (b - a));
+	}
+	for (auto &e : store) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+	store.clear();
 	return FQSK_OK;
 }
 

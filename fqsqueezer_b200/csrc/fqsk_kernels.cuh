@@ -157,7 +157,18 @@ __device__ __forceinline__ uint32_t dna_code(uint8_t ch) {  // dna.cpp:18-23
 	return ch == 'A' ? 0u : ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : 4u;
 }
 
-__global__ void __launch_bounds__(128) k_prep(SegDev S, uint32_t first_len_bytes, uint32_t b, uint32_t sorted) { pdl_enter();   // one warp per read
+// status words at their start-of-segment values (layout: fqsk_create): k_prep does this for the first evaluation of a segment, k_seg_reset for
+// a retry.  n_rec_dev (word 11) and the totals at +64 stay: k_scan_reads writes them.
+__device__ __forceinline__ void seg_reset_words(uint8_t *status, unsigned long long *counters, uint32_t t) {
+	uint32_t *w = reinterpret_cast<uint32_t *>(status);
+	if (t < 11) w[t] = 0;                                  // +0 flags[8], +32 n_miss, n_rscript, pool_used
+	if (t >= 12 && t < 16) w[t] = 0;                       // +48 hot-mode event counts / draws
+	if (t == 16) w[224 / 4] = 0;                           // s-mer fast-path verdict
+	if (t >= 32 && t < 40) w[304 / 4 + (t - 32)] = 0;      // flags of the ordered insert
+	if (t == 40) counters[4] = 0;                          // fresh p-mer fields
+}
+__global__ void __launch_bounds__(128) k_prep(SegDev S, uint32_t first_len_bytes, uint32_t b, uint32_t sorted, uint8_t *status, unsigned long long *counters) { pdl_enter();   // one warp per read
+	if (status && blockIdx.x == 0 && threadIdx.x < 64) seg_reset_words(status, counters, threadIdx.x);
 	uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (r >= S.n_reads) return;
 	const uint8_t *p = S.dna + S.off[r];

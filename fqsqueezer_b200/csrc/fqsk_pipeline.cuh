@@ -467,6 +467,83 @@ __global__ void k_hot_eval(EngineDev E, SegDev S, PipeDev P, const unsigned long
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// k_sorted_dif: compress_prefix_sorted's (flag, dif) of every read that goes through CompressSorted (dna.cpp:589-605):
+//   flag = 4 when the p-mer prefix equals the previous read's, else the prefix's field in the p-mer array;
+//   dif  = how many p-mers strictly between the two prefixes hold that same field value.
+// The reference counts with a linear scan over up to 4^p fields; here one CTA per read counts 16 fields per word, 4 words per load.
+// (In a sorted file the ranges of consecutive reads are disjoint: over a whole input the array is read about once.)
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t siv_word_count_eq(uint32_t w, uint32_t flag) {      // fields of the word equal to flag
+	const uint32_t x = w ^ (flag * 0x55555555u);
+	return __popc(~(x | (x >> 1)) & 0x55555555u);
+}
+__global__ void __launch_bounds__(256) k_sorted_dif(EngineDev E, SegDev S) { pdl_enter();
+	const uint32_t r = blockIdx.x, t = threadIdx.x;
+	if (r >= S.n_reads) return;
+	const bool sorted = item_sorted(S, E.sorted, r);
+	if (S.dup[r] || !sorted) { if (t == 0) { S.sorted_flag[r] = 0; S.sorted_dif[r] = 0; } return; }
+	const uint8_t *p = S.dna + S.off[r];
+	unsigned long long cur_dir = 0;
+	for (uint32_t i = 0; i < E.p; ++i) cur_dir |= (unsigned long long) sym_at(true, E, p, i) << (62 - 2 * i);
+	unsigned long long prev_dir; bool prev_valid;
+	const uint32_t back = S.iflags ? 3u : 1u;      // the previous read coded by CompressSorted: paired end -> the first mate of the previous pair
+	if (r < back) { prev_dir = S.carry->pprev_dir; prev_valid = S.carry->pprev_valid != 0; }
+	else {
+		const uint8_t *q = S.dna + S.off[r - back];
+		prev_dir = 0;
+		for (uint32_t i = 0; i < E.p; ++i) { uint32_t sy = dna_code(q[i]); if (sy == 4) sy = 3; prev_dir |= (unsigned long long) sy << (62 - 2 * i); }
+		prev_valid = true;
+	}
+	const uint64_t cur_al = cur_dir >> (64 - 2 * E.p);
+	const uint64_t prev_al = prev_valid ? prev_dir >> (64 - 2 * E.p) : 0;
+	const uint32_t flag = cur_dir == prev_dir ? 4u : siv_test(E.siv, cur_al);
+	unsigned long long cnt = 0;
+	const uint64_t lo = prev_al + 1, hi = cur_al;      // fields [lo, hi)
+	if (flag < 4 && lo < hi) {
+		const uint32_t *w = E.siv.w;                   // sorted order runs on unsharded engines only
+		const uint64_t w0 = lo >> 4, w1 = (hi - 1) >> 4;      // first and last word touched
+		auto masked = [&](uint64_t wd) {               // fields of word wd inside [lo, hi) that equal flag
+			const uint32_t a = wd == w0 ? (uint32_t) (lo & 15) : 0u, b = wd == w1 ? (uint32_t) ((hi - 1) & 15) + 1u : 16u;      // fields [a, b) of this word
+			const uint32_t x = __ldg(w + wd) ^ (flag * 0x55555555u);
+			uint32_t z = ~(x | (x >> 1)) & 0x55555555u;
+			z &= (b == 16 ? 0xFFFFFFFFu : ((1u << (2 * b)) - 1u)) & ~((1u << (2 * a)) - 1u);
+			return (uint32_t) __popc(z);
+		};
+		if (w1 - w0 < 8) { if (t <= w1 - w0) cnt = masked(w0 + t); }
+		else {
+			if (t == 0) cnt += masked(w0);
+			if (t == 1) cnt += masked(w1);
+			// whole words (w0, w1): a head up to the next 16-byte boundary, uint4 loads, a tail
+			const uint64_t a0 = w0 + 1, a1 = w1;       // [a0, a1)
+			const uint64_t v0 = (a0 + 3) & ~3ull, v1 = a1 & ~3ull;
+			if (v0 >= v1) { for (uint64_t wd = a0 + t; wd < a1; wd += 256) cnt += siv_word_count_eq(__ldg(w + wd), flag); }
+			else {
+				if (a0 + t < v0) cnt += siv_word_count_eq(__ldg(w + a0 + t), flag);
+				if (v1 + t < a1) cnt += siv_word_count_eq(__ldg(w + v1 + t), flag);
+				const uint4 *w4 = reinterpret_cast<const uint4 *>(w);
+				uint64_t q = (v0 >> 2) + t;
+				const uint64_t q1 = v1 >> 2;
+				for (; q + 256 < q1; q += 512) {
+					const uint4 x = __ldg(w4 + q), y = __ldg(w4 + q + 256);
+					cnt += siv_word_count_eq(x.x, flag) + siv_word_count_eq(x.y, flag) + siv_word_count_eq(x.z, flag) + siv_word_count_eq(x.w, flag)
+					     + siv_word_count_eq(y.x, flag) + siv_word_count_eq(y.y, flag) + siv_word_count_eq(y.z, flag) + siv_word_count_eq(y.w, flag);
+				}
+				for (; q < q1; q += 256) { const uint4 x = __ldg(w4 + q); cnt += siv_word_count_eq(x.x, flag) + siv_word_count_eq(x.y, flag) + siv_word_count_eq(x.z, flag) + siv_word_count_eq(x.w, flag); }
+			}
+		}
+	}
+	__shared__ unsigned long long part[8];
+	for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+	if ((t & 31) == 0) part[t >> 5] = cnt;
+	__syncthreads();
+	if (t == 0) {
+		unsigned long long tot = 0;
+		for (int q = 0; q < 8; ++q) tot += part[q];
+		S.sorted_flag[r] = flag; S.sorted_dif[r] = tot;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // k_walk: one WARP per read, "speculative chunks with commit-prefix".
 // The corrected registers of the reference are the registers of a CORRECTED READ: the original symbols with the patches
 // made by repair_kmers_existing / repair_kmers_missing (dna.cpp:363-365, 442-446); a bmer_unc hit (dna.cpp:697-705) drops
@@ -499,7 +576,6 @@ __global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P, 
 	__syncwarp();
 	if (lane == 0) P.dirty[r] = 0;
 	const bool sorted = item_sorted(S, E.sorted, r);      // this read goes through CompressSorted (dna.cpp:1716-1754)
-	if (S.dup[r] || (E.sorted && !sorted)) { if (lane == 0 && E.sorted) { S.sorted_flag[r] = 0; S.sorted_dif[r] = 0; } }
 	if (S.dup[r]) { if (lane == 0) { S.cnt_b[r] = S.cnt_s[r] = S.cnt_p[r] = S.hidden[r] = 0; } return; }
 	__shared__ uint8_t ringC_all[4][64], ringU_all[4][64];
 	uint8_t *ringC = ringC_all[threadIdx.x >> 5], *ringU = ringU_all[threadIdx.x >> 5];
@@ -530,28 +606,12 @@ __global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P, 
 		for (int o = 16; o; o >>= 1) { uint32_t y = __shfl_xor_sync(0xffffffffu, npos, o); npos = npos > y ? npos : y; }
 		if (!sorted && npos && !seeded) cor_pos = npos - 1;
 	}
-	if (sorted) {
+	if (sorted) {      // flag / dif of compress_prefix_sorted come from k_sorted_dif; here only the two p-mer pushes of the prefix (dna.cpp:655-660)
 		if (lane == 0) {
-			unsigned long long cur_dir = 0;
+			unsigned long long cur_dir = 0, cur_rc = 0;
 			for (uint32_t i = 0; i < E.p; ++i) cur_dir |= (unsigned long long) sym_at(sorted, E, p, i) << (62 - 2 * i);
-			unsigned long long cur_rc = 0;
 			for (uint32_t i = 0; i < E.p; ++i) cur_rc |= (unsigned long long) (3 - sym_at(sorted, E, p, E.p - 1 - i)) << (62 - 2 * i);
-			unsigned long long prev_dir; bool prev_valid;
-			const uint32_t back = S.iflags ? 3u : 1u;      // the previous read coded by CompressSorted: paired end -> the first mate of the previous pair
-			if (r < back) { prev_dir = S.carry->pprev_dir; prev_valid = S.carry->pprev_valid != 0; }
-			else {
-				const uint8_t *q = S.dna + S.off[r - back];
-				prev_dir = 0;
-				for (uint32_t i = 0; i < E.p; ++i) { uint32_t sy = dna_code(q[i]); if (sy == 4) sy = 3; prev_dir |= (unsigned long long) sy << (62 - 2 * i); }
-				prev_valid = true;
-			}
-			uint64_t cur_al = cur_dir >> (64 - 2 * E.p);
-			uint64_t prev_al = prev_valid ? prev_dir >> (64 - 2 * E.p) : 0;
-			uint32_t flag; unsigned long long dif = 0;
-			if (cur_dir == prev_dir) flag = 4; else flag = siv_test(E.siv, cur_al);
-			if (flag < 4) for (uint64_t i = prev_al + 1; i < cur_al; ++i) dif += siv_test(E.siv, i) == flag;
-			S.sorted_flag[r] = flag; S.sorted_dif[r] = dif;
-			out_p[0] = cur_al; out_p[1] = cur_rc >> (64 - 2 * E.p);
+			out_p[0] = cur_dir >> (64 - 2 * E.p); out_p[1] = cur_rc >> (64 - 2 * E.p);
 		}
 		np = 2;
 	}
@@ -703,7 +763,7 @@ __global__ void __launch_bounds__(128) k_walk(EngineDev E, SegDev S, PipeDev P, 
 			o.pos = i + bias; o.counts[0] = c[0]; o.counts[1] = c[1]; o.counts[2] = c[2]; o.counts[3] = c[3];
 			o.cor_pos = lane_cor; o.level = (uint8_t) lev; o.rough = 0; o.pad = 0;
 			P.recs[g] = o;
-			P.rkind[g] = rk;
+			P.rkind[g] = check ? (uint8_t) (rk | 0x80u) : rk;      // 0x80: written by a re-walk (the rough searches that started after walk 0 redo it)
 			if (rk) {
 				// register before the symbol became known: rebuild from the (possibly reverted) corrected view
 				KReg bq = ev_revert ? ring_breg(ringU, i, cb) : ring_breg(ringC, i, cb);
@@ -822,7 +882,10 @@ __global__ void __launch_bounds__(256) k_delta_build_flat(SegDev S, PipeDev P, u
 // k_rough: one warp per request.  find_counts_rough_{s,b} (dna.cpp:257-330): 4(k-1) single-substitution neighbours across the
 // lanes, non-empty ones appended in trial order to a merge script; find_counts_rough_p (dna.cpp:229-254) is a plain sum.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 8) k_rough(EngineDev E, PipeDev P) { pdl_enter();   // E.hb / E.hs carry occ_read while the tables are sparse (HtDev::occ)
+// only_marked = 0: every flagged position.  The first pass of a small segment starts this right behind walk 0, on a side stream next
+// to the thread-local pass (delta, k_local, walk 1); positions the re-walk wrote carry the 0x80 marker and are done again afterwards
+// with only_marked = 1 (their first scripts stay behind unreferenced).  Nothing here writes records: k_fold does.
+__global__ void __launch_bounds__(128, 8) k_rough(EngineDev E, PipeDev P, uint32_t only_marked) { pdl_enter();   // E.hb / E.hs carry occ_read while the tables are sparse (HtDev::occ)
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t n_rec = *P.n_rec_dev;
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
@@ -832,6 +895,8 @@ __global__ void __launch_bounds__(128, 8) k_rough(EngineDev E, PipeDev P) { pdl_
 	for (uint32_t g0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * RCHUNK; g0 < n_rec; g0 += warps * RCHUNK) {
 		// each warp owns RCHUNK consecutive positions: find the flagged ones, then work on them one at a time with all lanes
 		uint32_t mine = (lane < RCHUNK && g0 + lane < n_rec) ? P.rkind[g0 + lane] : 0;
+		mine = only_marked ? ((mine & 0x80u) ? (mine & 0x7Fu) : 0u) : (mine & 0x7Fu);
+		if (mine < 2 || mine > 4) mine = 0;      // (a value torn by a concurrent re-walk is redone by the marked pass)
 		KReg myreg{0, 0};
 		if (mine) myreg = P.rreg[g0 + lane];       // all registers of the chunk in one round trip, handed out by shuffles below
 		unsigned todo = __ballot_sync(0xffffffffu, mine != 0);
@@ -852,13 +917,19 @@ __global__ void __launch_bounds__(128, 8) k_rough(EngineDev E, PipeDev P) { pdl_
 				}
 				for (int qq = 0; qq < 4; ++qq) for (int o = 16; o; o >>= 1) c[qq] += __shfl_xor_sync(0xffffffffu, c[qq], o);
 				if (lane == 0) {
-					P.rslot[g] = 0xFFFFFFFFu;
-					if (any4(c)) {
-						fqsk_base_rec *rec = P.recs + g;
-						rec->counts[0] = c[0]; rec->counts[1] = c[1]; rec->counts[2] = c[2]; rec->counts[3] = c[3];
-						rec->level = FQSK_LEVEL_PMER; rec->rough = 1;
+					uint32_t slot = 0xFFFFFFFFu;
+					if (any4(c)) {      // at most 3 * 4 (p - 1) per symbol: fits the script's u16 entries
+						slot = atomicAdd(P.n_rscript, 1u);
+						if (slot >= P.rscript_cap) { P.flags[4] = 1; slot = 0xFFFFFFFFu; }
+						else {
+							sc.rec = g; sc.kind = 4; sc.valid = 1; sc.n = 1; sc.overflow = 0xFFFFFFFFu; sc.draws = 0;
+							for (int qq = 0; qq < 4; ++qq) { sc.c2[qq] = 0; sc.e[0][qq] = (uint16_t) c[qq]; }
+							P.rscripts[slot] = sc;
+						}
 					}
+					P.rslot[g] = slot;
 				}
+				__syncwarp();
 				continue;
 			}
 			const HtDev &t = kind == 2 ? E.hb : E.hs;
@@ -920,23 +991,35 @@ __global__ void __launch_bounds__(128, 8) k_rough(EngineDev E, PipeDev P) { pdl_
 // saturates); after a scan over reads pass 1 evaluates with the true offsets, writes the final counts and re-reports the
 // totals so the host can confirm the offsets.
 // ------------------------------------------------------------------------------------------------------------------
-__device__ void fold_script(const EngineDev &E, const PipeDev &P, const Script &sc, DrawCursor &dc, bool write) {
+// write: 0 = count the draws only, 1 = write the record, 2 = write it if the merge consumed no draw (its result then does not depend
+// on where the read's scripts sit in the mt19937 stream: final without the scan over reads)
+__device__ void fold_script(const EngineDev &E, const PipeDev &P, const Script &sc, DrawCursor &dc, int write) {
 	const bool is_b = (sc.kind == 0 || sc.kind == 2);
 	const bool rough = sc.kind >= 2;
 	const CIncP ci = is_b ? E.cib : E.cis;
 	uint32_t c[4] = {0, 0, 0, 0};
+	if (sc.kind == 4) {      // find_counts_rough_p (dna.cpp:229-254): a plain sum, already formed by k_rough
+		if (!write) return;
+		for (int q = 0; q < 4; ++q) c[q] = sc.e[0][q];
+		fqsk_base_rec *rec = P.recs + sc.rec;
+		rec->counts[0] = c[0]; rec->counts[1] = c[1]; rec->counts[2] = c[2]; rec->counts[3] = c[3];
+		rec->level = FQSK_LEVEL_PMER; rec->rough = 1;
+		return;
+	}
 	for (uint32_t n = 0; n < sc.n; ++n) {
 		uint32_t loc[4];
 		if (n < SCRIPT_INLINE) { for (int q = 0; q < 4; ++q) loc[q] = sc.e[n][q]; }
 		else { const unsigned short *d = P.pool + 4ull * (sc.overflow + (n - SCRIPT_INLINE)); for (int q = 0; q < 4; ++q) loc[q] = d[q]; }
 		for (int q = 0; q < 4; ++q) if (rough || loc[q]) c[q] = ci_plus(ci, c[q], loc[q], dc);
 	}
-	if (!write) return;
+	if (!write || (write == 2 && dc.used)) return;
 	fqsk_base_rec *rec = P.recs + sc.rec;
 	uint32_t lev = rec->level;
 	if (rough) { if (!any4(c)) return; lev = FQSK_LEVEL_PMER; rec->rough = 1; }
-	else if (sc.kind == 0) {
+	else if (sc.kind == 0) {      // a found front-truncated b lookup is level bmer (never inside a repair window: the register is not full), or mixed;
+		                          // written afresh, so that a merge evaluated again with other draws cannot inherit `mixed` from its first evaluation
 		int sat = (c[0] == ci.top) + (c[1] == ci.top) + (c[2] == ci.top) + (c[3] == ci.top);
+		lev = FQSK_LEVEL_BMER;
 		if (sat > 1) { for (int q = 0; q < 4; ++q) c[q] += sc.c2[q]; lev = FQSK_LEVEL_MIXED; }
 	}
 	rec->counts[0] = c[0]; rec->counts[1] = c[1]; rec->counts[2] = c[2]; rec->counts[3] = c[3];
@@ -958,6 +1041,7 @@ __device__ __forceinline__ uint32_t warp_excl_sum(uint32_t v, uint32_t lane, uin
 __global__ void __launch_bounds__(128) k_fold(EngineDev E, SegDev S, PipeDev P, int pass) { pdl_enter();
 	const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (r >= S.n_reads) return;
+	if (pass && P.rdraws_b[r] == 0 && P.rdraws_s[r] == 0) return;      // no draws in this read: pass 0 has written its records
 	uint32_t used[2] = {0, 0};          // draws of the scripts visited so far, per stream (b, s), as assumed by the offsets
 	uint32_t now[2] = {0, 0};           // ... as consumed by this pass
 	bool mismatch = false;
@@ -973,7 +1057,7 @@ __global__ void __launch_bounds__(128) k_fold(EngineDev E, SegDev S, PipeDev P, 
 			DrawCursor dc;
 			dc.ring = E.draws[st]; dc.mask = E.dmask[st]; dc.pos0 = E.dpos[st]; dc.avail = E.avail[st]; dc.used = 0; dc.overflow = E.flags + 0;
 			dc.base = base[st] + used[st] + (st ? ex1 : ex0);
-			fold_script(E, P, *sp, dc, pass != 0);
+			fold_script(E, P, *sp, dc, pass != 0 ? 1 : 2);
 			cnt = dc.used;
 			if (pass == 0) sp->draws = cnt;
 			else if (cnt != stored) { sp->draws = cnt; mismatch = true; }
@@ -996,9 +1080,9 @@ __global__ void __launch_bounds__(128) k_fold(EngineDev E, SegDev S, PipeDev P, 
 		for (uint32_t gs = g0; gs < g1; gs += 256) {
 			uint32_t kk[8], slot[8];
 #pragma unroll
-			for (int c = 0; c < 8; ++c) { const uint32_t g = gs + c * 32 + lane; kk[c] = g < g1 ? P.rkind[g] : 0; }
+			for (int c = 0; c < 8; ++c) { const uint32_t g = gs + c * 32 + lane; kk[c] = g < g1 ? (P.rkind[g] & 0x7Fu) : 0; }
 #pragma unroll
-			for (int c = 0; c < 8; ++c) { const uint32_t g = gs + c * 32 + lane; slot[c] = (kk[c] == 2 || kk[c] == 3) ? P.rslot[g] : 0xFFFFFFFFu; }
+			for (int c = 0; c < 8; ++c) { const uint32_t g = gs + c * 32 + lane; slot[c] = kk[c] >= 2 ? P.rslot[g] : 0xFFFFFFFFu; }
 #pragma unroll
 			for (int c = 0; c < 8; ++c) {
 				if (gs + c * 32 >= g1) break;
@@ -1297,15 +1381,9 @@ __global__ void __launch_bounds__(160) k_publish(const uint32_t *status, const u
 	__syncthreads();
 	if (t == 0) { *reinterpret_cast<volatile unsigned long long *>(seq) = want; __threadfence_system(); }
 }
-// status words at their start-of-segment values (layout: fqsk_create)
+// a segment evaluated again (retry): the reset k_prep did for the first evaluation
 __global__ void k_seg_reset(uint8_t *status, unsigned long long *counters) { pdl_enter();
-	const uint32_t t = threadIdx.x;
-	uint32_t *w = reinterpret_cast<uint32_t *>(status);
-	if (t < 11) w[t] = 0;                                  // +0 flags[8], +32 n_miss, n_rscript, pool_used
-	if (t >= 12 && t < 16) w[t] = 0;                       // +48 hot-mode event counts / draws
-	if (t == 16) w[224 / 4] = 0;                           // s-mer fast-path verdict
-	if (t >= 32 && t < 40) w[304 / 4 + (t - 32)] = 0;      // flags of the ordered insert
-	if (t == 40) counters[4] = 0;                          // fresh p-mer fields
+	seg_reset_words(status, counters, threadIdx.x);
 }
 // Verdict of a segment's first pass for the sync that is enqueued behind it without a host look + the state the next segment
 // inherits (read_prev, dna.cpp:1550-1551; in sorted order pmer_can_prev, dna.cpp:655), in one launch.  The pass settled when no

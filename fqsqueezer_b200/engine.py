@@ -19,7 +19,7 @@ READ_DESC_DTYPE = np.dtype([("dna_off", "<u8"), ("dna_len", "<u4"), ("flags", "<
 CTX_REC_DTYPE = np.dtype([("a", "<u8"), ("b", "<u8")])      # fqsk_ctx_rec (include/fqsk_ctx.h)
 TABLE_SIV, TABLE_SMER, TABLE_BMER, TABLE_PAIR = 0, 1, 2, 3
 MODE_SE_ORIGINAL, MODE_SE_SORTED, MODE_PE_ORIGINAL, MODE_PE_SORTED = 0, 1, 2, 3
-F_PROFILE, F_TRACE_ALLOC, F_TEST_HOOKS = 1, 2, 4
+F_PROFILE, F_TRACE_ALLOC, F_TEST_HOOKS, F_TRACE_LAUNCH, F_SERIAL = 1, 2, 4, 8, 16
 PHASES = ["prep", "lookup", "partial", "walk", "compact", "sort", "local", "rough", "fold", "sync_locate", "sync_apply", "sync_siv", "mt"]
 
 
@@ -47,7 +47,7 @@ class _Stats(C.Structure):
 
 EXPORTS = ["fqsk_create", "fqsk_destroy", "fqsk_last_error", "fqsk_block_start", "fqsk_segment", "fqsk_segment_device",
            "fqsk_device_recs", "fqsk_recs_checksum", "fqsk_sorted_prefix", "fqsk_pair_info", "fqsk_submit", "fqsk_submit_ctx", "fqsk_collect", "fqsk_sync", "fqsk_dump", "fqsk_stats_get", "fqsk_profile", "fqsk_ht_insert", "fqsk_ht_find",
-           "fqsk_ht_count", "fqsk_timer_begin", "fqsk_timer_end", "fqsk_siv_increment", "fqsk_siv_test", "fqsk_siv_counts", "fqsk_siv_test_shorter", "fqsk_mt_stream", "fqsk_host_alloc", "fqsk_host_free",
+           "fqsk_ht_count", "fqsk_timeline", "fqsk_timer_begin", "fqsk_timer_end", "fqsk_siv_increment", "fqsk_siv_test", "fqsk_siv_counts", "fqsk_siv_test_shorter", "fqsk_mt_stream", "fqsk_host_alloc", "fqsk_host_free",
            "fqsk_shard_export", "fqsk_shard_attach", "fqsk_sync_route", "fqsk_sync_apply", "fqsk_sync_finish"]
 
 _lib = None
@@ -82,6 +82,7 @@ def load_library():
     lib.fqsk_stats_get.argtypes = [vp, C.POINTER(_Stats)]
     lib.fqsk_profile.argtypes = [vp, C.POINTER(C.c_double), C.c_uint32]
     lib.fqsk_timer_begin.argtypes = [vp]
+    lib.fqsk_timeline.argtypes = [vp, C.c_int]
     lib.fqsk_timer_end.argtypes = [vp, C.POINTER(C.c_double)]
     lib.fqsk_ht_insert.argtypes = [vp, C.c_int, vp, C.c_uint64]
     lib.fqsk_ht_find.argtypes = [vp, C.c_int, vp, vp, vp, C.c_uint64, vp]
@@ -134,13 +135,13 @@ def _ptr(a):
 
 class KmerEngine:
     def __init__(self, p, s, b, prefix_len, mode=MODE_SE_ORIGINAL, device=0, expected_kmers=0, bmer_log2_buckets=0,
-                 smer_log2_buckets=0, profile=False, max_iterations=0, reserve_reads=0, reserve_bytes=0, test_fail_every=0, test_retry_every=0):
+                 smer_log2_buckets=0, profile=False, max_iterations=0, reserve_reads=0, reserve_bytes=0, test_fail_every=0, test_retry_every=0, flags=0):
         self.lib = load_library()
         hooks = (test_fail_every & 0xFFFF) | ((test_retry_every & 0xFFFF) << 16)      # fault injection of the recovery paths (tests only)
         prm = _Params(abi_version=1, pmer_len=p, smer_len=s, bmer_len=b, prefix_len=prefix_len, smer_counter_bits=12,
                       bmer_counter_bits=6, mode=mode, n_workers=1, device=device, bmer_log2_buckets=bmer_log2_buckets,
                       smer_log2_buckets=smer_log2_buckets, expected_kmers=expected_kmers, world_size=1, rank=0,
-                      max_iterations=max_iterations, flags=(F_PROFILE if profile else 0) | (F_TEST_HOOKS if hooks else 0), reserve_reads=reserve_reads, reserve_bytes=reserve_bytes,
+                      max_iterations=max_iterations, flags=(F_PROFILE if profile else 0) | (F_TEST_HOOKS if hooks else 0) | flags, reserve_reads=reserve_reads, reserve_bytes=reserve_bytes,
                       test_hooks=hooks)
         h = C.c_void_p()
         rc = self.lib.fqsk_create(C.byref(prm), C.byref(h))
@@ -305,6 +306,10 @@ class KmerEngine:
         d = {f: getattr(st, f) for f, _ in _Stats._fields_ if f != "draws"}
         d.update(draws_b=st.draws[0], draws_s=st.draws[1], draws_lb=st.draws[2], draws_ls=st.draws[3])
         return d
+
+    def timeline(self, on: bool):
+        """Measurement aid: bracket every launch with events on its own stream (on) / print the collected launches to stderr (off)."""
+        self._ck(self.lib.fqsk_timeline(self.h, 1 if on else 0))
 
     def timer_begin(self):
         self._ck(self.lib.fqsk_timer_begin(self.h))

@@ -106,6 +106,7 @@ public:
 		P.mode = mode;
 		P.n_workers = 1; P.world_size = 1; P.rank = 0;
 		P.device = getenv("FQSK_DEVICE") ? atoi(getenv("FQSK_DEVICE")) : 0;
+		if (const char *e = getenv("FQSK_FLAGS")) P.flags = (uint32_t) strtoul(e, nullptr, 0) & (FQSK_F_PROFILE | FQSK_F_TRACE_ALLOC | FQSK_F_TRACE_LAUNCH | FQSK_F_SERIAL);      // debugging aids of the library
 		uint64_t expect = genome_mbp * 3000000ull;                               // genomic + error k-mers; the tables grow when half full
 		if (const char *e = getenv("FQSK_EXPECTED_KMERS")) expect = strtoull(e, nullptr, 10);
 		P.expected_kmers = expect < (1ull << 22) ? (1ull << 22) : expect > (1ull << 30) ? (1ull << 30) : expect;

@@ -70,6 +70,8 @@ typedef struct fqsk_params {
 
 #define FQSK_F_PROFILE 1u        /* record CUDA-event timings per internal phase (fqsk_profile) */
 #define FQSK_F_TRACE_ALLOC 2u    /* print every device allocation of the segment scratch to stderr */
+#define FQSK_F_TRACE_LAUNCH 8u   /* debugging: synchronise the device after every kernel launch and print its source line to stderr */
+#define FQSK_F_SERIAL 16u        /* debugging / measurement: every kernel on the engine's one stream (no fork / join over side streams) */
 #define FQSK_F_TEST_HOOKS 4u     /* honour fqsk_params.test_hooks (tests of the recovery paths; never set by a host) */
 
 typedef struct fqsk_handle fqsk_handle;
@@ -128,7 +130,9 @@ int fqsk_segment(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const 
                  fqsk_base_rec *recs, uint64_t rec_cap, uint64_t *n_recs, uint8_t *dup, uint64_t *rec_off);
 
 /* Same, with the reads already resident in HBM (bench `value`): d_dna is a device pointer to the concatenated DNA bytes
- * (ASCII), d_off/d_len device arrays (u64 / u32); records stay on the device in the handle (fqsk_device_recs). */
+ * (ASCII), d_off/d_len device arrays (u64 / u32); records stay on the device in the handle (fqsk_device_recs).  The engine reads the
+ * three arrays on its own non-blocking stream: whatever filled them (a copy, a kernel on another stream) must have completed before
+ * the call, and they must stay untouched until the fqsk_sync that follows. */
 int fqsk_segment_device(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes, const uint64_t *d_off, const uint32_t *d_len,
                         uint32_t n_reads, uint64_t *n_recs);
 int fqsk_device_recs(fqsk_handle *h, const fqsk_base_rec **d_recs, uint64_t *n_recs);
@@ -216,6 +220,9 @@ int fqsk_stats_get(fqsk_handle *h, fqsk_stats *out);
 int fqsk_profile(fqsk_handle *h, double *ms, uint32_t n);   /* n <= FQSK_PH_COUNT */
 /* CUDA-event stopwatch on the engine's own stream (bench.py times steps on the device with it): begin records an event,
  * end records a second one, waits for it and returns the elapsed device milliseconds. */
+/* Measurement aid: on != 0 starts bracketing every kernel launch of the process with timing events on its own stream; on == 0 prints one
+ * line per launch (kernel, stream, begin / end in microseconds) to stderr.  Replaces nothing in the reference. */
+int fqsk_timeline(fqsk_handle *h, int on);
 int fqsk_timer_begin(fqsk_handle *h);
 int fqsk_timer_end(fqsk_handle *h, double *ms);
 
