@@ -120,11 +120,12 @@ struct fqsk_handle {
 	bool unsettled = false;                  // its first pass is enqueued, nobody has looked at the outcome yet
 	bool miss_fold_dirty = true; void *miss_fold_seen = nullptr;
 	uint32_t world = 1, rank = 0;            // reference worker `rank` of `world` (one per GPU)
+	unsigned long long sync_seq = 0;      // number of the sharded sync under way (posted to the owners' inbox headers)
 	unsigned long long *inbox = nullptr; uint64_t inbox_cap = 0;      // this rank's inbox: header + [3 tables][world sources][inbox_cap]
 	unsigned long long *peer_inbox[8] = {nullptr};
 	void *peer_ptrs[8][8] = {{nullptr}};     // IPC mappings to close
 	uint32_t attached = 0;                   // bit i: rank i's shard is mapped
-	DevBuf route_keys, route_keys2, route_sorted, route_hist, route_perm;
+	DevBuf route_keys, route_keys2, route_sorted, route_hist, route_perm, route_chunks;
 	uint64_t sync_fresh = 0, sync_updates = 0; bool routed = false, applied = false;
 	uint64_t siv_local_filled = 0;           // non-zero fields of THIS rank's p-mer shard (S.siv_no_filled is the global statistic)
 	DevBuf scan_vals; uint32_t scan_epoch2 = 0;
@@ -1305,6 +1306,20 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 // The reference's thread-local tables draw from cinc_lb / cinc_ls on every insert whose counter is above thr, looked up or
 // not (ht_kmer.h:433-436 via dna.cpp:826, 837, 862, 872).  When a sync row shows such a k-mer and the segment was not
 // evaluated in hot mode, the ordered evaluator runs in accounting mode to advance the stream position exactly.
+// first half of hot_account without the look: counts, per stream, the pushes of the segment that would draw from the thread-local
+// incrementer (rank >= thr + 1) into d_u32[4 + stream]; the caller has cleared the counters and reads them with its next look
+int hot_rank(fqsk_handle *h, int stream) {
+	DeltaDev D = stream ? h->seg_delta_s : h->seg_delta_b;
+	if (!D.keys || h->delta_filtered) return FQSK_OK;      // (a filtered delta exists on unsharded engines only; they account through hot_seen)
+	const size_t slots = (size_t) D.mask + 1;
+	DevBuf *hr = stream ? h->hr_s : h->hr_b;
+	for (int q = 0; q < 3; ++q) CK(hr[q].ensure(slots * 4));
+	D.rank_at = hr[0].as<uint32_t>(); D.prev_at = hr[1].as<uint32_t>(); D.cnt_at = hr[2].as<uint32_t>();
+	PipeDev P{};
+	P.ev_n = h->d_u32 + 4; P.ev_cap = 0; P.hot_draws = h->d_u32 + 6; P.flags = (int *) (h->d_status + 448);      // count only: ev_cap 0 stores nothing; its overflow flag goes to spare words of the status block
+	CK(pdl(k_delta_rank, 148 * 8, 256, h->st, D, P, (uint32_t) stream)); LAUNCHED(h);
+	return FQSK_OK;
+}
 int hot_account(fqsk_handle *h, int stream) {
 	if (h->delta_filtered) {    // the accounting needs every push of the segment: build the unfiltered delta (rare: repeats inside one segment)
 		CKR(seg_build_delta(h, true));
@@ -1473,7 +1488,7 @@ void fqsk_destroy(fqsk_handle *h) {
 	                  &h->y_tslot, &h->y_c0, &h->y_m, &h->y_draw, &h->y_j, &h->y_final, &h->y_flag_at, &h->y_own, &h->y_lead, &h->y_rank, &h->y_flag, &h->y_doff,
 	                  &h->idx_k, &h->idx_t, &h->idx_rt, &h->miss_fold, &h->hr_b[0], &h->hr_b[1], &h->hr_b[2], &h->hr_s[0], &h->hr_s[1], &h->hr_s[2],
 	                  &h->evk[0], &h->evk[1], &h->evv[0], &h->evv[1], &h->evk_s[0], &h->evk_s[1], &h->evv_s[0], &h->evv_s[1], &h->ctxrec[0], &h->ctxrec[1], &h->scan_part, &h->scan8_part, &h->rdx_hist, &h->rdx_k, &h->rdx_v, &h->scan_vals, &h->recs_alt, &h->dfilter, &h->pk,
-	                  &h->route_keys, &h->route_keys2, &h->route_sorted, &h->route_hist, &h->route_perm,
+	                  &h->route_keys, &h->route_keys2, &h->route_sorted, &h->route_hist, &h->route_perm, &h->route_chunks,
 	                  &h->pe_uk, &h->pe_uv, &h->pe_uc, &h->pe_tk, &h->pe_tv, &h->pe_q, &h->pe_sk, &h->pe_sv, &h->pe_sidx, &h->pe_t1, &h->pe_t2, &h->pe_pool, &h->pe_info, &h->it_src, &h->it_len,
 	                  &h->it_bytes, &h->it_first, &h->it_bias, &h->it_dupprev, &h->it_flags, &h->it_off32, &h->it_off64, &h->it_dna};
 
@@ -2087,17 +2102,16 @@ int fqsk_sync_route(fqsk_handle *h) {
 	CK(h->route_hist.ensure(4 * 8 * 4));
 	CK(cudaMemsetAsync(h->route_hist.p, 0, 4 * 8 * 4, h->st));
 	CK(cudaMemsetAsync(h->d_flags, 0, 8 * sizeof(int), h->st));
-	for (int t = 0; t < 3; ++t) {
-		const uint32_t n = ns[t];
-		uint32_t *hist = h->route_hist.as<uint32_t>() + 8 * t;
-		if (n) {
-			CK(h->route_keys.ensure(n)); CK(h->route_keys2.ensure(n)); CK(h->route_sorted.ensure((size_t) n * 8));
-			CK(pdl(k_owner_keys, nblk(n, 256), 256, h->st, rows[t], n, t == 0 ? 0u : 1u, 2 * h->P.pmer_len - 12, h->world, h->route_keys.as<uint8_t>(), hist)); LAUNCHED(h);
-			// one stable partition pass by owner: push order survives inside every owner group
-			CKR(rdx_scratch(h, n, false));
-			CKR((rdx_pass<3, OwnerOp>(h, h->st, rows[t], nullptr, h->route_sorted.as<unsigned long long>(), nullptr, n, OwnerOp{t == 0 ? 0u : 1u, 2 * h->P.pmer_len - 12, h->world})));
-		}
-		CK(pdl(k_route_scatter, nblk(std::max<uint32_t>(n, 8), 256), 256, h->st, h->route_sorted.as<unsigned long long>(), n, hist, I, (uint32_t) t, h->d_flags)); LAUNCHED(h);
+	{   // p / s / b rows: owner histogram per chunk, then every k-mer straight to its place in its owner's inbox (fqsk_kernels.cuh)
+		RouteRows R{};
+		uint32_t n_max = 0;
+		for (int t = 0; t < 3; ++t) { R.row[t] = rows[t]; R.n[t] = ns[t]; n_max = std::max(n_max, ns[t]); }
+		R.pshift = 2 * h->P.pmer_len - 12;
+		const uint32_t chunks = std::max<uint32_t>(nblk(n_max, ROUTE_CHUNK), 1);
+		const uint32_t chunks_max = std::max<uint32_t>(chunks, nblk((uint32_t) row_reserve(h, n_max), ROUTE_CHUNK));
+		CK(h->route_chunks.ensure((size_t) 3 * chunks_max * 8 * 4));
+		if (n_max) { CK(pdl(k_route_count, dim3(chunks, 3), 256, h->st, R, h->world, chunks_max, h->route_chunks.as<uint32_t>())); LAUNCHED(h); }
+		CK(pdl(k_route_move, dim3(chunks, 3), 256, h->st, R, chunks_max, (const uint32_t *) h->route_chunks.as<uint32_t>(), I, h->d_flags)); LAUNCHED(h);
 	}
 	if (h->pair.keys) {
 		// paired end: the distinct (key, value) pairs of the segment with summed weights, routed by (fmix64(key) >> 48) % world as three
@@ -2130,9 +2144,9 @@ int fqsk_sync_route(fqsk_handle *h) {
 		}
 		h->pe_nt = 0;
 	}
-	int fl[8];
-	CKR(read_flags(h, fl, 8));      // also drains the stream: the peer stores are complete when the caller enters its barrier
-	if (fl[4]) return fail(h, FQSK_E_CAPACITY, "an exchange row is longer than the inbox slot (%llu k-mers): create the engines with a larger reserve_bytes", (unsigned long long) h->inbox_cap);
+	// rows [rank][*] are on their way: post this sync's number at every owner (no host look: a row too long for its slot -- flags[4] -- is
+	// reported by the first look of fqsk_sync_apply, and the owner sees the oversized length itself)
+	CK(pdl(k_post_seq, 1, 32, h->st, I, ++h->sync_seq)); LAUNCHED(h);
 	h->routed = true;
 	return FQSK_OK;
 }
@@ -2141,11 +2155,26 @@ int fqsk_sync_apply(fqsk_handle *h, uint64_t *fresh, uint64_t *updates) {
 	if (!h) return FQSK_E_INVAL;
 	CK(cudaSetDevice(h->P.device));
 	if (h->world <= 1 || !h->routed) return fail(h, FQSK_E_INVAL, "fqsk_sync_apply needs fqsk_sync_route on a sharded engine first");
-	// posted slot lengths (every source wrote its own entry before the barrier)
+	// The thread-local PRNG streams of THIS worker advance with its own pushes above thr, whoever owns them (ht_kmer.h:433-436 via
+	// dna.cpp:826, 837, 862, 872): the ranks of the segment's pushes are counted now (no host look), the event counts come back with
+	// the look below, and only a segment that has such pushes (low-complexity reads) pays for the ordered evaluation.
+	const bool account = h->pending && h->seg_reads && !h->hot;
+	if (account) { CK(cudaMemsetAsync(h->d_u32 + 4, 0, 4 * 4, h->st)); CKR(hot_rank(h, 1)); CKR(hot_rank(h, 0)); }
+	// every source has posted this sync's number once its rows were in our inbox (k_post_seq): wait for them on the device, then read
+	// the posted slot lengths, the route's flags and the event counts with ONE look
+	int *d_err = (int *) (h->d_status + 480);      // spare word of the status block (cleared at create; set means the group is lost anyway)
+	CK(pdl(k_wait_seq, 1, 32, h->st, (const unsigned long long *) h->inbox, h->world, h->sync_seq, d_err)); LAUNCHED(h);
 	unsigned long long cnt[48];
+	uint32_t *hs0 = (uint32_t *) h->h_small;
 	CK(cudaMemcpyAsync(cnt, h->inbox, sizeof cnt, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaMemcpyAsync(hs0, h->d_status, 512, cudaMemcpyDeviceToHost, h->st));
 	CK(cudaStreamSynchronize(h->st));
+	if (hs0[480 / 4]) return fail(h, FQSK_E_CUDA, "sharded sync: a peer did not post its rows within the time limit");
+	if (((int *) hs0)[4]) return fail(h, FQSK_E_CAPACITY, "an exchange row is longer than the inbox slot (%llu k-mers): create the engines with a larger reserve_bytes", (unsigned long long) h->inbox_cap);
+	const uint32_t hot_en[2] = {hs0[8 + 4], hs0[8 + 5]};      // [0] b-stream events, [1] s-stream events
 	uint64_t tot[3] = {0, 0, 0};
+	for (int t = 0; t < 6; ++t) for (uint32_t i = 0; i < h->world; ++i)
+		if (cnt[t * 8 + i] > h->inbox_cap) return fail(h, FQSK_E_CAPACITY, "rank %u posted an exchange row longer than the inbox slot: create the engines with a larger reserve_bytes", i);
 	for (int t = 0; t < 3; ++t) for (uint32_t i = 0; i < h->world; ++i) tot[t] += cnt[t * 8 + i];
 	for (int t = 0; t < 3; ++t) if (tot[t] >= 0x80000000ull) return fail(h, FQSK_E_INVAL, "more than 2^31 k-mers in one sync row");
 	// rows [*][rank] in source order: one contiguous row per table
@@ -2160,9 +2189,7 @@ int fqsk_sync_apply(fqsk_handle *h, uint64_t *fresh, uint64_t *updates) {
 			at += c;
 		}
 	}
-	// the thread-local PRNG streams of THIS worker advance with its own pushes, whoever owns them (ht_kmer.h:433-436 via
-	// dna.cpp:826, 837, 862, 872): account for them from the segment's delta before it is dropped
-	if (h->pending && h->seg_reads && !h->hot) { CKR(hot_account(h, 1)); CKR(hot_account(h, 0)); }
+	if (account) { if (hot_en[1]) CKR(hot_account(h, 1)); if (hot_en[0]) CKR(hot_account(h, 0)); }      // rare: redoes the ranks, then evaluates in order
 	h->hot_seen[0] = h->hot_seen[1] = false;
 	CK(cudaMemsetAsync(h->d_counters + 4, 0, 8, h->st));
 	if (tot[0]) {

@@ -704,6 +704,106 @@ __global__ void k_route_scatter(const unsigned long long *sorted, uint32_t n, co
 	inbox_slot(I.base[o], I.cap, I.world, table, I.rank)[i - off[o]] = sorted[i];
 }
 
+// The three k-mer rows of a sync in two launches (blockIdx.y = table 0 p / 1 s / 2 b): k_route_count leaves the owner histogram of
+// every chunk of 2048 pending k-mers, k_route_move gives every k-mer its place inside its owner's group -- chunks in order, a warp's
+// 256 consecutive k-mers in order, lanes in order: push order survives (the owners insert in source order, dna.cpp:2421-2446) --
+// and stores it straight into slot [table][src = this rank] of the owner's inbox (NVLink peer stores); the CTA of chunk 0 posts the
+// slot lengths.  Replaces k_owner_keys + three radix launches + k_route_scatter per table.
+static const uint32_t ROUTE_CHUNK = 2048;
+struct RouteRows { const unsigned long long *row[3]; uint32_t n[3]; uint32_t pshift; };
+__device__ __forceinline__ uint32_t route_owner(uint32_t table, unsigned long long x, uint32_t pshift, uint32_t world) {
+	return table == 0 ? (uint32_t) ((x >> pshift) % world) : ht_owner(world, x);
+}
+__global__ void __launch_bounds__(256) k_route_count(RouteRows R, uint32_t world, uint32_t chunks_max, uint32_t *chunk_hist) { pdl_enter();      // chunk_hist[table][chunk][8]
+	const uint32_t table = blockIdx.y, c = blockIdx.x, n = R.n[table];
+	if ((unsigned long long) c * ROUTE_CHUNK >= n) return;
+	__shared__ uint32_t sh[8];
+	if (threadIdx.x < 8) sh[threadIdx.x] = 0;
+	__syncthreads();
+	const unsigned long long *row = R.row[table];
+	uint32_t mine[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	for (uint32_t q = 0; q < ROUTE_CHUNK / 256; ++q) {
+		const uint32_t i = c * ROUTE_CHUNK + q * 256 + threadIdx.x;
+		if (i < n) { const uint32_t o = route_owner(table, row[i], R.pshift, world); for (uint32_t k = 0; k < 8; ++k) mine[k] += (o == k); }
+	}
+	for (uint32_t k = 0; k < 8; ++k) {
+		uint32_t v = mine[k];
+		for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+		if ((threadIdx.x & 31) == 0 && v) atomicAdd(sh + k, v);
+	}
+	__syncthreads();
+	if (threadIdx.x < 8) chunk_hist[((size_t) table * chunks_max + c) * 8 + threadIdx.x] = sh[threadIdx.x];
+}
+__global__ void __launch_bounds__(256) k_route_move(RouteRows R, uint32_t chunks_max, const uint32_t *chunk_hist, InboxDev I, int *flags) { pdl_enter();
+	const uint32_t table = blockIdx.y, c = blockIdx.x, n = R.n[table], t = threadIdx.x, lane = t & 31, w = t >> 5;
+	const uint32_t n_chunks = (n + ROUTE_CHUNK - 1) / ROUTE_CHUNK;
+	__shared__ uint32_t base[8], total[8], wcnt[8][8];      // group position of the chunk's first k-mer per owner; row totals; per-warp counts
+	if (c > 0 && c >= n_chunks) return;
+	if (t < 8) {
+		uint32_t b = 0, tot = 0;
+		for (uint32_t q = 0; q < n_chunks; ++q) { const uint32_t v = chunk_hist[((size_t) table * chunks_max + q) * 8 + t]; if (q < c) b += v; tot += v; }
+		base[t] = b; total[t] = tot;
+	}
+	for (uint32_t q = t; q < 64; q += 256) (&wcnt[0][0])[q] = 0;
+	__syncthreads();
+	if (c == 0 && t < I.world) {
+		if (total[t] > I.cap) flags[4] = 1;
+		I.base[t][table * 8 + I.rank] = total[t];      // posted length of slot [table][src = rank] at owner t
+	}
+	if ((unsigned long long) c * ROUTE_CHUNK >= n) return;
+	const unsigned long long *row = R.row[table];
+	// a warp owns 256 consecutive k-mers of the chunk and visits them in 8 rounds of 32
+	unsigned long long x[8]; uint32_t own[8];
+	const uint32_t wbase = c * ROUTE_CHUNK + w * 256;
+#pragma unroll
+	for (uint32_t r = 0; r < 8; ++r) {
+		const uint32_t i = wbase + r * 32 + lane;
+		x[r] = i < n ? row[i] : 0ull;
+		own[r] = i < n ? route_owner(table, x[r], R.pshift, I.world) : 0xFFu;
+	}
+	uint32_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+	for (uint32_t r = 0; r < 8; ++r) for (uint32_t k = 0; k < 8; ++k) cnt[k] += __popc(__ballot_sync(0xffffffffu, own[r] == k));
+	if (lane < 8) { uint32_t v = 0; for (uint32_t k = 0; k < 8; ++k) if (k == lane) v = cnt[k]; wcnt[w][lane] = v; }
+	__syncthreads();
+	uint32_t pos[8];      // running position inside the owner's group for this warp
+	for (uint32_t k = 0; k < 8; ++k) { uint32_t b = base[k]; for (uint32_t q = 0; q < w; ++q) b += wcnt[q][k]; pos[k] = b; }
+#pragma unroll
+	for (uint32_t r = 0; r < 8; ++r) {
+		const uint32_t o = own[r];
+		uint32_t my = 0;
+		for (uint32_t k = 0; k < 8; ++k) {
+			const unsigned m = __ballot_sync(0xffffffffu, o == k);
+			if (o == k) my = pos[k] + __popc(m & ((1u << lane) - 1u));
+			pos[k] += __popc(m);
+		}
+		if (o < 8 && total[o] <= I.cap) inbox_slot(I.base[o], I.cap, I.world, table, I.rank)[my] = x[r];
+	}
+}
+
+// First barrier of the reference's sync (application.cpp:645-648: "every worker has filled its X_to_add rows") without the host: each
+// source posts the number of the sync into word [48 + src] of every owner's inbox header once its rows have landed there (a kernel of
+// its own behind the scatter kernels: their peer stores are complete when it starts); an owner waits for all its sources on the
+// device, in front of the copy that reads the posted lengths.  Bounded wait (~2 s): a rank that died must not hang the others.
+static const uint32_t INBOX_SEQ = 48;
+__global__ void k_post_seq(InboxDev I, unsigned long long seq) { pdl_enter();
+	const uint32_t i = threadIdx.x;
+	if (i >= I.world) return;
+	__threadfence_system();
+	*reinterpret_cast<volatile unsigned long long *>(I.base[i] + INBOX_SEQ + I.rank) = seq;
+	__threadfence_system();
+}
+__global__ void k_wait_seq(const unsigned long long *inbox, uint32_t world, unsigned long long seq, int *err) { pdl_enter();
+	const uint32_t i = threadIdx.x;
+	if (i >= world) return;
+	const long long t0 = clock64();
+	while (*reinterpret_cast<const volatile unsigned long long *>(inbox + INBOX_SEQ + i) < seq) {
+		if (clock64() - t0 > 4000000000ll) { *err = 1; break; }
+		__nanosleep(200);
+	}
+	__threadfence_system();
+}
+
 // checksum of a record stream (fqsk_recs_checksum): position-dependent term per record, summed mod 2^64
 __global__ void __launch_bounds__(256) k_recs_checksum(const fqsk_base_rec *recs, unsigned long long n, unsigned long long *out) { pdl_enter();
 	unsigned long long acc = 0;

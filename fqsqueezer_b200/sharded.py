@@ -3,9 +3,9 @@
 Rank r is the reference's worker thread r (application.cpp:575-671): it codes its own slice of every reads_block with its
 own PRNG streams and thread-local tables, and it OWNS the k-mers whose routing key maps to it (dna.cpp:825, 836, 845,
 2381-2388).  Lookups read every rank's shard through NVLink peer mappings (CUDA IPC, set up once here); at a sync the
-exchange matrices X_to_add[src][dst] are written straight into the owners' inboxes by the routing kernel (peer stores), and
-torch.distributed (NCCL) carries what is left of the reference's three barriers: one barrier and one all-reduce of the global
-p-mer statistics per sync.
+exchange matrices X_to_add[src][dst] are written straight into the owners' inboxes by the routing kernel (peer stores) together
+with the number of the sync, for which the owners wait on the device; torch.distributed (NCCL) carries what is left of the reference's
+three barriers: one all-reduce of the global p-mer statistics per sync (also the barrier in front of the next segment's lookups).
 
     grp = ShardedKmerEngine(p, s, b, prefix_len, rank, world, device=local_rank)   # after dist.init_process_group
     grp.block_start(); recs, dup = grp.segment(slab, off, ln); grp.sync()
@@ -96,9 +96,8 @@ class ShardedKmerEngine(E.KmerEngine):
         """InsertKmersToHT + ClearKmersToHT of all workers (dna.cpp:2393-2488) around the reference's barriers."""
         if self.world == 1:
             return super().sync()
-        self._ck(self.lib.fqsk_sync_route(self.h))
-        self.dist.barrier()                                     # every row [src][dst] is in its owner's inbox
-        fresh, upd = C.c_uint64(0), C.c_uint64(0)
+        self._ck(self.lib.fqsk_sync_route(self.h))              # rows [rank][*] into the owners' inboxes + this sync's number posted there
+        fresh, upd = C.c_uint64(0), C.c_uint64(0)                 # (the owners wait for their sources on the device: no host barrier here)
         self._ck(self.lib.fqsk_sync_apply(self.h, C.byref(fresh), C.byref(upd)))
         # global p-mer statistics; also the second barrier: every owner has finished its inserts before anybody looks up again
         f_all, u_all = allreduce_stats(self.dist, fresh.value, upd.value)
