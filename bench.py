@@ -113,21 +113,62 @@ def codes_to_slab(codes):
 
 
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons DURING the timed region.  NVML in-process (nvidia_ml_py): a query costs microseconds and does not touch
+    the CUDA context; spawning nvidia-smi five times a second next to a job that launches 60 000 kernels a second did (fork + NVML init per sample)."""
+
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.rows = index, False, []
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+            except Exception:
+                pass
+            self.dev = None
+            if uuid:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    hnd = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    u = pynvml.nvmlDeviceGetUUID(hnd)
+                    u = u.decode() if isinstance(u, bytes) else u
+                    if uuid in u or u.replace("GPU-", "") == uuid:
+                        self.dev = hnd
+            if self.dev is None:
+                self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.dev, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.dev, n.NVML_CLOCK_SM)
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.dev)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev)
+        act = lambda bit: "Active" if (r & bit) else "Not Active"
+        return [str(sm), str(mx), "0", act(n.nvmlClocksThrottleReasonHwSlowdown), act(n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                act(n.nvmlClocksThrottleReasonSwThermalSlowdown), act(n.nvmlClocksThrottleReasonSwPowerCap)]
 
     def run(self):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                if self.nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1 if self.nvml is not None else 0.5)
 
     def summary(self):
         if not self.rows:
@@ -136,7 +177,7 @@ class ClockSampler(threading.Thread):
         mx = max(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows if len(r) > 3 + i)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.rows)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def measured_peak():
@@ -410,9 +451,13 @@ def main():
         e.block_start()
         lo, t = d_blocks[g]
         base = t.data_ptr()
-        for a, bb in sched[g]:
+        segs = sched[g]
+        for k, (a, bb) in enumerate(segs):
             n = bb - a
             e.segment_device(base + (a - lo) * L, n * L, d_off.data_ptr(), d_len.data_ptr(), n, want_n_recs=False)
+            if k + 1 < len(segs) and not sharded:      # the worker loop knows its next segment (application.cpp:617-662): its read-only preparation runs ahead
+                a2, b2 = segs[k + 1]
+                e.announce_device(base + (a2 - lo) * L, (b2 - a2) * L, d_off.data_ptr(), d_len.data_ptr(), b2 - a2)
             e.sync()
 
     # warm-up: the first W steps of the job on a throw-away engine (a fresh box starts with idle clocks and a cold driver)

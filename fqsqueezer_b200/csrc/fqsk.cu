@@ -163,6 +163,12 @@ struct fqsk_handle {
 	bool seg_extra_pass = false;             // the last segment needed more than its first pass: records were rewritten after the pass
 	// fqsk_submit / fqsk_collect: double-buffered records, copies on their own stream
 	DevBuf pk;                                       // 2-bit packed reads of the segment (k_prep)
+	// fqsk_announce_device: k_prep / k_scan_reads of the NEXT segment run on a side stream while the segment in flight is still being evaluated;
+	// their outputs (dup, n_coded, letters, rec_off, sl_prefix, packed reads, totals) therefore exist twice, a segment uses instance seg_par
+	DevBuf f_dup, f_n_coded, f_letters, f_rec_off, f_sl_prefix, f_pk;
+	int seg_par = 0;
+	struct Front { bool valid = false; const uint8_t *dna = nullptr; uint64_t bytes = 0; const unsigned long long *off = nullptr; const uint32_t *len = nullptr; uint32_t n = 0; int par = 0; } front;
+	cudaStream_t st_front = nullptr; cudaEvent_t ev_front = nullptr;
 	DevBuf dfilter; bool delta_filtered = false;     // filter bits of the segment's delta (large segments), see seg_setup
 	DevBuf recs_alt; int rec_par = 0;
 	DevBuf ctxrec[2];                                // fqsk_submit_ctx: the 16-byte context records of the segment in flight, per parity
@@ -397,6 +403,15 @@ int stream_prefetch(fqsk_handle *h, Stream &s, uint64_t ahead) {
 	if (stream_avail_of(s) * 2 < ahead) return stream_generate(h, s, s.consumed + ahead);
 	return FQSK_OK;
 }
+// The b-mer stream of a long job: late in a file the ordered inserts of one reads_block consume 5-7 M draws and ask for a window as long
+// as their row before they know how many they need.  Whole parallel launches (MT_PAR chunks side by side, 8.4 M outputs, ~0.25 ms) keep
+// at least `low_water` outputs ahead of the consumer, so that neither the one-CTA path (2 G outputs/s) nor a wait is ever on the sync's
+// critical path (measured before: every other steady-state block waited 0.8 ms for a window generated on demand).
+int stream_keep_ahead(fqsk_handle *h, Stream &s, uint64_t low_water) {
+	const uint64_t launch = (uint64_t) MT_PAR * MT_CHUNK_BLOCKS * 624;
+	while (stream_avail_of(s) < low_water && s.generated + launch - s.consumed <= s.cap) CKR(stream_generate(h, s, s.generated + launch));
+	return FQSK_OK;
+}
 inline const uint32_t *stream_ptr(const Stream &s) { return s.buf; }
 inline uint64_t stream_avail(const Stream &s) { return (s.safe > s.consumed ? s.safe : s.consumed) - s.consumed; }
 
@@ -404,11 +419,12 @@ inline uint64_t stream_avail(const Stream &s) { return (s.safe > s.consumed ? s.
 int scan_chain(fqsk_handle *h, ScanChain &C, int which = 0) {      // which = 1: a scan that may run next to another one (side stream)
 	const size_t one = (size_t) SCAN_CHAIN_MAX * 8 * 8 + (size_t) SCAN_CHAIN_MAX * 4 + 64;
 	if (!h->scan_vals.p) {
-		CK(h->scan_vals.ensure(2 * one));
+		CK(h->scan_vals.ensure(3 * one));
 		CK(cudaMemsetAsync(h->scan_vals.p, 0, h->scan_vals.cap, h->st));
 		CK(cudaStreamSynchronize(h->st));
 	}
-	C.vals = (unsigned long long *) (h->scan_vals.as<uint8_t>() + (which ? one : 0)); C.flags = (uint32_t *) (C.vals + (size_t) SCAN_CHAIN_MAX * 8); C.epoch = ++h->scan_epoch2;
+	C.vals = (unsigned long long *) (h->scan_vals.as<uint8_t>() + (size_t) which * one);      // which = 0: engine stream, 1: compaction side stream, 2: front stream
+	C.flags = (uint32_t *) (C.vals + (size_t) SCAN_CHAIN_MAX * 8); C.epoch = ++h->scan_epoch2;
 	return FQSK_OK;
 }
 int ensure_iota(fqsk_handle *h, uint32_t n) {
@@ -839,6 +855,14 @@ int ensure_side(fqsk_handle *h) {
 	return FQSK_OK;
 }
 
+// totals of k_scan_reads per prep instance: instance 0 at +64 / word 11 of the status block, instance 1 at +408 / +484 (spare words)
+inline uint32_t seg_totals_off(int par) { return par ? 408u : 64u; }
+inline uint32_t *seg_nrec_dev(fqsk_handle *h, int par) { return par ? (uint32_t *) (h->d_status + 484) : h->d_u32 + 3; }
+struct PrepBufs { DevBuf *dup, *n_coded, *letters, *rec_off, *sl_prefix, *pk; };
+inline PrepBufs prep_bufs(fqsk_handle *h, int par) {
+	return par ? PrepBufs{&h->f_dup, &h->f_n_coded, &h->f_letters, &h->f_rec_off, &h->f_sl_prefix, &h->f_pk} : PrepBufs{&h->dup, &h->n_coded, &h->letters, &h->rec_off, &h->sl_prefix, &h->pk};
+}
+
 int seg_setup(fqsk_handle *h, bool reset_done = false) {      // reset_done: k_prep has just cleared the status words (first evaluation of the segment)
 	SegCtx &C = h->ctx;
 	SegDev &S = C.S;
@@ -875,7 +899,7 @@ int seg_setup(fqsk_handle *h, bool reset_done = false) {      // reset_done: k_p
 	P.rdraws_b = h->rdraws_b.as<uint32_t>(); P.rdraws_s = h->rdraws_s.as<uint32_t>();
 	P.doff_b = h->doff_b.as<unsigned long long>(); P.doff_s = h->doff_s.as<unsigned long long>();
 	P.time_b = h->time_b.as<uint32_t>(); P.time_s = h->time_s.as<uint32_t>();
-	P.flags = h->d_flags; P.n_rec_dev = h->d_u32 + 3;
+	P.flags = h->d_flags; P.n_rec_dev = seg_nrec_dev(h, h->seg_par);
 	S.recs = P.recs;
 
 	C.E = make_engine_dev(h);
@@ -903,7 +927,9 @@ int seg_setup(fqsk_handle *h, bool reset_done = false) {      // reset_done: k_p
 	// sorted order: (flag, dif) of compress_prefix_sorted per read, against the p-mer array as it is before this segment's sync
 	if (mode_sorted(h->P.mode)) { CK(pdl(k_sorted_dif, n, 256, h->st, C.E, S)); LAUNCHED(h); }
 	// full and front-truncated lookups touch disjoint positions: k_partial runs on a side stream next to k_lookup (not when profiling)
-	const bool fork = !h->serial && n < FORK_MAX_READS;      // side streams pay off where the chain is latency bound; large segments fill the GPU anyway
+	// k_partial is bound by the latency of its dependent probes (38 % of the warps active on a 51 000-read segment), k_lookup by DRAM: next to
+	// each other at every segment size
+	const bool fork = !h->serial;
 	if (fork) CKR(ensure_side(h));
 	cudaStream_t st_pt = fork ? h->st_side[1] : h->st;
 	if (fork) { CK(cudaEventRecord(h->ev_fork, h->st)); CK(cudaStreamWaitEvent(st_pt, h->ev_fork, 0)); }
@@ -990,6 +1016,7 @@ int seg_pass(fqsk_handle *h, bool with_prefix = false) {
 	if (h->world == 1 && h->items_main[0] < (1ull << h->tb.d.B)) Er.hb.occ_read = Er.hb.occ;
 	if (h->world == 1 && h->items_main[1] < (1ull << h->ts.d.B)) Er.hs.occ_read = Er.hs.occ;
 	const uint32_t rough_grid = std::max<uint32_t>(148, std::min<uint32_t>(nblk(rec_bound, 16), 148 * 32));
+	const bool rough_deep = !Er.hb.occ_read;      // the b-mer table is past one item per bucket: (nearly) every trial reads its sector
 	// First pass of a small segment: the rough searches -- the longest kernel of the chain -- start right behind walk 0 on a side stream,
 	// next to the thread-local pass (delta, k_local, walk 1).  The few positions walk 1 writes again carry a marker and are searched
 	// again below; k_rough writes scripts only (k_fold writes the records), so the two passes never race on a record.
@@ -1005,14 +1032,16 @@ int seg_pass(fqsk_handle *h, bool with_prefix = false) {
 		                               h->row_b[0].as<unsigned long long>(), h->row_s[0].as<unsigned long long>(), h->row_p.as<unsigned long long>(),
 		                               h->rt_b[0].as<uint32_t>(), h->rt_s[0].as<uint32_t>()));
 		LAUNCHED(h);
-		if (with_prefix) { CK(pdl(k_pre_verdict, 1, 32, st_c, (const int *) h->d_flags, (const uint32_t *) d_tot4, SYNC_INDEXED_MAX, h->d_syncin)); LAUNCHED(h); }
 		return FQSK_OK;
 	};
 	// grouping half of the b-mer sync (find-or-create per distinct k-mer, ranks, draw flags and their scan) behind the compaction, on the
 	// same side stream: it runs while k_rough / k_fold work on the records.  Predicated on the walk-level verdict; if the pass then fails
 	// to settle, the claimed slots are released again (sync_end: k_sync_unclaim).  Needs the segment's delta table (seg_build_delta).
+	// Only behind the last walk of the pass: a slot claimed for a k-mer that a later walk no longer pushes could never be given back (the
+	// tables have no deletion); behind walk 1 the verdict knows whether the pushes are final.
 	auto enqueue_grouping = [&](cudaStream_t st_c) -> int {
 		const uint32_t bound_b = (uint32_t) (2 * C.dna_bytes_actual + 2);
+		CK(pdl(k_pre_verdict, 1, 32, st_c, (const int *) h->d_flags, (const uint32_t *) d_tot4, SYNC_INDEXED_MAX, h->d_syncin)); LAUNCHED(h);
 		CKR(indexed_setup(h, S.delta_b, bound_b, h->d_syncin, true, h->spec_Y));
 		h->spec_g = nblk(bound_b, 256);
 		CKR(indexed_head(h, h->tb, h->spec_Y, h->row_b[0].as<unsigned long long>(), h->rt_b[0].as<uint32_t>(), h->spec_g, false, st_c));
@@ -1022,11 +1051,11 @@ int seg_pass(fqsk_handle *h, bool with_prefix = false) {
 	if (spec_rough) {
 		// Walk 1 only re-walks the reads whose thread-local answers differ and almost never changes a push; when it does, flags[2] fails
 		// the pass and everything here is done again.  So all three consumers of walk 0 start behind it: the rough searches (side stream
-		// 2), the compaction + early grouping (side stream 0) and the thread-local pass (this stream).
+		// 2), the compaction of the pushes (side stream 0) and the thread-local pass (this stream).
 		CKR(ensure_side(h));
 		CK(cudaEventRecord(h->ev_fork, h->st));
 		CK(cudaStreamWaitEvent(h->st_side[2], h->ev_fork, 0)); CK(cudaStreamWaitEvent(h->st_side[0], h->ev_fork, 0));
-		CK(pdl(k_rough, rough_grid, 128, h->st_side[2], Er, P, 0u)); LAUNCHED(h);
+		CK(pdl(rough_deep ? k_rough<true> : k_rough<false>, rough_grid, 128, h->st_side[2], Er, P, 0u)); LAUNCHED(h);
 		CK(cudaEventRecord(h->ev_side[2], h->st_side[2]));
 		CKR(enqueue_compaction(h->st_side[0]));
 	}
@@ -1034,12 +1063,12 @@ int seg_pass(fqsk_handle *h, bool with_prefix = false) {
 		if (++C.it >= max_it) return fail(h, FQSK_E_NO_CONVERGE, "segment did not reach its fixed point in %u iterations", max_it);
 		if (C.pass > 1) CK(cudaMemsetAsync(h->d_flags + 2, 0, sizeof(int), h->st));     // first pass: still clear from k_seg_reset
 		CKR(seg_build_delta(h));
-		if (spec_rough && with_prefix) {
-			CK(cudaEventRecord(h->ev_aux, h->st)); CK(cudaStreamWaitEvent(h->st_side[0], h->ev_aux, 0));      // the delta table is built
-			CKR(enqueue_grouping(h->st_side[0]));
-		}
 		{ Phase ph(h, FQSK_PH_LOCAL); CK(pdl(k_local, std::min<uint32_t>(nblk(std::max<uint32_t>(h->miss_cap, 1), 128), 148 * 16), 128, h->st, E, S, P, 1)); LAUNCHED(h); }
 		{ Phase ph(h, FQSK_PH_WALK); CK(pdl(k_walk, nblk((uint64_t) n * 32, 128), 128, h->st, E, S, P, C.it)); LAUNCHED(h); ++h->S.n_replays; }
+		if (spec_rough && with_prefix) {      // the rows were compacted behind walk 0; the grouping waits for walk 1 (and its flags)
+			CK(cudaEventRecord(h->ev_aux, h->st)); CK(cudaStreamWaitEvent(h->st_side[0], h->ev_aux, 0));
+			CKR(enqueue_grouping(h->st_side[0]));
+		}
 	}
 	if (C.redo_tail) {
 		// The compaction of the pushes (rows of the sync) and the rough searches + merges (records) only meet again at the verdict:
@@ -1056,7 +1085,7 @@ int seg_pass(fqsk_handle *h, bool with_prefix = false) {
 		if (fork) CK(cudaEventRecord(h->ev_side[0], st_c));
 		{ Phase ph(h, FQSK_PH_ROUGH);
 			if (spec_rough) CK(cudaStreamWaitEvent(h->st, h->ev_side[2], 0));      // join; then only the positions walk 1 wrote
-			CK(pdl(k_rough, rough_grid, 128, h->st, Er, P, spec_rough ? 1u : 0u)); LAUNCHED(h); }
+			CK(pdl(rough_deep ? k_rough<true> : k_rough<false>, rough_grid, 128, h->st, Er, P, spec_rough ? 1u : 0u)); LAUNCHED(h); }
 		{ Phase ph(h, FQSK_PH_FOLD); CK(pdl(k_fold, nblk((uint64_t) n * 32, 128), 128, h->st, E, S, P, 0)); LAUNCHED(h); }
 	}
 	{
@@ -1112,7 +1141,7 @@ int seg_finish(fqsk_handle *h, bool have_look) {
 	h->cur = 0;
 	{
 		uint32_t t4[4]; memcpy(t4, hs + 192, 16);
-		SegTotals tt; memcpy(&tt, hs + 64, sizeof tt);
+		SegTotals tt; memcpy(&tt, hs + seg_totals_off(h->seg_par), sizeof tt);
 		h->pend_b = t4[0]; h->pend_s = t4[1]; h->pend_p = t4[2];
 		h->hidden_p += t4[3];
 		for (int i = 0; i < 4; ++i) h->sl_base[i] += tt.letters.v[i];
@@ -1246,7 +1275,13 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 	if (n == 0) { h->pending = true; return FQSK_OK; }
 	if (dna_bytes >= (1ull << 30)) return fail(h, FQSK_E_INVAL, "segment larger than 1 GiB of DNA");   // push times are 2 * byte offset (+1) in 32 bits
 	const size_t n1 = (size_t) std::max<uint32_t>(n, pe ? h->P.reserve_reads / 2 * 3 : h->P.reserve_reads) + 1;
-	CK(h->dup.ensure(n1)); CK(h->n_coded.ensure(n1 * 4)); CK(h->letters.ensure(n1 * 32)); CK(h->rec_off.ensure(n1 * 8)); CK(h->sl_prefix.ensure(n1 * 32));
+	// announced (fqsk_announce_device)?  Then k_prep / k_scan_reads have run, or are running, on the front stream into the other instance
+	const bool fronted = h->front.valid && !pe && h->front.dna == d_dna && h->front.bytes == dna_bytes_actual && h->front.off == d_off && h->front.len == d_len && h->front.n == n;
+	if (h->front.valid && !fronted) CK(cudaStreamSynchronize(h->st_front));      // a hint that was not followed: let it drain, its outputs are dropped
+	h->front.valid = false;
+	if (fronted) h->seg_par = h->front.par;
+	const PrepBufs PB = prep_bufs(h, h->seg_par);
+	CK(PB.dup->ensure(n1)); CK(PB.n_coded->ensure(n1 * 4)); CK(PB.letters->ensure(n1 * 32)); CK(PB.rec_off->ensure(n1 * 8)); CK(PB.sl_prefix->ensure(n1 * 32));
 	CK(h->push_b.ensure((2 * dna_bytes + 2) * 8)); CK(h->push_s.ensure((dna_bytes + 1) * 8)); CK(h->push_p.ensure((2 * dna_bytes + 2 * n1) * 8));
 	CK(h->cnt_b.ensure(n1 * 4)); CK(h->cnt_s.ensure(n1 * 4)); CK(h->cnt_p.ensure(n1 * 4)); CK(h->hidden.ensure(n1 * 4));
 	CK(h->off_b[0].ensure(n1 * 4)); CK(h->off_s[0].ensure(n1 * 4));
@@ -1262,20 +1297,23 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 	if (pe) { S.first_a = h->it_first.as<uint32_t>(); S.bias_a = h->it_bias.as<uint32_t>(); S.dup_prev = h->it_dupprev.as<uint32_t>(); S.iflags = h->it_flags.as<uint8_t>(); }
 	CK(h->prev_read.ensure_keep((size_t) dna_bytes_actual + 64, h->st));     // a read is never longer than its segment
 	S.prev_read = h->prev_read.as<uint8_t>(); S.carry = h->d_carry;
-	S.dup = h->dup.as<uint8_t>(); S.n_coded = h->n_coded.as<uint32_t>(); S.letters = h->letters.as<U64x4>();
-	S.rec_off = h->rec_off.as<unsigned long long>(); S.sl_prefix = h->sl_prefix.as<U64x4>();
+	S.dup = PB.dup->as<uint8_t>(); S.n_coded = PB.n_coded->as<uint32_t>(); S.letters = PB.letters->as<U64x4>();
+	S.rec_off = PB.rec_off->as<unsigned long long>(); S.sl_prefix = PB.sl_prefix->as<U64x4>();
 	for (int i = 0; i < 4; ++i) S.sl_base.v[i] = h->sl_base[i];
 	S.push_b = h->push_b.as<unsigned long long>(); S.push_s = h->push_s.as<unsigned long long>(); S.push_p = h->push_p.as<unsigned long long>();
 	S.cnt_b = h->cnt_b.as<uint32_t>(); S.cnt_s = h->cnt_s.as<uint32_t>(); S.cnt_p = h->cnt_p.as<uint32_t>(); S.hidden = h->hidden.as<uint32_t>();
 	S.sorted_flag = h->sflag.as<uint32_t>(); S.sorted_dif = h->sdif.as<unsigned long long>();
-	CK(h->pk.ensure((dna_bytes / 32 + 2 * n1 + 8) * 8));
-	S.pk = h->pk.as<unsigned long long>();
-	{
+	CK(PB.pk->ensure((dna_bytes / 32 + 2 * n1 + 8) * 8));
+	S.pk = PB.pk->as<unsigned long long>();
+	if (n > SCAN_CHAIN_MAX * SCAN_READS_CHUNK) return fail(h, FQSK_E_INVAL, "more than %u reads in one segment", SCAN_CHAIN_MAX * SCAN_READS_CHUNK);
+	if (fronted) CK(cudaStreamWaitEvent(h->st, h->ev_front, 0));      // prep + scan of this segment: done ahead, next to the previous segment
+	else {
 		Phase ph(h, FQSK_PH_PREP);
-		CK(pdl(k_prep, nblk((uint64_t) n * 32, 128), 128, h->st, S, first, h->P.bmer_len, (uint32_t) mode_sorted(h->P.mode), h->d_status, h->d_counters)); LAUNCHED(h);      // + the segment's status words cleared
-		if (n > SCAN_CHAIN_MAX * SCAN_READS_CHUNK) return fail(h, FQSK_E_INVAL, "more than %u reads in one segment", SCAN_CHAIN_MAX * SCAN_READS_CHUNK);
+		CK(pdl(k_prep, nblk((uint64_t) n * 32, 128), 128, h->st, S, first, h->P.bmer_len, (uint32_t) mode_sorted(h->P.mode), h->d_status, h->d_counters,
+		       (const uint8_t *) nullptr, (const unsigned long long *) nullptr, (const uint32_t *) nullptr)); LAUNCHED(h);      // + the segment's status words cleared
 		ScanChain sc; CKR(scan_chain(h, sc));
-		CK(pdl(k_scan_reads, n <= 1024 ? 1u : nblk(n, SCAN_READS_CHUNK), n <= 1024 ? 256 : 1024, h->st, S, h->rec_off.as<unsigned long long>(), h->sl_prefix.as<U64x4>(), (SegTotals *) (h->d_status + 64), h->d_u32 + 3, sc)); LAUNCHED(h);
+		CK(pdl(k_scan_reads, n <= 1024 ? 1u : nblk(n, SCAN_READS_CHUNK), n <= 1024 ? 256 : 1024, h->st, S, PB.rec_off->as<unsigned long long>(), PB.sl_prefix->as<U64x4>(),
+		       (SegTotals *) (h->d_status + seg_totals_off(h->seg_par)), seg_nrec_dev(h, h->seg_par), sc)); LAUNCHED(h);
 	}
 	const uint32_t rec_bound = (uint32_t) dna_bytes;   // capacities follow the reserve as well
 	if (h->miss_cap < std::min<uint32_t>(rec_bound, 1u << 20)) h->miss_cap = std::min<uint32_t>(rec_bound, 1u << 20);
@@ -1284,7 +1322,7 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 	if (h->rreq_cap < rec_bound / 8) h->rreq_cap = rec_bound / 8 + 1024;
 	// draw windows: the merges of the segment and, for a sync enqueued unseen, the ordered inserts of its b-mers
 	CKR(stream_ensure(h, h->rng[ST_B], (1u << 16) + (dna_bytes_actual <= SPEC_MAX_BYTES ? 2 * dna_bytes_actual : 0))); CKR(stream_ensure(h, h->rng[ST_S], 1u << 12));
-	CKR(seg_setup(h, true));
+	CKR(seg_setup(h, !fronted));      // (an announced segment's k_prep ran before the previous look: it must not clear the status words)
 	if (h->delta_filtered) ++h->S.n_filtered_segments;
 	const bool prefix = h->world == 1 && h->fast_ok[0] && dna_bytes_actual <= SPEC_MAX_BYTES;     // the sync of this segment will be enqueued unseen
 	CKR(seg_pass(h, prefix));
@@ -1409,7 +1447,8 @@ int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
 		int prio_lo = 0, prio_hi = 0;
 		CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
 		CK(cudaStreamCreateWithPriority(&h->st, cudaStreamNonBlocking, prio_hi));         // see ensure_side
-		CK(cudaStreamCreateWithPriority(&h->st_mt, cudaStreamNonBlocking, prio_lo));      // the mt19937 generator works ahead: never in the way
+		CK(cudaStreamCreateWithPriority(&h->st_mt, cudaStreamNonBlocking, prio_hi));      // the mt19937 generator: 32 CTAs that work ahead; at a lower priority the full grids of
+		                                                                                  // a large segment starved it and the ordered b-mer insert waited 0.8 ms for its draws
 		CK(cudaMalloc(&h->d_status, 512)); CK(cudaMemset(h->d_status, 0, 512));
 		h->d_flags = (int *) h->d_status;                       // +0   : 8 ints
 		h->d_u32 = (uint32_t *) (h->d_status + 32);              // +32  : 8 counters
@@ -1488,7 +1527,7 @@ void fqsk_destroy(fqsk_handle *h) {
 	                  &h->y_tslot, &h->y_c0, &h->y_m, &h->y_draw, &h->y_j, &h->y_final, &h->y_flag_at, &h->y_own, &h->y_lead, &h->y_rank, &h->y_flag, &h->y_doff,
 	                  &h->idx_k, &h->idx_t, &h->idx_rt, &h->miss_fold, &h->hr_b[0], &h->hr_b[1], &h->hr_b[2], &h->hr_s[0], &h->hr_s[1], &h->hr_s[2],
 	                  &h->evk[0], &h->evk[1], &h->evv[0], &h->evv[1], &h->evk_s[0], &h->evk_s[1], &h->evv_s[0], &h->evv_s[1], &h->ctxrec[0], &h->ctxrec[1], &h->scan_part, &h->scan8_part, &h->rdx_hist, &h->rdx_k, &h->rdx_v, &h->scan_vals, &h->recs_alt, &h->dfilter, &h->pk,
-	                  &h->route_keys, &h->route_keys2, &h->route_sorted, &h->route_hist, &h->route_perm, &h->route_chunks,
+	                  &h->route_keys, &h->route_keys2, &h->route_sorted, &h->route_hist, &h->route_perm, &h->route_chunks, &h->f_dup, &h->f_n_coded, &h->f_letters, &h->f_rec_off, &h->f_sl_prefix, &h->f_pk,
 	                  &h->pe_uk, &h->pe_uv, &h->pe_uc, &h->pe_tk, &h->pe_tv, &h->pe_q, &h->pe_sk, &h->pe_sv, &h->pe_sidx, &h->pe_t1, &h->pe_t2, &h->pe_pool, &h->pe_info, &h->it_src, &h->it_len,
 	                  &h->it_bytes, &h->it_first, &h->it_bias, &h->it_dupprev, &h->it_flags, &h->it_off32, &h->it_off64, &h->it_dna};
 
@@ -1500,6 +1539,8 @@ void fqsk_destroy(fqsk_handle *h) {
 	for (int i = 0; i < 3; ++i) { if (h->st_side[i]) { cudaStreamSynchronize(h->st_side[i]); cudaStreamDestroy(h->st_side[i]); } if (h->ev_side[i]) cudaEventDestroy(h->ev_side[i]); }
 	if (h->ev_fork) cudaEventDestroy(h->ev_fork);
 	if (h->ev_aux) cudaEventDestroy(h->ev_aux);
+	if (h->st_front) { cudaStreamSynchronize(h->st_front); cudaStreamDestroy(h->st_front); }
+	if (h->ev_front) cudaEventDestroy(h->ev_front);
 	if (h->st_copy) { cudaStreamSynchronize(h->st_copy); cudaStreamDestroy(h->st_copy); }
 	if (h->h_small) cudaFreeHost(h->h_small);
 	for (auto &e : h->evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -1540,6 +1581,47 @@ int fqsk_segment_device(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes
 	h->tk_info = -1;
 	CKR(run_segment(h, d_dna, dna_bytes, (const unsigned long long *) d_off, d_len, n_reads));
 	if (n_recs) { CKR(seg_settle(h)); *n_recs = h->n_recs; }    // pass NULL to leave the look to fqsk_sync / fqsk_device_recs
+	return FQSK_OK;
+}
+
+// The caller names the segment its NEXT fqsk_segment_device call will bring while the current one is still in flight (between that
+// call and its fqsk_sync): duplicate flags, letter totals, packed reads and record offsets of the announced reads are functions of the
+// reads alone (read_prev of its first read = the last read of the segment in flight, dna.cpp:1521-1533), so k_prep / k_scan_reads run
+// now, on a side stream, instead of at the head of the next segment's dependent chain.  A hint: ignored where it does not apply.
+int fqsk_announce_device(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes, const uint64_t *d_off, const uint32_t *d_len, uint32_t n_reads) {
+	if (!h) return FQSK_E_INVAL;
+	CK(cudaSetDevice(h->P.device));
+	if (h->front.valid) { CK(cudaStreamSynchronize(h->st_front)); h->front.valid = false; }
+	const SegCtx &C = h->ctx;
+	if (mode_pe(h->P.mode) || h->serial || !n_reads || !d_dna || !d_off || !d_len || !h->pending || !h->seg_reads || !C.n) return FQSK_OK;
+	if (n_reads > SCAN_CHAIN_MAX * SCAN_READS_CHUNK || dna_bytes >= (1ull << 30)) return FQSK_OK;
+	const uint64_t bytes_r = std::max<uint64_t>(dna_bytes, h->P.reserve_bytes);
+	const size_t n1 = (size_t) std::max<uint32_t>(n_reads, h->P.reserve_reads) + 1;
+	const int par = h->seg_par ^ 1;
+	const PrepBufs PB = prep_bufs(h, par);
+	const size_t need[6] = {n1, n1 * 4, n1 * 32, n1 * 8, n1 * 32, (bytes_r / 32 + 2 * n1 + 8) * 8};
+	DevBuf *bufs[6] = {PB.dup, PB.n_coded, PB.letters, PB.rec_off, PB.sl_prefix, PB.pk};
+	for (int i = 0; i < 6; ++i) CK(bufs[i]->ensure(need[i]));
+	if (!h->st_front) {
+		int lo = 0, hi = 0;
+		CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+		CK(cudaStreamCreateWithPriority(&h->st_front, cudaStreamNonBlocking, lo));      // works ahead: yields to the chain of the segment in flight
+		CK(cudaEventCreateWithFlags(&h->ev_front, cudaEventDisableTiming));
+	}
+	SegDev S{};
+	S.dna = d_dna; S.off = (const unsigned long long *) d_off; S.len = d_len; S.n_reads = n_reads;
+	S.carry = h->d_carry; S.prev_read = h->prev_read.as<uint8_t>();      // (not read: read_prev comes from the segment in flight, below)
+	S.dup = PB.dup->as<uint8_t>(); S.n_coded = PB.n_coded->as<uint32_t>(); S.letters = PB.letters->as<U64x4>();
+	S.rec_off = PB.rec_off->as<unsigned long long>(); S.sl_prefix = PB.sl_prefix->as<U64x4>(); S.pk = PB.pk->as<unsigned long long>();
+	const uint32_t first = mode_sorted(h->P.mode) ? h->P.pmer_len : h->P.prefix_len;
+	const uint32_t last = C.n - 1;      // read_prev of the announced segment's first read: the last read of the segment in flight
+	CK(pdl(k_prep, nblk((uint64_t) n_reads * 32, 128), 128, h->st_front, S, first, h->P.bmer_len, (uint32_t) mode_sorted(h->P.mode), (uint8_t *) nullptr, (unsigned long long *) nullptr,
+	       C.S.dna, C.S.off + last, C.S.len + last)); LAUNCHED(h);
+	ScanChain sc; CKR(scan_chain(h, sc, 2));
+	CK(pdl(k_scan_reads, n_reads <= 1024 ? 1u : nblk(n_reads, SCAN_READS_CHUNK), n_reads <= 1024 ? 256 : 1024, h->st_front, S, PB.rec_off->as<unsigned long long>(), PB.sl_prefix->as<U64x4>(),
+	       (SegTotals *) (h->d_status + seg_totals_off(par)), seg_nrec_dev(h, par), sc)); LAUNCHED(h);
+	CK(cudaEventRecord(h->ev_front, h->st_front));
+	h->front.valid = true; h->front.dna = d_dna; h->front.bytes = dna_bytes; h->front.off = (const unsigned long long *) d_off; h->front.len = d_len; h->front.n = n_reads; h->front.par = par;
 	return FQSK_OK;
 }
 
@@ -1693,8 +1775,8 @@ int fqsk_segment(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const 
 		std::vector<uint8_t> idup(ni + 1);
 		std::vector<unsigned long long> ioff(ni + 1);
 		if (ni) {
-			CK(cudaMemcpyAsync(idup.data(), h->dup.p, ni, cudaMemcpyDeviceToHost, h->st));
-			CK(cudaMemcpyAsync(ioff.data(), h->rec_off.p, ((size_t) ni + 1) * 8, cudaMemcpyDeviceToHost, h->st));
+			CK(cudaMemcpyAsync(idup.data(), prep_bufs(h, h->seg_par).dup->p, ni, cudaMemcpyDeviceToHost, h->st));
+			CK(cudaMemcpyAsync(ioff.data(), prep_bufs(h, h->seg_par).rec_off->p, ((size_t) ni + 1) * 8, cudaMemcpyDeviceToHost, h->st));
 		}
 		CK(cudaStreamSynchronize(h->st));
 		for (uint32_t i = 0; i < n_reads / 2; ++i) {
@@ -1705,8 +1787,8 @@ int fqsk_segment(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const 
 		if (n_recs) *n_recs = h->n_recs;
 		return FQSK_OK;
 	}
-	if (n_reads && dup) CK(cudaMemcpyAsync(dup, h->dup.p, n_reads, cudaMemcpyDeviceToHost, h->st));
-	if (n_reads && rec_off) CK(cudaMemcpyAsync(rec_off, h->rec_off.p, ((size_t) n_reads + 1) * 8, cudaMemcpyDeviceToHost, h->st));
+	if (n_reads && dup) CK(cudaMemcpyAsync(dup, prep_bufs(h, h->seg_par).dup->p, n_reads, cudaMemcpyDeviceToHost, h->st));
+	if (n_reads && rec_off) CK(cudaMemcpyAsync(rec_off, prep_bufs(h, h->seg_par).rec_off->p, ((size_t) n_reads + 1) * 8, cudaMemcpyDeviceToHost, h->st));
 	CK(cudaStreamSynchronize(h->st));
 	if (n_recs) *n_recs = h->n_recs;
 	return FQSK_OK;
@@ -1886,7 +1968,7 @@ static int sync_end(fqsk_handle *h) {
 		h->hidden_p = 0;
 	}
 	for (int i = 0; i < 4; ++i) h->S.draws[i] = h->rng[i].consumed;
-	CKR(stream_prefetch(h, h->rng[ST_B], 1u << 23)); CKR(stream_prefetch(h, h->rng[ST_S], 1u << 18));
+	CKR(stream_keep_ahead(h, h->rng[ST_B], 12u << 20)); CKR(stream_prefetch(h, h->rng[ST_S], 1u << 18));
 	h->pending = false; h->pend_b = h->pend_s = h->pend_p = 0; h->seg_reads = 0;
 	resolve_phases(h);
 	return FQSK_OK;
@@ -1982,8 +2064,8 @@ static int submit_impl(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, 
 			CK(cudaMallocHost(&h->h_meta[par], want));
 			h->h_meta_cap[par] = want;
 		}
-		CK(cudaMemcpyAsync(h->h_meta[par], h->dup.p, ni, cudaMemcpyDeviceToHost, h->st));
-		CK(cudaMemcpyAsync(h->h_meta[par] + o_off, h->rec_off.p, ((size_t) ni + 1) * 8, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaMemcpyAsync(h->h_meta[par], prep_bufs(h, h->seg_par).dup->p, ni, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaMemcpyAsync(h->h_meta[par] + o_off, prep_bufs(h, h->seg_par).rec_off->p, ((size_t) ni + 1) * 8, cudaMemcpyDeviceToHost, h->st));
 		// what compress_prefix_sorted / CompressPE code per read / pair: functions of the reads and of the tables as they were when the
 		// segment started, so the values of the first pass are final
 		if (mode_sorted(h->P.mode)) {
@@ -2239,7 +2321,7 @@ int fqsk_sync_finish(fqsk_handle *h, uint64_t fresh_all, uint64_t updates_all) {
 	h->S.siv_no_filled += fresh_all;       // bit_vec.h:212-220: global atomics in the reference, read by every worker (dna.cpp:376)
 	h->S.siv_no_updates += updates_all;
 	for (int i = 0; i < 4; ++i) h->S.draws[i] = h->rng[i].consumed;
-	CKR(stream_prefetch(h, h->rng[ST_B], 1u << 23)); CKR(stream_prefetch(h, h->rng[ST_S], 1u << 18));
+	CKR(stream_keep_ahead(h, h->rng[ST_B], 12u << 20)); CKR(stream_prefetch(h, h->rng[ST_S], 1u << 18));
 	h->pending = false; h->pend_b = h->pend_s = h->pend_p = 0; h->seg_reads = 0;
 	h->routed = h->applied = false;
 	resolve_phases(h);

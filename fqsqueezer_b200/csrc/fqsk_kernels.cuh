@@ -167,7 +167,9 @@ __device__ __forceinline__ void seg_reset_words(uint8_t *status, unsigned long l
 	if (t >= 32 && t < 40) w[304 / 4 + (t - 32)] = 0;      // flags of the ordered insert
 	if (t == 40) counters[4] = 0;                          // fresh p-mer fields
 }
-__global__ void __launch_bounds__(128) k_prep(SegDev S, uint32_t first_len_bytes, uint32_t b, uint32_t sorted, uint8_t *status, unsigned long long *counters) { pdl_enter();   // one warp per read
+// pv_*: read_prev of the segment's first read when it is not the engine's own copy (fqsk_announce_device: the last read of the segment in flight)
+__global__ void __launch_bounds__(128) k_prep(SegDev S, uint32_t first_len_bytes, uint32_t b, uint32_t sorted, uint8_t *status, unsigned long long *counters,
+                                              const uint8_t *pv_dna, const unsigned long long *pv_off, const uint32_t *pv_len) { pdl_enter();   // one warp per read
 	if (status && blockIdx.x == 0 && threadIdx.x < 64) seg_reset_words(status, counters, threadIdx.x);
 	uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (r >= S.n_reads) return;
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(128) k_prep(SegDev S, uint32_t first_len_bytes
 	sorted = item_sorted(S, sorted, r);
 	const uint8_t *q; uint32_t qn;
 	uint32_t pr = S.dup_prev ? S.dup_prev[r] : (r ? r - 1 : 0xFFFFFFFFu);     // the read this one is compared with (read_prev)
-	if (pr == 0xFFFFFFFFu) { q = S.prev_read; qn = S.carry->prev_len; } else { q = S.dna + S.off[pr]; qn = S.len[pr]; }
+	if (pr == 0xFFFFFFFFu) { if (pv_off) { q = pv_dna + *pv_off; qn = *pv_len; } else { q = S.prev_read; qn = S.carry->prev_len; } } else { q = S.dna + S.off[pr]; qn = S.len[pr]; }
 	bool same = qn == n && !(ifl & IF_NO_DUPCHECK);
 	if (ifl & IF_SKIP) { same = true; n = 0; }
 	uint32_t cnt[4] = {0, 0, 0, 0};

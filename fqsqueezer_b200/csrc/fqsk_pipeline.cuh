@@ -885,12 +885,19 @@ __global__ void __launch_bounds__(256) k_delta_build_flat(SegDev S, PipeDev P, u
 // only_marked = 0: every flagged position.  The first pass of a small segment starts this right behind walk 0, on a side stream next
 // to the thread-local pass (delta, k_local, walk 1); positions the re-walk wrote carry the 0x80 marker and are done again afterwards
 // with only_marked = 1 (their first scripts stay behind unreferenced).  Nothing here writes records: k_fold does.
+// DEEP = false: one survivor per lane and round (sparse tables: a third of the trials survive the occupancy bits, one round; 55 registers);
+// DEEP = true: up to four sector reads per lane in flight (dense tables: every trial survives, the kernel lives on memory-level parallelism)
+template <bool DEEP>
 __global__ void __launch_bounds__(128, 8) k_rough(EngineDev E, PipeDev P, uint32_t only_marked) { pdl_enter();   // E.hb / E.hs carry occ_read while the tables are sparse (HtDev::occ)
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t n_rec = *P.n_rec_dev;
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
 	__shared__ Script stage[4];
+	__shared__ uint64_t surv_h_all[4][128];      // per warp: bucket hash of the trials that can hit, in trial order
+	__shared__ uint8_t surv_m_all[4][128];       //           trial number | orientation << 7
 	Script &sc = stage[threadIdx.x >> 5];
+	uint64_t *surv_h = surv_h_all[threadIdx.x >> 5];
+	uint8_t *surv_m = surv_m_all[threadIdx.x >> 5];
 	const uint32_t RCHUNK = 4;      // positions per warp iteration: small, so that a tiny segment still spreads over every SM
 	for (uint32_t g0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * RCHUNK; g0 < n_rec; g0 += warps * RCHUNK) {
 		// each warp owns RCHUNK consecutive positions: find the flagged ones, then work on them one at a time with all lanes
@@ -933,37 +940,92 @@ __global__ void __launch_bounds__(128, 8) k_rough(EngineDev E, PipeDev P, uint32
 				continue;
 			}
 			const HtDev &t = kind == 2 ? E.hb : E.hs;
-			uint32_t trials = 4 * (t.k - 1);
+			const uint32_t trials = 4 * (t.k - 1);      // <= 128
 			uint32_t n_ent = 0, ovf = 0xFFFFFFFFu;
-			// all sector reads of the request are issued before the first one is consumed (4(k-1) <= 128 trials: up to 4 per lane)
-			// Only the buckets stay live across the memory latency: the keys are recomputed when the sectors arrive, which keeps the
-			// kernel at 64 registers = 32 resident warps per SM (it is bound by the latency of one request's dependent steps).
-			Bucket bk[4]; bool live[4];
-#pragma unroll
-			for (int u = 0; u < 4; ++u) {
-				uint32_t tn = u * 32 + lane;
+			// Phase 1: every trial's bucket hash (the expensive part: two 64-bit multiplies) is computed ONCE; while the table is sparse the
+			// bucket-occupancy bit (L2-resident) decides which trials can hit at all.  The survivors -- about a third of the 4(k-1) trials in
+			// the first blocks of a file -- are compacted, in trial order, into the warp's list in shared memory.
+			// Phase 2: one survivor per lane: its sector is read and compared; non-empty results are appended to the script in list order =
+			// trial order (dna.cpp:283-287, 321-325).  (Before: three rounds of 32 trials, every hash computed twice: issue bound.)
+			uint32_t n_surv = 0;
+			for (uint32_t u = 0; u * 32 < trials; ++u) {
+				const uint32_t tn = u * 32 + lane;
 				// a trial that puts the original symbol back is the context itself, which the global table has just failed to
 				// answer (the level is `none`): known empty, no read
-				live[u] = tn < trials && (tn & 3) != kr_sym(reg, tn >> 2);
-				if (live[u]) {
+				bool keep = tn < trials && (tn & 3) != kr_sym(reg, tn >> 2);
+				uint64_t hsh = 0; bool isd = false;
+				if (keep) {
 					KReg tr = reg;
 					kr_set(tr, t.k, tn & 3, tn >> 2);
-					const bool isd = kr_is_dir(tr, t.k);
-					bk[u] = ht_load_bucket(t, ht_key(t, isd ? tr.dir : tr.rc));
+					isd = kr_is_dir(tr, t.k);
+					hsh = ht_mix(t, ht_kernel(t, isd ? tr.dir : tr.rc));
+					if (t.occ_read) { const uint64_t bucket = hsh >> t.rem_bits; keep = ((__ldg(t.occ_read + (bucket >> 5)) >> (bucket & 31)) & 1u) != 0; }
 				}
+				const unsigned m = __ballot_sync(0xffffffffu, keep);
+				if (keep) { const uint32_t at = n_surv + __popc(m & ((1u << lane) - 1u)); surv_h[at] = hsh; surv_m[at] = (uint8_t) (tn | (isd ? 0x80u : 0u)); }
+				n_surv += __popc(m);
 			}
-#pragma unroll
-			for (int u = 0; u < 4; ++u) {
-				if ((uint32_t) u * 32 >= trials) break;
-				uint32_t loc[4] = {0, 0, 0, 0};
-				if (live[u]) {
-					const uint32_t tn = u * 32 + lane;
-					KReg tr = reg;
-					kr_set(tr, t.k, tn & 3, tn >> 2);
-					const bool isd = kr_is_dir(tr, t.k);
-					ht_ctx_counts_from(t, ht_key(t, isd ? tr.dir : tr.rc), isd, bk[u], loc);
+			__syncwarp();
+			if (!DEEP) {
+				for (uint32_t s0 = 0; s0 < n_surv; s0 += 32) {
+					uint32_t loc[4] = {0, 0, 0, 0};
+					if (s0 + lane < n_surv) {
+						const uint32_t meta = surv_m[s0 + lane], tn = meta & 0x7Fu;
+						const bool isd = (meta & 0x80u) != 0;
+						KReg tr = reg;
+						kr_set(tr, t.k, tn & 3, tn >> 2);
+						const uint64_t x = isd ? tr.dir : tr.rc;
+						HtKey key;
+						key.h = surv_h[s0 + lane];
+						key.bucket = key.h >> t.rem_bits;
+						key.q = 0x80000000u | ((uint32_t) (key.h & ((1ull << t.rem_bits) - 1)) << (8 + t.cbits)) | (ht_ends(t, x) << t.cbits);
+						key.kal = x >> (64 - 2 * t.k);
+						key.owner = ht_owner(t.world, x);
+						const uint4 *bp = reinterpret_cast<const uint4 *>(t.peer_main[key.owner] + key.bucket * 8);
+						Bucket bk; bk.lo = __ldg(bp); bk.hi = __ldg(bp + 1);
+						ht_ctx_counts_from(t, key, isd, bk, loc);
+					}
+					script_append(P, sc, n_ent, ovf, loc, any4(loc), n_surv - s0);
 				}
-				script_append(P, sc, n_ent, ovf, loc, any4(loc), trials - u * 32);
+			} else {
+				// up to four survivors per lane: all their sector reads are issued before the first one is consumed (dense tables let every
+				// trial through: 4(k-1) reads per request, and the kernel lives on memory-level parallelism)
+				for (uint32_t s0 = 0; s0 < n_surv; s0 += 128) {
+					Bucket bk[4];
+	#pragma unroll
+					for (int u = 0; u < 4; ++u) {
+						const uint32_t i = s0 + u * 32 + lane;
+						if (i < n_surv) {
+							const uint32_t meta = surv_m[i], tn = meta & 0x7Fu;
+							KReg tr = reg;
+							kr_set(tr, t.k, tn & 3, tn >> 2);
+							const uint32_t owner = ht_owner(t.world, (meta & 0x80u) ? tr.dir : tr.rc);
+							const uint4 *bp = reinterpret_cast<const uint4 *>(t.peer_main[owner] + (surv_h[i] >> t.rem_bits) * 8);
+							bk[u].lo = __ldg(bp); bk[u].hi = __ldg(bp + 1);
+						}
+					}
+	#pragma unroll
+					for (int u = 0; u < 4; ++u) {
+						if (s0 + u * 32 >= n_surv) break;
+						const uint32_t i = s0 + u * 32 + lane;
+						uint32_t loc[4] = {0, 0, 0, 0};
+						if (i < n_surv) {
+							const uint32_t meta = surv_m[i], tn = meta & 0x7Fu;
+							const bool isd = (meta & 0x80u) != 0;
+							KReg tr = reg;
+							kr_set(tr, t.k, tn & 3, tn >> 2);
+							const uint64_t x = isd ? tr.dir : tr.rc;
+							HtKey key;
+							key.h = surv_h[i];
+							key.bucket = key.h >> t.rem_bits;
+							key.q = 0x80000000u | ((uint32_t) (key.h & ((1ull << t.rem_bits) - 1)) << (8 + t.cbits)) | (ht_ends(t, x) << t.cbits);
+							key.kal = x >> (64 - 2 * t.k);
+							key.owner = ht_owner(t.world, x);
+							ht_ctx_counts_from(t, key, isd, bk[u], loc);
+						}
+						script_append(P, sc, n_ent, ovf, loc, any4(loc), n_surv - (s0 + u * 32));
+					}
+				}
 			}
 			__syncwarp();
 			if (lane == 0) {

@@ -45,7 +45,7 @@ class _Stats(C.Structure):
                 ("n_filtered_segments", C.c_uint64)]
 
 
-EXPORTS = ["fqsk_create", "fqsk_destroy", "fqsk_last_error", "fqsk_block_start", "fqsk_segment", "fqsk_segment_device",
+EXPORTS = ["fqsk_create", "fqsk_destroy", "fqsk_last_error", "fqsk_block_start", "fqsk_segment", "fqsk_segment_device", "fqsk_announce_device",
            "fqsk_device_recs", "fqsk_recs_checksum", "fqsk_sorted_prefix", "fqsk_pair_info", "fqsk_submit", "fqsk_submit_ctx", "fqsk_collect", "fqsk_sync", "fqsk_dump", "fqsk_stats_get", "fqsk_profile", "fqsk_ht_insert", "fqsk_ht_find",
            "fqsk_ht_count", "fqsk_timeline", "fqsk_timer_begin", "fqsk_timer_end", "fqsk_siv_increment", "fqsk_siv_test", "fqsk_siv_counts", "fqsk_siv_test_shorter", "fqsk_mt_stream", "fqsk_host_alloc", "fqsk_host_free",
            "fqsk_shard_export", "fqsk_shard_attach", "fqsk_sync_route", "fqsk_sync_apply", "fqsk_sync_finish"]
@@ -70,6 +70,7 @@ def load_library():
     lib.fqsk_block_start.argtypes = [vp]
     lib.fqsk_segment.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint32, vp, C.c_uint64, u64p, vp, vp]
     lib.fqsk_segment_device.argtypes = [vp, vp, C.c_uint64, vp, vp, C.c_uint32, u64p]
+    lib.fqsk_announce_device.argtypes = [vp, vp, C.c_uint64, vp, vp, C.c_uint32]
     lib.fqsk_device_recs.argtypes = [vp, C.POINTER(vp), u64p]
     lib.fqsk_recs_checksum.argtypes = [vp, u64p, u64p]
     lib.fqsk_sorted_prefix.argtypes = [vp, vp, vp, C.c_uint32]
@@ -263,6 +264,11 @@ class KmerEngine:
         n_recs = C.c_uint64(0)
         self._ck(self.lib.fqsk_segment_device(self.h, C.c_void_p(d_dna_ptr), dna_bytes, C.c_void_p(d_off_ptr), C.c_void_p(d_len_ptr), n_reads, C.byref(n_recs)))
         return n_recs.value
+
+    def announce_device(self, d_dna_ptr: int, dna_bytes: int, d_off_ptr: int, d_len_ptr: int, n_reads: int):
+        """Hint between segment_device and its sync: the arguments of the NEXT segment_device call of the same reads_block (its
+        read-only preparation then runs next to the segment in flight)."""
+        self._ck(self.lib.fqsk_announce_device(self.h, C.c_void_p(d_dna_ptr), dna_bytes, C.c_void_p(d_off_ptr), C.c_void_p(d_len_ptr), n_reads))
 
     def device_recs(self):
         p = C.c_void_p()

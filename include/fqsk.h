@@ -135,6 +135,12 @@ int fqsk_segment(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const 
  * the call, and they must stay untouched until the fqsk_sync that follows. */
 int fqsk_segment_device(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes, const uint64_t *d_off, const uint32_t *d_len,
                         uint32_t n_reads, uint64_t *n_recs);
+/* Optional hint between fqsk_segment_device and its fqsk_sync: the arguments the NEXT fqsk_segment_device call will have.  What depends on
+ * the reads alone (duplicate flags -- dna.cpp:1521-1533 --, letter totals -- 2047-2057 --, record offsets) is then computed next to the
+ * segment in flight instead of at the head of the next one.  Same contract for the arrays as fqsk_segment_device; a hint that is not
+ * followed by the matching call is dropped.  The announced segment belongs to the same reads_block (no fqsk_block_start in between).
+ * Ignored for paired-end modes. */
+int fqsk_announce_device(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes, const uint64_t *d_off, const uint32_t *d_len, uint32_t n_reads);
 int fqsk_device_recs(fqsk_handle *h, const fqsk_base_rec **d_recs, uint64_t *n_recs);
 /* Order-sensitive checksum of the last segment's records, computed on the device (no record leaves HBM): the sum over the records i of
  * fmix64(a ^ fmix64(b ^ fmix64(c ^ fmix64(d + i)))) with a, b, c = the first three little-endian 64-bit words of record i, d = its last

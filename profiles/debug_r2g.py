@@ -62,8 +62,12 @@ if "parity" in what:
             d_len = torch.full((l - f,), B.L, dtype=torch.int32, device=dev)
             torch.cuda.synchronize()      # the engine reads these on its own non-blocking stream
             eng.block_start()
-            for a, bb in S.segments(0, l - f, S.calc_no_synchronizations(g, l - f, 1)):
+            segs = list(S.segments(0, l - f, S.calc_no_synchronizations(g, l - f, 1)))
+            for k, (a, bb) in enumerate(segs):
                 eng.segment_device(t.data_ptr() + a * B.L, (bb - a) * B.L, d_off.data_ptr(), d_len.data_ptr(), bb - a, want_n_recs=False)
+                if k + 1 < len(segs) and not os.environ.get("NO_ANNOUNCE"):
+                    a2, b2 = segs[k + 1]
+                    eng.announce_device(t.data_ptr() + a2 * B.L, (b2 - a2) * B.L, d_off.data_ptr(), d_len.data_ptr(), b2 - a2)
                 cs, n = eng.recs_checksum()
                 if n != int(z["seg_nrecs"][seg]) or cs != int(z["seg_sum"][seg]):
                     bad.append((seg, n, int(z["seg_nrecs"][seg]), bb - a))
@@ -86,8 +90,11 @@ if "timing" in what:
             p0 = eng.profile()
             eng.block_start()
             t0 = time.perf_counter()
-            for a, bb in sched:
+            for k, (a, bb) in enumerate(sched):
                 eng.segment_device(t.data_ptr() + a * B.L, (bb - a) * B.L, d_off.data_ptr(), d_len.data_ptr(), bb - a, want_n_recs=False)
+                if k + 1 < len(sched) and not os.environ.get("NO_ANNOUNCE"):
+                    a2, b2 = sched[k + 1]
+                    eng.announce_device(t.data_ptr() + a2 * B.L, (b2 - a2) * B.L, d_off.data_ptr(), d_len.data_ptr(), b2 - a2)
                 eng.sync()
             tot = time.perf_counter() - t0
             p1 = eng.profile()
@@ -131,11 +138,42 @@ if "timeline" in what:      # fork / join structure of three consecutive segment
         d_len = torch.full((l - f,), B.L, dtype=torch.int32, device=dev)
         torch.cuda.synchronize()
         eng.block_start()
-        for k, (a, bb) in enumerate(S.segments(0, l - f, S.calc_no_synchronizations(g, l - f, 1))):
-            if g == G and k == 40:
+        segs = list(S.segments(0, l - f, S.calc_no_synchronizations(g, l - f, 1)))
+        for k, (a, bb) in enumerate(segs):
+            if g == G and k == int(os.environ.get("TL_K0", "40")):
                 eng.timeline(True)
             eng.segment_device(t.data_ptr() + a * B.L, (bb - a) * B.L, d_off.data_ptr(), d_len.data_ptr(), bb - a, want_n_recs=False)
+            if k + 1 < len(segs) and not os.environ.get("NO_ANNOUNCE"):
+                a2, b2 = segs[k + 1]
+                eng.announce_device(t.data_ptr() + a2 * B.L, (b2 - a2) * B.L, d_off.data_ptr(), d_len.data_ptr(), b2 - a2)
             eng.sync()
-            if g == G and k == 42:
+            if g == G and k == int(os.environ.get("TL_K1", "42")):
                 eng.timeline(False)
+    eng.close()
+
+if "blocks" in what:      # wall clock per block over the early regime (tables fill up as in the job)
+    reads = B.JobReads(synth.make_genome(B.GENOME, B.SEED))
+    blocks = B.job_blocks()
+    eng = mk(E.F_SERIAL if os.environ.get("SERIAL") else 0)
+    for g in range(int(os.environ.get("NBLK", "104"))):
+        f, l = blocks[g]
+        t = torch.from_numpy(synth.codes_to_ascii(reads.codes(f, l)).reshape(-1)).to(dev)
+        d_off = torch.arange(l - f, dtype=torch.int64, device=dev) * B.L
+        d_len = torch.full((l - f,), B.L, dtype=torch.int32, device=dev)
+        segs = list(S.segments(0, l - f, S.calc_no_synchronizations(g, l - f, 1)))
+        torch.cuda.synchronize()
+        st0 = eng.stats()
+        eng.block_start()
+        t0 = time.perf_counter()
+        for k, (a, bb) in enumerate(segs):
+            eng.segment_device(t.data_ptr() + a * B.L, (bb - a) * B.L, d_off.data_ptr(), d_len.data_ptr(), bb - a, want_n_recs=False)
+            if k + 1 < len(segs) and not os.environ.get("NO_ANNOUNCE"):
+                a2, b2 = segs[k + 1]
+                eng.announce_device(t.data_ptr() + a2 * B.L, (b2 - a2) * B.L, d_off.data_ptr(), d_len.data_ptr(), b2 - a2)
+            eng.sync()
+        tot = time.perf_counter() - t0
+        st1 = eng.stats()
+        if g % 5 == 0 or g >= 95:
+            print(f"[blocks] block {g}: {len(segs)} segments of {segs[0][1] - segs[0][0]} reads, {1e3 * tot:.2f} ms, {1e6 * tot / len(segs):.0f} us / segment, "
+                  f"{(st1['kernel_launches'] - st0['kernel_launches']) / len(segs):.1f} launches / segment, {(st1['n_replays'] - st0['n_replays']) / len(segs):.2f} walks / segment, hot {st1['n_hot_segments'] - st0['n_hot_segments']}", flush=True)
     eng.close()
