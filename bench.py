@@ -14,7 +14,7 @@ block) -- which are also timed and reported separately (`regimes`).  The W warm-
 throw-away engine (same work, untimed).
 
 value  : bases/s with the reads already resident in HBM (fqsk_segment_device), timed with CUDA events on the engine's stream.
-e2e    : the same steps through the host-buffer C-ABI calls (fqsk_submit / fqsk_collect): H2D of the reads and D2H of every per-base
+e2e    : the same steps through the host-buffer C-ABI calls (fqsk_submit_ctx / fqsk_collect per sync segment): H2D of the reads and D2H of every per-base
          record inside the timed region.
 parity_check : device-side checksums (fqsk_recs_checksum) of every sync segment of the first blocks of the timed job against the
          REAL reference's records for the same reads (tests/golden/bench_config2_ref_checksums.npz, produced once by
@@ -545,13 +545,14 @@ def main():
         slabs = [codes_to_slab(reads.codes(*blocks[g])) for g in range(NB)]
 
         def run_block_host(g, pend, e):
-            """fqsk_submit / fqsk_collect, two segments in flight: segment n + 1 is submitted before n is collected -- the point where
-            the reference's host-side coder would consume the records of n."""
+            """fqsk_submit_ctx / fqsk_collect, two segments in flight: segment n + 1 is submitted before n is collected -- the point where
+            the reference's host-side coder consumes the records of n (host/fqsk_live.h does exactly this).  The pipeline runs across
+            block boundaries: the records of a 51 000-read segment take as long to reach the host as the next one takes to compute."""
             slab, off, ln = slabs[g]
             e.block_start()
             nb = 0
             for a, bb in sched[g]:
-                t = e.submit(slab, off[a:bb], ln[a:bb])
+                t = e.submit(slab, off[a:bb], ln[a:bb], ctx=True)
                 if pend is not None:
                     recs, dup, _ = e.collect(pend)
                     nb += recs.nbytes + dup.nbytes
@@ -577,12 +578,14 @@ def main():
             d2h += recs.nbytes + dup.nbytes
         barrier()
         e2e_s = time.time() - t0
+        st_e2e = eng2.stats()
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": total_bases / float(t.item()), "unit": UNIT,
                "h2d_bytes_per_step": (JOB_READS if not args.max_blocks else blocks[-1][1]) * (L + 12) // K, "d2h_bytes_per_step": d2h // K,
-               "note": "fqsk_submit / fqsk_collect with host slab + read descriptors (H2D inside), every per-base record (28 B) copied back into page-locked host memory on a second stream, two segments in flight; wall clock incl. ctypes/numpy host code"}
+               "host": {"api_ms": round(st_e2e["api_ns"] / 1e6, 1), "waiting_for_the_gpu_ms": round(st_e2e["look_wait_ns"] / 1e6, 1)},
+               "note": "fqsk_submit_ctx / fqsk_collect (what the compiled drop-in calls) with host slab + read descriptors (H2D inside), one 16-byte context record per coded base (the 7 context ids + rank the range coder consumes, built on the device) copied back into page-locked host memory on a second stream, two segments in flight; wall clock incl. ctypes/numpy host code"}
         eng2.close()
         del slabs
 
@@ -642,6 +645,9 @@ def main():
             "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic", "config": workload_config(world, args.replicas),
             "job": {"blocks_timed": NB, "segments_timed": int(n_seg), "bases": job_bases, "device_ms": dev_ms_max, "wall_ms": wall_ms, "create_seconds": round(create_s, 3),
+                    "host": {"api_ms": round((st1["api_ns"] - st0["api_ns"]) / 1e6, 1), "waiting_for_the_gpu_ms": round((st1["look_wait_ns"] - st0["look_wait_ns"]) / 1e6, 1),
+                             "looks": int(st1["n_looks"] - st0["n_looks"]),
+                             "note": "time of this rank inside the C-ABI calls and the part of it spent waiting for the device: the rest is launch work of the host; when the waiting share is small the early regime (thousands of ~200 us sync segments) is bound by the host's launch rate, not by the GPU"},
                     "warmup_blocks": len(warm_blocks), "note": "table construction (fqsk_create) lies outside the timed region, as the reference's does in its arm"},
             "regimes": regimes, "roofline": roof, "parity_check": parity, "cpu_baseline": cpu, "e2e": e2e, "compress_e2e": compress, "gpu_launches": int(launches),
             "clocks": sampler.summary(), "wall_ms_per_step": wall_ms / K}

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfqsk.so")
 SOURCES = [os.path.join(CSRC, "fqsk.cu")]
 HEADERS = [os.path.join(CSRC, "fqsk_dev.cuh"), os.path.join(CSRC, "fqsk_kernels.cuh"), os.path.join(CSRC, "fqsk_pipeline.cuh"), os.path.join(CSRC, "fqsk_pe.cuh"),
-           os.path.join(CSRC, "fqsk_sort.cuh"), os.path.join(CSRC, "fqsk_mtjump.h"),
+           os.path.join(CSRC, "fqsk_sort.cuh"), os.path.join(CSRC, "fqsk_front.cuh"), os.path.join(CSRC, "fqsk_mtjump.h"),
            os.path.join(os.path.dirname(HERE), "include", "fqsk.h"), os.path.join(os.path.dirname(HERE), "include", "fqsk_ctx.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--expt-relaxed-constexpr", "-diag-suppress", "177,550"]

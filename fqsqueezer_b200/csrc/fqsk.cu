@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cctype>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -20,6 +21,7 @@
 #include <vector>
 
 #include "fqsk_pipeline.cuh"
+#include "fqsk_front.cuh"
 #include "fqsk_pe.cuh"
 #include "fqsk_mtjump.h"
 #include <mutex>
@@ -172,7 +174,7 @@ struct fqsk_handle {
 	DevBuf dfilter; bool delta_filtered = false;     // filter bits of the segment's delta (large segments), see seg_setup
 	DevBuf recs_alt; int rec_par = 0;
 	DevBuf ctxrec[2];                                // fqsk_submit_ctx: the 16-byte context records of the segment in flight, per parity
-	cudaStream_t st_copy = nullptr; cudaEvent_t ev_recs = nullptr, ev_copied[2] = {nullptr, nullptr};
+	cudaStream_t st_copy = nullptr; cudaEvent_t ev_recs = nullptr, ev_copied[2] = {nullptr, nullptr}, ev_meta = nullptr; bool meta_pending = false;
 	uint8_t *h_stage2 = nullptr; size_t h_stage2_cap = 0;       // second pinned staging buffer (H2D of segment n + 1 while n is still needed)
 	uint8_t *h_meta[2] = {nullptr, nullptr}; size_t h_meta_cap[2] = {0, 0};   // pinned per-ticket copies of dup / rec_off (item arrays in paired-end mode)
 	struct Ticket { bool open = false, done = false; fqsk_ctx_rec *ctx = nullptr; fqsk_base_rec *recs = nullptr; uint64_t bound = 0, n_recs = 0; uint8_t *dup = nullptr; uint64_t *rec_off = nullptr; uint32_t n_reads = 0; int par = 0; uint64_t id = 0; } tk[2];
@@ -750,6 +752,8 @@ int indexed_tail(fqsk_handle *h, Table &t, Stream &rng, const SyncDev &Y, const 
 // one look at the device: the whole status block, the item counters and the fresh p-mer field count
 int look(fqsk_handle *h) {
 	uint8_t *hs = (uint8_t *) h->h_small;
+	struct WaitTimer { fqsk_handle *h; std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+	                   ~WaitTimer() { ++h->S.n_looks; h->S.look_wait_ns += (uint64_t) std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(); } } wait_timer{h};
 	if (h->prof) {
 		CK(cudaMemcpyAsync(hs, h->d_status, 512, cudaMemcpyDeviceToHost, h->st));
 		CK(cudaMemcpyAsync(hs + 512, h->d_counters, 48, cudaMemcpyDeviceToHost, h->st));
@@ -1536,6 +1540,7 @@ void fqsk_destroy(fqsk_handle *h) {
 	if (h->h_stage2) cudaFreeHost(h->h_stage2);
 	for (int i = 0; i < 2; ++i) { if (h->h_meta[i]) cudaFreeHost(h->h_meta[i]); if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]); }
 	if (h->ev_recs) cudaEventDestroy(h->ev_recs);
+	if (h->ev_meta) cudaEventDestroy(h->ev_meta);
 	for (int i = 0; i < 3; ++i) { if (h->st_side[i]) { cudaStreamSynchronize(h->st_side[i]); cudaStreamDestroy(h->st_side[i]); } if (h->ev_side[i]) cudaEventDestroy(h->ev_side[i]); }
 	if (h->ev_fork) cudaEventDestroy(h->ev_fork);
 	if (h->ev_aux) cudaEventDestroy(h->ev_aux);
@@ -1568,6 +1573,8 @@ static int prealloc_for_reserve(fqsk_handle *h) {
 	return FQSK_OK;
 }
 
+struct ApiTimer { fqsk_handle *h; std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+                  ~ApiTimer() { if (h) h->S.api_ns += (uint64_t) std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(); } };
 int fqsk_block_start(fqsk_handle *h) {
 	if (!h) return FQSK_E_INVAL;
 	CK(cudaSetDevice(h->P.device));
@@ -1577,8 +1584,10 @@ int fqsk_block_start(fqsk_handle *h) {
 
 int fqsk_segment_device(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes, const uint64_t *d_off, const uint32_t *d_len, uint32_t n_reads, uint64_t *n_recs) {
 	if (!h) return FQSK_E_INVAL;
+	ApiTimer api_timer{h};
 	CK(cudaSetDevice(h->P.device));
 	h->tk_info = -1;
+	if (h->meta_pending) { CK(cudaStreamWaitEvent(h->st, h->ev_meta, 0)); h->meta_pending = false; }
 	CKR(run_segment(h, d_dna, dna_bytes, (const unsigned long long *) d_off, d_len, n_reads));
 	if (n_recs) { CKR(seg_settle(h)); *n_recs = h->n_recs; }    // pass NULL to leave the look to fqsk_sync / fqsk_device_recs
 	return FQSK_OK;
@@ -1590,6 +1599,7 @@ int fqsk_segment_device(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes
 // now, on a side stream, instead of at the head of the next segment's dependent chain.  A hint: ignored where it does not apply.
 int fqsk_announce_device(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes, const uint64_t *d_off, const uint32_t *d_len, uint32_t n_reads) {
 	if (!h) return FQSK_E_INVAL;
+	ApiTimer api_timer{h};
 	CK(cudaSetDevice(h->P.device));
 	if (h->front.valid) { CK(cudaStreamSynchronize(h->st_front)); h->front.valid = false; }
 	const SegCtx &C = h->ctx;
@@ -1976,6 +1986,7 @@ static int sync_end(fqsk_handle *h) {
 
 int fqsk_sync(fqsk_handle *h) {
 	if (!h) return FQSK_E_INVAL;
+	ApiTimer api_timer{h};
 	CK(cudaSetDevice(h->P.device));
 	if (h->world > 1) return fail(h, FQSK_E_INVAL, "sharded engine: use fqsk_sync_route / fqsk_sync_apply / fqsk_sync_finish");
 	if (h->tk_open) return fail(h, FQSK_E_INVAL, "a submitted segment is in flight: fqsk_collect it first (fqsk_submit includes the sync)");
@@ -2031,11 +2042,13 @@ int fqsk_submit_ctx(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, con
 static int submit_impl(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const fqsk_read_desc *reads, uint32_t n_reads,
                        fqsk_base_rec *recs, fqsk_ctx_rec *ctx, uint64_t rec_cap, uint8_t *dup, uint64_t *rec_off, uint64_t *ticket) {
 	if (!h || !ticket || (!slab && n_reads) || (!reads && n_reads)) return FQSK_E_INVAL;
+	ApiTimer api_timer{h};
 	CK(cudaSetDevice(h->P.device));
 	if (h->world > 1) return fail(h, FQSK_E_UNSUPPORTED, "fqsk_submit: not available on a sharded engine");
 	if (!h->st_copy) {
 		CK(cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking));
 		CK(cudaEventCreateWithFlags(&h->ev_recs, cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&h->ev_meta, cudaEventDisableTiming));
 		for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
 	}
 	const int par = h->tk_open ? h->tk_cur ^ 1 : h->rec_par ^ 1;
@@ -2049,13 +2062,15 @@ static int submit_impl(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, 
 	CKR(submit_finish_compute(h));                                  // previous segment: settle + sync
 	CK(cudaStreamWaitEvent(h->st, h->ev_copied[par], 0));             // the device records of this parity have left for the host
 	h->rec_par = par;
+	if (h->meta_pending) { CK(cudaStreamWaitEvent(h->st, h->ev_meta, 0)); h->meta_pending = false; }      // the previous segment's per-read results have left the buffers this one rewrites
 	Uploaded U;
 	CKR(upload_segment(h, stage, total, n_reads, U));
 	CKR(run_segment(h, U.dna, total, U.off, U.len, n_reads));
 	const uint32_t ni = mode_pe(h->P.mode) ? n_reads / 2 * 3 : n_reads;
-	if (ni) {   // duplicate flags and record offsets are final after k_prep / k_scan_reads: main stream, ahead of the look that ends the sync
+	size_t o_off = 0, o_flag = 0, o_dif = 0, o_pair = 0;
+	if (ni) {
 		// layout: [dup: ni bytes, padded to 8][rec_off: (ni + 1) u64][sorted flag: ni u32, padded][sorted dif: ni u64][pair decisions: 3 u32 per pair]
-		const size_t o_off = ((size_t) ni + 8) & ~(size_t) 7, o_flag = o_off + ((size_t) ni + 1) * 8, o_dif = o_flag + ((((size_t) ni + 1) * 4 + 7) & ~(size_t) 7), o_pair = o_dif + (size_t) ni * 8;
+		o_off = ((size_t) ni + 8) & ~(size_t) 7; o_flag = o_off + ((size_t) ni + 1) * 8; o_dif = o_flag + ((((size_t) ni + 1) * 4 + 7) & ~(size_t) 7); o_pair = o_dif + (size_t) ni * 8;
 		const size_t need = o_pair + (size_t) (n_reads / 2 + 1) * 12;
 		if (need > h->h_meta_cap[par]) {
 			if (h->h_meta[par]) cudaFreeHost(h->h_meta[par]);
@@ -2064,21 +2079,28 @@ static int submit_impl(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, 
 			CK(cudaMallocHost(&h->h_meta[par], want));
 			h->h_meta_cap[par] = want;
 		}
-		CK(cudaMemcpyAsync(h->h_meta[par], prep_bufs(h, h->seg_par).dup->p, ni, cudaMemcpyDeviceToHost, h->st));
-		CK(cudaMemcpyAsync(h->h_meta[par] + o_off, prep_bufs(h, h->seg_par).rec_off->p, ((size_t) ni + 1) * 8, cudaMemcpyDeviceToHost, h->st));
-		// what compress_prefix_sorted / CompressPE code per read / pair: functions of the reads and of the tables as they were when the
-		// segment started, so the values of the first pass are final
-		if (mode_sorted(h->P.mode)) {
-			CK(cudaMemcpyAsync(h->h_meta[par] + o_flag, h->sflag.p, (size_t) ni * 4, cudaMemcpyDeviceToHost, h->st));
-			CK(cudaMemcpyAsync(h->h_meta[par] + o_dif, h->sdif.p, (size_t) ni * 8, cudaMemcpyDeviceToHost, h->st));
-		}
-		if (mode_pe(h->P.mode) && n_reads >= 2) CK(cudaMemcpyAsync(h->h_meta[par] + o_pair, h->pe_info.p, (size_t) (n_reads / 2) * 12, cudaMemcpyDeviceToHost, h->st));
 	}
 	if (bound && ctx && n_reads) CKR(enqueue_ctx_codes(h, par));      // the context ids of the segment's records, on the device
-	if (bound && (recs || ctx) && n_reads) {   // the records leave on their own stream while the sync and the next segment run
+	if (n_reads) {
+		// Everything the host gets back leaves on the copy stream while the sync and the next segment run: first the per-read results --
+		// duplicate flags and record offsets (final after k_prep / k_scan_reads), what compress_prefix_sorted / CompressPE code per read /
+		// pair (functions of the reads and of the tables as they were when the segment started: the first pass is final) --, then the records.
+		// (On the engine's stream the small copies sat between the segment and its sync: four stream-ordered copies on the critical path.)
 		CK(cudaEventRecord(h->ev_recs, h->st)); CK(cudaStreamWaitEvent(h->st_copy, h->ev_recs, 0));
-		if (ctx) CK(cudaMemcpyAsync(ctx, h->ctxrec[par].p, bound * sizeof(fqsk_ctx_rec), cudaMemcpyDeviceToHost, h->st_copy));
-		else CK(cudaMemcpyAsync(recs, dev_recs(h, par), bound * sizeof(fqsk_base_rec), cudaMemcpyDeviceToHost, h->st_copy));
+		if (ni) {
+			CK(cudaMemcpyAsync(h->h_meta[par], prep_bufs(h, h->seg_par).dup->p, ni, cudaMemcpyDeviceToHost, h->st_copy));
+			CK(cudaMemcpyAsync(h->h_meta[par] + o_off, prep_bufs(h, h->seg_par).rec_off->p, ((size_t) ni + 1) * 8, cudaMemcpyDeviceToHost, h->st_copy));
+			if (mode_sorted(h->P.mode)) {
+				CK(cudaMemcpyAsync(h->h_meta[par] + o_flag, h->sflag.p, (size_t) ni * 4, cudaMemcpyDeviceToHost, h->st_copy));
+				CK(cudaMemcpyAsync(h->h_meta[par] + o_dif, h->sdif.p, (size_t) ni * 8, cudaMemcpyDeviceToHost, h->st_copy));
+			}
+			if (mode_pe(h->P.mode) && n_reads >= 2) CK(cudaMemcpyAsync(h->h_meta[par] + o_pair, h->pe_info.p, (size_t) (n_reads / 2) * 12, cudaMemcpyDeviceToHost, h->st_copy));
+			CK(cudaEventRecord(h->ev_meta, h->st_copy)); h->meta_pending = true;
+		}
+		if (bound && (recs || ctx)) {
+			if (ctx) CK(cudaMemcpyAsync(ctx, h->ctxrec[par].p, bound * sizeof(fqsk_ctx_rec), cudaMemcpyDeviceToHost, h->st_copy));
+			else CK(cudaMemcpyAsync(recs, dev_recs(h, par), bound * sizeof(fqsk_base_rec), cudaMemcpyDeviceToHost, h->st_copy));
+		}
 		CK(cudaEventRecord(h->ev_copied[par], h->st_copy));
 	}
 	CKR(sync_begin(h));
@@ -2092,6 +2114,7 @@ static int submit_impl(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, 
 
 int fqsk_collect(fqsk_handle *h, uint64_t ticket, uint64_t *n_recs) {
 	if (!h) return FQSK_E_INVAL;
+	ApiTimer api_timer{h};
 	CK(cudaSetDevice(h->P.device));
 	int par = -1;
 	for (int i = 0; i < 2; ++i) if (h->tk[i].open && h->tk[i].id == ticket) par = i;
@@ -2101,7 +2124,7 @@ int fqsk_collect(fqsk_handle *h, uint64_t ticket, uint64_t *n_recs) {
 		if (par != h->tk_cur) return fail(h, FQSK_E_CUDA, "internal error: an older ticket was left unfinished");
 		CKR(submit_finish_compute(h));
 	}
-	if (T.bound && (T.recs || T.ctx) && T.n_reads) CK(cudaEventSynchronize(h->ev_copied[par]));
+	if (T.n_reads) CK(cudaEventSynchronize(h->ev_copied[par]));
 	const uint32_t n = T.n_reads;
 	if (n) {
 		const bool pe = mode_pe(h->P.mode);
@@ -2123,6 +2146,92 @@ int fqsk_collect(fqsk_handle *h, uint64_t ticket, uint64_t *n_recs) {
 	T.open = false;
 	h->tk_open = h->tk[0].open || h->tk[1].open;
 	h->tk_info = par;      // fqsk_sorted_prefix / fqsk_pair_info now describe this segment
+	return FQSK_OK;
+}
+
+// The worker loop of one reads_block (application.cpp:617-662) over the asynchronous pair: fqsk_block_start, then segment k + 1 is
+// submitted before segment k is collected -- the point where the host-side coder would consume the records of k.  Same calls a host makes
+// one by one (host/fqsk_live.h does), in one C call per block.
+int fqsk_block_host(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const fqsk_read_desc *reads, uint32_t n_reads, const uint32_t *seg_end, uint32_t n_segs,
+                    fqsk_base_rec *recs, uint64_t rec_cap, uint8_t *dup, uint64_t *seg_rec_off, uint64_t *seg_n_recs) {
+	if (!h || !seg_end || !n_segs || !seg_rec_off || !seg_n_recs || (n_reads && (!slab || !reads || !recs))) return FQSK_E_INVAL;
+	if (seg_end[n_segs - 1] != n_reads) return fail(h, FQSK_E_INVAL, "fqsk_block_host: the last segment must end at the last read");
+	uint64_t at = 0;
+	for (uint32_t k = 0, a = 0; k < n_segs; a = seg_end[k], ++k) {
+		if (seg_end[k] < a) return fail(h, FQSK_E_INVAL, "fqsk_block_host: segment ends must not decrease");
+		seg_rec_off[k] = at;
+		for (uint32_t r = a; r < seg_end[k]; ++r) at += reads[r].dna_len;      // upper bound of the coded positions
+	}
+	if (at > rec_cap) return fail(h, FQSK_E_CAPACITY, "record buffer holds %llu, the block can produce %llu", (unsigned long long) rec_cap, (unsigned long long) at);
+	CKR(fqsk_block_start(h));
+	uint64_t ticket[2] = {0, 0};
+	auto first_of = [&](uint32_t k) { return k ? seg_end[k - 1] : 0u; };
+	auto submit = [&](uint32_t k) {
+		const uint32_t a = first_of(k), n = seg_end[k] - a;
+		const uint64_t cap = (k + 1 < n_segs ? seg_rec_off[k + 1] : at) - seg_rec_off[k];
+		return fqsk_submit(h, slab, slab_size, reads + a, n, recs + seg_rec_off[k], cap, dup ? dup + a : nullptr, nullptr, &ticket[k & 1]);
+	};
+	CKR(submit(0));
+	for (uint32_t k = 0; k < n_segs; ++k) {
+		if (k + 1 < n_segs) CKR(submit(k + 1));      // the engine runs ahead of the consumer
+		CKR(fqsk_collect(h, ticket[k & 1], &seg_n_recs[k]));
+	}
+	return FQSK_OK;
+}
+
+// ---- sorted-mode front end ------------------------------------------------------------------------
+// rank[i] of read i: an integer order-isomorphic to the comparator of CSortedFASTQFile::sort_reads (io.h:499-528); see fqsk_front.cuh.
+// Needs no engine: its own stream and scratch on `device`, released before it returns (one call per bin file of a sorted-order job).
+int fqsk_sort_ranks(int device, const uint8_t *slab, uint64_t slab_size, const fqsk_read_desc *reads, uint32_t n_reads, uint32_t *rank) {
+	if ((!slab || !reads || !rank) && n_reads) return FQSK_E_INVAL;
+	if (!n_reads) return FQSK_OK;
+	for (uint32_t i = 0; i < n_reads; ++i) if (reads[i].dna_off > slab_size || reads[i].dna_len > slab_size - reads[i].dna_off) return FQSK_E_INVAL;
+	int n_dev = 0;
+	if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0) { cudaGetLastError(); g_create_error = "fqsk_sort_ranks: no CUDA device"; return FQSK_E_NO_DEVICE; }
+	if (device < 0 || device >= n_dev) return FQSK_E_INVAL;
+	struct Scratch {
+		std::vector<void *> ptrs; cudaStream_t st = nullptr;
+		~Scratch() { for (void *p : ptrs) cudaFree(p); if (st) cudaStreamDestroy(st); }
+		int get(void **p, size_t bytes) { void *q = nullptr; if (cudaMalloc(&q, std::max<size_t>(bytes, 16)) != cudaSuccess) { cudaGetLastError(); return FQSK_E_NOMEM; } ptrs.push_back(q); *p = q; return FQSK_OK; }
+	} X;
+#define FCK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { g_create_error = std::string("fqsk_sort_ranks: ") + cudaGetErrorString(e_); cudaGetLastError(); return FQSK_E_CUDA; } } while (0)
+	FCK(cudaSetDevice(device));
+	FCK(cudaStreamCreateWithFlags(&X.st, cudaStreamNonBlocking));
+	const uint32_t n = n_reads, tiles = nblk(n, RDX_TILE);
+	uint8_t *d_slab = nullptr; fqsk_read_desc *d_reads = nullptr;
+	unsigned long long *k0 = nullptr, *k1 = nullptr; uint32_t *v0 = nullptr, *v1 = nullptr, *gs = nullptr, *ge = nullptr, *d_rank = nullptr, *hist = nullptr, *d_max = nullptr;
+	CKR(X.get((void **) &d_slab, slab_size)); CKR(X.get((void **) &d_reads, (size_t) n * sizeof(fqsk_read_desc)));
+	CKR(X.get((void **) &k0, (size_t) n * 8)); CKR(X.get((void **) &k1, (size_t) n * 8)); CKR(X.get((void **) &v0, (size_t) n * 4)); CKR(X.get((void **) &v1, (size_t) n * 4));
+	CKR(X.get((void **) &gs, (size_t) n * 4)); CKR(X.get((void **) &ge, (size_t) n * 4)); CKR(X.get((void **) &d_rank, (size_t) n * 4));
+	CKR(X.get((void **) &hist, (((size_t) tiles + 1) << 8) * 4)); CKR(X.get((void **) &d_max, 4));
+	FCK(cudaMemcpyAsync(d_slab, slab, slab_size, cudaMemcpyHostToDevice, X.st));
+	FCK(cudaMemcpyAsync(d_reads, reads, (size_t) n * sizeof(fqsk_read_desc), cudaMemcpyHostToDevice, X.st));
+	FCK(cudaMemsetAsync(d_max, 0, 4, X.st));
+	FCK(pdl(k_front_key, nblk(n, 256), 256, X.st, (const uint8_t *) d_slab, (const fqsk_read_desc *) d_reads, n, k0));
+	// stable LSD radix sort of (key, read) by all 64 bits, 8 bits a pass (the engine's own partition kernels, fqsk_sort.cuh)
+	const unsigned long long *ks = k0; const uint32_t *vs = nullptr;
+	for (int p = 0; p < 8; ++p) {
+		unsigned long long *kd = (p & 1) ? k0 : k1; uint32_t *vd = (p & 1) ? v0 : v1;
+		uint32_t *totals = hist + ((size_t) tiles << 8);
+		const BitsOp op{(uint32_t) (8 * p), 0xFFu};
+		FCK(pdl(k_rdx_hist<8, BitsOp>, tiles, RDX_THREADS, X.st, ks, n, tiles, hist, op));
+		FCK(pdl(k_rdx_rowscan, 256u, 256, X.st, hist, tiles, totals));
+		FCK(pdl(k_rdx_scatter<8, BitsOp>, tiles, RDX_THREADS, X.st, ks, vs, kd, vd, n, tiles, (const uint32_t *) hist, (const uint32_t *) totals, op));
+		ks = kd; vs = vd;
+	}
+	// 8 passes: the result is in (k0, v0)
+	FCK(pdl(k_front_group, nblk(n, 256), 256, X.st, (const unsigned long long *) k0, n, gs, ge, d_max));
+	uint32_t max_run = 0;
+	FCK(cudaMemcpyAsync(&max_run, d_max, 4, cudaMemcpyDeviceToHost, X.st));
+	FCK(cudaStreamSynchronize(X.st));
+	if (max_run > (1u << 16)) {      // the members of a run are ranked by comparing each with all others: bounded, never approximated
+		g_create_error = "fqsk_sort_ranks: more than 65536 reads share their first 32 symbols; not supported";
+		return FQSK_E_UNSUPPORTED;
+	}
+	FCK(pdl(k_front_rank, nblk(n, 128), 128, X.st, (const uint8_t *) d_slab, (const fqsk_read_desc *) d_reads, (const uint32_t *) v0, (const uint32_t *) gs, (const uint32_t *) ge, n, d_rank));
+	FCK(cudaMemcpyAsync(rank, d_rank, (size_t) n * 4, cudaMemcpyDeviceToHost, X.st));
+	FCK(cudaStreamSynchronize(X.st));
+#undef FCK
 	return FQSK_OK;
 }
 

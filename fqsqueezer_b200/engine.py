@@ -42,13 +42,13 @@ class _Stats(C.Structure):
                 ("draws", C.c_uint64 * 4), ("n_segments", C.c_uint64), ("n_syncs", C.c_uint64), ("n_replays", C.c_uint64),
                 ("n_bases", C.c_uint64), ("n_reads", C.c_uint64), ("kernel_launches", C.c_uint64), ("bmer_buckets", C.c_uint64),
                 ("smer_buckets", C.c_uint64), ("bmer_stash_used", C.c_uint64), ("smer_stash_used", C.c_uint64), ("n_hot_segments", C.c_uint64),
-                ("n_filtered_segments", C.c_uint64)]
+                ("n_filtered_segments", C.c_uint64), ("n_looks", C.c_uint64), ("look_wait_ns", C.c_uint64), ("api_ns", C.c_uint64)]
 
 
 EXPORTS = ["fqsk_create", "fqsk_destroy", "fqsk_last_error", "fqsk_block_start", "fqsk_segment", "fqsk_segment_device", "fqsk_announce_device",
-           "fqsk_device_recs", "fqsk_recs_checksum", "fqsk_sorted_prefix", "fqsk_pair_info", "fqsk_submit", "fqsk_submit_ctx", "fqsk_collect", "fqsk_sync", "fqsk_dump", "fqsk_stats_get", "fqsk_profile", "fqsk_ht_insert", "fqsk_ht_find",
+           "fqsk_device_recs", "fqsk_recs_checksum", "fqsk_sorted_prefix", "fqsk_pair_info", "fqsk_submit", "fqsk_submit_ctx", "fqsk_collect", "fqsk_block_host", "fqsk_sync", "fqsk_dump", "fqsk_stats_get", "fqsk_profile", "fqsk_ht_insert", "fqsk_ht_find",
            "fqsk_ht_count", "fqsk_timeline", "fqsk_timer_begin", "fqsk_timer_end", "fqsk_siv_increment", "fqsk_siv_test", "fqsk_siv_counts", "fqsk_siv_test_shorter", "fqsk_mt_stream", "fqsk_host_alloc", "fqsk_host_free",
-           "fqsk_shard_export", "fqsk_shard_attach", "fqsk_sync_route", "fqsk_sync_apply", "fqsk_sync_finish"]
+           "fqsk_sort_ranks", "fqsk_shard_export", "fqsk_shard_attach", "fqsk_sync_route", "fqsk_sync_apply", "fqsk_sync_finish"]
 
 _lib = None
 
@@ -78,6 +78,7 @@ def load_library():
     lib.fqsk_submit.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint32, vp, C.c_uint64, vp, vp, u64p]
     lib.fqsk_submit_ctx.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint32, vp, C.c_uint64, vp, vp, u64p]
     lib.fqsk_collect.argtypes = [vp, C.c_uint64, u64p]
+    lib.fqsk_block_host.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint64, vp, vp, vp]
     lib.fqsk_sync.argtypes = [vp]
     lib.fqsk_dump.argtypes = [vp, C.c_int, vp, vp, C.c_uint64, u64p]
     lib.fqsk_stats_get.argtypes = [vp, C.POINTER(_Stats)]
@@ -94,6 +95,7 @@ def load_library():
     lib.fqsk_siv_test_shorter.argtypes = [vp, vp, vp, C.c_uint64, vp]
     lib.fqsk_mt_stream.argtypes = [vp, C.c_uint64, vp]
     lib.fqsk_host_alloc.argtypes = [C.c_uint64, C.POINTER(vp)]
+    lib.fqsk_sort_ranks.argtypes = [C.c_int, vp, C.c_uint64, vp, C.c_uint32, vp]
     lib.fqsk_host_free.argtypes = [vp]
     lib.fqsk_host_free.restype = None
     for n in EXPORTS:
@@ -128,6 +130,21 @@ def recs_checksum_host(recs: np.ndarray) -> int:
     with np.errstate(over="ignore"):
         h = fmix(a ^ fmix(b ^ fmix(c ^ fmix(d + np.arange(n, dtype=np.uint64)))))
         return int(h.sum(dtype=np.uint64))
+
+
+def sort_ranks(slab: np.ndarray, off: np.ndarray, length: np.ndarray, device: int = 0) -> np.ndarray:
+    """fqsk_sort_ranks: per read an integer order-isomorphic to the comparator of CSortedFASTQFile::sort_reads (io.h:499-528)."""
+    lib = load_library()
+    slab = np.ascontiguousarray(slab, np.uint8)
+    n = len(off)
+    desc = np.zeros(n, READ_DESC_DTYPE)
+    desc["dna_off"] = off
+    desc["dna_len"] = length
+    rank = np.zeros(n, np.uint32)
+    rc = lib.fqsk_sort_ranks(device, _ptr(slab), slab.size, _ptr(desc), n, _ptr(rank))
+    if rc != 0:
+        raise FqskError(rc, lib.fqsk_last_error(None).decode())
+    return rank
 
 
 def _ptr(a):
@@ -254,6 +271,30 @@ class KmerEngine:
         n_recs = C.c_uint64(0)
         self._ck(self.lib.fqsk_collect(self.h, ticket, C.byref(n_recs)))
         return recs[: n_recs.value], dup[:n], rec_off
+
+    def block_host(self, slab: np.ndarray, off: np.ndarray, length: np.ndarray, seg_end):
+        """One reads_block through fqsk_block_host: the worker loop of the reference (block start, then segment k + 1 submitted before
+        segment k is collected) in one call.  seg_end: exclusive end (read index) of every sync segment.  Returns (records buffer,
+        duplicate flags, first record of every segment, records of every segment); the buffers are page-locked, owned by the engine and
+        valid until the next block_host call."""
+        if slab.dtype != np.uint8 or not slab.flags.c_contiguous:
+            slab = np.ascontiguousarray(slab, np.uint8)
+        n = len(off)
+        seg_end = np.ascontiguousarray(seg_end, np.uint32)
+        ns = len(seg_end)
+        cap = int(length.sum(dtype=np.int64)) + 16
+        ent = self.__dict__.get("_block_cache")
+        n_cap, r_cap = max(n, self.reserve_reads, 1), max(cap, self.reserve_bytes + 16)
+        if ent is None or ent[0] < n_cap or ent[1] < r_cap:
+            ent = (n_cap, r_cap, np.zeros(n_cap, READ_DESC_DTYPE),
+                   self._pinned_array("brecs", r_cap * REC_DTYPE.itemsize)[: r_cap * REC_DTYPE.itemsize].view(REC_DTYPE), self._pinned_array("bdup", n_cap))
+            self._block_cache = ent
+        desc = ent[2]
+        desc["dna_off"][:n] = off
+        desc["dna_len"][:n] = length
+        seg_off, seg_n = np.zeros(ns, np.uint64), np.zeros(ns, np.uint64)
+        self._ck(self.lib.fqsk_block_host(self.h, _ptr(slab), slab.size, _ptr(desc), n, _ptr(seg_end), ns, _ptr(ent[3]), r_cap, _ptr(ent[4]), _ptr(seg_off), _ptr(seg_n)))
+        return ent[3], ent[4][: max(n, 1)], seg_off, seg_n
 
     def segment_device(self, d_dna_ptr: int, dna_bytes: int, d_off_ptr: int, d_len_ptr: int, n_reads: int, want_n_recs: bool = True):
         """Reads already in HBM.  want_n_recs=False only enqueues the segment: the library looks at the outcome when the

@@ -14,6 +14,7 @@ host/_bin/ is git-ignored and travels to the GPU box like our own .so files).  T
                    (549-661)                   scan; no p-mer pushes
                    CompressPE (1790-1880)      the shared-minimizer decision of mate 2 from fqsk_pair_info instead of find_minim_cand /
                                                generate_read_bmers / the candidate search; no append_pe_mers3
+  io.h             sort_reads (499-528)        the comparator of the per-bin std::sort compares ranks computed on the GPU (fqsk_sort_ranks)
   everything else (context model, range coders, id / quality / meta streams, container, decompressor) is untouched.
 
 host/fqsk_live.h (ours) holds the binding itself (dlopen of $FQSK_LIB, descriptors, record cursor).
@@ -199,6 +200,22 @@ def patch_dna(path):
     open(path, "w", encoding="latin-1").write(s)
 
 
+def patch_io(path):
+    """io.h:499-528 -- CSortedFASTQFile::sort_reads keeps its std::sort call; the comparator compares the ranks the GPU computed for the bin
+    (fqsk_sort_ranks): the same outcome for every pair of reads, so the same order, ties of the unstable sort included."""
+    s = open(path, encoding="latin-1").read()
+    s = replace_once(s, "#pragma once\n", '#pragma once\n#include "fqsk_live.h"\n', path) if "#pragma once\n" in s else replace_once(s, '#include "defs.h"\n', '#include "defs.h"\n#include "fqsk_live.h"\n', path)
+    a0 = s.index("\tvoid sort_reads()\n\t{\n")
+    a1 = s.index("\t//Return ordering of the sorted collection of reads", a0)
+    body = ("\tvoid sort_reads()\n\t{\n"
+            "\t\tstd::vector<uint32_t> fqsk_rank = CFqskLive::get().sort_ranks(buffer, buffer_filled, v_reads);\n"
+            "\t\tsort(v_reads.begin(), v_reads.end(), [&](pair<read_desc_t, uint32_t> &x, pair<read_desc_t, uint32_t> &y) {\n"
+            "\t\t\treturn fqsk_rank[x.second] < fqsk_rank[y.second];\n\t\t});\n\t}\n\n")
+    assert "dna_convert_NT[x.first.dna[i]]" in s[a0:a1]
+    s = s[:a0] + body + s[a1:]
+    open(path, "w", encoding="latin-1").write(s)
+
+
 def compile_dir(src_dir, build_dir, exe):
     os.makedirs(build_dir, exist_ok=True)
     cpps = sorted(f for f in os.listdir(src_dir) if f.endswith(".cpp"))
@@ -227,6 +244,7 @@ def main():
             shutil.copy(os.path.join(SRC, f), scratch)
     patch_application(os.path.join(scratch, "application.cpp"))
     patch_dna(os.path.join(scratch, "dna.cpp"))
+    patch_io(os.path.join(scratch, "io.h"))
     compile_dir(scratch, os.path.join(os.path.dirname(scratch), "host_obj"), EXE)
     print("[build_host] ok:", EXE)
     return 0

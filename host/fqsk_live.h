@@ -13,6 +13,7 @@
 // CPU test suite can point it at a mock built from the oracle (tests/mock_fqsk.cpp) to check the HOST half of the integration.
 #pragma once
 #include <dlfcn.h>
+#include <time.h>
 
 #include <cstdint>
 #include <cstdio>
@@ -40,6 +41,7 @@ class CFqskLive {
 	decltype(&fqsk_pair_info) p_pair_info = nullptr;
 	decltype(&fqsk_host_alloc) p_host_alloc = nullptr;
 	decltype(&fqsk_host_free) p_host_free = nullptr;
+	decltype(&fqsk_sort_ranks) p_sort_ranks = nullptr;      // sorted-order front end
 
 	fqsk_handle *h = nullptr;
 	const uint8_t *slab = nullptr;
@@ -76,14 +78,9 @@ class CFqskLive {
 public:
 	static CFqskLive &get() { static CFqskLive x; return x; }
 
-	// application.cpp:86-91 (AdjustToParams): the engine takes the place of siv_pmer / ht_smer / ht_bmer
-	// dna_mode: params.h:18 (0 se_original, 1 se_sorted, 2 pe_original, 3 pe_sorted) = FQSK_MODE_*
-	void create(uint32_t pmer_len, uint32_t smer_len, uint32_t bmer_len, uint32_t prefix_len, uint64_t genome_mbp, uint32_t dna_mode, uint32_t n_threads, bool dup_check) {
-		if (dna_mode > FQSK_MODE_PE_SORTED || n_threads != 1 || !dup_check) {
-			fprintf(stderr, "fqsk: the live host covers -t 1 with the duplicates check on (-s / -p, -om o / -om s); no CPU fallback for other modes\n");
-			exit(3);
-		}
-		mode = dna_mode;
+	// binds the library (once): create() needs it, and so does the sorted-order reader, which may open its first bin file earlier
+	void load() {
+		if (lib) return;
 		const char *path = getenv("FQSK_LIB");
 		lib = dlopen(path ? path : "libfqsk.so", RTLD_NOW | RTLD_LOCAL);
 		if (!lib) {   // the library needs the CUDA runtime: when the loader's search path does not have it, take it from $FQSK_CUDART or the toolkit
@@ -98,6 +95,34 @@ public:
 		// cor_zone, determine_ctx_codes and rank (dna.cpp:739-760) have run on the device.  FQSK_CTX=0 keeps the per-base records.
 		p_submit_ctx = (decltype(p_submit_ctx)) dlsym(lib, "fqsk_submit_ctx");
 		ctx_on = p_submit_ctx && !(getenv("FQSK_CTX") && !strcmp(getenv("FQSK_CTX"), "0"));
+		sym(p_sort_ranks, "fqsk_sort_ranks");
+	}
+
+	// io.h:499-528 (CSortedFASTQFile::sort_reads): the comparator's work -- two reads walked symbol by symbol per comparison -- is done once
+	// per bin file on the GPU: rank[read_id] is order-isomorphic to it, std::sort then compares integers (same outcomes, same final order)
+	template <typename V> std::vector<uint32_t> sort_ranks(const uint8_t *buffer, uint64_t size, V &v_reads) {
+		load();
+		const size_t n = v_reads.size();
+		std::vector<fqsk_read_desc> d(n);
+		for (size_t i = 0; i < n; ++i) {
+			if (v_reads[i].second != i) { fprintf(stderr, "fqsk: sort_reads expects the reads in file order\n"); exit(3); }
+			d[i].dna_off = (uint64_t) (v_reads[i].first.dna - buffer); d[i].dna_len = (uint32_t) v_reads[i].first.read_len(); d[i].flags = 0;
+		}
+		std::vector<uint32_t> rank(n);
+		int rc = p_sort_ranks(getenv("FQSK_DEVICE") ? atoi(getenv("FQSK_DEVICE")) : 0, buffer, size, d.data(), (uint32_t) n, rank.data());
+		if (rc != FQSK_OK) die("fqsk_sort_ranks", rc);
+		return rank;
+	}
+
+	// application.cpp:86-91 (AdjustToParams): the engine takes the place of siv_pmer / ht_smer / ht_bmer
+	// dna_mode: params.h:18 (0 se_original, 1 se_sorted, 2 pe_original, 3 pe_sorted) = FQSK_MODE_*
+	void create(uint32_t pmer_len, uint32_t smer_len, uint32_t bmer_len, uint32_t prefix_len, uint64_t genome_mbp, uint32_t dna_mode, uint32_t n_threads, bool dup_check) {
+		if (dna_mode > FQSK_MODE_PE_SORTED || n_threads != 1 || !dup_check) {
+			fprintf(stderr, "fqsk: the live host covers -t 1 with the duplicates check on (-s / -p, -om o / -om s); no CPU fallback for other modes\n");
+			exit(3);
+		}
+		mode = dna_mode;
+		load();
 		fqsk_params P;
 		memset(&P, 0, sizeof(P));
 		P.abi_version = FQSK_ABI_VERSION;

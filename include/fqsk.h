@@ -105,6 +105,9 @@ typedef struct fqsk_stats {
 	uint64_t bmer_buckets, smer_buckets, bmer_stash_used, smer_stash_used;
 	uint64_t n_hot_segments;                 /* segments redone with the ordered thread-local evaluator (cinc_lb / cinc_ls in use) */
 	uint64_t n_filtered_segments;            /* large segments whose thread-local delta held only the pushes a lookup could ask for */
+	uint64_t n_looks, look_wait_ns;          /* host looks at the device and the time the host spent WAITING in them: api time minus this = the
+	                                          * host's own work (launching); a job whose wait time is near zero is bound by its host, not the GPU */
+	uint64_t api_ns;                         /* time inside the segment / sync / submit / collect calls */
 } fqsk_stats;
 
 /* Named phases of fqsk_profile(): device milliseconds accumulated since create (only with FQSK_F_PROFILE). */
@@ -178,6 +181,12 @@ int fqsk_sync(fqsk_handle *h);
 int fqsk_submit(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const fqsk_read_desc *reads, uint32_t n_reads,
                 fqsk_base_rec *recs, uint64_t rec_cap, uint8_t *dup, uint64_t *rec_off, uint64_t *ticket);
 int fqsk_collect(fqsk_handle *h, uint64_t ticket, uint64_t *n_recs);
+/* One reads_block through the asynchronous pair, i.e. the reference's worker loop (application.cpp:617-662) with the k-mer engine one segment
+ * ahead of the consumer: fqsk_block_start, then fqsk_submit of segment k + 1 before fqsk_collect of segment k.  Segment k covers reads
+ * [seg_end[k - 1], seg_end[k]) (seg_end[-1] = 0; the segment after the last sync of a block may be empty).  recs: page-locked (fqsk_host_alloc),
+ * rec_cap >= sum of dna_len; the records of segment k start at recs[seg_rec_off[k]] and number seg_n_recs[k].  dup: n_reads bytes or NULL. */
+int fqsk_block_host(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const fqsk_read_desc *reads, uint32_t n_reads, const uint32_t *seg_end, uint32_t n_segs,
+                    fqsk_base_rec *recs, uint64_t rec_cap, uint8_t *dup, uint64_t *seg_rec_off, uint64_t *seg_n_recs);
 /* fqsk_submit with the context ids of the DNA stream built on the device: instead of fqsk_base_rec the
  * caller receives one fqsk_ctx_rec (16 bytes, include/fqsk_ctx.h) per coded base -- what cor_zone (dna.cpp:739-744),
  * CCodeContext::determine_ctx_codes (code_ctx.cpp:257-324), rank (dna.cpp:177-193) and update_ctx_r_sym (dna.cpp:664-671) compute on
@@ -187,14 +196,24 @@ int fqsk_collect(fqsk_handle *h, uint64_t ticket, uint64_t *n_recs);
 int fqsk_submit_ctx(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const fqsk_read_desc *reads, uint32_t n_reads,
                     fqsk_ctx_rec *ctx, uint64_t rec_cap, uint8_t *dup, uint64_t *rec_off, uint64_t *ticket);
 
+/* Sorted-order front end.  Replaces the comparator of CSortedFASTQFile::sort_reads (io.h:499-528: symbols with
+ * N read as T over the shorter length, then the shorter read first, then the raw bytes): rank[i] is an integer per read that is
+ * order-isomorphic to it -- rank[x] < rank[y] exactly when the comparator puts x before y, equal ranks for reads it calls equivalent.
+ * The host keeps its own std::sort call and compares ranks: the same comparison outcomes, hence the same order as the reference, ties of
+ * the unstable sort included.  slab: the bin file (or any buffer the descriptors point into); no engine handle is needed; `device` is the
+ * CUDA device to use.  More than 65 536 reads sharing their first 32 symbols: FQSK_E_UNSUPPORTED (message via fqsk_last_error(NULL)). */
+int fqsk_sort_ranks(int device, const uint8_t *slab, uint64_t slab_size, const fqsk_read_desc *reads, uint32_t n_reads, uint32_t *rank);
+
 /* ---- sharded operation (world_size > 1): one handle per GPU / process, reference `-t world_size` semantics --------------------
  * Replaces the shared-memory coupling of the reference's worker threads: global tables read by everybody between barriers
  * (application.cpp:645-654), X_to_add[src][dst] exchange matrices + InsertKmersToHT on the owner (dna.cpp:2393-2472).
  * Set-up: every rank calls fqsk_shard_export, the descriptors are exchanged by the caller (any transport) and every rank calls
  * fqsk_shard_attach for each peer: tables and inboxes become NVLink peer mappings (CUDA IPC).
- * Per sync, instead of fqsk_sync:  fqsk_sync_route  -> BARRIER ->  fqsk_sync_apply  -> ALL-REDUCE(sum) of (fresh, updates) ->
- * fqsk_sync_finish.  The barrier / all-reduce are the caller's (NCCL in fqsqueezer_b200/sharded.py); the payload itself moves
- * inside fqsk_sync_route as peer stores into the owners' inboxes.  Table growth is not supported in this mode: size the
+ * Per sync, instead of fqsk_sync:  fqsk_sync_route  ->  fqsk_sync_apply  -> ALL-REDUCE(sum) of (fresh, updates) -> fqsk_sync_finish.
+ * The reference's first barrier ("every row is filled") is a sequence number the routing step posts in the owners' inboxes and the
+ * apply step waits for ON THE DEVICE; the all-reduce -- the second barrier: every owner has inserted before anybody looks up again --
+ * is the caller's (NCCL in fqsqueezer_b200/sharded.py); the payload itself moves inside fqsk_sync_route as peer stores into the
+ * owners' inboxes.  Table growth is not supported in this mode: size the
  * tables with expected_kmers / *_log2_buckets / pair_log2_slots.  Paired-end (FQSK_MODE_PE_ORIGINAL): the pair table is
  * sharded by (fmix64(key) >> 48) % world_size (ht_kmer.h:599-602, dna.cpp:1076-1081) and the distinct (key, value, weight)
  * triples of a segment travel with the same exchange step. */

@@ -245,6 +245,17 @@ def ref_lib():
     return _ref_lib
 
 
+def sort_ranks(slab: np.ndarray, off: np.ndarray, length: np.ndarray) -> np.ndarray:
+    """rank[i] = number of reads the comparator of CSortedFASTQFile::sort_reads (io.h:499-528) puts strictly before read i."""
+    lib = oracle_lib()
+    lib.fqso_sort_ranks.argtypes = [_u8p, _u64p, _u32p, C.c_uint32, _u32p]
+    lib.fqso_sort_ranks.restype = None
+    n = len(off)
+    rank = np.zeros(max(n, 1), np.uint32)
+    lib.fqso_sort_ranks(np.ascontiguousarray(slab, np.uint8), np.ascontiguousarray(off, np.uint64), np.ascontiguousarray(length, np.uint32), n, rank)
+    return rank[:n]
+
+
 def oracle_units() -> _Units:
     return _Units(oracle_lib(), "fqso_", False)
 

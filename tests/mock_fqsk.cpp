@@ -105,3 +105,13 @@ int fqsk_host_alloc(uint64_t bytes, void **out) { *out = malloc(bytes); return *
 void fqsk_host_free(void *p) { free(p); }
 
 }
+
+// sorted-order front end: the oracle's restatement of the comparator of CSortedFASTQFile::sort_reads (io.h:499-528)
+extern "C" void fqso_sort_ranks(const uint8_t *slab, const uint64_t *off, const uint32_t *len, uint32_t n, uint32_t *rank);
+extern "C" int fqsk_sort_ranks(int, const uint8_t *slab, uint64_t, const fqsk_read_desc *reads, uint32_t n_reads, uint32_t *rank) {
+	std::vector<uint64_t> off(n_reads + 1);
+	std::vector<uint32_t> len(n_reads + 1);
+	for (uint32_t i = 0; i < n_reads; ++i) { off[i] = reads[i].dna_off; len[i] = reads[i].dna_len; }
+	fqso_sort_ranks(slab, off.data(), len.data(), n_reads, rank);
+	return FQSK_OK;
+}

@@ -1,7 +1,7 @@
 """Size-independent properties at BASELINE config-2 scale (p17/s20/b24, 51 000-read blocks, the reference's sync schedule), where
-the CPU oracle is too slow to be the checker: (1) the three ways into the engine -- reads resident in HBM (fqsk_segment_device),
-host buffers blocking (fqsk_segment + fqsk_sync) and host buffers asynchronous (fqsk_submit / fqsk_collect) -- must produce the
-same records, tables and PRNG positions; (2) a run is a pure function of its input (two runs, identical checksums);
+the CPU oracle is too slow to be the checker: (1) the ways into the engine -- reads resident in HBM (fqsk_segment_device, alone and with
+the next segment announced by fqsk_announce_device), host buffers blocking (fqsk_segment + fqsk_sync), host buffers asynchronous
+(fqsk_submit / fqsk_collect) and a whole reads_block per call (fqsk_block_host) -- must produce the same records, tables and PRNG positions; (2) a run is a pure function of its input (two runs, identical checksums);
 (3) conservation: every coded base yields exactly one record and the p-mer update count equals pushes + hidden updates."""
 import hashlib
 
@@ -50,15 +50,29 @@ def _run(mode, blocks):
         sched = list(S.segments(0, READS, S.calc_no_synchronizations(g, READS, 1)))
         slab, off, ln = _slab(codes)
         e.block_start()
-        if mode == "device":
+        if mode in ("device", "device_announce"):
             d = torch.from_numpy(synth.codes_to_ascii(codes).reshape(-1)).cuda()
             d_off = torch.from_numpy(np.arange(READS, dtype=np.int64) * L).cuda()
             d_len = torch.full((READS,), L, dtype=torch.int32, device="cuda")
-        for a, bb in sched:
-            if mode == "device":
-                n = e.segment_device(d.data_ptr() + a * L, (bb - a) * L, d_off.data_ptr(), d_len.data_ptr(), bb - a)
+            torch.cuda.synchronize()      # the engine reads them on its own non-blocking stream (include/fqsk.h)
+        if mode == "block":
+            recs, dup, seg_off, seg_n = e.block_host(slab, off, ln, np.array([bb for _, bb in sched], np.uint32))
+            for o, n in zip(seg_off.tolist(), seg_n.tolist()):
+                h.update(np.ascontiguousarray(recs[o:o + n]).view(np.uint8)); n_recs += n
+            continue
+        for k, (a, bb) in enumerate(sched):
+            if mode in ("device", "device_announce"):
+                if mode == "device":
+                    n = e.segment_device(d.data_ptr() + a * L, (bb - a) * L, d_off.data_ptr(), d_len.data_ptr(), bb - a)
+                else:
+                    e.segment_device(d.data_ptr() + a * L, (bb - a) * L, d_off.data_ptr(), d_len.data_ptr(), bb - a, want_n_recs=False)
+                    if k + 1 < len(sched):
+                        a2, b2 = sched[k + 1]
+                        e.announce_device(d.data_ptr() + a2 * L, (b2 - a2) * L, d_off.data_ptr(), d_len.data_ptr(), b2 - a2)
                 ptr, n2 = e.device_recs()
-                assert n == n2
+                if mode == "device":
+                    assert n == n2
+                n = n2
                 buf = torch.empty(n * E.REC_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
                 E.C.cdll.LoadLibrary("libcudart.so").cudaMemcpy(E.C.c_void_p(buf.data_ptr()), E.C.c_void_p(ptr), E.C.c_size_t(buf.numel()), 3)
                 recs = buf.cpu().numpy().view(E.REC_DTYPE)
@@ -82,13 +96,13 @@ def _run(mode, blocks):
     return h.hexdigest(), n_recs, tabs, st
 
 
-def test_three_entry_paths_agree_and_runs_are_deterministic():
+def test_entry_paths_agree_and_runs_are_deterministic():
     genome = synth.make_genome(GENOME, 5)
     blocks = [synth.make_reads(genome, READS, L=L, seed=100 + i)[0] for i in range(len(BLOCKS))]
     pref, p, s, b = E.kmer_params(GS)
-    res = {m: _run(m, blocks) for m in ("device", "blocking", "async")}
+    res = {m: _run(m, blocks) for m in ("device", "device_announce", "blocking", "async", "block")}
     again = _run("async", blocks)
-    assert res["device"] == res["blocking"] == res["async"] == again
+    assert res["device"] == res["device_announce"] == res["blocking"] == res["async"] == res["block"] == again
     digest, n_recs, tabs, st = res["async"]
     assert n_recs == len(BLOCKS) * READS * (L - pref)               # no duplicates in this stream: one record per coded suffix base
     assert st["siv_no_filled"] == tabs[0][0] and st["n_smers"] == tabs[1][0] and st["n_bmers"] == tabs[2][0]
