@@ -128,6 +128,7 @@ struct fqsk_handle {
 	void *peer_ptrs[8][8] = {{nullptr}};     // IPC mappings to close
 	uint32_t attached = 0;                   // bit i: rank i's shard is mapped
 	DevBuf route_keys, route_keys2, route_sorted, route_hist, route_perm, route_chunks;
+	DevBuf hot_tab;      // k_hot_eval: direct-indexed match table of a front-truncated thread-local lookup with many completions
 	uint64_t sync_fresh = 0, sync_updates = 0; bool routed = false, applied = false;
 	uint64_t siv_local_filled = 0;           // non-zero fields of THIS rank's p-mer shard (S.siv_no_filled is the global statistic)
 	DevBuf scan_vals; uint32_t scan_epoch2 = 0;
@@ -1000,7 +1001,8 @@ int seg_build_delta(fqsk_handle *h, bool force_full = false) {
 	}
 	CKR(stream_ensure(h, h->rng[ST_LB], (uint64_t) en[0] * 8 + 1024)); CKR(stream_ensure(h, h->rng[ST_LS], (uint64_t) en[1] * 8 + 1024));
 	C.E = make_engine_dev(h);
-	CK(pdl(k_hot_eval, 1, 64, h->st, C.E, S, P, h->evk_s[0].as<unsigned long long>(), h->evv_s[0].as<uint32_t>(), en[0], h->evk_s[1].as<unsigned long long>(), h->evv_s[1].as<uint32_t>(), en[1])); LAUNCHED(h);
+	CK(h->hot_tab.ensure((size_t) 2 * 3 * HOT_TAB_ENTRIES * 4)); CK(cudaMemsetAsync(h->hot_tab.p, 0, (size_t) 2 * 3 * HOT_TAB_ENTRIES * 4, h->st));
+	CK(pdl(k_hot_eval, 1, 64, h->st, C.E, S, P, h->evk_s[0].as<unsigned long long>(), h->evv_s[0].as<uint32_t>(), en[0], h->evk_s[1].as<unsigned long long>(), h->evv_s[1].as<uint32_t>(), en[1], h->hot_tab.as<uint32_t>())); LAUNCHED(h);
 	return FQSK_OK;
 }
 
@@ -1126,7 +1128,7 @@ int seg_finish(fqsk_handle *h, bool have_look) {
 		if (fl[1]) {
 			// a thread-local counter left the deterministic range: redo the segment with the ordered evaluator
 			if (!h->hot) { h->hot = true; ++h->S.n_hot_segments; h->seg_extra_pass = true; return RC_RETRY; }
-			return fail(h, FQSK_E_UNSUPPORTED, "a front-truncated thread-local lookup matched more than %u entries; not supported", DeltaCollect::CAP);
+			return fail(h, FQSK_E_CUDA, "internal error: the ordered thread-local evaluator met a lookup it cannot represent");
 		}
 		if (fl[2] || fl[0] || fl[7]) h->seg_extra_pass = true;
 		if (fl[2]) { C.redo_walk = true; C.redo_tail = true; CKR(seg_pass(h)); continue; }      // walk `it` changed pushes: one more thread-local pass
@@ -1394,8 +1396,9 @@ int hot_account(fqsk_handle *h, int stream) {
 	EngineDev E = make_engine_dev(h);
 	SegDev S{};
 	S.delta_b = stream ? DeltaDev{} : D; S.delta_s = stream ? D : DeltaDev{};
+	CK(h->hot_tab.ensure((size_t) 2 * 3 * HOT_TAB_ENTRIES * 4)); CK(cudaMemsetAsync(h->hot_tab.p, 0, (size_t) 2 * 3 * HOT_TAB_ENTRIES * 4, h->st));
 	CK(pdl(k_hot_eval, 1, 64, h->st, E, S, P, h->evk_s[0].as<unsigned long long>(), h->evv_s[0].as<uint32_t>(), stream ? 0 : en,
-	                               h->evk_s[1].as<unsigned long long>(), h->evv_s[1].as<uint32_t>(), stream ? en : 0));
+	                               h->evk_s[1].as<unsigned long long>(), h->evv_s[1].as<uint32_t>(), stream ? en : 0, h->hot_tab.as<uint32_t>()));
 	LAUNCHED(h);
 	CK(cudaMemcpyAsync(hs, h->d_status, 64, cudaMemcpyDeviceToHost, h->st));
 	CK(cudaStreamSynchronize(h->st));
@@ -1531,7 +1534,7 @@ void fqsk_destroy(fqsk_handle *h) {
 	                  &h->y_tslot, &h->y_c0, &h->y_m, &h->y_draw, &h->y_j, &h->y_final, &h->y_flag_at, &h->y_own, &h->y_lead, &h->y_rank, &h->y_flag, &h->y_doff,
 	                  &h->idx_k, &h->idx_t, &h->idx_rt, &h->miss_fold, &h->hr_b[0], &h->hr_b[1], &h->hr_b[2], &h->hr_s[0], &h->hr_s[1], &h->hr_s[2],
 	                  &h->evk[0], &h->evk[1], &h->evv[0], &h->evv[1], &h->evk_s[0], &h->evk_s[1], &h->evv_s[0], &h->evv_s[1], &h->ctxrec[0], &h->ctxrec[1], &h->scan_part, &h->scan8_part, &h->rdx_hist, &h->rdx_k, &h->rdx_v, &h->scan_vals, &h->recs_alt, &h->dfilter, &h->pk,
-	                  &h->route_keys, &h->route_keys2, &h->route_sorted, &h->route_hist, &h->route_perm, &h->route_chunks, &h->f_dup, &h->f_n_coded, &h->f_letters, &h->f_rec_off, &h->f_sl_prefix, &h->f_pk,
+	                  &h->route_keys, &h->route_keys2, &h->route_sorted, &h->route_hist, &h->route_perm, &h->route_chunks, &h->hot_tab, &h->f_dup, &h->f_n_coded, &h->f_letters, &h->f_rec_off, &h->f_sl_prefix, &h->f_pk,
 	                  &h->pe_uk, &h->pe_uv, &h->pe_uc, &h->pe_tk, &h->pe_tv, &h->pe_q, &h->pe_sk, &h->pe_sv, &h->pe_sidx, &h->pe_t1, &h->pe_t2, &h->pe_pool, &h->pe_info, &h->it_src, &h->it_len,
 	                  &h->it_bytes, &h->it_first, &h->it_bias, &h->it_dupprev, &h->it_flags, &h->it_off32, &h->it_off64, &h->it_dna};
 

@@ -412,8 +412,23 @@ struct DeltaCollect {    // matches of a front-truncated context: (trial index, 
 	}
 };
 
+// More than DeltaCollect::CAP distinct completions of one context (low-complexity reads: most of the 4^(m+1) possible ones pushed inside one
+// segment): the matches go into a table indexed directly by (trial, next symbol) -- at most 4^6 entries, tagged with the number of the
+// lookup so that it never has to be cleared -- and are read back in index order, which IS the merge order (ht_kmer.h:291-324).
+struct DeltaTable {
+	uint32_t *ep, *tm, *slot; uint32_t epoch, m, lsh;
+	FQSK_DEV void operator()(uint64_t Y, uint32_t t, uint32_t s) {
+		uint32_t trial = 0;
+		for (uint32_t j = 0; j < m; ++j) trial |= (uint32_t) ((Y >> (62 - 2 * j)) & 3) << (2 * j);
+		const uint32_t kk = (trial << 2) | (uint32_t) ((Y >> lsh) & 3);
+		if (ep[kk] != epoch) { ep[kk] = epoch; tm[kk] = t; slot[kk] = s; }
+		else if (t > tm[kk]) { tm[kk] = t; slot[kk] = s; }
+	}
+};
+static const uint32_t HOT_TAB_ENTRIES = 4096;      // 4^(m + 1), m <= 5 (b - s - 1 at the reference's largest k-mer lengths; s - p + 1 <= 4)
+
 __global__ void k_hot_eval(EngineDev E, SegDev S, PipeDev P, const unsigned long long *ek0, const uint32_t *ev0, uint32_t n0,
-                           const unsigned long long *ek1, const uint32_t *ev1, uint32_t n1) { pdl_enter();
+                           const unsigned long long *ek1, const uint32_t *ev1, uint32_t n1, uint32_t *tab) { pdl_enter();      // tab: 2 streams x 3 arrays x HOT_TAB_ENTRIES, zeroed by the caller
 	if ((threadIdx.x & 31) != 0) return;
 	const uint32_t st = threadIdx.x >> 5;     // 0: b / cinc_lb, 1: s / cinc_ls
 	if (st > 1) return;
@@ -425,6 +440,7 @@ __global__ void k_hot_eval(EngineDev E, SegDev S, PipeDev P, const unsigned long
 	const uint32_t n = st ? n1 : n0;
 	DrawCursor dc;
 	dc.ring = E.draws[2 + st]; dc.mask = E.dmask[2 + st]; dc.pos0 = E.dpos[2 + st]; dc.avail = E.avail[2 + st]; dc.base = 0; dc.used = 0; dc.overflow = E.flags + 0;
+	uint32_t tab_epoch = 0;
 	for (uint32_t i = 0; i < n; ++i) {
 		const uint32_t v = ev[i];
 		if (ek[i] & 1ull) {
@@ -443,16 +459,29 @@ __global__ void k_hot_eval(EngineDev E, SegDev S, PipeDev P, const unsigned long
 		const uint32_t cur = st ? cs : e.cb;
 		DeltaCollect M; M.n = 0; M.m = D.k - cur; M.lsh = 64 - 2 * D.k; M.overflow = false;
 		delta_scan(D, reg, cur, e.time, M);
-		if (M.overflow) { P.flags[1] = 1; continue; }
-		for (uint32_t a = 1; a < M.n; ++a) {   // insertion sort by (trial, symbol)
-			uint32_t kk = M.key[a], tt = M.tm[a], ss = M.slot[a]; uint32_t b = a;
-			while (b > 0 && M.key[b - 1] > kk) { M.key[b] = M.key[b - 1]; M.tm[b] = M.tm[b - 1]; M.slot[b] = M.slot[b - 1]; --b; }
-			M.key[b] = kk; M.tm[b] = tt; M.slot[b] = ss;
-		}
 		uint32_t c[4] = {0, 0, 0, 0};
-		for (uint32_t a = 0; a < M.n; ++a) {
-			uint32_t sym = M.key[a] & 3, loc = delta_count_at(D, M.slot[a]);
-			if (loc) c[sym] = ci_plus(ci, c[sym], loc, dc);
+		if (M.overflow) {
+			if (M.m > 5) { P.flags[1] = 1; continue; }      // cannot happen: the margins of the front-truncated lookups are at most 5 symbols
+			DeltaTable T;
+			T.ep = tab + (size_t) st * 3 * HOT_TAB_ENTRIES; T.tm = T.ep + HOT_TAB_ENTRIES; T.slot = T.tm + HOT_TAB_ENTRIES;
+			T.epoch = ++tab_epoch; T.m = M.m; T.lsh = M.lsh;
+			delta_scan(D, reg, cur, e.time, T);
+			const uint32_t n_keys = 4u << (2 * M.m);
+			for (uint32_t kk = 0; kk < n_keys; ++kk) {
+				if (T.ep[kk] != T.epoch) continue;
+				const uint32_t loc = delta_count_at(D, T.slot[kk]);
+				if (loc) c[kk & 3] = ci_plus(ci, c[kk & 3], loc, dc);
+			}
+		} else {
+			for (uint32_t a = 1; a < M.n; ++a) {   // insertion sort by (trial, symbol)
+				uint32_t kk = M.key[a], tt = M.tm[a], ss = M.slot[a]; uint32_t b = a;
+				while (b > 0 && M.key[b - 1] > kk) { M.key[b] = M.key[b - 1]; M.tm[b] = M.tm[b - 1]; M.slot[b] = M.slot[b - 1]; --b; }
+				M.key[b] = kk; M.tm[b] = tt; M.slot[b] = ss;
+			}
+			for (uint32_t a = 0; a < M.n; ++a) {
+				uint32_t sym = M.key[a] & 3, loc = delta_count_at(D, M.slot[a]);
+				if (loc) c[sym] = ci_plus(ci, c[sym], loc, dc);
+			}
 		}
 		const uint32_t lev = st ? FQSK_LEVEL_SMER : FQSK_LEVEL_BMER;
 		fqsk_base_rec *rec = P.prov + e.rec;

@@ -347,3 +347,46 @@ def test_large_paired_end_segments_match_oracle():
         assert sg[key] == so[key], key
     assert sg["n_filtered_segments"] == 2 and (io[:, 0] == 1).sum() > 100
     e.close(); o.close()
+
+
+def test_front_truncated_thread_local_lookup_with_hundreds_of_completions():
+    """Low-complexity input: inside ONE segment a fixed 30-mer is preceded by every possible 4-symbol prefix (256 distinct s-mers share
+    their last 13 symbols), the b-mers inside it are pushed hundreds of times (thread-local counters above thr: the ordered evaluator
+    runs, cinc_lb draws) and later reads START with the 30-mer -- their front-truncated thread-local s-mer lookups match 256 completions,
+    twice what the evaluator's in-register list holds (it then switches to its direct-indexed table).  Records, tables and all four PRNG
+    positions against the oracle."""
+    rng = np.random.default_rng(77)
+    L = 80
+    fixed = rng.integers(0, 4, 30).astype(np.uint8)
+    reads = []
+    for q in range(256):      # every 4-symbol prefix in front of the fixed 30-mer
+        pre = np.array([(q >> 6) & 3, (q >> 4) & 3, (q >> 2) & 3, q & 3], np.uint8)
+        reads.append(np.concatenate((rng.integers(0, 4, 16).astype(np.uint8), pre, fixed, rng.integers(0, 4, L - 50).astype(np.uint8))))
+    for _ in range(120):      # reads that start with the fixed 30-mer
+        reads.append(np.concatenate((fixed, rng.integers(0, 4, L - 30).astype(np.uint8))))
+    for _ in range(200):
+        reads.append(rng.integers(0, 4, L).astype(np.uint8))
+    codes = np.stack(reads)
+    slab = _fastq_slab(codes)
+    off, ln, _, _ = __import__("fqsqueezer_b200.schedule", fromlist=["x"]).parse_fastq(slab)
+    pref, p, s, b = E.kmer_params(1)
+    assert s - p + 1 == 4      # the front-truncated s-mer lookup misses up to 4 symbols: 4^4 completions x 1 next symbol
+    e = E.KmerEngine(p, s, b, pref)
+    o = O.OracleEngine(p, s, b, pref)
+    for eng in (e, o):
+        eng.block_start()
+    for a, bb in ((0, 376), (376, len(codes))):      # the second segment re-reads everything from the global tables
+        rg, dg = e.segment(slab, off[a:bb], ln[a:bb])
+        ro, do = o.segment(slab, off[a:bb], ln[a:bb])
+        H.assert_recs_equal(rg, ro[ro["pos"] < 0xFFFFFFF0])
+        assert np.array_equal(dg, do)
+        e.sync(); o.sync()
+    for which in (0, 1, 2):
+        kg, vg = e.dump(which)
+        ko, vo = o.dump(which)
+        assert np.array_equal(kg, ko) and np.array_equal(vg, vo), which
+    sg, so = e.stats(), o.stats()
+    for key in ("siv_no_filled", "siv_no_updates", "n_smers", "n_bmers", "draws_b", "draws_s", "draws_lb", "draws_ls"):
+        assert sg[key] == so[key], key
+    assert sg["n_hot_segments"] >= 1 and sg["draws_lb"] > 0
+    e.close(); o.close()
