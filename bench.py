@@ -455,7 +455,7 @@ def main():
         for k, (a, bb) in enumerate(segs):
             n = bb - a
             e.segment_device(base + (a - lo) * L, n * L, d_off.data_ptr(), d_len.data_ptr(), n, want_n_recs=False)
-            if k + 1 < len(segs) and not sharded:      # the worker loop knows its next segment (application.cpp:617-662): its read-only preparation runs ahead
+            if k + 1 < len(segs):      # the worker loop knows its next segment (application.cpp:617-662): its read-only preparation runs ahead
                 a2, b2 = segs[k + 1]
                 e.announce_device(base + (a2 - lo) * L, (b2 - a2) * L, d_off.data_ptr(), d_len.data_ptr(), b2 - a2)
             e.sync()

@@ -122,6 +122,7 @@ struct fqsk_handle {
 	bool unsettled = false;                  // its first pass is enqueued, nobody has looked at the outcome yet
 	bool miss_fold_dirty = true; void *miss_fold_seen = nullptr;
 	uint32_t world = 1, rank = 0;            // reference worker `rank` of `world` (one per GPU)
+	bool dev_finish = false;             // fqsk_sync_device: the apply step ends with the device-side second barrier
 	unsigned long long sync_seq = 0;      // number of the sharded sync under way (posted to the owners' inbox headers)
 	unsigned long long *inbox = nullptr; uint64_t inbox_cap = 0;      // this rank's inbox: header + [3 tables][world sources][inbox_cap]
 	unsigned long long *peer_inbox[8] = {nullptr};
@@ -2408,22 +2409,47 @@ int fqsk_sync_apply(fqsk_handle *h, uint64_t *fresh, uint64_t *updates) {
 		CK(cudaStreamSynchronize(h->st));
 		h->pair_items = *hsp;
 	}
-	unsigned long long hc[6];
+	unsigned long long hc[6], acc[2] = {0, 0};
+	h->sync_updates = tot[0] + h->hidden_p;
+	if (h->dev_finish) {
+		// this rank's inserts are enqueued: add its statistics to everybody's accumulators and post the sync's number (k_post_applied), then
+		// wait -- on the device -- until every rank has done the same: no lookup of the next segment can see a half-applied sync
+		InboxDev I{};
+		for (uint32_t i = 0; i < h->world; ++i) I.base[i] = h->peer_inbox[i];
+		I.cap = h->inbox_cap; I.world = h->world; I.rank = h->rank;
+		CK(pdl(k_post_applied, 1, 32, h->st, I, h->sync_seq, (const unsigned long long *) (h->d_counters + 4), (unsigned long long) h->sync_updates)); LAUNCHED(h);
+		CK(pdl(k_wait_applied, 1, 32, h->st, (const unsigned long long *) h->inbox, h->world, h->sync_seq, (int *) (h->d_status + 480))); LAUNCHED(h);
+		CK(cudaMemcpyAsync(acc, h->inbox + INBOX_ACC + 2 * (h->sync_seq & 1), 16, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaMemcpyAsync((uint8_t *) h->h_small + 480, h->d_status + 480, 4, cudaMemcpyDeviceToHost, h->st));
+	}
 	CK(cudaMemcpyAsync(hc, h->d_counters, 48, cudaMemcpyDeviceToHost, h->st));
 	CK(cudaStreamSynchronize(h->st));
 	resolve_phases(h);
+	if (h->dev_finish && *(const uint32_t *) ((uint8_t *) h->h_small + 480)) return fail(h, FQSK_E_CUDA, "sharded sync: a peer did not finish its inserts within the time limit");
 	for (int k = 0; k < 2; ++k) {
 		Table &t = k ? h->tb : h->ts;
 		if (hc[2 - 2 * k] > (4ull << t.d.B) || hc[3 - 2 * k] > (1ull << t.d.stash_log2) / 2) CKR(table_grow_if_needed(h, t));
 	}
 	h->sync_fresh = hc[4];
 	h->siv_local_filled += hc[4];
-	h->sync_updates = tot[0] + h->hidden_p;
 	h->hidden_p = 0;
-	if (fresh) *fresh = h->sync_fresh;
-	if (updates) *updates = h->sync_updates;
+	if (fresh) *fresh = h->dev_finish ? acc[0] : h->sync_fresh;
+	if (updates) *updates = h->dev_finish ? acc[1] : h->sync_updates;
 	h->applied = true;
 	return FQSK_OK;
+}
+
+// The whole sharded sync in one call and without a collective library: fqsk_sync_route, fqsk_sync_apply with the device-side second
+// barrier (k_post_applied / k_wait_applied: the global p-mer statistics travel as NVLink atomics), fqsk_sync_finish.
+int fqsk_sync_device(fqsk_handle *h) {
+	if (!h) return FQSK_E_INVAL;
+	CKR(fqsk_sync_route(h));
+	h->dev_finish = true;
+	uint64_t fresh_all = 0, updates_all = 0;
+	const int rc = fqsk_sync_apply(h, &fresh_all, &updates_all);
+	h->dev_finish = false;
+	if (rc != FQSK_OK) return rc;
+	return fqsk_sync_finish(h, fresh_all, updates_all);
 }
 
 int fqsk_sync_finish(fqsk_handle *h, uint64_t fresh_all, uint64_t updates_all) {

@@ -671,7 +671,8 @@ struct InboxDev {
 	unsigned long long cap;          // entries per (table, source) slot
 	uint32_t world, rank;
 };
-static const uint32_t INBOX_HDR = 64;    // u64 words: counts[3 tables][8 sources], then padding
+static const uint32_t INBOX_HDR = 128;   // u64 words: [0, 48) posted slot lengths [6 tables][8 sources]; [48, 56) routed and [56, 64) applied sync numbers per source;
+                                         // [64, 68) global p-mer statistics of the sync under way, two instances (k_post_applied)
 FQSK_HD unsigned long long *inbox_slot(unsigned long long *base, unsigned long long cap, uint32_t world, uint32_t table, uint32_t src) {
 	return base + INBOX_HDR + ((unsigned long long) table * world + src) * cap;
 }
@@ -800,6 +801,36 @@ __global__ void k_wait_seq(const unsigned long long *inbox, uint32_t world, unsi
 	if (i >= world) return;
 	const long long t0 = clock64();
 	while (*reinterpret_cast<const volatile unsigned long long *>(inbox + INBOX_SEQ + i) < seq) {
+		if (clock64() - t0 > 4000000000ll) { *err = 1; break; }
+		__nanosleep(200);
+	}
+	__threadfence_system();
+}
+
+// Second barrier of the reference's sync (application.cpp:651-654: "every owner has inserted") and the global p-mer statistics
+// (TSmallIntVector's atomics, bit_vec.h:212-220) without the host or a collective library: every rank adds its (fresh fields, updates)
+// into the accumulators of ALL ranks (NVLink atomics) and then posts the sync's number in their headers; a rank that has seen all N
+// numbers holds the complete sums.  Two accumulator instances alternate: a rank clears the next sync's instance before it posts this
+// sync's number, and nobody adds to that instance before having seen that number.
+static const uint32_t INBOX_APPLIED = 56, INBOX_ACC = 64;
+__global__ void k_post_applied(InboxDev I, unsigned long long seq, const unsigned long long *fresh_dev, unsigned long long updates) { pdl_enter();
+	const uint32_t t = threadIdx.x, par = (uint32_t) (seq & 1);
+	if (t == 0) { unsigned long long *own = I.base[I.rank] + INBOX_ACC + 2 * (par ^ 1); own[0] = 0; own[1] = 0; }
+	__threadfence_system();
+	__syncthreads();
+	if (t < I.world) {
+		atomicAdd_system(I.base[t] + INBOX_ACC + 2 * par, *fresh_dev);
+		atomicAdd_system(I.base[t] + INBOX_ACC + 2 * par + 1, updates);
+	}
+	__threadfence_system();
+	__syncthreads();
+	if (t < I.world) { *reinterpret_cast<volatile unsigned long long *>(I.base[t] + INBOX_APPLIED + I.rank) = seq; __threadfence_system(); }
+}
+__global__ void k_wait_applied(const unsigned long long *inbox, uint32_t world, unsigned long long seq, int *err) { pdl_enter();
+	const uint32_t i = threadIdx.x;
+	if (i >= world) return;
+	const long long t0 = clock64();
+	while (*reinterpret_cast<const volatile unsigned long long *>(inbox + INBOX_APPLIED + i) < seq) {
 		if (clock64() - t0 > 4000000000ll) { *err = 1; break; }
 		__nanosleep(200);
 	}

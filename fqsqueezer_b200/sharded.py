@@ -4,8 +4,9 @@ Rank r is the reference's worker thread r (application.cpp:575-671): it codes it
 own PRNG streams and thread-local tables, and it OWNS the k-mers whose routing key maps to it (dna.cpp:825, 836, 845,
 2381-2388).  Lookups read every rank's shard through NVLink peer mappings (CUDA IPC, set up once here); at a sync the
 exchange matrices X_to_add[src][dst] are written straight into the owners' inboxes by the routing kernel (peer stores) together
-with the number of the sync, for which the owners wait on the device; torch.distributed (NCCL) carries what is left of the reference's
-three barriers: one all-reduce of the global p-mer statistics per sync (also the barrier in front of the next segment's lookups).
+with the number of the sync, for which the owners wait on the device; the second barrier ("every owner has inserted") is a sequence
+number as well and the global p-mer statistics are NVLink atomics into every rank's accumulators (fqsk_sync_device): torch.distributed
+(NCCL) only carries the set-up (descriptor exchange) and, on request (host_collective=True), the three-step form with an all-reduce.
 
     grp = ShardedKmerEngine(p, s, b, prefix_len, rank, world, device=local_rank)   # after dist.init_process_group
     grp.block_start(); recs, dup = grp.segment(slab, off, ln); grp.sync()
@@ -56,6 +57,7 @@ class ShardedKmerEngine(E.KmerEngine):
 
     def __init__(self, p, s, b, prefix_len, rank, world, device=0, dist=None, expected_kmers=0, reserve_reads=0, reserve_bytes=0, mode=E.MODE_SE_ORIGINAL, **kw):
         self.rank, self.world, self.dist = rank, world, dist
+        self.host_collective = bool(kw.get("host_collective", False))      # True: the three-step form with the caller's all-reduce (NCCL / gloo)
         self.lib = E.load_library()
         self._bind()
         prm = E._Params(abi_version=1, pmer_len=p, smer_len=s, bmer_len=b, prefix_len=prefix_len, smer_counter_bits=12, bmer_counter_bits=6,
@@ -81,7 +83,8 @@ class ShardedKmerEngine(E.KmerEngine):
         lib.fqsk_sync_route.argtypes = [vp]
         lib.fqsk_sync_apply.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         lib.fqsk_sync_finish.argtypes = [vp, C.c_uint64, C.c_uint64]
-        for n in ("fqsk_shard_export", "fqsk_shard_attach", "fqsk_sync_route", "fqsk_sync_apply", "fqsk_sync_finish"):
+        lib.fqsk_sync_device.argtypes = [vp]
+        for n in ("fqsk_shard_export", "fqsk_shard_attach", "fqsk_sync_route", "fqsk_sync_apply", "fqsk_sync_finish", "fqsk_sync_device"):
             getattr(lib, n).restype = C.c_int
 
     def _attach_peers(self):
@@ -96,6 +99,11 @@ class ShardedKmerEngine(E.KmerEngine):
         """InsertKmersToHT + ClearKmersToHT of all workers (dna.cpp:2393-2488) around the reference's barriers."""
         if self.world == 1:
             return super().sync()
+        if not self.host_collective:
+            # rows into the owners' inboxes, both barriers as sequence numbers the ranks post in each other's inbox headers and wait for on
+            # the device, global p-mer statistics as NVLink atomics: no collective library on the path of a sync
+            self._ck(self.lib.fqsk_sync_device(self.h))
+            return
         self._ck(self.lib.fqsk_sync_route(self.h))              # rows [rank][*] into the owners' inboxes + this sync's number posted there
         fresh, upd = C.c_uint64(0), C.c_uint64(0)                 # (the owners wait for their sources on the device: no host barrier here)
         self._ck(self.lib.fqsk_sync_apply(self.h, C.byref(fresh), C.byref(upd)))

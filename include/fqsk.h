@@ -234,6 +234,10 @@ int fqsk_sync_apply(fqsk_handle *h, uint64_t *fresh, uint64_t *updates);
 /* After the all-reduce: the global p-mer statistics (bit_vec.h:204-220 -- they gate repair_kmers_missing on every worker) and
  * ClearKmersToHT.  The call sequence must be completed on all ranks before any of them starts its next segment. */
 int fqsk_sync_finish(fqsk_handle *h, uint64_t fresh_all_ranks, uint64_t updates_all_ranks);
+/* The three steps in one call, with NO collective of the caller's: the second barrier is a sequence number too (every rank posts it in
+ * every peer's inbox once its inserts are enqueued, and waits for all of them on the device), and the global p-mer statistics travel
+ * as NVLink atomics into every rank's accumulators.  All ranks must call it for every sync, as with the three-step form. */
+int fqsk_sync_device(fqsk_handle *h);
 
 /* Call after fqsk_sync, not between a segment and its sync (the grouping half of a small segment's sync may already be enqueued:
  * FQSK_E_INVAL).

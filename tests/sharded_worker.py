@@ -27,7 +27,7 @@ def main():
     slab = g["fastq"]
     paired = "-p" in [str(x) for x in g["extra"]]
     eng = sharded.ShardedKmerEngine(p, s, b, pref, rank, world, device=local, dist=dist, reserve_bytes=1 << 20, reserve_reads=1 << 14,
-                                    mode=E.MODE_PE_ORIGINAL if paired else E.MODE_SE_ORIGINAL)
+                                    mode=E.MODE_PE_ORIGINAL if paired else E.MODE_SE_ORIGINAL, host_collective="host" in sys.argv[2:])
     off, ln, roff, rsz = S.parse_fastq(slab)
     out, info = [], []
     for gen, (f, l) in enumerate(S.split_blocks(rsz, paired=paired)):
