@@ -787,7 +787,7 @@ __global__ void __launch_bounds__(256) k_route_move(RouteRows R, uint32_t chunks
 // First barrier of the reference's sync (application.cpp:645-648: "every worker has filled its X_to_add rows") without the host: each
 // source posts the number of the sync into word [48 + src] of every owner's inbox header once its rows have landed there (a kernel of
 // its own behind the scatter kernels: their peer stores are complete when it starts); an owner waits for all its sources on the
-// device, in front of the copy that reads the posted lengths.  Bounded wait (~2 s): a rank that died must not hang the others.
+// device, in front of the copy that reads the posted lengths.  Bounded wait (~20 s): a rank that died must not hang the others.
 static const uint32_t INBOX_SEQ = 48;
 __global__ void k_post_seq(InboxDev I, unsigned long long seq) { pdl_enter();
 	const uint32_t i = threadIdx.x;
@@ -801,7 +801,7 @@ __global__ void k_wait_seq(const unsigned long long *inbox, uint32_t world, unsi
 	if (i >= world) return;
 	const long long t0 = clock64();
 	while (*reinterpret_cast<const volatile unsigned long long *>(inbox + INBOX_SEQ + i) < seq) {
-		if (clock64() - t0 > 4000000000ll) { *err = 1; break; }
+		if (clock64() - t0 > 40000000000ll) { *err = 1; break; }      // ~20 s
 		__nanosleep(200);
 	}
 	__threadfence_system();
@@ -831,7 +831,7 @@ __global__ void k_wait_applied(const unsigned long long *inbox, uint32_t world, 
 	if (i >= world) return;
 	const long long t0 = clock64();
 	while (*reinterpret_cast<const volatile unsigned long long *>(inbox + INBOX_APPLIED + i) < seq) {
-		if (clock64() - t0 > 4000000000ll) { *err = 1; break; }
+		if (clock64() - t0 > 40000000000ll) { *err = 1; break; }      // ~20 s
 		__nanosleep(200);
 	}
 	__threadfence_system();
