@@ -361,6 +361,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-per-segment", action="store_true", help="e2e leg: one fqsk_submit_ctx / fqsk_collect call per sync segment from Python instead of one fqsk_block_stream call per reads_block")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--replicas", action="store_true", help="N > 1: N independent engines (weak scaling) instead of ONE job over hash-sharded tables")
     ap.add_argument("--shard", action="store_true", help="(default at N > 1; kept for compatibility)")
@@ -544,13 +545,21 @@ def main():
         eng2 = make_engine(e2e=True)
         slabs = [codes_to_slab(reads.codes(*blocks[g])) for g in range(NB)]
 
+        seg_ends = [np.array([bb for _, bb in sched[g]], np.uint32) for g in range(NB)]
+
         def run_block_host(g, pend, e):
-            """fqsk_submit_ctx / fqsk_collect, two segments in flight: segment n + 1 is submitted before n is collected -- the point where
-            the reference's host-side coder consumes the records of n (host/fqsk_live.h does exactly this).  The pipeline runs across
-            block boundaries: the records of a 51 000-read segment take as long to reach the host as the next one takes to compute."""
+            """One reads_block through fqsk_block_stream (fqsk_submit_ctx / fqsk_collect per sync segment, two segments in flight: segment
+            n + 1 is submitted before n is collected -- the point where the reference's host-side coder consumes the records of n;
+            host/fqsk_live.h makes the same calls one by one).  The pipeline runs across block boundaries: the block's last segment stays in
+            flight and is collected by the next call -- the records of a 51 000-read segment take as long to reach the host as the next one
+            takes to compute.  --e2e-per-segment: the same calls made one by one from Python (5 146 x 2 ctypes calls)."""
             slab, off, ln = slabs[g]
-            e.block_start()
             nb = 0
+            if not args.e2e_per_segment:
+                for recs in e.block_stream(slab, off, ln, seg_ends[g], ctx=True):
+                    nb += recs.nbytes
+                return nb + len(off), None
+            e.block_start()
             for a, bb in sched[g]:
                 t = e.submit(slab, off[a:bb], ln[a:bb], ctx=True)
                 if pend is not None:
@@ -559,13 +568,21 @@ def main():
                 pend = t
             return nb, pend
 
+        def drain(pend, e):
+            if not args.e2e_per_segment:
+                recs = e.stream_finish()
+                return recs.nbytes if recs is not None else 0
+            if pend is None:
+                return 0
+            recs, dup, _ = e.collect(pend)
+            return recs.nbytes + dup.nbytes
+
         scratch = make_engine(e2e=True)
         pend = None
         for g in warm_blocks:
             _, pend = run_block_host(g, pend, scratch)
-        if pend is not None:
-            scratch.collect(pend)
-            pend = None
+        drain(pend, scratch)
+        pend = None
         scratch.close()
         barrier()
         t0 = time.time()
@@ -573,9 +590,7 @@ def main():
         for g in range(NB):
             nb, pend = run_block_host(g, pend, eng2)
             d2h += nb
-        if pend is not None:
-            recs, dup, _ = eng2.collect(pend)
-            d2h += recs.nbytes + dup.nbytes
+        d2h += drain(pend, eng2)
         barrier()
         e2e_s = time.time() - t0
         st_e2e = eng2.stats()
@@ -585,7 +600,8 @@ def main():
         e2e = {"value": total_bases / float(t.item()), "unit": UNIT,
                "h2d_bytes_per_step": (JOB_READS if not args.max_blocks else blocks[-1][1]) * (L + 12) // K, "d2h_bytes_per_step": d2h // K,
                "host": {"api_ms": round(st_e2e["api_ns"] / 1e6, 1), "waiting_for_the_gpu_ms": round(st_e2e["look_wait_ns"] / 1e6, 1)},
-               "note": "fqsk_submit_ctx / fqsk_collect (what the compiled drop-in calls) with host slab + read descriptors (H2D inside), one 16-byte context record per coded base (the 7 context ids + rank the range coder consumes, built on the device) copied back into page-locked host memory on a second stream, two segments in flight; wall clock incl. ctypes/numpy host code"}
+               "call": "fqsk_submit_ctx + fqsk_collect per sync segment from Python" if args.e2e_per_segment else "fqsk_block_stream per reads_block (fqsk_submit_ctx + fqsk_collect per sync segment inside the library)",
+               "note": "fqsk_submit_ctx / fqsk_collect (what the compiled drop-in calls) with host slab + read descriptors (H2D inside), one 16-byte context record per coded base (the 7 context ids + rank the range coder consumes, built on the device) copied back into page-locked host memory on a second stream, two segments in flight, across block boundaries too; wall clock incl. ctypes/numpy host code"}
         eng2.close()
         del slabs
 

@@ -131,6 +131,11 @@ struct fqsk_handle {
 	DevBuf route_keys, route_keys2, route_sorted, route_hist, route_perm, route_chunks;
 	DevBuf hot_tab;      // k_hot_eval: direct-indexed match table of a front-truncated thread-local lookup with many completions
 	uint64_t sync_fresh = 0, sync_updates = 0; bool routed = false, applied = false;
+	// coordinated doubling of sharded tables: grow_local = what this rank's shards ask for after a sync (bit 0 s-mers, 1 b-mers, 2 pairs),
+	// grow_all = the OR over all ranks (every shard of a table has the same geometry: all grow or none), grow_pending = fqsk_sync_finish has
+	// returned FQSK_RESHARD and the doubling itself happens in the fqsk_shard_export that follows
+	uint32_t grow_local = 0, grow_all = 0; bool grow_pending = false;
+	uint32_t crowd_shift = 0;                // FQSK_F_TEST_CROWD: 6 -- tables double at 1/64 of the usual load (growth on small fixtures)
 	uint64_t siv_local_filled = 0;           // non-zero fields of THIS rank's p-mer shard (S.siv_no_filled is the global statistic)
 	DevBuf scan_vals; uint32_t scan_epoch2 = 0;
 	DevBuf scan_part; uint32_t scan_epoch = 0;   // published CTA sums of k_scan_flags, tagged with the launch epoch
@@ -173,6 +178,9 @@ struct fqsk_handle {
 	int seg_par = 0;
 	struct Front { bool valid = false; const uint8_t *dna = nullptr; uint64_t bytes = 0; const unsigned long long *off = nullptr; const uint32_t *len = nullptr; uint32_t n = 0; int par = 0; } front;
 	cudaStream_t st_front = nullptr; cudaEvent_t ev_front = nullptr;
+	// fqsk_submit: the reads of segment n + 1 go to the device (their own buffer, the front stream) and are prepared there while segment n is
+	// still in flight; block_fresh: fqsk_block_start has cleared read_prev and no segment has run since (nothing may be prepared ahead)
+	DevBuf dna2; cudaEvent_t ev_up = nullptr; bool block_fresh = false;
 	DevBuf dfilter; bool delta_filtered = false;     // filter bits of the segment's delta (large segments), see seg_setup
 	DevBuf recs_alt; int rec_par = 0;
 	DevBuf ctxrec[2];                                // fqsk_submit_ctx: the 16-byte context records of the segment in flight, per parity
@@ -286,6 +294,10 @@ void resolve_phases(fqsk_handle *h) {   // call after a stream synchronize
 
 uint64_t mod_inverse(uint64_t x) { uint64_t inv = x; for (int i = 0; i < 6; ++i) inv *= 2 - x * inv; return inv; }
 
+// Allocations other ranks map through CUDA IPC get a size that is a multiple of 2 MiB: smaller cudaMalloc blocks are sub-allocated from a
+// shared 2 MiB page, and an IPC handle then exports (and a close unmaps) the whole page with whatever else lives in it.
+inline size_t ipc_size(const fqsk_handle *h, size_t bytes) { return h->world > 1 ? (bytes + ((size_t) 2 << 20) - 1) & ~(((size_t) 2 << 20) - 1) : bytes; }
+
 int table_alloc(fqsk_handle *h, Table &t, uint32_t k, uint32_t cbits, uint32_t B, unsigned long long *counters) {
 	HtDev &d = t.d;
 	d.k = k; d.cbits = cbits; d.W = 2 * k - 8; d.top = (1u << cbits) - 1;
@@ -302,8 +314,8 @@ int table_alloc(fqsk_handle *h, Table &t, uint32_t k, uint32_t cbits, uint32_t B
 	d.err = (int *) (h->d_status + 400);      // +400 : a table's stash ran full (sticky)
 	t.inv.inv1 = mod_inverse(MIX_C1); t.inv.inv2 = mod_inverse(MIX_C2);
 	size_t mb = (size_t) 32 << B, sb = (size_t) 8 << d.stash_log2;
-	CK(cudaMalloc(&d.main, mb));
-	CK(cudaMalloc(&d.stash, sb));
+	CK(cudaMalloc(&d.main, ipc_size(h, mb)));
+	CK(cudaMalloc(&d.stash, ipc_size(h, sb)));
 	{
 		const size_t ob = std::max<size_t>(((size_t) 1 << B) / 8, 4);
 		CK(cudaMalloc(&d.occ, ob));
@@ -538,23 +550,35 @@ int table_dump_device(fqsk_handle *h, Table &t, uint64_t *n_out) {   // into h->
 	return FQSK_OK;
 }
 
-int table_grow_if_needed(fqsk_handle *h, Table &t) {
+int table_double(fqsk_handle *h, Table &t) {      // one doubling: dump, allocate 2^(B + 1) buckets, re-insert
+	uint64_t n = 0;
+	unsigned long long items[2];
+	CKR(table_dump_device(h, t, &n));
+	unsigned long long *counters = t.d.n_items;
+	CK(cudaFree(t.d.main)); CK(cudaFree(t.d.stash)); CK(cudaFree(t.d.occ));
+	t.d.main = nullptr; t.d.stash = nullptr; t.d.occ = nullptr;
+	uint32_t k = t.d.k, cb = t.d.cbits, B = t.d.B + 1;
+	CKR(table_alloc(h, t, k, cb, B, counters));
+	if (n) { CK(pdl(k_reinsert, nblk(n, 256), 256, h->st, t.d, h->dump_k.as<unsigned long long>(), h->dump_v.as<unsigned long long>(), n)); LAUNCHED(h); }
+	CK(cudaMemcpyAsync(items, t.d.n_items, 16, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaStreamSynchronize(h->st));
+	if (items[0] + items[1] != n) return fail(h, FQSK_E_CUDA, "table growth lost items (%llu -> %llu)", (unsigned long long) n, items[0] + items[1]);
+	++h->S.n_table_growths;
+	return FQSK_OK;
+}
+inline bool table_can_double(const Table &t) { return t.d.B + 1 < t.d.W && t.d.B + 1 <= 30 && t.d.W - (t.d.B + 1) >= 1; }
+inline unsigned long long crowd_main(const fqsk_handle *h, const Table &t) { return (4ull << t.d.B) >> h->crowd_shift; }      // half of the 8 << B slots (FQSK_F_TEST_CROWD: 1/64 of that)
+inline unsigned long long crowd_stash(const Table &t) { return (1ull << t.d.stash_log2) / 2; }
+inline bool table_crowded(const fqsk_handle *h, const Table &t, unsigned long long main_items, unsigned long long stash_items) { return main_items > crowd_main(h, t) || stash_items > crowd_stash(t); }
+
+int table_grow_if_needed(fqsk_handle *h, Table &t) {      // unsharded engines; shards double together (fqsk_sync_finish -> FQSK_RESHARD)
 	unsigned long long items[2];
 	CK(cudaMemcpyAsync(items, t.d.n_items, 16, cudaMemcpyDeviceToHost, h->st));
 	CK(cudaStreamSynchronize(h->st));
-	if (h->world > 1 && (items[0] > (4ull << t.d.B) || items[1] > (1ull << t.d.stash_log2) / 2))
-		return fail(h, FQSK_E_CAPACITY, "a table shard is more than half full and tables cannot grow in sharded mode: create the engines with a larger expected_kmers");
-	while (items[0] > (4ull << t.d.B) || items[1] > (1ull << t.d.stash_log2) / 2) {
-		uint64_t n = 0;
-		CKR(table_dump_device(h, t, &n));
-		unsigned long long *counters = t.d.n_items;
-		CK(cudaFree(t.d.main)); CK(cudaFree(t.d.stash)); CK(cudaFree(t.d.occ));
-		uint32_t k = t.d.k, cb = t.d.cbits, B = t.d.B + 1;
-		CKR(table_alloc(h, t, k, cb, B, counters));
-		if (n) { CK(pdl(k_reinsert, nblk(n, 256), 256, h->st, t.d, h->dump_k.as<unsigned long long>(), h->dump_v.as<unsigned long long>(), n)); LAUNCHED(h); }
+	while (table_crowded(h, t, items[0], items[1]) && table_can_double(t)) {
+		CKR(table_double(h, t));
 		CK(cudaMemcpyAsync(items, t.d.n_items, 16, cudaMemcpyDeviceToHost, h->st));
 		CK(cudaStreamSynchronize(h->st));
-		if (items[0] + items[1] != n) return fail(h, FQSK_E_CUDA, "table growth lost items (%llu -> %llu)", (unsigned long long) n, items[0] + items[1]);
 	}
 	return FQSK_OK;
 }
@@ -1183,25 +1207,35 @@ int seg_settle(fqsk_handle *h, bool have_look = false) {
 int pair_alloc(fqsk_handle *h, PairDev &t, uint64_t slots) {
 	t = PairDev{};
 	t.b = h->P.bmer_len; t.vm = (1ull << (2 * t.b)) - 1; t.top = ~0ull >> (2 * t.b); t.mask = slots - 1;
-	CK(cudaMalloc(&t.keys, slots * 8)); CK(cudaMalloc(&t.vcs, slots * 8));
+	CK(cudaMalloc(&t.keys, ipc_size(h, slots * 8))); CK(cudaMalloc(&t.vcs, ipc_size(h, slots * 8)));
 	CK(cudaMemsetAsync(t.keys, 0xFF, slots * 8, h->st)); CK(cudaMemsetAsync(t.vcs, 0xFF, slots * 8, h->st));
 	t.world = h->world;
 	for (uint32_t i = 0; i < 8; ++i) { t.peer_keys[i] = nullptr; t.peer_vcs[i] = nullptr; }
 	t.peer_keys[h->rank] = t.keys; t.peer_vcs[h->rank] = t.vcs;
 	return FQSK_OK;
 }
-int pair_reserve(fqsk_handle *h, uint64_t incoming) {     // keep the table at most half full (contents, not layout, are the contract)
-	uint64_t slots = h->pair.mask + 1;
-	if ((h->pair_items + incoming) * 2 <= slots) return FQSK_OK;
-	if (h->world > 1) return fail(h, FQSK_E_CAPACITY, "the pair-table shard would be more than half full and shards cannot grow: create the engines with a larger pair_log2_slots");
-	while ((h->pair_items + incoming) * 2 > slots) slots <<= 1;
+int pair_resize(fqsk_handle *h, uint64_t slots) {
 	PairDev nt;
 	CKR(pair_alloc(h, nt, slots));
 	CK(pdl(k_pair_rehash, 148 * 8, 256, h->st, h->pair, nt)); LAUNCHED(h);
 	CK(cudaStreamSynchronize(h->st));
 	cudaFree(h->pair.keys); cudaFree(h->pair.vcs);
 	h->pair = nt;
+	++h->S.n_table_growths;
 	return FQSK_OK;
+}
+int pair_reserve(fqsk_handle *h, uint64_t incoming) {     // keep the table at most half full (contents, not layout, are the contract)
+	uint64_t slots = h->pair.mask + 1;
+	if ((h->pair_items + incoming) * 2 <= slots) return FQSK_OK;
+	if (h->world > 1) {
+		// shards double together, after the sync that crowded one of them (fqsk_sync_finish -> FQSK_RESHARD): this sync's rows still go into
+		// the table as it is -- linear probing works at any load below 1 -- unless it would pass 7/8
+		if ((h->pair_items + incoming) * 8 > slots * 7) return fail(h, FQSK_E_CAPACITY, "one sync brings %llu pairs to a pair-table shard of %llu slots holding %llu: create the engines with a larger pair_log2_slots",
+		                                                            (unsigned long long) incoming, (unsigned long long) slots, (unsigned long long) h->pair_items);
+		return FQSK_OK;
+	}
+	while ((h->pair_items + incoming) * 2 > slots) slots <<= 1;
+	return pair_resize(h, slots);
 }
 PeSeg pe_seg(fqsk_handle *h) { return PeSeg{h->pe_sk.as<unsigned long long>(), h->pe_sv.as<unsigned long long>(), h->pe_sidx.as<uint32_t>(), h->pe_nt}; }
 
@@ -1266,6 +1300,7 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 	const uint32_t n_in = n;
 	const uint64_t bytes_in = dna_bytes_actual;
 	h->seg_reads_in = n_in; h->pe_nt = 0; h->pe_pairs = 0;
+	h->block_fresh = false;
 	if (pe && (n & 1)) return fail(h, FQSK_E_INVAL, "paired-end segment with an odd number of reads");
 	if (pe && n) {   // pairs -> work items: mate 1, mate 2 (whole or right of the shared minimizer), reversed left part
 		uint64_t bound = 0;
@@ -1274,6 +1309,7 @@ int run_segment(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes_actual,
 		n = 3 * (n / 2); dna_bytes_actual = bound;
 	}
 	const uint64_t dna_bytes = std::max<uint64_t>(dna_bytes_actual, pe ? (uint64_t) h->P.reserve_bytes + h->P.reserve_bytes / 4 : h->P.reserve_bytes);
+	if (h->world > 1 && h->grow_pending) return fail(h, FQSK_E_INVAL, "sharded engine: the last sync returned FQSK_RESHARD -- barrier, fqsk_shard_export, exchange, fqsk_shard_attach come first");
 	if (h->world > 1 && h->attached != (1u << h->world) - 1) return fail(h, FQSK_E_INVAL, "sharded engine: not every peer shard is attached (fqsk_shard_attach)");
 	const uint32_t first = mode_sorted(h->P.mode) ? h->P.pmer_len : h->P.prefix_len;
 	h->seg_reads = n; h->n_recs = 0; h->pend_b = h->pend_s = h->pend_p = 0;
@@ -1450,6 +1486,7 @@ int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
 	// plain sync), resp. is evaluated a second time from scratch as after a capacity overflow (exercises the release of claimed
 	// slots before the tables are read again).
 	if (p->flags & FQSK_F_TEST_HOOKS) { h->dbg_fail_every = p->test_hooks & 0xFFFFu; h->dbg_retry_every = p->test_hooks >> 16; }
+	if ((p->flags & FQSK_F_TEST_HOOKS) && (p->flags & FQSK_F_TEST_CROWD)) h->crowd_shift = 6;
 	if (p->flags & FQSK_F_TRACE_ALLOC) g_trace_alloc.store(true);
 	int rc = [&]() -> int {
 		int prio_lo = 0, prio_hi = 0;
@@ -1480,7 +1517,7 @@ int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
 		h->siv.key_bits = 2 * p->pmer_len;                                    // application.cpp:88
 		h->siv.world = world; h->siv.rank = p->rank; h->siv.top_shift = h->siv.key_bits - 12;
 		size_t sb = world > 1 ? ((((size_t) 4096 + world - 1) / world) << h->siv.top_shift) / 4 : ((size_t) 1 << h->siv.key_bits) / 4;
-		CK(cudaMalloc(&h->siv.w, sb));
+		CK(cudaMalloc(&h->siv.w, ipc_size(h, sb)));
 		CK(cudaMemsetAsync(h->siv.w, 0, sb, h->st));
 		for (uint32_t i = 0; i < FQSK_MAX_WORLD; ++i) h->siv.peer_w[i] = nullptr;
 		h->siv.peer_w[p->rank] = h->siv.w;
@@ -1489,7 +1526,7 @@ int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
 			const uint64_t rb = p->reserve_bytes ? p->reserve_bytes : (1u << 23), rr = p->reserve_reads ? p->reserve_reads : (1u << 16);
 			h->inbox_cap = 2 * rb + 2 * rr + 1024;
 			size_t ib = (INBOX_HDR + 6ull * world * h->inbox_cap) * 8;      // tables 0-2: p / s / b rows; 3-5: key / value / weight planes of the pair rows
-			CK(cudaMalloc(&h->inbox, ib));
+			CK(cudaMalloc(&h->inbox, ipc_size(h, ib)));
 			CK(cudaMemsetAsync(h->inbox, 0, INBOX_HDR * 8, h->st));
 			h->peer_inbox[p->rank] = h->inbox;
 			h->attached = 1u << p->rank;
@@ -1514,7 +1551,7 @@ void fqsk_destroy(fqsk_handle *h) {
 	if (!h) return;
 	cudaSetDevice(h->P.device);
 	if (h->st) cudaStreamSynchronize(h->st);
-	for (Table *t : {&h->tb, &h->ts}) { if (t->d.main) cudaFree(t->d.main); if (t->d.stash) cudaFree(t->d.stash); }
+	for (Table *t : {&h->tb, &h->ts}) { if (t->d.main) cudaFree(t->d.main); if (t->d.stash) cudaFree(t->d.stash); if (t->d.occ) cudaFree(t->d.occ); }
 	if (h->siv.w) cudaFree(h->siv.w);
 	for (uint32_t i = 0; i < FQSK_MAX_WORLD; ++i) for (int q = 0; q < 8; ++q) if (h->peer_ptrs[i][q]) cudaIpcCloseMemHandle(h->peer_ptrs[i][q]);
 	if (h->inbox) cudaFree(h->inbox);
@@ -1525,7 +1562,7 @@ void fqsk_destroy(fqsk_handle *h) {
 	for (auto &s : h->rng) { if (s.buf) cudaFree(s.buf); if (s.state) cudaFree(s.state); if (s.jstates) cudaFree(s.jstates); if (s.ev) cudaEventDestroy(s.ev); }
 	if (h->d_status) cudaFree(h->d_status);
 	if (h->d_counters) cudaFree(h->d_counters);
-	DevBuf *bufs[] = {&h->prev_read, &h->dna, &h->off, &h->len, &h->dup, &h->n_coded, &h->letters, &h->rec_off, &h->sl_prefix, &h->recs, &h->push_b, &h->push_s,
+	DevBuf *bufs[] = {&h->prev_read, &h->dna, &h->dna2, &h->off, &h->len, &h->dup, &h->n_coded, &h->letters, &h->rec_off, &h->sl_prefix, &h->recs, &h->push_b, &h->push_s,
 	                  &h->push_p, &h->cnt_b, &h->cnt_s, &h->cnt_p, &h->hidden, &h->draw_cnt, &h->draw_cnt_prev, &h->draw_scan, &h->off_b[0], &h->off_b[1], &h->off_s[0],
 	                  &h->off_s[1], &h->off_p, &h->row_b[0], &h->row_b[1], &h->row_s[0], &h->row_s[1], &h->row_p, &h->dk_b, &h->di_b, &h->dk_s, &h->di_s, &h->iota,
 	                  &h->cub_tmp, &h->flag8, &h->draw_off, &h->final_cnt, &h->slot_of, &h->dump_k, &h->dump_v, &h->q0, &h->q1,
@@ -1550,6 +1587,7 @@ void fqsk_destroy(fqsk_handle *h) {
 	if (h->ev_aux) cudaEventDestroy(h->ev_aux);
 	if (h->st_front) { cudaStreamSynchronize(h->st_front); cudaStreamDestroy(h->st_front); }
 	if (h->ev_front) cudaEventDestroy(h->ev_front);
+	if (h->ev_up) cudaEventDestroy(h->ev_up);
 	if (h->st_copy) { cudaStreamSynchronize(h->st_copy); cudaStreamDestroy(h->st_copy); }
 	if (h->h_small) cudaFreeHost(h->h_small);
 	for (auto &e : h->evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -1583,6 +1621,7 @@ int fqsk_block_start(fqsk_handle *h) {
 	if (!h) return FQSK_E_INVAL;
 	CK(cudaSetDevice(h->P.device));
 	CK(cudaMemsetAsync(&h->d_carry->prev_len, 0, 4, h->st));   // read_prev.clear(), application.cpp:624
+	h->block_fresh = true;
 	return FQSK_OK;
 }
 
@@ -1601,10 +1640,24 @@ int fqsk_segment_device(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes
 // call and its fqsk_sync): duplicate flags, letter totals, packed reads and record offsets of the announced reads are functions of the
 // reads alone (read_prev of its first read = the last read of the segment in flight, dna.cpp:1521-1533), so k_prep / k_scan_reads run
 // now, on a side stream, instead of at the head of the next segment's dependent chain.  A hint: ignored where it does not apply.
+static int ensure_front(fqsk_handle *h) {
+	if (h->st_front) return FQSK_OK;
+	int lo = 0, hi = 0;
+	CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+	CK(cudaStreamCreateWithPriority(&h->st_front, cudaStreamNonBlocking, lo));      // works ahead: yields to the chain of the segment in flight
+	CK(cudaEventCreateWithFlags(&h->ev_front, cudaEventDisableTiming));
+	CK(cudaEventCreateWithFlags(&h->ev_up, cudaEventDisableTiming));
+	return FQSK_OK;
+}
+static int announce_impl(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes, const uint64_t *d_off, const uint32_t *d_len, uint32_t n_reads);
 int fqsk_announce_device(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes, const uint64_t *d_off, const uint32_t *d_len, uint32_t n_reads) {
 	if (!h) return FQSK_E_INVAL;
 	ApiTimer api_timer{h};
 	CK(cudaSetDevice(h->P.device));
+	return announce_impl(h, d_dna, dna_bytes, d_off, d_len, n_reads);
+}
+// (the arrays may still be on their way: when they are filled by a copy on the front stream -- fqsk_submit -- the kernels below follow it in stream order)
+static int announce_impl(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_bytes, const uint64_t *d_off, const uint32_t *d_len, uint32_t n_reads) {
 	if (h->front.valid) { CK(cudaStreamSynchronize(h->st_front)); h->front.valid = false; }
 	const SegCtx &C = h->ctx;
 	if (mode_pe(h->P.mode) || h->serial || !n_reads || !d_dna || !d_off || !d_len || !h->pending || !h->seg_reads || !C.n) return FQSK_OK;
@@ -1616,12 +1669,7 @@ int fqsk_announce_device(fqsk_handle *h, const uint8_t *d_dna, uint64_t dna_byte
 	const size_t need[6] = {n1, n1 * 4, n1 * 32, n1 * 8, n1 * 32, (bytes_r / 32 + 2 * n1 + 8) * 8};
 	DevBuf *bufs[6] = {PB.dup, PB.n_coded, PB.letters, PB.rec_off, PB.sl_prefix, PB.pk};
 	for (int i = 0; i < 6; ++i) CK(bufs[i]->ensure(need[i]));
-	if (!h->st_front) {
-		int lo = 0, hi = 0;
-		CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-		CK(cudaStreamCreateWithPriority(&h->st_front, cudaStreamNonBlocking, lo));      // works ahead: yields to the chain of the segment in flight
-		CK(cudaEventCreateWithFlags(&h->ev_front, cudaEventDisableTiming));
-	}
+	CKR(ensure_front(h));
 	SegDev S{};
 	S.dna = d_dna; S.off = (const unsigned long long *) d_off; S.len = d_len; S.n_reads = n_reads;
 	S.carry = h->d_carry; S.prev_read = h->prev_read.as<uint8_t>();      // (not read: read_prev comes from the segment in flight, below)
@@ -1758,14 +1806,16 @@ static int stage_segment(fqsk_handle *h, uint8_t *&stage, size_t &stage_cap, con
 }
 // one H2D copy: the device buffer mirrors the staging layout [dna | off u64 | len u32]
 struct Uploaded { const uint8_t *dna; const unsigned long long *off; const uint32_t *len; };
-static int upload_segment(fqsk_handle *h, const uint8_t *stage, uint64_t total, uint32_t n_reads, Uploaded &U) {
+static int upload_segment(fqsk_handle *h, const uint8_t *stage, uint64_t total, uint32_t n_reads, Uploaded &U, DevBuf *buf = nullptr, cudaStream_t st = nullptr) {
+	if (!buf) buf = &h->dna;
+	if (!st) st = h->st;
 	const size_t off_pos = (total + 63) & ~(size_t) 63;
 	const size_t bytes = off_pos + (size_t) n_reads * 12;
-	CK(h->dna.ensure(std::max<size_t>(bytes, (size_t) h->P.reserve_bytes + (size_t) h->P.reserve_reads * 12 + 128) + 64));
-	if (n_reads) CK(cudaMemcpyAsync(h->dna.p, stage, bytes, cudaMemcpyHostToDevice, h->st));
-	U.dna = h->dna.as<uint8_t>();
-	U.off = (const unsigned long long *) (h->dna.as<uint8_t>() + off_pos);
-	U.len = (const uint32_t *) (h->dna.as<uint8_t>() + off_pos + (size_t) n_reads * 8);
+	CK(buf->ensure(std::max<size_t>(bytes, (size_t) h->P.reserve_bytes + (size_t) h->P.reserve_reads * 12 + 128) + 64));
+	if (n_reads) CK(cudaMemcpyAsync(buf->p, stage, bytes, cudaMemcpyHostToDevice, st));
+	U.dna = buf->as<uint8_t>();
+	U.off = (const unsigned long long *) (buf->as<uint8_t>() + off_pos);
+	U.len = (const uint32_t *) (buf->as<uint8_t>() + off_pos + (size_t) n_reads * 8);
 	return FQSK_OK;
 }
 
@@ -1974,7 +2024,7 @@ static int sync_end(fqsk_handle *h) {
 		h->items_main[0] = counters[0]; h->items_main[1] = counters[2];
 		for (int k = 0; k < 2; ++k) {
 			Table &t = k ? h->tb : h->ts;
-			if (counters[2 - 2 * k] > (4ull << t.d.B) || counters[3 - 2 * k] > (1ull << t.d.stash_log2) / 2) CKR(table_grow_if_needed(h, t));
+			if (table_crowded(h, t, counters[2 - 2 * k], counters[3 - 2 * k])) CKR(table_grow_if_needed(h, t));
 		}
 	} else {
 		CKR(seg_settle(h));
@@ -2063,12 +2113,26 @@ static int submit_impl(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, 
 	size_t &stage_cap = par ? h->h_stage2_cap : h->h_stage_cap;
 	CKR(stage_segment(h, stage, stage_cap, slab, slab_size, reads, n_reads, &total, &bound));
 	if (bound > rec_cap) return fail(h, FQSK_E_CAPACITY, "record buffer holds %llu, the segment can produce %llu", (unsigned long long) rec_cap, (unsigned long long) bound);
+	// Still ahead of the look at the previous segment: the reads travel to the device on the front stream, into the input buffer of this
+	// parity (the segment in flight reads the other one; the previous user of this one was settled two submits ago), and what depends on
+	// the reads alone -- duplicate flags, letter totals, packed reads, record offsets -- is computed behind the copy, next to the segment in
+	// flight (announce_impl: the same preparation fqsk_announce_device gives a device-resident caller).  Neither the copy nor k_prep /
+	// k_scan_reads then sits between the look at segment n and the first kernel of segment n + 1.  Not across a block start (read_prev
+	// was cleared), not with FQSK_F_SERIAL (one stream).
+	Uploaded U;
+	const bool ahead = !h->serial;
+	if (ahead) {
+		CKR(ensure_front(h));
+		CKR(upload_segment(h, stage, total, n_reads, U, par ? &h->dna2 : &h->dna, h->st_front));
+		CK(cudaEventRecord(h->ev_up, h->st_front));
+		if (!h->block_fresh && n_reads) CKR(announce_impl(h, U.dna, total, (const uint64_t *) U.off, U.len, n_reads));
+	}
 	CKR(submit_finish_compute(h));                                  // previous segment: settle + sync
 	CK(cudaStreamWaitEvent(h->st, h->ev_copied[par], 0));             // the device records of this parity have left for the host
 	h->rec_par = par;
 	if (h->meta_pending) { CK(cudaStreamWaitEvent(h->st, h->ev_meta, 0)); h->meta_pending = false; }      // the previous segment's per-read results have left the buffers this one rewrites
-	Uploaded U;
-	CKR(upload_segment(h, stage, total, n_reads, U));
+	if (ahead) CK(cudaStreamWaitEvent(h->st, h->ev_up, 0));
+	else CKR(upload_segment(h, stage, total, n_reads, U, par ? &h->dna2 : &h->dna));
 	CKR(run_segment(h, U.dna, total, U.off, U.len, n_reads));
 	const uint32_t ni = mode_pe(h->P.mode) ? n_reads / 2 * 3 : n_reads;
 	size_t o_off = 0, o_flag = 0, o_dif = 0, o_pair = 0;
@@ -2183,6 +2247,40 @@ int fqsk_block_host(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, con
 	return FQSK_OK;
 }
 
+// fqsk_block_host without the drain at the block end: the last segment of the block stays in flight and is collected by the NEXT call (or
+// by fqsk_collect), so that its records travel to the host while the first segments of the next reads_block are evaluated -- the worker
+// loop of application.cpp:617-662 running over consecutive blocks, the engine one segment ahead of the consumer throughout.
+int fqsk_block_stream(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const fqsk_read_desc *reads, uint32_t n_reads, const uint32_t *seg_end, uint32_t n_segs,
+                      fqsk_base_rec *recs, fqsk_ctx_rec *ctx, uint64_t rec_cap, uint8_t *dup, uint64_t *seg_rec_off, uint64_t *seg_n_recs,
+                      uint64_t *carry_ticket, uint64_t *carry_n_recs) {
+	if (!h || !seg_end || !n_segs || !seg_rec_off || !seg_n_recs || !carry_ticket || (n_reads && (!slab || !reads || (!recs == !ctx)))) return FQSK_E_INVAL;
+	if (seg_end[n_segs - 1] != n_reads) return fail(h, FQSK_E_INVAL, "fqsk_block_stream: the last segment must end at the last read");
+	uint64_t at = 0;
+	for (uint32_t k = 0, a = 0; k < n_segs; a = seg_end[k], ++k) {
+		if (seg_end[k] < a) return fail(h, FQSK_E_INVAL, "fqsk_block_stream: segment ends must not decrease");
+		seg_rec_off[k] = at;
+		for (uint32_t r = a; r < seg_end[k]; ++r) at += reads[r].dna_len;      // upper bound of the coded positions
+	}
+	if (at > rec_cap) return fail(h, FQSK_E_CAPACITY, "record buffer holds %llu, the block can produce %llu", (unsigned long long) rec_cap, (unsigned long long) at);
+	CKR(fqsk_block_start(h));
+	uint64_t pend = *carry_ticket, pend_k = ~0ull;      // pend_k: segment of THIS block the open ticket belongs to (~0: the carried one)
+	for (uint32_t k = 0, a = 0; k < n_segs; a = seg_end[k], ++k) {
+		const uint32_t n = seg_end[k] - a;
+		const uint64_t cap = (k + 1 < n_segs ? seg_rec_off[k + 1] : at) - seg_rec_off[k];
+		uint64_t t = 0;
+		if (ctx) CKR(fqsk_submit_ctx(h, slab, slab_size, reads + a, n, ctx + seg_rec_off[k], cap, dup ? dup + a : nullptr, nullptr, &t));
+		else CKR(fqsk_submit(h, slab, slab_size, reads + a, n, recs + seg_rec_off[k], cap, dup ? dup + a : nullptr, nullptr, &t));
+		if (pend) {
+			uint64_t nr = 0;
+			CKR(fqsk_collect(h, pend, &nr));
+			if (pend_k == ~0ull) { if (carry_n_recs) *carry_n_recs = nr; } else seg_n_recs[pend_k] = nr;
+		}
+		pend = t; pend_k = k;
+	}
+	*carry_ticket = pend;
+	return FQSK_OK;
+}
+
 // ---- sorted-mode front end ------------------------------------------------------------------------
 // rank[i] of read i: an integer order-isomorphic to the comparator of CSortedFASTQFile::sort_reads (io.h:499-528); see fqsk_front.cuh.
 // Needs no engine: its own stream and scratch on `device`, released before it returns (one call per bin file of a sorted-order job).
@@ -2244,6 +2342,13 @@ int fqsk_shard_export(fqsk_handle *h, fqsk_shard_desc *out) {
 	if (!h || !out) return FQSK_E_INVAL;
 	CK(cudaSetDevice(h->P.device));
 	if (h->world <= 1) return fail(h, FQSK_E_INVAL, "not a sharded engine");
+	if (h->grow_pending) {      // after FQSK_RESHARD and the caller's barrier: every peer has closed its mappings of the tables that double now
+		if (h->pending || h->tk_open) return fail(h, FQSK_E_INVAL, "fqsk_shard_export after FQSK_RESHARD: before the next segment");
+		if (h->grow_all & 1u) CKR(table_double(h, h->ts));
+		if (h->grow_all & 2u) CKR(table_double(h, h->tb));
+		if (h->grow_all & 4u) CKR(pair_resize(h, (h->pair.mask + 1) * 2));
+		h->grow_pending = false; h->grow_all = 0; h->grow_local = 0;
+	}
 	memset(out, 0, sizeof *out);
 	out->rank = h->rank; out->world_size = h->world;
 	out->geometry[0] = h->tb.d.B; out->geometry[1] = h->tb.d.stash_log2; out->geometry[2] = h->ts.d.B; out->geometry[3] = h->ts.d.stash_log2;
@@ -2409,7 +2514,7 @@ int fqsk_sync_apply(fqsk_handle *h, uint64_t *fresh, uint64_t *updates) {
 		CK(cudaStreamSynchronize(h->st));
 		h->pair_items = *hsp;
 	}
-	unsigned long long hc[6], acc[2] = {0, 0};
+	unsigned long long hc[6], acc[2] = {0, 0}, grow_word = 0;
 	h->sync_updates = tot[0] + h->hidden_p;
 	if (h->dev_finish) {
 		// this rank's inserts are enqueued: add its statistics to everybody's accumulators and post the sync's number (k_post_applied), then
@@ -2417,19 +2522,31 @@ int fqsk_sync_apply(fqsk_handle *h, uint64_t *fresh, uint64_t *updates) {
 		InboxDev I{};
 		for (uint32_t i = 0; i < h->world; ++i) I.base[i] = h->peer_inbox[i];
 		I.cap = h->inbox_cap; I.world = h->world; I.rank = h->rank;
-		CK(pdl(k_post_applied, 1, 32, h->st, I, h->sync_seq, (const unsigned long long *) (h->d_counters + 4), (unsigned long long) h->sync_updates)); LAUNCHED(h);
+		GrowLim lim;
+		for (int k = 0; k < 2; ++k) {      // [0, 1] b-mer table, [2, 3] s-mer table: the thresholds of table_crowded
+			const Table &t = k ? h->ts : h->tb;
+			lim.v[2 * k] = table_can_double(t) ? crowd_main(h, t) : ~0ull; lim.v[2 * k + 1] = table_can_double(t) ? crowd_stash(t) : ~0ull;
+		}
+		lim.v[4] = h->pair.keys ? (h->pair.mask + 1) / 2 : ~0ull;
+		CK(pdl(k_post_applied, 1, 32, h->st, I, h->sync_seq, (const unsigned long long *) (h->d_counters + 4), (unsigned long long) h->sync_updates,
+		       (const unsigned long long *) h->d_counters, (const unsigned long long *) (h->pair.keys ? (unsigned long long *) (h->d_pe + 6) : nullptr), lim)); LAUNCHED(h);
 		CK(pdl(k_wait_applied, 1, 32, h->st, (const unsigned long long *) h->inbox, h->world, h->sync_seq, (int *) (h->d_status + 480))); LAUNCHED(h);
 		CK(cudaMemcpyAsync(acc, h->inbox + INBOX_ACC + 2 * (h->sync_seq & 1), 16, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaMemcpyAsync(&grow_word, h->inbox + INBOX_GROW + (h->sync_seq & 1), 8, cudaMemcpyDeviceToHost, h->st));
 		CK(cudaMemcpyAsync((uint8_t *) h->h_small + 480, h->d_status + 480, 4, cudaMemcpyDeviceToHost, h->st));
 	}
 	CK(cudaMemcpyAsync(hc, h->d_counters, 48, cudaMemcpyDeviceToHost, h->st));
 	CK(cudaStreamSynchronize(h->st));
 	resolve_phases(h);
 	if (h->dev_finish && *(const uint32_t *) ((uint8_t *) h->h_small + 480)) return fail(h, FQSK_E_CUDA, "sharded sync: a peer did not finish its inserts within the time limit");
-	for (int k = 0; k < 2; ++k) {
-		Table &t = k ? h->tb : h->ts;
-		if (hc[2 - 2 * k] > (4ull << t.d.B) || hc[3 - 2 * k] > (1ull << t.d.stash_log2) / 2) CKR(table_grow_if_needed(h, t));
-	}
+	// shards double together: what this rank's shards ask for (three-step form: fqsk_shard_grow_request), resp. what all ranks asked for
+	// through the accumulators (device form)
+	h->grow_local = 0;
+	if (table_crowded(h, h->ts, hc[2], hc[3]) && table_can_double(h->ts)) h->grow_local |= 1u;
+	if (table_crowded(h, h->tb, hc[0], hc[1]) && table_can_double(h->tb)) h->grow_local |= 2u;
+	if (h->pair.keys && h->pair_items > (h->pair.mask + 1) / 2) h->grow_local |= 4u;
+	h->grow_all = 0;
+	if (h->dev_finish) h->grow_all = ((grow_word & 0xFFFFull) ? 1u : 0u) | (((grow_word >> 16) & 0xFFFFull) ? 2u : 0u) | (((grow_word >> 32) & 0xFFFFull) ? 4u : 0u);
 	h->sync_fresh = hc[4];
 	h->siv_local_filled += hc[4];
 	h->hidden_p = 0;
@@ -2463,6 +2580,39 @@ int fqsk_sync_finish(fqsk_handle *h, uint64_t fresh_all, uint64_t updates_all) {
 	h->pending = false; h->pend_b = h->pend_s = h->pend_p = 0; h->seg_reads = 0;
 	h->routed = h->applied = false;
 	resolve_phases(h);
+	if (h->grow_all) {
+		// Some rank's shard is past half full: every shard of that table doubles (one geometry per table).  The sync is complete and this
+		// rank's streams are idle (the apply step ended with a look), so the mappings of the peers' old tables can be closed here; the
+		// doubling itself waits for the caller's barrier -- a table must not be freed while a peer still maps it -- and happens in the
+		// fqsk_shard_export that follows.
+		// (all three tables are remapped, doubled or not: one rule, and the p-mer shards and inboxes -- never reallocated -- stay mapped)
+		for (uint32_t r = 0; r < h->world; ++r) {
+			if (r == h->rank) continue;
+			for (int q : {0, 1, 2, 3, 6, 7}) {      // ipc slots of the b-mer, s-mer and pair tables (fqsk_shard_desc)
+				void *&pp = h->peer_ptrs[r][q];
+				if (pp) { CK(cudaIpcCloseMemHandle(pp)); pp = nullptr; }
+			}
+			h->tb.d.peer_main[r] = nullptr; h->tb.d.peer_stash[r] = nullptr; h->ts.d.peer_main[r] = nullptr; h->ts.d.peer_stash[r] = nullptr;
+			if (h->pair.keys) { h->pair.peer_keys[r] = nullptr; h->pair.peer_vcs[r] = nullptr; }
+		}
+		h->attached = 1u << h->rank;
+		h->grow_pending = true;
+		return FQSK_RESHARD;
+	}
+	return FQSK_OK;
+}
+
+int fqsk_shard_grow_request(fqsk_handle *h, uint32_t *request) {
+	if (!h || !request) return FQSK_E_INVAL;
+	if (h->world <= 1 || !h->applied) return fail(h, FQSK_E_INVAL, "fqsk_shard_grow_request: between fqsk_sync_apply and fqsk_sync_finish of a sharded engine");
+	*request = h->grow_local;
+	return FQSK_OK;
+}
+int fqsk_shard_grow(fqsk_handle *h, uint32_t request_all_ranks) {
+	if (!h || request_all_ranks > 7u) return FQSK_E_INVAL;
+	if (h->world <= 1 || !h->applied) return fail(h, FQSK_E_INVAL, "fqsk_shard_grow: between fqsk_sync_apply and fqsk_sync_finish of a sharded engine");
+	if ((request_all_ranks & 4u) && !h->pair.keys) return fail(h, FQSK_E_INVAL, "fqsk_shard_grow: no pair table");
+	h->grow_all = request_all_ranks;
 	return FQSK_OK;
 }
 

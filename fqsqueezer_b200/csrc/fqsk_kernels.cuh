@@ -812,15 +812,26 @@ __global__ void k_wait_seq(const unsigned long long *inbox, uint32_t world, unsi
 // into the accumulators of ALL ranks (NVLink atomics) and then posts the sync's number in their headers; a rank that has seen all N
 // numbers holds the complete sums.  Two accumulator instances alternate: a rank clears the next sync's instance before it posts this
 // sync's number, and nobody adds to that instance before having seen that number.
-static const uint32_t INBOX_APPLIED = 56, INBOX_ACC = 64;
-__global__ void k_post_applied(InboxDev I, unsigned long long seq, const unsigned long long *fresh_dev, unsigned long long updates) { pdl_enter();
+static const uint32_t INBOX_APPLIED = 56, INBOX_ACC = 64, INBOX_GROW = 72;
+// Growth requests travel the same way: a rank whose shard of the s-mer / b-mer / pair table is past half full after its inserts adds 1 to
+// field 0 / 1 / 2 (16 bits each) of word INBOX_GROW + instance in every rank's header; every rank then reads the same word and all shards
+// of a requested table double together (fqsk_sync_finish -> FQSK_RESHARD).  lim: items in the buckets / in the stash of the b-mer table,
+// of the s-mer table, items of the pair table above which this rank asks (~0: the table cannot double any more).
+struct GrowLim { unsigned long long v[5]; };
+__global__ void k_post_applied(InboxDev I, unsigned long long seq, const unsigned long long *fresh_dev, unsigned long long updates,
+                               const unsigned long long *counters, const unsigned long long *pair_items, GrowLim lim) { pdl_enter();
 	const uint32_t t = threadIdx.x, par = (uint32_t) (seq & 1);
-	if (t == 0) { unsigned long long *own = I.base[I.rank] + INBOX_ACC + 2 * (par ^ 1); own[0] = 0; own[1] = 0; }
+	if (t == 0) { unsigned long long *own = I.base[I.rank] + INBOX_ACC + 2 * (par ^ 1); own[0] = 0; own[1] = 0; I.base[I.rank][INBOX_GROW + (par ^ 1)] = 0; }
 	__threadfence_system();
 	__syncthreads();
 	if (t < I.world) {
+		unsigned long long req = 0;
+		if (counters[2] > lim.v[2] || counters[3] > lim.v[3]) req |= 1ull;
+		if (counters[0] > lim.v[0] || counters[1] > lim.v[1]) req |= 1ull << 16;
+		if (pair_items && *pair_items > lim.v[4]) req |= 1ull << 32;
 		atomicAdd_system(I.base[t] + INBOX_ACC + 2 * par, *fresh_dev);
 		atomicAdd_system(I.base[t] + INBOX_ACC + 2 * par + 1, updates);
+		if (req) atomicAdd_system(I.base[t] + INBOX_GROW + par, req);
 	}
 	__threadfence_system();
 	__syncthreads();

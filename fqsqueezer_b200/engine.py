@@ -19,7 +19,7 @@ READ_DESC_DTYPE = np.dtype([("dna_off", "<u8"), ("dna_len", "<u4"), ("flags", "<
 CTX_REC_DTYPE = np.dtype([("a", "<u8"), ("b", "<u8")])      # fqsk_ctx_rec (include/fqsk_ctx.h)
 TABLE_SIV, TABLE_SMER, TABLE_BMER, TABLE_PAIR = 0, 1, 2, 3
 MODE_SE_ORIGINAL, MODE_SE_SORTED, MODE_PE_ORIGINAL, MODE_PE_SORTED = 0, 1, 2, 3
-F_PROFILE, F_TRACE_ALLOC, F_TEST_HOOKS, F_TRACE_LAUNCH, F_SERIAL = 1, 2, 4, 8, 16
+F_PROFILE, F_TRACE_ALLOC, F_TEST_HOOKS, F_TRACE_LAUNCH, F_SERIAL, F_TEST_CROWD = 1, 2, 4, 8, 16, 32
 PHASES = ["prep", "lookup", "partial", "walk", "compact", "sort", "local", "rough", "fold", "sync_locate", "sync_apply", "sync_siv", "mt"]
 
 
@@ -42,13 +42,15 @@ class _Stats(C.Structure):
                 ("draws", C.c_uint64 * 4), ("n_segments", C.c_uint64), ("n_syncs", C.c_uint64), ("n_replays", C.c_uint64),
                 ("n_bases", C.c_uint64), ("n_reads", C.c_uint64), ("kernel_launches", C.c_uint64), ("bmer_buckets", C.c_uint64),
                 ("smer_buckets", C.c_uint64), ("bmer_stash_used", C.c_uint64), ("smer_stash_used", C.c_uint64), ("n_hot_segments", C.c_uint64),
-                ("n_filtered_segments", C.c_uint64), ("n_looks", C.c_uint64), ("look_wait_ns", C.c_uint64), ("api_ns", C.c_uint64)]
+                ("n_filtered_segments", C.c_uint64), ("n_looks", C.c_uint64), ("look_wait_ns", C.c_uint64), ("api_ns", C.c_uint64),
+                ("n_table_growths", C.c_uint64)]
 
 
 EXPORTS = ["fqsk_create", "fqsk_destroy", "fqsk_last_error", "fqsk_block_start", "fqsk_segment", "fqsk_segment_device", "fqsk_announce_device",
-           "fqsk_device_recs", "fqsk_recs_checksum", "fqsk_sorted_prefix", "fqsk_pair_info", "fqsk_submit", "fqsk_submit_ctx", "fqsk_collect", "fqsk_block_host", "fqsk_sync", "fqsk_dump", "fqsk_stats_get", "fqsk_profile", "fqsk_ht_insert", "fqsk_ht_find",
+           "fqsk_device_recs", "fqsk_recs_checksum", "fqsk_sorted_prefix", "fqsk_pair_info", "fqsk_submit", "fqsk_submit_ctx", "fqsk_collect", "fqsk_block_host", "fqsk_block_stream", "fqsk_sync", "fqsk_dump", "fqsk_stats_get", "fqsk_profile", "fqsk_ht_insert", "fqsk_ht_find",
            "fqsk_ht_count", "fqsk_timeline", "fqsk_timer_begin", "fqsk_timer_end", "fqsk_siv_increment", "fqsk_siv_test", "fqsk_siv_counts", "fqsk_siv_test_shorter", "fqsk_mt_stream", "fqsk_host_alloc", "fqsk_host_free",
-           "fqsk_sort_ranks", "fqsk_shard_export", "fqsk_shard_attach", "fqsk_sync_route", "fqsk_sync_apply", "fqsk_sync_finish", "fqsk_sync_device"]
+           "fqsk_sort_ranks", "fqsk_shard_export", "fqsk_shard_attach", "fqsk_sync_route", "fqsk_sync_apply", "fqsk_sync_finish", "fqsk_sync_device",
+           "fqsk_shard_grow_request", "fqsk_shard_grow"]
 
 _lib = None
 
@@ -79,6 +81,7 @@ def load_library():
     lib.fqsk_submit_ctx.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint32, vp, C.c_uint64, vp, vp, u64p]
     lib.fqsk_collect.argtypes = [vp, C.c_uint64, u64p]
     lib.fqsk_block_host.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint64, vp, vp, vp]
+    lib.fqsk_block_stream.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint32, vp, C.c_uint32, vp, vp, C.c_uint64, vp, vp, vp, u64p, u64p]
     lib.fqsk_sync.argtypes = [vp]
     lib.fqsk_dump.argtypes = [vp, C.c_int, vp, vp, C.c_uint64, u64p]
     lib.fqsk_stats_get.argtypes = [vp, C.POINTER(_Stats)]
@@ -175,6 +178,7 @@ class KmerEngine:
         self._pinned = {}
         self.__dict__.pop("_submit_cache", None)
         self.__dict__.pop("_submit_cache_ctx", None)
+        self.__dict__.pop("_stream_state", None)
         if getattr(self, "h", None):
             self.lib.fqsk_destroy(self.h)
             self.h = None
@@ -295,6 +299,58 @@ class KmerEngine:
         seg_off, seg_n = np.zeros(ns, np.uint64), np.zeros(ns, np.uint64)
         self._ck(self.lib.fqsk_block_host(self.h, _ptr(slab), slab.size, _ptr(desc), n, _ptr(seg_end), ns, _ptr(ent[3]), r_cap, _ptr(ent[4]), _ptr(seg_off), _ptr(seg_n)))
         return ent[3], ent[4][: max(n, 1)], seg_off, seg_n
+
+    def block_stream(self, slab: np.ndarray, off: np.ndarray, length: np.ndarray, seg_end, ctx: bool = False):
+        """One reads_block of a run of consecutive blocks through fqsk_block_stream: like block_host, but the block's last segment stays in
+        flight and is collected by the next block_stream call (or by stream_finish after the last block).  Returns a list of record views
+        in stream order that became complete during this call: the previous block's last segment (if any), then this block's segments
+        0 .. n_segs - 2.  Page-locked buffers owned by the engine, two sets used alternately: the views stay valid until the second
+        block_stream call after this one."""
+        if slab.dtype != np.uint8 or not slab.flags.c_contiguous:
+            slab = np.ascontiguousarray(slab, np.uint8)
+        n = len(off)
+        seg_end = np.ascontiguousarray(seg_end, np.uint32)
+        ns = len(seg_end)
+        dt = CTX_REC_DTYPE if ctx else REC_DTYPE
+        cap = int(length.sum(dtype=np.int64)) + 16
+        st = self.__dict__.setdefault("_stream_state", {"slot": 0, "ticket": C.c_uint64(0), "tail": None, "cache": {}})
+        slot = st["slot"] ^ 1
+        st["slot"] = slot
+        key = (slot, bool(ctx))
+        ent = st["cache"].get(key)
+        n_cap, r_cap = max(n, self.reserve_reads, 1), max(cap, self.reserve_bytes + 16)
+        if ent is None or ent[0] < n_cap or ent[1] < r_cap:
+            ent = (n_cap, r_cap, np.zeros(n_cap, READ_DESC_DTYPE),
+                   self._pinned_array(f"trecs{slot}{'c' if ctx else ''}", r_cap * dt.itemsize)[: r_cap * dt.itemsize].view(dt), self._pinned_array(f"tdup{slot}", n_cap))
+            st["cache"][key] = ent
+        desc = ent[2]
+        desc["dna_off"][:n] = off
+        desc["dna_len"][:n] = length
+        seg_off, seg_n = np.zeros(ns, np.uint64), np.zeros(ns, np.uint64)
+        carry_n = C.c_uint64(0)
+        had = st["ticket"].value != 0
+        self._ck(self.lib.fqsk_block_stream(self.h, _ptr(slab), slab.size, _ptr(desc), n, _ptr(seg_end), ns, None if ctx else _ptr(ent[3]), _ptr(ent[3]) if ctx else None, r_cap,
+                                            _ptr(ent[4]), _ptr(seg_off), _ptr(seg_n), C.byref(st["ticket"]), C.byref(carry_n)))
+        out = []
+        if had:
+            buf, o = st["tail"]
+            out.append(buf[o:o + carry_n.value])
+        for k in range(ns - 1):
+            out.append(ent[3][int(seg_off[k]): int(seg_off[k]) + int(seg_n[k])])
+        st["tail"] = (ent[3], int(seg_off[ns - 1]))
+        st["keep"] = (slab, desc)
+        return out
+
+    def stream_finish(self):
+        """Collects the segment the last block_stream call left in flight; returns its records (or None when there is none)."""
+        st = self.__dict__.get("_stream_state")
+        if not st or not st["ticket"].value:
+            return None
+        n_recs = C.c_uint64(0)
+        self._ck(self.lib.fqsk_collect(self.h, st["ticket"].value, C.byref(n_recs)))
+        st["ticket"] = C.c_uint64(0)
+        buf, o = st["tail"]
+        return buf[o:o + n_recs.value]
 
     def segment_device(self, d_dna_ptr: int, dna_bytes: int, d_off_ptr: int, d_len_ptr: int, n_reads: int, want_n_recs: bool = True):
         """Reads already in HBM.  want_n_recs=False only enqueues the segment: the library looks at the outcome when the

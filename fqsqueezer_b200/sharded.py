@@ -42,14 +42,18 @@ def gather_descs(dist, my_blob: bytes, world: int):
     return [_ShardDesc.from_buffer_copy(x) for x in blobs]
 
 
-def allreduce_stats(dist, fresh: int, updates: int):
-    """Sum over the ranks of (fresh p-mer fields, p-mer updates): TSmallIntVector's global atomics (bit_vec.h:212-220)."""
+RESHARD = 1      # FQSK_RESHARD (include/fqsk.h): the sync is complete, table shards double before the next segment
+
+
+def allreduce_stats(dist, fresh: int, updates: int, grow_request: int = 0):
+    """Sum over the ranks of (fresh p-mer fields, p-mer updates): TSmallIntVector's global atomics (bit_vec.h:212-220) -- and, in the same
+    all-reduce, how many ranks ask for a doubling of the s-mer / b-mer / pair table (fqsk_shard_grow_request): returned as the OR of the requests."""
     import torch
     dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
-    t = torch.tensor([fresh, updates], dtype=torch.int64, device=dev)
+    t = torch.tensor([fresh, updates] + [(grow_request >> i) & 1 for i in range(3)], dtype=torch.int64, device=dev)
     dist.all_reduce(t)
-    a, b = t.tolist()
-    return int(a), int(b)
+    a, b, g0, g1, g2 = t.tolist()
+    return int(a), int(b), (1 if g0 else 0) | (2 if g1 else 0) | (4 if g2 else 0)
 
 
 class ShardedKmerEngine(E.KmerEngine):
@@ -63,7 +67,7 @@ class ShardedKmerEngine(E.KmerEngine):
         prm = E._Params(abi_version=1, pmer_len=p, smer_len=s, bmer_len=b, prefix_len=prefix_len, smer_counter_bits=12, bmer_counter_bits=6,
                         mode=mode, n_workers=world, device=device, bmer_log2_buckets=kw.get("bmer_log2_buckets", 0),
                         smer_log2_buckets=kw.get("smer_log2_buckets", 0), expected_kmers=expected_kmers, world_size=world, rank=rank,
-                        max_iterations=0, flags=E.F_PROFILE if kw.get("profile") else 0, reserve_reads=reserve_reads, reserve_bytes=reserve_bytes,
+                        max_iterations=0, flags=(E.F_PROFILE if kw.get("profile") else 0) | kw.get("flags", 0), reserve_reads=reserve_reads, reserve_bytes=reserve_bytes,
                         pair_log2_slots=kw.get("pair_log2_slots", 0))
         h = C.c_void_p()
         rc = self.lib.fqsk_create(C.byref(prm), C.byref(h))
@@ -84,7 +88,9 @@ class ShardedKmerEngine(E.KmerEngine):
         lib.fqsk_sync_apply.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         lib.fqsk_sync_finish.argtypes = [vp, C.c_uint64, C.c_uint64]
         lib.fqsk_sync_device.argtypes = [vp]
-        for n in ("fqsk_shard_export", "fqsk_shard_attach", "fqsk_sync_route", "fqsk_sync_apply", "fqsk_sync_finish", "fqsk_sync_device"):
+        lib.fqsk_shard_grow_request.argtypes = [vp, C.POINTER(C.c_uint32)]
+        lib.fqsk_shard_grow.argtypes = [vp, C.c_uint32]
+        for n in ("fqsk_shard_export", "fqsk_shard_attach", "fqsk_sync_route", "fqsk_sync_apply", "fqsk_sync_finish", "fqsk_sync_device", "fqsk_shard_grow_request", "fqsk_shard_grow"):
             getattr(lib, n).restype = C.c_int
 
     def _attach_peers(self):
@@ -102,14 +108,27 @@ class ShardedKmerEngine(E.KmerEngine):
         if not self.host_collective:
             # rows into the owners' inboxes, both barriers as sequence numbers the ranks post in each other's inbox headers and wait for on
             # the device, global p-mer statistics as NVLink atomics: no collective library on the path of a sync
-            self._ck(self.lib.fqsk_sync_device(self.h))
+            rc = self.lib.fqsk_sync_device(self.h)
+        else:
+            self._ck(self.lib.fqsk_sync_route(self.h))              # rows [rank][*] into the owners' inboxes + this sync's number posted there
+            fresh, upd = C.c_uint64(0), C.c_uint64(0)                 # (the owners wait for their sources on the device: no host barrier here)
+            self._ck(self.lib.fqsk_sync_apply(self.h, C.byref(fresh), C.byref(upd)))
+            req = C.c_uint32(0)
+            self._ck(self.lib.fqsk_shard_grow_request(self.h, C.byref(req)))
+            # global p-mer statistics; also the second barrier: every owner has finished its inserts before anybody looks up again
+            f_all, u_all, grow = allreduce_stats(self.dist, fresh.value, upd.value, req.value)
+            if grow:
+                self._ck(self.lib.fqsk_shard_grow(self.h, grow))
+            rc = self.lib.fqsk_sync_finish(self.h, f_all, u_all)
+        if rc == RESHARD:
+            # CHT_kmer::restruct (ht_kmer.h:88-112) for shards: some rank's shard is past half full, all shards of that table double.  Every
+            # rank got the same verdict; nobody frees a table before all peers have closed their mappings of it (the barrier), the doubling
+            # happens inside fqsk_shard_export, then the new descriptors are exchanged and attached as at set-up.
+            self.reshards = getattr(self, "reshards", 0) + 1
+            self.dist.barrier()
+            self._attach_peers()
             return
-        self._ck(self.lib.fqsk_sync_route(self.h))              # rows [rank][*] into the owners' inboxes + this sync's number posted there
-        fresh, upd = C.c_uint64(0), C.c_uint64(0)                 # (the owners wait for their sources on the device: no host barrier here)
-        self._ck(self.lib.fqsk_sync_apply(self.h, C.byref(fresh), C.byref(upd)))
-        # global p-mer statistics; also the second barrier: every owner has finished its inserts before anybody looks up again
-        f_all, u_all = allreduce_stats(self.dist, fresh.value, upd.value)
-        self._ck(self.lib.fqsk_sync_finish(self.h, f_all, u_all))
+        self._ck(rc)
 
     def dump_all(self, which):
         """Sorted contents of the whole (sharded) table, gathered on every rank -- parity check 1."""

@@ -7,7 +7,7 @@
  * needs per sync segment.  Everything below is plain C: pointers and sizes only.
  *
  * All `reference:` citations are relative to /root/reference/fqs/.
- * Every function returns 0 on success or a negative FQSK_E_* code; nothing throws across the ABI.
+ * Every function returns 0 on success or a negative FQSK_E_* code (one positive, non-error code: FQSK_RESHARD); nothing throws across the ABI.
  * There is NO CPU fallback: without a CUDA device fqsk_create fails with FQSK_E_NO_DEVICE.
  */
 #ifndef FQSK_H
@@ -25,6 +25,7 @@ extern "C" {
 
 enum {
 	FQSK_OK = 0,
+	FQSK_RESHARD = 1,         /* not an error -- sharded engines only: the sync is complete and table shards must double before the next segment (see fqsk_sync_finish) */
 	FQSK_E_INVAL = -1,        /* bad argument */
 	FQSK_E_NO_DEVICE = -2,    /* no usable CUDA device */
 	FQSK_E_CUDA = -3,         /* CUDA runtime error, see fqsk_last_error() */
@@ -63,7 +64,7 @@ typedef struct fqsk_params {
 	uint32_t flags;              /* FQSK_F_* */
 	uint32_t reserve_reads;      /* optional: largest segment the caller will submit (reads / DNA bytes); scratch is allocated once */
 	uint32_t reserve_bytes;
-	uint32_t pair_log2_slots;    /* paired-end: initial size of the pair table (0 = default); fixed on a sharded engine (shards cannot grow) */
+	uint32_t pair_log2_slots;    /* paired-end: initial size of the pair table (0 = default); it doubles when half full (sharded: all shards together, FQSK_RESHARD) */
 	uint32_t test_hooks;         /* only with FQSK_F_TEST_HOOKS, else must be 0: bits 0-15 = N -> every N-th segment's first-pass verdict is forced to
 	                              * "not settled"; bits 16-31 = M -> every M-th segment is evaluated a second time from scratch (fault injection) */
 } fqsk_params;
@@ -73,6 +74,7 @@ typedef struct fqsk_params {
 #define FQSK_F_TRACE_LAUNCH 8u   /* debugging: synchronise the device after every kernel launch and print its source line to stderr */
 #define FQSK_F_SERIAL 16u        /* debugging / measurement: every kernel on the engine's one stream (no fork / join over side streams) */
 #define FQSK_F_TEST_HOOKS 4u     /* honour fqsk_params.test_hooks (tests of the recovery paths; never set by a host) */
+#define FQSK_F_TEST_CROWD 32u    /* with FQSK_F_TEST_HOOKS: the s-mer / b-mer tables double at 1/64 of the usual load (growth paths on small fixtures) */
 
 typedef struct fqsk_handle fqsk_handle;
 
@@ -108,6 +110,7 @@ typedef struct fqsk_stats {
 	uint64_t n_looks, look_wait_ns;          /* host looks at the device and the time the host spent WAITING in them: api time minus this = the
 	                                          * host's own work (launching); a job whose wait time is near zero is bound by its host, not the GPU */
 	uint64_t api_ns;                         /* time inside the segment / sync / submit / collect calls */
+	uint64_t n_table_growths;                /* doublings of the s-mer / b-mer / pair table (ht_kmer.h:88-112 restruct) so far */
 } fqsk_stats;
 
 /* Named phases of fqsk_profile(): device milliseconds accumulated since create (only with FQSK_F_PROFILE). */
@@ -187,6 +190,16 @@ int fqsk_collect(fqsk_handle *h, uint64_t ticket, uint64_t *n_recs);
  * rec_cap >= sum of dna_len; the records of segment k start at recs[seg_rec_off[k]] and number seg_n_recs[k].  dup: n_reads bytes or NULL. */
 int fqsk_block_host(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const fqsk_read_desc *reads, uint32_t n_reads, const uint32_t *seg_end, uint32_t n_segs,
                     fqsk_base_rec *recs, uint64_t rec_cap, uint8_t *dup, uint64_t *seg_rec_off, uint64_t *seg_n_recs);
+/* fqsk_block_host for a run of consecutive reads_blocks: the last segment of the block is left in flight -- *carry_ticket names it on
+ * return -- and is collected by the next call right after that call's first submit (its record count goes to *carry_n_recs), so the engine
+ * stays one segment ahead of the consumer across block boundaries too (draining at every block end would leave the GPU idle while the
+ * last 51 000-read segment's records travel).  In: *carry_ticket = the ticket the previous call left, 0 on the first block; after the
+ * last block the caller collects *carry_ticket with fqsk_collect.  seg_n_recs[n_segs - 1] is NOT written (it is the next call's
+ * *carry_n_recs).  Exactly one of recs / ctx is given: 28-byte count records (fqsk_submit) or 16-byte context records (fqsk_submit_ctx).
+ * The buffers of a block (recs / ctx, dup) belong to the library until the carried ticket is collected: alternate between two sets. */
+int fqsk_block_stream(fqsk_handle *h, const uint8_t *slab, uint64_t slab_size, const fqsk_read_desc *reads, uint32_t n_reads, const uint32_t *seg_end, uint32_t n_segs,
+                      fqsk_base_rec *recs, fqsk_ctx_rec *ctx, uint64_t rec_cap, uint8_t *dup, uint64_t *seg_rec_off, uint64_t *seg_n_recs,
+                      uint64_t *carry_ticket, uint64_t *carry_n_recs);
 /* fqsk_submit with the context ids of the DNA stream built on the device: instead of fqsk_base_rec the
  * caller receives one fqsk_ctx_rec (16 bytes, include/fqsk_ctx.h) per coded base -- what cor_zone (dna.cpp:739-744),
  * CCodeContext::determine_ctx_codes (code_ctx.cpp:257-324), rank (dna.cpp:177-193) and update_ctx_r_sym (dna.cpp:664-671) compute on
@@ -213,8 +226,12 @@ int fqsk_sort_ranks(int device, const uint8_t *slab, uint64_t slab_size, const f
  * The reference's first barrier ("every row is filled") is a sequence number the routing step posts in the owners' inboxes and the
  * apply step waits for ON THE DEVICE; the all-reduce -- the second barrier: every owner has inserted before anybody looks up again --
  * is the caller's (NCCL in fqsqueezer_b200/sharded.py); the payload itself moves inside fqsk_sync_route as peer stores into the
- * owners' inboxes.  Table growth is not supported in this mode: size the
- * tables with expected_kmers / *_log2_buckets / pair_log2_slots.  Paired-end (FQSK_MODE_PE_ORIGINAL): the pair table is
+ * owners' inboxes.  Table growth (CHT_kmer::restruct, ht_kmer.h:88-112, ht_kmer.cpp:50-75) is coordinated: all shards of a table have the
+ * same geometry, so when ONE rank's shard of the s-mer, b-mer or pair table passes half full at a sync, fqsk_sync_finish / fqsk_sync_device
+ * return FQSK_RESHARD on EVERY rank (the sync itself is complete, peer mappings of the tables concerned are already closed); the caller then
+ * (1) synchronises all ranks -- nobody may free a table a peer still maps --, (2) calls fqsk_shard_export on every rank (the doubling
+ * happens here: dump, 2x buckets / slots, re-insert), (3) exchanges the descriptors and calls fqsk_shard_attach for every peer, exactly as
+ * at set-up.  Paired-end (FQSK_MODE_PE_ORIGINAL): the pair table is
  * sharded by (fmix64(key) >> 48) % world_size (ht_kmer.h:599-602, dna.cpp:1076-1081) and the distinct (key, value, weight)
  * triples of a segment travel with the same exchange step. */
 typedef struct fqsk_shard_desc {
@@ -231,8 +248,15 @@ int fqsk_sync_route(fqsk_handle *h);
 /* Owner side of InsertKmersToHT: applies the rows [*][rank] in source order (p-mers, s-mers, b-mers; this rank's cinc_s / cinc_b).
  * fresh = p-mer fields that became non-zero here, updates = p-mers applied here + this worker's hidden updates (dna.cpp:2416-2418). */
 int fqsk_sync_apply(fqsk_handle *h, uint64_t *fresh, uint64_t *updates);
+/* Three-step form only, between fqsk_sync_apply and fqsk_sync_finish: *request = the tables of which THIS rank's shard is past half full
+ * (bit 0 s-mers, bit 1 b-mers, bit 2 pairs).  The caller ORs the requests of all ranks -- they can travel with the all-reduce of the
+ * statistics -- and hands the result to fqsk_shard_grow on every rank; fqsk_sync_finish then returns FQSK_RESHARD when it is non-zero.
+ * (fqsk_sync_device needs neither call: the requests cross NVLink with the statistics.) */
+int fqsk_shard_grow_request(fqsk_handle *h, uint32_t *request);
+int fqsk_shard_grow(fqsk_handle *h, uint32_t request_all_ranks);
 /* After the all-reduce: the global p-mer statistics (bit_vec.h:204-220 -- they gate repair_kmers_missing on every worker) and
- * ClearKmersToHT.  The call sequence must be completed on all ranks before any of them starts its next segment. */
+ * ClearKmersToHT.  The call sequence must be completed on all ranks before any of them starts its next segment.
+ * Returns FQSK_RESHARD instead of FQSK_OK when table shards have to double first (see above). */
 int fqsk_sync_finish(fqsk_handle *h, uint64_t fresh_all_ranks, uint64_t updates_all_ranks);
 /* The three steps in one call, with NO collective of the caller's: the second barrier is a sequence number too (every rank posts it in
  * every peer's inbox once its inserts are enqueued, and waits for all of them on the device), and the global p-mer statistics travel

@@ -26,8 +26,10 @@ def main():
     pref, p, s, b = E.kmer_params(int(g["gs"]))
     slab = g["fastq"]
     paired = "-p" in [str(x) for x in g["extra"]]
+    grow = "grow" in sys.argv[2:]      # smallest legal tables + FQSK_F_TEST_CROWD: the shards have to double, together, several times during the run
+    kw = dict(bmer_log2_buckets=1, smer_log2_buckets=1, pair_log2_slots=10, flags=E.F_TEST_HOOKS | E.F_TEST_CROWD) if grow else {}
     eng = sharded.ShardedKmerEngine(p, s, b, pref, rank, world, device=local, dist=dist, reserve_bytes=1 << 20, reserve_reads=1 << 14,
-                                    mode=E.MODE_PE_ORIGINAL if paired else E.MODE_SE_ORIGINAL, host_collective="host" in sys.argv[2:])
+                                    mode=E.MODE_PE_ORIGINAL if paired else E.MODE_SE_ORIGINAL, host_collective="host" in sys.argv[2:], **kw)
     off, ln, roff, rsz = S.parse_fastq(slab)
     out, info = [], []
     for gen, (f, l) in enumerate(S.split_blocks(rsz, paired=paired)):
@@ -51,7 +53,9 @@ def main():
     st = eng.stats()
     assert st["siv_no_filled"] == int(g["siv_no_filled"]) and st["siv_no_updates"] == int(g["siv_no_updates"]), (st["siv_no_filled"], st["siv_no_updates"])
     assert st["kernel_launches"] > 0
-    print(f"rank {rank}/{world}: {len(recs)} records and the merged tables bit-exact vs fqs-1.1 -t {world} ({st['kernel_launches']} launches)", flush=True)
+    if grow:      # CHT_kmer::restruct for shards: FQSK_RESHARD -> barrier -> doubling inside fqsk_shard_export -> descriptors exchanged and attached again
+        assert getattr(eng, "reshards", 0) >= 2 and st["n_table_growths"] >= 4, (getattr(eng, "reshards", 0), st["n_table_growths"])
+    print(f"rank {rank}/{world}: {len(recs)} records and the merged tables bit-exact vs fqs-1.1 -t {world} ({st['kernel_launches']} launches, {getattr(eng, 'reshards', 0)} coordinated table doublings)", flush=True)
     eng.close()
     dist.barrier()
     dist.destroy_process_group()

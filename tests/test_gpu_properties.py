@@ -1,7 +1,8 @@
 """Size-independent properties at BASELINE config-2 scale (p17/s20/b24, 51 000-read blocks, the reference's sync schedule), where
 the CPU oracle is too slow to be the checker: (1) the ways into the engine -- reads resident in HBM (fqsk_segment_device, alone and with
 the next segment announced by fqsk_announce_device), host buffers blocking (fqsk_segment + fqsk_sync), host buffers asynchronous
-(fqsk_submit / fqsk_collect) and a whole reads_block per call (fqsk_block_host) -- must produce the same records, tables and PRNG positions; (2) a run is a pure function of its input (two runs, identical checksums);
+(fqsk_submit / fqsk_collect), a whole reads_block per call (fqsk_block_host) and a run of blocks with the last segment carried into the
+next call (fqsk_block_stream) -- must produce the same records, tables and PRNG positions; (2) a run is a pure function of its input (two runs, identical checksums);
 (3) conservation: every coded base yields exactly one record and the p-mer update count equals pushes + hidden updates."""
 import hashlib
 
@@ -60,6 +61,10 @@ def _run(mode, blocks):
             for o, n in zip(seg_off.tolist(), seg_n.tolist()):
                 h.update(np.ascontiguousarray(recs[o:o + n]).view(np.uint8)); n_recs += n
             continue
+        if mode in ("stream", "stream_ctx"):
+            for r2 in e.block_stream(slab, off, ln, np.array([bb for _, bb in sched], np.uint32), ctx=mode == "stream_ctx"):
+                h.update(np.ascontiguousarray(r2).view(np.uint8)); n_recs += len(r2)
+            continue
         for k, (a, bb) in enumerate(sched):
             if mode in ("device", "device_announce"):
                 if mode == "device":
@@ -81,7 +86,7 @@ def _run(mode, blocks):
                 recs, dup = e.segment(slab, off[a:bb], ln[a:bb])
                 e.sync()
             else:
-                t = e.submit(slab, off[a:bb], ln[a:bb])
+                t = e.submit(slab, off[a:bb], ln[a:bb], ctx=mode == "async_ctx")
                 if pend is not None:
                     r2, _, _ = e.collect(pend)
                     h.update(np.ascontiguousarray(r2).view(np.uint8)); n_recs += len(r2)
@@ -90,6 +95,9 @@ def _run(mode, blocks):
             h.update(np.ascontiguousarray(recs).view(np.uint8)); n_recs += len(recs)
     if pend is not None:
         r2, _, _ = e.collect(pend)
+        h.update(np.ascontiguousarray(r2).view(np.uint8)); n_recs += len(r2)
+    if mode in ("stream", "stream_ctx"):
+        r2 = e.stream_finish()
         h.update(np.ascontiguousarray(r2).view(np.uint8)); n_recs += len(r2)
     tabs, st = _tables(e)
     e.close()
@@ -100,9 +108,10 @@ def test_entry_paths_agree_and_runs_are_deterministic():
     genome = synth.make_genome(GENOME, 5)
     blocks = [synth.make_reads(genome, READS, L=L, seed=100 + i)[0] for i in range(len(BLOCKS))]
     pref, p, s, b = E.kmer_params(GS)
-    res = {m: _run(m, blocks) for m in ("device", "device_announce", "blocking", "async", "block")}
+    res = {m: _run(m, blocks) for m in ("device", "device_announce", "blocking", "async", "block", "stream", "async_ctx", "stream_ctx")}
     again = _run("async", blocks)
-    assert res["device"] == res["device_announce"] == res["blocking"] == res["async"] == res["block"] == again
+    assert res["device"] == res["device_announce"] == res["blocking"] == res["async"] == res["block"] == res["stream"] == again
+    assert res["async_ctx"] == res["stream_ctx"] and res["async_ctx"][1:] == res["async"][1:]      # context records: same count, tables and PRNG positions
     digest, n_recs, tabs, st = res["async"]
     assert n_recs == len(BLOCKS) * READS * (L - pref)               # no duplicates in this stream: one record per coded suffix base
     assert st["siv_no_filled"] == tabs[0][0] and st["n_smers"] == tabs[1][0] and st["n_bmers"] == tabs[2][0]

@@ -291,6 +291,26 @@ def test_recovery_paths_of_the_enqueued_sync(var, mode):
     e.close()
 
 
+@pytest.mark.parametrize("name,mode", [("se_orig_gs1", "blocking"), ("se_orig_gs1", "async"), ("se_orig_gs100", "blocking")])
+def test_tables_double_between_segments(name, mode):
+    """CHT_kmer::restruct (ht_kmer.h:88-112, ht_kmer.cpp:50-75) in the middle of a run: with FQSK_F_TEST_CROWD the s-mer and b-mer tables
+    count as crowded at 1/64 of the usual load, so they double several times between the sync segments of a small fixture (dump,
+    2x buckets, re-insert); records, table contents and PRNG positions must not notice."""
+    g = H.load_golden(name)
+    pref, p, s, b = E.kmer_params(int(g["gs"]))
+    e = E.KmerEngine(p, s, b, pref, bmer_log2_buckets=1, smer_log2_buckets=1, flags=E.F_TEST_HOOKS | E.F_TEST_CROWD)      # (log2 buckets are raised to the smallest legal geometry)
+    if mode == "async":
+        recs, _ = H.run_async(e, g["fastq"])
+    else:
+        recs = H.run_se(e, g["fastq"])
+    want = g["recs"]
+    H.assert_recs_equal(recs, want[want["pos"] < 0xFFFFFFF0])
+    H.assert_dump_equal(e, g)
+    st = e.stats()
+    assert st["n_table_growths"] >= 4, st["n_table_growths"]
+    e.close()
+
+
 def test_async_path_matches_oracle_config2_parameters_deep_coverage():
     """BASELINE config-2 k-mer lengths (p17/s20/b24) at 20x coverage through the reference's schedule (100 sync segments), via
     fqsk_submit / fqsk_collect: side streams, early grouping, enqueued syncs, saturating counters, the avg_filling_factor gate --

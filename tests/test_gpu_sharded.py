@@ -17,13 +17,15 @@ def _n_gpus():
 
 # sync: "device" = fqsk_sync_device (both barriers and the p-mer statistics on the device, no collective library per sync);
 #       "host"   = the three-step form with the caller's all-reduce (NCCL) as the second barrier
-@pytest.mark.parametrize("name,world,sync", [("se_orig_gs1_t2", 2, "device"), ("pe_orig_gs1_t2", 2, "device"), ("se_orig_gs16_t3", 3, "device"), ("se_orig_gs1_t2", 2, "host")])
+#       "... grow" = smallest legal tables that double -- all shards of a table together -- several times during the run (FQSK_RESHARD)
+@pytest.mark.parametrize("name,world,sync", [("se_orig_gs1_t2", 2, "device"), ("pe_orig_gs1_t2", 2, "device"), ("se_orig_gs16_t3", 3, "device"), ("se_orig_gs1_t2", 2, "host"),
+                                             ("se_orig_gs1_t2", 2, "device grow"), ("pe_orig_gs1_t2", 2, "device grow"), ("se_orig_gs1_t2", 2, "host grow")])
 def test_sharded_engine_matches_reference_threads(name, world, sync):
     if _n_gpus() < world:
         pytest.skip(f"needs {world} GPUs")
     port = 29500 + (os.getpid() % 400)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), os.path.join(ROOT, "tests", "sharded_worker.py"), name, sync]
+           "--master-port", str(port), os.path.join(ROOT, "tests", "sharded_worker.py"), name, *sync.split()]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-3000:])
     assert r.stdout.count("bit-exact") == world, r.stdout[-2000:]

@@ -81,7 +81,10 @@ def _gloo_rank(rank, world, port, q):
         got = sharded.gather_descs(dist, bytes(d), world)
         ok = all(x.rank == r and x.inbox_cap == 1234 + r and x.ipc[5][63] == (17 * r + 15 + 63) & 0xFF for r, x in enumerate(got))
         tot = sharded.allreduce_stats(dist, 10 + rank, 100 * (rank + 1))
-        ok = ok and tot == (sum(10 + r for r in range(world)), sum(100 * (r + 1) for r in range(world)))
+        ok = ok and tot == (sum(10 + r for r in range(world)), sum(100 * (r + 1) for r in range(world)), 0)
+        # growth requests ride in the same all-reduce and come back as the OR over the ranks: rank 0 asks for the b-mer table, rank 1 for the pair table
+        tot = sharded.allreduce_stats(dist, 1, 1, 2 if rank == 0 else 4 if rank == 1 else 0)
+        ok = ok and tot == (world, world, 6)
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()
