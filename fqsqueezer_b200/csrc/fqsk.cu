@@ -1463,7 +1463,7 @@ int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
 	const uint32_t world = p->world_size ? p->world_size : 1;
 	if (world > FQSK_MAX_WORLD || p->rank >= world) return fail(h, FQSK_E_INVAL, "need rank < world_size <= %u", FQSK_MAX_WORLD);
 	if (p->n_workers != world) return fail(h, FQSK_E_INVAL, "n_workers must equal world_size: one reference worker thread (-t) per GPU");
-	if (world > 1 && p->mode != FQSK_MODE_SE_ORIGINAL && p->mode != FQSK_MODE_PE_ORIGINAL) return fail(h, FQSK_E_UNSUPPORTED, "sharded operation is implemented for original order only (SE and PE)");
+	if (world > 1 && (p->mode == FQSK_MODE_SE_SORTED || p->mode == FQSK_MODE_PE_SORTED) && p->pmer_len < 8) return fail(h, FQSK_E_UNSUPPORTED, "sharded operation in sorted order needs pmer_len >= 8 (a 16-field word of the p-mer array must lie inside one owner's run)");
 	if (!(p->pmer_len >= 5 && p->pmer_len < p->smer_len && p->smer_len < p->bmer_len && p->bmer_len <= 31)) return fail(h, FQSK_E_INVAL, "need 5 <= p < s < b <= 31");
 	if (p->pmer_len > 18) return fail(h, FQSK_E_INVAL, "pmer_len > 18 not supported");
 	if (p->test_hooks && !(p->flags & FQSK_F_TEST_HOOKS)) return fail(h, FQSK_E_INVAL, "test_hooks without FQSK_F_TEST_HOOKS");

@@ -528,8 +528,21 @@ __global__ void __launch_bounds__(256) k_sorted_dif(EngineDev E, SegDev S) { pdl
 	const uint32_t flag = cur_dir == prev_dir ? 4u : siv_test(E.siv, cur_al);
 	unsigned long long cnt = 0;
 	const uint64_t lo = prev_al + 1, hi = cur_al;      // fields [lo, hi)
-	if (flag < 4 && lo < hi) {
-		const uint32_t *w = E.siv.w;                   // sorted order runs on unsharded engines only
+	if (flag < 4 && lo < hi && E.siv.world > 1) {
+		// sharded p-mer array: consecutive runs of 2^top_shift fields belong to the ranks in turn (dna.cpp:845), a word (16 fields) never
+		// spans two runs (top_shift >= 4, checked at create): every word is read from its owner's shard (NVLink peer mapping), one per thread
+		const uint64_t w0 = lo >> 4, w1 = (hi - 1) >> 4;
+		for (uint64_t wd = w0 + t; wd <= w1; wd += 256) {
+			const uint32_t a = wd == w0 ? (uint32_t) (lo & 15) : 0u, b = wd == w1 ? (uint32_t) ((hi - 1) & 15) + 1u : 16u;      // fields [a, b) of this word
+			uint64_t idx = wd << 4;
+			const uint32_t *w = siv_shard(E.siv, idx);
+			const uint32_t x = __ldg(w + (idx >> 4)) ^ (flag * 0x55555555u);
+			uint32_t z = ~(x | (x >> 1)) & 0x55555555u;
+			z &= (b == 16 ? 0xFFFFFFFFu : ((1u << (2 * b)) - 1u)) & ~((1u << (2 * a)) - 1u);
+			cnt += (uint32_t) __popc(z);
+		}
+	} else if (flag < 4 && lo < hi) {
+		const uint32_t *w = E.siv.w;                   // one array
 		const uint64_t w0 = lo >> 4, w1 = (hi - 1) >> 4;      // first and last word touched
 		auto masked = [&](uint64_t wd) {               // fields of word wd inside [lo, hi) that equal flag
 			const uint32_t a = wd == w0 ? (uint32_t) (lo & 15) : 0u, b = wd == w1 ? (uint32_t) ((hi - 1) & 15) + 1u : 16u;      // fields [a, b) of this word

@@ -245,6 +245,10 @@ def main():
     # paired end in the reference's default order (-p with -om s): mate 1 through the sorted prefix, bins and sort by mate 1
     if not only or "pe_sorted_gs1" in only:
         make_case_pe("pe_sorted_gs1", G=5000, n_pairs=1500, L=80, gs=1, seed=73, order="s", n_frac=0.002)
+    # the reference's default order at -t 2 (sorted bins, every reads_block split between two workers): SE and PE
+    make_case("se_sorted_gs1_t2", G=5000, n_reads=2600, L=70, gs=1, seed=46, n_frac=0.002, dup_frac=0.01, extra=("-om", "s"), threads=2)
+    if not only or "pe_sorted_gs1_t2" in only:
+        make_case_pe("pe_sorted_gs1_t2", G=5000, n_pairs=1500, L=80, gs=1, seed=74, order="s", n_frac=0.002, threads=2)
 
 
 if __name__ == "__main__":

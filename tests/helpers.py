@@ -253,3 +253,50 @@ def golden_sorted_expect(gold):
     flags = sp["c"][:, 0].astype(np.uint32)
     difs = sp["c"][:, 1].astype(np.uint64) | (sp["c"][:, 2].astype(np.uint64) << np.uint64(32))
     return r[r["pos"] < 0xFFFFFFF0], flags, difs
+
+
+def sorted_blocks(slab, off, rsz, paired=False):
+    """(generation, first, last) of every reads_block of a sorted-order run: one temp file per 4-symbol bin (of mate 1 when paired; N -> T)
+    goes through the block loop, so blocks never span bins while the generation keeps counting (application.cpp:349-412, 415-506, 538-570)."""
+    lut = np.full(256, 3, np.int64)
+    lut[ord("A")], lut[ord("C")], lut[ord("G")], lut[ord("T")] = 0, 1, 2, 3
+    step = 2 if paired else 1
+    o1 = off[0::step].astype(np.int64)
+    first4 = np.stack([lut[slab[o1 + k]] for k in range(4)], axis=1)
+    bins = first4[:, 0] * 64 + first4[:, 1] * 16 + first4[:, 2] * 4 + first4[:, 3]
+    cuts = [0] + list(step * (np.flatnonzero(np.diff(bins)) + 1)) + [len(off)]
+    gen = 0
+    for a0, a1 in zip(cuts[:-1], cuts[1:]):
+        for f, l in S.split_blocks(rsz[a0:a1], paired=paired):
+            yield gen, f + a0, l + a0
+            gen += 1
+
+
+def split_sorted_markers(recs, paired):
+    """(records, flags, difs[, pair_info]) of an oracle / tap record stream of a sorted-order run."""
+    sp = recs[recs["pos"] == O.POS_SORTED]
+    flags = sp["c"][:, 0].astype(np.uint32)
+    difs = sp["c"][:, 1].astype(np.uint64) | (sp["c"][:, 2].astype(np.uint64) << np.uint64(32))
+    out = [recs[recs["pos"] < 0xFFFFFFF0], flags, difs]
+    if paired:
+        out.append(recs[recs["pos"] == POS_PAIR]["c"][:, :3].astype(np.uint32))
+    return out
+
+
+def run_sorted_workers(group, slab, n_workers, paired=False):
+    """The reference's default order at -t T (-s / -p with -om s): the blocks of run_sorted / run_pe_sorted, each partitioned among the
+    workers as in run_se_workers / run_pe_workers.  Returns per worker the raw record stream (markers included: split_sorted_markers)."""
+    off, ln, roff, rsz = S.parse_fastq(slab)
+    out = [[] for _ in range(n_workers)]
+    for gen, f, l in sorted_blocks(slab, off, rsz, paired):
+        segs = [S.worker_segments(f, l, gen, n_workers, w, paired=paired) for w in range(n_workers)]
+        assert len({len(x) for x in segs}) == 1, "workers disagree on the number of syncs"
+        for w in group.workers:
+            w.block_start()
+        for q in range(len(segs[0])):
+            for wi, w in enumerate(group.workers):
+                a, b = segs[wi][q]
+                recs, dup = w.segment(slab, off[a:b], ln[a:b], 3 if paired else 2)
+                out[wi].append(recs)
+            group.sync()
+    return [np.concatenate(x) if x else np.zeros(0, O.REC_DTYPE) for x in out]

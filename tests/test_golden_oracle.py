@@ -125,3 +125,25 @@ def test_oracle_group_matches_reference_tap_paired_end_two_threads():
         H.assert_recs_equal(per_worker[w][0], want[want["pos"] < 0xFFFFFFF0])
     H.assert_dump_equal(grp, g, pairs=True)
     grp.close()
+
+
+@pytest.mark.parametrize("name,paired", [("se_sorted_gs1_t2", False), ("pe_sorted_gs1_t2", True)])
+def test_oracle_group_matches_reference_tap_sorted_order_two_threads(name, paired):
+    """The reference's default order at -t 2 (-s -om s / -p -om s): sorted bins, every reads_block split between two workers; per worker the
+    records, the (flag, dif) of compress_prefix_sorted and the pair decisions, and the shared tables after all syncs."""
+    import numpy as np
+    g = H.load_golden(name)
+    T = int(g["threads"])
+    pref, p, s, b = O.kmer_params(int(g["gs"]))
+    grp = O.OracleGroup(p, s, b, pref, T, mode=3 if paired else 1)
+    per_worker = H.run_sorted_workers(grp, g["fastq"], T, paired=paired)
+    n_dif = 0
+    for w in range(T):
+        got, want = H.split_sorted_markers(per_worker[w], paired), H.split_sorted_markers(g["recs_t%d" % w], paired)
+        for x, y in zip(got[1:], want[1:]):
+            assert np.array_equal(x, y), w
+        H.assert_recs_equal(got[0], want[0])
+        n_dif += int((want[2] > 0).sum())
+    assert n_dif > 100
+    H.assert_dump_equal(grp, g, pairs=paired)
+    grp.close()

@@ -19,7 +19,8 @@ def _n_gpus():
 #       "host"   = the three-step form with the caller's all-reduce (NCCL) as the second barrier
 #       "... grow" = smallest legal tables that double -- all shards of a table together -- several times during the run (FQSK_RESHARD)
 @pytest.mark.parametrize("name,world,sync", [("se_orig_gs1_t2", 2, "device"), ("pe_orig_gs1_t2", 2, "device"), ("se_orig_gs16_t3", 3, "device"), ("se_orig_gs1_t2", 2, "host"),
-                                             ("se_orig_gs1_t2", 2, "device grow"), ("pe_orig_gs1_t2", 2, "device grow"), ("se_orig_gs1_t2", 2, "host grow")])
+                                             ("se_orig_gs1_t2", 2, "device grow"), ("pe_orig_gs1_t2", 2, "device grow"), ("se_orig_gs1_t2", 2, "host grow"),
+                                             ("se_sorted_gs1_t2", 2, "device"), ("pe_sorted_gs1_t2", 2, "device")])      # the reference's default order (-om s) at -t 2
 def test_sharded_engine_matches_reference_threads(name, world, sync):
     if _n_gpus() < world:
         pytest.skip(f"needs {world} GPUs")
