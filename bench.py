@@ -116,9 +116,9 @@ class ClockSampler(threading.Thread):
     """SM clock and throttle reasons DURING the timed region.  NVML in-process (nvidia_ml_py): a query costs microseconds and does not touch
     the CUDA context; spawning nvidia-smi five times a second next to a job that launches 60 000 kernels a second did (fork + NVML init per sample)."""
 
-    def __init__(self, index):
+    def __init__(self, index, hz=2.0):
         super().__init__(daemon=True)
-        self.index, self.stop_flag, self.rows = index, False, []
+        self.index, self.stop_flag, self.rows, self.hz, self.mx = index, False, [], hz, None
         self.nvml = None
         try:
             import pynvml
@@ -146,7 +146,9 @@ class ClockSampler(threading.Thread):
     def _sample_nvml(self):
         n = self.nvml
         sm = n.nvmlDeviceGetClockInfo(self.dev, n.NVML_CLOCK_SM)
-        mx = n.nvmlDeviceGetMaxClockInfo(self.dev, n.NVML_CLOCK_SM)
+        if self.mx is None:
+            self.mx = n.nvmlDeviceGetMaxClockInfo(self.dev, n.NVML_CLOCK_SM)
+        mx = self.mx
         try:
             r = n.nvmlDeviceGetCurrentClocksEventReasons(self.dev)
         except Exception:
@@ -168,7 +170,7 @@ class ClockSampler(threading.Thread):
                         self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.1 if self.nvml is not None else 0.5)
+            time.sleep(1.0 / self.hz if self.nvml is not None else 0.5)
 
     def summary(self):
         if not self.rows:
@@ -363,6 +365,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-per-segment", action="store_true", help="e2e leg: one fqsk_submit_ctx / fqsk_collect call per sync segment from Python instead of one fqsk_block_stream call per reads_block")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--clock-hz", type=float, default=2.0, help="NVML samples per second of SM clock + throttle reasons during the timed region (0: one sample before and one after it)")
+    ap.add_argument("--short-warmup", action="store_true", help="warm up with the first W steps only (default: W steps, then the rest of the job, all on a throw-away engine)")
     ap.add_argument("--replicas", action="store_true", help="N > 1: N independent engines (weak scaling) instead of ONE job over hash-sharded tables")
     ap.add_argument("--shard", action="store_true", help="(default at N > 1; kept for compatibility)")
     ap.add_argument("--no-phase-events", action="store_true", help="skip the second pass that brackets the internal phases with CUDA events")
@@ -406,7 +410,10 @@ def main():
     NB = len(blocks)
     K = args.steps
     step_of_block = [min(K - 1, g * K // NB) for g in range(NB)] if K <= NB else list(range(NB))
-    warm_blocks = [g for g in range(NB) if step_of_block[g] < args.warmup]
+    # warm-up: W steps of the job on a throw-away engine -- and, unless --short-warmup, the rest of the job behind them: a fresh box needs
+    # seconds, not steps, until its host side runs at speed (the first bench run on a fresh box measured 3x the launch work of the second,
+    # profiles/r02_bench_first_run_on_a_fresh_box.json), and the later blocks use launch paths (51 000-read segments) the first W steps never touch
+    warm_blocks = [g for g in range(NB) if step_of_block[g] < args.warmup or not args.short_warmup]
     n_early = min(EARLY_BLOCKS, NB)
 
     # this rank's share of every block: everything (1 GPU / replicas) or worker `rank`'s slice (sharded: PartitionForWorkers)
@@ -468,8 +475,11 @@ def main():
     scratch.close()
     del scratch
     st0 = eng.stats()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler = ClockSampler(local_rank, hz=args.clock_hz or 2.0)
+    if args.clock_hz > 0:
+        sampler.start()
+    elif sampler.nvml is not None:
+        sampler.rows.append(sampler._sample_nvml())
     barrier()
     t_wall = time.time()
     prev_prof, t_prev = eng.profile(), time.time()
@@ -503,6 +513,8 @@ def main():
     barrier()
     wall_ms = (time.time() - t_wall) * 1e3
     sampler.stop_flag = True
+    if args.clock_hz <= 0 and sampler.nvml is not None:
+        sampler.rows.append(sampler._sample_nvml())
     st1 = eng.stats()
     dev_ms = regime_ms["early"] + regime_ms["steady"]
     ms = torch.tensor([dev_ms, regime_ms["early"], regime_ms["steady"]], dtype=torch.float64, device=dev)
@@ -664,7 +676,7 @@ def main():
                     "host": {"api_ms": round((st1["api_ns"] - st0["api_ns"]) / 1e6, 1), "waiting_for_the_gpu_ms": round((st1["look_wait_ns"] - st0["look_wait_ns"]) / 1e6, 1),
                              "looks": int(st1["n_looks"] - st0["n_looks"]),
                              "note": "time of this rank inside the C-ABI calls and the part of it spent waiting for the device: the rest is launch work of the host; when the waiting share is small the early regime (thousands of ~200 us sync segments) is bound by the host's launch rate, not by the GPU"},
-                    "warmup_blocks": len(warm_blocks), "note": "table construction (fqsk_create) lies outside the timed region, as the reference's does in its arm"},
+                    "warmup_blocks": len(warm_blocks), "warmup_note": "untimed, on a throw-away engine with its own tables: the W warm-up steps" + ("" if args.short_warmup else " and the rest of the job behind them"), "note": "table construction (fqsk_create) lies outside the timed region, as the reference's does in its arm"},
             "regimes": regimes, "roofline": roof, "parity_check": parity, "cpu_baseline": cpu, "e2e": e2e, "compress_e2e": compress, "gpu_launches": int(launches),
             "clocks": sampler.summary(), "wall_ms_per_step": wall_ms / K}
     print(json.dumps(line))

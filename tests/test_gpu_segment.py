@@ -291,7 +291,7 @@ def test_recovery_paths_of_the_enqueued_sync(var, mode):
     e.close()
 
 
-@pytest.mark.parametrize("name,mode", [("se_orig_gs1", "blocking"), ("se_orig_gs1", "async"), ("se_orig_gs100", "blocking")])
+@pytest.mark.parametrize("name,mode", [("se_orig_gs1", "blocking"), ("se_orig_gs1", "async"), ("se_orig_repeats_gs1", "blocking")])
 def test_tables_double_between_segments(name, mode):
     """CHT_kmer::restruct (ht_kmer.h:88-112, ht_kmer.cpp:50-75) in the middle of a run: with FQSK_F_TEST_CROWD the s-mer and b-mer tables
     count as crowded at 1/64 of the usual load, so they double several times between the sync segments of a small fixture (dump,
