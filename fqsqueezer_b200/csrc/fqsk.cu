@@ -2387,6 +2387,36 @@ int fqsk_shard_attach(fqsk_handle *h, const fqsk_shard_desc *peer) {
 	return FQSK_OK;
 }
 
+// fqsk_shard_attach for two handles of ONE process (a host with one worker thread per GPU -- host/fqsk_live.h at -t N): CUDA IPC handles
+// cannot be opened by the process that exported them, and need not be -- with peer access enabled the peer's allocations are directly
+// addressable (unified virtual addressing).  Same effect and same preconditions as fqsk_shard_attach; after FQSK_RESHARD it is called
+// again once BOTH handles have passed their fqsk_shard_export.
+int fqsk_shard_attach_local(fqsk_handle *h, fqsk_handle *peer) {
+	if (!h || !peer) return FQSK_E_INVAL;
+	CK(cudaSetDevice(h->P.device));
+	if (h->world <= 1 || peer->world != h->world || peer->rank >= h->world) return fail(h, FQSK_E_INVAL, "fqsk_shard_attach_local: the two handles do not belong to one group");
+	if (peer == h || peer->rank == h->rank) return peer == h ? FQSK_OK : fail(h, FQSK_E_INVAL, "fqsk_shard_attach_local: two handles with rank %u", h->rank);
+	if (peer->grow_pending || h->grow_pending) return fail(h, FQSK_E_INVAL, "fqsk_shard_attach_local: fqsk_shard_export (the doubling) comes first on both handles");
+	if (peer->tb.d.B != h->tb.d.B || peer->tb.d.stash_log2 != h->tb.d.stash_log2 || peer->ts.d.B != h->ts.d.B || peer->ts.d.stash_log2 != h->ts.d.stash_log2 ||
+	    peer->siv.key_bits != h->siv.key_bits || peer->inbox_cap != h->inbox_cap || !peer->pair.keys != !h->pair.keys || (h->pair.keys && peer->pair.mask != h->pair.mask))
+		return fail(h, FQSK_E_INVAL, "rank %u was created with a different table geometry", peer->rank);
+	if (peer->P.device != h->P.device) {
+		int can = 0;
+		CK(cudaDeviceCanAccessPeer(&can, h->P.device, peer->P.device));
+		if (!can) return fail(h, FQSK_E_UNSUPPORTED, "device %d cannot access device %d (no NVLink / PCIe peer path)", h->P.device, peer->P.device);
+		cudaError_t e = cudaDeviceEnablePeerAccess(peer->P.device, 0);
+		if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError(); else CK(e);
+	}
+	const uint32_t r = peer->rank;
+	h->tb.d.peer_main[r] = peer->tb.d.main; h->tb.d.peer_stash[r] = peer->tb.d.stash;
+	h->ts.d.peer_main[r] = peer->ts.d.main; h->ts.d.peer_stash[r] = peer->ts.d.stash;
+	h->siv.peer_w[r] = peer->siv.w;
+	h->peer_inbox[r] = peer->inbox;
+	if (h->pair.keys) { h->pair.peer_keys[r] = peer->pair.keys; h->pair.peer_vcs[r] = peer->pair.vcs; }
+	h->attached |= 1u << r;
+	return FQSK_OK;
+}
+
 int fqsk_sync_route(fqsk_handle *h) {
 	if (!h) return FQSK_E_INVAL;
 	CK(cudaSetDevice(h->P.device));

@@ -18,7 +18,7 @@ host/_bin/ is git-ignored and travels to the GPU box like our own .so files).  T
   everything else (context model, range coders, id / quality / meta streams, container, decompressor) is untouched.
 
 host/fqsk_live.h (ours) holds the binding itself (dlopen of $FQSK_LIB, descriptors, record cursor).
-Scope: -t 1; -s and -p, each with -om o and -om s.  No-op (exit 0) where /root/reference does not exist (the GPU box uses the prebuilt binary).
+Scope: -s and -p, each with -om o and -om s, at -t 1 (one engine) and -t N <= 8 (one sharded engine = one GPU per worker thread).  No-op (exit 0) where /root/reference does not exist (the GPU box uses the prebuilt binary).
 """
 import os
 import shutil
@@ -101,7 +101,9 @@ def patch_worker_loop(f, first_read_anchor, paired, where):
     # the helpers are done before the coders are flushed (application.cpp:663-664 / 1192-1193)
     f = replace_once(f, "\t\t\t\tfor(auto &x : c_rc_enc)\n\t\t\t\t\tx.End();\n", "\t\t\t\tfqsk_thr_ids.join();\n\t\t\t\tfqsk_thr_qual.join();\n\t\t\t\tfor(auto &x : c_rc_enc)\n\t\t\t\t\tx.End();\n", where)
     # the workers have joined (application.cpp:762 / 1310): engine statistics, release
-    f = replace_once(f, "\tv_thr_compress.clear();\n", "\tv_thr_compress.clear();\n\tCFqskLive::get().finish();\n", where)
+    f = replace_once(f, "\tv_thr_compress.clear();\n", "\tv_thr_compress.clear();\n\tCFqskLive::finish_all();\n", where)
+    # application.cpp:590-592 / 1118-1120: the worker thread takes its engine (one CFqskLive object per worker; -t N = N engines = N GPUs)
+    f = replace_once(f, "\t\t\tCDNACompressor &dna_comp = v_dna_comp[thread_id];\n", "\t\t\tCDNACompressor &dna_comp = v_dna_comp[thread_id];\n\t\t\tCFqskLive::bind_worker((uint32_t) thread_id);\n", where)
     return f
 
 
@@ -112,7 +114,7 @@ def patch_application(path):
     s = replace_once(s, "\tsiv_pmer = new TSmallIntVector<SIV_FIELD_SIZE>(2 * params.pmer_len);\n"
                         "\tht_smer = new CHT_kmer<uint32_t>(params.smer_len, SMER_COUNTER_BITS, params.ht_max_filling_factor);\n"
                         "\tht_bmer = new CHT_kmer<uint32_t>(params.bmer_len, BMER_COUNTER_BITS, params.ht_max_filling_factor);\n",
-                     "\tCFqskLive::get().create(params.pmer_len, params.smer_len, params.bmer_len, params.prefix_len, params.genome_size,\n"
+                     "\tCFqskLive::create(params.pmer_len, params.smer_len, params.bmer_len, params.prefix_len, params.genome_size,\n"
                      "\t\t(uint32_t) params.dna_mode, (uint32_t) params.no_threads, params.duplicates_check);\n"
                      "\tsiv_pmer = new TSmallIntVector<SIV_FIELD_SIZE>(8);\n"
                      "\tht_smer = new CHT_kmer<uint32_t>(12, SMER_COUNTER_BITS, params.ht_max_filling_factor);\n"

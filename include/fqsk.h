@@ -242,6 +242,11 @@ typedef struct fqsk_shard_desc {
 } fqsk_shard_desc;
 int fqsk_shard_export(fqsk_handle *h, fqsk_shard_desc *out);
 int fqsk_shard_attach(fqsk_handle *h, const fqsk_shard_desc *peer);
+/* fqsk_shard_attach for two handles that live in ONE process (one worker thread per GPU, as the reference's -t N worker threads of
+ * application.cpp:575-671 do): no descriptor, no IPC -- peer access is enabled between the two devices and the peer's shards are read
+ * directly.  Call for every ordered pair of handles after all of them are created (and again, after a barrier and every handle's
+ * fqsk_shard_export, when a sync returned FQSK_RESHARD). */
+int fqsk_shard_attach_local(fqsk_handle *h, fqsk_handle *peer);
 /* Routes this worker's pending rows (p, s, b) to their owners: rows [rank][*] of the exchange matrices, written into the owners'
  * inboxes.  Call on every rank, then synchronise all ranks (barrier). */
 int fqsk_sync_route(fqsk_handle *h);

@@ -5,7 +5,9 @@
 // library.  Only the entry points host/fqsk_live.h binds are provided.
 #include <cstdint>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "fqsk.h"
@@ -17,10 +19,22 @@ void fqso_block_start(void *h);
 uint64_t fqso_segment(void *h, const uint8_t *slab, const uint64_t *off, const uint32_t *len, uint32_t n, uint32_t kind, fqsk_base_rec *recs, uint64_t cap, uint8_t *dup);
 void fqso_sync(void *h);
 void fqso_stats(void *h, uint64_t *o);
+void *fqso_create_worker(void *first);
+void fqso_sync_group(void **hs, uint32_t T);
 }
 
+// -t N (host/fqsk_live.h: one engine per worker thread): the workers of one group share the oracle's tables (fqso_create_worker) and meet
+// in fqsk_sync_device, where the last one to arrive runs InsertKmersToHT + ClearKmersToHT of all of them (fqso_sync_group)
+struct MockGroup {
+	std::mutex mu; std::condition_variable cv;
+	uint32_t world = 1, arrived = 0, alive = 0; uint64_t generation = 0; void *owner_o = nullptr;
+	fqsk_handle *member[8] = {nullptr};
+};
+static std::mutex g_seg_mu;      // the oracle is sequential code: segments of different workers are served one at a time
+
 struct fqsk_handle {
-	void *o; uint32_t mode = 0; uint64_t n_segments = 0, n_syncs = 0;
+	void *o = nullptr; uint32_t mode = 0; uint64_t n_segments = 0, n_syncs = 0;
+	uint32_t world = 1, rank = 0; MockGroup *grp = nullptr; fqsk_params P{};
 	std::vector<uint32_t> s_flag, pair; std::vector<uint64_t> s_dif;      // the segment fqsk_sorted_prefix / fqsk_pair_info describe
 	struct Ticket { uint64_t id = 0, n_recs = 0; std::vector<uint32_t> s_flag, pair; std::vector<uint64_t> s_dif; } tk[2];
 	uint64_t next_ticket = 1;
@@ -29,16 +43,54 @@ struct fqsk_handle {
 extern "C" {
 
 int fqsk_create(const fqsk_params *p, fqsk_handle **out) {
-	if (!p || !out || p->abi_version != FQSK_ABI_VERSION || p->mode > FQSK_MODE_PE_SORTED || p->n_workers != 1) return FQSK_E_INVAL;
+	const uint32_t world = p && p->world_size ? p->world_size : 1;
+	if (!p || !out || p->abi_version != FQSK_ABI_VERSION || p->mode > FQSK_MODE_PE_SORTED || p->n_workers != world || world > 8 || p->rank >= world) return FQSK_E_INVAL;
 	fqsk_handle *h = new fqsk_handle();
-	h->mode = p->mode;
-	h->o = fqso_create(p->pmer_len, p->smer_len, p->bmer_len, p->prefix_len, p->mode);   // dna_mode_t = FQSK_MODE_*
+	h->mode = p->mode; h->world = world; h->rank = p->rank; h->P = *p;
+	if (p->rank == 0) {      // worker 0 owns the shared tables; the others join it in fqsk_shard_attach_local
+		h->o = fqso_create(p->pmer_len, p->smer_len, p->bmer_len, p->prefix_len, p->mode);   // dna_mode_t = FQSK_MODE_*
+		if (world > 1) { h->grp = new MockGroup(); h->grp->world = world; h->grp->member[0] = h; h->grp->alive = 1; }
+	}
 	*out = h;
 	return FQSK_OK;
 }
-void fqsk_destroy(fqsk_handle *h) { if (h) { fqso_destroy(h->o); delete h; } }
+// worker 0 owns the oracle's shared tables and must be released last; host/fqsk_live.h destroys in rank order, so its release is deferred
+void fqsk_destroy(fqsk_handle *h) {
+	if (!h) return;
+	MockGroup *g = h->grp;
+	if (!g) { if (h->o) fqso_destroy(h->o); delete h; return; }
+	if (h->rank == 0) g->owner_o = h->o; else if (h->o) fqso_destroy(h->o);
+	g->member[h->rank] = nullptr;
+	if (--g->alive == 0) { if (g->owner_o) fqso_destroy(g->owner_o); delete g; }
+	delete h;
+}
+int fqsk_shard_attach_local(fqsk_handle *h, fqsk_handle *peer) {
+	if (!h || !peer || h->world <= 1 || peer->world != h->world) return FQSK_E_INVAL;
+	if (h->rank != 0 && peer->rank == 0 && !h->o) {
+		h->o = fqso_create_worker(peer->o);
+		h->grp = peer->grp;
+		h->grp->member[h->rank] = h; ++h->grp->alive;
+	}
+	return FQSK_OK;
+}
+int fqsk_shard_export(fqsk_handle *h, fqsk_shard_desc *out) { if (!h || !out) return FQSK_E_INVAL; memset(out, 0, sizeof *out); out->rank = h->rank; out->world_size = h->world; return FQSK_OK; }
+int fqsk_sync_device(fqsk_handle *h) {
+	if (!h || h->world <= 1 || !h->grp) return FQSK_E_INVAL;
+	MockGroup *g = h->grp;
+	std::unique_lock<std::mutex> lk(g->mu);
+	const uint64_t gen = g->generation;
+	++h->n_syncs;
+	if (++g->arrived == g->world) {
+		void *hs[8];
+		for (uint32_t i = 0; i < g->world; ++i) { if (!g->member[i] || !g->member[i]->o) return FQSK_E_INVAL; hs[i] = g->member[i]->o; }
+		fqso_sync_group(hs, g->world);
+		g->arrived = 0; ++g->generation;
+		g->cv.notify_all();
+	} else g->cv.wait(lk, [&] { return g->generation != gen; });
+	return FQSK_OK;
+}
 const char *fqsk_last_error(fqsk_handle *) { return "mock"; }
-int fqsk_block_start(fqsk_handle *h) { fqso_block_start(h->o); return FQSK_OK; }
+int fqsk_block_start(fqsk_handle *h) { if (!h->o) return FQSK_E_INVAL; fqso_block_start(h->o); return FQSK_OK; }
 
 int fqsk_segment(fqsk_handle *h, const uint8_t *slab, uint64_t, const fqsk_read_desc *reads, uint32_t n_reads, fqsk_base_rec *recs, uint64_t rec_cap, uint64_t *n_recs, uint8_t *dup, uint64_t *) {
 	std::vector<uint64_t> off(n_reads + 1);
@@ -48,7 +100,9 @@ int fqsk_segment(fqsk_handle *h, const uint8_t *slab, uint64_t, const fqsk_read_
 	std::vector<fqsk_base_rec> tmp(total + 3 * (uint64_t) n_reads + 16);     // the oracle also emits per-read / duplicate markers (pos >= 0xFFFFFFF0)
 	std::vector<uint8_t> d(n_reads + 1);
 	const uint32_t kind = h->mode == FQSK_MODE_SE_SORTED ? 2 : (h->mode == FQSK_MODE_PE_ORIGINAL || h->mode == FQSK_MODE_PE_SORTED) ? 3 : 0;     // oracle: 0 CompressDirect, 2 CompressSorted, 3 CompressPE
-	uint64_t m = fqso_segment(h->o, slab, off.data(), len.data(), n_reads, kind, tmp.data(), tmp.size(), d.data());
+	if (!h->o) return FQSK_E_INVAL;
+	uint64_t m;
+	{ std::lock_guard<std::mutex> lk(g_seg_mu); m = fqso_segment(h->o, slab, off.data(), len.data(), n_reads, kind, tmp.data(), tmp.size(), d.data()); }
 	if (m > tmp.size()) return FQSK_E_CAPACITY;
 	h->s_flag.assign(n_reads + 1, 0); h->s_dif.assign(n_reads + 1, 0); h->pair.assign(3 * (n_reads / 2) + 3, 0);
 	uint64_t k = 0, rd = 0, pr = 0;       // rd: reads started so far (one 0xFFFFFFFF marker each; a with-minimizer mate 2 emits kind 1), pr: pairs decided

@@ -54,13 +54,14 @@ def _build_mock(tmp):
     return so
 
 
-def _check(lib, gs, tmp, fq, decode=True, layout=("-s", "-om", "o")):
-    """fq: one FASTQ path (single-end) or a pair of paths (paired-end).  layout: the reference's read layout / order options."""
+def _check(lib, gs, tmp, fq, decode=True, layout=("-s", "-om", "o"), threads=1, env=None):
+    """fq: one FASTQ path (single-end) or a pair of paths (paired-end).  layout: the reference's read layout / order options.
+    threads: the reference's -t (the live host runs one engine per worker thread; the comparison is with `fqs-1.1 -t threads`)."""
     files = [fq] if isinstance(fq, str) else list(fq)
-    base = ["e", *layout, "-qm", "o", "-im", "o", "-t", "1", "-gs", str(gs), "-v", "0"]
+    base = ["e", *layout, "-qm", "o", "-im", "o", "-t", str(threads), "-gs", str(gs), "-v", "0"]
     plain, ours = os.path.join(tmp, "plain.fqs"), os.path.join(tmp, "ours.fqs")
     subprocess.run([O.REF_BIN, *base, "-out", plain, *files], check=True, cwd=tmp, stdout=subprocess.DEVNULL)
-    r = subprocess.run([LIVE_BIN, *base, "-out", ours, *files], cwd=tmp, env=dict(os.environ, FQSK_LIB=lib, FQSK_VERBOSE="1"), capture_output=True, text=True)
+    r = subprocess.run([LIVE_BIN, *base, "-out", ours, *files], cwd=tmp, env=dict(os.environ, FQSK_LIB=lib, FQSK_VERBOSE="1", **(env or {})), capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-600:]
     a, b = open(plain, "rb").read(), open(ours, "rb").read()
     assert len(a) > 1000
@@ -241,8 +242,8 @@ def test_live_host_fails_loudly_without_engine():
         r = subprocess.run([LIVE_BIN, "e", "-s", "-om", "o", "-t", "1", "-gs", "1", "-v", "0", "-out", os.path.join(tmp, "x.fqs"), fq], cwd=tmp,
                            env=dict(os.environ, FQSK_LIB=os.path.join(tmp, "missing.so")), capture_output=True, text=True)
         assert r.returncode == 3 and "no CPU fallback" in r.stderr.replace("There is no", "no")
-        # modes the live host does not cover stop the same way (never silently served by the CPU classes)
-        r = subprocess.run([LIVE_BIN, "e", "-s", "-om", "o", "-t", "2", "-gs", "1", "-v", "0", "-out", os.path.join(tmp, "x.fqs"), fq], cwd=tmp,
+        # modes the live host does not cover (more worker threads than the 8 GPUs of a box) stop the same way (never silently served by the CPU classes)
+        r = subprocess.run([LIVE_BIN, "e", "-s", "-om", "o", "-t", "9", "-gs", "1", "-v", "0", "-out", os.path.join(tmp, "x.fqs"), fq], cwd=tmp,
                            env=dict(os.environ, FQSK_LIB=_build_mock(tmp)), capture_output=True, text=True)
         assert r.returncode == 3 and "no CPU fallback" in r.stderr
 
@@ -274,3 +275,51 @@ def test_live_host_on_gpu(case):
         log = _check(REAL_LIB, case[0], tmp, fq, decode=case is not BIG)
         assert "kernel launches" in log and " 0 kernel launches" not in log, log
         assert "16-byte context records built on the device" in log, log
+
+
+# ---- -t N: one engine per worker thread (host/fqsk_live.h), tables hash-sharded over the engines; the .fqs must equal `fqs-1.1 -t N` ----
+# (layout, gs, genome, reads or pairs, read length, seed, threads)
+WORKERS = [(("-s", "-om", "o"), 1, 6000, 4000, 100, 131, 2), (("-s", "-om", "s"), 1, 5000, 2500, 70, 145, 2), (("-p", "-om", "o"), 1, 5000, 1200, 80, 171, 2),
+           (("-p", "-om", "s"), 1, 5000, 1500, 80, 173, 2), (("-s", "-om", "o"), 16, 30000, 5000, 120, 132, 3)]
+
+
+def _run_workers(lib, case, env=None):
+    layout, gs, G, n, L, seed, T = case
+    with tempfile.TemporaryDirectory() as tmp:
+        fq = _fastq_pe(tmp, gs, G, n, L, seed) if layout[0] == "-p" else _fastq(tmp, gs, G, n, L, seed, 0.002, 0.01)
+        return _check(lib(tmp), gs, tmp, fq, layout=layout, threads=T, env=env)
+
+
+@needs_bins
+@pytest.mark.parametrize("case", WORKERS)
+def test_live_host_worker_threads_with_oracle_records(case):
+    """The worker loop at -t N over the C-ABI (application.cpp:575-671 / 1105-1193): every worker thread binds its own engine, codes its slice of
+    every reads_block from that engine's records and meets the others in the sync.  CPU leg: the mock serves N oracle workers on shared
+    tables (the reference's -t N semantics)."""
+    log = _run_workers(_build_mock, case)
+    assert log.count("segments") == case[-1], log
+
+
+def _n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count() if torch.cuda.is_available() else 0
+    except Exception:
+        return 0
+
+
+@needs_bins
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", WORKERS[:4])
+@pytest.mark.parametrize("grow", [False, True])
+def test_live_host_worker_threads_on_gpus(case, grow):
+    """-t 2 on two B200s: one sharded engine per worker thread in ONE process (fqsk_shard_attach_local: peer access instead of IPC),
+    fqsk_segment + fqsk_sync_device per sync segment; .fqs byte-identical to `fqs-1.1 -t 2`.  grow: smallest tables, crowded at 1/64 of the
+    usual load -- the shards double together several times (FQSK_RESHARD handled by the worker threads)."""
+    if _n_gpus() < case[-1]:
+        pytest.skip(f"needs {case[-1]} GPUs")
+    env = dict(FQSK_LOG2_BUCKETS="1", FQSK_PAIR_LOG2_SLOTS="10", FQSK_FLAGS=str(4 | 32)) if grow else None
+    log = _run_workers(lambda tmp: REAL_LIB, case, env=env)
+    assert "kernel launches" in log and " 0 kernel launches" not in log, log
+    if grow:
+        assert " 0 coordinated table doublings" not in log, log
