@@ -575,6 +575,8 @@ int table_grow_if_needed(fqsk_handle *h, Table &t) {      // unsharded engines; 
 	unsigned long long items[2];
 	CK(cudaMemcpyAsync(items, t.d.n_items, 16, cudaMemcpyDeviceToHost, h->st));
 	CK(cudaStreamSynchronize(h->st));
+	if (h->world > 1 && table_crowded(h, t, items[0], items[1]))      // (reached through the table-level mirrors only: fqsk_ht_insert)
+		return fail(h, FQSK_E_CAPACITY, "a table shard is more than half full: shards double together, at a sync (FQSK_RESHARD), not inside a table-level call");
 	while (table_crowded(h, t, items[0], items[1]) && table_can_double(t)) {
 		CKR(table_double(h, t));
 		CK(cudaMemcpyAsync(items, t.d.n_items, 16, cudaMemcpyDeviceToHost, h->st));
