@@ -302,6 +302,14 @@ def test_live_host_worker_threads_with_oracle_records(case):
     assert log.count("segments") == case[-1], log
 
 
+@needs_bins
+def test_live_host_worker_threads_multi_block_with_oracle_records():
+    """-t 2 over several reads_blocks: PartitionForWorkers per block (reads_block.h:197-214), the sync count of a block falling with its
+    generation and with the worker's share (application.h:85-92), end-of-block syncs of both workers."""
+    log = _run_workers(_build_mock, (("-s", "-om", "o"), 100, 400000, 60000, 150, 133, 2))
+    assert log.count("segments") == 2, log
+
+
 def _n_gpus():
     try:      # (no torch import: this file drives compiled binaries only)
         return len([x for x in subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=30).stdout.splitlines() if x.startswith("GPU ")])
