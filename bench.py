@@ -617,6 +617,57 @@ def main():
         eng2.close()
         del slabs
 
+    # ---------------- e2e of the sharded job: host buffers through the blocking pair, per rank ----------------
+    if not args.no_e2e and sharded:
+        def sharded_e2e():
+            """Every rank codes its slice of every reads_block from HOST buffers: fqsk_segment (H2D of the reads, the segment, D2H of the
+            28-byte count records into page-locked memory) + the device-driven sync, per sync segment -- the calls host/fqsk_live.h makes at
+            -t N (fqsk_submit is not available on a sharded engine, so nothing overlaps the copies).  Wall clock, max over the ranks."""
+            eng2 = make_engine(e2e=True)
+            mine = []
+            for g in range(NB):
+                f, _ = blocks[g]
+                lo, hi = sched[g][0][0], sched[g][-1][1]
+                mine.append(codes_to_slab(reads.codes(f + lo, f + hi)) + (lo,))
+
+            def run(g, e):
+                slab, off, ln, lo = mine[g]
+                e.block_start()
+                nb = 0
+                for a, bb in sched[g]:
+                    recs, dup = e.segment(slab, off[a - lo:bb - lo], ln[a - lo:bb - lo], pinned=True)
+                    nb += recs.nbytes + dup.nbytes
+                    e.sync()
+                return nb
+
+            scratch = make_engine(e2e=True)
+            for g in range(NB):
+                if step_of_block[g] < args.warmup:
+                    run(g, scratch)
+            scratch.close()
+            barrier()
+            t0 = time.time()
+            d2h = 0
+            for g in range(NB):
+                d2h += run(g, eng2)
+            barrier()
+            secs = time.time() - t0
+            st_e2e = eng2.stats()
+            eng2.close()
+            t = torch.tensor([secs], dtype=torch.float64, device=dev)
+            nbt = torch.tensor([d2h], dtype=torch.int64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(nbt)
+            return {"value": total_bases / float(t.item()), "unit": UNIT,
+                    "h2d_bytes_per_step": (JOB_READS if not args.max_blocks else blocks[-1][1]) * (L + 12) // K, "d2h_bytes_per_step": int(nbt.item()) // K,
+                    "host": {"api_ms": round(st_e2e["api_ns"] / 1e6, 1), "waiting_for_the_gpu_ms": round(st_e2e["look_wait_ns"] / 1e6, 1)},
+                    "call": "fqsk_segment + fqsk_sync_device per sync segment on every rank (blocking)",
+                    "note": "ONE job over the ranks with host slabs: per sync segment H2D of the rank's reads, the segment, D2H of one 28-byte count record per coded base into page-locked memory, then the device-driven sync; h2d / d2h bytes are summed over the ranks; wall clock incl. ctypes/numpy host code, max over the ranks"}
+        try:
+            e2e = sharded_e2e()
+        except Exception as ex:      # the device-timed line above stands on its own
+            e2e = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
